@@ -1,0 +1,76 @@
+"""ctypes binding of the C ABI in include/b200av1.h.
+
+The product library is dav1d_b200/libb200av1.so (CUDA, sm_100a). There is no CPU
+fallback: if it is missing it is built with nvcc, and if it cannot be built or loaded the
+import fails loudly. (tests/emu builds a *test-only* host-emulated copy of the same ABI and
+binds it through B200Lib(path) explicitly; the package itself never does.)
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200av1.so")
+
+
+class ItxBlock(C.Structure):
+    """struct B200ItxBlock (include/b200av1.h)"""
+    _fields_ = [("dst_off", C.c_uint32), ("coef_off", C.c_uint32), ("eob", C.c_int16),
+                ("txtp", C.c_uint8), ("plane", C.c_uint8)]
+
+
+ITXFM_FN_8 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int)
+ITXFM_FN_16 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int)
+
+_SIGS = {
+    "b200_version": (C.c_int, []),
+    "b200_last_error": (C.c_char_p, []),
+    "b200_launch_count": (C.c_uint64, []),
+    "b200_itx_dsp_init_8bpc": (None, [C.c_void_p, C.c_int]),
+    "b200_itx_dsp_init_16bpc": (None, [C.c_void_p, C.c_int]),
+    "b200_inv_txfm_add": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b200_itx_add_batch": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.POINTER(C.c_int32), C.c_int, C.c_void_p]),
+    "b200_itx_add_batch_host": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                          C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.c_int]),
+}
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class B200Lib:
+    """Thin typed wrapper; every symbol include/b200av1.h declares must resolve."""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise B200Error("b200av1 library not found: %s" % path)
+        self.path = path
+        self.dll = C.CDLL(path)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(self.dll, name)  # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, fn)
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise B200Error("%s failed (%d): %s" % (what, rc, self.b200_last_error().decode()))
+
+    @staticmethod
+    def symbols():
+        return list(_SIGS)
+
+
+_lib = None
+
+
+def get_lib():
+    """Load (building first if needed) the CUDA library. Never falls back to anything else."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            from . import build
+            build.build()
+        _lib = B200Lib(LIB_PATH)
+    return _lib

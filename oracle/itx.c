@@ -155,3 +155,31 @@ ORACLE_API int oracle_itx_defined(int tx, int txtp) {
     if (mx == 16 && o_min(w, h) == 16) return txtp <= 11;   /* 16x16: no 1-D ADST+identity */
     return 1;
 }
+
+/* Batched form over the same block records the CUDA kernels consume (layout of
+ * B200ItxBlock in include/b200av1.h, restated here so oracle/ stays self-contained). */
+typedef struct OracleItxBlock {
+    uint32_t dst_off, coef_off;
+    int16_t eob;
+    uint8_t txtp, plane;
+} OracleItxBlock;
+
+ORACLE_API int oracle_itx_add_batch(int bitdepth_max, int tx, const OracleItxBlock *blocks, int n,
+                                    void *coef, void *pic, const int32_t stride_px[3], int zero_coefs)
+{
+    const int hbd = bitdepth_max > 255;
+    const int sw = o_min(tx_w[tx], 32), sh = o_min(tx_h[tx], 32);
+    const size_t cs = hbd ? 4 : 2, ps = hbd ? 2 : 1;
+    for (int i = 0; i < n; i++) {
+        const OracleItxBlock *b = &blocks[i];
+        uint8_t *cf = (uint8_t *)coef + (size_t)b->coef_off * cs;
+        uint8_t save[32 * 32 * 4];
+        if (!zero_coefs) memcpy(save, cf, cs * sw * sh);
+        int r = oracle_inv_txfm_add((uint8_t *)pic + (size_t)b->dst_off * ps,
+                                    (ptrdiff_t)stride_px[b->plane] * (ptrdiff_t)ps, cf, b->eob, tx,
+                                    b->txtp, bitdepth_max);
+        if (!zero_coefs) memcpy(cf, save, cs * sw * sh);
+        if (r) return r;
+    }
+    return 0;
+}
