@@ -85,6 +85,108 @@ B200_API int b200_itx_add_batch_host(int bitdepth_max, int tx, const B200ItxBloc
                                      void *coef, size_t coef_bytes, void *pic, size_t pic_bytes,
                                      const int32_t stride_px[3], int zero_coefs);
 
+/* ==== mc (Dav1dMCDSPContext, reference src/mc.h:38-162, src/mc_tmpl.c) ================== */
+#define B200_N_2D_FILTERS 10          /* enum Filter2d, reference src/levels.h:184-196 (9 = bilinear) */
+
+/* ---- mc: Level 2 (batched, device-resident) ---- */
+/* Shared geometry of one b200_mc_*_batch call. Reference pictures are 3-plane allocations;
+ * ref_plane_off/ref_stride/ref_w/ref_h describe the planes (in pixels). Source coordinates that
+ * fall outside [0,ref_w) x [0,ref_h) are clamped — exactly the replicate padding dav1d's
+ * emu_edge builds for such blocks (reference src/recon_tmpl.c:960-977, src/mc_tmpl.c:868-916). */
+typedef struct B200McFrame {
+    const void *ref[8];          /* device base pointer per reference slot */
+    uint32_t ref_plane_off[3];
+    int32_t ref_stride[3];
+    int32_t ref_w[3], ref_h[3];
+    void *dst;                   /* device picture being reconstructed (dst_off includes the plane offset) */
+    int32_t dst_stride[3];
+    int16_t *tmp;                /* device int16 scratch: prep outputs / compound inputs */
+    uint8_t *mask;               /* device uint8 scratch: w_mask outputs, mask / blend inputs */
+    const void *px_tmp;          /* device pixel scratch: blend inputs (OBMC / inter-intra predictions) */
+} B200McFrame;
+
+/* one prediction block: dav1d's mc[filter2d] (op 0, "put") or mct[filter2d] (op 1, "prep") */
+typedef struct B200McBlock {
+    uint32_t dst_off;            /* put: pixel offset in dst; prep: int16 offset in tmp (dense, pitch w) */
+    int32_t src_x, src_y;        /* integer sample position of the block's top-left in the ref plane */
+    uint8_t w, h;                /* w in {2,4,..,128}; 2 <= h <= 128 */
+    uint8_t mx, my;              /* subpel phase 0..15 */
+    uint8_t filter2d;
+    uint8_t op;                  /* 0 put, 1 prep */
+    uint8_t plane;
+    uint8_t ref;
+} B200McBlock;
+B200_API int b200_mc_batch(int bitdepth_max, const B200McFrame *frame, const B200McBlock *d_blocks,
+                           int n_blocks, void *stream);
+
+/* compound combine of two prep outputs: avg / w_avg / mask / w_mask (reference src/mc_tmpl.c:628-781) */
+enum { B200_COMP_AVG = 0, B200_COMP_W_AVG = 1, B200_COMP_MASK = 2, B200_COMP_W_MASK_444 = 3,
+       B200_COMP_W_MASK_422 = 4, B200_COMP_W_MASK_420 = 5 };
+typedef struct B200CompBlock {
+    uint32_t dst_off;            /* pixel offset in dst */
+    uint32_t tmp1_off, tmp2_off; /* int16 offsets in frame->tmp */
+    uint32_t mask_off;           /* offset in frame->mask (mask: input; w_mask: output) */
+    uint8_t w, h;
+    uint8_t op;
+    uint8_t param;               /* w_avg: weight 0..16; w_mask: sign */
+    uint8_t plane;
+    uint8_t pad[3];
+} B200CompBlock;
+B200_API int b200_mc_comp_batch(int bitdepth_max, const B200McFrame *frame, const B200CompBlock *d_blocks,
+                                int n_blocks, void *stream);
+
+/* blend / blend_v / blend_h (reference src/mc_tmpl.c:683-722) */
+enum { B200_BLEND = 0, B200_BLEND_V = 1, B200_BLEND_H = 2 };
+typedef struct B200BlendBlock {
+    uint32_t dst_off;            /* pixel offset in dst */
+    uint32_t tmp_off;            /* pixel offset in frame->px_tmp (dense, pitch w) */
+    uint32_t mask_off;           /* B200_BLEND only: offset in frame->mask */
+    uint8_t w, h, op, plane;
+} B200BlendBlock;
+B200_API int b200_mc_blend_batch(int bitdepth_max, const B200McFrame *frame, const B200BlendBlock *d_blocks,
+                                 int n_blocks, void *stream);
+
+/* 8x8 affine warp: warp8x8 (op 0) / warp8x8t (op 1) (reference src/mc_tmpl.c:799-866) */
+typedef struct B200WarpBlock {
+    uint32_t dst_off;            /* op 0: pixel offset in dst; op 1: int16 offset in tmp */
+    int32_t src_x, src_y;        /* position of the 8x8 block's top-left (row 0, col 0 of the 15x15 window is -3,-3) */
+    int32_t mx, my;
+    int16_t abcd[4];
+    uint16_t tmp_stride;         /* op 1: pitch of tmp in int16 elements */
+    uint8_t op, plane, ref, pad;
+} B200WarpBlock;
+B200_API int b200_mc_warp_batch(int bitdepth_max, const B200McFrame *frame, const B200WarpBlock *d_blocks,
+                                int n_blocks, void *stream);
+
+/* ---- mc: Level 1 (host pointers, dav1d signatures; bitdepth_max appended like HIGHBD_DECL_SUFFIX) */
+B200_API int b200_mc_put(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
+                         int w, int h, int mx, int my, int filter2d, int bitdepth_max);
+B200_API int b200_mc_prep(int16_t *tmp, const void *src, ptrdiff_t src_stride, int w, int h,
+                          int mx, int my, int filter2d, int bitdepth_max);
+B200_API int b200_mc_comp(void *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2,
+                          int w, int h, int op, int param, uint8_t *mask, int bitdepth_max);
+B200_API int b200_mc_blend(void *dst, ptrdiff_t dst_stride, const void *tmp, int w, int h, int op,
+                           const uint8_t *mask, int bitdepth_max);
+B200_API int b200_mc_warp8x8(int op, void *out, ptrdiff_t out_stride, const void *src, ptrdiff_t src_stride,
+                             const int16_t *abcd, int mx, int my, int bitdepth_max);
+B200_API int b200_mc_emu_edge(intptr_t bw, intptr_t bh, intptr_t iw, intptr_t ih, intptr_t x, intptr_t y,
+                              void *dst, ptrdiff_t dst_stride, const void *ref, ptrdiff_t ref_stride,
+                              int bitdepth_max);
+B200_API int b200_mc_resize(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
+                            int dst_w, int h, int src_w, int dx, int mx, int bitdepth_max);
+
+/* same layout as Dav1dMCDSPContext (reference src/mc.h:146-162); *_scaled slots are NULL until the
+ * scaled-reference kernels land */
+typedef struct B200MCDSPContext {
+    void *mc[B200_N_2D_FILTERS];
+    void *mc_scaled[B200_N_2D_FILTERS];
+    void *mct[B200_N_2D_FILTERS];
+    void *mct_scaled[B200_N_2D_FILTERS];
+    void *avg, *w_avg, *mask, *w_mask[3], *blend, *blend_v, *blend_h, *warp8x8, *warp8x8t, *emu_edge, *resize;
+} B200MCDSPContext;
+B200_API void b200_mc_dsp_init_8bpc(B200MCDSPContext *c);
+B200_API void b200_mc_dsp_init_16bpc(B200MCDSPContext *c);
+
 #ifdef __cplusplus
 }
 #endif
