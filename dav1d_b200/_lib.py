@@ -18,6 +18,36 @@ class ItxBlock(C.Structure):
                 ("txtp", C.c_uint8), ("plane", C.c_uint8)]
 
 
+class McFrame(C.Structure):
+    """struct B200McFrame"""
+    _fields_ = [("ref", C.c_void_p * 8), ("ref_plane_off", C.c_uint32 * 3), ("ref_stride", C.c_int32 * 3),
+                ("ref_w", C.c_int32 * 3), ("ref_h", C.c_int32 * 3), ("dst", C.c_void_p),
+                ("dst_stride", C.c_int32 * 3), ("tmp", C.c_void_p), ("mask", C.c_void_p), ("px_tmp", C.c_void_p)]
+
+
+class McBlock(C.Structure):
+    _fields_ = [("dst_off", C.c_uint32), ("src_x", C.c_int32), ("src_y", C.c_int32), ("w", C.c_uint8),
+                ("h", C.c_uint8), ("mx", C.c_uint8), ("my", C.c_uint8), ("filter2d", C.c_uint8),
+                ("op", C.c_uint8), ("plane", C.c_uint8), ("ref", C.c_uint8)]
+
+
+class CompBlock(C.Structure):
+    _fields_ = [("dst_off", C.c_uint32), ("tmp1_off", C.c_uint32), ("tmp2_off", C.c_uint32),
+                ("mask_off", C.c_uint32), ("w", C.c_uint8), ("h", C.c_uint8), ("op", C.c_uint8),
+                ("param", C.c_uint8), ("plane", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+class BlendBlock(C.Structure):
+    _fields_ = [("dst_off", C.c_uint32), ("tmp_off", C.c_uint32), ("mask_off", C.c_uint32),
+                ("w", C.c_uint8), ("h", C.c_uint8), ("op", C.c_uint8), ("plane", C.c_uint8)]
+
+
+class WarpBlock(C.Structure):
+    _fields_ = [("dst_off", C.c_uint32), ("src_x", C.c_int32), ("src_y", C.c_int32), ("mx", C.c_int32),
+                ("my", C.c_int32), ("abcd", C.c_int16 * 4), ("tmp_stride", C.c_uint16), ("op", C.c_uint8),
+                ("plane", C.c_uint8), ("ref", C.c_uint8), ("pad", C.c_uint8)]
+
+
 ITXFM_FN_8 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int)
 ITXFM_FN_16 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int)
 
@@ -32,6 +62,22 @@ _SIGS = {
                                      C.POINTER(C.c_int32), C.c_int, C.c_void_p]),
     "b200_itx_add_batch_host": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
                                           C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.c_int]),
+    # ---- mc
+    "b200_mc_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_mc_comp_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_mc_blend_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_mc_warp_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_mc_put": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t] + [C.c_int] * 6),
+    "b200_mc_prep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ssize_t] + [C.c_int] * 6),
+    "b200_mc_comp": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                               C.c_int, C.c_void_p, C.c_int]),
+    "b200_mc_blend": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "b200_mc_warp8x8": (C.c_int, [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_void_p,
+                                  C.c_int, C.c_int, C.c_int]),
+    "b200_mc_emu_edge": (C.c_int, [C.c_ssize_t] * 6 + [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int]),
+    "b200_mc_resize": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t] + [C.c_int] * 6),
+    "b200_mc_dsp_init_8bpc": (None, [C.c_void_p]),
+    "b200_mc_dsp_init_16bpc": (None, [C.c_void_p]),
 }
 
 

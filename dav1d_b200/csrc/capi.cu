@@ -3,7 +3,7 @@
 // batched entry points. No CPU fallback anywhere: every path ends in a kernel launch.
 #include "common.cuh"
 #include "../../include/b200av1.h"
-#include "launch_count.h"
+#include "host_util.h"
 #include <atomic>
 #include <mutex>
 #include <stdarg.h>
@@ -18,6 +18,7 @@ int launch_itx(int tx, bool hbd, const B200ItxBlock *blocks, int n, void *coefs,
 }
 
 static thread_local char g_err[512];
+namespace b200 { std::mutex &host_lock() { static std::mutex m; return m; } }
 static std::atomic<uint64_t> g_launches{0};
 
 void b200_set_error(const char *fmt, ...) {
@@ -37,23 +38,10 @@ uint64_t b200_launch_count(void) { return g_launches.load(); }
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------
-// grow-only device scratch used by the host-pointer entry points
 namespace {
-struct Scratch {
-    void *p = nullptr;
-    size_t cap = 0;
-    int reserve(size_t n) {
-        if (n <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = n + (n >> 2) + 4096;
-        B200_CUDA_OK(cudaMalloc(&p, want));
-        cap = want;
-        return 0;
-    }
-};
-std::mutex g_mu;
+using b200::Scratch;
 Scratch g_s_blocks, g_s_coef, g_s_pic;
+#define g_mu (b200::host_lock())
 
 const uint8_t k_tx_w[19] = { 4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64 };
 const uint8_t k_tx_h[19] = { 4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16 };
@@ -69,10 +57,7 @@ bool itx_defined(int tx, int txtp) {
     return true;
 }
 
-[[noreturn]] void die(const char *what) {
-    fprintf(stderr, "b200av1: %s failed: %s\n", what, b200_last_error());
-    abort();
-}
+using b200::die;
 }  // namespace
 
 extern "C" {

@@ -1,0 +1,57 @@
+// Host-side helpers shared by the C-ABI translation units: grow-only device scratch buffers
+// for the host-pointer (Level-1 / end-to-end) entry points and the global lock that
+// serialises them. Device-pointer (Level-2) entry points never touch these.
+#pragma once
+#include "common.cuh"
+#include "launch_count.h"
+#include "../../include/b200av1.h"
+#include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace b200 {
+
+struct Scratch {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + (n >> 2) + 4096;
+        B200_CUDA_OK(cudaMalloc(&p, want));
+        cap = want;
+        return 0;
+    }
+    // host -> device (async on stream 0)
+    int upload(const void *src, size_t n) {
+        if (reserve(n)) return -1;
+        if (n) B200_CUDA_OK(cudaMemcpyAsync(p, src, n, cudaMemcpyHostToDevice, 0));
+        return 0;
+    }
+    int download(void *dst, size_t n) {
+        if (n) B200_CUDA_OK(cudaMemcpyAsync(dst, p, n, cudaMemcpyDeviceToHost, 0));
+        return 0;
+    }
+};
+
+std::mutex &host_lock();
+
+[[noreturn]] inline void die(const char *what) {
+    fprintf(stderr, "b200av1: %s failed: %s\n", what, b200_last_error());
+    abort();
+}
+
+// copy a w x h rectangle of `px`-byte pixels between a strided (possibly negative stride, bytes)
+// picture and a dense buffer
+inline void pack_rect(void *dense, const void *pic, ptrdiff_t stride, int w, int h, size_t px) {
+    for (int y = 0; y < h; y++)
+        memcpy((uint8_t *)dense + (size_t)y * w * px, (const uint8_t *)pic + (ptrdiff_t)y * stride, (size_t)w * px);
+}
+inline void unpack_rect(void *pic, ptrdiff_t stride, const void *dense, int w, int h, size_t px) {
+    for (int y = 0; y < h; y++)
+        memcpy((uint8_t *)pic + (ptrdiff_t)y * stride, (const uint8_t *)dense + (size_t)y * w * px, (size_t)w * px);
+}
+
+}  // namespace b200

@@ -1,0 +1,609 @@
+// Motion compensation (dav1d Dav1dMCDSPContext, reference src/mc_tmpl.c).
+//
+//   mc_pred_kernel   put / prep, 8-tap pairs + bilinear (:129-187, 246-305, 434-489, 533-586)
+//                    one CTA per prediction block; a lane owns one output column of an
+//                    8-row strip, keeps the 15 horizontally-filtered rows it needs in
+//                    registers and runs the vertical filter from them (no shared memory,
+//                    no int16 `mid` round trip). Source coordinates are clamped to the
+//                    reference plane = dav1d's emu_edge (:868-916) folded into the loads.
+//   mc_comp_kernel   avg / w_avg / mask / w_mask{444,422,420} (:628-681, 724-781)
+//   mc_blend_kernel  blend / blend_v / blend_h (:683-722)
+//   mc_warp_kernel   warp_affine_8x8 / 8x8t (:799-866), one warp per 8x8 block
+//   emu_edge / resize kernels (:868-944) for the Level-1 table
+// Integer only; bit-exact with the reference C path.
+#include "host_util.h"
+#define B200_TBL __constant__
+#include "tables_gen.h"
+
+namespace b200 {
+
+// enum Filter2d -> horizontal / vertical Dav1dFilterMode (reference src/levels.h:184-196)
+__constant__ uint8_t c_f2d_h[9] = { 0, 0, 0, 2, 2, 2, 1, 1, 1 };
+__constant__ uint8_t c_f2d_v[9] = { 0, 1, 2, 0, 1, 2, 0, 1, 2 };
+
+template <bool HBD> B200_DEV int inter_bits(int bdmax) {
+    if (!HBD) return 4;
+    return 14 - (32 - __clz(bdmax));   // 4 for 10-bit, 2 for 12-bit
+}
+
+#define RND_SH(v, sh) (((v) + ((1 << (sh)) >> 1)) >> (sh))
+
+constexpr int kMcWarps = 2;
+
+template <bool HBD>
+__global__ void __launch_bounds__(kMcWarps * 32)
+mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    const B200McBlock b = blocks[blockIdx.x];
+    const int w = b.w, h = b.h, pl = b.plane;
+    const pixel *__restrict__ ref = (const pixel *)fr.ref[b.ref] + fr.ref_plane_off[pl];
+    const int rs = fr.ref_stride[pl], rw1 = fr.ref_w[pl] - 1, rh1 = fr.ref_h[pl] - 1;
+    const int ib = inter_bits<HBD>(bdmax);
+    const int bias = HBD ? 8192 : 0;
+    const bool bilin = b.filter2d == 9;
+    const int mx = b.mx, my = b.my;
+    const bool has_h = mx != 0, has_v = my != 0;
+    const bool is_prep = b.op != 0;
+
+    int fh[8], fv[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) fh[k] = fv[k] = 0;
+    if (!bilin) {
+        // 4-tap sets for w <= 4 / h <= 4 (reference src/mc_tmpl.c:115-123)
+        if (has_h) {
+            const int t = c_f2d_h[b.filter2d];
+            const int idx = w > 4 ? t : 3 + (t & 1);
+#pragma unroll
+            for (int k = 0; k < 8; k++) fh[k] = b200_mc_subpel_filters[idx][mx - 1][k];
+        }
+        if (has_v) {
+            const int t = c_f2d_v[b.filter2d];
+            const int idx = h > 4 ? t : 3 + (t & 1);
+#pragma unroll
+            for (int k = 0; k < 8; k++) fv[k] = b200_mc_subpel_filters[idx][my - 1][k];
+        }
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tw = w < 32 ? w : 32;               // strip width (power of two)
+    const int tw_log = 31 - __clz(tw);
+    const int lx = lane & (tw - 1), lg = lane >> tw_log;
+    const int rows_per_unit = 8 << (5 - tw_log);
+    const int units_x = (w + 31) >> 5;
+    const int units_y = (h + rows_per_unit - 1) / rows_per_unit;
+    pixel *const dpx = (pixel *)fr.dst;
+    const int ds = fr.dst_stride[pl];
+
+    for (int u = warp; u < units_x * units_y; u += kMcWarps) {
+        const int ux = u % units_x, uy = u / units_x;
+        const int x = (ux << 5) + lx;
+        const int y0 = uy * rows_per_unit + lg * 8;
+        if (x >= w || y0 >= h) continue;
+        const int nrows = imin(8, h - y0);
+        const int sx = b.src_x + x, sy = b.src_y + y0;
+
+        // A[r]: horizontally filtered (or raw) sample of source row sy + r - 3 at column sx
+        int A[15];
+        const int r_lo = bilin ? 3 : (has_v ? 0 : 3);
+        const int r_hi = bilin ? 3 + nrows + (has_v ? 1 : 0) : (has_v ? nrows + 7 : 3 + nrows);
+#pragma unroll
+        for (int r = 0; r < 15; r++) {
+            A[r] = 0;
+            if (r >= r_lo && r < r_hi) {
+                const int yy = iclip(sy + r - 3, 0, rh1);
+                const pixel *row = ref + (ptrdiff_t)yy * rs;
+                if (bilin) {
+                    const int p0 = row[iclip(sx, 0, rw1)];
+                    if (has_h) {
+                        const int p1 = row[iclip(sx + 1, 0, rw1)];
+                        A[r] = RND_SH(16 * p0 + mx * (p1 - p0), 4 - ib);
+                    } else {
+                        A[r] = p0;
+                    }
+                } else if (has_h) {
+                    int s = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) s += fh[k] * (int)row[iclip(sx + k - 3, 0, rw1)];
+                    A[r] = RND_SH(s, 6 - ib);
+                } else {
+                    A[r] = row[iclip(sx, 0, rw1)];
+                }
+            }
+        }
+
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (j >= nrows) break;
+            int out;
+            if (bilin) {
+                if (has_v) {
+                    const int s = 16 * A[j + 3] + my * (A[j + 4] - A[j + 3]);
+                    if (has_h) out = is_prep ? RND_SH(s, 4) - bias : iclip(RND_SH(s, 4 + ib), 0, bdmax);
+                    else       out = is_prep ? RND_SH(s, 4 - ib) - bias : iclip(RND_SH(s, 4), 0, bdmax);
+                } else if (has_h) {
+                    out = is_prep ? A[j + 3] - bias : iclip((A[j + 3] + ((1 << ib) >> 1)) >> ib, 0, bdmax);
+                } else {
+                    out = is_prep ? (A[j + 3] << ib) - bias : A[j + 3];
+                }
+            } else if (has_v) {
+                int s = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) s += fv[k] * A[j + k];
+                if (has_h) out = is_prep ? RND_SH(s, 6) - bias : iclip(RND_SH(s, 6 + ib), 0, bdmax);
+                else       out = is_prep ? RND_SH(s, 6 - ib) - bias : iclip(RND_SH(s, 6), 0, bdmax);
+            } else if (has_h) {
+                out = is_prep ? A[j + 3] - bias : iclip((A[j + 3] + ((1 << ib) >> 1)) >> ib, 0, bdmax);
+            } else {
+                out = is_prep ? (A[j + 3] << ib) - bias : A[j + 3];
+            }
+            if (is_prep) fr.tmp[b.dst_off + (y0 + j) * w + x] = (int16_t)out;
+            else dpx[b.dst_off + (ptrdiff_t)(y0 + j) * ds + x] = (pixel)out;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+template <bool HBD>
+__global__ void __launch_bounds__(128)
+mc_comp_kernel(const B200CompBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    const B200CompBlock b = blocks[blockIdx.x];
+    const int w = b.w, h = b.h, op = b.op;
+    const int ib = inter_bits<HBD>(bdmax);
+    const int bias = HBD ? 8192 : 0;
+    const int16_t *__restrict__ t1 = fr.tmp + b.tmp1_off;
+    const int16_t *__restrict__ t2 = fr.tmp + b.tmp2_off;
+    pixel *const dst = (pixel *)fr.dst + b.dst_off;
+    const int ds = fr.dst_stride[b.plane];
+    uint8_t *const mask = fr.mask + b.mask_off;
+
+    if (op <= B200_COMP_MASK) {
+        for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+            const int y = i / w, x = i - y * w;
+            const int a = t1[i], c = t2[i];
+            int v;
+            if (op == B200_COMP_AVG) {
+                v = (a + c + (1 << ib) + bias * 2) >> (ib + 1);
+            } else if (op == B200_COMP_W_AVG) {
+                const int wt = b.param;
+                v = (a * wt + c * (16 - wt) + (8 << ib) + bias * 16) >> (ib + 4);
+            } else {
+                const int m = mask[i];
+                v = (a * m + c * (64 - m) + (32 << ib) + bias * 64) >> (ib + 6);
+            }
+            dst[(ptrdiff_t)y * ds + x] = (pixel)iclip(v, 0, bdmax);
+        }
+        return;
+    }
+    // w_mask: derive the blend mask from |tmp1 - tmp2|, blend, and emit the (sub-sampled) mask
+    const int ss_hor = op != B200_COMP_W_MASK_444, ss_ver = op == B200_COMP_W_MASK_420;
+    const int sign = b.param;
+    const int bitdepth = 32 - __clz(bdmax);
+    const int sh = ib + 6, rnd = (32 << ib) + bias * 64;
+    const int mask_sh = bitdepth + ib - 4, mask_rnd = 1 << (mask_sh - 5);
+    const int qw = w >> 1, qh = ss_ver ? h >> 1 : h;       // work items: 2 px wide, 1 or 2 rows tall
+    for (int i = threadIdx.x; i < qw * qh; i += blockDim.x) {
+        const int qy = i / qw, qx = i - qy * qw;
+        const int x = qx * 2;
+        int msum = 0;
+        for (int r = 0; r <= ss_ver; r++) {
+            const int y = ss_ver ? qy * 2 + r : qy;
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int idx = y * w + x + k;
+                const int c = t2[idx], d = t1[idx] - c;
+                const int m = imin(38 + ((iabs(d) + mask_rnd) >> mask_sh), 64);
+                dst[(ptrdiff_t)y * ds + x + k] = (pixel)iclip((d * m + c * 64 + rnd) >> sh, 0, bdmax);
+                if (!ss_hor) mask[idx] = (uint8_t)m;
+                msum += m;
+            }
+        }
+        if (ss_ver)      mask[qy * qw + qx] = (uint8_t)((msum + 2 - sign) >> 2);
+        else if (ss_hor) mask[qy * qw + qx] = (uint8_t)((msum + 1 - sign) >> 1);
+    }
+}
+
+template <bool HBD>
+__global__ void __launch_bounds__(128)
+mc_blend_kernel(const B200BlendBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    const B200BlendBlock b = blocks[blockIdx.x];
+    const int w = b.w, h = b.h, op = b.op;
+    pixel *const dst = (pixel *)fr.dst + b.dst_off;
+    const pixel *__restrict__ tmp = (const pixel *)fr.px_tmp + b.tmp_off;
+    const int ds = fr.dst_stride[b.plane];
+    const int bw = op == B200_BLEND_V ? (w * 3) >> 2 : w;
+    const int bh = op == B200_BLEND_H ? (h * 3) >> 2 : h;
+    for (int i = threadIdx.x; i < bw * bh; i += blockDim.x) {
+        const int y = i / bw, x = i - y * bw;
+        int m;
+        if (op == B200_BLEND) m = fr.mask[b.mask_off + y * w + x];
+        else if (op == B200_BLEND_V) m = b200_obmc_masks[w + x];
+        else m = b200_obmc_masks[h + y];
+        pixel *p = dst + (ptrdiff_t)y * ds + x;
+        *p = (pixel)(((int)*p * (64 - m) + (int)tmp[y * w + x] * m + 32) >> 6);
+    }
+}
+
+// one warp per 8x8 block; the 15x8 horizontally filtered rows go through shared memory
+constexpr int kWarpWarps = 4;
+template <bool HBD>
+__global__ void __launch_bounds__(kWarpWarps * 32)
+mc_warp_kernel(const B200WarpBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    __shared__ int mid[kWarpWarps][15 * 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bi = blockIdx.x * kWarpWarps + warp;
+    const bool valid = bi < n_blocks;
+    B200WarpBlock b;
+    if (valid) b = blocks[bi]; else { b = blocks[0]; }
+    const int pl = b.plane;
+    const pixel *__restrict__ ref = (const pixel *)fr.ref[b.ref] + fr.ref_plane_off[pl];
+    const int rs = fr.ref_stride[pl], rw1 = fr.ref_w[pl] - 1, rh1 = fr.ref_h[pl] - 1;
+    const int ib = inter_bits<HBD>(bdmax);
+    const int bias = HBD ? 8192 : 0;
+    if (valid) {
+        for (int i = lane; i < 15 * 8; i += 32) {
+            const int y = i >> 3, x = i & 7;
+            const int tmx = b.mx + y * b.abcd[1] + x * b.abcd[0];
+            const int8_t *f = b200_mc_warp_filter[64 + ((tmx + 512) >> 10)];
+            const pixel *row = ref + (ptrdiff_t)iclip(b.src_y + y - 3, 0, rh1) * rs;
+            int s = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) s += f[k] * (int)row[iclip(b.src_x + x + k - 3, 0, rw1)];
+            mid[warp][i] = RND_SH(s, 7 - ib);
+        }
+    }
+    __syncwarp();
+    if (valid) {
+        for (int i = lane; i < 64; i += 32) {
+            const int y = i >> 3, x = i & 7;
+            const int tmy = b.my + y * b.abcd[3] + x * b.abcd[2];
+            const int8_t *f = b200_mc_warp_filter[64 + ((tmy + 512) >> 10)];
+            int s = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) s += f[k] * mid[warp][(y + k) * 8 + x];
+            if (b.op) fr.tmp[b.dst_off + y * b.tmp_stride + x] = (int16_t)(RND_SH(s, 7) - bias);
+            else ((pixel *)fr.dst)[b.dst_off + (ptrdiff_t)y * fr.dst_stride[pl] + x] =
+                     (pixel)iclip(RND_SH(s, 7 + ib), 0, bdmax);
+        }
+    }
+}
+
+template <bool HBD>
+__global__ void emu_edge_kernel(int bw, int bh, int iw, int ih, int x0, int y0,
+                                typename Bd<HBD>::pixel *dst, const typename Bd<HBD>::pixel *ref)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < bw * bh; i += gridDim.x * blockDim.x) {
+        const int y = i / bw, x = i - y * bw;
+        dst[i] = ref[iclip(y0 + y, 0, ih - 1) * iw + iclip(x0 + x, 0, iw - 1)];
+    }
+}
+
+template <bool HBD>
+__global__ void resize_kernel(typename Bd<HBD>::pixel *dst, const typename Bd<HBD>::pixel *src, int dst_w,
+                              int h, int src_w, int dx, int mx0, int bdmax)
+{
+    // the x position recurrence (mx += dx; src_x += mx >> 14; mx &= 0x3fff) has the closed form below
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dst_w * h; i += gridDim.x * blockDim.x) {
+        const int y = i / dst_w, x = i - y * dst_w;
+        const long long pos = (long long)mx0 + (long long)x * dx;
+        const int src_x = -1 + (int)(pos >> 14), mx = (int)(pos & 0x3fff);
+        const int8_t *F = b200_resize_filter[mx >> 8];
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += F[k] * (int)src[y * src_w + iclip(src_x - 3 + k, 0, src_w - 1)];
+        dst[i] = (typename Bd<HBD>::pixel)iclip((-s + 64) >> 7, 0, bdmax);
+    }
+}
+
+}  // namespace b200
+
+// =======================================================================================
+using namespace b200;
+
+static int check_bd(int bdmax, const char *who) {
+    if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("%s: bad bitdepth_max %d", who, bdmax); return -2; }
+    return 0;
+}
+
+extern "C" {
+
+int b200_mc_batch(int bitdepth_max, const B200McFrame *frame, const B200McBlock *d_blocks, int n, void *stream) {
+    if (check_bd(bitdepth_max, "b200_mc_batch")) return -2;
+    if (n <= 0) return 0;
+    if (bitdepth_max > 255) { auto k = mc_pred_kernel<true>; B200_LAUNCH(k, dim3(n), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_pred_kernel<false>; B200_LAUNCH(k, dim3(n), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int b200_mc_comp_batch(int bitdepth_max, const B200McFrame *frame, const B200CompBlock *d_blocks, int n, void *stream) {
+    if (check_bd(bitdepth_max, "b200_mc_comp_batch")) return -2;
+    if (n <= 0) return 0;
+    if (bitdepth_max > 255) { auto k = mc_comp_kernel<true>; B200_LAUNCH(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_comp_kernel<false>; B200_LAUNCH(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int b200_mc_blend_batch(int bitdepth_max, const B200McFrame *frame, const B200BlendBlock *d_blocks, int n, void *stream) {
+    if (check_bd(bitdepth_max, "b200_mc_blend_batch")) return -2;
+    if (n <= 0) return 0;
+    if (bitdepth_max > 255) { auto k = mc_blend_kernel<true>; B200_LAUNCH(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_blend_kernel<false>; B200_LAUNCH(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int b200_mc_warp_batch(int bitdepth_max, const B200McFrame *frame, const B200WarpBlock *d_blocks, int n, void *stream) {
+    if (check_bd(bitdepth_max, "b200_mc_warp_batch")) return -2;
+    if (n <= 0) return 0;
+    const int grid = (n + kWarpWarps - 1) / kWarpWarps;
+    if (bitdepth_max > 255) { auto k = mc_warp_kernel<true>; B200_LAUNCH(k, dim3(grid), dim3(kWarpWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_warp_kernel<false>; B200_LAUNCH(k, dim3(grid), dim3(kWarpWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- Level 1: host pointers -------------------------------------------------------------
+namespace {
+Scratch s_ref, s_dst, s_tmp, s_mask, s_desc, s_px;
+uint8_t h_stage[2 * (128 + 8) * (128 + 8) * 2 + 64];
+}
+
+static int mc_l1(int op, void *out, ptrdiff_t out_stride, const void *src, ptrdiff_t src_stride, int w, int h,
+                 int mx, int my, int f2d, int bdmax)
+{
+    if (check_bd(bdmax, "b200_mc")) return -2;
+    if (f2d < 0 || f2d > 9 || w < 2 || w > 128 || (w & (w - 1)) || h < 2 || h > 128 || mx < 0 || mx > 15 || my < 0 || my > 15) {
+        b200_set_error("b200_mc: bad arguments (w=%d h=%d mx=%d my=%d filter=%d)", w, h, mx, my, f2d);
+        return -2;
+    }
+    std::lock_guard<std::mutex> lk(host_lock());
+    const size_t px = bdmax > 255 ? 2 : 1;
+    // the window the reference reads: 3 before / 4 after for 8-tap, 0 / 1 for bilinear, only on filtered axes
+    const int bl = f2d == 9 ? 0 : 3, al = f2d == 9 ? 1 : 4;
+    const int x0 = mx ? bl : 0, x1 = mx ? al : 0, y0 = my ? bl : 0, y1 = my ? al : 0;
+    const int ww = w + x0 + x1, wh = h + y0 + y1;
+    pack_rect(h_stage, (const uint8_t *)src - (ptrdiff_t)y0 * src_stride - (ptrdiff_t)x0 * (ptrdiff_t)px, src_stride, ww, wh, px);
+    if (s_ref.upload(h_stage, (size_t)ww * wh * px)) return -1;
+    if (s_dst.reserve((size_t)w * h * 2) || s_desc.reserve(sizeof(B200McBlock))) return -1;
+    B200McFrame fr;
+    memset(&fr, 0, sizeof(fr));
+    fr.ref[0] = s_ref.p; fr.ref_stride[0] = ww; fr.ref_w[0] = ww; fr.ref_h[0] = wh;
+    fr.dst = s_dst.p; fr.dst_stride[0] = w; fr.tmp = (int16_t *)s_dst.p;
+    B200McBlock b;
+    memset(&b, 0, sizeof(b));
+    b.dst_off = 0; b.src_x = x0; b.src_y = y0; b.w = (uint8_t)w; b.h = (uint8_t)h; b.mx = (uint8_t)mx; b.my = (uint8_t)my;
+    b.filter2d = (uint8_t)f2d; b.op = (uint8_t)op;
+    if (s_desc.upload(&b, sizeof(b))) return -1;
+    int r = b200_mc_batch(bdmax, &fr, (const B200McBlock *)s_desc.p, 1, 0);
+    if (r) return r;
+    if (op) {
+        if (s_dst.download(out, (size_t)w * h * 2)) return -1;
+        B200_CUDA_OK(cudaStreamSynchronize(0));
+    } else {
+        static uint8_t h_out[128 * 128 * 2];
+        if (s_dst.download(h_out, (size_t)w * h * px)) return -1;
+        B200_CUDA_OK(cudaStreamSynchronize(0));
+        unpack_rect(out, out_stride, h_out, w, h, px);
+    }
+    return 0;
+}
+
+extern "C" {
+
+int b200_mc_put(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride, int w, int h,
+                int mx, int my, int filter2d, int bitdepth_max) {
+    return mc_l1(0, dst, dst_stride, src, src_stride, w, h, mx, my, filter2d, bitdepth_max);
+}
+int b200_mc_prep(int16_t *tmp, const void *src, ptrdiff_t src_stride, int w, int h, int mx, int my,
+                 int filter2d, int bitdepth_max) {
+    return mc_l1(1, tmp, 0, src, src_stride, w, h, mx, my, filter2d, bitdepth_max);
+}
+
+int b200_mc_comp(void *dst, ptrdiff_t dst_stride, const int16_t *tmp1, const int16_t *tmp2, int w, int h,
+                 int op, int param, uint8_t *mask, int bdmax)
+{
+    if (check_bd(bdmax, "b200_mc_comp")) return -2;
+    if (op < 0 || op > B200_COMP_W_MASK_420 || w < 4 || w > 128 || h < 4 || h > 128 || (w & 1) || (op == B200_COMP_W_MASK_420 && (h & 1))) {
+        b200_set_error("b200_mc_comp: bad arguments (op=%d w=%d h=%d)", op, w, h);
+        return -2;
+    }
+    std::lock_guard<std::mutex> lk(host_lock());
+    const size_t px = bdmax > 255 ? 2 : 1, n = (size_t)w * h;
+    if (s_tmp.reserve(n * 4) || s_dst.reserve(n * 2) || s_mask.reserve(n) || s_desc.reserve(sizeof(B200CompBlock))) return -1;
+    B200_CUDA_OK(cudaMemcpyAsync(s_tmp.p, tmp1, n * 2, cudaMemcpyHostToDevice, 0));
+    B200_CUDA_OK(cudaMemcpyAsync((int16_t *)s_tmp.p + n, tmp2, n * 2, cudaMemcpyHostToDevice, 0));
+    if (op == B200_COMP_MASK) B200_CUDA_OK(cudaMemcpyAsync(s_mask.p, mask, n, cudaMemcpyHostToDevice, 0));
+    B200McFrame fr;
+    memset(&fr, 0, sizeof(fr));
+    fr.dst = s_dst.p; fr.dst_stride[0] = w; fr.tmp = (int16_t *)s_tmp.p; fr.mask = (uint8_t *)s_mask.p;
+    B200CompBlock b;
+    memset(&b, 0, sizeof(b));
+    b.tmp1_off = 0; b.tmp2_off = (uint32_t)n; b.w = (uint8_t)w; b.h = (uint8_t)h; b.op = (uint8_t)op; b.param = (uint8_t)param;
+    if (s_desc.upload(&b, sizeof(b))) return -1;
+    int r = b200_mc_comp_batch(bdmax, &fr, (const B200CompBlock *)s_desc.p, 1, 0);
+    if (r) return r;
+    static uint8_t h_out[128 * 128 * 2];
+    if (s_dst.download(h_out, n * px)) return -1;
+    if (op >= B200_COMP_W_MASK_444) {
+        const size_t mn = (size_t)(w >> (op != B200_COMP_W_MASK_444)) * (h >> (op == B200_COMP_W_MASK_420));
+        if (s_mask.download(mask, mn)) return -1;
+    }
+    B200_CUDA_OK(cudaStreamSynchronize(0));
+    unpack_rect(dst, dst_stride, h_out, w, h, px);
+    return 0;
+}
+
+int b200_mc_blend(void *dst, ptrdiff_t dst_stride, const void *tmp, int w, int h, int op, const uint8_t *mask, int bdmax)
+{
+    if (check_bd(bdmax, "b200_mc_blend")) return -2;
+    if (op < 0 || op > B200_BLEND_H || w < 1 || w > 128 || h < 1 || h > 128) { b200_set_error("b200_mc_blend: bad arguments"); return -2; }
+    std::lock_guard<std::mutex> lk(host_lock());
+    const size_t px = bdmax > 255 ? 2 : 1, n = (size_t)w * h;
+    static uint8_t h_io[128 * 128 * 2];
+    pack_rect(h_io, dst, dst_stride, w, h, px);
+    if (s_dst.upload(h_io, n * px) || s_px.upload(tmp, n * px) || s_desc.reserve(sizeof(B200BlendBlock))) return -1;
+    if (op == B200_BLEND && s_mask.upload(mask, n)) return -1;
+    B200McFrame fr;
+    memset(&fr, 0, sizeof(fr));
+    fr.dst = s_dst.p; fr.dst_stride[0] = w; fr.px_tmp = s_px.p; fr.mask = (uint8_t *)s_mask.p;
+    B200BlendBlock b;
+    memset(&b, 0, sizeof(b));
+    b.w = (uint8_t)w; b.h = (uint8_t)h; b.op = (uint8_t)op;
+    if (s_desc.upload(&b, sizeof(b))) return -1;
+    int r = b200_mc_blend_batch(bdmax, &fr, (const B200BlendBlock *)s_desc.p, 1, 0);
+    if (r) return r;
+    if (s_dst.download(h_io, n * px)) return -1;
+    B200_CUDA_OK(cudaStreamSynchronize(0));
+    unpack_rect(dst, dst_stride, h_io, w, h, px);
+    return 0;
+}
+
+int b200_mc_warp8x8(int op, void *out, ptrdiff_t out_stride, const void *src, ptrdiff_t src_stride,
+                    const int16_t *abcd, int mx, int my, int bdmax)
+{
+    if (check_bd(bdmax, "b200_mc_warp8x8")) return -2;
+    std::lock_guard<std::mutex> lk(host_lock());
+    const size_t px = bdmax > 255 ? 2 : 1;
+    pack_rect(h_stage, (const uint8_t *)src - 3 * src_stride - 3 * (ptrdiff_t)px, src_stride, 15, 15, px);
+    if (s_ref.upload(h_stage, 15 * 15 * px) || s_dst.reserve(64 * 2) || s_desc.reserve(sizeof(B200WarpBlock))) return -1;
+    B200McFrame fr;
+    memset(&fr, 0, sizeof(fr));
+    fr.ref[0] = s_ref.p; fr.ref_stride[0] = 15; fr.ref_w[0] = 15; fr.ref_h[0] = 15;
+    fr.dst = s_dst.p; fr.dst_stride[0] = 8; fr.tmp = (int16_t *)s_dst.p;
+    B200WarpBlock b;
+    memset(&b, 0, sizeof(b));
+    b.src_x = 3; b.src_y = 3; b.mx = mx; b.my = my; b.op = (uint8_t)op; b.tmp_stride = 8;
+    memcpy(b.abcd, abcd, 8);
+    if (s_desc.upload(&b, sizeof(b))) return -1;
+    int r = b200_mc_warp_batch(bdmax, &fr, (const B200WarpBlock *)s_desc.p, 1, 0);
+    if (r) return r;
+    uint8_t h_out[64 * 2];
+    if (s_dst.download(h_out, 64 * (op ? 2 : px))) return -1;
+    B200_CUDA_OK(cudaStreamSynchronize(0));
+    if (op) for (int y = 0; y < 8; y++) memcpy((int16_t *)out + (ptrdiff_t)y * out_stride, h_out + y * 16, 16);
+    else unpack_rect(out, out_stride, h_out, 8, 8, px);
+    return 0;
+}
+
+int b200_mc_emu_edge(intptr_t bw, intptr_t bh, intptr_t iw, intptr_t ih, intptr_t x, intptr_t y, void *dst,
+                     ptrdiff_t dst_stride, const void *ref, ptrdiff_t ref_stride, int bdmax)
+{
+    if (check_bd(bdmax, "b200_mc_emu_edge")) return -2;
+    if (bw < 1 || bh < 1 || iw < 1 || ih < 1 || bw * bh > (1 << 22) || iw * ih > (1 << 26)) { b200_set_error("b200_mc_emu_edge: bad geometry"); return -2; }
+    std::lock_guard<std::mutex> lk(host_lock());
+    const size_t px = bdmax > 255 ? 2 : 1;
+    // only the part of the plane the window can touch is shipped: rows/cols clamp(x..x+bw-1)
+    const int cx0 = iclip((int)x, 0, (int)iw - 1), cx1 = iclip((int)(x + bw - 1), 0, (int)iw - 1);
+    const int cy0 = iclip((int)y, 0, (int)ih - 1), cy1 = iclip((int)(y + bh - 1), 0, (int)ih - 1);
+    const int sw = cx1 - cx0 + 1, shh = cy1 - cy0 + 1;
+    uint8_t *stage = (uint8_t *)malloc((size_t)sw * shh * px + (size_t)bw * bh * px);
+    if (!stage) { b200_set_error("oom"); return -1; }
+    pack_rect(stage, (const uint8_t *)ref + (ptrdiff_t)cy0 * ref_stride + (ptrdiff_t)cx0 * (ptrdiff_t)px, ref_stride, sw, shh, px);
+    int rc = -1;
+    do {
+        if (s_ref.upload(stage, (size_t)sw * shh * px) || s_dst.reserve((size_t)bw * bh * px)) break;
+        const int n = (int)(bw * bh), grid = imin((n + 255) / 256, 1184);
+        if (bdmax > 255) { auto k = emu_edge_kernel<true>; B200_LAUNCH(k, dim3(grid), dim3(256), 0, (cudaStream_t)0, (int)bw, (int)bh, sw, shh, (int)x - cx0, (int)y - cy0, (uint16_t *)s_dst.p, (const uint16_t *)s_ref.p); }
+        else { auto k = emu_edge_kernel<false>; B200_LAUNCH(k, dim3(grid), dim3(256), 0, (cudaStream_t)0, (int)bw, (int)bh, sw, shh, (int)x - cx0, (int)y - cy0, (uint8_t *)s_dst.p, (const uint8_t *)s_ref.p); }
+        b200_count_launch();
+        uint8_t *outb = stage + (size_t)sw * shh * px;
+        if (s_dst.download(outb, (size_t)bw * bh * px)) break;
+        if (cudaStreamSynchronize(0) != cudaSuccess) { b200_set_error("sync failed"); break; }
+        unpack_rect(dst, dst_stride, outb, (int)bw, (int)bh, px);
+        rc = 0;
+    } while (0);
+    free(stage);
+    return rc;
+}
+
+int b200_mc_resize(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride, int dst_w, int h,
+                   int src_w, int dx, int mx, int bdmax)
+{
+    if (check_bd(bdmax, "b200_mc_resize")) return -2;
+    if (dst_w < 1 || h < 1 || src_w < 1 || (size_t)dst_w * h > (1u << 26)) { b200_set_error("b200_mc_resize: bad geometry"); return -2; }
+    std::lock_guard<std::mutex> lk(host_lock());
+    const size_t px = bdmax > 255 ? 2 : 1;
+    uint8_t *stage = (uint8_t *)malloc(((size_t)src_w + dst_w) * h * px);
+    if (!stage) { b200_set_error("oom"); return -1; }
+    pack_rect(stage, src, src_stride, src_w, h, px);
+    int rc = -1;
+    do {
+        if (s_ref.upload(stage, (size_t)src_w * h * px) || s_dst.reserve((size_t)dst_w * h * px)) break;
+        const int n = dst_w * h, grid = imin((n + 255) / 256, 1184);
+        if (bdmax > 255) { auto k = resize_kernel<true>; B200_LAUNCH(k, dim3(grid), dim3(256), 0, (cudaStream_t)0, (uint16_t *)s_dst.p, (const uint16_t *)s_ref.p, dst_w, h, src_w, dx, mx, bdmax); }
+        else { auto k = resize_kernel<false>; B200_LAUNCH(k, dim3(grid), dim3(256), 0, (cudaStream_t)0, (uint8_t *)s_dst.p, (const uint8_t *)s_ref.p, dst_w, h, src_w, dx, mx, bdmax); }
+        b200_count_launch();
+        uint8_t *outb = stage + (size_t)src_w * h * px;
+        if (s_dst.download(outb, (size_t)dst_w * h * px)) break;
+        if (cudaStreamSynchronize(0) != cudaSuccess) { b200_set_error("sync failed"); break; }
+        unpack_rect(dst, dst_stride, outb, dst_w, h, px);
+        rc = 0;
+    } while (0);
+    free(stage);
+    return rc;
+}
+
+}  // extern "C"
+
+// ---- Level-1 table: thunks with dav1d's exact signatures (reference src/mc.h:38-114) ---------
+namespace {
+#define DIE_IF(x, what) do { if (x) die(what); } while (0)
+template <int F> void put8(uint8_t *d, ptrdiff_t ds, const uint8_t *s, ptrdiff_t ss, int w, int h, int mx, int my) { DIE_IF(b200_mc_put(d, ds, s, ss, w, h, mx, my, F, 255), "mc"); }
+template <int F> void put16(uint16_t *d, ptrdiff_t ds, const uint16_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int bd) { DIE_IF(b200_mc_put(d, ds, s, ss, w, h, mx, my, F, bd), "mc"); }
+template <int F> void prep8(int16_t *t, const uint8_t *s, ptrdiff_t ss, int w, int h, int mx, int my) { DIE_IF(b200_mc_prep(t, s, ss, w, h, mx, my, F, 255), "mct"); }
+template <int F> void prep16(int16_t *t, const uint16_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int bd) { DIE_IF(b200_mc_prep(t, s, ss, w, h, mx, my, F, bd), "mct"); }
+void avg8(uint8_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h) { DIE_IF(b200_mc_comp(d, ds, a, b, w, h, B200_COMP_AVG, 0, nullptr, 255), "avg"); }
+void avg16(uint16_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, int bd) { DIE_IF(b200_mc_comp(d, ds, a, b, w, h, B200_COMP_AVG, 0, nullptr, bd), "avg"); }
+void wavg8(uint8_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, int wt) { DIE_IF(b200_mc_comp(d, ds, a, b, w, h, B200_COMP_W_AVG, wt, nullptr, 255), "w_avg"); }
+void wavg16(uint16_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, int wt, int bd) { DIE_IF(b200_mc_comp(d, ds, a, b, w, h, B200_COMP_W_AVG, wt, nullptr, bd), "w_avg"); }
+void mask8(uint8_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, const uint8_t *m) { DIE_IF(b200_mc_comp(d, ds, a, b, w, h, B200_COMP_MASK, 0, (uint8_t *)m, 255), "mask"); }
+void mask16(uint16_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, const uint8_t *m, int bd) { DIE_IF(b200_mc_comp(d, ds, a, b, w, h, B200_COMP_MASK, 0, (uint8_t *)m, bd), "mask"); }
+template <int L> void wmask8(uint8_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, uint8_t *m, int sign) { DIE_IF(b200_mc_comp(d, ds, a, b, w, h, B200_COMP_W_MASK_444 + L, sign, m, 255), "w_mask"); }
+template <int L> void wmask16(uint16_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, uint8_t *m, int sign, int bd) { DIE_IF(b200_mc_comp(d, ds, a, b, w, h, B200_COMP_W_MASK_444 + L, sign, m, bd), "w_mask"); }
+template <int BD> void blend_t(void *d, ptrdiff_t ds, const void *t, int w, int h, const uint8_t *m) { DIE_IF(b200_mc_blend(d, ds, t, w, h, B200_BLEND, m, BD), "blend"); }
+template <int BD> void blendv_t(void *d, ptrdiff_t ds, const void *t, int w, int h) { DIE_IF(b200_mc_blend(d, ds, t, w, h, B200_BLEND_V, nullptr, BD), "blend_v"); }
+template <int BD> void blendh_t(void *d, ptrdiff_t ds, const void *t, int w, int h) { DIE_IF(b200_mc_blend(d, ds, t, w, h, B200_BLEND_H, nullptr, BD), "blend_h"); }
+void warp8(uint8_t *d, ptrdiff_t ds, const uint8_t *s, ptrdiff_t ss, const int16_t *abcd, int mx, int my) { DIE_IF(b200_mc_warp8x8(0, d, ds, s, ss, abcd, mx, my, 255), "warp8x8"); }
+void warp16(uint16_t *d, ptrdiff_t ds, const uint16_t *s, ptrdiff_t ss, const int16_t *abcd, int mx, int my, int bd) { DIE_IF(b200_mc_warp8x8(0, d, ds, s, ss, abcd, mx, my, bd), "warp8x8"); }
+void warpt8(int16_t *t, ptrdiff_t ts, const uint8_t *s, ptrdiff_t ss, const int16_t *abcd, int mx, int my) { DIE_IF(b200_mc_warp8x8(1, t, ts, s, ss, abcd, mx, my, 255), "warp8x8t"); }
+void warpt16(int16_t *t, ptrdiff_t ts, const uint16_t *s, ptrdiff_t ss, const int16_t *abcd, int mx, int my, int bd) { DIE_IF(b200_mc_warp8x8(1, t, ts, s, ss, abcd, mx, my, bd), "warp8x8t"); }
+template <int BD> void emu_t(intptr_t bw, intptr_t bh, intptr_t iw, intptr_t ih, intptr_t x, intptr_t y, void *d, ptrdiff_t ds, const void *r, ptrdiff_t rs) { DIE_IF(b200_mc_emu_edge(bw, bh, iw, ih, x, y, d, ds, r, rs, BD), "emu_edge"); }
+void resize8(uint8_t *d, ptrdiff_t ds, const uint8_t *s, ptrdiff_t ss, int dw, int h, int sw, int dx, int mx) { DIE_IF(b200_mc_resize(d, ds, s, ss, dw, h, sw, dx, mx, 255), "resize"); }
+void resize16(uint16_t *d, ptrdiff_t ds, const uint16_t *s, ptrdiff_t ss, int dw, int h, int sw, int dx, int mx, int bd) { DIE_IF(b200_mc_resize(d, ds, s, ss, dw, h, sw, dx, mx, bd), "resize"); }
+
+template <int... F> void fill_mc8(B200MCDSPContext *c, std::integer_sequence<int, F...>) {
+    ((c->mc[F] = (void *)put8<F>, c->mct[F] = (void *)prep8<F>, c->mc_scaled[F] = nullptr, c->mct_scaled[F] = nullptr), ...);
+}
+template <int... F> void fill_mc16(B200MCDSPContext *c, std::integer_sequence<int, F...>) {
+    ((c->mc[F] = (void *)put16<F>, c->mct[F] = (void *)prep16<F>, c->mc_scaled[F] = nullptr, c->mct_scaled[F] = nullptr), ...);
+}
+}  // namespace
+
+extern "C" {
+void b200_mc_dsp_init_8bpc(B200MCDSPContext *c) {
+    fill_mc8(c, std::make_integer_sequence<int, B200_N_2D_FILTERS>{});
+    c->avg = (void *)avg8; c->w_avg = (void *)wavg8; c->mask = (void *)mask8;
+    c->w_mask[0] = (void *)wmask8<0>; c->w_mask[1] = (void *)wmask8<1>; c->w_mask[2] = (void *)wmask8<2>;
+    c->blend = (void *)blend_t<255>; c->blend_v = (void *)blendv_t<255>; c->blend_h = (void *)blendh_t<255>;
+    c->warp8x8 = (void *)warp8; c->warp8x8t = (void *)warpt8; c->emu_edge = (void *)emu_t<255>; c->resize = (void *)resize8;
+}
+void b200_mc_dsp_init_16bpc(B200MCDSPContext *c) {
+    fill_mc16(c, std::make_integer_sequence<int, B200_N_2D_FILTERS>{});
+    c->avg = (void *)avg16; c->w_avg = (void *)wavg16; c->mask = (void *)mask16;
+    c->w_mask[0] = (void *)wmask16<0>; c->w_mask[1] = (void *)wmask16<1>; c->w_mask[2] = (void *)wmask16<2>;
+    // blend*/emu_edge carry no bitdepth argument in dav1d: pixel width is all that matters (any hbd max works)
+    c->blend = (void *)blend_t<1023>; c->blend_v = (void *)blendv_t<1023>; c->blend_h = (void *)blendh_t<1023>;
+    c->warp8x8 = (void *)warp16; c->warp8x8t = (void *)warpt16; c->emu_edge = (void *)emu_t<1023>; c->resize = (void *)resize16;
+}
+}

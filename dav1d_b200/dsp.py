@@ -46,3 +46,70 @@ class InvTxfmDSPContext:
         fn = ITXFM_FN_16(ptr)
         bdmax = self.bitdepth_max
         return lambda dst, stride, coeff, eob: fn(_addr(dst), stride, _addr(coeff), eob, bdmax)
+
+
+# ------------------------------------------------------------------------------------------
+# Function-pointer prototypes of Dav1dMCDSPContext members (reference src/mc.h:38-114), as
+# (8 bpc argument list); the 16 bpc variants append `int bitdepth_max` (HIGHBD_DECL_SUFFIX)
+# except blend*, emu_edge which carry no bit-depth argument.
+_P, _S, _I, _L = C.c_void_p, C.c_ssize_t, C.c_int, C.c_ssize_t
+MC_PROTOS = {
+    "mc": ([_P, _S, _P, _S, _I, _I, _I, _I], True),
+    "mc_scaled": ([_P, _S, _P, _S, _I, _I, _I, _I, _I, _I], True),
+    "mct": ([_P, _P, _S, _I, _I, _I, _I], True),
+    "mct_scaled": ([_P, _P, _S, _I, _I, _I, _I, _I, _I], True),
+    "avg": ([_P, _S, _P, _P, _I, _I], True),
+    "w_avg": ([_P, _S, _P, _P, _I, _I, _I], True),
+    "mask": ([_P, _S, _P, _P, _I, _I, _P], True),
+    "w_mask": ([_P, _S, _P, _P, _I, _I, _P, _I], True),
+    "blend": ([_P, _S, _P, _I, _I, _P], False),
+    "blend_v": ([_P, _S, _P, _I, _I], False),
+    "blend_h": ([_P, _S, _P, _I, _I], False),
+    "warp8x8": ([_P, _S, _P, _S, _P, _I, _I], True),
+    "warp8x8t": ([_P, _S, _P, _S, _P, _I, _I], True),
+    "emu_edge": ([_L, _L, _L, _L, _L, _L, _P, _S, _P, _S], False),
+    "resize": ([_P, _S, _P, _S, _I, _I, _I, _I, _I], True),
+}
+# member order and array lengths of the struct (reference src/mc.h:146-162)
+MC_LAYOUT = [("mc", 10), ("mc_scaled", 10), ("mct", 10), ("mct_scaled", 10), ("avg", 1), ("w_avg", 1),
+             ("mask", 1), ("w_mask", 3), ("blend", 1), ("blend_v", 1), ("blend_h", 1), ("warp8x8", 1),
+             ("warp8x8t", 1), ("emu_edge", 1), ("resize", 1)]
+
+
+def wrap_dsp_table(tbl, layout, protos, hbd, bitdepth_max):
+    """Turn a flat table of C function pointers into attributes of callables taking numpy buffers /
+    ints in dav1d's argument order (bitdepth_max appended automatically for 16 bpc)."""
+    out, i = {}, 0
+    for name, n in layout:
+        args, has_bd = protos[name]
+        ft = C.CFUNCTYPE(None, *(args + ([_I] if (hbd and has_bd) else [])))
+        fns = []
+        for _ in range(n):
+            p = tbl[i]; i += 1
+            if not p:
+                fns.append(None)
+                continue
+            f = ft(p)
+
+            def call(*a, _f=f, _bd=(hbd and has_bd)):
+                a = [_addr(x) if isinstance(x, np.ndarray) else x for x in a]
+                if _bd:
+                    a.append(bitdepth_max)
+                return _f(*a)
+            fns.append(call)
+        out[name] = fns if n > 1 else fns[0]
+    return out
+
+
+class MCDSPContext:
+    """Dav1dMCDSPContext (reference src/mc.h:146-162): mc[10] mc_scaled[10] mct[10] mct_scaled[10] avg
+    w_avg mask w_mask[3] blend blend_v blend_h warp8x8 warp8x8t emu_edge resize."""
+
+    def __init__(self, bpc, lib=None):
+        assert bpc in (8, 10, 12)
+        self.bpc, self.bitdepth_max = bpc, (1 << bpc) - 1
+        self.lib = lib or get_lib()
+        self._tbl = (C.c_void_p * 53)()
+        (self.lib.b200_mc_dsp_init_8bpc if bpc == 8 else self.lib.b200_mc_dsp_init_16bpc)(self._tbl)
+        for k, v in wrap_dsp_table(self._tbl, MC_LAYOUT, MC_PROTOS, bpc > 8, self.bitdepth_max).items():
+            setattr(self, k, v)

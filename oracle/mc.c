@@ -369,3 +369,68 @@ ORACLE_API void oracle_resize(void *dst, ptrdiff_t dst_stride, const void *src, 
         }
     }
 }
+
+/* ---- batched forms over the records the CUDA kernels consume (layouts restate
+ * B200McFrame / B200McBlock / B200CompBlock / B200BlendBlock / B200WarpBlock of include/b200av1.h).
+ * Prediction follows dav1d's own route for blocks that leave the picture: emu_edge into a
+ * scratch window, then the regular mc function (reference src/recon_tmpl.c:956-988). */
+typedef struct {
+    const void *ref[8]; uint32_t ref_plane_off[3]; int32_t ref_stride[3], ref_w[3], ref_h[3];
+    void *dst; int32_t dst_stride[3]; int16_t *tmp; uint8_t *mask; const void *px_tmp;
+} OracleMcFrame;
+typedef struct { uint32_t dst_off; int32_t src_x, src_y; uint8_t w, h, mx, my, filter2d, op, plane, ref; } OracleMcBlock;
+typedef struct { uint32_t dst_off, tmp1_off, tmp2_off, mask_off; uint8_t w, h, op, param, plane, pad[3]; } OracleCompBlock;
+typedef struct { uint32_t dst_off, tmp_off, mask_off; uint8_t w, h, op, plane; } OracleBlendBlock;
+typedef struct { uint32_t dst_off; int32_t src_x, src_y, mx, my; int16_t abcd[4]; uint16_t tmp_stride; uint8_t op, plane, ref, pad; } OracleWarpBlock;
+
+ORACLE_API void oracle_mc_batch(int bdmax, const OracleMcFrame *f, const OracleMcBlock *b, int n) {
+    const int hbd = bdmax > 255; const size_t px = hbd ? 2 : 1;
+    static __thread uint8_t win[135 * 135 * 2];
+    for (int i = 0; i < n; i++, b++) {
+        const int pl = b->plane;
+        const uint8_t *ref = (const uint8_t *)f->ref[b->ref] + (size_t)f->ref_plane_off[pl] * px;
+        oracle_emu_edge(b->w + 7, b->h + 7, f->ref_w[pl], f->ref_h[pl], b->src_x - 3, b->src_y - 3, win,
+                        135 * (ptrdiff_t)px, ref, f->ref_stride[pl] * (ptrdiff_t)px, bdmax);
+        const uint8_t *src = win + (3 * 135 + 3) * px;
+        if (b->op) oracle_mc_prep(f->tmp + b->dst_off, src, 135 * (ptrdiff_t)px, b->w, b->h, b->mx, b->my, b->filter2d, bdmax);
+        else oracle_mc_put((uint8_t *)f->dst + (size_t)b->dst_off * px, f->dst_stride[pl] * (ptrdiff_t)px, src,
+                           135 * (ptrdiff_t)px, b->w, b->h, b->mx, b->my, b->filter2d, bdmax);
+    }
+}
+ORACLE_API void oracle_mc_comp_batch(int bdmax, const OracleMcFrame *f, const OracleCompBlock *b, int n) {
+    const size_t px = bdmax > 255 ? 2 : 1;
+    for (int i = 0; i < n; i++, b++) {
+        void *dst = (uint8_t *)f->dst + (size_t)b->dst_off * px;
+        const ptrdiff_t ds = f->dst_stride[b->plane] * (ptrdiff_t)px;
+        const int16_t *t1 = f->tmp + b->tmp1_off, *t2 = f->tmp + b->tmp2_off;
+        if (b->op == 0) oracle_avg(dst, ds, t1, t2, b->w, b->h, bdmax);
+        else if (b->op == 1) oracle_w_avg(dst, ds, t1, t2, b->w, b->h, b->param, bdmax);
+        else if (b->op == 2) oracle_mask(dst, ds, t1, t2, b->w, b->h, f->mask + b->mask_off, bdmax);
+        else oracle_w_mask(dst, ds, t1, t2, b->w, b->h, f->mask + b->mask_off, b->param, b->op - 3, bdmax);
+    }
+}
+ORACLE_API void oracle_mc_blend_batch(int bdmax, const OracleMcFrame *f, const OracleBlendBlock *b, int n) {
+    const size_t px = bdmax > 255 ? 2 : 1;
+    for (int i = 0; i < n; i++, b++) {
+        void *dst = (uint8_t *)f->dst + (size_t)b->dst_off * px;
+        const ptrdiff_t ds = f->dst_stride[b->plane] * (ptrdiff_t)px;
+        const void *tmp = (const uint8_t *)f->px_tmp + (size_t)b->tmp_off * px;
+        if (b->op == 0) oracle_blend(dst, ds, tmp, b->w, b->h, f->mask + b->mask_off, bdmax);
+        else if (b->op == 1) oracle_blend_v(dst, ds, tmp, b->w, b->h, bdmax);
+        else oracle_blend_h(dst, ds, tmp, b->w, b->h, bdmax);
+    }
+}
+ORACLE_API void oracle_mc_warp_batch(int bdmax, const OracleMcFrame *f, const OracleWarpBlock *b, int n) {
+    const int hbd = bdmax > 255; const size_t px = hbd ? 2 : 1;
+    uint8_t win[15 * 15 * 2];
+    for (int i = 0; i < n; i++, b++) {
+        const int pl = b->plane;
+        const uint8_t *ref = (const uint8_t *)f->ref[b->ref] + (size_t)f->ref_plane_off[pl] * px;
+        oracle_emu_edge(15, 15, f->ref_w[pl], f->ref_h[pl], b->src_x - 3, b->src_y - 3, win, 15 * (ptrdiff_t)px,
+                        ref, f->ref_stride[pl] * (ptrdiff_t)px, bdmax);
+        const uint8_t *src = win + (3 * 15 + 3) * px;
+        if (b->op) oracle_warp8x8(1, f->tmp + b->dst_off, b->tmp_stride, src, 15 * (ptrdiff_t)px, b->abcd, b->mx, b->my, bdmax);
+        else oracle_warp8x8(0, (uint8_t *)f->dst + (size_t)b->dst_off * px, f->dst_stride[pl] * (ptrdiff_t)px, src,
+                            15 * (ptrdiff_t)px, b->abcd, b->mx, b->my, bdmax);
+    }
+}

@@ -229,3 +229,52 @@ def coef_dtype(bpc):
 
 def pixel_dtype(bpc):
     return np.uint8 if bpc == 8 else np.uint16
+
+
+# ---------------------------------------------------------------- mc
+def ref_mc_ctx(bpc):
+    """The reference's Dav1dMCDSPContext (C path) wrapped like dav1d_b200.dsp.MCDSPContext."""
+    key = ("mc", bpc)
+    if key not in _cache:
+        from dav1d_b200 import dsp
+        tbl = (C.c_void_p * 53)()
+        (ref().dav1d_mc_dsp_init_8bpc if bpc == 8 else ref().dav1d_mc_dsp_init_16bpc)(tbl)
+
+        class Ctx:
+            pass
+        c = Ctx()
+        c._tbl = tbl
+        for k, v in dsp.wrap_dsp_table(tbl, dsp.MC_LAYOUT, dsp.MC_PROTOS, bpc > 8, (1 << bpc) - 1).items():
+            setattr(c, k, v)
+        _cache[key] = c
+    return _cache[key]
+
+
+def oracle_mc_ctx(bpc):
+    """oracle/mc.c behind the same member names / call signatures."""
+    o = oracle()
+    bd = (1 << bpc) - 1
+    P, S, I = C.c_void_p, C.c_ssize_t, C.c_int
+
+    def a(x):
+        return x.ctypes.data if isinstance(x, np.ndarray) else x
+
+    class Ctx:
+        pass
+    c = Ctx()
+    c.mc = [(lambda d, ds, s, ss, w, h, mx, my, f=f: o.oracle_mc_put(P(a(d)), S(ds), P(a(s)), S(ss), w, h, mx, my, f, bd)) for f in range(10)]
+    c.mct = [(lambda t, s, ss, w, h, mx, my, f=f: o.oracle_mc_prep(P(a(t)), P(a(s)), S(ss), w, h, mx, my, f, bd)) for f in range(10)]
+    c.mc_scaled = [(lambda d, ds, s, ss, w, h, mx, my, dx, dy, f=f: o.oracle_mc_put_scaled(P(a(d)), S(ds), P(a(s)), S(ss), w, h, mx, my, dx, dy, f, bd)) for f in range(10)]
+    c.mct_scaled = [(lambda t, s, ss, w, h, mx, my, dx, dy, f=f: o.oracle_mc_prep_scaled(P(a(t)), P(a(s)), S(ss), w, h, mx, my, dx, dy, f, bd)) for f in range(10)]
+    c.avg = lambda d, ds, t1, t2, w, h: o.oracle_avg(P(a(d)), S(ds), P(a(t1)), P(a(t2)), w, h, bd)
+    c.w_avg = lambda d, ds, t1, t2, w, h, wt: o.oracle_w_avg(P(a(d)), S(ds), P(a(t1)), P(a(t2)), w, h, wt, bd)
+    c.mask = lambda d, ds, t1, t2, w, h, m: o.oracle_mask(P(a(d)), S(ds), P(a(t1)), P(a(t2)), w, h, P(a(m)), bd)
+    c.w_mask = [(lambda d, ds, t1, t2, w, h, m, sign, l=l: o.oracle_w_mask(P(a(d)), S(ds), P(a(t1)), P(a(t2)), w, h, P(a(m)), sign, l, bd)) for l in range(3)]
+    c.blend = lambda d, ds, t, w, h, m: o.oracle_blend(P(a(d)), S(ds), P(a(t)), w, h, P(a(m)), bd)
+    c.blend_v = lambda d, ds, t, w, h: o.oracle_blend_v(P(a(d)), S(ds), P(a(t)), w, h, bd)
+    c.blend_h = lambda d, ds, t, w, h: o.oracle_blend_h(P(a(d)), S(ds), P(a(t)), w, h, bd)
+    c.warp8x8 = lambda d, ds, s, ss, abcd, mx, my: o.oracle_warp8x8(0, P(a(d)), S(ds), P(a(s)), S(ss), P(a(abcd)), mx, my, bd)
+    c.warp8x8t = lambda t, ts, s, ss, abcd, mx, my: o.oracle_warp8x8(1, P(a(t)), S(ts), P(a(s)), S(ss), P(a(abcd)), mx, my, bd)
+    c.emu_edge = lambda bw, bh, iw, ih, x, y, d, ds, r, rs: o.oracle_emu_edge(S(bw), S(bh), S(iw), S(ih), S(x), S(y), P(a(d)), S(ds), P(a(r)), S(rs), bd)
+    c.resize = lambda d, ds, s, ss, dw, h, sw, dx, mx: o.oracle_resize(P(a(d)), S(ds), P(a(s)), S(ss), dw, h, sw, dx, mx, bd)
+    return c
