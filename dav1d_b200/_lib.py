@@ -48,6 +48,24 @@ class WarpBlock(C.Structure):
                 ("plane", C.c_uint8), ("ref", C.c_uint8), ("pad", C.c_uint8)]
 
 
+class FilterLUT(C.Structure):
+    """Av1FilterLUT / B200FilterLUT"""
+    _fields_ = [("e", C.c_uint8 * 64), ("i", C.c_uint8 * 64), ("sharp", C.c_uint64 * 2)]
+
+
+class Av1Filter(C.Structure):
+    """Av1Filter / B200Av1Filter (1348 bytes)"""
+    _fields_ = [("filter_y", C.c_uint16 * 2 * 3 * 32 * 2), ("filter_uv", C.c_uint16 * 2 * 2 * 32 * 2),
+                ("cdef_idx", C.c_int8 * 4), ("noskip_mask", C.c_uint16 * 2 * 16)]
+
+
+class LfFrame(C.Structure):
+    _fields_ = [("pic", C.c_void_p), ("plane_off", C.c_uint32 * 3), ("stride", C.c_int32 * 3),
+                ("w4", C.c_int32), ("h4", C.c_int32), ("sb128w", C.c_int32), ("b4_stride", C.c_int32),
+                ("ss_hor", C.c_int32), ("ss_ver", C.c_int32), ("sb128", C.c_int32), ("filter_y", C.c_int32),
+                ("filter_uv", C.c_int32), ("mask", C.c_void_p), ("level", C.c_void_p), ("lut", FilterLUT)]
+
+
 ITXFM_FN_8 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int)
 ITXFM_FN_16 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int)
 
@@ -78,6 +96,12 @@ _SIGS = {
     "b200_mc_resize": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t] + [C.c_int] * 6),
     "b200_mc_dsp_init_8bpc": (None, [C.c_void_p]),
     "b200_mc_dsp_init_16bpc": (None, [C.c_void_p]),
+    # ---- loopfilter
+    "b200_lf_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "b200_loop_filter_sb": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p,
+                                      C.c_ssize_t, C.c_void_p, C.c_int, C.c_int]),
+    "b200_loop_filter_dsp_init_8bpc": (None, [C.c_void_p]),
+    "b200_loop_filter_dsp_init_16bpc": (None, [C.c_void_p]),
 }
 
 

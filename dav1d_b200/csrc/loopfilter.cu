@@ -1,0 +1,265 @@
+// Deblocking filter (dav1d Dav1dLoopFilterDSPContext; reference src/loopfilter_tmpl.c:37-245,
+// frame driver src/lf_apply_tmpl.c:176-466).
+//
+// Within one direction every edge segment is independent (a width-wd filter reads <= wd/2 and
+// writes < wd/2 samples per side, and wd is bounded by the transform size on both sides), so a
+// picture is deblocked by two flat sweeps instead of dav1d's per-superblock-row calls:
+//   lf_cols_kernel  all column (vertical) edges: thread = (edge x4, picture line); threadIdx.x
+//                   walks consecutive edges of one line so a warp touches one contiguous row span
+//   lf_rows_kernel  all row (horizontal) edges: thread = (pixel column, edge y4); threadIdx.x walks
+//                   consecutive pixel columns, every tap is a coalesced row access
+// Masks and levels are consumed in dav1d's own layout (Av1Filter bit masks, level[4] per 4x4).
+#include "host_util.h"
+
+namespace b200 {
+
+// one line across one edge; p points at the first sample after the edge, sb = step across it
+template <bool HBD>
+B200_DEV void lf_line(typename Bd<HBD>::pixel *p, ptrdiff_t sb, int E, int I, int H, int wd, int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    const int b8 = HBD ? (32 - __clz(bdmax)) - 8 : 0;
+    const int F = 1 << b8;
+    E <<= b8; I <<= b8; H <<= b8;
+    const int p1 = p[-2 * sb], p0 = p[-1 * sb], q0 = p[0], q1 = p[sb];
+    int fm = iabs(p1 - p0) <= I && iabs(q1 - q0) <= I && iabs(p0 - q0) * 2 + (iabs(p1 - q1) >> 1) <= E;
+    int p2 = 0, q2 = 0, p3 = 0, q3 = 0;
+    if (wd > 4) {
+        p2 = p[-3 * sb]; q2 = p[2 * sb];
+        fm &= iabs(p2 - p1) <= I && iabs(q2 - q1) <= I;
+        if (wd > 6) {
+            p3 = p[-4 * sb]; q3 = p[3 * sb];
+            fm &= iabs(p3 - p2) <= I && iabs(q3 - q2) <= I;
+        }
+    }
+    if (!fm) return;
+    int flat8in = 0;
+    if (wd >= 6) flat8in = iabs(p2 - p0) <= F && iabs(p1 - p0) <= F && iabs(q1 - q0) <= F && iabs(q2 - q0) <= F;
+    if (wd >= 8) flat8in &= iabs(p3 - p0) <= F && iabs(q3 - q0) <= F;
+    if (wd >= 16) {
+        const int p6 = p[-7 * sb], p5 = p[-6 * sb], p4 = p[-5 * sb], q4 = p[4 * sb], q5 = p[5 * sb], q6 = p[6 * sb];
+        const int flat8out = iabs(p6 - p0) <= F && iabs(p5 - p0) <= F && iabs(p4 - p0) <= F &&
+                             iabs(q4 - q0) <= F && iabs(q5 - q0) <= F && iabs(q6 - q0) <= F;
+        if (flat8out & flat8in) {
+            // sliding 16-term window over p6*6 p6 p5 .. q5 q6 q6*6 (reference :95-118)
+            int s = p6 * 7 + p5 * 2 + p4 * 2 + p3 + p2 + p1 + p0 + q0 + 8;
+            p[-6 * sb] = (pixel)(s >> 4); s += -2 * p6 + p3 + q1;
+            p[-5 * sb] = (pixel)(s >> 4); s += -p6 - p5 + p2 + q2;
+            p[-4 * sb] = (pixel)(s >> 4); s += -p6 - p4 + p1 + q3;
+            p[-3 * sb] = (pixel)(s >> 4); s += -p6 - p3 + p0 + q4;
+            p[-2 * sb] = (pixel)(s >> 4); s += -p6 - p2 + q0 + q5;
+            p[-1 * sb] = (pixel)(s >> 4); s += -p6 - p1 + q1 + q6;
+            p[0]       = (pixel)(s >> 4); s += -p5 - p0 + q2 + q6;
+            p[1 * sb]  = (pixel)(s >> 4); s += -p4 - q0 + q3 + q6;
+            p[2 * sb]  = (pixel)(s >> 4); s += -p3 - q1 + q4 + q6;
+            p[3 * sb]  = (pixel)(s >> 4); s += -p2 - q2 + q5 + q6;
+            p[4 * sb]  = (pixel)(s >> 4); s += -p1 - q3 + q6 + q6;
+            p[5 * sb]  = (pixel)(s >> 4);
+            return;
+        }
+    }
+    if (wd >= 8 && flat8in) {
+        p[-3 * sb] = (pixel)((p3 + p3 + p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3);
+        p[-2 * sb] = (pixel)((p3 + p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3);
+        p[-1 * sb] = (pixel)((p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3);
+        p[0]       = (pixel)((p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3);
+        p[1 * sb]  = (pixel)((p1 + p0 + q0 + 2 * q1 + q2 + q3 + q3 + 4) >> 3);
+        p[2 * sb]  = (pixel)((p0 + q0 + q1 + 2 * q2 + q3 + q3 + q3 + 4) >> 3);
+    } else if (wd == 6 && flat8in) {
+        p[-2 * sb] = (pixel)((p2 + 2 * p2 + 2 * p1 + 2 * p0 + q0 + 4) >> 3);
+        p[-1 * sb] = (pixel)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+        p[0]       = (pixel)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+        p[1 * sb]  = (pixel)((p0 + 2 * q0 + 2 * q1 + 2 * q2 + q2 + 4) >> 3);
+    } else {
+        const int lo = -128 * (1 << b8), hi = 128 * (1 << b8) - 1;
+        const bool hev = iabs(p1 - p0) > H || iabs(q1 - q0) > H;
+        int f = hev ? iclip(p1 - q1, lo, hi) : 0;
+        f = iclip(3 * (q0 - p0) + f, lo, hi);
+        const int f1 = imin(f + 4, hi) >> 3, f2 = imin(f + 3, hi) >> 3;
+        p[-1 * sb] = (pixel)iclip(p0 + f2, 0, bdmax);
+        p[0]       = (pixel)iclip(q0 - f1, 0, bdmax);
+        if (!hev) {
+            const int g = (f1 + 1) >> 1;
+            p[-2 * sb] = (pixel)iclip(p1 + g, 0, bdmax);
+            p[1 * sb]  = (pixel)iclip(q1 - g, 0, bdmax);
+        }
+    }
+}
+
+// decode the filter width of unit `a` (index along the edge direction inside the 128x128 area) for
+// the line of units `b` (index across it); returns 0 when no edge is filtered there
+B200_DEV int lf_width(const B200Av1Filter &m, int plane, int dir, int b, int a, int ss_a)
+{
+    if (plane == 0) {
+        const int half = a >> 4, bit = a & 15;
+        if ((m.filter_y[dir][b][2][half] >> bit) & 1) return 16;
+        if ((m.filter_y[dir][b][1][half] >> bit) & 1) return 8;
+        if ((m.filter_y[dir][b][0][half] >> bit) & 1) return 4;
+        return 0;
+    }
+    const int hs = 16 >> ss_a;                       // units per 16-bit half along the edge direction
+    const int half = a >= hs, bit = a - half * hs;
+    if ((m.filter_uv[dir][b][1][half] >> bit) & 1) return 6;
+    if ((m.filter_uv[dir][b][0][half] >> bit) & 1) return 4;
+    return 0;
+}
+
+// grid: (ceil(units_x / 32), ceil(lines / 8), 3 planes); block (32, 8)
+template <bool HBD>
+__global__ void __launch_bounds__(256) lf_cols_kernel(B200LfFrame f, int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    const int plane = blockIdx.z;
+    if (plane ? !f.filter_uv : !f.filter_y) return;
+    const int ssh = plane ? f.ss_hor : 0, ssv = plane ? f.ss_ver : 0;
+    const int x4 = blockIdx.x * 32 + threadIdx.x;            // 4-px unit (plane units)
+    const int y = blockIdx.y * 8 + threadIdx.y;              // picture line (plane units)
+    const int pw4 = (f.w4 + ssh) >> ssh, ph4 = (f.h4 + ssv) >> ssv;
+    if (x4 >= pw4 || x4 == 0 || y >= ph4 * 4) return;
+    const int upsb_x = 32 >> ssh, upsb_y = 32 >> ssv;        // units per 128x128 area
+    const int sbx = x4 / upsb_x, xi = x4 - sbx * upsb_x;
+    const int y4 = y >> 2, sby = y4 / upsb_y, yi = y4 - sby * upsb_y;
+    const B200Av1Filter &m = f.mask[sby * f.sb128w + sbx];
+    const int wd = lf_width(m, plane, 0, xi, yi, ssv);
+    if (!wd) return;
+    const uint8_t (*l)[4] = f.level + (ptrdiff_t)y4 * f.b4_stride + x4;
+    const int c = plane == 0 ? 0 : plane + 1;
+    const int L = l[0][c] ? l[0][c] : l[-1][c];
+    if (!L) return;
+    pixel *p = (pixel *)f.pic + f.plane_off[plane] + (ptrdiff_t)y * f.stride[plane] + x4 * 4;
+    lf_line<HBD>(p, 1, f.lut.e[L], f.lut.i[L], L >> 4, wd, bdmax);
+}
+
+// grid: (ceil(width_px / 128), ceil(units_y / 2), 3); block (128, 2)
+template <bool HBD>
+__global__ void __launch_bounds__(256) lf_rows_kernel(B200LfFrame f, int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    const int plane = blockIdx.z;
+    if (plane ? !f.filter_uv : !f.filter_y) return;
+    const int ssh = plane ? f.ss_hor : 0, ssv = plane ? f.ss_ver : 0;
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    const int y4 = blockIdx.y * 2 + threadIdx.y;
+    const int pw4 = (f.w4 + ssh) >> ssh, ph4 = (f.h4 + ssv) >> ssv;
+    if (x >= pw4 * 4 || y4 >= ph4 || y4 == 0) return;
+    const int upsb_x = 32 >> ssh, upsb_y = 32 >> ssv;
+    const int x4 = x >> 2, sbx = x4 / upsb_x, xi = x4 - sbx * upsb_x;
+    const int sby = y4 / upsb_y, yi = y4 - sby * upsb_y;
+    const B200Av1Filter &m = f.mask[sby * f.sb128w + sbx];
+    const int wd = lf_width(m, plane, 1, yi, xi, ssh);
+    if (!wd) return;
+    const uint8_t (*l)[4] = f.level + (ptrdiff_t)y4 * f.b4_stride + x4;
+    const int c = plane == 0 ? 1 : plane + 1;
+    const int L = l[0][c] ? l[0][c] : l[-f.b4_stride][c];
+    if (!L) return;
+    pixel *p = (pixel *)f.pic + f.plane_off[plane] + (ptrdiff_t)(y4 * 4) * f.stride[plane] + x;
+    lf_line<HBD>(p, f.stride[plane], f.lut.e[L], f.lut.i[L], L >> 4, wd, bdmax);
+}
+
+// Level-1 form: one call of loop_filter_sb = up to 32 segments along one line of units
+struct LfSbArgs {
+    uint32_t mask[3];
+    uint8_t cur[32], prev[32];
+    B200FilterLUT lut;
+    int plane_class, dir, n_units, stride;
+};
+template <bool HBD>
+__global__ void lf_sb_kernel(typename Bd<HBD>::pixel *dst, LfSbArgs a, int bdmax)
+{
+    const int line = blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= a.n_units * 4) return;
+    const int u = line >> 2;
+    int wd = 0;
+    if (a.plane_class) wd = (a.mask[1] >> u) & 1 ? 6 : ((a.mask[0] >> u) & 1 ? 4 : 0);
+    else wd = (a.mask[2] >> u) & 1 ? 16 : ((a.mask[1] >> u) & 1 ? 8 : ((a.mask[0] >> u) & 1 ? 4 : 0));
+    if (!wd) return;
+    const int L = a.cur[u] ? a.cur[u] : a.prev[u];
+    if (!L) return;
+    // dense window: dir 0 -> 16 px wide rows, edge at column 8; dir 1 -> 16 rows, edge at row 8
+    typename Bd<HBD>::pixel *p = a.dir ? dst + 8 * a.stride + line : dst + (ptrdiff_t)line * a.stride + 8;
+    lf_line<HBD>(p, a.dir ? a.stride : 1, a.lut.e[L], a.lut.i[L], L >> 4, wd, bdmax);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_lf_frame(int bdmax, const B200LfFrame *f, void *stream)
+{
+    if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_lf_frame: bad bitdepth_max %d", bdmax); return -2; }
+    if (!f->filter_y) return 0;   // dav1d skips deblocking entirely when both luma levels are 0 (src/recon_tmpl.c:1988)
+    const int w4 = f->w4, h4 = f->h4;
+    dim3 g1((w4 + 31) / 32, (h4 * 4 + 7) / 8, 3), b1(32, 8);
+    dim3 g2((w4 * 4 + 127) / 128, (h4 + 1) / 2, 3), b2(128, 2);
+    if (bdmax > 255) {
+        auto k1 = lf_cols_kernel<true>; B200_LAUNCH(k1, g1, b1, 0, (cudaStream_t)stream, *f, bdmax);
+        auto k2 = lf_rows_kernel<true>; B200_LAUNCH(k2, g2, b2, 0, (cudaStream_t)stream, *f, bdmax);
+    } else {
+        auto k1 = lf_cols_kernel<false>; B200_LAUNCH(k1, g1, b1, 0, (cudaStream_t)stream, *f, bdmax);
+        auto k2 = lf_rows_kernel<false>; B200_LAUNCH(k2, g2, b2, 0, (cudaStream_t)stream, *f, bdmax);
+    }
+    b200_count_launch(); b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int b200_loop_filter_sb(int plane_class, int dir, void *dst, ptrdiff_t stride, const uint32_t *mask,
+                        const uint8_t (*lvl)[4], ptrdiff_t lvl_stride, const B200FilterLUT *lut, int w, int bdmax)
+{
+    (void)w;   // like the C reference, the extent comes from the highest set mask bit
+    if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_loop_filter_sb: bad bitdepth_max"); return -2; }
+    const uint32_t vm = mask[0] | mask[1] | (plane_class ? 0 : mask[2]);
+    if (!vm) return 0;
+    int n_units = 32 - __builtin_clz(vm);
+    std::lock_guard<std::mutex> lk(host_lock());
+    static Scratch s_win;
+    static uint8_t h_win[16 * 128 * 2];
+    const size_t px = bdmax > 255 ? 2 : 1;
+    LfSbArgs a;
+    memset(&a, 0, sizeof(a));
+    a.mask[0] = mask[0]; a.mask[1] = mask[1]; a.mask[2] = plane_class ? 0 : mask[2];
+    a.lut = *lut; a.plane_class = plane_class; a.dir = dir; a.n_units = n_units;
+    for (int u = 0; u < n_units; u++) {
+        const uint8_t (*l)[4] = lvl + (dir ? u : u * lvl_stride);
+        a.cur[u] = l[0][0];
+        a.prev[u] = dir ? l[-lvl_stride][0] : l[-1][0];
+    }
+    const int lines = n_units * 4;
+    int ww, wh; const uint8_t *org;
+    if (dir) { ww = lines; wh = 16; org = (const uint8_t *)dst - 8 * stride; }
+    else { ww = 16; wh = lines; org = (const uint8_t *)dst - 8 * (ptrdiff_t)px; }
+    a.stride = ww;
+    pack_rect(h_win, org, stride, ww, wh, px);
+    if (s_win.upload(h_win, (size_t)ww * wh * px)) return -1;
+    const int grid = (lines + 127) / 128;
+    if (bdmax > 255) { auto k = lf_sb_kernel<true>; B200_LAUNCH(k, dim3(grid), dim3(128), 0, (cudaStream_t)0, (uint16_t *)s_win.p, a, bdmax); }
+    else { auto k = lf_sb_kernel<false>; B200_LAUNCH(k, dim3(grid), dim3(128), 0, (cudaStream_t)0, (uint8_t *)s_win.p, a, bdmax); }
+    b200_count_launch();
+    if (s_win.download(h_win, (size_t)ww * wh * px)) return -1;
+    B200_CUDA_OK(cudaStreamSynchronize(0));
+    unpack_rect((uint8_t *)org, stride, h_win, ww, wh, px);
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+template <int PC, int DIR> void lf8(uint8_t *d, ptrdiff_t s, const uint32_t *m, const uint8_t (*l)[4], ptrdiff_t ls, const B200FilterLUT *lut, int w) {
+    if (b200_loop_filter_sb(PC, DIR, d, s, m, l, ls, lut, w, 255)) die("loop_filter_sb");
+}
+template <int PC, int DIR> void lf16(uint16_t *d, ptrdiff_t s, const uint32_t *m, const uint8_t (*l)[4], ptrdiff_t ls, const B200FilterLUT *lut, int w, int bd) {
+    if (b200_loop_filter_sb(PC, DIR, d, s, m, l, ls, lut, w, bd)) die("loop_filter_sb");
+}
+}
+extern "C" {
+void b200_loop_filter_dsp_init_8bpc(B200LoopFilterDSPContext *c) {
+    c->loop_filter_sb[0][0] = (void *)lf8<0, 0>; c->loop_filter_sb[0][1] = (void *)lf8<0, 1>;
+    c->loop_filter_sb[1][0] = (void *)lf8<1, 0>; c->loop_filter_sb[1][1] = (void *)lf8<1, 1>;
+}
+void b200_loop_filter_dsp_init_16bpc(B200LoopFilterDSPContext *c) {
+    c->loop_filter_sb[0][0] = (void *)lf16<0, 0>; c->loop_filter_sb[0][1] = (void *)lf16<0, 1>;
+    c->loop_filter_sb[1][0] = (void *)lf16<1, 0>; c->loop_filter_sb[1][1] = (void *)lf16<1, 1>;
+}
+}

@@ -113,3 +113,18 @@ class MCDSPContext:
         (self.lib.b200_mc_dsp_init_8bpc if bpc == 8 else self.lib.b200_mc_dsp_init_16bpc)(self._tbl)
         for k, v in wrap_dsp_table(self._tbl, MC_LAYOUT, MC_PROTOS, bpc > 8, self.bitdepth_max).items():
             setattr(self, k, v)
+
+
+LF_PROTO = [_P, _S, _P, _P, _S, _P, _I]   # decl_loopfilter_sb_fn (reference src/loopfilter.h:39-43)
+
+
+class LoopFilterDSPContext:
+    """Dav1dLoopFilterDSPContext (reference src/loopfilter.h:45-53): loop_filter_sb[plane_class][dir]."""
+
+    def __init__(self, bpc, lib=None):
+        self.bpc, self.bitdepth_max = bpc, (1 << bpc) - 1
+        self.lib = lib or get_lib()
+        self._tbl = (C.c_void_p * 4)()
+        (self.lib.b200_loop_filter_dsp_init_8bpc if bpc == 8 else self.lib.b200_loop_filter_dsp_init_16bpc)(self._tbl)
+        t = wrap_dsp_table(self._tbl, [("f", 4)], {"f": (LF_PROTO, True)}, bpc > 8, self.bitdepth_max)["f"]
+        self.loop_filter_sb = [[t[0], t[1]], [t[2], t[3]]]

@@ -1,0 +1,171 @@
+"""Synthetic frame records for tests and bench.py.
+
+No AV1 stream or encoder exists in this environment (SURVEY.md §7 hard part 7), so the "host
+side" that dav1d's entropy decoder would play is synthesised at the RECORD level: random block
+tilings, transform sizes, filter levels, masks ... in exactly the layouts dav1d's pass 1 leaves
+in memory (Av1Filter bit masks, level[4] per 4x4, ...). Everything here is seeded and pure numpy.
+"""
+import numpy as np
+
+# byte-identical to dav1d's Av1Filter (reference src/lf_mask.h:51-57), 1348 bytes
+AV1FILTER_DT = np.dtype([("filter_y", "<u2", (2, 32, 3, 2)), ("filter_uv", "<u2", (2, 32, 2, 2)),
+                         ("cdef_idx", "i1", (4,)), ("noskip_mask", "<u2", (16, 2))])
+assert AV1FILTER_DT.itemsize == 1348
+
+
+def random_tiling(rng, w4, h4, max_log=4, min_log=0, p_split=0.55):
+    """Random block tiling of a w4 x h4 grid of 4x4 units. Returns int arrays (h4, w4):
+    bx, by (origin of the block covering each unit) and lw, lh (log2 of block width/height in units)."""
+    bx = np.zeros((h4, w4), np.int32); by = np.zeros((h4, w4), np.int32)
+    lw = np.zeros((h4, w4), np.int8); lh = np.zeros((h4, w4), np.int8)
+    S = 1 << max_log
+
+    def fill(x, y, lwv, lhv):
+        x1, y1 = min(w4, x + (1 << lwv)), min(h4, y + (1 << lhv))
+        bx[y:y1, x:x1] = x; by[y:y1, x:x1] = y; lw[y:y1, x:x1] = lwv; lh[y:y1, x:x1] = lhv
+
+    def rec(x, y, lwv, lhv):
+        if x >= w4 or y >= h4:
+            return
+        can_w, can_h = lwv > min_log, lhv > min_log
+        if (can_w or can_h) and rng.random() < p_split:
+            mode = rng.integers(0, 3)
+            if mode == 0 and can_w and can_h:
+                for dy in (0, 1):
+                    for dx in (0, 1):
+                        rec(x + (dx << (lwv - 1)), y + (dy << (lhv - 1)), lwv - 1, lhv - 1)
+                return
+            if (mode == 1 or not can_h) and can_w and lwv >= lhv:       # keep aspect within 1:2 .. 2:1 .. 4:1
+                rec(x, y, lwv - 1, lhv); rec(x + (1 << (lwv - 1)), y, lwv - 1, lhv)
+                return
+            if can_h and lhv >= lwv:
+                rec(x, y, lwv, lhv - 1); rec(x, y + (1 << (lhv - 1)), lwv, lhv - 1)
+                return
+        fill(x, y, lwv, lhv)
+
+    for y in range(0, h4, S):
+        for x in range(0, w4, S):
+            rec(x, y, max_log, max_log)
+    return bx, by, lw, lh
+
+
+def _pack_bits(flags, axis_units, halves_len):
+    """flags: bool [n_sb_a, units_a(<=32), ...]; pack `axis_units` along axis 1 into 2 uint16 halves."""
+    n = flags.shape[1]
+    out = []
+    for h in range(2):
+        lo, hi = h * halves_len, min(n, (h + 1) * halves_len)
+        if lo >= hi:
+            out.append(np.zeros(flags.shape[:1] + flags.shape[2:], np.uint16))
+            continue
+        w = (1 << np.arange(hi - lo)).astype(np.uint32)
+        shape = [1] * flags.ndim; shape[1] = hi - lo
+        out.append((flags[:, lo:hi] * w.reshape(shape)).sum(axis=1).astype(np.uint16))
+    return out
+
+
+def build_lf_masks(w4, h4, til_y, til_uv, ss_hor, ss_ver):
+    """Av1Filter[] (one per 128x128 area, row-major sb128h x sb128w) from a luma tiling and a chroma
+    tiling (chroma tiling in chroma 4x4 units). Edge filter size = min(size class of the two
+    transform blocks that meet, capped: luma 4/8/16 -> 0/1/2, chroma 4/6 -> 0/1), as
+    dav1d_create_lf_mask_* does (reference src/lf_mask.c)."""
+    sb128w, sb128h = (w4 + 31) // 32, (h4 + 31) // 32
+    masks = np.zeros(sb128h * sb128w, AV1FILTER_DT)
+
+    def edges(til, cap):
+        bx, by, lw, lh = til
+        hh, ww = bx.shape
+        xs = np.arange(ww)[None, :]; ys = np.arange(hh)[:, None]
+        cw, ch = np.minimum(lw, cap), np.minimum(lh, cap)
+        col = np.full((hh, ww), -1, np.int8)
+        is_l = (bx == xs) & (xs > 0)
+        col[:, 1:] = np.where(is_l[:, 1:], np.minimum(cw[:, 1:], cw[:, :-1]), -1)
+        row = np.full((hh, ww), -1, np.int8)
+        is_t = (by == ys) & (ys > 0)
+        row[1:, :] = np.where(is_t[1:, :], np.minimum(ch[1:, :], ch[:-1, :]), -1)
+        return col, row
+
+    def put(field, col, row, ux, uy, ncls):
+        # ux / uy: units per 128x128 area in x / y; pad to whole areas
+        hh, ww = col.shape
+        H, W = sb128h * uy, sb128w * ux
+        for d, cls_map in ((0, col), (1, row)):
+            full = np.full((H, W), -1, np.int8); full[:hh, :ww] = cls_map
+            t = full.reshape(sb128h, uy, sb128w, ux)           # [sby, yi, sbx, xi]
+            for k in range(ncls):
+                f = (t == k)
+                if d == 0:   # col edges: index [xi][k][half(yi)] bit yi
+                    a = f.transpose(0, 1, 2, 3)                # [sby, yi, sbx, xi]
+                    halves = _pack_bits(a, uy, 16 * uy // 32)
+                    for h in range(2):
+                        masks[field][:, 0, :ux, k, h] = halves[h].reshape(sb128h * sb128w, ux)
+                else:        # row edges: index [yi][k][half(xi)] bit xi
+                    a = f.transpose(0, 3, 2, 1)                # [sby, xi, sbx, yi]
+                    halves = _pack_bits(a, ux, 16 * ux // 32)
+                    for h in range(2):
+                        masks[field][:, 1, :uy, k, h] = halves[h].reshape(sb128h * sb128w, uy)
+
+    cy, ry = edges(til_y, 2)
+    put("filter_y", cy, ry, 32, 32, 3)
+    if til_uv is not None:
+        cu, ru = edges(til_uv, 1)
+        put("filter_uv", cu, ru, 32 >> ss_hor, 32 >> ss_ver, 2)
+    return masks
+
+
+def filter_lut(sharp):
+    """Av1FilterLUT from the frame's sharpness (dav1d_calc_eih, reference src/lf_mask.c:385-...;
+    same formula as tests/checkasm/loopfilter.c:122-137)."""
+    e = np.zeros(64, np.uint8); i = np.zeros(64, np.uint8)
+    for level in range(64):
+        limit = level
+        if sharp > 0:
+            limit >>= (sharp + 3) >> 2
+            limit = min(limit, 9 - sharp)
+        limit = max(limit, 1)
+        i[level] = limit
+        e[level] = 2 * (level + 2) + limit
+    return e, i, [(sharp + 3) >> 2, (9 - sharp) if sharp else 0xff]
+
+
+def make_lf_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, sharp=None, smooth=True):
+    """Picture + deblocking records for one frame. Returns a dict of numpy arrays / ints."""
+    bd = (1 << bpc) - 1
+    dt = np.uint8 if bpc == 8 else np.uint16
+    w4, h4 = (W + 3) // 4, (H + 3) // 4
+    cw4, ch4 = (w4 + ss_hor) >> ss_hor, (h4 + ss_ver) >> ss_ver
+    sb128w = (w4 + 31) // 32
+    b4_stride = (w4 + 31) & ~31
+    # planes: stride padded like dav1d's allocator (reference src/picture.c:46-78)
+    aw, ah = (W + 127) & ~127, (H + 127) & ~127
+    stride = [aw + 64, (aw >> ss_hor) + 64, (aw >> ss_hor) + 64]
+    rows = [ah, ah >> ss_ver, ah >> ss_ver]
+    off = [0, stride[0] * rows[0], stride[0] * rows[0] + stride[1] * rows[1]]
+    total = off[2] + stride[2] * rows[2]
+    if smooth:   # low-amplitude texture so that the flat / narrow decisions all occur
+        base = rng.integers(0, bd + 1, total // 64 + 2)
+        pic = (np.repeat(base, 64)[:total] + rng.integers(-3 << (bpc - 8), (3 << (bpc - 8)) + 1, total)).clip(0, bd).astype(dt)
+    else:
+        pic = rng.integers(0, bd + 1, total).astype(dt)
+    til_y = random_tiling(rng, w4, h4)
+    til_uv = random_tiling(rng, cw4, ch4, max_log=3)
+    masks = build_lf_masks(w4, h4, til_y, til_uv, ss_hor, ss_ver)
+    # levels per block (0 sometimes, to exercise the neighbour fallback and the L == 0 skip)
+    level = np.zeros((h4 + 32) * b4_stride * 4, np.uint8).reshape(-1, 4)
+    lv = level.reshape(h4 + 32, b4_stride, 4)
+
+    def per_block(til, hh, ww):
+        bx, by, _, _ = til
+        key = by.astype(np.int64) * 65536 + bx
+        uniq, inv = np.unique(key, return_inverse=True)
+        vals = rng.integers(0, 64, len(uniq)).astype(np.uint8)
+        vals[rng.random(len(uniq)) < 0.15] = 0
+        return vals[inv].reshape(hh, ww)
+    lv[:h4, :w4, 0] = per_block(til_y, h4, w4)
+    lv[:h4, :w4, 1] = per_block(til_y, h4, w4)
+    lv[:ch4, :cw4, 2] = per_block(til_uv, ch4, cw4)
+    lv[:ch4, :cw4, 3] = per_block(til_uv, ch4, cw4)
+    e, i, sh = filter_lut(int(rng.integers(0, 8)) if sharp is None else sharp)
+    return dict(bpc=bpc, bd=bd, W=W, H=H, w4=w4, h4=h4, sb128w=sb128w, b4_stride=b4_stride, ss_hor=ss_hor,
+                ss_ver=ss_ver, stride=stride, off=off, rows=rows, pic=pic, masks=masks, level=level,
+                lut_e=e, lut_i=i, lut_sharp=sh, til_y=til_y, til_uv=til_uv)

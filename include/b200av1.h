@@ -187,6 +187,49 @@ typedef struct B200MCDSPContext {
 B200_API void b200_mc_dsp_init_8bpc(B200MCDSPContext *c);
 B200_API void b200_mc_dsp_init_16bpc(B200MCDSPContext *c);
 
+/* ==== loopfilter (Dav1dLoopFilterDSPContext, reference src/loopfilter.h:39-53) =========== */
+/* byte-identical to dav1d's Av1FilterLUT / Av1Filter (reference src/lf_mask.h:36-57): a dav1d
+ * record emitter ships f->lf.lim_lut and f->lf.mask[] (after the tile-edge fix-ups of
+ * src/lf_apply_tmpl.c:331-401) and f->lf.level[] to HBM unchanged. */
+typedef struct B200FilterLUT {
+    uint8_t e[64];
+    uint8_t i[64];
+    uint64_t sharp[2];
+} B200FilterLUT;
+typedef struct B200Av1Filter {
+    uint16_t filter_y[2 /* 0=col, 1=row */][32][3][2];
+    uint16_t filter_uv[2 /* 0=col, 1=row */][32][2][2];
+    int8_t cdef_idx[4];
+    uint16_t noskip_mask[16][2];
+} B200Av1Filter;
+
+/* Level 2: deblock a whole picture in HBM (replaces dav1d_loopfilter_sbrow_cols/_rows for every
+ * superblock row, reference src/lf_apply_tmpl.c:313-466): one sweep over all column edges of
+ * all planes, then one over all row edges. */
+typedef struct B200LfFrame {
+    void *pic;                     /* device picture, 3 planes */
+    uint32_t plane_off[3];         /* pixels */
+    int32_t stride[3];             /* pixels */
+    int32_t w4, h4;                /* f->w4, f->h4: picture size in luma 4-px units */
+    int32_t sb128w;                /* f->sb128w */
+    int32_t b4_stride;             /* f->b4_stride */
+    int32_t ss_hor, ss_ver;        /* chroma subsampling */
+    int32_t sb128;                 /* informational (walk order only matters on the CPU) */
+    int32_t filter_y, filter_uv;   /* frame header: level_y[0]|level_y[1], level_u|level_v */
+    const B200Av1Filter *mask;     /* device, sb128w * ceil(h4/32) entries */
+    const uint8_t (*level)[4];     /* device, f->lf.level */
+    B200FilterLUT lut;
+} B200LfFrame;
+B200_API int b200_lf_frame(int bitdepth_max, const B200LfFrame *frame, void *stream);
+
+/* Level 1: loop_filter_sb[plane_class][dir] with host pointers (decl_loopfilter_sb_fn) */
+B200_API int b200_loop_filter_sb(int plane_class, int dir, void *dst, ptrdiff_t stride, const uint32_t *mask,
+                                 const uint8_t (*lvl)[4], ptrdiff_t lvl_stride, const B200FilterLUT *lut,
+                                 int w, int bitdepth_max);
+typedef struct B200LoopFilterDSPContext { void *loop_filter_sb[2][2]; } B200LoopFilterDSPContext;
+B200_API void b200_loop_filter_dsp_init_8bpc(B200LoopFilterDSPContext *c);
+B200_API void b200_loop_filter_dsp_init_16bpc(B200LoopFilterDSPContext *c);
+
 #ifdef __cplusplus
 }
 #endif

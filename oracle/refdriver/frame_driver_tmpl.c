@@ -1,0 +1,80 @@
+/*
+ * oracle/refdriver/frame_driver_tmpl.c — TEST INFRASTRUCTURE, compiled at BITDEPTH 8 and 16 and
+ * linked into oracle/_ref/libdav1d_ref.so.
+ *
+ * Drives the reference's OWN frame-level drivers (src/lf_apply_tmpl.c, ...) from a hand-built
+ * Dav1dFrameContext holding just the fields those drivers read, so that the frame-wide CUDA
+ * sweeps can be checked against dav1d's real per-superblock-row code, not only against our
+ * restatement. The caller's frame description restates B200LfFrame (include/b200av1.h).
+ */
+#include "config.h"
+#include <stdlib.h>
+#include <string.h>
+#include "common/bitdepth.h"
+#include "src/internal.h"
+#include "src/lf_apply.h"
+#include "src/loopfilter.h"
+
+#define API __attribute__((visibility("default")))
+
+typedef struct {
+    void *pic;
+    uint32_t plane_off[3];
+    int32_t stride[3];
+    int32_t w4, h4, sb128w, b4_stride, ss_hor, ss_ver, sb128, filter_y, filter_uv;
+    Av1Filter *mask;
+    uint8_t (*level)[4];
+    struct { uint8_t e[64], i[64]; uint64_t sharp[2]; } lut;   /* unaligned, as the caller packs it */
+} RefLfFrame;
+
+API void bitfn(refdrv_lf_frame)(const int bitdepth_max, const RefLfFrame *const fr)
+{
+    Dav1dFrameContext *const f = calloc(1, sizeof(*f));
+    Dav1dSequenceHeader *const seq = calloc(1, sizeof(*seq));
+    Dav1dFrameHeader *const hdr = calloc(1, sizeof(*hdr));
+    Dav1dDSPContext *const dsp = calloc(1, sizeof(*dsp));
+    bitfn(dav1d_loop_filter_dsp_init)(&dsp->lf);
+    f->dsp = dsp;
+    f->seq_hdr = seq;
+    f->frame_hdr = hdr;
+    seq->sb128 = fr->sb128;
+    f->w4 = fr->w4; f->h4 = fr->h4;
+    f->bw = fr->w4; f->bh = fr->h4;            /* no super-res, frame size == picture size here */
+    f->sb128w = fr->sb128w;
+    f->b4_stride = fr->b4_stride;
+    f->sb_step = 32 >> !fr->sb128;
+    f->sbh = (fr->h4 + f->sb_step - 1) / f->sb_step;
+    f->cur.p.layout = !fr->ss_hor ? DAV1D_PIXEL_LAYOUT_I444 : fr->ss_ver ? DAV1D_PIXEL_LAYOUT_I420 : DAV1D_PIXEL_LAYOUT_I422;
+    f->cur.stride[0] = fr->stride[0] * (ptrdiff_t)sizeof(pixel);
+    f->cur.stride[1] = fr->stride[1] * (ptrdiff_t)sizeof(pixel);
+#if BITDEPTH == 16
+    f->bitdepth_max = bitdepth_max;
+#endif
+    f->lf.level = fr->level;
+    memcpy(f->lf.lim_lut.e, fr->lut.e, 64);
+    memcpy(f->lf.lim_lut.i, fr->lut.i, 64);
+    f->lf.lim_lut.sharp[0] = fr->lut.sharp[0]; f->lf.lim_lut.sharp[1] = fr->lut.sharp[1];
+    f->lf.mask = fr->mask;
+    hdr->loopfilter.level_u = hdr->loopfilter.level_v = fr->filter_uv;
+    hdr->tiling.cols = 1;
+    hdr->tiling.col_start_sb[0] = 0;
+    hdr->tiling.col_start_sb[1] = 1 << 14;    /* single tile column: loop at lf_apply_tmpl.c:334 exits at once */
+    static uint8_t lpf_edge[2][8192];
+    f->lf.tx_lpf_right_edge[0] = lpf_edge[0];
+    f->lf.tx_lpf_right_edge[1] = lpf_edge[1];
+    pixel *const base = fr->pic;
+    if (fr->filter_y) {
+        for (int sby = 0; sby < f->sbh; sby++) {
+            const int y = sby * f->sb_step * 4;
+            pixel *const p[3] = {
+                base + fr->plane_off[0] + (ptrdiff_t)y * fr->stride[0],
+                base + fr->plane_off[1] + (ptrdiff_t)(y >> fr->ss_ver) * fr->stride[1],
+                base + fr->plane_off[2] + (ptrdiff_t)(y >> fr->ss_ver) * fr->stride[2],
+            };
+            Av1Filter *const mask = f->lf.mask + (sby >> !seq->sb128) * f->sb128w;
+            bytefn(dav1d_loopfilter_sbrow_cols)(f, p, mask, sby, 0);
+            bytefn(dav1d_loopfilter_sbrow_rows)(f, p, mask, sby);
+        }
+    }
+    free(dsp); free(hdr); free(seq); free(f);
+}
