@@ -66,6 +66,13 @@ class LfFrame(C.Structure):
                 ("filter_uv", C.c_int32), ("mask", C.c_void_p), ("level", C.c_void_p), ("lut", FilterLUT)]
 
 
+class CdefFrame(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("plane_off", C.c_uint32 * 3), ("stride", C.c_int32 * 3),
+                ("bw", C.c_int32), ("bh", C.c_int32), ("sb128w", C.c_int32), ("ss_hor", C.c_int32),
+                ("ss_ver", C.c_int32), ("damping", C.c_int32), ("y_strength", C.c_int32 * 8),
+                ("uv_strength", C.c_int32 * 8), ("mask", C.c_void_p)]
+
+
 ITXFM_FN_8 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int)
 ITXFM_FN_16 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int)
 
@@ -102,6 +109,12 @@ _SIGS = {
                                       C.c_ssize_t, C.c_void_p, C.c_int, C.c_int]),
     "b200_loop_filter_dsp_init_8bpc": (None, [C.c_void_p]),
     "b200_loop_filter_dsp_init_16bpc": (None, [C.c_void_p]),
+    # ---- cdef
+    "b200_cdef_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "b200_cdef_dir": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int]),
+    "b200_cdef_fb": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 8),
+    "b200_cdef_dsp_init_8bpc": (None, [C.c_void_p]),
+    "b200_cdef_dsp_init_16bpc": (None, [C.c_void_p]),
 }
 
 

@@ -1,0 +1,339 @@
+// CDEF (dav1d Dav1dCdefDSPContext; reference src/cdef_tmpl.c:37-305, driver src/cdef_apply_tmpl.c).
+//
+// Frame-wide and out of place: one warp owns one 8x8 luma block and its chroma blocks. The warp
+// finds the block's direction/variance from the (pre-CDEF) luma samples, derives the strengths
+// exactly like dav1d_cdef_brow, then every lane filters its pixels reading taps straight from the
+// source picture; taps outside the block's available rectangle (picture edges) are skipped, which is
+// what the reference's INT16_MIN padding achieves. Unfiltered blocks are copied through.
+#include "host_util.h"
+
+namespace b200 {
+
+// taps of direction d: [k = near/far][dy, dx]  (reference src/tables.c:400-413, stride 12 removed)
+__constant__ int8_t c_cdef_off[8][2][2] = {
+    { { -1, 1 }, { -2, 2 } }, { { 0, 1 }, { -1, 2 } }, { { 0, 1 }, { 0, 2 } }, { { 0, 1 }, { 1, 2 } },
+    { { 1, 1 }, { 2, 2 } },   { { 1, 0 }, { 2, 1 } },  { { 1, 0 }, { 2, 0 } }, { { 1, 0 }, { 2, -1 } },
+};
+__constant__ uint16_t c_cdef_div[7] = { 840, 420, 280, 210, 168, 140, 120 };
+__constant__ uint8_t c_uv_dir422[8] = { 7, 0, 2, 4, 5, 6, 6, 6 };
+
+B200_DEV int cdef_constrain(int diff, int threshold, int shift) {
+    const int adiff = iabs(diff);
+    const int v = imin(adiff, imax(0, threshold - (adiff >> shift)));
+    return diff < 0 ? -v : v;
+}
+
+struct CdefRect { int xmin, xmax, ymin, ymax; };   // available samples: [xmin, xmax) x [ymin, ymax)
+
+template <bool HBD>
+B200_DEV int cdef_pixel(const typename Bd<HBD>::pixel *__restrict__ plane, int stride, int ax, int ay,
+                        const CdefRect &r, int pri, int sec, int dir, int pri_shift, int sec_shift, int pri_tap0)
+{
+    const int px = plane[(ptrdiff_t)ay * stride + ax];
+    int sum = 0, mx = px, mn = px;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        if (pri) {
+            const int tap = k ? ((pri_tap0 & 3) | 2) : pri_tap0;
+            const int dy = c_cdef_off[dir][k][0], dx = c_cdef_off[dir][k][1];
+#pragma unroll
+            for (int s = -1; s <= 1; s += 2) {
+                const int x = ax + s * dx, y = ay + s * dy;
+                if (x < r.xmin || x >= r.xmax || y < r.ymin || y >= r.ymax) continue;
+                const int p = plane[(ptrdiff_t)y * stride + x];
+                sum += tap * cdef_constrain(p - px, pri, pri_shift);
+                mn = imin(mn, p); mx = imax(mx, p);
+            }
+        }
+        if (sec) {
+            const int tap = 2 - k;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int d2 = (dir + (j ? 6 : 2)) & 7;
+                const int dy = c_cdef_off[d2][k][0], dx = c_cdef_off[d2][k][1];
+#pragma unroll
+                for (int s = -1; s <= 1; s += 2) {
+                    const int x = ax + s * dx, y = ay + s * dy;
+                    if (x < r.xmin || x >= r.xmax || y < r.ymin || y >= r.ymax) continue;
+                    const int p = plane[(ptrdiff_t)y * stride + x];
+                    sum += tap * cdef_constrain(p - px, sec, sec_shift);
+                    mn = imin(mn, p); mx = imax(mx, p);
+                }
+            }
+        }
+    }
+    int v = px + ((sum - (sum < 0) + 8) >> 4);
+    if (pri && sec) v = iclip(v, mn, mx);
+    return v;
+}
+
+// direction search over an 8x8 block held in shared memory as (px >> (bitdepth-8)) - 128;
+// lanes 0..7 each own one direction's cost. Returns dir in all lanes, *var likewise.
+B200_DEV int cdef_find_dir(const int *v, int lane, unsigned *var)
+{
+    unsigned cost = 0;
+    if (lane < 8) {
+        int sums[15];
+#pragma unroll
+        for (int i = 0; i < 15; i++) sums[i] = 0;
+        for (int i = 0; i < 64; i++) {
+            const int y = i >> 3, x = i & 7, p = v[i];
+            int idx;
+            switch (lane) {
+            case 0: idx = y + x; break;
+            case 1: idx = y + (x >> 1); break;
+            case 2: idx = y; break;
+            case 3: idx = 3 + y - (x >> 1); break;
+            case 4: idx = 7 + y - x; break;
+            case 5: idx = 3 - (y >> 1) + x; break;
+            case 6: idx = x; break;
+            default: idx = (y >> 1) + x; break;
+            }
+#pragma unroll
+            for (int k = 0; k < 15; k++) if (k == idx) sums[k] += p;
+        }
+        if (lane == 2 || lane == 6) {
+#pragma unroll
+            for (int n = 0; n < 8; n++) cost += sums[n] * sums[n];
+            cost *= 105;
+        } else if (lane == 0 || lane == 4) {
+#pragma unroll
+            for (int n = 0; n < 7; n++) cost += (sums[n] * sums[n] + sums[14 - n] * sums[14 - n]) * c_cdef_div[n];
+            cost += sums[7] * sums[7] * 105;
+        } else {
+#pragma unroll
+            for (int m = 0; m < 5; m++) cost += sums[3 + m] * sums[3 + m];
+            cost *= 105;
+#pragma unroll
+            for (int m = 0; m < 3; m++) cost += (sums[m] * sums[m] + sums[10 - m] * sums[10 - m]) * c_cdef_div[2 * m + 1];
+        }
+    }
+    unsigned c[8];
+#pragma unroll
+    for (int n = 0; n < 8; n++) c[n] = __shfl_sync(0xffffffffu, cost, n);
+    int best = 0; unsigned bc = c[0];
+#pragma unroll
+    for (int n = 1; n < 8; n++) if (c[n] > bc) { bc = c[n]; best = n; }
+    unsigned opp = c[0];
+#pragma unroll
+    for (int n = 1; n < 8; n++) if (n == (best ^ 4)) opp = c[n];
+    if ((best ^ 4) == 0) opp = c[0];
+    *var = (bc - opp) >> 10;
+    return best;
+}
+
+B200_DEV int cdef_adjust_strength(int strength, unsigned var) {
+    if (!var) return 0;
+    const int i = (var >> 6) ? imin(ulog2(var >> 6), 12) : 0;
+    return (strength * (4 + i) + 8) >> 4;
+}
+
+constexpr int kCdefWarps = 4;
+
+template <bool HBD>
+__global__ void __launch_bounds__(kCdefWarps * 32) cdef_frame_kernel(B200CdefFrame f, int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    __shared__ int luma[kCdefWarps][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bx = (blockIdx.x * kCdefWarps + warp) * 2, by = blockIdx.y * 2;   // 4-px units
+    const bool inside = bx < f.bw;
+    const int b8 = HBD ? (32 - __clz(bdmax)) - 8 : 0;
+    const pixel *const src = (const pixel *)f.src;
+    pixel *const dst = (pixel *)f.dst;
+
+    int y_lvl = 0, uv_lvl = 0;
+    if (inside) {
+        const B200Av1Filter &m = f.mask[(by >> 5) * f.sb128w + (bx >> 5)];
+        const int cdef_idx = m.cdef_idx[((by & 16) >> 3) + ((bx & 16) >> 4)];
+        const uint16_t *nr = m.noskip_mask[(by & 30) >> 1];
+        const unsigned noskip = (unsigned)nr[1] << 16 | nr[0];
+        if (cdef_idx != -1 && (noskip & (3u << (bx & 30)))) {
+            y_lvl = f.y_strength[cdef_idx];
+            uv_lvl = f.uv_strength[cdef_idx];
+        }
+    }
+    const int y_pri = (y_lvl >> 2) << b8;
+    int y_sec = y_lvl & 3; y_sec += y_sec == 3; y_sec <<= b8;
+    const int uv_pri = (uv_lvl >> 2) << b8;
+    int uv_sec = uv_lvl & 3; uv_sec += uv_sec == 3; uv_sec <<= b8;
+
+    // direction / variance from the pre-CDEF luma block (only when a primary strength needs it)
+    int dir = 0; unsigned var = 0;
+    const bool need_dir = inside && (y_pri || uv_pri);
+    if (inside) {
+        const pixel *p = src + f.plane_off[0] + (ptrdiff_t)(by * 4) * f.stride[0] + bx * 4;
+        for (int i = lane; i < 64; i += 32) luma[warp][i] = ((int)p[(i >> 3) * f.stride[0] + (i & 7)] >> b8) - 128;
+    }
+    __syncwarp();
+    // every lane takes part in the shuffles; the result is only used when need_dir
+    {
+        unsigned vv;
+        const int d = cdef_find_dir(luma[warp], lane, &vv);
+        if (need_dir) { dir = d; var = vv; }
+    }
+    if (!inside) return;
+
+    const int have_l = bx > 0, have_r = bx + 2 < f.bw, have_t = by > 0, have_b = by + 2 < f.bh;
+    const int damping = f.damping + b8;
+#pragma unroll 1
+    for (int pl = 0; pl < 3; pl++) {
+        const int sh = pl ? f.ss_hor : 0, sv = pl ? f.ss_ver : 0;
+        const int w = 8 >> sh, h = 8 >> sv;
+        int pri = 0, sec = 0, d = 0, damp = damping;
+        if (pl == 0) {
+            if (y_pri) { pri = cdef_adjust_strength(y_pri, var); sec = y_sec; d = dir; }
+            else { sec = y_sec; }
+        } else if (uv_lvl) {
+            pri = uv_pri; sec = uv_sec; damp = damping - 1;
+            d = uv_pri ? ((f.ss_hor && !f.ss_ver) ? c_uv_dir422[dir] : dir) : 0;
+        }
+        const int x0 = bx * 4 >> sh, y0 = by * 4 >> sv;
+        const pixel *sp = src + f.plane_off[pl];
+        pixel *dp = dst + f.plane_off[pl];
+        const int st = f.stride[pl];
+        if (!pri && !sec) {
+            for (int i = lane; i < w * h; i += 32) {
+                const int x = x0 + (i % w), y = y0 + (i / w);
+                dp[(ptrdiff_t)y * st + x] = sp[(ptrdiff_t)y * st + x];
+            }
+            continue;
+        }
+        CdefRect r;
+        r.xmin = x0 - 2 * have_l; r.xmax = x0 + w + 2 * have_r;
+        r.ymin = y0 - 2 * have_t; r.ymax = y0 + h + 2 * have_b;
+        const int pri_tap0 = 4 - ((pri >> b8) & 1);
+        const int pri_shift = pri ? imax(0, damp - ulog2(pri)) : 0;
+        const int sec_shift = sec ? damp - ulog2(sec) : 0;
+        for (int i = lane; i < w * h; i += 32) {
+            const int x = x0 + (i % w), y = y0 + (i / w);
+            dp[(ptrdiff_t)y * st + x] = (pixel)cdef_pixel<HBD>(sp, st, x, y, r, pri, sec, d, pri_shift, sec_shift, pri_tap0);
+        }
+    }
+}
+
+// Level-1 kernels ---------------------------------------------------------------------------
+template <bool HBD>
+__global__ void cdef_fb_kernel(const typename Bd<HBD>::pixel *win, typename Bd<HBD>::pixel *out, int w, int h,
+                               int pri, int sec, int dir, int damping, int edges, int bdmax)
+{
+    // win: dense (w+4) x (h+4) window, block at (2,2)
+    const int b8 = HBD ? (32 - __clz(bdmax)) - 8 : 0;
+    CdefRect r;
+    r.xmin = (edges & B200_CDEF_HAVE_LEFT) ? 0 : 2; r.xmax = w + 2 + ((edges & B200_CDEF_HAVE_RIGHT) ? 2 : 0);
+    r.ymin = (edges & B200_CDEF_HAVE_TOP) ? 0 : 2;  r.ymax = h + 2 + ((edges & B200_CDEF_HAVE_BOTTOM) ? 2 : 0);
+    const int pri_tap0 = 4 - ((pri >> b8) & 1);
+    const int pri_shift = pri ? imax(0, damping - ulog2(pri)) : 0;
+    const int sec_shift = sec ? damping - ulog2(sec) : 0;
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x)
+        out[i] = (typename Bd<HBD>::pixel)cdef_pixel<HBD>(win, w + 4, 2 + (i % w), 2 + (i / w), r, pri, sec, dir,
+                                                          pri_shift, sec_shift, pri_tap0);
+}
+
+template <bool HBD>
+__global__ void cdef_dir_kernel(const typename Bd<HBD>::pixel *img, int *out, int bdmax)
+{
+    __shared__ int v[64];
+    const int b8 = HBD ? (32 - __clz(bdmax)) - 8 : 0;
+    for (int i = threadIdx.x; i < 64; i += 32) v[i] = ((int)img[i] >> b8) - 128;
+    __syncwarp();
+    unsigned var;
+    const int d = cdef_find_dir(v, threadIdx.x, &var);
+    if (threadIdx.x == 0) { out[0] = d; out[1] = (int)var; }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+static int cdef_check_bd(int bdmax, const char *who) {
+    if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("%s: bad bitdepth_max %d", who, bdmax); return -2; }
+    return 0;
+}
+
+extern "C" {
+
+int b200_cdef_frame(int bdmax, const B200CdefFrame *f, void *stream)
+{
+    if (cdef_check_bd(bdmax, "b200_cdef_frame")) return -2;
+    dim3 grid(((f->bw + 1) / 2 + kCdefWarps - 1) / kCdefWarps, (f->bh + 1) / 2);
+    if (bdmax > 255) { auto k = cdef_frame_kernel<true>; B200_LAUNCH(k, grid, dim3(kCdefWarps * 32), 0, (cudaStream_t)stream, *f, bdmax); }
+    else { auto k = cdef_frame_kernel<false>; B200_LAUNCH(k, grid, dim3(kCdefWarps * 32), 0, (cudaStream_t)stream, *f, bdmax); }
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int b200_cdef_dir(const void *img, ptrdiff_t stride, unsigned *var, int bdmax)
+{
+    if (cdef_check_bd(bdmax, "b200_cdef_dir")) return -2;
+    std::lock_guard<std::mutex> lk(host_lock());
+    static Scratch s_in, s_out;
+    const size_t px = bdmax > 255 ? 2 : 1;
+    uint8_t blk[64 * 2];
+    pack_rect(blk, img, stride, 8, 8, px);
+    if (s_in.upload(blk, 64 * px) || s_out.reserve(8)) return -1;
+    if (bdmax > 255) { auto k = cdef_dir_kernel<true>; B200_LAUNCH(k, dim3(1), dim3(32), 0, (cudaStream_t)0, (const uint16_t *)s_in.p, (int *)s_out.p, bdmax); }
+    else { auto k = cdef_dir_kernel<false>; B200_LAUNCH(k, dim3(1), dim3(32), 0, (cudaStream_t)0, (const uint8_t *)s_in.p, (int *)s_out.p, bdmax); }
+    b200_count_launch();
+    int res[2];
+    if (s_out.download(res, 8)) return -1;
+    B200_CUDA_OK(cudaStreamSynchronize(0));
+    *var = (unsigned)res[1];
+    return res[0];   // 0..7
+}
+
+int b200_cdef_fb(void *dst, ptrdiff_t stride, const void *left, const void *top, const void *bottom, int pri,
+                 int sec, int dir, int damping, int w, int h, int edges, int bdmax)
+{
+    if (cdef_check_bd(bdmax, "b200_cdef_fb")) return -2;
+    if (!((w == 4 || w == 8) && (h == 4 || h == 8)) || dir < 0 || dir > 7 || (!pri && !sec)) { b200_set_error("b200_cdef_fb: bad arguments"); return -2; }
+    std::lock_guard<std::mutex> lk(host_lock());
+    static Scratch s_in, s_out;
+    const size_t px = bdmax > 255 ? 2 : 1;
+    const int ww = w + 4;
+    uint8_t win[12 * 12 * 2];
+    memset(win, 0, sizeof(win));
+    auto put = [&](int wx, int wy, const void *p) { memcpy(win + ((size_t)wy * ww + wx) * px, p, px); };
+    const int xs = (edges & B200_CDEF_HAVE_LEFT) ? -2 : 0, xe = w + ((edges & B200_CDEF_HAVE_RIGHT) ? 2 : 0);
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < xe; x++) put(2 + x, 2 + y, (const uint8_t *)dst + (ptrdiff_t)y * stride + (ptrdiff_t)x * (ptrdiff_t)px);
+        if (edges & B200_CDEF_HAVE_LEFT) for (int x = -2; x < 0; x++) put(2 + x, 2 + y, (const uint8_t *)left + (size_t)(y * 2 + 2 + x) * px);
+    }
+    if (edges & B200_CDEF_HAVE_TOP)
+        for (int y = -2; y < 0; y++) for (int x = xs; x < xe; x++)
+            put(2 + x, 2 + y, (const uint8_t *)top + (ptrdiff_t)(y + 2) * stride + (ptrdiff_t)x * (ptrdiff_t)px);
+    if (edges & B200_CDEF_HAVE_BOTTOM)
+        for (int y = 0; y < 2; y++) for (int x = xs; x < xe; x++)
+            put(2 + x, 2 + h + y, (const uint8_t *)bottom + (ptrdiff_t)y * stride + (ptrdiff_t)x * (ptrdiff_t)px);
+    if (s_in.upload(win, (size_t)ww * (h + 4) * px) || s_out.reserve(64 * 2)) return -1;
+    if (bdmax > 255) { auto k = cdef_fb_kernel<true>; B200_LAUNCH(k, dim3(1), dim3(64), 0, (cudaStream_t)0, (const uint16_t *)s_in.p, (uint16_t *)s_out.p, w, h, pri, sec, dir, damping, edges, bdmax); }
+    else { auto k = cdef_fb_kernel<false>; B200_LAUNCH(k, dim3(1), dim3(64), 0, (cudaStream_t)0, (const uint8_t *)s_in.p, (uint8_t *)s_out.p, w, h, pri, sec, dir, damping, edges, bdmax); }
+    b200_count_launch();
+    uint8_t out[64 * 2];
+    if (s_out.download(out, (size_t)w * h * px)) return -1;
+    B200_CUDA_OK(cudaStreamSynchronize(0));
+    unpack_rect(dst, stride, out, w, h, px);
+    return 0;
+}
+
+}  // extern "C"
+
+namespace {
+int dir8(const uint8_t *img, ptrdiff_t st, unsigned *var) { int r = b200_cdef_dir(img, st, var, 255); if (r < 0) die("cdef.dir"); return r; }
+int dir16(const uint16_t *img, ptrdiff_t st, unsigned *var, int bd) { int r = b200_cdef_dir(img, st, var, bd); if (r < 0) die("cdef.dir"); return r; }
+template <int W, int H> void fb8(uint8_t *d, ptrdiff_t st, const void *l, const uint8_t *t, const uint8_t *b, int pri, int sec, int dir, int damp, int edges) {
+    if (b200_cdef_fb(d, st, l, t, b, pri, sec, dir, damp, W, H, edges, 255)) die("cdef.fb");
+}
+template <int W, int H> void fb16(uint16_t *d, ptrdiff_t st, const void *l, const uint16_t *t, const uint16_t *b, int pri, int sec, int dir, int damp, int edges, int bd) {
+    if (b200_cdef_fb(d, st, l, t, b, pri, sec, dir, damp, W, H, edges, bd)) die("cdef.fb");
+}
+}
+extern "C" {
+void b200_cdef_dsp_init_8bpc(B200CdefDSPContext *c) {
+    c->dir = (void *)dir8; c->fb[0] = (void *)fb8<8, 8>; c->fb[1] = (void *)fb8<4, 8>; c->fb[2] = (void *)fb8<4, 4>;
+}
+void b200_cdef_dsp_init_16bpc(B200CdefDSPContext *c) {
+    c->dir = (void *)dir16; c->fb[0] = (void *)fb16<8, 8>; c->fb[1] = (void *)fb16<4, 8>; c->fb[2] = (void *)fb16<4, 4>;
+}
+}

@@ -128,3 +128,29 @@ class LoopFilterDSPContext:
         (self.lib.b200_loop_filter_dsp_init_8bpc if bpc == 8 else self.lib.b200_loop_filter_dsp_init_16bpc)(self._tbl)
         t = wrap_dsp_table(self._tbl, [("f", 4)], {"f": (LF_PROTO, True)}, bpc > 8, self.bitdepth_max)["f"]
         self.loop_filter_sb = [[t[0], t[1]], [t[2], t[3]]]
+
+
+class CdefDSPContext:
+    """Dav1dCdefDSPContext (reference src/cdef.h:64-67): dir, fb[3] (8x8 / 4x8 / 4x4).
+    dir(img, stride) -> (dir, var); fb[i](dst, stride, left, top, bottom, pri, sec, dir, damping, edges)."""
+
+    def __init__(self, bpc, lib=None):
+        self.bpc, self.bitdepth_max = bpc, (1 << bpc) - 1
+        self.lib = lib or get_lib()
+        self._tbl = (C.c_void_p * 4)()
+        (self.lib.b200_cdef_dsp_init_8bpc if bpc == 8 else self.lib.b200_cdef_dsp_init_16bpc)(self._tbl)
+        hbd = bpc > 8
+        dir_ft = C.CFUNCTYPE(_I, _P, _S, C.POINTER(C.c_uint), *([_I] if hbd else []))
+        fb_ft = C.CFUNCTYPE(None, _P, _S, _P, _P, _P, _I, _I, _I, _I, _I, *([_I] if hbd else []))
+        self._dir = dir_ft(self._tbl[0])
+        self._fb = [fb_ft(self._tbl[1 + i]) for i in range(3)]
+        bd = [self.bitdepth_max] if hbd else []
+
+        def dir_(img, stride):
+            var = C.c_uint(0)
+            d = self._dir(_addr(img), stride, C.byref(var), *bd)
+            return d, var.value
+        self.dir = dir_
+        self.fb = [(lambda dst, st, left, top, bot, pri, sec, d, damp, edges, _f=f:
+                    _f(_addr(dst), st, _addr(left), _addr(top), _addr(bot), pri, sec, d, damp, edges, *bd))
+                   for f in self._fb]

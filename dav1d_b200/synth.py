@@ -169,3 +169,23 @@ def make_lf_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, sharp=None, smooth=True):
     return dict(bpc=bpc, bd=bd, W=W, H=H, w4=w4, h4=h4, sb128w=sb128w, b4_stride=b4_stride, ss_hor=ss_hor,
                 ss_ver=ss_ver, stride=stride, off=off, rows=rows, pic=pic, masks=masks, level=level,
                 lut_e=e, lut_i=i, lut_sharp=sh, til_y=til_y, til_uv=til_uv)
+
+
+def make_cdef_params(rng, bw, bh, sb128w, masks, p_unset=0.1, p_noskip=0.8):
+    """Fill cdef_idx / noskip_mask of an Av1Filter array in place and draw the frame header strengths
+    (frame_hdr->cdef, reference include/dav1d/headers.h). Returns (damping, y_strength[8], uv_strength[8])."""
+    sb128h = (bh + 31) // 32
+    idx = rng.integers(0, 8, (sb128h * sb128w, 4)).astype(np.int8)
+    idx[rng.random(idx.shape) < p_unset] = -1
+    masks["cdef_idx"] = idx
+    ns = rng.random((sb128h * sb128w, 16, 16)) < p_noskip          # [sb][8x8 row][8x8 col]
+    bits = np.zeros((sb128h * sb128w, 16, 2), np.uint16)
+    for h in range(2):
+        w = (3 << (2 * np.arange(8))).astype(np.uint32)
+        bits[:, :, h] = (ns[:, :, h * 8:(h + 1) * 8] * w[None, None, :]).sum(axis=2).astype(np.uint16)
+    masks["noskip_mask"] = bits
+    y = rng.integers(0, 64, 8); uv = rng.integers(0, 64, 8)
+    y[rng.random(8) < 0.2] = 0; uv[rng.random(8) < 0.2] = 0
+    y[0] &= 3                     # one entry with secondary-only luma
+    uv[1] &= ~3                   # one with primary-only chroma
+    return int(rng.integers(3, 7)), [int(v) for v in y], [int(v) for v in uv]

@@ -230,6 +230,35 @@ typedef struct B200LoopFilterDSPContext { void *loop_filter_sb[2][2]; } B200Loop
 B200_API void b200_loop_filter_dsp_init_8bpc(B200LoopFilterDSPContext *c);
 B200_API void b200_loop_filter_dsp_init_16bpc(B200LoopFilterDSPContext *c);
 
+/* ==== cdef (Dav1dCdefDSPContext, reference src/cdef.h:53-67) ============================= */
+enum { B200_CDEF_HAVE_LEFT = 1, B200_CDEF_HAVE_RIGHT = 2, B200_CDEF_HAVE_TOP = 4, B200_CDEF_HAVE_BOTTOM = 8 };
+
+/* Level 2: CDEF over a whole deblocked picture, OUT OF PLACE (src -> dst; every 8x8 of the
+ * bw x bh area is written, unfiltered blocks are copied through). Replaces dav1d_cdef_brow for
+ * every superblock row (reference src/cdef_apply_tmpl.c:97-308); CDEF only ever reads pre-CDEF
+ * samples, which is what the reference's cdef_line / lr_bak backups emulate in place. */
+typedef struct B200CdefFrame {
+    const void *src;               /* device, deblocked picture */
+    void *dst;                     /* device, same geometry */
+    uint32_t plane_off[3];
+    int32_t stride[3];
+    int32_t bw, bh;                /* f->bw, f->bh (4-px units) */
+    int32_t sb128w, ss_hor, ss_ver;
+    int32_t damping;               /* frame_hdr->cdef.damping */
+    int32_t y_strength[8], uv_strength[8];   /* frame_hdr->cdef.{y,uv}_strength */
+    const B200Av1Filter *mask;     /* device: cdef_idx[] and noskip_mask[] are read */
+} B200CdefFrame;
+B200_API int b200_cdef_frame(int bitdepth_max, const B200CdefFrame *frame, void *stream);
+
+/* Level 1 (host pointers): cdef.dir and cdef.fb[0..2] = 8x8 / 4x8 / 4x4 */
+B200_API int b200_cdef_dir(const void *img, ptrdiff_t stride, unsigned *var, int bitdepth_max);
+B200_API int b200_cdef_fb(void *dst, ptrdiff_t stride, const void *left, const void *top, const void *bottom,
+                          int pri_strength, int sec_strength, int dir, int damping, int w, int h, int edges,
+                          int bitdepth_max);
+typedef struct B200CdefDSPContext { void *dir; void *fb[3]; } B200CdefDSPContext;
+B200_API void b200_cdef_dsp_init_8bpc(B200CdefDSPContext *c);
+B200_API void b200_cdef_dsp_init_16bpc(B200CdefDSPContext *c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,3 +78,60 @@ API void bitfn(refdrv_lf_frame)(const int bitdepth_max, const RefLfFrame *const 
     }
     free(dsp); free(hdr); free(seq); free(f);
 }
+
+
+/* ---- CDEF: the reference's own dav1d_cdef_brow over a fully deblocked picture, in place ---- */
+#include "src/cdef_apply.h"
+#include "src/cdef.h"
+typedef struct {
+    void *src, *dst;               /* dst unused: the reference filters `src` in place */
+    uint32_t plane_off[3];
+    int32_t stride[3];
+    int32_t bw, bh, sb128w, ss_hor, ss_ver, damping;
+    int32_t y_strength[8], uv_strength[8];
+    Av1Filter *mask;
+} RefCdefFrame;
+
+API void bitfn(refdrv_cdef_frame)(const int bitdepth_max, const RefCdefFrame *const fr)
+{
+    Dav1dFrameContext *const f = calloc(1, sizeof(*f));
+    Dav1dContext *const c = calloc(1, sizeof(*c));
+    Dav1dSequenceHeader *const seq = calloc(1, sizeof(*seq));
+    Dav1dFrameHeader *const hdr = calloc(1, sizeof(*hdr));
+    Dav1dDSPContext *const dsp = calloc(1, sizeof(*dsp));
+    Dav1dTaskContext *const tc = calloc(1, sizeof(*tc));
+    bitfn(dav1d_cdef_dsp_init)(&dsp->cdef);
+    f->dsp = dsp; f->seq_hdr = seq; f->frame_hdr = hdr; f->c = c;
+    c->n_tc = 1;
+    tc->f = f;
+    f->bw = fr->bw; f->bh = fr->bh; f->sb128w = fr->sb128w;
+    f->cur.p.layout = !fr->ss_hor ? DAV1D_PIXEL_LAYOUT_I444 : fr->ss_ver ? DAV1D_PIXEL_LAYOUT_I420 : DAV1D_PIXEL_LAYOUT_I422;
+    f->cur.p.bpc = 32 - clz(bitdepth_max);
+    f->cur.stride[0] = fr->stride[0] * (ptrdiff_t)sizeof(pixel);
+    f->cur.stride[1] = fr->stride[1] * (ptrdiff_t)sizeof(pixel);
+#if BITDEPTH == 16
+    f->bitdepth_max = bitdepth_max;
+#endif
+    hdr->cdef.damping = fr->damping;
+    for (int i = 0; i < 8; i++) { hdr->cdef.y_strength[i] = fr->y_strength[i]; hdr->cdef.uv_strength[i] = fr->uv_strength[i]; }
+    hdr->width[0] = hdr->width[1] = fr->bw * 4;
+    /* two-line pre-filter backups, toggled per 8-row band (src/decode.c:2916-2936, have_tt == 0 layout) */
+    pixel *const lines = calloc((size_t)(fr->stride[0] * 4 + fr->stride[1] * 8 + 64), sizeof(pixel));
+    f->lf.cdef_line[0][0] = lines;
+    f->lf.cdef_line[1][0] = lines + fr->stride[0] * 2;
+    pixel *const uvl = lines + fr->stride[0] * 4;
+    f->lf.cdef_line[0][1] = uvl; f->lf.cdef_line[0][2] = uvl + fr->stride[1] * 2;
+    f->lf.cdef_line[1][1] = uvl + fr->stride[1] * 4; f->lf.cdef_line[1][2] = uvl + fr->stride[1] * 6;
+    pixel *const base = fr->src;
+    for (int r = 0; r * 32 < fr->bh; r++) {
+        const int y = r * 128;
+        pixel *const p[3] = {
+            base + fr->plane_off[0] + (ptrdiff_t)y * fr->stride[0],
+            base + fr->plane_off[1] + (ptrdiff_t)(y >> fr->ss_ver) * fr->stride[1],
+            base + fr->plane_off[2] + (ptrdiff_t)(y >> fr->ss_ver) * fr->stride[2],
+        };
+        const int end = r * 32 + 32 < fr->bh ? r * 32 + 32 : fr->bh;
+        bytefn(dav1d_cdef_brow)(tc, p, fr->mask + r * fr->sb128w, r * 32, end, 0, 0);
+    }
+    free(lines); free(tc); free(dsp); free(hdr); free(seq); free(c); free(f);
+}
