@@ -73,6 +73,13 @@ class CdefFrame(C.Structure):
                 ("uv_strength", C.c_int32 * 8), ("mask", C.c_void_p)]
 
 
+class LrFrame(C.Structure):
+    _fields_ = [("cdef", C.c_void_p), ("dbl", C.c_void_p), ("dst", C.c_void_p), ("plane_off", C.c_uint32 * 3),
+                ("stride", C.c_int32 * 3), ("w", C.c_int32), ("h", C.c_int32), ("ss_hor", C.c_int32),
+                ("ss_ver", C.c_int32), ("sb128", C.c_int32), ("sr_sb128w", C.c_int32),
+                ("unit_size_log2", C.c_int32 * 2), ("restore_planes", C.c_int32), ("lr_mask", C.c_void_p)]
+
+
 ITXFM_FN_8 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int)
 ITXFM_FN_16 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int)
 
@@ -115,6 +122,12 @@ _SIGS = {
     "b200_cdef_fb": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 8),
     "b200_cdef_dsp_init_8bpc": (None, [C.c_void_p]),
     "b200_cdef_dsp_init_16bpc": (None, [C.c_void_p]),
+    # ---- looprestoration
+    "b200_lr_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "b200_lr_filter": (C.c_int, [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_int, C.c_int]),
+    "b200_loop_restoration_dsp_init_8bpc": (None, [C.c_void_p, C.c_int]),
+    "b200_loop_restoration_dsp_init_16bpc": (None, [C.c_void_p, C.c_int]),
 }
 
 

@@ -154,3 +154,21 @@ class CdefDSPContext:
         self.fb = [(lambda dst, st, left, top, bot, pri, sec, d, damp, edges, _f=f:
                     _f(_addr(dst), st, _addr(left), _addr(top), _addr(bot), pri, sec, d, damp, edges, *bd))
                    for f in self._fb]
+
+
+LR_PROTO = [_P, _S, _P, _P, _I, _I, _P, _I]   # decl_lr_filter_fn (reference src/looprestoration.h:64-70)
+
+
+class LoopRestorationDSPContext:
+    """Dav1dLoopRestorationDSPContext (reference src/looprestoration.h:72-75): wiener[2] (7-/5-tap), sgr[3]
+    (5x5, 3x3, mix). fn(dst, stride, left, lpf, w, h, params, edges); `params` = address of a
+    16-byte aligned LooprestorationParams."""
+
+    def __init__(self, bpc, lib=None):
+        self.bpc, self.bitdepth_max = bpc, (1 << bpc) - 1
+        self.lib = lib or get_lib()
+        self._tbl = (C.c_void_p * 5)()
+        (self.lib.b200_loop_restoration_dsp_init_8bpc if bpc == 8 else self.lib.b200_loop_restoration_dsp_init_16bpc)(self._tbl, bpc)
+        t = wrap_dsp_table(self._tbl, [("wiener", 2), ("sgr", 3)], {"wiener": (LR_PROTO, True), "sgr": (LR_PROTO, True)},
+                           bpc > 8, self.bitdepth_max)
+        self.wiener, self.sgr = t["wiener"], t["sgr"]

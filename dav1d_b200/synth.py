@@ -189,3 +189,31 @@ def make_cdef_params(rng, bw, bh, sb128w, masks, p_unset=0.1, p_noskip=0.8):
     y[0] &= 3                     # one entry with secondary-only luma
     uv[1] &= ~3                   # one with primary-only chroma
     return int(rng.integers(3, 7)), [int(v) for v in y], [int(v) for v in uv]
+
+
+# byte-identical to dav1d's Av1Restoration (reference src/lf_mask.h:42-62): lr[3 planes][4 units] x 9 bytes
+LR_UNIT_DT = np.dtype([("type", "u1"), ("filter_h", "i1", (3,)), ("filter_v", "i1", (3,)), ("sgr_weights", "i1", (2,))])
+AV1RESTORATION_DT = np.dtype([("lr", LR_UNIT_DT, (3, 4))])
+assert AV1RESTORATION_DT.itemsize == 108
+SGR_PARAMS = [(140, 3236), (112, 2158), (93, 1618), (80, 1438), (70, 1295), (58, 1177), (47, 1079), (37, 996),
+              (30, 925), (25, 863), (0, 2589), (0, 1618), (0, 1177), (0, 925), (56, 0), (22, 0)]
+
+
+def make_lr_params(rng, W, H, p_none=0.25):
+    """Random legal loop-restoration units in dav1d's lr_mask layout. type: 0 none, 2 Wiener,
+    3 + sgr_idx self-guided (reference src/lr_apply_tmpl.c:53-84)."""
+    sb128w, sb128h = (W + 127) >> 7, (H + 127) >> 7
+    m = np.zeros(sb128h * sb128w, AV1RESTORATION_DT)
+    u = m["lr"]
+    n = u["type"].shape
+    kind = rng.random(n)
+    typ = np.where(kind < p_none, 0, np.where(kind < p_none + (1 - p_none) / 2, 2, 3 + rng.integers(0, 16, n))).astype(np.uint8)
+    u["type"] = typ
+    u["filter_h"][..., 0] = rng.integers(-5, 11, n); u["filter_h"][..., 1] = rng.integers(-23, 9, n); u["filter_h"][..., 2] = rng.integers(-17, 47, n)
+    u["filter_v"][..., 0] = rng.integers(-5, 11, n); u["filter_v"][..., 1] = rng.integers(-23, 9, n); u["filter_v"][..., 2] = rng.integers(-17, 47, n)
+    u["filter_h"][:, 1:, :, 0] = 0; u["filter_v"][:, 1:, :, 0] = 0          # chroma uses the 5-tap form
+    idx = np.clip(typ.astype(np.int32) - 3, 0, 15)
+    s0 = np.array([p[0] for p in SGR_PARAMS])[idx]; s1 = np.array([p[1] for p in SGR_PARAMS])[idx]
+    u["sgr_weights"][..., 0] = np.where(s0 > 0, rng.integers(-96, 32, n), 0)
+    u["sgr_weights"][..., 1] = np.where(s1 > 0, rng.integers(-32, 96, n), 95)
+    return m

@@ -259,6 +259,42 @@ typedef struct B200CdefDSPContext { void *dir; void *fb[3]; } B200CdefDSPContext
 B200_API void b200_cdef_dsp_init_8bpc(B200CdefDSPContext *c);
 B200_API void b200_cdef_dsp_init_16bpc(B200CdefDSPContext *c);
 
+/* ==== looprestoration (Dav1dLoopRestorationDSPContext, reference src/looprestoration.h:49-75) == */
+enum { B200_LR_HAVE_LEFT = 1, B200_LR_HAVE_RIGHT = 2, B200_LR_HAVE_TOP = 4, B200_LR_HAVE_BOTTOM = 8 };
+/* byte-identical to dav1d's Av1RestorationUnit / Av1Restoration (reference src/lf_mask.h:42-62) */
+typedef struct B200RestorationUnit {
+    uint8_t type;                  /* 0 none, 2 Wiener, 3 + sgr_idx self-guided */
+    int8_t filter_h[3], filter_v[3];
+    int8_t sgr_weights[2];
+} B200RestorationUnit;
+typedef struct B200Av1Restoration { B200RestorationUnit lr[3][4]; } B200Av1Restoration;
+
+/* Level 2: restore a whole picture, OUT OF PLACE. `cdef` is the picture after CDEF (rows inside a
+ * 64-row stripe), `dbl` the picture after deblocking / before CDEF (the two rows above and below each
+ * stripe boundary: what dav1d_copy_lpf saves, reference src/lf_apply_tmpl.c:40-174), `dst` receives the
+ * restored picture (unrestored units are copied through). Replaces dav1d_lr_sbrow for every superblock
+ * row (reference src/lr_apply_tmpl.c:36-202); the unit lookup in lr_mask[] is dav1d's. */
+typedef struct B200LrFrame {
+    const void *cdef, *dbl;
+    void *dst;
+    uint32_t plane_off[3];
+    int32_t stride[3];
+    int32_t w, h;                  /* picture size in luma pixels (f->sr_cur.p.p.w / h) */
+    int32_t ss_hor, ss_ver, sb128, sr_sb128w;
+    int32_t unit_size_log2[2];     /* frame_hdr->restoration.unit_size[y, uv] */
+    int32_t restore_planes;        /* f->lf.restore_planes */
+    const B200Av1Restoration *lr_mask;   /* device, f->lf.lr_mask */
+} B200LrFrame;
+B200_API int b200_lr_frame(int bitdepth_max, const B200LrFrame *frame, void *stream);
+
+/* Level 1 (host pointers, decl_lr_filter_fn): kind 0 = wiener (7- and 5-tap), 1..3 = sgr 5x5 / 3x3 / mix.
+ * `params` points at a LooprestorationParams (int16 filter[2][8] or {uint32 s0, s1; int16 w0, w1}). */
+B200_API int b200_lr_filter(int kind, void *dst, ptrdiff_t stride, const void *left, const void *lpf, int w, int h,
+                            const void *params, int edges, int bitdepth_max);
+typedef struct B200LoopRestorationDSPContext { void *wiener[2]; void *sgr[3]; } B200LoopRestorationDSPContext;
+B200_API void b200_loop_restoration_dsp_init_8bpc(B200LoopRestorationDSPContext *c, int bpc);
+B200_API void b200_loop_restoration_dsp_init_16bpc(B200LoopRestorationDSPContext *c, int bpc);
+
 #ifdef __cplusplus
 }
 #endif

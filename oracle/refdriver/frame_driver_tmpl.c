@@ -135,3 +135,66 @@ API void bitfn(refdrv_cdef_frame)(const int bitdepth_max, const RefCdefFrame *co
     }
     free(lines); free(tc); free(dsp); free(hdr); free(seq); free(c); free(f);
 }
+
+/* ---- loop restoration: the reference's own dav1d_copy_lpf + dav1d_lr_sbrow, in place on `cdef` ---- */
+#include "src/lr_apply.h"
+#include "src/looprestoration.h"
+typedef struct {
+    void *cdef; const void *dbl; void *dst;   /* dst unused: the reference restores `cdef` in place */
+    uint32_t plane_off[3]; int32_t stride[3];
+    int32_t w, h, ss_hor, ss_ver, sb128, sr_sb128w;
+    int32_t unit_size_log2[2];
+    int32_t restore_planes;
+    Av1Restoration *lr_mask;
+} RefLrFrame;
+
+API void bitfn(refdrv_lr_frame)(const int bitdepth_max, const RefLrFrame *const fr)
+{
+    Dav1dFrameContext *const f = calloc(1, sizeof(*f));
+    Dav1dContext *const c = calloc(1, sizeof(*c));
+    Dav1dSequenceHeader *const seq = calloc(1, sizeof(*seq));
+    Dav1dFrameHeader *const hdr = calloc(1, sizeof(*hdr));
+    Dav1dDSPContext *const dsp = calloc(1, sizeof(*dsp));
+    bitfn(dav1d_loop_restoration_dsp_init)(&dsp->lr, 32 - clz(bitdepth_max));
+    f->dsp = dsp; f->seq_hdr = seq; f->frame_hdr = hdr; f->c = c;
+    c->n_tc = 1;
+    seq->sb128 = fr->sb128; seq->cdef = 1;
+    const enum Dav1dPixelLayout layout = !fr->ss_hor ? DAV1D_PIXEL_LAYOUT_I444 : fr->ss_ver ? DAV1D_PIXEL_LAYOUT_I420 : DAV1D_PIXEL_LAYOUT_I422;
+    f->cur.p.w = f->sr_cur.p.p.w = fr->w; f->cur.p.h = f->sr_cur.p.p.h = fr->h;
+    f->cur.p.layout = f->sr_cur.p.p.layout = layout;
+    f->cur.p.bpc = f->sr_cur.p.p.bpc = 32 - clz(bitdepth_max);
+    f->cur.stride[0] = f->sr_cur.p.stride[0] = fr->stride[0] * (ptrdiff_t)sizeof(pixel);
+    f->cur.stride[1] = f->sr_cur.p.stride[1] = fr->stride[1] * (ptrdiff_t)sizeof(pixel);
+#if BITDEPTH == 16
+    f->bitdepth_max = bitdepth_max;
+#endif
+    f->bw = (fr->w + 3) >> 2; f->bh = (fr->h + 3) >> 2;
+    f->sb_step = 16 << fr->sb128;
+    f->sbh = (f->bh + f->sb_step - 1) / f->sb_step;
+    f->sr_sb128w = fr->sr_sb128w;
+    f->lf.lr_mask = fr->lr_mask;
+    f->lf.restore_planes = fr->restore_planes;
+    hdr->width[0] = hdr->width[1] = fr->w;
+    hdr->restoration.unit_size[0] = fr->unit_size_log2[0];
+    hdr->restoration.unit_size[1] = fr->unit_size_log2[1];
+    pixel *lines[3];
+    for (int p = 0; p < 3; p++) {
+        lines[p] = calloc((size_t)fr->stride[p] * 16 + 64, sizeof(pixel));
+        f->lf.lr_lpf_line[p] = lines[p];
+    }
+    pixel *const C = fr->cdef;
+    pixel *const D = (pixel *)fr->dbl;
+    for (int sby = 0; sby < f->sbh; sby++) {
+        const int y = sby * f->sb_step * 4;
+        pixel *const d[3] = { D + fr->plane_off[0] + (ptrdiff_t)y * fr->stride[0],
+                              D + fr->plane_off[1] + (ptrdiff_t)(y >> fr->ss_ver) * fr->stride[1],
+                              D + fr->plane_off[2] + (ptrdiff_t)(y >> fr->ss_ver) * fr->stride[2] };
+        pixel *const s[3] = { C + fr->plane_off[0] + (ptrdiff_t)y * fr->stride[0],
+                              C + fr->plane_off[1] + (ptrdiff_t)(y >> fr->ss_ver) * fr->stride[1],
+                              C + fr->plane_off[2] + (ptrdiff_t)(y >> fr->ss_ver) * fr->stride[2] };
+        bytefn(dav1d_copy_lpf)(f, d, sby);
+        bytefn(dav1d_lr_sbrow)(f, s, sby);
+    }
+    for (int p = 0; p < 3; p++) free(lines[p]);
+    free(dsp); free(hdr); free(seq); free(c); free(f);
+}
