@@ -80,6 +80,24 @@ class LrFrame(C.Structure):
                 ("unit_size_log2", C.c_int32 * 2), ("restore_planes", C.c_int32), ("lr_mask", C.c_void_p)]
 
 
+class FrameJob(C.Structure):
+    """struct B200FrameJob"""
+    _fields_ = [("bitdepth_max", C.c_int32), ("zero_coefs", C.c_int32), ("mc", McFrame),
+                ("d_pred", C.c_void_p), ("n_pred", C.c_int32), ("pad0", C.c_int32),
+                ("d_warp", C.c_void_p), ("n_warp", C.c_int32), ("pad1", C.c_int32),
+                ("d_comp", C.c_void_p), ("n_comp", C.c_int32), ("pad2", C.c_int32),
+                ("d_comp2", C.c_void_p), ("n_comp2", C.c_int32), ("pad2b", C.c_int32),
+                ("d_blend", C.c_void_p), ("n_blend", C.c_int32), ("pad3", C.c_int32),
+                ("d_itx", C.c_void_p * 19), ("n_itx", C.c_int32 * 19), ("pad4", C.c_int32),
+                ("d_coef", C.c_void_p), ("itx_stride", C.c_int32 * 3),
+                ("run_lf", C.c_int32), ("run_cdef", C.c_int32), ("run_lr", C.c_int32),
+                ("lf", LfFrame), ("cdef", CdefFrame), ("lr", LrFrame)]
+
+
+class Xfer(C.Structure):
+    _fields_ = [("host", C.c_void_p), ("dev", C.c_void_p), ("bytes", C.c_uint64)]
+
+
 ITXFM_FN_8 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int)
 ITXFM_FN_16 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int)
 
@@ -128,6 +146,10 @@ _SIGS = {
                                  C.c_void_p, C.c_int, C.c_int]),
     "b200_loop_restoration_dsp_init_8bpc": (None, [C.c_void_p, C.c_int]),
     "b200_loop_restoration_dsp_init_16bpc": (None, [C.c_void_p, C.c_int]),
+    # ---- whole frame
+    "b200_frame_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_struct_size": (C.c_int, [C.c_int]),
+    "b200_frame_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
 }
 
 
@@ -148,6 +170,11 @@ class B200Lib:
             fn.restype = res
             fn.argtypes = args
             setattr(self, name, fn)
+        for i, cls in enumerate(ABI_STRUCTS):
+            got = self.b200_struct_size(i)
+            if got != C.sizeof(cls):
+                raise B200Error("ABI mismatch: sizeof(%s) is %d in %s but %d in the Python binding"
+                                % (cls.__name__, got, path, C.sizeof(cls)))
 
     def check(self, rc, what):
         if rc != 0:
@@ -157,6 +184,8 @@ class B200Lib:
     def symbols():
         return list(_SIGS)
 
+
+ABI_STRUCTS = None   # filled below: index -> ctypes class, checked against b200_struct_size() on load
 
 _lib = None
 
@@ -170,3 +199,11 @@ def get_lib():
             build.build()
         _lib = B200Lib(LIB_PATH)
     return _lib
+
+
+class Av1Restoration(C.Structure):
+    _fields_ = [("lr", C.c_uint8 * 108)]
+
+
+ABI_STRUCTS = [McFrame, McBlock, CompBlock, BlendBlock, WarpBlock, ItxBlock, LfFrame, CdefFrame, LrFrame, FrameJob,
+               Av1Filter, Av1Restoration]

@@ -1,0 +1,54 @@
+// Whole-frame job: sequences the batched kernels of one frame on a stream (include/b200av1.h,
+// B200FrameJob). The device-side counterpart of dav1d's per-frame task graph
+// (TILE_RECONSTRUCTION -> DEBLOCK_COLS -> DEBLOCK_ROWS -> CDEF -> LOOP_RESTORATION,
+// reference src/thread_task.c:699-854) with whole-frame stages instead of superblock rows.
+#include "host_util.h"
+
+extern "C" {
+
+int b200_frame_run(const B200FrameJob *j, void *stream)
+{
+    int r;
+    const int bd = j->bitdepth_max;
+    if ((r = b200_mc_batch(bd, &j->mc, j->d_pred, j->n_pred, stream))) return r;
+    if ((r = b200_mc_warp_batch(bd, &j->mc, j->d_warp, j->n_warp, stream))) return r;
+    if ((r = b200_mc_comp_batch(bd, &j->mc, j->d_comp, j->n_comp, stream))) return r;
+    if ((r = b200_mc_comp_batch(bd, &j->mc, j->d_comp2, j->n_comp2, stream))) return r;
+    if ((r = b200_mc_blend_batch(bd, &j->mc, j->d_blend, j->n_blend, stream))) return r;
+    for (int tx = 0; tx < B200_N_RECT_TX_SIZES; tx++)
+        if (j->n_itx[tx] > 0 &&
+            (r = b200_itx_add_batch(bd, tx, j->d_itx[tx], j->n_itx[tx], j->d_coef, j->mc.dst, j->itx_stride,
+                                    j->zero_coefs, stream)))
+            return r;
+    if (j->run_lf && (r = b200_lf_frame(bd, &j->lf, stream))) return r;
+    if (j->run_cdef && (r = b200_cdef_frame(bd, &j->cdef, stream))) return r;
+    if (j->run_lr && (r = b200_lr_frame(bd, &j->lr, stream))) return r;
+    return 0;
+}
+
+int b200_struct_size(int which)
+{
+    switch (which) {
+    case 0: return sizeof(B200McFrame); case 1: return sizeof(B200McBlock); case 2: return sizeof(B200CompBlock);
+    case 3: return sizeof(B200BlendBlock); case 4: return sizeof(B200WarpBlock); case 5: return sizeof(B200ItxBlock);
+    case 6: return sizeof(B200LfFrame); case 7: return sizeof(B200CdefFrame); case 8: return sizeof(B200LrFrame);
+    case 9: return sizeof(B200FrameJob); case 10: return sizeof(B200Av1Filter); case 11: return sizeof(B200Av1Restoration);
+    }
+    return -1;
+}
+
+int b200_frame_run_host(const B200FrameJob *job, const B200Xfer *up, int n_up, const B200Xfer *down, int n_down,
+                        void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < n_up; i++)
+        if (up[i].bytes) B200_CUDA_OK(cudaMemcpyAsync(up[i].dev, up[i].host, up[i].bytes, cudaMemcpyHostToDevice, st));
+    int r = b200_frame_run(job, stream);
+    if (r) return r;
+    for (int i = 0; i < n_down; i++)
+        if (down[i].bytes) B200_CUDA_OK(cudaMemcpyAsync(down[i].host, down[i].dev, down[i].bytes, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+"""Host side of the whole-frame job (include/b200av1.h, B200FrameJob).
+
+FrameBuffers turns one frame's records (numpy arrays in dav1d's layouts, e.g. from synth.py — the
+role dav1d's pass-1 entropy decode plays in a real integration) into device buffers + a B200FrameJob,
+and runs it. `alloc` abstracts where the buffers live: torch CUDA tensors on the GPU, or plain numpy
+when the same C ABI is bound to the test-only host emulator.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+
+class TorchAlloc:
+    """device buffers as torch CUDA tensors (torch is plumbing: memory + streams only)"""
+
+    def __init__(self, device=None):
+        import torch
+        self.torch = torch
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+
+    def upload(self, a):
+        t = self.torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(self.device)
+        return t, t.data_ptr()
+
+    def zeros(self, nbytes):
+        t = self.torch.zeros(max(nbytes, 16), dtype=self.torch.uint8, device=self.device)
+        return t, t.data_ptr()
+
+    def download(self, t, like):
+        return t.cpu().numpy()[:like.nbytes].view(like.dtype)
+
+    def pinned(self, a):
+        t = self.torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()).pin_memory()
+        return t, t.data_ptr()
+
+    def sync(self):
+        self.torch.cuda.synchronize()
+
+    def stream(self):
+        return self.torch.cuda.current_stream().cuda_stream
+
+
+class NumpyAlloc:
+    """'device' == host: only valid with the emulated library (tests/emu)"""
+
+    def upload(self, a):
+        c = np.ascontiguousarray(a).view(np.uint8).reshape(-1).copy()
+        return c, c.ctypes.data
+
+    def zeros(self, nbytes):
+        c = np.zeros(max(nbytes, 16), np.uint8)
+        return c, c.ctypes.data
+
+    def download(self, t, like):
+        return t[:like.nbytes].view(like.dtype)
+
+    def pinned(self, a):
+        return self.upload(a)
+
+    def sync(self):
+        pass
+
+    def stream(self):
+        return None
+
+
+class FrameBuffers:
+    def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True):
+        self.S, self.lib = S, lib or _lib.get_lib()
+        self.alloc = alloc or TorchAlloc()
+        A = self.alloc
+        self.keep = {}
+        px = S["pic"].itemsize
+
+        def up(name, arr):
+            self.keep[name] = A.upload(arr)
+            return self.keep[name][1]
+
+        def zeros(name, nbytes):
+            self.keep[name] = A.zeros(nbytes)
+            return self.keep[name][1]
+        nbytes = S["pic"].nbytes
+        refs = [up("ref%d" % i, r) for i, r in enumerate(S["refs"])]
+        p0, p1, p2 = zeros("p0", nbytes), zeros("p1", nbytes), zeros("p2", nbytes)
+        tmp = zeros("tmp", S["tmp_len"] * 2)
+        mask = up("mask", S["mask"])
+        j = _lib.FrameJob()
+        j.bitdepth_max, j.zero_coefs = S["bd"], 0
+        for i, r in enumerate(refs):
+            j.mc.ref[i] = r
+        ssh, ssv = [0, S["ss_hor"], S["ss_hor"]], [0, S["ss_ver"], S["ss_ver"]]
+        for p in range(3):
+            j.mc.ref_plane_off[p] = S["off"][p]; j.mc.ref_stride[p] = S["stride"][p]
+            j.mc.ref_w[p] = (S["W"] + ssh[p]) >> ssh[p]; j.mc.ref_h[p] = (S["H"] + ssv[p]) >> ssv[p]
+            j.mc.dst_stride[p] = S["stride"][p]; j.itx_stride[p] = S["stride"][p]
+        j.mc.dst, j.mc.tmp, j.mc.mask, j.mc.px_tmp = p0, tmp, mask, None
+        self.uploads = []          # (name, host array) re-sent per frame on the end-to-end path
+
+        def rec(field_ptr, field_n, name, arr):
+            if len(arr):
+                setattr(j, field_ptr, up(name, arr)); setattr(j, field_n, len(arr))
+                self.uploads.append((name, arr))
+        rec("d_pred", "n_pred", "pred", S["pred"])
+        rec("d_comp", "n_comp", "comp", S["comp"])
+        rec("d_comp2", "n_comp2", "comp2", S["comp2"])
+        for tx in range(19):
+            a = S["itx"][tx]
+            if len(a):
+                j.d_itx[tx] = up("itx%d" % tx, a); j.n_itx[tx] = len(a)
+                self.uploads.append(("itx%d" % tx, a))
+        j.d_coef = up("coef", S["coefs"]); self.uploads.append(("coef", S["coefs"]))
+        if len(S["mask"]) > 1:
+            self.uploads.append(("mask", S["mask"]))
+        # post filters
+        j.run_lf, j.run_cdef, j.run_lr = int(run_lf), int(run_cdef), int(run_lr)
+        d_masks = up("masks", S["masks"]); self.uploads.append(("masks", S["masks"]))
+        d_level = up("level", S["level"]); self.uploads.append(("level", S["level"]))
+        d_lrm = up("lr_mask", S["lr_mask"]); self.uploads.append(("lr_mask", S["lr_mask"]))
+        lf = j.lf
+        lf.pic = p0
+        for p in range(3):
+            lf.plane_off[p] = S["off"][p]; lf.stride[p] = S["stride"][p]
+        lf.w4, lf.h4, lf.sb128w, lf.b4_stride = S["w4"], S["h4"], S["sb128w"], S["b4_stride"]
+        lf.ss_hor, lf.ss_ver, lf.sb128, lf.filter_y, lf.filter_uv = S["ss_hor"], S["ss_ver"], S["sb128"], 1, 1
+        lf.mask, lf.level = d_masks, d_level
+        for k in range(64):
+            lf.lut.e[k], lf.lut.i[k] = int(S["lut_e"][k]), int(S["lut_i"][k])
+        lf.lut.sharp[0], lf.lut.sharp[1] = S["lut_sharp"]
+        cd = j.cdef
+        cd.src, cd.dst = p0, p1
+        for p in range(3):
+            cd.plane_off[p] = S["off"][p]; cd.stride[p] = S["stride"][p]
+        cd.bw, cd.bh, cd.sb128w, cd.ss_hor, cd.ss_ver, cd.damping = S["bw"], S["bh"], S["sb128w"], S["ss_hor"], S["ss_ver"], S["damping"]
+        for i in range(8):
+            cd.y_strength[i], cd.uv_strength[i] = S["y_strength"][i], S["uv_strength"][i]
+        cd.mask = d_masks
+        lr = j.lr
+        lr.cdef, lr.dbl, lr.dst = (p1 if run_cdef else p0), p0, p2
+        for p in range(3):
+            lr.plane_off[p] = S["off"][p]; lr.stride[p] = S["stride"][p]
+        lr.w, lr.h, lr.ss_hor, lr.ss_ver, lr.sb128 = S["W"], S["H"], S["ss_hor"], S["ss_ver"], S["sb128"]
+        lr.sr_sb128w = (S["W"] + 127) >> 7
+        lr.unit_size_log2[0], lr.unit_size_log2[1] = S["us"]
+        lr.restore_planes, lr.lr_mask = S["rp"], d_lrm
+        self.job = j
+        self.out_name = "p2" if run_lr else ("p1" if run_cdef else "p0")
+        self.n_launches = (1 if j.n_pred else 0) + (1 if j.n_comp else 0) + (1 if j.n_comp2 else 0) + \
+            sum(1 for tx in range(19) if j.n_itx[tx]) + 2 * int(run_lf) + int(run_cdef) + int(run_lr)
+        self._host = None
+
+    # ---- device-resident run (records already in HBM) ----
+    def run(self, stream=None):
+        st = self.alloc.stream() if stream is None else stream
+        self.lib.check(self.lib.b200_frame_run(C.byref(self.job), st), "b200_frame_run")
+
+    def set_refs(self, ptrs):
+        for i, p in enumerate(ptrs):
+            self.job.mc.ref[i] = p
+
+    def output(self, name=None):
+        return self.alloc.download(self.keep[name or self.out_name][0], self.S["pic"])
+
+    def picture_ptr(self, name=None):
+        return self.keep[name or self.out_name][1]
+
+    # ---- end-to-end run: records from pinned host memory, picture back to the host ----
+    def prepare_host(self):
+        A = self.alloc
+        ups = []
+        self._host_keep = []
+        for name, arr in self.uploads:
+            t, p = A.pinned(arr)
+            self._host_keep.append(t)
+            ups.append((p, self.keep[name][1], arr.nbytes))
+        out_t, out_p = A.pinned(np.zeros(self.S["pic"].nbytes, np.uint8))
+        self._host_out = out_t
+        self._ups = (_lib.Xfer * len(ups))(*[_lib.Xfer(h, d, n) for h, d, n in ups])
+        self._downs = (_lib.Xfer * 1)(_lib.Xfer(out_p, self.keep[self.out_name][1], self.S["pic"].nbytes))
+        self.h2d_bytes = sum(n for _, _, n in ups)
+        self.d2h_bytes = self.S["pic"].nbytes
+
+    def run_host(self, stream=None):
+        if self._host is None:
+            self.prepare_host(); self._host = True
+        st = self.alloc.stream() if stream is None else stream
+        self.lib.check(self.lib.b200_frame_run_host(C.byref(self.job), self._ups, len(self._ups), self._downs, 1, st),
+                       "b200_frame_run_host")
+
+    def host_output(self):
+        t = self._host_out
+        a = t.numpy() if hasattr(t, "numpy") else t
+        return a[:self.S["pic"].nbytes].view(self.S["pic"].dtype)

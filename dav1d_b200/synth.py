@@ -217,3 +217,197 @@ def make_lr_params(rng, W, H, p_none=0.25):
     u["sgr_weights"][..., 0] = np.where(s0 > 0, rng.integers(-96, 32, n), 0)
     u["sgr_weights"][..., 1] = np.where(s1 > 0, rng.integers(-32, 96, n), 95)
     return m
+
+
+# ------------------------------------------------------------------------------------------
+# whole inter frame (BASELINE configs 2-4): prediction + residual + post-filter records
+# ------------------------------------------------------------------------------------------
+import os as _os
+from . import levels as _L
+
+MC_BLOCK_DT = np.dtype([("dst_off", "<u4"), ("src_x", "<i4"), ("src_y", "<i4"), ("w", "u1"), ("h", "u1"), ("mx", "u1"),
+                        ("my", "u1"), ("filter2d", "u1"), ("op", "u1"), ("plane", "u1"), ("ref", "u1")])
+COMP_BLOCK_DT = np.dtype([("dst_off", "<u4"), ("tmp1_off", "<u4"), ("tmp2_off", "<u4"), ("mask_off", "<u4"), ("w", "u1"),
+                          ("h", "u1"), ("op", "u1"), ("param", "u1"), ("plane", "u1"), ("pad", "u1", (3,))])
+ITX_BLOCK_DT = np.dtype([("dst_off", "<u4"), ("coef_off", "<u4"), ("eob", "<i2"), ("txtp", "u1"), ("plane", "u1")])
+assert MC_BLOCK_DT.itemsize == 20 and COMP_BLOCK_DT.itemsize == 24 and ITX_BLOCK_DT.itemsize == 12
+TX_FROM_WH = {(_L.TX_W[t], _L.TX_H[t]): t for t in range(19)}
+_scans = None
+
+
+def scan_table(tx):
+    """dav1d_scans[tx] (committed copy generated from the reference, tests/golden/make_golden.py)."""
+    global _scans
+    if _scans is None:
+        _scans = np.load(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "data", "scans.npz"))
+    return _scans["tx%d" % tx].astype(np.int64)
+
+
+def smooth_picture(rng, total, bd, dt):
+    """low-pass filtered noise so that sub-pel interpolation is non-trivial"""
+    base = rng.integers(0, bd + 1, total // 16 + 2).astype(np.int32)
+    up = np.repeat(base, 16)[:total]
+    up = (up + np.roll(up, 5) + np.roll(up, 11) + np.roll(up, 23)) // 4
+    return (up + rng.integers(-6, 7, total)).clip(0, bd).astype(dt)
+
+
+def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.3, p_skip=0.25, min_log=1, max_log=4):
+    """Synthetic inter frame: every block is predicted from `n_refs` reference pictures (single or
+    compound), carries a residual (unless skipped) and the frame has deblock / CDEF / LR parameters."""
+    bd = (1 << bpc) - 1
+    dt = np.uint8 if bpc == 8 else np.uint16
+    cdt = np.int16 if bpc == 8 else np.int32
+    S = make_lf_frame(rng, bpc, W, H, ss_hor, ss_ver)          # geometry + placeholder masks (rebuilt below)
+    stride, off = S["stride"], S["off"]
+    total = len(S["pic"])
+    w4, h4 = S["w4"], S["h4"]
+    ssh, ssv = [0, ss_hor, ss_hor], [0, ss_ver, ss_ver]
+    refs = [smooth_picture(rng, total, bd, dt) for _ in range(n_refs)]
+    bx, by, lw, lh = random_tiling(rng, w4, h4, max_log=max_log, min_log=min_log)
+    key = by.astype(np.int64) * 65536 + bx
+    _, first = np.unique(key, return_index=True)
+    blocks = [(int(bx.flat[i]), int(by.flat[i]), int(lw.flat[i]), int(lh.flat[i])) for i in first]
+
+    pred, comp, comp2 = [], [], []
+    itx = {t: [] for t in range(19)}          # tx -> list of (dst_off, plane, txtp)
+    tmp_off, mask_off = 0, 0
+    # transform tilings for the deblocking masks (tx granularity)
+    ty = [np.zeros((h4, w4), np.int32), np.zeros((h4, w4), np.int32), np.zeros((h4, w4), np.int8), np.zeros((h4, w4), np.int8)]
+    cw4, ch4 = (w4 + ss_hor) >> ss_hor, (h4 + ss_ver) >> ss_ver
+    tuv = [np.zeros((ch4, cw4), np.int32), np.zeros((ch4, cw4), np.int32), np.zeros((ch4, cw4), np.int8), np.zeros((ch4, cw4), np.int8)]
+    skip_map = np.zeros((h4, w4), bool)
+
+    def paint(t, x, y, lwv, lhv, hh, ww):
+        x1, y1 = min(ww, x + (1 << lwv)), min(hh, y + (1 << lhv))
+        if x < ww and y < hh:
+            t[0][y:y1, x:x1] = x; t[1][y:y1, x:x1] = y; t[2][y:y1, x:x1] = lwv; t[3][y:y1, x:x1] = lhv
+
+    for (x4, y4, lwv, lhv) in blocks:
+        bw, bh = 4 << lwv, 4 << lhv
+        compound = rng.random() < p_compound
+        mv = [(int(rng.integers(-512, 513)), int(rng.integers(-512, 513))) for _ in range(2)]   # 1/8 luma pixels
+        if rng.random() < 0.05:
+            mv[0] = (mv[0][0] & ~7, mv[0][1] & ~7)                                              # integer-pel sometimes
+        f2d = int(rng.integers(0, 10))
+        rf = [int(rng.integers(0, n_refs)), int(rng.integers(0, n_refs))]
+        cop = int(rng.choice([0, 0, 0, 0, 0, 1, 1, 1, 2, 5])) if compound else -1   # avg 50 / w_avg 30 / wedge 10 / seg 10
+        cparam = int(rng.integers(1, 16)) if cop == 1 else int(rng.integers(0, 2))
+        luma_mask_off = None
+        for pl in range(3):
+            w, h = bw >> ssh[pl], bh >> ssv[pl]
+            px, py = (x4 * 4) >> ssh[pl], (y4 * 4) >> ssv[pl]
+            dst_off = off[pl] + py * stride[pl] + px
+            n = 2 if compound else 1
+            offs = []
+            for k in range(n):
+                mvx, mvy = mv[k]
+                if pl == 0 or not ss_hor:
+                    sx, mx = px + (mvx >> 3), (mvx & 7) << 1
+                else:
+                    sx, mx = px + (mvx >> 4), mvx & 15
+                if pl == 0 or not ss_ver:
+                    sy, my = py + (mvy >> 3), (mvy & 7) << 1
+                else:
+                    sy, my = py + (mvy >> 4), mvy & 15
+                if compound:
+                    pred.append((tmp_off, sx, sy, w, h, mx, my, f2d, 1, pl, rf[k])); offs.append(tmp_off); tmp_off += w * h
+                else:
+                    pred.append((dst_off, sx, sy, w, h, mx, my, f2d, 0, pl, rf[k]))
+            if compound:
+                if cop == 5:           # segment mask: luma derives it (w_mask), chroma consumes it (mask)
+                    if pl == 0:
+                        lay = 3 + (ss_hor + ss_ver)           # w_mask_444 / 422 / 420
+                        luma_mask_off = mask_off
+                        comp.append((dst_off, offs[0], offs[1], mask_off, w, h, lay, cparam, pl, (0, 0, 0)))
+                        mask_off += w * h
+                    else:
+                        comp2.append((dst_off, offs[0], offs[1], luma_mask_off, w, h, 2, 0, pl, (0, 0, 0)))
+                elif cop == 2:         # wedge: explicit mask from the host
+                    comp.append((dst_off, offs[0], offs[1], mask_off, w, h, 2, 0, pl, (0, 0, 0))); mask_off += w * h
+                else:
+                    comp.append((dst_off, offs[0], offs[1], 0, w, h, cop, cparam, pl, (0, 0, 0)))
+        # residual: transform tiling of the block (var-tx split depth <= 1), capped at 64
+        skip = rng.random() < p_skip
+        skip_map[y4:y4 + (1 << lhv), x4:x4 + (1 << lwv)] = skip
+        tlw, tlh = min(lwv, 4), min(lhv, 4)
+        if rng.random() < 0.3 and tlw > 0 and tlh > 0:
+            tlw -= 1; tlh -= 1
+        for yy in range(y4, y4 + (1 << lhv), 1 << tlh):
+            for xx in range(x4, x4 + (1 << lwv), 1 << tlw):
+                paint(ty, xx, yy, tlw, tlh, h4, w4)
+                if not skip and xx < w4 and yy < h4:
+                    tx = TX_FROM_WH[(4 << tlw, 4 << tlh)]
+                    itx[tx].append((off[0] + yy * 4 * stride[0] + xx * 4, 0))
+        # chroma: one transform per block, capped at 32 (64x64 luma -> 32x32 chroma)
+        clw, clh = max(lwv - ss_hor, 0), max(lhv - ss_ver, 0)
+        cx4, cy4 = x4 >> ss_hor, y4 >> ss_ver
+        ctl, cth = min(clw, 3), min(clh, 3)
+        for yy in range(cy4, cy4 + (1 << clh), 1 << cth):
+            for xx in range(cx4, cx4 + (1 << clw), 1 << ctl):
+                paint(tuv, xx, yy, ctl, cth, ch4, cw4)
+                if not skip and xx < cw4 and yy < ch4:
+                    tx = TX_FROM_WH[(4 << ctl, 4 << cth)]
+                    for pl in (1, 2):
+                        itx[tx].append((off[pl] + yy * 4 * stride[pl] + xx * 4, pl))
+
+    # ---- coefficient stream (vectorised per transform size) ----
+    coef_chunks, itx_arrays, coef_off = [], {}, 0
+    for tx in range(19):
+        lst = itx[tx]
+        if not lst:
+            itx_arrays[tx] = np.zeros(0, ITX_BLOCK_DT)
+            continue
+        n = len(lst)
+        sw, sh = _L.tx_coef_dims(tx)
+        ncf = sw * sh
+        legal = [tp for tp in range(10) if _L.itx_defined(tx, tp)]          # 2-D transform classes only
+        txtp = rng.choice(legal, n, p=None if len(legal) == 1 else [0.55] + [0.45 / (len(legal) - 1)] * (len(legal) - 1))
+        scan = scan_table(tx)
+        inv = np.empty(ncf, np.int64); inv[scan] = np.arange(ncf)          # coefficient index -> scan position
+        eob = np.minimum((rng.exponential(ncf / 10.0, n)).astype(np.int64), ncf - 1)
+        eob[rng.random(n) < 0.25] = 0                                        # dc-only blocks
+        amp = (bd + 1) / 2.0
+        pos = inv[None, :]
+        mag = rng.laplace(0.0, amp * 0.35, (n, ncf)) / (1.0 + pos / 6.0)
+        c = np.rint(mag).astype(np.int64)
+        c[pos > eob[:, None]] = 0
+        c[np.arange(n), scan[eob]] = np.where(c[np.arange(n), scan[eob]] == 0, 1, c[np.arange(n), scan[eob]])
+        arr = np.zeros(n, ITX_BLOCK_DT)
+        arr["dst_off"] = [d for d, _ in lst]; arr["plane"] = [p for _, p in lst]
+        arr["coef_off"] = coef_off + np.arange(n) * ncf
+        arr["eob"] = eob; arr["txtp"] = txtp
+        itx_arrays[tx] = arr
+        coef_chunks.append(c.astype(cdt).reshape(-1))
+        coef_off += n * ncf
+    coefs = np.concatenate(coef_chunks) if coef_chunks else np.zeros(1, cdt)
+
+    def to_arr(lst, dtp):
+        a = np.zeros(len(lst), dtp)
+        for i, rec in enumerate(lst):
+            a[i] = rec
+        return a
+    S.update(refs=refs, pred=to_arr(pred, MC_BLOCK_DT), comp=to_arr(comp, COMP_BLOCK_DT), comp2=to_arr(comp2, COMP_BLOCK_DT),
+             itx=itx_arrays, coefs=coefs, tmp_len=tmp_off + 64, mask=rng.integers(0, 65, max(1, mask_off)).astype(np.uint8))
+    S["pic"] = np.zeros(total, dt)                     # the picture being reconstructed
+    # post-filter records from the transform tilings
+    S["masks"] = build_lf_masks(w4, h4, tuple(ty), tuple(tuv), ss_hor, ss_ver)
+    S["til_y"], S["til_uv"] = tuple(ty), tuple(tuv)
+    S["bw"], S["bh"] = w4, h4
+    S["damping"], S["y_strength"], S["uv_strength"] = make_cdef_params(rng, w4, h4, S["sb128w"], S["masks"])
+    # noskip_mask from the real skip flags (reference src/decode.c:1946-1955)
+    sb128h = (h4 + 31) // 32
+    ns8 = np.zeros((sb128h * 16, S["sb128w"] * 16), bool)
+    nsk = ~skip_map
+    hh, ww = (h4 + 1) // 2, (w4 + 1) // 2
+    pad = np.zeros((hh * 2, ww * 2), bool); pad[:h4, :w4] = nsk
+    ns8[:hh, :ww] = pad.reshape(hh, 2, ww, 2).any(axis=(1, 3))
+    t = ns8.reshape(sb128h, 16, S["sb128w"], 16).transpose(0, 2, 1, 3).reshape(-1, 16, 16)
+    bits = np.zeros((t.shape[0], 16, 2), np.uint16)
+    wgt = (3 << (2 * np.arange(8))).astype(np.uint32)
+    for h in range(2):
+        bits[:, :, h] = (t[:, :, h * 8:(h + 1) * 8] * wgt[None, None, :]).sum(axis=2).astype(np.uint16)
+    S["masks"]["noskip_mask"] = bits
+    S["lr_mask"] = make_lr_params(rng, W, H)
+    S["us"] = (6, 6 - (1 if ss_hor else 0))
+    S["rp"], S["sb128"] = 7, 0
+    return S

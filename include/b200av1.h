@@ -295,6 +295,48 @@ typedef struct B200LoopRestorationDSPContext { void *wiener[2]; void *sgr[3]; } 
 B200_API void b200_loop_restoration_dsp_init_8bpc(B200LoopRestorationDSPContext *c, int bpc);
 B200_API void b200_loop_restoration_dsp_init_16bpc(B200LoopRestorationDSPContext *c, int bpc);
 
+/* ==== whole-frame job: reconstruction + post-filter sweep ================================= */
+/* What a dav1d `f->bd_fn` record emitter hands over per frame (SURVEY.md §8b level 2): the block
+ * records of pass 2 (prediction blocks, compound / blend / warp records, transform blocks bucketed by
+ * transform size with their coefficient stream) and the post-filter parameters, all already in HBM.
+ * b200_frame_run enqueues, on `stream`:
+ *    prediction (put/prep) -> warp -> compound -> compound stage 2 -> blend -> inverse transforms (one launch per size)
+ *    -> deblock (2 sweeps, in place on the reconstructed picture) -> CDEF (out of place) -> loop
+ *    restoration (out of place).
+ * Stages whose counts / run_* flags are zero are skipped. Picture chaining is the caller's: typically
+ * mc.dst == lf.pic == cdef.src == lr.dbl, cdef.dst == lr.cdef, lr.dst = output. */
+typedef struct B200FrameJob {
+    int32_t bitdepth_max;
+    int32_t zero_coefs;
+    B200McFrame mc;
+    const B200McBlock *d_pred;   int32_t n_pred;   int32_t pad0;
+    const B200WarpBlock *d_warp; int32_t n_warp;   int32_t pad1;
+    const B200CompBlock *d_comp; int32_t n_comp;   int32_t pad2;
+    const B200CompBlock *d_comp2; int32_t n_comp2; int32_t pad2b;  /* second compound stage: chroma `mask` blocks that
+                                                                      consume the mask a luma w_mask of stage 1 produced */
+    const B200BlendBlock *d_blend; int32_t n_blend; int32_t pad3;
+    const B200ItxBlock *d_itx[B200_N_RECT_TX_SIZES];
+    int32_t n_itx[B200_N_RECT_TX_SIZES];
+    int32_t pad4;
+    void *d_coef;
+    int32_t itx_stride[3];       /* picture strides (pixels) for the transform add */
+    int32_t run_lf, run_cdef, run_lr;
+    B200LfFrame lf;
+    B200CdefFrame cdef;
+    B200LrFrame lr;
+} B200FrameJob;
+B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
+/* sizeof() of the ABI structs as compiled into the library (binding self-check): 0 McFrame, 1 McBlock, 2 CompBlock,
+ * 3 BlendBlock, 4 WarpBlock, 5 ItxBlock, 6 LfFrame, 7 CdefFrame, 8 LrFrame, 9 FrameJob, 10 Av1Filter, 11 Av1Restoration */
+B200_API int b200_struct_size(int which);
+
+/* The same job fed from HOST buffers (the end-to-end path): every (host, dev, bytes) pair of `uploads`
+ * is copied host->device first, the job runs, then every pair of `downloads` is copied device->host and
+ * the stream is synchronised. Device buffers are the ones the job's pointers refer to. */
+typedef struct B200Xfer { void *host; void *dev; uint64_t bytes; } B200Xfer;
+B200_API int b200_frame_run_host(const B200FrameJob *job, const B200Xfer *uploads, int n_uploads,
+                                 const B200Xfer *downloads, int n_downloads, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,101 @@
+"""Whole-frame parity: reconstruction (prediction + compound + inverse transforms) followed by the
+post-filter sweep (deblock -> CDEF -> loop restoration) over one synthetic inter frame, CUDA job vs the
+oracle running the same stages in the same order on the CPU (each stage of the oracle is itself pinned
+against the reference: test_itx / test_mc / test_loopfilter / test_cdef / test_looprestoration)."""
+import ctypes as C
+import numpy as np
+import pytest
+
+import refs
+from dav1d_b200 import _lib, synth, frame
+import test_loopfilter as TLF
+import test_cdef as TCD
+import test_looprestoration as TLR
+
+
+def oracle_frame(S, run_lf=True, run_cdef=True, run_lr=True):
+    """returns dict of the pictures after each stage"""
+    o = refs.oracle()
+    bd = S["bd"]
+    pic = np.zeros_like(S["pic"])
+    tmp = np.zeros(S["tmp_len"], np.int16)
+    mask = S["mask"].copy()
+    fr = _lib.McFrame()
+    keep = [r.copy() for r in S["refs"]]
+    for i, r in enumerate(keep):
+        fr.ref[i] = r.ctypes.data
+    ssh, ssv = [0, S["ss_hor"], S["ss_hor"]], [0, S["ss_ver"], S["ss_ver"]]
+    for p in range(3):
+        fr.ref_plane_off[p] = S["off"][p]; fr.ref_stride[p] = S["stride"][p]
+        fr.ref_w[p] = (S["W"] + ssh[p]) >> ssh[p]; fr.ref_h[p] = (S["H"] + ssv[p]) >> ssv[p]
+        fr.dst_stride[p] = S["stride"][p]
+    fr.dst, fr.tmp, fr.mask = pic.ctypes.data, tmp.ctypes.data, mask.ctypes.data
+    o.oracle_mc_batch(bd, C.byref(fr), S["pred"].ctypes.data, len(S["pred"]))
+    o.oracle_mc_comp_batch(bd, C.byref(fr), S["comp"].ctypes.data, len(S["comp"]))
+    o.oracle_mc_comp_batch(bd, C.byref(fr), S["comp2"].ctypes.data, len(S["comp2"]))
+    st = (C.c_int32 * 3)(*S["stride"])
+    coefs = S["coefs"].copy()
+    for tx in range(19):
+        a = S["itx"][tx]
+        if len(a):
+            assert o.oracle_itx_add_batch(bd, tx, a.ctypes.data, len(a), coefs.ctypes.data, pic.ctypes.data, st, 0) == 0
+    out = {"recon": pic.copy()}
+    S2 = dict(S); S2["pic"] = pic
+    if run_lf:
+        pic = TLF.lf_frame_oracle(S2); S2["pic"] = pic
+    out["dbl"] = pic.copy()
+    if run_cdef:
+        cd = TCD.cdef_frame_oracle(S2)
+    else:
+        cd = pic
+    out["cdef"] = cd
+    if run_lr:
+        S3 = dict(S2); S3["cdef"], S3["dbl"] = cd, pic
+        out["lr"] = TLR.lr_frame_oracle(S3)
+    return out
+
+
+def check_frame(S, fb, exp):
+    """the frame area of every stage's picture must match"""
+    got_recon_dbl = fb.output("p0")
+    assert TCD.frame_area_equal(S, got_recon_dbl, exp["dbl"]), "reconstruction + deblock mismatch"
+    assert TCD.frame_area_equal(S, fb.output("p1"), exp["cdef"]), "cdef mismatch"
+    assert TLR.picture_equal(S, fb.output("p2"), exp["lr"]), "loop restoration mismatch"
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", [(8, 200, 136, 1, 1), (10, 136, 72, 1, 1)])
+def test_emu_frame(bpc, W, H, ssh, ssv):
+    S = synth.make_inter_frame(np.random.default_rng(600 + bpc), bpc, W, H, ssh, ssv)
+    exp = oracle_frame(S)
+    assert (exp["recon"] != 0).mean() > 0.3 and not np.array_equal(exp["recon"], exp["dbl"])
+    fb = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
+    fb.run()
+    check_frame(S, fb, exp)
+    # the host-buffer path must give the same picture
+    fb2 = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
+    fb2.run_host()
+    assert TLR.picture_equal(S, fb2.host_output(), exp["lr"])
+
+
+def test_abi_struct_sizes_match_binding():
+    from dav1d_b200 import build
+    build.build()
+    lib = _lib.B200Lib(_lib.LIB_PATH)            # raises on any sizeof mismatch
+    assert lib.b200_struct_size(9) == C.sizeof(_lib.FrameJob)
+    assert C.sizeof(_lib.Av1Filter) == synth.AV1FILTER_DT.itemsize == 1348
+    assert synth.MC_BLOCK_DT.itemsize == C.sizeof(_lib.McBlock) and synth.COMP_BLOCK_DT.itemsize == C.sizeof(_lib.CompBlock)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", [(8, 640, 360, 1, 1), (10, 648, 368, 1, 1), (12, 328, 200, 0, 0), (8, 1920, 1080, 1, 1)])
+def test_gpu_frame(bpc, W, H, ssh, ssv):
+    S = synth.make_inter_frame(np.random.default_rng(610 + bpc + W), bpc, W, H, ssh, ssv)
+    exp = oracle_frame(S)
+    fb = frame.FrameBuffers(S)
+    fb.run()
+    fb.alloc.sync()
+    check_frame(S, fb, exp)
+    fb2 = frame.FrameBuffers(S)
+    fb2.run_host()
+    assert TLR.picture_equal(S, fb2.host_output(), exp["lr"])
