@@ -1,18 +1,25 @@
 #!/usr/bin/env python3
-"""bench.py — throughput of the B200 AV1 reconstruction back end on BASELINE.json's metric.
+"""bench.py — throughput of the B200 AV1 reconstruction + post-filter back end (BASELINE.json metric:
+Mpixels/s recon+postfilter @ 4K).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-One "step" = one pass of the hot path over one batch of synthetic block records.
-Prints ONE JSON line (rank 0). See DESIGN.md §Measurement for the byte accounting.
+One "step" = one pass of the hot path over one batch of synthetic records, per GPU.
 
 Workloads
-  itx8x8   BASELINE config 0: 2^20 inv_txfm_add DCT_DCT 8x8, 8-bit, checkasm-style coefficients
-           on an 8192x8192 plane (67.1 Mpx / step). Algorithmic bytes: 256 B / block
-           (128 B coefs + 64 B dst read + 64 B dst write).
+  4k8_inter (default)  BASELINE config 2/3: one 3840x2160 8-bit 4:2:0 inter frame per GPU per step:
+             prediction (put / prep + avg / w_avg / mask / w_mask from 2 reference pictures, 8-tap and
+             bilinear, MVs that also leave the picture) -> inverse transforms (var-tx, 4x4..64x64) ->
+             deblock (2 sweeps) -> CDEF -> loop restoration (Wiener + self-guided). Records are
+             synthesised at the record level (no AV1 streams / encoder exist here).
+             Mpixels = luma pixels (3840*2160 = 8.29 Mpx per frame).
+  itx8x8     BASELINE config 0: 2^20 inv_txfm_add DCT_DCT 8x8 8-bit blocks (67.1 Mpx) per step.
+Multi-GPU: frames shard over GPUs (one frame per GPU per step, weak scaling); for the inter workload every
+rank's restored picture is all-gathered over NCCL after each step (the reference-picture broadcast: frame
+n+1.. may reference it), inside the timed region.
 
---impl reference times dav1d's own C functions (oracle/_ref, unmodified reference sources)
-on the host cores over a bounded sample of the same records.
+--impl reference times dav1d's own C functions (oracle/_ref, unmodified reference sources, HAVE_ASM=0:
+no nasm in this image) on the host cores: one frame per thread (dav1d's frame threading), all cores.
 """
 import argparse
 import ctypes as C
@@ -30,9 +37,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 ITX_DT = np.dtype([("dst_off", "<u4"), ("coef_off", "<u4"), ("eob", "<i2"), ("txtp", "u1"), ("plane", "u1")])
+W4K, H4K = 3840, 2160
 
 
-# ------------------------------------------------------------------------------ workload
+# ------------------------------------------------------------------------------ itx8x8 workload
 def fdct_matrix(n):
     i = np.arange(n)[:, None].astype(np.float64)
     j = np.arange(n)[None, :].astype(np.float64)
@@ -45,12 +53,12 @@ def make_itx8x8(seed, n_blocks, plane_w):
     """BASELINE config 0 records (vectorised port of the checkasm generator's distribution:
     random +-255 residual -> float forward DCT x 2.0 -> round; eob uniform over the dc-only /
     full classes; reference tests/checkasm/itx.c:185-242)."""
+    from dav1d_b200 import synth
     rng = np.random.default_rng(seed)
     m = fdct_matrix(8)
     coefs = np.empty((n_blocks, 64), np.int16)
     eobs = np.empty(n_blocks, np.int16)
-    import refs
-    order = refs.scan_table(1)          # dav1d_scans[TX_8X8]: scan position -> coefficient index
+    order = synth.scan_table(1)          # dav1d_scans[TX_8X8]: scan position -> coefficient index
     inv = np.empty(64, np.int32)
     inv[order] = np.arange(64)
     chunk = 1 << 16
@@ -95,7 +103,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(f)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
@@ -114,67 +122,136 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-# ------------------------------------------------------------------------------ reference arm
-def run_reference(args):
+def frame_algorithmic_bytes(S):
+    """SURVEY.md §8(d) accounting for one frame, per stage (bytes); px = bytes per pixel."""
+    px = S["pic"].itemsize
+    cps = S["coefs"].itemsize
+    ssh, ssv = [0, S["ss_hor"], S["ss_hor"]], [0, S["ss_ver"], S["ss_ver"]]
+    samples = sum(((S["W"] + ssh[p]) >> ssh[p]) * ((S["H"] + ssv[p]) >> ssv[p]) for p in range(3))
+    b = S["pred"]
+    foot = ((b["w"].astype(np.int64) + 7 * (b["mx"] != 0)) * (b["h"].astype(np.int64) + 7 * (b["my"] != 0))).sum() * px
+    out = (b["w"].astype(np.int64) * b["h"] * np.where(b["op"] == 1, 2, px)).sum()
+    c = np.concatenate([S["comp"], S["comp2"]])
+    comp = (c["w"].astype(np.int64) * c["h"] * (4 + px)).sum()
+    itx = 0
+    from dav1d_b200 import levels as L
+    for tx in range(19):
+        n = len(S["itx"][tx])
+        sw, sh = L.tx_coef_dims(tx)
+        itx += n * (sw * sh * cps + 2 * L.TX_W[tx] * L.TX_H[tx] * px)
+    return {"mc": int(foot + out), "comp": int(comp), "itx": int(itx), "deblock": int(4 * samples * px),
+            "cdef": int(2 * samples * px), "lr": int(2 * samples * px), "samples": int(samples)}
+
+
+# ------------------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_frames(S, n_threads, reps, use_ref=True):
+    """`n_threads` frames in parallel, one per thread (frame threading), each through the reference's own
+    functions (oracle/refdriver refdrv_frame_run) or, when oracle/_ref is absent, the oracle port."""
     import refs
+    from dav1d_b200 import frame
+    if use_ref and refs.have_ref():
+        fn = refs.ref().refdrv_frame_run_8bpc if S["bpc"] == 8 else refs.ref().refdrv_frame_run_16bpc
+        kind = "reference"
+    else:
+        import test_frame
+        fn, kind = None, "port"
+    fbs = [frame.FrameBuffers(S, lib=object(), alloc=frame.NumpyAlloc()) for _ in range(n_threads)] if fn else None
+
+    def work(i):
+        for _ in range(reps):
+            if fn:
+                fn(C.byref(fbs[i].job))
+            else:
+                test_frame.oracle_frame(S)
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return n_threads * reps * S["W"] * S["H"] / dt / 1e6, dt, kind
+
+
+def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from dav1d_b200 import synth
     ncores = os.cpu_count() or 1
-    n = 1 << 18                                        # bounded sample of the same workload
-    blocks, coefs, pic = make_itx8x8(1, n, 8192)
-    lib = refs.ref()
-    st = (C.c_int32 * 3)(8192, 8192, 8192)
+    if args.workload == "itx8x8":
+        import refs
+        n = 1 << 18
+        blocks, coefs, pic = make_itx8x8(1, n, 8192)
+        st = (C.c_int32 * 3)(8192, 8192, 8192)
+        lib = refs.ref()
 
-    def step():
-        return lib.refdrv_itx_add_batch(255, 1, blocks.ctypes.data, n, coefs.ctypes.data, pic.ctypes.data, st, 0, ncores)
-    for _ in range(args.warmup):
-        step()
-    t = [step() for _ in range(args.steps)]
-    ms = 1e3 * sum(t) / len(t)
-    val = n * 64 / (ms * 1e-3) / 1e6
+        def step():
+            return lib.refdrv_itx_add_batch(255, 1, blocks.ctypes.data, n, coefs.ctypes.data, pic.ctypes.data, st, 0, ncores)
+        for _ in range(args.warmup):
+            step()
+        t = [step() for _ in range(args.steps)]
+        ms = 1e3 * sum(t) / len(t)
+        val = n * 64 / (ms * 1e-3) / 1e6
+        wl = "itx8x8: inv_txfm_add DCT_DCT 8x8 8-bit (BASELINE config 0), sample of 2^18 of the 2^20 blocks per step"
+        sample = "2^18 blocks/step, %d threads" % ncores
+        kind = "reference"
+    else:
+        S = synth.make_inter_frame(np.random.default_rng(1), 8, W4K, H4K)
+        nthr = min(ncores, 64)
+        for _ in range(min(args.warmup, 1)):
+            cpu_frames(S, nthr, 1)
+        vals, dts = [], []
+        for _ in range(args.steps):
+            v, dt, kind = cpu_frames(S, nthr, 1)
+            vals.append(v); dts.append(dt)
+        val = float(np.mean(vals)); ms = 1e3 * float(np.mean(dts))
+        wl = "4k8_inter: 3840x2160 8-bit 4:2:0 inter frame (mc + itx + deblock + CDEF + LR), %d frames per step, one per thread" % nthr
+        sample = "%d whole 4K frames per step (one per thread, %d of %d cores), dav1d C path HAVE_ASM=0" % (nthr, nthr, ncores)
+        ncores = nthr
     line = {"impl": "reference", "metric": "Mpixels/s", "value": val, "unit": "Mpixels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/i16->i32", "data": "synthetic",
-            "config": {"workload": "itx8x8: inv_txfm_add DCT_DCT 8x8 8-bit (BASELINE config 0), sample of 2^18 of the 2^20 blocks",
-                       "l2": "n/a (host)"},
-            "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": ncores, "kind": "reference",
-                             "sample": "2^18 blocks/step, dav1d C path (HAVE_ASM=0, gcc -O3 -march=x86-64-v3), %d threads" % ncores},
+            "config": {"workload": wl, "l2": "n/a (host)"},
+            "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": ncores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------ our arm
-def run_ours(args):
+def dist_setup():
     import torch
     import torch.distributed as dist
-    from dav1d_b200 import batch, get_lib
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = get_lib()
+    return torch, dist, world, rank, local
 
-    n_blocks, plane_w, nsets = 1 << 20, 8192, 3
-    px_per_step = n_blocks * 64
-    # every rank processes its own, differently-seeded frame batch (frames shard over GPUs)
-    sets = []
-    host = None
+
+def run_ours_frame(args):
+    torch, dist, world, rank, local = dist_setup()
+    from dav1d_b200 import synth, frame, get_lib
+    lib = get_lib()
+    nsets = 3
+    fbs, Ss = [], []
     for k in range(nsets):
-        blocks, coefs, pic = make_itx8x8(1 + rank * 16 + k, n_blocks, plane_w)
-        if k == 0:
-            host = (blocks, coefs, pic)
-        sets.append((torch.from_numpy(blocks.view(np.uint8)).cuda(), torch.from_numpy(coefs).cuda(),
-                     torch.from_numpy(pic).cuda()))
-    strides = [plane_w] * 3
+        S = synth.make_inter_frame(np.random.default_rng(1 + rank * 16 + k), 8, W4K, H4K)
+        Ss.append(S)
+        fbs.append(frame.FrameBuffers(S))
+    px_per_step = W4K * H4K
+    gather = None
+    if world > 1:   # reference-picture exchange buffer: every rank's restored picture
+        gather = torch.empty(world * Ss[0]["pic"].nbytes, dtype=torch.uint8, device="cuda")
 
     def step(i):
-        b, c, p = sets[i % nsets]
-        batch.itx_add_batch(255, 1, b, c, p, strides)
+        fb = fbs[i % nsets]
+        fb.run()
+        if world > 1:
+            dist.all_gather_into_tensor(gather, fb.keep[fb.out_name][0][:Ss[0]["pic"].nbytes])
 
     def sync_all():
         torch.cuda.synchronize()
@@ -196,15 +273,146 @@ def run_ours(args):
     sync_all()
     launches = lib.b200_launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
+    t = torch.tensor([total_ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * px_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # per-stage device times (CUDA events around each stage's launches, same stream, same rotation)
+    stage_ms = stage_times(torch, lib, fbs, nsets)
+
+    # end to end: records from pinned host memory through b200_frame_run_host, picture back to the host
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        fbs[i % nsets].run_host()
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        fbs[i % nsets].run_host()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * px_per_step / (float(t.item()) * 1e-3) / 1e6
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg = frame_algorithmic_bytes(Ss[0])
+        stages = {}
+        for name, ms in stage_ms.items():
+            key = {"pred": "mc", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr"}[name]
+            stages[name] = {"ms": ms, "algorithmic_bytes": alg[key], "GBps": alg[key] / (ms * 1e-3) / 1e9 if ms > 0 else None}
+        dom = max(stage_ms, key=lambda k: stage_ms[k])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "frame_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom)
+        achieved = stages[dom]["GBps"]
+        total_alg = sum(alg[k] for k in ("mc", "comp", "itx", "deblock", "cdef", "lr"))
+        nthr = min(os.cpu_count() or 1, 32)
+        v, dt, kind = cpu_frames(Ss[0], nthr, 1)
+        cpu = {"value": v, "unit": "Mpixels/s", "cores": nthr, "kind": kind,
+               "sample": "%d whole 4K frames, one per thread (frame threading), dav1d C path HAVE_ASM=0 (no nasm in image), %.1f s" % (nthr, dt)}
+        line = {"metric": "Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8/i16->i32", "data": "synthetic",
+                "config": {"workload": "4k8_inter: one 3840x2160 8-bit 4:2:0 inter frame per GPU per step: prediction (put/prep+"
+                                       "compound, 2 refs) + inverse transforms + deblock + CDEF + loop restoration (BASELINE configs 2-3)",
+                           "l2": "3 rotating frame sets (~%d MB) > 126 MB L2" % (3 * (5 * Ss[0]["pic"].nbytes + Ss[0]["coefs"].nbytes) // 1000000),
+                           "records": {"pred_blocks": int(len(Ss[0]["pred"])), "compound": int(len(Ss[0]["comp"]) + len(Ss[0]["comp2"])),
+                                       "tx_blocks": int(sum(len(a) for a in Ss[0]["itx"].values())), "coefs": int(len(Ss[0]["coefs"]))},
+                           "exchange": "all_gather of each rank's restored picture per step (NCCL)" if world > 1 else "none"},
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "whole_frame": {"algorithmic_bytes": total_alg, "GBps": total_alg / (ms_per_step * 1e-3) / 1e9,
+                                             "frac": total_alg / (ms_per_step * 1e-3) / 1e9 / peak},
+                             "stages": stages},
+                "cpu_baseline": cpu,
+                "e2e": {"value": e2e_val, "unit": "Mpixels/s", "h2d_bytes_per_step": int(fbs[0].h2d_bytes),
+                        "d2h_bytes_per_step": int(fbs[0].d2h_bytes)},
+                "gpu_launches": int(launches), "clocks": sampler.summary()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def stage_times(torch, lib, fbs, nsets, reps=6):
+    """average device time of each stage of the frame job (events on the launching stream)"""
+    from dav1d_b200 import _lib
+    names = ["pred", "comp", "itx", "deblock", "cdef", "lr"]
+    acc = {n: 0.0 for n in names}
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(reps):
+        fb = fbs[r % nsets]
+        j = fb.job
+        bd = j.bitdepth_max
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+        evs[0].record()
+        lib.b200_mc_batch(bd, C.byref(j.mc), j.d_pred, j.n_pred, st); evs[1].record()
+        lib.b200_mc_comp_batch(bd, C.byref(j.mc), j.d_comp, j.n_comp, st)
+        lib.b200_mc_comp_batch(bd, C.byref(j.mc), j.d_comp2, j.n_comp2, st); evs[2].record()
+        for tx in range(19):
+            if j.n_itx[tx]:
+                lib.b200_itx_add_batch(bd, tx, j.d_itx[tx], j.n_itx[tx], j.d_coef, j.mc.dst, j.itx_stride, 0, st)
+        evs[3].record()
+        lib.b200_lf_frame(bd, C.byref(j.lf), st); evs[4].record()
+        lib.b200_cdef_frame(bd, C.byref(j.cdef), st); evs[5].record()
+        lib.b200_lr_frame(bd, C.byref(j.lr), st); evs[6].record()
+        torch.cuda.synchronize()
+        if r >= 1:
+            for k, n in enumerate(names):
+                acc[n] += evs[k].elapsed_time(evs[k + 1])
+    return {n: acc[n] / (reps - 1) for n in names}
+
+
+def run_ours_itx(args):
+    torch, dist, world, rank, local = dist_setup()
+    from dav1d_b200 import batch, get_lib
+    lib = get_lib()
+    n_blocks, plane_w, nsets = 1 << 20, 8192, 3
+    px_per_step = n_blocks * 64
+    sets, host = [], None
+    for k in range(nsets):
+        blocks, coefs, pic = make_itx8x8(1 + rank * 16 + k, n_blocks, plane_w)
+        if k == 0:
+            host = (blocks, coefs, pic)
+        sets.append((torch.from_numpy(blocks.view(np.uint8)).cuda(), torch.from_numpy(coefs).cuda(),
+                     torch.from_numpy(pic).cuda()))
+    strides = [plane_w] * 3
+
+    def step(i):
+        b, c, p = sets[i % nsets]
+        batch.itx_add_batch(255, 1, b, c, p, strides)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for i in range(args.warmup):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = lib.b200_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step(i)
+        ev[i + 1].record()
+    sync_all()
+    launches = lib.b200_launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
     kern_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     t = torch.tensor([total_ms], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
+    ms_per_step = float(t.item()) / args.steps
     value = world * px_per_step / (ms_per_step * 1e-3) / 1e6
-
-    # end to end: host (pinned) buffers through the C ABI, copies inside the timed region
     hb = torch.from_numpy(host[0].view(np.uint8)).pin_memory()
     hc = torch.from_numpy(host[1]).pin_memory()
     hp = torch.from_numpy(host[2].copy()).pin_memory()
@@ -223,8 +431,8 @@ def run_ours(args):
     e2e_val = world * px_per_step / (float(t.item()) * 1e-3) / 1e6
     sampler.stop_flag = True
     sampler.join(timeout=2)
-
     if rank == 0:
+        import refs
         peak, peak_src = measured_peak()
         alg_bytes = n_blocks * 256
         k_ms = sum(kern_ms) / len(kern_ms)
@@ -233,7 +441,18 @@ def run_ours(args):
         tp = os.path.join(ROOT, "profiles", "itx8x8_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        cpu = cpu_baseline()
+        n = 1 << 18
+        blocks, coefs, pic = make_itx8x8(1, n, 8192)
+        st = (C.c_int32 * 3)(8192, 8192, 8192)
+        ncores = os.cpu_count() or 1
+        lib_r = refs.ref()
+        lib_r.refdrv_itx_add_batch(255, 1, blocks.ctypes.data, n, coefs.ctypes.data, pic.ctypes.data, st, 0, ncores)
+        reps, tot = 0, 0.0
+        while tot < 3.0 and reps < 200:
+            tot += lib_r.refdrv_itx_add_batch(255, 1, blocks.ctypes.data, n, coefs.ctypes.data, pic.ctypes.data, st, 0, ncores)
+            reps += 1
+        cpu = {"value": reps * n * 64 / tot / 1e6, "unit": "Mpixels/s", "cores": ncores, "kind": "reference",
+               "sample": "2^18 of the 2^20 blocks x %d reps, dav1d C path HAVE_ASM=0 (no nasm in image), %d threads" % (reps, ncores)}
         line = {"metric": "Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/i16->i32", "data": "synthetic",
@@ -252,43 +471,20 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline():
-    """dav1d's C path (oracle/_ref) when shipped, else the oracle port, on a bounded sample."""
-    import refs
-    n = 1 << 18
-    blocks, coefs, pic = make_itx8x8(1, n, 8192)
-    st = (C.c_int32 * 3)(8192, 8192, 8192)
-    ncores = os.cpu_count() or 1
-    if refs.have_ref():
-        lib = refs.ref()
-        lib.refdrv_itx_add_batch(255, 1, blocks.ctypes.data, n, coefs.ctypes.data, pic.ctypes.data, st, 0, ncores)
-        reps, tot = 0, 0.0
-        while tot < 3.0 and reps < 200:
-            tot += lib.refdrv_itx_add_batch(255, 1, blocks.ctypes.data, n, coefs.ctypes.data, pic.ctypes.data, st, 0, ncores)
-            reps += 1
-        t1 = lib.refdrv_itx_add_batch(255, 1, blocks.ctypes.data, n, coefs.ctypes.data, pic.ctypes.data, st, 0, 1)
-        return {"value": reps * n * 64 / tot / 1e6, "unit": "Mpixels/s", "cores": ncores, "kind": "reference",
-                "sample": "2^18 of the 2^20 blocks x %d reps, dav1d C path HAVE_ASM=0 (no nasm in image), %d threads" % (reps, ncores),
-                "single_core_value": n * 64 / t1 / 1e6}
-    o = refs.oracle()
-    t0 = time.perf_counter()
-    o.oracle_itx_add_batch(255, 1, blocks.ctypes.data, n, coefs.ctypes.data, pic.ctypes.data, st, 0)
-    dt = time.perf_counter() - t0
-    return {"value": n * 64 / dt / 1e6, "unit": "Mpixels/s", "cores": 1, "kind": "port", "sample": "2^18 blocks, oracle port, 1 thread"}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "itx8x8"])
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
+        args.steps = min(args.steps, 5)      # bounded: each step is tens of whole 4K frames on the CPU
         run_reference(args)
     else:
-        run_ours(args)
+        args.warmup = max(args.warmup, 3)
+        (run_ours_itx if args.workload == "itx8x8" else run_ours_frame)(args)
 
 
 if __name__ == "__main__":

@@ -198,3 +198,111 @@ API void bitfn(refdrv_lr_frame)(const int bitdepth_max, const RefLrFrame *const 
     for (int p = 0; p < 3; p++) free(lines[p]);
     free(dsp); free(hdr); free(seq); free(c); free(f);
 }
+
+/* ---- whole frame on the CPU with the reference's own functions (bench.py --impl reference,
+ *      cpu_baseline): same B200FrameJob records, host pointers, single thread per call ---- */
+#include "../../include/b200av1.h"
+#include "src/mc.h"
+#include "src/itx.h"
+
+API void bitfn(refdrv_frame_run)(const B200FrameJob *const j)
+{
+    static __thread Dav1dMCDSPContext mc;
+    static __thread Dav1dInvTxfmDSPContext itx;
+    static __thread int inited;
+    if (!inited) {
+        bitfn(dav1d_mc_dsp_init)(&mc);
+        bitfn(dav1d_itx_dsp_init)(&itx, BITDEPTH == 8 ? 8 : 32 - clz(j->bitdepth_max));
+        inited = 1;
+    }
+    const int bitdepth_max = j->bitdepth_max;
+    (void)bitdepth_max;
+    pixel *const dst = j->mc.dst;
+    ALIGN_STK_64(pixel, emu, 192 * 160,);
+    /* prediction: emu_edge when the footprint leaves the picture, like mc() in src/recon_tmpl.c:956-988 */
+    for (int i = 0; i < j->n_pred; i++) {
+        const B200McBlock *b = &j->d_pred[i];
+        const int pl = b->plane, w = b->w, h = b->h, mx = b->mx, my = b->my;
+        const pixel *ref = (const pixel *)j->mc.ref[b->ref] + j->mc.ref_plane_off[pl];
+        ptrdiff_t rs = j->mc.ref_stride[pl] * (ptrdiff_t)sizeof(pixel);
+        const int dx = b->src_x, dy = b->src_y, iw = j->mc.ref_w[pl], ih = j->mc.ref_h[pl];
+        const pixel *src;
+        if (dx < !!mx * 3 || dy < !!my * 3 || dx + w + !!mx * 4 > iw || dy + h + !!my * 4 > ih) {
+            mc.emu_edge(w + !!mx * 7, h + !!my * 7, iw, ih, dx - !!mx * 3, dy - !!my * 3, emu, 192 * sizeof(pixel), ref, rs);
+            src = &emu[192 * !!my * 3 + !!mx * 3];
+            rs = 192 * sizeof(pixel);
+        } else {
+            src = ref + (ptrdiff_t)dy * j->mc.ref_stride[pl] + dx;
+        }
+        if (b->op) mc.mct[b->filter2d](j->mc.tmp + b->dst_off, src, rs, w, h, mx, my HIGHBD_TAIL_SUFFIX);
+        else mc.mc[b->filter2d](dst + b->dst_off, j->mc.dst_stride[pl] * (ptrdiff_t)sizeof(pixel), src, rs, w, h, mx, my HIGHBD_TAIL_SUFFIX);
+    }
+    for (int pass = 0; pass < 2; pass++) {
+        const B200CompBlock *cb = pass ? j->d_comp2 : j->d_comp;
+        const int n = pass ? j->n_comp2 : j->n_comp;
+        for (int i = 0; i < n; i++, cb++) {
+            pixel *d = dst + cb->dst_off;
+            const ptrdiff_t ds = j->mc.dst_stride[cb->plane] * (ptrdiff_t)sizeof(pixel);
+            const int16_t *t1 = j->mc.tmp + cb->tmp1_off, *t2 = j->mc.tmp + cb->tmp2_off;
+            uint8_t *m = j->mc.mask + cb->mask_off;
+            switch (cb->op) {
+            case B200_COMP_AVG:   mc.avg(d, ds, t1, t2, cb->w, cb->h HIGHBD_TAIL_SUFFIX); break;
+            case B200_COMP_W_AVG: mc.w_avg(d, ds, t1, t2, cb->w, cb->h, cb->param HIGHBD_TAIL_SUFFIX); break;
+            case B200_COMP_MASK:  mc.mask(d, ds, t1, t2, cb->w, cb->h, m HIGHBD_TAIL_SUFFIX); break;
+            default: mc.w_mask[cb->op - B200_COMP_W_MASK_444](d, ds, t1, t2, cb->w, cb->h, m, cb->param HIGHBD_TAIL_SUFFIX); break;
+            }
+        }
+    }
+    for (int tx = 0; tx < N_RECT_TX_SIZES; tx++) {
+        const TxfmInfo *t = &dav1d_txfm_dimensions[tx];
+        const int n_cf = imin(t->w * 4, 32) * imin(t->h * 4, 32);
+        for (int i = 0; i < j->n_itx[tx]; i++) {
+            const B200ItxBlock *b = &j->d_itx[tx][i];
+            coef *cf = (coef *)j->d_coef + b->coef_off, save[1024];
+            memcpy(save, cf, sizeof(coef) * n_cf);
+            itx.itxfm_add[tx][b->txtp](dst + b->dst_off, j->itx_stride[b->plane] * (ptrdiff_t)sizeof(pixel), cf, b->eob HIGHBD_TAIL_SUFFIX);
+            memcpy(cf, save, sizeof(coef) * n_cf);
+        }
+    }
+    /* the three frame drivers take frame structs with the same leading layout as the B200 ones */
+    if (j->run_lf) {
+        RefLfFrame lf;
+        memset(&lf, 0, sizeof(lf));
+        lf.pic = j->lf.pic;
+        for (int p = 0; p < 3; p++) { lf.plane_off[p] = j->lf.plane_off[p]; lf.stride[p] = j->lf.stride[p]; }
+        lf.w4 = j->lf.w4; lf.h4 = j->lf.h4; lf.sb128w = j->lf.sb128w; lf.b4_stride = j->lf.b4_stride;
+        lf.ss_hor = j->lf.ss_hor; lf.ss_ver = j->lf.ss_ver; lf.sb128 = j->lf.sb128; lf.filter_y = j->lf.filter_y; lf.filter_uv = j->lf.filter_uv;
+        lf.mask = (Av1Filter *)j->lf.mask; lf.level = (uint8_t (*)[4])j->lf.level;
+        memcpy(&lf.lut, &j->lf.lut, sizeof(lf.lut));
+        bitfn(refdrv_lf_frame)(bitdepth_max, &lf);
+    }
+    size_t pic_bytes = 0;
+    {   /* extent of the picture allocation: last plane offset + its rows */
+        const int ssv = j->lf.ss_ver;
+        const int rows = (((j->lf.h4 * 4 + 127) & ~127) >> ssv);
+        pic_bytes = ((size_t)j->lf.plane_off[2] + (size_t)rows * j->lf.stride[2]) * sizeof(pixel);
+    }
+    if (j->run_cdef) {
+        memcpy(j->cdef.dst, j->cdef.src, pic_bytes);
+        RefCdefFrame cd;
+        memset(&cd, 0, sizeof(cd));
+        cd.src = j->cdef.dst;
+        for (int p = 0; p < 3; p++) { cd.plane_off[p] = j->cdef.plane_off[p]; cd.stride[p] = j->cdef.stride[p]; }
+        cd.bw = j->cdef.bw; cd.bh = j->cdef.bh; cd.sb128w = j->cdef.sb128w; cd.ss_hor = j->cdef.ss_hor; cd.ss_ver = j->cdef.ss_ver;
+        cd.damping = j->cdef.damping;
+        for (int i = 0; i < 8; i++) { cd.y_strength[i] = j->cdef.y_strength[i]; cd.uv_strength[i] = j->cdef.uv_strength[i]; }
+        cd.mask = (Av1Filter *)j->cdef.mask;
+        bitfn(refdrv_cdef_frame)(bitdepth_max, &cd);
+    }
+    if (j->run_lr) {
+        memcpy(j->lr.dst, j->lr.cdef, pic_bytes);
+        RefLrFrame lr;
+        memset(&lr, 0, sizeof(lr));
+        lr.cdef = j->lr.dst; lr.dbl = j->lr.dbl;
+        for (int p = 0; p < 3; p++) { lr.plane_off[p] = j->lr.plane_off[p]; lr.stride[p] = j->lr.stride[p]; }
+        lr.w = j->lr.w; lr.h = j->lr.h; lr.ss_hor = j->lr.ss_hor; lr.ss_ver = j->lr.ss_ver; lr.sb128 = j->lr.sb128;
+        lr.sr_sb128w = j->lr.sr_sb128w; lr.unit_size_log2[0] = j->lr.unit_size_log2[0]; lr.unit_size_log2[1] = j->lr.unit_size_log2[1];
+        lr.restore_planes = j->lr.restore_planes; lr.lr_mask = (Av1Restoration *)j->lr.lr_mask;
+        bitfn(refdrv_lr_frame)(bitdepth_max, &lr);
+    }
+}

@@ -99,3 +99,22 @@ def test_gpu_frame(bpc, W, H, ssh, ssv):
     fb2 = frame.FrameBuffers(S)
     fb2.run_host()
     assert TLR.picture_equal(S, fb2.host_output(), exp["lr"])
+
+
+def reference_frame(S):
+    """the same job through the reference's own functions on the CPU (oracle/refdriver: refdrv_frame_run)"""
+    fb = frame.FrameBuffers(S, lib=object(), alloc=frame.NumpyAlloc())
+    fn = refs.ref().refdrv_frame_run_8bpc if S["bpc"] == 8 else refs.ref().refdrv_frame_run_16bpc
+    fn(C.byref(fb.job))
+    return fb
+
+
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", [(8, 328, 200, 1, 1), (10, 264, 136, 1, 1), (12, 136, 200, 0, 0)])
+def test_oracle_frame_vs_reference_functions(bpc, W, H, ssh, ssv):
+    """whole-frame pin of the oracle: every stage run by dav1d's own C functions / frame drivers"""
+    if not refs.have_ref():
+        pytest.skip("reference build (oracle/_ref) not present")
+    S = synth.make_inter_frame(np.random.default_rng(620 + bpc), bpc, W, H, ssh, ssv)
+    exp = oracle_frame(S)
+    fb = reference_frame(S)
+    check_frame(S, fb, exp)
