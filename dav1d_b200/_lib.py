@@ -150,6 +150,14 @@ _SIGS = {
     "b200_frame_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_struct_size": (C.c_int, [C.c_int]),
     "b200_frame_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    # ---- ipred
+    "b200_ipred_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_ipred": (C.c_int, [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p] + [C.c_int] * 6),
+    "b200_cfl_ac": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ssize_t] + [C.c_int] * 7),
+    "b200_cfl_pred": (C.c_int, [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "b200_pal_pred": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "b200_intra_pred_dsp_init_8bpc": (None, [C.c_void_p]),
+    "b200_intra_pred_dsp_init_16bpc": (None, [C.c_void_p]),
 }
 
 

@@ -172,3 +172,25 @@ class LoopRestorationDSPContext:
         t = wrap_dsp_table(self._tbl, [("wiener", 2), ("sgr", 3)], {"wiener": (LR_PROTO, True), "sgr": (LR_PROTO, True)},
                            bpc > 8, self.bitdepth_max)
         self.wiener, self.sgr = t["wiener"], t["sgr"]
+
+
+IPRED_LAYOUT = [("intra_pred", 14), ("cfl_ac", 3), ("cfl_pred", 6), ("pal_pred", 1)]
+IPRED_PROTOS = {   # reference src/ipred.h:44-79
+    "intra_pred": ([_P, _S, _P, _I, _I, _I, _I, _I], True),
+    "cfl_ac": ([_P, _P, _S, _I, _I, _I, _I], False),
+    "cfl_pred": ([_P, _S, _P, _I, _I, _P, _I], True),
+    "pal_pred": ([_P, _S, _P, _P, _I, _I], False),
+}
+
+
+class IntraPredDSPContext:
+    """Dav1dIntraPredDSPContext (reference src/ipred.h:81-90): intra_pred[14], cfl_ac[3], cfl_pred[6] (slots
+    DC / LEFT_DC / TOP_DC / DC_128 used), pal_pred."""
+
+    def __init__(self, bpc, lib=None):
+        self.bpc, self.bitdepth_max = bpc, (1 << bpc) - 1
+        self.lib = lib or get_lib()
+        self._tbl = (C.c_void_p * 24)()
+        (self.lib.b200_intra_pred_dsp_init_8bpc if bpc == 8 else self.lib.b200_intra_pred_dsp_init_16bpc)(self._tbl)
+        for k, v in wrap_dsp_table(self._tbl, IPRED_LAYOUT, IPRED_PROTOS, bpc > 8, self.bitdepth_max).items():
+            setattr(self, k, v)

@@ -295,6 +295,53 @@ typedef struct B200LoopRestorationDSPContext { void *wiener[2]; void *sgr[3]; } 
 B200_API void b200_loop_restoration_dsp_init_8bpc(B200LoopRestorationDSPContext *c, int bpc);
 B200_API void b200_loop_restoration_dsp_init_16bpc(B200LoopRestorationDSPContext *c, int bpc);
 
+/* ==== ipred (Dav1dIntraPredDSPContext, reference src/ipred.h:44-90) ======================= */
+/* DSP-table mode indices (reference src/levels.h:112-136) */
+enum { B200_DC_PRED = 0, B200_VERT_PRED = 1, B200_HOR_PRED = 2, B200_LEFT_DC_PRED = 3, B200_TOP_DC_PRED = 4,
+       B200_DC_128_PRED = 5, B200_Z1_PRED = 6, B200_Z2_PRED = 7, B200_Z3_PRED = 8, B200_SMOOTH_PRED = 9,
+       B200_SMOOTH_V_PRED = 10, B200_SMOOTH_H_PRED = 11, B200_PAETH_PRED = 12, B200_FILTER_PRED = 13 };
+enum { B200_IPRED_OP_PRED = 0, B200_IPRED_OP_CFL_PRED = 1, B200_IPRED_OP_PAL_PRED = 2, B200_IPRED_OP_CFL_AC = 3 };
+
+/* Level 2: independent intra blocks whose edge arrays are already assembled (what
+ * dav1d_prepare_intra_edges produces, reference src/ipred_prepare_tmpl.c:75-204). */
+typedef struct B200IpredFrame {
+    void *dst;                     /* device picture */
+    int32_t dst_stride[3];
+    int32_t ss_hor, ss_ver;        /* for cfl_ac */
+    const void *edge;              /* device pixel buffer holding every block's edge array / palette */
+    int16_t *ac;                   /* device int16 buffer: cfl_ac outputs, cfl_pred inputs (dense, pitch w) */
+    const uint8_t *pal_idx;        /* device palette index bytes (two 3-bit indices per byte) */
+} B200IpredFrame;
+typedef struct B200IpredBlock {
+    uint32_t dst_off;              /* pixel offset in dst (cfl_ac: of the luma block in dst) */
+    uint32_t edge_off;             /* pixel index of `topleft` inside edge (pal_pred: of pal[8]) */
+    uint32_t ac_off;               /* int16 offset in ac (pal_pred: byte offset in pal_idx) */
+    int32_t max_w, max_h;          /* Z2 only */
+    int16_t angle;                 /* angle | flags (Z modes), filter index (FILTER), w_pad | h_pad << 8 (cfl_ac) */
+    int8_t alpha;                  /* cfl_pred */
+    uint8_t w, h, mode, op, plane;
+} B200IpredBlock;
+B200_API int b200_ipred_batch(int bitdepth_max, const B200IpredFrame *frame, const B200IpredBlock *d_blocks,
+                              int n_blocks, void *stream);
+
+/* Level 1 (host pointers) */
+B200_API int b200_ipred(int mode, void *dst, ptrdiff_t stride, const void *topleft, int w, int h, int angle,
+                        int max_w, int max_h, int bitdepth_max);
+B200_API int b200_cfl_ac(int16_t *ac, const void *ypx, ptrdiff_t stride, int w_pad, int h_pad, int cw, int ch,
+                         int ss_hor, int ss_ver, int bitdepth_max);
+B200_API int b200_cfl_pred(int mode, void *dst, ptrdiff_t stride, const void *topleft, int w, int h,
+                           const int16_t *ac, int alpha, int bitdepth_max);
+B200_API int b200_pal_pred(void *dst, ptrdiff_t stride, const void *pal, const uint8_t *idx, int w, int h,
+                           int bitdepth_max);
+typedef struct B200IntraPredDSPContext {
+    void *intra_pred[14];
+    void *cfl_ac[3];               /* 420, 422, 444 */
+    void *cfl_pred[6];
+    void *pal_pred;
+} B200IntraPredDSPContext;
+B200_API void b200_intra_pred_dsp_init_8bpc(B200IntraPredDSPContext *c);
+B200_API void b200_intra_pred_dsp_init_16bpc(B200IntraPredDSPContext *c);
+
 /* ==== whole-frame job: reconstruction + post-filter sweep ================================= */
 /* What a dav1d `f->bd_fn` record emitter hands over per frame (SURVEY.md §8b level 2): the block
  * records of pass 2 (prediction blocks, compound / blend / warp records, transform blocks bucketed by
