@@ -98,6 +98,22 @@ class Xfer(C.Structure):
     _fields_ = [("host", C.c_void_p), ("dev", C.c_void_p), ("bytes", C.c_uint64)]
 
 
+class FilmGrainData(C.Structure):
+    """Dav1dFilmGrainData / B200FilmGrainData (224 bytes)"""
+    _fields_ = [("seed", C.c_uint), ("num_y_points", C.c_int), ("y_points", (C.c_uint8 * 2) * 14),
+                ("chroma_scaling_from_luma", C.c_int), ("num_uv_points", C.c_int * 2),
+                ("uv_points", ((C.c_uint8 * 2) * 10) * 2), ("scaling_shift", C.c_int), ("ar_coeff_lag", C.c_int),
+                ("ar_coeffs_y", C.c_int8 * 24), ("ar_coeffs_uv", (C.c_int8 * 28) * 2), ("ar_coeff_shift", C.c_uint64),
+                ("grain_scale_shift", C.c_int), ("uv_mult", C.c_int * 2), ("uv_luma_mult", C.c_int * 2),
+                ("uv_offset", C.c_int * 2), ("overlap_flag", C.c_int), ("clip_to_restricted_range", C.c_int)]
+
+
+class FgFrame(C.Structure):
+    _fields_ = [("in_", C.c_void_p), ("out", C.c_void_p), ("plane_off", C.c_uint32 * 3), ("stride", C.c_int32 * 3),
+                ("w", C.c_int32), ("h", C.c_int32), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32), ("is_id", C.c_int32),
+                ("data", FilmGrainData), ("scratch", C.c_void_p)]
+
+
 ITXFM_FN_8 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int)
 ITXFM_FN_16 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int)
 
@@ -146,6 +162,15 @@ _SIGS = {
                                  C.c_void_p, C.c_int, C.c_int]),
     "b200_loop_restoration_dsp_init_8bpc": (None, [C.c_void_p, C.c_int]),
     "b200_loop_restoration_dsp_init_16bpc": (None, [C.c_void_p, C.c_int]),
+    # ---- filmgrain
+    "b200_fg_apply_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "b200_fg_generate_grain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b200_fgy_32x32xn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_int]),
+    "b200_fguv_32x32xn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_int, C.c_void_p, C.c_ssize_t] + [C.c_int] * 5),
+    "b200_film_grain_dsp_init_8bpc": (None, [C.c_void_p]),
+    "b200_film_grain_dsp_init_16bpc": (None, [C.c_void_p]),
     # ---- whole frame
     "b200_frame_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_struct_size": (C.c_int, [C.c_int]),
@@ -214,4 +239,4 @@ class Av1Restoration(C.Structure):
 
 
 ABI_STRUCTS = [McFrame, McBlock, CompBlock, BlendBlock, WarpBlock, ItxBlock, LfFrame, CdefFrame, LrFrame, FrameJob,
-               Av1Filter, Av1Restoration]
+               Av1Filter, Av1Restoration, FgFrame, FilmGrainData]

@@ -33,6 +33,7 @@ int b200_struct_size(int which)
     case 3: return sizeof(B200BlendBlock); case 4: return sizeof(B200WarpBlock); case 5: return sizeof(B200ItxBlock);
     case 6: return sizeof(B200LfFrame); case 7: return sizeof(B200CdefFrame); case 8: return sizeof(B200LrFrame);
     case 9: return sizeof(B200FrameJob); case 10: return sizeof(B200Av1Filter); case 11: return sizeof(B200Av1Restoration);
+    case 12: return sizeof(B200FgFrame); case 13: return sizeof(B200FilmGrainData);
     }
     return -1;
 }

@@ -194,3 +194,26 @@ class IntraPredDSPContext:
         (self.lib.b200_intra_pred_dsp_init_8bpc if bpc == 8 else self.lib.b200_intra_pred_dsp_init_16bpc)(self._tbl)
         for k, v in wrap_dsp_table(self._tbl, IPRED_LAYOUT, IPRED_PROTOS, bpc > 8, self.bitdepth_max).items():
             setattr(self, k, v)
+
+
+FG_LAYOUT = [("generate_grain_y", 1), ("generate_grain_uv", 3), ("fgy_32x32xn", 1), ("fguv_32x32xn", 3)]
+FG_PROTOS = {   # reference src/filmgrain.h:46-73
+    "generate_grain_y": ([_P, _P], True),
+    "generate_grain_uv": ([_P, _P, _P, C.c_ssize_t], True),
+    "fgy_32x32xn": ([_P, _P, _S, _P, C.c_size_t, _P, _P, _I, _I], True),
+    "fguv_32x32xn": ([_P, _P, _S, _P, C.c_size_t, _P, _P, _I, _I, _P, _S, _I, _I], True),
+}
+
+
+class FilmGrainDSPContext:
+    """Dav1dFilmGrainDSPContext (reference src/filmgrain.h:75-80): generate_grain_y, generate_grain_uv[3]
+    (420 / 422 / 444), fgy_32x32xn, fguv_32x32xn[3]. Film grain parameter blocks are passed as the address of
+    a _lib.FilmGrainData (ctypes.addressof)."""
+
+    def __init__(self, bpc, lib=None):
+        self.bpc, self.bitdepth_max = bpc, (1 << bpc) - 1
+        self.lib = lib or get_lib()
+        self._tbl = (C.c_void_p * 8)()
+        (self.lib.b200_film_grain_dsp_init_8bpc if bpc == 8 else self.lib.b200_film_grain_dsp_init_16bpc)(self._tbl)
+        for k, v in wrap_dsp_table(self._tbl, FG_LAYOUT, FG_PROTOS, bpc > 8, self.bitdepth_max).items():
+            setattr(self, k, v)

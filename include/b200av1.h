@@ -342,6 +342,67 @@ typedef struct B200IntraPredDSPContext {
 B200_API void b200_intra_pred_dsp_init_8bpc(B200IntraPredDSPContext *c);
 B200_API void b200_intra_pred_dsp_init_16bpc(B200IntraPredDSPContext *c);
 
+/* ==== filmgrain (Dav1dFilmGrainDSPContext, reference src/filmgrain.h:46-80) ================ */
+/* byte-identical to Dav1dFilmGrainData (reference include/dav1d/headers.h:315-333), 224 bytes */
+typedef struct B200FilmGrainData {
+    unsigned seed;
+    int num_y_points;
+    uint8_t y_points[14][2];
+    int chroma_scaling_from_luma;
+    int num_uv_points[2];
+    uint8_t uv_points[2][10][2];
+    int scaling_shift;
+    int ar_coeff_lag;
+    int8_t ar_coeffs_y[24];
+    int8_t ar_coeffs_uv[2][25 + 3];
+    uint64_t ar_coeff_shift;
+    int grain_scale_shift;
+    int uv_mult[2];
+    int uv_luma_mult[2];
+    int uv_offset[2];
+    int overlap_flag;
+    int clip_to_restricted_range;
+} B200FilmGrainData;
+#define B200_GRAIN_WIDTH 82
+#define B200_GRAIN_HEIGHT 73
+#define B200_FG_SCRATCH_BYTES (256 * 1024)
+
+/* Level 2: grain synthesis + application for a whole picture, out of place (in -> out), like
+ * dav1d_apply_grain (reference src/fg_apply_tmpl.c:100-240): one small kernel builds the three grain
+ * LUTs (LFSR + Gaussian table + AR filter run as a skewed wavefront), the scaling LUTs and the
+ * per-32x32-block offsets in `scratch` (device, >= B200_FG_SCRATCH_BYTES), then one sweep applies the
+ * noise to all planes. */
+typedef struct B200FgFrame {
+    const void *in;
+    void *out;
+    uint32_t plane_off[3];
+    int32_t stride[3];
+    int32_t w, h, ss_hor, ss_ver;
+    int32_t is_id;                 /* seq_hdr->mtrx == DAV1D_MC_IDENTITY */
+    B200FilmGrainData data;
+    void *scratch;
+} B200FgFrame;
+B200_API int b200_fg_apply_frame(int bitdepth_max, const B200FgFrame *frame, void *stream);
+
+/* Level 1 (host pointers). Grain LUT entries are int8 (8 bpc) / int16 (10, 12 bpc), pitch 82. */
+B200_API int b200_fg_generate_grain(void *buf, const void *buf_y, const B200FilmGrainData *data, int uv,
+                                    int ss_hor, int ss_ver, int bitdepth_max);   /* uv < 0: luma */
+B200_API int b200_fgy_32x32xn(void *dst_row, const void *src_row, ptrdiff_t stride, const B200FilmGrainData *data,
+                              size_t pw, const uint8_t *scaling, const void *grain_lut, int bh, int row_num,
+                              int bitdepth_max);
+B200_API int b200_fguv_32x32xn(void *dst_row, const void *src_row, ptrdiff_t stride, const B200FilmGrainData *data,
+                               size_t pw, const uint8_t *scaling, const void *grain_lut, int bh, int row_num,
+                               const void *luma_row, ptrdiff_t luma_stride, int uv_pl, int is_id, int ss_hor,
+                               int ss_ver, int bitdepth_max);
+typedef struct B200FilmGrainDSPContext {
+    void *generate_grain_y;
+    void *generate_grain_uv[3];
+    void *fgy_32x32xn;
+    void *fguv_32x32xn[3];
+} B200FilmGrainDSPContext;
+B200_API void b200_film_grain_dsp_init_8bpc(B200FilmGrainDSPContext *c);
+B200_API void b200_film_grain_dsp_init_16bpc(B200FilmGrainDSPContext *c);
+
 /* ==== whole-frame job: reconstruction + post-filter sweep ================================= */
 /* What a dav1d `f->bd_fn` record emitter hands over per frame (SURVEY.md §8b level 2): the block
  * records of pass 2 (prediction blocks, compound / blend / warp records, transform blocks bucketed by
@@ -374,7 +435,8 @@ typedef struct B200FrameJob {
 } B200FrameJob;
 B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check): 0 McFrame, 1 McBlock, 2 CompBlock,
- * 3 BlendBlock, 4 WarpBlock, 5 ItxBlock, 6 LfFrame, 7 CdefFrame, 8 LrFrame, 9 FrameJob, 10 Av1Filter, 11 Av1Restoration */
+ * 3 BlendBlock, 4 WarpBlock, 5 ItxBlock, 6 LfFrame, 7 CdefFrame, 8 LrFrame, 9 FrameJob, 10 Av1Filter, 11 Av1Restoration,
+ * 12 FgFrame, 13 FilmGrainData */
 B200_API int b200_struct_size(int which);
 
 /* The same job fed from HOST buffers (the end-to-end path): every (host, dev, bytes) pair of `uploads`

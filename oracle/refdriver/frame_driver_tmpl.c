@@ -306,3 +306,38 @@ API void bitfn(refdrv_frame_run)(const B200FrameJob *const j)
         bitfn(refdrv_lr_frame)(bitdepth_max, &lr);
     }
 }
+
+/* ---- film grain: the reference's own dav1d_apply_grain (prep + every 32-row strip) ---- */
+#include "src/fg_apply.h"
+#include "src/filmgrain.h"
+typedef struct {
+    const void *in; void *out;
+    uint32_t plane_off[3]; int32_t stride[3];
+    int32_t w, h, ss_hor, ss_ver, is_id;
+    Dav1dFilmGrainData data;
+} RefFgFrame;
+
+API void bitfn(refdrv_fg_frame)(const int bitdepth_max, const RefFgFrame *const fr)
+{
+    Dav1dFilmGrainDSPContext dsp;
+    bitfn(dav1d_film_grain_dsp_init)(&dsp);
+    Dav1dPicture in, out;
+    Dav1dFrameHeader *const hdr = calloc(1, sizeof(*hdr));
+    Dav1dSequenceHeader *const seq = calloc(1, sizeof(*seq));
+    memset(&in, 0, sizeof(in)); memset(&out, 0, sizeof(out));
+    hdr->film_grain.data = fr->data;
+    seq->mtrx = fr->is_id ? DAV1D_MC_IDENTITY : DAV1D_MC_BT709;
+    const enum Dav1dPixelLayout layout = !fr->ss_hor ? DAV1D_PIXEL_LAYOUT_I444 : fr->ss_ver ? DAV1D_PIXEL_LAYOUT_I420 : DAV1D_PIXEL_LAYOUT_I422;
+    Dav1dPicture *pics[2] = { &in, &out };
+    for (int i = 0; i < 2; i++) {
+        Dav1dPicture *p = pics[i];
+        pixel *base = (pixel *)(i ? fr->out : (void *)fr->in);
+        for (int pl = 0; pl < 3; pl++) p->data[pl] = base + fr->plane_off[pl];
+        p->stride[0] = fr->stride[0] * (ptrdiff_t)sizeof(pixel);
+        p->stride[1] = fr->stride[1] * (ptrdiff_t)sizeof(pixel);
+        p->p.w = fr->w; p->p.h = fr->h; p->p.layout = layout; p->p.bpc = 32 - clz(bitdepth_max);
+        p->frame_hdr = hdr; p->seq_hdr = seq;
+    }
+    bitfn(dav1d_apply_grain)(&dsp, &out, &in);
+    free(hdr); free(seq);
+}
