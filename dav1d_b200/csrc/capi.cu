@@ -13,6 +13,8 @@
 #include <utility>
 
 namespace b200 {
+int launch_itx_grouped(bool hbd, const void *const *blocks, const int32_t *n, void *coefs, void *pic, const int32_t *st,
+                       int bdmax, int zero, cudaStream_t stream);
 int launch_itx(int tx, bool hbd, const B200ItxBlock *blocks, int n, void *coefs, void *pic,
                const int32_t *st, int bdmax, int zero, cudaStream_t stream);
 }
@@ -75,6 +77,20 @@ int b200_itx_add_batch(int bitdepth_max, int tx, const B200ItxBlock *d_blocks, i
     if (b200::launch_itx(tx, bitdepth_max > 255, d_blocks, n_blocks, d_coef, d_pic, stride_px,
                          bitdepth_max, zero_coefs, (cudaStream_t)stream))
         { b200_set_error("b200_itx_add_batch: launch failed"); return -1; }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int b200_itx_add_frame(int bitdepth_max, const void *const d_blocks[19], const int32_t n_blocks[19], void *d_coef,
+                       void *d_pic, const int32_t stride_px[3], int zero_coefs, void *stream)
+{
+    if (bitdepth_max != 255 && bitdepth_max != 1023 && bitdepth_max != 4095) {
+        b200_set_error("b200_itx_add_frame: bad bitdepth_max %d", bitdepth_max);
+        return -2;
+    }
+    if (b200::launch_itx_grouped(bitdepth_max > 255, d_blocks, n_blocks, d_coef, d_pic, stride_px, bitdepth_max,
+                                 zero_coefs, (cudaStream_t)stream))
+        { b200_set_error("b200_itx_add_frame: launch failed"); return -1; }
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -128,86 +128,228 @@ B200_DEV int cdef_adjust_strength(int strength, unsigned var) {
     return (strength * (4 + i) + 8) >> 4;
 }
 
-constexpr int kCdefWarps = 4;
+// ---- frame kernel ---------------------------------------------------------------------------------
+// One CTA filters a 64x32 luma tile (half a 64x64 superblock: cdef_idx is uniform) and the matching chroma
+// tiles. The pre-CDEF samples are staged once in shared memory as 32-bit words holding the vertical pair
+// (p[y][x], p[y+1][x]) in its two int16 halves, samples outside the picture replaced by a sentinel, so
+// that a thread filters two vertically adjacent pixels at once with the 16x2 SIMD integer instructions
+// (VIADD.16x2 / VIMNMX.S16x2[.RELU]) and every tap is a single conflict-free LDS.32.
+//
+// constrain(diff) = sign(diff) * min(|diff|, max(0, thr - (|diff| >> shift))) is accumulated as
+//   P = relu(min(diff, t)), N = relu(min(-diff, t)), t = thr - (|diff| >> shift)   (sum = sum(P) - sum(N)),
+// which needs no sign restore. The sentinel (-16384) keeps diff inside int16 and makes t <= 0 for every
+// legal damping, so out-of-picture taps contribute nothing and are ignored by the signed max / unsigned min.
+constexpr int kCdefTW = 64, kCdefTH = 32, kCdefPitch = kCdefTW + 8, kCdefRows = kCdefTH + 3;
+constexpr int kCdefThreads = 256;
+constexpr unsigned kCdefSentinel = 0xC000u;
+
+struct CdefBlockInfo { int16_t y_pri, y_sec, uv_pri, uv_sec; int8_t y_dir, uv_dir, inside, pad; };
+
+struct CdefShared {
+    uint32_t tile[3][kCdefRows * kCdefPitch];   // pair rows -2 .. TH, columns -4 .. TW+3
+    CdefBlockInfo info[32];
+    int16_t off[8][2];                          // word offset of direction d, tap k (filled per plane pitch: constant pitch)
+};
+
+template <int D> B200_DEV unsigned cdef_dir_cost(const int (&v)[8][8])
+{
+    constexpr int NB = (D == 2 || D == 6) ? 8 : (D == 0 || D == 4) ? 15 : 11;
+    int sums[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) sums[i] = 0;
+#pragma unroll
+    for (int y = 0; y < 8; y++)
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            constexpr int dummy = 0; (void)dummy;
+            const int idx = D == 0 ? y + x : D == 1 ? y + (x >> 1) : D == 2 ? y : D == 3 ? 3 + y - (x >> 1)
+                          : D == 4 ? 7 + y - x : D == 5 ? 3 - (y >> 1) + x : D == 6 ? x : (y >> 1) + x;
+            sums[idx] += v[y][x];
+        }
+    unsigned cost = 0;
+    if (D == 2 || D == 6) {
+#pragma unroll
+        for (int n = 0; n < 8; n++) cost += sums[n] * sums[n];
+        cost *= 105;
+    } else if (D == 0 || D == 4) {
+#pragma unroll
+        for (int n = 0; n < 7; n++) cost += (sums[n] * sums[n] + sums[14 - n] * sums[14 - n]) * c_cdef_div[n];
+        cost += sums[7] * sums[7] * 105;
+    } else {
+#pragma unroll
+        for (int m = 0; m < 5; m++) cost += sums[3 + m] * sums[3 + m];
+        cost *= 105;
+#pragma unroll
+        for (int m = 0; m < 3; m++) cost += (sums[m] * sums[m] + sums[10 - m] * sums[10 - m]) * c_cdef_div[2 * m + 1];
+    }
+    return cost;
+}
+
+// one tap pair (+off / -off) on two packed pixels
+B200_DEV void cdef_tap2(const uint32_t *t, int idx, int off, unsigned negpx, unsigned thr1, int shift, unsigned smask, int tap,
+                        unsigned &sumP, unsigned &sumN, unsigned &mx, unsigned &mn)
+{
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const unsigned p = t[idx + (s ? -off : off)];
+        const unsigned diff = __vadd2(p, negpx);
+        const unsigned ndiff = __vadd2(~diff, 0x00010001u);
+        const unsigned adiff = __vmaxs2(diff, ndiff);
+        const unsigned th = __vadd2(thr1, ~((adiff >> shift) & smask));
+        sumP += tap * __vimin_s16x2_relu(diff, th);
+        sumN += tap * __vimin_s16x2_relu(ndiff, th);
+        mx = __vmaxs2(mx, p);
+        mn = __vminu2(mn, p);
+    }
+}
 
 template <bool HBD>
-__global__ void __launch_bounds__(kCdefWarps * 32) cdef_frame_kernel(B200CdefFrame f, int bdmax)
+__global__ void __launch_bounds__(kCdefThreads, 3) cdef_frame_kernel(B200CdefFrame f, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
-    __shared__ int luma[kCdefWarps][64];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bx = (blockIdx.x * kCdefWarps + warp) * 2, by = blockIdx.y * 2;   // 4-px units
-    const bool inside = bx < f.bw;
+    __shared__ CdefShared S;
+    const int tid = threadIdx.x;
+    const int bx0 = blockIdx.x * 16, by0 = blockIdx.y * 8;      // tile origin, 4-px units
     const int b8 = HBD ? (32 - __clz(bdmax)) - 8 : 0;
     const pixel *const src = (const pixel *)f.src;
     pixel *const dst = (pixel *)f.dst;
 
-    int y_lvl = 0, uv_lvl = 0;
-    if (inside) {
-        const B200Av1Filter &m = f.mask[(by >> 5) * f.sb128w + (bx >> 5)];
-        const int cdef_idx = m.cdef_idx[((by & 16) >> 3) + ((bx & 16) >> 4)];
-        const uint16_t *nr = m.noskip_mask[(by & 30) >> 1];
-        const unsigned noskip = (unsigned)nr[1] << 16 | nr[0];
-        if (cdef_idx != -1 && (noskip & (3u << (bx & 30)))) {
-            y_lvl = f.y_strength[cdef_idx];
-            uv_lvl = f.uv_strength[cdef_idx];
-        }
-    }
-    const int y_pri = (y_lvl >> 2) << b8;
-    int y_sec = y_lvl & 3; y_sec += y_sec == 3; y_sec <<= b8;
-    const int uv_pri = (uv_lvl >> 2) << b8;
-    int uv_sec = uv_lvl & 3; uv_sec += uv_sec == 3; uv_sec <<= b8;
-
-    // direction / variance from the pre-CDEF luma block (only when a primary strength needs it)
-    int dir = 0; unsigned var = 0;
-    const bool need_dir = inside && (y_pri || uv_pri);
-    if (inside) {
-        const pixel *p = src + f.plane_off[0] + (ptrdiff_t)(by * 4) * f.stride[0] + bx * 4;
-        for (int i = lane; i < 64; i += 32) luma[warp][i] = ((int)p[(i >> 3) * f.stride[0] + (i & 7)] >> b8) - 128;
-    }
-    __syncwarp();
-    // every lane takes part in the shuffles; the result is only used when need_dir
-    {
-        unsigned vv;
-        const int d = cdef_find_dir(luma[warp], lane, &vv);
-        if (need_dir) { dir = d; var = vv; }
-    }
-    if (!inside) return;
-
-    const int have_l = bx > 0, have_r = bx + 2 < f.bw, have_t = by > 0, have_b = by + 2 < f.bh;
-    const int damping = f.damping + b8;
+    // ---- stage the three planes (4 samples of two consecutive rows per thread and step)
 #pragma unroll 1
     for (int pl = 0; pl < 3; pl++) {
         const int sh = pl ? f.ss_hor : 0, sv = pl ? f.ss_ver : 0;
-        const int w = 8 >> sh, h = 8 >> sv;
-        int pri = 0, sec = 0, d = 0, damp = damping;
-        if (pl == 0) {
-            if (y_pri) { pri = cdef_adjust_strength(y_pri, var); sec = y_sec; d = dir; }
-            else { sec = y_sec; }
-        } else if (uv_lvl) {
-            pri = uv_pri; sec = uv_sec; damp = damping - 1;
-            d = uv_pri ? ((f.ss_hor && !f.ss_ver) ? c_uv_dir422[dir] : dir) : 0;
-        }
-        const int x0 = bx * 4 >> sh, y0 = by * 4 >> sv;
+        const int tw = kCdefTW >> sh, th = kCdefTH >> sv;
+        const int availw = ((f.bw + 1) >> 1) * 8 >> sh, availh = ((f.bh + 1) >> 1) * 8 >> sv;
+        const int x0 = bx0 * 4 >> sh, y0 = by0 * 4 >> sv;
+        const int groups = (tw + 8) >> 2, rows = th + 3;
         const pixel *sp = src + f.plane_off[pl];
+        const int st = f.stride[pl];
+        for (int i = tid; i < groups * rows; i += kCdefThreads) {
+            const int r = i / groups, g = i - r * groups;
+            const int x = x0 - 4 + g * 4, y = y0 - 2 + r;
+            unsigned a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) a[k] = b[k] = kCdefSentinel;
+            if (x >= 0 && x < availw) {
+                if (y >= 0 && y < availh) {
+                    if (HBD) { const uint2 q = *(const uint2 *)(sp + (ptrdiff_t)y * st + x); a[0] = q.x & 0xffff; a[1] = q.x >> 16; a[2] = q.y & 0xffff; a[3] = q.y >> 16; }
+                    else { const unsigned q = *(const unsigned *)(sp + (ptrdiff_t)y * st + x); a[0] = q & 0xff; a[1] = (q >> 8) & 0xff; a[2] = (q >> 16) & 0xff; a[3] = q >> 24; }
+                }
+                if (y + 1 >= 0 && y + 1 < availh) {
+                    if (HBD) { const uint2 q = *(const uint2 *)(sp + (ptrdiff_t)(y + 1) * st + x); b[0] = q.x & 0xffff; b[1] = q.x >> 16; b[2] = q.y & 0xffff; b[3] = q.y >> 16; }
+                    else { const unsigned q = *(const unsigned *)(sp + (ptrdiff_t)(y + 1) * st + x); b[0] = q & 0xff; b[1] = (q >> 8) & 0xff; b[2] = (q >> 16) & 0xff; b[3] = q >> 24; }
+                }
+            }
+            uint4 w;
+            w.x = a[0] | b[0] << 16; w.y = a[1] | b[1] << 16; w.z = a[2] | b[2] << 16; w.w = a[3] | b[3] << 16;
+            *(uint4 *)&S.tile[pl][r * kCdefPitch + g * 4] = w;
+        }
+    }
+    if (tid < 16) {
+        const int d = tid >> 1, k = tid & 1;
+        S.off[d][k] = (int16_t)(c_cdef_off[d][k][0] * kCdefPitch + c_cdef_off[d][k][1]);
+    }
+    __syncthreads();
+
+    // ---- per-8x8 parameters: one thread per block (direction search over all 8 directions)
+    if (tid < 32) {
+        const int bxi = tid & 7, byi = tid >> 3;
+        const int bx = bx0 + bxi * 2, by = by0 + byi * 2;
+        CdefBlockInfo bi; bi.y_pri = bi.y_sec = bi.uv_pri = bi.uv_sec = 0; bi.y_dir = bi.uv_dir = 0; bi.pad = 0;
+        bi.inside = bx < f.bw && by < f.bh;
+        if (bi.inside) {
+            int y_lvl = 0, uv_lvl = 0;
+            const B200Av1Filter &m = f.mask[(by >> 5) * f.sb128w + (bx >> 5)];
+            const int cdef_idx = m.cdef_idx[((by & 16) >> 3) + ((bx & 16) >> 4)];
+            const uint16_t *nr = m.noskip_mask[(by & 30) >> 1];
+            const unsigned noskip = (unsigned)nr[1] << 16 | nr[0];
+            if (cdef_idx != -1 && (noskip & (3u << (bx & 30)))) { y_lvl = f.y_strength[cdef_idx]; uv_lvl = f.uv_strength[cdef_idx]; }
+            const int y_pri = (y_lvl >> 2) << b8;
+            int y_sec = y_lvl & 3; y_sec += y_sec == 3; y_sec <<= b8;
+            const int uv_pri = (uv_lvl >> 2) << b8;
+            int uv_sec = uv_lvl & 3; uv_sec += uv_sec == 3; uv_sec <<= b8;
+            int dir = 0; unsigned var = 0;
+            if (y_pri || uv_pri) {
+                int v[8][8];
+                const uint32_t *t = &S.tile[0][(2 + byi * 8) * kCdefPitch + 4 + bxi * 8];
+#pragma unroll
+                for (int y = 0; y < 8; y += 2)
+#pragma unroll
+                    for (int x = 0; x < 8; x++) {
+                        const unsigned w = t[y * kCdefPitch + x];
+                        v[y][x] = (int)((w & 0xffff) >> b8) - 128;
+                        v[y + 1][x] = (int)((w >> 16) >> b8) - 128;
+                    }
+                unsigned c[8];
+                c[0] = cdef_dir_cost<0>(v); c[1] = cdef_dir_cost<1>(v); c[2] = cdef_dir_cost<2>(v); c[3] = cdef_dir_cost<3>(v);
+                c[4] = cdef_dir_cost<4>(v); c[5] = cdef_dir_cost<5>(v); c[6] = cdef_dir_cost<6>(v); c[7] = cdef_dir_cost<7>(v);
+                unsigned bc = c[0];
+#pragma unroll
+                for (int n = 1; n < 8; n++) if (c[n] > bc) { bc = c[n]; dir = n; }
+                unsigned opp = 0;
+#pragma unroll
+                for (int n = 0; n < 8; n++) if (n == (dir ^ 4)) opp = c[n];
+                var = (bc - opp) >> 10;
+            }
+            if (y_pri) { bi.y_pri = (int16_t)cdef_adjust_strength(y_pri, var); bi.y_sec = (int16_t)y_sec; bi.y_dir = (int8_t)dir; }
+            else bi.y_sec = (int16_t)y_sec;
+            if (uv_lvl) {
+                bi.uv_pri = (int16_t)uv_pri; bi.uv_sec = (int16_t)uv_sec;
+                bi.uv_dir = (int8_t)(uv_pri ? ((f.ss_hor && !f.ss_ver) ? c_uv_dir422[dir] : dir) : 0);
+            }
+        }
+        S.info[tid] = bi;
+    }
+    __syncthreads();
+
+    // ---- filter: one thread per vertical pixel pair
+#pragma unroll 1
+    for (int pl = 0; pl < 3; pl++) {
+        const int sh = pl ? f.ss_hor : 0, sv = pl ? f.ss_ver : 0;
+        const int tw = kCdefTW >> sh, th = kCdefTH >> sv;
+        const int x0 = bx0 * 4 >> sh, y0 = by0 * 4 >> sv;
         pixel *dp = dst + f.plane_off[pl];
         const int st = f.stride[pl];
-        if (!pri && !sec) {
-            for (int i = lane; i < w * h; i += 32) {
-                const int x = x0 + (i % w), y = y0 + (i / w);
-                dp[(ptrdiff_t)y * st + x] = sp[(ptrdiff_t)y * st + x];
+        const int damp = f.damping + b8 - (pl ? 1 : 0);
+        const uint32_t *t = S.tile[pl];
+        for (int i = tid; i < tw * (th >> 1); i += kCdefThreads) {
+            const int yp = i / tw, x = i - yp * tw, y = yp * 2;
+            const CdefBlockInfo bi = S.info[(y >> (3 - sv)) * 8 + (x >> (3 - sh))];
+            if (!bi.inside) continue;
+            const int idx = (y + 2) * kCdefPitch + x + 4;
+            const unsigned px2 = t[idx];
+            int o0 = px2 & 0xffff, o1 = px2 >> 16;
+            const int pri = pl ? bi.uv_pri : bi.y_pri, sec = pl ? bi.uv_sec : bi.y_sec, dir = pl ? bi.uv_dir : bi.y_dir;
+            if (pri | sec) {
+                const unsigned negpx = __vadd2(~px2, 0x00010001u);
+                unsigned sumP = 0, sumN = 0, mx = px2, mn = px2;
+                if (pri) {
+                    const int shift = imax(0, damp - ulog2(pri));
+                    const unsigned thr1 = (unsigned)(pri + 1) * 0x00010001u, smask = (0xffffu >> shift) * 0x00010001u;
+                    const int tap0 = 4 - ((pri >> b8) & 1);
+                    cdef_tap2(t, idx, S.off[dir][0], negpx, thr1, shift, smask, tap0, sumP, sumN, mx, mn);
+                    cdef_tap2(t, idx, S.off[dir][1], negpx, thr1, shift, smask, (tap0 & 3) | 2, sumP, sumN, mx, mn);
+                }
+                if (sec) {
+                    const int shift = damp - ulog2(sec);
+                    const unsigned thr1 = (unsigned)(sec + 1) * 0x00010001u, smask = (0xffffu >> shift) * 0x00010001u;
+                    const int d2 = (dir + 2) & 7, d6 = (dir + 6) & 7;
+                    cdef_tap2(t, idx, S.off[d2][0], negpx, thr1, shift, smask, 2, sumP, sumN, mx, mn);
+                    cdef_tap2(t, idx, S.off[d6][0], negpx, thr1, shift, smask, 2, sumP, sumN, mx, mn);
+                    cdef_tap2(t, idx, S.off[d2][1], negpx, thr1, shift, smask, 1, sumP, sumN, mx, mn);
+                    cdef_tap2(t, idx, S.off[d6][1], negpx, thr1, shift, smask, 1, sumP, sumN, mx, mn);
+                }
+                const int s0 = (int)(sumP & 0xffff) - (int)(sumN & 0xffff), s1 = (int)(sumP >> 16) - (int)(sumN >> 16);
+                o0 += (s0 - (s0 < 0) + 8) >> 4;
+                o1 += (s1 - (s1 < 0) + 8) >> 4;
+                if (pri && sec) {
+                    o0 = iclip(o0, (int)(mn & 0xffff), (int)(mx & 0xffff));
+                    o1 = iclip(o1, (int)(mn >> 16), (int)(mx >> 16));
+                }
             }
-            continue;
-        }
-        CdefRect r;
-        r.xmin = x0 - 2 * have_l; r.xmax = x0 + w + 2 * have_r;
-        r.ymin = y0 - 2 * have_t; r.ymax = y0 + h + 2 * have_b;
-        const int pri_tap0 = 4 - ((pri >> b8) & 1);
-        const int pri_shift = pri ? imax(0, damp - ulog2(pri)) : 0;
-        const int sec_shift = sec ? damp - ulog2(sec) : 0;
-        for (int i = lane; i < w * h; i += 32) {
-            const int x = x0 + (i % w), y = y0 + (i / w);
-            dp[(ptrdiff_t)y * st + x] = (pixel)cdef_pixel<HBD>(sp, st, x, y, r, pri, sec, d, pri_shift, sec_shift, pri_tap0);
+            pixel *o = dp + (ptrdiff_t)(y0 + y) * st + x0 + x;
+            o[0] = (pixel)o0;
+            o[st] = (pixel)o1;
         }
     }
 }
@@ -256,9 +398,12 @@ extern "C" {
 int b200_cdef_frame(int bdmax, const B200CdefFrame *f, void *stream)
 {
     if (cdef_check_bd(bdmax, "b200_cdef_frame")) return -2;
-    dim3 grid(((f->bw + 1) / 2 + kCdefWarps - 1) / kCdefWarps, (f->bh + 1) / 2);
-    if (bdmax > 255) { auto k = cdef_frame_kernel<true>; B200_LAUNCH(k, grid, dim3(kCdefWarps * 32), 0, (cudaStream_t)stream, *f, bdmax); }
-    else { auto k = cdef_frame_kernel<false>; B200_LAUNCH(k, grid, dim3(kCdefWarps * 32), 0, (cudaStream_t)stream, *f, bdmax); }
+    const size_t px = bdmax > 255 ? 2 : 1;
+    for (int pl = 0; pl < 3; pl++)   // the tile loader reads 4 samples at a time
+        if ((f->stride[pl] & 3) || (f->plane_off[pl] & 3) || ((uintptr_t)f->src * 1 % (4 * px))) { b200_set_error("b200_cdef_frame: planes must be 4-sample aligned"); return -2; }
+    dim3 grid((f->bw + 15) / 16, (f->bh + 7) / 8);
+    if (bdmax > 255) { auto k = cdef_frame_kernel<true>; B200_LAUNCH(k, grid, dim3(kCdefThreads), 0, (cudaStream_t)stream, *f, bdmax); }
+    else { auto k = cdef_frame_kernel<false>; B200_LAUNCH(k, grid, dim3(kCdefThreads), 0, (cudaStream_t)stream, *f, bdmax); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -15,11 +15,9 @@ int b200_frame_run(const B200FrameJob *j, void *stream)
     if ((r = b200_mc_comp_batch(bd, &j->mc, j->d_comp, j->n_comp, stream))) return r;
     if ((r = b200_mc_comp_batch(bd, &j->mc, j->d_comp2, j->n_comp2, stream))) return r;
     if ((r = b200_mc_blend_batch(bd, &j->mc, j->d_blend, j->n_blend, stream))) return r;
-    for (int tx = 0; tx < B200_N_RECT_TX_SIZES; tx++)
-        if (j->n_itx[tx] > 0 &&
-            (r = b200_itx_add_batch(bd, tx, j->d_itx[tx], j->n_itx[tx], j->d_coef, j->mc.dst, j->itx_stride,
-                                    j->zero_coefs, stream)))
-            return r;
+    if ((r = b200_itx_add_frame(bd, (const void *const *)j->d_itx, j->n_itx, j->d_coef, j->mc.dst, j->itx_stride,
+                                j->zero_coefs, stream)))
+        return r;
     if (j->run_lf && (r = b200_lf_frame(bd, &j->lf, stream))) return r;
     if (j->run_cdef && (r = b200_cdef_frame(bd, &j->cdef, stream))) return r;
     if (j->run_lr && (r = b200_lr_frame(bd, &j->lr, stream))) return r;
@@ -38,8 +36,8 @@ int b200_struct_size(int which)
     return -1;
 }
 
-int b200_frame_run_host(const B200FrameJob *job, const B200Xfer *up, int n_up, const B200Xfer *down, int n_down,
-                        void *stream)
+int b200_frame_submit_host(const B200FrameJob *job, const B200Xfer *up, int n_up, const B200Xfer *down, int n_down,
+                           void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     for (int i = 0; i < n_up; i++)
@@ -48,8 +46,20 @@ int b200_frame_run_host(const B200FrameJob *job, const B200Xfer *up, int n_up, c
     if (r) return r;
     for (int i = 0; i < n_down; i++)
         if (down[i].bytes) B200_CUDA_OK(cudaMemcpyAsync(down[i].host, down[i].dev, down[i].bytes, cudaMemcpyDeviceToHost, st));
-    B200_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
+}
+
+int b200_frame_wait(void *stream)
+{
+    B200_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+int b200_frame_run_host(const B200FrameJob *job, const B200Xfer *up, int n_up, const B200Xfer *down, int n_down,
+                        void *stream)
+{
+    int r = b200_frame_submit_host(job, up, n_up, down, n_down, stream);
+    return r ? r : b200_frame_wait(stream);
 }
 
 }  // extern "C"

@@ -37,22 +37,21 @@ template <int W, int H> struct ItxGeom {
 
 constexpr int kItxWarps = 4;
 
+// the work of one CTA (`cta` = its index among the CTAs of this transform size); smem: kItxWarps * NB * SLOT words
 template <int W, int H, int TX, int SHIFT, bool HBD>
-__global__ void __launch_bounds__(kItxWarps * 32)
-itx_add_kernel(const B200ItxBlock *__restrict__ blocks, int n_blocks,
-               typename Bd<HBD>::coef *__restrict__ coefs, typename Bd<HBD>::pixel *__restrict__ pic,
-               int stride0, int stride1, int stride2, int bitdepth_max, int zero_coefs)
+B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *__restrict__ blocks, int n_blocks,
+                           typename Bd<HBD>::coef *__restrict__ coefs, typename Bd<HBD>::pixel *__restrict__ pic,
+                           int stride0, int stride1, int stride2, int bitdepth_max, int zero_coefs)
 {
     typedef ItxGeom<W, H> G;
     typedef typename Bd<HBD>::pixel pixel;
     typedef typename Bd<HBD>::coef coef;
-    __shared__ int tile[kItxWarps][G::NB * G::SLOT];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G::L, li = lane % G::L;
-    const int bi = (blockIdx.x * kItxWarps + warp) * G::NB + grp;
+    const int bi = (cta * kItxWarps + warp) * G::NB + grp;
     const bool valid = bi < n_blocks;
-    int *const t = &tile[warp][grp * G::SLOT];
+    int *const t = smem + (warp * G::NB + grp) * G::SLOT;
 
     B200ItxBlock blk;
     blk.dst_off = 0; blk.coef_off = 0; blk.eob = 0; blk.txtp = 0; blk.plane = 0;
@@ -165,6 +164,67 @@ itx_add_kernel(const B200ItxBlock *__restrict__ blocks, int n_blocks,
             }
         }
     }
+}
+
+template <int W, int H, int TX, int SHIFT, bool HBD>
+__global__ void __launch_bounds__(kItxWarps * 32)
+itx_add_kernel(const B200ItxBlock *__restrict__ blocks, int n_blocks,
+               typename Bd<HBD>::coef *__restrict__ coefs, typename Bd<HBD>::pixel *__restrict__ pic,
+               int stride0, int stride1, int stride2, int bitdepth_max, int zero_coefs)
+{
+    typedef ItxGeom<W, H> G;
+    __shared__ int tile[kItxWarps * G::NB * G::SLOT];
+    itx_add_body<W, H, TX, SHIFT, HBD>(blockIdx.x, tile, blocks, n_blocks, coefs, pic, stride0, stride1, stride2,
+                                       bitdepth_max, zero_coefs);
+}
+
+// ---- all transform sizes of a frame in ONE launch: CTAs are dealt to the sizes largest-first -------------
+// tx -> (w, h, inter-pass shift): reference src/itx_tmpl.c:160-178
+#define B200_ITX_SIZES(X) \
+    X(4, 64, 64, 2) X(11, 32, 64, 1) X(12, 64, 32, 1) X(17, 16, 64, 2) X(18, 64, 16, 2) X(3, 32, 32, 2) X(9, 16, 32, 1) \
+    X(10, 32, 16, 1) X(15, 8, 32, 2) X(16, 32, 8, 2) X(2, 16, 16, 2) X(7, 8, 16, 1) X(8, 16, 8, 1) X(13, 4, 16, 1) \
+    X(14, 16, 4, 1) X(1, 8, 8, 1) X(5, 4, 8, 0) X(6, 8, 4, 0) X(0, 4, 4, 0)
+
+struct ItxGroups {
+    const B200ItxBlock *blocks[B200_N_RECT_TX_SIZES];
+    int n[B200_N_RECT_TX_SIZES];
+    int cta_begin[B200_N_RECT_TX_SIZES], cta_end[B200_N_RECT_TX_SIZES];
+};
+
+template <bool HBD>
+__global__ void __launch_bounds__(kItxWarps * 32)
+itx_add_grouped_kernel(const ItxGroups g, typename Bd<HBD>::coef *__restrict__ coefs, typename Bd<HBD>::pixel *__restrict__ pic,
+                       int stride0, int stride1, int stride2, int bitdepth_max, int zero_coefs)
+{
+    __shared__ int tile[kItxWarps * ItxGeom<64, 64>::NB * ItxGeom<64, 64>::SLOT];
+    const int c = blockIdx.x;
+#define X(TX, W, H, SH) \
+    if (c < g.cta_end[TX]) { \
+        itx_add_body<W, H, TX, SH, HBD>(c - g.cta_begin[TX], tile, g.blocks[TX], g.n[TX], coefs, pic, stride0, stride1, stride2, \
+                                        bitdepth_max, zero_coefs); \
+        return; \
+    }
+    B200_ITX_SIZES(X)
+#undef X
+}
+
+int launch_itx_grouped(bool hbd, const void *const *blocks, const int32_t *n, void *coefs, void *pic, const int32_t *st,
+                       int bdmax, int zero, cudaStream_t stream)
+{
+    ItxGroups g;
+    int total = 0;
+#define X(TX, W, H, SH) { \
+        const int per_cta = kItxWarps * ItxGeom<W, H>::NB; \
+        const int ctas = n[TX] > 0 ? (n[TX] + per_cta - 1) / per_cta : 0; \
+        g.blocks[TX] = (const B200ItxBlock *)blocks[TX]; g.n[TX] = n[TX] > 0 ? n[TX] : 0; \
+        g.cta_begin[TX] = total; total += ctas; g.cta_end[TX] = total; }
+    B200_ITX_SIZES(X)
+#undef X
+    if (!total) return 0;
+    if (hbd) { auto k = itx_add_grouped_kernel<true>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int32_t *)coefs, (uint16_t *)pic, st[0], st[1], st[2], bdmax, zero); }
+    else { auto k = itx_add_grouped_kernel<false>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int16_t *)coefs, (uint8_t *)pic, st[0], st[1], st[2], bdmax, zero); }
+    b200_count_launch();
+    return 0;
 }
 
 template <int W, int H, int TX, int SHIFT>

@@ -40,6 +40,10 @@ class TorchAlloc:
     def stream(self):
         return self.torch.cuda.current_stream().cuda_stream
 
+    def new_stream(self):
+        s = self.torch.cuda.Stream(device=self.device)
+        return s, s.cuda_stream
+
 
 class NumpyAlloc:
     """'device' == host: only valid with the emulated library (tests/emu)"""
@@ -63,6 +67,9 @@ class NumpyAlloc:
 
     def stream(self):
         return None
+
+    def new_stream(self):
+        return None, None
 
 
 class FrameBuffers:
@@ -146,7 +153,7 @@ class FrameBuffers:
         self.job = j
         self.out_name = "p2" if run_lr else ("p1" if run_cdef else "p0")
         self.n_launches = (1 if j.n_pred else 0) + (1 if j.n_comp else 0) + (1 if j.n_comp2 else 0) + \
-            sum(1 for tx in range(19) if j.n_itx[tx]) + 2 * int(run_lf) + int(run_cdef) + int(run_lr)
+            (1 if any(j.n_itx[tx] for tx in range(19)) else 0) + 2 * int(run_lf) + int(run_cdef) + int(run_lr)
         self._host = None
 
     # ---- device-resident run (records already in HBM) ----
@@ -186,6 +193,18 @@ class FrameBuffers:
         st = self.alloc.stream() if stream is None else stream
         self.lib.check(self.lib.b200_frame_run_host(C.byref(self.job), self._ups, len(self._ups), self._downs, 1, st),
                        "b200_frame_run_host")
+
+    # frame-threaded variant: each FrameBuffers owns a stream; submit() returns at once, wait() joins
+    def submit_host(self):
+        if self._host is None:
+            self.prepare_host(); self._host = True
+        if getattr(self, "_own_stream", None) is None:
+            self._own_stream = self.alloc.new_stream()
+        self.lib.check(self.lib.b200_frame_submit_host(C.byref(self.job), self._ups, len(self._ups), self._downs, 1,
+                                                       self._own_stream[1]), "b200_frame_submit_host")
+
+    def wait(self):
+        self.lib.check(self.lib.b200_frame_wait(self._own_stream[1]), "b200_frame_wait")
 
     def host_output(self):
         t = self._host_out

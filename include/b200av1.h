@@ -79,6 +79,11 @@ B200_API int b200_itx_add_batch(int bitdepth_max, int tx, const B200ItxBlock *d_
                                 void *d_coef, void *d_pic, const int32_t stride_px[3],
                                 int zero_coefs, void *stream);
 
+/* All 19 transform sizes of a frame in one launch (d_blocks[tx] / n_blocks[tx] as above, sizes with
+ * n_blocks[tx] <= 0 are skipped). Blocks of different sizes must not overlap in the picture. */
+B200_API int b200_itx_add_frame(int bitdepth_max, const void *const d_blocks[19], const int32_t n_blocks[19],
+                                void *d_coef, void *d_pic, const int32_t stride_px[3], int zero_coefs, void *stream);
+
 /* Same work through HOST buffers (the end-to-end leg of bench.py): copies blocks, coefficients
  * and the picture to HBM, runs b200_itx_add_batch, copies the picture back, synchronises. */
 B200_API int b200_itx_add_batch_host(int bitdepth_max, int tx, const B200ItxBlock *blocks, int n_blocks,
@@ -445,6 +450,13 @@ B200_API int b200_struct_size(int which);
 typedef struct B200Xfer { void *host; void *dev; uint64_t bytes; } B200Xfer;
 B200_API int b200_frame_run_host(const B200FrameJob *job, const B200Xfer *uploads, int n_uploads,
                                  const B200Xfer *downloads, int n_downloads, void *stream);
+/* Asynchronous halves of the above, for callers that keep several frames in flight on different streams
+ * (the device-side counterpart of dav1d's frame threading, n_fc frame contexts): submit enqueues
+ * uploads + job + downloads and returns; wait blocks until everything enqueued on `stream` is done.
+ * Host buffers must be page-locked for the copies to overlap other streams' work. */
+B200_API int b200_frame_submit_host(const B200FrameJob *job, const B200Xfer *uploads, int n_uploads,
+                                    const B200Xfer *downloads, int n_downloads, void *stream);
+B200_API int b200_frame_wait(void *stream);
 
 #ifdef __cplusplus
 }

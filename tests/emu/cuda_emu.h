@@ -188,6 +188,19 @@ static inline int __dp4a_us(unsigned a, int b, int c) { /* helper: u8 x s8 */
     for (int i = 0; i < 4; i++) c += (int)((a >> (8 * i)) & 0xff) * (int)(int8_t)(b >> (8 * i));
     return c;
 }
+// 16x2 SIMD integer intrinsics (semantics per the CUDA math API: per-halfword, wrapping unless noted)
+#define EMU_H2(expr_lo, expr_hi) ((unsigned)((expr_lo) & 0xffff) | ((unsigned)((expr_hi) & 0xffff) << 16))
+static inline int emu_s16(unsigned v) { return (int)(int16_t)(v & 0xffff); }
+static inline unsigned __vadd2(unsigned a, unsigned b) { return EMU_H2((a & 0xffff) + (b & 0xffff), (a >> 16) + (b >> 16)); }
+static inline unsigned __vsub2(unsigned a, unsigned b) { return EMU_H2((a & 0xffff) - (b & 0xffff), (a >> 16) - (b >> 16)); }
+static inline unsigned __vmaxs2(unsigned a, unsigned b) { return EMU_H2(std::max(emu_s16(a), emu_s16(b)), std::max(emu_s16(a >> 16), emu_s16(b >> 16))); }
+static inline unsigned __vmins2(unsigned a, unsigned b) { return EMU_H2(std::min(emu_s16(a), emu_s16(b)), std::min(emu_s16(a >> 16), emu_s16(b >> 16))); }
+static inline unsigned __vmaxu2(unsigned a, unsigned b) { return EMU_H2(std::max(a & 0xffff, b & 0xffff), std::max(a >> 16, b >> 16)); }
+static inline unsigned __vminu2(unsigned a, unsigned b) { return EMU_H2(std::min(a & 0xffff, b & 0xffff), std::min(a >> 16, b >> 16)); }
+static inline unsigned __vimin_s16x2_relu(unsigned a, unsigned b) { return EMU_H2(std::max(0, std::min(emu_s16(a), emu_s16(b))), std::max(0, std::min(emu_s16(a >> 16), emu_s16(b >> 16)))); }
+static inline unsigned __vimax_s16x2_relu(unsigned a, unsigned b) { return EMU_H2(std::max(0, std::max(emu_s16(a), emu_s16(b))), std::max(0, std::max(emu_s16(a >> 16), emu_s16(b >> 16)))); }
+static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vadd2(a, b), c); }
+static inline unsigned __viaddmin_s16x2(unsigned a, unsigned b, unsigned c) { return __vmins2(__vadd2(a, b), c); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 static inline void __nanosleep(unsigned) { emu_yield(); }
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }

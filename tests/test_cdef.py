@@ -169,7 +169,8 @@ def test_emu_cdef_level1(bpc):
 
 
 @pytest.mark.emu
-@pytest.mark.parametrize("bpc,W,H,ssh,ssv", [(8, 136, 72, 1, 1), (10, 72, 72, 1, 0), (8, 72, 40, 0, 0)])
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", [(8, 136, 72, 1, 1), (10, 72, 72, 1, 0), (8, 72, 40, 0, 0), (8, 68, 44, 1, 1), (12, 140, 76, 1, 1),
+                                                (12, 68, 36, 0, 0), (10, 204, 100, 1, 1)])
 def test_emu_cdef_frame(bpc, W, H, ssh, ssv):
     S = make_cdef_frame(np.random.default_rng(430 + bpc + W), bpc, W, H, ssh, ssv)
     exp = cdef_frame_oracle(S)

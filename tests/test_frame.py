@@ -76,6 +76,9 @@ def test_emu_frame(bpc, W, H, ssh, ssv):
     fb2 = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
     fb2.run_host()
     assert TLR.picture_equal(S, fb2.host_output(), exp["lr"])
+    fb3 = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
+    fb3.submit_host(); fb3.wait()
+    assert TLR.picture_equal(S, fb3.host_output(), exp["lr"])
 
 
 def test_abi_struct_sizes_match_binding():
@@ -99,6 +102,12 @@ def test_gpu_frame(bpc, W, H, ssh, ssv):
     fb2 = frame.FrameBuffers(S)
     fb2.run_host()
     assert TLR.picture_equal(S, fb2.host_output(), exp["lr"])
+    # two frames in flight on their own streams (frame-threaded end-to-end path)
+    fb3, fb4 = frame.FrameBuffers(S), frame.FrameBuffers(S)
+    for _ in range(3):
+        fb3.submit_host(); fb4.submit_host()
+        fb3.wait(); fb4.wait()
+    assert TLR.picture_equal(S, fb3.host_output(), exp["lr"]) and TLR.picture_equal(S, fb4.host_output(), exp["lr"])
 
 
 def reference_frame(S):
