@@ -81,15 +81,6 @@ def test_emu_frame(bpc, W, H, ssh, ssv):
     assert TLR.picture_equal(S, fb3.host_output(), exp["lr"])
 
 
-def test_abi_struct_sizes_match_binding():
-    from dav1d_b200 import build
-    build.build()
-    lib = _lib.B200Lib(_lib.LIB_PATH)            # raises on any sizeof mismatch
-    assert lib.b200_struct_size(9) == C.sizeof(_lib.FrameJob)
-    assert C.sizeof(_lib.Av1Filter) == synth.AV1FILTER_DT.itemsize == 1348
-    assert synth.MC_BLOCK_DT.itemsize == C.sizeof(_lib.McBlock) and synth.COMP_BLOCK_DT.itemsize == C.sizeof(_lib.CompBlock)
-
-
 @pytest.mark.gpu
 @pytest.mark.parametrize("bpc,W,H,ssh,ssv", [(8, 640, 360, 1, 1), (10, 648, 368, 1, 1), (12, 328, 200, 0, 0), (8, 1920, 1080, 1, 1)])
 def test_gpu_frame(bpc, W, H, ssh, ssv):
