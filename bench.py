@@ -139,8 +139,27 @@ def frame_algorithmic_bytes(S):
         n = len(S["itx"][tx])
         sw, sh = L.tx_coef_dims(tx)
         itx += n * (sw * sh * cps + 2 * L.TX_W[tx] * L.TX_H[tx] * px)
+    luma = S["W"] * S["H"]
     return {"mc": int(foot + out), "comp": int(comp), "itx": int(itx), "deblock": int(4 * samples * px),
-            "cdef": int(2 * samples * px), "lr": int(2 * samples * px), "samples": int(samples)}
+            "cdef": int(2 * samples * px), "lr": int(2 * samples * px),
+            "fg": int((2 * samples + luma) * px) if S.get("fg") is not None else 0,   # + luma re-read by the chroma planes
+            "samples": int(samples)}
+
+
+FRAME_WORKLOADS = {
+    "4k8_inter": dict(bpc=8, W=3840, H=2160, fg=False, dtype="u8/i16->i32",
+                      desc="one 3840x2160 8-bit 4:2:0 inter frame per GPU per step: prediction (put/prep+compound, 2 refs) + "
+                           "inverse transforms + deblock + CDEF + loop restoration (BASELINE configs[2])"),
+    "4k10_full": dict(bpc=10, W=3840, H=2160, fg=True, dtype="u16/i32->i32",
+                      desc="one 3840x2160 10-bit 4:2:0 inter frame per GPU per step, full pipeline: prediction + inverse "
+                           "transforms + deblock + CDEF + loop restoration + film grain (BASELINE configs[3])"),
+}
+
+
+def make_workload_frame(name, seed):
+    from dav1d_b200 import synth
+    wl = FRAME_WORKLOADS[name]
+    return synth.make_inter_frame(np.random.default_rng(seed), wl["bpc"], wl["W"], wl["H"], film_grain=wl["fg"])
 
 
 # ------------------------------------------------------------------------------ reference arm / cpu baseline
@@ -197,7 +216,7 @@ def run_reference(args):
         sample = "2^18 blocks/step, %d threads" % ncores
         kind = "reference"
     else:
-        S = synth.make_inter_frame(np.random.default_rng(1), 8, W4K, H4K)
+        S = make_workload_frame(args.workload, 1)
         nthr = min(ncores, 64)
         for _ in range(min(args.warmup, 1)):
             cpu_frames(S, nthr, 1)
@@ -206,12 +225,13 @@ def run_reference(args):
             v, dt, kind = cpu_frames(S, nthr, 1)
             vals.append(v); dts.append(dt)
         val = float(np.mean(vals)); ms = 1e3 * float(np.mean(dts))
-        wl = "4k8_inter: 3840x2160 8-bit 4:2:0 inter frame (mc + itx + deblock + CDEF + LR), %d frames per step, one per thread" % nthr
+        wl = "%s: %s; reference arm: %d frames per step, one per host thread" % (args.workload, FRAME_WORKLOADS[args.workload]["desc"], nthr)
         sample = "%d whole 4K frames per step (one per thread, %d of %d cores), dav1d C path HAVE_ASM=0" % (nthr, nthr, ncores)
         ncores = nthr
     line = {"impl": "reference", "metric": "Mpixels/s", "value": val, "unit": "Mpixels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/i16->i32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": FRAME_WORKLOADS.get(args.workload, {"dtype": "u8/i16->i32"})["dtype"], "data": "synthetic",
             "config": {"workload": wl, "l2": "n/a (host)"},
             "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": ncores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -239,7 +259,7 @@ def run_ours_frame(args):
     nsets = 3
     fbs, Ss = [], []
     for k in range(nsets):
-        S = synth.make_inter_frame(np.random.default_rng(1 + rank * 16 + k), 8, W4K, H4K)
+        S = make_workload_frame(args.workload, 1 + rank * 16 + k)
         Ss.append(S)
         fbs.append(frame.FrameBuffers(S))
     px_per_step = W4K * H4K
@@ -251,7 +271,7 @@ def run_ours_frame(args):
         fb = fbs[i % nsets]
         fb.run()
         if world > 1:
-            dist.all_gather_into_tensor(gather, fb.keep[fb.out_name][0][:Ss[0]["pic"].nbytes])
+            dist.all_gather_into_tensor(gather, fb.keep[fb.ref_name][0][:Ss[0]["pic"].nbytes])   # un-grained picture
 
     def sync_all():
         torch.cuda.synchronize()
@@ -314,7 +334,7 @@ def run_ours_frame(args):
         alg = frame_algorithmic_bytes(Ss[0])
         stages = {}
         for name, ms in stage_ms.items():
-            key = {"pred": "mc", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr"}[name]
+            key = {"pred": "mc", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg"}[name]
             stages[name] = {"ms": ms, "algorithmic_bytes": alg[key], "GBps": alg[key] / (ms * 1e-3) / 1e9 if ms > 0 else None}
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         traffic = None
@@ -322,16 +342,21 @@ def run_ours_frame(args):
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(dom)
         achieved = stages[dom]["GBps"]
-        total_alg = sum(alg[k] for k in ("mc", "comp", "itx", "deblock", "cdef", "lr"))
+        total_alg = sum(alg[k] for k in ("mc", "comp", "itx", "deblock", "cdef", "lr", "fg"))
+        recon_ms = stage_ms["pred"] + stage_ms["comp"] + stage_ms["itx"]
+        post_ms = sum(v for k, v in stage_ms.items() if k in ("deblock", "cdef", "lr", "fg"))
+        split = {"recon": {"ms": recon_ms, "Mpixels/s": px_per_step / (recon_ms * 1e-3) / 1e6,
+                           "GBps": (alg["mc"] + alg["comp"] + alg["itx"]) / (recon_ms * 1e-3) / 1e9},
+                 "postfilter": {"ms": post_ms, "Mpixels/s": px_per_step / (post_ms * 1e-3) / 1e6,
+                                "GBps": (alg["deblock"] + alg["cdef"] + alg["lr"] + alg["fg"]) / (post_ms * 1e-3) / 1e9}}
         nthr = min(os.cpu_count() or 1, 32)
         v, dt, kind = cpu_frames(Ss[0], nthr, 1)
         cpu = {"value": v, "unit": "Mpixels/s", "cores": nthr, "kind": kind,
-               "sample": "%d whole 4K frames, one per thread (frame threading), dav1d C path HAVE_ASM=0 (no nasm in image), %.1f s" % (nthr, dt)}
+               "sample": "%d whole 4K frames of this workload, one per thread (frame threading), dav1d C path HAVE_ASM=0 (no nasm in image), %.1f s" % (nthr, dt)}
         line = {"metric": "Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8/i16->i32", "data": "synthetic",
-                "config": {"workload": "4k8_inter: one 3840x2160 8-bit 4:2:0 inter frame per GPU per step: prediction (put/prep+"
-                                       "compound, 2 refs) + inverse transforms + deblock + CDEF + loop restoration (BASELINE configs 2-3)",
+                "vs_baseline": None, "dtype": FRAME_WORKLOADS[args.workload]["dtype"], "data": "synthetic",
+                "config": {"workload": "%s: %s" % (args.workload, FRAME_WORKLOADS[args.workload]["desc"]),
                            "l2": "3 rotating frame sets (~%d MB) > 126 MB L2" % (3 * (5 * Ss[0]["pic"].nbytes + Ss[0]["coefs"].nbytes) // 1000000),
                            "records": {"pred_blocks": int(len(Ss[0]["pred"])), "compound": int(len(Ss[0]["comp"]) + len(Ss[0]["comp2"])),
                                        "tx_blocks": int(sum(len(a) for a in Ss[0]["itx"].values())), "coefs": int(len(Ss[0]["coefs"]))},
@@ -340,7 +365,7 @@ def run_ours_frame(args):
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "whole_frame": {"algorithmic_bytes": total_alg, "GBps": total_alg / (ms_per_step * 1e-3) / 1e9,
                                              "frac": total_alg / (ms_per_step * 1e-3) / 1e9 / peak},
-                             "stages": stages},
+                             "stages": stages, "split": split},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_val, "unit": "Mpixels/s", "h2d_bytes_per_step": int(fbs[0].h2d_bytes),
                         "d2h_bytes_per_step": int(fbs[0].d2h_bytes)},
@@ -353,25 +378,24 @@ def run_ours_frame(args):
 def stage_times(torch, lib, fbs, nsets, reps=6):
     """average device time of each stage of the frame job (events on the launching stream)"""
     from dav1d_b200 import _lib
-    names = ["pred", "comp", "itx", "deblock", "cdef", "lr"]
+    names = ["pred", "comp", "itx", "deblock", "cdef", "lr"] + (["fg"] if fbs[0].job.run_fg else [])
     acc = {n: 0.0 for n in names}
     st = torch.cuda.current_stream().cuda_stream
     for r in range(reps):
         fb = fbs[r % nsets]
         j = fb.job
         bd = j.bitdepth_max
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
         evs[0].record()
         lib.b200_mc_batch(bd, C.byref(j.mc), j.d_pred, j.n_pred, st); evs[1].record()
         lib.b200_mc_comp_batch(bd, C.byref(j.mc), j.d_comp, j.n_comp, st)
         lib.b200_mc_comp_batch(bd, C.byref(j.mc), j.d_comp2, j.n_comp2, st); evs[2].record()
-        for tx in range(19):
-            if j.n_itx[tx]:
-                lib.b200_itx_add_batch(bd, tx, j.d_itx[tx], j.n_itx[tx], j.d_coef, j.mc.dst, j.itx_stride, 0, st)
-        evs[3].record()
+        lib.b200_itx_add_frame(bd, j.d_itx, j.n_itx, j.d_coef, j.mc.dst, j.itx_stride, 0, st); evs[3].record()
         lib.b200_lf_frame(bd, C.byref(j.lf), st); evs[4].record()
         lib.b200_cdef_frame(bd, C.byref(j.cdef), st); evs[5].record()
         lib.b200_lr_frame(bd, C.byref(j.lr), st); evs[6].record()
+        if j.run_fg:   # apply only: the LUT preparation overlaps reconstruction on the side stream in the real job
+            lib.b200_fg_apply(bd, C.byref(j.fg), st); evs[7].record()
         torch.cuda.synchronize()
         if r >= 1:
             for k, n in enumerate(names):
@@ -487,7 +511,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "itx8x8"])
+    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k10_full", "itx8x8"])
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 5)      # bounded: each step is tens of whole 4K frames on the CPU

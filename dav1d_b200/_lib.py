@@ -80,24 +80,6 @@ class LrFrame(C.Structure):
                 ("unit_size_log2", C.c_int32 * 2), ("restore_planes", C.c_int32), ("lr_mask", C.c_void_p)]
 
 
-class FrameJob(C.Structure):
-    """struct B200FrameJob"""
-    _fields_ = [("bitdepth_max", C.c_int32), ("zero_coefs", C.c_int32), ("mc", McFrame),
-                ("d_pred", C.c_void_p), ("n_pred", C.c_int32), ("pad0", C.c_int32),
-                ("d_warp", C.c_void_p), ("n_warp", C.c_int32), ("pad1", C.c_int32),
-                ("d_comp", C.c_void_p), ("n_comp", C.c_int32), ("pad2", C.c_int32),
-                ("d_comp2", C.c_void_p), ("n_comp2", C.c_int32), ("pad2b", C.c_int32),
-                ("d_blend", C.c_void_p), ("n_blend", C.c_int32), ("pad3", C.c_int32),
-                ("d_itx", C.c_void_p * 19), ("n_itx", C.c_int32 * 19), ("pad4", C.c_int32),
-                ("d_coef", C.c_void_p), ("itx_stride", C.c_int32 * 3),
-                ("run_lf", C.c_int32), ("run_cdef", C.c_int32), ("run_lr", C.c_int32),
-                ("lf", LfFrame), ("cdef", CdefFrame), ("lr", LrFrame)]
-
-
-class Xfer(C.Structure):
-    _fields_ = [("host", C.c_void_p), ("dev", C.c_void_p), ("bytes", C.c_uint64)]
-
-
 class FilmGrainData(C.Structure):
     """Dav1dFilmGrainData / B200FilmGrainData (224 bytes)"""
     _fields_ = [("seed", C.c_uint), ("num_y_points", C.c_int), ("y_points", (C.c_uint8 * 2) * 14),
@@ -112,6 +94,25 @@ class FgFrame(C.Structure):
     _fields_ = [("in_", C.c_void_p), ("out", C.c_void_p), ("plane_off", C.c_uint32 * 3), ("stride", C.c_int32 * 3),
                 ("w", C.c_int32), ("h", C.c_int32), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32), ("is_id", C.c_int32),
                 ("data", FilmGrainData), ("scratch", C.c_void_p)]
+
+
+class FrameJob(C.Structure):
+    """struct B200FrameJob"""
+    _fields_ = [("bitdepth_max", C.c_int32), ("zero_coefs", C.c_int32), ("mc", McFrame),
+                ("d_pred", C.c_void_p), ("n_pred", C.c_int32), ("pad0", C.c_int32),
+                ("d_warp", C.c_void_p), ("n_warp", C.c_int32), ("pad1", C.c_int32),
+                ("d_comp", C.c_void_p), ("n_comp", C.c_int32), ("pad2", C.c_int32),
+                ("d_comp2", C.c_void_p), ("n_comp2", C.c_int32), ("pad2b", C.c_int32),
+                ("d_blend", C.c_void_p), ("n_blend", C.c_int32), ("pad3", C.c_int32),
+                ("d_itx", C.c_void_p * 19), ("n_itx", C.c_int32 * 19), ("pad4", C.c_int32),
+                ("d_coef", C.c_void_p), ("itx_stride", C.c_int32 * 3),
+                ("run_lf", C.c_int32), ("run_cdef", C.c_int32), ("run_lr", C.c_int32),
+                ("lf", LfFrame), ("cdef", CdefFrame), ("lr", LrFrame),
+                ("run_fg", C.c_int32), ("pad5", C.c_int32), ("fg", FgFrame)]
+
+
+class Xfer(C.Structure):
+    _fields_ = [("host", C.c_void_p), ("dev", C.c_void_p), ("bytes", C.c_uint64)]
 
 
 ITXFM_FN_8 = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int)
@@ -165,6 +166,8 @@ _SIGS = {
     "b200_loop_restoration_dsp_init_16bpc": (None, [C.c_void_p, C.c_int]),
     # ---- filmgrain
     "b200_fg_apply_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "b200_fg_prep": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "b200_fg_apply": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "b200_fg_generate_grain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200_fgy_32x32xn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int, C.c_int]),

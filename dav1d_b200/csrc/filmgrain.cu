@@ -257,18 +257,38 @@ using namespace b200;
 
 extern "C" {
 
-int b200_fg_apply_frame(int bdmax, const B200FgFrame *f, void *stream)
+static int fg_check(int bdmax, const B200FgFrame *f, const char *who)
 {
-    if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_fg_apply_frame: bad bitdepth_max"); return -2; }
+    if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("%s: bad bitdepth_max", who); return -2; }
     const int rows = (f->h + 31) / 32, nbx = (f->w + 31) / 32;
-    if (nbx > kMaxBlocksX || (size_t)rows * kMaxBlocksX > sizeof(((FgScratch *)0)->offsets)) { b200_set_error("b200_fg_apply_frame: picture too large"); return -2; }
+    if (nbx > kMaxBlocksX || (size_t)rows * kMaxBlocksX > sizeof(((FgScratch *)0)->offsets)) { b200_set_error("%s: picture too large", who); return -2; }
+    return 0;
+}
+
+int b200_fg_prep(int bdmax, const B200FgFrame *f, void *stream)
+{
+    if (fg_check(bdmax, f, "b200_fg_prep")) return -2;
     B200_LAUNCH(fg_prep_kernel, dim3(1), dim3(128), 0, (cudaStream_t)stream, *f, bdmax);
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int b200_fg_apply(int bdmax, const B200FgFrame *f, void *stream)
+{
+    if (fg_check(bdmax, f, "b200_fg_apply")) return -2;
     dim3 grid((f->w + 127) / 128, (f->h + 1) / 2, 3);
     if (bdmax > 255) { auto k = fg_apply_kernel<true>; B200_LAUNCH(k, grid, dim3(128, 2), 0, (cudaStream_t)stream, *f, bdmax); }
     else { auto k = fg_apply_kernel<false>; B200_LAUNCH(k, grid, dim3(128, 2), 0, (cudaStream_t)stream, *f, bdmax); }
-    b200_count_launch(); b200_count_launch();
+    b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+int b200_fg_apply_frame(int bdmax, const B200FgFrame *f, void *stream)
+{
+    int r = b200_fg_prep(bdmax, f, stream);
+    return r ? r : b200_fg_apply(bdmax, f, stream);
 }
 
 int b200_fg_generate_grain(void *buf, const void *buf_y, const B200FilmGrainData *data, int uv, int ss_hor, int ss_ver, int bdmax)

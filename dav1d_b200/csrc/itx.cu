@@ -191,18 +191,28 @@ struct ItxGroups {
     int cta_begin[B200_N_RECT_TX_SIZES], cta_end[B200_N_RECT_TX_SIZES];
 };
 
-template <bool HBD>
-__global__ void __launch_bounds__(kItxWarps * 32)
+// Two register classes, one launch each: sizes with a 64-point dimension (long butterflies, up to ~170 live
+// registers, 33 KB tile) and everything else (<= 64 registers, 17 KB tile, 8 CTAs per SM).
+template <bool BIG> struct ItxClass {
+    static constexpr int kMinCtas = BIG ? 3 : 8;
+    static constexpr int kTileWords = kItxWarps * (BIG ? ItxGeom<64, 64>::NB * ItxGeom<64, 64>::SLOT
+                                                       : ItxGeom<32, 32>::NB * ItxGeom<32, 32>::SLOT);
+};
+
+template <bool HBD, bool BIG>
+__global__ void __launch_bounds__(kItxWarps * 32, ItxClass<BIG>::kMinCtas)
 itx_add_grouped_kernel(const ItxGroups g, typename Bd<HBD>::coef *__restrict__ coefs, typename Bd<HBD>::pixel *__restrict__ pic,
                        int stride0, int stride1, int stride2, int bitdepth_max, int zero_coefs)
 {
-    __shared__ int tile[kItxWarps * ItxGeom<64, 64>::NB * ItxGeom<64, 64>::SLOT];
+    __shared__ int tile[ItxClass<BIG>::kTileWords];
     const int c = blockIdx.x;
 #define X(TX, W, H, SH) \
-    if (c < g.cta_end[TX]) { \
-        itx_add_body<W, H, TX, SH, HBD>(c - g.cta_begin[TX], tile, g.blocks[TX], g.n[TX], coefs, pic, stride0, stride1, stride2, \
-                                        bitdepth_max, zero_coefs); \
-        return; \
+    if constexpr ((W == 64 || H == 64) == BIG) { \
+        if (c < g.cta_end[TX]) { \
+            itx_add_body<W, H, TX, SH, HBD>(c - g.cta_begin[TX], tile, g.blocks[TX], g.n[TX], coefs, pic, stride0, stride1, \
+                                            stride2, bitdepth_max, zero_coefs); \
+            return; \
+        } \
     }
     B200_ITX_SIZES(X)
 #undef X
@@ -211,19 +221,27 @@ itx_add_grouped_kernel(const ItxGroups g, typename Bd<HBD>::coef *__restrict__ c
 int launch_itx_grouped(bool hbd, const void *const *blocks, const int32_t *n, void *coefs, void *pic, const int32_t *st,
                        int bdmax, int zero, cudaStream_t stream)
 {
-    ItxGroups g;
-    int total = 0;
+    for (int big = 1; big >= 0; big--) {
+        ItxGroups g;
+        int total = 0;
 #define X(TX, W, H, SH) { \
-        const int per_cta = kItxWarps * ItxGeom<W, H>::NB; \
-        const int ctas = n[TX] > 0 ? (n[TX] + per_cta - 1) / per_cta : 0; \
-        g.blocks[TX] = (const B200ItxBlock *)blocks[TX]; g.n[TX] = n[TX] > 0 ? n[TX] : 0; \
-        g.cta_begin[TX] = total; total += ctas; g.cta_end[TX] = total; }
-    B200_ITX_SIZES(X)
+            const int per_cta = kItxWarps * ItxGeom<W, H>::NB; \
+            const int mine = ((W == 64 || H == 64) ? 1 : 0) == big; \
+            const int ctas = (mine && n[TX] > 0) ? (n[TX] + per_cta - 1) / per_cta : 0; \
+            g.blocks[TX] = (const B200ItxBlock *)blocks[TX]; g.n[TX] = n[TX] > 0 ? n[TX] : 0; \
+            g.cta_begin[TX] = total; total += ctas; g.cta_end[TX] = total; }
+        B200_ITX_SIZES(X)
 #undef X
-    if (!total) return 0;
-    if (hbd) { auto k = itx_add_grouped_kernel<true>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int32_t *)coefs, (uint16_t *)pic, st[0], st[1], st[2], bdmax, zero); }
-    else { auto k = itx_add_grouped_kernel<false>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int16_t *)coefs, (uint8_t *)pic, st[0], st[1], st[2], bdmax, zero); }
-    b200_count_launch();
+        if (!total) continue;
+        if (hbd) {
+            if (big) { auto k = itx_add_grouped_kernel<true, true>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int32_t *)coefs, (uint16_t *)pic, st[0], st[1], st[2], bdmax, zero); }
+            else { auto k = itx_add_grouped_kernel<true, false>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int32_t *)coefs, (uint16_t *)pic, st[0], st[1], st[2], bdmax, zero); }
+        } else {
+            if (big) { auto k = itx_add_grouped_kernel<false, true>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int16_t *)coefs, (uint8_t *)pic, st[0], st[1], st[2], bdmax, zero); }
+            else { auto k = itx_add_grouped_kernel<false, false>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int16_t *)coefs, (uint8_t *)pic, st[0], st[1], st[2], bdmax, zero); }
+        }
+        b200_count_launch();
+    }
     return 0;
 }
 

@@ -28,28 +28,127 @@ template <bool HBD> B200_DEV int inter_bits(int bdmax) {
 
 #define RND_SH(v, sh) (((v) + ((1 << (sh)) >> 1)) >> (sh))
 
-constexpr int kMcWarps = 2;
+// ---- put / prep ---------------------------------------------------------------------------------
+// One warp per prediction block (4 blocks per CTA), blocks larger than 32x32 walked in 32x32 sub-blocks:
+//   1. the source window (sub-block + 3/4 taps of margin on filtered axes) is staged in the warp's shared
+//      memory: 32-bit aligned words straight from the reference when the window lies inside the plane,
+//      per-sample clamped loads otherwise (= dav1d's emu_edge, reference src/mc_tmpl.c:868-916);
+//   2. horizontal pass: an item = S consecutive columns of one window row, lanes run along rows (odd word
+//      pitch: conflict-free), sliding the 8-tap window through registers -> int16 `mid` tile;
+//   3. vertical pass: an item = S consecutive rows of one column, lanes run along x (conflict-free reads,
+//      coalesced stores), same sliding window, final rounding / clip / prep bias.
+// S = 2 / 4 / 8 by sub-block area so that small blocks still fill the warp. Bilinear is the same machinery
+// with the taps {16-m, m} at positions 3, 4 and a base shift of 4 instead of 6.
+constexpr int kMcWarps = 4;
+constexpr int kMcSub = 32, kMcWin = kMcSub + 7;          // sub-block edge, window edge
+constexpr int kMcMidPitch = kMcSub + 2;                   // int16 elements; (pitch * 2 / 4) odd
+
+template <bool HBD> struct alignas(16) McSmem {
+    typedef typename Bd<HBD>::pixel pixel;
+    static constexpr int kRawPitch = HBD ? 42 : 44;       // elements; word pitch 21 / 11 (odd)
+    pixel raw[kMcWin * kRawPitch];
+    int16_t mid[kMcWin * kMcMidPitch];
+};
+
+template <bool HBD, int S>
+B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int sh, const int nr, const int shift0,
+                        const bool has_h, const bool has_v, const int (&fh)[8], const int (&fv)[8], const int fsh,
+                        const int ib, const int bias, const bool is_prep, const int bdmax,
+                        typename Bd<HBD>::pixel *dpx, const int ds, int16_t *dtmp, const int tw)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    constexpr int RP = McSmem<HBD>::kRawPitch;
+    // ---- horizontal: mid[r][x] for r < nr, x < sw
+    const int ngx = (sw + S - 1) / S;
+    for (int it = lane; it < nr * ngx; it += 32) {
+        const int g = it / nr, r = it - g * nr;
+        const int x0 = g * S;
+        const pixel *row = &sm.raw[r * RP + shift0 + x0];
+        int16_t *m = &sm.mid[r * kMcMidPitch + x0];
+        if (has_h) {
+            int win[S + 7];
+#pragma unroll
+            for (int k = 0; k < S + 7; k++) win[k] = row[k];
+#pragma unroll
+            for (int j = 0; j < S; j++) {
+                int sacc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) sacc += fh[k] * win[j + k];
+                if (x0 + j < sw) m[j] = (int16_t)RND_SH(sacc, fsh - ib);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; j++) if (x0 + j < sw) m[j] = (int16_t)row[j];
+        }
+    }
+    __syncwarp();
+    // ---- vertical + store
+    const int ngy = (sh + S - 1) / S;
+    for (int it = lane; it < sw * ngy; it += 32) {
+        const int g = it / sw, x = it - g * sw;
+        const int y0 = g * S;
+        const int16_t *m = &sm.mid[y0 * kMcMidPitch + x];
+        int out[S];
+        if (has_v) {
+            int win[S + 7];
+#pragma unroll
+            for (int k = 0; k < S + 7; k++) win[k] = (y0 + k < nr) ? m[k * kMcMidPitch] : 0;
+#pragma unroll
+            for (int j = 0; j < S; j++) {
+                int sacc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) sacc += fv[k] * win[j + k];
+                if (has_h) out[j] = is_prep ? RND_SH(sacc, fsh) - bias : iclip(RND_SH(sacc, fsh + ib), 0, bdmax);
+                else       out[j] = is_prep ? RND_SH(sacc, fsh - ib) - bias : iclip(RND_SH(sacc, fsh), 0, bdmax);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; j++) {
+                const int a = (y0 + j < nr) ? m[j * kMcMidPitch] : 0;
+                if (has_h) out[j] = is_prep ? a - bias : iclip((a + ((1 << ib) >> 1)) >> ib, 0, bdmax);
+                else       out[j] = is_prep ? (a << ib) - bias : a;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < S; j++) {
+            if (y0 + j >= sh) break;
+            if (is_prep) dtmp[(y0 + j) * tw + x] = (int16_t)out[j];
+            else dpx[(ptrdiff_t)(y0 + j) * ds + x] = (pixel)out[j];
+        }
+    }
+    __syncwarp();
+}
 
 template <bool HBD>
 __global__ void __launch_bounds__(kMcWarps * 32)
 mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
-    const B200McBlock b = blocks[blockIdx.x];
+    __shared__ McSmem<HBD> smem[kMcWarps];
+    constexpr int RP = McSmem<HBD>::kRawPitch;
+    constexpr int PPW = HBD ? 2 : 4;                       // pixels per 32-bit word
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bi = blockIdx.x * kMcWarps + warp;
+    if (bi >= n_blocks) return;
+    McSmem<HBD> &sm = smem[warp];
+    const B200McBlock b = blocks[bi];
     const int w = b.w, h = b.h, pl = b.plane;
     const pixel *__restrict__ ref = (const pixel *)fr.ref[b.ref] + fr.ref_plane_off[pl];
-    const int rs = fr.ref_stride[pl], rw1 = fr.ref_w[pl] - 1, rh1 = fr.ref_h[pl] - 1;
+    const int rs = fr.ref_stride[pl], rw = fr.ref_w[pl], rh = fr.ref_h[pl];
     const int ib = inter_bits<HBD>(bdmax);
     const int bias = HBD ? 8192 : 0;
     const bool bilin = b.filter2d == 9;
     const int mx = b.mx, my = b.my;
     const bool has_h = mx != 0, has_v = my != 0;
     const bool is_prep = b.op != 0;
+    const int fsh = bilin ? 4 : 6;
 
     int fh[8], fv[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) fh[k] = fv[k] = 0;
-    if (!bilin) {
+    if (bilin) {
+        fh[3] = 16 - mx; fh[4] = mx; fv[3] = 16 - my; fv[4] = my;
+    } else {
         // 4-tap sets for w <= 4 / h <= 4 (reference src/mc_tmpl.c:115-123)
         if (has_h) {
             const int t = c_f2d_h[b.filter2d];
@@ -64,83 +163,46 @@ mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, B200McFrame
             for (int k = 0; k < 8; k++) fv[k] = b200_mc_subpel_filters[idx][my - 1][k];
         }
     }
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tw = w < 32 ? w : 32;               // strip width (power of two)
-    const int tw_log = 31 - __clz(tw);
-    const int lx = lane & (tw - 1), lg = lane >> tw_log;
-    const int rows_per_unit = 8 << (5 - tw_log);
-    const int units_x = (w + 31) >> 5;
-    const int units_y = (h + rows_per_unit - 1) / rows_per_unit;
     pixel *const dpx = (pixel *)fr.dst;
     const int ds = fr.dst_stride[pl];
+    const bool words_ok = ((rs & (PPW - 1)) == 0) && ((((uintptr_t)ref) & 3) == 0);
 
-    for (int u = warp; u < units_x * units_y; u += kMcWarps) {
-        const int ux = u % units_x, uy = u / units_x;
-        const int x = (ux << 5) + lx;
-        const int y0 = uy * rows_per_unit + lg * 8;
-        if (x >= w || y0 >= h) continue;
-        const int nrows = imin(8, h - y0);
-        const int sx = b.src_x + x, sy = b.src_y + y0;
-
-        // A[r]: horizontally filtered (or raw) sample of source row sy + r - 3 at column sx
-        int A[15];
-        const int r_lo = bilin ? 3 : (has_v ? 0 : 3);
-        const int r_hi = bilin ? 3 + nrows + (has_v ? 1 : 0) : (has_v ? nrows + 7 : 3 + nrows);
-#pragma unroll
-        for (int r = 0; r < 15; r++) {
-            A[r] = 0;
-            if (r >= r_lo && r < r_hi) {
-                const int yy = iclip(sy + r - 3, 0, rh1);
-                const pixel *row = ref + (ptrdiff_t)yy * rs;
-                if (bilin) {
-                    const int p0 = row[iclip(sx, 0, rw1)];
-                    if (has_h) {
-                        const int p1 = row[iclip(sx + 1, 0, rw1)];
-                        A[r] = RND_SH(16 * p0 + mx * (p1 - p0), 4 - ib);
-                    } else {
-                        A[r] = p0;
-                    }
-                } else if (has_h) {
-                    int s = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) s += fh[k] * (int)row[iclip(sx + k - 3, 0, rw1)];
-                    A[r] = RND_SH(s, 6 - ib);
-                } else {
-                    A[r] = row[iclip(sx, 0, rw1)];
+    for (int sy0 = 0; sy0 < h; sy0 += kMcSub)
+        for (int sx0 = 0; sx0 < w; sx0 += kMcSub) {
+            const int sw = imin(kMcSub, w - sx0), sh = imin(kMcSub, h - sy0);
+            const int nc = sw + (has_h ? 7 : 0), nr = sh + (has_v ? 7 : 0);
+            const int gx = b.src_x + sx0 - (has_h ? 3 : 0), gy = b.src_y + sy0 - (has_v ? 3 : 0);
+            int shift0 = 0;
+            if (words_ok && gx >= 0 && gy >= 0 && gx + nc <= rw && gy + nr <= rh &&
+                (((gx & ~(PPW - 1)) + ((nc + (gx & (PPW - 1)) + PPW - 1) & ~(PPW - 1))) <= rs)) {
+                // interior: aligned words, the window starts `shift0` samples into the tile row
+                shift0 = gx & (PPW - 1);
+                const int nw = (nc + shift0 + PPW - 1) / PPW;
+                const int gxa = gx - shift0;
+                const unsigned magic = (65536u + nw - 1) / nw;
+                for (int it = lane; it < nr * nw; it += 32) {
+                    const int r = (int)((it * magic) >> 16), c = it - r * nw;
+                    const unsigned v = *(const unsigned *)(ref + (ptrdiff_t)(gy + r) * rs + gxa + c * PPW);
+                    *(unsigned *)&sm.raw[r * RP + c * PPW] = v;
                 }
-            }
-        }
-
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (j >= nrows) break;
-            int out;
-            if (bilin) {
-                if (has_v) {
-                    const int s = 16 * A[j + 3] + my * (A[j + 4] - A[j + 3]);
-                    if (has_h) out = is_prep ? RND_SH(s, 4) - bias : iclip(RND_SH(s, 4 + ib), 0, bdmax);
-                    else       out = is_prep ? RND_SH(s, 4 - ib) - bias : iclip(RND_SH(s, 4), 0, bdmax);
-                } else if (has_h) {
-                    out = is_prep ? A[j + 3] - bias : iclip((A[j + 3] + ((1 << ib) >> 1)) >> ib, 0, bdmax);
-                } else {
-                    out = is_prep ? (A[j + 3] << ib) - bias : A[j + 3];
-                }
-            } else if (has_v) {
-                int s = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) s += fv[k] * A[j + k];
-                if (has_h) out = is_prep ? RND_SH(s, 6) - bias : iclip(RND_SH(s, 6 + ib), 0, bdmax);
-                else       out = is_prep ? RND_SH(s, 6 - ib) - bias : iclip(RND_SH(s, 6), 0, bdmax);
-            } else if (has_h) {
-                out = is_prep ? A[j + 3] - bias : iclip((A[j + 3] + ((1 << ib) >> 1)) >> ib, 0, bdmax);
             } else {
-                out = is_prep ? (A[j + 3] << ib) - bias : A[j + 3];
+                const unsigned magic = (65536u + nc - 1) / nc;
+                for (int it = lane; it < nr * nc; it += 32) {
+                    const int r = (int)((it * magic) >> 16), c = it - r * nc;
+                    sm.raw[r * RP + c] = ref[(ptrdiff_t)iclip(gy + r, 0, rh - 1) * rs + iclip(gx + c, 0, rw - 1)];
+                }
             }
-            if (is_prep) fr.tmp[b.dst_off + (y0 + j) * w + x] = (int16_t)out;
-            else dpx[b.dst_off + (ptrdiff_t)(y0 + j) * ds + x] = (pixel)out;
+            __syncwarp();
+            pixel *dsub = dpx + b.dst_off + (ptrdiff_t)sy0 * ds + sx0;
+            int16_t *tsub = fr.tmp + b.dst_off + sy0 * w + sx0;
+            const int area = sw * sh;
+            if (area <= 64)
+                mc_passes<HBD, 2>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
+            else if (area <= 256)
+                mc_passes<HBD, 4>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
+            else
+                mc_passes<HBD, 8>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
         }
-    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -316,8 +378,8 @@ extern "C" {
 int b200_mc_batch(int bitdepth_max, const B200McFrame *frame, const B200McBlock *d_blocks, int n, void *stream) {
     if (check_bd(bitdepth_max, "b200_mc_batch")) return -2;
     if (n <= 0) return 0;
-    if (bitdepth_max > 255) { auto k = mc_pred_kernel<true>; B200_LAUNCH(k, dim3(n), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
-    else { auto k = mc_pred_kernel<false>; B200_LAUNCH(k, dim3(n), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    if (bitdepth_max > 255) { auto k = mc_pred_kernel<true>; B200_LAUNCH(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_pred_kernel<false>; B200_LAUNCH(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;

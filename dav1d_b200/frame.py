@@ -150,10 +150,25 @@ class FrameBuffers:
         lr.sr_sb128w = (S["W"] + 127) >> 7
         lr.unit_size_log2[0], lr.unit_size_log2[1] = S["us"]
         lr.restore_planes, lr.lr_mask = S["rp"], d_lrm
-        self.job = j
         self.out_name = "p2" if run_lr else ("p1" if run_cdef else "p0")
+        n_fg = 0
+        self.ref_name = self.out_name          # the picture later frames predict from (never the grained copy)
+        if S.get("fg") is not None:
+            # film grain goes into a separate display copy; the un-grained picture stays the reference picture
+            fg = j.fg
+            j.run_fg = 1
+            fg.in_, fg.out = self.keep[self.out_name][1], zeros("p3", nbytes)
+            for p in range(3):
+                fg.plane_off[p] = S["off"][p]; fg.stride[p] = S["stride"][p]
+            fg.w, fg.h, fg.ss_hor, fg.ss_ver, fg.is_id = S["W"], S["H"], S["ss_hor"], S["ss_ver"], 0
+            fg.data = S["fg"]
+            fg.scratch = zeros("fg_scratch", 256 * 1024)
+            self.ref_name, self.out_name = self.out_name, "p3"
+            n_fg = 2
+        self.job = j
         self.n_launches = (1 if j.n_pred else 0) + (1 if j.n_comp else 0) + (1 if j.n_comp2 else 0) + \
-            (1 if any(j.n_itx[tx] for tx in range(19)) else 0) + 2 * int(run_lf) + int(run_cdef) + int(run_lr)
+            (1 if any(j.n_itx[tx] for tx in (4, 11, 12, 17, 18)) else 0) + \
+            (1 if any(j.n_itx[tx] for tx in range(19) if tx not in (4, 11, 12, 17, 18)) else 0) + 2 * int(run_lf) + int(run_cdef) + int(run_lr) + n_fg
         self._host = None
 
     # ---- device-resident run (records already in HBM) ----

@@ -251,7 +251,42 @@ def smooth_picture(rng, total, bd, dt):
     return (up + rng.integers(-6, 7, total)).clip(0, bd).astype(dt)
 
 
-def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.3, p_skip=0.25, min_log=1, max_log=4):
+def make_film_grain(rng, full=True):
+    """random Dav1dFilmGrainData in the ranges of tests/checkasm/filmgrain.c (:62-75, :160-215)"""
+    from . import _lib
+    d = _lib.FilmGrainData()
+    d.seed = int(rng.integers(0, 1 << 16))
+    d.grain_scale_shift = int(rng.integers(0, 4))
+    d.ar_coeff_shift = int(rng.integers(6, 10))
+    d.ar_coeff_lag = int(rng.integers(0, 4))
+    for i in range(24):
+        d.ar_coeffs_y[i] = int(rng.integers(-128, 128))
+    for uv in range(2):
+        for i in range(25):
+            d.ar_coeffs_uv[uv][i] = int(rng.integers(-128, 128))
+    d.num_y_points = int(rng.integers(0, 15)) if full else 2 + int(rng.integers(0, 13))
+
+    def points(dst, n):
+        pad = 0xff // n if n else 0
+        for i in range(n):
+            dst[i][0] = min(255, 0xff * i // n + int(rng.integers(0, max(pad, 1))))
+            dst[i][1] = int(rng.integers(0, 256))
+    points(d.y_points, d.num_y_points)
+    d.chroma_scaling_from_luma = int(rng.integers(0, 2))
+    for uv in range(2):
+        d.num_uv_points[uv] = int(rng.integers(0, 11))
+        points(d.uv_points[uv], d.num_uv_points[uv])
+        d.uv_mult[uv] = int(rng.integers(-128, 128))
+        d.uv_luma_mult[uv] = int(rng.integers(-128, 128))
+        d.uv_offset[uv] = int(rng.integers(-256, 256))
+    d.scaling_shift = int(rng.integers(8, 12))
+    d.overlap_flag = int(rng.integers(0, 2))
+    d.clip_to_restricted_range = int(rng.integers(0, 2))
+    return d
+
+
+def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.3, p_skip=0.25, min_log=1, max_log=4,
+                     film_grain=False):
     """Synthetic inter frame: every block is predicted from `n_refs` reference pictures (single or
     compound), carries a residual (unless skipped) and the frame has deblock / CDEF / LR parameters."""
     bd = (1 << bpc) - 1
@@ -410,4 +445,8 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
     S["lr_mask"] = make_lr_params(rng, W, H)
     S["us"] = (6, 6 - (1 if ss_hor else 0))
     S["rp"], S["sb128"] = 7, 0
+    if film_grain:
+        d = make_film_grain(rng, full=False)
+        d.overlap_flag = 1
+        S["fg"] = d
     return S

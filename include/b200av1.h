@@ -388,6 +388,9 @@ typedef struct B200FgFrame {
     void *scratch;
 } B200FgFrame;
 B200_API int b200_fg_apply_frame(int bitdepth_max, const B200FgFrame *frame, void *stream);
+/* the two halves of the above: prep touches only frame->data / geometry / scratch, apply needs in / out too */
+B200_API int b200_fg_prep(int bitdepth_max, const B200FgFrame *frame, void *stream);
+B200_API int b200_fg_apply(int bitdepth_max, const B200FgFrame *frame, void *stream);
 
 /* Level 1 (host pointers). Grain LUT entries are int8 (8 bpc) / int16 (10, 12 bpc), pitch 82. */
 B200_API int b200_fg_generate_grain(void *buf, const void *buf_y, const B200FilmGrainData *data, int uv,
@@ -415,7 +418,7 @@ B200_API void b200_film_grain_dsp_init_16bpc(B200FilmGrainDSPContext *c);
  * b200_frame_run enqueues, on `stream`:
  *    prediction (put/prep) -> warp -> compound -> compound stage 2 -> blend -> inverse transforms (one launch per size)
  *    -> deblock (2 sweeps, in place on the reconstructed picture) -> CDEF (out of place) -> loop
- *    restoration (out of place).
+ *    restoration (out of place) -> film grain (out of place, into the display copy).
  * Stages whose counts / run_* flags are zero are skipped. Picture chaining is the caller's: typically
  * mc.dst == lf.pic == cdef.src == lr.dbl, cdef.dst == lr.cdef, lr.dst = output. */
 typedef struct B200FrameJob {
@@ -437,6 +440,9 @@ typedef struct B200FrameJob {
     B200LfFrame lf;
     B200CdefFrame cdef;
     B200LrFrame lr;
+    int32_t run_fg, pad5;        /* film grain on the output copy (fg.in = lr.dst typically); the grain LUT preparation
+                                    runs on an internal side stream concurrently with reconstruction */
+    B200FgFrame fg;
 } B200FrameJob;
 B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check): 0 McFrame, 1 McBlock, 2 CompBlock,

@@ -205,6 +205,7 @@ API void bitfn(refdrv_lr_frame)(const int bitdepth_max, const RefLrFrame *const 
 #include "src/mc.h"
 #include "src/itx.h"
 
+static void bitfn(frame_run_fg)(int bitdepth_max, const B200FrameJob *j);
 API void bitfn(refdrv_frame_run)(const B200FrameJob *const j)
 {
     static __thread Dav1dMCDSPContext mc;
@@ -305,6 +306,7 @@ API void bitfn(refdrv_frame_run)(const B200FrameJob *const j)
         lr.restore_planes = j->lr.restore_planes; lr.lr_mask = (Av1Restoration *)j->lr.lr_mask;
         bitfn(refdrv_lr_frame)(bitdepth_max, &lr);
     }
+    if (j->run_fg) bitfn(frame_run_fg)(bitdepth_max, j);
 }
 
 /* ---- film grain: the reference's own dav1d_apply_grain (prep + every 32-row strip) ---- */
@@ -340,4 +342,15 @@ API void bitfn(refdrv_fg_frame)(const int bitdepth_max, const RefFgFrame *const 
     }
     bitfn(dav1d_apply_grain)(&dsp, &out, &in);
     free(hdr); free(seq);
+}
+
+static void bitfn(frame_run_fg)(const int bitdepth_max, const B200FrameJob *const j)
+{
+    RefFgFrame fr;
+    memset(&fr, 0, sizeof(fr));
+    fr.in = j->fg.in; fr.out = j->fg.out;
+    for (int p = 0; p < 3; p++) { fr.plane_off[p] = j->fg.plane_off[p]; fr.stride[p] = j->fg.stride[p]; }
+    fr.w = j->fg.w; fr.h = j->fg.h; fr.ss_hor = j->fg.ss_hor; fr.ss_ver = j->fg.ss_ver; fr.is_id = j->fg.is_id;
+    memcpy(&fr.data, &j->fg.data, sizeof(fr.data));
+    bitfn(refdrv_fg_frame)(bitdepth_max, &fr);
 }

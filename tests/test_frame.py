@@ -52,6 +52,14 @@ def oracle_frame(S, run_lf=True, run_cdef=True, run_lr=True):
     if run_lr:
         S3 = dict(S2); S3["cdef"], S3["dbl"] = cd, pic
         out["lr"] = TLR.lr_frame_oracle(S3)
+    if S.get("fg") is not None:
+        import test_filmgrain as TFG
+        fr = _lib.FgFrame()
+        for p in range(3):
+            fr.plane_off[p] = S["off"][p]; fr.stride[p] = S["stride"][p]
+        fr.w, fr.h, fr.ss_hor, fr.ss_ver, fr.is_id = S["W"], S["H"], S["ss_hor"], S["ss_ver"], 0
+        fr.data = S["fg"]
+        out["fg"] = TFG.run_oracle_frame(fr, np.ascontiguousarray(out["lr"]), S["bpc"])
     return out
 
 
@@ -61,12 +69,14 @@ def check_frame(S, fb, exp):
     assert TCD.frame_area_equal(S, got_recon_dbl, exp["dbl"]), "reconstruction + deblock mismatch"
     assert TCD.frame_area_equal(S, fb.output("p1"), exp["cdef"]), "cdef mismatch"
     assert TLR.picture_equal(S, fb.output("p2"), exp["lr"]), "loop restoration mismatch"
+    if "fg" in exp:
+        assert TLR.picture_equal(S, fb.output("p3"), exp["fg"]), "film grain mismatch"
 
 
 @pytest.mark.emu
 @pytest.mark.parametrize("bpc,W,H,ssh,ssv", [(8, 200, 136, 1, 1), (10, 136, 72, 1, 1)])
 def test_emu_frame(bpc, W, H, ssh, ssv):
-    S = synth.make_inter_frame(np.random.default_rng(600 + bpc), bpc, W, H, ssh, ssv)
+    S = synth.make_inter_frame(np.random.default_rng(600 + bpc), bpc, W, H, ssh, ssv, film_grain=bpc > 8)
     exp = oracle_frame(S)
     assert (exp["recon"] != 0).mean() > 0.3 and not np.array_equal(exp["recon"], exp["dbl"])
     fb = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
@@ -75,30 +85,32 @@ def test_emu_frame(bpc, W, H, ssh, ssv):
     # the host-buffer path must give the same picture
     fb2 = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
     fb2.run_host()
-    assert TLR.picture_equal(S, fb2.host_output(), exp["lr"])
+    last = exp["fg"] if "fg" in exp else exp["lr"]
+    assert TLR.picture_equal(S, fb2.host_output(), last)
     fb3 = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
     fb3.submit_host(); fb3.wait()
-    assert TLR.picture_equal(S, fb3.host_output(), exp["lr"])
+    assert TLR.picture_equal(S, fb3.host_output(), last)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("bpc,W,H,ssh,ssv", [(8, 640, 360, 1, 1), (10, 648, 368, 1, 1), (12, 328, 200, 0, 0), (8, 1920, 1080, 1, 1)])
 def test_gpu_frame(bpc, W, H, ssh, ssv):
-    S = synth.make_inter_frame(np.random.default_rng(610 + bpc + W), bpc, W, H, ssh, ssv)
+    S = synth.make_inter_frame(np.random.default_rng(610 + bpc + W), bpc, W, H, ssh, ssv, film_grain=bpc > 8)
     exp = oracle_frame(S)
     fb = frame.FrameBuffers(S)
     fb.run()
     fb.alloc.sync()
     check_frame(S, fb, exp)
+    last = exp["fg"] if "fg" in exp else exp["lr"]
     fb2 = frame.FrameBuffers(S)
     fb2.run_host()
-    assert TLR.picture_equal(S, fb2.host_output(), exp["lr"])
+    assert TLR.picture_equal(S, fb2.host_output(), last)
     # two frames in flight on their own streams (frame-threaded end-to-end path)
     fb3, fb4 = frame.FrameBuffers(S), frame.FrameBuffers(S)
     for _ in range(3):
         fb3.submit_host(); fb4.submit_host()
         fb3.wait(); fb4.wait()
-    assert TLR.picture_equal(S, fb3.host_output(), exp["lr"]) and TLR.picture_equal(S, fb4.host_output(), exp["lr"])
+    assert TLR.picture_equal(S, fb3.host_output(), last) and TLR.picture_equal(S, fb4.host_output(), last)
 
 
 def reference_frame(S):
@@ -114,7 +126,7 @@ def test_oracle_frame_vs_reference_functions(bpc, W, H, ssh, ssv):
     """whole-frame pin of the oracle: every stage run by dav1d's own C functions / frame drivers"""
     if not refs.have_ref():
         pytest.skip("reference build (oracle/_ref) not present")
-    S = synth.make_inter_frame(np.random.default_rng(620 + bpc), bpc, W, H, ssh, ssv)
+    S = synth.make_inter_frame(np.random.default_rng(620 + bpc), bpc, W, H, ssh, ssv, film_grain=bpc > 8)
     exp = oracle_frame(S)
     fb = reference_frame(S)
     check_frame(S, fb, exp)

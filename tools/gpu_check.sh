@@ -14,13 +14,15 @@ if [[ $what == all || $what == bench ]]; then
   timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
   timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
   timeout 600 python bench.py --workload itx8x8 > gpurun_out/bench_itx8x8.json 2> gpurun_out/bench_itx8x8.err
+  timeout 900 python bench.py --impl reference --workload 4k10_full --steps 2 --warmup 1 > gpurun_out/bench_ref_4k10.json 2> gpurun_out/bench_ref_4k10.err
+  timeout 900 python bench.py --workload 4k10_full > gpurun_out/bench_4k10.json 2> gpurun_out/bench_4k10.err
 fi
 if [[ $what == all || $what == ncu ]]; then
-  # launch list of 3 timed frames after the warm-up (5 warm-up frames x 8 launches are skipped)
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 24 --csv \
+  # launch list of 3 timed frames after the warm-up (5 warm-up frames x 9 launches are skipped)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 45 -c 27 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 5 > gpurun_out/ncu_bench.log 2>&1
   # full capture of one whole frame's kernels
-  timeout 1200 ncu --set full --clock-control none --import-source on -s 40 -c 8 \
+  timeout 1200 ncu --set full --clock-control none --import-source on -s 45 -c 9 \
       -f -o gpurun_out/prof_frame python bench.py --steps 3 --warmup 5 > gpurun_out/ncu_full.log 2>&1
 fi
 echo done > gpurun_out/done.txt
