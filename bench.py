@@ -140,7 +140,15 @@ def frame_algorithmic_bytes(S):
         sw, sh = L.tx_coef_dims(tx)
         itx += n * (sw * sh * cps + 2 * L.TX_W[tx] * L.TX_H[tx] * px)
     luma = S["W"] * S["H"]
-    return {"mc": int(foot + out), "comp": int(comp), "itx": int(itx), "deblock": int(4 * samples * px),
+    intra = 0
+    if S.get("intra_tx") is not None and len(S["intra_tx"]):
+        t = S["intra_tx"]
+        tw = np.array(L.TX_W)[t["tx"]].astype(np.int64); th = np.array(L.TX_H)[t["tx"]].astype(np.int64)
+        coded = t["eob"] >= 0
+        # prediction written + edge read; residual: coefficients read + picture read-modify-write
+        intra = int(((tw * th + 2 * (tw + th) + 1) * px).sum() +
+                    ((np.minimum(tw, 32) * np.minimum(th, 32) * cps + 2 * tw * th * px) * coded).sum())
+    return {"intra": intra, "mc": int(foot + out), "comp": int(comp), "itx": int(itx), "deblock": int(4 * samples * px),
             "cdef": int(2 * samples * px), "lr": int(2 * samples * px),
             "fg": int((2 * samples + luma) * px) if S.get("fg") is not None else 0,   # + luma re-read by the chroma planes
             "samples": int(samples)}
@@ -153,13 +161,25 @@ FRAME_WORKLOADS = {
     "4k10_full": dict(bpc=10, W=3840, H=2160, fg=True, dtype="u16/i32->i32",
                       desc="one 3840x2160 10-bit 4:2:0 inter frame per GPU per step, full pipeline: prediction + inverse "
                            "transforms + deblock + CDEF + loop restoration + film grain (BASELINE configs[3])"),
+    "1080p8_intra": dict(bpc=8, W=1920, H=1080, fg=False, dtype="u8/i16->i32", intra=True,
+                         desc="one 1920x1080 8-bit 4:2:0 intra-only frame per GPU per step: device-side edge preparation + "
+                              "intra prediction + inverse transforms (dependency-driven kernel) + deblock (BASELINE configs[1])"),
 }
 
 
 def make_workload_frame(name, seed):
     from dav1d_b200 import synth
     wl = FRAME_WORKLOADS[name]
+    if wl.get("intra"):
+        return synth.make_intra_frame(np.random.default_rng(seed), wl["bpc"], wl["W"], wl["H"])
     return synth.make_inter_frame(np.random.default_rng(seed), wl["bpc"], wl["W"], wl["H"], film_grain=wl["fg"])
+
+
+def workload_buffers(name, S, **kw):
+    from dav1d_b200 import frame
+    if FRAME_WORKLOADS[name].get("intra"):
+        return frame.FrameBuffers(S, run_cdef=False, run_lr=False, **kw)
+    return frame.FrameBuffers(S, **kw)
 
 
 # ------------------------------------------------------------------------------ reference arm / cpu baseline
@@ -174,7 +194,8 @@ def cpu_frames(S, n_threads, reps, use_ref=True):
     else:
         import test_frame
         fn, kind = None, "port"
-    fbs = [frame.FrameBuffers(S, lib=object(), alloc=frame.NumpyAlloc()) for _ in range(n_threads)] if fn else None
+    wl = next((k for k, v in FRAME_WORKLOADS.items() if v.get("intra")), None) if S.get("intra_tx") is not None else "4k8_inter"
+    fbs = [workload_buffers(wl, S, lib=object(), alloc=frame.NumpyAlloc()) for _ in range(n_threads)] if fn else None
 
     def work(i):
         for _ in range(reps):
@@ -226,7 +247,7 @@ def run_reference(args):
             vals.append(v); dts.append(dt)
         val = float(np.mean(vals)); ms = 1e3 * float(np.mean(dts))
         wl = "%s: %s; reference arm: %d frames per step, one per host thread" % (args.workload, FRAME_WORKLOADS[args.workload]["desc"], nthr)
-        sample = "%d whole 4K frames per step (one per thread, %d of %d cores), dav1d C path HAVE_ASM=0" % (nthr, nthr, ncores)
+        sample = "%d whole frames per step (one per thread, %d of %d cores), dav1d C path HAVE_ASM=0" % (nthr, nthr, ncores)
         ncores = nthr
     line = {"impl": "reference", "metric": "Mpixels/s", "value": val, "unit": "Mpixels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -256,13 +277,13 @@ def run_ours_frame(args):
     torch, dist, world, rank, local = dist_setup()
     from dav1d_b200 import synth, frame, get_lib
     lib = get_lib()
-    nsets = 3
+    nsets = 24 if FRAME_WORKLOADS[args.workload].get("intra") else 3
     fbs, Ss = [], []
     for k in range(nsets):
         S = make_workload_frame(args.workload, 1 + rank * 16 + k)
         Ss.append(S)
-        fbs.append(frame.FrameBuffers(S))
-    px_per_step = W4K * H4K
+        fbs.append(workload_buffers(args.workload, S))
+    px_per_step = FRAME_WORKLOADS[args.workload]["W"] * FRAME_WORKLOADS[args.workload]["H"]
     gather = None
     if world > 1:   # reference-picture exchange buffer: every rank's restored picture
         gather = torch.empty(world * Ss[0]["pic"].nbytes, dtype=torch.uint8, device="cuda")
@@ -334,7 +355,7 @@ def run_ours_frame(args):
         alg = frame_algorithmic_bytes(Ss[0])
         stages = {}
         for name, ms in stage_ms.items():
-            key = {"pred": "mc", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg"}[name]
+            key = {"pred": "mc", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg", "intra": "intra"}[name]
             stages[name] = {"ms": ms, "algorithmic_bytes": alg[key], "GBps": alg[key] / (ms * 1e-3) / 1e9 if ms > 0 else None}
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         traffic = None
@@ -342,24 +363,26 @@ def run_ours_frame(args):
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(dom)
         achieved = stages[dom]["GBps"]
-        total_alg = sum(alg[k] for k in ("mc", "comp", "itx", "deblock", "cdef", "lr", "fg"))
-        recon_ms = stage_ms["pred"] + stage_ms["comp"] + stage_ms["itx"]
+        run_keys = {"pred": "mc", "comp": "comp", "itx": "itx", "intra": "intra", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg"}
+        total_alg = sum(alg[run_keys[k]] for k in stage_ms)
+        recon_ms = sum(v for k, v in stage_ms.items() if k in ("pred", "comp", "itx", "intra"))
         post_ms = sum(v for k, v in stage_ms.items() if k in ("deblock", "cdef", "lr", "fg"))
         split = {"recon": {"ms": recon_ms, "Mpixels/s": px_per_step / (recon_ms * 1e-3) / 1e6,
-                           "GBps": (alg["mc"] + alg["comp"] + alg["itx"]) / (recon_ms * 1e-3) / 1e9},
+                           "GBps": sum(alg[run_keys[k]] for k in stage_ms if k in ("pred", "comp", "itx", "intra")) / (recon_ms * 1e-3) / 1e9},
                  "postfilter": {"ms": post_ms, "Mpixels/s": px_per_step / (post_ms * 1e-3) / 1e6,
-                                "GBps": (alg["deblock"] + alg["cdef"] + alg["lr"] + alg["fg"]) / (post_ms * 1e-3) / 1e9}}
+                                "GBps": sum(alg[run_keys[k]] for k in stage_ms if k in ("deblock", "cdef", "lr", "fg")) / (post_ms * 1e-3) / 1e9}}
         nthr = min(os.cpu_count() or 1, 32)
         v, dt, kind = cpu_frames(Ss[0], nthr, 1)
         cpu = {"value": v, "unit": "Mpixels/s", "cores": nthr, "kind": kind,
-               "sample": "%d whole 4K frames of this workload, one per thread (frame threading), dav1d C path HAVE_ASM=0 (no nasm in image), %.1f s" % (nthr, dt)}
+               "sample": "%d whole frames of this workload, one per thread (frame threading), dav1d C path HAVE_ASM=0 (no nasm in image), %.1f s" % (nthr, dt)}
         line = {"metric": "Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": FRAME_WORKLOADS[args.workload]["dtype"], "data": "synthetic",
                 "config": {"workload": "%s: %s" % (args.workload, FRAME_WORKLOADS[args.workload]["desc"]),
-                           "l2": "3 rotating frame sets (~%d MB) > 126 MB L2" % (3 * (5 * Ss[0]["pic"].nbytes + Ss[0]["coefs"].nbytes) // 1000000),
+                           "l2": "%d rotating frame sets (~%d MB) > 126 MB L2" % (nsets, nsets * ((2 + len(Ss[0]["refs"]) + fbs[0].job.run_cdef + fbs[0].job.run_lr + fbs[0].job.run_fg) * Ss[0]["pic"].nbytes + Ss[0]["coefs"].nbytes) // 1000000),
                            "records": {"pred_blocks": int(len(Ss[0]["pred"])), "compound": int(len(Ss[0]["comp"]) + len(Ss[0]["comp2"])),
-                                       "tx_blocks": int(sum(len(a) for a in Ss[0]["itx"].values())), "coefs": int(len(Ss[0]["coefs"]))},
+                                       "tx_blocks": int(sum(len(a) for a in Ss[0]["itx"].values())), "coefs": int(len(Ss[0]["coefs"])),
+                                       "intra_tx_blocks": int(len(Ss[0].get("intra_tx", []))), "intra_waves": int(Ss[0].get("intra_waves", 0))},
                            "exchange": "all_gather of each rank's restored picture per step (NCCL)" if world > 1 else "none"},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -378,29 +401,40 @@ def run_ours_frame(args):
 def stage_times(torch, lib, fbs, nsets, reps=6):
     """average device time of each stage of the frame job (events on the launching stream)"""
     from dav1d_b200 import _lib
-    names = ["pred", "comp", "itx", "deblock", "cdef", "lr"] + (["fg"] if fbs[0].job.run_fg else [])
-    acc = {n: 0.0 for n in names}
+    j0 = fbs[0].job
+    stages = []
+    if j0.n_pred:
+        stages.append(("pred", lambda j, bd, st: lib.b200_mc_batch(bd, C.byref(j.mc), j.d_pred, j.n_pred, st)))
+    if j0.n_comp or j0.n_comp2:
+        stages.append(("comp", lambda j, bd, st: (lib.b200_mc_comp_batch(bd, C.byref(j.mc), j.d_comp, j.n_comp, st),
+                                                  lib.b200_mc_comp_batch(bd, C.byref(j.mc), j.d_comp2, j.n_comp2, st))))
+    if any(j0.n_itx[t] for t in range(19)):
+        stages.append(("itx", lambda j, bd, st: lib.b200_itx_add_frame(bd, j.d_itx, j.n_itx, j.d_coef, j.mc.dst, j.itx_stride, 0, st)))
+    if j0.n_intra:
+        stages.append(("intra", lambda j, bd, st: lib.b200_intra_frame(bd, C.byref(j.intra), j.d_intra, j.n_intra, st)))
+    if j0.run_lf:
+        stages.append(("deblock", lambda j, bd, st: lib.b200_lf_frame(bd, C.byref(j.lf), st)))
+    if j0.run_cdef:
+        stages.append(("cdef", lambda j, bd, st: lib.b200_cdef_frame(bd, C.byref(j.cdef), st)))
+    if j0.run_lr:
+        stages.append(("lr", lambda j, bd, st: lib.b200_lr_frame(bd, C.byref(j.lr), st)))
+    if j0.run_fg:   # apply only: the LUT preparation overlaps reconstruction on the side stream in the real job
+        stages.append(("fg", lambda j, bd, st: lib.b200_fg_apply(bd, C.byref(j.fg), st)))
+    acc = {n: 0.0 for n, _ in stages}
     st = torch.cuda.current_stream().cuda_stream
     for r in range(reps):
         fb = fbs[r % nsets]
         j = fb.job
-        bd = j.bitdepth_max
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)]
         evs[0].record()
-        lib.b200_mc_batch(bd, C.byref(j.mc), j.d_pred, j.n_pred, st); evs[1].record()
-        lib.b200_mc_comp_batch(bd, C.byref(j.mc), j.d_comp, j.n_comp, st)
-        lib.b200_mc_comp_batch(bd, C.byref(j.mc), j.d_comp2, j.n_comp2, st); evs[2].record()
-        lib.b200_itx_add_frame(bd, j.d_itx, j.n_itx, j.d_coef, j.mc.dst, j.itx_stride, 0, st); evs[3].record()
-        lib.b200_lf_frame(bd, C.byref(j.lf), st); evs[4].record()
-        lib.b200_cdef_frame(bd, C.byref(j.cdef), st); evs[5].record()
-        lib.b200_lr_frame(bd, C.byref(j.lr), st); evs[6].record()
-        if j.run_fg:   # apply only: the LUT preparation overlaps reconstruction on the side stream in the real job
-            lib.b200_fg_apply(bd, C.byref(j.fg), st); evs[7].record()
+        for k, (_, fn) in enumerate(stages):
+            fn(j, j.bitdepth_max, st)
+            evs[k + 1].record()
         torch.cuda.synchronize()
         if r >= 1:
-            for k, n in enumerate(names):
+            for k, (n, _) in enumerate(stages):
                 acc[n] += evs[k].elapsed_time(evs[k + 1])
-    return {n: acc[n] / (reps - 1) for n in names}
+    return {n: acc[n] / (reps - 1) for n in acc}
 
 
 def run_ours_itx(args):
@@ -511,7 +545,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k10_full", "itx8x8"])
+    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k10_full", "1080p8_intra", "itx8x8"])
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 5)      # bounded: each step is tens of whole 4K frames on the CPU

@@ -96,6 +96,21 @@ class FgFrame(C.Structure):
                 ("data", FilmGrainData), ("scratch", C.c_void_p)]
 
 
+class IntraTx(C.Structure):
+    """struct B200IntraTx (40 bytes)"""
+    _fields_ = [("dst_off", C.c_uint32), ("coef_off", C.c_uint32), ("luma_off", C.c_uint32), ("eob", C.c_int16),
+                ("x4", C.c_uint16), ("y4", C.c_uint16), ("xend4", C.c_uint16), ("yend4", C.c_uint16),
+                ("max_w", C.c_int16), ("max_h", C.c_int16), ("angle_flags", C.c_uint16), ("tx", C.c_uint8),
+                ("txtp", C.c_uint8), ("mode", C.c_uint8), ("angle", C.c_int8), ("plane", C.c_uint8), ("flags", C.c_uint8),
+                ("cfl_alpha", C.c_int8), ("cfl_w_pad", C.c_uint8), ("cfl_h_pad", C.c_uint8), ("pad", C.c_uint8 * 3)]
+
+
+class IntraFrame(C.Structure):
+    _fields_ = [("pic", C.c_void_p), ("stride", C.c_int32 * 3), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32),
+                ("w4", C.c_int32 * 3), ("h4", C.c_int32 * 3), ("d_coef", C.c_void_p), ("zero_coefs", C.c_int32),
+                ("pad", C.c_int32), ("scratch", C.c_void_p)]
+
+
 class FrameJob(C.Structure):
     """struct B200FrameJob"""
     _fields_ = [("bitdepth_max", C.c_int32), ("zero_coefs", C.c_int32), ("mc", McFrame),
@@ -108,6 +123,7 @@ class FrameJob(C.Structure):
                 ("d_coef", C.c_void_p), ("itx_stride", C.c_int32 * 3),
                 ("run_lf", C.c_int32), ("run_cdef", C.c_int32), ("run_lr", C.c_int32),
                 ("lf", LfFrame), ("cdef", CdefFrame), ("lr", LrFrame),
+                ("d_intra", C.c_void_p), ("n_intra", C.c_int32), ("pad6", C.c_int32), ("intra", IntraFrame),
                 ("run_fg", C.c_int32), ("pad5", C.c_int32), ("fg", FgFrame)]
 
 
@@ -164,6 +180,9 @@ _SIGS = {
                                  C.c_void_p, C.c_int, C.c_int]),
     "b200_loop_restoration_dsp_init_8bpc": (None, [C.c_void_p, C.c_int]),
     "b200_loop_restoration_dsp_init_16bpc": (None, [C.c_void_p, C.c_int]),
+    # ---- intra frame
+    "b200_intra_scratch_bytes": (C.c_size_t, [C.c_void_p]),
+    "b200_intra_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     # ---- filmgrain
     "b200_fg_apply_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "b200_fg_prep": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
@@ -245,4 +264,4 @@ class Av1Restoration(C.Structure):
 
 
 ABI_STRUCTS = [McFrame, McBlock, CompBlock, BlendBlock, WarpBlock, ItxBlock, LfFrame, CdefFrame, LrFrame, FrameJob,
-               Av1Filter, Av1Restoration, FgFrame, FilmGrainData]
+               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame]

@@ -52,6 +52,7 @@ int b200_frame_run(const B200FrameJob *j, void *stream)
     if ((r = b200_itx_add_frame(bd, (const void *const *)j->d_itx, j->n_itx, j->d_coef, j->mc.dst, j->itx_stride,
                                 j->zero_coefs, stream)))
         return r;
+    if (j->n_intra > 0 && (r = b200_intra_frame(bd, &j->intra, j->d_intra, j->n_intra, stream))) return r;
     if (j->run_lf && (r = b200_lf_frame(bd, &j->lf, stream))) return r;
     if (j->run_cdef && (r = b200_cdef_frame(bd, &j->cdef, stream))) return r;
     if (j->run_lr && (r = b200_lr_frame(bd, &j->lr, stream))) return r;
@@ -73,6 +74,7 @@ int b200_struct_size(int which)
     case 6: return sizeof(B200LfFrame); case 7: return sizeof(B200CdefFrame); case 8: return sizeof(B200LrFrame);
     case 9: return sizeof(B200FrameJob); case 10: return sizeof(B200Av1Filter); case 11: return sizeof(B200Av1Restoration);
     case 12: return sizeof(B200FgFrame); case 13: return sizeof(B200FilmGrainData);
+    case 14: return sizeof(B200IntraTx); case 15: return sizeof(B200IntraFrame);
     }
     return -1;
 }

@@ -1,0 +1,245 @@
+// Intra reconstruction of a whole frame (dav1d_recon_b_intra, reference src/recon_tmpl.c:1176-1555, with
+// dav1d_prepare_intra_edges, reference src/ipred_prepare_tmpl.c:75-204, run on the device).
+//
+// Intra prediction reads the *reconstructed* pixels left of / above the block, so transform blocks form a
+// dependency graph (left, top, top-left, and — when the bitstream order made them available — top-right and
+// bottom-left neighbours; CFL chroma additionally needs its luma block). The kernel is a dataflow machine:
+//   * a persistent grid; each CTA repeatedly takes the next record (atomic ticket). Records are in a
+//     topological order, so everything a record waits for has already been taken by a running CTA;
+//   * the CTA polls the per-4x4 "done" map of the cells its edge pixels come from, then gathers the edge array
+//     into shared memory with L1-bypassing loads (the rules of dav1d_prepare_intra_edges: replication past the
+//     tile end, default values without neighbours, Z2 corner smoothing);
+//   * predicts (ipred_body.cuh), adds the inverse transform (itx_body.cuh), fences, publishes its cells.
+// Integer, bit-exact with the reference C path.
+#include "ipred_body.cuh"
+#include "itx_body.cuh"
+#include "launch_count.h"
+
+namespace b200 {
+
+// scratch layout: [ticket counter: 256 B][done maps of the three planes, bytes][cfl ac: per CTA 32*32 int16]
+struct IntraScratch {
+    size_t done_off[3], ac_off, total;
+};
+static inline IntraScratch intra_scratch_layout(const B200IntraFrame *f, int grid)
+{
+    IntraScratch L;
+    size_t o = 256;
+    for (int p = 0; p < 3; p++) { L.done_off[p] = o; o += ((size_t)f->w4[p] * f->h4[p] + 255) & ~(size_t)255; }
+    L.ac_off = o; o += (size_t)grid * 32 * 32 * sizeof(int16_t);
+    L.total = o;
+    return L;
+}
+constexpr int kIntraGrid = 148 * 4;
+
+struct IntraParams {
+    B200IntraFrame f;
+    const B200IntraTx *tx;
+    int n;
+    int *ticket;
+    uint8_t *done[3];
+    int16_t *ac;
+};
+
+B200_DEV int ld_cell(const uint8_t *p) { return *(const volatile uint8_t *)p; }
+
+template <bool HBD> B200_DEV int ld_px(const typename Bd<HBD>::pixel *p) {
+#ifdef B200_EMU
+    return *p;
+#else
+    return __ldcg(p);          // L2 only: another SM wrote it, this SM's L1 may hold a stale line
+#endif
+}
+
+template <bool HBD>
+__global__ void __launch_bounds__(kIpT) intra_frame_kernel(const IntraParams P, const int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    typedef typename Bd<HBD>::coef coef;
+    __shared__ IpShared S;
+    __shared__ int s_itx[ItxGeom<64, 64>::NB * ItxGeom<64, 64>::SLOT];
+    __shared__ B200ItxBlock s_blk;
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x;
+    const B200IntraFrame &f = P.f;
+    const int bitdepth = 32 - __clz(bdmax);
+    int *const tl = S.edge + 128;
+    int16_t *const ac = P.ac + (size_t)blockIdx.x * 32 * 32;
+
+    for (;;) {
+        if (tid == 0) s_ticket = atomicAdd(P.ticket, 1);
+        __syncthreads();
+        const int ti = s_ticket;
+        if (ti >= P.n) break;
+        const B200IntraTx r = P.tx[ti];
+        const int pl = r.plane, st = f.stride[pl];
+        const int tw = c_tx_w4[r.tx], th = c_tx_h4[r.tx];              // 4-sample units
+        const int w = tw * 4, h = th * 4;
+        const int x = r.x4, y = r.y4, xe = r.xend4, ye = r.yend4;
+        const bool have_left = r.flags & B200_INTRA_HAVE_LEFT, have_top = r.flags & B200_INTRA_HAVE_TOP;
+        const bool have_tr = have_top && x + tw < xe && (r.flags & B200_INTRA_TOP_HAS_RIGHT);
+        const bool have_bl = have_left && y + th < ye && (r.flags & B200_INTRA_LEFT_HAS_BOTTOM);
+        const bool is_cfl = r.mode == B200_INTRA_MODE_CFL && r.cfl_alpha != 0;
+        const uint8_t *const dmap = P.done[pl];
+        const int mw = f.w4[pl];
+
+        // ---- wait for the neighbours whose pixels the edge array reads
+        {
+            const int n_left = have_left ? imin(th, ye - y) + (have_bl ? imin(th, ye - y - th) : 0) : 0;
+            const int n_top = have_top ? imin(tw, xe - x) + (have_tr ? imin(tw, xe - x - tw) : 0) : 0;
+            const int n_tl = have_left && have_top;
+            int n_luma = 0, lw4 = 0, lx4 = 0, ly4 = 0;
+            if (is_cfl) {
+                lx4 = x << f.ss_hor; ly4 = y << f.ss_ver;
+                lw4 = imin((tw - r.cfl_w_pad) << f.ss_hor, f.w4[0] - lx4);
+                const int lh4 = imin((th - r.cfl_h_pad) << f.ss_ver, f.h4[0] - ly4);
+                n_luma = lw4 * lh4;
+            }
+            for (int c = tid; c < n_left + n_top + n_tl + n_luma; c += kIpT) {
+                const uint8_t *cell;
+                if (c < n_left) cell = dmap + (y + c) * mw + x - 1;
+                else if (c < n_left + n_top) cell = dmap + (y - 1) * mw + x + (c - n_left);
+                else if (c < n_left + n_top + n_tl) cell = dmap + (y - 1) * mw + x - 1;
+                else { const int k = c - n_left - n_top - n_tl; cell = P.done[0] + (ly4 + k / lw4) * f.w4[0] + lx4 + k % lw4; }
+                while (!ld_cell(cell)) __nanosleep(64);
+            }
+            __threadfence();
+            __syncthreads();
+        }
+
+        pixel *const dst = (pixel *)f.pic + r.dst_off;
+        // ---- dav1d_prepare_intra_edges: mode conversion (:97-120)
+        int mode = r.mode, angle = r.angle;
+        if (mode == B200_INTRA_MODE_CFL) mode = 0;                             // DC_PRED (:1446, :1373)
+        if (mode >= 1 && mode <= 8) {                                          // VERT_PRED .. VERT_LEFT_PRED
+            const int base = mode == 1 ? 90 : mode == 2 ? 180 : mode == 3 ? 45 : mode == 4 ? 135 : mode == 5 ? 113
+                           : mode == 6 ? 157 : mode == 7 ? 203 : 67;
+            angle = base + 3 * angle;
+            if (angle <= 90) mode = angle < 90 && have_top ? B200_Z1_PRED : B200_VERT_PRED;
+            else if (angle < 180) mode = B200_Z2_PRED;
+            else mode = angle > 180 && have_left ? B200_Z3_PRED : B200_HOR_PRED;
+        } else if (mode == 0) {
+            mode = have_left ? (have_top ? B200_DC_PRED : B200_LEFT_DC_PRED) : (have_top ? B200_TOP_DC_PRED : B200_DC_128_PRED);
+        } else if (mode == 12) {
+            mode = have_left ? (have_top ? B200_PAETH_PRED : B200_HOR_PRED) : (have_top ? B200_VERT_PRED : B200_DC_128_PRED);
+        }
+        // ---- edge gather (every part is filled; the predictors read only what the reference fills)
+        {
+            const pixel *const top = dst - st;
+            const int half = (1 << bitdepth) >> 1;
+            const int lpx = imin(h, (ye - y) << 2), lpx2 = imin(h, (ye - y - th) << 2);
+            const int tpx = imin(w, (xe - x) << 2), tpx2 = imin(w, (xe - x - tw) << 2);
+            const int left_fill = have_top ? ld_px<HBD>(top) : half + 1;
+            const int top_fill = have_left ? ld_px<HBD>(dst - 1) : half - 1;
+            for (int i = tid; i < 2 * h; i += kIpT) {                           // tl[-(1+i)]: left, then bottom-left
+                int v;
+                if (i < h) v = have_left ? ld_px<HBD>(dst + (ptrdiff_t)imin(i, lpx - 1) * st - 1) : left_fill;
+                else if (have_bl) v = ld_px<HBD>(dst + (ptrdiff_t)(h + imin(i - h, lpx2 - 1)) * st - 1);
+                else v = have_left ? ld_px<HBD>(dst + (ptrdiff_t)(lpx - 1) * st - 1) : left_fill;
+                tl[-(1 + i)] = v;
+            }
+            for (int i = tid; i < 2 * w; i += kIpT) {                           // tl[1+i]: top, then top-right
+                int v;
+                if (i < w) v = have_top ? ld_px<HBD>(top + imin(i, tpx - 1)) : top_fill;
+                else if (have_tr) v = ld_px<HBD>(top + w + imin(i - w, tpx2 - 1));
+                else v = have_top ? ld_px<HBD>(top + tpx - 1) : top_fill;
+                tl[1 + i] = v;
+            }
+            if (tid == 0)
+                tl[0] = have_left ? (have_top ? ld_px<HBD>(top - 1) : ld_px<HBD>(dst - 1)) : (have_top ? ld_px<HBD>(top) : half);
+            __syncthreads();
+            if (tid == 0 && mode == B200_Z2_PRED && tw + th >= 6 && (r.angle_flags & 1024))
+                tl[0] = ((tl[-1] + tl[1]) * 5 + tl[0] * 6 + 8) >> 4;
+            __syncthreads();
+        }
+
+        // ---- predict
+        if (is_cfl) {
+            const pixel *ypx = (const pixel *)f.pic + r.luma_off;
+            // cfl_ac reads pixels another SM may have written: stage through ld_px by way of the body's plain loads
+            // is not possible, so the (tiny) ac computation is done here with L2 loads.
+            {
+                const int ssh = f.ss_hor, ssv = f.ss_ver, ys = f.stride[0];
+                int part = 0;
+                for (int i = tid; i < w * h; i += kIpT) {
+                    const int yy = i / w, xx = i - yy * w;
+                    const int sy = imin(yy, h - 4 * r.cfl_h_pad - 1), sx = imin(xx, w - 4 * r.cfl_w_pad - 1);
+                    const pixel *p = ypx + (ptrdiff_t)(sy << ssv) * ys + (sx << ssh);
+                    int s = ld_px<HBD>(p);
+                    if (ssh) s += ld_px<HBD>(p + 1);
+                    if (ssv) { s += ld_px<HBD>(p + ys); if (ssh) s += ld_px<HBD>(p + ys + 1); }
+                    s <<= 1 + !ssv + !ssh;
+                    ac[i] = (int16_t)s;
+                    part += s;
+                }
+                S.tile[tid] = part;
+                __syncthreads();
+                if (tid == 0) {
+                    const int log2sz = (__ffs(w) - 1) + (__ffs(h) - 1);
+                    int sum = (1 << log2sz) >> 1;
+                    for (int i = 0; i < kIpT; i++) sum += S.tile[i];
+                    S.dc = sum >> log2sz;
+                }
+                __syncthreads();
+                const int dc = S.dc;
+                for (int i = tid; i < w * h; i += kIpT) ac[i] = (int16_t)(ac[i] - dc);
+                __syncthreads();
+            }
+            ipred_cfl_pred_body<HBD>(S, dst, st, w, h, mode, r.cfl_alpha, ac, bdmax);
+        } else {
+            const int a = (mode == B200_FILTER_PRED ? r.angle : angle) | r.angle_flags;
+            ipred_pred_body<HBD>(S, dst, st, w, h, mode, a, r.max_w, r.max_h, bdmax);
+        }
+        __syncthreads();
+
+        // ---- residual
+        if (r.eob >= 0) {
+            if (tid == 0) { s_blk.dst_off = r.dst_off; s_blk.coef_off = r.coef_off; s_blk.eob = r.eob; s_blk.txtp = r.txtp; s_blk.plane = (uint8_t)pl; }
+            __syncthreads();
+            switch (r.tx) {
+#define X(TX, W, H, SH) case TX: itx_add_body<W, H, TX, SH, HBD>(0, s_itx, &s_blk, 1, (coef *)f.d_coef, (pixel *)f.pic, f.stride[0], f.stride[1], f.stride[2], bdmax, f.zero_coefs); break;
+            B200_ITX_SIZES(X)
+#undef X
+            }
+        }
+        // ---- publish
+        __threadfence();
+        __syncthreads();
+        {
+            uint8_t *const dm = P.done[pl];
+            const int cw = imin(tw, mw - x), chh = imin(th, f.h4[pl] - y);
+            for (int c = tid; c < cw * chh; c += kIpT) *(volatile uint8_t *)(dm + (y + c / cw) * mw + x + c % cw) = 1;
+        }
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+size_t b200_intra_scratch_bytes(const B200IntraFrame *f) { return intra_scratch_layout(f, kIntraGrid).total; }
+
+int b200_intra_frame(int bdmax, const B200IntraFrame *f, const B200IntraTx *d_tx, int n, void *stream)
+{
+    if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_intra_frame: bad bitdepth_max"); return -2; }
+    if (n <= 0) return 0;
+    if (!f->scratch) { b200_set_error("b200_intra_frame: no scratch"); return -2; }
+    const IntraScratch L = intra_scratch_layout(f, kIntraGrid);
+    IntraParams P;
+    P.f = *f; P.tx = d_tx; P.n = n;
+    uint8_t *base = (uint8_t *)f->scratch;
+    P.ticket = (int *)base;
+    for (int p = 0; p < 3; p++) P.done[p] = base + L.done_off[p];
+    P.ac = (int16_t *)(base + L.ac_off);
+    B200_CUDA_OK(cudaMemsetAsync(base, 0, L.ac_off, (cudaStream_t)stream));     // ticket + done maps
+    const int grid = n < kIntraGrid ? n : kIntraGrid;
+    if (bdmax > 255) { auto k = intra_frame_kernel<true>; B200_LAUNCH(k, dim3(grid), dim3(kIpT), 0, (cudaStream_t)stream, P, bdmax); }
+    else { auto k = intra_frame_kernel<false>; B200_LAUNCH(k, dim3(grid), dim3(kIpT), 0, (cudaStream_t)stream, P, bdmax); }
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -11,160 +11,10 @@
 //     lanes touch consecutive pixels of a row (coalesced).
 // Integer only, bit-exact with the reference C path for every input (including coefficient
 // garbage: rows beyond the eob-derived bound are treated as zero exactly like the reference).
-#include "itx_1d.cuh"
-#define B200_TBL __constant__
-#include "tables_gen.h"
-#include "../../include/b200av1.h"
+#include "itx_body.cuh"
 #include "launch_count.h"
 
 namespace b200 {
-
-// per TxfmType slot: 1-D type of the row pass (first) and of the column pass (second).
-// Slot X_Y = X vertical, Y horizontal (reference src/levels.h:81-83, src/itx_tmpl.c:232-262).
-__constant__ uint8_t c_tx_first[16]  = { 0, 0, 1, 1, 0, 2, 2, 2, 1, 3, 3, 0, 3, 1, 3, 2 };
-__constant__ uint8_t c_tx_second[16] = { 0, 1, 0, 1, 2, 0, 2, 1, 2, 3, 0, 3, 1, 3, 2, 3 };
-
-template <int W, int H> struct ItxGeom {
-    static constexpr int SW = W < 32 ? W : 32;
-    static constexpr int SH = H < 32 ? H : 32;
-    static constexpr int L = SH > SW ? SH : SW;          // lanes per block
-    static constexpr int NB = 32 / L;                     // blocks per warp
-    static constexpr int P = W + 1;                       // tile pitch (words)
-    static constexpr int SLOT = SH * P;                   // words per block tile
-    static constexpr int LW = W == 4 ? 0 : W == 8 ? 1 : W == 16 ? 2 : W == 32 ? 3 : 4;
-    static constexpr bool RECT2 = (W * 2 == H) || (H * 2 == W);
-};
-
-constexpr int kItxWarps = 4;
-
-// the work of one CTA (`cta` = its index among the CTAs of this transform size); smem: kItxWarps * NB * SLOT words
-template <int W, int H, int TX, int SHIFT, bool HBD>
-B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *__restrict__ blocks, int n_blocks,
-                           typename Bd<HBD>::coef *__restrict__ coefs, typename Bd<HBD>::pixel *__restrict__ pic,
-                           int stride0, int stride1, int stride2, int bitdepth_max, int zero_coefs)
-{
-    typedef ItxGeom<W, H> G;
-    typedef typename Bd<HBD>::pixel pixel;
-    typedef typename Bd<HBD>::coef coef;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = lane / G::L, li = lane % G::L;
-    const int bi = (cta * kItxWarps + warp) * G::NB + grp;
-    const bool valid = bi < n_blocks;
-    int *const t = smem + (warp * G::NB + grp) * G::SLOT;
-
-    B200ItxBlock blk;
-    blk.dst_off = 0; blk.coef_off = 0; blk.eob = 0; blk.txtp = 0; blk.plane = 0;
-    if (valid) blk = blocks[bi];
-    const int txtp = blk.txtp;
-    const int eob = blk.eob;
-    coef *const cf = coefs + blk.coef_off;
-    const int stride = blk.plane == 0 ? stride0 : blk.plane == 1 ? stride1 : stride2;
-    pixel *const dst = pic + blk.dst_off;
-
-    constexpr int rnd = (1 << SHIFT) >> 1;
-    const bool is_wht = (W == 4 && H == 4) && txtp == B200_WHT_WHT;
-    const bool dc_only = !is_wht && eob < (txtp == 0 ? 1 : 0);
-
-    int row_lo, col_lo;
-    if (HBD) {
-        row_lo = (int)((unsigned)~bitdepth_max << 7);
-        col_lo = (int)((unsigned)~bitdepth_max << 5);
-    } else {
-        row_lo = col_lo = -32768;
-    }
-    const int row_hi = ~row_lo, col_hi = ~col_lo;
-
-    const int t_first = is_wht ? 0 : c_tx_first[txtp & 15];
-    const int t_second = is_wht ? 0 : c_tx_second[txtp & 15];
-
-    // ---------------- pass 1: one lane per coefficient row ----------------
-    if (valid && !dc_only && li < G::SH) {
-        const int y = li;
-        int c[W];
-        if (is_wht) {
-            if constexpr (W == 4 && H == 4) {
-#pragma unroll
-                for (int x = 0; x < 4; x++) c[x] = (int)cf[y + x * 4] >> 2;
-                iwht4(c);
-#pragma unroll
-                for (int x = 0; x < 4; x++) t[y * G::P + x] = c[x];
-            }
-        } else {
-            // rows past this bound are zero by definition (reference src/itx_tmpl.c:86-105)
-            int last;
-            if (t_second == TX1D_IDENTITY && t_first != TX1D_IDENTITY) last = imin(G::SH - 1, eob);
-            else if (t_first == TX1D_IDENTITY && t_second != TX1D_IDENTITY) last = eob >> (G::LW + 2);
-            else last = b200_lnz_col[b200_lnz_col_off[TX] + eob];
-            if (y <= last) {
-#pragma unroll
-                for (int x = 0; x < W; x++) {
-                    if (x < G::SW) {
-                        const int v = (int)cf[y + x * G::SH];
-                        c[x] = G::RECT2 ? (int)((unsigned)v * 181u + 128u) >> 8 : v;
-                    } else {
-                        c[x] = 0;
-                    }
-                }
-                tx1d_apply<W>(c, t_first, row_lo, row_hi);
-#pragma unroll
-                for (int x = 0; x < W; x++)
-                    t[y * G::P + x] = iclip((c[x] + rnd) >> SHIFT, col_lo, col_hi);
-            } else {
-#pragma unroll
-                for (int x = 0; x < W; x++) t[y * G::P + x] = 0;
-            }
-        }
-        if (zero_coefs) {
-#pragma unroll
-            for (int x = 0; x < G::SW; x++) cf[y + x * G::SH] = 0;
-        }
-    }
-    int dc = 0;
-    if (valid && dc_only) dc = (int)cf[0];
-    __syncwarp();
-    if (valid && dc_only && zero_coefs && li == 0) cf[0] = 0;
-
-    // ---------------- pass 2: one lane per picture column ----------------
-    if (valid) {
-        if (dc_only) {
-            if (G::RECT2) dc = (dc * 181 + 128) >> 8;
-            dc = (dc * 181 + 128) >> 8;
-            dc = (dc + rnd) >> SHIFT;
-            dc = (dc * 181 + 128 + 2048) >> 12;
-            for (int x = li; x < W; x += G::L) {
-#pragma unroll 4
-                for (int y = 0; y < H; y++) {
-                    pixel *p = dst + (ptrdiff_t)y * stride + x;
-                    *p = (pixel)iclip((int)*p + dc, 0, bitdepth_max);
-                }
-            }
-        } else {
-            for (int x = li; x < W; x += G::L) {
-                int c[H];
-#pragma unroll
-                for (int y = 0; y < H; y++) c[y] = y < G::SH ? t[y * G::P + x] : 0;
-                if (is_wht) {
-                    if constexpr (W == 4 && H == 4) {
-                        iwht4(c);
-#pragma unroll
-                        for (int y = 0; y < 4; y++) {
-                            pixel *p = dst + (ptrdiff_t)y * stride + x;
-                            *p = (pixel)iclip((int)*p + c[y], 0, bitdepth_max);
-                        }
-                    }
-                } else {
-                    tx1d_apply<H>(c, t_second, col_lo, col_hi);
-#pragma unroll
-                    for (int y = 0; y < H; y++) {
-                        pixel *p = dst + (ptrdiff_t)y * stride + x;
-                        *p = (pixel)iclip((int)*p + ((c[y] + 8) >> 4), 0, bitdepth_max);
-                    }
-                }
-            }
-        }
-    }
-}
 
 template <int W, int H, int TX, int SHIFT, bool HBD>
 __global__ void __launch_bounds__(kItxWarps * 32)
@@ -178,13 +28,7 @@ itx_add_kernel(const B200ItxBlock *__restrict__ blocks, int n_blocks,
                                        bitdepth_max, zero_coefs);
 }
 
-// ---- all transform sizes of a frame in ONE launch: CTAs are dealt to the sizes largest-first -------------
-// tx -> (w, h, inter-pass shift): reference src/itx_tmpl.c:160-178
-#define B200_ITX_SIZES(X) \
-    X(4, 64, 64, 2) X(11, 32, 64, 1) X(12, 64, 32, 1) X(17, 16, 64, 2) X(18, 64, 16, 2) X(3, 32, 32, 2) X(9, 16, 32, 1) \
-    X(10, 32, 16, 1) X(15, 8, 32, 2) X(16, 32, 8, 2) X(2, 16, 16, 2) X(7, 8, 16, 1) X(8, 16, 8, 1) X(13, 4, 16, 1) \
-    X(14, 16, 4, 1) X(1, 8, 8, 1) X(5, 4, 8, 0) X(6, 8, 4, 0) X(0, 4, 4, 0)
-
+// ---- all transform sizes of a frame in two launches (one per register class), CTAs dealt largest size first ---
 struct ItxGroups {
     const B200ItxBlock *blocks[B200_N_RECT_TX_SIZES];
     int n[B200_N_RECT_TX_SIZES];

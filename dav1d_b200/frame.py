@@ -119,6 +119,19 @@ class FrameBuffers:
         j.d_coef = up("coef", S["coefs"]); self.uploads.append(("coef", S["coefs"]))
         if len(S["mask"]) > 1:
             self.uploads.append(("mask", S["mask"]))
+        n_intra = 0
+        if S.get("intra_tx") is not None and len(S["intra_tx"]):
+            it = j.intra
+            it.pic, it.d_coef, it.zero_coefs = p0, j.d_coef, 0
+            it.ss_hor, it.ss_ver = S["ss_hor"], S["ss_ver"]
+            for p in range(3):
+                it.stride[p] = S["stride"][p]
+                it.w4[p] = S["w4"] >> ssh[p]; it.h4[p] = S["h4"] >> ssv[p]
+            nb = self.lib.b200_intra_scratch_bytes(C.byref(it)) if hasattr(self.lib, "b200_intra_scratch_bytes") else 1 << 22
+            it.scratch = zeros("intra_scratch", nb)
+            j.d_intra = up("intra_tx", S["intra_tx"]); j.n_intra = len(S["intra_tx"])
+            self.uploads.append(("intra_tx", S["intra_tx"]))
+            n_intra = 1
         # post filters
         j.run_lf, j.run_cdef, j.run_lr = int(run_lf), int(run_cdef), int(run_lr)
         d_masks = up("masks", S["masks"]); self.uploads.append(("masks", S["masks"]))
@@ -168,7 +181,7 @@ class FrameBuffers:
         self.job = j
         self.n_launches = (1 if j.n_pred else 0) + (1 if j.n_comp else 0) + (1 if j.n_comp2 else 0) + \
             (1 if any(j.n_itx[tx] for tx in (4, 11, 12, 17, 18)) else 0) + \
-            (1 if any(j.n_itx[tx] for tx in range(19) if tx not in (4, 11, 12, 17, 18)) else 0) + 2 * int(run_lf) + int(run_cdef) + int(run_lr) + n_fg
+            (1 if any(j.n_itx[tx] for tx in range(19) if tx not in (4, 11, 12, 17, 18)) else 0) + 2 * int(run_lf) + int(run_cdef) + int(run_lr) + n_fg + n_intra
         self._host = None
 
     # ---- device-resident run (records already in HBM) ----

@@ -450,3 +450,221 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
         d.overlap_flag = 1
         S["fg"] = d
     return S
+
+
+# ---------------------------------------------------------------------------------------------------------
+# intra frames: transform-block records for b200_intra_frame (include/b200av1.h, B200IntraTx)
+INTRA_TX_DT = np.dtype([("dst_off", "<u4"), ("coef_off", "<u4"), ("luma_off", "<u4"), ("eob", "<i2"), ("x4", "<u2"), ("y4", "<u2"),
+                        ("xend4", "<u2"), ("yend4", "<u2"), ("max_w", "<i2"), ("max_h", "<i2"), ("angle_flags", "<u2"),
+                        ("tx", "u1"), ("txtp", "u1"), ("mode", "u1"), ("angle", "i1"), ("plane", "u1"), ("flags", "u1"),
+                        ("cfl_alpha", "i1"), ("cfl_w_pad", "u1"), ("cfl_h_pad", "u1"), ("pad", "u1", (3,))])
+assert INTRA_TX_DT.itemsize == 40
+_SMOOTH_MODES = (9, 10, 11)
+MODE_FILTER, MODE_CFL = 13, 14
+
+
+def ordered_tiling(rng, w4, h4, max_log=4, min_log=1, p_split=0.6):
+    """Blocks (x4, y4, lw, lh) in decode order: superblock raster, recursive partition order inside."""
+    out = []
+    S = 1 << max_log
+
+    def rec(x, y, lwv, lhv):
+        if x >= w4 or y >= h4:
+            return
+        can_w, can_h = lwv > min_log, lhv > min_log
+        if (can_w or can_h) and rng.random() < p_split:
+            mode = rng.integers(0, 3)
+            if mode == 0 and can_w and can_h:
+                for dy in (0, 1):
+                    for dx in (0, 1):
+                        rec(x + (dx << (lwv - 1)), y + (dy << (lhv - 1)), lwv - 1, lhv - 1)
+                return
+            if (mode == 1 or not can_h) and can_w and lwv >= lhv:
+                rec(x, y, lwv - 1, lhv); rec(x + (1 << (lwv - 1)), y, lwv - 1, lhv)
+                return
+            if can_h and lhv >= lwv:
+                rec(x, y, lwv, lhv - 1); rec(x, y + (1 << (lhv - 1)), lwv, lhv - 1)
+                return
+        out.append((x, y, lwv, lhv))
+    for y in range(0, h4, S):
+        for x in range(0, w4, S):
+            rec(x, y, max_log, max_log)
+    return out
+
+
+def make_intra_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, p_skip=0.2, p_cfl=0.25):
+    """Synthetic intra-only frame (BASELINE configs[1]): every block intra predicted (all 13 modes with angle deltas,
+    filter-intra, CFL) at transform-block granularity + residual, deblocking parameters. W, H multiples of 8
+    (dav1d's f->bw / f->bh are even). Availability of the top-right / bottom-left neighbours follows decode order
+    geometrically (a superset of the bitstream rule; what matters to the kernels is that it is consistent)."""
+    assert W % 8 == 0 and H % 8 == 0
+    bd = (1 << bpc) - 1
+    dt = np.uint8 if bpc == 8 else np.uint16
+    cdt = np.int16 if bpc == 8 else np.int32
+    S = make_lf_frame(rng, bpc, W, H, ss_hor, ss_ver)
+    stride, off = S["stride"], S["off"]
+    w4, h4 = S["w4"], S["h4"]
+    ssh, ssv = [0, ss_hor, ss_hor], [0, ss_ver, ss_ver]
+    pw4 = [w4, w4 >> ss_hor, w4 >> ss_hor]; ph4 = [h4, h4 >> ss_ver, h4 >> ss_ver]
+    edge_filter = int(rng.integers(0, 2))
+    order = [np.full((ph4[p], pw4[p]), -1, np.int64) for p in range(3)]       # owning record (decode order) per 4x4 cell
+    ymode = np.zeros((h4, w4), np.int8); uvmode = np.zeros((h4, w4), np.int8)
+    ty = [np.zeros((h4, w4), np.int32), np.zeros((h4, w4), np.int32), np.zeros((h4, w4), np.int8), np.zeros((h4, w4), np.int8)]
+    cw4, ch4 = (w4 + ss_hor) >> ss_hor, (h4 + ss_ver) >> ss_ver
+    tuv = [np.zeros((ch4, cw4), np.int32), np.zeros((ch4, cw4), np.int32), np.zeros((ch4, cw4), np.int8), np.zeros((ch4, cw4), np.int8)]
+    recs = []
+
+    def paint(t, x, y, lwv, lhv, hh, ww):
+        x1, y1 = min(ww, x + (1 << lwv)), min(hh, y + (1 << lhv))
+        t[0][y:y1, x:x1] = x; t[1][y:y1, x:x1] = y; t[2][y:y1, x:x1] = lwv; t[3][y:y1, x:x1] = lhv
+
+    def is_sm(m):
+        return 512 if m in _SMOOTH_MODES else 0
+
+    def add(pl, x, y, tlw, tlh, mode, angle, sm, skip, bx4, by4, cfl=None):
+        """one transform block of plane pl at (x, y) [plane 4-sample units]"""
+        tw, th = 1 << tlw, 1 << tlh
+        idx = len(recs)
+        om = order[pl]
+        fl = (1 if x > 0 else 0) | (2 if y > 0 else 0)
+        if cfl is None or cfl[0] == 0:
+            if y > 0 and x + tw < pw4[pl] and 0 <= om[y - 1, x + tw]:
+                fl |= 4
+            if x > 0 and y + th < ph4[pl] and 0 <= om[y + th, x - 1]:
+                fl |= 8
+        om[y:y + th, x:x + tw] = idx
+        r = np.zeros(1, INTRA_TX_DT)[0]
+        r["dst_off"] = off[pl] + y * 4 * stride[pl] + x * 4
+        r["x4"], r["y4"], r["xend4"], r["yend4"] = x, y, pw4[pl], ph4[pl]
+        if pl == 0:
+            r["max_w"], r["max_h"] = 4 * w4 - 4 * x, 4 * h4 - 4 * y
+        else:
+            r["max_w"] = (4 * w4 + ss_hor - 4 * (x << ss_hor)) >> ss_hor
+            r["max_h"] = (4 * h4 + ss_ver - 4 * (y << ss_ver)) >> ss_ver
+        r["angle_flags"] = sm | (edge_filter << 10)
+        r["tx"] = TX_FROM_WH[(4 * tw, 4 * th)]
+        r["mode"], r["angle"], r["plane"], r["flags"] = mode, angle, pl, fl
+        r["eob"] = -1 if skip else 0           # residual filled in below
+        if cfl is not None:
+            r["cfl_alpha"], r["cfl_w_pad"], r["cfl_h_pad"] = cfl
+            r["luma_off"] = off[0] + (by4 & ~ss_ver) * 4 * stride[0] + (bx4 & ~ss_hor) * 4
+        recs.append(r)
+
+    for (x4, y4, lwv, lhv) in ordered_tiling(rng, w4, h4):
+        bw4, bh4 = 1 << lwv, 1 << lhv
+        cw, chh = min(bw4, w4 - x4), min(bh4, h4 - y4)                         # clipped block size (w4, h4 in :1188)
+        skip = rng.random() < p_skip
+        small = bw4 <= 8 and bh4 <= 8
+        # ---- luma
+        m = int(rng.integers(0, 13))
+        ang = int(rng.integers(-3, 4)) if 1 <= m <= 8 else 0
+        if m == 0 and small and rng.random() < 0.4:
+            m, ang = MODE_FILTER, int(rng.integers(0, 5))
+        sm = (is_sm(ymode[y4 - 1, x4]) if y4 > 0 else 0) | (is_sm(ymode[y4, x4 - 1]) if x4 > 0 else 0)
+        ymode[y4:y4 + chh, x4:x4 + cw] = 0 if m == MODE_FILTER else m          # filter-intra blocks store DC_PRED
+        tlw, tlh = min(lwv, 4), min(lhv, 4)
+        for _ in range(int(rng.integers(0, 3))):                               # tx split depth 0..2
+            if tlw >= tlh and tlw > 0:
+                tlw -= 1
+                if tlh > tlw + 2:
+                    tlh -= 1
+            elif tlh > 0:
+                tlh -= 1
+            if tlw > tlh + 2:
+                tlw = tlh + 2
+            if tlh > tlw + 2:
+                tlh = tlw + 2
+        for yy in range(0, chh, 1 << tlh):
+            for xx in range(0, cw, 1 << tlw):
+                paint(ty, x4 + xx, y4 + yy, tlw, tlh, h4, w4)
+                add(0, x4 + xx, y4 + yy, tlw, tlh, m, ang, sm, skip, x4, y4)
+        # ---- chroma (every block is at least 8x8 luma, so every block carries chroma)
+        clw, clh = lwv - ss_hor, lhv - ss_ver
+        cx4, cy4 = x4 >> ss_hor, y4 >> ss_ver
+        ccw, cch = (cw + ss_hor) >> ss_hor, (chh + ss_ver) >> ss_ver
+        um = int(rng.integers(0, 13))
+        uang = int(rng.integers(-3, 4)) if 1 <= um <= 8 else 0
+        cfl = None
+        if small and rng.random() < p_cfl:
+            um, uang = MODE_CFL, 0
+        smu = (is_sm(uvmode[y4 - 1, x4]) if y4 > 0 else 0) | (is_sm(uvmode[y4, x4 - 1]) if x4 > 0 else 0)
+        uvmode[y4:y4 + chh, x4:x4 + cw] = 0 if um == MODE_CFL else um
+        ctl, cth = min(clw, 3), min(clh, 3)
+        for pl in (1, 2):
+            if um == MODE_CFL:
+                fr = ((ccw << ss_hor) + (1 << tlw) - 1) & ~((1 << tlw) - 1)
+                fb = ((cch << ss_ver) + (1 << tlh) - 1) & ~((1 << tlh) - 1)
+                alpha = int(rng.integers(-16, 17)) if rng.random() < 0.85 else 0
+                cfl = (alpha, (1 << clw) - (fr >> ss_hor), (1 << clh) - (fb >> ss_ver))
+            for yy in range(0, cch, 1 << cth):
+                for xx in range(0, ccw, 1 << ctl):
+                    if pl == 1:
+                        paint(tuv, cx4 + xx, cy4 + yy, ctl, cth, ch4, cw4)
+                    add(pl, cx4 + xx, cy4 + yy, ctl, cth, um, uang, smu, skip, x4, y4, cfl)
+
+    tx = np.array(recs, INTRA_TX_DT)
+    n = len(tx)
+    # ---- residuals (same generator as the inter frames)
+    coef_off = 0
+    chunks = []
+    for t in range(19):
+        sel = np.nonzero((tx["tx"] == t) & (tx["eob"] >= 0))[0]
+        if not len(sel):
+            continue
+        k = len(sel)
+        sw, sh = _L.tx_coef_dims(t)
+        ncf = sw * sh
+        legal = [tp for tp in range(10) if _L.itx_defined(t, tp)]
+        txtp = rng.choice(legal, k, p=None if len(legal) == 1 else [0.55] + [0.45 / (len(legal) - 1)] * (len(legal) - 1))
+        scan = scan_table(t)
+        inv = np.empty(ncf, np.int64); inv[scan] = np.arange(ncf)
+        eob = np.minimum((rng.exponential(ncf / 10.0, k)).astype(np.int64), ncf - 1)
+        eob[rng.random(k) < 0.25] = 0
+        amp = (bd + 1) / 2.0
+        pos = inv[None, :]
+        c = np.rint(rng.laplace(0.0, amp * 0.25, (k, ncf)) / (1.0 + pos / 6.0)).astype(np.int64)
+        c[pos > eob[:, None]] = 0
+        c[np.arange(k), scan[eob]] = np.where(c[np.arange(k), scan[eob]] == 0, 1, c[np.arange(k), scan[eob]])
+        tx["coef_off"][sel] = coef_off + np.arange(k) * ncf
+        tx["eob"][sel] = eob; tx["txtp"][sel] = txtp
+        chunks.append(c.astype(cdt).reshape(-1))
+        coef_off += k * ncf
+    coefs = np.concatenate(chunks) if chunks else np.zeros(1, cdt)
+
+    # ---- wavefront numbers: 1 + the latest wave among the cells the device waits for (same cells as intra.cu)
+    wave_map = [np.zeros((ph4[p], pw4[p]), np.int32) for p in range(3)]
+    wave = np.zeros(n, np.int64)
+    for i in range(n):
+        r = tx[i]
+        pl, x, y = int(r["plane"]), int(r["x4"]), int(r["y4"])
+        tw, th = _L.TX_W[r["tx"]] // 4, _L.TX_H[r["tx"]] // 4
+        wm = wave_map[pl]
+        fl = int(r["flags"])
+        dep = 0
+        if fl & 1:
+            nrow = min(th, ph4[pl] - y) + (min(th, ph4[pl] - y - th) if (fl & 8) and y + th < ph4[pl] else 0)
+            dep = max(dep, int(wm[y:y + nrow, x - 1].max()))
+        if fl & 2:
+            ncol = min(tw, pw4[pl] - x) + (min(tw, pw4[pl] - x - tw) if (fl & 4) and x + tw < pw4[pl] else 0)
+            dep = max(dep, int(wm[y - 1, x:x + ncol].max()))
+        if (fl & 3) == 3:
+            dep = max(dep, int(wm[y - 1, x - 1]))
+        if r["mode"] == MODE_CFL and r["cfl_alpha"] != 0:
+            lx, ly = x << ss_hor, y << ss_ver
+            lw_ = min((tw - int(r["cfl_w_pad"])) << ss_hor, w4 - lx); lh_ = min((th - int(r["cfl_h_pad"])) << ss_ver, h4 - ly)
+            dep = max(dep, int(wave_map[0][ly:ly + lh_, lx:lx + lw_].max()))
+        wave[i] = dep + 1
+        wm[y:y + th, x:x + tw] = dep + 1
+    sorted_idx = np.argsort(wave, kind="stable")
+    S.update(intra_tx=tx[sorted_idx].copy(), intra_tx_decode_order=tx, intra_waves=int(wave.max()), coefs=coefs,
+             refs=[], pred=np.zeros(0, MC_BLOCK_DT), comp=np.zeros(0, COMP_BLOCK_DT), comp2=np.zeros(0, COMP_BLOCK_DT),
+             itx={t: np.zeros(0, ITX_BLOCK_DT) for t in range(19)}, tmp_len=64, mask=np.zeros(1, np.uint8))
+    S["pic"] = np.zeros(len(S["pic"]), dt)
+    S["masks"] = build_lf_masks(w4, h4, tuple(ty), tuple(tuv), ss_hor, ss_ver)
+    S["til_y"], S["til_uv"] = tuple(ty), tuple(tuv)
+    S["bw"], S["bh"] = w4, h4
+    S["damping"], S["y_strength"], S["uv_strength"] = make_cdef_params(rng, w4, h4, S["sb128w"], S["masks"])
+    S["lr_mask"] = make_lr_params(rng, W, H)
+    S["us"] = (6, 6 - (1 if ss_hor else 0))
+    S["rp"], S["sb128"] = 7, 0
+    return S

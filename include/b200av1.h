@@ -411,6 +411,47 @@ typedef struct B200FilmGrainDSPContext {
 B200_API void b200_film_grain_dsp_init_8bpc(B200FilmGrainDSPContext *c);
 B200_API void b200_film_grain_dsp_init_16bpc(B200FilmGrainDSPContext *c);
 
+/* ==== intra reconstruction of a whole frame ================================================== */
+/* One record per TRANSFORM block of an intra-coded block, because dav1d predicts, then adds the residual, at
+ * transform-block granularity (dav1d_recon_b_intra, reference src/recon_tmpl.c:1176-1555): each block's edge
+ * pixels are the reconstructed pixels of its neighbours. The device prepares the edge arrays itself
+ * (dav1d_prepare_intra_edges, reference src/ipred_prepare_tmpl.c:75-204), predicts, adds the inverse transform
+ * and publishes the block in a per-4x4 "done" map; a persistent grid takes records in order and each CTA waits
+ * for the map cells its edges read. Records must therefore be in a topological order of those dependencies
+ * (decode order is one; sorted by wavefront number is the efficient one). */
+enum { B200_INTRA_HAVE_LEFT = 1, B200_INTRA_HAVE_TOP = 2, B200_INTRA_TOP_HAS_RIGHT = 4, B200_INTRA_LEFT_HAS_BOTTOM = 8 };
+enum { B200_INTRA_MODE_FILTER = 13, B200_INTRA_MODE_CFL = 14 };   /* besides enum IntraPredMode DC_PRED(0)..PAETH_PRED(12) */
+typedef struct B200IntraTx {
+    uint32_t dst_off;              /* sample offset of the transform block in the picture (plane offset included) */
+    uint32_t coef_off;             /* into d_coef, dav1d's transposed layout, min(w,32) x min(h,32) */
+    uint32_t luma_off;             /* CFL only: sample offset of the co-located luma block (y_src, :1346) */
+    int16_t eob;                   /* < 0: no residual */
+    uint16_t x4, y4;               /* position in this plane, 4-sample units (t->bx >> ss_hor, t->by >> ss_ver) */
+    uint16_t xend4, yend4;         /* ts->tiling.col_end / row_end (>> ss) : where available edge pixels stop */
+    int16_t max_w, max_h;          /* the Z2 limits handed to intra_pred (:1276-1277, :1474-1477) */
+    uint16_t angle_flags;          /* sm_flag | sm_uv_flag (512), intra_edge_filter << 10 (:1205, :1233) */
+    uint8_t tx, txtp;              /* enum RectTxfmSize, enum TxfmType */
+    uint8_t mode;                  /* y_mode / uv_mode as coded, B200_INTRA_MODE_FILTER, B200_INTRA_MODE_CFL */
+    int8_t angle;                  /* y_angle / uv_angle (-3..3); filter-intra: the filter index */
+    uint8_t plane;
+    uint8_t flags;                 /* B200_INTRA_* availability bits (have_left/have_top and enum EdgeFlags) */
+    int8_t cfl_alpha;              /* CFL: alpha of this plane (0 = plain DC_PRED, :1446-1451) */
+    uint8_t cfl_w_pad, cfl_h_pad;  /* CFL: cfl_ac padding arguments, 4-sample units (:1359-1362) */
+    uint8_t pad[3];
+} B200IntraTx;
+typedef struct B200IntraFrame {
+    void *pic;                     /* device picture being reconstructed */
+    int32_t stride[3];
+    int32_t ss_hor, ss_ver;
+    int32_t w4[3], h4[3];          /* per plane: frame size in 4-sample units (done-map geometry) */
+    void *d_coef;
+    int32_t zero_coefs, pad;
+    void *scratch;                 /* device, >= b200_intra_scratch_bytes(frame) */
+} B200IntraFrame;
+B200_API size_t b200_intra_scratch_bytes(const B200IntraFrame *frame);
+B200_API int b200_intra_frame(int bitdepth_max, const B200IntraFrame *frame, const B200IntraTx *d_tx, int n_tx,
+                              void *stream);
+
 /* ==== whole-frame job: reconstruction + post-filter sweep ================================= */
 /* What a dav1d `f->bd_fn` record emitter hands over per frame (SURVEY.md §8b level 2): the block
  * records of pass 2 (prediction blocks, compound / blend / warp records, transform blocks bucketed by
@@ -440,6 +481,9 @@ typedef struct B200FrameJob {
     B200LfFrame lf;
     B200CdefFrame cdef;
     B200LrFrame lr;
+    const B200IntraTx *d_intra;  /* intra transform blocks (run after the inter stages, before the post filters) */
+    int32_t n_intra, pad6;
+    B200IntraFrame intra;
     int32_t run_fg, pad5;        /* film grain on the output copy (fg.in = lr.dst typically); the grain LUT preparation
                                     runs on an internal side stream concurrently with reconstruction */
     B200FgFrame fg;
@@ -447,7 +491,7 @@ typedef struct B200FrameJob {
 B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check): 0 McFrame, 1 McBlock, 2 CompBlock,
  * 3 BlendBlock, 4 WarpBlock, 5 ItxBlock, 6 LfFrame, 7 CdefFrame, 8 LrFrame, 9 FrameJob, 10 Av1Filter, 11 Av1Restoration,
- * 12 FgFrame, 13 FilmGrainData */
+ * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame */
 B200_API int b200_struct_size(int which);
 
 /* The same job fed from HOST buffers (the end-to-end path): every (host, dev, bytes) pair of `uploads`

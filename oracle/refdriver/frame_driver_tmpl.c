@@ -206,6 +206,7 @@ API void bitfn(refdrv_lr_frame)(const int bitdepth_max, const RefLrFrame *const 
 #include "src/itx.h"
 
 static void bitfn(frame_run_fg)(int bitdepth_max, const B200FrameJob *j);
+static void bitfn(intra_records)(int bitdepth_max, const B200IntraFrame *fr, const B200IntraTx *tx, int n);
 API void bitfn(refdrv_frame_run)(const B200FrameJob *const j)
 {
     static __thread Dav1dMCDSPContext mc;
@@ -265,6 +266,7 @@ API void bitfn(refdrv_frame_run)(const B200FrameJob *const j)
             memcpy(cf, save, sizeof(coef) * n_cf);
         }
     }
+    if (j->n_intra > 0) bitfn(intra_records)(bitdepth_max, &j->intra, j->d_intra, j->n_intra);
     /* the three frame drivers take frame structs with the same leading layout as the B200 ones */
     if (j->run_lf) {
         RefLfFrame lf;
@@ -353,4 +355,58 @@ static void bitfn(frame_run_fg)(const int bitdepth_max, const B200FrameJob *cons
     fr.w = j->fg.w; fr.h = j->fg.h; fr.ss_hor = j->fg.ss_hor; fr.ss_ver = j->fg.ss_ver; fr.is_id = j->fg.is_id;
     memcpy(&fr.data, &j->fg.data, sizeof(fr.data));
     bitfn(refdrv_fg_frame)(bitdepth_max, &fr);
+}
+
+/* ---- intra reconstruction: the reference's own dav1d_prepare_intra_edges + intra_pred / cfl / itxfm_add per
+ * transform-block record, in record order (what dav1d_recon_b_intra does per tx block, src/recon_tmpl.c:1235-1330,
+ * 1342-1398, 1418-1540). The top edge is read from the picture: with whole-frame reconstruction the row above is
+ * still unfiltered, which is what f->ipred_edge preserves in the sbrow pipeline. */
+#include "src/ipred.h"
+#include "src/ipred_prepare.h"
+static void bitfn(intra_records)(const int bitdepth_max, const B200IntraFrame *const fr, const B200IntraTx *const tx, const int n)
+{
+    Dav1dIntraPredDSPContext ip;
+    Dav1dInvTxfmDSPContext itx;
+    bitfn(dav1d_intra_pred_dsp_init)(&ip);
+    bitfn(dav1d_itx_dsp_init)(&itx, 32 - clz(bitdepth_max));
+    pixel edge_buf[257];
+    pixel *const edge = edge_buf + 128;
+    int16_t ac[32 * 32];
+    const int layout_idx = !fr->ss_hor ? 2 : fr->ss_ver ? 0 : 1;
+    for (int i = 0; i < n; i++) {
+        const B200IntraTx *const r = &tx[i];
+        const TxfmInfo *const t = &dav1d_txfm_dimensions[r->tx];
+        pixel *const dst = (pixel *)fr->pic + r->dst_off;
+        const ptrdiff_t stride = fr->stride[r->plane] * (ptrdiff_t)sizeof(pixel);
+        const int have_left = !!(r->flags & B200_INTRA_HAVE_LEFT), have_top = !!(r->flags & B200_INTRA_HAVE_TOP);
+        const enum EdgeFlags ef = ((r->flags & B200_INTRA_TOP_HAS_RIGHT) ? EDGE_I444_TOP_HAS_RIGHT : 0) |
+                                  ((r->flags & B200_INTRA_LEFT_HAS_BOTTOM) ? EDGE_I444_LEFT_HAS_BOTTOM : 0);
+        int angle = r->angle;
+        if (r->mode == B200_INTRA_MODE_CFL && r->cfl_alpha) {
+            angle = 0;
+            ip.cfl_ac[layout_idx](ac, (const pixel *)fr->pic + r->luma_off, fr->stride[0] * (ptrdiff_t)sizeof(pixel),
+                                  r->cfl_w_pad, r->cfl_h_pad, t->w * 4, t->h * 4);
+            const enum IntraPredMode m = bytefn(dav1d_prepare_intra_edges)(r->x4, have_left, r->y4, have_top, r->xend4, r->yend4,
+                                                                          0, dst, stride, NULL, DC_PRED, &angle, t->w, t->h, 0,
+                                                                          edge HIGHBD_TAIL_SUFFIX);
+            ip.cfl_pred[m](dst, stride, edge, t->w * 4, t->h * 4, ac, r->cfl_alpha HIGHBD_TAIL_SUFFIX);
+        } else {
+            const enum IntraPredMode in = r->mode == B200_INTRA_MODE_CFL ? DC_PRED : (enum IntraPredMode)r->mode;
+            const enum IntraPredMode m = bytefn(dav1d_prepare_intra_edges)(r->x4, have_left, r->y4, have_top, r->xend4, r->yend4,
+                                                                          ef, dst, stride, NULL, in, &angle, t->w, t->h,
+                                                                          (r->angle_flags >> 10) & 1, edge HIGHBD_TAIL_SUFFIX);
+            ip.intra_pred[m](dst, stride, edge, t->w * 4, t->h * 4, angle | r->angle_flags, r->max_w, r->max_h HIGHBD_TAIL_SUFFIX);
+        }
+        if (r->eob >= 0) {
+            const int n_cf = imin(t->w * 4, 32) * imin(t->h * 4, 32);
+            coef *cf = (coef *)fr->d_coef + r->coef_off, save[1024];
+            memcpy(save, cf, sizeof(coef) * n_cf);
+            itx.itxfm_add[r->tx][r->txtp](dst, stride, cf, r->eob HIGHBD_TAIL_SUFFIX);
+            if (!fr->zero_coefs) memcpy(cf, save, sizeof(coef) * n_cf);
+        }
+    }
+}
+API void bitfn(refdrv_intra_frame)(const int bitdepth_max, const B200IntraFrame *const fr, const B200IntraTx *const tx, const int n)
+{
+    bitfn(intra_records)(bitdepth_max, fr, tx, n);
 }

@@ -1,0 +1,117 @@
+"""Parity tests for intra-frame reconstruction (device-side dav1d_prepare_intra_edges + predictors + itx in a
+dependency-driven kernel; include/b200av1.h B200IntraTx / b200_intra_frame).
+
+The oracle restatement (oracle/intra.c) is pinned against the reference's own dav1d_prepare_intra_edges,
+intra_pred / cfl_ac / cfl_pred and itxfm_add functions driven record by record (oracle/refdriver); the CUDA
+kernel is then checked against the oracle, with the records in decode order and in wavefront order.
+"""
+import ctypes as C
+import numpy as np
+import pytest
+
+import refs
+from dav1d_b200 import _lib, synth, frame
+
+CASES = [(8, 136, 72, 1, 1), (10, 200, 136, 1, 1), (12, 72, 136, 0, 0), (8, 264, 136, 1, 0)]
+
+
+def intra_frame_struct(S, pic, coefs):
+    fr = _lib.IntraFrame()
+    ssh, ssv = [0, S["ss_hor"], S["ss_hor"]], [0, S["ss_ver"], S["ss_ver"]]
+    fr.pic, fr.d_coef, fr.zero_coefs = pic.ctypes.data, coefs.ctypes.data, 0
+    fr.ss_hor, fr.ss_ver = S["ss_hor"], S["ss_ver"]
+    for p in range(3):
+        fr.stride[p] = S["stride"][p]; fr.w4[p] = S["w4"] >> ssh[p]; fr.h4[p] = S["h4"] >> ssv[p]
+    return fr
+
+
+def run_cpu(fn, S, order="intra_tx"):
+    pic = np.zeros_like(S["pic"]); coefs = S["coefs"].copy()
+    fr = intra_frame_struct(S, pic, coefs)
+    tx = np.ascontiguousarray(S[order])
+    fn.restype = None
+    fn(C.c_int(S["bd"]), C.byref(fr), C.c_void_p(tx.ctypes.data), C.c_int(len(tx)))
+    assert np.array_equal(coefs, S["coefs"])
+    return pic
+
+
+def oracle_intra(S, order="intra_tx"):
+    return run_cpu(refs.oracle().oracle_intra_frame, S, order)
+
+
+def reference_intra(S, order="intra_tx"):
+    r = refs.ref()
+    return run_cpu(r.refdrv_intra_frame_8bpc if S["bpc"] == 8 else r.refdrv_intra_frame_16bpc, S, order)
+
+
+def planes_equal(S, a, b):
+    ssh, ssv = [0, S["ss_hor"], S["ss_hor"]], [0, S["ss_ver"], S["ss_ver"]]
+    for p in range(3):
+        w, h = S["W"] >> ssh[p], S["H"] >> ssv[p]
+        st, o = S["stride"][p], S["off"][p]
+        va = a[o:o + st * h].reshape(h, st)[:, :w]; vb = b[o:o + st * h].reshape(h, st)[:, :w]
+        if not np.array_equal(va, vb):
+            ys, xs = np.nonzero(va != vb)
+            return False, (p, int(ys[0]), int(xs[0]), int(va[ys[0], xs[0]]), int(vb[ys[0], xs[0]]), len(ys))
+    return True, None
+
+
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", CASES)
+def test_oracle_intra_vs_reference_functions(bpc, W, H, ssh, ssv):
+    if not refs.have_ref():
+        pytest.skip("oracle/_ref not built")
+    S = synth.make_intra_frame(np.random.default_rng(700 + bpc + W), bpc, W, H, ssh, ssv)
+    a = reference_intra(S); b = oracle_intra(S)
+    ok, where = planes_equal(S, a, b)
+    assert ok, where
+    assert (a != 0).mean() > 0.15
+    # any topological order gives the same picture: decode order vs wavefront order
+    c = oracle_intra(S, "intra_tx_decode_order")
+    ok, where = planes_equal(S, a, c)
+    assert ok, where
+    if W * H >= 200 * 136:
+        modes = set(S["intra_tx"]["mode"].tolist())
+        assert modes >= set(range(13)) | {synth.MODE_CFL, synth.MODE_FILTER}, modes
+
+
+def run_lib(lib, alloc, S, order="intra_tx"):
+    S2 = dict(S); S2["intra_tx"] = np.ascontiguousarray(S[order])
+    fb = frame.FrameBuffers(S2, lib=lib, alloc=alloc, run_lf=False, run_cdef=False, run_lr=False)
+    fb.run()
+    fb.alloc.sync()
+    return fb.output("p0")
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", CASES)
+def test_emu_intra_frame(bpc, W, H, ssh, ssv):
+    S = synth.make_intra_frame(np.random.default_rng(720 + bpc + W), bpc, W, H, ssh, ssv)
+    exp = oracle_intra(S)
+    got = run_lib(refs.emu_lib(), frame.NumpyAlloc(), S)
+    ok, where = planes_equal(S, exp, got)
+    assert ok, where
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", CASES + [(8, 1920, 1080, 1, 1), (10, 1280, 720, 1, 1)])
+def test_gpu_intra_frame(bpc, W, H, ssh, ssv):
+    S = synth.make_intra_frame(np.random.default_rng(740 + bpc + W), bpc, W, H, ssh, ssv)
+    exp = oracle_intra(S)
+    for order in ("intra_tx", "intra_tx_decode_order"):
+        got = run_lib(_lib.get_lib(), None, S, order)
+        ok, where = planes_equal(S, exp, got)
+        assert ok, (order, where)
+
+
+@pytest.mark.gpu
+def test_gpu_intra_frame_with_deblock():
+    """BASELINE configs[1]: intra reconstruction followed by the deblocking sweeps, whole job through the C ABI"""
+    import test_loopfilter as TLF
+    S = synth.make_intra_frame(np.random.default_rng(760), 8, 640, 360)
+    rec = oracle_intra(S)
+    S2 = dict(S); S2["pic"] = rec
+    exp = TLF.lf_frame_oracle(S2)
+    fb = frame.FrameBuffers(S, run_cdef=False, run_lr=False)
+    fb.run(); fb.alloc.sync()
+    import test_cdef as TCD
+    assert TCD.frame_area_equal(S, fb.output("p0"), exp)

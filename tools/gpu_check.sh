@@ -16,6 +16,8 @@ if [[ $what == all || $what == bench ]]; then
   timeout 600 python bench.py --workload itx8x8 > gpurun_out/bench_itx8x8.json 2> gpurun_out/bench_itx8x8.err
   timeout 900 python bench.py --impl reference --workload 4k10_full --steps 2 --warmup 1 > gpurun_out/bench_ref_4k10.json 2> gpurun_out/bench_ref_4k10.err
   timeout 900 python bench.py --workload 4k10_full > gpurun_out/bench_4k10.json 2> gpurun_out/bench_4k10.err
+  timeout 900 python bench.py --impl reference --workload 1080p8_intra --steps 2 --warmup 1 > gpurun_out/bench_ref_intra.json 2> gpurun_out/bench_ref_intra.err
+  timeout 900 python bench.py --workload 1080p8_intra > gpurun_out/bench_intra.json 2> gpurun_out/bench_intra.err
 fi
 if [[ $what == all || $what == ncu ]]; then
   # launch list of 3 timed frames after the warm-up (5 warm-up frames x 9 launches are skipped)
