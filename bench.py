@@ -161,9 +161,11 @@ FRAME_WORKLOADS = {
     "4k10_full": dict(bpc=10, W=3840, H=2160, fg=True, dtype="u16/i32->i32",
                       desc="one 3840x2160 10-bit 4:2:0 inter frame per GPU per step, full pipeline: prediction + inverse "
                            "transforms + deblock + CDEF + loop restoration + film grain (BASELINE configs[3])"),
-    "1080p8_intra": dict(bpc=8, W=1920, H=1080, fg=False, dtype="u8/i16->i32", intra=True,
+    "1080p8_intra": dict(bpc=8, W=1920, H=1080, fg=False, dtype="u8/i16->i32", intra=True, frames_per_step=12,
                          desc="one 1920x1080 8-bit 4:2:0 intra-only frame per GPU per step: device-side edge preparation + "
-                              "intra prediction + inverse transforms (dependency-driven kernel) + deblock (BASELINE configs[1])"),
+                              "intra prediction + inverse transforms (dependency-driven kernel) + deblock (BASELINE configs[1]); a step is 12 "
+                              "independent frames in flight on 12 streams (an intra frame is a ~1000-deep dependency chain, so "
+                              "frames, like dav1d's frame threads, are the parallel axis)"),
 }
 
 
@@ -178,7 +180,8 @@ def make_workload_frame(name, seed):
 def workload_buffers(name, S, **kw):
     from dav1d_b200 import frame
     if FRAME_WORKLOADS[name].get("intra"):
-        return frame.FrameBuffers(S, run_cdef=False, run_lr=False, **kw)
+        # 12 frames in flight x 48 CTAs = 576 <= the 592 CTAs (4 per SM) that can be resident at once
+        return frame.FrameBuffers(S, run_cdef=False, run_lr=False, intra_grid=48, **kw)
     return frame.FrameBuffers(S, **kw)
 
 
@@ -283,12 +286,25 @@ def run_ours_frame(args):
         S = make_workload_frame(args.workload, 1 + rank * 16 + k)
         Ss.append(S)
         fbs.append(workload_buffers(args.workload, S))
-    px_per_step = FRAME_WORKLOADS[args.workload]["W"] * FRAME_WORKLOADS[args.workload]["H"]
+    fps = FRAME_WORKLOADS[args.workload].get("frames_per_step", 1)
+    px_per_step = fps * FRAME_WORKLOADS[args.workload]["W"] * FRAME_WORKLOADS[args.workload]["H"]
+    side = [torch.cuda.Stream() for _ in range(fps)] if fps > 1 else []
+    ev_go = torch.cuda.Event() if fps > 1 else None
+    ev_done = [torch.cuda.Event() for _ in range(fps)]
     gather = None
     if world > 1:   # reference-picture exchange buffer: every rank's restored picture
         gather = torch.empty(world * Ss[0]["pic"].nbytes, dtype=torch.uint8, device="cuda")
 
     def step(i):
+        if fps > 1:      # fps frames in flight, one stream each, joined back into the timing stream
+            cur = torch.cuda.current_stream()
+            ev_go.record(cur)
+            for k in range(fps):
+                side[k].wait_event(ev_go)
+                fbs[(i * fps + k) % nsets].run(side[k].cuda_stream)
+                ev_done[k].record(side[k])
+                cur.wait_event(ev_done[k])
+            return
         fb = fbs[i % nsets]
         fb.run()
         if world > 1:

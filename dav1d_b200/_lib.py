@@ -96,6 +96,12 @@ class FgFrame(C.Structure):
                 ("data", FilmGrainData), ("scratch", C.c_void_p)]
 
 
+class McScaledBlock(C.Structure):
+    _fields_ = [("dst_off", C.c_uint32), ("src_x", C.c_int32), ("src_y", C.c_int32), ("mx", C.c_uint16), ("my", C.c_uint16),
+                ("dx", C.c_uint16), ("dy", C.c_uint16), ("w", C.c_uint8), ("h", C.c_uint8), ("filter2d", C.c_uint8),
+                ("op", C.c_uint8), ("plane", C.c_uint8), ("ref", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
 class IntraTx(C.Structure):
     """struct B200IntraTx (40 bytes)"""
     _fields_ = [("dst_off", C.c_uint32), ("coef_off", C.c_uint32), ("luma_off", C.c_uint32), ("eob", C.c_int16),
@@ -108,7 +114,7 @@ class IntraTx(C.Structure):
 class IntraFrame(C.Structure):
     _fields_ = [("pic", C.c_void_p), ("stride", C.c_int32 * 3), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32),
                 ("w4", C.c_int32 * 3), ("h4", C.c_int32 * 3), ("d_coef", C.c_void_p), ("zero_coefs", C.c_int32),
-                ("pad", C.c_int32), ("scratch", C.c_void_p)]
+                ("grid", C.c_int32), ("scratch", C.c_void_p)]
 
 
 class FrameJob(C.Structure):
@@ -124,6 +130,7 @@ class FrameJob(C.Structure):
                 ("run_lf", C.c_int32), ("run_cdef", C.c_int32), ("run_lr", C.c_int32),
                 ("lf", LfFrame), ("cdef", CdefFrame), ("lr", LrFrame),
                 ("d_intra", C.c_void_p), ("n_intra", C.c_int32), ("pad6", C.c_int32), ("intra", IntraFrame),
+                ("d_scaled", C.c_void_p), ("n_scaled", C.c_int32), ("pad7", C.c_int32),
                 ("run_fg", C.c_int32), ("pad5", C.c_int32), ("fg", FgFrame)]
 
 
@@ -151,6 +158,9 @@ _SIGS = {
     "b200_mc_comp_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_mc_blend_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_mc_warp_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_mc_scaled_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_mc_put_scaled": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t] + [C.c_int] * 8),
+    "b200_mc_prep_scaled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ssize_t] + [C.c_int] * 8),
     "b200_mc_put": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t] + [C.c_int] * 6),
     "b200_mc_prep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ssize_t] + [C.c_int] * 6),
     "b200_mc_comp": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -264,4 +274,4 @@ class Av1Restoration(C.Structure):
 
 
 ABI_STRUCTS = [McFrame, McBlock, CompBlock, BlendBlock, WarpBlock, ItxBlock, LfFrame, CdefFrame, LrFrame, FrameJob,
-               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame]
+               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame, McScaledBlock]

@@ -4,28 +4,6 @@
 // reference src/thread_task.c:699-854) with whole-frame stages instead of superblock rows.
 #include "host_util.h"
 
-#ifndef B200_EMU
-#include <map>
-namespace {
-// per caller stream: a side stream + two events, so that the film grain LUT preparation (one CTA, latency bound,
-// depends only on the frame header) overlaps reconstruction instead of serialising behind it
-struct FgSide { cudaStream_t side; cudaEvent_t start, done; };
-FgSide *fg_side_for(cudaStream_t main)
-{
-    static std::map<cudaStream_t, FgSide> pool;
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
-    auto it = pool.find(main);
-    if (it != pool.end()) return &it->second;
-    FgSide s;
-    if (cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&s.start, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    return &(pool[main] = s);
-}
-}
-#endif
-
 extern "C" {
 
 int b200_frame_run(const B200FrameJob *j, void *stream)
@@ -34,17 +12,16 @@ int b200_frame_run(const B200FrameJob *j, void *stream)
     const int bd = j->bitdepth_max;
     bool fg_prepped = false;
 #ifndef B200_EMU
-    FgSide *fs = nullptr;
-    if (j->run_fg && (fs = fg_side_for((cudaStream_t)stream))) {
-        // the scratch is reused frame after frame on this stream: order the prep after everything enqueued so far
-        B200_CUDA_OK(cudaEventRecord(fs->start, (cudaStream_t)stream));
-        B200_CUDA_OK(cudaStreamWaitEvent(fs->side, fs->start, 0));
+    // film grain LUT preparation: one CTA, latency bound, depends only on the frame header -> side stream. The
+    // scratch is reused frame after frame on this stream, hence the fork (after everything enqueued so far).
+    SideStream *fs = nullptr;
+    if (j->run_fg && (fs = side_stream_for((cudaStream_t)stream, 0)) && fs->fork((cudaStream_t)stream)) {
         if ((r = b200_fg_prep(bd, &j->fg, fs->side))) return r;
-        B200_CUDA_OK(cudaEventRecord(fs->done, fs->side));
         fg_prepped = true;
     }
 #endif
     if ((r = b200_mc_batch(bd, &j->mc, j->d_pred, j->n_pred, stream))) return r;
+    if ((r = b200_mc_scaled_batch(bd, &j->mc, j->d_scaled, j->n_scaled, stream))) return r;
     if ((r = b200_mc_warp_batch(bd, &j->mc, j->d_warp, j->n_warp, stream))) return r;
     if ((r = b200_mc_comp_batch(bd, &j->mc, j->d_comp, j->n_comp, stream))) return r;
     if ((r = b200_mc_comp_batch(bd, &j->mc, j->d_comp2, j->n_comp2, stream))) return r;
@@ -58,7 +35,7 @@ int b200_frame_run(const B200FrameJob *j, void *stream)
     if (j->run_lr && (r = b200_lr_frame(bd, &j->lr, stream))) return r;
     if (j->run_fg) {
 #ifndef B200_EMU
-        if (fg_prepped) B200_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, fs->done, 0));
+        if (fg_prepped && !fs->join((cudaStream_t)stream)) { b200_set_error("b200_frame_run: stream join failed"); return -1; }
 #endif
         if (!fg_prepped && (r = b200_fg_prep(bd, &j->fg, stream))) return r;
         if ((r = b200_fg_apply(bd, &j->fg, stream))) return r;
@@ -74,7 +51,7 @@ int b200_struct_size(int which)
     case 6: return sizeof(B200LfFrame); case 7: return sizeof(B200CdefFrame); case 8: return sizeof(B200LrFrame);
     case 9: return sizeof(B200FrameJob); case 10: return sizeof(B200Av1Filter); case 11: return sizeof(B200Av1Restoration);
     case 12: return sizeof(B200FgFrame); case 13: return sizeof(B200FilmGrainData);
-    case 14: return sizeof(B200IntraTx); case 15: return sizeof(B200IntraFrame);
+    case 14: return sizeof(B200IntraTx); case 15: return sizeof(B200IntraFrame); case 16: return sizeof(B200McScaledBlock);
     }
     return -1;
 }

@@ -55,3 +55,34 @@ inline void unpack_rect(void *pic, ptrdiff_t stride, const void *dense, int w, i
 }
 
 }  // namespace b200
+
+#ifndef B200_EMU
+#include <map>
+// A side stream + fork/join events per (caller stream, slot): lets a stage that is latency bound on few CTAs run
+// beside the next stage instead of in front of it. fork(): side waits for everything enqueued on `main` so far;
+// join(): `main` waits for everything enqueued on the side stream.
+struct SideStream {
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool fork(cudaStream_t main) {
+        return cudaEventRecord(ev_fork, main) == cudaSuccess && cudaStreamWaitEvent(side, ev_fork, 0) == cudaSuccess;
+    }
+    bool join(cudaStream_t main) {
+        return cudaEventRecord(ev_join, side) == cudaSuccess && cudaStreamWaitEvent(main, ev_join, 0) == cudaSuccess;
+    }
+};
+inline SideStream *side_stream_for(cudaStream_t main, int slot)
+{
+    static std::map<std::pair<cudaStream_t, int>, SideStream> pool;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(main, slot);
+    auto it = pool.find(key);
+    if (it != pool.end()) return &it->second;
+    SideStream s;
+    if (cudaStreamCreateWithFlags(&s.side, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    return &(pool[key] = s);
+}
+#endif

@@ -9,7 +9,10 @@
 //   * the CTA polls the per-4x4 "done" map of the cells its edge pixels come from, then gathers the edge array
 //     into shared memory with L1-bypassing loads (the rules of dav1d_prepare_intra_edges: replication past the
 //     tile end, default values without neighbours, Z2 corner smoothing);
-//   * predicts (ipred_body.cuh), adds the inverse transform (itx_body.cuh), fences, publishes its cells.
+//   * predicts (ipred_body.cuh) into a shared-memory tile, adds the inverse transform (itx_body.cuh) there, writes
+//     the finished block to the picture with row-contiguous stores, fences, publishes its cells;
+//   * the next ticket, the next record and an L2 prefetch of its coefficients are issued while the current block is
+//     in flight, so that only [poll -> edge loads -> predict -> transform -> store -> fence] is on the dependency chain.
 // Integer, bit-exact with the reference C path.
 #include "ipred_body.cuh"
 #include "itx_body.cuh"
@@ -17,20 +20,21 @@
 
 namespace b200 {
 
-// scratch layout: [ticket counter: 256 B][done maps of the three planes, bytes][cfl ac: per CTA 32*32 int16]
+// scratch layout: [ticket counter: 256 B][done maps of the three planes, one byte per 4x4 cell]
 struct IntraScratch {
-    size_t done_off[3], ac_off, total;
+    size_t done_off[3], total;
 };
-static inline IntraScratch intra_scratch_layout(const B200IntraFrame *f, int grid)
+static inline IntraScratch intra_scratch_layout(const B200IntraFrame *f)
 {
     IntraScratch L;
     size_t o = 256;
     for (int p = 0; p < 3; p++) { L.done_off[p] = o; o += ((size_t)f->w4[p] * f->h4[p] + 255) & ~(size_t)255; }
-    L.ac_off = o; o += (size_t)grid * 32 * 32 * sizeof(int16_t);
     L.total = o;
     return L;
 }
-constexpr int kIntraGrid = 148 * 4;
+// CTAs per launch: a frame's wavefront is a few dozen blocks wide; a modest grid leaves room for other frames'
+// kernels (other streams) to run beside this one
+constexpr int kIntraGrid = 148;
 
 struct IntraParams {
     B200IntraFrame f;
@@ -38,7 +42,6 @@ struct IntraParams {
     int n;
     int *ticket;
     uint8_t *done[3];
-    int16_t *ac;
 };
 
 B200_DEV int ld_cell(const uint8_t *p) { return *(const volatile uint8_t *)p; }
@@ -51,27 +54,45 @@ template <bool HBD> B200_DEV int ld_px(const typename Bd<HBD>::pixel *p) {
 #endif
 }
 
+B200_DEV void prefetch_l2(const void *p) {
+#ifndef B200_EMU
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
+
 template <bool HBD>
 __global__ void __launch_bounds__(kIpT) intra_frame_kernel(const IntraParams P, const int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     typedef typename Bd<HBD>::coef coef;
+    constexpr int kRecWords = sizeof(B200IntraTx) / 4;
     __shared__ IpShared S;
     __shared__ int s_itx[ItxGeom<64, 64>::NB * ItxGeom<64, 64>::SLOT];
+    __shared__ pixel s_px[64 * 64];                 // the block being reconstructed (pitch = its width)
+    __shared__ int16_t s_ac[32 * 32];
     __shared__ B200ItxBlock s_blk;
-    __shared__ int s_ticket;
+    __shared__ int s_ticket, s_next;
+    __shared__ uint32_t s_rec[kRecWords];
     const int tid = threadIdx.x;
     const B200IntraFrame &f = P.f;
     const int bitdepth = 32 - __clz(bdmax);
     int *const tl = S.edge + 128;
-    int16_t *const ac = P.ac + (size_t)blockIdx.x * 32 * 32;
+
+    if (tid == 0) s_ticket = atomicAdd(P.ticket, 1);
+    __syncthreads();
+    if (tid < kRecWords && s_ticket < P.n) s_rec[tid] = ((const uint32_t *)&P.tx[s_ticket])[tid];
+    __syncthreads();
 
     for (;;) {
-        if (tid == 0) s_ticket = atomicAdd(P.ticket, 1);
-        __syncthreads();
         const int ti = s_ticket;
         if (ti >= P.n) break;
-        const B200IntraTx r = P.tx[ti];
+        B200IntraTx r;
+#pragma unroll
+        for (int k = 0; k < kRecWords; k++) ((uint32_t *)&r)[k] = s_rec[k];
+        int nxt = 0;
+        if (tid == 0) nxt = atomicAdd(P.ticket, 1);          // consumed at the end of this iteration
         const int pl = r.plane, st = f.stride[pl];
         const int tw = c_tx_w4[r.tx], th = c_tx_h4[r.tx];              // 4-sample units
         const int w = tw * 4, h = th * 4;
@@ -101,9 +122,10 @@ __global__ void __launch_bounds__(kIpT) intra_frame_kernel(const IntraParams P, 
                 else if (c < n_left + n_top) cell = dmap + (y - 1) * mw + x + (c - n_left);
                 else if (c < n_left + n_top + n_tl) cell = dmap + (y - 1) * mw + x - 1;
                 else { const int k = c - n_left - n_top - n_tl; cell = P.done[0] + (ly4 + k / lw4) * f.w4[0] + lx4 + k % lw4; }
-                while (!ld_cell(cell)) __nanosleep(64);
+                while (!ld_cell(cell)) __nanosleep(20);
             }
             __threadfence();
+            if (tid == 0) s_next = nxt;
             __syncthreads();
         }
 
@@ -147,62 +169,68 @@ __global__ void __launch_bounds__(kIpT) intra_frame_kernel(const IntraParams P, 
             }
             if (tid == 0)
                 tl[0] = have_left ? (have_top ? ld_px<HBD>(top - 1) : ld_px<HBD>(dst - 1)) : (have_top ? ld_px<HBD>(top) : half);
-            __syncthreads();
-            if (tid == 0 && mode == B200_Z2_PRED && tw + th >= 6 && (r.angle_flags & 1024))
-                tl[0] = ((tl[-1] + tl[1]) * 5 + tl[0] * 6 + 8) >> 4;
-            __syncthreads();
-        }
-
-        // ---- predict
-        if (is_cfl) {
-            const pixel *ypx = (const pixel *)f.pic + r.luma_off;
-            // cfl_ac reads pixels another SM may have written: stage through ld_px by way of the body's plain loads
-            // is not possible, so the (tiny) ac computation is done here with L2 loads.
-            {
+            // CFL: the (sub-sampled, padded) luma block -> s_ac (mean removed below)
+            int part = 0;
+            if (is_cfl) {
+                const pixel *ypx = (const pixel *)f.pic + r.luma_off;
                 const int ssh = f.ss_hor, ssv = f.ss_ver, ys = f.stride[0];
-                int part = 0;
                 for (int i = tid; i < w * h; i += kIpT) {
                     const int yy = i / w, xx = i - yy * w;
                     const int sy = imin(yy, h - 4 * r.cfl_h_pad - 1), sx = imin(xx, w - 4 * r.cfl_w_pad - 1);
                     const pixel *p = ypx + (ptrdiff_t)(sy << ssv) * ys + (sx << ssh);
-                    int s = ld_px<HBD>(p);
-                    if (ssh) s += ld_px<HBD>(p + 1);
-                    if (ssv) { s += ld_px<HBD>(p + ys); if (ssh) s += ld_px<HBD>(p + ys + 1); }
-                    s <<= 1 + !ssv + !ssh;
-                    ac[i] = (int16_t)s;
-                    part += s;
+                    int sacc = ld_px<HBD>(p);
+                    if (ssh) sacc += ld_px<HBD>(p + 1);
+                    if (ssv) { sacc += ld_px<HBD>(p + ys); if (ssh) sacc += ld_px<HBD>(p + ys + 1); }
+                    sacc <<= 1 + !ssv + !ssh;
+                    s_ac[i] = (int16_t)sacc;
+                    part += sacc;
                 }
                 S.tile[tid] = part;
-                __syncthreads();
-                if (tid == 0) {
-                    const int log2sz = (__ffs(w) - 1) + (__ffs(h) - 1);
-                    int sum = (1 << log2sz) >> 1;
-                    for (int i = 0; i < kIpT; i++) sum += S.tile[i];
-                    S.dc = sum >> log2sz;
-                }
-                __syncthreads();
-                const int dc = S.dc;
-                for (int i = tid; i < w * h; i += kIpT) ac[i] = (int16_t)(ac[i] - dc);
-                __syncthreads();
             }
-            ipred_cfl_pred_body<HBD>(S, dst, st, w, h, mode, r.cfl_alpha, ac, bdmax);
+            __syncthreads();
+            if (tid == 0 && mode == B200_Z2_PRED && tw + th >= 6 && (r.angle_flags & 1024))
+                tl[0] = ((tl[-1] + tl[1]) * 5 + tl[0] * 6 + 8) >> 4;
+            if (is_cfl && tid == 0) {
+                const int log2sz = (__ffs(w) - 1) + (__ffs(h) - 1);
+                int sum = (1 << log2sz) >> 1;
+                for (int i = 0; i < kIpT; i++) sum += S.tile[i];
+                S.dc = sum >> log2sz;
+            }
+            __syncthreads();
+        }
+        // the next record (its ticket has arrived by now): loads issued here, consumed at the end of the iteration
+        uint32_t next_word = 0;
+        const int nti = s_next;
+        if (tid < kRecWords && nti < P.n) next_word = ((const uint32_t *)&P.tx[nti])[tid];
+
+        // ---- predict into the shared tile
+        if (is_cfl) {
+            const int dc = S.dc;
+            for (int i = tid; i < w * h; i += kIpT) s_ac[i] = (int16_t)(s_ac[i] - dc);
+            __syncthreads();
+            ipred_cfl_pred_body<HBD>(S, s_px, w, w, h, mode, r.cfl_alpha, s_ac, bdmax);
         } else {
             const int a = (mode == B200_FILTER_PRED ? r.angle : angle) | r.angle_flags;
-            ipred_pred_body<HBD>(S, dst, st, w, h, mode, a, r.max_w, r.max_h, bdmax);
+            ipred_pred_body<HBD>(S, s_px, w, w, h, mode, a, r.max_w, r.max_h, bdmax);
         }
         __syncthreads();
 
-        // ---- residual
+        // ---- residual, added in the shared tile
         if (r.eob >= 0) {
-            if (tid == 0) { s_blk.dst_off = r.dst_off; s_blk.coef_off = r.coef_off; s_blk.eob = r.eob; s_blk.txtp = r.txtp; s_blk.plane = (uint8_t)pl; }
+            if (tid == 0) { s_blk.dst_off = 0; s_blk.coef_off = r.coef_off; s_blk.eob = r.eob; s_blk.txtp = r.txtp; s_blk.plane = 0; }
             __syncthreads();
             switch (r.tx) {
-#define X(TX, W, H, SH) case TX: itx_add_body<W, H, TX, SH, HBD>(0, s_itx, &s_blk, 1, (coef *)f.d_coef, (pixel *)f.pic, f.stride[0], f.stride[1], f.stride[2], bdmax, f.zero_coefs); break;
+#define X(TX, W, H, SH) case TX: itx_add_body<W, H, TX, SH, HBD>(0, s_itx, &s_blk, 1, (coef *)f.d_coef, s_px, W, W, W, bdmax, f.zero_coefs); break;
             B200_ITX_SIZES(X)
 #undef X
             }
+            __syncthreads();
         }
-        // ---- publish
+        // ---- write the block, publish
+        for (int i = tid; i < w * h; i += kIpT) {
+            const int yy = i / w, xx = i - yy * w;
+            dst[(ptrdiff_t)yy * st + xx] = s_px[i];
+        }
         __threadfence();
         __syncthreads();
         {
@@ -210,6 +238,14 @@ __global__ void __launch_bounds__(kIpT) intra_frame_kernel(const IntraParams P, 
             const int cw = imin(tw, mw - x), chh = imin(th, f.h4[pl] - y);
             for (int c = tid; c < cw * chh; c += kIpT) *(volatile uint8_t *)(dm + (y + c / cw) * mw + x + c % cw) = 1;
         }
+        // ---- hand over to the next record
+        if (tid < kRecWords) s_rec[tid] = next_word;
+        if (tid == 0) s_ticket = nti;
+        if (tid == 1 && nti < P.n) {                     // word 1 of the record = coef_off: warm L2 with its coefficients
+            const char *cf = (const char *)((const coef *)f.d_coef + next_word);
+            for (int k = 0; k < 8; k++) prefetch_l2(cf + k * 256);
+        }
+        __syncthreads();
     }
 }
 
@@ -219,22 +255,22 @@ using namespace b200;
 
 extern "C" {
 
-size_t b200_intra_scratch_bytes(const B200IntraFrame *f) { return intra_scratch_layout(f, kIntraGrid).total; }
+size_t b200_intra_scratch_bytes(const B200IntraFrame *f) { return intra_scratch_layout(f).total; }
 
 int b200_intra_frame(int bdmax, const B200IntraFrame *f, const B200IntraTx *d_tx, int n, void *stream)
 {
     if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_intra_frame: bad bitdepth_max"); return -2; }
     if (n <= 0) return 0;
     if (!f->scratch) { b200_set_error("b200_intra_frame: no scratch"); return -2; }
-    const IntraScratch L = intra_scratch_layout(f, kIntraGrid);
+    const IntraScratch L = intra_scratch_layout(f);
     IntraParams P;
     P.f = *f; P.tx = d_tx; P.n = n;
     uint8_t *base = (uint8_t *)f->scratch;
     P.ticket = (int *)base;
     for (int p = 0; p < 3; p++) P.done[p] = base + L.done_off[p];
-    P.ac = (int16_t *)(base + L.ac_off);
-    B200_CUDA_OK(cudaMemsetAsync(base, 0, L.ac_off, (cudaStream_t)stream));     // ticket + done maps
-    const int grid = n < kIntraGrid ? n : kIntraGrid;
+    B200_CUDA_OK(cudaMemsetAsync(base, 0, L.total, (cudaStream_t)stream));      // ticket + done maps
+    const int want = f->grid > 0 ? f->grid : kIntraGrid;
+    const int grid = n < want ? n : want;
     if (bdmax > 255) { auto k = intra_frame_kernel<true>; B200_LAUNCH(k, dim3(grid), dim3(kIpT), 0, (cudaStream_t)stream, P, bdmax); }
     else { auto k = intra_frame_kernel<false>; B200_LAUNCH(k, dim3(grid), dim3(kIpT), 0, (cudaStream_t)stream, P, bdmax); }
     b200_count_launch();

@@ -205,6 +205,73 @@ mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, B200McFrame
         }
 }
 
+// ---- scaled references -----------------------------------------------------------------------------
+// One CTA per block, one thread per output sample: column x reads the source at (mx + x*dx) >> 10 with the
+// filter phase ((mx + x*dx) & 1023) >> 6, row y at (my + y*dy) >> 10 likewise (closed form of the reference's
+// running imx / ioff, src/mc_tmpl.c:213-222); the 8 horizontally filtered rows a sample needs are computed on the
+// fly (scaled prediction is rare: super-resolution / reference scaling only). Clamped loads = emu_edge.
+template <bool HBD>
+__global__ void __launch_bounds__(256)
+mc_scaled_kernel(const B200McScaledBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    const B200McScaledBlock b = blocks[blockIdx.x];
+    const int w = b.w, h = b.h, pl = b.plane;
+    const pixel *__restrict__ ref = (const pixel *)fr.ref[b.ref] + fr.ref_plane_off[pl];
+    const int rs = fr.ref_stride[pl], rw1 = fr.ref_w[pl] - 1, rh1 = fr.ref_h[pl] - 1;
+    const int ib = inter_bits<HBD>(bdmax);
+    const int bias = HBD ? 8192 : 0;
+    const bool bilin = b.filter2d == 9, is_prep = b.op != 0;
+    const int th = bilin ? 0 : c_f2d_h[b.filter2d], tv = bilin ? 0 : c_f2d_v[b.filter2d];
+    const int hidx = w > 4 ? th : 3 + (th & 1), vidx = h > 4 ? tv : 3 + (tv & 1);
+    pixel *const dpx = (pixel *)fr.dst;
+    const int ds = fr.dst_stride[pl];
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+        const int y = i / w, x = i - y * w;
+        const int px = b.mx + x * b.dx, py = b.my + y * b.dy;
+        const int sx = b.src_x + (px >> 10), sy = b.src_y + (py >> 10);
+        int out;
+        if (bilin) {
+            const int fx = (px & 0x3ff) >> 6, fy = (py & 0x3ff) >> 6;
+            int m[2];
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const pixel *row = ref + (ptrdiff_t)iclip(sy + r, 0, rh1) * rs;
+                const int p0 = row[iclip(sx, 0, rw1)], p1 = row[iclip(sx + 1, 0, rw1)];
+                m[r] = RND_SH(16 * p0 + fx * (p1 - p0), 4 - ib);
+            }
+            const int s = 16 * m[0] + fy * (m[1] - m[0]);
+            out = is_prep ? RND_SH(s, 4) - bias : iclip(RND_SH(s, 4 + ib), 0, bdmax);
+        } else {
+            const int fx = (px & 0x3ff) >> 6, fy = (py & 0x3ff) >> 6;
+            int mid[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                if (!fy && r != 3) { mid[r] = 0; continue; }
+                const pixel *row = ref + (ptrdiff_t)iclip(sy + r - 3, 0, rh1) * rs;
+                if (fx) {
+                    int sacc = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) sacc += b200_mc_subpel_filters[hidx][fx - 1][k] * (int)row[iclip(sx + k - 3, 0, rw1)];
+                    mid[r] = RND_SH(sacc, 6 - ib);
+                } else {
+                    mid[r] = (int)row[iclip(sx, 0, rw1)] << ib;
+                }
+            }
+            if (fy) {
+                int sacc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) sacc += b200_mc_subpel_filters[vidx][fy - 1][k] * mid[k];
+                out = is_prep ? RND_SH(sacc, 6) - bias : iclip(RND_SH(sacc, 6 + ib), 0, bdmax);
+            } else {
+                out = is_prep ? mid[3] - bias : iclip((mid[3] + ((1 << ib) >> 1)) >> ib, 0, bdmax);
+            }
+        }
+        if (is_prep) fr.tmp[b.dst_off + y * w + x] = (int16_t)out;
+        else dpx[b.dst_off + (ptrdiff_t)y * ds + x] = (pixel)out;
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 template <bool HBD>
 __global__ void __launch_bounds__(128)
@@ -384,6 +451,15 @@ int b200_mc_batch(int bitdepth_max, const B200McFrame *frame, const B200McBlock 
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
+int b200_mc_scaled_batch(int bitdepth_max, const B200McFrame *frame, const B200McScaledBlock *d_blocks, int n, void *stream) {
+    if (check_bd(bitdepth_max, "b200_mc_scaled_batch")) return -2;
+    if (n <= 0) return 0;
+    if (bitdepth_max > 255) { auto k = mc_scaled_kernel<true>; B200_LAUNCH(k, dim3(n), dim3(256), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_scaled_kernel<false>; B200_LAUNCH(k, dim3(n), dim3(256), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 int b200_mc_comp_batch(int bitdepth_max, const B200McFrame *frame, const B200CompBlock *d_blocks, int n, void *stream) {
     if (check_bd(bitdepth_max, "b200_mc_comp_batch")) return -2;
     if (n <= 0) return 0;
@@ -461,7 +537,59 @@ static int mc_l1(int op, void *out, ptrdiff_t out_stride, const void *src, ptrdi
     return 0;
 }
 
+static int mc_scaled_l1(int op, void *out, ptrdiff_t out_stride, const void *src, ptrdiff_t src_stride, int w, int h,
+                        int mx, int my, int dx, int dy, int f2d, int bdmax)
+{
+    if (check_bd(bdmax, "b200_mc_scaled")) return -2;
+    if (f2d < 0 || f2d > 9 || w < 2 || w > 128 || h < 2 || h > 128 || mx < 0 || mx > 1023 || my < 0 || my > 1023 ||
+        dx < 1 || dx > 2048 || dy < 1 || dy > 2048) {
+        b200_set_error("b200_mc_scaled: bad arguments (w=%d h=%d mx=%d my=%d dx=%d dy=%d filter=%d)", w, h, mx, my, dx, dy, f2d);
+        return -2;
+    }
+    std::lock_guard<std::mutex> lk(host_lock());
+    const size_t px = bdmax > 255 ? 2 : 1;
+    // the window the reference reads (8-tap: 3 before / 4 after the integer position; bilinear: 0 / 1)
+    const int bl = f2d == 9 ? 0 : 3, al = f2d == 9 ? 1 : 4;
+    const int ww = ((mx + (w - 1) * dx) >> 10) + 1 + bl + al, wh = ((my + (h - 1) * dy) >> 10) + 1 + bl + al;
+    static uint8_t *stage = nullptr; static size_t stage_sz = 0;
+    const size_t need = (size_t)ww * wh * px;
+    if (need > stage_sz) { free(stage); stage = (uint8_t *)malloc(need); stage_sz = stage ? need : 0; if (!stage) { b200_set_error("oom"); return -1; } }
+    pack_rect(stage, (const uint8_t *)src - (ptrdiff_t)bl * src_stride - (ptrdiff_t)bl * (ptrdiff_t)px, src_stride, ww, wh, px);
+    if (s_ref.upload(stage, need)) return -1;
+    if (s_dst.reserve((size_t)w * h * 2)) return -1;
+    B200McFrame fr;
+    memset(&fr, 0, sizeof(fr));
+    fr.ref[0] = s_ref.p; fr.ref_stride[0] = ww; fr.ref_w[0] = ww; fr.ref_h[0] = wh;
+    fr.dst = s_dst.p; fr.dst_stride[0] = w; fr.tmp = (int16_t *)s_dst.p;
+    B200McScaledBlock b;
+    memset(&b, 0, sizeof(b));
+    b.src_x = bl; b.src_y = bl; b.w = (uint8_t)w; b.h = (uint8_t)h; b.mx = (uint16_t)mx; b.my = (uint16_t)my;
+    b.dx = (uint16_t)dx; b.dy = (uint16_t)dy; b.filter2d = (uint8_t)f2d; b.op = (uint8_t)op;
+    if (s_desc.upload(&b, sizeof(b))) return -1;
+    int r = b200_mc_scaled_batch(bdmax, &fr, (const B200McScaledBlock *)s_desc.p, 1, 0);
+    if (r) return r;
+    if (op) {
+        if (s_dst.download(out, (size_t)w * h * 2)) return -1;
+        B200_CUDA_OK(cudaStreamSynchronize(0));
+    } else {
+        static uint8_t h_out[128 * 128 * 2];
+        if (s_dst.download(h_out, (size_t)w * h * px)) return -1;
+        B200_CUDA_OK(cudaStreamSynchronize(0));
+        unpack_rect(out, out_stride, h_out, w, h, px);
+    }
+    return 0;
+}
+
 extern "C" {
+
+int b200_mc_put_scaled(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride, int w, int h,
+                       int mx, int my, int dx, int dy, int filter2d, int bitdepth_max) {
+    return mc_scaled_l1(0, dst, dst_stride, src, src_stride, w, h, mx, my, dx, dy, filter2d, bitdepth_max);
+}
+int b200_mc_prep_scaled(int16_t *tmp, const void *src, ptrdiff_t src_stride, int w, int h, int mx, int my,
+                        int dx, int dy, int filter2d, int bitdepth_max) {
+    return mc_scaled_l1(1, tmp, 0, src, src_stride, w, h, mx, my, dx, dy, filter2d, bitdepth_max);
+}
 
 int b200_mc_put(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride, int w, int h,
                 int mx, int my, int filter2d, int bitdepth_max) {
@@ -625,6 +753,10 @@ template <int F> void put8(uint8_t *d, ptrdiff_t ds, const uint8_t *s, ptrdiff_t
 template <int F> void put16(uint16_t *d, ptrdiff_t ds, const uint16_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int bd) { DIE_IF(b200_mc_put(d, ds, s, ss, w, h, mx, my, F, bd), "mc"); }
 template <int F> void prep8(int16_t *t, const uint8_t *s, ptrdiff_t ss, int w, int h, int mx, int my) { DIE_IF(b200_mc_prep(t, s, ss, w, h, mx, my, F, 255), "mct"); }
 template <int F> void prep16(int16_t *t, const uint16_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int bd) { DIE_IF(b200_mc_prep(t, s, ss, w, h, mx, my, F, bd), "mct"); }
+template <int F> void puts8(uint8_t *d, ptrdiff_t ds, const uint8_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int dx, int dy) { DIE_IF(b200_mc_put_scaled(d, ds, s, ss, w, h, mx, my, dx, dy, F, 255), "mc_scaled"); }
+template <int F> void puts16(uint16_t *d, ptrdiff_t ds, const uint16_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int dx, int dy, int bd) { DIE_IF(b200_mc_put_scaled(d, ds, s, ss, w, h, mx, my, dx, dy, F, bd), "mc_scaled"); }
+template <int F> void preps8(int16_t *t, const uint8_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int dx, int dy) { DIE_IF(b200_mc_prep_scaled(t, s, ss, w, h, mx, my, dx, dy, F, 255), "mct_scaled"); }
+template <int F> void preps16(int16_t *t, const uint16_t *s, ptrdiff_t ss, int w, int h, int mx, int my, int dx, int dy, int bd) { DIE_IF(b200_mc_prep_scaled(t, s, ss, w, h, mx, my, dx, dy, F, bd), "mct_scaled"); }
 void avg8(uint8_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h) { DIE_IF(b200_mc_comp(d, ds, a, b, w, h, B200_COMP_AVG, 0, nullptr, 255), "avg"); }
 void avg16(uint16_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, int bd) { DIE_IF(b200_mc_comp(d, ds, a, b, w, h, B200_COMP_AVG, 0, nullptr, bd), "avg"); }
 void wavg8(uint8_t *d, ptrdiff_t ds, const int16_t *a, const int16_t *b, int w, int h, int wt) { DIE_IF(b200_mc_comp(d, ds, a, b, w, h, B200_COMP_W_AVG, wt, nullptr, 255), "w_avg"); }
@@ -645,10 +777,10 @@ void resize8(uint8_t *d, ptrdiff_t ds, const uint8_t *s, ptrdiff_t ss, int dw, i
 void resize16(uint16_t *d, ptrdiff_t ds, const uint16_t *s, ptrdiff_t ss, int dw, int h, int sw, int dx, int mx, int bd) { DIE_IF(b200_mc_resize(d, ds, s, ss, dw, h, sw, dx, mx, bd), "resize"); }
 
 template <int... F> void fill_mc8(B200MCDSPContext *c, std::integer_sequence<int, F...>) {
-    ((c->mc[F] = (void *)put8<F>, c->mct[F] = (void *)prep8<F>, c->mc_scaled[F] = nullptr, c->mct_scaled[F] = nullptr), ...);
+    ((c->mc[F] = (void *)put8<F>, c->mct[F] = (void *)prep8<F>, c->mc_scaled[F] = (void *)puts8<F>, c->mct_scaled[F] = (void *)preps8<F>), ...);
 }
 template <int... F> void fill_mc16(B200MCDSPContext *c, std::integer_sequence<int, F...>) {
-    ((c->mc[F] = (void *)put16<F>, c->mct[F] = (void *)prep16<F>, c->mc_scaled[F] = nullptr, c->mct_scaled[F] = nullptr), ...);
+    ((c->mc[F] = (void *)put16<F>, c->mct[F] = (void *)prep16<F>, c->mc_scaled[F] = (void *)puts16<F>, c->mct_scaled[F] = (void *)preps16<F>), ...);
 }
 }  // namespace
 

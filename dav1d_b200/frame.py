@@ -73,7 +73,7 @@ class NumpyAlloc:
 
 
 class FrameBuffers:
-    def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True):
+    def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True, intra_grid=0):
         self.S, self.lib = S, lib or _lib.get_lib()
         self.alloc = alloc or TorchAlloc()
         A = self.alloc
@@ -122,7 +122,7 @@ class FrameBuffers:
         n_intra = 0
         if S.get("intra_tx") is not None and len(S["intra_tx"]):
             it = j.intra
-            it.pic, it.d_coef, it.zero_coefs = p0, j.d_coef, 0
+            it.pic, it.d_coef, it.zero_coefs, it.grid = p0, j.d_coef, 0, intra_grid
             it.ss_hor, it.ss_ver = S["ss_hor"], S["ss_ver"]
             for p in range(3):
                 it.stride[p] = S["stride"][p]

@@ -163,7 +163,27 @@ typedef struct B200WarpBlock {
 B200_API int b200_mc_warp_batch(int bitdepth_max, const B200McFrame *frame, const B200WarpBlock *d_blocks,
                                 int n_blocks, void *stream);
 
+/* scaled references: mc_scaled[filter2d] (op 0) / mct_scaled[filter2d] (op 1) (reference src/mc_tmpl.c:189-244,
+ * 307-358, 491-531, 588-626; caller src/recon_tmpl.c:991-1046). Positions advance by dx / dy 1/1024ths of a sample
+ * per output column / row; src_x, src_y is the sample that (mx, my) = (0, 0) addresses. Source coordinates are
+ * clamped to the reference plane (= emu_edge). */
+typedef struct B200McScaledBlock {
+    uint32_t dst_off;            /* put: pixel offset in dst; prep: int16 offset in tmp (dense, pitch w) */
+    int32_t src_x, src_y;
+    uint16_t mx, my;             /* 0 .. 1023 */
+    uint16_t dx, dy;             /* 1 .. 2048 */
+    uint8_t w, h;                /* 2 .. 128 */
+    uint8_t filter2d, op, plane, ref;
+    uint8_t pad[2];
+} B200McScaledBlock;
+B200_API int b200_mc_scaled_batch(int bitdepth_max, const B200McFrame *frame, const B200McScaledBlock *d_blocks,
+                                  int n_blocks, void *stream);
+
 /* ---- mc: Level 1 (host pointers, dav1d signatures; bitdepth_max appended like HIGHBD_DECL_SUFFIX) */
+B200_API int b200_mc_put_scaled(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride, int w, int h,
+                                int mx, int my, int dx, int dy, int filter2d, int bitdepth_max);
+B200_API int b200_mc_prep_scaled(int16_t *tmp, const void *src, ptrdiff_t src_stride, int w, int h, int mx, int my,
+                                 int dx, int dy, int filter2d, int bitdepth_max);
 B200_API int b200_mc_put(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
                          int w, int h, int mx, int my, int filter2d, int bitdepth_max);
 B200_API int b200_mc_prep(int16_t *tmp, const void *src, ptrdiff_t src_stride, int w, int h,
@@ -180,8 +200,7 @@ B200_API int b200_mc_emu_edge(intptr_t bw, intptr_t bh, intptr_t iw, intptr_t ih
 B200_API int b200_mc_resize(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride,
                             int dst_w, int h, int src_w, int dx, int mx, int bitdepth_max);
 
-/* same layout as Dav1dMCDSPContext (reference src/mc.h:146-162); *_scaled slots are NULL until the
- * scaled-reference kernels land */
+/* same layout as Dav1dMCDSPContext (reference src/mc.h:146-162) */
 typedef struct B200MCDSPContext {
     void *mc[B200_N_2D_FILTERS];
     void *mc_scaled[B200_N_2D_FILTERS];
@@ -445,7 +464,8 @@ typedef struct B200IntraFrame {
     int32_t ss_hor, ss_ver;
     int32_t w4[3], h4[3];          /* per plane: frame size in 4-sample units (done-map geometry) */
     void *d_coef;
-    int32_t zero_coefs, pad;
+    int32_t zero_coefs;
+    int32_t grid;                  /* CTAs to launch; 0 = default (one per SM) */
     void *scratch;                 /* device, >= b200_intra_scratch_bytes(frame) */
 } B200IntraFrame;
 B200_API size_t b200_intra_scratch_bytes(const B200IntraFrame *frame);
@@ -484,6 +504,8 @@ typedef struct B200FrameJob {
     const B200IntraTx *d_intra;  /* intra transform blocks (run after the inter stages, before the post filters) */
     int32_t n_intra, pad6;
     B200IntraFrame intra;
+    const B200McScaledBlock *d_scaled;   /* predictions from scaled references (run with the put / prep stage) */
+    int32_t n_scaled, pad7;
     int32_t run_fg, pad5;        /* film grain on the output copy (fg.in = lr.dst typically); the grain LUT preparation
                                     runs on an internal side stream concurrently with reconstruction */
     B200FgFrame fg;
@@ -491,7 +513,7 @@ typedef struct B200FrameJob {
 B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check): 0 McFrame, 1 McBlock, 2 CompBlock,
  * 3 BlendBlock, 4 WarpBlock, 5 ItxBlock, 6 LfFrame, 7 CdefFrame, 8 LrFrame, 9 FrameJob, 10 Av1Filter, 11 Av1Restoration,
- * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame */
+ * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame, 16 McScaledBlock */
 B200_API int b200_struct_size(int which);
 
 /* The same job fed from HOST buffers (the end-to-end path): every (host, dev, bytes) pair of `uploads`

@@ -268,7 +268,7 @@ def test_oracle_mc_vs_reference(bpc):
 def test_emu_mc(bpc):
     from dav1d_b200.dsp import MCDSPContext
     new = MCDSPContext(bpc, lib=refs.emu_lib())
-    run_mc_checks(new, refs.oracle_mc_ctx(bpc), bpc, seed=50 + bpc, light=True)
+    run_mc_checks(new, refs.oracle_mc_ctx(bpc), bpc, seed=50 + bpc, light=True, scaled=True)
 
 
 # ------------------------------------------------------------------ GPU parity (Level-1 table)
@@ -278,7 +278,7 @@ def test_gpu_mc_level1(bpc):
     from dav1d_b200.dsp import MCDSPContext
     new = MCDSPContext(bpc)
     chk = refs.ref_mc_ctx(bpc) if refs.have_ref() else refs.oracle_mc_ctx(bpc)
-    n = run_mc_checks(new, chk, bpc, seed=60 + bpc)
+    n = run_mc_checks(new, chk, bpc, seed=60 + bpc, scaled=True)
     assert n > 1500
     run_mc_checks(new, refs.oracle_mc_ctx(bpc), bpc, seed=70 + bpc, light=True)
 
