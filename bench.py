@@ -185,6 +185,9 @@ def workload_buffers(name, S, **kw):
     return frame.FrameBuffers(S, **kw)
 
 
+OURS = dict(compact=True)    # our arm ships coefficients 0 .. eob in scan order (the reference arm needs the dense plane)
+
+
 # ------------------------------------------------------------------------------ reference arm / cpu baseline
 def cpu_frames(S, n_threads, reps, use_ref=True):
     """`n_threads` frames in parallel, one per thread (frame threading), each through the reference's own
@@ -285,7 +288,7 @@ def run_ours_frame(args):
     for k in range(nsets):
         S = make_workload_frame(args.workload, 1 + rank * 16 + k)
         Ss.append(S)
-        fbs.append(workload_buffers(args.workload, S))
+        fbs.append(workload_buffers(args.workload, S, **OURS))
     fps = FRAME_WORKLOADS[args.workload].get("frames_per_step", 1)
     px_per_step = fps * FRAME_WORKLOADS[args.workload]["W"] * FRAME_WORKLOADS[args.workload]["H"]
     side = [torch.cuda.Stream() for _ in range(fps)] if fps > 1 else []
@@ -399,6 +402,7 @@ def run_ours_frame(args):
                            "records": {"pred_blocks": int(len(Ss[0]["pred"])), "compound": int(len(Ss[0]["comp"]) + len(Ss[0]["comp2"])),
                                        "tx_blocks": int(sum(len(a) for a in Ss[0]["itx"].values())), "coefs": int(len(Ss[0]["coefs"])),
                                        "intra_tx_blocks": int(len(Ss[0].get("intra_tx", []))), "intra_waves": int(Ss[0].get("intra_waves", 0))},
+                           "upload": "per coded transform block the coefficients 0..eob in scan order (expanded on the device inside the timed job) + block records + masks/levels",
                            "exchange": "all_gather of each rank's restored picture per step (NCCL)" if world > 1 else "none"},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

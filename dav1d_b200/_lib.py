@@ -102,6 +102,10 @@ class McScaledBlock(C.Structure):
                 ("op", C.c_uint8), ("plane", C.c_uint8), ("ref", C.c_uint8), ("pad", C.c_uint8 * 2)]
 
 
+class CoefBlock(C.Structure):
+    _fields_ = [("dense_off", C.c_uint32), ("compact_off", C.c_uint32), ("eob", C.c_int16), ("tx", C.c_uint8), ("pad", C.c_uint8)]
+
+
 class IntraTx(C.Structure):
     """struct B200IntraTx (40 bytes)"""
     _fields_ = [("dst_off", C.c_uint32), ("coef_off", C.c_uint32), ("luma_off", C.c_uint32), ("eob", C.c_int16),
@@ -131,6 +135,8 @@ class FrameJob(C.Structure):
                 ("lf", LfFrame), ("cdef", CdefFrame), ("lr", LrFrame),
                 ("d_intra", C.c_void_p), ("n_intra", C.c_int32), ("pad6", C.c_int32), ("intra", IntraFrame),
                 ("d_scaled", C.c_void_p), ("n_scaled", C.c_int32), ("pad7", C.c_int32),
+                ("d_expand", C.c_void_p), ("n_expand", C.c_int32), ("pad8", C.c_int32), ("d_ccoef", C.c_void_p),
+                ("coef_bytes", C.c_uint64),
                 ("run_fg", C.c_int32), ("pad5", C.c_int32), ("fg", FgFrame)]
 
 
@@ -190,6 +196,7 @@ _SIGS = {
                                  C.c_void_p, C.c_int, C.c_int]),
     "b200_loop_restoration_dsp_init_8bpc": (None, [C.c_void_p, C.c_int]),
     "b200_loop_restoration_dsp_init_16bpc": (None, [C.c_void_p, C.c_int]),
+    "b200_coef_expand": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     # ---- intra frame
     "b200_intra_scratch_bytes": (C.c_size_t, [C.c_void_p]),
     "b200_intra_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
@@ -274,4 +281,4 @@ class Av1Restoration(C.Structure):
 
 
 ABI_STRUCTS = [McFrame, McBlock, CompBlock, BlendBlock, WarpBlock, ItxBlock, LfFrame, CdefFrame, LrFrame, FrameJob,
-               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame, McScaledBlock]
+               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame, McScaledBlock, CoefBlock]

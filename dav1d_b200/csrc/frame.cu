@@ -20,6 +20,10 @@ int b200_frame_run(const B200FrameJob *j, void *stream)
         fg_prepped = true;
     }
 #endif
+    if (j->n_expand > 0) {
+        B200_CUDA_OK(cudaMemsetAsync(j->d_coef, 0, j->coef_bytes, (cudaStream_t)stream));
+        if ((r = b200_coef_expand(bd, j->d_expand, j->n_expand, j->d_ccoef, j->d_coef, stream))) return r;
+    }
     if ((r = b200_mc_batch(bd, &j->mc, j->d_pred, j->n_pred, stream))) return r;
     if ((r = b200_mc_scaled_batch(bd, &j->mc, j->d_scaled, j->n_scaled, stream))) return r;
     if ((r = b200_mc_warp_batch(bd, &j->mc, j->d_warp, j->n_warp, stream))) return r;
@@ -51,7 +55,7 @@ int b200_struct_size(int which)
     case 6: return sizeof(B200LfFrame); case 7: return sizeof(B200CdefFrame); case 8: return sizeof(B200LrFrame);
     case 9: return sizeof(B200FrameJob); case 10: return sizeof(B200Av1Filter); case 11: return sizeof(B200Av1Restoration);
     case 12: return sizeof(B200FgFrame); case 13: return sizeof(B200FilmGrainData);
-    case 14: return sizeof(B200IntraTx); case 15: return sizeof(B200IntraFrame); case 16: return sizeof(B200McScaledBlock);
+    case 14: return sizeof(B200IntraTx); case 15: return sizeof(B200IntraFrame); case 16: return sizeof(B200McScaledBlock); case 17: return sizeof(B200CoefBlock);
     }
     return -1;
 }

@@ -73,7 +73,7 @@ class NumpyAlloc:
 
 
 class FrameBuffers:
-    def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True, intra_grid=0):
+    def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True, intra_grid=0, compact=False):
         self.S, self.lib = S, lib or _lib.get_lib()
         self.alloc = alloc or TorchAlloc()
         A = self.alloc
@@ -116,7 +116,17 @@ class FrameBuffers:
             if len(a):
                 j.d_itx[tx] = up("itx%d" % tx, a); j.n_itx[tx] = len(a)
                 self.uploads.append(("itx%d" % tx, a))
-        j.d_coef = up("coef", S["coefs"]); self.uploads.append(("coef", S["coefs"]))
+        if compact:
+            # the emitter ships coefficients 0 .. eob in scan order; the job zeroes + rebuilds the dense buffer
+            from . import synth
+            cc, ex = synth.compact_coefs(S)
+            j.d_coef = zeros("coef", S["coefs"].nbytes)
+            j.coef_bytes = S["coefs"].nbytes
+            j.d_ccoef = up("ccoef", cc); self.uploads.append(("ccoef", cc))
+            if len(ex):
+                j.d_expand = up("expand", ex); j.n_expand = len(ex); self.uploads.append(("expand", ex))
+        else:
+            j.d_coef = up("coef", S["coefs"]); self.uploads.append(("coef", S["coefs"]))
         if len(S["mask"]) > 1:
             self.uploads.append(("mask", S["mask"]))
         n_intra = 0
@@ -214,6 +224,9 @@ class FrameBuffers:
         self._downs = (_lib.Xfer * 1)(_lib.Xfer(out_p, self.keep[self.out_name][1], self.S["pic"].nbytes))
         self.h2d_bytes = sum(n for _, _, n in ups)
         self.d2h_bytes = self.S["pic"].nbytes
+
+    def h2d_bytes_estimate(self):
+        return sum(a.nbytes for _, a in self.uploads)
 
     def run_host(self, stream=None):
         if self._host is None:

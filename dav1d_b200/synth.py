@@ -668,3 +668,40 @@ def make_intra_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, p_skip=0.2, p_cfl=0.25)
     S["us"] = (6, 6 - (1 if ss_hor else 0))
     S["rp"], S["sb128"] = 7, 0
     return S
+
+
+# ---------------------------------------------------------------------------------------------------------
+COEF_BLOCK_DT = np.dtype([("dense_off", "<u4"), ("compact_off", "<u4"), ("eob", "<i2"), ("tx", "u1"), ("pad", "u1")])
+
+
+def compact_coefs(S):
+    """What a record emitter would ship instead of the dense coefficient plane: per coded transform block the
+    coefficients 0 .. eob in scan order, plus one B200CoefBlock record each (include/b200av1.h). Returns
+    (compact stream, records)."""
+    dense = S["coefs"]
+    recs, chunks, pos = [], [], 0
+    groups = [(tx, S["itx"][tx]["coef_off"].astype(np.int64), S["itx"][tx]["eob"].astype(np.int64)) for tx in range(19) if len(S["itx"][tx])]
+    it = S.get("intra_tx")
+    if it is not None and len(it):
+        for tx in range(19):
+            sel = (it["tx"] == tx) & (it["eob"] >= 0)
+            if sel.any():
+                groups.append((tx, it["coef_off"][sel].astype(np.int64), it["eob"][sel].astype(np.int64)))
+    for tx, offs, eobs in groups:
+        scan = scan_table(tx)
+        n = len(offs)
+        cnt = eobs + 1
+        # gather dense[off + scan[k]] for k <= eob, block after block
+        k = np.arange(int(cnt.max()))[None, :]
+        valid = k < cnt[:, None]
+        idx = offs[:, None] + scan[np.minimum(k, len(scan) - 1)]
+        chunks.append(dense[idx[valid]])
+        a = np.zeros(n, COEF_BLOCK_DT)
+        a["dense_off"] = offs
+        a["compact_off"] = pos + np.concatenate([[0], np.cumsum(cnt)[:-1]])
+        a["eob"] = eobs; a["tx"] = tx
+        recs.append(a)
+        pos += int(cnt.sum())
+    if not recs:
+        return np.zeros(1, dense.dtype), np.zeros(0, COEF_BLOCK_DT)
+    return np.concatenate(chunks).astype(dense.dtype), np.concatenate(recs)

@@ -472,6 +472,20 @@ B200_API size_t b200_intra_scratch_bytes(const B200IntraFrame *frame);
 B200_API int b200_intra_frame(int bitdepth_max, const B200IntraFrame *frame, const B200IntraTx *d_tx, int n_tx,
                               void *stream);
 
+/* ==== compact coefficient upload ============================================================= */
+/* Per coded transform block the emitter may ship only coefficients 0 .. eob in scan order (dav1d_scans[tx],
+ * reference src/scan.c) instead of the dense block: b200_coef_expand scatters them into the (zeroed) dense buffer
+ * the transform kernels read. In a B200FrameJob: d_expand / n_expand / d_ccoef / coef_bytes; b200_frame_run then
+ * zeroes d_coef[0 .. coef_bytes) and expands before anything else. */
+typedef struct B200CoefBlock {
+    uint32_t dense_off;            /* coefficient index of the block in the dense buffer (= its coef_off) */
+    uint32_t compact_off;          /* coefficient index of its first value in the compact stream */
+    int16_t eob;
+    uint8_t tx, pad;
+} B200CoefBlock;
+B200_API int b200_coef_expand(int bitdepth_max, const B200CoefBlock *d_blocks, int n_blocks, const void *d_compact,
+                              void *d_dense, void *stream);
+
 /* ==== whole-frame job: reconstruction + post-filter sweep ================================= */
 /* What a dav1d `f->bd_fn` record emitter hands over per frame (SURVEY.md §8b level 2): the block
  * records of pass 2 (prediction blocks, compound / blend / warp records, transform blocks bucketed by
@@ -506,6 +520,10 @@ typedef struct B200FrameJob {
     B200IntraFrame intra;
     const B200McScaledBlock *d_scaled;   /* predictions from scaled references (run with the put / prep stage) */
     int32_t n_scaled, pad7;
+    const B200CoefBlock *d_expand;       /* compact coefficient upload (optional, see b200_coef_expand) */
+    int32_t n_expand, pad8;
+    const void *d_ccoef;
+    uint64_t coef_bytes;
     int32_t run_fg, pad5;        /* film grain on the output copy (fg.in = lr.dst typically); the grain LUT preparation
                                     runs on an internal side stream concurrently with reconstruction */
     B200FgFrame fg;
@@ -513,7 +531,7 @@ typedef struct B200FrameJob {
 B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check): 0 McFrame, 1 McBlock, 2 CompBlock,
  * 3 BlendBlock, 4 WarpBlock, 5 ItxBlock, 6 LfFrame, 7 CdefFrame, 8 LrFrame, 9 FrameJob, 10 Av1Filter, 11 Av1Restoration,
- * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame, 16 McScaledBlock */
+ * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame, 16 McScaledBlock, 17 CoefBlock */
 B200_API int b200_struct_size(int which);
 
 /* The same job fed from HOST buffers (the end-to-end path): every (host, dev, bytes) pair of `uploads`

@@ -87,7 +87,8 @@ def test_emu_frame(bpc, W, H, ssh, ssv):
     fb2.run_host()
     last = exp["fg"] if "fg" in exp else exp["lr"]
     assert TLR.picture_equal(S, fb2.host_output(), last)
-    fb3 = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
+    fb3 = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc(), compact=True)   # compact coefficient upload
+    assert fb3.h2d_bytes_estimate() < fb2.h2d_bytes_estimate()
     fb3.submit_host(); fb3.wait()
     assert TLR.picture_equal(S, fb3.host_output(), last)
 
@@ -106,7 +107,7 @@ def test_gpu_frame(bpc, W, H, ssh, ssv):
     fb2.run_host()
     assert TLR.picture_equal(S, fb2.host_output(), last)
     # two frames in flight on their own streams (frame-threaded end-to-end path)
-    fb3, fb4 = frame.FrameBuffers(S), frame.FrameBuffers(S)
+    fb3, fb4 = frame.FrameBuffers(S, compact=True), frame.FrameBuffers(S, compact=True)
     for _ in range(3):
         fb3.submit_host(); fb4.submit_host()
         fb3.wait(); fb4.wait()

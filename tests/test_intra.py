@@ -74,9 +74,9 @@ def test_oracle_intra_vs_reference_functions(bpc, W, H, ssh, ssv):
         assert modes >= set(range(13)) | {synth.MODE_CFL, synth.MODE_FILTER}, modes
 
 
-def run_lib(lib, alloc, S, order="intra_tx"):
+def run_lib(lib, alloc, S, order="intra_tx", compact=False):
     S2 = dict(S); S2["intra_tx"] = np.ascontiguousarray(S[order])
-    fb = frame.FrameBuffers(S2, lib=lib, alloc=alloc, run_lf=False, run_cdef=False, run_lr=False)
+    fb = frame.FrameBuffers(S2, lib=lib, alloc=alloc, run_lf=False, run_cdef=False, run_lr=False, compact=compact)
     fb.run()
     fb.alloc.sync()
     return fb.output("p0")
@@ -90,6 +90,9 @@ def test_emu_intra_frame(bpc, W, H, ssh, ssv):
     got = run_lib(refs.emu_lib(), frame.NumpyAlloc(), S)
     ok, where = planes_equal(S, exp, got)
     assert ok, where
+    got = run_lib(refs.emu_lib(), frame.NumpyAlloc(), S, compact=True)      # coefficients shipped in scan order up to eob
+    ok, where = planes_equal(S, exp, got)
+    assert ok, where
 
 
 @pytest.mark.gpu
@@ -98,7 +101,7 @@ def test_gpu_intra_frame(bpc, W, H, ssh, ssv):
     S = synth.make_intra_frame(np.random.default_rng(740 + bpc + W), bpc, W, H, ssh, ssv)
     exp = oracle_intra(S)
     for order in ("intra_tx", "intra_tx_decode_order"):
-        got = run_lib(_lib.get_lib(), None, S, order)
+        got = run_lib(_lib.get_lib(), None, S, order, compact=order == "intra_tx")
         ok, where = planes_equal(S, exp, got)
         assert ok, (order, where)
 
