@@ -161,11 +161,11 @@ FRAME_WORKLOADS = {
     "4k10_full": dict(bpc=10, W=3840, H=2160, fg=True, dtype="u16/i32->i32",
                       desc="one 3840x2160 10-bit 4:2:0 inter frame per GPU per step, full pipeline: prediction + inverse "
                            "transforms + deblock + CDEF + loop restoration + film grain (BASELINE configs[3])"),
-    "1080p8_intra": dict(bpc=8, W=1920, H=1080, fg=False, dtype="u8/i16->i32", intra=True, frames_per_step=12,
+    "1080p8_intra": dict(bpc=8, W=1920, H=1080, fg=False, dtype="u8/i16->i32", intra=True, frames_per_step=int(os.environ.get("B200_INTRA_FPS", "24")),
                          desc="one 1920x1080 8-bit 4:2:0 intra-only frame per GPU per step: device-side edge preparation + "
-                              "intra prediction + inverse transforms (dependency-driven kernel) + deblock (BASELINE configs[1]); a step is 12 "
-                              "independent frames in flight on 12 streams (an intra frame is a ~1000-deep dependency chain, so "
-                              "frames, like dav1d's frame threads, are the parallel axis)"),
+                              "intra prediction + inverse transforms (dependency-driven kernel) + deblock (BASELINE configs[1]); a step is %s "
+                              "independent frames in flight on as many streams (an intra frame is a ~1000-deep dependency chain, so "
+                              "frames, like dav1d's frame threads, are the parallel axis)" % os.environ.get("B200_INTRA_FPS", "24")),
 }
 
 
@@ -180,8 +180,8 @@ def make_workload_frame(name, seed):
 def workload_buffers(name, S, **kw):
     from dav1d_b200 import frame
     if FRAME_WORKLOADS[name].get("intra"):
-        # 12 frames in flight x 48 CTAs = 576 <= the 592 CTAs (4 per SM) that can be resident at once
-        return frame.FrameBuffers(S, run_cdef=False, run_lr=False, intra_grid=48, **kw)
+        # frames in flight x CTAs per frame <= the 592 CTAs (4 per SM) that can be resident at once
+        return frame.FrameBuffers(S, run_cdef=False, run_lr=False, intra_grid=int(os.environ.get("B200_INTRA_GRID", "24")), **kw)
     return frame.FrameBuffers(S, **kw)
 
 
@@ -365,7 +365,7 @@ def run_ours_frame(args):
     t = torch.tensor([e2e_ms], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * px_per_step / (float(t.item()) * 1e-3) / 1e6
+    e2e_val = world * (px_per_step // fps) / (float(t.item()) * 1e-3) / 1e6      # one frame per submit
     sampler.stop_flag = True
     sampler.join(timeout=2)
 

@@ -141,7 +141,7 @@ B200_DEV int fg_pixel_grain(const B200FilmGrainData &d, const int16_t *lut, cons
                             int b8, int row, int x, int y, int pw, int bh, int sx, int sy)
 {
     const int gmin = -(128 << b8), gmax = (128 << b8) - 1;
-    const int bs = 32 >> sx, bsy = 32 >> sy, bi = x / bs, xin = x - bi * bs;
+    const int bs = 32 >> sx, bsy = 32 >> sy, bi = x >> (5 - sx), xin = x & (bs - 1);
     const int bw = imin(bs, pw - bi * bs);
     const bool xov = d.overlap_flag && bi && xin < imin(2 >> sx, bw);
     const bool yov = d.overlap_flag && row > 0 && y < imin(2 >> sy, bh);
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) fg_apply_kernel(B200FgFrame f, int bdmax)
     const FgScratch *S = (const FgScratch *)f.scratch;
     const int b8 = HBD ? (32 - __clz(bdmax)) - 8 : 0;
     const int srows = 32 >> sy;                       // strip height in plane rows
-    const int row = yp / srows, y = yp - row * srows;
+    const int row = yp >> (5 - sy), y = yp & (srows - 1);
     const int bh_l = imin(f.h - row * 32, 32), bh = (bh_l + sy) >> sy;
     const int g = fg_pixel_grain(d, S->lut[pl], &S->offsets[row * kMaxBlocksX], &S->offsets[(row ? row - 1 : 0) * kMaxBlocksX],
                                  b8, row, x, y, pw, bh, sx, sy);

@@ -66,24 +66,7 @@ itx_add_grouped_kernel(const ItxGroups g, typename Bd<HBD>::coef *__restrict__ c
 int launch_itx_grouped(bool hbd, const void *const *blocks, const int32_t *n, void *coefs, void *pic, const int32_t *st,
                        int bdmax, int zero, cudaStream_t stream)
 {
-    // the 64-point class is a few hundred long-running CTAs: it runs on a side stream beside the other sizes
-    // (the two classes never touch the same pixels)
-    cudaStream_t main_stream = stream;
-#ifndef B200_EMU
-    SideStream *ss = nullptr;
-    bool forked = false;
-    {
-        int n_big = 0, n_small = 0;
-#define X(TX, W, H, SH) if (n[TX] > 0) { if (W == 64 || H == 64) n_big += n[TX]; else n_small += n[TX]; }
-        B200_ITX_SIZES(X)
-#undef X
-        if (n_big && n_small && (ss = side_stream_for(main_stream, 1))) forked = ss->fork(main_stream);
-    }
-#endif
     for (int big = 1; big >= 0; big--) {
-#ifndef B200_EMU
-        stream = (big && forked) ? ss->side : main_stream;
-#endif
         ItxGroups g;
         int total = 0;
 #define X(TX, W, H, SH) { \
@@ -104,9 +87,6 @@ int launch_itx_grouped(bool hbd, const void *const *blocks, const int32_t *n, vo
         }
         b200_count_launch();
     }
-#ifndef B200_EMU
-    if (forked && !ss->join(main_stream)) return -1;
-#endif
     return 0;
 }
 

@@ -45,8 +45,9 @@ B200_DEV void lr_tile_compute(LrShared &sm, const LrTileParams &P, int tw, int t
     if (P.type == 1) {
         const int rbh = 3 + (bitdepth == 12) * 2, rbv = 11 - (bitdepth == 12) * 2;
         const int clip_limit = 1 << (bitdepth + 1 + 7 - rbh);
-        for (int i = tid; i < (th + 6) * tw; i += nt) {
-            const int y = i / tw, x = i - y * tw;
+        for (int i = tid; i < (th + 6) * kTW; i += nt) {      // constant pitch: the divisions become shifts
+            const int y = i / kTW, x = i - y * kTW;
+            if (x >= tw) continue;
             int sum = 1 << (bitdepth + 6);
             if (!HBD) sum += (int)sm.src[y][x + 3] * 128;
 #pragma unroll
@@ -55,8 +56,9 @@ B200_DEV void lr_tile_compute(LrShared &sm, const LrTileParams &P, int tw, int t
         }
         __syncthreads();
         const int round_offset = 1 << (bitdepth + (rbv - 1));
-        for (int i = tid; i < th * tw; i += nt) {
-            const int y = i / tw, x = i - y * tw;
+        for (int i = tid; i < th * kTW; i += nt) {
+            const int y = i / kTW, x = i - y * kTW;
+            if (x >= tw) continue;
             int sum = -round_offset;
 #pragma unroll
             for (int k = 0; k < 7; k++) sum += (int)sm.u.hor[y + k][x] * P.fv[k];
@@ -67,8 +69,9 @@ B200_DEV void lr_tile_compute(LrShared &sm, const LrTileParams &P, int tw, int t
     // ---- self-guided ----
     const int b8 = bitdepth - 8;
     if (P.s1) {      // 3x3 surfaces at rows -1 .. th, cols -1 .. tw
-        for (int i = tid; i < (th + 2) * (tw + 2); i += nt) {
-            const int yy = i / (tw + 2), xx = i - yy * (tw + 2);     // surface index; source centre (xx + 2, yy + 2)
+        for (int i = tid; i < (th + 2) * (kTW + 2); i += nt) {
+            const int yy = i / (kTW + 2), xx = i - yy * (kTW + 2);   // surface index; source centre (xx + 2, yy + 2)
+            if (xx >= tw + 2) continue;
             int sum = 0, sq = 0;
 #pragma unroll
             for (int dy = -1; dy <= 1; dy++)
@@ -85,8 +88,9 @@ B200_DEV void lr_tile_compute(LrShared &sm, const LrTileParams &P, int tw, int t
     }
     if (P.s0) {      // 5x5 surfaces at odd rows -1, 1, 3, ... (index j <-> row 2j - 1)
         const int nrow = (th + 1) / 2 + 1;
-        for (int i = tid; i < nrow * (tw + 2); i += nt) {
-            const int j = i / (tw + 2), xx = i - j * (tw + 2);
+        for (int i = tid; i < nrow * (kTW + 2); i += nt) {
+            const int j = i / (kTW + 2), xx = i - j * (kTW + 2);
+            if (xx >= tw + 2) continue;
             const int cy = 2 * j - 1 + 3;                            // source row index of the centre
             int sum = 0, sq = 0;
 #pragma unroll
@@ -103,8 +107,9 @@ B200_DEV void lr_tile_compute(LrShared &sm, const LrTileParams &P, int tw, int t
         }
     }
     __syncthreads();
-    for (int i = tid; i < th * tw; i += nt) {
-        const int y = i / tw, x = i - y * tw;
+    for (int i = tid; i < th * kTW; i += nt) {
+        const int y = i / kTW, x = i - y * kTW;
+        if (x >= tw) continue;
         const int src = sm.src[y + 3][x + 3];
         int t5 = 0, t3 = 0;
         if (P.s0) {
@@ -194,16 +199,18 @@ __global__ void __launch_bounds__(256) lr_frame_kernel(B200LrFrame f, int bdmax)
         lr_unit_params(u, HBD, P);
     }
     if (P.type == 0) {
-        for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
-            const int y = i / tw, x = i - y * tw;
+        for (int i = threadIdx.x; i < kTW * th; i += blockDim.x) {
+            const int y = i / kTW, x = i - y * kTW;
+            if (x >= tw) continue;
             O[(ptrdiff_t)(ty0 + y) * st + x0 + x] = C[(ptrdiff_t)(ty0 + y) * st + x0 + x];
         }
         return;
     }
     // stage the virtual source: rows ty0-3 .. ty0+th+2, cols x0-3 .. x0+tw+2
     const bool have_top = y0s > 0, have_bot = y1s < h;
-    for (int i = threadIdx.x; i < (th + 6) * (tw + 6); i += blockDim.x) {
-        const int yy = i / (tw + 6), xx = i - yy * (tw + 6);
+    for (int i = threadIdx.x; i < (th + 6) * kSW; i += blockDim.x) {
+        const int yy = i / kSW, xx = i - yy * kSW;
+        if (xx >= tw + 6) continue;
         int Y = ty0 - 3 + yy;
         const int X = iclip(x0 - 3 + xx, 0, w - 1);
         const pixel *base = C;
@@ -227,8 +234,9 @@ __global__ void __launch_bounds__(256) lr_window_kernel(const typename Bd<HBD>::
     __shared__ LrShared sm;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
     const int tw = imin(kTW, w - x0), th = imin(kTH, h - y0);
-    for (int i = threadIdx.x; i < (th + 6) * (tw + 6); i += blockDim.x) {
-        const int yy = i / (tw + 6), xx = i - yy * (tw + 6);
+    for (int i = threadIdx.x; i < (th + 6) * kSW; i += blockDim.x) {
+        const int yy = i / kSW, xx = i - yy * kSW;
+        if (xx >= tw + 6) continue;
         sm.src[yy][xx] = win[(size_t)(y0 + yy) * (w + 6) + x0 + xx];
     }
     __syncthreads();

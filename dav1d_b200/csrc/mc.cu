@@ -37,7 +37,7 @@ template <bool HBD> B200_DEV int inter_bits(int bdmax) {
 //      pitch: conflict-free), sliding the 8-tap window through registers -> int16 `mid` tile;
 //   3. vertical pass: an item = S consecutive rows of one column, lanes run along x (conflict-free reads,
 //      coalesced stores), same sliding window, final rounding / clip / prep bias.
-// S = 2 / 4 / 8 by sub-block area so that small blocks still fill the warp. Bilinear is the same machinery
+// S = 1 / 2 / 4 / 8 by sub-block area so that small blocks still fill the warp. Bilinear is the same machinery
 // with the taps {16-m, m} at positions 3, 4 and a base shift of 4 instead of 6.
 constexpr int kMcWarps = 4;
 constexpr int kMcSub = 32, kMcWin = kMcSub + 7;          // sub-block edge, window edge
@@ -60,8 +60,9 @@ B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int
     constexpr int RP = McSmem<HBD>::kRawPitch;
     // ---- horizontal: mid[r][x] for r < nr, x < sw
     const int ngx = (sw + S - 1) / S;
+    const unsigned magic_r = (65536u + nr - 1) / nr;       // exact it / nr for it < 65536 / nr (it < 39 * 32)
     for (int it = lane; it < nr * ngx; it += 32) {
-        const int g = it / nr, r = it - g * nr;
+        const int g = (int)((it * magic_r) >> 16), r = it - g * nr;
         const int x0 = g * S;
         const pixel *row = &sm.raw[r * RP + shift0 + x0];
         int16_t *m = &sm.mid[r * kMcMidPitch + x0];
@@ -84,8 +85,9 @@ B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int
     __syncwarp();
     // ---- vertical + store
     const int ngy = (sh + S - 1) / S;
+    const unsigned magic_w = (65536u + sw - 1) / sw;
     for (int it = lane; it < sw * ngy; it += 32) {
-        const int g = it / sw, x = it - g * sw;
+        const int g = (int)((it * magic_w) >> 16), x = it - g * sw;
         const int y0 = g * S;
         const int16_t *m = &sm.mid[y0 * kMcMidPitch + x];
         int out[S];
@@ -120,7 +122,7 @@ B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int
 }
 
 template <bool HBD>
-__global__ void __launch_bounds__(kMcWarps * 32)
+__global__ void __launch_bounds__(kMcWarps * 32, 8)
 mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
@@ -196,7 +198,9 @@ mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, B200McFrame
             pixel *dsub = dpx + b.dst_off + (ptrdiff_t)sy0 * ds + sx0;
             int16_t *tsub = fr.tmp + b.dst_off + sy0 * w + sx0;
             const int area = sw * sh;
-            if (area <= 64)
+            if (area <= 32)
+                mc_passes<HBD, 1>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
+            else if (area <= 64)
                 mc_passes<HBD, 2>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
             else if (area <= 256)
                 mc_passes<HBD, 4>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
