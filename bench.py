@@ -85,25 +85,40 @@ def make_itx8x8(seed, n_blocks, plane_w):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region: ONE long-running
+    `nvidia-smi ... -lms 200` process (the recipe of B200_PROFILING.md) read by this thread, so that the run is
+    not perturbed by a process spawn + driver attach per sample."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.stop_flag, self.samples = index, False, []
+        self.index, self.stop_flag, self.samples, self.proc = index, False, [], None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                f = [x.strip() for x in r.stdout.strip().split(",")]
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
                 if len(f) >= 6:
                     self.samples.append(f)
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+        finally:
+            self.stop()
+
+    def stop(self):
+        self.stop_flag = True
+        p = self.proc
+        if p is not None and p.poll() is None:
+            try:
+                p.terminate()          # exactly the process this object started
             except Exception:
                 pass
-            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
@@ -283,7 +298,7 @@ def run_ours_frame(args):
     torch, dist, world, rank, local = dist_setup()
     from dav1d_b200 import synth, frame, get_lib
     lib = get_lib()
-    nsets = 24 if FRAME_WORKLOADS[args.workload].get("intra") else 3
+    nsets = max(24, FRAME_WORKLOADS[args.workload].get("frames_per_step", 1)) if FRAME_WORKLOADS[args.workload].get("intra") else 3
     fbs, Ss = [], []
     for k in range(nsets):
         S = make_workload_frame(args.workload, 1 + rank * 16 + k)
@@ -345,7 +360,7 @@ def run_ours_frame(args):
     # end to end: records from pinned host memory through b200_frame_run_host, picture back to the host
     # nsets frames in flight, one stream each (the GPU-side analogue of dav1d's frame threads): every step
     # copies that frame's records host->device and its restored picture device->host.
-    e2e_steps = max(6, min(args.steps, 60))
+    e2e_steps = max(6, min(args.steps, 400))
     for i in range(2 * nsets):
         if i >= nsets:
             fbs[i % nsets].wait()
@@ -366,7 +381,7 @@ def run_ours_frame(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * (px_per_step // fps) / (float(t.item()) * 1e-3) / 1e6      # one frame per submit
-    sampler.stop_flag = True
+    sampler.stop()
     sampler.join(timeout=2)
 
     if rank == 0:
@@ -517,7 +532,7 @@ def run_ours_itx(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * px_per_step / (float(t.item()) * 1e-3) / 1e6
-    sampler.stop_flag = True
+    sampler.stop()
     sampler.join(timeout=2)
     if rank == 0:
         import refs
@@ -562,8 +577,8 @@ def run_ours_itx(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k10_full", "1080p8_intra", "itx8x8"])
     args = ap.parse_args()

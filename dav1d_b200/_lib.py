@@ -269,6 +269,9 @@ def get_lib():
     """Load (building first if needed) the CUDA library. Never falls back to anything else."""
     global _lib
     if _lib is None:
+        if os.environ.get("B200AV1_LIB"):          # tuning aid: an alternative build of the same library
+            _lib = B200Lib(os.environ["B200AV1_LIB"])
+            return _lib
         if not os.path.exists(LIB_PATH):
             from . import build
             build.build()

@@ -31,6 +31,25 @@ def _stamp():
     return h.hexdigest()
 
 
+def build_variant(name, defines):
+    """Tuning aid: a second library `libb200av1_<name>.so` compiled with extra -D flags (selected at run time with
+    B200AV1_LIB=<path>). Never used by the tests or the driver."""
+    out = os.path.join(HERE, "libb200av1_%s.so" % name)
+    obj = os.path.join(OBJ, "var_" + name)
+    os.makedirs(obj, exist_ok=True)
+    objs = []
+    for src in _sources():
+        o = os.path.join(obj, src[:-3] + ".o")
+        r = subprocess.run([NVCC] + FLAGS + ["-D%s" % d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", o], capture_output=True, text=True)
+        if r.returncode:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, r.stderr[-4000:]))
+        objs.append(o)
+    r = subprocess.run([NVCC, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"], capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError("link failed:\n" + r.stderr[-4000:])
+    return out
+
+
 def build(verbose=False, force=False):
     os.makedirs(OBJ, exist_ok=True)
     stamp_file = os.path.join(OBJ, "stamp.json")

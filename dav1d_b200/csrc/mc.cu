@@ -122,7 +122,13 @@ B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int
 }
 
 template <bool HBD>
-__global__ void __launch_bounds__(kMcWarps * 32, 8)
+#ifndef B200_MC_MINB
+#define B200_MC_MINB 8
+#endif
+#ifndef B200_MC_S1
+#define B200_MC_S1 1
+#endif
+__global__ void __launch_bounds__(kMcWarps * 32, B200_MC_MINB)
 mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
@@ -198,7 +204,7 @@ mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, B200McFrame
             pixel *dsub = dpx + b.dst_off + (ptrdiff_t)sy0 * ds + sx0;
             int16_t *tsub = fr.tmp + b.dst_off + sy0 * w + sx0;
             const int area = sw * sh;
-            if (area <= 32)
+            if (B200_MC_S1 && area <= 32)
                 mc_passes<HBD, 1>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
             else if (area <= 64)
                 mc_passes<HBD, 2>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
