@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(kIpT) intra_frame_kernel(const IntraParams P, 
     __shared__ int s_itx[ItxGeom<64, 64>::NB * ItxGeom<64, 64>::SLOT];
     __shared__ pixel s_px[64 * 64];                 // the block being reconstructed (pitch = its width)
     __shared__ int16_t s_ac[32 * 32];
+    __shared__ coef s_cf[32 * 32];                  // this block's coefficients, fetched while waiting
     __shared__ B200ItxBlock s_blk;
     __shared__ int s_ticket, s_next;
     __shared__ uint32_t s_rec[kRecWords];
@@ -103,6 +104,14 @@ __global__ void __launch_bounds__(kIpT) intra_frame_kernel(const IntraParams P, 
         const bool is_cfl = r.mode == B200_INTRA_MODE_CFL && r.cfl_alpha != 0;
         const uint8_t *const dmap = P.done[pl];
         const int mw = f.w4[pl];
+        // coefficients: loads issued before the wait, parked in shared memory after it (off the dependency chain)
+        const int ncf = imin(w, 32) * imin(h, 32);
+        coef *const gcf = (coef *)f.d_coef + r.coef_off;
+        coef creg[1024 / kIpT];
+        if (r.eob >= 0) {
+#pragma unroll
+            for (int k = 0; k < 1024 / kIpT; k++) { const int i = tid + k * kIpT; creg[k] = i < ncf ? gcf[i] : (coef)0; }
+        }
 
         // ---- wait for the neighbours whose pixels the edge array reads
         {
@@ -116,16 +125,24 @@ __global__ void __launch_bounds__(kIpT) intra_frame_kernel(const IntraParams P, 
                 const int lh4 = imin((th - r.cfl_h_pad) << f.ss_ver, f.h4[0] - ly4);
                 n_luma = lw4 * lh4;
             }
-            for (int c = tid; c < n_left + n_top + n_tl + n_luma; c += kIpT) {
-                const uint8_t *cell;
-                if (c < n_left) cell = dmap + (y + c) * mw + x - 1;
-                else if (c < n_left + n_top) cell = dmap + (y - 1) * mw + x + (c - n_left);
-                else if (c < n_left + n_top + n_tl) cell = dmap + (y - 1) * mw + x - 1;
-                else { const int k = c - n_left - n_top - n_tl; cell = P.done[0] + (ly4 + k / lw4) * f.w4[0] + lx4 + k % lw4; }
-                while (!ld_cell(cell)) __nanosleep(20);
+            // only warp 0 polls (the other warps park at the barrier and cost no issue slots)
+            if (tid < 32) {
+                for (int c = tid; c < n_left + n_top + n_tl + n_luma; c += 32) {
+                    const uint8_t *cell;
+                    if (c < n_left) cell = dmap + (y + c) * mw + x - 1;
+                    else if (c < n_left + n_top) cell = dmap + (y - 1) * mw + x + (c - n_left);
+                    else if (c < n_left + n_top + n_tl) cell = dmap + (y - 1) * mw + x - 1;
+                    else { const int k = c - n_left - n_top - n_tl; cell = P.done[0] + (ly4 + k / lw4) * f.w4[0] + lx4 + k % lw4; }
+                    unsigned ns = 32;
+                    while (!ld_cell(cell)) { __nanosleep(ns); if (ns < 256) ns += 32; }
+                }
             }
             __threadfence();
             if (tid == 0) s_next = nxt;
+            if (r.eob >= 0) {
+#pragma unroll
+                for (int k = 0; k < 1024 / kIpT; k++) { const int i = tid + k * kIpT; if (i < ncf) s_cf[i] = creg[k]; }
+            }
             __syncthreads();
         }
 
@@ -217,14 +234,16 @@ __global__ void __launch_bounds__(kIpT) intra_frame_kernel(const IntraParams P, 
 
         // ---- residual, added in the shared tile
         if (r.eob >= 0) {
-            if (tid == 0) { s_blk.dst_off = 0; s_blk.coef_off = r.coef_off; s_blk.eob = r.eob; s_blk.txtp = r.txtp; s_blk.plane = 0; }
+            if (tid == 0) { s_blk.dst_off = 0; s_blk.coef_off = 0; s_blk.eob = r.eob; s_blk.txtp = r.txtp; s_blk.plane = 0; }
             __syncthreads();
             switch (r.tx) {
-#define X(TX, W, H, SH) case TX: itx_add_body<W, H, TX, SH, HBD>(0, s_itx, &s_blk, 1, (coef *)f.d_coef, s_px, W, W, W, bdmax, f.zero_coefs); break;
+#define X(TX, W, H, SH) case TX: itx_add_body<W, H, TX, SH, HBD>(0, s_itx, &s_blk, 1, s_cf, s_px, W, W, W, bdmax, 0); break;
             B200_ITX_SIZES(X)
 #undef X
             }
             __syncthreads();
+            if (f.zero_coefs)
+                for (int i = tid; i < ncf; i += kIpT) gcf[i] = 0;
         }
         // ---- write the block, publish
         for (int i = tid; i < w * h; i += kIpT) {

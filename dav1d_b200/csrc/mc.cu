@@ -299,20 +299,38 @@ mc_comp_kernel(const B200CompBlock *__restrict__ blocks, int n_blocks, B200McFra
     uint8_t *const mask = fr.mask + b.mask_off;
 
     if (op <= B200_COMP_MASK) {
-        for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
-            const int y = i / w, x = i - y * w;
-            const int a = t1[i], c = t2[i];
-            int v;
-            if (op == B200_COMP_AVG) {
-                v = (a + c + (1 << ib) + bias * 2) >> (ib + 1);
-            } else if (op == B200_COMP_W_AVG) {
-                const int wt = b.param;
-                v = (a * wt + c * (16 - wt) + (8 << ib) + bias * 16) >> (ib + 4);
+        // two horizontally adjacent samples per thread: one 32-bit load per int16 source when the block is 2-aligned
+        const int qw = w >> 1, qsh = 31 - __clz(qw);
+        const bool pow2 = (qw & (qw - 1)) == 0;
+        const bool vec = !((b.tmp1_off | b.tmp2_off) & 1u);
+        const bool vst = !((b.dst_off | (unsigned)ds) & 1u);
+        const int wt = b.param;
+        for (int i = threadIdx.x; i < qw * h; i += blockDim.x) {
+            const int y = pow2 ? i >> qsh : i / qw, x = (i - y * qw) * 2;
+            int a[2], c[2], v[2];
+            if (vec) {
+                const unsigned ua = *(const unsigned *)(t1 + 2 * i), uc = *(const unsigned *)(t2 + 2 * i);
+                a[0] = (int16_t)(ua & 0xffff); a[1] = (int)ua >> 16; c[0] = (int16_t)(uc & 0xffff); c[1] = (int)uc >> 16;
             } else {
-                const int m = mask[i];
-                v = (a * m + c * (64 - m) + (32 << ib) + bias * 64) >> (ib + 6);
+                a[0] = t1[2 * i]; a[1] = t1[2 * i + 1]; c[0] = t2[2 * i]; c[1] = t2[2 * i + 1];
             }
-            dst[(ptrdiff_t)y * ds + x] = (pixel)iclip(v, 0, bdmax);
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                if (op == B200_COMP_AVG) {
+                    v[k] = (a[k] + c[k] + (1 << ib) + bias * 2) >> (ib + 1);
+                } else if (op == B200_COMP_W_AVG) {
+                    v[k] = (a[k] * wt + c[k] * (16 - wt) + (8 << ib) + bias * 16) >> (ib + 4);
+                } else {
+                    const int m = mask[2 * i + k];
+                    v[k] = (a[k] * m + c[k] * (64 - m) + (32 << ib) + bias * 64) >> (ib + 6);
+                }
+                v[k] = iclip(v[k], 0, bdmax);
+            }
+            pixel *o = dst + (ptrdiff_t)y * ds + x;
+            if (vst) {
+                if (HBD) *(unsigned *)o = (unsigned)v[0] | (unsigned)v[1] << 16;
+                else *(uint16_t *)o = (uint16_t)(v[0] | v[1] << 8);
+            } else { o[0] = (pixel)v[0]; o[1] = (pixel)v[1]; }
         }
         return;
     }
