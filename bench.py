@@ -21,6 +21,10 @@ n+1.. may reference it), inside the timed region.
 --impl reference times dav1d's own C functions (oracle/_ref, unmodified reference sources, HAVE_ASM=0:
 no nasm in this image) on the host cores: one frame per thread (dav1d's frame threading), all cores.
 """
+import os as _os
+# up to 32 hardware work queues, so that the frames in flight (one stream each) really run side by side: with the
+# default of 8, kernels of streams that share a queue are dispatched one after the other
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import argparse
 import ctypes as C
 import json

@@ -123,10 +123,10 @@ B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int
 
 template <bool HBD>
 #ifndef B200_MC_MINB
-#define B200_MC_MINB 8
+#define B200_MC_MINB 6
 #endif
 #ifndef B200_MC_S1
-#define B200_MC_S1 1
+#define B200_MC_S1 0
 #endif
 __global__ void __launch_bounds__(kMcWarps * 32, B200_MC_MINB)
 mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
