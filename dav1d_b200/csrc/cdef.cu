@@ -204,7 +204,10 @@ B200_DEV void cdef_tap2(const uint32_t *t, int idx, int off, unsigned negpx, uns
 }
 
 template <bool HBD>
-__global__ void __launch_bounds__(kCdefThreads, 3) cdef_frame_kernel(B200CdefFrame f, int bdmax)
+#ifndef B200_CDEF_MINB
+#define B200_CDEF_MINB 4
+#endif
+__global__ void __launch_bounds__(kCdefThreads, B200_CDEF_MINB) cdef_frame_kernel(B200CdefFrame f, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ CdefShared S;

@@ -160,7 +160,10 @@ B200_DEV void lr_unit_params(const B200RestorationUnit &u, bool hbd, LrTileParam
 }
 
 template <bool HBD>
-__global__ void __launch_bounds__(256) lr_frame_kernel(B200LrFrame f, int bdmax)
+#ifndef B200_LR_MINB
+#define B200_LR_MINB 6
+#endif
+__global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(B200LrFrame f, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ LrShared sm;

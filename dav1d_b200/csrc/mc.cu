@@ -50,6 +50,30 @@ template <bool HBD> struct alignas(16) McSmem {
     int16_t mid[kMcWin * kMcMidPitch];
 };
 
+// sum of 4 unsigned bytes of `px` times 4 signed bytes of `taps`, plus acc
+B200_DEV int dp4a_us(unsigned px, int taps, int acc) {
+#ifdef B200_EMU
+    return __dp4a_us(px, taps, acc);
+#else
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(taps), "r"(acc));
+    return d;
+#endif
+}
+
+// two unsigned halfwords of `px` times signed bytes {0,1} (HI = false) or {2,3} (HI = true) of `taps`, plus acc
+template <bool HI> B200_DEV int dp2a_us(unsigned px, int taps, int acc) {
+#ifdef B200_EMU
+    const int t0 = (int8_t)(taps >> (HI ? 16 : 0)), t1 = (int8_t)(taps >> (HI ? 24 : 8));
+    return acc + (int)(px & 0xffff) * t0 + (int)(px >> 16) * t1;
+#else
+    int d;
+    if (HI) asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(taps), "r"(acc));
+    else asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(taps), "r"(acc));
+    return d;
+#endif
+}
+
 template <bool HBD, int S>
 B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int sh, const int nr, const int shift0,
                         const bool has_h, const bool has_v, const int (&fh)[8], const int (&fv)[8], const int fsh,
@@ -59,6 +83,8 @@ B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int
     typedef typename Bd<HBD>::pixel pixel;
     constexpr int RP = McSmem<HBD>::kRawPitch;
     // ---- horizontal: mid[r][x] for r < nr, x < sw
+    const int fh_lo = (fh[0] & 0xff) | (fh[1] & 0xff) << 8 | (fh[2] & 0xff) << 16 | (fh[3] & 0xff) << 24;
+    const int fh_hi = (fh[4] & 0xff) | (fh[5] & 0xff) << 8 | (fh[6] & 0xff) << 16 | (fh[7] & 0xff) << 24;
     const int ngx = (sw + S - 1) / S;
     const unsigned magic_r = (65536u + nr - 1) / nr;       // exact it / nr for it < 65536 / nr (it < 39 * 32)
     for (int it = lane; it < nr * ngx; it += 32) {
@@ -67,15 +93,55 @@ B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int
         const pixel *row = &sm.raw[r * RP + shift0 + x0];
         int16_t *m = &sm.mid[r * kMcMidPitch + x0];
         if (has_h) {
-            int win[S + 7];
+            if constexpr (!HBD) {
+                // 8-bit: the S+7 source bytes as aligned words, realigned once to the item's first byte, then per
+                // output two funnel shifts + two dp4a (4 taps each) instead of 8 loads + 8 multiply-adds
+                constexpr int NW = (S + 7 + 3) / 4 + 1;
+                const int b0 = shift0 + x0;
+                const unsigned *rw = (const unsigned *)&sm.raw[r * RP + (b0 & ~3)];
+                unsigned wv[NW + 1];
 #pragma unroll
-            for (int k = 0; k < S + 7; k++) win[k] = row[k];
+                for (int k = 0; k < NW; k++) wv[k] = rw[k];
+                wv[NW] = 0;
+                const unsigned sh8 = (b0 & 3) * 8;
+                unsigned a[NW];
 #pragma unroll
-            for (int j = 0; j < S; j++) {
-                int sacc = 0;
+                for (int k = 0; k < NW; k++) a[k] = __funnelshift_r(wv[k], wv[k + 1], sh8);
 #pragma unroll
-                for (int k = 0; k < 8; k++) sacc += fh[k] * win[j + k];
-                if (x0 + j < sw) m[j] = (int16_t)RND_SH(sacc, fsh - ib);
+                for (int j = 0; j < S; j++) {
+                    const unsigned lo = __funnelshift_r(a[j >> 2], a[(j >> 2) + 1], (j & 3) * 8);
+                    const unsigned hi = __funnelshift_r(a[(j >> 2) + 1], a[(j >> 2) + 2 < NW ? (j >> 2) + 2 : NW - 1], (j & 3) * 8);
+                    const int sacc = dp4a_us(hi, fh_hi, dp4a_us(lo, fh_lo, 0));
+                    if (x0 + j < sw) m[j] = (int16_t)RND_SH(sacc, fsh - ib);
+                }
+            } else {
+                // 10/12-bit: pixel pairs as words, realigned once to the item's first sample; per output 4 dp2a
+                constexpr int NW = (S + 7 + 1) / 2 + 1;
+                const int b0 = shift0 + x0;
+                const unsigned *rw = (const unsigned *)&sm.raw[r * RP + (b0 & ~1)];
+                unsigned wv[NW + 1];
+#pragma unroll
+                for (int k = 0; k < NW; k++) wv[k] = rw[k];
+                wv[NW] = 0;
+                const unsigned sh16 = (b0 & 1) * 16;
+                unsigned a[NW + 1];
+#pragma unroll
+                for (int k = 0; k < NW; k++) a[k] = __funnelshift_r(wv[k], wv[k + 1], sh16);
+                a[NW] = 0;
+#pragma unroll
+                for (int j = 0; j < S; j++) {
+                    const int q = j >> 1;
+                    unsigned p0, p1, p2, p3;
+                    if (j & 1) {
+                        p0 = __funnelshift_r(a[q], a[q + 1], 16); p1 = __funnelshift_r(a[q + 1], a[q + 2], 16);
+                        p2 = __funnelshift_r(a[q + 2], a[q + 3], 16); p3 = __funnelshift_r(a[q + 3], a[q + 4 < NW ? q + 4 : NW], 16);
+                    } else { p0 = a[q]; p1 = a[q + 1]; p2 = a[q + 2]; p3 = a[q + 3]; }
+                    int sacc = dp2a_us<false>(p0, fh_lo, 0);
+                    sacc = dp2a_us<true>(p1, fh_lo, sacc);
+                    sacc = dp2a_us<false>(p2, fh_hi, sacc);
+                    sacc = dp2a_us<true>(p3, fh_hi, sacc);
+                    if (x0 + j < sw) m[j] = (int16_t)RND_SH(sacc, fsh - ib);
+                }
             }
         } else {
 #pragma unroll

@@ -201,6 +201,8 @@ static inline unsigned __vimin_s16x2_relu(unsigned a, unsigned b) { return EMU_H
 static inline unsigned __vimax_s16x2_relu(unsigned a, unsigned b) { return EMU_H2(std::max(0, std::max(emu_s16(a), emu_s16(b))), std::max(0, std::max(emu_s16(a >> 16), emu_s16(b >> 16)))); }
 static inline unsigned __viaddmax_s16x2(unsigned a, unsigned b, unsigned c) { return __vmaxs2(__vadd2(a, b), c); }
 static inline unsigned __viaddmin_s16x2(unsigned a, unsigned b, unsigned c) { return __vmins2(__vadd2(a, b), c); }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { sh &= 31; return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { sh &= 31; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 static inline void __nanosleep(unsigned) { emu_yield(); }
 template <class T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
