@@ -508,9 +508,6 @@ def run_ours_itx(args):
         batch.itx_add_batch(255, 1, b, c, p, strides)
 
     def sync_all():
-        for k in range(nsets):
-            if pending[k] is not None:
-                pending[k].wait(); pending[k] = None
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

@@ -20,11 +20,11 @@ if [[ $what == all || $what == bench ]]; then
   timeout 900 python bench.py --workload 1080p8_intra > gpurun_out/bench_intra.json 2> gpurun_out/bench_intra.err
 fi
 if [[ $what == all || $what == ncu ]]; then
-  # launch list of 3 timed frames after the warm-up (5 warm-up frames x 9 launches are skipped)
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 45 -c 27 --csv \
+  # launch list of 3 timed frames after the warm-up (5 warm-up frames x 10 launches are skipped)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 50 -c 30 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 5 > gpurun_out/ncu_bench.log 2>&1
   # full capture of one whole frame's kernels
-  timeout 1200 ncu --set full --clock-control none --import-source on -s 45 -c 9 \
+  timeout 1200 ncu --set full --clock-control none --import-source on -s 50 -c 10 \
       -f -o gpurun_out/prof_frame python bench.py --steps 3 --warmup 5 > gpurun_out/ncu_full.log 2>&1
 fi
 echo done > gpurun_out/done.txt
