@@ -199,6 +199,8 @@ _SIGS = {
     "b200_coef_expand": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     # ---- intra frame
     "b200_intra_scratch_bytes": (C.c_size_t, [C.c_void_p]),
+    "b200_intra_frames": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_frame_run_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b200_intra_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     # ---- filmgrain
     "b200_fg_apply_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
@@ -216,6 +218,7 @@ _SIGS = {
     "b200_struct_size": (C.c_int, [C.c_int]),
     "b200_frame_run_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_frame_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_frame_submit_host_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_frame_wait": (C.c_int, [C.c_void_p]),
     # ---- ipred
     "b200_ipred_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

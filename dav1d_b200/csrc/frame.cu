@@ -6,18 +6,19 @@
 
 extern "C" {
 
-int b200_frame_run(const B200FrameJob *j, void *stream)
+// the stages before intra reconstruction; *fg_side is set when the film grain preparation was forked to a side stream
+static int frame_phase_recon(const B200FrameJob *j, void *stream, void **fg_side)
 {
     int r;
     const int bd = j->bitdepth_max;
-    bool fg_prepped = false;
+    *fg_side = nullptr;
 #ifndef B200_EMU
     // film grain LUT preparation: one CTA, latency bound, depends only on the frame header -> side stream. The
     // scratch is reused frame after frame on this stream, hence the fork (after everything enqueued so far).
     SideStream *fs = nullptr;
     if (j->run_fg && (fs = side_stream_for((cudaStream_t)stream, 0)) && fs->fork((cudaStream_t)stream)) {
         if ((r = b200_fg_prep(bd, &j->fg, fs->side))) return r;
-        fg_prepped = true;
+        *fg_side = fs;
     }
 #endif
     if (j->n_expand > 0) {
@@ -33,17 +34,53 @@ int b200_frame_run(const B200FrameJob *j, void *stream)
     if ((r = b200_itx_add_frame(bd, (const void *const *)j->d_itx, j->n_itx, j->d_coef, j->mc.dst, j->itx_stride,
                                 j->zero_coefs, stream)))
         return r;
-    if (j->n_intra > 0 && (r = b200_intra_frame(bd, &j->intra, j->d_intra, j->n_intra, stream))) return r;
+    return 0;
+}
+
+static int frame_phase_post(const B200FrameJob *j, void *stream, void *fg_side)
+{
+    int r;
+    const int bd = j->bitdepth_max;
     if (j->run_lf && (r = b200_lf_frame(bd, &j->lf, stream))) return r;
     if (j->run_cdef && (r = b200_cdef_frame(bd, &j->cdef, stream))) return r;
     if (j->run_lr && (r = b200_lr_frame(bd, &j->lr, stream))) return r;
     if (j->run_fg) {
 #ifndef B200_EMU
-        if (fg_prepped && !fs->join((cudaStream_t)stream)) { b200_set_error("b200_frame_run: stream join failed"); return -1; }
+        if (fg_side && !((SideStream *)fg_side)->join((cudaStream_t)stream)) { b200_set_error("b200_frame_run: stream join failed"); return -1; }
 #endif
-        if (!fg_prepped && (r = b200_fg_prep(bd, &j->fg, stream))) return r;
+        if (!fg_side && (r = b200_fg_prep(bd, &j->fg, stream))) return r;
         if ((r = b200_fg_apply(bd, &j->fg, stream))) return r;
     }
+    return 0;
+}
+
+int b200_frame_run(const B200FrameJob *j, void *stream)
+{
+    int r;
+    void *fg_side;
+    if ((r = frame_phase_recon(j, stream, &fg_side))) return r;
+    if (j->n_intra > 0 && (r = b200_intra_frame(j->bitdepth_max, &j->intra, j->d_intra, j->n_intra, stream))) return r;
+    return frame_phase_post(j, stream, fg_side);
+}
+
+int b200_frame_run_batch(const B200FrameJob *const *jobs, int n, void *stream)
+{
+    if (n <= 0) return 0;
+    if (n > 256) { b200_set_error("b200_frame_run_batch: too many jobs"); return -2; }
+    int r;
+    void *fg_side[256];
+    B200IntraFrame frames[256];
+    const B200IntraTx *tx[256];
+    int32_t ntx[256];
+    for (int i = 0; i < n; i++) {
+        if (jobs[i]->bitdepth_max != jobs[0]->bitdepth_max) { b200_set_error("b200_frame_run_batch: mixed bit depths"); return -2; }
+        if (jobs[i]->run_fg) { b200_set_error("b200_frame_run_batch: film grain jobs must be run one by one"); return -2; }
+        if ((r = frame_phase_recon(jobs[i], stream, &fg_side[i]))) return r;
+        frames[i] = jobs[i]->intra; tx[i] = jobs[i]->d_intra; ntx[i] = jobs[i]->n_intra;
+    }
+    if ((r = b200_intra_frames(jobs[0]->bitdepth_max, frames, tx, ntx, n, stream))) return r;
+    for (int i = 0; i < n; i++)
+        if ((r = frame_phase_post(jobs[i], stream, fg_side[i]))) return r;
     return 0;
 }
 
@@ -67,6 +104,19 @@ int b200_frame_submit_host(const B200FrameJob *job, const B200Xfer *up, int n_up
     for (int i = 0; i < n_up; i++)
         if (up[i].bytes) B200_CUDA_OK(cudaMemcpyAsync(up[i].dev, up[i].host, up[i].bytes, cudaMemcpyHostToDevice, st));
     int r = b200_frame_run(job, stream);
+    if (r) return r;
+    for (int i = 0; i < n_down; i++)
+        if (down[i].bytes) B200_CUDA_OK(cudaMemcpyAsync(down[i].host, down[i].dev, down[i].bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int b200_frame_submit_host_batch(const B200FrameJob *const *jobs, int n_jobs, const B200Xfer *up, int n_up,
+                                 const B200Xfer *down, int n_down, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < n_up; i++)
+        if (up[i].bytes) B200_CUDA_OK(cudaMemcpyAsync(up[i].dev, up[i].host, up[i].bytes, cudaMemcpyHostToDevice, st));
+    int r = b200_frame_run_batch(jobs, n_jobs, stream);
     if (r) return r;
     for (int i = 0; i < n_down; i++)
         if (down[i].bytes) B200_CUDA_OK(cudaMemcpyAsync(down[i].host, down[i].dev, down[i].bytes, cudaMemcpyDeviceToHost, st));

@@ -43,6 +43,11 @@ struct IntraParams {
     int *ticket;
     uint8_t *done[3];
 };
+// several independent frames per launch (blockIdx.y = frame): frames are the parallel axis of intra decoding and
+// one launch is not limited by the number of hardware work queues the way one stream per frame is
+constexpr int kIntraMaxBatch = 24;
+struct IntraBatch { IntraParams p[kIntraMaxBatch]; };
+static_assert(sizeof(IntraBatch) <= 4000, "kernel parameter space");
 
 B200_DEV int ld_cell(const uint8_t *p) { return *(const volatile uint8_t *)p; }
 
@@ -63,8 +68,9 @@ B200_DEV void prefetch_l2(const void *p) {
 }
 
 template <bool HBD>
-__global__ void __launch_bounds__(kIpT) intra_frame_kernel(const IntraParams P, const int bdmax)
+__global__ void __launch_bounds__(kIpT, 5) intra_frame_kernel(const __grid_constant__ IntraBatch B, const int bdmax)
 {
+    const IntraParams &P = B.p[blockIdx.y];
     typedef typename Bd<HBD>::pixel pixel;
     typedef typename Bd<HBD>::coef coef;
     constexpr int kRecWords = sizeof(B200IntraTx) / 4;
@@ -276,25 +282,42 @@ extern "C" {
 
 size_t b200_intra_scratch_bytes(const B200IntraFrame *f) { return intra_scratch_layout(f).total; }
 
+int b200_intra_frames(int bdmax, const B200IntraFrame *frames, const B200IntraTx *const *d_tx, const int32_t *n_tx,
+                      int n_frames, void *stream)
+{
+    if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_intra_frames: bad bitdepth_max"); return -2; }
+    for (int base = 0; base < n_frames; base += kIntraMaxBatch) {
+        IntraBatch B;
+        memset(&B, 0, sizeof(B));
+        int nb = 0, grid = 0;
+        for (int i = base; i < n_frames && nb < kIntraMaxBatch; i++) {
+            if (n_tx[i] <= 0) continue;
+            const B200IntraFrame *f = &frames[i];
+            if (!f->scratch) { b200_set_error("b200_intra_frames: no scratch"); return -2; }
+            const IntraScratch L = intra_scratch_layout(f);
+            IntraParams &P = B.p[nb++];
+            P.f = *f; P.tx = d_tx[i]; P.n = n_tx[i];
+            uint8_t *base_p = (uint8_t *)f->scratch;
+            P.ticket = (int *)base_p;
+            for (int p = 0; p < 3; p++) P.done[p] = base_p + L.done_off[p];
+            B200_CUDA_OK(cudaMemsetAsync(base_p, 0, L.total, (cudaStream_t)stream));      // ticket + done maps
+            const int want = f->grid > 0 ? f->grid : kIntraGrid;
+            grid = imax(grid, n_tx[i] < want ? n_tx[i] : want);
+        }
+        if (!nb) continue;
+        if (bdmax > 255) { auto k = intra_frame_kernel<true>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIpT), 0, (cudaStream_t)stream, B, bdmax); }
+        else { auto k = intra_frame_kernel<false>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIpT), 0, (cudaStream_t)stream, B, bdmax); }
+        b200_count_launch();
+        B200_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
 int b200_intra_frame(int bdmax, const B200IntraFrame *f, const B200IntraTx *d_tx, int n, void *stream)
 {
-    if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_intra_frame: bad bitdepth_max"); return -2; }
     if (n <= 0) return 0;
-    if (!f->scratch) { b200_set_error("b200_intra_frame: no scratch"); return -2; }
-    const IntraScratch L = intra_scratch_layout(f);
-    IntraParams P;
-    P.f = *f; P.tx = d_tx; P.n = n;
-    uint8_t *base = (uint8_t *)f->scratch;
-    P.ticket = (int *)base;
-    for (int p = 0; p < 3; p++) P.done[p] = base + L.done_off[p];
-    B200_CUDA_OK(cudaMemsetAsync(base, 0, L.total, (cudaStream_t)stream));      // ticket + done maps
-    const int want = f->grid > 0 ? f->grid : kIntraGrid;
-    const int grid = n < want ? n : want;
-    if (bdmax > 255) { auto k = intra_frame_kernel<true>; B200_LAUNCH(k, dim3(grid), dim3(kIpT), 0, (cudaStream_t)stream, P, bdmax); }
-    else { auto k = intra_frame_kernel<false>; B200_LAUNCH(k, dim3(grid), dim3(kIpT), 0, (cudaStream_t)stream, P, bdmax); }
-    b200_count_launch();
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
+    const int32_t nn = n;
+    return b200_intra_frames(bdmax, f, &d_tx, &nn, 1, stream);
 }
 
 }  // extern "C"

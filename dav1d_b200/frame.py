@@ -72,6 +72,48 @@ class NumpyAlloc:
         return None, None
 
 
+def run_batch(fbs, stream=None):
+    """b200_frame_run_batch over several FrameBuffers (same library, same bit depth) on one stream: their intra
+    stages share launches (frames are the parallel axis of intra decoding)."""
+    lib = fbs[0].lib
+    arr = (C.POINTER(_lib.FrameJob) * len(fbs))(*[C.pointer(fb.job) for fb in fbs])
+    st = fbs[0].alloc.stream() if stream is None else stream
+    lib.check(lib.b200_frame_run_batch(arr, len(fbs), st), "b200_frame_run_batch")
+
+
+class FrameGroup:
+    """Several FrameBuffers driven as one unit on one stream (b200_frame_run_batch / b200_frame_submit_host_batch)."""
+
+    def __init__(self, fbs):
+        self.fbs, self.lib = fbs, fbs[0].lib
+        self.jobs = (C.POINTER(_lib.FrameJob) * len(fbs))(*[C.pointer(fb.job) for fb in fbs])
+        self._stream = None
+        self._host = False
+
+    def stream(self):
+        if self._stream is None:
+            self._stream = self.fbs[0].alloc.new_stream()
+        return self._stream[1]
+
+    def run(self, stream=None):
+        self.lib.check(self.lib.b200_frame_run_batch(self.jobs, len(self.fbs), self.stream() if stream is None else stream),
+                       "b200_frame_run_batch")
+
+    def submit_host(self):
+        if not self._host:
+            ups, downs = [], []
+            for fb in self.fbs:
+                fb.prepare_host(); fb._host = True
+                ups += list(fb._ups); downs += list(fb._downs)
+            self._ups = (_lib.Xfer * len(ups))(*ups); self._downs = (_lib.Xfer * len(downs))(*downs)
+            self._host = True
+        self.lib.check(self.lib.b200_frame_submit_host_batch(self.jobs, len(self.fbs), self._ups, len(self._ups), self._downs,
+                                                             len(self._downs), self.stream()), "b200_frame_submit_host_batch")
+
+    def wait(self):
+        self.lib.check(self.lib.b200_frame_wait(self.stream()), "b200_frame_wait")
+
+
 class FrameBuffers:
     def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True, intra_grid=0, compact=False):
         self.S, self.lib = S, lib or _lib.get_lib()

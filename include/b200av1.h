@@ -471,6 +471,10 @@ typedef struct B200IntraFrame {
 B200_API size_t b200_intra_scratch_bytes(const B200IntraFrame *frame);
 B200_API int b200_intra_frame(int bitdepth_max, const B200IntraFrame *frame, const B200IntraTx *d_tx, int n_tx,
                               void *stream);
+/* Several independent frames (same bit depth) in one call: up to 24 frames share a launch (one grid row per frame), so
+ * the number of frames in flight is not tied to the number of streams / hardware work queues. */
+B200_API int b200_intra_frames(int bitdepth_max, const B200IntraFrame *frames, const B200IntraTx *const *d_tx,
+                               const int32_t *n_tx, int n_frames, void *stream);
 
 /* ==== compact coefficient upload ============================================================= */
 /* Per coded transform block the emitter may ship only coefficients 0 .. eob in scan order (dav1d_scans[tx],
@@ -529,6 +533,9 @@ typedef struct B200FrameJob {
     B200FgFrame fg;
 } B200FrameJob;
 B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
+/* n independent jobs of the same bit depth on one stream: reconstruction of every job, then ONE batched intra launch
+ * (b200_intra_frames), then every job's post filters. */
+B200_API int b200_frame_run_batch(const B200FrameJob *const *jobs, int n_jobs, void *stream);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check): 0 McFrame, 1 McBlock, 2 CompBlock,
  * 3 BlendBlock, 4 WarpBlock, 5 ItxBlock, 6 LfFrame, 7 CdefFrame, 8 LrFrame, 9 FrameJob, 10 Av1Filter, 11 Av1Restoration,
  * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame, 16 McScaledBlock, 17 CoefBlock */
@@ -546,6 +553,8 @@ B200_API int b200_frame_run_host(const B200FrameJob *job, const B200Xfer *upload
  * Host buffers must be page-locked for the copies to overlap other streams' work. */
 B200_API int b200_frame_submit_host(const B200FrameJob *job, const B200Xfer *uploads, int n_uploads,
                                     const B200Xfer *downloads, int n_downloads, void *stream);
+B200_API int b200_frame_submit_host_batch(const B200FrameJob *const *jobs, int n_jobs, const B200Xfer *uploads,
+                                          int n_uploads, const B200Xfer *downloads, int n_downloads, void *stream);
 B200_API int b200_frame_wait(void *stream);
 
 #ifdef __cplusplus

@@ -35,6 +35,7 @@
 #define __global__
 #define __device__
 #define __host__
+#define __grid_constant__
 #define __forceinline__ inline __attribute__((always_inline))
 #define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)

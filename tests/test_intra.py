@@ -95,6 +95,35 @@ def test_emu_intra_frame(bpc, W, H, ssh, ssv):
     assert ok, where
 
 
+def check_batch(lib, alloc_fn, n, bpc=8, W=136, H=72, with_lf=True):
+    """n different frames through b200_frame_run_batch (one intra launch for all of them) against the oracle"""
+    import test_loopfilter as TLF
+    import test_cdef as TCD
+    Ss = [synth.make_intra_frame(np.random.default_rng(780 + k), bpc, W, H) for k in range(n)]
+    fbs = [frame.FrameBuffers(S, lib=lib, alloc=alloc_fn(), run_lf=with_lf, run_cdef=False, run_lr=False, compact=k & 1, intra_grid=7)
+           for k, S in enumerate(Ss)]
+    frame.run_batch(fbs)
+    fbs[0].alloc.sync()
+    for S, fb in zip(Ss, fbs):
+        rec = oracle_intra(S)
+        if with_lf:
+            S2 = dict(S); S2["pic"] = rec
+            assert TCD.frame_area_equal(S, fb.output("p0"), TLF.lf_frame_oracle(S2))
+        else:
+            ok, where = planes_equal(S, rec, fb.output("p0"))
+            assert ok, where
+
+
+@pytest.mark.emu
+def test_emu_intra_batch():
+    check_batch(refs.emu_lib(), frame.NumpyAlloc, 3)
+
+
+@pytest.mark.gpu
+def test_gpu_intra_batch():
+    check_batch(_lib.get_lib(), frame.TorchAlloc, 30, W=264, H=136)      # > 24 frames: two launches
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("bpc,W,H,ssh,ssv", CASES + [(8, 1920, 1080, 1, 1), (10, 1280, 720, 1, 1)])
 def test_gpu_intra_frame(bpc, W, H, ssh, ssv):
