@@ -282,7 +282,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": ncores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -450,7 +450,7 @@ def run_ours_frame(args):
                 "e2e": {"value": e2e_val, "unit": "Mpixels/s", "h2d_bytes_per_step": int(fbs[0].h2d_bytes),
                         "d2h_bytes_per_step": int(fbs[0].d2h_bytes)},
                 "gpu_launches": int(launches), "clocks": sampler.summary()}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -591,12 +591,26 @@ def run_ours_itx(args):
                 "e2e": {"value": e2e_val, "unit": "Mpixels/s", "h2d_bytes_per_step": int(hb.numel() + hc.numel() * 2 + hp.numel()),
                         "d2h_bytes_per_step": int(hp.numel())},
                 "gpu_launches": int(launches), "clocks": sampler.summary()}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """the one JSON line, on the process's real stdout"""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries the JSON line and nothing else: libraries that print to fd 1 (e.g. NCCL's version banner) go to stderr
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -45,99 +45,144 @@ B200_DEV void lr_tile_compute(LrShared &sm, const LrTileParams &P, int tw, int t
     if (P.type == 1) {
         const int rbh = 3 + (bitdepth == 12) * 2, rbv = 11 - (bitdepth == 12) * 2;
         const int clip_limit = 1 << (bitdepth + 1 + 7 - rbh);
-        for (int i = tid; i < (th + 6) * kTW; i += nt) {      // constant pitch: the divisions become shifts
-            const int y = i / kTW, x = i - y * kTW;
+        // horizontal: 4 consecutive outputs per thread share their 10 source samples
+        for (int i = tid; i < (th + 6) * (kTW / 4); i += nt) {
+            const int y = i / (kTW / 4), x = (i - y * (kTW / 4)) * 4;
             if (x >= tw) continue;
-            int sum = 1 << (bitdepth + 6);
-            if (!HBD) sum += (int)sm.src[y][x + 3] * 128;
+            int v[10];
 #pragma unroll
-            for (int k = 0; k < 7; k++) sum += (int)sm.src[y][x + k] * P.fh[k];
-            sm.u.hor[y][x] = (uint16_t)iclip((sum + (1 << (rbh - 1))) >> rbh, 0, clip_limit - 1);
+            for (int k = 0; k < 10; k++) v[k] = sm.src[y][x + k];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int sum = 1 << (bitdepth + 6);
+                if (!HBD) sum += v[j + 3] * 128;
+#pragma unroll
+                for (int k = 0; k < 7; k++) sum += v[j + k] * P.fh[k];
+                sm.u.hor[y][x + j] = (uint16_t)iclip((sum + (1 << (rbh - 1))) >> rbh, 0, clip_limit - 1);
+            }
         }
         __syncthreads();
+        // vertical: 4 consecutive rows per thread share their 10 intermediate samples
         const int round_offset = 1 << (bitdepth + (rbv - 1));
-        for (int i = tid; i < th * kTW; i += nt) {
-            const int y = i / kTW, x = i - y * kTW;
+        for (int i = tid; i < ((th + 3) / 4) * kTW; i += nt) {
+            const int yq = i / kTW, x = i - yq * kTW, y = yq * 4;
             if (x >= tw) continue;
-            int sum = -round_offset;
+            int v[10];
 #pragma unroll
-            for (int k = 0; k < 7; k++) sum += (int)sm.u.hor[y + k][x] * P.fv[k];
-            store(x, y, iclip((sum + (1 << (rbv - 1))) >> rbv, 0, bdmax));
+            for (int k = 0; k < 10; k++) v[k] = y + k < th + 6 ? (int)sm.u.hor[y + k][x] : 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (y + j >= th) break;
+                int sum = -round_offset;
+#pragma unroll
+                for (int k = 0; k < 7; k++) sum += v[j + k] * P.fv[k];
+                store(x, y + j, iclip((sum + (1 << (rbv - 1))) >> rbv, 0, bdmax));
+            }
         }
         return;
     }
     // ---- self-guided ----
     const int b8 = bitdepth - 8;
     if (P.s1) {      // 3x3 surfaces at rows -1 .. th, cols -1 .. tw
-        for (int i = tid; i < (th + 2) * (kTW + 2); i += nt) {
-            const int yy = i / (kTW + 2), xx = i - yy * (kTW + 2);   // surface index; source centre (xx + 2, yy + 2)
+        // 4 consecutive surface points per thread: 3 x 6 source samples -> column sums -> sliding 3-wide sums
+        constexpr int NS = (kTW + 2 + 3) / 4;
+        for (int i = tid; i < (th + 2) * NS; i += nt) {
+            const int yy = i / NS, xx = (i - yy * NS) * 4;           // surface index; source centre (xx + 2, yy + 2)
             if (xx >= tw + 2) continue;
-            int sum = 0, sq = 0;
+            int cs[6], cq[6];
 #pragma unroll
-            for (int dy = -1; dy <= 1; dy++)
+            for (int k = 0; k < 6; k++) {
+                const int v0 = sm.src[yy + 1][xx + 1 + k], v1 = sm.src[yy + 2][xx + 1 + k], v2 = sm.src[yy + 3][xx + 1 + k];
+                cs[k] = v0 + v1 + v2; cq[k] = v0 * v0 + v1 * v1 + v2 * v2;
+            }
 #pragma unroll
-                for (int dx = -1; dx <= 1; dx++) { const int v = sm.src[yy + 2 + dy][xx + 2 + dx]; sum += v; sq += v * v; }
-            const int a = (sq + ((1 << (2 * b8)) >> 1)) >> (2 * b8);
-            const int b = (sum + ((1 << b8) >> 1)) >> b8;
-            const unsigned p = (unsigned)imax(a * 9 - b * b, 0);
-            const unsigned z = (p * P.s1 + (1u << 19)) >> 20;
-            const unsigned x = b200_sgr_x_by_x[z < 255u ? z : 255u];
-            sm.u.s.A3[yy][xx] = (int)((x * (unsigned)sum * 455u + (1u << 11)) >> 12);
-            sm.u.s.B3[yy][xx] = (uint16_t)x;
+            for (int k = 0; k < 4; k++) {
+                if (xx + k >= tw + 2) break;
+                const int sum = cs[k] + cs[k + 1] + cs[k + 2], sq = cq[k] + cq[k + 1] + cq[k + 2];
+                const int a = (sq + ((1 << (2 * b8)) >> 1)) >> (2 * b8);
+                const int b = (sum + ((1 << b8) >> 1)) >> b8;
+                const unsigned p = (unsigned)imax(a * 9 - b * b, 0);
+                const unsigned z = (p * P.s1 + (1u << 19)) >> 20;
+                const unsigned x = b200_sgr_x_by_x[z < 255u ? z : 255u];
+                sm.u.s.A3[yy][xx + k] = (int)((x * (unsigned)sum * 455u + (1u << 11)) >> 12);
+                sm.u.s.B3[yy][xx + k] = (uint16_t)x;
+            }
         }
     }
     if (P.s0) {      // 5x5 surfaces at odd rows -1, 1, 3, ... (index j <-> row 2j - 1)
         const int nrow = (th + 1) / 2 + 1;
-        for (int i = tid; i < nrow * (kTW + 2); i += nt) {
-            const int j = i / (kTW + 2), xx = i - j * (kTW + 2);
+        constexpr int NS = (kTW + 2 + 3) / 4;
+        for (int i = tid; i < nrow * NS; i += nt) {
+            const int j = i / NS, xx = (i - j * NS) * 4;
             if (xx >= tw + 2) continue;
             const int cy = 2 * j - 1 + 3;                            // source row index of the centre
-            int sum = 0, sq = 0;
+            int cs[8], cq[8];
 #pragma unroll
-            for (int dy = -2; dy <= 2; dy++)
+            for (int k = 0; k < 8; k++) {
+                int su = 0, sq = 0;
 #pragma unroll
-                for (int dx = -2; dx <= 2; dx++) { const int v = sm.src[cy + dy][xx + 2 + dx]; sum += v; sq += v * v; }
-            const int a = (sq + ((1 << (2 * b8)) >> 1)) >> (2 * b8);
-            const int b = (sum + ((1 << b8) >> 1)) >> b8;
-            const unsigned p = (unsigned)imax(a * 25 - b * b, 0);
-            const unsigned z = (p * P.s0 + (1u << 19)) >> 20;
-            const unsigned x = b200_sgr_x_by_x[z < 255u ? z : 255u];
-            sm.u.s.A5[j][xx] = (int)((x * (unsigned)sum * 164u + (1u << 11)) >> 12);
-            sm.u.s.B5[j][xx] = (uint16_t)x;
+                for (int dy = -2; dy <= 2; dy++) { const int v = sm.src[cy + dy][xx + k]; su += v; sq += v * v; }
+                cs[k] = su; cq[k] = sq;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (xx + k >= tw + 2) break;
+                const int sum = cs[k] + cs[k + 1] + cs[k + 2] + cs[k + 3] + cs[k + 4];
+                const int sq = cq[k] + cq[k + 1] + cq[k + 2] + cq[k + 3] + cq[k + 4];
+                const int a = (sq + ((1 << (2 * b8)) >> 1)) >> (2 * b8);
+                const int b = (sum + ((1 << b8) >> 1)) >> b8;
+                const unsigned p = (unsigned)imax(a * 25 - b * b, 0);
+                const unsigned z = (p * P.s0 + (1u << 19)) >> 20;
+                const unsigned x = b200_sgr_x_by_x[z < 255u ? z : 255u];
+                sm.u.s.A5[j][xx + k] = (int)((x * (unsigned)sum * 164u + (1u << 11)) >> 12);
+                sm.u.s.B5[j][xx + k] = (uint16_t)x;
+            }
         }
     }
     __syncthreads();
-    for (int i = tid; i < th * kTW; i += nt) {
-        const int y = i / kTW, x = i - y * kTW;
+    // 4 consecutive pixels of a row per thread: the neighbourhood sums are built from per-column partial sums
+    for (int i = tid; i < th * (kTW / 4); i += nt) {
+        const int y = i / (kTW / 4), x = (i - y * (kTW / 4)) * 4;
         if (x >= tw) continue;
-        const int src = sm.src[y + 3][x + 3];
-        int t5 = 0, t3 = 0;
+        int t5a[4] = { 0, 0, 0, 0 }, t5b[4] = { 0, 0, 0, 0 }, t3a[4] = { 0, 0, 0, 0 }, t3b[4] = { 0, 0, 0, 0 };
         if (P.s0) {
-            const int xs = x + 1;
+            int ca[6], cb[6];
             if (!(y & 1)) {
                 const int j0 = y >> 1, j1 = j0 + 1;                   // rows y - 1 and y + 1
-                const int a = ((int)sm.u.s.B5[j0][xs] + sm.u.s.B5[j1][xs]) * 6 +
-                              ((int)sm.u.s.B5[j0][xs - 1] + sm.u.s.B5[j1][xs - 1] + sm.u.s.B5[j0][xs + 1] + sm.u.s.B5[j1][xs + 1]) * 5;
-                const int b = (sm.u.s.A5[j0][xs] + sm.u.s.A5[j1][xs]) * 6 +
-                              (sm.u.s.A5[j0][xs - 1] + sm.u.s.A5[j1][xs - 1] + sm.u.s.A5[j0][xs + 1] + sm.u.s.A5[j1][xs + 1]) * 5;
-                t5 = (b - a * src + (1 << 8)) >> 9;
+#pragma unroll
+                for (int k = 0; k < 6; k++) { ca[k] = (int)sm.u.s.B5[j0][x + k] + sm.u.s.B5[j1][x + k]; cb[k] = sm.u.s.A5[j0][x + k] + sm.u.s.A5[j1][x + k]; }
             } else {
                 const int j = (y + 1) >> 1;                           // row y
-                const int a = (int)sm.u.s.B5[j][xs] * 6 + ((int)sm.u.s.B5[j][xs - 1] + sm.u.s.B5[j][xs + 1]) * 5;
-                const int b = sm.u.s.A5[j][xs] * 6 + (sm.u.s.A5[j][xs - 1] + sm.u.s.A5[j][xs + 1]) * 5;
-                t5 = (b - a * src + (1 << 7)) >> 8;
+#pragma unroll
+                for (int k = 0; k < 6; k++) { ca[k] = sm.u.s.B5[j][x + k]; cb[k] = sm.u.s.A5[j][x + k]; }
             }
+#pragma unroll
+            for (int k = 0; k < 4; k++) { t5a[k] = ca[k + 1] * 6 + (ca[k] + ca[k + 2]) * 5; t5b[k] = cb[k + 1] * 6 + (cb[k] + cb[k + 2]) * 5; }
         }
         if (P.s1) {
-            const int xs = x + 1, ys = y + 1;
-#define B200_EIGHT(PL) (((int)PL[ys][xs] + PL[ys][xs - 1] + PL[ys][xs + 1] + PL[ys - 1][xs] + PL[ys + 1][xs]) * 4 + \
-                        ((int)PL[ys - 1][xs - 1] + PL[ys + 1][xs - 1] + PL[ys - 1][xs + 1] + PL[ys + 1][xs + 1]) * 3)
-            const int a = B200_EIGHT(sm.u.s.B3), b = B200_EIGHT(sm.u.s.A3);
-#undef B200_EIGHT
-            t3 = (b - a * src + (1 << 8)) >> 9;
+            const int ys = y + 1;
+            int ma[6], va[6], mb[6], vb[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                ma[k] = sm.u.s.B3[ys][x + k]; va[k] = (int)sm.u.s.B3[ys - 1][x + k] + sm.u.s.B3[ys + 1][x + k];
+                mb[k] = sm.u.s.A3[ys][x + k]; vb[k] = sm.u.s.A3[ys - 1][x + k] + sm.u.s.A3[ys + 1][x + k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                t3a[k] = (ma[k + 1] + ma[k] + ma[k + 2] + va[k + 1]) * 4 + (va[k] + va[k + 2]) * 3;
+                t3b[k] = (mb[k + 1] + mb[k] + mb[k + 2] + vb[k + 1]) * 4 + (vb[k] + vb[k + 2]) * 3;
+            }
         }
-        const int v = P.w0 * t5 + P.w1 * t3;     // the unused term is zero (w0 = 0 without s0; t3 = 0 without s1)
-        store(x, y, iclip(src + ((v + (1 << 10)) >> 11), 0, bdmax));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (x + k >= tw) break;
+            const int src = sm.src[y + 3][x + k + 3];
+            int t5 = 0, t3 = 0;
+            if (P.s0) t5 = !(y & 1) ? (t5b[k] - t5a[k] * src + (1 << 8)) >> 9 : (t5b[k] - t5a[k] * src + (1 << 7)) >> 8;
+            if (P.s1) t3 = (t3b[k] - t3a[k] * src + (1 << 8)) >> 9;
+            const int v = P.w0 * t5 + P.w1 * t3;     // the unused term is zero (w0 = 0 without s0; t3 = 0 without s1)
+            store(x + k, y, iclip(src + ((v + (1 << 10)) >> 11), 0, bdmax));
+        }
     }
 }
 
