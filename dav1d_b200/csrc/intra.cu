@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(kIpT, 5) intra_frame_kernel(const __grid_const
                     unsigned ns = 32;
                     while (!ld_cell(cell)) { __nanosleep(ns); if (ns < 256) ns += 32; }
                 }
+                __threadfence();          // acquire side, by the polling warp only (the barrier below publishes it)
             }
-            __threadfence();
             if (tid == 0) s_next = nxt;
             if (r.eob >= 0) {
 #pragma unroll
@@ -256,12 +256,15 @@ __global__ void __launch_bounds__(kIpT, 5) intra_frame_kernel(const __grid_const
             const int yy = i / w, xx = i - yy * w;
             dst[(ptrdiff_t)yy * st + xx] = s_px[i];
         }
-        __threadfence();
+        // one device-scope fence per block: the barrier orders every thread's stores before thread 0's fence (causality
+        // through bar.sync, fences are cumulative), the warp barrier orders the fence before the flag stores of warp 0
         __syncthreads();
-        {
+        if (tid < 32) {
+            if (tid == 0) __threadfence();
+            __syncwarp();
             uint8_t *const dm = P.done[pl];
             const int cw = imin(tw, mw - x), chh = imin(th, f.h4[pl] - y);
-            for (int c = tid; c < cw * chh; c += kIpT) *(volatile uint8_t *)(dm + (y + c / cw) * mw + x + c % cw) = 1;
+            for (int c = tid; c < cw * chh; c += 32) *(volatile uint8_t *)(dm + (y + c / cw) * mw + x + c % cw) = 1;
         }
         // ---- hand over to the next record
         if (tid < kRecWords) s_rec[tid] = next_word;

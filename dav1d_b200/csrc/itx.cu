@@ -38,8 +38,11 @@ struct ItxGroups {
 
 // Two register classes, one launch each: sizes with a 64-point dimension (long butterflies, up to ~170 live
 // registers, 33 KB tile) and everything else (<= 64 registers, 17 KB tile, 8 CTAs per SM).
+#ifndef B200_ITX_SMALL_MINB
+#define B200_ITX_SMALL_MINB 7
+#endif
 template <bool BIG> struct ItxClass {
-    static constexpr int kMinCtas = BIG ? 3 : 8;
+    static constexpr int kMinCtas = BIG ? 3 : B200_ITX_SMALL_MINB;
     static constexpr int kTileWords = kItxWarps * (BIG ? ItxGeom<64, 64>::NB * ItxGeom<64, 64>::SLOT
                                                        : ItxGeom<32, 32>::NB * ItxGeom<32, 32>::SLOT);
 };

@@ -123,11 +123,15 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
             dc = (dc * 181 + 128) >> 8;
             dc = (dc + rnd) >> SHIFT;
             dc = (dc * 181 + 128 + 2048) >> 12;
+            // read-modify-write in load batches: the stores of one row must not serialise the loads of the next
+            constexpr int CH = H < 16 ? H : 16;
             for (int x = li; x < W; x += G::L) {
-#pragma unroll 4
-                for (int y = 0; y < H; y++) {
-                    pixel *p = dst + (ptrdiff_t)y * stride + x;
-                    *p = (pixel)iclip((int)*p + dc, 0, bitdepth_max);
+                for (int y0 = 0; y0 < H; y0 += CH) {
+                    int v[CH];
+#pragma unroll
+                    for (int y = 0; y < CH; y++) v[y] = dst[(ptrdiff_t)(y0 + y) * stride + x];
+#pragma unroll
+                    for (int y = 0; y < CH; y++) dst[(ptrdiff_t)(y0 + y) * stride + x] = (pixel)iclip(v[y] + dc, 0, bitdepth_max);
                 }
             }
         } else {
@@ -145,11 +149,26 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
                         }
                     }
                 } else {
+                    // The picture column is read in batches of up to 16 rows whose loads are all issued before the
+                    // first store of the batch (a store may alias the next load, so row-by-row read-modify-write
+                    // would serialise on memory latency); for H <= 16 the batch is issued before the transform so
+                    // that the loads fly while the butterflies run.
+                    constexpr int CH = H < 16 ? H : 16;
+                    int pv[CH];
+                    if (H <= 16) {
+#pragma unroll
+                        for (int y = 0; y < CH; y++) pv[y] = dst[(ptrdiff_t)y * stride + x];
+                    }
                     tx1d_apply<H>(c, t_second, col_lo, col_hi);
 #pragma unroll
-                    for (int y = 0; y < H; y++) {
-                        pixel *p = dst + (ptrdiff_t)y * stride + x;
-                        *p = (pixel)iclip((int)*p + ((c[y] + 8) >> 4), 0, bitdepth_max);
+                    for (int y0 = 0; y0 < H; y0 += CH) {
+                        if (H > 16) {
+#pragma unroll
+                            for (int y = 0; y < CH; y++) pv[y] = dst[(ptrdiff_t)(y0 + y) * stride + x];
+                        }
+#pragma unroll
+                        for (int y = 0; y < CH; y++)
+                            dst[(ptrdiff_t)(y0 + y) * stride + x] = (pixel)iclip(pv[y] + ((c[y0 + y] + 8) >> 4), 0, bitdepth_max);
                     }
                 }
             }
