@@ -229,6 +229,10 @@ __global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(B200LrFrame
     pixel *O = (pixel *)f.dst + f.plane_off[pl];
     const int st = f.stride[pl];
 
+    // the unit lookup and the tap / weight set-up are per-tile work: one thread does them, the tile reads them from
+    // shared memory (they used to be a quarter of the kernel's instructions, executed by all 256 threads)
+    __shared__ LrTileParams sP;
+    if (threadIdx.x == 0) {
     LrTileParams P;
     P.type = 0;
     if (f.restore_planes & (1 << pl)) {
@@ -246,6 +250,10 @@ __global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(B200LrFrame
         const B200RestorationUnit u = f.lr_mask[sb_idx + (xu >> shift_hor)].lr[pl][unit_idx + ((xu >> (shift_hor - 1)) & 1)];
         lr_unit_params(u, HBD, P);
     }
+    sP = P;
+    }
+    __syncthreads();
+    const LrTileParams &P = sP;
     if (P.type == 0) {
         for (int i = threadIdx.x; i < kTW * th; i += blockDim.x) {
             const int y = i / kTW, x = i - y * kTW;
@@ -256,6 +264,31 @@ __global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(B200LrFrame
     }
     // stage the virtual source: rows ty0-3 .. ty0+th+2, cols x0-3 .. x0+tw+2
     const bool have_top = y0s > 0, have_bot = y1s < h;
+    constexpr int PPW = HBD ? 2 : 4;                                 // samples per 32-bit word
+    const bool interior = x0 >= 4 && x0 + tw + 4 <= w && !(tw & 3) && !(x0 & 3) && !(st & (PPW - 1)) &&
+                          !(((uintptr_t)C | (uintptr_t)D) & 3);
+    if (interior) {
+        // aligned words over picture columns x0-4 .. x0+tw+3 (one more column on each side than needed)
+        const int NW = (tw + 8) / PPW;
+        const unsigned magic = (65536u + NW - 1) / NW;               // exact i / NW for i < 38 * 36
+        for (int i = threadIdx.x; i < (th + 6) * NW; i += blockDim.x) {
+            const int yy = (int)((i * magic) >> 16), g = i - yy * NW;
+            int Y = ty0 - 3 + yy;
+            const pixel *base = C;
+            if (Y < y0s) {
+                if (have_top) { base = D; Y = imax(Y, y0s - 2); } else Y = y0s;
+            } else if (Y >= y1s) {
+                if (have_bot) { base = D; Y = imin(imin(Y, y1s + 1), h - 1); } else Y = y1s - 1;
+            }
+            const unsigned wv = *(const unsigned *)(base + (ptrdiff_t)Y * st + x0 - 4 + g * PPW);
+            const int c0 = g * PPW - 1;                              // tile column of the word's first sample
+#pragma unroll
+            for (int k = 0; k < PPW; k++) {
+                const int c = c0 + k;
+                if (c >= 0 && c < tw + 6) sm.src[yy][c] = (uint16_t)(HBD ? (wv >> (16 * k)) & 0xffff : (wv >> (8 * k)) & 0xff);
+            }
+        }
+    } else
     for (int i = threadIdx.x; i < (th + 6) * kSW; i += blockDim.x) {
         const int yy = i / kSW, xx = i - yy * kSW;
         if (xx >= tw + 6) continue;
