@@ -68,7 +68,10 @@ B200_DEV void prefetch_l2(const void *p) {
 }
 
 template <bool HBD>
-__global__ void __launch_bounds__(kIpT, 5) intra_frame_kernel(const __grid_constant__ IntraBatch B, const int bdmax)
+#ifndef B200_INTRA_MINB
+#define B200_INTRA_MINB 5
+#endif
+__global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(const __grid_constant__ IntraBatch B, const int bdmax)
 {
     const IntraParams &P = B.p[blockIdx.y];
     typedef typename Bd<HBD>::pixel pixel;

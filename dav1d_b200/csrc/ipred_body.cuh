@@ -11,7 +11,10 @@
 namespace b200 {
 
 
-constexpr int kIpT = 128;   // threads per block
+#ifndef B200_IPT
+#define B200_IPT 128
+#endif
+constexpr int kIpT = B200_IPT;   // threads per block
 
 B200_DEV int ip_filter_strength(int wh, int angle, int is_sm) {
     if (is_sm) {

@@ -153,22 +153,33 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
                     // first store of the batch (a store may alias the next load, so row-by-row read-modify-write
                     // would serialise on memory latency); for H <= 16 the batch is issued before the transform so
                     // that the loads fly while the butterflies run.
-                    constexpr int CH = H < 16 ? H : 16;
-                    int pv[CH];
-                    if (H <= 16) {
+                    if constexpr (H <= 8) {
+                        // short columns: plain row-by-row read-modify-write (other warps hide the latency, and the
+                        // extra registers of a batch would cost occupancy in the 8x8 / 4x4 bulk)
+                        tx1d_apply<H>(c, t_second, col_lo, col_hi);
 #pragma unroll
-                        for (int y = 0; y < CH; y++) pv[y] = dst[(ptrdiff_t)y * stride + x];
-                    }
-                    tx1d_apply<H>(c, t_second, col_lo, col_hi);
-#pragma unroll
-                    for (int y0 = 0; y0 < H; y0 += CH) {
-                        if (H > 16) {
-#pragma unroll
-                            for (int y = 0; y < CH; y++) pv[y] = dst[(ptrdiff_t)(y0 + y) * stride + x];
+                        for (int y = 0; y < H; y++) {
+                            pixel *p = dst + (ptrdiff_t)y * stride + x;
+                            *p = (pixel)iclip((int)*p + ((c[y] + 8) >> 4), 0, bitdepth_max);
                         }
+                    } else {
+                        constexpr int CH = 16;
+                        int pv[CH];
+                        if (H <= 16) {
 #pragma unroll
-                        for (int y = 0; y < CH; y++)
-                            dst[(ptrdiff_t)(y0 + y) * stride + x] = (pixel)iclip(pv[y] + ((c[y0 + y] + 8) >> 4), 0, bitdepth_max);
+                            for (int y = 0; y < CH; y++) pv[y] = dst[(ptrdiff_t)y * stride + x];
+                        }
+                        tx1d_apply<H>(c, t_second, col_lo, col_hi);
+#pragma unroll
+                        for (int y0 = 0; y0 < H; y0 += CH) {
+                            if (H > 16) {
+#pragma unroll
+                                for (int y = 0; y < CH; y++) pv[y] = dst[(ptrdiff_t)(y0 + y) * stride + x];
+                            }
+#pragma unroll
+                            for (int y = 0; y < CH; y++)
+                                dst[(ptrdiff_t)(y0 + y) * stride + x] = (pixel)iclip(pv[y] + ((c[y0 + y] + 8) >> 4), 0, bitdepth_max);
+                        }
                     }
                 }
             }
