@@ -200,7 +200,9 @@ def workload_buffers(name, S, **kw):
     from dav1d_b200 import frame
     if FRAME_WORKLOADS[name].get("intra"):
         # frames in flight x CTAs per frame <= the 592 CTAs (4 per SM) that can be resident at once
-        return frame.FrameBuffers(S, run_cdef=False, run_lr=False, intra_grid=int(os.environ.get("B200_INTRA_GRID", "8")), **kw)
+        sb = bool(int(os.environ.get("B200_INTRA_SB", "1"))) and kw.get("lib") is None      # superblock-granular schedule
+        return frame.FrameBuffers(S, run_cdef=False, run_lr=False, intra_grid=int(os.environ.get("B200_INTRA_GRID", "8")),
+                                  intra_sb=sb, **kw)
     return frame.FrameBuffers(S, **kw)
 
 

@@ -115,10 +115,15 @@ class IntraTx(C.Structure):
                 ("cfl_alpha", C.c_int8), ("cfl_w_pad", C.c_uint8), ("cfl_h_pad", C.c_uint8), ("pad", C.c_uint8 * 3)]
 
 
+class IntraSb(C.Structure):
+    _fields_ = [("first", C.c_uint32), ("count", C.c_uint32), ("sx", C.c_uint16), ("sy", C.c_uint16)]
+
+
 class IntraFrame(C.Structure):
     _fields_ = [("pic", C.c_void_p), ("stride", C.c_int32 * 3), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32),
                 ("w4", C.c_int32 * 3), ("h4", C.c_int32 * 3), ("d_coef", C.c_void_p), ("zero_coefs", C.c_int32),
-                ("grid", C.c_int32), ("scratch", C.c_void_p)]
+                ("grid", C.c_int32), ("scratch", C.c_void_p), ("plane_off", C.c_uint32 * 3), ("n_sb", C.c_int32),
+                ("sb_w", C.c_int32), ("sb_h", C.c_int32), ("sb", C.c_void_p)]
 
 
 class FrameJob(C.Structure):
@@ -287,4 +292,4 @@ class Av1Restoration(C.Structure):
 
 
 ABI_STRUCTS = [McFrame, McBlock, CompBlock, BlendBlock, WarpBlock, ItxBlock, LfFrame, CdefFrame, LrFrame, FrameJob,
-               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame, McScaledBlock, CoefBlock]
+               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame, McScaledBlock, CoefBlock, IntraSb]

@@ -41,7 +41,7 @@ struct IntraParams {
     const B200IntraTx *tx;
     int n;
     int *ticket;
-    uint8_t *done[3];
+    uint8_t *done[3];       // superblock mode: done[0] = one flag per superblock
 };
 // several independent frames per launch (blockIdx.y = frame): frames are the parallel axis of intra decoding and
 // one launch is not limited by the number of hardware work queues the way one stream per frame is
@@ -68,6 +68,10 @@ B200_DEV void prefetch_l2(const void *p) {
 }
 
 template <bool HBD>
+#ifndef B200_POLL_NS0
+#define B200_POLL_NS0 32
+#define B200_POLL_NSMAX 256
+#endif
 #ifndef B200_INTRA_MINB
 #define B200_INTRA_MINB 5
 #endif
@@ -142,8 +146,8 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
                     else if (c < n_left + n_top) cell = dmap + (y - 1) * mw + x + (c - n_left);
                     else if (c < n_left + n_top + n_tl) cell = dmap + (y - 1) * mw + x - 1;
                     else { const int k = c - n_left - n_top - n_tl; cell = P.done[0] + (ly4 + k / lw4) * f.w4[0] + lx4 + k % lw4; }
-                    unsigned ns = 32;
-                    while (!ld_cell(cell)) { __nanosleep(ns); if (ns < 256) ns += 32; }
+                    unsigned ns = B200_POLL_NS0;
+                    while (!ld_cell(cell)) { __nanosleep(ns); if (ns < B200_POLL_NSMAX) ns += ns >> 1; }
                 }
                 __threadfence();          // acquire side, by the polling warp only (the barrier below publishes it)
             }
@@ -280,6 +284,225 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
     }
 }
 
+
+// ---- superblock-granular variant -------------------------------------------------------------------------
+// A CTA takes a whole 64x64 superblock (ticket order = wavefront order of superblocks) and reconstructs its
+// transform blocks one after the other in decode order on a shared-memory canvas (superblock + the row above,
+// reaching 64 samples into the top-right superblock, + the column to the left). Dependencies inside the
+// superblock therefore cost a barrier instead of a global-memory flag round trip; only the four neighbouring
+// superblocks (left, top-left, top, top-right) are waited for through global flags, and the picture is read /
+// written once per superblock. The next record and its coefficients are fetched while the current block runs.
+template <bool HBD>
+__global__ void __launch_bounds__(kIpT, 3) intra_sb_kernel(const __grid_constant__ IntraBatch B, const int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    typedef typename Bd<HBD>::coef coef;
+    constexpr int kRecWords = sizeof(B200IntraTx) / 4;
+    const IntraParams &P = B.p[blockIdx.y];
+    __shared__ IpShared S;
+    __shared__ int s_itx[ItxGeom<64, 64>::NB * ItxGeom<64, 64>::SLOT];
+    __shared__ int16_t s_ac[32 * 32];
+    __shared__ coef s_cf[32 * 32];
+    __shared__ B200ItxBlock s_blk;
+    __shared__ int s_ticket;
+    __shared__ uint32_t s_rec[kRecWords];
+#ifdef B200_EMU
+    pixel *const canvas = (pixel *)B200_EMU_DYN_SMEM;
+#else
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    pixel *const canvas = (pixel *)dyn_smem;
+#endif
+    const int tid = threadIdx.x;
+    const B200IntraFrame &f = P.f;
+    const int bitdepth = 32 - __clz(bdmax);
+    int *const tl = S.edge + 128;
+    // canvas geometry per plane: pitch cs, origin of the superblock's top-left sample at co + cs + 1
+    int cs[3], co[3], sbw[3], sbh[3];
+    {
+        int o = 0;
+        for (int p = 0; p < 3; p++) {
+            sbw[p] = 64 >> (p ? f.ss_hor : 0); sbh[p] = 64 >> (p ? f.ss_ver : 0);
+            cs[p] = 2 * sbw[p] + 2;                       // left column + 2 superblock widths (+1 pad: even pitch)
+            co[p] = o; o += cs[p] * (sbh[p] + 1);
+        }
+    }
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(P.ticket, 1);
+        __syncthreads();
+        const int si = s_ticket;
+        if (si >= f.n_sb) break;
+        const B200IntraSb sb = f.sb[si];
+        const int sx = sb.sx, sy = sb.sy;
+        // first record + its coefficients (exposed once per superblock)
+        if (tid < kRecWords && sb.count) s_rec[tid] = ((const uint32_t *)&P.tx[sb.first])[tid];
+        // ---- wait for the neighbouring superblocks, then load the halos
+        if (tid < 4) {
+            const int dx = tid == 3 ? 1 : tid == 2 ? 0 : -1, dy = tid == 0 ? 0 : -1;   // left, top-left, top, top-right
+            const int nx = sx + dx, ny = sy + dy;
+            if (nx >= 0 && nx < f.sb_w && ny >= 0) {
+                const uint8_t *cell = P.done[0] + ny * f.sb_w + nx;
+                unsigned ns = 64;
+                while (!ld_cell(cell)) { __nanosleep(ns); if (ns < 1024) ns += ns >> 1; }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        for (int p = 0; p < 3; p++) {
+            const pixel *pic = (const pixel *)f.pic + f.plane_off[p];
+            const int st = f.stride[p], pw = f.w4[p] * 4;
+            const int X0 = sx * sbw[p], Y0 = sy * sbh[p];
+            pixel *cv = canvas + co[p];
+            if (sy > 0)      // row above: x = X0-1 .. X0 + 2*sbw - 1, limited to the plane
+                for (int i = tid; i < 2 * sbw[p] + 1; i += kIpT) {
+                    const int x = X0 - 1 + i;
+                    if (x >= 0 && x < pw) cv[i] = (pixel)ld_px<HBD>(pic + (ptrdiff_t)(Y0 - 1) * st + x);
+                }
+            if (sx > 0)      // column to the left
+                for (int i = tid; i < sbh[p]; i += kIpT)
+                    if (Y0 + i < f.h4[p] * 4) cv[(1 + i) * cs[p]] = (pixel)ld_px<HBD>(pic + (ptrdiff_t)(Y0 + i) * st + X0 - 1);
+        }
+        __syncthreads();
+
+        // ---- the superblock's transform blocks, in decode order
+        for (unsigned ri = 0; ri < sb.count; ri++) {
+            B200IntraTx r;
+#pragma unroll
+            for (int k = 0; k < kRecWords; k++) ((uint32_t *)&r)[k] = s_rec[k];
+            const int pl = r.plane;
+            const int tw = c_tx_w4[r.tx], th = c_tx_h4[r.tx];
+            const int w = tw * 4, h = th * 4;
+            const int x = r.x4, y = r.y4, xe = r.xend4, ye = r.yend4;
+            const bool have_left = r.flags & B200_INTRA_HAVE_LEFT, have_top = r.flags & B200_INTRA_HAVE_TOP;
+            const bool have_tr = have_top && x + tw < xe && (r.flags & B200_INTRA_TOP_HAS_RIGHT);
+            const bool have_bl = have_left && y + th < ye && (r.flags & B200_INTRA_LEFT_HAS_BOTTOM);
+            const bool is_cfl = r.mode == B200_INTRA_MODE_CFL && r.cfl_alpha != 0;
+            const int ncf = imin(w, 32) * imin(h, 32);
+            coef *const gcf = (coef *)f.d_coef + r.coef_off;
+            // this block's coefficients -> shared memory (for ri > 0 they were prefetched to L2 one block ago)
+            if (r.eob >= 0)
+                for (int i = tid; i < ncf; i += kIpT) s_cf[i] = gcf[i];
+            // next record: load issued now, parked at the end of the iteration
+            uint32_t next_word = 0;
+            if (tid < kRecWords && ri + 1 < sb.count) next_word = ((const uint32_t *)&P.tx[sb.first + ri + 1])[tid];
+            const int st = cs[pl];
+            pixel *const dst = canvas + co[pl] + (1 + (y * 4 - sy * sbh[pl])) * st + 1 + (x * 4 - sx * sbw[pl]);
+
+            int mode = r.mode, angle = r.angle;
+            if (mode == B200_INTRA_MODE_CFL) mode = 0;
+            if (mode >= 1 && mode <= 8) {
+                const int base = mode == 1 ? 90 : mode == 2 ? 180 : mode == 3 ? 45 : mode == 4 ? 135 : mode == 5 ? 113
+                               : mode == 6 ? 157 : mode == 7 ? 203 : 67;
+                angle = base + 3 * angle;
+                if (angle <= 90) mode = angle < 90 && have_top ? B200_Z1_PRED : B200_VERT_PRED;
+                else if (angle < 180) mode = B200_Z2_PRED;
+                else mode = angle > 180 && have_left ? B200_Z3_PRED : B200_HOR_PRED;
+            } else if (mode == 0) {
+                mode = have_left ? (have_top ? B200_DC_PRED : B200_LEFT_DC_PRED) : (have_top ? B200_TOP_DC_PRED : B200_DC_128_PRED);
+            } else if (mode == 12) {
+                mode = have_left ? (have_top ? B200_PAETH_PRED : B200_HOR_PRED) : (have_top ? B200_VERT_PRED : B200_DC_128_PRED);
+            }
+            {   // edge gather from the canvas (same rules as the global-memory kernel above)
+                const pixel *const top = dst - st;
+                const int half = (1 << bitdepth) >> 1;
+                const int lpx = imin(h, (ye - y) << 2), lpx2 = imin(h, (ye - y - th) << 2);
+                const int tpx = imin(w, (xe - x) << 2), tpx2 = imin(w, (xe - x - tw) << 2);
+                const int left_fill = have_top ? (int)top[0] : half + 1;
+                const int top_fill = have_left ? (int)dst[-1] : half - 1;
+                for (int i = tid; i < 2 * h; i += kIpT) {
+                    int v;
+                    if (i < h) v = have_left ? (int)dst[(ptrdiff_t)imin(i, lpx - 1) * st - 1] : left_fill;
+                    else if (have_bl) v = dst[(ptrdiff_t)(h + imin(i - h, lpx2 - 1)) * st - 1];
+                    else v = have_left ? (int)dst[(ptrdiff_t)(lpx - 1) * st - 1] : left_fill;
+                    tl[-(1 + i)] = v;
+                }
+                for (int i = tid; i < 2 * w; i += kIpT) {
+                    int v;
+                    if (i < w) v = have_top ? (int)top[imin(i, tpx - 1)] : top_fill;
+                    else if (have_tr) v = top[w + imin(i - w, tpx2 - 1)];
+                    else v = have_top ? (int)top[tpx - 1] : top_fill;
+                    tl[1 + i] = v;
+                }
+                if (tid == 0)
+                    tl[0] = have_left ? (have_top ? (int)top[-1] : (int)dst[-1]) : (have_top ? (int)top[0] : half);
+                if (is_cfl) {
+                    const int ssh = f.ss_hor, ssv = f.ss_ver, ys = cs[0];
+                    // co-located luma block inside the luma canvas (:1346: position rounded down to even units)
+                    const int lx = ((x << ssh) & ~ssh) * 4 - sx * 64, ly = ((y << ssv) & ~ssv) * 4 - sy * 64;
+                    const pixel *ypx = canvas + co[0] + (1 + ly) * ys + 1 + lx;
+                    int part = 0;
+                    for (int i = tid; i < w * h; i += kIpT) {
+                        const int yy = i / w, xx = i - yy * w;
+                        const int syy = imin(yy, h - 4 * r.cfl_h_pad - 1), sxx = imin(xx, w - 4 * r.cfl_w_pad - 1);
+                        const pixel *q = ypx + (ptrdiff_t)(syy << ssv) * ys + (sxx << ssh);
+                        int sacc = q[0];
+                        if (ssh) sacc += q[1];
+                        if (ssv) { sacc += q[ys]; if (ssh) sacc += q[ys + 1]; }
+                        sacc <<= 1 + !ssv + !ssh;
+                        s_ac[i] = (int16_t)sacc;
+                        part += sacc;
+                    }
+                    S.tile[tid] = part;
+                }
+                __syncthreads();
+                if (tid == 0 && mode == B200_Z2_PRED && tw + th >= 6 && (r.angle_flags & 1024))
+                    tl[0] = ((tl[-1] + tl[1]) * 5 + tl[0] * 6 + 8) >> 4;
+                if (is_cfl && tid == 0) {
+                    const int log2sz = (__ffs(w) - 1) + (__ffs(h) - 1);
+                    int sum = (1 << log2sz) >> 1;
+                    for (int i = 0; i < kIpT; i++) sum += S.tile[i];
+                    S.dc = sum >> log2sz;
+                }
+                __syncthreads();
+            }
+            if (is_cfl) {
+                const int dc = S.dc;
+                for (int i = tid; i < w * h; i += kIpT) s_ac[i] = (int16_t)(s_ac[i] - dc);
+                __syncthreads();
+                ipred_cfl_pred_body<HBD>(S, dst, st, w, h, mode, r.cfl_alpha, s_ac, bdmax);
+            } else {
+                const int a = (mode == B200_FILTER_PRED ? r.angle : angle) | r.angle_flags;
+                ipred_pred_body<HBD>(S, dst, st, w, h, mode, a, r.max_w, r.max_h, bdmax);
+            }
+            __syncthreads();
+            if (r.eob >= 0) {
+                if (tid == 0) { s_blk.dst_off = 0; s_blk.coef_off = 0; s_blk.eob = r.eob; s_blk.txtp = r.txtp; s_blk.plane = 0; }
+                __syncthreads();
+                switch (r.tx) {
+#define X(TX, W, H, SH) case TX: itx_add_body<W, H, TX, SH, HBD>(0, s_itx, &s_blk, 1, s_cf, dst, st, st, st, bdmax, 0); break;
+                B200_ITX_SIZES(X)
+#undef X
+                }
+                if (f.zero_coefs)
+                    for (int i = tid; i < ncf; i += kIpT) gcf[i] = 0;
+            }
+            __syncthreads();
+            if (tid < kRecWords) s_rec[tid] = next_word;
+            if (tid == 1 && ri + 1 < sb.count) {          // word 1 of the next record = coef_off: warm L2
+                const char *cf = (const char *)((const coef *)f.d_coef + next_word);
+                for (int k = 0; k < 8; k++) prefetch_l2(cf + k * 256);
+            }
+            __syncthreads();
+        }
+
+        // ---- write the superblock (the part inside the plane), publish
+        for (int p = 0; p < 3; p++) {
+            pixel *pic = (pixel *)f.pic + f.plane_off[p];
+            const int st = f.stride[p];
+            const int X0 = sx * sbw[p], Y0 = sy * sbh[p];
+            const int ww = imin(sbw[p], f.w4[p] * 4 - X0), hh = imin(sbh[p], f.h4[p] * 4 - Y0);
+            const pixel *cv = canvas + co[p] + cs[p] + 1;
+            for (int i = tid; i < sbw[p] * hh; i += kIpT) {
+                const int yy = i / sbw[p], xx = i - yy * sbw[p];
+                if (xx < ww) pic[(ptrdiff_t)(Y0 + yy) * st + X0 + xx] = cv[yy * cs[p] + xx];
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); *(volatile uint8_t *)(P.done[0] + sy * f.sb_w + sx) = 1; }
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -288,31 +511,62 @@ extern "C" {
 
 size_t b200_intra_scratch_bytes(const B200IntraFrame *f) { return intra_scratch_layout(f).total; }
 
+static size_t intra_canvas_bytes(const B200IntraFrame *f, size_t px)
+{
+    size_t n = 0;
+    for (int p = 0; p < 3; p++) {
+        const int bw = 64 >> (p ? f->ss_hor : 0), bh = 64 >> (p ? f->ss_ver : 0);
+        n += (size_t)(2 * bw + 2) * (bh + 1);
+    }
+    return (n * px + 15) & ~(size_t)15;
+}
+
 int b200_intra_frames(int bdmax, const B200IntraFrame *frames, const B200IntraTx *const *d_tx, const int32_t *n_tx,
                       int n_frames, void *stream)
 {
     if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_intra_frames: bad bitdepth_max"); return -2; }
-    for (int base = 0; base < n_frames; base += kIntraMaxBatch) {
+    const size_t px = bdmax > 255 ? 2 : 1;
+    for (int mode = 0; mode < 2; mode++)          // 0: per-transform-block dataflow, 1: superblock-granular
+    for (int base = 0; base < n_frames; ) {
         IntraBatch B;
         memset(&B, 0, sizeof(B));
-        int nb = 0, grid = 0;
-        for (int i = base; i < n_frames && nb < kIntraMaxBatch; i++) {
+        int nb = 0, grid = 0, i = base;
+        size_t dyn = 0;
+        for (; i < n_frames && nb < kIntraMaxBatch; i++) {
             if (n_tx[i] <= 0) continue;
             const B200IntraFrame *f = &frames[i];
+            if ((f->sb != nullptr) != (mode == 1)) continue;
             if (!f->scratch) { b200_set_error("b200_intra_frames: no scratch"); return -2; }
+            if (mode == 1 && nb && (f->ss_hor != B.p[0].f.ss_hor || f->ss_ver != B.p[0].f.ss_ver)) break;   // one canvas layout per launch
             const IntraScratch L = intra_scratch_layout(f);
             IntraParams &P = B.p[nb++];
             P.f = *f; P.tx = d_tx[i]; P.n = n_tx[i];
             uint8_t *base_p = (uint8_t *)f->scratch;
             P.ticket = (int *)base_p;
             for (int p = 0; p < 3; p++) P.done[p] = base_p + L.done_off[p];
-            B200_CUDA_OK(cudaMemsetAsync(base_p, 0, L.total, (cudaStream_t)stream));      // ticket + done maps
-            const int want = f->grid > 0 ? f->grid : kIntraGrid;
-            grid = imax(grid, n_tx[i] < want ? n_tx[i] : want);
+            B200_CUDA_OK(cudaMemsetAsync(base_p, 0, mode ? 256 + (size_t)f->sb_w * f->sb_h : L.total, (cudaStream_t)stream));
+            const int units = mode ? f->n_sb : n_tx[i];
+            const int want = f->grid > 0 ? f->grid : (mode ? 16 : kIntraGrid);
+            grid = imax(grid, units < want ? units : want);
+            if (mode) dyn = intra_canvas_bytes(f, px);
         }
+        base = i;
         if (!nb) continue;
-        if (bdmax > 255) { auto k = intra_frame_kernel<true>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIpT), 0, (cudaStream_t)stream, B, bdmax); }
-        else { auto k = intra_frame_kernel<false>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIpT), 0, (cudaStream_t)stream, B, bdmax); }
+        if (mode == 0) {
+            if (bdmax > 255) { auto k = intra_frame_kernel<true>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIpT), 0, (cudaStream_t)stream, B, bdmax); }
+            else { auto k = intra_frame_kernel<false>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIpT), 0, (cudaStream_t)stream, B, bdmax); }
+        } else {
+#ifndef B200_EMU
+            static bool attr_set[2] = { false, false };
+            if (!attr_set[bdmax > 255]) {
+                if (bdmax > 255) B200_CUDA_OK(cudaFuncSetAttribute(intra_sb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                else B200_CUDA_OK(cudaFuncSetAttribute(intra_sb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                attr_set[bdmax > 255] = true;
+            }
+#endif
+            if (bdmax > 255) { auto k = intra_sb_kernel<true>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIpT), dyn, (cudaStream_t)stream, B, bdmax); }
+            else { auto k = intra_sb_kernel<false>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIpT), dyn, (cudaStream_t)stream, B, bdmax); }
+        }
         b200_count_launch();
         B200_CUDA_OK(cudaGetLastError());
     }

@@ -115,7 +115,7 @@ class FrameGroup:
 
 
 class FrameBuffers:
-    def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True, intra_grid=0, compact=False):
+    def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True, intra_grid=0, compact=False, intra_sb=False):
         self.S, self.lib = S, lib or _lib.get_lib()
         self.alloc = alloc or TorchAlloc()
         A = self.alloc
@@ -181,8 +181,17 @@ class FrameBuffers:
                 it.w4[p] = S["w4"] >> ssh[p]; it.h4[p] = S["h4"] >> ssv[p]
             nb = self.lib.b200_intra_scratch_bytes(C.byref(it)) if hasattr(self.lib, "b200_intra_scratch_bytes") else 1 << 22
             it.scratch = zeros("intra_scratch", nb)
-            j.d_intra = up("intra_tx", S["intra_tx"]); j.n_intra = len(S["intra_tx"])
-            self.uploads.append(("intra_tx", S["intra_tx"]))
+            if intra_sb:     # superblock-granular schedule (records grouped by 64x64 superblock)
+                j.d_intra = up("intra_tx", S["intra_tx_sb"]); j.n_intra = len(S["intra_tx_sb"])
+                self.uploads.append(("intra_tx", S["intra_tx_sb"]))
+                it.sb = up("intra_sb", S["intra_sb"]); it.n_sb = len(S["intra_sb"])
+                it.sb_w, it.sb_h = S["intra_sb_grid"]
+                self.uploads.append(("intra_sb", S["intra_sb"]))
+                for p in range(3):
+                    it.plane_off[p] = S["off"][p]
+            else:
+                j.d_intra = up("intra_tx", S["intra_tx"]); j.n_intra = len(S["intra_tx"])
+                self.uploads.append(("intra_tx", S["intra_tx"]))
             n_intra = 1
         # post filters
         j.run_lf, j.run_cdef, j.run_lr = int(run_lf), int(run_cdef), int(run_lr)

@@ -459,6 +459,7 @@ INTRA_TX_DT = np.dtype([("dst_off", "<u4"), ("coef_off", "<u4"), ("luma_off", "<
                         ("tx", "u1"), ("txtp", "u1"), ("mode", "u1"), ("angle", "i1"), ("plane", "u1"), ("flags", "u1"),
                         ("cfl_alpha", "i1"), ("cfl_w_pad", "u1"), ("cfl_h_pad", "u1"), ("pad", "u1", (3,))])
 assert INTRA_TX_DT.itemsize == 40
+INTRA_SB_DT = np.dtype([("first", "<u4"), ("count", "<u4"), ("sx", "<u2"), ("sy", "<u2")])
 _SMOOTH_MODES = (9, 10, 11)
 MODE_FILTER, MODE_CFL = 13, 14
 
@@ -656,7 +657,25 @@ def make_intra_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, p_skip=0.2, p_cfl=0.25)
         wave[i] = dep + 1
         wm[y:y + th, x:x + tw] = dep + 1
     sorted_idx = np.argsort(wave, kind="stable")
+    # superblock-granular schedule: records grouped by 64x64 superblock (decode order inside), superblocks in
+    # wavefront order sx + 2*sy (left / top-left / top / top-right neighbours always earlier)
+    sbw_n, sbh_n = (w4 + 15) // 16, (h4 + 15) // 16
+    shx = np.array([4, 4 - ss_hor, 4 - ss_hor])[tx["plane"]]; shy = np.array([4, 4 - ss_ver, 4 - ss_ver])[tx["plane"]]
+    rsx = (tx["x4"].astype(np.int64) >> shx); rsy = (tx["y4"].astype(np.int64) >> shy)
+    sb_of = rsy * sbw_n + rsx
+    order_sb = sorted(range(sbw_n * sbh_n), key=lambda k: ((k % sbw_n) + 2 * (k // sbw_n), k // sbw_n))
+    by_sb = np.argsort(sb_of, kind="stable")                      # keeps decode order inside a superblock
+    counts = np.bincount(sb_of, minlength=sbw_n * sbh_n)
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    sb_recs = np.zeros(len(order_sb), INTRA_SB_DT)
+    pieces, pos = [], 0
+    for t, k in enumerate(order_sb):
+        pieces.append(by_sb[starts[k]:starts[k] + counts[k]])
+        sb_recs[t] = (pos, counts[k], k % sbw_n, k // sbw_n)
+        pos += counts[k]
+    tx_sb = tx[np.concatenate(pieces)].copy() if pieces else tx.copy()
     S.update(intra_tx=tx[sorted_idx].copy(), intra_tx_decode_order=tx, intra_waves=int(wave.max()), coefs=coefs,
+             intra_tx_sb=tx_sb, intra_sb=sb_recs, intra_sb_grid=(sbw_n, sbh_n),
              refs=[], pred=np.zeros(0, MC_BLOCK_DT), comp=np.zeros(0, COMP_BLOCK_DT), comp2=np.zeros(0, COMP_BLOCK_DT),
              itx={t: np.zeros(0, ITX_BLOCK_DT) for t in range(19)}, tmp_len=64, mask=np.zeros(1, np.uint8))
     S["pic"] = np.zeros(len(S["pic"]), dt)

@@ -458,6 +458,13 @@ typedef struct B200IntraTx {
     uint8_t cfl_w_pad, cfl_h_pad;  /* CFL: cfl_ac padding arguments, 4-sample units (:1359-1362) */
     uint8_t pad[3];
 } B200IntraTx;
+/* Superblock-granular scheduling (optional, 64x64 superblocks): records sorted by superblock, decode order inside;
+ * one B200IntraSb per superblock in ticket order, which must be a topological order of the superblock
+ * dependencies left / top-left / top / top-right (raster order is one; sorted by sx + 2*sy is the efficient one). */
+typedef struct B200IntraSb {
+    uint32_t first, count;         /* records [first, first + count) of d_tx */
+    uint16_t sx, sy;               /* superblock position */
+} B200IntraSb;
 typedef struct B200IntraFrame {
     void *pic;                     /* device picture being reconstructed */
     int32_t stride[3];
@@ -465,8 +472,11 @@ typedef struct B200IntraFrame {
     int32_t w4[3], h4[3];          /* per plane: frame size in 4-sample units (done-map geometry) */
     void *d_coef;
     int32_t zero_coefs;
-    int32_t grid;                  /* CTAs to launch; 0 = default (one per SM) */
+    int32_t grid;                  /* CTAs to launch; 0 = default */
     void *scratch;                 /* device, >= b200_intra_scratch_bytes(frame) */
+    uint32_t plane_off[3];         /* superblock mode: sample offset of each plane in pic */
+    int32_t n_sb, sb_w, sb_h;      /* superblock mode: number of B200IntraSb, superblock grid */
+    const B200IntraSb *sb;         /* device; NULL = per-transform-block dataflow */
 } B200IntraFrame;
 B200_API size_t b200_intra_scratch_bytes(const B200IntraFrame *frame);
 B200_API int b200_intra_frame(int bitdepth_max, const B200IntraFrame *frame, const B200IntraTx *d_tx, int n_tx,
@@ -538,7 +548,7 @@ B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
 B200_API int b200_frame_run_batch(const B200FrameJob *const *jobs, int n_jobs, void *stream);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check): 0 McFrame, 1 McBlock, 2 CompBlock,
  * 3 BlendBlock, 4 WarpBlock, 5 ItxBlock, 6 LfFrame, 7 CdefFrame, 8 LrFrame, 9 FrameJob, 10 Av1Filter, 11 Av1Restoration,
- * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame, 16 McScaledBlock, 17 CoefBlock */
+ * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame, 16 McScaledBlock, 17 CoefBlock, 18 IntraSb */
 B200_API int b200_struct_size(int which);
 
 /* The same job fed from HOST buffers (the end-to-end path): every (host, dev, bytes) pair of `uploads`

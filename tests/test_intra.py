@@ -74,9 +74,9 @@ def test_oracle_intra_vs_reference_functions(bpc, W, H, ssh, ssv):
         assert modes >= set(range(13)) | {synth.MODE_CFL, synth.MODE_FILTER}, modes
 
 
-def run_lib(lib, alloc, S, order="intra_tx", compact=False):
+def run_lib(lib, alloc, S, order="intra_tx", compact=False, sb=False):
     S2 = dict(S); S2["intra_tx"] = np.ascontiguousarray(S[order])
-    fb = frame.FrameBuffers(S2, lib=lib, alloc=alloc, run_lf=False, run_cdef=False, run_lr=False, compact=compact)
+    fb = frame.FrameBuffers(S2, lib=lib, alloc=alloc, run_lf=False, run_cdef=False, run_lr=False, compact=compact, intra_sb=sb)
     fb.run()
     fb.alloc.sync()
     return fb.output("p0")
@@ -93,6 +93,9 @@ def test_emu_intra_frame(bpc, W, H, ssh, ssv):
     got = run_lib(refs.emu_lib(), frame.NumpyAlloc(), S, compact=True)      # coefficients shipped in scan order up to eob
     ok, where = planes_equal(S, exp, got)
     assert ok, where
+    got = run_lib(refs.emu_lib(), frame.NumpyAlloc(), S, sb=True)            # superblock-granular schedule
+    ok, where = planes_equal(S, exp, got)
+    assert ok, ("sb", where)
 
 
 def check_batch(lib, alloc_fn, n, bpc=8, W=136, H=72, with_lf=True):
@@ -100,7 +103,7 @@ def check_batch(lib, alloc_fn, n, bpc=8, W=136, H=72, with_lf=True):
     import test_loopfilter as TLF
     import test_cdef as TCD
     Ss = [synth.make_intra_frame(np.random.default_rng(780 + k), bpc, W, H) for k in range(n)]
-    fbs = [frame.FrameBuffers(S, lib=lib, alloc=alloc_fn(), run_lf=with_lf, run_cdef=False, run_lr=False, compact=k & 1, intra_grid=7)
+    fbs = [frame.FrameBuffers(S, lib=lib, alloc=alloc_fn(), run_lf=with_lf, run_cdef=False, run_lr=False, compact=k & 1, intra_grid=7, intra_sb=bool(k & 2))
            for k, S in enumerate(Ss)]
     frame.run_batch(fbs)
     fbs[0].alloc.sync()
@@ -116,7 +119,7 @@ def check_batch(lib, alloc_fn, n, bpc=8, W=136, H=72, with_lf=True):
 
 @pytest.mark.emu
 def test_emu_intra_batch():
-    check_batch(refs.emu_lib(), frame.NumpyAlloc, 3)
+    check_batch(refs.emu_lib(), frame.NumpyAlloc, 4)
 
 
 @pytest.mark.gpu
@@ -133,6 +136,9 @@ def test_gpu_intra_frame(bpc, W, H, ssh, ssv):
         got = run_lib(_lib.get_lib(), None, S, order, compact=order == "intra_tx")
         ok, where = planes_equal(S, exp, got)
         assert ok, (order, where)
+    got = run_lib(_lib.get_lib(), None, S, sb=True, compact=True)
+    ok, where = planes_equal(S, exp, got)
+    assert ok, ("sb", where)
 
 
 @pytest.mark.gpu
