@@ -304,7 +304,7 @@ def run_ours_frame(args):
     torch, dist, world, rank, local = dist_setup()
     from dav1d_b200 import synth, frame, get_lib
     lib = get_lib()
-    nsets = max(24, FRAME_WORKLOADS[args.workload].get("frames_per_step", 1)) if FRAME_WORKLOADS[args.workload].get("intra") else int(os.environ.get("B200_NSETS", "3"))
+    nsets = max(24, FRAME_WORKLOADS[args.workload].get("frames_per_step", 1)) if FRAME_WORKLOADS[args.workload].get("intra") else int(os.environ.get("B200_NSETS", "5"))
     fbs, Ss = [], []
     for k in range(nsets):
         # at most 8 distinct synthetic frames; every set still owns its device buffers (that is what defeats L2)

@@ -13,22 +13,32 @@
 
 namespace b200 {
 
-// one line across one edge; p points at the first sample after the edge, sb = step across it
-template <bool HBD>
-B200_DEV void lf_line(typename Bd<HBD>::pixel *p, ptrdiff_t sb, int E, int I, int H, int wd, int bdmax)
+// sample accessors for one line across one edge: index i = offset from the first sample after the edge (-8 .. 7)
+template <bool HBD> struct LfMem {            // straight from the picture, sb = step across the edge
+    typename Bd<HBD>::pixel *p; ptrdiff_t sb;
+    B200_DEV int get(int i) const { return p[i * sb]; }
+    B200_DEV void set(int i, int v) { p[i * sb] = (typename Bd<HBD>::pixel)v; }
+};
+struct LfRegs {                               // a register window (column edges: loaded / stored as aligned words)
+    int v[16]; unsigned dirty;
+    B200_DEV int get(int i) const { return v[i + 8]; }
+    B200_DEV void set(int i, int val) { v[i + 8] = val; dirty |= 1u << (i + 8); }
+};
+
+template <bool HBD, class Acc>
+B200_DEV void lf_line_acc(Acc &px, int E, int I, int H, int wd, int bdmax)
 {
-    typedef typename Bd<HBD>::pixel pixel;
     const int b8 = HBD ? (32 - __clz(bdmax)) - 8 : 0;
     const int F = 1 << b8;
     E <<= b8; I <<= b8; H <<= b8;
-    const int p1 = p[-2 * sb], p0 = p[-1 * sb], q0 = p[0], q1 = p[sb];
+    const int p1 = px.get(-2), p0 = px.get(-1), q0 = px.get(0), q1 = px.get(1);
     int fm = iabs(p1 - p0) <= I && iabs(q1 - q0) <= I && iabs(p0 - q0) * 2 + (iabs(p1 - q1) >> 1) <= E;
     int p2 = 0, q2 = 0, p3 = 0, q3 = 0;
     if (wd > 4) {
-        p2 = p[-3 * sb]; q2 = p[2 * sb];
+        p2 = px.get(-3); q2 = px.get(2);
         fm &= iabs(p2 - p1) <= I && iabs(q2 - q1) <= I;
         if (wd > 6) {
-            p3 = p[-4 * sb]; q3 = p[3 * sb];
+            p3 = px.get(-4); q3 = px.get(3);
             fm &= iabs(p3 - p2) <= I && iabs(q3 - q2) <= I;
         }
     }
@@ -37,53 +47,60 @@ B200_DEV void lf_line(typename Bd<HBD>::pixel *p, ptrdiff_t sb, int E, int I, in
     if (wd >= 6) flat8in = iabs(p2 - p0) <= F && iabs(p1 - p0) <= F && iabs(q1 - q0) <= F && iabs(q2 - q0) <= F;
     if (wd >= 8) flat8in &= iabs(p3 - p0) <= F && iabs(q3 - q0) <= F;
     if (wd >= 16) {
-        const int p6 = p[-7 * sb], p5 = p[-6 * sb], p4 = p[-5 * sb], q4 = p[4 * sb], q5 = p[5 * sb], q6 = p[6 * sb];
+        const int p6 = px.get(-7), p5 = px.get(-6), p4 = px.get(-5), q4 = px.get(4), q5 = px.get(5), q6 = px.get(6);
         const int flat8out = iabs(p6 - p0) <= F && iabs(p5 - p0) <= F && iabs(p4 - p0) <= F &&
                              iabs(q4 - q0) <= F && iabs(q5 - q0) <= F && iabs(q6 - q0) <= F;
         if (flat8out & flat8in) {
             // sliding 16-term window over p6*6 p6 p5 .. q5 q6 q6*6 (reference :95-118)
             int s = p6 * 7 + p5 * 2 + p4 * 2 + p3 + p2 + p1 + p0 + q0 + 8;
-            p[-6 * sb] = (pixel)(s >> 4); s += -2 * p6 + p3 + q1;
-            p[-5 * sb] = (pixel)(s >> 4); s += -p6 - p5 + p2 + q2;
-            p[-4 * sb] = (pixel)(s >> 4); s += -p6 - p4 + p1 + q3;
-            p[-3 * sb] = (pixel)(s >> 4); s += -p6 - p3 + p0 + q4;
-            p[-2 * sb] = (pixel)(s >> 4); s += -p6 - p2 + q0 + q5;
-            p[-1 * sb] = (pixel)(s >> 4); s += -p6 - p1 + q1 + q6;
-            p[0]       = (pixel)(s >> 4); s += -p5 - p0 + q2 + q6;
-            p[1 * sb]  = (pixel)(s >> 4); s += -p4 - q0 + q3 + q6;
-            p[2 * sb]  = (pixel)(s >> 4); s += -p3 - q1 + q4 + q6;
-            p[3 * sb]  = (pixel)(s >> 4); s += -p2 - q2 + q5 + q6;
-            p[4 * sb]  = (pixel)(s >> 4); s += -p1 - q3 + q6 + q6;
-            p[5 * sb]  = (pixel)(s >> 4);
+            px.set(-6, (s >> 4)); s += -2 * p6 + p3 + q1;
+            px.set(-5, (s >> 4)); s += -p6 - p5 + p2 + q2;
+            px.set(-4, (s >> 4)); s += -p6 - p4 + p1 + q3;
+            px.set(-3, (s >> 4)); s += -p6 - p3 + p0 + q4;
+            px.set(-2, (s >> 4)); s += -p6 - p2 + q0 + q5;
+            px.set(-1, (s >> 4)); s += -p6 - p1 + q1 + q6;
+            px.set(0, (s >> 4)); s += -p5 - p0 + q2 + q6;
+            px.set(1, (s >> 4)); s += -p4 - q0 + q3 + q6;
+            px.set(2, (s >> 4)); s += -p3 - q1 + q4 + q6;
+            px.set(3, (s >> 4)); s += -p2 - q2 + q5 + q6;
+            px.set(4, (s >> 4)); s += -p1 - q3 + q6 + q6;
+            px.set(5, (s >> 4));
             return;
         }
     }
     if (wd >= 8 && flat8in) {
-        p[-3 * sb] = (pixel)((p3 + p3 + p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3);
-        p[-2 * sb] = (pixel)((p3 + p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3);
-        p[-1 * sb] = (pixel)((p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3);
-        p[0]       = (pixel)((p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3);
-        p[1 * sb]  = (pixel)((p1 + p0 + q0 + 2 * q1 + q2 + q3 + q3 + 4) >> 3);
-        p[2 * sb]  = (pixel)((p0 + q0 + q1 + 2 * q2 + q3 + q3 + q3 + 4) >> 3);
+        px.set(-3, ((p3 + p3 + p3 + 2 * p2 + p1 + p0 + q0 + 4) >> 3));
+        px.set(-2, ((p3 + p3 + p2 + 2 * p1 + p0 + q0 + q1 + 4) >> 3));
+        px.set(-1, ((p3 + p2 + p1 + 2 * p0 + q0 + q1 + q2 + 4) >> 3));
+        px.set(0, ((p2 + p1 + p0 + 2 * q0 + q1 + q2 + q3 + 4) >> 3));
+        px.set(1, ((p1 + p0 + q0 + 2 * q1 + q2 + q3 + q3 + 4) >> 3));
+        px.set(2, ((p0 + q0 + q1 + 2 * q2 + q3 + q3 + q3 + 4) >> 3));
     } else if (wd == 6 && flat8in) {
-        p[-2 * sb] = (pixel)((p2 + 2 * p2 + 2 * p1 + 2 * p0 + q0 + 4) >> 3);
-        p[-1 * sb] = (pixel)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
-        p[0]       = (pixel)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
-        p[1 * sb]  = (pixel)((p0 + 2 * q0 + 2 * q1 + 2 * q2 + q2 + 4) >> 3);
+        px.set(-2, ((p2 + 2 * p2 + 2 * p1 + 2 * p0 + q0 + 4) >> 3));
+        px.set(-1, ((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3));
+        px.set(0, ((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3));
+        px.set(1, ((p0 + 2 * q0 + 2 * q1 + 2 * q2 + q2 + 4) >> 3));
     } else {
         const int lo = -128 * (1 << b8), hi = 128 * (1 << b8) - 1;
         const bool hev = iabs(p1 - p0) > H || iabs(q1 - q0) > H;
         int f = hev ? iclip(p1 - q1, lo, hi) : 0;
         f = iclip(3 * (q0 - p0) + f, lo, hi);
         const int f1 = imin(f + 4, hi) >> 3, f2 = imin(f + 3, hi) >> 3;
-        p[-1 * sb] = (pixel)iclip(p0 + f2, 0, bdmax);
-        p[0]       = (pixel)iclip(q0 - f1, 0, bdmax);
+        px.set(-1, iclip(p0 + f2, 0, bdmax));
+        px.set(0, iclip(q0 - f1, 0, bdmax));
         if (!hev) {
             const int g = (f1 + 1) >> 1;
-            p[-2 * sb] = (pixel)iclip(p1 + g, 0, bdmax);
-            p[1 * sb]  = (pixel)iclip(q1 - g, 0, bdmax);
+            px.set(-2, iclip(p1 + g, 0, bdmax));
+            px.set(1, iclip(q1 - g, 0, bdmax));
         }
     }
+}
+
+template <bool HBD>
+B200_DEV void lf_line(typename Bd<HBD>::pixel *p, ptrdiff_t sb, int E, int I, int H, int wd, int bdmax)
+{
+    LfMem<HBD> m{ p, sb };
+    lf_line_acc<HBD>(m, E, I, H, wd, bdmax);
 }
 
 // decode the filter width of unit `a` (index along the edge direction inside the 128x128 area) for
@@ -127,6 +144,32 @@ __global__ void __launch_bounds__(256) lf_cols_kernel(B200LfFrame f, int bdmax)
     const int L = l[0][c] ? l[0][c] : l[-1][c];
     if (!L) return;
     pixel *p = (pixel *)f.pic + f.plane_off[plane] + (ptrdiff_t)y * f.stride[plane] + x4 * 4;
+    constexpr int PPW = HBD ? 2 : 4;                          // samples per 32-bit word
+    if (((uintptr_t)p & 3) == 0) {
+        // the 8 (16 for the widest filter) samples around the edge as aligned words, filtered in registers,
+        // modified samples written back one by one
+        LfRegs r;
+        r.dirty = 0;
+        const int lo = wd == 16 ? -8 : -4, n = wd == 16 ? 16 : 8;
+        const unsigned *wp = (const unsigned *)(p + lo);
+#pragma unroll
+        for (int k = 0; k < 16 / PPW; k++) {
+            if (k * PPW >= n) break;
+            const unsigned wv = wp[k];
+#pragma unroll
+            for (int j = 0; j < PPW; j++) {
+                const int val = HBD ? (wv >> (16 * j)) & 0xffff : (wv >> (8 * j)) & 0xff;
+                // window slot: lo + k*PPW + j + 8
+                if (wd == 16) r.v[k * PPW + j] = val; else if (k * PPW + j + 4 < 16) r.v[k * PPW + j + 4] = val;
+            }
+        }
+        lf_line_acc<HBD>(r, f.lut.e[L], f.lut.i[L], L >> 4, wd, bdmax);
+        // stores stay per sample: the word also holds samples that the neighbouring edge's thread may be changing
+#pragma unroll
+        for (int sl = 2; sl < 14; sl++)
+            if (r.dirty & (1u << sl)) p[sl - 8] = (pixel)r.v[sl];
+        return;
+    }
     lf_line<HBD>(p, 1, f.lut.e[L], f.lut.i[L], L >> 4, wd, bdmax);
 }
 

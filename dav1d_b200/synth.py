@@ -421,7 +421,14 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
         for i, rec in enumerate(lst):
             a[i] = rec
         return a
-    S.update(refs=refs, pred=to_arr(pred, MC_BLOCK_DT), comp=to_arr(comp, COMP_BLOCK_DT), comp2=to_arr(comp2, COMP_BLOCK_DT),
+    def by_area(a):
+        """records bucketed by block area, largest first (what a record emitter would do with one list per size class):
+        the warps of a CTA then work on blocks of the same size and the long blocks start first"""
+        if not len(a):
+            return a
+        return a[np.argsort(-(a["w"].astype(np.int64) * a["h"]), kind="stable")]
+    S.update(refs=refs, pred=by_area(to_arr(pred, MC_BLOCK_DT)), comp=by_area(to_arr(comp, COMP_BLOCK_DT)),
+             comp2=by_area(to_arr(comp2, COMP_BLOCK_DT)),
              itx=itx_arrays, coefs=coefs, tmp_len=tmp_off + 64, mask=rng.integers(0, 65, max(1, mask_off)).astype(np.uint8))
     S["pic"] = np.zeros(total, dt)                     # the picture being reconstructed
     # post-filter records from the transform tilings
