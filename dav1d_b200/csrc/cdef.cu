@@ -207,7 +207,7 @@ template <bool HBD>
 #ifndef B200_CDEF_MINB
 #define B200_CDEF_MINB 4
 #endif
-__global__ void __launch_bounds__(kCdefThreads, B200_CDEF_MINB) cdef_frame_kernel(B200CdefFrame f, int bdmax)
+__global__ void __launch_bounds__(kCdefThreads, B200_CDEF_MINB) cdef_frame_kernel(const __grid_constant__ B200CdefFrame f, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ CdefShared S;

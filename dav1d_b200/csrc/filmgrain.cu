@@ -110,7 +110,7 @@ B200_DEV void fg_scaling(int bitdepth, const uint8_t (*points)[2], int num, uint
     }
 }
 
-__global__ void __launch_bounds__(128) fg_prep_kernel(B200FgFrame f, int bdmax)
+__global__ void __launch_bounds__(128) fg_prep_kernel(const __grid_constant__ B200FgFrame f, int bdmax)
 {
     FgScratch *S = (FgScratch *)f.scratch;
     const B200FilmGrainData &d = f.data;
@@ -166,7 +166,7 @@ B200_DEV int fg_pixel_grain(const B200FilmGrainData &d, const int16_t *lut, cons
 
 // grid: (ceil(w / 128), h_plane rows / 2 .. , 3 planes); block (128, 2)
 template <bool HBD>
-__global__ void __launch_bounds__(256) fg_apply_kernel(B200FgFrame f, int bdmax)
+__global__ void __launch_bounds__(256) fg_apply_kernel(const __grid_constant__ B200FgFrame f, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     const int pl = blockIdx.z;

@@ -8,7 +8,7 @@
 namespace b200 {
 
 template <bool HBD>
-__global__ void __launch_bounds__(kIpT) ipred_kernel(const B200IpredBlock *__restrict__ blocks, int n, B200IpredFrame f, int bdmax)
+__global__ void __launch_bounds__(kIpT) ipred_kernel(const B200IpredBlock *__restrict__ blocks, int n, const __grid_constant__ B200IpredFrame f, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ IpShared S;

@@ -49,7 +49,7 @@ template <bool BIG> struct ItxClass {
 
 template <bool HBD, bool BIG>
 __global__ void __launch_bounds__(kItxWarps * 32, ItxClass<BIG>::kMinCtas)
-itx_add_grouped_kernel(const ItxGroups g, typename Bd<HBD>::coef *__restrict__ coefs, typename Bd<HBD>::pixel *__restrict__ pic,
+itx_add_grouped_kernel(const __grid_constant__ ItxGroups g, typename Bd<HBD>::coef *__restrict__ coefs, typename Bd<HBD>::pixel *__restrict__ pic,
                        int stride0, int stride1, int stride2, int bitdepth_max, int zero_coefs)
 {
     __shared__ int tile[ItxClass<BIG>::kTileWords];

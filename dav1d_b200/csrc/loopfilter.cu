@@ -118,7 +118,7 @@ B200_DEV int lf_width(const B200Av1Filter &m, int plane, int dir, int b, int a, 
 
 // grid: (ceil(units_x / 32), ceil(lines / 8), 3 planes); block (32, 8)
 template <bool HBD>
-__global__ void __launch_bounds__(256) lf_cols_kernel(B200LfFrame f, int bdmax)
+__global__ void __launch_bounds__(256) lf_cols_kernel(const __grid_constant__ B200LfFrame f, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     const int plane = blockIdx.z;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) lf_cols_kernel(B200LfFrame f, int bdmax)
 
 // grid: (ceil(width_px / 128), ceil(units_y / 2), 3); block (128, 2)
 template <bool HBD>
-__global__ void __launch_bounds__(256) lf_rows_kernel(B200LfFrame f, int bdmax)
+__global__ void __launch_bounds__(256) lf_rows_kernel(const __grid_constant__ B200LfFrame f, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     const int plane = blockIdx.z;

@@ -208,7 +208,7 @@ template <bool HBD>
 #ifndef B200_LR_MINB
 #define B200_LR_MINB 6
 #endif
-__global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(B200LrFrame f, int bdmax)
+__global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(const __grid_constant__ B200LrFrame f, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ LrShared sm;

@@ -195,7 +195,7 @@ template <bool HBD>
 #define B200_MC_S1 0
 #endif
 __global__ void __launch_bounds__(kMcWarps * 32, B200_MC_MINB)
-mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
+mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ McSmem<HBD> smem[kMcWarps];
@@ -288,7 +288,7 @@ mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, B200McFrame
 // fly (scaled prediction is rare: super-resolution / reference scaling only). Clamped loads = emu_edge.
 template <bool HBD>
 __global__ void __launch_bounds__(256)
-mc_scaled_kernel(const B200McScaledBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
+mc_scaled_kernel(const B200McScaledBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     const B200McScaledBlock b = blocks[blockIdx.x];
@@ -351,7 +351,7 @@ mc_scaled_kernel(const B200McScaledBlock *__restrict__ blocks, int n_blocks, B20
 // ---------------------------------------------------------------------------------------
 template <bool HBD>
 __global__ void __launch_bounds__(128)
-mc_comp_kernel(const B200CompBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
+mc_comp_kernel(const B200CompBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     const B200CompBlock b = blocks[blockIdx.x];
@@ -430,7 +430,7 @@ mc_comp_kernel(const B200CompBlock *__restrict__ blocks, int n_blocks, B200McFra
 
 template <bool HBD>
 __global__ void __launch_bounds__(128)
-mc_blend_kernel(const B200BlendBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
+mc_blend_kernel(const B200BlendBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     const B200BlendBlock b = blocks[blockIdx.x];
@@ -455,7 +455,7 @@ mc_blend_kernel(const B200BlendBlock *__restrict__ blocks, int n_blocks, B200McF
 constexpr int kWarpWarps = 4;
 template <bool HBD>
 __global__ void __launch_bounds__(kWarpWarps * 32)
-mc_warp_kernel(const B200WarpBlock *__restrict__ blocks, int n_blocks, B200McFrame fr, int bdmax)
+mc_warp_kernel(const B200WarpBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ int mid[kWarpWarps][15 * 8];
