@@ -6,7 +6,7 @@
 //                    raster-order AR filter runs as a skewed wavefront, one thread per LUT row, row y
 //                    trailing row y-1 by lag+1 columns; (3) scaling LUTs (closed form of the `d += delta`
 //                    recurrence) and (4) the per-row block-offset chains.
-//   fg_apply_kernel  one thread per pixel of every plane: LUT sample of its own 32x32 block blended with
+//   fg_apply_kernel  one thread per 4 consecutive pixels: LUT samples of their own 32x32 block blended with
 //                    the left / top / top-left blocks' samples inside the 2-sample overlap, scaled by
 //                    scaling[] of the (luma-mixed) sample value, clipped.
 #include "host_util.h"
@@ -164,7 +164,8 @@ B200_DEV int fg_pixel_grain(const B200FilmGrainData &d, const int16_t *lut, cons
     return g;
 }
 
-// grid: (ceil(w / 128), h_plane rows / 2 .. , 3 planes); block (128, 2)
+// grid: (ceil(w / 128), ceil(h / 8), 3 planes); block (32, 8); a thread owns 4 consecutive samples of one row
+// (always inside one 32-wide grain block: 4 divides the block width of every layout)
 template <bool HBD>
 __global__ void __launch_bounds__(256) fg_apply_kernel(const __grid_constant__ B200FgFrame f, int bdmax)
 {
@@ -173,39 +174,69 @@ __global__ void __launch_bounds__(256) fg_apply_kernel(const __grid_constant__ B
     const B200FilmGrainData &d = f.data;
     const int sx = pl ? f.ss_hor : 0, sy = pl ? f.ss_ver : 0;
     const int pw = (f.w + sx) >> sx, ph = (f.h + sy) >> sy;
-    const int x = blockIdx.x * 128 + threadIdx.x, yp = blockIdx.y * 2 + threadIdx.y;
-    if (x >= pw || yp >= ph) return;
-    const pixel *in = (const pixel *)f.in + f.plane_off[pl];
-    pixel *out = (pixel *)f.out + f.plane_off[pl];
-    const int st = f.stride[pl];
-    const int s = in[(ptrdiff_t)yp * st + x];
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4, yp = blockIdx.y * 8 + threadIdx.y;
+    if (x0 >= pw || yp >= ph) return;
+    const int nx = imin(4, pw - x0);
+    const pixel *in = (const pixel *)f.in + f.plane_off[pl] + (ptrdiff_t)yp * f.stride[pl] + x0;
+    pixel *out = (pixel *)f.out + f.plane_off[pl] + (ptrdiff_t)yp * f.stride[pl] + x0;
+    int s[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) s[k] = k < nx ? (int)in[k] : 0;
     const bool grained = pl ? (d.chroma_scaling_from_luma || d.num_uv_points[pl - 1]) : d.num_y_points != 0;
-    if (!grained) { out[(ptrdiff_t)yp * st + x] = (pixel)s; return; }
+    if (!grained) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (k < nx) out[k] = (pixel)s[k];
+        return;
+    }
     const FgScratch *S = (const FgScratch *)f.scratch;
     const int b8 = HBD ? (32 - __clz(bdmax)) - 8 : 0;
-    const int srows = 32 >> sy;                       // strip height in plane rows
+    const int srows = 32 >> sy, bs = 32 >> sx;        // strip height / block width in plane samples
     const int row = yp >> (5 - sy), y = yp & (srows - 1);
     const int bh_l = imin(f.h - row * 32, 32), bh = (bh_l + sy) >> sy;
-    const int g = fg_pixel_grain(d, S->lut[pl], &S->offsets[row * kMaxBlocksX], &S->offsets[(row ? row - 1 : 0) * kMaxBlocksX],
-                                 b8, row, x, y, pw, bh, sx, sy);
-    int val = s, mn, mx;
+    const uint8_t *off_cur = &S->offsets[row * kMaxBlocksX], *off_prev = &S->offsets[(row ? row - 1 : 0) * kMaxBlocksX];
+    const int bi = x0 >> (5 - sx), xin0 = x0 & (bs - 1);
+    int g[4];
+    const bool any_ov = d.overlap_flag && ((bi && xin0 < (2 >> sx)) || (row > 0 && y < imin(2 >> sy, bh)));
+    if (any_ov) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) g[k] = k < nx ? fg_pixel_grain(d, S->lut[pl], off_cur, off_prev, b8, row, x0 + k, y, pw, bh, sx, sy) : 0;
+    } else {      // the common case: 4 consecutive samples of this block's window into the grain LUT
+        const int rv = off_cur[bi];
+        const int offx = 3 + (2 >> sx) * (3 + (rv >> 4)), offy = 3 + (2 >> sy) * (3 + (rv & 0xF));
+        const int16_t *gp = S->lut[pl] + (offy + y) * GW + offx + xin0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) g[k] = gp[k];
+    }
+    int mn, mx;
     if (d.clip_to_restricted_range) { mn = 16 << b8; mx = (pl && !f.is_id ? 240 : 235) << b8; }
     else { mn = 0; mx = bdmax; }
     const uint8_t *scaling = S->scaling[0];
+    int val[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) val[k] = s[k];
     if (pl) {
         const pixel *luma = (const pixel *)f.in + f.plane_off[0] + (ptrdiff_t)(yp << sy) * f.stride[0];
-        const int lx = x << sx;
-        int avg = luma[lx];
-        if (sx) avg = (avg + (int)luma[imin(lx + 1, f.w - 1)] + 1) >> 1;   // odd widths: replicate the last column (:196-203)
-        val = avg;
-        if (!d.chroma_scaling_from_luma) {
-            const int combined = avg * d.uv_luma_mult[pl - 1] + s * d.uv_mult[pl - 1];
-            val = iclip((combined >> 6) + d.uv_offset[pl - 1] * (1 << b8), 0, bdmax);
-            scaling = S->scaling[pl];
+        const bool mix = !d.chroma_scaling_from_luma;
+        if (mix) scaling = S->scaling[pl];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k >= nx) break;
+            const int lx = (x0 + k) << sx;
+            int avg = luma[lx];
+            if (sx) avg = (avg + (int)luma[imin(lx + 1, f.w - 1)] + 1) >> 1;   // odd widths: replicate the last column (:196-203)
+            val[k] = avg;
+            if (mix) {
+                const int combined = avg * d.uv_luma_mult[pl - 1] + s[k] * d.uv_mult[pl - 1];
+                val[k] = iclip((combined >> 6) + d.uv_offset[pl - 1] * (1 << b8), 0, bdmax);
+            }
         }
     }
-    const int noise = fg_round2((int)scaling[val] * g, d.scaling_shift);
-    out[(ptrdiff_t)yp * st + x] = (pixel)iclip(s + noise, mn, mx);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k >= nx) break;
+        const int noise = fg_round2((int)scaling[val[k]] * g[k], d.scaling_shift);
+        out[k] = (pixel)iclip(s[k] + noise, mn, mx);
+    }
 }
 
 // ---- Level-1 kernels ----
@@ -277,9 +308,9 @@ int b200_fg_prep(int bdmax, const B200FgFrame *f, void *stream)
 int b200_fg_apply(int bdmax, const B200FgFrame *f, void *stream)
 {
     if (fg_check(bdmax, f, "b200_fg_apply")) return -2;
-    dim3 grid((f->w + 127) / 128, (f->h + 1) / 2, 3);
-    if (bdmax > 255) { auto k = fg_apply_kernel<true>; B200_LAUNCH(k, grid, dim3(128, 2), 0, (cudaStream_t)stream, *f, bdmax); }
-    else { auto k = fg_apply_kernel<false>; B200_LAUNCH(k, grid, dim3(128, 2), 0, (cudaStream_t)stream, *f, bdmax); }
+    dim3 grid((f->w + 127) / 128, (f->h + 7) / 8, 3);
+    if (bdmax > 255) { auto k = fg_apply_kernel<true>; B200_LAUNCH(k, grid, dim3(32, 8), 0, (cudaStream_t)stream, *f, bdmax); }
+    else { auto k = fg_apply_kernel<false>; B200_LAUNCH(k, grid, dim3(32, 8), 0, (cudaStream_t)stream, *f, bdmax); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
