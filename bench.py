@@ -180,6 +180,10 @@ FRAME_WORKLOADS = {
     "4k10_full": dict(bpc=10, W=3840, H=2160, fg=True, dtype="u16/i32->i32",
                       desc="one 3840x2160 10-bit 4:2:0 inter frame per GPU per step, full pipeline: prediction + inverse "
                            "transforms + deblock + CDEF + loop restoration + film grain (BASELINE configs[3])"),
+    "8k10_full": dict(bpc=10, W=7680, H=4320, fg=True, dtype="u16/i32->i32",
+                      desc="one 7680x4320 10-bit 4:2:0 inter frame per GPU per step, full pipeline incl. film grain "
+                           "(BASELINE configs[4]: with --gpus N every rank reconstructs its own frame and the restored pictures "
+                           "are exchanged over NCCL as reference pictures)"),
     "1080p8_intra": dict(bpc=8, W=1920, H=1080, fg=False, dtype="u8/i16->i32", intra=True, frames_per_step=int(os.environ.get("B200_INTRA_FPS", "96")),
                          desc="one 1920x1080 8-bit 4:2:0 intra-only frame per GPU per step: device-side edge preparation + "
                               "intra prediction + inverse transforms (dependency-driven kernel) + deblock (BASELINE configs[1]); a step is %s "
@@ -304,7 +308,7 @@ def run_ours_frame(args):
     torch, dist, world, rank, local = dist_setup()
     from dav1d_b200 import synth, frame, get_lib
     lib = get_lib()
-    nsets = max(24, FRAME_WORKLOADS[args.workload].get("frames_per_step", 1)) if FRAME_WORKLOADS[args.workload].get("intra") else int(os.environ.get("B200_NSETS", "5"))
+    nsets = max(24, FRAME_WORKLOADS[args.workload].get("frames_per_step", 1)) if FRAME_WORKLOADS[args.workload].get("intra") else int(os.environ.get("B200_NSETS", "3" if args.workload == "8k10_full" else "5"))
     fbs, Ss = [], []
     for k in range(nsets):
         # at most 8 distinct synthetic frames; every set still owns its device buffers (that is what defeats L2)
@@ -618,7 +622,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k10_full", "1080p8_intra", "itx8x8"])
+    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k10_full", "8k10_full", "1080p8_intra", "itx8x8"])
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = min(args.steps, 5)      # bounded: each step is tens of whole 4K frames on the CPU

@@ -24,9 +24,13 @@ template <int W, int H> struct ItxGeom {
     static constexpr int SLOT = SH * P;                   // words per block tile
     static constexpr int LW = W == 4 ? 0 : W == 8 ? 1 : W == 16 ? 2 : W == 32 ? 3 : 4;
     static constexpr bool RECT2 = (W * 2 == H) || (H * 2 == W);
+    // 64-wide blocks are shared by a pair of warps: one warp runs the row pass (32 coefficient rows), then each warp
+    // takes 32 of the 64 picture columns of the column pass
+    static constexpr bool PAIR = W == 64;
 };
 
 constexpr int kItxWarps = 4;
+template <int W, int H> constexpr int itx_blocks_per_cta() { return ItxGeom<W, H>::PAIR ? kItxWarps / 2 : kItxWarps * ItxGeom<W, H>::NB; }
 
 // the work of one CTA (`cta` = its index among the CTAs of this transform size); smem: kItxWarps * NB * SLOT words
 template <int W, int H, int TX, int SHIFT, bool HBD>
@@ -40,9 +44,11 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G::L, li = lane % G::L;
-    const int bi = (cta * kItxWarps + warp) * G::NB + grp;
+    const int half = G::PAIR ? warp & 1 : 0;                       // which 32 columns of a 64-wide block
+    const int slot = G::PAIR ? warp >> 1 : warp * G::NB + grp;     // block slot inside the CTA
+    const int bi = cta * itx_blocks_per_cta<W, H>() + slot;
     const bool valid = bi < n_blocks;
-    int *const t = smem + (warp * G::NB + grp) * G::SLOT;
+    int *const t = smem + slot * G::SLOT;
 
     B200ItxBlock blk;
     blk.dst_off = 0; blk.coef_off = 0; blk.eob = 0; blk.txtp = 0; blk.plane = 0;
@@ -70,7 +76,7 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
     const int t_second = is_wht ? 0 : c_tx_second[txtp & 15];
 
     // ---------------- pass 1: one lane per coefficient row ----------------
-    if (valid && !dc_only && li < G::SH) {
+    if (valid && !dc_only && li < G::SH && half == 0) {
         const int y = li;
         int c[W];
         if (is_wht) {
@@ -113,8 +119,8 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
     }
     int dc = 0;
     if (valid && dc_only) dc = (int)cf[0];
-    __syncwarp();
-    if (valid && dc_only && zero_coefs && li == 0) cf[0] = 0;
+    if (G::PAIR) __syncthreads(); else __syncwarp();               // (every thread of the CTA runs this function)
+    if (valid && dc_only && zero_coefs && li == 0 && half == 0) cf[0] = 0;
 
     // ---------------- pass 2: one lane per picture column ----------------
     if (valid) {
@@ -125,7 +131,7 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
             dc = (dc * 181 + 128 + 2048) >> 12;
             // read-modify-write in load batches: the stores of one row must not serialise the loads of the next
             constexpr int CH = H < 16 ? H : 16;
-            for (int x = li; x < W; x += G::L) {
+            for (int x = li + half * 32; x < W; x += G::PAIR ? 64 : G::L) {
                 for (int y0 = 0; y0 < H; y0 += CH) {
                     int v[CH];
 #pragma unroll
@@ -135,7 +141,7 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
                 }
             }
         } else {
-            for (int x = li; x < W; x += G::L) {
+            for (int x = li + half * 32; x < W; x += G::PAIR ? 64 : G::L) {
                 int c[H];
 #pragma unroll
                 for (int y = 0; y < H; y++) c[y] = y < G::SH ? t[y * G::P + x] : 0;
