@@ -24,7 +24,7 @@ itx_add_kernel(const B200ItxBlock *__restrict__ blocks, int n_blocks,
                int stride0, int stride1, int stride2, int bitdepth_max, int zero_coefs)
 {
     typedef ItxGeom<W, H> G;
-    __shared__ int tile[itx_blocks_per_cta<W, H>() * G::SLOT];
+    __shared__ int tile[ItxGeom<W, H>::BPC * G::SLOT];
     itx_add_body<W, H, TX, SHIFT, HBD>(blockIdx.x, tile, blocks, n_blocks, coefs, pic, stride0, stride1, stride2,
                                        bitdepth_max, zero_coefs);
 }
@@ -73,7 +73,7 @@ int launch_itx_grouped(bool hbd, const void *const *blocks, const int32_t *n, vo
         ItxGroups g;
         int total = 0;
 #define X(TX, W, H, SH) { \
-            const int per_cta = itx_blocks_per_cta<W, H>(); \
+            const int per_cta = ItxGeom<W, H>::BPC; \
             const int mine = ((W == 64 || H == 64) ? 1 : 0) == big; \
             const int ctas = (mine && n[TX] > 0) ? (n[TX] + per_cta - 1) / per_cta : 0; \
             g.blocks[TX] = (const B200ItxBlock *)blocks[TX]; g.n[TX] = n[TX] > 0 ? n[TX] : 0; \
@@ -98,7 +98,7 @@ static int launch_itx_wh(bool hbd, const B200ItxBlock *blocks, int n, void *coef
                          const int32_t *st, int bdmax, int zero, cudaStream_t stream)
 {
     typedef ItxGeom<W, H> G;
-    const int per_cta = itx_blocks_per_cta<W, H>();
+    const int per_cta = ItxGeom<W, H>::BPC;
     const int grid = (n + per_cta - 1) / per_cta;
     if (grid <= 0) return 0;
     if (hbd) {

@@ -15,6 +15,8 @@ namespace b200 {
 static __constant__ uint8_t c_tx_first[16]  = { 0, 0, 1, 1, 0, 2, 2, 2, 1, 3, 3, 0, 3, 1, 3, 2 };
 static __constant__ uint8_t c_tx_second[16] = { 0, 1, 0, 1, 2, 0, 2, 1, 2, 3, 0, 3, 1, 3, 2, 3 };
 
+constexpr int kItxWarps = 4;
+
 template <int W, int H> struct ItxGeom {
     static constexpr int SW = W < 32 ? W : 32;
     static constexpr int SH = H < 32 ? H : 32;
@@ -27,10 +29,8 @@ template <int W, int H> struct ItxGeom {
     // 64-wide blocks are shared by a pair of warps: one warp runs the row pass (32 coefficient rows), then each warp
     // takes 32 of the 64 picture columns of the column pass
     static constexpr bool PAIR = W == 64;
+    static constexpr int BPC = PAIR ? kItxWarps / 2 : kItxWarps * NB;   // blocks per CTA
 };
-
-constexpr int kItxWarps = 4;
-template <int W, int H> constexpr int itx_blocks_per_cta() { return ItxGeom<W, H>::PAIR ? kItxWarps / 2 : kItxWarps * ItxGeom<W, H>::NB; }
 
 // the work of one CTA (`cta` = its index among the CTAs of this transform size); smem: kItxWarps * NB * SLOT words
 template <int W, int H, int TX, int SHIFT, bool HBD>
@@ -46,7 +46,7 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
     const int grp = lane / G::L, li = lane % G::L;
     const int half = G::PAIR ? warp & 1 : 0;                       // which 32 columns of a 64-wide block
     const int slot = G::PAIR ? warp >> 1 : warp * G::NB + grp;     // block slot inside the CTA
-    const int bi = cta * itx_blocks_per_cta<W, H>() + slot;
+    const int bi = cta * G::BPC + slot;
     const bool valid = bi < n_blocks;
     int *const t = smem + slot * G::SLOT;
 
