@@ -293,7 +293,10 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
 // superblocks (left, top-left, top, top-right) are waited for through global flags, and the picture is read /
 // written once per superblock. The next record and its coefficients are fetched while the current block runs.
 template <bool HBD>
-__global__ void __launch_bounds__(kIpT, 3) intra_sb_kernel(const __grid_constant__ IntraBatch B, const int bdmax)
+#ifndef B200_INTRA_SB_MINB
+#define B200_INTRA_SB_MINB 3
+#endif
+__global__ void __launch_bounds__(kIpT, B200_INTRA_SB_MINB) intra_sb_kernel(const __grid_constant__ IntraBatch B, const int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     typedef typename Bd<HBD>::coef coef;
