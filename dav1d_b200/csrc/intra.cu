@@ -50,6 +50,14 @@ struct IntraBatch { IntraParams p[kIntraMaxBatch]; };
 static_assert(sizeof(IntraBatch) <= 4000, "kernel parameter space");
 
 B200_DEV int ld_cell(const uint8_t *p) { return *(const volatile uint8_t *)p; }
+// a dependency that never arrives (records not in a topological order) must not hang the GPU: fail the launch
+B200_DEV void intra_stuck() {
+#ifndef B200_EMU
+    __trap();
+#else
+    abort();
+#endif
+}
 
 template <bool HBD> B200_DEV int ld_px(const typename Bd<HBD>::pixel *p) {
 #ifdef B200_EMU
@@ -146,8 +154,11 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
                     else if (c < n_left + n_top) cell = dmap + (y - 1) * mw + x + (c - n_left);
                     else if (c < n_left + n_top + n_tl) cell = dmap + (y - 1) * mw + x - 1;
                     else { const int k = c - n_left - n_top - n_tl; cell = P.done[0] + (ly4 + k / lw4) * f.w4[0] + lx4 + k % lw4; }
-                    unsigned ns = B200_POLL_NS0;
-                    while (!ld_cell(cell)) { __nanosleep(ns); if (ns < B200_POLL_NSMAX) ns += ns >> 1; }
+                    unsigned ns = B200_POLL_NS0, spins = 0;
+                    while (!ld_cell(cell)) {
+                        __nanosleep(ns); if (ns < B200_POLL_NSMAX) ns += ns >> 1;
+                        if (++spins > (1u << 23)) intra_stuck();      // seconds: records are not in a valid order
+                    }
                 }
                 __threadfence();          // acquire side, by the polling warp only (the barrier below publishes it)
             }
@@ -346,8 +357,11 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_SB_MINB) intra_sb_kernel(cons
             const int nx = sx + dx, ny = sy + dy;
             if (nx >= 0 && nx < f.sb_w && ny >= 0) {
                 const uint8_t *cell = P.done[0] + ny * f.sb_w + nx;
-                unsigned ns = 64;
-                while (!ld_cell(cell)) { __nanosleep(ns); if (ns < 1024) ns += ns >> 1; }
+                unsigned ns = 64, spins = 0;
+                while (!ld_cell(cell)) {
+                    __nanosleep(ns); if (ns < 1024) ns += ns >> 1;
+                    if (++spins > (1u << 22)) intra_stuck();
+                }
             }
             __threadfence();
         }
