@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
             if (tid == 0) { s_blk.dst_off = 0; s_blk.coef_off = 0; s_blk.eob = r.eob; s_blk.txtp = r.txtp; s_blk.plane = 0; }
             __syncthreads();
             switch (r.tx) {
-#define X(TX, W, H, SH) case TX: itx_add_body<W, H, TX, SH, HBD>(0, s_itx, &s_blk, 1, s_cf, s_px, W, W, W, bdmax, 0); break;
+#define X(TX, W, H, SH) case TX: itx_add_body<W, H, TX, SH, HBD, true>(0, s_itx, &s_blk, 1, s_cf, s_px, W, W, W, bdmax, 0); break;
             B200_ITX_SIZES(X)
 #undef X
             }
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_SB_MINB) intra_sb_kernel(cons
                 if (tid == 0) { s_blk.dst_off = 0; s_blk.coef_off = 0; s_blk.eob = r.eob; s_blk.txtp = r.txtp; s_blk.plane = 0; }
                 __syncthreads();
                 switch (r.tx) {
-#define X(TX, W, H, SH) case TX: itx_add_body<W, H, TX, SH, HBD>(0, s_itx, &s_blk, 1, s_cf, dst, st, st, st, bdmax, 0); break;
+#define X(TX, W, H, SH) case TX: itx_add_body<W, H, TX, SH, HBD, true>(0, s_itx, &s_blk, 1, s_cf, dst, st, st, st, bdmax, 0); break;
                 B200_ITX_SIZES(X)
 #undef X
                 }

@@ -32,8 +32,47 @@ template <int W, int H> struct ItxGeom {
     static constexpr int BPC = PAIR ? kItxWarps / 2 : kItxWarps * NB;   // blocks per CTA
 };
 
+// Out-of-line passes shared by every block size with the same row length W / column length H. Used by the intra
+// reconstruction kernels, whose code size (every size x type inlined: 48 K instructions) thrashes the instruction cache
+// once several CTAs share an SM; the batched itx kernels keep the fully inlined form.
+template <int W, bool HBD>
+__device__ __noinline__ void itx_row_pass_shared(const typename Bd<HBD>::coef *cfy, int sh_stride, int *trow, int rect2,
+                                                 int shift, int t_first, int row_lo, int row_hi, int col_lo, int col_hi)
+{
+    constexpr int SW = W < 32 ? W : 32;
+    int c[W];
+#pragma unroll
+    for (int x = 0; x < W; x++) {
+        if (x < SW) {
+            const int v = (int)cfy[x * sh_stride];
+            c[x] = rect2 ? (int)((unsigned)v * 181u + 128u) >> 8 : v;
+        } else {
+            c[x] = 0;
+        }
+    }
+    tx1d_apply<W>(c, t_first, row_lo, row_hi);
+    const int rnd = (1 << shift) >> 1;
+#pragma unroll
+    for (int x = 0; x < W; x++) trow[x] = iclip((c[x] + rnd) >> shift, col_lo, col_hi);
+}
+
+template <int H, bool HBD>
+__device__ __noinline__ void itx_col_pass_shared(const int *tcol, int pitch, typename Bd<HBD>::pixel *dcol, int stride,
+                                                 int t_second, int col_lo, int col_hi, int bitdepth_max)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    constexpr int SH = H < 32 ? H : 32;
+    int c[H];
+#pragma unroll
+    for (int y = 0; y < H; y++) c[y] = y < SH ? tcol[y * pitch] : 0;
+    tx1d_apply<H>(c, t_second, col_lo, col_hi);
+#pragma unroll
+    for (int y = 0; y < H; y++)
+        dcol[(ptrdiff_t)y * stride] = (pixel)iclip((int)dcol[(ptrdiff_t)y * stride] + ((c[y] + 8) >> 4), 0, bitdepth_max);
+}
+
 // the work of one CTA (`cta` = its index among the CTAs of this transform size); smem: kItxWarps * NB * SLOT words
-template <int W, int H, int TX, int SHIFT, bool HBD>
+template <int W, int H, int TX, int SHIFT, bool HBD, bool SHARED = false>
 B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *__restrict__ blocks, int n_blocks,
                            typename Bd<HBD>::coef *__restrict__ coefs, typename Bd<HBD>::pixel *__restrict__ pic,
                            int stride0, int stride1, int stride2, int bitdepth_max, int zero_coefs)
@@ -93,7 +132,9 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
             if (t_second == TX1D_IDENTITY && t_first != TX1D_IDENTITY) last = imin(G::SH - 1, eob);
             else if (t_first == TX1D_IDENTITY && t_second != TX1D_IDENTITY) last = eob >> (G::LW + 2);
             else last = b200_lnz_col[b200_lnz_col_off[TX] + eob];
-            if (y <= last) {
+            if (SHARED && y <= last) {
+                itx_row_pass_shared<W, HBD>(cf + y, G::SH, t + y * G::P, G::RECT2, SHIFT, t_first, row_lo, row_hi, col_lo, col_hi);
+            } else if (y <= last) {
 #pragma unroll
                 for (int x = 0; x < W; x++) {
                     if (x < G::SW) {
@@ -142,6 +183,10 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
             }
         } else {
             for (int x = li + half * 32; x < W; x += G::PAIR ? 64 : G::L) {
+                if (SHARED && !is_wht) {
+                    itx_col_pass_shared<H, HBD>(t + x, G::P, dst + x, stride, t_second, col_lo, col_hi, bitdepth_max);
+                    continue;
+                }
                 int c[H];
 #pragma unroll
                 for (int y = 0; y < H; y++) c[y] = y < G::SH ? t[y * G::P + x] : 0;
