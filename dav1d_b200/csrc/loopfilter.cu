@@ -4,7 +4,7 @@
 // Within one direction every edge segment is independent (a width-wd filter reads <= wd/2 and
 // writes < wd/2 samples per side, and wd is bounded by the transform size on both sides), so a
 // picture is deblocked by two flat sweeps instead of dav1d's per-superblock-row calls:
-//   lf_cols_kernel  all column (vertical) edges: thread = (edge x4, picture line); threadIdx.x
+//   lf_cols_kernel  all column (vertical) edges: thread = (edge x4, unit row y4), 4 lines each; threadIdx.x
 //                   walks consecutive edges of one line so a warp touches one contiguous row span
 //   lf_rows_kernel  all row (horizontal) edges: thread = (pixel column, edge y4); threadIdx.x walks
 //                   consecutive pixel columns, every tap is a coalesced row access
@@ -116,7 +116,8 @@ B200_DEV int lf_width(const B200Av1Filter &m, int plane, int dir, int b, int a, 
     return 0;
 }
 
-// grid: (ceil(units_x / 32), ceil(lines / 8), 3 planes); block (32, 8)
+// grid: (ceil(units_x / 32), ceil(units_y / 8), 3 planes); block (32, 8); a thread owns the 4 lines of one 4x4 unit
+// edge: mask decoding and level look-up are per unit, and the 4 lines give the memory system independent loads
 template <bool HBD>
 __global__ void __launch_bounds__(256) lf_cols_kernel(const __grid_constant__ B200LfFrame f, int bdmax)
 {
@@ -125,12 +126,12 @@ __global__ void __launch_bounds__(256) lf_cols_kernel(const __grid_constant__ B2
     if (plane ? !f.filter_uv : !f.filter_y) return;
     const int ssh = plane ? f.ss_hor : 0, ssv = plane ? f.ss_ver : 0;
     const int x4 = blockIdx.x * 32 + threadIdx.x;            // 4-px unit (plane units)
-    const int y = blockIdx.y * 8 + threadIdx.y;              // picture line (plane units)
+    const int y4 = blockIdx.y * 8 + threadIdx.y;
     const int pw4 = (f.w4 + ssh) >> ssh, ph4 = (f.h4 + ssv) >> ssv;
-    if (x4 >= pw4 || x4 == 0 || y >= ph4 * 4) return;
+    if (x4 >= pw4 || x4 == 0 || y4 >= ph4) return;
     const int upsb_x = 32 >> ssh, upsb_y = 32 >> ssv;        // units per 128x128 area
     const int sbx = x4 / upsb_x, xi = x4 - sbx * upsb_x;
-    const int y4 = y >> 2, sby = y4 / upsb_y, yi = y4 - sby * upsb_y;
+    const int sby = y4 / upsb_y, yi = y4 - sby * upsb_y;
     const B200Av1Filter &m = f.mask[sby * f.sb128w + sbx];
     const int wd = lf_width(m, plane, 0, xi, yi, ssv);
     if (!wd) return;
@@ -138,8 +139,10 @@ __global__ void __launch_bounds__(256) lf_cols_kernel(const __grid_constant__ B2
     const int c = plane == 0 ? 0 : plane + 1;
     const int L = l[0][c] ? l[0][c] : l[-1][c];
     if (!L) return;
-    pixel *p = (pixel *)f.pic + f.plane_off[plane] + (ptrdiff_t)y * f.stride[plane] + x4 * 4;
-    lf_line<HBD>(p, 1, f.lut.e[L], f.lut.i[L], L >> 4, wd, bdmax);
+    const int E = f.lut.e[L], I = f.lut.i[L];
+    pixel *p = (pixel *)f.pic + f.plane_off[plane] + (ptrdiff_t)(y4 * 4) * f.stride[plane] + x4 * 4;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++, p += f.stride[plane]) lf_line<HBD>(p, 1, E, I, L >> 4, wd, bdmax);
 }
 
 // grid: (ceil(width_px / 128), ceil(units_y / 2), 3); block (128, 2)
@@ -203,7 +206,7 @@ int b200_lf_frame(int bdmax, const B200LfFrame *f, void *stream)
     if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_lf_frame: bad bitdepth_max %d", bdmax); return -2; }
     if (!f->filter_y) return 0;   // dav1d skips deblocking entirely when both luma levels are 0 (src/recon_tmpl.c:1988)
     const int w4 = f->w4, h4 = f->h4;
-    dim3 g1((w4 + 31) / 32, (h4 * 4 + 7) / 8, 3), b1(32, 8);
+    dim3 g1((w4 + 31) / 32, (h4 + 7) / 8, 3), b1(32, 8);
     dim3 g2((w4 * 4 + 127) / 128, (h4 + 1) / 2, 3), b2(128, 2);
     if (bdmax > 255) {
         auto k1 = lf_cols_kernel<true>; B200_LAUNCH(k1, g1, b1, 0, (cudaStream_t)stream, *f, bdmax);
