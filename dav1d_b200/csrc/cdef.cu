@@ -143,7 +143,8 @@ constexpr int kCdefTW = 64, kCdefTH = 32, kCdefPitch = kCdefTW + 8, kCdefRows = 
 constexpr int kCdefThreads = 256;
 constexpr unsigned kCdefSentinel = 0xC000u;
 
-struct CdefBlockInfo { int16_t y_pri, y_sec, uv_pri, uv_sec; int8_t y_dir, uv_dir, inside, pad; };
+struct CdefBlockInfo { int16_t y_pri, y_sec, uv_pri, uv_sec; int8_t y_dir, uv_dir, inside, pad;
+                       uint8_t y_pri_shift, y_sec_shift, uv_pri_shift, uv_sec_shift; };   // constrain shifts, computed once per block
 
 struct CdefShared {
     uint32_t tile[3][kCdefRows * kCdefPitch];   // pair rows -2 .. TH, columns -4 .. TW+3
@@ -227,24 +228,35 @@ __global__ void __launch_bounds__(kCdefThreads, B200_CDEF_MINB) cdef_frame_kerne
         const int groups = (tw + 8) >> 2, rows = th + 3;
         const pixel *sp = src + f.plane_off[pl];
         const int st = f.stride[pl];
+        const unsigned magic = (65536u + groups - 1) / groups;            // exact i / groups for i < 36 * 18
         for (int i = tid; i < groups * rows; i += kCdefThreads) {
-            const int r = i / groups, g = i - r * groups;
+            const int r = (int)((i * magic) >> 16), g = i - r * groups;
             const int x = x0 - 4 + g * 4, y = y0 - 2 + r;
-            unsigned a[4], b[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) a[k] = b[k] = kCdefSentinel;
+            uint4 w;
+            w.x = w.y = w.z = w.w = kCdefSentinel * 0x00010001u;
             if (x >= 0 && x < availw) {
-                if (y >= 0 && y < availh) {
-                    if (HBD) { const uint2 q = *(const uint2 *)(sp + (ptrdiff_t)y * st + x); a[0] = q.x & 0xffff; a[1] = q.x >> 16; a[2] = q.y & 0xffff; a[3] = q.y >> 16; }
-                    else { const unsigned q = *(const unsigned *)(sp + (ptrdiff_t)y * st + x); a[0] = q & 0xff; a[1] = (q >> 8) & 0xff; a[2] = (q >> 16) & 0xff; a[3] = q >> 24; }
-                }
-                if (y + 1 >= 0 && y + 1 < availh) {
-                    if (HBD) { const uint2 q = *(const uint2 *)(sp + (ptrdiff_t)(y + 1) * st + x); b[0] = q.x & 0xffff; b[1] = q.x >> 16; b[2] = q.y & 0xffff; b[3] = q.y >> 16; }
-                    else { const unsigned q = *(const unsigned *)(sp + (ptrdiff_t)(y + 1) * st + x); b[0] = q & 0xff; b[1] = (q >> 8) & 0xff; b[2] = (q >> 16) & 0xff; b[3] = q >> 24; }
+                const bool ha = y >= 0 && y < availh, hb = y + 1 >= 0 && y + 1 < availh;
+                if (HBD) {
+                    uint2 qa, qb;
+                    qa.x = qa.y = qb.x = qb.y = kCdefSentinel * 0x00010001u;
+                    if (ha) qa = *(const uint2 *)(sp + (ptrdiff_t)y * st + x);
+                    if (hb) qb = *(const uint2 *)(sp + (ptrdiff_t)(y + 1) * st + x);
+                    // (a0 a1 | a2 a3) x (b0 b1 | b2 b3) -> (a0 b0) (a1 b1) (a2 b2) (a3 b3): one byte permute each
+                    w.x = __byte_perm(qa.x, qb.x, 0x5410); w.y = __byte_perm(qa.x, qb.x, 0x7632);
+                    w.z = __byte_perm(qa.y, qb.y, 0x5410); w.w = __byte_perm(qa.y, qb.y, 0x7632);
+                } else {
+                    const unsigned sent4 = 0;         // per-byte sentinel impossible: handled after the permutes
+                    unsigned qa = sent4, qb = sent4;
+                    if (ha) qa = *(const unsigned *)(sp + (ptrdiff_t)y * st + x);
+                    if (hb) qb = *(const unsigned *)(sp + (ptrdiff_t)(y + 1) * st + x);
+                    // bytes a_k, b_k -> halfwords (a_k | b_k << 16): two byte permutes per word
+                    const unsigned t01 = __byte_perm(qa, qb, 0x5140), t23 = __byte_perm(qa, qb, 0x7362);   // a0 b0 a1 b1 | a2 b2 a3 b3
+                    w.x = __byte_perm(t01, 0, 0x4140); w.y = __byte_perm(t01, 0, 0x4342);
+                    w.z = __byte_perm(t23, 0, 0x4140); w.w = __byte_perm(t23, 0, 0x4342);
+                    if (!ha) { w.x = (w.x & 0xffff0000u) | kCdefSentinel; w.y = (w.y & 0xffff0000u) | kCdefSentinel; w.z = (w.z & 0xffff0000u) | kCdefSentinel; w.w = (w.w & 0xffff0000u) | kCdefSentinel; }
+                    if (!hb) { w.x = (w.x & 0xffffu) | kCdefSentinel << 16; w.y = (w.y & 0xffffu) | kCdefSentinel << 16; w.z = (w.z & 0xffffu) | kCdefSentinel << 16; w.w = (w.w & 0xffffu) | kCdefSentinel << 16; }
                 }
             }
-            uint4 w;
-            w.x = a[0] | b[0] << 16; w.y = a[1] | b[1] << 16; w.z = a[2] | b[2] << 16; w.w = a[3] | b[3] << 16;
             *(uint4 *)&S.tile[pl][r * kCdefPitch + g * 4] = w;
         }
     }
@@ -301,6 +313,13 @@ __global__ void __launch_bounds__(kCdefThreads, B200_CDEF_MINB) cdef_frame_kerne
                 bi.uv_dir = (int8_t)(uv_pri ? ((f.ss_hor && !f.ss_ver) ? c_uv_dir422[dir] : dir) : 0);
             }
         }
+        {   // shift = max(0, damping - ulog2(strength)) per class (luma damping, chroma damping - 1)
+            const int dl = f.damping + b8, dc = dl - 1;
+            bi.y_pri_shift = (uint8_t)(bi.y_pri ? imax(0, dl - ulog2(bi.y_pri)) : 0);
+            bi.y_sec_shift = (uint8_t)(bi.y_sec ? dl - ulog2(bi.y_sec) : 0);
+            bi.uv_pri_shift = (uint8_t)(bi.uv_pri ? imax(0, dc - ulog2(bi.uv_pri)) : 0);
+            bi.uv_sec_shift = (uint8_t)(bi.uv_sec ? dc - ulog2(bi.uv_sec) : 0);
+        }
         S.info[tid] = bi;
     }
     __syncthreads();
@@ -313,10 +332,10 @@ __global__ void __launch_bounds__(kCdefThreads, B200_CDEF_MINB) cdef_frame_kerne
         const int x0 = bx0 * 4 >> sh, y0 = by0 * 4 >> sv;
         pixel *dp = dst + f.plane_off[pl];
         const int st = f.stride[pl];
-        const int damp = f.damping + b8 - (pl ? 1 : 0);
         const uint32_t *t = S.tile[pl];
+        const int twl = 6 - sh;                                   // tw = 64 >> sh is a power of two
         for (int i = tid; i < tw * (th >> 1); i += kCdefThreads) {
-            const int yp = i / tw, x = i - yp * tw, y = yp * 2;
+            const int yp = i >> twl, x = i & (tw - 1), y = yp * 2;
             const CdefBlockInfo bi = S.info[(y >> (3 - sv)) * 8 + (x >> (3 - sh))];
             if (!bi.inside) continue;
             const int idx = (y + 2) * kCdefPitch + x + 4;
@@ -327,14 +346,14 @@ __global__ void __launch_bounds__(kCdefThreads, B200_CDEF_MINB) cdef_frame_kerne
                 const unsigned negpx = __vadd2(~px2, 0x00010001u);
                 unsigned sumP = 0, sumN = 0, mx = px2, mn = px2;
                 if (pri) {
-                    const int shift = imax(0, damp - ulog2(pri));
+                    const int shift = pl ? bi.uv_pri_shift : bi.y_pri_shift;
                     const unsigned thr1 = (unsigned)(pri + 1) * 0x00010001u, smask = (0xffffu >> shift) * 0x00010001u;
                     const int tap0 = 4 - ((pri >> b8) & 1);
                     cdef_tap2(t, idx, S.off[dir][0], negpx, thr1, shift, smask, tap0, sumP, sumN, mx, mn);
                     cdef_tap2(t, idx, S.off[dir][1], negpx, thr1, shift, smask, (tap0 & 3) | 2, sumP, sumN, mx, mn);
                 }
                 if (sec) {
-                    const int shift = damp - ulog2(sec);
+                    const int shift = pl ? bi.uv_sec_shift : bi.y_sec_shift;
                     const unsigned thr1 = (unsigned)(sec + 1) * 0x00010001u, smask = (0xffffu >> shift) * 0x00010001u;
                     const int d2 = (dir + 2) & 7, d6 = (dir + 6) & 7;
                     cdef_tap2(t, idx, S.off[d2][0], negpx, thr1, shift, smask, 2, sumP, sumN, mx, mn);
