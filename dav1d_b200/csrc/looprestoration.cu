@@ -204,21 +204,27 @@ B200_DEV void lr_unit_params(const B200RestorationUnit &u, bool hbd, LrTileParam
     }
 }
 
+struct LrGrid { int base[3], nx[3]; };       // flattened tile list: plane p owns CTAs base[p] .. , nx[p] tiles per row
+
 template <bool HBD>
 #ifndef B200_LR_MINB
 #define B200_LR_MINB 6
 #endif
-__global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(const __grid_constant__ B200LrFrame f, int bdmax)
+__global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(const __grid_constant__ B200LrFrame f, const __grid_constant__ LrGrid lg, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ LrShared sm;
-    const int pl = blockIdx.z;
+    const int bid = blockIdx.x;
+    const int pl = bid >= lg.base[2] ? 2 : bid >= lg.base[1] ? 1 : 0;
     const int ssh = pl ? f.ss_hor : 0, ssv = pl ? f.ss_ver : 0;
     const int w = (f.w + ssh) >> ssh, h = (f.h + ssv) >> ssv;
     const int us_log2 = f.unit_size_log2[pl ? 1 : 0], unit = 1 << us_log2, half = unit >> 1;
     const int tw_full = unit < kTW ? unit : kTW;
-    const int x0 = blockIdx.x * tw_full;
-    const int k = blockIdx.y >> 1, ty = blockIdx.y & 1;
+    const int local = bid - lg.base[pl], nxp = lg.nx[pl];
+    const int tyi = local / nxp, txi = local - tyi * nxp;
+    const int x0 = txi * tw_full;
+    // a 64-row luma stripe is 2 tiles tall; a vertically subsampled stripe (32 rows) is 1
+    const int k = ssv ? tyi : tyi >> 1, ty = ssv ? 0 : tyi & 1;
     const int y0s = k ? (64 * k - 8) >> ssv : 0;
     const int y1s = imin(h, (64 * (k + 1) - 8) >> ssv);
     const int ty0 = y0s + ty * kTH;
@@ -336,11 +342,20 @@ int b200_lr_frame(int bdmax, const B200LrFrame *f, void *stream)
     if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_lr_frame: bad bitdepth_max %d", bdmax); return -2; }
     for (int i = 0; i < 2; i++)
         if (f->unit_size_log2[i] < 5 || f->unit_size_log2[i] > 8) { b200_set_error("b200_lr_frame: bad unit size"); return -2; }
-    const int min_tw = 32;
     const int n_stripes = (f->h + 8 + 63) / 64;
-    dim3 grid((f->w + min_tw - 1) / min_tw, n_stripes * 2, 3);
-    if (bdmax > 255) { auto k = lr_frame_kernel<true>; B200_LAUNCH(k, grid, dim3(256), 0, (cudaStream_t)stream, *f, bdmax); }
-    else { auto k = lr_frame_kernel<false>; B200_LAUNCH(k, grid, dim3(256), 0, (cudaStream_t)stream, *f, bdmax); }
+    LrGrid lg;
+    int total = 0;
+    for (int p = 0; p < 3; p++) {
+        const int ssh = p ? f->ss_hor : 0, ssv = p ? f->ss_ver : 0;
+        const int w = (f->w + ssh) >> ssh;
+        const int unit = 1 << f->unit_size_log2[p ? 1 : 0], tw_full = unit < kTW ? unit : kTW;
+        lg.nx[p] = (w + tw_full - 1) / tw_full;
+        lg.base[p] = total;
+        total += lg.nx[p] * n_stripes * (ssv ? 1 : 2);
+    }
+    dim3 grid(total);
+    if (bdmax > 255) { auto k = lr_frame_kernel<true>; B200_LAUNCH(k, grid, dim3(256), 0, (cudaStream_t)stream, *f, lg, bdmax); }
+    else { auto k = lr_frame_kernel<false>; B200_LAUNCH(k, grid, dim3(256), 0, (cudaStream_t)stream, *f, lg, bdmax); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
