@@ -141,17 +141,23 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def frame_algorithmic_bytes(S):
+def frame_algorithmic_bytes(S, fused=False):
     """SURVEY.md §8(d) accounting for one frame, per stage (bytes); px = bytes per pixel."""
     px = S["pic"].itemsize
     cps = S["coefs"].itemsize
     ssh, ssv = [0, S["ss_hor"], S["ss_hor"]], [0, S["ss_ver"], S["ss_ver"]]
     samples = sum(((S["W"] + ssh[p]) >> ssh[p]) * ((S["H"] + ssv[p]) >> ssv[p]) for p in range(3))
-    b = S["pred"]
+    fused = fused and "cfused" in S
+    b = S["pred_single"] if fused else S["pred"]
     foot = ((b["w"].astype(np.int64) + 7 * (b["mx"] != 0)) * (b["h"].astype(np.int64) + 7 * (b["my"] != 0))).sum() * px
     out = (b["w"].astype(np.int64) * b["h"] * np.where(b["op"] == 1, 2, px)).sum()
-    c = np.concatenate([S["comp"], S["comp2"]])
-    comp = (c["w"].astype(np.int64) * c["h"] * (4 + px)).sum()
+    if fused:      # a fused compound block: two footprints read + one block written (SURVEY §8d)
+        c = np.concatenate([S["cfused"], S["cfused2"]])
+        w_, h_ = c["w"].astype(np.int64), c["h"].astype(np.int64)
+        comp = (sum((w_ + 7 * (c["mx"][:, k] != 0)) * (h_ + 7 * (c["my"][:, k] != 0)) for k in range(2)) * px + w_ * h_ * px).sum() if len(c) else 0
+    else:
+        c = np.concatenate([S["comp"], S["comp2"]])
+        comp = (c["w"].astype(np.int64) * c["h"] * (4 + px)).sum()
     itx = 0
     from dav1d_b200 import levels as L
     for tx in range(19):
@@ -210,7 +216,7 @@ def workload_buffers(name, S, **kw):
     return frame.FrameBuffers(S, **kw)
 
 
-OURS = dict(compact=True)    # our arm ships coefficients 0 .. eob in scan order (the reference arm needs the dense plane)
+OURS = dict(compact=True, fused=True)   # ... and runs compound blocks through the fused prediction kernel    # our arm ships coefficients 0 .. eob in scan order (the reference arm needs the dense plane)
 
 
 # ------------------------------------------------------------------------------ reference arm / cpu baseline
@@ -414,7 +420,7 @@ def run_ours_frame(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        alg = frame_algorithmic_bytes(Ss[0])
+        alg = frame_algorithmic_bytes(Ss[0], fused=bool(fbs[0].job.n_cfused))
         stages = {}
         for name, ms in stage_ms.items():
             key = {"pred": "mc", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg", "intra": "intra"}[name]
@@ -445,6 +451,7 @@ def run_ours_frame(args):
                            "records": {"pred_blocks": int(len(Ss[0]["pred"])), "compound": int(len(Ss[0]["comp"]) + len(Ss[0]["comp2"])),
                                        "tx_blocks": int(sum(len(a) for a in Ss[0]["itx"].values())), "coefs": int(len(Ss[0]["coefs"])),
                                        "intra_tx_blocks": int(len(Ss[0].get("intra_tx", []))), "intra_waves": int(Ss[0].get("intra_waves", 0))},
+                           "compound": "fused: both predictions + avg/w_avg/mask/w_mask in one kernel, int16 intermediates stay on the SM",
                            "upload": "per coded transform block the coefficients 0..eob in scan order (expanded on the device inside the timed job) + block records + masks/levels",
                            "exchange": "all_gather of each rank's restored picture per step (NCCL, asynchronous: overlaps the next frame)" if world > 1 else "none"},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -468,6 +475,9 @@ def stage_times(torch, lib, fbs, nsets, reps=6):
     stages = []
     if j0.n_pred:
         stages.append(("pred", lambda j, bd, st: lib.b200_mc_batch(bd, C.byref(j.mc), j.d_pred, j.n_pred, st)))
+    if j0.n_cfused or j0.n_cfused2:
+        stages.append(("comp", lambda j, bd, st: (lib.b200_mc_comp_fused_batch(bd, C.byref(j.mc), j.d_cfused, j.n_cfused, st),
+                                                  lib.b200_mc_comp_fused_batch(bd, C.byref(j.mc), j.d_cfused2, j.n_cfused2, st))))
     if j0.n_comp or j0.n_comp2:
         stages.append(("comp", lambda j, bd, st: (lib.b200_mc_comp_batch(bd, C.byref(j.mc), j.d_comp, j.n_comp, st),
                                                   lib.b200_mc_comp_batch(bd, C.byref(j.mc), j.d_comp2, j.n_comp2, st))))

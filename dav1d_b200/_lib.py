@@ -96,6 +96,12 @@ class FgFrame(C.Structure):
                 ("data", FilmGrainData), ("scratch", C.c_void_p)]
 
 
+class CompFusedBlock(C.Structure):
+    _fields_ = [("dst_off", C.c_uint32), ("mask_off", C.c_uint32), ("src_x", C.c_int32 * 2), ("src_y", C.c_int32 * 2),
+                ("w", C.c_uint8), ("h", C.c_uint8), ("mx", C.c_uint8 * 2), ("my", C.c_uint8 * 2), ("ref", C.c_uint8 * 2),
+                ("filter2d", C.c_uint8), ("op", C.c_uint8), ("param", C.c_uint8), ("plane", C.c_uint8), ("pad", C.c_uint8 * 4)]
+
+
 class McScaledBlock(C.Structure):
     _fields_ = [("dst_off", C.c_uint32), ("src_x", C.c_int32), ("src_y", C.c_int32), ("mx", C.c_uint16), ("my", C.c_uint16),
                 ("dx", C.c_uint16), ("dy", C.c_uint16), ("w", C.c_uint8), ("h", C.c_uint8), ("filter2d", C.c_uint8),
@@ -140,6 +146,7 @@ class FrameJob(C.Structure):
                 ("lf", LfFrame), ("cdef", CdefFrame), ("lr", LrFrame),
                 ("d_intra", C.c_void_p), ("n_intra", C.c_int32), ("pad6", C.c_int32), ("intra", IntraFrame),
                 ("d_scaled", C.c_void_p), ("n_scaled", C.c_int32), ("pad7", C.c_int32),
+                ("d_cfused", C.c_void_p), ("d_cfused2", C.c_void_p), ("n_cfused", C.c_int32), ("n_cfused2", C.c_int32),
                 ("d_expand", C.c_void_p), ("n_expand", C.c_int32), ("pad8", C.c_int32), ("d_ccoef", C.c_void_p),
                 ("coef_bytes", C.c_uint64),
                 ("run_fg", C.c_int32), ("pad5", C.c_int32), ("fg", FgFrame)]
@@ -169,6 +176,7 @@ _SIGS = {
     "b200_mc_comp_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_mc_blend_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_mc_warp_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_mc_comp_fused_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_mc_scaled_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_mc_put_scaled": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t] + [C.c_int] * 8),
     "b200_mc_prep_scaled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_ssize_t] + [C.c_int] * 8),
@@ -292,4 +300,4 @@ class Av1Restoration(C.Structure):
 
 
 ABI_STRUCTS = [McFrame, McBlock, CompBlock, BlendBlock, WarpBlock, ItxBlock, LfFrame, CdefFrame, LrFrame, FrameJob,
-               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame, McScaledBlock, CoefBlock, IntraSb]
+               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame, McScaledBlock, CoefBlock, IntraSb, CompFusedBlock]

@@ -28,6 +28,8 @@ static int frame_phase_recon(const B200FrameJob *j, void *stream, void **fg_side
     if ((r = b200_mc_batch(bd, &j->mc, j->d_pred, j->n_pred, stream))) return r;
     if ((r = b200_mc_scaled_batch(bd, &j->mc, j->d_scaled, j->n_scaled, stream))) return r;
     if ((r = b200_mc_warp_batch(bd, &j->mc, j->d_warp, j->n_warp, stream))) return r;
+    if ((r = b200_mc_comp_fused_batch(bd, &j->mc, j->d_cfused, j->n_cfused, stream))) return r;
+    if ((r = b200_mc_comp_fused_batch(bd, &j->mc, j->d_cfused2, j->n_cfused2, stream))) return r;
     if ((r = b200_mc_comp_batch(bd, &j->mc, j->d_comp, j->n_comp, stream))) return r;
     if ((r = b200_mc_comp_batch(bd, &j->mc, j->d_comp2, j->n_comp2, stream))) return r;
     if ((r = b200_mc_blend_batch(bd, &j->mc, j->d_blend, j->n_blend, stream))) return r;
@@ -92,7 +94,7 @@ int b200_struct_size(int which)
     case 6: return sizeof(B200LfFrame); case 7: return sizeof(B200CdefFrame); case 8: return sizeof(B200LrFrame);
     case 9: return sizeof(B200FrameJob); case 10: return sizeof(B200Av1Filter); case 11: return sizeof(B200Av1Restoration);
     case 12: return sizeof(B200FgFrame); case 13: return sizeof(B200FilmGrainData);
-    case 14: return sizeof(B200IntraTx); case 15: return sizeof(B200IntraFrame); case 16: return sizeof(B200McScaledBlock); case 17: return sizeof(B200CoefBlock); case 18: return sizeof(B200IntraSb);
+    case 14: return sizeof(B200IntraTx); case 15: return sizeof(B200IntraFrame); case 16: return sizeof(B200McScaledBlock); case 17: return sizeof(B200CoefBlock); case 18: return sizeof(B200IntraSb); case 19: return sizeof(B200CompFusedBlock);
     }
     return -1;
 }

@@ -187,20 +187,91 @@ B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int
     __syncwarp();
 }
 
-template <bool HBD>
 #ifndef B200_MC_MINB
 #define B200_MC_MINB 6
 #endif
 #ifndef B200_MC_S1
 #define B200_MC_S1 0
 #endif
+
+// filter taps of one prediction (registers): 8-tap / 4-tap sets or the bilinear pair, and the base shift
+struct McTaps { int fh[8], fv[8]; int fsh; bool has_h, has_v; };
+B200_DEV void mc_taps(McTaps &t, int filter2d, int mx, int my, int w, int h)
+{
+    const bool bilin = filter2d == 9;
+    t.has_h = mx != 0; t.has_v = my != 0; t.fsh = bilin ? 4 : 6;
+#pragma unroll
+    for (int k = 0; k < 8; k++) t.fh[k] = t.fv[k] = 0;
+    if (bilin) {
+        t.fh[3] = 16 - mx; t.fh[4] = mx; t.fv[3] = 16 - my; t.fv[4] = my;
+    } else {
+        // 4-tap sets for w <= 4 / h <= 4 (reference src/mc_tmpl.c:115-123)
+        if (t.has_h) {
+            const int f = c_f2d_h[filter2d];
+            const int idx = w > 4 ? f : 3 + (f & 1);
+#pragma unroll
+            for (int k = 0; k < 8; k++) t.fh[k] = b200_mc_subpel_filters[idx][mx - 1][k];
+        }
+        if (t.has_v) {
+            const int f = c_f2d_v[filter2d];
+            const int idx = h > 4 ? f : 3 + (f & 1);
+#pragma unroll
+            for (int k = 0; k < 8; k++) t.fv[k] = b200_mc_subpel_filters[idx][my - 1][k];
+        }
+    }
+}
+
+// one sub-block (<= 32x32) of one prediction by one warp: stage the source window, run the two passes.
+// (sx, sy): reference sample of the sub-block's top-left output; put -> dsub / ds, prep -> tsub / tw.
+template <bool HBD>
+B200_DEV void mc_subblock(McSmem<HBD> &sm, const int lane, const typename Bd<HBD>::pixel *__restrict__ ref, const int rs,
+                          const int rw, const int rh, const int sx, const int sy, const int sw, const int sh,
+                          const McTaps &t, const int ib, const int bias, const bool is_prep, const int bdmax,
+                          typename Bd<HBD>::pixel *dsub, const int ds, int16_t *tsub, const int tw)
+{
+    constexpr int RP = McSmem<HBD>::kRawPitch;
+    constexpr int PPW = HBD ? 2 : 4;                       // pixels per 32-bit word
+    const bool words_ok = ((rs & (PPW - 1)) == 0) && ((((uintptr_t)ref) & 3) == 0);
+    const int nc = sw + (t.has_h ? 7 : 0), nr = sh + (t.has_v ? 7 : 0);
+    const int gx = sx - (t.has_h ? 3 : 0), gy = sy - (t.has_v ? 3 : 0);
+    int shift0 = 0;
+    if (words_ok && gx >= 0 && gy >= 0 && gx + nc <= rw && gy + nr <= rh &&
+        (((gx & ~(PPW - 1)) + ((nc + (gx & (PPW - 1)) + PPW - 1) & ~(PPW - 1))) <= rs)) {
+        // interior: aligned words, the window starts `shift0` samples into the tile row
+        shift0 = gx & (PPW - 1);
+        const int nw = (nc + shift0 + PPW - 1) / PPW;
+        const int gxa = gx - shift0;
+        const unsigned magic = (65536u + nw - 1) / nw;
+        for (int it = lane; it < nr * nw; it += 32) {
+            const int r = (int)((it * magic) >> 16), c = it - r * nw;
+            const unsigned v = *(const unsigned *)(ref + (ptrdiff_t)(gy + r) * rs + gxa + c * PPW);
+            *(unsigned *)&sm.raw[r * RP + c * PPW] = v;
+        }
+    } else {
+        const unsigned magic = (65536u + nc - 1) / nc;
+        for (int it = lane; it < nr * nc; it += 32) {
+            const int r = (int)((it * magic) >> 16), c = it - r * nc;
+            sm.raw[r * RP + c] = ref[(ptrdiff_t)iclip(gy + r, 0, rh - 1) * rs + iclip(gx + c, 0, rw - 1)];
+        }
+    }
+    __syncwarp();
+    const int area = sw * sh;
+    if (B200_MC_S1 && area <= 32)
+        mc_passes<HBD, 1>(sm, lane, sw, sh, nr, shift0, t.has_h, t.has_v, t.fh, t.fv, t.fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, tw);
+    else if (area <= 64)
+        mc_passes<HBD, 2>(sm, lane, sw, sh, nr, shift0, t.has_h, t.has_v, t.fh, t.fv, t.fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, tw);
+    else if (area <= 256)
+        mc_passes<HBD, 4>(sm, lane, sw, sh, nr, shift0, t.has_h, t.has_v, t.fh, t.fv, t.fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, tw);
+    else
+        mc_passes<HBD, 8>(sm, lane, sw, sh, nr, shift0, t.has_h, t.has_v, t.fh, t.fv, t.fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, tw);
+}
+
+template <bool HBD>
 __global__ void __launch_bounds__(kMcWarps * 32, B200_MC_MINB)
 mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ McSmem<HBD> smem[kMcWarps];
-    constexpr int RP = McSmem<HBD>::kRawPitch;
-    constexpr int PPW = HBD ? 2 : 4;                       // pixels per 32-bit word
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bi = blockIdx.x * kMcWarps + warp;
     if (bi >= n_blocks) return;
@@ -211,73 +282,95 @@ mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, const __gri
     const int rs = fr.ref_stride[pl], rw = fr.ref_w[pl], rh = fr.ref_h[pl];
     const int ib = inter_bits<HBD>(bdmax);
     const int bias = HBD ? 8192 : 0;
-    const bool bilin = b.filter2d == 9;
-    const int mx = b.mx, my = b.my;
-    const bool has_h = mx != 0, has_v = my != 0;
     const bool is_prep = b.op != 0;
-    const int fsh = bilin ? 4 : 6;
-
-    int fh[8], fv[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) fh[k] = fv[k] = 0;
-    if (bilin) {
-        fh[3] = 16 - mx; fh[4] = mx; fv[3] = 16 - my; fv[4] = my;
-    } else {
-        // 4-tap sets for w <= 4 / h <= 4 (reference src/mc_tmpl.c:115-123)
-        if (has_h) {
-            const int t = c_f2d_h[b.filter2d];
-            const int idx = w > 4 ? t : 3 + (t & 1);
-#pragma unroll
-            for (int k = 0; k < 8; k++) fh[k] = b200_mc_subpel_filters[idx][mx - 1][k];
-        }
-        if (has_v) {
-            const int t = c_f2d_v[b.filter2d];
-            const int idx = h > 4 ? t : 3 + (t & 1);
-#pragma unroll
-            for (int k = 0; k < 8; k++) fv[k] = b200_mc_subpel_filters[idx][my - 1][k];
-        }
-    }
+    McTaps t;
+    mc_taps(t, b.filter2d, b.mx, b.my, w, h);
     pixel *const dpx = (pixel *)fr.dst;
     const int ds = fr.dst_stride[pl];
-    const bool words_ok = ((rs & (PPW - 1)) == 0) && ((((uintptr_t)ref) & 3) == 0);
+    for (int sy0 = 0; sy0 < h; sy0 += kMcSub)
+        for (int sx0 = 0; sx0 < w; sx0 += kMcSub)
+            mc_subblock<HBD>(sm, lane, ref, rs, rw, rh, b.src_x + sx0, b.src_y + sy0, imin(kMcSub, w - sx0), imin(kMcSub, h - sy0),
+                             t, ib, bias, is_prep, bdmax, dpx + b.dst_off + (ptrdiff_t)sy0 * ds + sx0, ds,
+                             fr.tmp + b.dst_off + sy0 * w + sx0, w);
+}
 
+// ---- fused compound prediction -----------------------------------------------------------------------
+// Both predictions of a compound block and their combination in one pass: the two int16 intermediates of a
+// 32x32 sub-block stay in the warp's shared memory instead of making the round trip through mc.tmp in HBM
+// (prep store + compound load: 4 bytes per sample each way), and the separate compound launch disappears.
+// Same arithmetic as prep + avg / w_avg / mask / w_mask (reference src/mc_tmpl.c:628-781): bit-identical.
+template <bool HBD>
+__global__ void __launch_bounds__(kMcWarps * 32, B200_MC_MINB)
+mc_comp_fused_kernel(const B200CompFusedBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    __shared__ McSmem<HBD> smem[kMcWarps];
+    __shared__ int16_t s_pred[kMcWarps][2][kMcSub * kMcSub];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bi = blockIdx.x * kMcWarps + warp;
+    if (bi >= n_blocks) return;
+    McSmem<HBD> &sm = smem[warp];
+    const B200CompFusedBlock b = blocks[bi];
+    const int w = b.w, h = b.h, pl = b.plane, op = b.op;
+    const int rs = fr.ref_stride[pl], rw = fr.ref_w[pl], rh = fr.ref_h[pl];
+    const int ib = inter_bits<HBD>(bdmax);
+    const int bias = HBD ? 8192 : 0;
+    const int bitdepth = 32 - __clz(bdmax);
+    pixel *const dpx = (pixel *)fr.dst + b.dst_off;
+    const int ds = fr.dst_stride[pl];
+    uint8_t *const mask = fr.mask + b.mask_off;
+    const int ss_hor = op >= B200_COMP_W_MASK_422, ss_ver = op == B200_COMP_W_MASK_420;
     for (int sy0 = 0; sy0 < h; sy0 += kMcSub)
         for (int sx0 = 0; sx0 < w; sx0 += kMcSub) {
             const int sw = imin(kMcSub, w - sx0), sh = imin(kMcSub, h - sy0);
-            const int nc = sw + (has_h ? 7 : 0), nr = sh + (has_v ? 7 : 0);
-            const int gx = b.src_x + sx0 - (has_h ? 3 : 0), gy = b.src_y + sy0 - (has_v ? 3 : 0);
-            int shift0 = 0;
-            if (words_ok && gx >= 0 && gy >= 0 && gx + nc <= rw && gy + nr <= rh &&
-                (((gx & ~(PPW - 1)) + ((nc + (gx & (PPW - 1)) + PPW - 1) & ~(PPW - 1))) <= rs)) {
-                // interior: aligned words, the window starts `shift0` samples into the tile row
-                shift0 = gx & (PPW - 1);
-                const int nw = (nc + shift0 + PPW - 1) / PPW;
-                const int gxa = gx - shift0;
-                const unsigned magic = (65536u + nw - 1) / nw;
-                for (int it = lane; it < nr * nw; it += 32) {
-                    const int r = (int)((it * magic) >> 16), c = it - r * nw;
-                    const unsigned v = *(const unsigned *)(ref + (ptrdiff_t)(gy + r) * rs + gxa + c * PPW);
-                    *(unsigned *)&sm.raw[r * RP + c * PPW] = v;
+#pragma unroll 1
+            for (int r = 0; r < 2; r++) {
+                const pixel *__restrict__ ref = (const pixel *)fr.ref[b.ref[r]] + fr.ref_plane_off[pl];
+                McTaps t;
+                mc_taps(t, b.filter2d, b.mx[r], b.my[r], w, h);
+                mc_subblock<HBD>(sm, lane, ref, rs, rw, rh, b.src_x[r] + sx0, b.src_y[r] + sy0, sw, sh, t, ib, bias, true, bdmax,
+                                 nullptr, 0, s_pred[warp][r], sw);
+            }
+            __syncwarp();
+            const int16_t *t1 = s_pred[warp][0], *t2 = s_pred[warp][1];
+            if (op <= B200_COMP_MASK) {
+                for (int i = lane; i < sw * sh; i += 32) {
+                    const int y = i / sw, x = i - y * sw;
+                    const int a = t1[i], c = t2[i];
+                    int v;
+                    if (op == B200_COMP_AVG) v = (a + c + (1 << ib) + bias * 2) >> (ib + 1);
+                    else if (op == B200_COMP_W_AVG) v = (a * b.param + c * (16 - b.param) + (8 << ib) + bias * 16) >> (ib + 4);
+                    else { const int m = mask[(sy0 + y) * w + sx0 + x]; v = (a * m + c * (64 - m) + (32 << ib) + bias * 64) >> (ib + 6); }
+                    dpx[(ptrdiff_t)(sy0 + y) * ds + sx0 + x] = (pixel)iclip(v, 0, bdmax);
                 }
             } else {
-                const unsigned magic = (65536u + nc - 1) / nc;
-                for (int it = lane; it < nr * nc; it += 32) {
-                    const int r = (int)((it * magic) >> 16), c = it - r * nc;
-                    sm.raw[r * RP + c] = ref[(ptrdiff_t)iclip(gy + r, 0, rh - 1) * rs + iclip(gx + c, 0, rw - 1)];
+                // w_mask: derive the blend mask from |tmp1 - tmp2|, blend, emit the (sub-sampled) mask
+                const int sign = b.param;
+                const int shc = ib + 6, rnd = (32 << ib) + bias * 64;
+                const int mask_sh = bitdepth + ib - 4, mask_rnd = 1 << (mask_sh - 5);
+                const int qw = sw >> 1, qh = ss_ver ? sh >> 1 : sh;
+                const int mw = ss_hor ? w >> 1 : w;                    // pitch of the emitted mask
+                for (int i = lane; i < qw * qh; i += 32) {
+                    const int qy = i / qw, qx = i - qy * qw;
+                    const int x = qx * 2;
+                    int msum = 0;
+                    for (int rr = 0; rr <= ss_ver; rr++) {
+                        const int y = ss_ver ? qy * 2 + rr : qy;
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const int idx = y * sw + x + k;
+                            const int c = t2[idx], d = t1[idx] - c;
+                            const int m = imin(38 + ((iabs(d) + mask_rnd) >> mask_sh), 64);
+                            dpx[(ptrdiff_t)(sy0 + y) * ds + sx0 + x + k] = (pixel)iclip((d * m + c * 64 + rnd) >> shc, 0, bdmax);
+                            if (!ss_hor) mask[(sy0 + y) * w + sx0 + x + k] = (uint8_t)m;
+                            msum += m;
+                        }
+                    }
+                    if (ss_ver)      mask[((sy0 >> 1) + qy) * mw + (sx0 >> 1) + qx] = (uint8_t)((msum + 2 - sign) >> 2);
+                    else if (ss_hor) mask[(sy0 + qy) * mw + (sx0 >> 1) + qx] = (uint8_t)((msum + 1 - sign) >> 1);
                 }
             }
             __syncwarp();
-            pixel *dsub = dpx + b.dst_off + (ptrdiff_t)sy0 * ds + sx0;
-            int16_t *tsub = fr.tmp + b.dst_off + sy0 * w + sx0;
-            const int area = sw * sh;
-            if (B200_MC_S1 && area <= 32)
-                mc_passes<HBD, 1>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
-            else if (area <= 64)
-                mc_passes<HBD, 2>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
-            else if (area <= 256)
-                mc_passes<HBD, 4>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
-            else
-                mc_passes<HBD, 8>(sm, lane, sw, sh, nr, shift0, has_h, has_v, fh, fv, fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, w);
         }
 }
 
@@ -550,6 +643,15 @@ int b200_mc_scaled_batch(int bitdepth_max, const B200McFrame *frame, const B200M
     if (n <= 0) return 0;
     if (bitdepth_max > 255) { auto k = mc_scaled_kernel<true>; B200_LAUNCH(k, dim3(n), dim3(256), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
     else { auto k = mc_scaled_kernel<false>; B200_LAUNCH(k, dim3(n), dim3(256), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int b200_mc_comp_fused_batch(int bitdepth_max, const B200McFrame *frame, const B200CompFusedBlock *d_blocks, int n, void *stream) {
+    if (check_bd(bitdepth_max, "b200_mc_comp_fused_batch")) return -2;
+    if (n <= 0) return 0;
+    if (bitdepth_max > 255) { auto k = mc_comp_fused_kernel<true>; B200_LAUNCH(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_comp_fused_kernel<false>; B200_LAUNCH(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -115,7 +115,7 @@ class FrameGroup:
 
 
 class FrameBuffers:
-    def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True, intra_grid=0, compact=False, intra_sb=False):
+    def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True, intra_grid=0, compact=False, intra_sb=False, fused=False):
         self.S, self.lib = S, lib or _lib.get_lib()
         self.alloc = alloc or TorchAlloc()
         A = self.alloc
@@ -150,9 +150,14 @@ class FrameBuffers:
             if len(arr):
                 setattr(j, field_ptr, up(name, arr)); setattr(j, field_n, len(arr))
                 self.uploads.append((name, arr))
-        rec("d_pred", "n_pred", "pred", S["pred"])
-        rec("d_comp", "n_comp", "comp", S["comp"])
-        rec("d_comp2", "n_comp2", "comp2", S["comp2"])
+        if fused and "cfused" in S:      # compound blocks: both predictions + the combination in one kernel
+            rec("d_pred", "n_pred", "pred", S["pred_single"])
+            rec("d_cfused", "n_cfused", "cfused", S["cfused"])
+            rec("d_cfused2", "n_cfused2", "cfused2", S["cfused2"])
+        else:
+            rec("d_pred", "n_pred", "pred", S["pred"])
+            rec("d_comp", "n_comp", "comp", S["comp"])
+            rec("d_comp2", "n_comp2", "comp2", S["comp2"])
         for tx in range(19):
             a = S["itx"][tx]
             if len(a):
@@ -241,6 +246,7 @@ class FrameBuffers:
             n_fg = 2
         self.job = j
         self.n_launches = (1 if j.n_pred else 0) + (1 if j.n_comp else 0) + (1 if j.n_comp2 else 0) + \
+            (1 if j.n_cfused else 0) + (1 if j.n_cfused2 else 0) + \
             (1 if any(j.n_itx[tx] for tx in (4, 11, 12, 17, 18)) else 0) + \
             (1 if any(j.n_itx[tx] for tx in range(19) if tx not in (4, 11, 12, 17, 18)) else 0) + 2 * int(run_lf) + int(run_cdef) + int(run_lr) + n_fg + n_intra
         self._host = None

@@ -229,6 +229,10 @@ MC_BLOCK_DT = np.dtype([("dst_off", "<u4"), ("src_x", "<i4"), ("src_y", "<i4"), 
                         ("my", "u1"), ("filter2d", "u1"), ("op", "u1"), ("plane", "u1"), ("ref", "u1")])
 COMP_BLOCK_DT = np.dtype([("dst_off", "<u4"), ("tmp1_off", "<u4"), ("tmp2_off", "<u4"), ("mask_off", "<u4"), ("w", "u1"),
                           ("h", "u1"), ("op", "u1"), ("param", "u1"), ("plane", "u1"), ("pad", "u1", (3,))])
+COMP_FUSED_DT = np.dtype([("dst_off", "<u4"), ("mask_off", "<u4"), ("src_x", "<i4", (2,)), ("src_y", "<i4", (2,)), ("w", "u1"), ("h", "u1"),
+                          ("mx", "u1", (2,)), ("my", "u1", (2,)), ("ref", "u1", (2,)), ("filter2d", "u1"), ("op", "u1"), ("param", "u1"),
+                          ("plane", "u1"), ("pad", "u1", (4,))])
+assert COMP_FUSED_DT.itemsize == 40
 ITX_BLOCK_DT = np.dtype([("dst_off", "<u4"), ("coef_off", "<u4"), ("eob", "<i2"), ("txtp", "u1"), ("plane", "u1")])
 assert MC_BLOCK_DT.itemsize == 20 and COMP_BLOCK_DT.itemsize == 24 and ITX_BLOCK_DT.itemsize == 12
 TX_FROM_WH = {(_L.TX_W[t], _L.TX_H[t]): t for t in range(19)}
@@ -304,6 +308,7 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
     blocks = [(int(bx.flat[i]), int(by.flat[i]), int(lw.flat[i]), int(lh.flat[i])) for i in first]
 
     pred, comp, comp2 = [], [], []
+    pred_single, cfused, cfused2 = [], [], []  # the same predictions for the fused compound kernel
     itx = {t: [] for t in range(19)}          # tx -> list of (dst_off, plane, txtp)
     tmp_off, mask_off = 0, 0
     # transform tilings for the deblocking masks (tx granularity)
@@ -333,7 +338,7 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
             px, py = (x4 * 4) >> ssh[pl], (y4 * 4) >> ssv[pl]
             dst_off = off[pl] + py * stride[pl] + px
             n = 2 if compound else 1
-            offs = []
+            offs, srcs = [], []
             for k in range(n):
                 mvx, mvy = mv[k]
                 if pl == 0 or not ss_hor:
@@ -344,23 +349,32 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
                     sy, my = py + (mvy >> 3), (mvy & 7) << 1
                 else:
                     sy, my = py + (mvy >> 4), mvy & 15
+                srcs.append((sx, sy, mx, my))
                 if compound:
                     pred.append((tmp_off, sx, sy, w, h, mx, my, f2d, 1, pl, rf[k])); offs.append(tmp_off); tmp_off += w * h
                 else:
                     pred.append((dst_off, sx, sy, w, h, mx, my, f2d, 0, pl, rf[k]))
+                    pred_single.append(pred[-1])
             if compound:
+                def fused(moff, op_, par):
+                    return (dst_off, moff, (srcs[0][0], srcs[1][0]), (srcs[0][1], srcs[1][1]), w, h, (srcs[0][2], srcs[1][2]),
+                            (srcs[0][3], srcs[1][3]), (rf[0], rf[1]), f2d, op_, par, pl, (0, 0, 0, 0))
                 if cop == 5:           # segment mask: luma derives it (w_mask), chroma consumes it (mask)
                     if pl == 0:
                         lay = 3 + (ss_hor + ss_ver)           # w_mask_444 / 422 / 420
                         luma_mask_off = mask_off
                         comp.append((dst_off, offs[0], offs[1], mask_off, w, h, lay, cparam, pl, (0, 0, 0)))
+                        cfused.append(fused(mask_off, lay, cparam))
                         mask_off += w * h
                     else:
                         comp2.append((dst_off, offs[0], offs[1], luma_mask_off, w, h, 2, 0, pl, (0, 0, 0)))
+                        cfused2.append(fused(luma_mask_off, 2, 0))
                 elif cop == 2:         # wedge: explicit mask from the host
-                    comp.append((dst_off, offs[0], offs[1], mask_off, w, h, 2, 0, pl, (0, 0, 0))); mask_off += w * h
+                    comp.append((dst_off, offs[0], offs[1], mask_off, w, h, 2, 0, pl, (0, 0, 0)))
+                    cfused.append(fused(mask_off, 2, 0)); mask_off += w * h
                 else:
                     comp.append((dst_off, offs[0], offs[1], 0, w, h, cop, cparam, pl, (0, 0, 0)))
+                    cfused.append(fused(0, cop, cparam))
         # residual: transform tiling of the block (var-tx split depth <= 1), capped at 64
         skip = rng.random() < p_skip
         skip_map[y4:y4 + (1 << lhv), x4:x4 + (1 << lwv)] = skip
@@ -428,7 +442,8 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
             return a
         return a[np.argsort(-(a["w"].astype(np.int64) * a["h"]), kind="stable")]
     S.update(refs=refs, pred=by_area(to_arr(pred, MC_BLOCK_DT)), comp=by_area(to_arr(comp, COMP_BLOCK_DT)),
-             comp2=by_area(to_arr(comp2, COMP_BLOCK_DT)),
+             comp2=by_area(to_arr(comp2, COMP_BLOCK_DT)), pred_single=by_area(to_arr(pred_single, MC_BLOCK_DT)),
+             cfused=by_area(to_arr(cfused, COMP_FUSED_DT)), cfused2=by_area(to_arr(cfused2, COMP_FUSED_DT)),
              itx=itx_arrays, coefs=coefs, tmp_len=tmp_off + 64, mask=rng.integers(0, 65, max(1, mask_off)).astype(np.uint8))
     S["pic"] = np.zeros(total, dt)                     # the picture being reconstructed
     # post-filter records from the transform tilings

@@ -140,6 +140,22 @@ typedef struct B200CompBlock {
 B200_API int b200_mc_comp_batch(int bitdepth_max, const B200McFrame *frame, const B200CompBlock *d_blocks,
                                 int n_blocks, void *stream);
 
+/* Fused compound prediction: both mct[] predictions and avg / w_avg / mask / w_mask in one pass, the int16
+ * intermediates never leave the SM (same arithmetic, bit-identical to prep + compound). `mask` / `w_mask` use
+ * frame->mask at mask_off exactly like B200CompBlock (mask: input, pitch w; w_mask: output). */
+typedef struct B200CompFusedBlock {
+    uint32_t dst_off;            /* pixel offset in dst */
+    uint32_t mask_off;
+    int32_t src_x[2], src_y[2];  /* integer sample position of the block's top-left in each reference plane */
+    uint8_t w, h;
+    uint8_t mx[2], my[2];        /* subpel phases 0..15 */
+    uint8_t ref[2];
+    uint8_t filter2d, op, param, plane;
+    uint8_t pad[4];
+} B200CompFusedBlock;
+B200_API int b200_mc_comp_fused_batch(int bitdepth_max, const B200McFrame *frame, const B200CompFusedBlock *d_blocks,
+                                      int n_blocks, void *stream);
+
 /* blend / blend_v / blend_h (reference src/mc_tmpl.c:683-722) */
 enum { B200_BLEND = 0, B200_BLEND_V = 1, B200_BLEND_H = 2 };
 typedef struct B200BlendBlock {
@@ -534,6 +550,9 @@ typedef struct B200FrameJob {
     B200IntraFrame intra;
     const B200McScaledBlock *d_scaled;   /* predictions from scaled references (run with the put / prep stage) */
     int32_t n_scaled, pad7;
+    const B200CompFusedBlock *d_cfused;  /* fused compound prediction, stage 1 and stage 2 (stage 2 = blocks that consume */
+    const B200CompFusedBlock *d_cfused2; /* a mask emitted by a w_mask block of stage 1) */
+    int32_t n_cfused, n_cfused2;
     const B200CoefBlock *d_expand;       /* compact coefficient upload (optional, see b200_coef_expand) */
     int32_t n_expand, pad8;
     const void *d_ccoef;
@@ -548,7 +567,7 @@ B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
 B200_API int b200_frame_run_batch(const B200FrameJob *const *jobs, int n_jobs, void *stream);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check): 0 McFrame, 1 McBlock, 2 CompBlock,
  * 3 BlendBlock, 4 WarpBlock, 5 ItxBlock, 6 LfFrame, 7 CdefFrame, 8 LrFrame, 9 FrameJob, 10 Av1Filter, 11 Av1Restoration,
- * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame, 16 McScaledBlock, 17 CoefBlock, 18 IntraSb */
+ * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame, 16 McScaledBlock, 17 CoefBlock, 18 IntraSb, 19 CompFusedBlock */
 B200_API int b200_struct_size(int which);
 
 /* The same job fed from HOST buffers (the end-to-end path): every (host, dev, bytes) pair of `uploads`

@@ -82,6 +82,10 @@ def test_emu_frame(bpc, W, H, ssh, ssv):
     fb = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
     fb.run()
     check_frame(S, fb, exp)
+    fbf = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc(), fused=True)     # fused compound prediction
+    assert fbf.job.n_cfused > 0 and fbf.job.n_comp == 0
+    fbf.run()
+    check_frame(S, fbf, exp)
     # the host-buffer path must give the same picture
     fb2 = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
     fb2.run_host()
@@ -102,6 +106,10 @@ def test_gpu_frame(bpc, W, H, ssh, ssv):
     fb.run()
     fb.alloc.sync()
     check_frame(S, fb, exp)
+    fbf = frame.FrameBuffers(S, fused=True, compact=True)
+    fbf.run()
+    fbf.alloc.sync()
+    check_frame(S, fbf, exp)
     last = exp["fg"] if "fg" in exp else exp["lr"]
     fb2 = frame.FrameBuffers(S)
     fb2.run_host()
