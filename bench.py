@@ -216,7 +216,9 @@ def workload_buffers(name, S, **kw):
     return frame.FrameBuffers(S, **kw)
 
 
-OURS = dict(compact=True, fused=True)   # ... and runs compound blocks through the fused prediction kernel    # our arm ships coefficients 0 .. eob in scan order (the reference arm needs the dense plane)
+# ... compound blocks go through prep + compound (the fused prediction kernel, B200_FUSED=1, measured slower: the stages
+# are instruction bound, not HBM bound, so saving the int16 round trip does not pay: 114 us vs 33 + 29 us at 4K)
+OURS = dict(compact=True, fused=bool(int(os.environ.get("B200_FUSED", "0"))))    # our arm ships coefficients 0 .. eob in scan order (the reference arm needs the dense plane)
 
 
 # ------------------------------------------------------------------------------ reference arm / cpu baseline
