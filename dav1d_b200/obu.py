@@ -1,0 +1,206 @@
+"""Synthetic AV1 elementary streams (low-overhead OBU format, AV1 spec section 5) for driving a real dav1d
+front end: hand-written sequence / frame headers in front of tile payloads of random bytes.
+
+There is no AV1 encoder in this environment. An AV1 tile payload is one arithmetic-coded symbol stream, and
+every byte string decodes to *some* legal symbol sequence, so random tile bytes behind valid headers give
+frames that exercise the whole block layer of the decoder (partitions, every intra mode, directional deltas,
+filter-intra, CFL, transform sizes / types, coefficient magnitudes up to the clipping range, per-block
+delta-q / delta-lf, CDEF indices, loop-restoration units) with the contexts and CDF adaptation of a real
+stream. The header syntax follows the order in which the reference parses it (reference src/obu.c:
+parse_seq_hdr :71-307, parse_frame_hdr :399-1164, parse_tile_hdr :1166-1180; tile size bytes src/decode.c,
+dav1d_decode_frame_init_cdf).
+
+Used by tests/test_stream.py and bench.py's `stream` workloads; not a general AV1 muxer."""
+import numpy as np
+
+
+class BitWriter:
+    def __init__(self):
+        self.bits = []
+
+    def f(self, n, v):
+        v = int(v)
+        assert 0 <= v < (1 << n), (n, v)
+        for i in range(n - 1, -1, -1):
+            self.bits.append((v >> i) & 1)
+
+    def su(self, n, v):                      # signed, n bits two's complement (dav1d_get_sbits)
+        self.f(n, v & ((1 << n) - 1))
+
+    def align(self):
+        while len(self.bits) % 8:
+            self.bits.append(0)
+
+    def trailing(self):                      # trailing_bits(): a one, then zeros up to the byte boundary
+        self.bits.append(1)
+        self.align()
+
+    def bytes(self):
+        assert len(self.bits) % 8 == 0
+        a = np.array(self.bits, np.uint8).reshape(-1, 8)
+        return bytes(np.packbits(a, axis=1).reshape(-1))
+
+
+def leb128(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7f
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+def obu(obu_type, payload):
+    # obu_header: forbidden 0 | type(4) | extension 0 | has_size_field 1 | reserved 0
+    return bytes([(obu_type << 3) | 2]) + leb128(len(payload)) + payload
+
+
+OBU_SEQ_HDR, OBU_TD, OBU_FRAME = 1, 2, 6
+
+
+def sequence_header(w, h, bpc=8, sb128=0, film_grain=0, filter_intra=1, intra_edge_filter=1, cdef=1, restoration=1):
+    b = BitWriter()
+    b.f(3, 0)                                # seq_profile 0: 4:2:0, 8 / 10 bit
+    b.f(1, 0); b.f(1, 0)                     # still_picture, reduced_still_picture_header
+    b.f(1, 0)                                # timing_info_present
+    b.f(1, 0)                                # initial_display_delay_present
+    b.f(5, 0)                                # operating_points_cnt_minus_1
+    b.f(12, 0)                               # operating_point_idc
+    b.f(3, 3); b.f(2, 1)                     # seq_level_idx (major 5, minor 1)
+    b.f(1, 0)                                # seq_tier (major level > 3)
+    wn, hn = max(1, int(w - 1).bit_length()), max(1, int(h - 1).bit_length())
+    b.f(4, wn - 1); b.f(4, hn - 1)
+    b.f(wn, w - 1); b.f(hn, h - 1)
+    b.f(1, 0)                                # frame_id_numbers_present
+    b.f(1, sb128); b.f(1, filter_intra); b.f(1, intra_edge_filter)
+    b.f(1, 1); b.f(1, 1); b.f(1, 1); b.f(1, 1)   # interintra, masked compound, warped motion, dual filter
+    b.f(1, 1)                                # enable_order_hint
+    b.f(1, 1); b.f(1, 0)                     # jnt_comp, ref_frame_mvs
+    b.f(1, 0); b.f(1, 0)                     # seq_choose_screen_content_tools = 0, seq_force_screen_content_tools = 0
+    b.f(3, 6)                                # order_hint_bits_minus_1
+    b.f(1, 0); b.f(1, cdef); b.f(1, restoration)   # superres, cdef, restoration
+    b.f(1, 1 if bpc > 8 else 0)              # high_bitdepth (profile 0: 10 bit)
+    b.f(1, 0)                                # mono_chrome
+    b.f(1, 0)                                # color_description_present
+    b.f(1, 0)                                # color_range
+    b.f(2, 0)                                # chroma_sample_position
+    b.f(1, 0)                                # separate_uv_delta_q
+    b.f(1, film_grain)
+    b.trailing()
+    return obu(OBU_SEQ_HDR, b.bytes())
+
+
+def _tile_log2(sz, tgt):
+    k = 0
+    while (sz << k) < tgt:
+        k += 1
+    return k
+
+
+def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None, lf=None, cdef=True,
+              restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0):
+    """One shown key frame (OBU_FRAME). Returns the OBU bytes. `cdef_on` / `restoration_on` must match the sequence
+    header (the fields are absent when the sequence disables the tool)."""
+    b = BitWriter()
+    b.f(1, 0)                                # show_existing_frame
+    b.f(2, 0); b.f(1, 1)                     # frame_type KEY, show_frame
+    b.f(1, 0)                                # disable_cdf_update
+    b.f(1, 0)                                # frame_size_override
+    b.f(7, 0)                                # order_hint
+    b.f(1, 0)                                # render_and_frame_size_different
+    b.f(1, 0)                                # disable_frame_end_update_cdf
+    # tile info (uniform)
+    sbl = 6 + sb128
+    sbw, sbh = (w + (1 << sbl) - 1) >> sbl, (h + (1 << sbl) - 1) >> sbl
+    b.f(1, 1)
+    min_cols = _tile_log2(4096 >> sbl, sbw)
+    max_cols, max_rows = _tile_log2(1, min(sbw, 64)), _tile_log2(1, min(sbh, 64))
+    min_tiles = max(_tile_log2(4096 * 2304 >> (2 * sbl), sbw * sbh), min_cols)
+    log2_cols = min(max(log2_cols, min_cols), max_cols)
+    for _ in range(min_cols, log2_cols):
+        b.f(1, 1)
+    if log2_cols < max_cols:
+        b.f(1, 0)
+    min_rows = max(min_tiles - log2_cols, 0)
+    log2_rows = min(max(log2_rows, min_rows), max_rows)
+    for _ in range(min_rows, log2_rows):
+        b.f(1, 1)
+    if log2_rows < max_rows:
+        b.f(1, 0)
+    tile_w = 1 + ((sbw - 1) >> log2_cols); cols = (sbw + tile_w - 1) // tile_w
+    tile_h = 1 + ((sbh - 1) >> log2_rows); rows = (sbh + tile_h - 1) // tile_h
+    if log2_cols or log2_rows:
+        b.f(log2_cols + log2_rows, 0)        # context_update_tile_id
+        b.f(2, 3)                            # tile_size_bytes_minus_1
+    # quantizer
+    q = int(rng.integers(40, 200)) if q is None else q
+    b.f(8, q)
+    b.f(1, 0); b.f(1, 0); b.f(1, 0)          # no y dc / u dc / u ac deltas
+    b.f(1, 0)                                # using_qmatrix
+    b.f(1, 0)                                # segmentation_enabled
+    if q:
+        b.f(1, 1 if delta_q else 0)          # delta_q_present
+        if delta_q:
+            b.f(2, int(rng.integers(0, 4)))
+            b.f(1, 1); b.f(2, int(rng.integers(0, 4))); b.f(1, int(rng.integers(0, 2)))   # delta_lf present, res, multi
+    # loop filter
+    lf = [int(rng.integers(1, 64)), int(rng.integers(1, 64)), int(rng.integers(0, 64)), int(rng.integers(0, 64))] if lf is None else lf
+    b.f(6, lf[0]); b.f(6, lf[1])
+    if lf[0] or lf[1]:
+        b.f(6, lf[2]); b.f(6, lf[3])
+    b.f(3, int(rng.integers(0, 8)))          # sharpness
+    b.f(1, 1); b.f(1, 0)                     # mode_ref_delta_enabled, no update
+    if cdef_on:
+        nb = int(rng.integers(0, 4)) if cdef else 0
+        b.f(2, int(rng.integers(0, 4))); b.f(2, nb)
+        for _ in range(1 << nb):
+            b.f(6, int(rng.integers(0, 64)) if cdef else 0)
+            b.f(6, int(rng.integers(0, 64)) if cdef else 0)
+    if restoration_on:
+        types = [int(rng.integers(0, 4)) for _ in range(3)] if restoration else [0, 0, 0]
+        for t in types:
+            b.f(2, t)
+        if any(types):
+            if sb128:
+                b.f(1, int(rng.integers(0, 2)))
+            else:
+                s = int(rng.integers(0, 2)); b.f(1, s)
+                if s:
+                    b.f(1, int(rng.integers(0, 2)))
+            if types[1] or types[2]:
+                b.f(1, int(rng.integers(0, 2)))
+    b.f(1, 1)                                # tx_mode_select
+    b.f(1, int(rng.integers(0, 2)))          # reduced_tx_set
+    if film_grain_seq:
+        b.f(1, 0)                            # apply_grain
+    b.align()
+    n_tiles = cols * rows
+    if n_tiles > 1:
+        b.f(1, 0)                            # tile_start_and_end_present_flag
+    b.align()
+    out = bytearray(b.bytes())
+    for t in range(n_tiles):
+        tc, tr = t % cols, t // cols
+        nsb = (min(sbw, (tc + 1) * tile_w) - tc * tile_w) * (min(sbh, (tr + 1) * tile_h) - tr * tile_h)
+        n = max(64, (payload_bytes_per_sb64 << (2 * sb128)) * nsb)   # the symbol decoder must never run dry (src/decode.c:2743)
+        data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        if t < n_tiles - 1:
+            out += int(n - 1).to_bytes(4, "little")
+        out += data
+    return obu(OBU_FRAME, bytes(out))
+
+
+def temporal_unit(*obus):
+    return obu(OBU_TD, b"") + b"".join(obus)
+
+
+def intra_stream(seed, w, h, n_frames=1, bpc=8, sb128=0, log2_cols=0, log2_rows=0, **kw):
+    """A list of temporal units (bytes), each holding one shown key frame."""
+    rng = np.random.default_rng(seed)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128)
+    tus = []
+    for i in range(n_frames):
+        fr = key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, **kw)
+        tus.append(temporal_unit(seq, fr) if i == 0 else temporal_unit(fr))
+    return tus
