@@ -226,6 +226,14 @@ _SIGS = {
                                     C.c_int, C.c_int, C.c_void_p, C.c_ssize_t] + [C.c_int] * 5),
     "b200_film_grain_dsp_init_8bpc": (None, [C.c_void_p]),
     "b200_film_grain_dsp_init_16bpc": (None, [C.c_void_p]),
+    # ---- memory / streams for C hosts
+    "b200_dev_alloc": (C.c_void_p, [C.c_size_t]),
+    "b200_dev_free": (None, [C.c_void_p]),
+    "b200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "b200_host_free": (None, [C.c_void_p]),
+    "b200_stream_create": (C.c_void_p, []),
+    "b200_stream_destroy": (None, [C.c_void_p]),
+    "b200_dev_memset": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
     # ---- whole frame
     "b200_frame_run": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_struct_size": (C.c_int, [C.c_int]),

@@ -37,6 +37,35 @@ int b200_version(void) { return 100; }
 const char *b200_last_error(void) { return g_err; }
 uint64_t b200_launch_count(void) { return g_launches.load(); }
 
+void *b200_dev_alloc(size_t bytes) {
+    void *p = nullptr;
+    const cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { b200_set_error("b200_dev_alloc(%zu): %s", bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+void b200_dev_free(void *p) { if (p) cudaFree(p); }
+void *b200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    const cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { b200_set_error("b200_host_alloc(%zu): %s", bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+void b200_host_free(void *p) { if (p) cudaFreeHost(p); }
+void *b200_stream_create(void) {
+    cudaStream_t s = nullptr;
+    const cudaError_t e = cudaStreamCreate(&s);
+    if (e != cudaSuccess) { b200_set_error("b200_stream_create: %s", cudaGetErrorString(e)); return nullptr; }
+#ifdef B200_EMU
+    if (!s) return (void *)(uintptr_t)1;      // the host emulator has no stream objects; NULL means failure to callers
+#endif
+    return (void *)s;
+}
+void b200_stream_destroy(void *stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream); }
+int b200_dev_memset(void *p, int value, size_t bytes, void *stream) {
+    B200_CUDA_OK(cudaMemsetAsync(p, value, bytes, (cudaStream_t)stream));
+    return 0;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------

@@ -34,6 +34,16 @@ B200_API const char *b200_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 B200_API uint64_t b200_launch_count(void);
 
+/* Device / pinned-host memory and streams for C hosts (a dav1d build has no other way to own HBM): thin
+ * wrappers over cudaMalloc / cudaMallocHost / cudaStreamCreate. NULL on failure (b200_last_error() says why). */
+B200_API void *b200_dev_alloc(size_t bytes);
+B200_API void b200_dev_free(void *p);
+B200_API void *b200_host_alloc(size_t bytes);      /* page-locked */
+B200_API void b200_host_free(void *p);
+B200_API void *b200_stream_create(void);
+B200_API void b200_stream_destroy(void *stream);
+B200_API int b200_dev_memset(void *p, int value, size_t bytes, void *stream);
+
 /* enum RectTxfmSize / enum TxfmType numbering is dav1d's (reference src/levels.h:38-110) */
 #define B200_N_RECT_TX_SIZES 19
 #define B200_N_TX_TYPES_PLUS_LL 17

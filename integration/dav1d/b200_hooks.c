@@ -1,0 +1,144 @@
+/*
+ * integration/dav1d/b200_hooks.c — back-end loading and per-frame-context state for the dav1d record emitters.
+ * The back end (dav1d_b200/libb200av1.so) is bound at run time through its C ABI (include/b200av1.h); there is no
+ * CPU fallback: without a back end every frame fails with an error.
+ */
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "b200_hooks.h"
+
+#define API __attribute__((visibility("default")))
+
+static B200Backend g_be;
+static int g_be_ok;
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static HookFrame g_frames[64];
+static B200HookStats g_stats;
+
+API int b200hook_set_backend(const char *path)
+{
+    pthread_mutex_lock(&g_lock);
+    g_be_ok = 0;
+    void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) { fprintf(stderr, "b200hook: cannot load back end %s: %s\n", path, dlerror()); pthread_mutex_unlock(&g_lock); return -1; }
+    memset(&g_be, 0, sizeof(g_be));
+    g_be.handle = h;
+#define SYM(field, name) do { *(void **)&g_be.field = dlsym(h, name); \
+        if (!g_be.field) { fprintf(stderr, "b200hook: back end lacks %s\n", name); pthread_mutex_unlock(&g_lock); return -1; } } while (0)
+    SYM(last_error, "b200_last_error");
+    SYM(dev_alloc, "b200_dev_alloc"); SYM(dev_free, "b200_dev_free");
+    SYM(host_alloc, "b200_host_alloc"); SYM(host_free, "b200_host_free");
+    SYM(stream_create, "b200_stream_create"); SYM(stream_destroy, "b200_stream_destroy");
+    SYM(intra_scratch_bytes, "b200_intra_scratch_bytes");
+    SYM(frame_run_host, "b200_frame_run_host");
+    SYM(struct_size, "b200_struct_size");
+#undef SYM
+    /* binding self-check: the structs this file was compiled with are the ones the library was compiled with */
+    if (g_be.struct_size(9) != (int)sizeof(B200FrameJob) || g_be.struct_size(14) != (int)sizeof(B200IntraTx) ||
+        g_be.struct_size(10) != (int)sizeof(B200Av1Filter) || g_be.struct_size(11) != (int)sizeof(B200Av1Restoration)) {
+        fprintf(stderr, "b200hook: ABI struct size mismatch with %s\n", path);
+        pthread_mutex_unlock(&g_lock);
+        return -1;
+    }
+    g_be_ok = 1;
+    pthread_mutex_unlock(&g_lock);
+    return 0;
+}
+
+/* Device jobs of different frame contexts normally overlap (one stream each). A back end that is not re-entrant
+ * (the host emulator the CPU tests bind) asks for one job at a time. */
+static int g_serialize;
+static pthread_mutex_t g_job_lock = PTHREAD_MUTEX_INITIALIZER;
+API void b200hook_set_serialize(int on) { g_serialize = on; }
+void b200hook_job_enter(void) { if (g_serialize) pthread_mutex_lock(&g_job_lock); }
+void b200hook_job_leave(void) { if (g_serialize) pthread_mutex_unlock(&g_job_lock); }
+
+const B200Backend *b200hook_backend(void)
+{
+    if (!g_be_ok) {
+        const char *env = getenv("B200AV1_LIB");
+        if (!env || b200hook_set_backend(env)) {
+            fprintf(stderr, "b200hook: no back end loaded (b200hook_set_backend / B200AV1_LIB) - frame fails\n");
+            return NULL;
+        }
+    }
+    return &g_be;
+}
+
+int b200hook_buf_reserve(HookBuf *b, size_t bytes, int need_host, int keep)
+{
+    const B200Backend *be = b200hook_backend();
+    if (!be) return -1;
+    if (bytes <= b->cap && b->dev && (!need_host || b->host)) return 0;
+    size_t cap = b->cap ? b->cap : 4096;
+    while (cap < bytes) cap *= 2;
+    void *host = NULL, *dev = be->dev_alloc(cap);
+    if (!dev) { fprintf(stderr, "b200hook: %s\n", be->last_error()); return -1; }
+    if (need_host) {
+        host = be->host_alloc(cap);
+        if (!host) { fprintf(stderr, "b200hook: %s\n", be->last_error()); be->dev_free(dev); return -1; }
+        if (keep && b->host) memcpy(host, b->host, b->cap);
+    }
+    if (b->host) be->host_free(b->host);
+    if (b->dev) be->dev_free(b->dev);
+    b->host = host; b->dev = dev; b->cap = cap;
+    return 0;
+}
+
+void b200hook_buf_free(HookBuf *b)
+{
+    if (g_be_ok) { if (b->host) g_be.host_free(b->host); if (b->dev) g_be.dev_free(b->dev); }
+    memset(b, 0, sizeof(*b));
+}
+
+HookFrame *b200hook_frame(const void *key)
+{
+    HookFrame *r = NULL;
+    pthread_mutex_lock(&g_lock);
+    for (int i = 0; i < 64 && !r; i++)
+        if (g_frames[i].key == key) r = &g_frames[i];
+    for (int i = 0; i < 64 && !r; i++)
+        if (!g_frames[i].key) {
+            r = &g_frames[i];
+            memset(r, 0, sizeof(*r));
+            pthread_mutex_init(&r->lock, NULL);
+            r->key = key;
+        }
+    pthread_mutex_unlock(&g_lock);
+    return r;
+}
+
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms)
+{
+    pthread_mutex_lock(&g_lock);
+    g_stats.frames++; g_stats.records += records; g_stats.coefs += coefs;
+    g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += d2h; g_stats.device_ms += ms;
+    pthread_mutex_unlock(&g_lock);
+}
+
+API void b200hook_get_stats(B200HookStats *out, int reset)
+{
+    pthread_mutex_lock(&g_lock);
+    *out = g_stats;
+    if (reset) memset(&g_stats, 0, sizeof(g_stats));
+    pthread_mutex_unlock(&g_lock);
+}
+
+/* frees every per-frame-context buffer (call after dav1d_close) */
+API void b200hook_release(void)
+{
+    pthread_mutex_lock(&g_lock);
+    for (int i = 0; i < 64; i++) {
+        HookFrame *h = &g_frames[i];
+        if (!h->key) continue;
+        b200hook_buf_free(&h->tx); b200hook_buf_free(&h->coef); b200hook_buf_free(&h->mask);
+        b200hook_buf_free(&h->level); b200hook_buf_free(&h->lr_mask); b200hook_buf_free(&h->scratch);
+        for (int p = 0; p < 3; p++) b200hook_buf_free(&h->pic[p]);
+        if (h->stream && g_be_ok) g_be.stream_destroy(h->stream);
+        pthread_mutex_destroy(&h->lock);
+        memset(h, 0, sizeof(*h));
+    }
+    pthread_mutex_unlock(&g_lock);
+}

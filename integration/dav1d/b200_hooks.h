@@ -1,0 +1,58 @@
+/*
+ * integration/dav1d/b200_hooks.h — state shared by the dav1d `f->bd_fn` record emitters
+ * (b200_hooks_tmpl.c, compiled at BITDEPTH 8 and 16) and the back-end loader (b200_hooks.c).
+ *
+ * This directory is the reference-side half of the drop-in: it is compiled against dav1d's
+ * internal headers where they lie under $(REF) and linked with dav1d's own objects into ONE library whose
+ * decode.c was compiled with the f->bd_fn targets renamed (-Ddav1d_recon_b_intra_8bpc=b200hook_recon_b_intra_8bpc
+ * ..., reference src/decode.c:3418-3442) — no reference source is modified or copied.
+ */
+#ifndef B200_HOOKS_H
+#define B200_HOOKS_H
+#include <pthread.h>
+#include <stddef.h>
+#include <stdint.h>
+#include "../../include/b200av1.h"
+
+/* libb200av1.so entry points, resolved once with dlopen/dlsym (b200hook_set_backend) */
+typedef struct B200Backend {
+    void *handle;
+    const char *(*last_error)(void);
+    void *(*dev_alloc)(size_t);
+    void (*dev_free)(void *);
+    void *(*host_alloc)(size_t);
+    void (*host_free)(void *);
+    void *(*stream_create)(void);
+    void (*stream_destroy)(void *);
+    size_t (*intra_scratch_bytes)(const B200IntraFrame *);
+    int (*frame_run_host)(const B200FrameJob *, const B200Xfer *, int, const B200Xfer *, int, void *);
+    int (*struct_size)(int);
+} B200Backend;
+const B200Backend *b200hook_backend(void);   /* NULL (after logging) when no back end is loaded: the decode fails */
+
+/* a device buffer paired with its pinned host staging copy, grown on demand */
+typedef struct HookBuf { void *host, *dev; size_t cap; } HookBuf;
+int b200hook_buf_reserve(HookBuf *b, size_t bytes, int need_host, int keep);
+void b200hook_buf_free(HookBuf *b);
+
+/* per frame context (dav1d's n_fc frames in flight): the records of the frame being reconstructed */
+typedef struct HookFrame {
+    const void *key;               /* the Dav1dFrameContext this slot serves */
+    pthread_mutex_t lock;
+    int n_tx;                      /* B200IntraTx records emitted so far (tx.host) */
+    size_t n_coef;                 /* coefficients staged so far (coef.host), in elements */
+    int tile_sbrows_done;          /* completed pass-2 tile superblock rows of the current frame */
+    int unsupported;               /* a block used a tool the emitters do not translate yet */
+    HookBuf tx, coef, mask, level, lr_mask, pic[3], scratch;
+    void *stream;
+    /* statistics */
+    uint64_t frames, records;
+} HookFrame;
+HookFrame *b200hook_frame(const void *key);
+void b200hook_job_enter(void);
+void b200hook_job_leave(void);
+
+typedef struct B200HookStats { uint64_t frames, records, coefs, h2d_bytes, d2h_bytes; double device_ms; } B200HookStats;
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms);
+
+#endif

@@ -1,0 +1,105 @@
+"""Real-stream drop-in test: the same AV1 elementary stream decoded (a) by the stock reference (oracle/_ref, dav1d's own
+CPU back end) and (b) by integration/_ref/libdav1d_b200.so = the same dav1d front end with the f->bd_fn hooks emitting
+B200 records and libb200av1 reconstructing + filtering every frame. Output pictures must be byte-identical.
+Streams: dav1d_b200/obu.py (valid headers, random tile payloads: every intra tool, per-block delta q / lf, CDEF, LR).
+CPU tests bind the hooks to the host emulator build of the CUDA sources; GPU tests bind the real library."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import refs
+from dav1d_b200 import obu, stream
+
+pytestmark = pytest.mark.skipif(not (os.path.exists(stream.HOOKED_SO) or os.path.isdir("/root/reference/src")),
+                                reason="integration/_ref/libdav1d_b200.so not built")
+
+
+def _ref_decode(tus, **kw):
+    assert refs.have_ref()
+    return stream.decode_stream(C.CDLL(refs.REF_SO), tus, **kw)
+
+
+def _check(dec, tus, expect_frames):
+    r0, info0, out0 = _ref_decode(tus)
+    assert r0 == expect_frames, "the stock reference could not decode the synthetic stream (%d)" % r0
+    r1, info1, out1 = dec.decode(tus)
+    assert r1 == r0, "hooked decoder returned %d" % r1
+    assert np.array_equal(info0, info1)
+    if not np.array_equal(out0, out1):
+        d = np.nonzero(out0 != out1)[0]
+        raise AssertionError("%d of %d output bytes differ, first at %d" % (len(d), len(out0), d[0]))
+    st = dec.stats(reset=True)
+    assert st["frames"] == expect_frames and st["records"] > 0
+
+
+CASES_CPU = [
+    # w, h, bpc, sb128, log2 tile cols, rows, frames
+    (256, 192, 8, 0, 0, 0, 2),
+    (256, 192, 10, 0, 1, 1, 2),
+    (328, 250, 8, 1, 1, 0, 1),          # sizes that are not multiples of 8, 128x128 superblocks
+    (640, 360, 8, 0, 2, 1, 2),
+    (330, 250, 10, 1, 0, 1, 1),
+]
+
+
+@pytest.fixture(scope="module")
+def emu_decoder():
+    refs.emu_lib()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(refs.ROOT, "tests", "emu", "build_emu.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    if os.path.isdir("/root/reference/src"):
+        stream.build_hooked()
+    d = stream.HookedDecoder(backend=m.build(), serialize=True)
+    yield d
+    d.release()
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("case", CASES_CPU)
+def test_stream_emu_matches_stock_dav1d(emu_decoder, case):
+    w, h, bpc, sb128, lc, lr, nf = case
+    tus = obu.intra_stream(hash(case) & 0xffff, w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=lc, log2_rows=lr)
+    _check(emu_decoder, tus, nf)
+
+
+def test_stream_without_backend_fails_loudly():
+    """no CPU fallback: with no back end bound the hooked decoder reports an error instead of decoding (own process:
+    the binding is process-wide state of the library)"""
+    import subprocess, sys
+    if os.path.isdir("/root/reference/src"):
+        stream.build_hooked()
+    code = ("import ctypes as C, os, sys; sys.path.insert(0, %r); os.environ.pop('B200AV1_LIB', None)\n"
+            "from dav1d_b200 import obu, stream\n"
+            "dll = C.CDLL(stream.HOOKED_SO)\n"
+            "r, _, _ = stream.decode_stream(dll, obu.intra_stream(1, 128, 128, n_frames=1))\n"
+            "print('RESULT', r)\n") % refs.ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "RESULT -" in out.stdout, out.stdout + out.stderr
+    assert "no back end loaded" in out.stderr
+
+
+CASES_GPU = [
+    (640, 360, 8, 0, 1, 1, 3),
+    (1920, 1080, 8, 0, 2, 1, 3),
+    (1920, 1080, 10, 1, 1, 1, 2),
+    (3840, 2160, 8, 0, 2, 2, 2),
+    (1000, 602, 10, 0, 0, 0, 2),
+]
+
+
+@pytest.fixture(scope="module")
+def gpu_decoder():
+    d = stream.HookedDecoder()
+    yield d
+    d.release()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES_GPU)
+def test_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
+    w, h, bpc, sb128, lc, lr, nf = case
+    tus = obu.intra_stream(1000 + (hash(case) & 0xfff), w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=lc, log2_rows=lr)
+    _check(gpu_decoder, tus, nf)
