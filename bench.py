@@ -299,6 +299,113 @@ def run_reference(args):
     emit(line)
 
 
+# ------------------------------------------------------------------------------ real streams behind dav1d's front end
+STREAM_WORKLOADS = {
+    "stream1080p8": dict(W=1920, H=1080, bpc=8, frames=8, log2_cols=2, log2_rows=1,
+                         desc="AV1 elementary stream, 8 key frames 1920x1080 8-bit 4:2:0, 4x2 tiles (valid headers, random tile "
+                              "payloads: dav1d_b200/obu.py) decoded through dav1d's public API; front end (OBU parsing, entropy "
+                              "decoding, threading) = unmodified dav1d on the host, back end = f->bd_fn record emitters + "
+                              "libb200av1 (intra reconstruction, deblock, CDEF, loop restoration)"),
+    "stream4k10": dict(W=3840, H=2160, bpc=10, frames=4, log2_cols=2, log2_rows=2,
+                       desc="AV1 elementary stream, 4 key frames 3840x2160 10-bit 4:2:0, 4x4 tiles, decoded through dav1d's public API "
+                            "(host front end = unmodified dav1d, back end = libb200av1)"),
+}
+
+
+def run_stream(args):
+    """e2e = pixels / wall time of the whole decode (dav1d_send_data -> pictures out); value = pixels / time spent in the
+    device jobs (record upload + kernels + picture download, from the hooks' own clock). Reference arm = the stock
+    reference decoding the same stream with the same number of threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from dav1d_b200 import obu, stream
+    W = STREAM_WORKLOADS[args.workload]
+    nthr = min(os.cpu_count() or 1, 32)
+    mfd = min(8, W["frames"])
+    tus = obu.intra_stream(100 + rank, W["W"], W["H"], n_frames=W["frames"], bpc=W["bpc"], log2_cols=W["log2_cols"], log2_rows=W["log2_rows"])
+    px = W["W"] * W["H"] * W["frames"]
+    stream.decode_stream.capacity = (W["W"] * W["H"] * 3 // 2) * (2 if W["bpc"] > 8 else 1) * W["frames"] + (1 << 20)
+    steps = min(args.steps, 10)
+    wl = "%s: %s; %d dav1d threads, %d frames in flight" % (args.workload, W["desc"], nthr, mfd)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import refs
+        dll = C.CDLL(refs.REF_SO)
+        for _ in range(min(args.warmup, 1)):
+            stream.decode_stream(dll, tus, n_threads=nthr, max_frame_delay=mfd)
+        dts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            r, _, _ = stream.decode_stream(dll, tus, n_threads=nthr, max_frame_delay=mfd)
+            dts.append(time.perf_counter() - t0)
+            assert r == W["frames"], r
+        ms = 1e3 * float(np.mean(dts)); val = px / (ms * 1e-3) / 1e6
+        emit({"impl": "reference", "metric": "Mpixels/s", "value": val, "unit": "Mpixels/s", "n_gpus": args.gpus, "steps": steps,
+              "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "u8/i16->i32" if W["bpc"] == 8 else "u16/i32", "data": "synthetic", "config": {"workload": wl, "l2": "n/a (host)"},
+              "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": nthr, "kind": "reference",
+                               "sample": "the whole stream per step, stock dav1d (C path, HAVE_ASM=0), %d threads" % nthr},
+              "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+        return
+    torch, dist, world, rank, local = dist_setup()
+    from dav1d_b200 import get_lib
+    lib = get_lib()
+    dec = stream.HookedDecoder()
+    for _ in range(max(args.warmup, 3) if steps > 1 else 1):
+        r, _, _ = dec.decode(tus, n_threads=nthr, max_frame_delay=mfd)
+        assert r == W["frames"], "hooked decode failed: %d" % r
+    dec.stats(reset=True)
+    before = lib.b200_launch_count()
+    sampler = ClockSampler(local); sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r, _, out = dec.decode(tus, n_threads=nthr, max_frame_delay=mfd)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    sampler.stop()
+    st = dec.stats()
+    if world > 1:
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    launches = lib.b200_launch_count() - before
+    ms = 1e3 * dt / steps
+    e2e = world * px / (ms * 1e-3) / 1e6
+    dev_ms = st["device_ms"] / max(st["frames"], 1)
+    value = world * W["W"] * W["H"] / (dev_ms * 1e-3) / 1e6
+    pxb = 2 if W["bpc"] > 8 else 1
+    S_ = W["W"] * W["H"] * 3 // 2
+    alg = st["coefs"] / max(st["frames"], 1) * (2 * pxb) + S_ * pxb * (1 + 2 + 4 + 2 + 2)   # coefs + pred write + itx rmw + deblock + cdef + lr
+    peak, src = measured_peak()
+    # the CPU arm beside it (bounded: one decode of the same stream by the stock reference)
+    cpu = None
+    if rank == 0:
+        import refs
+        dll = C.CDLL(refs.REF_SO)
+        t1 = time.perf_counter(); rr, _, ref_out = stream.decode_stream(dll, tus, n_threads=nthr, max_frame_delay=mfd); tc = time.perf_counter() - t1
+        assert rr == W["frames"] and np.array_equal(ref_out, out), "stream bench: output differs from the stock reference"
+        cpu = {"value": px / tc / 1e6, "unit": "Mpixels/s", "cores": nthr, "kind": "reference",
+               "sample": "one decode of the same stream by stock dav1d (C path, HAVE_ASM=0), %d threads, %.2f s; outputs compared byte for byte" % (nthr, tc)}
+    if rank == 0:
+        emit({"metric": "Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+              "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "u8/i16->i32" if W["bpc"] == 8 else "u16/i32", "data": "synthetic",
+              "config": {"workload": wl, "l2": "every frame's records and pictures are fresh (uploaded per frame)",
+                         "value_is": "pixels / time inside the per-frame device jobs (H2D of records + kernels + D2H of the picture), host clock",
+                         "records_per_frame": st["records"] // max(st["frames"], 1)},
+              "roofline": {"bound": "hbm", "kernel": "frame job (intra reconstruction + deblock + CDEF + LR, incl. PCIe copies)",
+                           "achieved": alg / (dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": alg / (dev_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": src},
+              "cpu_baseline": cpu,
+              "e2e": {"value": e2e, "unit": "Mpixels/s", "h2d_bytes_per_step": st["h2d_bytes"] // steps, "d2h_bytes_per_step": st["d2h_bytes"] // steps},
+              "gpu_launches": int(launches), "clocks": sampler.summary()})
+    dec.release()
+
+
 # ------------------------------------------------------------------------------ our arm
 def dist_setup():
     import torch
@@ -634,8 +741,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k10_full", "8k10_full", "1080p8_intra", "itx8x8"])
+    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k10_full", "8k10_full", "1080p8_intra", "itx8x8", "stream1080p8", "stream4k10"])
     args = ap.parse_args()
+    if args.workload in STREAM_WORKLOADS:
+        return run_stream(args)
     if args.impl == "reference":
         args.steps = min(args.steps, 5)      # bounded: each step is tens of whole 4K frames on the CPU
         run_reference(args)

@@ -110,6 +110,62 @@ HookFrame *b200hook_frame(const void *key)
     return r;
 }
 
+/* Wavefront order for the device's dataflow kernel (dav1d_b200/csrc/intra.cu): records arrive in decode order, where a
+ * window of consecutive records spans only a couple of superblocks; sorted by dependency depth ("wave": 1 + the
+ * deepest record among the cells whose pixels the block's edge array reads, the same cells the kernel polls) a window
+ * of consecutive tickets spans a whole anti-diagonal of the frame. Stable counting sort: any order in which every
+ * record follows its dependencies is valid for the kernel. Returns the number of waves, < 0 on allocation failure. */
+static const uint8_t k_tx_w4[19] = { 1, 2, 4, 8, 16, 1, 2, 2, 4, 4, 8, 8, 16, 1, 4, 2, 8, 4, 16 };
+static const uint8_t k_tx_h4[19] = { 1, 2, 4, 8, 16, 2, 1, 4, 2, 8, 4, 16, 8, 4, 1, 8, 2, 16, 4 };
+static inline int mini(int a, int b) { return a < b ? a : b; }
+int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int32_t w4[3], const int32_t h4[3],
+                       int ss_hor, int ss_ver)
+{
+    size_t cells = 0, off[3];
+    for (int p = 0; p < 3; p++) { off[p] = cells; cells += (size_t)w4[p] * h4[p]; }
+    int32_t *const map = calloc(cells, sizeof(*map));
+    int32_t *const wave = malloc((size_t)(n + 1) * sizeof(*wave));
+    if (!map || !wave) { free(map); free(wave); return -1; }
+    int n_waves = 0;
+    for (int i = 0; i < n; i++) {
+        const B200IntraTx *const r = &in[i];
+        const int pl = r->plane, mw = w4[pl], mh = h4[pl];
+        int32_t *const m = map + off[pl];
+        const int x = r->x4, y = r->y4, tw = k_tx_w4[r->tx], th = k_tx_h4[r->tx], xe = r->xend4, ye = r->yend4;
+        const int hl = r->flags & B200_INTRA_HAVE_LEFT, ht = r->flags & B200_INTRA_HAVE_TOP;
+        int dep = 0;
+        if (hl) {
+            int rows = mini(th, ye - y);
+            if ((r->flags & B200_INTRA_LEFT_HAS_BOTTOM) && y + th < ye) rows += mini(th, ye - y - th);
+            for (int k = 0; k < rows && y + k < mh; k++) { const int v = m[(size_t)(y + k) * mw + x - 1]; if (v > dep) dep = v; }
+        }
+        if (ht) {
+            int cols = mini(tw, xe - x);
+            if ((r->flags & B200_INTRA_TOP_HAS_RIGHT) && x + tw < xe) cols += mini(tw, xe - x - tw);
+            for (int k = 0; k < cols && x + k < mw; k++) { const int v = m[(size_t)(y - 1) * mw + x + k]; if (v > dep) dep = v; }
+        }
+        if (hl && ht) { const int v = m[(size_t)(y - 1) * mw + x - 1]; if (v > dep) dep = v; }
+        if (r->mode == B200_INTRA_MODE_CFL && r->cfl_alpha) {
+            const int lx = x << ss_hor, ly = y << ss_ver;
+            const int lw = mini((tw - r->cfl_w_pad) << ss_hor, w4[0] - lx), lh = mini((th - r->cfl_h_pad) << ss_ver, h4[0] - ly);
+            for (int yy = 0; yy < lh; yy++)
+                for (int xx = 0; xx < lw; xx++) { const int v = map[(size_t)(ly + yy) * w4[0] + lx + xx]; if (v > dep) dep = v; }
+        }
+        const int wv = dep + 1;
+        wave[i] = wv;
+        if (wv > n_waves) n_waves = wv;
+        for (int yy = y; yy < y + th && yy < mh; yy++)
+            for (int xx = x; xx < x + tw && xx < mw; xx++) m[(size_t)yy * mw + xx] = wv;
+    }
+    int32_t *const start = calloc((size_t)n_waves + 2, sizeof(*start));
+    if (!start) { free(map); free(wave); return -1; }
+    for (int i = 0; i < n; i++) start[wave[i] + 1]++;
+    for (int k = 1; k <= n_waves + 1; k++) start[k] += start[k - 1];
+    for (int i = 0; i < n; i++) out[start[wave[i]]++] = in[i];
+    free(start); free(map); free(wave);
+    return n_waves;
+}
+
 void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms)
 {
     pthread_mutex_lock(&g_lock);
@@ -133,7 +189,7 @@ API void b200hook_release(void)
     for (int i = 0; i < 64; i++) {
         HookFrame *h = &g_frames[i];
         if (!h->key) continue;
-        b200hook_buf_free(&h->tx); b200hook_buf_free(&h->coef); b200hook_buf_free(&h->mask);
+        b200hook_buf_free(&h->tx); b200hook_buf_free(&h->tx_sorted); b200hook_buf_free(&h->coef); b200hook_buf_free(&h->mask);
         b200hook_buf_free(&h->level); b200hook_buf_free(&h->lr_mask); b200hook_buf_free(&h->scratch);
         for (int p = 0; p < 3; p++) b200hook_buf_free(&h->pic[p]);
         if (h->stream && g_be_ok) g_be.stream_destroy(h->stream);

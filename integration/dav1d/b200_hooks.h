@@ -43,12 +43,14 @@ typedef struct HookFrame {
     size_t n_coef;                 /* coefficients staged so far (coef.host), in elements */
     int tile_sbrows_done;          /* completed pass-2 tile superblock rows of the current frame */
     int unsupported;               /* a block used a tool the emitters do not translate yet */
-    HookBuf tx, coef, mask, level, lr_mask, pic[3], scratch;
+    HookBuf tx, tx_sorted, coef, mask, level, lr_mask, pic[3], scratch;
     void *stream;
     /* statistics */
     uint64_t frames, records;
 } HookFrame;
 HookFrame *b200hook_frame(const void *key);
+int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int32_t w4[3], const int32_t h4[3],
+                       int ss_hor, int ss_ver);
 void b200hook_job_enter(void);
 void b200hook_job_leave(void);
 

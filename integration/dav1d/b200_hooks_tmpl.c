@@ -325,6 +325,17 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     }
     if (b200hook_buf_reserve(&hf->scratch, be->intra_scratch_bytes(&j.intra), 0, 0)) return -1;
     j.intra.scratch = hf->scratch.dev;
+    /* decode order -> wavefront order (B200HOOK_WAVE_SORT=0 keeps decode order, which is also valid) */
+    const HookBuf *txb = &hf->tx;
+    static int wave_sort = -1;
+    if (wave_sort < 0) { const char *e = getenv("B200HOOK_WAVE_SORT"); wave_sort = !e || atoi(e) != 0; }
+    if (wave_sort && hf->n_tx > 0) {
+        if (b200hook_buf_reserve(&hf->tx_sorted, (size_t)hf->n_tx * sizeof(B200IntraTx), 1, 0)) return -1;
+        if (b200hook_wave_sort((const B200IntraTx *)hf->tx.host, (B200IntraTx *)hf->tx_sorted.host, hf->n_tx,
+                               j.intra.w4, j.intra.h4, ss_hor, ss_ver) < 0) return -1;
+        txb = &hf->tx_sorted;
+        j.d_intra = (const B200IntraTx *)txb->dev;
+    }
     /* deblock (reference src/recon_tmpl.c:1987-2027), in place on p0 */
     const int do_lf = (f->c->inloop_filters & DAV1D_INLOOPFILTER_DEBLOCK) && (hdr->loopfilter.level_y[0] || hdr->loopfilter.level_y[1]);
     j.run_lf = do_lf;
@@ -358,7 +369,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     j.lr.lr_mask = (const B200Av1Restoration *)hf->lr_mask.dev;
 
     const B200Xfer up[5] = {
-        { hf->tx.host, hf->tx.dev, (uint64_t)hf->n_tx * sizeof(B200IntraTx) },
+        { txb->host, txb->dev, (uint64_t)hf->n_tx * sizeof(B200IntraTx) },
         { hf->coef.host, hf->coef.dev, (uint64_t)hf->n_coef * sizeof(coef) },
         { hf->mask.host, hf->mask.dev, mask_bytes },
         { hf->level.host, hf->level.dev, level_bytes },
