@@ -47,7 +47,7 @@ struct IntraParams {
 // one launch is not limited by the number of hardware work queues the way one stream per frame is
 constexpr int kIntraMaxBatch = 24;
 struct IntraBatch { IntraParams p[kIntraMaxBatch]; };
-static_assert(sizeof(IntraBatch) <= 4000, "kernel parameter space");
+static_assert(sizeof(IntraBatch) <= 4080, "kernel parameter space (4 KB with the trailing int)");
 
 B200_DEV int ld_cell(const uint8_t *p) { return *(const volatile uint8_t *)p; }
 // a dependency that never arrives (records not in a topological order) must not hang the GPU: fail the launch
@@ -561,7 +561,10 @@ int b200_intra_frames(int bdmax, const B200IntraFrame *frames, const B200IntraTx
             uint8_t *base_p = (uint8_t *)f->scratch;
             P.ticket = (int *)base_p;
             for (int p = 0; p < 3; p++) P.done[p] = base_p + L.done_off[p];
-            B200_CUDA_OK(cudaMemsetAsync(base_p, 0, mode ? 256 + (size_t)f->sb_w * f->sb_h : L.total, (cudaStream_t)stream));
+            if (!mode && f->done_init)
+                B200_CUDA_OK(cudaMemcpyAsync(base_p, f->done_init, L.total, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+            else
+                B200_CUDA_OK(cudaMemsetAsync(base_p, 0, mode ? 256 + (size_t)f->sb_w * f->sb_h : L.total, (cudaStream_t)stream));
             const int units = mode ? f->n_sb : n_tx[i];
             const int want = f->grid > 0 ? f->grid : (mode ? 16 : kIntraGrid);
             grid = imax(grid, units < want ? units : want);

@@ -59,7 +59,8 @@ def obu(obu_type, payload):
 OBU_SEQ_HDR, OBU_TD, OBU_FRAME = 1, 2, 6
 
 
-def sequence_header(w, h, bpc=8, sb128=0, film_grain=0, filter_intra=1, intra_edge_filter=1, cdef=1, restoration=1):
+def sequence_header(w, h, bpc=8, sb128=0, film_grain=0, filter_intra=1, intra_edge_filter=1, cdef=1, restoration=1,
+                    inter_intra=1, masked_compound=1, warped_motion=1):
     b = BitWriter()
     b.f(3, 0)                                # seq_profile 0: 4:2:0, 8 / 10 bit
     b.f(1, 0); b.f(1, 0)                     # still_picture, reduced_still_picture_header
@@ -74,7 +75,7 @@ def sequence_header(w, h, bpc=8, sb128=0, film_grain=0, filter_intra=1, intra_ed
     b.f(wn, w - 1); b.f(hn, h - 1)
     b.f(1, 0)                                # frame_id_numbers_present
     b.f(1, sb128); b.f(1, filter_intra); b.f(1, intra_edge_filter)
-    b.f(1, 1); b.f(1, 1); b.f(1, 1); b.f(1, 1)   # interintra, masked compound, warped motion, dual filter
+    b.f(1, inter_intra); b.f(1, masked_compound); b.f(1, warped_motion); b.f(1, 1)   # ..., dual filter
     b.f(1, 1)                                # enable_order_hint
     b.f(1, 1); b.f(1, 0)                     # jnt_comp, ref_frame_mvs
     b.f(1, 0); b.f(1, 0)                     # seq_choose_screen_content_tools = 0, seq_force_screen_content_tools = 0
@@ -98,18 +99,9 @@ def _tile_log2(sz, tgt):
     return k
 
 
-def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None, lf=None, cdef=True,
-              restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0):
-    """One shown key frame (OBU_FRAME). Returns the OBU bytes. `cdef_on` / `restoration_on` must match the sequence
-    header (the fields are absent when the sequence disables the tool)."""
-    b = BitWriter()
-    b.f(1, 0)                                # show_existing_frame
-    b.f(2, 0); b.f(1, 1)                     # frame_type KEY, show_frame
-    b.f(1, 0)                                # disable_cdf_update
-    b.f(1, 0)                                # frame_size_override
-    b.f(7, 0)                                # order_hint
-    b.f(1, 0)                                # render_and_frame_size_different
-    b.f(1, 0)                                # disable_frame_end_update_cdf
+def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on):
+    """tile info, quantizer, segmentation, delta q / lf, loop filter, CDEF, loop restoration (same syntax in key and
+    inter frames when primary_ref_frame is NONE)"""
     # tile info (uniform)
     sbl = 6 + sb128
     sbw, sbh = (w + (1 << sbl) - 1) >> sbl, (h + (1 << sbl) - 1) >> sbl
@@ -170,10 +162,10 @@ def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb
                     b.f(1, int(rng.integers(0, 2)))
             if types[1] or types[2]:
                 b.f(1, int(rng.integers(0, 2)))
-    b.f(1, 1)                                # tx_mode_select
-    b.f(1, int(rng.integers(0, 2)))          # reduced_tx_set
-    if film_grain_seq:
-        b.f(1, 0)                            # apply_grain
+    return cols, rows, tile_w, tile_h, sbw, sbh
+
+
+def _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_bytes_per_sb64):
     b.align()
     n_tiles = cols * rows
     if n_tiles > 1:
@@ -188,7 +180,27 @@ def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb
         if t < n_tiles - 1:
             out += int(n - 1).to_bytes(4, "little")
         out += data
-    return obu(OBU_FRAME, bytes(out))
+    return bytes(out)
+
+
+def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None, lf=None, cdef=True,
+              restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0):
+    """One shown key frame (OBU_FRAME). Returns the OBU bytes. `cdef_on` / `restoration_on` must match the sequence
+    header (the fields are absent when the sequence disables the tool)."""
+    b = BitWriter()
+    b.f(1, 0)                                # show_existing_frame
+    b.f(2, 0); b.f(1, 1)                     # frame_type KEY, show_frame
+    b.f(1, 0)                                # disable_cdf_update
+    b.f(1, 0)                                # frame_size_override
+    b.f(7, 0)                                # order_hint
+    b.f(1, 0)                                # render_and_frame_size_different
+    b.f(1, 0)                                # disable_frame_end_update_cdf
+    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on)
+    b.f(1, 1)                                # tx_mode_select
+    b.f(1, int(rng.integers(0, 2)))          # reduced_tx_set
+    if film_grain_seq:
+        b.f(1, 0)                            # apply_grain
+    return obu(OBU_FRAME, _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_bytes_per_sb64))
 
 
 def temporal_unit(*obus):
@@ -203,4 +215,89 @@ def intra_stream(seed, w, h, n_frames=1, bpc=8, sb128=0, log2_cols=0, log2_rows=
     for i in range(n_frames):
         fr = key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, **kw)
         tus.append(temporal_unit(seq, fr) if i == 0 else temporal_unit(fr))
+    return tus
+
+
+def _poc_diff(bits, a, b):
+    mask = 1 << (bits - 1)
+    d = a - b
+    return (d & (mask - 1)) - (d & mask)
+
+
+def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None,
+                lf=None, cdef=True, restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0,
+                refresh=None, switchable_motion_mode=0, warped_motion_seq=0, comp_refs=1):
+    """One shown inter frame (OBU_FRAME), primary_ref_frame = NONE. `ref_hints` = order hints held by the 8 reference slots
+    (updated in place for the slots this frame refreshes). Global motion is identity."""
+    bits = 7
+    b = BitWriter()
+    b.f(1, 0)                                # show_existing_frame
+    b.f(2, 1); b.f(1, 1)                     # frame_type INTER, show_frame
+    b.f(1, 0)                                # error_resilient_mode
+    b.f(1, 0)                                # disable_cdf_update
+    b.f(1, 0)                                # frame_size_override
+    b.f(bits, order_hint)
+    b.f(3, 7)                                # primary_ref_frame NONE
+    refresh = int(rng.integers(1, 256)) if refresh is None else refresh
+    b.f(8, refresh)
+    b.f(1, 0)                                # frame_refs_short_signaling
+    refidx = [int(rng.integers(0, 8)) for _ in range(7)]
+    for r in refidx:
+        b.f(3, r)
+    b.f(1, 0)                                # render_and_frame_size_different
+    b.f(1, int(rng.integers(0, 2)))          # allow_high_precision_mv
+    if rng.integers(0, 2):
+        b.f(1, 1)                            # is_filter_switchable
+    else:
+        b.f(1, 0); b.f(2, int(rng.integers(0, 4)))
+    b.f(1, switchable_motion_mode)
+    b.f(1, 0)                                # disable_frame_end_update_cdf
+    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on)
+    b.f(1, 1)                                # tx_mode_select
+    b.f(1, comp_refs)                        # reference_select
+    if comp_refs:                            # skip_mode_present exists only when two suitable references do (src/obu.c:929-987)
+        off_before = off_after = -1
+        for r in refidx:
+            rp = ref_hints[r]
+            d = _poc_diff(bits, rp, order_hint)
+            if d > 0:
+                if off_after < 0 or _poc_diff(bits, off_after, rp) > 0:
+                    off_after = rp
+            elif d < 0 and (off_before < 0 or _poc_diff(bits, rp, off_before) > 0):
+                off_before = rp
+        allowed = False
+        if off_before >= 0 and off_after >= 0:
+            allowed = True
+        elif off_before >= 0:
+            off2 = -1
+            for r in refidx:
+                rp = ref_hints[r]
+                if _poc_diff(bits, rp, off_before) < 0 and (off2 < 0 or _poc_diff(bits, rp, off2) > 0):
+                    off2 = rp
+            allowed = off2 >= 0
+        if allowed:
+            b.f(1, int(rng.integers(0, 2)))  # skip_mode_present
+    if warped_motion_seq:
+        b.f(1, 0)                            # allow_warped_motion
+    b.f(1, int(rng.integers(0, 2)))          # reduced_tx_set
+    for _ in range(7):
+        b.f(1, 0)                            # is_global: identity
+    if film_grain_seq:
+        b.f(1, 0)
+    for i in range(8):
+        if refresh & (1 << i):
+            ref_hints[i] = order_hint
+    return obu(OBU_FRAME, _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_bytes_per_sb64))
+
+
+def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, **kw):
+    """Temporal units: one key frame, then n_frames - 1 inter frames (single and compound references incl. wedge /
+    difference-weighted masks and distance weights, switchable interpolation filters, variable transform trees, intra
+    blocks; no OBMC / warped motion / inter-intra, identity global motion)."""
+    rng = np.random.default_rng(seed)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=0, warped_motion=0)
+    hints = [0] * 8
+    tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows))]
+    for i in range(1, n_frames):
+        tus.append(temporal_unit(inter_frame(rng, w, h, i, hints, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, **kw)))
     return tus

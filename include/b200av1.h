@@ -503,6 +503,11 @@ typedef struct B200IntraFrame {
     uint32_t plane_off[3];         /* superblock mode: sample offset of each plane in pic */
     int32_t n_sb, sb_w, sb_h;      /* superblock mode: number of B200IntraSb, superblock grid */
     const B200IntraSb *sb;         /* device; NULL = per-transform-block dataflow */
+    const uint8_t *done_init;      /* device or NULL; per-transform-block mode only. Frames that mix inter and intra blocks:
+                                      an image of the scratch (b200_intra_scratch_bytes: 256 zero bytes, then one byte per
+                                      4x4 cell for plane 0, 1, 2, each map padded to a multiple of 256 bytes) in which the
+                                      cells NOT covered by an intra record are 1 — their pixels are final before the
+                                      kernel starts (the inter stages ran) — and the cells of intra records are 0 */
 } B200IntraFrame;
 B200_API size_t b200_intra_scratch_bytes(const B200IntraFrame *frame);
 B200_API int b200_intra_frame(int bitdepth_max, const B200IntraFrame *frame, const B200IntraTx *d_tx, int n_tx,

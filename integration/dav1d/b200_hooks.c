@@ -93,6 +93,50 @@ void b200hook_buf_free(HookBuf *b)
     memset(b, 0, sizeof(*b));
 }
 
+void *b200hook_append(HookBuf *b, int *n, size_t elem)
+{
+    if (b200hook_buf_reserve(b, (size_t)(*n + 1) * elem, 1, 1)) return NULL;
+    void *const p = (uint8_t *)b->host + (size_t)(*n)++ * elem;
+    memset(p, 0, elem);
+    return p;
+}
+
+static HookRefPic g_refs[64];
+static pthread_cond_t g_ref_cond = PTHREAD_COND_INITIALIZER;
+HookRefPic *b200hook_refpic(const void *key, size_t bytes, int create)
+{
+    const B200Backend *be = b200hook_backend();
+    HookRefPic *r = NULL;
+    if (!be || !key) return NULL;
+    pthread_mutex_lock(&g_lock);
+    for (int i = 0; i < 64 && !r; i++)
+        if (g_refs[i].key == key) r = &g_refs[i];
+    if (!r && create)
+        for (int i = 0; i < 64 && !r; i++)
+            if (!g_refs[i].key) { r = &g_refs[i]; memset(r, 0, sizeof(*r)); r->key = key; }
+    if (r && create && r->bytes < bytes) {
+        if (r->dev) be->dev_free(r->dev);
+        r->dev = be->dev_alloc(bytes);
+        r->bytes = r->dev ? bytes : 0;
+        if (!r->dev) { fprintf(stderr, "b200hook: %s\n", be->last_error()); r->key = NULL; r = NULL; }
+    }
+    pthread_mutex_unlock(&g_lock);
+    return r;
+}
+void b200hook_refpic_set_ready(HookRefPic *r, int ready)
+{
+    pthread_mutex_lock(&g_lock);
+    r->ready = ready;
+    pthread_cond_broadcast(&g_ref_cond);
+    pthread_mutex_unlock(&g_lock);
+}
+void b200hook_refpic_wait(HookRefPic *r)
+{
+    pthread_mutex_lock(&g_lock);
+    while (!r->ready) pthread_cond_wait(&g_ref_cond, &g_lock);
+    pthread_mutex_unlock(&g_lock);
+}
+
 HookFrame *b200hook_frame(const void *key)
 {
     HookFrame *r = NULL;
@@ -192,9 +236,16 @@ API void b200hook_release(void)
         b200hook_buf_free(&h->tx); b200hook_buf_free(&h->tx_sorted); b200hook_buf_free(&h->coef); b200hook_buf_free(&h->mask);
         b200hook_buf_free(&h->level); b200hook_buf_free(&h->lr_mask); b200hook_buf_free(&h->scratch);
         for (int p = 0; p < 3; p++) b200hook_buf_free(&h->pic[p]);
+        b200hook_buf_free(&h->pred); b200hook_buf_free(&h->comp); b200hook_buf_free(&h->comp2);
+        for (int t = 0; t < 19; t++) b200hook_buf_free(&h->itx[t]);
+        b200hook_buf_free(&h->tmp16); b200hook_buf_free(&h->cmask); b200hook_buf_free(&h->done_init);
         if (h->stream && g_be_ok) g_be.stream_destroy(h->stream);
         pthread_mutex_destroy(&h->lock);
         memset(h, 0, sizeof(*h));
+    }
+    for (int i = 0; i < 64; i++) {
+        if (g_refs[i].dev && g_be_ok) g_be.dev_free(g_refs[i].dev);
+        memset(&g_refs[i], 0, sizeof(g_refs[i]));
     }
     pthread_mutex_unlock(&g_lock);
 }

@@ -44,6 +44,14 @@ typedef struct HookFrame {
     int tile_sbrows_done;          /* completed pass-2 tile superblock rows of the current frame */
     int unsupported;               /* a block used a tool the emitters do not translate yet */
     HookBuf tx, tx_sorted, coef, mask, level, lr_mask, pic[3], scratch;
+    /* inter frames: prediction / compound / transform records (B200McBlock, B200CompBlock x 2 stages, B200ItxBlock
+     * per transform size), the int16 scratch of the compound predictions (device only), the mask buffer (dav1d's
+     * wedge tables at its head, difference-weighted masks behind them) and the initial done map of the intra kernel
+     * (cells of inter blocks are "done" before it starts) */
+    HookBuf pred, comp, comp2, itx[19], tmp16, cmask, done_init;
+    int n_pred, n_comp, n_comp2, n_itx[19];
+    size_t n_tmp16, n_cmask;
+    int started, is_inter;
     void *stream;
     /* statistics */
     uint64_t frames, records;
@@ -51,6 +59,14 @@ typedef struct HookFrame {
 HookFrame *b200hook_frame(const void *key);
 int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int32_t w4[3], const int32_t h4[3],
                        int ss_hor, int ss_ver);
+void *b200hook_append(HookBuf *b, int *n, size_t elem);
+
+/* device pictures that outlive their frame context: every decoded picture, keyed by the host picture's data[0]
+ * (dav1d recycles a host buffer only when no reference to it is left, so a key is reused only for a dead picture) */
+typedef struct HookRefPic { const void *key; void *dev; size_t bytes; int ready; } HookRefPic;
+HookRefPic *b200hook_refpic(const void *key, size_t bytes, int create);
+void b200hook_refpic_set_ready(HookRefPic *r, int ready);
+void b200hook_refpic_wait(HookRefPic *r);
 void b200hook_job_enter(void);
 void b200hook_job_leave(void);
 

@@ -13,8 +13,11 @@
  *                      parameters are shipped to HBM, b200_frame_run_host reconstructs and filters the whole frame,
  *                      and the finished picture is copied into f->cur (what the output / reference logic reads)
  *   filter_sbrow_*  -> nothing left to do on the CPU (the device job already ran the whole post-filter sweep)
- *   recon_b_inter   -> not translated yet: the tile fails loudly (no CPU fallback)
- * Palette blocks are not translated yet either (streams with allow_screen_content_tools fail loudly).
+ *   recon_b_inter   -> B200McBlock (put / prep) per prediction incl. the shared 4x4 chroma of sub-8x8 blocks,
+ *                      B200CompBlock per compound combination (avg, distance weights, wedge and difference-weighted
+ *                      masks), one B200ItxBlock per leaf of the transform tree (reference src/recon_tmpl.c:1557-1985)
+ * Not translated yet (the frame fails loudly, there is no CPU fallback): palette, intra block copy, OBMC, warped /
+ * global motion, inter-intra, scaled references.
  */
 #include "config.h"
 #include <stdio.h>
@@ -23,11 +26,13 @@
 #include <time.h>
 #include "common/attributes.h"
 #include "common/bitdepth.h"
+#include "common/frame.h"
 #include "common/intops.h"
 #include "src/internal.h"
 #include "src/ipred_prepare.h"
 #include "src/recon.h"
 #include "src/tables.h"
+#include "src/wedge.h"
 #include "b200_hooks.h"
 
 static inline double bitfn(now_ms)(void)
@@ -50,6 +55,19 @@ static void bitfn(pic_geom)(const Dav1dFrameContext *const f, PicGeom *const g)
     g->off[1] = (uint32_t)g->stride[0] * rows;
     g->off[2] = g->off[1] + (uint32_t)g->stride[1] * g->rows[1];
     g->bytes = ((size_t)g->off[2] + (size_t)g->stride[2] * g->rows[2]) * sizeof(pixel);
+}
+
+/* first pass-2 hook call of a frame: its output picture (keyed by the host buffer) is not valid any more / yet */
+static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *const f)
+{
+    if (hf->started) return;
+    hf->started = 1;
+    hf->n_cmask = (sizeof(dav1d_masks) + 63) & ~(size_t)63;      /* dav1d's wedge tables sit at the head of the mask buffer */
+    PicGeom g;
+    bitfn(pic_geom)(f, &g);
+    HookRefPic *const out = b200hook_refpic(f->cur.data[0], g.bytes, 1);
+    if (out) b200hook_refpic_set_ready(out, 0);
+    else hf->unsupported |= 8;
 }
 
 /* ---- one transform block -> one record ------------------------------------------------------------------ */
@@ -127,6 +145,7 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
     const int layout_shift = f->cur.p.layout - 1;      /* EDGE_I420_* >> (layout - 1) selects this layout's chroma flags */
 
     pthread_mutex_lock(&hf->lock);
+    bitfn(frame_started)(hf, f);
     if (b->pal_sz[0] || (has_chroma && b->pal_sz[1])) hf->unsupported |= 1;
     /* the reference walks a block in 64x64-luma chunks: luma transform blocks of the chunk, then its chroma */
     for (int iy = 0; iy < h4; iy += 16) {
@@ -208,12 +227,214 @@ out:
     pthread_mutex_unlock(&hf->lock);
 }
 
+/* ---- inter blocks (what dav1d_recon_b_inter does, reference src/recon_tmpl.c:1557-1985) -------------------- */
+/* one motion-compensated prediction: the arguments of the reference's mc() (:938-988), as a B200McBlock.
+ * Source samples outside the reference plane are clamped by the kernel (= emu_edge). */
+static int bitfn(emit_mc)(HookFrame *const hf, const Dav1dFrameContext *const f, const int prep, const uint32_t dst_off,
+                          const int bw4, const int bh4, const int bx, const int by, const int pl, const mv mv,
+                          const int refidx, const enum Filter2d filter_2d)
+{
+    const Dav1dThreadPicture *const refp = &f->refp[refidx];
+    if (refp->p.p.w != f->cur.p.w || refp->p.p.h != f->cur.p.h) { hf->unsupported |= 32; return 0; }   /* scaled reference */
+    const int ss_ver = !!pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
+    const int ss_hor = !!pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    const int h_mul = 4 >> ss_hor, v_mul = 4 >> ss_ver;
+    const int mx = mv.x & (15 >> !ss_hor), my = mv.y & (15 >> !ss_ver);
+    B200McBlock *const r = b200hook_append(&hf->pred, &hf->n_pred, sizeof(*r));
+    if (!r) return -1;
+    r->dst_off = dst_off;
+    r->src_x = bx * h_mul + (mv.x >> (3 + ss_hor));
+    r->src_y = by * v_mul + (mv.y >> (3 + ss_ver));
+    r->w = bw4 * h_mul; r->h = bh4 * v_mul;
+    r->mx = mx << !ss_hor; r->my = my << !ss_ver;
+    r->filter2d = filter_2d; r->op = prep; r->plane = pl; r->ref = refidx;
+    return 0;
+}
+
+static int bitfn(emit_itx)(TxCtx *const c, const int tx, const int pl, const uint32_t dst_off, const int chroma)
+{
+    HookFrame *const hf = c->hf;
+    B200IntraTx tmp;          /* take_residual fills eob / txtp / coef_off of any record with these fields */
+    memset(&tmp, 0, sizeof(tmp));
+    if (bitfn(take_residual)(c, &tmp, &dav1d_txfm_dimensions[tx], chroma)) return -1;
+    if (tmp.eob < 0) return 0;
+    B200ItxBlock *const r = b200hook_append(&hf->itx[tx], &hf->n_itx[tx], sizeof(*r));
+    if (!r) return -1;
+    r->dst_off = dst_off; r->coef_off = tmp.coef_off; r->eob = tmp.eob; r->txtp = tmp.txtp; r->plane = pl;
+    return 0;
+}
+
+/* the luma transform tree of an inter block (read_coef_tree, :731-822): (x4, y4) = position of this node */
+static int bitfn(emit_tx_tree)(TxCtx *const c, const enum RectTxfmSize tx, const int depth, const uint16_t *const split,
+                               const int x_off, const int y_off, const int x4, const int y4)
+{
+    const Dav1dFrameContext *const f = c->t->f;
+    const TxfmInfo *const td = &dav1d_txfm_dimensions[tx];
+    if (depth < 2 && split[depth] && (split[depth] & (1 << (y_off * 4 + x_off)))) {
+        const enum RectTxfmSize sub = td->sub;
+        const TxfmInfo *const sd = &dav1d_txfm_dimensions[sub];
+        const int two_cols = td->w >= td->h && x4 + sd->w < f->bw, two_rows = td->h >= td->w && y4 + sd->h < f->bh;
+        if (bitfn(emit_tx_tree)(c, sub, depth + 1, split, x_off * 2, y_off * 2, x4, y4)) return -1;
+        if (two_cols && bitfn(emit_tx_tree)(c, sub, depth + 1, split, x_off * 2 + 1, y_off * 2, x4 + sd->w, y4)) return -1;
+        if (two_rows) {
+            if (bitfn(emit_tx_tree)(c, sub, depth + 1, split, x_off * 2, y_off * 2 + 1, x4, y4 + sd->h)) return -1;
+            if (two_cols && bitfn(emit_tx_tree)(c, sub, depth + 1, split, x_off * 2 + 1, y_off * 2 + 1, x4 + sd->w, y4 + sd->h)) return -1;
+        }
+        return 0;
+    }
+    return bitfn(emit_itx)(c, tx, 0, c->g.off[0] + (uint32_t)(4 * y4) * c->g.stride[0] + 4 * x4, 0);
+}
+
 int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSize bs, const Av1Block *const b)
 {
-    (void)bs; (void)b;
-    HookFrame *const hf = b200hook_frame(t->f);
-    if (hf) { pthread_mutex_lock(&hf->lock); hf->unsupported |= 2; pthread_mutex_unlock(&hf->lock); }
-    return -1;      /* aborts the tile (reference src/decode.c:771): inter blocks are not translated yet */
+    const Dav1dFrameContext *const f = t->f;
+    HookFrame *const hf = b200hook_frame(f);
+    if (!hf) return -1;
+    if (t->frame_thread.pass != 2) {
+        pthread_mutex_lock(&hf->lock); hf->unsupported |= 4; pthread_mutex_unlock(&hf->lock);
+        return -1;
+    }
+    TxCtx c = { hf, t, b };
+    bitfn(pic_geom)(f, &c.g);
+    const PicGeom *const g = &c.g;
+    const int ss_ver = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
+    const int ss_hor = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    const int bx = t->bx, by = t->by, bx4 = bx & 31, by4 = by & 31;
+    const uint8_t *const dim = dav1d_block_dimensions[bs];
+    const int bw4 = dim[0], bh4 = dim[1];
+    const int w4 = imin(bw4, f->bw - bx), h4 = imin(bh4, f->bh - by);
+    const int cw4 = (w4 + ss_hor) >> ss_hor, ch4 = (h4 + ss_ver) >> ss_ver;
+    const int cbw4 = (bw4 + ss_hor) >> ss_hor, cbh4 = (bh4 + ss_ver) >> ss_ver;
+    const int has_chroma = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I400 && (bw4 > ss_hor || bx & 1) && (bh4 > ss_ver || by & 1);
+    const int chr_layout_idx = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I400 ? 0 : DAV1D_PIXEL_LAYOUT_I444 - f->cur.p.layout;
+    const uint32_t ydst = g->off[0] + (uint32_t)(4 * by) * g->stride[0] + 4 * bx;
+    const uint32_t uvrel = (uint32_t)(4 * (by >> ss_ver)) * g->stride[1] + 4 * (bx >> ss_hor);   /* + g->off[pl] */
+    int rc = -1;
+
+    pthread_mutex_lock(&hf->lock);
+    bitfn(frame_started)(hf, f);
+    hf->is_inter = 1;
+    if (IS_KEY_OR_INTRA(f->frame_hdr)) { hf->unsupported |= 64; goto out; }          /* intra block copy */
+    if (b->comp_type == COMP_INTER_NONE) {
+        const enum Filter2d filter_2d = b->filter2d;
+        const int warp = (b->inter_mode == GLOBALMV && f->gmv_warp_allowed[b->ref[0]]) ||
+                         (b->motion_mode == MM_WARP && t->warpmv.type > DAV1D_WM_TYPE_TRANSLATION);
+        if (warp && (imin(bw4, bh4) > 1 || imin(cbw4, cbh4) > 1)) hf->unsupported |= 16;
+        if (b->motion_mode == MM_OBMC) hf->unsupported |= 128;
+        if (b->interintra_type) hf->unsupported |= 256;
+        if (bitfn(emit_mc)(hf, f, 0, ydst, bw4, bh4, bx, by, 0, b->mv[0], b->ref[0], filter_2d)) goto out;
+        if (has_chroma) {
+            /* a 4-wide / 4-tall luma block shares its 4x4 chroma block with its left / top neighbours: each quarter is
+             * predicted with the motion of the luma block above it, if all of them are inter (:1652-1724) */
+            int sub8 = bw4 == ss_hor || bh4 == ss_ver;
+            refmvs_block *const *rr = NULL;
+            if (sub8) {
+                rr = &t->rt.r[(by & 31) + 5];
+                if (bw4 == 1) sub8 &= rr[0][bx - 1].ref.ref[0] > 0;
+                if (bh4 == ss_ver) sub8 &= rr[-1][bx].ref.ref[0] > 0;
+                if (bw4 == 1 && bh4 == ss_ver) sub8 &= rr[-1][bx - 1].ref.ref[0] > 0;
+            }
+            if (sub8) {
+                uint32_t h_off = 0, v_off = 0;
+                if (bw4 == 1 && bh4 == ss_ver) {
+                    const refmvs_block *const n = &rr[-1][bx - 1];
+                    for (int pl = 1; pl <= 2; pl++)
+                        if (bitfn(emit_mc)(hf, f, 0, g->off[pl] + uvrel, bw4, bh4, bx - 1, by - 1, pl, n->mv.mv[0], n->ref.ref[0] - 1,
+                                           f->frame_thread.b[(by - 1) * f->b4_stride + bx - 1].filter2d)) goto out;
+                    v_off = 2 * g->stride[1]; h_off = 2;
+                }
+                if (bw4 == 1) {
+                    const refmvs_block *const n = &rr[0][bx - 1];
+                    for (int pl = 1; pl <= 2; pl++)
+                        if (bitfn(emit_mc)(hf, f, 0, g->off[pl] + uvrel + v_off, bw4, bh4, bx - 1, by, pl, n->mv.mv[0], n->ref.ref[0] - 1,
+                                           f->frame_thread.b[by * f->b4_stride + bx - 1].filter2d)) goto out;
+                    h_off = 2;
+                }
+                if (bh4 == ss_ver) {
+                    const refmvs_block *const n = &rr[-1][bx];
+                    for (int pl = 1; pl <= 2; pl++)
+                        if (bitfn(emit_mc)(hf, f, 0, g->off[pl] + uvrel + h_off, bw4, bh4, bx, by - 1, pl, n->mv.mv[0], n->ref.ref[0] - 1,
+                                           f->frame_thread.b[(by - 1) * f->b4_stride + bx].filter2d)) goto out;
+                    v_off = 2 * g->stride[1];
+                }
+                for (int pl = 1; pl <= 2; pl++)
+                    if (bitfn(emit_mc)(hf, f, 0, g->off[pl] + uvrel + h_off + v_off, bw4, bh4, bx, by, pl, b->mv[0], b->ref[0], filter_2d)) goto out;
+            } else {
+                for (int pl = 1; pl <= 2; pl++)
+                    if (bitfn(emit_mc)(hf, f, 0, g->off[pl] + uvrel, bw4 << (bw4 == ss_hor), bh4 << (bh4 == ss_ver),
+                                       bx & ~ss_hor, by & ~ss_ver, pl, b->mv[0], b->ref[0], filter_2d)) goto out;
+            }
+        }
+    } else {
+        /* compound: two int16 predictions per plane, then avg / w_avg / mask / w_mask (:1782-1866) */
+        const enum Filter2d filter_2d = b->filter2d;
+        if (b->inter_mode == GLOBALMV_GLOBALMV && (f->gmv_warp_allowed[b->ref[0]] || f->gmv_warp_allowed[b->ref[1]])) hf->unsupported |= 16;
+        uint32_t mask_off = 0;          /* luma mask, then the mask the chroma planes read */
+        for (int pl = 0; pl < (has_chroma ? 3 : 1); pl++) {
+            const int pw = pl ? bw4 * 4 >> ss_hor : bw4 * 4, ph = pl ? bh4 * 4 >> ss_ver : bh4 * 4;
+            uint32_t tmp_off[2];
+            for (int i = 0; i < 2; i++) {
+                tmp_off[i] = (uint32_t)hf->n_tmp16;
+                hf->n_tmp16 += (size_t)pw * ph;
+                if (bitfn(emit_mc)(hf, f, 1, tmp_off[i], bw4, bh4, bx, by, pl, b->mv[i], b->ref[i], filter_2d)) goto out;
+            }
+            const int seg = b->comp_type == COMP_INTER_SEG, wedge = b->comp_type == COMP_INTER_WEDGE;
+            /* chroma of a difference-weighted block reads the mask its luma block writes: second compound stage */
+            B200CompBlock *const r = (pl && seg) ? b200hook_append(&hf->comp2, &hf->n_comp2, sizeof(*r))
+                                                 : b200hook_append(&hf->comp, &hf->n_comp, sizeof(*r));
+            if (!r) goto out;
+            r->dst_off = pl ? g->off[pl] + uvrel : ydst;
+            r->w = pw; r->h = ph; r->plane = pl;
+            r->tmp1_off = tmp_off[0]; r->tmp2_off = tmp_off[1];
+            switch (b->comp_type) {
+            case COMP_INTER_AVG: r->op = B200_COMP_AVG; break;
+            case COMP_INTER_WEIGHTED_AVG: r->op = B200_COMP_W_AVG; r->param = f->jnt_weights[b->ref[0]][b->ref[1]]; break;
+            default:
+                r->tmp1_off = tmp_off[b->mask_sign]; r->tmp2_off = tmp_off[!b->mask_sign];
+                if (!pl) {
+                    if (seg) {
+                        /* w_mask writes the (sub-sampled) mask the chroma planes blend with */
+                        r->op = B200_COMP_W_MASK_444 + chr_layout_idx; r->param = b->mask_sign;
+                        hf->n_cmask = (hf->n_cmask + 63) & ~(size_t)63;
+                        r->mask_off = mask_off = (uint32_t)hf->n_cmask;
+                        hf->n_cmask += (size_t)(bw4 * 4 >> ss_hor) * (bh4 * 4 >> ss_ver);
+                    } else {
+                        r->op = B200_COMP_MASK;
+                        r->mask_off = (uint32_t)(WEDGE_MASK(0, bs, 0, b->wedge_idx) - (const uint8_t *)&dav1d_masks);
+                        if (has_chroma)
+                            mask_off = (uint32_t)(WEDGE_MASK(chr_layout_idx, bs, b->mask_sign, b->wedge_idx) - (const uint8_t *)&dav1d_masks);
+                    }
+                } else {
+                    r->op = B200_COMP_MASK; r->mask_off = mask_off;
+                }
+                (void)wedge;
+            }
+        }
+    }
+    /* residual (:1888-1983) */
+    if (!b->skip) {
+        const TxfmInfo *const uvtx = &dav1d_txfm_dimensions[b->uvtx], *const ytx = &dav1d_txfm_dimensions[b->max_ytx];
+        const uint16_t tx_split[2] = { b->tx_split0, b->tx_split1 };
+        for (int iy = 0; iy < bh4; iy += 16)
+            for (int ix = 0; ix < bw4; ix += 16) {
+                int y_off = !!iy;
+                for (int y = iy; y < imin(h4, iy + 16); y += ytx->h, y_off++) {
+                    int x_off = !!ix;
+                    for (int x = ix; x < imin(w4, ix + 16); x += ytx->w, x_off++)
+                        if (bitfn(emit_tx_tree)(&c, b->max_ytx, 0, tx_split, x_off, y_off, bx + x, by + y)) goto out;
+                }
+                if (has_chroma)
+                    for (int pl = 1; pl <= 2; pl++)
+                        for (int y = iy >> ss_ver; y < imin(ch4, (iy + 16) >> ss_ver); y += uvtx->h)
+                            for (int x = ix >> ss_hor; x < imin(cw4, (ix + 16) >> ss_hor); x += uvtx->w)
+                                if (bitfn(emit_itx)(&c, b->uvtx, pl, g->off[pl] + uvrel + (uint32_t)(4 * y) * g->stride[1] + 4 * x, 1)) goto out;
+            }
+    }
+    rc = 0;
+out:
+    if (rc) hf->unsupported |= 8;
+    pthread_mutex_unlock(&hf->lock);
+    return 0;       /* problems are reported when the frame completes (the whole frame fails, loudly) */
 }
 
 /* ---- frame completion ------------------------------------------------------------------------------------- */
@@ -281,6 +502,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         fprintf(stderr, "b200hook: frame uses tools the emitters do not translate yet (%s%s%s%s)\n",
                 hf->unsupported & 1 ? " palette" : "", hf->unsupported & 2 ? " inter" : "",
                 hf->unsupported & 4 ? " single-pass-decoding" : "", hf->unsupported & 8 ? " out-of-memory" : "");
+        fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 scaled reference, 64 intra block copy, 128 OBMC, 256 inter-intra)\n", hf->unsupported);
         return -1;
     }
     PicGeom g;
@@ -310,8 +532,47 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
 #else
     j.bitdepth_max = f->bitdepth_max;
 #endif
-    void *const p0 = hf->pic[0].dev, *const p1 = hf->pic[1].dev, *const p2 = hf->pic[2].dev;
+    /* the finished picture goes into a buffer that outlives this frame context (later frames predict from it); the
+     * other stages ping-pong through the context's own pictures */
+    HookRefPic *const outp = b200hook_refpic(f->cur.data[0], g.bytes, 1);
+    if (!outp) return -1;
+    const int will_cdef = f->seq_hdr->cdef && (f->c->inloop_filters & DAV1D_INLOOPFILTER_CDEF);
+    const int will_lr = f->lf.restore_planes && (f->c->inloop_filters & DAV1D_INLOOPFILTER_RESTORATION);
+    void *const p2 = will_lr ? outp->dev : hf->pic[2].dev;
+    void *const p1 = !will_lr && will_cdef ? outp->dev : hf->pic[1].dev;
+    void *const p0 = !will_lr && !will_cdef ? outp->dev : hf->pic[0].dev;
     j.mc.dst = p0;
+    const int inter = hf->is_inter;
+    if (inter) {
+        for (int k = 0; k < 7; k++) {
+            const void *const key = f->refp[k].p.data[0];
+            if (!key) continue;
+            HookRefPic *const rp = b200hook_refpic(key, 0, 0);
+            if (!rp || !rp->dev) { fprintf(stderr, "b200hook: reference %d was not decoded by this back end\n", k); return -1; }
+            b200hook_refpic_wait(rp);          /* its device job (another frame context) must have finished */
+            j.mc.ref[k] = rp->dev;
+        }
+        for (int p = 0; p < 3; p++) {
+            j.mc.ref_plane_off[p] = g.off[p]; j.mc.ref_stride[p] = g.stride[p];
+            j.mc.ref_w[p] = p ? (f->cur.p.w + ss_hor) >> ss_hor : f->cur.p.w;
+            j.mc.ref_h[p] = p ? (f->cur.p.h + ss_ver) >> ss_ver : f->cur.p.h;
+        }
+        if (b200hook_buf_reserve(&hf->tmp16, (hf->n_tmp16 + 1) * sizeof(int16_t), 0, 0) ||
+            b200hook_buf_reserve(&hf->cmask, hf->n_cmask + 64, 1, 0) ||
+            b200hook_buf_reserve(&hf->pred, (size_t)imax(hf->n_pred, 1) * sizeof(B200McBlock), 1, 1) ||
+            b200hook_buf_reserve(&hf->comp, (size_t)imax(hf->n_comp, 1) * sizeof(B200CompBlock), 1, 1) ||
+            b200hook_buf_reserve(&hf->comp2, (size_t)imax(hf->n_comp2, 1) * sizeof(B200CompBlock), 1, 1))
+            return -1;
+        memcpy(hf->cmask.host, &dav1d_masks, sizeof(dav1d_masks));
+        j.mc.tmp = (int16_t *)hf->tmp16.dev; j.mc.mask = (uint8_t *)hf->cmask.dev;
+        j.d_pred = (const B200McBlock *)hf->pred.dev; j.n_pred = hf->n_pred;
+        j.d_comp = (const B200CompBlock *)hf->comp.dev; j.n_comp = hf->n_comp;
+        j.d_comp2 = (const B200CompBlock *)hf->comp2.dev; j.n_comp2 = hf->n_comp2;
+        for (int t = 0; t < N_RECT_TX_SIZES; t++) {
+            if (!hf->n_itx[t]) continue;
+            j.d_itx[t] = (const B200ItxBlock *)hf->itx[t].dev; j.n_itx[t] = hf->n_itx[t];
+        }
+    }
     j.d_coef = hf->coef.dev;
     for (int p = 0; p < 3; p++) { j.itx_stride[p] = g.stride[p]; j.mc.dst_stride[p] = g.stride[p]; }
     /* intra reconstruction */
@@ -325,6 +586,24 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     }
     if (b200hook_buf_reserve(&hf->scratch, be->intra_scratch_bytes(&j.intra), 0, 0)) return -1;
     j.intra.scratch = hf->scratch.dev;
+    if (inter && hf->n_tx > 0) {
+        /* intra blocks inside an inter frame: everything that is not an intra transform block is already final */
+        const size_t total = be->intra_scratch_bytes(&j.intra);
+        if (b200hook_buf_reserve(&hf->done_init, total, 1, 0)) return -1;
+        uint8_t *const img = hf->done_init.host;
+        memset(img, 0, 256); memset(img + 256, 1, total - 256);
+        size_t moff[3], o = 256;
+        for (int p = 0; p < 3; p++) { moff[p] = o; o += ((size_t)j.intra.w4[p] * j.intra.h4[p] + 255) & ~(size_t)255; }
+        const B200IntraTx *const recs = (const B200IntraTx *)hf->tx.host;
+        for (int i = 0; i < hf->n_tx; i++) {
+            const B200IntraTx *const r = &recs[i];
+            const TxfmInfo *const td = &dav1d_txfm_dimensions[r->tx];
+            const int mw = j.intra.w4[r->plane], mh = j.intra.h4[r->plane];
+            for (int y = r->y4; y < imin(r->y4 + td->h, mh); y++)
+                memset(img + moff[r->plane] + (size_t)y * mw + r->x4, 0, imin(td->w, mw - r->x4));
+        }
+        j.intra.done_init = (const uint8_t *)hf->done_init.dev;
+    }
     /* decode order -> wavefront order (B200HOOK_WAVE_SORT=0 keeps decode order, which is also valid) */
     const HookBuf *txb = &hf->tx;
     static int wave_sort = -1;
@@ -368,14 +647,23 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     j.lr.restore_planes = f->lf.restore_planes;
     j.lr.lr_mask = (const B200Av1Restoration *)hf->lr_mask.dev;
 
-    const B200Xfer up[5] = {
-        { txb->host, txb->dev, (uint64_t)hf->n_tx * sizeof(B200IntraTx) },
-        { hf->coef.host, hf->coef.dev, (uint64_t)hf->n_coef * sizeof(coef) },
-        { hf->mask.host, hf->mask.dev, mask_bytes },
-        { hf->level.host, hf->level.dev, level_bytes },
-        { hf->lr_mask.host, hf->lr_mask.dev, lr_bytes },
-    };
-    uint8_t *const out = do_lr ? p2 : do_cdef ? p1 : p0;
+    B200Xfer up[32];
+    int n_up = 0;
+#define UP(buf, nbytes) do { up[n_up].host = (buf).host; up[n_up].dev = (buf).dev; up[n_up].bytes = (uint64_t)(nbytes); n_up++; } while (0)
+    UP(*txb, (size_t)hf->n_tx * sizeof(B200IntraTx));
+    UP(hf->coef, hf->n_coef * sizeof(coef));
+    UP(hf->mask, mask_bytes); UP(hf->level, level_bytes); UP(hf->lr_mask, lr_bytes);
+    if (inter) {
+        UP(hf->pred, (size_t)hf->n_pred * sizeof(B200McBlock));
+        UP(hf->comp, (size_t)hf->n_comp * sizeof(B200CompBlock));
+        UP(hf->comp2, (size_t)hf->n_comp2 * sizeof(B200CompBlock));
+        UP(hf->cmask, sizeof(dav1d_masks));
+        for (int t = 0; t < N_RECT_TX_SIZES; t++)
+            if (hf->n_itx[t]) UP(hf->itx[t], (size_t)hf->n_itx[t] * sizeof(B200ItxBlock));
+        if (j.intra.done_init) UP(hf->done_init, be->intra_scratch_bytes(&j.intra));
+    }
+#undef UP
+    uint8_t *const out = outp->dev;
     B200Xfer down[3];
     uint64_t d2h = 0, h2d = 0;
     for (int p = 0; p < 3; p++) {
@@ -385,13 +673,15 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         down[p].bytes = (uint64_t)rows * g.stride[p] * sizeof(pixel);
         d2h += down[p].bytes;
     }
-    for (int i = 0; i < 5; i++) h2d += up[i].bytes;
+    for (int i = 0; i < n_up; i++) h2d += up[i].bytes;
     const double t0 = bitfn(now_ms)();
     b200hook_job_enter();
-    const int r = be->frame_run_host(&j, up, 5, down, 3, hf->stream);
+    const int r = be->frame_run_host(&j, up, n_up, down, 3, hf->stream);
     b200hook_job_leave();
     if (r) { fprintf(stderr, "b200hook: b200_frame_run_host failed (%d): %s\n", r, be->last_error()); return -1; }
-    b200hook_account((uint64_t)hf->n_tx, hf->n_coef, h2d, d2h, bitfn(now_ms)() - t0);
+    uint64_t n_rec = (uint64_t)hf->n_tx + hf->n_pred + hf->n_comp + hf->n_comp2;
+    for (int t = 0; t < N_RECT_TX_SIZES; t++) n_rec += hf->n_itx[t];
+    b200hook_account(n_rec, hf->n_coef, h2d, d2h, bitfn(now_ms)() - t0);
     return 0;
 }
 
@@ -408,7 +698,11 @@ void bitfn(b200hook_backup_ipred_edge)(Dav1dTaskContext *const t)
     if (++hf->tile_sbrows_done >= total) {
         if (bitfn(run_frame)(hf, f))
             atomic_fetch_or(&f->task_thread.error, 1);      /* the frame is reported as a decoding error */
+        HookRefPic *const outp = b200hook_refpic(f->cur.data[0], 0, 0);
+        if (outp) b200hook_refpic_set_ready(outp, 1);       /* also after a failure: nobody may wait for ever */
         hf->tile_sbrows_done = 0; hf->n_tx = 0; hf->n_coef = 0; hf->unsupported = 0;
+        hf->n_pred = hf->n_comp = hf->n_comp2 = 0; hf->n_tmp16 = 0; hf->started = 0; hf->is_inter = 0;
+        memset(hf->n_itx, 0, sizeof(hf->n_itx));
     }
     pthread_mutex_unlock(&hf->lock);
 }

@@ -65,6 +65,26 @@ def test_stream_emu_matches_stock_dav1d(emu_decoder, case):
     _check(emu_decoder, tus, nf)
 
 
+CASES_INTER_CPU = [
+    # w, h, bpc, sb128, log2 tile cols, rows, frames (1 key frame + inter frames)
+    (320, 192, 8, 0, 0, 0, 3),
+    (320, 192, 10, 0, 1, 1, 4),
+    (640, 360, 8, 1, 1, 0, 3),
+    (330, 250, 8, 0, 0, 0, 5),
+]
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("case", CASES_INTER_CPU)
+def test_inter_stream_emu_matches_stock_dav1d(emu_decoder, case):
+    """key frame + inter frames: single and compound references (average, distance weights, wedge and
+    difference-weighted masks), sub-8x8 chroma, variable transform trees, intra blocks inside inter frames,
+    references kept in device memory across frames and frame contexts"""
+    w, h, bpc, sb128, lc, lr, nf = case
+    tus = obu.inter_stream(hash(case) & 0xffff, w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=lc, log2_rows=lr)
+    _check(emu_decoder, tus, nf)
+
+
 def test_stream_without_backend_fails_loudly():
     """no CPU fallback: with no back end bound the hooked decoder reports an error instead of decoding (own process:
     the binding is process-wide state of the library)"""
@@ -90,6 +110,14 @@ CASES_GPU = [
 ]
 
 
+CASES_INTER_GPU = [
+    (640, 360, 8, 0, 1, 1, 4),
+    (1920, 1080, 8, 0, 2, 1, 4),
+    (1920, 1080, 10, 1, 1, 1, 3),
+    (3840, 2160, 8, 0, 2, 2, 3),
+]
+
+
 @pytest.fixture(scope="module")
 def gpu_decoder():
     d = stream.HookedDecoder()
@@ -102,4 +130,12 @@ def gpu_decoder():
 def test_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
     w, h, bpc, sb128, lc, lr, nf = case
     tus = obu.intra_stream(1000 + (hash(case) & 0xfff), w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=lc, log2_rows=lr)
+    _check(gpu_decoder, tus, nf)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES_INTER_GPU)
+def test_inter_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
+    w, h, bpc, sb128, lc, lr, nf = case
+    tus = obu.inter_stream(2000 + (hash(case) & 0xfff), w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=lc, log2_rows=lr)
     _check(gpu_decoder, tus, nf)
