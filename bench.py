@@ -306,6 +306,14 @@ STREAM_WORKLOADS = {
                               "payloads: dav1d_b200/obu.py) decoded through dav1d's public API; front end (OBU parsing, entropy "
                               "decoding, threading) = unmodified dav1d on the host, back end = f->bd_fn record emitters + "
                               "libb200av1 (intra reconstruction, deblock, CDEF, loop restoration)"),
+    "stream1080p8_inter": dict(W=1920, H=1080, bpc=8, frames=16, log2_cols=2, log2_rows=1, inter=1,
+                               desc="AV1 elementary stream, 1 key frame + 15 inter frames 1920x1080 8-bit 4:2:0, 4x2 tiles (valid headers, "
+                                    "random tile payloads: single / compound references incl. wedge and difference-weighted masks, OBMC, "
+                                    "locally warped motion, transform trees, intra blocks) decoded through dav1d's public API; host front "
+                                    "end = unmodified dav1d, back end = f->bd_fn record emitters + libb200av1, references resident in HBM"),
+    "stream4k8_inter": dict(W=3840, H=2160, bpc=8, frames=8, log2_cols=2, log2_rows=2, inter=1,
+                            desc="AV1 elementary stream, 1 key frame + 7 inter frames 3840x2160 8-bit 4:2:0, 4x4 tiles, all inter tools of "
+                                 "stream1080p8_inter, decoded through dav1d's public API (host front end = unmodified dav1d, back end = libb200av1)"),
     "stream4k10": dict(W=3840, H=2160, bpc=10, frames=4, log2_cols=2, log2_rows=2,
                        desc="AV1 elementary stream, 4 key frames 3840x2160 10-bit 4:2:0, 4x4 tiles, decoded through dav1d's public API "
                             "(host front end = unmodified dav1d, back end = libb200av1)"),
@@ -322,7 +330,8 @@ def run_stream(args):
     W = STREAM_WORKLOADS[args.workload]
     nthr = min(os.cpu_count() or 1, 32)
     mfd = min(8, W["frames"])
-    tus = obu.intra_stream(100 + rank, W["W"], W["H"], n_frames=W["frames"], bpc=W["bpc"], log2_cols=W["log2_cols"], log2_rows=W["log2_rows"])
+    gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=1, **k)) if W.get("inter") else obu.intra_stream
+    tus = gen(100 + rank, W["W"], W["H"], n_frames=W["frames"], bpc=W["bpc"], log2_cols=W["log2_cols"], log2_rows=W["log2_rows"])
     px = W["W"] * W["H"] * W["frames"]
     stream.decode_stream.capacity = (W["W"] * W["H"] * 3 // 2) * (2 if W["bpc"] > 8 else 1) * W["frames"] + (1 << 20)
     steps = min(args.steps, 10)
@@ -396,7 +405,7 @@ def run_stream(args):
               "dtype": "u8/i16->i32" if W["bpc"] == 8 else "u16/i32", "data": "synthetic",
               "config": {"workload": wl, "l2": "every frame's records and pictures are fresh (uploaded per frame)",
                          "value_is": "pixels / time inside the per-frame device jobs (H2D of records + kernels + D2H of the picture), host clock",
-                         "records_per_frame": st["records"] // max(st["frames"], 1)},
+                         "records_per_frame": {k: st[k] // max(st["frames"], 1) for k in ("intra_tx", "pred", "comp", "warp", "blend", "itx")}},
               "roofline": {"bound": "hbm", "kernel": "frame job (intra reconstruction + deblock + CDEF + LR, incl. PCIe copies)",
                            "achieved": alg / (dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": alg / (dev_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": src},
@@ -741,7 +750,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k10_full", "8k10_full", "1080p8_intra", "itx8x8", "stream1080p8", "stream4k10"])
+    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k10_full", "8k10_full", "1080p8_intra", "itx8x8"] + sorted(STREAM_WORKLOADS))
     args = ap.parse_args()
     if args.workload in STREAM_WORKLOADS:
         return run_stream(args)

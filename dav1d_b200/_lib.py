@@ -149,7 +149,8 @@ class FrameJob(C.Structure):
                 ("d_cfused", C.c_void_p), ("d_cfused2", C.c_void_p), ("n_cfused", C.c_int32), ("n_cfused2", C.c_int32),
                 ("d_expand", C.c_void_p), ("n_expand", C.c_int32), ("pad8", C.c_int32), ("d_ccoef", C.c_void_p),
                 ("coef_bytes", C.c_uint64),
-                ("run_fg", C.c_int32), ("pad5", C.c_int32), ("fg", FgFrame)]
+                ("run_fg", C.c_int32), ("pad5", C.c_int32), ("fg", FgFrame),
+                ("d_blend2", C.c_void_p), ("n_blend2", C.c_int32), ("pad9", C.c_int32)]
 
 
 class Xfer(C.Structure):

@@ -33,6 +33,7 @@ static int frame_phase_recon(const B200FrameJob *j, void *stream, void **fg_side
     if ((r = b200_mc_comp_batch(bd, &j->mc, j->d_comp, j->n_comp, stream))) return r;
     if ((r = b200_mc_comp_batch(bd, &j->mc, j->d_comp2, j->n_comp2, stream))) return r;
     if ((r = b200_mc_blend_batch(bd, &j->mc, j->d_blend, j->n_blend, stream))) return r;
+    if ((r = b200_mc_blend_batch(bd, &j->mc, j->d_blend2, j->n_blend2, stream))) return r;
     if ((r = b200_itx_add_frame(bd, (const void *const *)j->d_itx, j->n_itx, j->d_coef, j->mc.dst, j->itx_stride,
                                 j->zero_coefs, stream)))
         return r;

@@ -282,11 +282,12 @@ mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, const __gri
     const int rs = fr.ref_stride[pl], rw = fr.ref_w[pl], rh = fr.ref_h[pl];
     const int ib = inter_bits<HBD>(bdmax);
     const int bias = HBD ? 8192 : 0;
-    const bool is_prep = b.op != 0;
+    const bool is_prep = b.op == 1;
     McTaps t;
     mc_taps(t, b.filter2d, b.mx, b.my, w, h);
-    pixel *const dpx = (pixel *)fr.dst;
-    const int ds = fr.dst_stride[pl];
+    // op 2: "put" into the dense pixel scratch (pitch w) that the blend stages read (OBMC neighbour predictions)
+    pixel *const dpx = b.op == 2 ? (pixel *)fr.px_tmp : (pixel *)fr.dst;
+    const int ds = b.op == 2 ? w : fr.dst_stride[pl];
     for (int sy0 = 0; sy0 < h; sy0 += kMcSub)
         for (int sx0 = 0; sx0 < w; sx0 += kMcSub)
             mc_subblock<HBD>(sm, lane, ref, rs, rw, rh, b.src_x + sx0, b.src_y + sy0, imin(kMcSub, w - sx0), imin(kMcSub, h - sy0),

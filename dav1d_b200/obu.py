@@ -226,7 +226,7 @@ def _poc_diff(bits, a, b):
 
 def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None,
                 lf=None, cdef=True, restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0,
-                refresh=None, switchable_motion_mode=0, warped_motion_seq=0, comp_refs=1):
+                refresh=None, switchable_motion_mode=0, warped_motion_seq=0, comp_refs=1, allow_warped_motion=0):
     """One shown inter frame (OBU_FRAME), primary_ref_frame = NONE. `ref_hints` = order hints held by the 8 reference slots
     (updated in place for the slots this frame refreshes). Global motion is identity."""
     bits = 7
@@ -278,7 +278,7 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
         if allowed:
             b.f(1, int(rng.integers(0, 2)))  # skip_mode_present
     if warped_motion_seq:
-        b.f(1, 0)                            # allow_warped_motion
+        b.f(1, allow_warped_motion)
     b.f(1, int(rng.integers(0, 2)))          # reduced_tx_set
     for _ in range(7):
         b.f(1, 0)                            # is_global: identity
@@ -290,12 +290,15 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
     return obu(OBU_FRAME, _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_bytes_per_sb64))
 
 
-def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, **kw):
+def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, **kw):
     """Temporal units: one key frame, then n_frames - 1 inter frames (single and compound references incl. wedge /
     difference-weighted masks and distance weights, switchable interpolation filters, variable transform trees, intra
-    blocks; no OBMC / warped motion / inter-intra, identity global motion)."""
+    blocks; identity global motion, no inter-intra). motion_mods=1 additionally enables the per-block motion mode:
+    overlapped block motion compensation and locally warped motion."""
     rng = np.random.default_rng(seed)
-    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=0, warped_motion=0)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=0, warped_motion=motion_modes)
+    if motion_modes:
+        kw = dict(kw, switchable_motion_mode=1, warped_motion_seq=1, allow_warped_motion=1)
     hints = [0] * 8
     tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows))]
     for i in range(1, n_frames):

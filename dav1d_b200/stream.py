@@ -15,7 +15,9 @@ HOOKED_SO = os.path.join(ROOT, "integration", "_ref", "libdav1d_b200.so")
 
 class HookStats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("records", C.c_uint64), ("coefs", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64), ("device_ms", C.c_double)]
+                ("d2h_bytes", C.c_uint64), ("device_ms", C.c_double), ("intra_tx", C.c_uint64), ("pred", C.c_uint64),
+                ("comp", C.c_uint64), ("warp", C.c_uint64), ("blend", C.c_uint64), ("itx", C.c_uint64),
+                ("inter_frames", C.c_uint64), ("host_prep_ms", C.c_double)]
 
 
 def build_hooked(verbose=False):

@@ -117,17 +117,17 @@ typedef struct B200McFrame {
     int32_t dst_stride[3];
     int16_t *tmp;                /* device int16 scratch: prep outputs / compound inputs */
     uint8_t *mask;               /* device uint8 scratch: w_mask outputs, mask / blend inputs */
-    const void *px_tmp;          /* device pixel scratch: blend inputs (OBMC / inter-intra predictions) */
+    const void *px_tmp;          /* device pixel scratch: blend inputs (OBMC / inter-intra predictions); written by B200McBlock op 2 */
 } B200McFrame;
 
 /* one prediction block: dav1d's mc[filter2d] (op 0, "put") or mct[filter2d] (op 1, "prep") */
 typedef struct B200McBlock {
-    uint32_t dst_off;            /* put: pixel offset in dst; prep: int16 offset in tmp (dense, pitch w) */
+    uint32_t dst_off;            /* put: pixel offset in dst (op 2: in px_tmp); prep: int16 offset in tmp (dense, pitch w) */
     int32_t src_x, src_y;        /* integer sample position of the block's top-left in the ref plane */
     uint8_t w, h;                /* w in {2,4,..,128}; 2 <= h <= 128 */
     uint8_t mx, my;              /* subpel phase 0..15 */
     uint8_t filter2d;
-    uint8_t op;                  /* 0 put, 1 prep */
+    uint8_t op;                  /* 0 put, 1 prep, 2 put into px_tmp (dst_off = pixel offset there, dense, pitch w) */
     uint8_t plane;
     uint8_t ref;
 } B200McBlock;
@@ -536,7 +536,7 @@ B200_API int b200_coef_expand(int bitdepth_max, const B200CoefBlock *d_blocks, i
  * records of pass 2 (prediction blocks, compound / blend / warp records, transform blocks bucketed by
  * transform size with their coefficient stream) and the post-filter parameters, all already in HBM.
  * b200_frame_run enqueues, on `stream`:
- *    prediction (put/prep) -> warp -> compound -> compound stage 2 -> blend -> inverse transforms (one launch per size)
+ *    prediction (put/prep) -> warp -> compound -> compound stage 2 -> blend -> blend stage 2 -> inverse transforms (one launch per size)
  *    -> deblock (2 sweeps, in place on the reconstructed picture) -> CDEF (out of place) -> loop
  *    restoration (out of place) -> film grain (out of place, into the display copy).
  * Stages whose counts / run_* flags are zero are skipped. Picture chaining is the caller's: typically
@@ -575,6 +575,8 @@ typedef struct B200FrameJob {
     int32_t run_fg, pad5;        /* film grain on the output copy (fg.in = lr.dst typically); the grain LUT preparation
                                     runs on an internal side stream concurrently with reconstruction */
     B200FgFrame fg;
+    const B200BlendBlock *d_blend2;      /* second blend stage, after d_blend: OBMC blends the predictions of the blocks above */
+    int32_t n_blend2, pad9;              /* (blend_h, stage 1) and then those of the blocks to the left (blend_v, stage 2) */
 } B200FrameJob;
 B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
 /* n independent jobs of the same bit depth on one stream: reconstruction of every job, then ONE batched intra launch

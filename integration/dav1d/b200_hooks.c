@@ -16,6 +16,7 @@ static int g_be_ok;
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static HookFrame g_frames[64];
 static B200HookStats g_stats;
+static uint64_t g_clock;            /* LRU stamps of the frame-context and picture tables */
 
 API int b200hook_set_backend(const char *path)
 {
@@ -111,9 +112,18 @@ HookRefPic *b200hook_refpic(const void *key, size_t bytes, int create)
     pthread_mutex_lock(&g_lock);
     for (int i = 0; i < 64 && !r; i++)
         if (g_refs[i].key == key) r = &g_refs[i];
-    if (!r && create)
+    if (!r && create) {
         for (int i = 0; i < 64 && !r; i++)
             if (!g_refs[i].key) { r = &g_refs[i]; memset(r, 0, sizeof(*r)); r->key = key; }
+        if (!r) {
+            /* host pictures of closed decoders never come back: recycle the least recently used entry (the live set —
+             * 8 reference slots + frames in flight + pictures waiting for output — is far smaller than the table) */
+            for (int i = 0; i < 64; i++)
+                if (g_refs[i].ready && (!r || g_refs[i].last_use < r->last_use)) r = &g_refs[i];
+            if (r) { r->key = key; r->ready = 0; }
+        }
+    }
+    if (r) r->last_use = ++g_clock;
     if (r && create && r->bytes < bytes) {
         if (r->dev) be->dev_free(r->dev);
         r->dev = be->dev_alloc(bytes);
@@ -137,9 +147,11 @@ void b200hook_refpic_wait(HookRefPic *r)
     pthread_mutex_unlock(&g_lock);
 }
 
+/* Frame contexts come and go with dav1d_open / dav1d_close (there is no hook for either): a context that is not in the
+ * table takes over the least recently used idle slot, together with that slot's buffers. */
 HookFrame *b200hook_frame(const void *key)
 {
-    HookFrame *r = NULL;
+    HookFrame *r = NULL, *lru = NULL;
     pthread_mutex_lock(&g_lock);
     for (int i = 0; i < 64 && !r; i++)
         if (g_frames[i].key == key) r = &g_frames[i];
@@ -150,6 +162,16 @@ HookFrame *b200hook_frame(const void *key)
             pthread_mutex_init(&r->lock, NULL);
             r->key = key;
         }
+    if (!r) {
+        for (int i = 0; i < 64; i++) {
+            HookFrame *const h = &g_frames[i];
+            if (h->started || h->tile_sbrows_done) continue;          /* a frame is being emitted into this slot */
+            if (!lru || h->last_use < lru->last_use) lru = h;
+        }
+        if (lru) { lru->key = key; lru->unsupported = 0; r = lru; }
+        else fprintf(stderr, "b200hook: more than 64 frame contexts in flight\n");
+    }
+    if (r) r->last_use = ++g_clock;
     pthread_mutex_unlock(&g_lock);
     return r;
 }
@@ -210,11 +232,14 @@ int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int
     return n_waves;
 }
 
-void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms)
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[7], double prep_ms)
 {
     pthread_mutex_lock(&g_lock);
     g_stats.frames++; g_stats.records += records; g_stats.coefs += coefs;
     g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += d2h; g_stats.device_ms += ms;
+    g_stats.intra_tx += kinds[0]; g_stats.pred += kinds[1]; g_stats.comp += kinds[2]; g_stats.warp += kinds[3];
+    g_stats.host_prep_ms += prep_ms;
+    g_stats.blend += kinds[4]; g_stats.itx += kinds[5]; g_stats.inter_frames += kinds[6];
     pthread_mutex_unlock(&g_lock);
 }
 
@@ -239,6 +264,7 @@ API void b200hook_release(void)
         b200hook_buf_free(&h->pred); b200hook_buf_free(&h->comp); b200hook_buf_free(&h->comp2);
         for (int t = 0; t < 19; t++) b200hook_buf_free(&h->itx[t]);
         b200hook_buf_free(&h->tmp16); b200hook_buf_free(&h->cmask); b200hook_buf_free(&h->done_init);
+        b200hook_buf_free(&h->warp); b200hook_buf_free(&h->blend); b200hook_buf_free(&h->blend2); b200hook_buf_free(&h->pxtmp);
         if (h->stream && g_be_ok) g_be.stream_destroy(h->stream);
         pthread_mutex_destroy(&h->lock);
         memset(h, 0, sizeof(*h));

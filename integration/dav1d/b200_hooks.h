@@ -39,8 +39,8 @@ void b200hook_buf_free(HookBuf *b);
 typedef struct HookFrame {
     const void *key;               /* the Dav1dFrameContext this slot serves */
     pthread_mutex_t lock;
-    int n_tx;                      /* B200IntraTx records emitted so far (tx.host) */
-    size_t n_coef;                 /* coefficients staged so far (coef.host), in elements */
+    int n_tx, cap_tx;              /* B200IntraTx records emitted so far (tx.host); slots are taken atomically */
+    size_t n_coef, cap_coef;       /* coefficients staged so far (coef.host), in elements; taken atomically */
     int tile_sbrows_done;          /* completed pass-2 tile superblock rows of the current frame */
     int unsupported;               /* a block used a tool the emitters do not translate yet */
     HookBuf tx, tx_sorted, coef, mask, level, lr_mask, pic[3], scratch;
@@ -49,9 +49,11 @@ typedef struct HookFrame {
      * wedge tables at its head, difference-weighted masks behind them) and the initial done map of the intra kernel
      * (cells of inter blocks are "done" before it starts) */
     HookBuf pred, comp, comp2, itx[19], tmp16, cmask, done_init;
-    int n_pred, n_comp, n_comp2, n_itx[19];
-    size_t n_tmp16, n_cmask;
+    HookBuf warp, blend, blend2, pxtmp;      /* warped-motion 8x8 blocks; OBMC: blend_h stage, blend_v stage, pixel scratch (device only) */
+    int n_pred, n_comp, n_comp2, n_itx[19], n_warp, n_blend, n_blend2;
+    size_t n_tmp16, n_cmask, n_pxtmp;
     int started, is_inter;
+    uint64_t last_use;             /* slot recycling: least recently used idle slot is taken over (its buffers are kept) */
     void *stream;
     /* statistics */
     uint64_t frames, records;
@@ -63,14 +65,18 @@ void *b200hook_append(HookBuf *b, int *n, size_t elem);
 
 /* device pictures that outlive their frame context: every decoded picture, keyed by the host picture's data[0]
  * (dav1d recycles a host buffer only when no reference to it is left, so a key is reused only for a dead picture) */
-typedef struct HookRefPic { const void *key; void *dev; size_t bytes; int ready; } HookRefPic;
+typedef struct HookRefPic { const void *key; void *dev; size_t bytes; int ready; uint64_t last_use; } HookRefPic;
 HookRefPic *b200hook_refpic(const void *key, size_t bytes, int create);
 void b200hook_refpic_set_ready(HookRefPic *r, int ready);
 void b200hook_refpic_wait(HookRefPic *r);
 void b200hook_job_enter(void);
 void b200hook_job_leave(void);
 
-typedef struct B200HookStats { uint64_t frames, records, coefs, h2d_bytes, d2h_bytes; double device_ms; } B200HookStats;
-void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms);
+typedef struct B200HookStats {
+    uint64_t frames, records, coefs, h2d_bytes, d2h_bytes; double device_ms;
+    uint64_t intra_tx, pred, comp, warp, blend, itx, inter_frames;      /* records by kind */
+    double host_prep_ms;            /* frame completion on the host before the job: mask fix-ups, wavefront sort, staging */
+} B200HookStats;
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[7], double prep_ms);
 
 #endif

@@ -16,8 +16,10 @@
  *   recon_b_inter   -> B200McBlock (put / prep) per prediction incl. the shared 4x4 chroma of sub-8x8 blocks,
  *                      B200CompBlock per compound combination (avg, distance weights, wedge and difference-weighted
  *                      masks), one B200ItxBlock per leaf of the transform tree (reference src/recon_tmpl.c:1557-1985)
- * Not translated yet (the frame fails loudly, there is no CPU fallback): palette, intra block copy, OBMC, warped /
- * global motion, inter-intra, scaled references.
+ *                      B200WarpBlock per 8x8 of a warped block (local and global motion), OBMC as neighbour predictions
+ *                      into a pixel scratch + two ordered blend stages
+ * Not translated yet (the frame fails loudly, there is no CPU fallback): palette, intra block copy, inter-intra,
+ * scaled references.
  */
 #include "config.h"
 #include <stdio.h>
@@ -60,14 +62,30 @@ static void bitfn(pic_geom)(const Dav1dFrameContext *const f, PicGeom *const g)
 /* first pass-2 hook call of a frame: its output picture (keyed by the host buffer) is not valid any more / yet */
 static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *const f)
 {
-    if (hf->started) return;
-    hf->started = 1;
-    hf->n_cmask = (sizeof(dav1d_masks) + 63) & ~(size_t)63;      /* dav1d's wedge tables sit at the head of the mask buffer */
-    PicGeom g;
-    bitfn(pic_geom)(f, &g);
-    HookRefPic *const out = b200hook_refpic(f->cur.data[0], g.bytes, 1);
-    if (out) b200hook_refpic_set_ready(out, 0);
-    else hf->unsupported |= 8;
+    if (__atomic_load_n(&hf->started, __ATOMIC_ACQUIRE)) return;
+    pthread_mutex_lock(&hf->lock);
+    if (!hf->started) {
+        hf->n_cmask = (sizeof(dav1d_masks) + 63) & ~(size_t)63;      /* dav1d's wedge tables sit at the head of the mask buffer */
+        PicGeom g;
+        bitfn(pic_geom)(f, &g);
+        HookRefPic *const out = b200hook_refpic(f->cur.data[0], g.bytes, 1);
+        if (out) b200hook_refpic_set_ready(out, 0);
+        else __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
+        /* intra records and coefficients are appended without a lock by every tile thread of the frame (slots are taken
+         * with atomic counters), so their buffers are sized for the worst case up front: one record per 4x4 cell of each
+         * plane, 16 coefficients per cell, over the 128-aligned frame area */
+        const int ss_ver = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+        const size_t aw4 = (f->bw + 31) & ~31, ah4 = (f->bh + 31) & ~31;
+        const size_t cells = aw4 * ah4 + (f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I400 ? 2 * ((aw4 >> ss_hor) * (ah4 >> ss_ver)) : 0);
+        hf->cap_tx = (int)cells; hf->cap_coef = cells * 16;
+        if (b200hook_buf_reserve(&hf->tx, cells * sizeof(B200IntraTx), 1, 0) ||
+            b200hook_buf_reserve(&hf->coef, cells * 16 * sizeof(coef), 1, 0)) {
+            __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
+            hf->cap_tx = 0; hf->cap_coef = 0;       /* nothing can be emitted: the frame fails when it completes */
+        }
+        __atomic_store_n(&hf->started, 1, __ATOMIC_RELEASE);
+    }
+    pthread_mutex_unlock(&hf->lock);
 }
 
 /* ---- one transform block -> one record ------------------------------------------------------------------ */
@@ -82,18 +100,19 @@ typedef struct TxCtx {
  * inverse transform would have: the buffer must be all zero for the next frame's pass 1) */
 static int bitfn(stage_coefs)(HookFrame *const hf, coef *const cf, const int n, uint32_t *const off)
 {
-    if (b200hook_buf_reserve(&hf->coef, (hf->n_coef + n) * sizeof(coef), 1, 1)) return -1;
-    memcpy((coef *)hf->coef.host + hf->n_coef, cf, n * sizeof(coef));
+    const size_t at = __atomic_fetch_add(&hf->n_coef, (size_t)n, __ATOMIC_RELAXED);
+    if (at + n > hf->cap_coef) return -1;
+    memcpy((coef *)hf->coef.host + at, cf, n * sizeof(coef));
     memset(cf, 0, n * sizeof(coef));
-    *off = (uint32_t)hf->n_coef;
-    hf->n_coef += n;
+    *off = (uint32_t)at;
     return 0;
 }
 
 static B200IntraTx *bitfn(new_record)(HookFrame *const hf)
 {
-    if (b200hook_buf_reserve(&hf->tx, (size_t)(hf->n_tx + 1) * sizeof(B200IntraTx), 1, 1)) return NULL;
-    B200IntraTx *const r = (B200IntraTx *)hf->tx.host + hf->n_tx++;
+    const int at = __atomic_fetch_add(&hf->n_tx, 1, __ATOMIC_RELAXED);
+    if (at >= hf->cap_tx) return NULL;
+    B200IntraTx *const r = (B200IntraTx *)hf->tx.host + at;
     memset(r, 0, sizeof(*r));
     return r;
 }
@@ -122,11 +141,11 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
     const Dav1dFrameContext *const f = t->f;
     Dav1dTileState *const ts = t->ts;
     HookFrame *const hf = b200hook_frame(f);
-    if (!hf) return;
+    if (!hf) { atomic_fetch_or(&((Dav1dFrameContext *)f)->task_thread.error, 1); return; }
     if (t->frame_thread.pass != 2) {
         /* single-pass decoding interleaves entropy decoding with reconstruction inside this hook; the B200 back end
          * needs dav1d's two-pass mode (n_threads >= 2 with max_frame_delay >= 2, reference src/lib.c get_num_threads) */
-        pthread_mutex_lock(&hf->lock); hf->unsupported |= 4; pthread_mutex_unlock(&hf->lock);
+        __atomic_fetch_or(&hf->unsupported, 4, __ATOMIC_RELAXED);
         return;
     }
     TxCtx c = { hf, t, b };
@@ -144,9 +163,8 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
     const int edge_filter_bit = f->seq_hdr->intra_edge_filter << 10;
     const int layout_shift = f->cur.p.layout - 1;      /* EDGE_I420_* >> (layout - 1) selects this layout's chroma flags */
 
-    pthread_mutex_lock(&hf->lock);
     bitfn(frame_started)(hf, f);
-    if (b->pal_sz[0] || (has_chroma && b->pal_sz[1])) hf->unsupported |= 1;
+    if (b->pal_sz[0] || (has_chroma && b->pal_sz[1])) __atomic_fetch_or(&hf->unsupported, 1, __ATOMIC_RELAXED);
     /* the reference walks a block in 64x64-luma chunks: luma transform blocks of the chunk, then its chroma */
     for (int iy = 0; iy < h4; iy += 16) {
         const int y_end = imin(h4, iy + 16), cy_end = imin(ch4, (iy + 16) >> ss_ver);
@@ -159,7 +177,7 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
             for (int y = iy; y < y_end; y += yt->h)
                 for (int x = ix; x < x_end; x += yt->w) {
                     B200IntraTx *const r = bitfn(new_record)(hf);
-                    if (!r) { hf->unsupported |= 8; goto out; }
+                    if (!r) { __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED); goto out; }
                     const int px = bx + x, py = by + y;
                     r->plane = 0; r->tx = b->tx;
                     r->x4 = px; r->y4 = py; r->xend4 = ts->tiling.col_end; r->yend4 = ts->tiling.row_end;
@@ -172,7 +190,7 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
                                (py > ts->tiling.row_start ? B200_INTRA_HAVE_TOP : 0) |
                                (((y > iy || !chunk_tr) && last_col) ? 0 : B200_INTRA_TOP_HAS_RIGHT) |
                                ((x > ix || (!chunk_bl && last_row)) ? 0 : B200_INTRA_LEFT_HAS_BOTTOM);
-                    if (bitfn(take_residual)(&c, r, yt, 0)) { hf->unsupported |= 8; goto out; }
+                    if (bitfn(take_residual)(&c, r, yt, 0)) { __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED); goto out; }
                 }
             if (!has_chroma) continue;
             /* ---- chroma ---- */
@@ -194,7 +212,7 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
                 for (int y = iy >> ss_ver; y < cy_end; y += ct->h)
                     for (int x = ix >> ss_hor; x < cx_end; x += ct->w) {
                         B200IntraTx *const r = bitfn(new_record)(hf);
-                        if (!r) { hf->unsupported |= 8; goto out; }
+                        if (!r) { __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED); goto out; }
                         /* luma-unit position the reference's t->bx / t->by would hold here */
                         const int lx = bx + (x << ss_hor), ly = by + (y << ss_ver);
                         const int px = lx >> ss_hor, py = ly >> ss_ver;
@@ -219,23 +237,22 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
                         if (!is_cfl || !r->cfl_alpha)      /* alpha == 0 is a plain DC_PRED with the usual edge rules */
                             r->flags |= (((y > (iy >> ss_ver) || !uv_tr) && last_col) ? 0 : B200_INTRA_TOP_HAS_RIGHT) |
                                         ((x > (ix >> ss_hor) || (!uv_bl && last_row)) ? 0 : B200_INTRA_LEFT_HAS_BOTTOM);
-                        if (bitfn(take_residual)(&c, r, ct, 1)) { hf->unsupported |= 8; goto out; }
+                        if (bitfn(take_residual)(&c, r, ct, 1)) { __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED); goto out; }
                     }
         }
     }
-out:
-    pthread_mutex_unlock(&hf->lock);
+out:;
 }
 
 /* ---- inter blocks (what dav1d_recon_b_inter does, reference src/recon_tmpl.c:1557-1985) -------------------- */
 /* one motion-compensated prediction: the arguments of the reference's mc() (:938-988), as a B200McBlock.
  * Source samples outside the reference plane are clamped by the kernel (= emu_edge). */
-static int bitfn(emit_mc)(HookFrame *const hf, const Dav1dFrameContext *const f, const int prep, const uint32_t dst_off,
+static int bitfn(emit_mc)(HookFrame *const hf, const Dav1dFrameContext *const f, const int op, const uint32_t dst_off,
                           const int bw4, const int bh4, const int bx, const int by, const int pl, const mv mv,
                           const int refidx, const enum Filter2d filter_2d)
 {
     const Dav1dThreadPicture *const refp = &f->refp[refidx];
-    if (refp->p.p.w != f->cur.p.w || refp->p.p.h != f->cur.p.h) { hf->unsupported |= 32; return 0; }   /* scaled reference */
+    if (refp->p.p.w != f->cur.p.w || refp->p.p.h != f->cur.p.h) { __atomic_fetch_or(&hf->unsupported, 32, __ATOMIC_RELAXED); return 0; }   /* scaled reference */
     const int ss_ver = !!pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
     const int ss_hor = !!pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
     const int h_mul = 4 >> ss_hor, v_mul = 4 >> ss_ver;
@@ -247,7 +264,88 @@ static int bitfn(emit_mc)(HookFrame *const hf, const Dav1dFrameContext *const f,
     r->src_y = by * v_mul + (mv.y >> (3 + ss_ver));
     r->w = bw4 * h_mul; r->h = bh4 * v_mul;
     r->mx = mx << !ss_hor; r->my = my << !ss_ver;
-    r->filter2d = filter_2d; r->op = prep; r->plane = pl; r->ref = refidx;
+    r->filter2d = filter_2d; r->op = op; r->plane = pl; r->ref = refidx;      /* op: 0 put, 1 prep, 2 put into the pixel scratch */
+    return 0;
+}
+
+/* warped motion: one B200WarpBlock per 8x8 of the block (warp_affine, :1115-1174); op 0 -> pixels at dst_off,
+ * op 1 -> int16 prediction at dst_off in tmp (pitch tmp_stride) */
+static int bitfn(emit_warp)(HookFrame *const hf, const Dav1dFrameContext *const f, const Dav1dTaskContext *const t, const int op,
+                            const uint32_t dst_off, const int pitch, const uint8_t *const b_dim, const int pl, const int refidx,
+                            const Dav1dWarpedMotionParams *const wmp)
+{
+    const Dav1dThreadPicture *const refp = &f->refp[refidx];
+    if (refp->p.p.w != f->cur.p.w || refp->p.p.h != f->cur.p.h) { __atomic_fetch_or(&hf->unsupported, 32, __ATOMIC_RELAXED); return 0; }
+    const int ss_ver = !!pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
+    const int ss_hor = !!pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    const int h_mul = 4 >> ss_hor, v_mul = 4 >> ss_ver;
+    const int32_t *const mat = wmp->matrix;
+    for (int y = 0; y < b_dim[1] * v_mul; y += 8) {
+        const int src_y = t->by * 4 + ((y + 4) << ss_ver);
+        const int64_t mat3_y = (int64_t)mat[3] * src_y + mat[0], mat5_y = (int64_t)mat[5] * src_y + mat[1];
+        for (int x = 0; x < b_dim[0] * h_mul; x += 8) {
+            const int src_x = t->bx * 4 + ((x + 4) << ss_hor);
+            const int64_t mvx = ((int64_t)mat[2] * src_x + mat3_y) >> ss_hor, mvy = ((int64_t)mat[4] * src_x + mat5_y) >> ss_ver;
+            B200WarpBlock *const r = b200hook_append(&hf->warp, &hf->n_warp, sizeof(*r));
+            if (!r) return -1;
+            r->dst_off = dst_off + (uint32_t)y * pitch + x;
+            r->src_x = (int)(mvx >> 16) - 4; r->src_y = (int)(mvy >> 16) - 4;
+            r->mx = (((int)mvx & 0xffff) - wmp->u.p.alpha * 4 - wmp->u.p.beta * 7) & ~0x3f;
+            r->my = (((int)mvy & 0xffff) - wmp->u.p.gamma * 4 - wmp->u.p.delta * 4) & ~0x3f;
+            for (int k = 0; k < 4; k++) r->abcd[k] = wmp->u.abcd[k];
+            r->tmp_stride = pitch; r->op = op; r->plane = pl; r->ref = refidx;
+        }
+    }
+    return 0;
+}
+
+/* overlapped block motion compensation (obmc, :1052-1113): the block's top rows are blended with predictions made with
+ * the motion of the blocks above (blend_h, first blend stage), then its left columns with those of the blocks to the left
+ * (blend_v, second stage: the two overlap in the top-left corner and the order matters) */
+static int bitfn(emit_obmc)(HookFrame *const hf, const Dav1dFrameContext *const f, const Dav1dTaskContext *const t,
+                            const uint32_t dst_off, const int dst_stride, const uint8_t *const b_dim, const int pl,
+                            const int bx4, const int by4, const int w4, const int h4)
+{
+    refmvs_block *const *const r = &t->rt.r[(t->by & 31) + 5];
+    const int ss_ver = !!pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
+    const int ss_hor = !!pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    const int h_mul = 4 >> ss_hor, v_mul = 4 >> ss_ver;
+    if (t->by > t->ts->tiling.row_start && (!pl || b_dim[0] * h_mul + b_dim[1] * v_mul >= 16))
+        for (int i = 0, x = 0; x < w4 && i < imin(b_dim[2], 4); ) {
+            const refmvs_block *const a_r = &r[-1][t->bx + x + 1];          /* odd column: the block covering it */
+            const int step4 = iclip(dav1d_block_dimensions[a_r->bs][0], 2, 16);
+            if (a_r->ref.ref[0] > 0) {
+                const int ow4 = imin(step4, b_dim[0]), oh4 = imin(b_dim[1], 16) >> 1;
+                const uint32_t scratch = (uint32_t)hf->n_pxtmp;
+                hf->n_pxtmp += (size_t)(ow4 * h_mul) * (((oh4 * 3 + 3) >> 2) * v_mul);
+                if (bitfn(emit_mc)(hf, f, 2, scratch, ow4, (oh4 * 3 + 3) >> 2, t->bx + x, t->by, pl, a_r->mv.mv[0], a_r->ref.ref[0] - 1,
+                                   dav1d_filter_2d[t->a->filter[1][bx4 + x + 1]][t->a->filter[0][bx4 + x + 1]])) return -1;
+                B200BlendBlock *const bl = b200hook_append(&hf->blend, &hf->n_blend, sizeof(*bl));
+                if (!bl) return -1;
+                bl->dst_off = dst_off + x * h_mul; bl->tmp_off = scratch;
+                bl->w = h_mul * ow4; bl->h = v_mul * oh4; bl->op = B200_BLEND_H; bl->plane = pl;
+                i++;
+            }
+            x += step4;
+        }
+    if (t->bx > t->ts->tiling.col_start)
+        for (int i = 0, y = 0; y < h4 && i < imin(b_dim[3], 4); ) {
+            const refmvs_block *const l_r = &r[y + 1][t->bx - 1];
+            const int step4 = iclip(dav1d_block_dimensions[l_r->bs][1], 2, 16);
+            if (l_r->ref.ref[0] > 0) {
+                const int ow4 = imin(b_dim[0], 16) >> 1, oh4 = imin(step4, b_dim[1]);
+                const uint32_t scratch = (uint32_t)hf->n_pxtmp;
+                hf->n_pxtmp += (size_t)(ow4 * h_mul) * (oh4 * v_mul);
+                if (bitfn(emit_mc)(hf, f, 2, scratch, ow4, oh4, t->bx, t->by + y, pl, l_r->mv.mv[0], l_r->ref.ref[0] - 1,
+                                   dav1d_filter_2d[t->l.filter[1][by4 + y + 1]][t->l.filter[0][by4 + y + 1]])) return -1;
+                B200BlendBlock *const bl = b200hook_append(&hf->blend2, &hf->n_blend2, sizeof(*bl));
+                if (!bl) return -1;
+                bl->dst_off = dst_off + (uint32_t)(y * v_mul) * dst_stride; bl->tmp_off = scratch;
+                bl->w = h_mul * ow4; bl->h = v_mul * oh4; bl->op = B200_BLEND_V; bl->plane = pl;
+                i++;
+            }
+            y += step4;
+        }
     return 0;
 }
 
@@ -289,9 +387,9 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
 {
     const Dav1dFrameContext *const f = t->f;
     HookFrame *const hf = b200hook_frame(f);
-    if (!hf) return -1;
+    if (!hf) { atomic_fetch_or(&((Dav1dFrameContext *)f)->task_thread.error, 1); return -1; }
     if (t->frame_thread.pass != 2) {
-        pthread_mutex_lock(&hf->lock); hf->unsupported |= 4; pthread_mutex_unlock(&hf->lock);
+        __atomic_fetch_or(&hf->unsupported, 4, __ATOMIC_RELAXED);
         return -1;
     }
     TxCtx c = { hf, t, b };
@@ -311,18 +409,22 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
     const uint32_t uvrel = (uint32_t)(4 * (by >> ss_ver)) * g->stride[1] + 4 * (bx >> ss_hor);   /* + g->off[pl] */
     int rc = -1;
 
-    pthread_mutex_lock(&hf->lock);
     bitfn(frame_started)(hf, f);
+    pthread_mutex_lock(&hf->lock);          /* protects the inter record lists; intra records / coefficients are lock-free */
     hf->is_inter = 1;
-    if (IS_KEY_OR_INTRA(f->frame_hdr)) { hf->unsupported |= 64; goto out; }          /* intra block copy */
+    if (IS_KEY_OR_INTRA(f->frame_hdr)) { __atomic_fetch_or(&hf->unsupported, 64, __ATOMIC_RELAXED); goto out; }          /* intra block copy */
     if (b->comp_type == COMP_INTER_NONE) {
         const enum Filter2d filter_2d = b->filter2d;
         const int warp = (b->inter_mode == GLOBALMV && f->gmv_warp_allowed[b->ref[0]]) ||
                          (b->motion_mode == MM_WARP && t->warpmv.type > DAV1D_WM_TYPE_TRANSLATION);
-        if (warp && (imin(bw4, bh4) > 1 || imin(cbw4, cbh4) > 1)) hf->unsupported |= 16;
-        if (b->motion_mode == MM_OBMC) hf->unsupported |= 128;
-        if (b->interintra_type) hf->unsupported |= 256;
-        if (bitfn(emit_mc)(hf, f, 0, ydst, bw4, bh4, bx, by, 0, b->mv[0], b->ref[0], filter_2d)) goto out;
+        const Dav1dWarpedMotionParams *const wmp = b->motion_mode == MM_WARP ? &t->warpmv : &f->frame_hdr->gmv[b->ref[0]];
+        if (b->interintra_type) __atomic_fetch_or(&hf->unsupported, 256, __ATOMIC_RELAXED);
+        if (warp && imin(bw4, bh4) > 1) {
+            if (bitfn(emit_warp)(hf, f, t, 0, ydst, g->stride[0], dim, 0, b->ref[0], wmp)) goto out;
+        } else {
+            if (bitfn(emit_mc)(hf, f, 0, ydst, bw4, bh4, bx, by, 0, b->mv[0], b->ref[0], filter_2d)) goto out;
+            if (b->motion_mode == MM_OBMC && bitfn(emit_obmc)(hf, f, t, ydst, g->stride[0], dim, 0, bx4, by4, w4, h4)) goto out;
+        }
         if (has_chroma) {
             /* a 4-wide / 4-tall luma block shares its 4x4 chroma block with its left / top neighbours: each quarter is
              * predicted with the motion of the luma block above it, if all of them are inter (:1652-1724) */
@@ -359,16 +461,20 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
                 }
                 for (int pl = 1; pl <= 2; pl++)
                     if (bitfn(emit_mc)(hf, f, 0, g->off[pl] + uvrel + h_off + v_off, bw4, bh4, bx, by, pl, b->mv[0], b->ref[0], filter_2d)) goto out;
-            } else {
+            } else if (warp && imin(cbw4, cbh4) > 1) {
                 for (int pl = 1; pl <= 2; pl++)
+                    if (bitfn(emit_warp)(hf, f, t, 0, g->off[pl] + uvrel, g->stride[1], dim, pl, b->ref[0], wmp)) goto out;
+            } else {
+                for (int pl = 1; pl <= 2; pl++) {
                     if (bitfn(emit_mc)(hf, f, 0, g->off[pl] + uvrel, bw4 << (bw4 == ss_hor), bh4 << (bh4 == ss_ver),
                                        bx & ~ss_hor, by & ~ss_ver, pl, b->mv[0], b->ref[0], filter_2d)) goto out;
+                    if (b->motion_mode == MM_OBMC && bitfn(emit_obmc)(hf, f, t, g->off[pl] + uvrel, g->stride[1], dim, pl, bx4, by4, w4, h4)) goto out;
+                }
             }
         }
     } else {
         /* compound: two int16 predictions per plane, then avg / w_avg / mask / w_mask (:1782-1866) */
         const enum Filter2d filter_2d = b->filter2d;
-        if (b->inter_mode == GLOBALMV_GLOBALMV && (f->gmv_warp_allowed[b->ref[0]] || f->gmv_warp_allowed[b->ref[1]])) hf->unsupported |= 16;
         uint32_t mask_off = 0;          /* luma mask, then the mask the chroma planes read */
         for (int pl = 0; pl < (has_chroma ? 3 : 1); pl++) {
             const int pw = pl ? bw4 * 4 >> ss_hor : bw4 * 4, ph = pl ? bh4 * 4 >> ss_ver : bh4 * 4;
@@ -376,7 +482,9 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
             for (int i = 0; i < 2; i++) {
                 tmp_off[i] = (uint32_t)hf->n_tmp16;
                 hf->n_tmp16 += (size_t)pw * ph;
-                if (bitfn(emit_mc)(hf, f, 1, tmp_off[i], bw4, bh4, bx, by, pl, b->mv[i], b->ref[i], filter_2d)) goto out;
+                if (b->inter_mode == GLOBALMV_GLOBALMV && f->gmv_warp_allowed[b->ref[i]] && (!pl || imin(cbw4, cbh4) > 1)) {
+                    if (bitfn(emit_warp)(hf, f, t, 1, tmp_off[i], pw, dim, pl, b->ref[i], &f->frame_hdr->gmv[b->ref[i]])) goto out;
+                } else if (bitfn(emit_mc)(hf, f, 1, tmp_off[i], bw4, bh4, bx, by, pl, b->mv[i], b->ref[i], filter_2d)) goto out;
             }
             const int seg = b->comp_type == COMP_INTER_SEG, wedge = b->comp_type == COMP_INTER_WEDGE;
             /* chroma of a difference-weighted block reads the mask its luma block writes: second compound stage */
@@ -432,7 +540,7 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
     }
     rc = 0;
 out:
-    if (rc) hf->unsupported |= 8;
+    if (rc) __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
     pthread_mutex_unlock(&hf->lock);
     return 0;       /* problems are reported when the frame completes (the whole frame fails, loudly) */
 }
@@ -496,6 +604,7 @@ static void bitfn(fix_tile_edges)(const Dav1dFrameContext *const f, Av1Filter *c
 
 static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const f)
 {
+    const double t_enter = bitfn(now_ms)();
     const B200Backend *const be = b200hook_backend();
     if (!be) return -1;
     if (hf->unsupported) {
@@ -516,10 +625,9 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     for (int k = 0; k < 3; k++)
         if (b200hook_buf_reserve(&hf->pic[k], g.bytes, 0, 0)) return -1;
     if (b200hook_buf_reserve(&hf->mask, mask_bytes, 1, 0) || b200hook_buf_reserve(&hf->level, level_bytes, 1, 0) ||
-        b200hook_buf_reserve(&hf->lr_mask, lr_bytes, 1, 0) ||
-        b200hook_buf_reserve(&hf->tx, (size_t)imax(hf->n_tx, 1) * sizeof(B200IntraTx), 1, 1) ||
-        b200hook_buf_reserve(&hf->coef, (hf->n_coef + 1) * sizeof(coef), 1, 1))
+        b200hook_buf_reserve(&hf->lr_mask, lr_bytes, 1, 0))
         return -1;
+    if (hf->n_tx > hf->cap_tx || hf->n_coef > hf->cap_coef) { fprintf(stderr, "b200hook: record buffers overflowed\n"); return -1; }
     memcpy(hf->mask.host, f->lf.mask, mask_bytes);
     bitfn(fix_tile_edges)(f, (Av1Filter *)hf->mask.host);
     memcpy(hf->level.host, f->lf.level, level_bytes);
@@ -561,13 +669,21 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
             b200hook_buf_reserve(&hf->cmask, hf->n_cmask + 64, 1, 0) ||
             b200hook_buf_reserve(&hf->pred, (size_t)imax(hf->n_pred, 1) * sizeof(B200McBlock), 1, 1) ||
             b200hook_buf_reserve(&hf->comp, (size_t)imax(hf->n_comp, 1) * sizeof(B200CompBlock), 1, 1) ||
-            b200hook_buf_reserve(&hf->comp2, (size_t)imax(hf->n_comp2, 1) * sizeof(B200CompBlock), 1, 1))
+            b200hook_buf_reserve(&hf->comp2, (size_t)imax(hf->n_comp2, 1) * sizeof(B200CompBlock), 1, 1) ||
+            b200hook_buf_reserve(&hf->warp, (size_t)imax(hf->n_warp, 1) * sizeof(B200WarpBlock), 1, 1) ||
+            b200hook_buf_reserve(&hf->blend, (size_t)imax(hf->n_blend, 1) * sizeof(B200BlendBlock), 1, 1) ||
+            b200hook_buf_reserve(&hf->blend2, (size_t)imax(hf->n_blend2, 1) * sizeof(B200BlendBlock), 1, 1) ||
+            b200hook_buf_reserve(&hf->pxtmp, (hf->n_pxtmp + 1) * sizeof(pixel), 0, 0))
             return -1;
         memcpy(hf->cmask.host, &dav1d_masks, sizeof(dav1d_masks));
         j.mc.tmp = (int16_t *)hf->tmp16.dev; j.mc.mask = (uint8_t *)hf->cmask.dev;
         j.d_pred = (const B200McBlock *)hf->pred.dev; j.n_pred = hf->n_pred;
         j.d_comp = (const B200CompBlock *)hf->comp.dev; j.n_comp = hf->n_comp;
         j.d_comp2 = (const B200CompBlock *)hf->comp2.dev; j.n_comp2 = hf->n_comp2;
+        j.mc.px_tmp = hf->pxtmp.dev;
+        j.d_warp = (const B200WarpBlock *)hf->warp.dev; j.n_warp = hf->n_warp;
+        j.d_blend = (const B200BlendBlock *)hf->blend.dev; j.n_blend = hf->n_blend;
+        j.d_blend2 = (const B200BlendBlock *)hf->blend2.dev; j.n_blend2 = hf->n_blend2;
         for (int t = 0; t < N_RECT_TX_SIZES; t++) {
             if (!hf->n_itx[t]) continue;
             j.d_itx[t] = (const B200ItxBlock *)hf->itx[t].dev; j.n_itx[t] = hf->n_itx[t];
@@ -657,6 +773,9 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         UP(hf->pred, (size_t)hf->n_pred * sizeof(B200McBlock));
         UP(hf->comp, (size_t)hf->n_comp * sizeof(B200CompBlock));
         UP(hf->comp2, (size_t)hf->n_comp2 * sizeof(B200CompBlock));
+        UP(hf->warp, (size_t)hf->n_warp * sizeof(B200WarpBlock));
+        UP(hf->blend, (size_t)hf->n_blend * sizeof(B200BlendBlock));
+        UP(hf->blend2, (size_t)hf->n_blend2 * sizeof(B200BlendBlock));
         UP(hf->cmask, sizeof(dav1d_masks));
         for (int t = 0; t < N_RECT_TX_SIZES; t++)
             if (hf->n_itx[t]) UP(hf->itx[t], (size_t)hf->n_itx[t] * sizeof(B200ItxBlock));
@@ -679,9 +798,13 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     const int r = be->frame_run_host(&j, up, n_up, down, 3, hf->stream);
     b200hook_job_leave();
     if (r) { fprintf(stderr, "b200hook: b200_frame_run_host failed (%d): %s\n", r, be->last_error()); return -1; }
-    uint64_t n_rec = (uint64_t)hf->n_tx + hf->n_pred + hf->n_comp + hf->n_comp2;
-    for (int t = 0; t < N_RECT_TX_SIZES; t++) n_rec += hf->n_itx[t];
-    b200hook_account(n_rec, hf->n_coef, h2d, d2h, bitfn(now_ms)() - t0);
+    uint64_t n_rec = (uint64_t)hf->n_tx + hf->n_pred + hf->n_comp + hf->n_comp2 + hf->n_warp + hf->n_blend + hf->n_blend2;
+    uint64_t n_itx = 0;
+    for (int t = 0; t < N_RECT_TX_SIZES; t++) n_itx += hf->n_itx[t];
+    n_rec += n_itx;
+    const uint64_t kinds[7] = { (uint64_t)hf->n_tx, (uint64_t)hf->n_pred, (uint64_t)hf->n_comp + hf->n_comp2, (uint64_t)hf->n_warp,
+                                (uint64_t)hf->n_blend + hf->n_blend2, n_itx, (uint64_t)inter };
+    b200hook_account(n_rec, hf->n_coef, h2d, d2h, bitfn(now_ms)() - t0, kinds, t0 - t_enter);
     return 0;
 }
 
@@ -691,9 +814,9 @@ void bitfn(b200hook_backup_ipred_edge)(Dav1dTaskContext *const t)
 {
     Dav1dFrameContext *const f = (Dav1dFrameContext *)t->f;
     HookFrame *const hf = b200hook_frame(f);
-    if (!hf) return;
+    if (!hf) { atomic_fetch_or(&f->task_thread.error, 1); return; }
     pthread_mutex_lock(&hf->lock);
-    if (t->frame_thread.pass != 2) hf->unsupported |= 4;
+    if (t->frame_thread.pass != 2) __atomic_fetch_or(&hf->unsupported, 4, __ATOMIC_RELAXED);
     const int total = f->sbh * f->frame_hdr->tiling.cols;
     if (++hf->tile_sbrows_done >= total) {
         if (bitfn(run_frame)(hf, f))
@@ -701,7 +824,8 @@ void bitfn(b200hook_backup_ipred_edge)(Dav1dTaskContext *const t)
         HookRefPic *const outp = b200hook_refpic(f->cur.data[0], 0, 0);
         if (outp) b200hook_refpic_set_ready(outp, 1);       /* also after a failure: nobody may wait for ever */
         hf->tile_sbrows_done = 0; hf->n_tx = 0; hf->n_coef = 0; hf->unsupported = 0;
-        hf->n_pred = hf->n_comp = hf->n_comp2 = 0; hf->n_tmp16 = 0; hf->started = 0; hf->is_inter = 0;
+        hf->n_pred = hf->n_comp = hf->n_comp2 = hf->n_warp = hf->n_blend = hf->n_blend2 = 0;
+        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->started = 0; hf->is_inter = 0;
         memset(hf->n_itx, 0, sizeof(hf->n_itx));
     }
     pthread_mutex_unlock(&hf->lock);

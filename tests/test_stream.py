@@ -31,6 +31,7 @@ def _check(dec, tus, expect_frames):
         d = np.nonzero(out0 != out1)[0]
         raise AssertionError("%d of %d output bytes differ, first at %d" % (len(d), len(out0), d[0]))
     st = dec.stats(reset=True)
+    dec.last_stats = st
     assert st["frames"] == expect_frames and st["records"] > 0
 
 
@@ -66,11 +67,13 @@ def test_stream_emu_matches_stock_dav1d(emu_decoder, case):
 
 
 CASES_INTER_CPU = [
-    # w, h, bpc, sb128, log2 tile cols, rows, frames (1 key frame + inter frames)
-    (320, 192, 8, 0, 0, 0, 3),
-    (320, 192, 10, 0, 1, 1, 4),
-    (640, 360, 8, 1, 1, 0, 3),
-    (330, 250, 8, 0, 0, 0, 5),
+    # w, h, bpc, sb128, log2 tile cols, rows, frames (1 key frame + inter frames), per-block motion modes (OBMC, local warp)
+    (320, 192, 8, 0, 0, 0, 3, 0),
+    (320, 192, 10, 0, 1, 1, 4, 0),
+    (640, 360, 8, 1, 1, 0, 3, 0),
+    (330, 250, 8, 0, 0, 0, 5, 1),
+    (320, 192, 10, 0, 1, 1, 4, 1),
+    (640, 360, 8, 1, 1, 0, 4, 1),
 ]
 
 
@@ -80,9 +83,23 @@ def test_inter_stream_emu_matches_stock_dav1d(emu_decoder, case):
     """key frame + inter frames: single and compound references (average, distance weights, wedge and
     difference-weighted masks), sub-8x8 chroma, variable transform trees, intra blocks inside inter frames,
     references kept in device memory across frames and frame contexts"""
-    w, h, bpc, sb128, lc, lr, nf = case
-    tus = obu.inter_stream(hash(case) & 0xffff, w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=lc, log2_rows=lr)
+    w, h, bpc, sb128, lc, lr, nf, mm = case
+    tus = obu.inter_stream(hash(case) & 0xffff, w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=lc, log2_rows=lr, motion_modes=mm)
     _check(emu_decoder, tus, nf)
+    if mm:
+        assert emu_decoder.last_stats["blend"] > 0, "no OBMC block in the stream"
+
+
+@pytest.mark.emu
+def test_stream_many_decoders_recycle_slots(emu_decoder):
+    """frame contexts and host pictures of closed decoders must not exhaust the hook's tables (each decode opens a new
+    dav1d context; the tables are recycled least-recently-used)"""
+    tus = obu.inter_stream(5, 192, 128, n_frames=5, motion_modes=1)
+    r0, _, out0 = _ref_decode(tus)
+    for _ in range(20):
+        r1, _, out1 = emu_decoder.decode(tus, n_threads=8, max_frame_delay=4)
+        assert r1 == r0 and np.array_equal(out0, out1)
+    emu_decoder.stats(reset=True)
 
 
 def test_stream_without_backend_fails_loudly():
@@ -111,10 +128,12 @@ CASES_GPU = [
 
 
 CASES_INTER_GPU = [
-    (640, 360, 8, 0, 1, 1, 4),
-    (1920, 1080, 8, 0, 2, 1, 4),
-    (1920, 1080, 10, 1, 1, 1, 3),
-    (3840, 2160, 8, 0, 2, 2, 3),
+    (640, 360, 8, 0, 1, 1, 4, 0),
+    (1920, 1080, 8, 0, 2, 1, 4, 0),
+    (1920, 1080, 10, 1, 1, 1, 3, 0),
+    (3840, 2160, 8, 0, 2, 2, 3, 0),
+    (1920, 1080, 8, 0, 2, 1, 6, 1),
+    (1280, 720, 10, 1, 1, 0, 6, 1),
 ]
 
 
@@ -136,6 +155,19 @@ def test_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", CASES_INTER_GPU)
 def test_inter_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
-    w, h, bpc, sb128, lc, lr, nf = case
-    tus = obu.inter_stream(2000 + (hash(case) & 0xfff), w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=lc, log2_rows=lr)
+    w, h, bpc, sb128, lc, lr, nf, mm = case
+    tus = obu.inter_stream(2000 + (hash(case) & 0xfff), w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=lc, log2_rows=lr, motion_modes=mm)
     _check(gpu_decoder, tus, nf)
+
+
+@pytest.mark.gpu
+def test_stream_gpu_many_frames_in_flight(gpu_decoder):
+    """8 frame contexts, 32 threads, decoders opened again and again (slot recycling), device jobs of several frames
+    overlapping on their own streams"""
+    tus = obu.inter_stream(77, 1280, 720, n_frames=10, log2_cols=1, log2_rows=1, motion_modes=1)
+    r0, _, out0 = _ref_decode(tus, n_threads=16, max_frame_delay=8)
+    assert r0 == 10
+    for _ in range(12):
+        r1, _, out1 = gpu_decoder.decode(tus, n_threads=32, max_frame_delay=8)
+        assert r1 == r0 and np.array_equal(out0, out1)
+    gpu_decoder.stats(reset=True)

@@ -11,7 +11,7 @@ if [[ $what == *" tests "* ]]; then
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1
 fi
 if [[ $what == *" stream "* ]]; then
-  for wl in stream1080p8 stream4k10; do
+  for wl in stream1080p8 stream1080p8_inter stream4k8_inter stream4k10; do
     timeout 300 python bench.py --workload $wl --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$wl.json 2> gpurun_out/bench_ref_$wl.err
     timeout 300 python bench.py --workload $wl --steps 5 > gpurun_out/bench_$wl.json 2> gpurun_out/bench_$wl.err
   done
