@@ -26,6 +26,7 @@ import os as _os
 # default of 8, kernels of streams that share a queue are dispatched one after the other
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import argparse
+import contextlib
 import ctypes as C
 import json
 import os
@@ -405,7 +406,9 @@ def run_stream(args):
               "dtype": "u8/i16->i32" if W["bpc"] == 8 else "u16/i32", "data": "synthetic",
               "config": {"workload": wl, "l2": "every frame's records and pictures are fresh (uploaded per frame)",
                          "value_is": "pixels / time inside the per-frame device jobs (H2D of records + kernels + D2H of the picture), host clock",
-                         "records_per_frame": {k: st[k] // max(st["frames"], 1) for k in ("intra_tx", "pred", "comp", "warp", "blend", "itx")}},
+                         "records_per_frame": {k: st[k] // max(st["frames"], 1) for k in ("intra_tx", "pred", "comp", "warp", "blend", "itx")},
+                         "host_ms_per_frame": {"completion_before_job (mask fix-ups, wavefront sort, staging)": st["host_prep_ms"] / max(st["frames"], 1),
+                                               "device_job": dev_ms, "whole_decode_wall": ms / W["frames"]}},
               "roofline": {"bound": "hbm", "kernel": "frame job (intra reconstruction + deblock + CDEF + LR, incl. PCIe copies)",
                            "achieved": alg / (dev_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": alg / (dev_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": src},
@@ -432,7 +435,14 @@ def run_ours_frame(args):
     torch, dist, world, rank, local = dist_setup()
     from dav1d_b200 import synth, frame, get_lib
     lib = get_lib()
-    nsets = max(24, FRAME_WORKLOADS[args.workload].get("frames_per_step", 1)) if FRAME_WORKLOADS[args.workload].get("intra") else int(os.environ.get("B200_NSETS", "3" if args.workload == "8k10_full" else "5"))
+    # frames in flight for the device-resident measurement: consecutive frames go round-robin to this many streams (the
+    # device-side analogue of dav1d's frame threads, n_fc): one frame's kernel tails and launch gaps are filled by the
+    # next frame's kernels. Every frame set always runs on the same stream (nsets is a multiple of the stream count).
+    n_streams = max(1, int(os.environ.get("B200_FRAMES_IN_FLIGHT", "2")))
+    nsets = max(24, FRAME_WORKLOADS[args.workload].get("frames_per_step", 1)) if FRAME_WORKLOADS[args.workload].get("intra") else int(os.environ.get("B200_NSETS", "3" if args.workload == "8k10_full" else "6"))
+    if not FRAME_WORKLOADS[args.workload].get("intra"):
+        nsets = -(-nsets // n_streams) * n_streams
+    side = [torch.cuda.Stream() for _ in range(n_streams)] if n_streams > 1 else []
     fbs, Ss = [], []
     for k in range(nsets):
         # at most 8 distinct synthetic frames; every set still owns its device buffers (that is what defeats L2)
@@ -463,12 +473,14 @@ def run_ours_frame(args):
             return
         k = i % nsets
         fb = fbs[k]
-        if pending[k] is not None:      # the exchange that still reads this frame set's picture (issued nsets steps ago)
-            pending[k].wait()
-        fb.run()
-        if world > 1:
-            # the exchange of frame i overlaps the reconstruction of frame i + 1 (NCCL stream; un-grained picture)
-            pending[k] = dist.all_gather_into_tensor(gather[k], fb.keep[fb.ref_name][0][:Ss[0]["pic"].nbytes], async_op=True)
+        ctx = torch.cuda.stream(side[k % n_streams]) if side else contextlib.nullcontext()
+        with ctx:
+            if pending[k] is not None:      # the exchange that still reads this frame set's picture (issued nsets steps ago)
+                pending[k].wait()
+            fb.run()
+            if world > 1:
+                # the exchange of frame i overlaps the reconstruction of frame i + 1 (NCCL stream; un-grained picture)
+                pending[k] = dist.all_gather_into_tensor(gather[k], fb.keep[fb.ref_name][0][:Ss[0]["pic"].nbytes], async_op=True)
 
     def sync_all():
         for k in range(nsets):
@@ -485,14 +497,18 @@ def run_ours_frame(args):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = lib.b200_launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True)]
     ev[0].record()
+    main = torch.cuda.current_stream()
+    for s_ in side:
+        s_.wait_stream(main)            # the timed region starts on every stream after ev[0]
     for i in range(args.steps):
         step(i)
-        ev[i + 1].record()
     for k in range(nsets):              # the timed region ends when the last exchanges have landed too
         if pending[k] is not None:
             pending[k].wait(); pending[k] = None
+    for s_ in side:
+        main.wait_stream(s_)            # ... and when every stream has drained
     ev_end = torch.cuda.Event(enable_timing=True)
     ev_end.record()
     sync_all()
@@ -565,7 +581,7 @@ def run_ours_frame(args):
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": FRAME_WORKLOADS[args.workload]["dtype"], "data": "synthetic",
                 "config": {"workload": "%s: %s" % (args.workload, FRAME_WORKLOADS[args.workload]["desc"]),
-                           "l2": "%d rotating frame sets (~%d MB) > 126 MB L2" % (nsets, nsets * ((2 + len(Ss[0]["refs"]) + fbs[0].job.run_cdef + fbs[0].job.run_lr + fbs[0].job.run_fg) * Ss[0]["pic"].nbytes + Ss[0]["coefs"].nbytes) // 1000000),
+                           "frames_in_flight": n_streams, "l2": "%d rotating frame sets (~%d MB) > 126 MB L2" % (nsets, nsets * ((2 + len(Ss[0]["refs"]) + fbs[0].job.run_cdef + fbs[0].job.run_lr + fbs[0].job.run_fg) * Ss[0]["pic"].nbytes + Ss[0]["coefs"].nbytes) // 1000000),
                            "records": {"pred_blocks": int(len(Ss[0]["pred"])), "compound": int(len(Ss[0]["comp"]) + len(Ss[0]["comp2"])),
                                        "tx_blocks": int(sum(len(a) for a in Ss[0]["itx"].values())), "coefs": int(len(Ss[0]["coefs"])),
                                        "intra_tx_blocks": int(len(Ss[0].get("intra_tx", []))), "intra_waves": int(Ss[0].get("intra_waves", 0))},
