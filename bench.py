@@ -315,9 +315,10 @@ STREAM_WORKLOADS = {
     "stream4k8_inter": dict(W=3840, H=2160, bpc=8, frames=8, log2_cols=2, log2_rows=2, inter=1,
                             desc="AV1 elementary stream, 1 key frame + 7 inter frames 3840x2160 8-bit 4:2:0, 4x4 tiles, all inter tools of "
                                  "stream1080p8_inter, decoded through dav1d's public API (host front end = unmodified dav1d, back end = libb200av1)"),
-    "stream4k10": dict(W=3840, H=2160, bpc=10, frames=4, log2_cols=2, log2_rows=2,
-                       desc="AV1 elementary stream, 4 key frames 3840x2160 10-bit 4:2:0, 4x4 tiles, decoded through dav1d's public API "
-                            "(host front end = unmodified dav1d, back end = libb200av1)"),
+    "stream4k10": dict(W=3840, H=2160, bpc=10, frames=6, log2_cols=2, log2_rows=2, inter=1, film_grain=1,
+                       desc="AV1 elementary stream, 1 key frame + 5 inter frames 3840x2160 10-bit 4:2:0, 4x4 tiles, all inter tools of "
+                            "stream1080p8_inter plus film grain on every frame (the full pipeline of BASELINE configs[3]) decoded through "
+                            "dav1d's public API (host front end = unmodified dav1d, back end incl. film grain = libb200av1)"),
 }
 
 
@@ -332,7 +333,8 @@ def run_stream(args):
     nthr = min(os.cpu_count() or 1, 32)
     mfd = min(8, W["frames"])
     gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=1, **k)) if W.get("inter") else obu.intra_stream
-    tus = gen(100 + rank, W["W"], W["H"], n_frames=W["frames"], bpc=W["bpc"], log2_cols=W["log2_cols"], log2_rows=W["log2_rows"])
+    fg = int(W.get("film_grain", 0))
+    tus = gen(100 + rank, W["W"], W["H"], n_frames=W["frames"], bpc=W["bpc"], log2_cols=W["log2_cols"], log2_rows=W["log2_rows"], film_grain=fg)
     px = W["W"] * W["H"] * W["frames"]
     stream.decode_stream.capacity = (W["W"] * W["H"] * 3 // 2) * (2 if W["bpc"] > 8 else 1) * W["frames"] + (1 << 20)
     steps = min(args.steps, 10)
@@ -343,11 +345,11 @@ def run_stream(args):
         import refs
         dll = C.CDLL(refs.REF_SO)
         for _ in range(min(args.warmup, 1)):
-            stream.decode_stream(dll, tus, n_threads=nthr, max_frame_delay=mfd)
+            stream.decode_stream(dll, tus, n_threads=nthr, max_frame_delay=mfd, apply_grain=fg)
         dts = []
         for _ in range(steps):
             t0 = time.perf_counter()
-            r, _, _ = stream.decode_stream(dll, tus, n_threads=nthr, max_frame_delay=mfd)
+            r, _, _ = stream.decode_stream(dll, tus, n_threads=nthr, max_frame_delay=mfd, apply_grain=fg)
             dts.append(time.perf_counter() - t0)
             assert r == W["frames"], r
         ms = 1e3 * float(np.mean(dts)); val = px / (ms * 1e-3) / 1e6
@@ -363,7 +365,7 @@ def run_stream(args):
     lib = get_lib()
     dec = stream.HookedDecoder()
     for _ in range(max(args.warmup, 3) if steps > 1 else 1):
-        r, _, _ = dec.decode(tus, n_threads=nthr, max_frame_delay=mfd)
+        r, _, _ = dec.decode(tus, n_threads=nthr, max_frame_delay=mfd, apply_grain=fg)
         assert r == W["frames"], "hooked decode failed: %d" % r
     dec.stats(reset=True)
     before = lib.b200_launch_count()
@@ -373,7 +375,7 @@ def run_stream(args):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        r, _, out = dec.decode(tus, n_threads=nthr, max_frame_delay=mfd)
+        r, _, out = dec.decode(tus, n_threads=nthr, max_frame_delay=mfd, apply_grain=fg)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     sampler.stop()
@@ -396,7 +398,7 @@ def run_stream(args):
     if rank == 0:
         import refs
         dll = C.CDLL(refs.REF_SO)
-        t1 = time.perf_counter(); rr, _, ref_out = stream.decode_stream(dll, tus, n_threads=nthr, max_frame_delay=mfd); tc = time.perf_counter() - t1
+        t1 = time.perf_counter(); rr, _, ref_out = stream.decode_stream(dll, tus, n_threads=nthr, max_frame_delay=mfd, apply_grain=fg); tc = time.perf_counter() - t1
         assert rr == W["frames"] and np.array_equal(ref_out, out), "stream bench: output differs from the stock reference"
         cpu = {"value": px / tc / 1e6, "unit": "Mpixels/s", "cores": nthr, "kind": "reference",
                "sample": "one decode of the same stream by stock dav1d (C path, HAVE_ASM=0), %d threads, %.2f s; outputs compared byte for byte" % (nthr, tc)}

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kCdefThreads, B200_CDEF_MINB) cdef_frame_kerne
         const int groups = (tw + 8) >> 2, rows = th + 3;
         const pixel *sp = src + f.plane_off[pl];
         const int st = f.stride[pl];
-        const unsigned magic = (65536u + groups - 1) / groups;            // exact i / groups for i < 36 * 18
+        const unsigned magic = recip16(groups);            // exact i / groups for i < 36 * 18
         for (int i = tid; i < groups * rows; i += kCdefThreads) {
             const int r = (int)((i * magic) >> 16), g = i - r * groups;
             const int x = x0 - 4 + g * 4, y = y0 - 2 + r;

@@ -204,7 +204,8 @@ B200_DEV void lr_unit_params(const B200RestorationUnit &u, bool hbd, LrTileParam
     }
 }
 
-struct LrGrid { int base[3], nx[3]; };       // flattened tile list: plane p owns CTAs base[p] .. , nx[p] tiles per row
+struct LrGrid { int base[3], nx[3]; unsigned nx_recip[3]; };   // flattened tile list: plane p owns CTAs base[p] .. , nx[p] tiles per row;
+                                                               // nx_recip = ceil(2^32 / nx): local / nx == mulhi(local, nx_recip) while local * nx < 2^32
 
 template <bool HBD>
 #ifndef B200_LR_MINB
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(const __gri
     const int us_log2 = f.unit_size_log2[pl ? 1 : 0], unit = 1 << us_log2, half = unit >> 1;
     const int tw_full = unit < kTW ? unit : kTW;
     const int local = bid - lg.base[pl], nxp = lg.nx[pl];
-    const int tyi = local / nxp, txi = local - tyi * nxp;
+    const int tyi = nxp > 1 ? (int)__umulhi((unsigned)local, lg.nx_recip[pl]) : local, txi = local - tyi * nxp;
     const int x0 = txi * tw_full;
     // a 64-row luma stripe is 2 tiles tall; a vertically subsampled stripe (32 rows) is 1
     const int k = ssv ? tyi : tyi >> 1, ty = ssv ? 0 : tyi & 1;
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(const __gri
     if (interior) {
         // aligned words over picture columns x0-4 .. x0+tw+3 (one more column on each side than needed)
         const int NW = (tw + 8) / PPW;
-        const unsigned magic = (65536u + NW - 1) / NW;               // exact i / NW for i < 38 * 36
+        const unsigned magic = recip16(NW);               // exact i / NW for i < 38 * 36
         for (int i = threadIdx.x; i < (th + 6) * NW; i += blockDim.x) {
             const int yy = (int)((i * magic) >> 16), g = i - yy * NW;
             int Y = ty0 - 3 + yy;
@@ -350,6 +351,7 @@ int b200_lr_frame(int bdmax, const B200LrFrame *f, void *stream)
         const int w = (f->w + ssh) >> ssh;
         const int unit = 1 << f->unit_size_log2[p ? 1 : 0], tw_full = unit < kTW ? unit : kTW;
         lg.nx[p] = (w + tw_full - 1) / tw_full;
+        lg.nx_recip[p] = lg.nx[p] > 1 ? (unsigned)(((1ull << 32) + lg.nx[p] - 1) / lg.nx[p]) : 0u;
         lg.base[p] = total;
         total += lg.nx[p] * n_stripes * (ssv ? 1 : 2);
     }

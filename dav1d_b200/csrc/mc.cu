@@ -86,7 +86,7 @@ B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int
     const int fh_lo = (fh[0] & 0xff) | (fh[1] & 0xff) << 8 | (fh[2] & 0xff) << 16 | (fh[3] & 0xff) << 24;
     const int fh_hi = (fh[4] & 0xff) | (fh[5] & 0xff) << 8 | (fh[6] & 0xff) << 16 | (fh[7] & 0xff) << 24;
     const int ngx = (sw + S - 1) / S;
-    const unsigned magic_r = (65536u + nr - 1) / nr;       // exact it / nr for it < 65536 / nr (it < 39 * 32)
+    const unsigned magic_r = recip16(nr);       // exact it / nr for it < 65536 / nr (it < 39 * 32)
     for (int it = lane; it < nr * ngx; it += 32) {
         const int g = (int)((it * magic_r) >> 16), r = it - g * nr;
         const int x0 = g * S;
@@ -151,7 +151,7 @@ B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int
     __syncwarp();
     // ---- vertical + store
     const int ngy = (sh + S - 1) / S;
-    const unsigned magic_w = (65536u + sw - 1) / sw;
+    const unsigned magic_w = recip16(sw);
     for (int it = lane; it < sw * ngy; it += 32) {
         const int g = (int)((it * magic_w) >> 16), x = it - g * sw;
         const int y0 = g * S;
@@ -241,14 +241,14 @@ B200_DEV void mc_subblock(McSmem<HBD> &sm, const int lane, const typename Bd<HBD
         shift0 = gx & (PPW - 1);
         const int nw = (nc + shift0 + PPW - 1) / PPW;
         const int gxa = gx - shift0;
-        const unsigned magic = (65536u + nw - 1) / nw;
+        const unsigned magic = recip16(nw);
         for (int it = lane; it < nr * nw; it += 32) {
             const int r = (int)((it * magic) >> 16), c = it - r * nw;
             const unsigned v = *(const unsigned *)(ref + (ptrdiff_t)(gy + r) * rs + gxa + c * PPW);
             *(unsigned *)&sm.raw[r * RP + c * PPW] = v;
         }
     } else {
-        const unsigned magic = (65536u + nc - 1) / nc;
+        const unsigned magic = recip16(nc);
         for (int it = lane; it < nr * nc; it += 32) {
             const int r = (int)((it * magic) >> 16), c = it - r * nc;
             sm.raw[r * RP + c] = ref[(ptrdiff_t)iclip(gy + r, 0, rh - 1) * rs + iclip(gx + c, 0, rw - 1)];

@@ -199,7 +199,7 @@ def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb
     b.f(1, 1)                                # tx_mode_select
     b.f(1, int(rng.integers(0, 2)))          # reduced_tx_set
     if film_grain_seq:
-        b.f(1, 0)                            # apply_grain
+        _film_grain_params(b, rng, 0)
     return obu(OBU_FRAME, _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_bytes_per_sb64))
 
 
@@ -207,15 +207,59 @@ def temporal_unit(*obus):
     return obu(OBU_TD, b"") + b"".join(obus)
 
 
-def intra_stream(seed, w, h, n_frames=1, bpc=8, sb128=0, log2_cols=0, log2_rows=0, **kw):
+def intra_stream(seed, w, h, n_frames=1, bpc=8, sb128=0, log2_cols=0, log2_rows=0, film_grain=0, **kw):
     """A list of temporal units (bytes), each holding one shown key frame."""
     rng = np.random.default_rng(seed)
-    seq = sequence_header(w, h, bpc=bpc, sb128=sb128)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, film_grain=film_grain)
+    if film_grain:
+        kw = dict(kw, film_grain_seq=1)
     tus = []
     for i in range(n_frames):
         fr = key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, **kw)
         tus.append(temporal_unit(seq, fr) if i == 0 else temporal_unit(fr))
     return tus
+
+
+def _film_grain_params(b, rng, inter):
+    """film_grain_params() with apply_grain = 1 and fresh parameters (reference src/obu.c:1064-1155): random scaling
+    points, auto-regression lag 0..3 with random coefficients, overlap, optional chroma-from-luma scaling"""
+    b.f(1, 1)                                # apply_grain
+    b.f(16, int(rng.integers(0, 1 << 16)))   # grain_seed
+    if inter:
+        b.f(1, 1)                            # update_grain
+    ny = int(rng.integers(0, 15))
+    b.f(4, ny)
+    xs = sorted(rng.choice(256, ny, replace=False).tolist())
+    for x in xs:
+        b.f(8, x); b.f(8, int(rng.integers(0, 256)))
+    csfl = int(rng.integers(0, 2))
+    b.f(1, csfl)
+    nuv = [0, 0]
+    if not (csfl or ny == 0):                # 4:2:0 without luma points carries no chroma points either
+        n = int(rng.integers(0, 11))
+        nuv = [n, int(rng.integers(1, 11)) if n else 0]      # both planes or neither (4:2:0)
+        for pl in range(2):
+            b.f(4, nuv[pl])
+            for x in sorted(rng.choice(256, nuv[pl], replace=False).tolist()):
+                b.f(8, x); b.f(8, int(rng.integers(0, 256)))
+    b.f(2, int(rng.integers(0, 4)))          # grain_scaling_minus_8
+    lag = int(rng.integers(0, 4))
+    b.f(2, lag)
+    npos = 2 * lag * (lag + 1)
+    if ny:
+        for _ in range(npos):
+            b.f(8, int(rng.integers(0, 256)))
+    for pl in range(2):
+        if nuv[pl] or csfl:
+            for _ in range(npos + (1 if ny else 0)):
+                b.f(8, int(rng.integers(0, 256)))
+    b.f(2, int(rng.integers(0, 4)))          # ar_coeff_shift_minus_6
+    b.f(2, int(rng.integers(0, 4)))          # grain_scale_shift
+    for pl in range(2):
+        if nuv[pl]:
+            b.f(8, int(rng.integers(0, 256))); b.f(8, int(rng.integers(0, 256))); b.f(9, int(rng.integers(0, 512)))
+    b.f(1, int(rng.integers(0, 2)))          # overlap_flag
+    b.f(1, int(rng.integers(0, 2)))          # clip_to_restricted_range
 
 
 def _poc_diff(bits, a, b):
@@ -283,24 +327,26 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
     for _ in range(7):
         b.f(1, 0)                            # is_global: identity
     if film_grain_seq:
-        b.f(1, 0)
+        _film_grain_params(b, rng, 1)
     for i in range(8):
         if refresh & (1 << i):
             ref_hints[i] = order_hint
     return obu(OBU_FRAME, _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_bytes_per_sb64))
 
 
-def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, **kw):
+def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, film_grain=0, **kw):
     """Temporal units: one key frame, then n_frames - 1 inter frames (single and compound references incl. wedge /
     difference-weighted masks and distance weights, switchable interpolation filters, variable transform trees, intra
     blocks; identity global motion, no inter-intra). motion_mods=1 additionally enables the per-block motion mode:
     overlapped block motion compensation and locally warped motion."""
     rng = np.random.default_rng(seed)
-    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=0, warped_motion=motion_modes)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=0, warped_motion=motion_modes, film_grain=film_grain)
     if motion_modes:
         kw = dict(kw, switchable_motion_mode=1, warped_motion_seq=1, allow_warped_motion=1)
+    if film_grain:
+        kw = dict(kw, film_grain_seq=1)
     hints = [0] * 8
-    tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows))]
+    tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, film_grain_seq=film_grain))]
     for i in range(1, n_frames):
         tus.append(temporal_unit(inter_frame(rng, w, h, i, hints, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, **kw)))
     return tus

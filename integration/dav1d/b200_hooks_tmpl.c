@@ -18,6 +18,8 @@
  *                      masks), one B200ItxBlock per leaf of the transform tree (reference src/recon_tmpl.c:1557-1985)
  *                      B200WarpBlock per 8x8 of a warped block (local and global motion), OBMC as neighbour predictions
  *                      into a pixel scratch + two ordered blend stages
+ *   apply_grain / prep_grain / apply_grain_row (output stage, renamed in lib.c / thread_task.c) -> one device film
+ *                      grain job on the HBM-resident picture, result copied into the output picture
  * Not translated yet (the frame fails loudly, there is no CPU fallback): palette, intra block copy, inter-intra,
  * scaled references.
  */
@@ -838,3 +840,79 @@ void bitfn(b200hook_filter_sbrow_deblock_rows)(Dav1dFrameContext *const f, const
 void bitfn(b200hook_filter_sbrow_cdef)(Dav1dTaskContext *const tc, const int sby) { (void)tc; (void)sby; }
 void bitfn(b200hook_filter_sbrow_resize)(Dav1dFrameContext *const f, const int sby) { (void)f; (void)sby; }
 void bitfn(b200hook_filter_sbrow_lr)(Dav1dFrameContext *const f, const int sby) { (void)f; (void)sby; }
+
+
+/* ---- film grain on the output copy (dav1d_apply_grain, reference src/lib.c:485-520; with worker threads the
+ * delayed_fg tasks of src/thread_task.c:470-545 call prep_grain once and apply_grain_row per 32-row strip) ---------
+ * The decoded picture is still in HBM (keyed by its host buffer), so the whole job — grain LUTs, scaling LUTs, every
+ * strip of every plane — runs as one b200 frame job when `prep` is called; the per-row calls have nothing left to do. */
+#include "src/fg_apply.h"
+static void bitfn(fg_whole_picture)(Dav1dPicture *const out, const Dav1dPicture *const in)
+{
+    const B200Backend *const be = b200hook_backend();
+    HookRefPic *const src = b200hook_refpic(in->data[0], 0, 0);
+    if (!be || !src || !src->dev || out->stride[0] != in->stride[0] || out->stride[1] != in->stride[1]) {
+        fprintf(stderr, "b200hook: film grain: the picture is not resident on the device (or the output copy has another layout)\n");
+        abort();                                    /* no error channel here (void, like dav1d's), no CPU fallback */
+    }
+    b200hook_refpic_wait(src);
+    const int ss_ver = in->p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = in->p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    const int rows = (in->p.h + 127) & ~127;
+    const int st0 = (int)PXSTRIDE(in->stride[0]), st1 = (int)PXSTRIDE(in->stride[1]);
+    const uint32_t off1 = (uint32_t)st0 * rows, off2 = off1 + (uint32_t)st1 * (rows >> ss_ver);
+    const size_t bytes = ((size_t)off2 + (size_t)st1 * (rows >> ss_ver)) * sizeof(pixel);
+    static const char fg_slot_key = 0;
+    HookFrame *const hf = b200hook_frame(&fg_slot_key);                  /* a slot of its own for the output stage */
+    if (!hf) abort();
+    pthread_mutex_lock(&hf->lock);
+    if ((!hf->stream && !(hf->stream = be->stream_create())) || b200hook_buf_reserve(&hf->pic[0], bytes, 0, 0) ||
+        b200hook_buf_reserve(&hf->scratch, B200_FG_SCRATCH_BYTES, 0, 0)) {
+        fprintf(stderr, "b200hook: film grain: %s\n", be->last_error());
+        abort();
+    }
+    B200FrameJob j;
+    memset(&j, 0, sizeof(j));
+#if BITDEPTH == 8
+    j.bitdepth_max = 255;
+#else
+    j.bitdepth_max = (1 << in->p.bpc) - 1;
+#endif
+    j.run_fg = 1;
+    j.fg.in = src->dev; j.fg.out = hf->pic[0].dev; j.fg.scratch = hf->scratch.dev;
+    j.fg.plane_off[0] = 0; j.fg.plane_off[1] = off1; j.fg.plane_off[2] = off2;
+    j.fg.stride[0] = st0; j.fg.stride[1] = j.fg.stride[2] = st1;
+    j.fg.w = in->p.w; j.fg.h = in->p.h; j.fg.ss_hor = ss_hor; j.fg.ss_ver = ss_ver;
+    j.fg.is_id = in->seq_hdr->mtrx == DAV1D_MC_IDENTITY;
+    memcpy(&j.fg.data, &in->frame_hdr->film_grain.data, sizeof(j.fg.data));
+    B200Xfer down[3];
+    const int npl = in->p.layout == DAV1D_PIXEL_LAYOUT_I400 ? 1 : 3;
+    for (int p = 0; p < npl; p++) {
+        const int prow = p ? (in->p.h + ss_ver) >> ss_ver : in->p.h;
+        down[p].host = out->data[p];
+        down[p].dev = (uint8_t *)hf->pic[0].dev + (size_t)j.fg.plane_off[p] * sizeof(pixel);
+        down[p].bytes = (uint64_t)prow * j.fg.stride[p] * sizeof(pixel);
+    }
+    b200hook_job_enter();
+    const int r = be->frame_run_host(&j, NULL, 0, down, npl, hf->stream);
+    b200hook_job_leave();
+    pthread_mutex_unlock(&hf->lock);
+    if (r) { fprintf(stderr, "b200hook: film grain job failed: %s\n", be->last_error()); abort(); }
+}
+
+void bitfn(b200hook_apply_grain)(const Dav1dFilmGrainDSPContext *const dsp, Dav1dPicture *const out, const Dav1dPicture *const in)
+{
+    (void)dsp;
+    bitfn(fg_whole_picture)(out, in);
+}
+void bitfn(b200hook_prep_grain)(const Dav1dFilmGrainDSPContext *const dsp, Dav1dPicture *const out, const Dav1dPicture *const in,
+                                uint8_t scaling[3][SCALING_SIZE], entry grain_lut[3][GRAIN_HEIGHT + 1][GRAIN_WIDTH])
+{
+    (void)dsp; (void)scaling; (void)grain_lut;
+    bitfn(fg_whole_picture)(out, in);
+}
+void bitfn(b200hook_apply_grain_row)(const Dav1dFilmGrainDSPContext *const dsp, Dav1dPicture *const out, const Dav1dPicture *const in,
+                                     const uint8_t scaling[3][SCALING_SIZE], const entry grain_lut[3][GRAIN_HEIGHT + 1][GRAIN_WIDTH],
+                                     const int row)
+{
+    (void)dsp; (void)out; (void)in; (void)scaling; (void)grain_lut; (void)row;      /* done by the job prep started */
+}

@@ -21,10 +21,10 @@ def _ref_decode(tus, **kw):
     return stream.decode_stream(C.CDLL(refs.REF_SO), tus, **kw)
 
 
-def _check(dec, tus, expect_frames):
-    r0, info0, out0 = _ref_decode(tus)
+def _check(dec, tus, expect_frames, **kw):
+    r0, info0, out0 = _ref_decode(tus, **kw)
     assert r0 == expect_frames, "the stock reference could not decode the synthetic stream (%d)" % r0
-    r1, info1, out1 = dec.decode(tus)
+    r1, info1, out1 = dec.decode(tus, **kw)
     assert r1 == r0, "hooked decoder returned %d" % r1
     assert np.array_equal(info0, info1)
     if not np.array_equal(out0, out1):
@@ -88,6 +88,20 @@ def test_inter_stream_emu_matches_stock_dav1d(emu_decoder, case):
     _check(emu_decoder, tus, nf)
     if mm:
         assert emu_decoder.last_stats["blend"] > 0, "no OBMC block in the stream"
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("case", [(256, 192, 8, 2, 0), (320, 192, 10, 3, 1), (330, 250, 8, 4, 1)])
+def test_film_grain_stream_emu_matches_stock_dav1d(emu_decoder, case):
+    """film grain on the output copy (dav1d's apply_grain / delayed_fg tasks) runs as a device job on the HBM-resident
+    picture: random scaling points, AR lags 0..3, overlap, chroma scaling from luma, 8 / 10 bit"""
+    w, h, bpc, nf, inter = case
+    gen = obu.inter_stream if inter else obu.intra_stream
+    tus = gen(40 + (hash(case) & 0xff), w, h, n_frames=nf, bpc=bpc, film_grain=1)
+    r0, _, with_grain = _ref_decode(tus, apply_grain=1)
+    _, _, without = _ref_decode(tus, apply_grain=0)
+    assert r0 == nf and not np.array_equal(with_grain, without), "the stream carries no visible grain"
+    _check(emu_decoder, tus, nf, apply_grain=1)
 
 
 @pytest.mark.emu
@@ -171,3 +185,12 @@ def test_stream_gpu_many_frames_in_flight(gpu_decoder):
         r1, _, out1 = gpu_decoder.decode(tus, n_threads=32, max_frame_delay=8)
         assert r1 == r0 and np.array_equal(out0, out1)
     gpu_decoder.stats(reset=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(1920, 1080, 8, 3, 1), (3840, 2160, 10, 3, 1), (1280, 720, 10, 2, 0)])
+def test_film_grain_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
+    w, h, bpc, nf, inter = case
+    gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=1, **k)) if inter else obu.intra_stream
+    tus = gen(60 + (hash(case) & 0xff), w, h, n_frames=nf, bpc=bpc, log2_cols=1, log2_rows=1, film_grain=1)
+    _check(gpu_decoder, tus, nf, apply_grain=1)
