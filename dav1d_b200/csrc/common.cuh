@@ -15,7 +15,9 @@ namespace b200 {
 
 B200_HD int imin(int a, int b) { return a < b ? a : b; }
 B200_HD int imax(int a, int b) { return a > b ? a : b; }
-B200_HD int iclip(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// min / max form (lo <= hi everywhere): sm_100a fuses the producing add into VIADDMNMX, so add + clamp is two instructions
+// instead of four (ISETP + predicated VIMNMX sequence); iclip was 29 % of the transform kernel's instructions
+B200_HD int iclip(int v, int lo, int hi) { return imax(lo, imin(v, hi)); }
 B200_HD int iabs(int v) { return v < 0 ? -v : v; }
 B200_HD int ulog2(unsigned v) {
 #if defined(__CUDA_ARCH__)

@@ -129,9 +129,9 @@ __global__ void __launch_bounds__(256) lf_cols_kernel(const __grid_constant__ B2
     const int y4 = blockIdx.y * 8 + threadIdx.y;
     const int pw4 = (f.w4 + ssh) >> ssh, ph4 = (f.h4 + ssv) >> ssv;
     if (x4 >= pw4 || x4 == 0 || y4 >= ph4) return;
-    const int upsb_x = 32 >> ssh, upsb_y = 32 >> ssv;        // units per 128x128 area
-    const int sbx = x4 / upsb_x, xi = x4 - sbx * upsb_x;
-    const int sby = y4 / upsb_y, yi = y4 - sby * upsb_y;
+    // 32 >> ss units per 128x128 area: shifts, not divisions (a run-time divisor costs ~20 instructions per thread)
+    const int sbx = x4 >> (5 - ssh), xi = x4 & ((32 >> ssh) - 1);
+    const int sby = y4 >> (5 - ssv), yi = y4 & ((32 >> ssv) - 1);
     const B200Av1Filter &m = f.mask[sby * f.sb128w + sbx];
     const int wd = lf_width(m, plane, 0, xi, yi, ssv);
     if (!wd) return;
@@ -157,9 +157,8 @@ __global__ void __launch_bounds__(256) lf_rows_kernel(const __grid_constant__ B2
     const int y4 = blockIdx.y * 2 + threadIdx.y;
     const int pw4 = (f.w4 + ssh) >> ssh, ph4 = (f.h4 + ssv) >> ssv;
     if (x >= pw4 * 4 || y4 >= ph4 || y4 == 0) return;
-    const int upsb_x = 32 >> ssh, upsb_y = 32 >> ssv;
-    const int x4 = x >> 2, sbx = x4 / upsb_x, xi = x4 - sbx * upsb_x;
-    const int sby = y4 / upsb_y, yi = y4 - sby * upsb_y;
+    const int x4 = x >> 2, sbx = x4 >> (5 - ssh), xi = x4 & ((32 >> ssh) - 1);
+    const int sby = y4 >> (5 - ssv), yi = y4 & ((32 >> ssv) - 1);
     const B200Av1Filter &m = f.mask[sby * f.sb128w + sbx];
     const int wd = lf_width(m, plane, 1, yi, xi, ssh);
     if (!wd) return;
