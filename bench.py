@@ -310,7 +310,7 @@ STREAM_WORKLOADS = {
     "stream1080p8_inter": dict(W=1920, H=1080, bpc=8, frames=16, log2_cols=2, log2_rows=1, inter=1,
                                desc="AV1 elementary stream, 1 key frame + 15 inter frames 1920x1080 8-bit 4:2:0, 4x2 tiles (valid headers, "
                                     "random tile payloads: single / compound references incl. wedge and difference-weighted masks, OBMC, "
-                                    "locally warped motion, transform trees, intra blocks) decoded through dav1d's public API; host front "
+                                    "locally warped motion, inter-intra, transform trees, intra blocks) decoded through dav1d's public API; host front "
                                     "end = unmodified dav1d, back end = f->bd_fn record emitters + libb200av1, references resident in HBM"),
     "stream4k8_inter": dict(W=3840, H=2160, bpc=8, frames=8, log2_cols=2, log2_rows=2, inter=1,
                             desc="AV1 elementary stream, 1 key frame + 7 inter frames 3840x2160 8-bit 4:2:0, 4x4 tiles, all inter tools of "
@@ -332,7 +332,7 @@ def run_stream(args):
     W = STREAM_WORKLOADS[args.workload]
     nthr = min(os.cpu_count() or 1, 32)
     mfd = min(8, W["frames"])
-    gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=1, **k)) if W.get("inter") else obu.intra_stream
+    gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=2, **k)) if W.get("inter") else obu.intra_stream
     fg = int(W.get("film_grain", 0))
     tus = gen(100 + rank, W["W"], W["H"], n_frames=W["frames"], bpc=W["bpc"], log2_cols=W["log2_cols"], log2_rows=W["log2_rows"], film_grain=fg)
     px = W["W"] * W["H"] * W["frames"]

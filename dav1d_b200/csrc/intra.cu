@@ -36,8 +36,21 @@ static inline IntraScratch intra_scratch_layout(const B200IntraFrame *f)
 // kernels (other streams) to run beside this one
 constexpr int kIntraGrid = 148;
 
+// what the kernels read of a B200IntraFrame (same member names; keeps 24 frames per launch inside the parameter space)
+struct IntraFrameDev {
+    void *pic;
+    int32_t stride[3];
+    int32_t ss_hor, ss_ver;
+    int32_t w4[3], h4[3];
+    void *d_coef;
+    int32_t zero_coefs;
+    uint32_t plane_off[3];
+    int32_t n_sb, sb_w, sb_h;
+    const B200IntraSb *sb;
+    const uint8_t *mask;
+};
 struct IntraParams {
-    B200IntraFrame f;
+    IntraFrameDev f;
     const B200IntraTx *tx;
     int n;
     int *ticket;
@@ -98,7 +111,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
     __shared__ int s_ticket, s_next;
     __shared__ uint32_t s_rec[kRecWords];
     const int tid = threadIdx.x;
-    const B200IntraFrame &f = P.f;
+    const IntraFrameDev &f = P.f;
     const int bitdepth = 32 - __clz(bdmax);
     int *const tl = S.edge + 128;
 
@@ -123,6 +136,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
         const bool have_tr = have_top && x + tw < xe && (r.flags & B200_INTRA_TOP_HAS_RIGHT);
         const bool have_bl = have_left && y + th < ye && (r.flags & B200_INTRA_LEFT_HAS_BOTTOM);
         const bool is_cfl = r.mode == B200_INTRA_MODE_CFL && r.cfl_alpha != 0;
+        const bool is_ii = r.mode == B200_INTRA_MODE_II, is_resid = r.mode == B200_INTRA_MODE_RESID;
         const uint8_t *const dmap = P.done[pl];
         const int mw = f.w4[pl];
         // coefficients: loads issued before the wait, parked in shared memory after it (off the dependency chain)
@@ -136,9 +150,12 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
 
         // ---- wait for the neighbours whose pixels the edge array reads
         {
-            const int n_left = have_left ? imin(th, ye - y) + (have_bl ? imin(th, ye - y - th) : 0) : 0;
-            const int n_top = have_top ? imin(tw, xe - x) + (have_tr ? imin(tw, xe - x - tw) : 0) : 0;
-            const int n_tl = have_left && have_top;
+            // a residual-only record waits for its own cells to be "predicted" (2), everything else for final neighbours (1)
+            const int n_left = is_resid ? 0 : have_left ? imin(th, ye - y) + (have_bl ? imin(th, ye - y - th) : 0) : 0;
+            const int n_top = is_resid ? 0 : have_top ? imin(tw, xe - x) + (have_tr ? imin(tw, xe - x - tw) : 0) : 0;
+            const int n_tl = !is_resid && have_left && have_top;
+            const int self_w = imin(tw, mw - x), n_self = is_resid ? self_w * imin(th, f.h4[pl] - y) : 0;
+            const int want = is_resid ? 2 : 1;
             int n_luma = 0, lw4 = 0, lx4 = 0, ly4 = 0;
             if (is_cfl) {
                 lx4 = x << f.ss_hor; ly4 = y << f.ss_ver;
@@ -148,14 +165,15 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
             }
             // only warp 0 polls (the other warps park at the barrier and cost no issue slots)
             if (tid < 32) {
-                for (int c = tid; c < n_left + n_top + n_tl + n_luma; c += 32) {
+                for (int c = tid; c < n_left + n_top + n_tl + n_luma + n_self; c += 32) {
                     const uint8_t *cell;
-                    if (c < n_left) cell = dmap + (y + c) * mw + x - 1;
+                    if (c >= n_left + n_top + n_tl + n_luma) { const int k = c - n_left - n_top - n_tl - n_luma; cell = dmap + (y + k / self_w) * mw + x + k % self_w; }
+                    else if (c < n_left) cell = dmap + (y + c) * mw + x - 1;
                     else if (c < n_left + n_top) cell = dmap + (y - 1) * mw + x + (c - n_left);
                     else if (c < n_left + n_top + n_tl) cell = dmap + (y - 1) * mw + x - 1;
                     else { const int k = c - n_left - n_top - n_tl; cell = P.done[0] + (ly4 + k / lw4) * f.w4[0] + lx4 + k % lw4; }
                     unsigned ns = B200_POLL_NS0, spins = 0;
-                    while (!ld_cell(cell)) {
+                    while (ld_cell(cell) != want) {
                         __nanosleep(ns); if (ns < B200_POLL_NSMAX) ns += ns >> 1;
                         if (++spins > (1u << 23)) intra_stuck();      // seconds: records are not in a valid order
                     }
@@ -173,6 +191,8 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
         pixel *const dst = (pixel *)f.pic + r.dst_off;
         // ---- dav1d_prepare_intra_edges: mode conversion (:97-120)
         int mode = r.mode, angle = r.angle;
+        if (is_ii) { mode = r.angle; angle = 0; }                              // inter-intra: the predictor is in `angle`
+        if (is_resid) mode = 0;
         if (mode == B200_INTRA_MODE_CFL) mode = 0;                             // DC_PRED (:1446, :1373)
         if (mode >= 1 && mode <= 8) {                                          // VERT_PRED .. VERT_LEFT_PRED
             const int base = mode == 1 ? 90 : mode == 2 ? 180 : mode == 3 ? 45 : mode == 4 ? 135 : mode == 5 ? 113
@@ -245,7 +265,10 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
         if (tid < kRecWords && nti < P.n) next_word = ((const uint32_t *)&P.tx[nti])[tid];
 
         // ---- predict into the shared tile
-        if (is_cfl) {
+        if (is_resid) {
+            // residual only: the tile is what the inter-intra record of this block left in the picture (another SM wrote it)
+            for (int i = tid; i < w * h; i += kIpT) { const int yy = i / w, xx = i - yy * w; s_px[i] = (pixel)ld_px<HBD>(dst + (ptrdiff_t)yy * st + xx); }
+        } else if (is_cfl) {
             const int dc = S.dc;
             for (int i = tid; i < w * h; i += kIpT) s_ac[i] = (int16_t)(s_ac[i] - dc);
             __syncthreads();
@@ -255,6 +278,16 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
             ipred_pred_body<HBD>(S, s_px, w, w, h, mode, a, r.max_w, r.max_h, bdmax);
         }
         __syncthreads();
+        if (is_ii) {
+            // inter-intra: blend the intra prediction into the inter prediction already in the picture (earlier launch),
+            // dst = (inter * (64 - m) + intra * m + 32) >> 6 (dsp->mc.blend, reference src/mc_tmpl.c:683-694)
+            const uint8_t *const msk = f.mask + r.luma_off;
+            for (int i = tid; i < w * h; i += kIpT) {
+                const int yy = i / w, xx = i - yy * w, m = msk[i];
+                s_px[i] = (pixel)(((int)dst[(ptrdiff_t)yy * st + xx] * (64 - m) + (int)s_px[i] * m + 32) >> 6);
+            }
+            __syncthreads();
+        }
 
         // ---- residual, added in the shared tile
         if (r.eob >= 0) {
@@ -282,7 +315,8 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
             __syncwarp();
             uint8_t *const dm = P.done[pl];
             const int cw = imin(tw, mw - x), chh = imin(th, f.h4[pl] - y);
-            for (int c = tid; c < cw * chh; c += 32) *(volatile uint8_t *)(dm + (y + c / cw) * mw + x + c % cw) = 1;
+            const uint8_t state = is_ii && r.cfl_alpha ? 2 : 1;          // 2: predicted, the block's residual records follow
+            for (int c = tid; c < cw * chh; c += 32) *(volatile uint8_t *)(dm + (y + c / cw) * mw + x + c % cw) = state;
         }
         // ---- hand over to the next record
         if (tid < kRecWords) s_rec[tid] = next_word;
@@ -327,7 +361,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_SB_MINB) intra_sb_kernel(cons
     pixel *const canvas = (pixel *)dyn_smem;
 #endif
     const int tid = threadIdx.x;
-    const B200IntraFrame &f = P.f;
+    const IntraFrameDev &f = P.f;
     const int bitdepth = 32 - __clz(bdmax);
     int *const tl = S.edge + 128;
     // canvas geometry per plane: pitch cs, origin of the superblock's top-left sample at co + cs + 1
@@ -557,7 +591,10 @@ int b200_intra_frames(int bdmax, const B200IntraFrame *frames, const B200IntraTx
             if (mode == 1 && nb && (f->ss_hor != B.p[0].f.ss_hor || f->ss_ver != B.p[0].f.ss_ver)) break;   // one canvas layout per launch
             const IntraScratch L = intra_scratch_layout(f);
             IntraParams &P = B.p[nb++];
-            P.f = *f; P.tx = d_tx[i]; P.n = n_tx[i];
+            P.f.pic = f->pic; P.f.ss_hor = f->ss_hor; P.f.ss_ver = f->ss_ver; P.f.d_coef = f->d_coef; P.f.zero_coefs = f->zero_coefs;
+            for (int p = 0; p < 3; p++) { P.f.stride[p] = f->stride[p]; P.f.w4[p] = f->w4[p]; P.f.h4[p] = f->h4[p]; P.f.plane_off[p] = f->plane_off[p]; }
+            P.f.n_sb = f->n_sb; P.f.sb_w = f->sb_w; P.f.sb_h = f->sb_h; P.f.sb = f->sb; P.f.mask = f->mask;
+            P.tx = d_tx[i]; P.n = n_tx[i];
             uint8_t *base_p = (uint8_t *)f->scratch;
             P.ticket = (int *)base_p;
             for (int p = 0; p < 3; p++) P.done[p] = base_p + L.done_off[p];

@@ -337,10 +337,10 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
 def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, film_grain=0, **kw):
     """Temporal units: one key frame, then n_frames - 1 inter frames (single and compound references incl. wedge /
     difference-weighted masks and distance weights, switchable interpolation filters, variable transform trees, intra
-    blocks; identity global motion, no inter-intra). motion_mods=1 additionally enables the per-block motion mode:
-    overlapped block motion compensation and locally warped motion."""
+    blocks; identity global motion). motion_modes=1 additionally enables the per-block motion mode (overlapped block
+    motion compensation, locally warped motion), motion_modes=2 inter-intra prediction as well."""
     rng = np.random.default_rng(seed)
-    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=0, warped_motion=motion_modes, film_grain=film_grain)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=1 if motion_modes >= 2 else 0, warped_motion=1 if motion_modes else 0, film_grain=film_grain)
     if motion_modes:
         kw = dict(kw, switchable_motion_mode=1, warped_motion_seq=1, allow_warped_motion=1)
     if film_grain:

@@ -465,7 +465,14 @@ B200_API void b200_film_grain_dsp_init_16bpc(B200FilmGrainDSPContext *c);
  * for the map cells its edges read. Records must therefore be in a topological order of those dependencies
  * (decode order is one; sorted by wavefront number is the efficient one). */
 enum { B200_INTRA_HAVE_LEFT = 1, B200_INTRA_HAVE_TOP = 2, B200_INTRA_TOP_HAS_RIGHT = 4, B200_INTRA_LEFT_HAS_BOTTOM = 8 };
-enum { B200_INTRA_MODE_FILTER = 13, B200_INTRA_MODE_CFL = 14 };   /* besides enum IntraPredMode DC_PRED(0)..PAETH_PRED(12) */
+enum { B200_INTRA_MODE_FILTER = 13, B200_INTRA_MODE_CFL = 14,   /* besides enum IntraPredMode DC_PRED(0)..PAETH_PRED(12) */
+       /* inter-intra (reference src/recon_tmpl.c:1601-1626, 1737-1777): the block's inter prediction is already in the
+        * picture (prediction stage); an II record predicts `angle` (= DC / VERT / HOR / SMOOTH_PRED) over the whole
+        * block (`tx` = the block's size) from the reconstructed neighbours and blends it in with the mask at `luma_off`
+        * bytes into B200IntraFrame.mask (pitch = block width). It carries no residual: the block's transform blocks
+        * follow as RESID records, which add their residual to the pixels in place. cfl_alpha != 0 in the II record says
+        * that RESID records follow (the done map then holds 2 = "predicted" until they publish 1 = "final"). */
+       B200_INTRA_MODE_II = 15, B200_INTRA_MODE_RESID = 16 };
 typedef struct B200IntraTx {
     uint32_t dst_off;              /* sample offset of the transform block in the picture (plane offset included) */
     uint32_t coef_off;             /* into d_coef, dav1d's transposed layout, min(w,32) x min(h,32) */
@@ -503,6 +510,7 @@ typedef struct B200IntraFrame {
     uint32_t plane_off[3];         /* superblock mode: sample offset of each plane in pic */
     int32_t n_sb, sb_w, sb_h;      /* superblock mode: number of B200IntraSb, superblock grid */
     const B200IntraSb *sb;         /* device; NULL = per-transform-block dataflow */
+    const uint8_t *mask;           /* device or NULL: blend masks of B200_INTRA_MODE_II records (per-transform-block mode only) */
     const uint8_t *done_init;      /* device or NULL; per-transform-block mode only. Frames that mix inter and intra blocks:
                                       an image of the scratch (b200_intra_scratch_bytes: 256 zero bytes, then one byte per
                                       4x4 cell for plane 0, 1, 2, each map padded to a multiple of 256 bytes) in which the

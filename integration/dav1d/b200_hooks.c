@@ -200,17 +200,20 @@ int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int
         const int x = r->x4, y = r->y4, tw = k_tx_w4[r->tx], th = k_tx_h4[r->tx], xe = r->xend4, ye = r->yend4;
         const int hl = r->flags & B200_INTRA_HAVE_LEFT, ht = r->flags & B200_INTRA_HAVE_TOP;
         int dep = 0;
-        if (hl) {
+        if (r->mode == B200_INTRA_MODE_RESID) {           /* waits for the inter-intra record that covers it */
+            for (int yy = y; yy < y + th && yy < mh; yy++)
+                for (int xx = x; xx < x + tw && xx < mw; xx++) { const int v = m[(size_t)yy * mw + xx]; if (v > dep) dep = v; }
+        } else if (hl) {
             int rows = mini(th, ye - y);
             if ((r->flags & B200_INTRA_LEFT_HAS_BOTTOM) && y + th < ye) rows += mini(th, ye - y - th);
             for (int k = 0; k < rows && y + k < mh; k++) { const int v = m[(size_t)(y + k) * mw + x - 1]; if (v > dep) dep = v; }
         }
-        if (ht) {
+        if (ht && r->mode != B200_INTRA_MODE_RESID) {
             int cols = mini(tw, xe - x);
             if ((r->flags & B200_INTRA_TOP_HAS_RIGHT) && x + tw < xe) cols += mini(tw, xe - x - tw);
             for (int k = 0; k < cols && x + k < mw; k++) { const int v = m[(size_t)(y - 1) * mw + x + k]; if (v > dep) dep = v; }
         }
-        if (hl && ht) { const int v = m[(size_t)(y - 1) * mw + x - 1]; if (v > dep) dep = v; }
+        if (hl && ht && r->mode != B200_INTRA_MODE_RESID) { const int v = m[(size_t)(y - 1) * mw + x - 1]; if (v > dep) dep = v; }
         if (r->mode == B200_INTRA_MODE_CFL && r->cfl_alpha) {
             const int lx = x << ss_hor, ly = y << ss_ver;
             const int lw = mini((tw - r->cfl_w_pad) << ss_hor, w4[0] - lx), lh = mini((th - r->cfl_h_pad) << ss_ver, h4[0] - ly);
@@ -232,13 +235,13 @@ int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int
     return n_waves;
 }
 
-void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[7], double prep_ms)
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[8], double prep_ms)
 {
     pthread_mutex_lock(&g_lock);
     g_stats.frames++; g_stats.records += records; g_stats.coefs += coefs;
     g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += d2h; g_stats.device_ms += ms;
     g_stats.intra_tx += kinds[0]; g_stats.pred += kinds[1]; g_stats.comp += kinds[2]; g_stats.warp += kinds[3];
-    g_stats.host_prep_ms += prep_ms;
+    g_stats.host_prep_ms += prep_ms; g_stats.interintra += kinds[7];
     g_stats.blend += kinds[4]; g_stats.itx += kinds[5]; g_stats.inter_frames += kinds[6];
     pthread_mutex_unlock(&g_lock);
 }

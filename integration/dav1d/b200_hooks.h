@@ -52,7 +52,7 @@ typedef struct HookFrame {
     HookBuf warp, blend, blend2, pxtmp;      /* warped-motion 8x8 blocks; OBMC: blend_h stage, blend_v stage, pixel scratch (device only) */
     int n_pred, n_comp, n_comp2, n_itx[19], n_warp, n_blend, n_blend2;
     size_t n_tmp16, n_cmask, n_pxtmp;
-    int started, is_inter;
+    int started, is_inter, n_ii;
     uint64_t last_use;             /* slot recycling: least recently used idle slot is taken over (its buffers are kept) */
     void *stream;
     /* statistics */
@@ -76,7 +76,8 @@ typedef struct B200HookStats {
     uint64_t frames, records, coefs, h2d_bytes, d2h_bytes; double device_ms;
     uint64_t intra_tx, pred, comp, warp, blend, itx, inter_frames;      /* records by kind */
     double host_prep_ms;            /* frame completion on the host before the job: mask fix-ups, wavefront sort, staging */
+    uint64_t interintra;            /* inter-intra records (a subset of intra_tx) */
 } B200HookStats;
-void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[7], double prep_ms);
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[8], double prep_ms);
 
 #endif

@@ -20,8 +20,9 @@
  *                      into a pixel scratch + two ordered blend stages
  *   apply_grain / prep_grain / apply_grain_row (output stage, renamed in lib.c / thread_task.c) -> one device film
  *                      grain job on the HBM-resident picture, result copied into the output picture
- * Not translated yet (the frame fails loudly, there is no CPU fallback): palette, intra block copy, inter-intra,
- * scaled references.
+ *                      inter-intra: an II record per plane (intra predictor over the block, blended into the inter
+ *                      prediction by the intra dataflow kernel) + the block's residual as RESID records
+ * Not translated yet (the frame fails loudly, there is no CPU fallback): palette, intra block copy, scaled references.
  */
 #include "config.h"
 #include <stdio.h>
@@ -96,6 +97,7 @@ typedef struct TxCtx {
     const Dav1dTaskContext *t;
     const Av1Block *b;
     PicGeom g;
+    int ii;                 /* the block is an inter-intra block: its residual goes through the intra kernel */
 } TxCtx;
 
 /* copies the block's coefficients out of dav1d's pass-1 buffer (and clears them there, as the reference's
@@ -351,9 +353,56 @@ static int bitfn(emit_obmc)(HookFrame *const hf, const Dav1dFrameContext *const 
     return 0;
 }
 
+/* inter-intra (reference :1601-1626 luma, :1737-1777 chroma): one II record per plane of the block; the predictor runs
+ * over the whole block, whose size is also a transform size (8x8 .. 32x32 luma, halved for sub-sampled chroma) */
+static int bitfn(emit_interintra)(TxCtx *const c, const enum BlockSize bs, const int pl, const uint32_t dst_off,
+                                  const int bx, const int by, const uint8_t *const mask)
+{
+    static const int8_t tx_of[9][9] = {      /* [w4][h4] -> enum RectTxfmSize, -1 where dav1d has no such transform */
+        { -1, -1, -1, -1, -1, -1, -1, -1, -1 },
+        { -1, TX_4X4, RTX_4X8, -1, RTX_4X16, -1, -1, -1, -1 },
+        { -1, RTX_8X4, TX_8X8, -1, RTX_8X16, -1, -1, -1, RTX_8X32 },
+        { -1, -1, -1, -1, -1, -1, -1, -1, -1 },
+        { -1, RTX_16X4, RTX_16X8, -1, TX_16X16, -1, -1, -1, RTX_16X32 },
+        { -1, -1, -1, -1, -1, -1, -1, -1, -1 }, { -1, -1, -1, -1, -1, -1, -1, -1, -1 }, { -1, -1, -1, -1, -1, -1, -1, -1, -1 },
+        { -1, -1, RTX_32X8, -1, RTX_32X16, -1, -1, -1, TX_32X32 },
+    };
+    HookFrame *const hf = c->hf;
+    const Dav1dFrameContext *const f = c->t->f;
+    const Dav1dTileState *const ts = c->t->ts;
+    const int ss_ver = pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    const uint8_t *const dim = dav1d_block_dimensions[bs];
+    const int pw4 = (dim[0] + ss_hor) >> ss_hor, ph4 = (dim[1] + ss_ver) >> ss_ver;
+    const int tx = pw4 <= 8 && ph4 <= 8 ? tx_of[pw4][ph4] : -1;
+    if (tx < 0) { __atomic_fetch_or(&hf->unsupported, 256, __ATOMIC_RELAXED); return 0; }
+    B200IntraTx *const r = bitfn(new_record)(hf);
+    if (!r) return -1;
+    const int px = bx >> ss_hor, py = by >> ss_ver;
+    r->mode = B200_INTRA_MODE_II; r->plane = pl; r->tx = tx; r->dst_off = dst_off; r->eob = -1;
+    r->angle = c->b->interintra_mode == II_SMOOTH_PRED ? SMOOTH_PRED : c->b->interintra_mode;     /* DC / VERT / HOR / SMOOTH */
+    r->x4 = px; r->y4 = py; r->xend4 = ts->tiling.col_end >> ss_hor; r->yend4 = ts->tiling.row_end >> ss_ver;
+    r->flags = (px > (ts->tiling.col_start >> ss_hor) ? B200_INTRA_HAVE_LEFT : 0) | (py > (ts->tiling.row_start >> ss_ver) ? B200_INTRA_HAVE_TOP : 0);
+    r->luma_off = (uint32_t)(mask - (const uint8_t *)&dav1d_masks);
+    r->cfl_alpha = !c->b->skip;               /* residual records follow */
+    __atomic_fetch_add(&hf->n_ii, 1, __ATOMIC_RELAXED);
+    return 0;
+}
+
 static int bitfn(emit_itx)(TxCtx *const c, const int tx, const int pl, const uint32_t dst_off, const int chroma)
 {
     HookFrame *const hf = c->hf;
+    if (c->ii) {
+        /* inter-intra block: the residual is added by the intra dataflow kernel after the block's blend (a RESID record
+         * per transform block, also when it has no coefficients: it turns the cells from "predicted" into "final") */
+        B200IntraTx *const r = bitfn(new_record)(hf);
+        if (!r || bitfn(take_residual)(c, r, &dav1d_txfm_dimensions[tx], chroma)) return -1;
+        const int ss_ver = pl && c->t->f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = pl && c->t->f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+        const uint32_t rel = dst_off - c->g.off[pl];
+        r->mode = B200_INTRA_MODE_RESID; r->plane = pl; r->tx = tx; r->dst_off = dst_off;
+        r->y4 = (rel / c->g.stride[pl]) >> 2; r->x4 = (rel % c->g.stride[pl]) >> 2;
+        r->xend4 = c->t->ts->tiling.col_end >> ss_hor; r->yend4 = c->t->ts->tiling.row_end >> ss_ver;
+        return 0;
+    }
     B200IntraTx tmp;          /* take_residual fills eob / txtp / coef_off of any record with these fields */
     memset(&tmp, 0, sizeof(tmp));
     if (bitfn(take_residual)(c, &tmp, &dav1d_txfm_dimensions[tx], chroma)) return -1;
@@ -420,13 +469,14 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
         const int warp = (b->inter_mode == GLOBALMV && f->gmv_warp_allowed[b->ref[0]]) ||
                          (b->motion_mode == MM_WARP && t->warpmv.type > DAV1D_WM_TYPE_TRANSLATION);
         const Dav1dWarpedMotionParams *const wmp = b->motion_mode == MM_WARP ? &t->warpmv : &f->frame_hdr->gmv[b->ref[0]];
-        if (b->interintra_type) __atomic_fetch_or(&hf->unsupported, 256, __ATOMIC_RELAXED);
+        c.ii = !!b->interintra_type;
         if (warp && imin(bw4, bh4) > 1) {
             if (bitfn(emit_warp)(hf, f, t, 0, ydst, g->stride[0], dim, 0, b->ref[0], wmp)) goto out;
         } else {
             if (bitfn(emit_mc)(hf, f, 0, ydst, bw4, bh4, bx, by, 0, b->mv[0], b->ref[0], filter_2d)) goto out;
             if (b->motion_mode == MM_OBMC && bitfn(emit_obmc)(hf, f, t, ydst, g->stride[0], dim, 0, bx4, by4, w4, h4)) goto out;
         }
+        if (c.ii && bitfn(emit_interintra)(&c, bs, 0, ydst, bx, by, II_MASK(0, bs, b))) goto out;
         if (has_chroma) {
             /* a 4-wide / 4-tall luma block shares its 4x4 chroma block with its left / top neighbours: each quarter is
              * predicted with the motion of the luma block above it, if all of them are inter (:1652-1724) */
@@ -473,6 +523,9 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
                     if (b->motion_mode == MM_OBMC && bitfn(emit_obmc)(hf, f, t, g->off[pl] + uvrel, g->stride[1], dim, pl, bx4, by4, w4, h4)) goto out;
                 }
             }
+            if (c.ii && !sub8)
+                for (int pl = 1; pl <= 2; pl++)
+                    if (bitfn(emit_interintra)(&c, bs, pl, g->off[pl] + uvrel, bx, by, II_MASK(chr_layout_idx, bs, b))) goto out;
         }
     } else {
         /* compound: two int16 predictions per plane, then avg / w_avg / mask / w_mask (:1782-1866) */
@@ -704,6 +757,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     }
     if (b200hook_buf_reserve(&hf->scratch, be->intra_scratch_bytes(&j.intra), 0, 0)) return -1;
     j.intra.scratch = hf->scratch.dev;
+    j.intra.mask = inter ? (const uint8_t *)hf->cmask.dev : NULL;
     if (inter && hf->n_tx > 0) {
         /* intra blocks inside an inter frame: everything that is not an intra transform block is already final */
         const size_t total = be->intra_scratch_bytes(&j.intra);
@@ -804,8 +858,8 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     uint64_t n_itx = 0;
     for (int t = 0; t < N_RECT_TX_SIZES; t++) n_itx += hf->n_itx[t];
     n_rec += n_itx;
-    const uint64_t kinds[7] = { (uint64_t)hf->n_tx, (uint64_t)hf->n_pred, (uint64_t)hf->n_comp + hf->n_comp2, (uint64_t)hf->n_warp,
-                                (uint64_t)hf->n_blend + hf->n_blend2, n_itx, (uint64_t)inter };
+    const uint64_t kinds[8] = { (uint64_t)hf->n_tx, (uint64_t)hf->n_pred, (uint64_t)hf->n_comp + hf->n_comp2, (uint64_t)hf->n_warp,
+                                (uint64_t)hf->n_blend + hf->n_blend2, n_itx, (uint64_t)inter, (uint64_t)hf->n_ii };
     b200hook_account(n_rec, hf->n_coef, h2d, d2h, bitfn(now_ms)() - t0, kinds, t0 - t_enter);
     return 0;
 }
@@ -827,7 +881,7 @@ void bitfn(b200hook_backup_ipred_edge)(Dav1dTaskContext *const t)
         if (outp) b200hook_refpic_set_ready(outp, 1);       /* also after a failure: nobody may wait for ever */
         hf->tile_sbrows_done = 0; hf->n_tx = 0; hf->n_coef = 0; hf->unsupported = 0;
         hf->n_pred = hf->n_comp = hf->n_comp2 = hf->n_warp = hf->n_blend = hf->n_blend2 = 0;
-        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->started = 0; hf->is_inter = 0;
+        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->started = 0; hf->is_inter = 0; hf->n_ii = 0;
         memset(hf->n_itx, 0, sizeof(hf->n_itx));
     }
     pthread_mutex_unlock(&hf->lock);

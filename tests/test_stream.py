@@ -72,8 +72,8 @@ CASES_INTER_CPU = [
     (320, 192, 10, 0, 1, 1, 4, 0),
     (640, 360, 8, 1, 1, 0, 3, 0),
     (330, 250, 8, 0, 0, 0, 5, 1),
-    (320, 192, 10, 0, 1, 1, 4, 1),
-    (640, 360, 8, 1, 1, 0, 4, 1),
+    (320, 192, 10, 0, 1, 1, 4, 2),      # 2: inter-intra prediction as well
+    (640, 360, 8, 1, 1, 0, 4, 2),
 ]
 
 
@@ -88,6 +88,8 @@ def test_inter_stream_emu_matches_stock_dav1d(emu_decoder, case):
     _check(emu_decoder, tus, nf)
     if mm:
         assert emu_decoder.last_stats["blend"] > 0, "no OBMC block in the stream"
+    if mm >= 2:
+        assert emu_decoder.last_stats["interintra"] > 0, "no inter-intra block in the stream"
 
 
 @pytest.mark.emu
@@ -146,8 +148,8 @@ CASES_INTER_GPU = [
     (1920, 1080, 8, 0, 2, 1, 4, 0),
     (1920, 1080, 10, 1, 1, 1, 3, 0),
     (3840, 2160, 8, 0, 2, 2, 3, 0),
-    (1920, 1080, 8, 0, 2, 1, 6, 1),
-    (1280, 720, 10, 1, 1, 0, 6, 1),
+    (1920, 1080, 8, 0, 2, 1, 6, 2),
+    (1280, 720, 10, 1, 1, 0, 6, 2),
 ]
 
 
@@ -178,7 +180,7 @@ def test_inter_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
 def test_stream_gpu_many_frames_in_flight(gpu_decoder):
     """8 frame contexts, 32 threads, decoders opened again and again (slot recycling), device jobs of several frames
     overlapping on their own streams"""
-    tus = obu.inter_stream(77, 1280, 720, n_frames=10, log2_cols=1, log2_rows=1, motion_modes=1)
+    tus = obu.inter_stream(77, 1280, 720, n_frames=10, log2_cols=1, log2_rows=1, motion_modes=2)
     r0, _, out0 = _ref_decode(tus, n_threads=16, max_frame_delay=8)
     assert r0 == 10
     for _ in range(12):
@@ -191,6 +193,6 @@ def test_stream_gpu_many_frames_in_flight(gpu_decoder):
 @pytest.mark.parametrize("case", [(1920, 1080, 8, 3, 1), (3840, 2160, 10, 3, 1), (1280, 720, 10, 2, 0)])
 def test_film_grain_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
     w, h, bpc, nf, inter = case
-    gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=1, **k)) if inter else obu.intra_stream
+    gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=2, **k)) if inter else obu.intra_stream
     tus = gen(60 + (hash(case) & 0xff), w, h, n_frames=nf, bpc=bpc, log2_cols=1, log2_rows=1, film_grain=1)
     _check(gpu_decoder, tus, nf, apply_grain=1)
