@@ -330,8 +330,8 @@ def run_stream(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from dav1d_b200 import obu, stream
     W = STREAM_WORKLOADS[args.workload]
-    nthr = min(os.cpu_count() or 1, 32)
-    mfd = min(8, W["frames"])
+    nthr = int(os.environ.get("B200_STREAM_THREADS", min(os.cpu_count() or 1, 32)))     # dav1d worker threads, both arms
+    mfd = min(8, W["frames"], nthr)
     gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=2, **k)) if W.get("inter") else obu.intra_stream
     fg = int(W.get("film_grain", 0))
     tus = gen(100 + rank, W["W"], W["H"], n_frames=W["frames"], bpc=W["bpc"], log2_cols=W["log2_cols"], log2_rows=W["log2_rows"], film_grain=fg)
