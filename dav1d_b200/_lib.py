@@ -129,7 +129,7 @@ class IntraFrame(C.Structure):
     _fields_ = [("pic", C.c_void_p), ("stride", C.c_int32 * 3), ("ss_hor", C.c_int32), ("ss_ver", C.c_int32),
                 ("w4", C.c_int32 * 3), ("h4", C.c_int32 * 3), ("d_coef", C.c_void_p), ("zero_coefs", C.c_int32),
                 ("grid", C.c_int32), ("scratch", C.c_void_p), ("plane_off", C.c_uint32 * 3), ("n_sb", C.c_int32),
-                ("sb_w", C.c_int32), ("sb_h", C.c_int32), ("sb", C.c_void_p), ("mask", C.c_void_p), ("done_init", C.c_void_p)]
+                ("sb_w", C.c_int32), ("sb_h", C.c_int32), ("sb", C.c_void_p), ("mask", C.c_void_p), ("pal", C.c_void_p), ("done_init", C.c_void_p)]
 
 
 class FrameJob(C.Structure):

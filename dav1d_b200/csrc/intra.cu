@@ -47,14 +47,14 @@ struct IntraFrameDev {
     uint32_t plane_off[3];
     int32_t n_sb, sb_w, sb_h;
     const B200IntraSb *sb;
-    const uint8_t *mask;
+    const uint8_t *mask, *pal;
 };
 struct IntraParams {
     IntraFrameDev f;
     const B200IntraTx *tx;
     int n;
-    int *ticket;
-    uint8_t *done[3];       // superblock mode: done[0] = one flag per superblock
+    uint8_t *scratch;       // [ticket counter: 256 B][done maps]; superblock mode: one flag per superblock at done_off[0]
+    uint32_t done_off[3];
 };
 // several independent frames per launch (blockIdx.y = frame): frames are the parallel axis of intra decoding and
 // one launch is not limited by the number of hardware work queues the way one stream per frame is
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
     const int bitdepth = 32 - __clz(bdmax);
     int *const tl = S.edge + 128;
 
-    if (tid == 0) s_ticket = atomicAdd(P.ticket, 1);
+    if (tid == 0) s_ticket = atomicAdd(((int *)P.scratch), 1);
     __syncthreads();
     if (tid < kRecWords && s_ticket < P.n) s_rec[tid] = ((const uint32_t *)&P.tx[s_ticket])[tid];
     __syncthreads();
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
 #pragma unroll
         for (int k = 0; k < kRecWords; k++) ((uint32_t *)&r)[k] = s_rec[k];
         int nxt = 0;
-        if (tid == 0) nxt = atomicAdd(P.ticket, 1);          // consumed at the end of this iteration
+        if (tid == 0) nxt = atomicAdd(((int *)P.scratch), 1);          // consumed at the end of this iteration
         const int pl = r.plane, st = f.stride[pl];
         const int tw = c_tx_w4[r.tx], th = c_tx_h4[r.tx];              // 4-sample units
         const int w = tw * 4, h = th * 4;
@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
         const bool have_tr = have_top && x + tw < xe && (r.flags & B200_INTRA_TOP_HAS_RIGHT);
         const bool have_bl = have_left && y + th < ye && (r.flags & B200_INTRA_LEFT_HAS_BOTTOM);
         const bool is_cfl = r.mode == B200_INTRA_MODE_CFL && r.cfl_alpha != 0;
-        const bool is_ii = r.mode == B200_INTRA_MODE_II, is_resid = r.mode == B200_INTRA_MODE_RESID;
-        const uint8_t *const dmap = P.done[pl];
+        const bool is_ii = r.mode == B200_INTRA_MODE_II, is_resid = r.mode == B200_INTRA_MODE_RESID, is_pal = r.mode == B200_INTRA_MODE_PAL;
+        const uint8_t *const dmap = (P.scratch + P.done_off[pl]);
         const int mw = f.w4[pl];
         // coefficients: loads issued before the wait, parked in shared memory after it (off the dependency chain)
         const int ncf = imin(w, 32) * imin(h, 32);
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
                     else if (c < n_left) cell = dmap + (y + c) * mw + x - 1;
                     else if (c < n_left + n_top) cell = dmap + (y - 1) * mw + x + (c - n_left);
                     else if (c < n_left + n_top + n_tl) cell = dmap + (y - 1) * mw + x - 1;
-                    else { const int k = c - n_left - n_top - n_tl; cell = P.done[0] + (ly4 + k / lw4) * f.w4[0] + lx4 + k % lw4; }
+                    else { const int k = c - n_left - n_top - n_tl; cell = (P.scratch + P.done_off[0]) + (ly4 + k / lw4) * f.w4[0] + lx4 + k % lw4; }
                     unsigned ns = B200_POLL_NS0, spins = 0;
                     while (ld_cell(cell) != want) {
                         __nanosleep(ns); if (ns < B200_POLL_NSMAX) ns += ns >> 1;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
         // ---- dav1d_prepare_intra_edges: mode conversion (:97-120)
         int mode = r.mode, angle = r.angle;
         if (is_ii) { mode = r.angle; angle = 0; }                              // inter-intra: the predictor is in `angle`
-        if (is_resid) mode = 0;
+        if (is_resid || is_pal) mode = 0;
         if (mode == B200_INTRA_MODE_CFL) mode = 0;                             // DC_PRED (:1446, :1373)
         if (mode >= 1 && mode <= 8) {                                          // VERT_PRED .. VERT_LEFT_PRED
             const int base = mode == 1 ? 90 : mode == 2 ? 180 : mode == 3 ? 45 : mode == 4 ? 135 : mode == 5 ? 113
@@ -268,6 +268,11 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
         if (is_resid) {
             // residual only: the tile is what the inter-intra record of this block left in the picture (another SM wrote it)
             for (int i = tid; i < w * h; i += kIpT) { const int yy = i / w, xx = i - yy * w; s_px[i] = (pixel)ld_px<HBD>(dst + (ptrdiff_t)yy * st + xx); }
+        } else if (is_pal) {
+            // palette: 8 colours, then the index map (two 4-bit indices per byte, low nibble first)
+            const pixel *const colours = (const pixel *)(f.pal + r.luma_off);
+            const uint8_t *const idx = f.pal + r.luma_off + 8 * sizeof(pixel);
+            for (int i = tid; i < w * h; i += kIpT) s_px[i] = colours[(idx[i >> 1] >> ((i & 1) * 4)) & 7];
         } else if (is_cfl) {
             const int dc = S.dc;
             for (int i = tid; i < w * h; i += kIpT) s_ac[i] = (int16_t)(s_ac[i] - dc);
@@ -313,9 +318,9 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
         if (tid < 32) {
             if (tid == 0) __threadfence();
             __syncwarp();
-            uint8_t *const dm = P.done[pl];
+            uint8_t *const dm = (P.scratch + P.done_off[pl]);
             const int cw = imin(tw, mw - x), chh = imin(th, f.h4[pl] - y);
-            const uint8_t state = is_ii && r.cfl_alpha ? 2 : 1;          // 2: predicted, the block's residual records follow
+            const uint8_t state = (is_ii || is_pal) && r.cfl_alpha ? 2 : 1;   // 2: predicted, the block's residual records follow
             for (int c = tid; c < cw * chh; c += 32) *(volatile uint8_t *)(dm + (y + c / cw) * mw + x + c % cw) = state;
         }
         // ---- hand over to the next record
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_SB_MINB) intra_sb_kernel(cons
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_ticket = atomicAdd(P.ticket, 1);
+        if (tid == 0) s_ticket = atomicAdd(((int *)P.scratch), 1);
         __syncthreads();
         const int si = s_ticket;
         if (si >= f.n_sb) break;
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_SB_MINB) intra_sb_kernel(cons
             const int dx = tid == 3 ? 1 : tid == 2 ? 0 : -1, dy = tid == 0 ? 0 : -1;   // left, top-left, top, top-right
             const int nx = sx + dx, ny = sy + dy;
             if (nx >= 0 && nx < f.sb_w && ny >= 0) {
-                const uint8_t *cell = P.done[0] + ny * f.sb_w + nx;
+                const uint8_t *cell = (P.scratch + P.done_off[0]) + ny * f.sb_w + nx;
                 unsigned ns = 64, spins = 0;
                 while (!ld_cell(cell)) {
                     __nanosleep(ns); if (ns < 1024) ns += ns >> 1;
@@ -550,7 +555,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_SB_MINB) intra_sb_kernel(cons
             }
         }
         __syncthreads();
-        if (tid == 0) { __threadfence(); *(volatile uint8_t *)(P.done[0] + sy * f.sb_w + sx) = 1; }
+        if (tid == 0) { __threadfence(); *(volatile uint8_t *)((P.scratch + P.done_off[0]) + sy * f.sb_w + sx) = 1; }
     }
 }
 
@@ -593,11 +598,11 @@ int b200_intra_frames(int bdmax, const B200IntraFrame *frames, const B200IntraTx
             IntraParams &P = B.p[nb++];
             P.f.pic = f->pic; P.f.ss_hor = f->ss_hor; P.f.ss_ver = f->ss_ver; P.f.d_coef = f->d_coef; P.f.zero_coefs = f->zero_coefs;
             for (int p = 0; p < 3; p++) { P.f.stride[p] = f->stride[p]; P.f.w4[p] = f->w4[p]; P.f.h4[p] = f->h4[p]; P.f.plane_off[p] = f->plane_off[p]; }
-            P.f.n_sb = f->n_sb; P.f.sb_w = f->sb_w; P.f.sb_h = f->sb_h; P.f.sb = f->sb; P.f.mask = f->mask;
+            P.f.n_sb = f->n_sb; P.f.sb_w = f->sb_w; P.f.sb_h = f->sb_h; P.f.sb = f->sb; P.f.mask = f->mask; P.f.pal = f->pal;
             P.tx = d_tx[i]; P.n = n_tx[i];
             uint8_t *base_p = (uint8_t *)f->scratch;
-            P.ticket = (int *)base_p;
-            for (int p = 0; p < 3; p++) P.done[p] = base_p + L.done_off[p];
+            P.scratch = base_p;
+            for (int p = 0; p < 3; p++) P.done_off[p] = (uint32_t)L.done_off[p];
             if (!mode && f->done_init)
                 B200_CUDA_OK(cudaMemcpyAsync(base_p, f->done_init, L.total, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
             else

@@ -60,7 +60,7 @@ OBU_SEQ_HDR, OBU_TD, OBU_FRAME = 1, 2, 6
 
 
 def sequence_header(w, h, bpc=8, sb128=0, film_grain=0, filter_intra=1, intra_edge_filter=1, cdef=1, restoration=1,
-                    inter_intra=1, masked_compound=1, warped_motion=1):
+                    inter_intra=1, masked_compound=1, warped_motion=1, screen_content=0):
     b = BitWriter()
     b.f(3, 0)                                # seq_profile 0: 4:2:0, 8 / 10 bit
     b.f(1, 0); b.f(1, 0)                     # still_picture, reduced_still_picture_header
@@ -78,7 +78,9 @@ def sequence_header(w, h, bpc=8, sb128=0, film_grain=0, filter_intra=1, intra_ed
     b.f(1, inter_intra); b.f(1, masked_compound); b.f(1, warped_motion); b.f(1, 1)   # ..., dual filter
     b.f(1, 1)                                # enable_order_hint
     b.f(1, 1); b.f(1, 0)                     # jnt_comp, ref_frame_mvs
-    b.f(1, 0); b.f(1, 0)                     # seq_choose_screen_content_tools = 0, seq_force_screen_content_tools = 0
+    b.f(1, 0); b.f(1, screen_content)        # seq_choose_screen_content_tools = 0, seq_force_screen_content_tools
+    if screen_content:
+        b.f(1, 0); b.f(1, 0)                 # seq_choose_integer_mv = 0, seq_force_integer_mv = 0
     b.f(3, 6)                                # order_hint_bits_minus_1
     b.f(1, 0); b.f(1, cdef); b.f(1, restoration)   # superres, cdef, restoration
     b.f(1, 1 if bpc > 8 else 0)              # high_bitdepth (profile 0: 10 bit)
@@ -184,7 +186,7 @@ def _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_byt
 
 
 def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None, lf=None, cdef=True,
-              restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0):
+              restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0, screen_content=0):
     """One shown key frame (OBU_FRAME). Returns the OBU bytes. `cdef_on` / `restoration_on` must match the sequence
     header (the fields are absent when the sequence disables the tool)."""
     b = BitWriter()
@@ -194,6 +196,8 @@ def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb
     b.f(1, 0)                                # frame_size_override
     b.f(7, 0)                                # order_hint
     b.f(1, 0)                                # render_and_frame_size_different
+    if screen_content:
+        b.f(1, 0)                            # allow_intrabc
     b.f(1, 0)                                # disable_frame_end_update_cdf
     cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on)
     b.f(1, 1)                                # tx_mode_select
@@ -207,12 +211,14 @@ def temporal_unit(*obus):
     return obu(OBU_TD, b"") + b"".join(obus)
 
 
-def intra_stream(seed, w, h, n_frames=1, bpc=8, sb128=0, log2_cols=0, log2_rows=0, film_grain=0, **kw):
+def intra_stream(seed, w, h, n_frames=1, bpc=8, sb128=0, log2_cols=0, log2_rows=0, film_grain=0, screen_content=0, **kw):
     """A list of temporal units (bytes), each holding one shown key frame."""
     rng = np.random.default_rng(seed)
-    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, film_grain=film_grain)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, film_grain=film_grain, screen_content=screen_content)
     if film_grain:
         kw = dict(kw, film_grain_seq=1)
+    if screen_content:
+        kw = dict(kw, screen_content=1)
     tus = []
     for i in range(n_frames):
         fr = key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, **kw)
@@ -334,19 +340,19 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
     return obu(OBU_FRAME, _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_bytes_per_sb64))
 
 
-def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, film_grain=0, **kw):
+def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, film_grain=0, screen_content=0, **kw):
     """Temporal units: one key frame, then n_frames - 1 inter frames (single and compound references incl. wedge /
     difference-weighted masks and distance weights, switchable interpolation filters, variable transform trees, intra
     blocks; identity global motion). motion_modes=1 additionally enables the per-block motion mode (overlapped block
     motion compensation, locally warped motion), motion_modes=2 inter-intra prediction as well."""
     rng = np.random.default_rng(seed)
-    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=1 if motion_modes >= 2 else 0, warped_motion=1 if motion_modes else 0, film_grain=film_grain)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=1 if motion_modes >= 2 else 0, warped_motion=1 if motion_modes else 0, film_grain=film_grain, screen_content=screen_content)
     if motion_modes:
         kw = dict(kw, switchable_motion_mode=1, warped_motion_seq=1, allow_warped_motion=1)
     if film_grain:
         kw = dict(kw, film_grain_seq=1)
     hints = [0] * 8
-    tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, film_grain_seq=film_grain))]
+    tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, film_grain_seq=film_grain, screen_content=screen_content))]
     for i in range(1, n_frames):
         tus.append(temporal_unit(inter_frame(rng, w, h, i, hints, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, **kw)))
     return tus

@@ -472,7 +472,12 @@ enum { B200_INTRA_MODE_FILTER = 13, B200_INTRA_MODE_CFL = 14,   /* besides enum 
         * bytes into B200IntraFrame.mask (pitch = block width). It carries no residual: the block's transform blocks
         * follow as RESID records, which add their residual to the pixels in place. cfl_alpha != 0 in the II record says
         * that RESID records follow (the done map then holds 2 = "predicted" until they publish 1 = "final"). */
-       B200_INTRA_MODE_II = 15, B200_INTRA_MODE_RESID = 16 };
+       B200_INTRA_MODE_II = 15, B200_INTRA_MODE_RESID = 16,
+       /* palette (reference src/recon_tmpl.c:1201-1223, 1400-1419; pal_pred_c src/ipred_tmpl.c:717-730): a PAL record covers
+        * the whole block (`tx` = the block's size); `luma_off` = byte offset into B200IntraFrame.pal of 8 palette entries
+        * (pixels) followed by the w x h index map, two 4-bit indices per byte, low nibble first, pitch w / 2 (dav1d's
+        * packed pal_idx). Like II it carries no residual: RESID records follow when cfl_alpha != 0. */
+       B200_INTRA_MODE_PAL = 17 };
 typedef struct B200IntraTx {
     uint32_t dst_off;              /* sample offset of the transform block in the picture (plane offset included) */
     uint32_t coef_off;             /* into d_coef, dav1d's transposed layout, min(w,32) x min(h,32) */
@@ -511,6 +516,7 @@ typedef struct B200IntraFrame {
     int32_t n_sb, sb_w, sb_h;      /* superblock mode: number of B200IntraSb, superblock grid */
     const B200IntraSb *sb;         /* device; NULL = per-transform-block dataflow */
     const uint8_t *mask;           /* device or NULL: blend masks of B200_INTRA_MODE_II records (per-transform-block mode only) */
+    const uint8_t *pal;            /* device or NULL: palettes + index maps of B200_INTRA_MODE_PAL records */
     const uint8_t *done_init;      /* device or NULL; per-transform-block mode only. Frames that mix inter and intra blocks:
                                       an image of the scratch (b200_intra_scratch_bytes: 256 zero bytes, then one byte per
                                       4x4 cell for plane 0, 1, 2, each map padded to a multiple of 256 bytes) in which the

@@ -235,13 +235,13 @@ int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int
     return n_waves;
 }
 
-void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[8], double prep_ms)
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[9], double prep_ms)
 {
     pthread_mutex_lock(&g_lock);
     g_stats.frames++; g_stats.records += records; g_stats.coefs += coefs;
     g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += d2h; g_stats.device_ms += ms;
     g_stats.intra_tx += kinds[0]; g_stats.pred += kinds[1]; g_stats.comp += kinds[2]; g_stats.warp += kinds[3];
-    g_stats.host_prep_ms += prep_ms; g_stats.interintra += kinds[7];
+    g_stats.host_prep_ms += prep_ms; g_stats.interintra += kinds[7]; g_stats.palette_bytes += kinds[8];
     g_stats.blend += kinds[4]; g_stats.itx += kinds[5]; g_stats.inter_frames += kinds[6];
     pthread_mutex_unlock(&g_lock);
 }
@@ -267,6 +267,7 @@ API void b200hook_release(void)
         b200hook_buf_free(&h->pred); b200hook_buf_free(&h->comp); b200hook_buf_free(&h->comp2);
         for (int t = 0; t < 19; t++) b200hook_buf_free(&h->itx[t]);
         b200hook_buf_free(&h->tmp16); b200hook_buf_free(&h->cmask); b200hook_buf_free(&h->done_init);
+        b200hook_buf_free(&h->pal);
         b200hook_buf_free(&h->warp); b200hook_buf_free(&h->blend); b200hook_buf_free(&h->blend2); b200hook_buf_free(&h->pxtmp);
         if (h->stream && g_be_ok) g_be.stream_destroy(h->stream);
         pthread_mutex_destroy(&h->lock);

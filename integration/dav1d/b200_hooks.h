@@ -49,6 +49,8 @@ typedef struct HookFrame {
      * wedge tables at its head, difference-weighted masks behind them) and the initial done map of the intra kernel
      * (cells of inter blocks are "done" before it starts) */
     HookBuf pred, comp, comp2, itx[19], tmp16, cmask, done_init;
+    HookBuf pal;                             /* palettes + packed index maps of palette blocks (slots taken atomically) */
+    size_t n_pal, cap_pal;
     HookBuf warp, blend, blend2, pxtmp;      /* warped-motion 8x8 blocks; OBMC: blend_h stage, blend_v stage, pixel scratch (device only) */
     int n_pred, n_comp, n_comp2, n_itx[19], n_warp, n_blend, n_blend2;
     size_t n_tmp16, n_cmask, n_pxtmp;
@@ -77,7 +79,8 @@ typedef struct B200HookStats {
     uint64_t intra_tx, pred, comp, warp, blend, itx, inter_frames;      /* records by kind */
     double host_prep_ms;            /* frame completion on the host before the job: mask fix-ups, wavefront sort, staging */
     uint64_t interintra;            /* inter-intra records (a subset of intra_tx) */
+    uint64_t palette_bytes;         /* palettes + index maps shipped for palette blocks */
 } B200HookStats;
-void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[8], double prep_ms);
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[9], double prep_ms);
 
 #endif

@@ -22,7 +22,8 @@
  *                      grain job on the HBM-resident picture, result copied into the output picture
  *                      inter-intra: an II record per plane (intra predictor over the block, blended into the inter
  *                      prediction by the intra dataflow kernel) + the block's residual as RESID records
- * Not translated yet (the frame fails loudly, there is no CPU fallback): palette, intra block copy, scaled references.
+ *                      palette blocks: a PAL record per plane (palette + dav1d's packed index map) + RESID records
+ * Not translated yet (the frame fails loudly, there is no CPU fallback): intra block copy, scaled references.
  */
 #include "config.h"
 #include <stdio.h>
@@ -81,10 +82,14 @@ static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *c
         const size_t aw4 = (f->bw + 31) & ~31, ah4 = (f->bh + 31) & ~31;
         const size_t cells = aw4 * ah4 + (f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I400 ? 2 * ((aw4 >> ss_hor) * (ah4 >> ss_ver)) : 0);
         hf->cap_tx = (int)cells; hf->cap_coef = cells * 16;
+        /* palette blocks: 8 bytes of packed indices per 4x4 cell + 8 palette entries per block (>= 1 cell) */
+        hf->cap_pal = f->frame_hdr->allow_screen_content_tools ? cells * (8 + 8 * sizeof(pixel)) : 0;
+        hf->n_pal = 0;
         if (b200hook_buf_reserve(&hf->tx, cells * sizeof(B200IntraTx), 1, 0) ||
-            b200hook_buf_reserve(&hf->coef, cells * 16 * sizeof(coef), 1, 0)) {
+            b200hook_buf_reserve(&hf->coef, cells * 16 * sizeof(coef), 1, 0) ||
+            (hf->cap_pal && b200hook_buf_reserve(&hf->pal, hf->cap_pal, 1, 0))) {
             __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
-            hf->cap_tx = 0; hf->cap_coef = 0;       /* nothing can be emitted: the frame fails when it completes */
+            hf->cap_tx = 0; hf->cap_coef = 0; hf->cap_pal = 0;      /* nothing can be emitted: the frame fails when it completes */
         }
         __atomic_store_n(&hf->started, 1, __ATOMIC_RELEASE);
     }
@@ -139,6 +144,37 @@ static int bitfn(take_residual)(TxCtx *const c, B200IntraTx *const r, const Txfm
     return 0;
 }
 
+/* the transform size with the dimensions of a w4 x h4 block (4-sample units), -1 if dav1d has none */
+static int bitfn(tx_of_dims)(const int w4, const int h4)
+{
+    for (int tx = 0; tx < N_RECT_TX_SIZES; tx++)
+        if (dav1d_txfm_dimensions[tx].w == w4 && dav1d_txfm_dimensions[tx].h == h4) return tx;
+    return -1;
+}
+
+/* palette block of one plane (reference :1201-1223 luma, :1400-1419 chroma): a PAL record over the whole block, the
+ * palette and dav1d's packed index map copied into the frame's palette buffer */
+static int bitfn(emit_palette)(TxCtx *const c, const int pl, const int pw4, const int ph4, const uint32_t dst_off,
+                               const int x4, const int y4, const pixel *const pal, const uint8_t *const idx)
+{
+    HookFrame *const hf = c->hf;
+    const int tx = bitfn(tx_of_dims)(pw4, ph4);
+    const size_t idx_bytes = (size_t)pw4 * ph4 * 8, need = (8 * sizeof(pixel) + idx_bytes + 15) & ~(size_t)15;
+    if (tx < 0) { __atomic_fetch_or(&hf->unsupported, 1, __ATOMIC_RELAXED); return 0; }
+    const size_t at = __atomic_fetch_add(&hf->n_pal, need, __ATOMIC_RELAXED);
+    B200IntraTx *const r = bitfn(new_record)(hf);
+    if (!r || at + need > hf->cap_pal) return -1;
+    memcpy((uint8_t *)hf->pal.host + at, pal, 8 * sizeof(pixel));
+    memcpy((uint8_t *)hf->pal.host + at + 8 * sizeof(pixel), idx, idx_bytes);
+    r->mode = B200_INTRA_MODE_PAL; r->plane = pl; r->tx = tx; r->dst_off = dst_off; r->eob = -1;
+    r->x4 = x4; r->y4 = y4;
+    r->xend4 = c->t->ts->tiling.col_end >> (pl && c->t->f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444);
+    r->yend4 = c->t->ts->tiling.row_end >> (pl && c->t->f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420);
+    r->luma_off = (uint32_t)at;
+    r->cfl_alpha = !c->b->skip;               /* residual records follow */
+    return 0;
+}
+
 void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSize bs,
                                    const enum EdgeFlags intra_edge_flags, const Av1Block *const b)
 {
@@ -168,18 +204,29 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
     const int layout_shift = f->cur.p.layout - 1;      /* EDGE_I420_* >> (layout - 1) selects this layout's chroma flags */
 
     bitfn(frame_started)(hf, f);
-    if (b->pal_sz[0] || (has_chroma && b->pal_sz[1])) __atomic_fetch_or(&hf->unsupported, 1, __ATOMIC_RELAXED);
+    /* palette: the colours live in f->frame_thread.pal (one entry per 8x8 area, indexed like the reference does), the
+     * packed index maps are consumed from the tile's pal_idx cursor exactly like the reference consumes them */
+    const pixel (*const pal)[8] = !(b->pal_sz[0] | b->pal_sz[1]) ? NULL :
+        f->frame_thread.pal[((by >> 1) + (bx & 1)) * (f->b4_stride >> 1) + ((bx >> 1) + (by & 1))];
+    const int pass_idx = t->frame_thread.pass & 1;
     /* the reference walks a block in 64x64-luma chunks: luma transform blocks of the chunk, then its chroma */
     for (int iy = 0; iy < h4; iy += 16) {
         const int y_end = imin(h4, iy + 16), cy_end = imin(ch4, (iy + 16) >> ss_ver);
         for (int ix = 0; ix < w4; ix += 16) {
             const int x_end = imin(w4, ix + 16), cx_end = imin(cw4, (ix + 16) >> ss_hor);
             /* ---- luma ---- */
+            if (b->pal_sz[0]) {
+                const uint8_t *const idx = ts->frame_thread[pass_idx].pal_idx;
+                ts->frame_thread[pass_idx].pal_idx += bw4 * bh4 * 8;
+                if (bitfn(emit_palette)(&c, 0, bw4, bh4, c.g.off[0] + (uint32_t)(4 * by) * c.g.stride[0] + 4 * bx, bx, by, pal[0], idx))
+                    { __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED); goto out; }
+            }
             const int y_flags = sm_flag(t->a, bx4) | sm_flag(&t->l, by4) | edge_filter_bit;
             const int chunk_tr = ix + 16 < w4 ? 1 : iy ? 0 : !!(intra_edge_flags & EDGE_I444_TOP_HAS_RIGHT);
             const int chunk_bl = ix ? 0 : iy + 16 < h4 ? 1 : !!(intra_edge_flags & EDGE_I444_LEFT_HAS_BOTTOM);
             for (int y = iy; y < y_end; y += yt->h)
                 for (int x = ix; x < x_end; x += yt->w) {
+                    if (b->pal_sz[0] && b->skip) continue;      /* palette block without residual: the PAL record is final */
                     B200IntraTx *const r = bitfn(new_record)(hf);
                     if (!r) { __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED); goto out; }
                     const int px = bx + x, py = by + y;
@@ -188,12 +235,14 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
                     r->dst_off = c.g.off[0] + (uint32_t)(4 * py) * c.g.stride[0] + 4 * px;
                     r->mode = b->y_mode; r->angle = b->y_angle;
                     r->angle_flags = y_flags;
+                    if (b->pal_sz[0]) r->mode = B200_INTRA_MODE_RESID;      /* the palette record predicted the whole block */
                     r->max_w = 4 * f->bw - 4 * px; r->max_h = 4 * f->bh - 4 * py;
                     const int last_col = x + yt->w >= x_end, last_row = y + yt->h >= y_end;
                     r->flags = (px > ts->tiling.col_start ? B200_INTRA_HAVE_LEFT : 0) |
                                (py > ts->tiling.row_start ? B200_INTRA_HAVE_TOP : 0) |
                                (((y > iy || !chunk_tr) && last_col) ? 0 : B200_INTRA_TOP_HAS_RIGHT) |
                                ((x > ix || (!chunk_bl && last_row)) ? 0 : B200_INTRA_LEFT_HAS_BOTTOM);
+                    if (b->pal_sz[0]) r->flags = 0;
                     if (bitfn(take_residual)(&c, r, yt, 0)) { __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED); goto out; }
                 }
             if (!has_chroma) continue;
@@ -212,9 +261,19 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
                 const int far_b = ((ch4 << ss_ver) + yt->h - 1) & ~(yt->h - 1);
                 cfl_wpad = cbw4 - (far_r >> ss_hor); cfl_hpad = cbh4 - (far_b >> ss_ver);
             }
+            const int uv_pal = !is_cfl && b->pal_sz[1];
+            if (uv_pal) {
+                const uint8_t *const idx = ts->frame_thread[pass_idx].pal_idx;
+                ts->frame_thread[pass_idx].pal_idx += cbw4 * cbh4 * 8;
+                for (int pl = 1; pl <= 2; pl++)
+                    if (bitfn(emit_palette)(&c, pl, cbw4, cbh4, c.g.off[pl] + (uint32_t)(4 * (by >> ss_ver)) * c.g.stride[pl] + 4 * (bx >> ss_hor),
+                                            bx >> ss_hor, by >> ss_ver, pal[pl], idx))
+                        { __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED); goto out; }
+            }
             for (int pl = 1; pl <= 2; pl++)
                 for (int y = iy >> ss_ver; y < cy_end; y += ct->h)
                     for (int x = ix >> ss_hor; x < cx_end; x += ct->w) {
+                        if (uv_pal && b->skip) continue;
                         B200IntraTx *const r = bitfn(new_record)(hf);
                         if (!r) { __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED); goto out; }
                         /* luma-unit position the reference's t->bx / t->by would hold here */
@@ -238,7 +297,8 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
                         } else {
                             r->mode = b->uv_mode; r->angle = b->uv_angle;
                         }
-                        if (!is_cfl || !r->cfl_alpha)      /* alpha == 0 is a plain DC_PRED with the usual edge rules */
+                        if (uv_pal) { r->mode = B200_INTRA_MODE_RESID; r->flags = 0; }
+                        else if (!is_cfl || !r->cfl_alpha)      /* alpha == 0 is a plain DC_PRED with the usual edge rules */
                             r->flags |= (((y > (iy >> ss_ver) || !uv_tr) && last_col) ? 0 : B200_INTRA_TOP_HAS_RIGHT) |
                                         ((x > (ix >> ss_hor) || (!uv_bl && last_row)) ? 0 : B200_INTRA_LEFT_HAS_BOTTOM);
                         if (bitfn(take_residual)(&c, r, ct, 1)) { __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED); goto out; }
@@ -358,22 +418,13 @@ static int bitfn(emit_obmc)(HookFrame *const hf, const Dav1dFrameContext *const 
 static int bitfn(emit_interintra)(TxCtx *const c, const enum BlockSize bs, const int pl, const uint32_t dst_off,
                                   const int bx, const int by, const uint8_t *const mask)
 {
-    static const int8_t tx_of[9][9] = {      /* [w4][h4] -> enum RectTxfmSize, -1 where dav1d has no such transform */
-        { -1, -1, -1, -1, -1, -1, -1, -1, -1 },
-        { -1, TX_4X4, RTX_4X8, -1, RTX_4X16, -1, -1, -1, -1 },
-        { -1, RTX_8X4, TX_8X8, -1, RTX_8X16, -1, -1, -1, RTX_8X32 },
-        { -1, -1, -1, -1, -1, -1, -1, -1, -1 },
-        { -1, RTX_16X4, RTX_16X8, -1, TX_16X16, -1, -1, -1, RTX_16X32 },
-        { -1, -1, -1, -1, -1, -1, -1, -1, -1 }, { -1, -1, -1, -1, -1, -1, -1, -1, -1 }, { -1, -1, -1, -1, -1, -1, -1, -1, -1 },
-        { -1, -1, RTX_32X8, -1, RTX_32X16, -1, -1, -1, TX_32X32 },
-    };
     HookFrame *const hf = c->hf;
     const Dav1dFrameContext *const f = c->t->f;
     const Dav1dTileState *const ts = c->t->ts;
     const int ss_ver = pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
     const uint8_t *const dim = dav1d_block_dimensions[bs];
     const int pw4 = (dim[0] + ss_hor) >> ss_hor, ph4 = (dim[1] + ss_ver) >> ss_ver;
-    const int tx = pw4 <= 8 && ph4 <= 8 ? tx_of[pw4][ph4] : -1;
+    const int tx = bitfn(tx_of_dims)(pw4, ph4);
     if (tx < 0) { __atomic_fetch_or(&hf->unsupported, 256, __ATOMIC_RELAXED); return 0; }
     B200IntraTx *const r = bitfn(new_record)(hf);
     if (!r) return -1;
@@ -758,6 +809,8 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     if (b200hook_buf_reserve(&hf->scratch, be->intra_scratch_bytes(&j.intra), 0, 0)) return -1;
     j.intra.scratch = hf->scratch.dev;
     j.intra.mask = inter ? (const uint8_t *)hf->cmask.dev : NULL;
+    j.intra.pal = hf->n_pal ? (const uint8_t *)hf->pal.dev : NULL;
+    if (hf->n_pal > hf->cap_pal) { fprintf(stderr, "b200hook: palette buffer overflowed\n"); return -1; }
     if (inter && hf->n_tx > 0) {
         /* intra blocks inside an inter frame: everything that is not an intra transform block is already final */
         const size_t total = be->intra_scratch_bytes(&j.intra);
@@ -825,6 +878,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     UP(*txb, (size_t)hf->n_tx * sizeof(B200IntraTx));
     UP(hf->coef, hf->n_coef * sizeof(coef));
     UP(hf->mask, mask_bytes); UP(hf->level, level_bytes); UP(hf->lr_mask, lr_bytes);
+    if (hf->n_pal) UP(hf->pal, hf->n_pal);
     if (inter) {
         UP(hf->pred, (size_t)hf->n_pred * sizeof(B200McBlock));
         UP(hf->comp, (size_t)hf->n_comp * sizeof(B200CompBlock));
@@ -858,8 +912,8 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     uint64_t n_itx = 0;
     for (int t = 0; t < N_RECT_TX_SIZES; t++) n_itx += hf->n_itx[t];
     n_rec += n_itx;
-    const uint64_t kinds[8] = { (uint64_t)hf->n_tx, (uint64_t)hf->n_pred, (uint64_t)hf->n_comp + hf->n_comp2, (uint64_t)hf->n_warp,
-                                (uint64_t)hf->n_blend + hf->n_blend2, n_itx, (uint64_t)inter, (uint64_t)hf->n_ii };
+    const uint64_t kinds[9] = { (uint64_t)hf->n_tx, (uint64_t)hf->n_pred, (uint64_t)hf->n_comp + hf->n_comp2, (uint64_t)hf->n_warp,
+                                (uint64_t)hf->n_blend + hf->n_blend2, n_itx, (uint64_t)inter, (uint64_t)hf->n_ii, (uint64_t)hf->n_pal };
     b200hook_account(n_rec, hf->n_coef, h2d, d2h, bitfn(now_ms)() - t0, kinds, t0 - t_enter);
     return 0;
 }

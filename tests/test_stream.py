@@ -107,6 +107,17 @@ def test_film_grain_stream_emu_matches_stock_dav1d(emu_decoder, case):
 
 
 @pytest.mark.emu
+@pytest.mark.parametrize("case", [(256, 192, 8, 2, 0, 0), (320, 192, 10, 3, 1, 0), (640, 360, 8, 2, 0, 1)])
+def test_screen_content_stream_emu_matches_stock_dav1d(emu_decoder, case):
+    """allow_screen_content_tools: palette blocks (luma and chroma palettes, packed index maps) in key and inter frames"""
+    w, h, bpc, nf, inter, sb128 = case
+    gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=2, **k)) if inter else obu.intra_stream
+    tus = gen(7, w, h, n_frames=nf, bpc=bpc, sb128=sb128, screen_content=1)
+    _check(emu_decoder, tus, nf)
+    assert emu_decoder.last_stats["palette_bytes"] > 0, "no palette block in the stream"
+
+
+@pytest.mark.emu
 def test_stream_many_decoders_recycle_slots(emu_decoder):
     """frame contexts and host pictures of closed decoders must not exhaust the hook's tables (each decode opens a new
     dav1d context; the tables are recycled least-recently-used)"""
@@ -196,3 +207,12 @@ def test_film_grain_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
     gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=2, **k)) if inter else obu.intra_stream
     tus = gen(60 + (hash(case) & 0xff), w, h, n_frames=nf, bpc=bpc, log2_cols=1, log2_rows=1, film_grain=1)
     _check(gpu_decoder, tus, nf, apply_grain=1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(1280, 720, 8, 2, 0, 0), (1920, 1080, 10, 3, 1, 1)])
+def test_screen_content_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
+    w, h, bpc, nf, inter, sb128 = case
+    gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=2, **k)) if inter else obu.intra_stream
+    tus = gen(9, w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=1, log2_rows=1, screen_content=1)
+    _check(gpu_decoder, tus, nf)
