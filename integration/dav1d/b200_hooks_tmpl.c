@@ -872,9 +872,9 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     j.lr.restore_planes = f->lf.restore_planes;
     j.lr.lr_mask = (const B200Av1Restoration *)hf->lr_mask.dev;
 
-    B200Xfer up[32];
+    B200Xfer up[48];          /* 6 fixed + 8 inter lists + 19 transform sizes + done map: 34 at most */
     int n_up = 0;
-#define UP(buf, nbytes) do { up[n_up].host = (buf).host; up[n_up].dev = (buf).dev; up[n_up].bytes = (uint64_t)(nbytes); n_up++; } while (0)
+#define UP(buf, nbytes) do { if (n_up >= 48) abort(); up[n_up].host = (buf).host; up[n_up].dev = (buf).dev; up[n_up].bytes = (uint64_t)(nbytes); n_up++; } while (0)
     UP(*txb, (size_t)hf->n_tx * sizeof(B200IntraTx));
     UP(hf->coef, hf->n_coef * sizeof(coef));
     UP(hf->mask, mask_bytes); UP(hf->level, level_bytes); UP(hf->lr_mask, lr_bytes);
