@@ -1,11 +1,12 @@
 /*
- * oracle/refdriver/stream_driver.c — TEST INFRASTRUCTURE.
+ * integration/dav1d/stream_driver.c — a minimal dav1d client (what tools/dav1d.c does, without the muxers).
  *
  * Decodes an AV1 elementary stream (a list of temporal units) through dav1d's PUBLIC API only
  * (dav1d_open / dav1d_send_data / dav1d_get_picture, reference include/dav1d/dav1d.h, src/lib.c)
- * and packs every output picture tightly into one buffer. Linked both into oracle/_ref/libdav1d_ref.so
- * (the stock CPU decoder = the checker) and into integration/_ref/libdav1d_b200.so (the same front end
- * with the B200 back end behind f->bd_fn), so a test can compare the two byte for byte.
+ * and packs every output picture tightly into one buffer. It knows nothing about either back end: it is linked
+ * into integration/_ref/libdav1d_b200.so (dav1d's front end with the B200 back end behind f->bd_fn) and — by
+ * oracle/Makefile — into oracle/_ref/libdav1d_ref.so (the stock CPU decoder = the checker), so a test can compare
+ * the two byte for byte.
  */
 #include <errno.h>
 #include <stdint.h>
