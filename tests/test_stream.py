@@ -216,3 +216,60 @@ def test_screen_content_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
     gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=2, **k)) if inter else obu.intra_stream
     tus = gen(9, w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=1, log2_rows=1, screen_content=1)
     _check(gpu_decoder, tus, nf)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_synthetic_headers_are_accepted_by_the_stock_decoder():
+    """the bit-level header writer (dav1d_b200/obu.py) against dav1d's own parser over many random parameter draws:
+    tile layouts, quantiser / delta-q / delta-lf, loop filter, CDEF, restoration unit sizes, interpolation filters,
+    reference lists (skip-mode signalling depends on the order hints), film grain parameters, screen content"""
+    n = 0
+    for seed in range(24):
+        rng = np.random.default_rng(seed)
+        w, h = int(rng.integers(3, 12)) * 16, int(rng.integers(3, 10)) * 16
+        kw = dict(bpc=int(rng.choice([8, 10])), sb128=int(rng.integers(0, 2)), log2_cols=int(rng.integers(0, 2)),
+                  log2_rows=int(rng.integers(0, 2)), film_grain=int(rng.integers(0, 2)), screen_content=int(rng.integers(0, 2)))
+        if seed & 1:
+            tus = obu.inter_stream(seed, w, h, n_frames=4, motion_modes=int(rng.integers(0, 3)), **kw)
+        else:
+            tus = obu.intra_stream(seed, w, h, n_frames=2, **kw)
+        r, info, _ = _ref_decode(tus, apply_grain=1)
+        assert r == len(tus), "seed %d: stock dav1d rejected the stream (%d)" % (seed, r)
+        assert (info[:, 0] == w).all() and (info[:, 1] == h).all() and (info[:, 2] == kw["bpc"]).all()
+        n += r
+    assert n == 12 * 2 + 12 * 4
+
+
+def test_hook_wavefront_sort_is_a_valid_order():
+    """b200hook_wave_sort (integration/dav1d/b200_hooks.c): the order it produces must keep every intra record behind the
+    records whose pixels its edge array reads (the kernel's ticket order requirement), for records in decode order"""
+    from dav1d_b200 import synth, levels as L
+    if os.path.isdir("/root/reference/src"):
+        stream.build_hooked()
+    dll = C.CDLL(stream.HOOKED_SO)
+    S = synth.make_intra_frame(np.random.default_rng(11), 8, 328, 200)
+    tx = S["intra_tx_decode_order"]
+    n = len(tx)
+    out = np.zeros_like(tx)
+    w4 = (C.c_int32 * 3)(S["w4"], S["w4"] >> 1, S["w4"] >> 1)
+    h4 = (C.c_int32 * 3)(S["h4"], S["h4"] >> 1, S["h4"] >> 1)
+    dll.b200hook_wave_sort.restype = C.c_int
+    waves = dll.b200hook_wave_sort(tx.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n, w4, h4, 1, 1)
+    assert waves == S["intra_waves"], (waves, S["intra_waves"])          # same depth as the generator's own numbering
+    # same multiset of records, and every record's dependency cells are owned by earlier records
+    assert sorted(out.tobytes()[i * tx.itemsize:(i + 1) * tx.itemsize] for i in range(n)) == \
+           sorted(tx.tobytes()[i * tx.itemsize:(i + 1) * tx.itemsize] for i in range(n))
+    owner = [np.full((h4[p], w4[p]), -1, np.int64) for p in range(3)]
+    for i in range(n):
+        r = out[i]
+        pl, x, y = int(r["plane"]), int(r["x4"]), int(r["y4"])
+        tw, th = L.TX_W[r["tx"]] // 4, L.TX_H[r["tx"]] // 4
+        fl = int(r["flags"])
+        om = owner[pl]
+        if fl & 1:
+            rows = min(th, h4[pl] - y) + (min(th, h4[pl] - y - th) if (fl & 8) and y + th < h4[pl] else 0)
+            assert (om[y:y + rows, x - 1] >= 0).all(), "record %d reads a left neighbour that comes later" % i
+        if fl & 2:
+            cols = min(tw, w4[pl] - x) + (min(tw, w4[pl] - x - tw) if (fl & 4) and x + tw < w4[pl] else 0)
+            assert (om[y - 1, x:x + cols] >= 0).all(), "record %d reads a top neighbour that comes later" % i
+        om[y:y + th, x:x + tw] = i
