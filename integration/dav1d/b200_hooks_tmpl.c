@@ -188,7 +188,7 @@ void bitfn(b200hook_recon_b_intra)(Dav1dTaskContext *const t, const enum BlockSi
         __atomic_fetch_or(&hf->unsupported, 4, __ATOMIC_RELAXED);
         return;
     }
-    TxCtx c = { hf, t, b };
+    TxCtx c = { .hf = hf, .t = t, .b = b };
     bitfn(pic_geom)(f, &c.g);
     const int ss_ver = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
     const int ss_hor = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
@@ -494,7 +494,7 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
         __atomic_fetch_or(&hf->unsupported, 4, __ATOMIC_RELAXED);
         return -1;
     }
-    TxCtx c = { hf, t, b };
+    TxCtx c = { .hf = hf, .t = t, .b = b };
     bitfn(pic_geom)(f, &c.g);
     const PicGeom *const g = &c.g;
     const int ss_ver = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
@@ -592,7 +592,7 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
                     if (bitfn(emit_warp)(hf, f, t, 1, tmp_off[i], pw, dim, pl, b->ref[i], &f->frame_hdr->gmv[b->ref[i]])) goto out;
                 } else if (bitfn(emit_mc)(hf, f, 1, tmp_off[i], bw4, bh4, bx, by, pl, b->mv[i], b->ref[i], filter_2d)) goto out;
             }
-            const int seg = b->comp_type == COMP_INTER_SEG, wedge = b->comp_type == COMP_INTER_WEDGE;
+            const int seg = b->comp_type == COMP_INTER_SEG;
             /* chroma of a difference-weighted block reads the mask its luma block writes: second compound stage */
             B200CompBlock *const r = (pl && seg) ? b200hook_append(&hf->comp2, &hf->n_comp2, sizeof(*r))
                                                  : b200hook_append(&hf->comp, &hf->n_comp, sizeof(*r));
@@ -621,7 +621,6 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
                 } else {
                     r->op = B200_COMP_MASK; r->mask_off = mask_off;
                 }
-                (void)wedge;
             }
         }
     }
