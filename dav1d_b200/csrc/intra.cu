@@ -13,6 +13,13 @@
 //     the finished block to the picture with row-contiguous stores, fences, publishes its cells;
 //   * the next ticket, the next record and an L2 prefetch of its coefficients are issued while the current block is
 //     in flight, so that only [poll -> edge loads -> predict -> transform -> store -> fence] is on the dependency chain.
+// Three more record kinds ride on the same machine (frames that mix prediction types, reference src/recon_tmpl.c:1201-1223,
+// 1601-1626, 1737-1777): B200_INTRA_MODE_PAL writes a palette block from its 8 colours + packed index map,
+// B200_INTRA_MODE_II blends an intra predictor over a whole inter block into the inter prediction that an earlier launch
+// left in the picture (inter-intra), and B200_INTRA_MODE_RESID adds a transform block's residual to such a block in place.
+// The done map therefore has three states per 4x4 cell: 0 = not written, 2 = predicted (PAL / II with residual records to
+// come), 1 = final. Neighbours wait for 1, a RESID record waits for 2 on its own cells. In frames with inter blocks the map
+// starts from `done_init` (every cell that no intra record covers is already final when the kernel starts).
 // Integer, bit-exact with the reference C path.
 #include "ipred_body.cuh"
 #include "itx_body.cuh"
