@@ -4,6 +4,8 @@
  * Plain-C restatement of intra reconstruction at transform-block granularity:
  *   edge preparation            reference src/ipred_prepare_tmpl.c:75-204 (dav1d_prepare_intra_edges)
  *   per-tx-block glue           reference src/recon_tmpl.c:1235-1330 (luma), 1342-1398 (CFL), 1418-1540 (chroma)
+ *   palette / inter-intra glue  reference src/recon_tmpl.c:1201-1223, 1400-1419 (pal_pred over the whole block),
+ *                               1601-1626, 1737-1777 (intra predictor over the block, blended into the inter prediction)
  * Records (B200IntraTx, include/b200av1.h) are processed sequentially in the order given. The top edge is
  * read from the picture itself: with whole-frame reconstruction the row above is still unfiltered, which is
  * what f->ipred_edge preserves in the reference's superblock-row pipeline.
@@ -14,6 +16,8 @@
 void oracle_ipred(int mode, void *dst, ptrdiff_t stride_bytes, const void *topleft, int w, int h, int angle, int max_w, int max_h, int bdmax);
 void oracle_cfl_ac(int16_t *ac, const void *ypx, ptrdiff_t stride_bytes, int w_pad, int h_pad, int w, int h, int ss_hor, int ss_ver, int bdmax);
 void oracle_cfl_pred(int mode, void *dst, ptrdiff_t stride_bytes, const void *topleft, int w, int h, const int16_t *ac, int alpha, int bdmax);
+void oracle_pal_pred(void *dst, ptrdiff_t stride_bytes, const void *pal, const uint8_t *idx, int w, int h, int bdmax);
+void oracle_blend(void *dst, ptrdiff_t dst_stride, const void *tmp, int w, int h, const uint8_t *mask, int bdmax);
 int oracle_inv_txfm_add(void *dst, ptrdiff_t stride_bytes, void *coeff, int eob, int tx, int txtp, int bdmax);
 
 static const uint8_t k_w4[19] = { 1, 2, 4, 8, 16, 1, 2, 2, 4, 4, 8, 8, 16, 1, 4, 2, 8, 4, 16 };
@@ -88,7 +92,20 @@ ORACLE_API void oracle_intra_frame(int bdmax, const B200IntraFrame *f, const B20
         const int hl = !!(r->flags & B200_INTRA_HAVE_LEFT), ht = !!(r->flags & B200_INTRA_HAVE_TOP);
         int angle = r->angle;
         const void *tl = (const uint8_t *)edge + 128 * px;
-        if (r->mode == B200_INTRA_MODE_CFL && r->cfl_alpha) {
+        if (r->mode == B200_INTRA_MODE_RESID) {
+            /* nothing to predict: the block was predicted by a PAL / II record, only the residual below is added */
+        } else if (r->mode == B200_INTRA_MODE_PAL) {
+            const uint8_t *pd = f->pal + r->luma_off;
+            oracle_pal_pred(dst, st * (ptrdiff_t)px, pd, pd + 8 * px, w, h, bdmax);
+        } else if (r->mode == B200_INTRA_MODE_II) {
+            /* the predictor named by `angle` over the whole block into a scratch, then dsp->mc.blend with the mask */
+            uint16_t tmp16[64 * 64];
+            int a0 = 0;
+            const int m = oracle_prepare_intra_edges(r->x4, hl, r->y4, ht, r->xend4, r->yend4, 0, f->pic, r->dst_off, st, r->angle,
+                                                     &a0, tw, th, 0, edge, bdmax);
+            oracle_ipred(m, tmp16, w * (ptrdiff_t)px, tl, w, h, 0, 0, 0, bdmax);
+            oracle_blend(dst, st * (ptrdiff_t)px, tmp16, w, h, f->mask + r->luma_off, bdmax);
+        } else if (r->mode == B200_INTRA_MODE_CFL && r->cfl_alpha) {
             angle = 0;
             oracle_cfl_ac(ac, (const uint8_t *)f->pic + (size_t)r->luma_off * px, f->stride[0] * (ptrdiff_t)px, r->cfl_w_pad,
                           r->cfl_h_pad, w, h, f->ss_hor, f->ss_ver, bdmax);

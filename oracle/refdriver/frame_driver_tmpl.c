@@ -367,6 +367,8 @@ static void bitfn(intra_records)(const int bitdepth_max, const B200IntraFrame *c
 {
     Dav1dIntraPredDSPContext ip;
     Dav1dInvTxfmDSPContext itx;
+    Dav1dMCDSPContext mcd;
+    bitfn(dav1d_mc_dsp_init)(&mcd);
     bitfn(dav1d_intra_pred_dsp_init)(&ip);
     bitfn(dav1d_itx_dsp_init)(&itx, 32 - clz(bitdepth_max));
     pixel edge_buf[257];
@@ -382,7 +384,22 @@ static void bitfn(intra_records)(const int bitdepth_max, const B200IntraFrame *c
         const enum EdgeFlags ef = ((r->flags & B200_INTRA_TOP_HAS_RIGHT) ? EDGE_I444_TOP_HAS_RIGHT : 0) |
                                   ((r->flags & B200_INTRA_LEFT_HAS_BOTTOM) ? EDGE_I444_LEFT_HAS_BOTTOM : 0);
         int angle = r->angle;
-        if (r->mode == B200_INTRA_MODE_CFL && r->cfl_alpha) {
+        if (r->mode == B200_INTRA_MODE_RESID) {
+            /* residual only */
+        } else if (r->mode == B200_INTRA_MODE_PAL) {
+            /* the reference's own pal_pred over the whole block (src/recon_tmpl.c:1220) */
+            const pixel *const pal = (const pixel *)(fr->pal + r->luma_off);
+            ip.pal_pred(dst, stride, pal, (const uint8_t *)(pal + 8), t->w * 4, t->h * 4);
+        } else if (r->mode == B200_INTRA_MODE_II) {
+            /* the reference's own edge preparation, predictor and blend (src/recon_tmpl.c:1601-1626) */
+            pixel tmp[64 * 64];
+            int a0 = 0;
+            const enum IntraPredMode m = bytefn(dav1d_prepare_intra_edges)(r->x4, have_left, r->y4, have_top, r->xend4, r->yend4, 0, dst, stride,
+                                                                          NULL, (enum IntraPredMode)r->angle, &a0, t->w, t->h, 0,
+                                                                          edge HIGHBD_TAIL_SUFFIX);
+            ip.intra_pred[m](tmp, t->w * 4 * sizeof(pixel), edge, t->w * 4, t->h * 4, 0, 0, 0 HIGHBD_TAIL_SUFFIX);
+            mcd.blend(dst, stride, tmp, t->w * 4, t->h * 4, fr->mask + r->luma_off);
+        } else if (r->mode == B200_INTRA_MODE_CFL && r->cfl_alpha) {
             angle = 0;
             ip.cfl_ac[layout_idx](ac, (const pixel *)fr->pic + r->luma_off, fr->stride[0] * (ptrdiff_t)sizeof(pixel),
                                   r->cfl_w_pad, r->cfl_h_pad, t->w * 4, t->h * 4);

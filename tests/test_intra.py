@@ -153,3 +153,85 @@ def test_gpu_intra_frame_with_deblock():
     fb.run(); fb.alloc.sync()
     import test_cdef as TCD
     assert TCD.frame_area_equal(S, fb.output("p0"), exp)
+
+
+# ---- record kinds of mixed frames: palette blocks, inter-intra blends, residual-only transform blocks -----------------
+def make_mixed(S, rng, p_pal=0.2, p_ii=0.25):
+    """Turns a share of the transform blocks of a synthetic intra frame into PAL / II records (+ a RESID record when the
+    block had a residual), the way the dav1d hooks emit palette and inter-intra blocks (include/b200av1.h). The picture
+    starts as random pixels: what the prediction stage would have left in an inter-intra block."""
+    px = 2 if S["bpc"] > 8 else 1
+    bd = S["bd"]
+    src = S["intra_tx_decode_order"]
+    out, pal, mask = [], bytearray(), bytearray()
+    from dav1d_b200 import levels as L
+    for r in src:
+        w, h = L.TX_W[r["tx"]], L.TX_H[r["tx"]]
+        u = rng.random()
+        if r["mode"] == synth.MODE_CFL or u >= p_pal + p_ii:
+            out.append(r.copy()); continue
+        head = r.copy()
+        head["eob"] = -1; head["flags"] = int(r["flags"]) & 3; head["angle_flags"] = 0
+        head["cfl_alpha"] = 1 if r["eob"] >= 0 else 0
+        if u < p_pal:
+            head["mode"], head["flags"], head["angle"] = 17, 0, 0
+            while len(pal) % 16:
+                pal.append(0)
+            head["luma_off"] = len(pal)
+            cols = rng.integers(0, bd + 1, 8).astype(np.uint16 if px == 2 else np.uint8)
+            idx = rng.integers(0, 8, (h, w)).astype(np.uint8)
+            pal += cols.tobytes() + (idx[:, 0::2] | (idx[:, 1::2] << 4)).astype(np.uint8).tobytes()
+        else:
+            head["mode"] = 15
+            head["angle"] = int(rng.choice([0, 1, 2, 9]))            # DC / VERT / HOR / SMOOTH
+            head["luma_off"] = len(mask)
+            mask += rng.integers(0, 65, w * h).astype(np.uint8).tobytes()
+        out.append(head)
+        if r["eob"] >= 0:
+            res = r.copy()
+            res["mode"], res["flags"], res["angle"], res["angle_flags"] = 16, 0, 0, 0
+            out.append(res)
+    S2 = dict(S)
+    S2["mixed_tx"] = np.array(out, dtype=src.dtype)
+    S2["mixed_pal"] = np.frombuffer(bytes(pal) + b"\0" * 16, np.uint8).copy()
+    S2["mixed_mask"] = np.frombuffer(bytes(mask) + b"\0" * 16, np.uint8).copy()
+    S2["mixed_pic0"] = rng.integers(0, bd + 1, len(S["pic"])).astype(S["pic"].dtype)
+    return S2
+
+
+def run_mixed(fn, S, emu=None):
+    pic = S["mixed_pic0"].copy(); coefs = S["coefs"].copy()
+    fr = intra_frame_struct(S, pic, coefs)
+    fr.mask, fr.pal = S["mixed_mask"].ctypes.data, S["mixed_pal"].ctypes.data
+    for p in range(3):
+        fr.plane_off[p] = S["off"][p]
+    tx = np.ascontiguousarray(S["mixed_tx"])
+    if emu is None:
+        fn.restype = None
+        fn(C.c_int(S["bd"]), C.byref(fr), C.c_void_p(tx.ctypes.data), C.c_int(len(tx)))
+    else:
+        scratch = np.zeros(int(emu.b200_intra_scratch_bytes(C.byref(fr))) + 256, np.uint8)
+        fr.scratch = scratch.ctypes.data
+        emu.check(emu.b200_intra_frame(S["bd"], C.byref(fr), tx.ctypes.data, len(tx), None), "b200_intra_frame")
+    return pic
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", CASES)
+def test_mixed_record_kinds_oracle_reference_and_kernel(bpc, W, H, ssh, ssv):
+    """PAL / II / RESID records: oracle restatement == the reference's own pal_pred / prepare_intra_edges / intra_pred /
+    blend / itxfm_add driven record by record == the kernel (host emulator build)"""
+    if not refs.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(900 + bpc + W)
+    S = make_mixed(synth.make_intra_frame(rng, bpc, W, H, ssh, ssv), rng)
+    kinds = set(S["mixed_tx"]["mode"].tolist())
+    assert {15, 16, 17} <= kinds, kinds
+    r = refs.ref()
+    a = run_mixed(r.refdrv_intra_frame_8bpc if bpc == 8 else r.refdrv_intra_frame_16bpc, S)
+    b = run_mixed(refs.oracle().oracle_intra_frame, S)
+    ok, where = planes_equal(S, a, b)
+    assert ok, ("oracle vs reference", where)
+    c = run_mixed(None, S, emu=refs.emu_lib())
+    ok, where = planes_equal(S, b, c)
+    assert ok, ("kernel vs oracle", where)
