@@ -59,10 +59,21 @@ def obu(obu_type, payload):
 OBU_SEQ_HDR, OBU_TD, OBU_FRAME = 1, 2, 6
 
 
+# 4:2:2 is expressible in the headers below, but random tile payloads are not legal 4:2:2 streams: partitions whose
+# chroma blocks would be 2 samples wide are forbidden there and the decoder rejects them (reference src/decode.c,
+# decode_sb). The stream generators therefore offer 4:2:0, 4:4:4 and 4:0:0.
+def _profile(bpc, layout):
+    """seq_profile for a bit depth / chroma layout: 0 = 4:2:0 (and 4:0:0) 8 / 10 bit, 1 = 4:4:4 8 / 10 bit, 2 = 4:2:2 and everything 12 bit"""
+    if bpc == 12 or layout == "422":
+        return 2
+    return 1 if layout == "444" else 0
+
+
 def sequence_header(w, h, bpc=8, sb128=0, film_grain=0, filter_intra=1, intra_edge_filter=1, cdef=1, restoration=1,
-                    inter_intra=1, masked_compound=1, warped_motion=1, screen_content=0):
+                    inter_intra=1, masked_compound=1, warped_motion=1, screen_content=0, layout="420"):
     b = BitWriter()
-    b.f(3, 0)                                # seq_profile 0: 4:2:0, 8 / 10 bit
+    profile = _profile(bpc, layout)
+    b.f(3, profile)
     b.f(1, 0); b.f(1, 0)                     # still_picture, reduced_still_picture_header
     b.f(1, 0)                                # timing_info_present
     b.f(1, 0)                                # initial_display_delay_present
@@ -83,12 +94,22 @@ def sequence_header(w, h, bpc=8, sb128=0, film_grain=0, filter_intra=1, intra_ed
         b.f(1, 0); b.f(1, 0)                 # seq_choose_integer_mv = 0, seq_force_integer_mv = 0
     b.f(3, 6)                                # order_hint_bits_minus_1
     b.f(1, 0); b.f(1, cdef); b.f(1, restoration)   # superres, cdef, restoration
-    b.f(1, 1 if bpc > 8 else 0)              # high_bitdepth (profile 0: 10 bit)
-    b.f(1, 0)                                # mono_chrome
+    b.f(1, 1 if bpc > 8 else 0)              # high_bitdepth
+    if profile == 2 and bpc > 8:
+        b.f(1, 1 if bpc == 12 else 0)        # twelve_bit
+    mono = layout == "400"
+    if profile != 1:
+        b.f(1, 1 if mono else 0)             # mono_chrome
     b.f(1, 0)                                # color_description_present
     b.f(1, 0)                                # color_range
-    b.f(2, 0)                                # chroma_sample_position
-    b.f(1, 0)                                # separate_uv_delta_q
+    if not mono:
+        if profile == 2 and bpc == 12:       # explicit subsampling
+            b.f(1, 0 if layout == "444" else 1)
+            if layout != "444":
+                b.f(1, 1 if layout == "420" else 0)
+        if layout == "420":
+            b.f(2, 0)                        # chroma_sample_position
+        b.f(1, 0)                            # separate_uv_delta_q
     b.f(1, film_grain)
     b.trailing()
     return obu(OBU_SEQ_HDR, b.bytes())
@@ -101,7 +122,7 @@ def _tile_log2(sz, tgt):
     return k
 
 
-def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on):
+def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout="420"):
     """tile info, quantizer, segmentation, delta q / lf, loop filter, CDEF, loop restoration (same syntax in key and
     inter frames when primary_ref_frame is NONE)"""
     # tile info (uniform)
@@ -130,7 +151,10 @@ def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restor
     # quantizer
     q = int(rng.integers(40, 200)) if q is None else q
     b.f(8, q)
-    b.f(1, 0); b.f(1, 0); b.f(1, 0)          # no y dc / u dc / u ac deltas
+    mono = layout == "400"
+    b.f(1, 0)                                # no y dc delta
+    if not mono:
+        b.f(1, 0); b.f(1, 0)                 # no u dc / u ac deltas
     b.f(1, 0)                                # using_qmatrix
     b.f(1, 0)                                # segmentation_enabled
     if q:
@@ -141,7 +165,7 @@ def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restor
     # loop filter
     lf = [int(rng.integers(1, 64)), int(rng.integers(1, 64)), int(rng.integers(0, 64)), int(rng.integers(0, 64))] if lf is None else lf
     b.f(6, lf[0]); b.f(6, lf[1])
-    if lf[0] or lf[1]:
+    if (lf[0] or lf[1]) and not mono:
         b.f(6, lf[2]); b.f(6, lf[3])
     b.f(3, int(rng.integers(0, 8)))          # sharpness
     b.f(1, 1); b.f(1, 0)                     # mode_ref_delta_enabled, no update
@@ -150,10 +174,13 @@ def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restor
         b.f(2, int(rng.integers(0, 4))); b.f(2, nb)
         for _ in range(1 << nb):
             b.f(6, int(rng.integers(0, 64)) if cdef else 0)
-            b.f(6, int(rng.integers(0, 64)) if cdef else 0)
+            if not mono:
+                b.f(6, int(rng.integers(0, 64)) if cdef else 0)
     if restoration_on:
         types = [int(rng.integers(0, 4)) for _ in range(3)] if restoration else [0, 0, 0]
-        for t in types:
+        if mono:
+            types[1] = types[2] = 0
+        for t in (types[:1] if mono else types):
             b.f(2, t)
         if any(types):
             if sb128:
@@ -162,7 +189,7 @@ def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restor
                 s = int(rng.integers(0, 2)); b.f(1, s)
                 if s:
                     b.f(1, int(rng.integers(0, 2)))
-            if types[1] or types[2]:
+            if (types[1] or types[2]) and layout == "420":
                 b.f(1, int(rng.integers(0, 2)))
     return cols, rows, tile_w, tile_h, sbw, sbh
 
@@ -186,7 +213,7 @@ def _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_byt
 
 
 def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None, lf=None, cdef=True,
-              restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0, screen_content=0):
+              restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0, screen_content=0, layout="420"):
     """One shown key frame (OBU_FRAME). Returns the OBU bytes. `cdef_on` / `restoration_on` must match the sequence
     header (the fields are absent when the sequence disables the tool)."""
     b = BitWriter()
@@ -199,11 +226,11 @@ def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb
     if screen_content:
         b.f(1, 0)                            # allow_intrabc
     b.f(1, 0)                                # disable_frame_end_update_cdf
-    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on)
+    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout)
     b.f(1, 1)                                # tx_mode_select
     b.f(1, int(rng.integers(0, 2)))          # reduced_tx_set
     if film_grain_seq:
-        _film_grain_params(b, rng, 0)
+        _film_grain_params(b, rng, 0, layout)
     return obu(OBU_FRAME, _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_bytes_per_sb64))
 
 
@@ -211,10 +238,11 @@ def temporal_unit(*obus):
     return obu(OBU_TD, b"") + b"".join(obus)
 
 
-def intra_stream(seed, w, h, n_frames=1, bpc=8, sb128=0, log2_cols=0, log2_rows=0, film_grain=0, screen_content=0, **kw):
+def intra_stream(seed, w, h, n_frames=1, bpc=8, sb128=0, log2_cols=0, log2_rows=0, film_grain=0, screen_content=0, layout="420", **kw):
     """A list of temporal units (bytes), each holding one shown key frame."""
     rng = np.random.default_rng(seed)
-    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, film_grain=film_grain, screen_content=screen_content)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, film_grain=film_grain, screen_content=screen_content, layout=layout)
+    kw = dict(kw, layout=layout)
     if film_grain:
         kw = dict(kw, film_grain_seq=1)
     if screen_content:
@@ -226,7 +254,7 @@ def intra_stream(seed, w, h, n_frames=1, bpc=8, sb128=0, log2_cols=0, log2_rows=
     return tus
 
 
-def _film_grain_params(b, rng, inter):
+def _film_grain_params(b, rng, inter, layout="420"):
     """film_grain_params() with apply_grain = 1 and fresh parameters (reference src/obu.c:1064-1155): random scaling
     points, auto-regression lag 0..3 with random coefficients, overlap, optional chroma-from-luma scaling"""
     b.f(1, 1)                                # apply_grain
@@ -238,12 +266,14 @@ def _film_grain_params(b, rng, inter):
     xs = sorted(rng.choice(256, ny, replace=False).tolist())
     for x in xs:
         b.f(8, x); b.f(8, int(rng.integers(0, 256)))
-    csfl = int(rng.integers(0, 2))
-    b.f(1, csfl)
+    mono = layout == "400"
+    csfl = 0 if mono else int(rng.integers(0, 2))
+    if not mono:
+        b.f(1, csfl)
     nuv = [0, 0]
-    if not (csfl or ny == 0):                # 4:2:0 without luma points carries no chroma points either
+    if not (mono or csfl or (layout == "420" and ny == 0)):   # 4:2:0 without luma points carries no chroma points either
         n = int(rng.integers(0, 11))
-        nuv = [n, int(rng.integers(1, 11)) if n else 0]      # both planes or neither (4:2:0)
+        nuv = [n, int(rng.integers(1, 11)) if n else 0] if layout == "420" else [n, int(rng.integers(0, 11))]   # 4:2:0: both or neither
         for pl in range(2):
             b.f(4, nuv[pl])
             for x in sorted(rng.choice(256, nuv[pl], replace=False).tolist()):
@@ -276,7 +306,7 @@ def _poc_diff(bits, a, b):
 
 def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None,
                 lf=None, cdef=True, restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0,
-                refresh=None, switchable_motion_mode=0, warped_motion_seq=0, comp_refs=1, allow_warped_motion=0):
+                refresh=None, switchable_motion_mode=0, warped_motion_seq=0, comp_refs=1, allow_warped_motion=0, layout="420"):
     """One shown inter frame (OBU_FRAME), primary_ref_frame = NONE. `ref_hints` = order hints held by the 8 reference slots
     (updated in place for the slots this frame refreshes). Global motion is identity."""
     bits = 7
@@ -302,7 +332,7 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
         b.f(1, 0); b.f(2, int(rng.integers(0, 4)))
     b.f(1, switchable_motion_mode)
     b.f(1, 0)                                # disable_frame_end_update_cdf
-    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on)
+    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout)
     b.f(1, 1)                                # tx_mode_select
     b.f(1, comp_refs)                        # reference_select
     if comp_refs:                            # skip_mode_present exists only when two suitable references do (src/obu.c:929-987)
@@ -333,26 +363,27 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
     for _ in range(7):
         b.f(1, 0)                            # is_global: identity
     if film_grain_seq:
-        _film_grain_params(b, rng, 1)
+        _film_grain_params(b, rng, 1, layout)
     for i in range(8):
         if refresh & (1 << i):
             ref_hints[i] = order_hint
     return obu(OBU_FRAME, _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_bytes_per_sb64))
 
 
-def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, film_grain=0, screen_content=0, **kw):
+def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, film_grain=0, screen_content=0, layout="420", **kw):
     """Temporal units: one key frame, then n_frames - 1 inter frames (single and compound references incl. wedge /
     difference-weighted masks and distance weights, switchable interpolation filters, variable transform trees, intra
     blocks; identity global motion). motion_modes=1 additionally enables the per-block motion mode (overlapped block
     motion compensation, locally warped motion), motion_modes=2 inter-intra prediction as well."""
     rng = np.random.default_rng(seed)
-    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=1 if motion_modes >= 2 else 0, warped_motion=1 if motion_modes else 0, film_grain=film_grain, screen_content=screen_content)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=1 if motion_modes >= 2 else 0, warped_motion=1 if motion_modes else 0, film_grain=film_grain, screen_content=screen_content, layout=layout)
+    kw = dict(kw, layout=layout)
     if motion_modes:
         kw = dict(kw, switchable_motion_mode=1, warped_motion_seq=1, allow_warped_motion=1)
     if film_grain:
         kw = dict(kw, film_grain_seq=1)
     hints = [0] * 8
-    tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, film_grain_seq=film_grain, screen_content=screen_content))]
+    tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, film_grain_seq=film_grain, screen_content=screen_content, layout=layout))]
     for i in range(1, n_frames):
         tus.append(temporal_unit(inter_frame(rng, w, h, i, hints, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, **kw)))
     return tus

@@ -75,6 +75,8 @@ static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *c
         HookRefPic *const out = b200hook_refpic(f->cur.data[0], g.bytes, 1);
         if (out) b200hook_refpic_set_ready(out, 0);
         else __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
+        if (f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I400)      /* the post-filter sweeps always walk three planes */
+            __atomic_fetch_or(&hf->unsupported, 512, __ATOMIC_RELAXED);
         /* intra records and coefficients are appended without a lock by every tile thread of the frame (slots are taken
          * with atomic counters), so their buffers are sized for the worst case up front: one record per 4x4 cell of each
          * plane, 16 coefficients per cell, over the 128-aligned frame area */
@@ -716,7 +718,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         fprintf(stderr, "b200hook: frame uses tools the emitters do not translate yet (%s%s%s%s)\n",
                 hf->unsupported & 1 ? " palette" : "", hf->unsupported & 2 ? " inter" : "",
                 hf->unsupported & 4 ? " single-pass-decoding" : "", hf->unsupported & 8 ? " out-of-memory" : "");
-        fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 scaled reference, 64 intra block copy, 128 OBMC, 256 inter-intra)\n", hf->unsupported);
+        fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 scaled reference, 64 intra block copy, 256 inter-intra block size, 512 monochrome)\n", hf->unsupported);
         return -1;
     }
     PicGeom g;

@@ -118,6 +118,26 @@ def test_screen_content_stream_emu_matches_stock_dav1d(emu_decoder, case):
 
 
 @pytest.mark.emu
+@pytest.mark.parametrize("case", [("444", 8, 0, 0, 0), ("444", 10, 1, 1, 1), ("444", 12, 1, 0, 0), ("420", 12, 1, 1, 1)])
+def test_other_layouts_and_12bit_stream_emu_matches_stock_dav1d(emu_decoder, case):
+    """profile 1 (4:4:4) and profile 2 (12 bit) streams: same hooks, chroma at full resolution / 12-bit clipping ranges.
+    (4:2:2 cannot be driven with random payloads: its illegal partitions make the decoder reject the tile.)"""
+    layout, bpc, inter, fg, sc = case
+    gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=2, **k)) if inter else obu.intra_stream
+    tus = gen(5, 200, 136, n_frames=3, bpc=bpc, layout=layout, film_grain=fg, screen_content=sc)
+    _check(emu_decoder, tus, 3, apply_grain=1)
+
+
+def test_monochrome_stream_fails_loudly(emu_decoder):
+    """4:0:0 is not supported by the whole-frame post filters (they walk three planes): the hooked decoder must report an
+    error, not decode something else"""
+    tus = obu.intra_stream(5, 128, 128, n_frames=1, layout="400")
+    assert _ref_decode(tus)[0] == 1
+    assert emu_decoder.decode(tus)[0] < 0
+    emu_decoder.stats(reset=True)
+
+
+@pytest.mark.emu
 def test_stream_many_decoders_recycle_slots(emu_decoder):
     """frame contexts and host pictures of closed decoders must not exhaust the hook's tables (each decode opens a new
     dav1d context; the tables are recycled least-recently-used)"""
