@@ -56,7 +56,7 @@ def obu(obu_type, payload):
     return bytes([(obu_type << 3) | 2]) + leb128(len(payload)) + payload
 
 
-OBU_SEQ_HDR, OBU_TD, OBU_FRAME = 1, 2, 6
+OBU_SEQ_HDR, OBU_TD, OBU_FRAME_HDR, OBU_FRAME = 1, 2, 3, 6
 
 
 # 4:2:2 is expressible in the headers below, but random tile payloads are not legal 4:2:2 streams: partitions whose
@@ -306,13 +306,16 @@ def _poc_diff(bits, a, b):
 
 def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None,
                 lf=None, cdef=True, restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0,
-                refresh=None, switchable_motion_mode=0, warped_motion_seq=0, comp_refs=1, allow_warped_motion=0, layout="420"):
+                refresh=None, switchable_motion_mode=0, warped_motion_seq=0, comp_refs=1, allow_warped_motion=0, layout="420",
+                show_frame=1):
     """One shown inter frame (OBU_FRAME), primary_ref_frame = NONE. `ref_hints` = order hints held by the 8 reference slots
     (updated in place for the slots this frame refreshes). Global motion is identity."""
     bits = 7
     b = BitWriter()
     b.f(1, 0)                                # show_existing_frame
-    b.f(2, 1); b.f(1, 1)                     # frame_type INTER, show_frame
+    b.f(2, 1); b.f(1, show_frame)            # frame_type INTER, show_frame
+    if not show_frame:
+        b.f(1, 1)                            # showable_frame: a later show_existing_frame header outputs it
     b.f(1, 0)                                # error_resilient_mode
     b.f(1, 0)                                # disable_cdf_update
     b.f(1, 0)                                # frame_size_override
@@ -370,11 +373,23 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
     return obu(OBU_FRAME, _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_bytes_per_sb64))
 
 
-def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, film_grain=0, screen_content=0, layout="420", **kw):
+def show_existing_frame(slot):
+    """a frame header OBU that outputs the (hidden, showable) frame held by reference slot `slot`"""
+    b = BitWriter()
+    b.f(1, 1)                                # show_existing_frame
+    b.f(3, slot)                             # frame_to_show_map_idx
+    b.trailing()
+    return obu(OBU_FRAME_HDR, b.bytes())
+
+
+def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, film_grain=0, screen_content=0, layout="420",
+                 hidden_every=0, **kw):
     """Temporal units: one key frame, then n_frames - 1 inter frames (single and compound references incl. wedge /
     difference-weighted masks and distance weights, switchable interpolation filters, variable transform trees, intra
     blocks; identity global motion). motion_modes=1 additionally enables the per-block motion mode (overlapped block
-    motion compensation, locally warped motion), motion_modes=2 inter-intra prediction as well."""
+    motion compensation, locally warped motion), motion_modes=2 inter-intra prediction as well. hidden_every=k makes
+    every k-th inter frame a hidden future frame (decoded early, referenced with backward prediction, output later by a
+    show_existing_frame header)."""
     rng = np.random.default_rng(seed)
     seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=1 if motion_modes >= 2 else 0, warped_motion=1 if motion_modes else 0, film_grain=film_grain, screen_content=screen_content, layout=layout)
     kw = dict(kw, layout=layout)
@@ -385,5 +400,14 @@ def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=
     hints = [0] * 8
     tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, film_grain_seq=film_grain, screen_content=screen_content, layout=layout))]
     for i in range(1, n_frames):
-        tus.append(temporal_unit(inter_frame(rng, w, h, i, hints, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, **kw)))
+        if hidden_every and i % hidden_every == 0:
+            # an "alt-ref": decoded now into slot 7 but not shown (it carries a later order hint), then a shown frame in
+            # the same temporal unit, and one unit later a show_existing_frame header that outputs the hidden frame
+            hid = inter_frame(rng, w, h, (i + 1) % 128, hints, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, show_frame=0,
+                              refresh=0x80, **kw)
+            shown = inter_frame(rng, w, h, i % 128, hints, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, refresh=int(rng.integers(1, 128)), **kw)
+            tus.append(temporal_unit(hid, shown))
+            tus.append(temporal_unit(show_existing_frame(7)))
+        else:
+            tus.append(temporal_unit(inter_frame(rng, w, h, i % 128, hints, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, **kw)))
     return tus
