@@ -213,15 +213,23 @@ def _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_byt
 
 
 def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None, lf=None, cdef=True,
-              restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0, screen_content=0, layout="420"):
-    """One shown key frame (OBU_FRAME). Returns the OBU bytes. `cdef_on` / `restoration_on` must match the sequence
+              restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0, screen_content=0, layout="420",
+              intra_only=None):
+    """One shown key frame (OBU_FRAME), or with intra_only=(order_hint, refresh_frame_flags) a shown INTRA_ONLY frame
+    (intra coded, but it only replaces the reference slots it names). Returns the OBU bytes. `cdef_on` / `restoration_on` must match the sequence
     header (the fields are absent when the sequence disables the tool)."""
     b = BitWriter()
     b.f(1, 0)                                # show_existing_frame
-    b.f(2, 0); b.f(1, 1)                     # frame_type KEY, show_frame
+    if intra_only is None:
+        b.f(2, 0); b.f(1, 1)                 # frame_type KEY, show_frame
+    else:
+        b.f(2, 2); b.f(1, 1)                 # frame_type INTRA_ONLY, show_frame
+        b.f(1, 0)                            # error_resilient_mode
     b.f(1, 0)                                # disable_cdf_update
     b.f(1, 0)                                # frame_size_override
-    b.f(7, 0)                                # order_hint
+    b.f(7, 0 if intra_only is None else intra_only[0])   # order_hint
+    if intra_only is not None:
+        b.f(8, intra_only[1])                # refresh_frame_flags (a shown key frame refreshes all slots implicitly)
     b.f(1, 0)                                # render_and_frame_size_different
     if screen_content:
         b.f(1, 0)                            # allow_intrabc
@@ -383,7 +391,7 @@ def show_existing_frame(slot):
 
 
 def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, film_grain=0, screen_content=0, layout="420",
-                 hidden_every=0, **kw):
+                 hidden_every=0, intra_only_every=0, **kw):
     """Temporal units: one key frame, then n_frames - 1 inter frames (single and compound references incl. wedge /
     difference-weighted masks and distance weights, switchable interpolation filters, variable transform trees, intra
     blocks; identity global motion). motion_modes=1 additionally enables the per-block motion mode (overlapped block
@@ -400,6 +408,14 @@ def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=
     hints = [0] * 8
     tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, film_grain_seq=film_grain, screen_content=screen_content, layout=layout))]
     for i in range(1, n_frames):
+        if intra_only_every and i % intra_only_every == 0:
+            refresh = int(rng.integers(1, 255))
+            tus.append(temporal_unit(key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, film_grain_seq=film_grain,
+                                               screen_content=screen_content, layout=layout, intra_only=(i % 128, refresh))))
+            for k in range(8):
+                if refresh & (1 << k):
+                    hints[k] = i % 128
+            continue
         if hidden_every and i % hidden_every == 0:
             # an "alt-ref": decoded now into slot 7 but not shown (it carries a later order hint), then a shown frame in
             # the same temporal unit, and one unit later a show_existing_frame header that outputs the hidden frame

@@ -139,6 +139,13 @@ def test_hidden_frames_and_show_existing_emu_matches_stock_dav1d(emu_decoder, ca
     _check(emu_decoder, tus, 10, apply_grain=1)
 
 
+@pytest.mark.emu
+def test_intra_only_frames_emu_matches_stock_dav1d(emu_decoder):
+    """INTRA_ONLY frames between inter frames: intra coded, replace only the reference slots they name"""
+    tus = obu.inter_stream(31, 256, 192, n_frames=8, bpc=10, film_grain=1, motion_modes=2, screen_content=1, intra_only_every=3)
+    _check(emu_decoder, tus, 8, apply_grain=1)
+
+
 def test_monochrome_stream_fails_loudly(emu_decoder):
     """4:0:0 is not supported by the whole-frame post filters (they walk three planes): the hooked decoder must report an
     error, not decode something else"""
