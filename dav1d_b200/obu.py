@@ -306,6 +306,37 @@ def _film_grain_params(b, rng, inter, layout="420"):
     b.f(1, int(rng.integers(0, 2)))          # clip_to_restricted_range
 
 
+def _subexp_near_ref(b, rng, steps=2):
+    """one dav1d_get_bits_subexp() field (reference src/getbits.c:139-164) whose decoded value is the prediction plus or
+    minus a few units: `k` escape bits, a stop bit, then the 3 + max(k - 1, 0) literal bits of that bucket"""
+    k = int(rng.integers(0, steps + 1))
+    for _ in range(k):
+        b.f(1, 1)
+    b.f(1, 0)
+    nb = 3 if k == 0 else 3 + k - 1
+    b.f(nb, int(rng.integers(0, 1 << nb)))
+
+
+def _global_motion_params(b, rng, hp):
+    """global_motion_params() for the 7 references with primary_ref_frame = NONE (predictions = the default parameters,
+    reference src/obu.c:1014-1060): a mix of identity, translation, rotation-zoom and affine models close to identity, so
+    that the shear parameters are valid and GLOBALMV blocks are really warped"""
+    for _ in range(7):
+        kind = int(rng.integers(0, 4))           # 0 identity, 1 translation, 2 rot-zoom, 3 affine
+        if kind == 0:
+            b.f(1, 0); continue
+        b.f(1, 1)
+        if kind == 2:
+            b.f(1, 1)
+        else:
+            b.f(1, 0); b.f(1, 1 if kind == 1 else 0)
+        if kind >= 2:
+            _subexp_near_ref(b, rng); _subexp_near_ref(b, rng)          # mat[2], mat[3]
+            if kind == 3:
+                _subexp_near_ref(b, rng); _subexp_near_ref(b, rng)      # mat[4], mat[5]
+        _subexp_near_ref(b, rng, 3); _subexp_near_ref(b, rng, 3)        # mat[0], mat[1] (translation part)
+
+
 def _poc_diff(bits, a, b):
     mask = 1 << (bits - 1)
     d = a - b
@@ -315,7 +346,7 @@ def _poc_diff(bits, a, b):
 def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None,
                 lf=None, cdef=True, restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0,
                 refresh=None, switchable_motion_mode=0, warped_motion_seq=0, comp_refs=1, allow_warped_motion=0, layout="420",
-                show_frame=1):
+                show_frame=1, global_motion=0):
     """One shown inter frame (OBU_FRAME), primary_ref_frame = NONE. `ref_hints` = order hints held by the 8 reference slots
     (updated in place for the slots this frame refreshes). Global motion is identity."""
     bits = 7
@@ -336,7 +367,8 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
     for r in refidx:
         b.f(3, r)
     b.f(1, 0)                                # render_and_frame_size_different
-    b.f(1, int(rng.integers(0, 2)))          # allow_high_precision_mv
+    hp = int(rng.integers(0, 2))
+    b.f(1, hp)                               # allow_high_precision_mv
     if rng.integers(0, 2):
         b.f(1, 1)                            # is_filter_switchable
     else:
@@ -371,8 +403,11 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
     if warped_motion_seq:
         b.f(1, allow_warped_motion)
     b.f(1, int(rng.integers(0, 2)))          # reduced_tx_set
-    for _ in range(7):
-        b.f(1, 0)                            # is_global: identity
+    if global_motion:
+        _global_motion_params(b, rng, hp)
+    else:
+        for _ in range(7):
+            b.f(1, 0)                        # is_global: identity
     if film_grain_seq:
         _film_grain_params(b, rng, 1, layout)
     for i in range(8):

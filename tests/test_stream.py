@@ -146,6 +146,17 @@ def test_intra_only_frames_emu_matches_stock_dav1d(emu_decoder):
     _check(emu_decoder, tus, 8, apply_grain=1)
 
 
+@pytest.mark.emu
+@pytest.mark.parametrize("case", [(8, 0), (10, 2)])
+def test_global_motion_stream_emu_matches_stock_dav1d(emu_decoder, case):
+    """non-identity global motion (translation, rotation-zoom, affine models written with the sub-exponential code):
+    GLOBALMV blocks become warped predictions (warp8x8 into the picture, warp8x8t into the compound scratch)"""
+    bpc, mm = case
+    tus = obu.inter_stream(50 + bpc, 320, 192, n_frames=5, bpc=bpc, motion_modes=mm, global_motion=1)
+    _check(emu_decoder, tus, 5)
+    assert emu_decoder.last_stats["warp"] > 0, "no warped block in the stream"
+
+
 def test_monochrome_stream_fails_loudly(emu_decoder):
     """4:0:0 is not supported by the whole-frame post filters (they walk three planes): the hooked decoder must report an
     error, not decode something else"""
