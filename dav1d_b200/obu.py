@@ -122,7 +122,8 @@ def _tile_log2(sz, tgt):
     return k
 
 
-def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout="420"):
+def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout="420",
+                  segmentation=0):
     """tile info, quantizer, segmentation, delta q / lf, loop filter, CDEF, loop restoration (same syntax in key and
     inter frames when primary_ref_frame is NONE)"""
     # tile info (uniform)
@@ -156,7 +157,26 @@ def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restor
     if not mono:
         b.f(1, 0); b.f(1, 0)                 # no u dc / u ac deltas
     b.f(1, 0)                                # using_qmatrix
-    b.f(1, 0)                                # segmentation_enabled
+    b.f(1, segmentation)                     # segmentation_enabled (primary_ref_frame NONE: map and data are always updated)
+    if segmentation:
+        for _ in range(8):
+            # per segment: quantiser delta (may reach qidx 0 = lossless: 4x4 Walsh-Hadamard blocks, no filtering), four
+            # loop-filter deltas, forced reference, forced skip, forced global motion
+            if rng.random() < 0.5:
+                b.f(1, 1); b.su(9, int(rng.choice([-q, int(rng.integers(-60, 61))])))
+            else:
+                b.f(1, 0)
+            for _k in range(4):
+                if rng.random() < 0.3:
+                    b.f(1, 1); b.su(7, int(rng.integers(-30, 31)))
+                else:
+                    b.f(1, 0)
+            if rng.random() < 0.2:
+                b.f(1, 1); b.f(3, int(rng.integers(0, 8)))
+            else:
+                b.f(1, 0)
+            b.f(1, int(rng.random() < 0.15))
+            b.f(1, int(rng.random() < 0.15))
     if q:
         b.f(1, 1 if delta_q else 0)          # delta_q_present
         if delta_q:
@@ -214,7 +234,7 @@ def _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_byt
 
 def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None, lf=None, cdef=True,
               restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0, screen_content=0, layout="420",
-              intra_only=None):
+              intra_only=None, segmentation=0):
     """One shown key frame (OBU_FRAME), or with intra_only=(order_hint, refresh_frame_flags) a shown INTRA_ONLY frame
     (intra coded, but it only replaces the reference slots it names). Returns the OBU bytes. `cdef_on` / `restoration_on` must match the sequence
     header (the fields are absent when the sequence disables the tool)."""
@@ -234,7 +254,7 @@ def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb
     if screen_content:
         b.f(1, 0)                            # allow_intrabc
     b.f(1, 0)                                # disable_frame_end_update_cdf
-    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout)
+    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout, segmentation)
     b.f(1, 1)                                # tx_mode_select
     b.f(1, int(rng.integers(0, 2)))          # reduced_tx_set
     if film_grain_seq:
@@ -346,7 +366,7 @@ def _poc_diff(bits, a, b):
 def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None,
                 lf=None, cdef=True, restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0,
                 refresh=None, switchable_motion_mode=0, warped_motion_seq=0, comp_refs=1, allow_warped_motion=0, layout="420",
-                show_frame=1, global_motion=0):
+                show_frame=1, global_motion=0, segmentation=0):
     """One shown inter frame (OBU_FRAME), primary_ref_frame = NONE. `ref_hints` = order hints held by the 8 reference slots
     (updated in place for the slots this frame refreshes). Global motion is identity."""
     bits = 7
@@ -375,7 +395,7 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
         b.f(1, 0); b.f(2, int(rng.integers(0, 4)))
     b.f(1, switchable_motion_mode)
     b.f(1, 0)                                # disable_frame_end_update_cdf
-    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout)
+    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout, segmentation)
     b.f(1, 1)                                # tx_mode_select
     b.f(1, comp_refs)                        # reference_select
     if comp_refs:                            # skip_mode_present exists only when two suitable references do (src/obu.c:929-987)

@@ -157,6 +157,18 @@ def test_global_motion_stream_emu_matches_stock_dav1d(emu_decoder, case):
     assert emu_decoder.last_stats["warp"] > 0, "no warped block in the stream"
 
 
+@pytest.mark.emu
+@pytest.mark.parametrize("seed", [70, 71, 75])
+def test_segmentation_stream_emu_matches_stock_dav1d(emu_decoder, seed):
+    """segmentation: per-segment quantiser deltas (down to qidx 0 = lossless segments: 4x4 Walsh-Hadamard blocks, loop
+    filter off for them), loop-filter deltas, forced reference / skip / global motion"""
+    if seed & 1:
+        tus = obu.inter_stream(seed, 256, 192, n_frames=4, bpc=10, motion_modes=2, segmentation=1, global_motion=1)
+    else:
+        tus = obu.intra_stream(seed, 256, 192, n_frames=2, bpc=8, segmentation=1)
+    _check(emu_decoder, tus, len(tus))
+
+
 def test_monochrome_stream_fails_loudly(emu_decoder):
     """4:0:0 is not supported by the whole-frame post filters (they walk three planes): the hooked decoder must report an
     error, not decode something else"""
