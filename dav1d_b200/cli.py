@@ -3,6 +3,7 @@
 
     python -m dav1d_b200.cli -i stream.obu -o out.y4m            # Section-5 ("low overhead") OBU file -> y4m
     python -m dav1d_b200.cli -i stream.obu --muxer md5            # md5 of the decoded frames (like `dav1d --muxer md5`)
+    python -m dav1d_b200.cli -i clip.ivf --verify <md5>           # IVF / Annex B input too; exit status 2 on a mismatch
     python -m dav1d_b200.cli --synth inter:1280x720:10:8:grain,mm --muxer md5   # synthetic stream (dav1d_b200/obu.py)
     python -m dav1d_b200.cli --synth key:640x360:8:2 -w s.obu     # just write the synthetic stream to a file
 
@@ -46,6 +47,61 @@ def split_temporal_units(data):
     if n > start:
         tus.append(bytes(data[start:n]))
     return tus
+
+
+def split_ivf(data):
+    """IVF container (reference tools/input/ivf.c): 32-byte file header ('DKIF', fourcc 'AV01'), then per frame a 12-byte
+    header (payload size u32, timestamp u64) and one temporal unit of Section-5 OBUs"""
+    if data[:4] != b"DKIF" or data[8:12] not in (b"AV01", b"av01"):
+        raise ValueError("not an AV1 IVF file")
+    pos, tus = int.from_bytes(data[6:8], "little"), []
+    while pos + 12 <= len(data):
+        sz = int.from_bytes(data[pos:pos + 4], "little")
+        pos += 12
+        if pos + sz > len(data):
+            raise ValueError("truncated IVF frame")
+        tus.append(bytes(data[pos:pos + sz])); pos += sz
+    return tus
+
+
+def _leb128(data, pos):
+    v, shift = 0, 0
+    while True:
+        b = data[pos]; pos += 1
+        v |= (b & 0x7f) << shift; shift += 7
+        if not b & 0x80:
+            return v, pos
+
+
+def split_annexb(data):
+    """Annex B length-delimited stream (reference tools/input/annexb.c): temporal_unit_size, frame_unit_size, obu_length
+    prefixes; the OBUs inside carry no size field, so each is rewritten into the Section-5 form (has_size_field = 1) the
+    stream driver feeds to dav1d"""
+    pos, tus = 0, []
+    while pos < len(data):
+        tu_size, pos = _leb128(data, pos)
+        tu_end, out = pos + tu_size, bytearray()
+        while pos < tu_end:
+            fu_size, pos = _leb128(data, pos)
+            fu_end = pos + fu_size
+            while pos < fu_end:
+                ol, pos = _leb128(data, pos)
+                hdr = data[pos]
+                ext = (hdr >> 2) & 1
+                if hdr & 2:                      # already carries a size field: keep as is
+                    out += data[pos:pos + ol]
+                else:
+                    payload = data[pos + 1 + ext:pos + ol]
+                    out += bytes([hdr | 2]) + data[pos + 1:pos + 1 + ext] + obu.leb128(len(payload)) + payload
+                pos += ol
+        tus.append(bytes(out))
+    return tus
+
+
+def demux(data, kind="auto"):
+    if kind == "auto":
+        kind = "ivf" if data[:4] == b"DKIF" else "obu"
+    return {"ivf": split_ivf, "obu": split_temporal_units, "annexb": split_annexb}[kind](data)
 
 
 def synth_stream(spec, seed=1):
@@ -104,7 +160,9 @@ def md5_of(frames):
 
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="python -m dav1d_b200.cli", description=__doc__.split("\n")[0])
-    ap.add_argument("-i", "--input", help="Section-5 OBU file")
+    ap.add_argument("-i", "--input", help="input file: Section-5 OBU stream, IVF, or Annex B")
+    ap.add_argument("--demuxer", choices=["auto", "obu", "ivf", "annexb"], default="auto")
+    ap.add_argument("--verify", metavar="MD5", help="compare the md5 of the decoded frames with this digest (like `dav1d --verify`)")
     ap.add_argument("--synth", help="synthetic stream kind:WxH:bpc:frames[:grain,screen,mm]")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("-w", "--write-stream", help="write the (synthetic) stream to this .obu file")
@@ -118,11 +176,11 @@ def main(argv=None):
     args = ap.parse_args(argv)
     if bool(args.input) == bool(args.synth):
         ap.error("give exactly one of -i / --synth")
-    tus = synth_stream(args.synth, args.seed) if args.synth else split_temporal_units(open(args.input, "rb").read())
+    tus = synth_stream(args.synth, args.seed) if args.synth else demux(open(args.input, "rb").read(), args.demuxer)
     if args.write_stream:
         with open(args.write_stream, "wb") as fh:
             fh.write(b"".join(tus))
-        if not (args.output or args.muxer):
+        if not (args.output or args.muxer or args.verify):
             print("wrote %d temporal units, %d bytes" % (len(tus), sum(map(len, tus))))
             return 0
     kw = dict(n_threads=max(2, args.threads), max_frame_delay=max(2, args.framedelay), apply_grain=args.filmgrain, max_pics=len(tus) + 8)
@@ -142,6 +200,11 @@ def main(argv=None):
     elif muxer == "md5":
         digest, cnt = md5_of(frames_of(info, packed))
         print(digest)
+    if args.verify:
+        digest, _ = md5_of(frames_of(info, packed))
+        if digest != args.verify.lower():
+            print("md5 mismatch: %s != %s" % (digest, args.verify), file=sys.stderr)
+            return 2
     px = sum(int(w) * int(h) for w, h, _, _ in info)
     print("decoded %d frames in %.3f s (%.1f fps, %.1f Mpixels/s)" % (n, dt, n / dt, px / dt / 1e6), file=sys.stderr)
     return 0

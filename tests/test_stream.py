@@ -357,6 +357,29 @@ def test_cli_md5_y4m_and_obu_file_roundtrip(tmp_path, capsys):
     r0, info0, out0 = _ref_decode(tus, apply_grain=1)
     want, n = cli.md5_of(cli.frames_of(info0, out0))
     assert r0 == 3 and n == 3 and got == want
+    # the same stream wrapped in IVF and in Annex B (size-less OBUs) demuxes to the same temporal units and the same md5
+    ivf = b"DKIF" + (0).to_bytes(2, "little") + (32).to_bytes(2, "little") + b"AV01" + (208).to_bytes(2, "little") + \
+          (144).to_bytes(2, "little") + (25).to_bytes(4, "little") + (1).to_bytes(4, "little") + (3).to_bytes(4, "little") + bytes(4)
+    for k, tu in enumerate(tus):
+        ivf += len(tu).to_bytes(4, "little") + k.to_bytes(8, "little") + tu
+    ivf_file = str(tmp_path / "s.ivf")
+    open(ivf_file, "wb").write(ivf)
+    assert cli.demux(ivf) == tus
+    assert cli.main(["-i", ivf_file] + common[2:] + ["--verify", want]) == 0
+    assert cli.main(["-i", ivf_file] + common[2:] + ["--verify", "0" * 32]) == 2
+
+    def annexb(tu):
+        out, pos = bytearray(), 0
+        while pos < len(tu):                      # strip the size fields, add obu_length prefixes; one frame unit per TU
+            hdr = tu[pos]
+            size, p = cli._leb128(tu, pos + 1)
+            body = bytes([hdr & ~2]) + tu[p:p + size]
+            out += obu.leb128(len(body)) + body
+            pos = p + size
+        fu = obu.leb128(len(out)) + bytes(out)
+        return obu.leb128(len(fu)) + fu
+    ab = b"".join(annexb(tu) for tu in tus)
+    assert cli.split_annexb(ab) == tus
     assert cli.main(common + ["-o", y4m]) == 0
     assert open(y4m, "rb").read(64).startswith(b"YUV4MPEG2 W208 H144 F25:1 Ip C420p10\nFRAME\n")
     assert os.path.getsize(y4m) == len(b"YUV4MPEG2 W208 H144 F25:1 Ip C420p10\n") + 3 * (6 + 208 * 144 * 3)
