@@ -70,7 +70,7 @@ def _profile(bpc, layout):
 
 
 def sequence_header(w, h, bpc=8, sb128=0, film_grain=0, filter_intra=1, intra_edge_filter=1, cdef=1, restoration=1,
-                    inter_intra=1, masked_compound=1, warped_motion=1, screen_content=0, layout="420"):
+                    inter_intra=1, masked_compound=1, warped_motion=1, screen_content=0, layout="420", super_res=0):
     b = BitWriter()
     profile = _profile(bpc, layout)
     b.f(3, profile)
@@ -93,7 +93,7 @@ def sequence_header(w, h, bpc=8, sb128=0, film_grain=0, filter_intra=1, intra_ed
     if screen_content:
         b.f(1, 0); b.f(1, 0)                 # seq_choose_integer_mv = 0, seq_force_integer_mv = 0
     b.f(3, 6)                                # order_hint_bits_minus_1
-    b.f(1, 0); b.f(1, cdef); b.f(1, restoration)   # superres, cdef, restoration
+    b.f(1, super_res); b.f(1, cdef); b.f(1, restoration)   # superres, cdef, restoration
     b.f(1, 1 if bpc > 8 else 0)              # high_bitdepth
     if profile == 2 and bpc > 8:
         b.f(1, 1 if bpc == 12 else 0)        # twelve_bit
@@ -234,7 +234,7 @@ def _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_byt
 
 def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None, lf=None, cdef=True,
               restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0, screen_content=0, layout="420",
-              intra_only=None, segmentation=0):
+              intra_only=None, segmentation=0, super_res=0):
     """One shown key frame (OBU_FRAME), or with intra_only=(order_hint, refresh_frame_flags) a shown INTRA_ONLY frame
     (intra coded, but it only replaces the reference slots it names). Returns the OBU bytes. `cdef_on` / `restoration_on` must match the sequence
     header (the fields are absent when the sequence disables the tool)."""
@@ -250,8 +250,10 @@ def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb
     b.f(7, 0 if intra_only is None else intra_only[0])   # order_hint
     if intra_only is not None:
         b.f(8, intra_only[1])                # refresh_frame_flags (a shown key frame refreshes all slots implicitly)
+    if super_res:
+        b.f(1, 1); b.f(3, int(rng.integers(0, 8)))   # use_superres, coded_denom
     b.f(1, 0)                                # render_and_frame_size_different
-    if screen_content:
+    if screen_content and not super_res:
         b.f(1, 0)                            # allow_intrabc
     b.f(1, 0)                                # disable_frame_end_update_cdf
     cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout, segmentation)
@@ -266,11 +268,12 @@ def temporal_unit(*obus):
     return obu(OBU_TD, b"") + b"".join(obus)
 
 
-def intra_stream(seed, w, h, n_frames=1, bpc=8, sb128=0, log2_cols=0, log2_rows=0, film_grain=0, screen_content=0, layout="420", **kw):
+def intra_stream(seed, w, h, n_frames=1, bpc=8, sb128=0, log2_cols=0, log2_rows=0, film_grain=0, screen_content=0, layout="420",
+                 super_res=0, **kw):
     """A list of temporal units (bytes), each holding one shown key frame."""
     rng = np.random.default_rng(seed)
-    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, film_grain=film_grain, screen_content=screen_content, layout=layout)
-    kw = dict(kw, layout=layout)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, film_grain=film_grain, screen_content=screen_content, layout=layout, super_res=super_res)
+    kw = dict(kw, layout=layout, super_res=super_res)
     if film_grain:
         kw = dict(kw, film_grain_seq=1)
     if screen_content:

@@ -77,6 +77,8 @@ static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *c
         else __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
         if (f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I400)      /* the post-filter sweeps always walk three planes */
             __atomic_fetch_or(&hf->unsupported, 512, __ATOMIC_RELAXED);
+        if (f->frame_hdr->width[0] != f->frame_hdr->width[1])        /* super-resolution: no upscaling stage in the frame job yet */
+            __atomic_fetch_or(&hf->unsupported, 1024, __ATOMIC_RELAXED);
         /* intra records and coefficients are appended without a lock by every tile thread of the frame (slots are taken
          * with atomic counters), so their buffers are sized for the worst case up front: one record per 4x4 cell of each
          * plane, 16 coefficients per cell, over the 128-aligned frame area */
@@ -718,7 +720,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         fprintf(stderr, "b200hook: frame uses tools the emitters do not translate yet (%s%s%s%s)\n",
                 hf->unsupported & 1 ? " palette" : "", hf->unsupported & 2 ? " inter" : "",
                 hf->unsupported & 4 ? " single-pass-decoding" : "", hf->unsupported & 8 ? " out-of-memory" : "");
-        fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 scaled reference, 64 intra block copy, 256 inter-intra block size, 512 monochrome)\n", hf->unsupported);
+        fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 scaled reference, 64 intra block copy, 256 inter-intra block size, 512 monochrome, 1024 super-resolution)\n", hf->unsupported);
         return -1;
     }
     PicGeom g;

@@ -169,6 +169,14 @@ def test_segmentation_stream_emu_matches_stock_dav1d(emu_decoder, seed):
     _check(emu_decoder, tus, len(tus))
 
 
+def test_super_resolution_stream_fails_loudly(emu_decoder):
+    """super-resolution needs an upscaling stage the frame job does not have yet: an error, not a wrong picture"""
+    tus = obu.intra_stream(3, 256, 192, n_frames=1, super_res=1)
+    assert _ref_decode(tus)[0] == 1
+    assert emu_decoder.decode(tus)[0] < 0
+    emu_decoder.stats(reset=True)
+
+
 def test_monochrome_stream_fails_loudly(emu_decoder):
     """4:0:0 is not supported by the whole-frame post filters (they walk three planes): the hooked decoder must report an
     error, not decode something else"""
