@@ -169,6 +169,15 @@ def test_segmentation_stream_emu_matches_stock_dav1d(emu_decoder, seed):
     _check(emu_decoder, tus, len(tus))
 
 
+@pytest.mark.emu
+def test_sequence_changes_within_one_decode(emu_decoder):
+    """new sequence headers mid-stream (other picture size, other bit depth): per-frame geometry, buffers that grow, the
+    8-bit and the 16-bit hook sets alternating on the same frame contexts"""
+    tus = obu.inter_stream(1, 320, 192, n_frames=3, motion_modes=2) + obu.inter_stream(2, 200, 136, n_frames=3, motion_modes=1) + \
+          obu.inter_stream(3, 456, 264, n_frames=3, bpc=10, motion_modes=2, film_grain=1)
+    _check(emu_decoder, tus, 9, apply_grain=1)
+
+
 def test_super_resolution_stream_fails_loudly(emu_decoder):
     """super-resolution needs an upscaling stage the frame job does not have yet: an error, not a wrong picture"""
     tus = obu.intra_stream(3, 256, 192, n_frames=1, super_res=1)
