@@ -29,6 +29,8 @@ if [[ $what == *" bench2 "* ]]; then
   timeout 600 python bench.py --workload itx8x8 > gpurun_out/bench_itx8x8.json 2> gpurun_out/bench_itx8x8.err
 fi
 if [[ $what == *" ncu "* ]]; then
+  # one frame at a time: the launch order of a frame is then the stage order (the default bench interleaves two frames)
+  export B200_FRAMES_IN_FLIGHT=1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 50 -c 30 --csv \
       --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 5 > gpurun_out/ncu_bench.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -s 50 -c 10 \
