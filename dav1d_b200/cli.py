@@ -118,16 +118,13 @@ def synth_stream(spec, seed=1):
 
 
 def frames_of(info, packed):
-    """(w, h, bpc, [Y, U, V] arrays) per decoded picture out of the driver's packed output (4:2:0 / 4:0:0 layouts)"""
+    """(w, h, bpc, [Y, U, V] arrays) per decoded picture out of the driver's packed output"""
     pos = 0
     for w, h, bpc, layout in info:
         px = 2 if bpc > 8 else 1
         dt = np.uint16 if px == 2 else np.uint8
         planes = []
-        dims = [(w, h)] if layout == 0 else [(w, h), ((w + 1) // 2, (h + 1) // 2), ((w + 1) // 2, (h + 1) // 2)]
-        if layout not in (0, 1):
-            raise ValueError("only 4:0:0 and 4:2:0 output is handled by this tool (layout %d)" % layout)
-        for pw, ph in dims:
+        for pw, ph in stream.plane_dims(int(w), int(h), int(layout)):
             nbytes = pw * ph * px
             planes.append(packed[pos:pos + nbytes].view(dt).reshape(ph, pw)); pos += nbytes
         yield int(w), int(h), int(bpc), planes
@@ -139,7 +136,8 @@ def write_y4m(path, frames, fps=(25, 1)):
         first = True
         for w, h, bpc, planes in frames:
             if first:
-                cs = ("mono" if len(planes) == 1 else "420jpeg") if bpc == 8 else ("mono%d" % bpc if len(planes) == 1 else "420p%d" % bpc)
+                ss = "mono" if len(planes) == 1 else {1: "420", 2: "422", 3: "444"}[1 if planes[1].shape[0] < h else (2 if planes[1].shape[1] < w else 3)]
+                cs = ("420jpeg" if ss == "420" else ss) if bpc == 8 else (ss + str(bpc) if ss == "mono" else "%sp%d" % (ss, bpc))
                 fh.write(("YUV4MPEG2 W%d H%d F%d:%d Ip C%s\n" % (w, h, fps[0], fps[1], cs)).encode())
                 first = False
             fh.write(b"FRAME\n")

@@ -31,6 +31,15 @@ def build_hooked(verbose=False):
     return HOOKED_SO
 
 
+def plane_dims(w, h, layout):
+    """(width, height) of the planes of a picture; layout = enum Dav1dPixelLayout (0 4:0:0, 1 4:2:0, 2 4:2:2, 3 4:4:4)"""
+    if layout == 0:
+        return [(w, h)]
+    cw = w if layout == 3 else (w + 1) // 2
+    ch = (h + 1) // 2 if layout == 1 else h
+    return [(w, h), (cw, ch), (cw, ch)]
+
+
 def decode_stream(dll, tus, n_threads=4, max_frame_delay=2, max_pics=64, apply_grain=0):
     """Decode a list of temporal units with `dll` (a CDLL exporting refdrv_decode_stream: the hooked library or the
     stock checker). Returns (n_pictures or negative dav1d error, info[n][4] = w, h, bpc, layout, packed pictures)."""
@@ -48,8 +57,8 @@ def decode_stream(dll, tus, n_threads=4, max_frame_delay=2, max_pics=64, apply_g
                                  info.ctypes.data, max_pics)
     n = 0
     for i in range(max(r, 0)):
-        w, h, bpc = (int(v) for v in info[4 * i:4 * i + 3])
-        n += (w * h + 2 * ((w + 1) // 2) * ((h + 1) // 2)) * (2 if bpc > 8 else 1)
+        w, h, bpc, layout = (int(v) for v in info[4 * i:4 * i + 4])
+        n += sum(pw * ph for pw, ph in plane_dims(w, h, layout)) * (2 if bpc > 8 else 1)
     return r, info[:4 * max(r, 0)].reshape(-1, 4).copy(), out[:n]
 
 

@@ -1,0 +1,41 @@
+"""Regenerates tests/golden/stream_golden.json + the .obu files next to it: small synthetic AV1 streams (dav1d_b200/obu.py)
+and the md5 of the pictures the UNMODIFIED reference decoder (oracle/_ref/libdav1d_ref.so, built from /root/reference by
+oracle/Makefile) produces for them, film grain applied. Run where the reference is built:
+
+    python tests/golden/make_stream_golden.py
+"""
+import ctypes as C
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from dav1d_b200 import cli, obu, stream  # noqa: E402
+
+CASES = {
+    "key_8bit_tiles": lambda: obu.intra_stream(1, 136, 96, n_frames=2, log2_cols=1, payload_bytes_per_sb64=700),
+    "inter_10bit_all_tools": lambda: obu.inter_stream(2, 136, 96, n_frames=4, bpc=10, motion_modes=2, film_grain=1, screen_content=1,
+                                                      global_motion=1, segmentation=1, hidden_every=2, payload_bytes_per_sb64=700),
+    "inter_444_12bit": lambda: obu.inter_stream(3, 72, 72, n_frames=3, bpc=12, layout="444", motion_modes=1, payload_bytes_per_sb64=1500),
+}
+
+
+def main():
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libdav1d_ref.so"))
+    out = {}
+    for name, gen in CASES.items():
+        tus = gen()
+        with open(os.path.join(HERE, "stream_%s.obu" % name), "wb") as fh:
+            fh.write(b"".join(tus))
+        n, info, packed = stream.decode_stream(ref, tus, apply_grain=1)
+        assert n > 0, (name, n)
+        digest, frames = cli.md5_of(cli.frames_of(info, packed))
+        out[name] = {"md5": digest, "frames": frames, "temporal_units": len(tus), "bytes": sum(map(len, tus))}
+        print(name, out[name])
+    json.dump(out, open(os.path.join(HERE, "stream_golden.json"), "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

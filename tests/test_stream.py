@@ -400,3 +400,41 @@ def test_cli_md5_y4m_and_obu_file_roundtrip(tmp_path, capsys):
     assert cli.main(common + ["-o", y4m]) == 0
     assert open(y4m, "rb").read(64).startswith(b"YUV4MPEG2 W208 H144 F25:1 Ip C420p10\nFRAME\n")
     assert os.path.getsize(y4m) == len(b"YUV4MPEG2 W208 H144 F25:1 Ip C420p10\n") + 3 * (6 + 208 * 144 * 3)
+
+
+# ---- committed golden streams: tests/golden/stream_*.obu + the md5 of the stock reference's output (make_stream_golden.py)
+def _golden():
+    import json
+    from dav1d_b200 import cli
+    g = json.load(open(os.path.join(refs.ROOT, "tests", "golden", "stream_golden.json")))
+    return {k: (cli.demux(open(os.path.join(refs.ROOT, "tests", "golden", "stream_%s.obu" % k), "rb").read()), v) for k, v in g.items()}
+
+
+def _md5(dec_result):
+    from dav1d_b200 import cli
+    n, info, packed = dec_result
+    assert n > 0, n
+    return cli.md5_of(cli.frames_of(info, packed))
+
+
+def test_golden_streams_reference_md5():
+    """the committed streams decode with the stock reference to the committed digests (pins the reference build and the files)"""
+    for name, (tus, want) in _golden().items():
+        assert len(tus) == want["temporal_units"] and sum(map(len, tus)) == want["bytes"]
+        assert _md5(_ref_decode(tus, apply_grain=1)) == (want["md5"], want["frames"]), name
+
+
+@pytest.mark.emu
+def test_golden_streams_hooked_emu_md5(emu_decoder):
+    for name, (tus, want) in _golden().items():
+        assert _md5(emu_decoder.decode(tus, apply_grain=1)) == (want["md5"], want["frames"]), name
+    emu_decoder.stats(reset=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["key_8bit_tiles", "inter_10bit_all_tools"])
+def test_golden_streams_hooked_gpu_md5(gpu_decoder, name):
+    """needs neither /root/reference nor oracle/: the digest of the reference's output is committed"""
+    tus, want = _golden()[name]
+    assert _md5(gpu_decoder.decode(tus, apply_grain=1)) == (want["md5"], want["frames"])
+    gpu_decoder.stats(reset=True)
