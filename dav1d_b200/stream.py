@@ -11,6 +11,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOOKED_SO = os.path.join(ROOT, "integration", "_ref", "libdav1d_b200.so")
+LEVEL1_SO = os.path.join(ROOT, "integration", "_ref", "libdav1d_b200_l1.so")
+FAMILIES = {"itx": 1, "mc": 2, "ipred": 4, "loopfilter": 8, "cdef": 16, "looprestoration": 32, "filmgrain": 64}
 
 
 class HookStats(C.Structure):
@@ -21,7 +23,7 @@ class HookStats(C.Structure):
 
 
 def build_hooked(verbose=False):
-    """(Re)build integration/_ref/libdav1d_b200.so where the reference sources exist; a no-op on the GPU box."""
+    """(Re)build integration/_ref/libdav1d_b200.so (+ the Level-1 variant) where the reference sources exist; a no-op on the GPU box."""
     import subprocess
     r = subprocess.run(["make", "-j8", "-C", os.path.join(ROOT, "integration", "dav1d"), "all"], capture_output=True, text=True)
     if r.returncode:
@@ -94,3 +96,29 @@ class HookedDecoder:
 
     def release(self):
         self.dll.b200hook_release()
+
+
+class Level1Decoder:
+    """dav1d with its own reconstruction code, but every DSP table slot (`Dav1dDSPContext`: itx, mc, ipred, loopfilter,
+    cdef, looprestoration, filmgrain) overridden by libb200av1's Level-1 functions — the architecture-hook form of the
+    drop-in (integration/dav1d/b200_level1.c). One kernel launch per DSP call: a parity harness, not a throughput path.
+    `families` = iterable of FAMILIES keys (default: all seven)."""
+
+    def __init__(self, backend=None, families=None):
+        if not os.path.exists(LEVEL1_SO):
+            if os.path.isdir("/root/reference/src"):
+                build_hooked()
+            else:
+                raise RuntimeError("integration/_ref/libdav1d_b200_l1.so missing (it is built where the reference sources exist)")
+        if backend is None:
+            from . import _lib
+            backend = _lib.get_lib().path
+        self.dll = C.CDLL(LEVEL1_SO)
+        mask = sum(FAMILIES[f] for f in (families or FAMILIES))
+        if self.dll.b200l1_set_backend(backend.encode(), mask) != 0:
+            raise RuntimeError("b200l1_set_backend(%s) failed" % backend)
+
+    def decode(self, tus, **kw):
+        kw.setdefault("n_threads", 1)            # the Level-1 thunks serialise on one lock anyway
+        kw.setdefault("max_frame_delay", 1)
+        return decode_stream(self.dll, tus, **kw)

@@ -438,3 +438,36 @@ def test_golden_streams_hooked_gpu_md5(gpu_decoder, name):
     tus, want = _golden()[name]
     assert _md5(gpu_decoder.decode(tus, apply_grain=1)) == (want["md5"], want["frames"])
     gpu_decoder.stats(reset=True)
+
+
+# ---- Level 1 inside a real dav1d: Dav1dDSPContext filled by b200_*_dsp_init (integration/dav1d/b200_level1.c) ----------
+def _level1_case(dec, launches):
+    n0 = launches()
+    for gen, kw in ((obu.intra_stream, dict(n_frames=1)),
+                    (obu.inter_stream, dict(n_frames=3, bpc=10, motion_modes=2, film_grain=1, global_motion=1))):
+        tus = gen(4, 136, 96, payload_bytes_per_sb64=600, **kw)
+        r0, _, out0 = _ref_decode(tus, n_threads=1, max_frame_delay=1, apply_grain=1)
+        r1, _, out1 = dec.decode(tus, apply_grain=1)
+        assert r0 == len(tus) and r1 == r0 and np.array_equal(out0, out1), gen.__name__
+    assert launches() - n0 > 1000, "the DSP calls did not reach the back end"
+
+
+@pytest.mark.emu
+def test_level1_tables_inside_dav1d_emu():
+    """dav1d's own recon_tmpl.c / lf_apply / cdef_apply / lr_apply / fg_apply running on the B200 function tables (all seven
+    families): decoded pictures identical to stock dav1d, thousands of kernel launches behind the DSP pointers"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(refs.ROOT, "tests", "emu", "build_emu.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    emu_path = m.build()
+    if os.path.isdir("/root/reference/src"):
+        stream.build_hooked()
+    emu = refs.emu_lib()
+    _level1_case(stream.Level1Decoder(backend=emu_path), lambda: int(emu.b200_launch_count()))
+
+
+@pytest.mark.gpu
+def test_level1_tables_inside_dav1d_gpu():
+    from dav1d_b200 import _lib
+    lib = _lib.get_lib()
+    _level1_case(stream.Level1Decoder(), lambda: int(lib.b200_launch_count()))
