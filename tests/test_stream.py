@@ -468,6 +468,13 @@ def test_level1_tables_inside_dav1d_emu():
 
 @pytest.mark.gpu
 def test_level1_tables_inside_dav1d_gpu():
-    from dav1d_b200 import _lib
-    lib = _lib.get_lib()
-    _level1_case(stream.Level1Decoder(), lambda: int(lib.b200_launch_count()))
+    """own process: the Level-1 thunks have no error channel (like dav1d's DSP functions) and abort on a CUDA failure"""
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import test_stream as T\n"
+            "from dav1d_b200 import _lib, stream\n"
+            "lib = _lib.get_lib()\n"
+            "T._level1_case(stream.Level1Decoder(), lambda: int(lib.b200_launch_count()))\n"
+            "print('LEVEL1 OK', lib.b200_launch_count())\n") % (refs.ROOT, os.path.join(refs.ROOT, "tests"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert "LEVEL1 OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
