@@ -466,6 +466,28 @@ def test_level1_tables_inside_dav1d_emu():
     _level1_case(stream.Level1Decoder(backend=emu_path), lambda: int(emu.b200_launch_count()))
 
 
+@pytest.mark.emu
+def test_level1_tables_inside_dav1d_many_streams_emu():
+    """the same harness over randomly parameterised streams: 8 / 10 / 12 bit, 4:2:0 / 4:4:4 / 4:0:0, screen content (pal_pred),
+    segmentation with lossless segments (the WHT slot), global motion (warp8x8 / warp8x8t), film grain"""
+    emu = refs.emu_lib()
+    dec = stream.Level1Decoder(backend=emu.path)
+    for seed in range(5000, 5016):
+        rng = np.random.default_rng(seed)
+        w, h = int(rng.integers(4, 20)) * 8 + int(rng.choice([0, 0, 2, 6])), int(rng.integers(4, 14)) * 8 + int(rng.choice([0, 0, 4]))
+        kw = dict(bpc=int(rng.choice([8, 10, 12])), sb128=int(rng.integers(0, 2)), log2_cols=int(rng.integers(0, 2)),
+                  film_grain=int(rng.integers(0, 2)), screen_content=int(rng.integers(0, 2)), layout=str(rng.choice(["420", "420", "444", "400"])),
+                  segmentation=int(rng.integers(0, 2)), payload_bytes_per_sb64=800)
+        if seed % 3:
+            tus = obu.inter_stream(seed, w, h, n_frames=int(rng.integers(2, 5)), motion_modes=int(rng.integers(0, 3)),
+                                   global_motion=int(rng.integers(0, 2)), hidden_every=int(rng.choice([0, 2])), **kw)
+        else:
+            tus = obu.intra_stream(seed, w, h, n_frames=2, **kw)
+        r0, _, out0 = _ref_decode(tus, n_threads=1, max_frame_delay=1, apply_grain=1)
+        r1, _, out1 = dec.decode(tus, apply_grain=1)
+        assert r0 > 0 and r1 == r0 and np.array_equal(out0, out1), (seed, kw)
+
+
 @pytest.mark.gpu
 def test_level1_tables_inside_dav1d_gpu():
     """own process: the Level-1 thunks have no error channel (like dav1d's DSP functions) and abort on a CUDA failure"""
