@@ -120,7 +120,10 @@ HookRefPic *b200hook_refpic(const void *key, size_t bytes, int create)
              * 8 reference slots + frames in flight + pictures waiting for output — is far smaller than the table) */
             for (int i = 0; i < 64; i++)
                 if (g_refs[i].ready && (!r || g_refs[i].last_use < r->last_use)) r = &g_refs[i];
-            if (r) { r->key = key; r->ready = 0; }
+            if (!r)                              /* only pictures of abandoned frames (never completed) are left: oldest one */
+                for (int i = 0; i < 64; i++)
+                    if (!r || g_refs[i].last_use < r->last_use) r = &g_refs[i];
+            r->key = key; r->ready = 0;
         }
     }
     if (r) r->last_use = ++g_clock;
@@ -168,8 +171,14 @@ HookFrame *b200hook_frame(const void *key)
             if (h->started || h->tile_sbrows_done) continue;          /* a frame is being emitted into this slot */
             if (!lru || h->last_use < lru->last_use) lru = h;
         }
-        if (lru) { lru->key = key; lru->unsupported = 0; r = lru; }
-        else fprintf(stderr, "b200hook: more than 64 frame contexts in flight\n");
+        if (!lru) {
+            /* every slot looks busy: contexts of decoders that were closed in the middle of a frame never finish it. Live
+             * contexts are looked up all the time, so the least recently used slot is one of those leftovers. */
+            for (int i = 0; i < 64; i++)
+                if (!lru || g_frames[i].last_use < lru->last_use) lru = &g_frames[i];
+            lru->started = 0; lru->tile_sbrows_done = 0; lru->cur_pic = NULL;
+        }
+        lru->key = key; lru->unsupported = 0; r = lru;
     }
     if (r) r->last_use = ++g_clock;
     pthread_mutex_unlock(&g_lock);

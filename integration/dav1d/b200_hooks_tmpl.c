@@ -66,9 +66,18 @@ static void bitfn(pic_geom)(const Dav1dFrameContext *const f, PicGeom *const g)
 /* first pass-2 hook call of a frame: its output picture (keyed by the host buffer) is not valid any more / yet */
 static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *const f)
 {
-    if (__atomic_load_n(&hf->started, __ATOMIC_ACQUIRE)) return;
+    if (__atomic_load_n(&hf->started, __ATOMIC_ACQUIRE) && hf->cur_pic == f->cur.data[0]) return;
     pthread_mutex_lock(&hf->lock);
+    if (hf->started && hf->cur_pic != f->cur.data[0]) {
+        /* the context's previous frame never completed (dav1d flushed or closed while it was being reconstructed) */
+        hf->tile_sbrows_done = 0; hf->n_tx = 0; hf->n_coef = 0; hf->unsupported = 0;
+        hf->n_pred = hf->n_comp = hf->n_comp2 = hf->n_warp = hf->n_blend = hf->n_blend2 = 0;
+        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->is_inter = 0; hf->n_ii = 0;
+        memset(hf->n_itx, 0, sizeof(hf->n_itx));
+        hf->started = 0;
+    }
     if (!hf->started) {
+        hf->cur_pic = f->cur.data[0];
         hf->n_cmask = (sizeof(dav1d_masks) + 63) & ~(size_t)63;      /* dav1d's wedge tables sit at the head of the mask buffer */
         PicGeom g;
         bitfn(pic_geom)(f, &g);

@@ -88,3 +88,33 @@ done:
     dav1d_close(&c);
     return res;
 }
+
+/* Sends the first n_tu temporal units and closes the decoder at once, without draining: whatever frames are still
+ * being decoded are flushed by dav1d_close (reference src/lib.c, dav1d_flush / close_internal). Test hook for the
+ * back end's handling of abandoned frames. Returns the number of pictures that happened to come out. */
+API int refdrv_decode_and_abandon(const uint8_t *data, const uint64_t *tu_sz, int n_tu, int n_threads, int max_frame_delay)
+{
+    Dav1dSettings s;
+    Dav1dContext *c = NULL;
+    dav1d_default_settings(&s);
+    s.n_threads = n_threads;
+    s.max_frame_delay = max_frame_delay;
+    if (dav1d_open(&c, &s) < 0) return -1;
+    int n_pics = 0;
+    const uint8_t *ptr = data;
+    for (int i = 0; i < n_tu; i++) {
+        Dav1dData d;
+        memset(&d, 0, sizeof(d));
+        if (dav1d_data_wrap(&d, ptr, (size_t)tu_sz[i], nop_free, NULL) < 0) break;
+        ptr += tu_sz[i];
+        while (d.sz) {
+            const int r = dav1d_send_data(c, &d);
+            if (r < 0 && r != DAV1D_ERR(EAGAIN)) { dav1d_data_unref(&d); break; }
+            Dav1dPicture p;
+            memset(&p, 0, sizeof(p));
+            if (dav1d_get_picture(c, &p) == 0) { n_pics++; dav1d_picture_unref(&p); }
+        }
+    }
+    dav1d_close(&c);
+    return n_pics;
+}

@@ -178,6 +178,24 @@ def test_sequence_changes_within_one_decode(emu_decoder):
     _check(emu_decoder, tus, 9, apply_grain=1)
 
 
+@pytest.mark.emu
+def test_abandoned_frames_do_not_poison_later_decodes(emu_decoder):
+    """decoders closed while frames are still in flight (dav1d_close flushes them half way through pass 2): the frame
+    contexts' slots keep half-emitted frames; later decodes must neither pick up their records nor run out of slots"""
+    good = obu.inter_stream(1, 256, 192, n_frames=4, motion_modes=2)
+    r0, _, out0 = _ref_decode(good)
+    long_ = obu.inter_stream(2, 320, 256, n_frames=10, motion_modes=1, log2_cols=1, log2_rows=1)
+    data = b"".join(long_)
+    sz = (C.c_uint64 * len(long_))(*[len(t) for t in long_])
+    dll = emu_decoder.dll
+    dll.refdrv_decode_and_abandon.restype = C.c_int
+    for k in range(14):                       # 14 x 8 frame contexts > the 64 slots of the hook's table
+        assert dll.refdrv_decode_and_abandon(data, sz, 3 + k % 6, 8, 8) >= 0
+        r1, _, out1 = emu_decoder.decode(good)
+        assert r1 == r0 and np.array_equal(out0, out1), k
+    emu_decoder.stats(reset=True)
+
+
 def test_super_resolution_stream_fails_loudly(emu_decoder):
     """super-resolution needs an upscaling stage the frame job does not have yet: an error, not a wrong picture"""
     tus = obu.intra_stream(3, 256, 192, n_frames=1, super_res=1)
