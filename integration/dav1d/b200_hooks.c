@@ -244,6 +244,33 @@ int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int
     return n_waves;
 }
 
+/* dav1d's "this frame is over" (completed, failed or flushed; reference src/decode.c:3242, called from src/thread_task.c and
+ * src/lib.c:588, which are compiled with the call renamed to this wrapper). A frame that ends without having been handed to
+ * the device leaves half a frame of records in its slot: drop them, and release anybody waiting for its picture. */
+struct Dav1dFrameContext;
+void dav1d_decode_frame_exit(struct Dav1dFrameContext *f, int retval);
+void b200hook_decode_frame_exit(struct Dav1dFrameContext *const f, const int retval)
+{
+    HookFrame *h = NULL;
+    pthread_mutex_lock(&g_lock);
+    for (int i = 0; i < 64 && !h; i++)
+        if (g_frames[i].key == (const void *)f) h = &g_frames[i];
+    pthread_mutex_unlock(&g_lock);
+    if (h) {
+        pthread_mutex_lock(&h->lock);
+        if (h->started) {
+            HookRefPic *const out = h->cur_pic ? b200hook_refpic(h->cur_pic, 0, 0) : NULL;
+            if (out) b200hook_refpic_set_ready(out, 1);
+            h->started = 0; h->tile_sbrows_done = 0; h->n_tx = 0; h->n_coef = 0; h->unsupported = 0;
+            h->n_pred = h->n_comp = h->n_comp2 = h->n_warp = h->n_blend = h->n_blend2 = 0;
+            h->n_tmp16 = 0; h->n_pxtmp = 0; h->is_inter = 0; h->n_ii = 0; h->n_pal = 0;
+            memset(h->n_itx, 0, sizeof(h->n_itx));
+        }
+        pthread_mutex_unlock(&h->lock);
+    }
+    dav1d_decode_frame_exit(f, retval);
+}
+
 void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[9], double prep_ms)
 {
     pthread_mutex_lock(&g_lock);
