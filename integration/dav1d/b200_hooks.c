@@ -168,17 +168,22 @@ HookFrame *b200hook_frame(const void *key)
     if (!r) {
         for (int i = 0; i < 64; i++) {
             HookFrame *const h = &g_frames[i];
-            if (h->started || h->tile_sbrows_done) continue;          /* a frame is being emitted into this slot */
+            if (h->pinned || h->started || h->tile_sbrows_done) continue;    /* a frame is being emitted into this slot */
             if (!lru || h->last_use < lru->last_use) lru = h;
         }
         if (!lru) {
             /* every slot looks busy: contexts of decoders that were closed in the middle of a frame never finish it. Live
              * contexts are looked up all the time, so the least recently used slot is one of those leftovers. */
             for (int i = 0; i < 64; i++)
-                if (!lru || g_frames[i].last_use < lru->last_use) lru = &g_frames[i];
-            lru->started = 0; lru->tile_sbrows_done = 0; lru->cur_pic = NULL;
+                if (!g_frames[i].pinned && (!lru || g_frames[i].last_use < lru->last_use)) lru = &g_frames[i];
         }
-        lru->key = key; lru->unsupported = 0; r = lru;
+        /* a slot whose job is still running (its lock is held) is not taken over */
+        if (lru && pthread_mutex_trylock(&lru->lock) == 0) {
+            lru->started = 0; lru->tile_sbrows_done = 0; lru->cur_pic = NULL;
+            lru->key = key; lru->unsupported = 0; r = lru;
+            pthread_mutex_unlock(&lru->lock);
+        } else
+            fprintf(stderr, "b200hook: no frame-context slot available\n");
     }
     if (r) r->last_use = ++g_clock;
     pthread_mutex_unlock(&g_lock);

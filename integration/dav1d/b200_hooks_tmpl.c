@@ -984,6 +984,7 @@ static void bitfn(fg_whole_picture)(Dav1dPicture *const out, const Dav1dPicture 
     static const char fg_slot_key = 0;
     HookFrame *const hf = b200hook_frame(&fg_slot_key);                  /* a slot of its own for the output stage */
     if (!hf) abort();
+    hf->pinned = 1;
     pthread_mutex_lock(&hf->lock);
     if ((!hf->stream && !(hf->stream = be->stream_create())) || b200hook_buf_reserve(&hf->pic[0], bytes, 0, 0) ||
         b200hook_buf_reserve(&hf->scratch, B200_FG_SCRATCH_BYTES, 0, 0)) {
