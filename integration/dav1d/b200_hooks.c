@@ -165,26 +165,29 @@ HookFrame *b200hook_frame(const void *key)
             pthread_mutex_init(&r->lock, NULL);
             r->key = key;
         }
-    if (!r) {
-        for (int i = 0; i < 64; i++) {
-            HookFrame *const h = &g_frames[i];
-            if (h->pinned || h->started || h->tile_sbrows_done) continue;    /* a frame is being emitted into this slot */
-            if (!lru || h->last_use < lru->last_use) lru = h;
+    /* table full: take over the least recently used slot — idle ones first (pass 0), then leftovers of decoders that were
+     * closed in the middle of a frame (pass 1: live contexts are looked up all the time, so an old busy-looking slot is dead).
+     * A slot whose lock is held (its job or its exit handler is running) is skipped. */
+    for (int pass = 0; pass < 2 && !r; pass++) {
+        uint64_t floor_use = 0;
+        for (int tries = 0; tries < 64 && !r; tries++) {
+            for (int i = 0; i < 64; i++) {
+                HookFrame *const h = &g_frames[i];
+                if (h->pinned || h->last_use <= floor_use) continue;
+                if (!pass && (h->started || h->tile_sbrows_done)) continue;
+                if (!lru || h->last_use < lru->last_use) lru = h;
+            }
+            if (!lru) break;
+            if (pthread_mutex_trylock(&lru->lock) == 0) {
+                lru->started = 0; lru->tile_sbrows_done = 0; lru->cur_pic = NULL;
+                lru->key = key; lru->unsupported = 0; r = lru;
+                pthread_mutex_unlock(&lru->lock);
+            } else {
+                floor_use = lru->last_use; lru = NULL;          /* busy right now: next oldest */
+            }
         }
-        if (!lru) {
-            /* every slot looks busy: contexts of decoders that were closed in the middle of a frame never finish it. Live
-             * contexts are looked up all the time, so the least recently used slot is one of those leftovers. */
-            for (int i = 0; i < 64; i++)
-                if (!g_frames[i].pinned && (!lru || g_frames[i].last_use < lru->last_use)) lru = &g_frames[i];
-        }
-        /* a slot whose job is still running (its lock is held) is not taken over */
-        if (lru && pthread_mutex_trylock(&lru->lock) == 0) {
-            lru->started = 0; lru->tile_sbrows_done = 0; lru->cur_pic = NULL;
-            lru->key = key; lru->unsupported = 0; r = lru;
-            pthread_mutex_unlock(&lru->lock);
-        } else
-            fprintf(stderr, "b200hook: no frame-context slot available\n");
     }
+    if (!r) fprintf(stderr, "b200hook: no frame-context slot available\n");
     if (r) r->last_use = ++g_clock;
     pthread_mutex_unlock(&g_lock);
     return r;
