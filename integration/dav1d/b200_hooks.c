@@ -271,7 +271,7 @@ void b200hook_decode_frame_exit(struct Dav1dFrameContext *const f, const int ret
             if (out) b200hook_refpic_set_ready(out, 1);
             h->started = 0; h->tile_sbrows_done = 0; h->n_tx = 0; h->n_coef = 0; h->unsupported = 0;
             h->n_pred = h->n_comp = h->n_comp2 = h->n_warp = h->n_blend = h->n_blend2 = 0;
-            h->n_tmp16 = 0; h->n_pxtmp = 0; h->is_inter = 0; h->n_ii = 0; h->n_pal = 0;
+            h->n_tmp16 = 0; h->n_pxtmp = 0; h->is_inter = 0; h->n_ii = 0; h->n_pal = 0; h->refs_used = 0;
             memset(h->n_itx, 0, sizeof(h->n_itx));
         }
         pthread_mutex_unlock(&h->lock);

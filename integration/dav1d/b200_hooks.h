@@ -55,6 +55,7 @@ typedef struct HookFrame {
     int n_pred, n_comp, n_comp2, n_itx[19], n_warp, n_blend, n_blend2;
     size_t n_tmp16, n_cmask, n_pxtmp;
     int started, is_inter, n_ii;
+    unsigned refs_used;            /* bit k: some prediction of this frame reads reference k (f->refp[k]) */
     int pinned;                    /* never recycled for another key (the output-stage slots) */
     const void *cur_pic;           /* f->cur.data[0] of the frame being emitted: a different picture means the previous frame of this
                                       context was abandoned half way (flush / close) and its records are stale */

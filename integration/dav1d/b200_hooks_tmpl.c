@@ -72,7 +72,7 @@ static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *c
         /* the context's previous frame never completed (dav1d flushed or closed while it was being reconstructed) */
         hf->tile_sbrows_done = 0; hf->n_tx = 0; hf->n_coef = 0; hf->unsupported = 0;
         hf->n_pred = hf->n_comp = hf->n_comp2 = hf->n_warp = hf->n_blend = hf->n_blend2 = 0;
-        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->is_inter = 0; hf->n_ii = 0;
+        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->is_inter = 0; hf->n_ii = 0; hf->refs_used = 0;
         memset(hf->n_itx, 0, sizeof(hf->n_itx));
         hf->started = 0;
     }
@@ -342,6 +342,7 @@ static int bitfn(emit_mc)(HookFrame *const hf, const Dav1dFrameContext *const f,
     r->w = bw4 * h_mul; r->h = bh4 * v_mul;
     r->mx = mx << !ss_hor; r->my = my << !ss_ver;
     r->filter2d = filter_2d; r->op = op; r->plane = pl; r->ref = refidx;      /* op: 0 put, 1 prep, 2 put into the pixel scratch */
+    hf->refs_used |= 1u << refidx;
     return 0;
 }
 
@@ -371,6 +372,7 @@ static int bitfn(emit_warp)(HookFrame *const hf, const Dav1dFrameContext *const 
             r->my = (((int)mvy & 0xffff) - wmp->u.p.gamma * 4 - wmp->u.p.delta * 4) & ~0x3f;
             for (int k = 0; k < 4; k++) r->abcd[k] = wmp->u.abcd[k];
             r->tmp_stride = pitch; r->op = op; r->plane = pl; r->ref = refidx;
+            hf->refs_used |= 1u << refidx;
         }
     }
     return 0;
@@ -771,8 +773,11 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     const int inter = hf->is_inter;
     if (inter) {
         for (int k = 0; k < 7; k++) {
+            /* only the references some block really predicts from: dav1d made this frame wait for those (their pass 2 has
+             * begun, so their device picture exists and will become ready); a reference nobody reads may not even have
+             * started its second pass yet */
             const void *const key = f->refp[k].p.data[0];
-            if (!key) continue;
+            if (!key || !(hf->refs_used & (1u << k))) continue;
             HookRefPic *const rp = b200hook_refpic(key, 0, 0);
             if (!rp || !rp->dev) { fprintf(stderr, "b200hook: reference %d was not decoded by this back end\n", k); return -1; }
             b200hook_refpic_wait(rp);          /* its device job (another frame context) must have finished */
@@ -947,7 +952,7 @@ void bitfn(b200hook_backup_ipred_edge)(Dav1dTaskContext *const t)
         if (outp) b200hook_refpic_set_ready(outp, 1);       /* also after a failure: nobody may wait for ever */
         hf->tile_sbrows_done = 0; hf->n_tx = 0; hf->n_coef = 0; hf->unsupported = 0;
         hf->n_pred = hf->n_comp = hf->n_comp2 = hf->n_warp = hf->n_blend = hf->n_blend2 = 0;
-        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->started = 0; hf->is_inter = 0; hf->n_ii = 0;
+        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->started = 0; hf->is_inter = 0; hf->n_ii = 0; hf->refs_used = 0;
         memset(hf->n_itx, 0, sizeof(hf->n_itx));
     }
     pthread_mutex_unlock(&hf->lock);

@@ -196,6 +196,27 @@ def test_abandoned_frames_do_not_poison_later_decodes(emu_decoder):
     emu_decoder.stats(reset=True)
 
 
+@pytest.mark.emu
+@pytest.mark.parametrize("seed", [6002, 6070, 6363])
+def test_unused_references_are_not_waited_for(emu_decoder, seed):
+    """a frame lists 7 references but its blocks may read only some of them; dav1d makes it wait only for those, so an
+    unused reference may not even have started its second pass when the frame completes (found by fuzzing: the frame
+    used to fail with "reference was not decoded"). Several repeats: the outcome depended on thread timing."""
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.integers(4, 30)) * 8 + int(rng.choice([0, 0, 2, 6])), int(rng.integers(4, 22)) * 8 + int(rng.choice([0, 0, 4]))
+    kw = dict(bpc=int(rng.choice([8, 10, 12])), sb128=int(rng.integers(0, 2)), log2_cols=int(rng.integers(0, 2)), log2_rows=int(rng.integers(0, 2)),
+              film_grain=int(rng.integers(0, 2)), screen_content=int(rng.integers(0, 2)), layout=str(rng.choice(["420", "420", "444"])),
+              segmentation=int(rng.integers(0, 2)))
+    tus = obu.inter_stream(seed, w, h, n_frames=int(rng.integers(2, 7)), motion_modes=int(rng.integers(0, 3)), global_motion=int(rng.integers(0, 2)),
+                           hidden_every=int(rng.choice([0, 0, 2, 3])), intra_only_every=int(rng.choice([0, 0, 0, 4])), **kw)
+    r0, _, out0 = _ref_decode(tus, apply_grain=1)
+    assert r0 > 0
+    for _ in range(6):
+        r1, _, out1 = emu_decoder.decode(tus, apply_grain=1, n_threads=4, max_frame_delay=3)
+        assert r1 == r0 and np.array_equal(out0, out1)
+    emu_decoder.stats(reset=True)
+
+
 def test_super_resolution_stream_fails_loudly(emu_decoder):
     """super-resolution needs an upscaling stage the frame job does not have yet: an error, not a wrong picture"""
     tus = obu.intra_stream(3, 256, 192, n_frames=1, super_res=1)
