@@ -154,6 +154,14 @@ void b200hook_refpic_wait(HookRefPic *r)
  * table takes over the least recently used idle slot, together with that slot's buffers. */
 HookFrame *b200hook_frame(const void *key)
 {
+    /* called by every hook, i.e. once per block: the thread's last answer is almost always still right (a slot is only
+     * handed to another key while it is idle), so the table lock is taken once per tile superblock row, not per block */
+    static __thread const void *tl_key;
+    static __thread HookFrame *tl_slot;
+    if (tl_key == key && tl_slot && __atomic_load_n(&tl_slot->key, __ATOMIC_ACQUIRE) == key) {
+        tl_slot->last_use = g_clock;
+        return tl_slot;
+    }
     HookFrame *r = NULL, *lru = NULL;
     pthread_mutex_lock(&g_lock);
     for (int i = 0; i < 64 && !r; i++)
@@ -190,6 +198,7 @@ HookFrame *b200hook_frame(const void *key)
     if (!r) fprintf(stderr, "b200hook: no frame-context slot available\n");
     if (r) r->last_use = ++g_clock;
     pthread_mutex_unlock(&g_lock);
+    tl_key = key; tl_slot = r;
     return r;
 }
 
