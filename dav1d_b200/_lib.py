@@ -153,6 +153,13 @@ class FrameJob(C.Structure):
                 ("d_blend2", C.c_void_p), ("n_blend2", C.c_int32), ("pad9", C.c_int32)]
 
 
+class FrameBand(C.Structure):
+    """struct B200FrameBand"""
+    _fields_ = [("y0", C.c_int32), ("y1", C.c_int32), ("last", C.c_int32), ("pad", C.c_int32)] + \
+               [(n, C.c_int32 * 2) for n in ("pred", "warp", "comp", "comp2", "blend", "blend2", "scaled", "cfused", "cfused2", "expand")] + \
+               [("itx", (C.c_int32 * 2) * 19)]
+
+
 class Xfer(C.Structure):
     _fields_ = [("host", C.c_void_p), ("dev", C.c_void_p), ("bytes", C.c_uint64)]
 
@@ -242,6 +249,19 @@ _SIGS = {
     "b200_frame_submit_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_frame_submit_host_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_frame_wait": (C.c_int, [C.c_void_p]),
+    # ---- band-sliced job + cross-GPU exchange
+    "b200_frame_run_band": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200_band_progress": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_ipc_open": (C.c_void_p, [C.c_void_p]),
+    "b200_ipc_close": (C.c_int, [C.c_void_p]),
+    "b200_copy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200_flag_signal": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "b200_flag_wait_geq": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "b200_event_create": (C.c_void_p, []),
+    "b200_event_destroy": (None, [C.c_void_p]),
+    "b200_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_stream_wait_event": (C.c_int, [C.c_void_p, C.c_void_p]),
     # ---- ipred
     "b200_ipred_batch": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_ipred": (C.c_int, [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p] + [C.c_int] * 6),
@@ -309,4 +329,4 @@ class Av1Restoration(C.Structure):
 
 
 ABI_STRUCTS = [McFrame, McBlock, CompBlock, BlendBlock, WarpBlock, ItxBlock, LfFrame, CdefFrame, LrFrame, FrameJob,
-               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame, McScaledBlock, CoefBlock, IntraSb, CompFusedBlock]
+               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame, McScaledBlock, CoefBlock, IntraSb, CompFusedBlock, FrameBand]

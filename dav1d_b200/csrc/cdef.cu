@@ -208,12 +208,12 @@ template <bool HBD>
 #ifndef B200_CDEF_MINB
 #define B200_CDEF_MINB 4
 #endif
-__global__ void __launch_bounds__(kCdefThreads, B200_CDEF_MINB) cdef_frame_kernel(const __grid_constant__ B200CdefFrame f, int bdmax)
+__global__ void __launch_bounds__(kCdefThreads, B200_CDEF_MINB) cdef_frame_kernel(const __grid_constant__ B200CdefFrame f, int bdmax, int tile_row0)
 {
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ CdefShared S;
     const int tid = threadIdx.x;
-    const int bx0 = blockIdx.x * 16, by0 = blockIdx.y * 8;      // tile origin, 4-px units
+    const int bx0 = blockIdx.x * 16, by0 = (tile_row0 + blockIdx.y) * 8;      // tile origin, 4-px units
     const int b8 = HBD ? (32 - __clz(bdmax)) - 8 : 0;
     const pixel *const src = (const pixel *)f.src;
     pixel *const dst = (pixel *)f.dst;
@@ -415,20 +415,30 @@ static int cdef_check_bd(int bdmax, const char *who) {
     return 0;
 }
 
-extern "C" {
-
-int b200_cdef_frame(int bdmax, const B200CdefFrame *f, void *stream)
+namespace b200 {
+// tile rows [t0, t1) of the sweep: a tile row is 32 luma rows (16 subsampled chroma rows) and reads 2 rows beyond each side
+int cdef_frame_rows(int bdmax, const B200CdefFrame *f, int t0, int t1, cudaStream_t stream)
 {
     if (cdef_check_bd(bdmax, "b200_cdef_frame")) return -2;
     const size_t px = bdmax > 255 ? 2 : 1;
     for (int pl = 0; pl < 3; pl++)   // the tile loader reads 4 samples at a time
         if ((f->stride[pl] & 3) || (f->plane_off[pl] & 3) || ((uintptr_t)f->src * 1 % (4 * px))) { b200_set_error("b200_cdef_frame: planes must be 4-sample aligned"); return -2; }
-    dim3 grid((f->bw + 15) / 16, (f->bh + 7) / 8);
-    if (bdmax > 255) { auto k = cdef_frame_kernel<true>; B200_LAUNCH(k, grid, dim3(kCdefThreads), 0, (cudaStream_t)stream, *f, bdmax); }
-    else { auto k = cdef_frame_kernel<false>; B200_LAUNCH(k, grid, dim3(kCdefThreads), 0, (cudaStream_t)stream, *f, bdmax); }
+    t0 = imax(t0, 0); t1 = imin(t1, (f->bh + 7) / 8);
+    if (t1 <= t0) return 0;
+    dim3 grid((f->bw + 15) / 16, t1 - t0);
+    if (bdmax > 255) { auto k = cdef_frame_kernel<true>; B200_LAUNCH(k, grid, dim3(kCdefThreads), 0, stream, *f, bdmax, t0); }
+    else { auto k = cdef_frame_kernel<false>; B200_LAUNCH(k, grid, dim3(kCdefThreads), 0, stream, *f, bdmax, t0); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
+}
+}  // namespace b200
+
+extern "C" {
+
+int b200_cdef_frame(int bdmax, const B200CdefFrame *f, void *stream)
+{
+    return b200::cdef_frame_rows(bdmax, f, 0, (f->bh + 7) / 8, (cudaStream_t)stream);
 }
 
 int b200_cdef_dir(const void *img, ptrdiff_t stride, unsigned *var, int bdmax)

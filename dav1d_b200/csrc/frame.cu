@@ -87,6 +87,234 @@ int b200_frame_run_batch(const B200FrameJob *const *jobs, int n, void *stream)
     return 0;
 }
 
+// ---- band-sliced job (include/b200av1.h, B200FrameBand) --------------------------------------------------------
+static int job_luma_h(const B200FrameJob *j) { return j->lr.h > 0 ? j->lr.h : j->lf.h4 * 4; }
+
+int b200_band_progress(const B200FrameJob *j, int y1, int last, int plane)
+{
+    const int ssv = plane ? j->lf.ss_ver : 0;
+    const int ph = (job_luma_h(j) + ssv) >> ssv;
+    if (last) return ph;
+    int p;
+    if (j->run_lr)        p = ssv ? (y1 >> 1) - 36 : y1 - 40;      // the last tile row whose stripe is complete (see b200_frame_run_band)
+    else if (j->run_cdef) p = (y1 - 32) >> ssv;
+    else if (j->run_lf)   p = ssv ? (y1 >> 1) - 4 : y1 - 8;        // a row edge at y1 still changes up to 6 (chroma: 2) rows above it
+    else                  p = y1 >> ssv;
+    return p < 0 ? 0 : (p > ph ? ph : p);
+}
+
+int b200_frame_run_band(const B200FrameJob *j, const B200FrameBand *b, void *stream)
+{
+    int r;
+    const int bd = j->bitdepth_max;
+    const int H = job_luma_h(j);
+    if ((b->y0 & 63) || b->y0 < 0 || b->y1 <= b->y0 || (!b->last && (b->y1 & 63)) || (b->last && b->y1 < H)) {
+        b200_set_error("b200_frame_run_band: band [%d, %d) must be 64-row aligned (last band: down to the picture height %d)", b->y0, b->y1, H);
+        return -2;
+    }
+    if (j->n_intra > 0) { b200_set_error("b200_frame_run_band: intra records are not band-sliced (use b200_frame_run)"); return -2; }
+    const bool first = b->y0 == 0;
+#ifndef B200_EMU
+    bool fg_forked = false;
+    if (first && j->run_fg) {       // grain LUTs depend on the frame header only: beside the first band, joined before the last one's apply
+        SideStream *fs = side_stream_for((cudaStream_t)stream, 0);
+        if (fs && fs->fork((cudaStream_t)stream)) { if ((r = b200_fg_prep(bd, &j->fg, fs->side))) return r; fg_forked = true; }
+    }
+    if (first && j->run_fg && !fg_forked && (r = b200_fg_prep(bd, &j->fg, stream))) return r;
+#else
+    if (first && j->run_fg && (r = b200_fg_prep(bd, &j->fg, stream))) return r;
+#endif
+    if (first && j->n_expand > 0) B200_CUDA_OK(cudaMemsetAsync(j->d_coef, 0, j->coef_bytes, (cudaStream_t)stream));
+#define SUB(ptr, rng) ((ptr) ? (ptr) + (rng)[0] : (ptr)), (rng)[1]
+    if (j->n_expand > 0 && (r = b200_coef_expand(bd, SUB(j->d_expand, b->expand), j->d_ccoef, j->d_coef, stream))) return r;
+    if ((r = b200_mc_batch(bd, &j->mc, SUB(j->d_pred, b->pred), stream))) return r;
+    if ((r = b200_mc_scaled_batch(bd, &j->mc, SUB(j->d_scaled, b->scaled), stream))) return r;
+    if ((r = b200_mc_warp_batch(bd, &j->mc, SUB(j->d_warp, b->warp), stream))) return r;
+    if ((r = b200_mc_comp_fused_batch(bd, &j->mc, SUB(j->d_cfused, b->cfused), stream))) return r;
+    if ((r = b200_mc_comp_fused_batch(bd, &j->mc, SUB(j->d_cfused2, b->cfused2), stream))) return r;
+    if ((r = b200_mc_comp_batch(bd, &j->mc, SUB(j->d_comp, b->comp), stream))) return r;
+    if ((r = b200_mc_comp_batch(bd, &j->mc, SUB(j->d_comp2, b->comp2), stream))) return r;
+    if ((r = b200_mc_blend_batch(bd, &j->mc, SUB(j->d_blend, b->blend), stream))) return r;
+    if ((r = b200_mc_blend_batch(bd, &j->mc, SUB(j->d_blend2, b->blend2), stream))) return r;
+#undef SUB
+    const void *itx_p[B200_N_RECT_TX_SIZES];
+    int32_t itx_n[B200_N_RECT_TX_SIZES];
+    for (int t = 0; t < B200_N_RECT_TX_SIZES; t++) {
+        itx_p[t] = j->d_itx[t] ? j->d_itx[t] + b->itx[t][0] : nullptr;
+        itx_n[t] = j->d_itx[t] ? b->itx[t][1] : 0;
+    }
+    if ((r = b200_itx_add_frame(bd, itx_p, itx_n, j->d_coef, j->mc.dst, j->itx_stride, j->zero_coefs, stream))) return r;
+    // sweeps: what this band's reconstruction makes final. Deblock: the band's own rows (a row-edge filter at y1 will still
+    // change rows >= y1 - 6). CDEF tile rows (32 luma rows, reading 2 more on each side): those ending at or above y1 - 32.
+    // Loop restoration tile rows (32 rows inside the 64-row stripes that end at 64 k - 8, reading CDEF output up to 3 rows
+    // further inside the stripe and 2 deblocked rows beyond it): luma tile rows ending at or above y1 - 40, a subsampled
+    // chroma stripe (one tile) once it ends at or above (y1 - 32) / 2 - 12.
+    const cudaStream_t st = (cudaStream_t)stream;
+    if (j->run_lf && (r = b200::lf_frame_rows(bd, &j->lf, b->y0 >> 2, b->last ? j->lf.h4 : b->y1 >> 2, st))) return r;
+    const int big = 1 << 28;
+    if (j->run_cdef && (r = b200::cdef_frame_rows(bd, &j->cdef, b->y0 ? (b->y0 >> 5) - 1 : 0, b->last ? big : (b->y1 >> 5) - 1, st))) return r;
+    if (j->run_lr && (r = b200::lr_frame_rows(bd, &j->lr, b->y0 ? 2 * (b->y0 >> 6) - 1 : 0, b->last ? big : 2 * (b->y1 >> 6) - 1, st))) return r;
+    if (b->last && j->run_fg) {
+#ifndef B200_EMU
+        SideStream *fs = side_stream_for(st, 0);
+        if (fs && !fs->join(st)) { b200_set_error("b200_frame_run_band: stream join failed"); return -1; }
+#endif
+        if ((r = b200_fg_apply(bd, &j->fg, stream))) return r;
+    }
+    return 0;
+}
+
+// ---- cross-GPU exchange primitives -------------------------------------------------------------------------------
+#ifndef B200_EMU
+namespace {
+__global__ void flag_signal_kernel(uint32_t *flag, uint32_t value)
+{
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(value) : "memory");
+}
+__global__ void flag_wait_kernel(const uint32_t *flag, uint32_t value)
+{
+    uint32_t v;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - value) >= 0) break;
+        __nanosleep(200);
+    }
+}
+// cuStreamWaitValue32 through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned);
+WaitValue32Fn wait_value_fn()
+{
+    static WaitValue32Fn fn = [] {
+        void *p = nullptr;
+        if (getenv("B200_FLAG_KERNELS")) return (WaitValue32Fn) nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        cudaGetLastError();
+        return (WaitValue32Fn)p;
+    }();
+    return fn;
+}
+}
+#endif
+
+int b200_ipc_export(void *dev_ptr, uint8_t handle[B200_IPC_HANDLE_BYTES])
+{
+#ifndef B200_EMU
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200_IPC_HANDLE_BYTES, "ipc handle size");
+    cudaIpcMemHandle_t h;
+    B200_CUDA_OK(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, sizeof(h));
+    return 0;
+#else
+    (void)dev_ptr; (void)handle;
+    b200_set_error("b200_ipc_export: no peer memory on the host emulator");
+    return -1;
+#endif
+}
+
+void *b200_ipc_open(const uint8_t handle[B200_IPC_HANDLE_BYTES])
+{
+#ifndef B200_EMU
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { b200_set_error("b200_ipc_open: %s", cudaGetErrorString(e)); return nullptr; }
+    return p;
+#else
+    (void)handle;
+    b200_set_error("b200_ipc_open: no peer memory on the host emulator");
+    return nullptr;
+#endif
+}
+
+int b200_ipc_close(void *p)
+{
+#ifndef B200_EMU
+    if (p) B200_CUDA_OK(cudaIpcCloseMemHandle(p));
+#else
+    (void)p;
+#endif
+    return 0;
+}
+
+int b200_copy_async(void *dst, const void *src, size_t bytes, void *stream)
+{
+    if (bytes) B200_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return 0;
+}
+
+int b200_flag_signal(uint32_t *flag, uint32_t value, void *stream)
+{
+#ifndef B200_EMU
+    flag_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+#else
+    (void)stream;
+    *flag = value;
+#endif
+    return 0;
+}
+
+int b200_flag_wait_geq(const uint32_t *flag, uint32_t value, void *stream)
+{
+#ifndef B200_EMU
+    if (WaitValue32Fn fn = wait_value_fn()) {
+        const int rc = fn((cudaStream_t)stream, (unsigned long long)(uintptr_t)flag, value, 1 /* CU_STREAM_WAIT_VALUE_GEQ */);
+        if (rc == 0) return 0;
+        b200_set_error("b200_flag_wait_geq: cuStreamWaitValue32 -> %d", rc);
+        return -1;
+    }
+    flag_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+#else
+    (void)stream;
+    if ((int32_t)(*flag - value) < 0) { b200_set_error("b200_flag_wait_geq: flag %u < %u (the emulator executes in program order)", *flag, value); return -1; }
+#endif
+    return 0;
+}
+
+void *b200_event_create(void)
+{
+#ifndef B200_EMU
+    cudaEvent_t e = nullptr;
+    const cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (r != cudaSuccess) { b200_set_error("b200_event_create: %s", cudaGetErrorString(r)); return nullptr; }
+    return (void *)e;
+#else
+    return (void *)(uintptr_t)1;
+#endif
+}
+void b200_event_destroy(void *ev)
+{
+#ifndef B200_EMU
+    if (ev) cudaEventDestroy((cudaEvent_t)ev);
+#else
+    (void)ev;
+#endif
+}
+int b200_event_record(void *ev, void *stream)
+{
+#ifndef B200_EMU
+    B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream));
+#else
+    (void)ev; (void)stream;
+#endif
+    return 0;
+}
+int b200_stream_wait_event(void *stream, void *ev)
+{
+#ifndef B200_EMU
+    B200_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)ev, 0));
+#else
+    (void)ev; (void)stream;
+#endif
+    return 0;
+}
+
 int b200_struct_size(int which)
 {
     switch (which) {
@@ -95,7 +323,7 @@ int b200_struct_size(int which)
     case 6: return sizeof(B200LfFrame); case 7: return sizeof(B200CdefFrame); case 8: return sizeof(B200LrFrame);
     case 9: return sizeof(B200FrameJob); case 10: return sizeof(B200Av1Filter); case 11: return sizeof(B200Av1Restoration);
     case 12: return sizeof(B200FgFrame); case 13: return sizeof(B200FilmGrainData);
-    case 14: return sizeof(B200IntraTx); case 15: return sizeof(B200IntraFrame); case 16: return sizeof(B200McScaledBlock); case 17: return sizeof(B200CoefBlock); case 18: return sizeof(B200IntraSb); case 19: return sizeof(B200CompFusedBlock);
+    case 14: return sizeof(B200IntraTx); case 15: return sizeof(B200IntraFrame); case 16: return sizeof(B200McScaledBlock); case 17: return sizeof(B200CoefBlock); case 18: return sizeof(B200IntraSb); case 19: return sizeof(B200CompFusedBlock); case 20: return sizeof(B200FrameBand);
     }
     return -1;
 }

@@ -38,6 +38,11 @@ struct Scratch {
 
 std::mutex &host_lock();
 
+// row-range forms of the frame-wide sweeps (a band of a frame job, frame.cu; the b200_*_frame entry points pass the whole range)
+int lf_frame_rows(int bdmax, const B200LfFrame *f, int ya4, int yb4, cudaStream_t stream);
+int cdef_frame_rows(int bdmax, const B200CdefFrame *f, int t0, int t1, cudaStream_t stream);
+int lr_frame_rows(int bdmax, const B200LrFrame *f, int r0, int r1, cudaStream_t stream);
+
 [[noreturn]] inline void die(const char *what) {
     fprintf(stderr, "b200av1: %s failed: %s\n", what, b200_last_error());
     abort();

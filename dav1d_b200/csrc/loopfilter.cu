@@ -119,15 +119,15 @@ B200_DEV int lf_width(const B200Av1Filter &m, int plane, int dir, int b, int a, 
 // grid: (ceil(units_x / 32), ceil(units_y / 8), 3 planes); block (32, 8); a thread owns the 4 lines of one 4x4 unit
 // edge: mask decoding and level look-up are per unit, and the 4 lines give the memory system independent loads
 template <bool HBD>
-__global__ void __launch_bounds__(256) lf_cols_kernel(const __grid_constant__ B200LfFrame f, int bdmax)
+__global__ void __launch_bounds__(256) lf_cols_kernel(const __grid_constant__ B200LfFrame f, int bdmax, int ya4, int yb4)
 {
     typedef typename Bd<HBD>::pixel pixel;
     const int plane = blockIdx.z;
     if (plane ? !f.filter_uv : !f.filter_y) return;
     const int ssh = plane ? f.ss_hor : 0, ssv = plane ? f.ss_ver : 0;
     const int x4 = blockIdx.x * 32 + threadIdx.x;            // 4-px unit (plane units)
-    const int y4 = blockIdx.y * 8 + threadIdx.y;
-    const int pw4 = (f.w4 + ssh) >> ssh, ph4 = (f.h4 + ssv) >> ssv;
+    const int y4 = (ya4 >> ssv) + blockIdx.y * 8 + threadIdx.y;     // rows [ya4, yb4) in luma units: one band (or the frame)
+    const int pw4 = (f.w4 + ssh) >> ssh, ph4 = imin((f.h4 + ssv) >> ssv, (yb4 + ssv) >> ssv);
     if (x4 >= pw4 || x4 == 0 || y4 >= ph4) return;
     // 32 >> ss units per 128x128 area: shifts, not divisions (a run-time divisor costs ~20 instructions per thread)
     const int sbx = x4 >> (5 - ssh), xi = x4 & ((32 >> ssh) - 1);
@@ -147,15 +147,15 @@ __global__ void __launch_bounds__(256) lf_cols_kernel(const __grid_constant__ B2
 
 // grid: (ceil(width_px / 128), ceil(units_y / 2), 3); block (128, 2)
 template <bool HBD>
-__global__ void __launch_bounds__(256) lf_rows_kernel(const __grid_constant__ B200LfFrame f, int bdmax)
+__global__ void __launch_bounds__(256) lf_rows_kernel(const __grid_constant__ B200LfFrame f, int bdmax, int ya4, int yb4)
 {
     typedef typename Bd<HBD>::pixel pixel;
     const int plane = blockIdx.z;
     if (plane ? !f.filter_uv : !f.filter_y) return;
     const int ssh = plane ? f.ss_hor : 0, ssv = plane ? f.ss_ver : 0;
     const int x = blockIdx.x * 128 + threadIdx.x;
-    const int y4 = blockIdx.y * 2 + threadIdx.y;
-    const int pw4 = (f.w4 + ssh) >> ssh, ph4 = (f.h4 + ssv) >> ssv;
+    const int y4 = (ya4 >> ssv) + blockIdx.y * 2 + threadIdx.y;
+    const int pw4 = (f.w4 + ssh) >> ssh, ph4 = imin((f.h4 + ssv) >> ssv, (yb4 + ssv) >> ssv);
     if (x >= pw4 * 4 || y4 >= ph4 || y4 == 0) return;
     const int x4 = x >> 2, sbx = x4 >> (5 - ssh), xi = x4 & ((32 >> ssh) - 1);
     const int sby = y4 >> (5 - ssv), yi = y4 & ((32 >> ssv) - 1);
@@ -194,6 +194,31 @@ __global__ void lf_sb_kernel(typename Bd<HBD>::pixel *dst, LfSbArgs a, int bdmax
     lf_line<HBD>(p, a.dir ? a.stride : 1, a.lut.e[L], a.lut.i[L], L >> 4, wd, bdmax);
 }
 
+// rows [ya4, yb4) (luma 4-px units; even, so that subsampled chroma rows split at the same place) of both sweeps:
+// the column edges of those rows, then the row edges at ya4 .. yb4 - 1. Run band after band from the top this is the
+// whole-frame order: a row-edge filter at y touches rows y - 7 .. y + 6 only, all of them column-filtered already.
+int lf_frame_rows(int bdmax, const B200LfFrame *f, int ya4, int yb4, cudaStream_t stream)
+{
+    if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_lf_frame: bad bitdepth_max %d", bdmax); return -2; }
+    if (!f->filter_y) return 0;   // dav1d skips deblocking entirely when both luma levels are 0 (src/recon_tmpl.c:1988)
+    ya4 = imax(ya4, 0); yb4 = imin(yb4, f->h4);
+    if (yb4 <= ya4) return 0;
+    if ((ya4 & 1) || ((yb4 & 1) && yb4 != f->h4)) { b200_set_error("b200_lf_frame: odd band boundary"); return -2; }
+    const int w4 = f->w4, n4 = yb4 - ya4;
+    dim3 g1((w4 + 31) / 32, (n4 + 7) / 8, 3), b1(32, 8);
+    dim3 g2((w4 * 4 + 127) / 128, (n4 + 1) / 2, 3), b2(128, 2);
+    if (bdmax > 255) {
+        auto k1 = lf_cols_kernel<true>; B200_LAUNCH(k1, g1, b1, 0, stream, *f, bdmax, ya4, yb4);
+        auto k2 = lf_rows_kernel<true>; B200_LAUNCH(k2, g2, b2, 0, stream, *f, bdmax, ya4, yb4);
+    } else {
+        auto k1 = lf_cols_kernel<false>; B200_LAUNCH(k1, g1, b1, 0, stream, *f, bdmax, ya4, yb4);
+        auto k2 = lf_rows_kernel<false>; B200_LAUNCH(k2, g2, b2, 0, stream, *f, bdmax, ya4, yb4);
+    }
+    b200_count_launch(); b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -202,21 +227,7 @@ extern "C" {
 
 int b200_lf_frame(int bdmax, const B200LfFrame *f, void *stream)
 {
-    if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_lf_frame: bad bitdepth_max %d", bdmax); return -2; }
-    if (!f->filter_y) return 0;   // dav1d skips deblocking entirely when both luma levels are 0 (src/recon_tmpl.c:1988)
-    const int w4 = f->w4, h4 = f->h4;
-    dim3 g1((w4 + 31) / 32, (h4 + 7) / 8, 3), b1(32, 8);
-    dim3 g2((w4 * 4 + 127) / 128, (h4 + 1) / 2, 3), b2(128, 2);
-    if (bdmax > 255) {
-        auto k1 = lf_cols_kernel<true>; B200_LAUNCH(k1, g1, b1, 0, (cudaStream_t)stream, *f, bdmax);
-        auto k2 = lf_rows_kernel<true>; B200_LAUNCH(k2, g2, b2, 0, (cudaStream_t)stream, *f, bdmax);
-    } else {
-        auto k1 = lf_cols_kernel<false>; B200_LAUNCH(k1, g1, b1, 0, (cudaStream_t)stream, *f, bdmax);
-        auto k2 = lf_rows_kernel<false>; B200_LAUNCH(k2, g2, b2, 0, (cudaStream_t)stream, *f, bdmax);
-    }
-    b200_count_launch(); b200_count_launch();
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
+    return b200::lf_frame_rows(bdmax, f, 0, f->h4, (cudaStream_t)stream);
 }
 
 int b200_loop_filter_sb(int plane_class, int dir, void *dst, ptrdiff_t stride, const uint32_t *mask,

@@ -204,7 +204,7 @@ B200_DEV void lr_unit_params(const B200RestorationUnit &u, bool hbd, LrTileParam
     }
 }
 
-struct LrGrid { int base[3], nx[3]; unsigned nx_recip[3]; };   // flattened tile list: plane p owns CTAs base[p] .. , nx[p] tiles per row;
+struct LrGrid { int base[3], nx[3]; unsigned nx_recip[3]; int ty0[3]; };   // flattened tile list: plane p owns CTAs base[p] .. , nx[p] tiles per row;
                                                                // nx_recip = ceil(2^32 / nx): local / nx == mulhi(local, nx_recip) while local * nx < 2^32
 
 template <bool HBD>
@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(const __gri
     const int us_log2 = f.unit_size_log2[pl ? 1 : 0], unit = 1 << us_log2, half = unit >> 1;
     const int tw_full = unit < kTW ? unit : kTW;
     const int local = bid - lg.base[pl], nxp = lg.nx[pl];
-    const int tyi = nxp > 1 ? (int)__umulhi((unsigned)local, lg.nx_recip[pl]) : local, txi = local - tyi * nxp;
+    const int tyl = nxp > 1 ? (int)__umulhi((unsigned)local, lg.nx_recip[pl]) : local, txi = local - tyl * nxp;
+    const int tyi = tyl + lg.ty0[pl];                     // first tile row of this launch (a band, or 0 for the frame)
     const int x0 = txi * tw_full;
     // a 64-row luma stripe is 2 tiles tall; a vertically subsampled stripe (32 rows) is 1
     const int k = ssv ? tyi : tyi >> 1, ty = ssv ? 0 : tyi & 1;
@@ -332,18 +333,16 @@ __global__ void __launch_bounds__(256) lr_window_kernel(const typename Bd<HBD>::
                          [&](int x, int y, int v) { out[(size_t)(y0 + y) * w + x0 + x] = (typename Bd<HBD>::pixel)v; });
 }
 
-}  // namespace b200
-
-using namespace b200;
-
-extern "C" {
-
-int b200_lr_frame(int bdmax, const B200LrFrame *f, void *stream)
+// tile rows [r0, r1) of the sweep, counted in half stripes: tile row r is rows 32 r - 8 .. 32 r + 23 of the luma plane
+// (the first one starts at row 0); a vertically subsampled plane has one tile per stripe, so it runs its stripes
+// [r0 / 2, r1 / 2) — callers that cut a frame into bands pass r0, r1 odd: a chroma stripe runs with the band that completes it.
+int lr_frame_rows(int bdmax, const B200LrFrame *f, int r0, int r1, cudaStream_t stream)
 {
     if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_lr_frame: bad bitdepth_max %d", bdmax); return -2; }
     for (int i = 0; i < 2; i++)
         if (f->unit_size_log2[i] < 5 || f->unit_size_log2[i] > 8) { b200_set_error("b200_lr_frame: bad unit size"); return -2; }
     const int n_stripes = (f->h + 8 + 63) / 64;
+    r0 = imax(r0, 0); r1 = imin(r1, 2 * n_stripes);
     LrGrid lg;
     int total = 0;
     for (int p = 0; p < 3; p++) {
@@ -353,14 +352,28 @@ int b200_lr_frame(int bdmax, const B200LrFrame *f, void *stream)
         lg.nx[p] = (w + tw_full - 1) / tw_full;
         lg.nx_recip[p] = lg.nx[p] > 1 ? (unsigned)(((1ull << 32) + lg.nx[p] - 1) / lg.nx[p]) : 0u;
         lg.base[p] = total;
-        total += lg.nx[p] * n_stripes * (ssv ? 1 : 2);
+        const int a = ssv ? r0 >> 1 : r0, b = ssv ? r1 >> 1 : r1;
+        lg.ty0[p] = a;
+        total += lg.nx[p] * imax(b - a, 0);
     }
+    if (!total) return 0;
     dim3 grid(total);
-    if (bdmax > 255) { auto k = lr_frame_kernel<true>; B200_LAUNCH(k, grid, dim3(256), 0, (cudaStream_t)stream, *f, lg, bdmax); }
-    else { auto k = lr_frame_kernel<false>; B200_LAUNCH(k, grid, dim3(256), 0, (cudaStream_t)stream, *f, lg, bdmax); }
+    if (bdmax > 255) { auto k = lr_frame_kernel<true>; B200_LAUNCH(k, grid, dim3(256), 0, stream, *f, lg, bdmax); }
+    else { auto k = lr_frame_kernel<false>; B200_LAUNCH(k, grid, dim3(256), 0, stream, *f, lg, bdmax); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_lr_frame(int bdmax, const B200LrFrame *f, void *stream)
+{
+    return b200::lr_frame_rows(bdmax, f, 0, 1 << 30, (cudaStream_t)stream);
 }
 
 int b200_lr_filter(int kind, void *dst, ptrdiff_t stride, const void *left, const void *lpf, int w, int h,

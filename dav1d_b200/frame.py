@@ -72,6 +72,93 @@ class NumpyAlloc:
         return None, None
 
 
+def band_plan(S, band_rows, compact=False, fused=False):
+    """Cut a frame's records into horizontal bands of `band_rows` luma rows (a multiple of 64: blocks never straddle a
+    band). Returns (S2, bands, need): S2 = shallow copy of S whose record arrays are stably sorted by band (the by-area
+    order is kept inside a band), bands = list of dicts {y0, y1, last, <record list>: (first, count)} and need[k][ref] =
+    (luma rows, chroma rows) of reference `ref` that band k's predictions read — the `lowest_pixel` of dav1d's
+    check_tile (reference src/thread_task.c:415, src/decode.c lowest_pixel bookkeeping)."""
+    assert band_rows % 64 == 0 and band_rows > 0
+    H, off, stride = S["H"], S["off"], S["stride"]
+    ssv = [0, S["ss_ver"], S["ss_ver"]]
+    nb = -(-H // band_rows)
+    S2 = dict(S)
+
+    def luma_y(dst_off, plane):
+        pl = np.asarray(plane).astype(np.int64)
+        o = np.asarray(off, np.int64)[pl]; st = np.asarray(stride, np.int64)[pl]
+        return ((np.asarray(dst_off).astype(np.int64) - o) // st) << np.asarray(ssv, np.int64)[pl]
+
+    def sort_by_band(arr, y):
+        band = (y // band_rows).astype(np.int64)
+        assert not len(band) or (band.min() >= 0 and band.max() < nb)
+        order = np.argsort(band, kind="stable")
+        cnt = np.bincount(band, minlength=nb)
+        first = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+        return arr[order], first, cnt, band[order]
+
+    ranges = {}
+    # compound records first: they tell where the int16 predictions (op 1, addressed in `tmp`) belong
+    tmp_y = {}
+    for name in ("comp", "comp2"):
+        a = S[name]
+        y = luma_y(a["dst_off"], a["plane"]) if len(a) else np.zeros(0, np.int64)
+        for t1, t2, yy in zip(a["tmp1_off"].tolist(), a["tmp2_off"].tolist(), y.tolist()):
+            tmp_y[t1] = yy; tmp_y[t2] = yy
+        S2[name], f, c, _ = sort_by_band(a, y)
+        ranges[name] = (f, c)
+    pname = "pred_single" if (fused and "cfused" in S) else "pred"
+    a = S[pname]
+    y = np.zeros(len(a), np.int64)
+    put = a["op"] != 1
+    if put.any():
+        y[put] = luma_y(a["dst_off"][put], a["plane"][put])
+    if (~put).any():
+        y[~put] = [tmp_y[t] for t in a["dst_off"][~put].tolist()]
+    S2[pname], f, c, pband = sort_by_band(a, y)
+    ranges["pred"] = (f, c)
+    for name in ("cfused", "cfused2"):
+        if name in S:
+            a = S[name]
+            S2[name], f, c, _ = sort_by_band(a, luma_y(a["dst_off"], a["plane"]) if len(a) else np.zeros(0, np.int64))
+            ranges[name] = (f, c)
+    S2["itx"] = {}
+    itx_ranges = {}
+    for tx in range(19):
+        a = S["itx"][tx]
+        S2["itx"][tx], f, c, _ = sort_by_band(a, luma_y(a["dst_off"], a["plane"]) if len(a) else np.zeros(0, np.int64))
+        itx_ranges[tx] = (f, c)
+    expand = None
+    if compact:
+        from . import synth
+        cc, ex = synth.compact_coefs(S2)
+        # compact_coefs emits its records size class after size class, each in the (band-sorted) order of S2["itx"][tx]
+        eb = np.concatenate([np.repeat(np.arange(nb), itx_ranges[tx][1]) for tx in range(19) if len(S2["itx"][tx])]) if len(ex) else np.zeros(0, np.int64)
+        assert len(eb) == len(ex)
+        order = np.argsort(eb, kind="stable")
+        cnt = np.bincount(eb, minlength=nb)
+        expand = (cc, ex[order])
+        ranges["expand"] = (np.concatenate([[0], np.cumsum(cnt)[:-1]]), cnt)
+    bands = []
+    for k in range(nb):
+        b = {"y0": k * band_rows, "y1": min(H, (k + 1) * band_rows), "last": int(k == nb - 1)}
+        for name, (f, c) in ranges.items():
+            b[name] = (int(f[k]), int(c[k]))
+        b["itx"] = [(int(itx_ranges[tx][0][k]), int(itx_ranges[tx][1][k])) for tx in range(19)]
+        bands.append(b)
+    # rows of each reference that a band reads: block bottom + 4 rows of filter support (8-tap: 3 above, 4 below)
+    P = S2[pname]
+    n_refs = len(S["refs"])
+    need = np.zeros((nb, max(n_refs, 1), 2), np.int64)
+    if len(P):
+        low = P["src_y"].astype(np.int64) + P["h"] + 4
+        cls = (P["plane"] > 0).astype(np.int64)
+        np.maximum.at(need, (pband, P["ref"].astype(np.int64), cls), low)
+    ph = [H, (H + ssv[1]) >> ssv[1]]
+    need[:, :, 0] = np.minimum(need[:, :, 0], ph[0]); need[:, :, 1] = np.minimum(need[:, :, 1], ph[1])
+    return S2, bands, need, expand
+
+
 def run_batch(fbs, stream=None):
     """b200_frame_run_batch over several FrameBuffers (same library, same bit depth) on one stream: their intra
     stages share launches (frames are the parallel axis of intra decoding)."""
@@ -115,7 +202,21 @@ class FrameGroup:
 
 
 class FrameBuffers:
-    def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True, intra_grid=0, compact=False, intra_sb=False, fused=False):
+    def __init__(self, S, lib=None, alloc=None, run_lf=True, run_cdef=True, run_lr=True, intra_grid=0, compact=False, intra_sb=False, fused=False,
+                 band_rows=0):
+        self.bands = None
+        expand = None
+        if band_rows:            # records sorted by band + the B200FrameBand list (b200_frame_run_band)
+            S, plan, self.band_need, expand = band_plan(S, band_rows, compact=compact, fused=fused)
+            self.bands = (_lib.FrameBand * len(plan))()
+            for k, b in enumerate(plan):
+                fbn = self.bands[k]
+                fbn.y0, fbn.y1, fbn.last = b["y0"], b["y1"], b["last"]
+                for name in ("pred", "comp", "comp2", "cfused", "cfused2", "expand"):
+                    if name in b:
+                        getattr(fbn, name)[0], getattr(fbn, name)[1] = b[name]
+                for tx in range(19):
+                    fbn.itx[tx][0], fbn.itx[tx][1] = b["itx"][tx]
         self.S, self.lib = S, lib or _lib.get_lib()
         self.alloc = alloc or TorchAlloc()
         A = self.alloc
@@ -166,7 +267,7 @@ class FrameBuffers:
         if compact:
             # the emitter ships coefficients 0 .. eob in scan order; the job zeroes + rebuilds the dense buffer
             from . import synth
-            cc, ex = synth.compact_coefs(S)
+            cc, ex = expand if expand is not None else synth.compact_coefs(S)
             j.d_coef = zeros("coef", S["coefs"].nbytes)
             j.coef_bytes = S["coefs"].nbytes
             j.d_ccoef = up("ccoef", cc); self.uploads.append(("ccoef", cc))
@@ -255,6 +356,23 @@ class FrameBuffers:
     def run(self, stream=None):
         st = self.alloc.stream() if stream is None else stream
         self.lib.check(self.lib.b200_frame_run(C.byref(self.job), st), "b200_frame_run")
+
+    # ---- band by band (b200_frame_run_band): same result as run(); what the frame pipeline over GPUs schedules ----
+    def n_bands(self):
+        return len(self.bands) if self.bands is not None else 0
+
+    def run_band(self, k, stream=None):
+        st = self.alloc.stream() if stream is None else stream
+        self.lib.check(self.lib.b200_frame_run_band(C.byref(self.job), C.byref(self.bands[k]), st), "b200_frame_run_band")
+
+    def run_bands(self, stream=None):
+        for k in range(len(self.bands)):
+            self.run_band(k, stream)
+
+    def band_progress(self, k, plane):
+        """rows of `plane` of the restored picture that are final after band k"""
+        b = self.bands[k]
+        return self.lib.b200_band_progress(C.byref(self.job), b.y1, b.last, plane)
 
     def set_refs(self, ptrs):
         for i, p in enumerate(ptrs):

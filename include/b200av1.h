@@ -598,8 +598,53 @@ B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
 B200_API int b200_frame_run_batch(const B200FrameJob *const *jobs, int n_jobs, void *stream);
 /* sizeof() of the ABI structs as compiled into the library (binding self-check): 0 McFrame, 1 McBlock, 2 CompBlock,
  * 3 BlendBlock, 4 WarpBlock, 5 ItxBlock, 6 LfFrame, 7 CdefFrame, 8 LrFrame, 9 FrameJob, 10 Av1Filter, 11 Av1Restoration,
- * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame, 16 McScaledBlock, 17 CoefBlock, 18 IntraSb, 19 CompFusedBlock */
+ * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame, 16 McScaledBlock, 17 CoefBlock, 18 IntraSb, 19 CompFusedBlock,
+ * 20 FrameBand */
 B200_API int b200_struct_size(int which);
+
+/* ==== band-sliced frame job + cross-GPU reference exchange ===================== */
+/* dav1d lets frame n+1 start while frame n is still being decoded: a tile superblock row may run as soon as every
+ * reference picture has progressed past the lowest pixel row it reads (check_tile, reference src/thread_task.c:393-436,
+ * `lowest_pixel` :415; progress counters src/picture.h:52-63). The device-side counterpart: a frame job is cut into
+ * horizontal BANDS (luma rows [y0, y1), multiples of 64 except the bottom of the picture; blocks never straddle a band
+ * because bands are superblock aligned). b200_frame_run_band enqueues, for one band,
+ *     coefficient expansion / prediction / compound / blends / inverse transforms of the band's records,
+ *     deblock of its rows (column edges, then the row edges at y0 .. y1-1),
+ *     then the part of CDEF and loop restoration whose inputs that makes final:
+ *       CDEF tile rows (32 luma rows) below y1 - 32, loop-restoration tile rows whose stripe ends at or above y1 - 8,
+ *     and, for the last band, everything down to the bottom edge + film grain.
+ * After band k the restored picture is final down to b200_band_progress(): the rows a dependent frame may predict from.
+ * Bands must be run in order, top to bottom, on one stream; the result is bit-identical to b200_frame_run. */
+typedef struct B200FrameBand {
+    int32_t y0, y1;                 /* luma rows reconstructed by this band */
+    int32_t last;                   /* 1: bottom band (y1 = picture height; sweeps run to the bottom edge) */
+    int32_t pad;
+    /* [first, count) of the job's record arrays that belong to this band */
+    int32_t pred[2], warp[2], comp[2], comp2[2], blend[2], blend2[2], scaled[2], cfused[2], cfused2[2], expand[2];
+    int32_t itx[B200_N_RECT_TX_SIZES][2];
+} B200FrameBand;
+B200_API int b200_frame_run_band(const B200FrameJob *job, const B200FrameBand *band, void *stream);
+/* rows of plane `plane` of the restored picture (lr.dst, or cdef.dst / the reconstruction when later stages are off) that
+ * are final once the band ending at luma row y1 has run (`last` != 0: the plane height) */
+B200_API int b200_band_progress(const B200FrameJob *job, int y1, int last, int plane);
+
+/* Reference pictures cross GPUs as one-sided puts over NVLink peer memory (one process per GPU: the consumer exports
+ * its landing buffer with b200_ipc_export, the producer maps it with b200_ipc_open): after a band, the producer copies
+ * the rows that became final into each consumer's buffer (b200_copy_async: cudaMemcpyAsync, peer pointers allowed) and
+ * then raises that consumer's progress flag (b200_flag_signal, a system-scope store issued behind the copy on the same
+ * stream); the consumer's stream waits for the value it needs (b200_flag_wait_geq) before the band that reads those rows.
+ * On one GPU the same dependency is a CUDA event (b200_event_*). */
+#define B200_IPC_HANDLE_BYTES 64
+B200_API int b200_ipc_export(void *dev_ptr, uint8_t handle[B200_IPC_HANDLE_BYTES]);
+B200_API void *b200_ipc_open(const uint8_t handle[B200_IPC_HANDLE_BYTES]);
+B200_API int b200_ipc_close(void *peer_ptr);
+B200_API int b200_copy_async(void *dst, const void *src, size_t bytes, void *stream);
+B200_API int b200_flag_signal(uint32_t *flag, uint32_t value, void *stream);           /* flag: device memory, local or peer */
+B200_API int b200_flag_wait_geq(const uint32_t *flag, uint32_t value, void *stream);   /* flag: local device memory */
+B200_API void *b200_event_create(void);
+B200_API void b200_event_destroy(void *event);
+B200_API int b200_event_record(void *event, void *stream);
+B200_API int b200_stream_wait_event(void *stream, void *event);
 
 /* The same job fed from HOST buffers (the end-to-end path): every (host, dev, bytes) pair of `uploads`
  * is copied host->device first, the job runs, then every pair of `downloads` is copied device->host and

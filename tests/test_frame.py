@@ -122,6 +122,60 @@ def test_gpu_frame(bpc, W, H, ssh, ssv):
     assert TLR.picture_equal(S, fb3.host_output(), last) and TLR.picture_equal(S, fb4.host_output(), last)
 
 
+def _banded_variants(S, **kw):
+    """band-sliced jobs of frame S that must all reproduce the whole-frame job (b200_frame_run_band)"""
+    out = []
+    for rows, opts in ((64, {}), (128, dict(compact=True)), (64, dict(fused=True, compact=True))):
+        fb = frame.FrameBuffers(S, band_rows=rows, **opts, **kw)
+        assert fb.n_bands() == -(-S["H"] // rows)
+        out.append(fb)
+    return out
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", [(8, 200, 264, 1, 1), (10, 136, 200, 1, 1), (8, 72, 136, 0, 0)])
+def test_emu_frame_bands(bpc, W, H, ssh, ssv):
+    """a frame cut into 64 / 128-row bands (reconstruction, deblock, and the CDEF / LR / grain rows each band makes final)
+    equals the whole-frame job and the oracle; the progress a band reports is really final at that point"""
+    S = synth.make_inter_frame(np.random.default_rng(630 + bpc + H), bpc, W, H, ssh, ssv, film_grain=bpc > 8)
+    exp = oracle_frame(S)
+    kw = dict(lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
+    for fb in _banded_variants(S, **kw):
+        fb.run_bands()
+        check_frame(S, fb, exp)
+    # progress: after band k the rows b200_band_progress reports must already hold their final values
+    fb = frame.FrameBuffers(S, band_rows=64, **kw)
+    final = exp["lr"]
+    hs = [S["H"], (S["H"] + ssv) >> ssv, (S["H"] + ssv) >> ssv]
+    ws = [S["W"], (S["W"] + ssh) >> ssh, (S["W"] + ssh) >> ssh]
+    prev = [0, 0, 0]
+    for k in range(fb.n_bands()):
+        fb.run_band(k)
+        got = fb.output("p2")
+        for pl in range(3):
+            rows = fb.band_progress(k, pl)
+            assert prev[pl] <= rows <= hs[pl]
+            prev[pl] = rows
+            o, st = S["off"][pl], S["stride"][pl]
+            a = got[o:o + hs[pl] * st].reshape(hs[pl], st)[:rows, :ws[pl]]
+            b = final[o:o + hs[pl] * st].reshape(hs[pl], st)[:rows, :ws[pl]]
+            assert np.array_equal(a, b), "band %d plane %d: rows reported final are not" % (k, pl)
+    assert prev == hs
+    # the rows a band's predictions read from each reference stay inside the picture and grow with the band
+    assert (fb.band_need[:, :, 0] <= S["H"]).all() and (fb.band_need[-1].max() > 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", [(8, 640, 360, 1, 1), (10, 648, 520, 1, 1)])
+def test_gpu_frame_bands(bpc, W, H, ssh, ssv):
+    S = synth.make_inter_frame(np.random.default_rng(640 + bpc), bpc, W, H, ssh, ssv, film_grain=bpc > 8)
+    exp = oracle_frame(S)
+    for fb in _banded_variants(S):
+        fb.run_bands()
+        fb.alloc.sync()
+        check_frame(S, fb, exp)
+
+
 def reference_frame(S):
     """the same job through the reference's own functions on the CPU (oracle/refdriver: refdrv_frame_run)"""
     fb = frame.FrameBuffers(S, lib=object(), alloc=frame.NumpyAlloc())
