@@ -96,7 +96,7 @@ int b200_band_progress(const B200FrameJob *j, int y1, int last, int plane)
     const int ph = (job_luma_h(j) + ssv) >> ssv;
     if (last) return ph;
     int p;
-    if (j->run_lr)        p = ssv ? (y1 >> 1) - 36 : y1 - 40;      // the last tile row whose stripe is complete (see b200_frame_run_band)
+    if (j->run_lr)        p = ssv ? (y1 >> 1) - 36 : (y1 <= 64 ? 0 : y1 - 40);   // the last tile row that could run (see b200_frame_run_band)
     else if (j->run_cdef) p = (y1 - 32) >> ssv;
     else if (j->run_lf)   p = ssv ? (y1 >> 1) - 4 : y1 - 8;        // a row edge at y1 still changes up to 6 (chroma: 2) rows above it
     else                  p = y1 >> ssv;
@@ -125,7 +125,7 @@ int b200_frame_run_band(const B200FrameJob *j, const B200FrameBand *b, void *str
     if (first && j->run_fg && (r = b200_fg_prep(bd, &j->fg, stream))) return r;
 #endif
     if (first && j->n_expand > 0) B200_CUDA_OK(cudaMemsetAsync(j->d_coef, 0, j->coef_bytes, (cudaStream_t)stream));
-#define SUB(ptr, rng) ((ptr) ? (ptr) + (rng)[0] : (ptr)), (rng)[1]
+#define SUB(ptr, rng) ((ptr) ? (ptr) + (rng)[0] : (ptr)), ((ptr) ? (rng)[1] : 0)
     if (j->n_expand > 0 && (r = b200_coef_expand(bd, SUB(j->d_expand, b->expand), j->d_ccoef, j->d_coef, stream))) return r;
     if ((r = b200_mc_batch(bd, &j->mc, SUB(j->d_pred, b->pred), stream))) return r;
     if ((r = b200_mc_scaled_batch(bd, &j->mc, SUB(j->d_scaled, b->scaled), stream))) return r;
@@ -153,7 +153,9 @@ int b200_frame_run_band(const B200FrameJob *j, const B200FrameBand *b, void *str
     if (j->run_lf && (r = b200::lf_frame_rows(bd, &j->lf, b->y0 >> 2, b->last ? j->lf.h4 : b->y1 >> 2, st))) return r;
     const int big = 1 << 28;
     if (j->run_cdef && (r = b200::cdef_frame_rows(bd, &j->cdef, b->y0 ? (b->y0 >> 5) - 1 : 0, b->last ? big : (b->y1 >> 5) - 1, st))) return r;
-    if (j->run_lr && (r = b200::lr_frame_rows(bd, &j->lr, b->y0 ? 2 * (b->y0 >> 6) - 1 : 0, b->last ? big : 2 * (b->y1 >> 6) - 1, st))) return r;
+    // (the top stripe is 8 rows shorter and its first tile row spans rows 0 .. 31: it needs CDEF rows up to 34, i.e. the band below)
+    const int lr0 = b->y0 > 64 ? 2 * (b->y0 >> 6) - 1 : 0, lr1 = b->last ? big : (b->y1 > 64 ? 2 * (b->y1 >> 6) - 1 : 0);
+    if (j->run_lr && (r = b200::lr_frame_rows(bd, &j->lr, lr0, lr1, st))) return r;
     if (b->last && j->run_fg) {
 #ifndef B200_EMU
         SideStream *fs = side_stream_for(st, 0);

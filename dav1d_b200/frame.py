@@ -77,7 +77,8 @@ def band_plan(S, band_rows, compact=False, fused=False):
     band). Returns (S2, bands, need): S2 = shallow copy of S whose record arrays are stably sorted by band (the by-area
     order is kept inside a band), bands = list of dicts {y0, y1, last, <record list>: (first, count)} and need[k][ref] =
     (luma rows, chroma rows) of reference `ref` that band k's predictions read — the `lowest_pixel` of dav1d's
-    check_tile (reference src/thread_task.c:415, src/decode.c lowest_pixel bookkeeping)."""
+    check_tile (reference src/thread_task.c:415, src/decode.c lowest_pixel bookkeeping); expand = the compact coefficient
+    stream and its band-sorted B200CoefBlock records when `compact`."""
     assert band_rows % 64 == 0 and band_rows > 0
     H, off, stride = S["H"], S["off"], S["stride"]
     ssv = [0, S["ss_ver"], S["ss_ver"]]
@@ -118,7 +119,7 @@ def band_plan(S, band_rows, compact=False, fused=False):
     S2[pname], f, c, pband = sort_by_band(a, y)
     ranges["pred"] = (f, c)
     for name in ("cfused", "cfused2"):
-        if name in S:
+        if fused and name in S:
             a = S[name]
             S2[name], f, c, _ = sort_by_band(a, luma_y(a["dst_off"], a["plane"]) if len(a) else np.zeros(0, np.int64))
             ranges[name] = (f, c)
