@@ -1,37 +1,344 @@
-"""Frame sharding over GPUs: frame n is reconstructed by rank n mod G — the device-side
-analogue of dav1d's frame threads (`n_fc`, reference src/thread_task.c:409-436 for the dependency rule) — and
-the only exchange on the data path is the finished reference picture, broadcast from its owner to every rank
-that predicts from it. `torch.distributed` is plumbing: NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests.
+"""Frame sharding over GPUs: frame n is reconstructed by rank n mod G — the device-side analogue of
+dav1d's frame threads (`n_fc`) — and frame n predicts from the restored pictures of frames n-1 and n-2, which other
+ranks own. The dependency rule is dav1d's check_tile (reference src/thread_task.c:393-436): a band of frame n may start
+once each reference has progressed past the lowest row the band reads (`lowest_pixel`, :415; progress counters
+src/picture.h:52-63). Here a frame job is cut into horizontal bands (b200_frame_run_band); after each band the
+producer PUTS the rows that became final into the consumers' landing buffers over NVLink peer memory and raises their
+progress flag; the consumer's stream waits for exactly the flag value its band needs. No collective, no host
+synchronisation on the data path; `torch.distributed` only exchanges the IPC handles (and carries the CPU tests).
+
+    PeerExchange   CUDA IPC peer pointers + copy engine puts + stream-ordered flags (the product path on GPUs)
+    DistExchange   the same schedule over torch.distributed isend / recv (gloo, in the CPU tests on the host emulator)
 """
+import ctypes as C
+
 import numpy as np
+
+K_SLOTS = 2            # landing buffers per (consumer, reference distance): frame seq of a producer lands in slot seq % K_SLOTS
+FLAG_BYTES = 4096      # flag area at the head of every rank's arena
+SEQ_SHIFT = 10         # progress flag value = (producer frame seq << SEQ_SHIFT) + bands done
 
 
 def frame_owner(n, world):
     return n % world
 
 
-def decode_gop(frames, make_buffers, dist, rank, world, as_tensor, n_refs=2):
-    """Reconstruct `frames` (list of synth frame dicts, decode order). Frame k predicts from the restored pictures
-    of frames k-1 and k-2 (its own synthetic references stand in for pictures before the GOP).
+def rows_to_bytes(S, plane, r0, r1):
+    """byte range [a, b) inside a picture allocation that holds rows [r0, r1) of `plane` (whole rows, pitch included)"""
+    px = S["pic"].itemsize
+    o, st = S["off"][plane], S["stride"][plane]
+    return (o + r0 * st) * px, (o + r1 * st) * px
 
-    make_buffers(S) -> FrameBuffers on this rank's device; as_tensor(fb, name) -> the torch tensor aliasing one of
-    its buffers (what broadcast sends / receives). Returns the list of restored pictures (numpy) on every rank."""
-    pics = []          # per frame: tensor holding the restored picture on this rank
-    keep = []
-    for k, S in enumerate(frames):
-        owner = frame_owner(k, world)
-        fb = make_buffers(S)
-        keep.append(fb)
-        out = as_tensor(fb, fb.out_name)
-        if rank == owner:
-            # reference slots: most recent restored pictures first
-            for slot in range(n_refs):
-                if k - 1 - slot >= 0:
-                    as_tensor(fb, "ref%d" % slot).copy_(pics[k - 1 - slot][:as_tensor(fb, "ref%d" % slot).numel()])
-            fb.run()
-            fb.alloc.sync()
+
+class PeerExchange:
+    """One arena per rank (flags + K_SLOTS landing pictures per reference distance), exported with CUDA IPC; every rank
+    maps the arenas of the ranks it sends to (rank + d) and of those it acknowledges to (rank - d)."""
+
+    def __init__(self, lib, dist, rank, world, pic_bytes, n_refs):
+        self.lib, self.rank, self.world, self.n_refs, self.pic_bytes = lib, rank, world, n_refs, pic_bytes
+        self.arena_bytes = FLAG_BYTES + n_refs * K_SLOTS * pic_bytes
+        self.arena = lib.b200_dev_alloc(self.arena_bytes)
+        if not self.arena:
+            raise RuntimeError("b200_dev_alloc: " + lib.b200_last_error().decode())
+        lib.check(lib.b200_dev_memset(self.arena, 0, FLAG_BYTES, None), "b200_dev_memset")
+        lib.check(lib.b200_frame_wait(None), "b200_frame_wait")
+        h = (C.c_uint8 * 64)()
+        lib.check(lib.b200_ipc_export(self.arena, h), "b200_ipc_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h))
+        self.peer = {rank: self.arena}
+        for d in range(1, n_refs + 1):
+            for r in ((rank + d) % world, (rank - d) % world):
+                if r not in self.peer:
+                    hb = (C.c_uint8 * 64).from_buffer_copy(handles[r])
+                    p = lib.b200_ipc_open(hb)
+                    if not p:
+                        raise RuntimeError("b200_ipc_open(rank %d): %s" % (r, lib.b200_last_error().decode()))
+                    self.peer[r] = p
+        dist.barrier()
+
+    # layout inside an arena (the same on every rank)
+    def landing_off(self, d, slot):
+        return FLAG_BYTES + ((d - 1) * K_SLOTS + slot) * self.pic_bytes
+
+    @staticmethod
+    def prog_flag_off(d):          # written by the producer at distance d, waited on by the owner
+        return 64 * d
+
+    @staticmethod
+    def ack_flag_off(d):           # written by the consumer at distance d ("frame seq consumed"), waited on by the owner
+        return 2048 + 64 * d
+
+    def landing_ptr(self, d, slot):
+        return self.arena + self.landing_off(d, slot)
+
+    def put(self, consumer, d, slot, a, b, src_ptr, stream):
+        self.lib.check(self.lib.b200_copy_async(self.peer[consumer] + self.landing_off(d, slot) + a, src_ptr + a, b - a, stream), "b200_copy_async")
+
+    def signal_progress(self, consumer, d, value, stream):
+        self.lib.check(self.lib.b200_flag_signal(self.peer[consumer] + self.prog_flag_off(d), value, stream), "b200_flag_signal")
+
+    def wait_progress(self, d, value, stream, **_):
+        self.lib.check(self.lib.b200_flag_wait_geq(self.arena + self.prog_flag_off(d), value, stream), "b200_flag_wait_geq")
+
+    def signal_ack(self, producer, d, value, stream):
+        self.lib.check(self.lib.b200_flag_signal(self.peer[producer] + self.ack_flag_off(d), value, stream), "b200_flag_signal")
+
+    def wait_ack(self, d, value, stream):
+        self.lib.check(self.lib.b200_flag_wait_geq(self.arena + self.ack_flag_off(d), value, stream), "b200_flag_wait_geq")
+
+    def close(self):
+        for r, p in self.peer.items():
+            if r != self.rank:
+                self.lib.b200_ipc_close(p)
+        self.lib.b200_dev_free(self.arena)
+        self.peer = {}
+
+
+class DistExchange:
+    """The same puts / progress waits as messages: put = isend of the byte range, wait_progress = blocking recv of the
+    producer's messages until the flag value is reached. Works on numpy 'device' memory (host emulator, gloo) and is
+    what the gloo tests run. Only valid where a band has finished when run_band returns (the emulator): a message is
+    received when its consumer asks for it, so a slot's previous occupant has been consumed by then and the
+    acknowledgements are implicit."""
+
+    def __init__(self, dist, rank, world, pic_bytes, n_refs, as_tensor, new_buffer):
+        self.dist, self.rank, self.world, self.n_refs, self.pic_bytes = dist, rank, world, n_refs, pic_bytes
+        self.as_tensor = as_tensor
+        self.land = {(d, s): new_buffer(pic_bytes) for d in range(1, n_refs + 1) for s in range(K_SLOTS)}   # (keep, ptr)
+        self.have = {d: 0 for d in range(1, n_refs + 1)}          # flag value reached per distance
+        self.plan = {d: [] for d in range(1, n_refs + 1)}         # messages the producer at distance d will send, in order
+        self.pending = []
+
+    def landing_ptr(self, d, slot):
+        return self.land[(d, slot)][1]
+
+    def expect(self, d, slot, value, ranges):
+        """consumer-side mirror of the producer's put sequence (both sides derive it from the same band plan)"""
+        self.plan[d].append((slot, value, ranges))
+
+    def put(self, consumer, d, slot, a, b, src_ptr, stream, src_keep=None):
+        t = self.as_tensor(src_keep)[a:b]
+        self.pending.append(self.dist.isend(t, dst=consumer))
+
+    def signal_progress(self, consumer, d, value, stream):
+        pass                                   # the arrival of the band's messages is the signal
+
+    def wait_progress(self, d, value, stream, **_):
+        producer = (self.rank - d) % self.world
+        while self.have[d] < value:
+            slot, v, ranges = self.plan[d].pop(0)
+            for a, b in ranges:
+                self.dist.recv(self.as_tensor(self.land[(d, slot)][0])[a:b], src=producer)
+            self.have[d] = v
+
+    def signal_ack(self, producer, d, value, stream):
+        pass
+
+    def wait_ack(self, d, value, stream):
+        pass
+
+    def close(self):
+        for d in self.plan:                    # drain what the producers sent but no band asked for
+            if self.plan[d]:
+                self.wait_progress(d, self.plan[d][-1][1], None)
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+
+
+class GopPipeline:
+    """This rank's share of a dependent group of pictures. Frame `seq` of this rank is global frame n = seq * world + rank;
+    it is decoded in set seq % n_sets (a FrameBuffers with band plan) and predicts from frames n-1 .. n-n_refs.
+
+    make_buffers(i) -> FrameBuffers (band_rows set) for set i; all sets share geometry. exchange: PeerExchange /
+    DistExchange / None (world == 1)."""
+
+    def __init__(self, lib, rank, world, sets, exchange=None, n_refs=2, n_streams=1, host_io=False, n_total=None):
+        self.n_total = n_total          # frames in the group of pictures (None: endless stream): later frames do not exist as consumers
+        self.lib, self.rank, self.world, self.sets, self.x, self.n_refs = lib, rank, world, sets, exchange, n_refs
+        self.n_sets = len(sets)
+        assert self.n_sets * world > n_refs, "a set would be overwritten while later frames still predict from it"
+        fb = sets[0]
+        self.S = fb.S
+        self.nb = fb.n_bands()
+        assert self.nb >= 1 and all(s.n_bands() == self.nb for s in sets)
+        self.ref_name = fb.ref_name
+        self.host_io = host_io
+        A = fb.alloc
+        self.streams = [A.new_stream() for _ in range(max(1, n_streams))]          # (keep, handle)
+        self.copy_stream = A.new_stream() if world > 1 else (None, None)
+        # progress after each band, per plane class (luma, chroma): what a consumer's `need` is compared with
+        self.prog = np.array([[fb.band_progress(k, 0), fb.band_progress(k, 1)] for k in range(self.nb)], np.int64)
+        # events: per set and band (local consumers on another stream), per set "frame done", "puts done"
+        ev = lib.b200_event_create
+        self.ev_band = [[ev() for _ in range(self.nb)] for _ in sets] if len(self.streams) > 1 else None
+        self.ev_done = [ev() for _ in sets]
+        self.ev_puts = [ev() for _ in sets] if world > 1 else None
+        self.ev_band_copy = [ev() for _ in sets] if world > 1 else None
+        self.submitted = 0
+        self.set_seq = [-1] * self.n_sets
+        self.bytes_put = 0
+        if host_io:
+            for s in sets:
+                s.prepare_host(); s._host = True
+
+    def band_needed(self, need_luma, need_chroma):
+        """first band of the producer after which rows [0, need) of both plane classes are final"""
+        if need_luma <= 0 and need_chroma <= 0:
+            return -1
+        ok = (self.prog[:, 0] >= need_luma) & (self.prog[:, 1] >= need_chroma)
+        return int(np.argmax(ok))                        # the last band always satisfies it
+
+    def ref_source(self, n, d):
+        """where frame n's reference at distance d lives on this rank: (kind, ...)"""
+        m = n - d
+        if m < 0:
+            return ("own", None)
+        owner, mseq = m % self.world, m // self.world
+        if owner == self.rank:
+            return ("local", mseq)
+        return ("remote", mseq)
+
+    def submit(self):
+        """enqueue this rank's next frame (all its bands, waits and puts); returns its local sequence number"""
+        lib, x, world, rank = self.lib, self.x, self.world, self.rank
+        seq = self.submitted
+        self.submitted += 1
+        n = seq * world + rank
+        si = seq % self.n_sets
+        fb = self.sets[si]
+        sidx = seq % len(self.streams)
+        st = self.streams[sidx][1]
+        # ---- the set is free again: its previous frame finished, its puts left, nobody predicts from it any more
+        if self.set_seq[si] >= 0:
+            prev = self.set_seq[si]
+            if (prev % len(self.streams)) != sidx:
+                lib.check(lib.b200_stream_wait_event(st, self.ev_done[si]), "wait")
+            if world > 1:
+                lib.check(lib.b200_stream_wait_event(st, self.ev_puts[si]), "wait")
+            for d in range(1, self.n_refs + 1):                 # local frames that predicted from it
+                r = (prev * world + rank) + d
+                if r % world == rank:
+                    rs = r // world
+                    if rs < seq and (rs % len(self.streams)) != sidx:
+                        lib.check(lib.b200_stream_wait_event(st, self.ev_done[rs % self.n_sets]), "wait")
+        self.set_seq[si] = seq
+        # ---- reference pointers
+        srcs = []
+        for d in range(1, self.n_refs + 1):
+            kind, mseq = self.ref_source(n, d)
+            srcs.append((kind, mseq))
+            if kind == "local":
+                fb.job.mc.ref[d - 1] = self.sets[mseq % self.n_sets].picture_ptr(self.ref_name)
+            elif kind == "remote":
+                fb.job.mc.ref[d - 1] = x.landing_ptr(d, mseq % K_SLOTS)
+            else:
+                fb.job.mc.ref[d - 1] = fb.keep["ref%d" % (d - 1)][1]
+        if self.host_io:
+            for u in fb._ups:
+                lib.check(lib.b200_copy_async(u.dev, u.host, u.bytes, st), "h2d")
+        S = self.S
+        ph = [S["H"], (S["H"] + S["ss_ver"]) >> S["ss_ver"]]
+        consumers = [(d, (rank + d) % world) for d in range(1, self.n_refs + 1)
+                     if (rank + d) % world != rank and (self.n_total is None or n + d < self.n_total)] if world > 1 else []
+        if isinstance(x, DistExchange):       # tell the exchange what the producers of my references will send
+            for d in range(1, self.n_refs + 1):
+                if srcs[d - 1][0] == "remote":
+                    mseq = srcs[d - 1][1]
+                    for k in range(self.nb):
+                        x.expect(d, mseq % K_SLOTS, (mseq << SEQ_SHIFT) + k + 1, self._band_ranges(k))
+        waited = [-1] * (self.n_refs + 1)
+        for k in range(self.nb):
+            # ---- dependencies of band k: each reference must be final down to the lowest row the band reads
+            for d in range(1, self.n_refs + 1):
+                kind, mseq = srcs[d - 1]
+                if kind == "own":
+                    continue
+                kn = self.band_needed(int(fb.band_need[k, d - 1, 0]), int(fb.band_need[k, d - 1, 1]))
+                if kn <= waited[d]:
+                    continue
+                waited[d] = kn
+                if kind == "local":
+                    if (mseq % len(self.streams)) != sidx:
+                        lib.check(lib.b200_stream_wait_event(st, self.ev_band[mseq % self.n_sets][kn]), "wait")
+                else:
+                    x.wait_progress(d, (mseq << SEQ_SHIFT) + kn + 1, st)
+            fb.run_band(k, st)
+            if self.ev_band is not None:
+                lib.check(lib.b200_event_record(self.ev_band[si][k], st), "record")
+            # ---- put the rows that became final into the consumers' landing buffers, then raise their flag
+            if consumers:
+                cs = self.copy_stream[1]
+                lib.check(lib.b200_event_record(self.ev_band_copy[si], st), "record")
+                lib.check(lib.b200_stream_wait_event(cs, self.ev_band_copy[si]), "wait")
+                src_keep, src_ptr = fb.keep[self.ref_name]
+                for d, c in consumers:
+                    if k == 0 and seq >= K_SLOTS:
+                        x.wait_ack(d, seq - K_SLOTS + 1, cs)          # the slot's previous occupant has been consumed
+                    for a, b in self._band_ranges(k):
+                        if isinstance(x, DistExchange):
+                            x.put(c, d, seq % K_SLOTS, a, b, src_ptr, cs, src_keep=src_keep)
+                        else:
+                            x.put(c, d, seq % K_SLOTS, a, b, src_ptr, cs)
+                        self.bytes_put += b - a
+                    x.signal_progress(c, d, (seq << SEQ_SHIFT) + k + 1, cs)
+        # ---- the frame is enqueued: acknowledge the references (their slots may be overwritten once this point is reached)
+        for d in range(1, self.n_refs + 1):
+            kind, mseq = srcs[d - 1]
+            if kind == "remote":
+                x.signal_ack((rank - d) % world, d, mseq + 1, st)
+        if self.host_io:
+            for dn in fb._downs:
+                lib.check(lib.b200_copy_async(dn.host, dn.dev, dn.bytes, st), "d2h")
+        lib.check(lib.b200_event_record(self.ev_done[si], st), "record")
         if world > 1:
-            dist.broadcast(out, src=owner)
-        pics.append(out)
-    nbytes = frames[0]["pic"].nbytes
-    return [p.cpu().numpy()[:nbytes].view(frames[0]["pic"].dtype).copy() for p in pics]
+            lib.check(lib.b200_event_record(self.ev_puts[si], self.copy_stream[1]), "record")
+        return seq
+
+    def _band_ranges(self, k):
+        """byte ranges of the restored picture that became final with band k (per plane: rows [progress(k-1), progress(k)))"""
+        out = []
+        for pl in range(3):
+            cls = 1 if pl else 0
+            r0 = int(self.prog[k - 1, cls]) if k else 0
+            r1 = int(self.prog[k, cls])
+            if r1 > r0:
+                out.append(rows_to_bytes(self.S, pl, r0, r1))
+        return out
+
+    def sync(self):
+        for _, h in self.streams:
+            self.lib.check(self.lib.b200_frame_wait(h), "b200_frame_wait")
+        if self.copy_stream[1] is not None:
+            self.lib.check(self.lib.b200_frame_wait(self.copy_stream[1]), "b200_frame_wait")
+
+    def output(self, seq, name=None):
+        return self.sets[seq % self.n_sets].output(name or self.ref_name)
+
+
+def decode_gop(frames, make_buffers, dist, rank, world, lib, exchange="peer", band_rows=64, n_refs=2, n_sets=None, n_streams=1,
+               as_tensor=None, new_buffer=None):
+    """Reconstruct `frames` (synthetic frame dicts, decode order): frame k on rank k mod world, predicting from the restored
+    pictures of frames k-1 and k-2 (its own synthetic references stand in for pictures before the GOP). Every rank returns
+    {k: restored picture} for the frames it owns. make_buffers(S, band_rows) -> FrameBuffers on this rank's device."""
+    mine = [k for k in range(len(frames)) if k % world == rank]
+    n_sets = n_sets or max(len(mine), 1)
+    assert n_sets >= len(mine), "decode_gop keeps every owned frame resident"
+    sets = [make_buffers(frames[k], band_rows) for k in mine] or [make_buffers(frames[0], band_rows)]
+    x = None
+    pic_bytes = frames[0]["pic"].nbytes
+    if world > 1:
+        if exchange == "peer":
+            x = PeerExchange(lib, dist, rank, world, pic_bytes, n_refs)
+        else:
+            x = DistExchange(dist, rank, world, pic_bytes, n_refs, as_tensor, new_buffer)
+    pipe = GopPipeline(lib, rank, world, sets, exchange=x, n_refs=n_refs, n_streams=n_streams, n_total=len(frames))
+    for _ in mine:
+        pipe.submit()
+    pipe.sync()
+    if x is not None:
+        if dist is not None:
+            dist.barrier()
+        x.close()
+    return {k: pipe.output(i).copy() for i, k in enumerate(mine)}

@@ -1,6 +1,10 @@
-"""The N>1 path on CPU: two gloo ranks shard a 4-frame GOP (frame n -> rank n mod 2) through the emulated
-library, broadcasting every restored picture as the next frames' reference; both ranks must end with the same
-pictures as a single-rank decode, and frame 0 must equal the oracle's."""
+"""The N>1 path: a dependent group of pictures sharded over ranks (frame n -> rank n mod world, predicting from the restored
+pictures of frames n-1 and n-2 that OTHER ranks produce), band by band, gated like dav1d's check_tile (dav1d_b200/shard.py).
+
+CPU: gloo ranks drive the emulated library, reference rows travel as messages (DistExchange).
+GPU: one process per rank, reference rows travel as puts into peer memory mapped with CUDA IPC, gated by stream-ordered
+     flags (PeerExchange). With fewer GPUs than ranks the ranks share a device (IPC works between processes on one GPU).
+Every rank's pictures must equal a single-rank decode of the same GOP and the oracle's chained decode."""
 import os
 import sys
 
@@ -12,59 +16,151 @@ import torch.multiprocessing as mp
 
 import refs
 
-W, H, N = 136, 72, 4
+W, H, N = 136, 200, 6
 
 
-def _frames():
+def _frames(bpc=8, w=W, h=H, n=N, seed=900):
     from dav1d_b200 import synth
-    return [synth.make_inter_frame(np.random.default_rng(900 + k), 8, W, H) for k in range(N)]
+    return [synth.make_inter_frame(np.random.default_rng(seed + k), bpc, w, h, film_grain=False) for k in range(n)]
 
 
-def _decode(rank, world):
+def oracle_gop(frames, n_refs=2):
+    """the chained decode on the CPU: frame k's references are the restored pictures of frames k-1, k-2"""
+    import test_frame as TF
+    out = []
+    for k, S in enumerate(frames):
+        S2 = dict(S)
+        S2["refs"] = [out[k - 1 - d] if k - 1 - d >= 0 else S["refs"][d] for d in range(n_refs)]
+        out.append(TF.oracle_frame(S2)["lr"])
+    return out
+
+
+def _decode_emu(rank, world, frames, band_rows=64):
     from dav1d_b200 import frame, shard
     lib = refs.emu_lib()
 
-    def make(S):
-        return frame.FrameBuffers(S, lib=lib, alloc=frame.NumpyAlloc())
+    def make(S, rows):
+        return frame.FrameBuffers(S, lib=lib, alloc=frame.NumpyAlloc(), band_rows=rows)
 
-    def as_tensor(fb, name):
-        return torch.from_numpy(fb.keep[name][0])
-    return shard.decode_gop(_frames(), make, dist, rank, world, as_tensor)
+    def new_buffer(nbytes):
+        a = np.zeros(nbytes, np.uint8)
+        return a, a.ctypes.data
+    return shard.decode_gop(frames, make, dist if world > 1 else None, rank, world, lib, exchange="dist", band_rows=band_rows,
+                            as_tensor=torch.from_numpy, new_buffer=new_buffer)
 
 
-def _worker(rank, world, port, outdir):
+def _worker_emu(rank, world, port, outdir):
     sys.path.insert(0, os.path.dirname(__file__))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        pics = _decode(rank, world)
-        np.save(os.path.join(outdir, "r%d.npy" % rank), np.stack(pics))
+        pics = _decode_emu(rank, world, _frames())
+        np.savez(os.path.join(outdir, "r%d.npz" % rank), **{str(k): v for k, v in pics.items()})
     finally:
         dist.destroy_process_group()
 
 
+def _collect(outdir, world, n):
+    got = {}
+    for r in range(world):
+        z = np.load(os.path.join(outdir, "r%d.npz" % r))
+        for k in z.files:
+            assert int(k) % world == r and int(k) not in got
+            got[int(k)] = z[k]
+    assert sorted(got) == list(range(n))
+    return [got[k] for k in range(n)]
+
+
 @pytest.mark.emu
-def test_two_ranks_shard_a_gop(tmp_path):
-    port = 29500 + os.getpid() % 2000
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    a = np.load(tmp_path / "r0.npy"); b = np.load(tmp_path / "r1.npy")
-    assert np.array_equal(a, b), "ranks disagree"
-    single = np.stack(_decode(0, 1))
-    assert np.array_equal(a, single), "sharded decode differs from single-rank decode"
-    # frame 0 against the oracle
-    import test_frame as TF
+@pytest.mark.parametrize("world", [2, 3])
+def test_ranks_shard_a_dependent_gop(tmp_path, world):
+    port = 29500 + (os.getpid() + world * 7) % 2000
+    mp.spawn(_worker_emu, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    frames = _frames()
+    got = _collect(str(tmp_path), world, N)
+    single = _decode_emu(0, 1, frames)
     import test_looprestoration as TLR
-    S0 = _frames()[0]
-    exp = TF.oracle_frame(S0)
-    assert TLR.picture_equal(S0, a[0], exp["lr"])
+    exp = oracle_gop(frames)
+    for k in range(N):
+        assert np.array_equal(got[k], single[k]), "frame %d: sharded decode differs from the single-rank decode" % k
+        assert TLR.picture_equal(frames[k], got[k], exp[k]), "frame %d differs from the oracle's chained decode" % k
     # later frames really depend on the exchanged pictures
     from dav1d_b200 import frame
-    lone = frame.FrameBuffers(_frames()[1], lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
+    lone = frame.FrameBuffers(frames[1], lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
     lone.run()
-    assert not np.array_equal(lone.output(), a[1])
+    assert not np.array_equal(lone.output(), got[1])
+
+
+@pytest.mark.emu
+def test_single_rank_pipeline_two_band_sizes():
+    """world = 1: the band pipeline is just a chained decode; 64- and 128-row bands agree with the oracle"""
+    import test_looprestoration as TLR
+    frames = _frames(n=4)
+    exp = oracle_gop(frames)
+    for rows in (64, 128):
+        got = _decode_emu(0, 1, frames, band_rows=rows)
+        for k in range(4):
+            assert TLR.picture_equal(frames[k], got[k], exp[k]), (rows, k)
 
 
 def test_frame_owner_round_robin():
     from dav1d_b200 import shard
     assert [shard.frame_owner(n, 4) for n in range(6)] == [0, 1, 2, 3, 0, 1]
+
+
+# ------------------------------------------------------------------------------------------ GPU: peer memory
+GW, GH, GN = 648, 520, 8
+
+
+def _worker_gpu(rank, world, port, outdir, n_streams):
+    sys.path.insert(0, os.path.dirname(__file__))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    ndev = torch.cuda.device_count()
+    torch.cuda.set_device(rank % ndev)
+    # NCCL needs one device per rank; ranks that share a device exchange the IPC handles over gloo instead
+    backend = "nccl" if ndev >= world else "gloo"
+    dist.init_process_group(backend, rank=rank, world_size=world, **({"device_id": torch.device("cuda", rank)} if backend == "nccl" else {}))
+    try:
+        from dav1d_b200 import frame, shard, get_lib
+        lib = get_lib()
+        frames = _frames(10, GW, GH, GN, seed=950)
+
+        def make(S, rows):
+            return frame.FrameBuffers(S, band_rows=rows, compact=True)
+        pics = shard.decode_gop(frames, make, dist, rank, world, lib, exchange="peer", band_rows=64, n_streams=n_streams)
+        np.savez(os.path.join(outdir, "r%d.npz" % rank), **{str(k): v for k, v in pics.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,n_streams", [(2, 1), (3, 1), (2, 2)])
+def test_gpu_ranks_shard_a_dependent_gop(tmp_path, world, n_streams):
+    """one process per rank; reference rows cross ranks as peer-memory puts gated by flags (NVLink when the ranks have
+    their own GPUs); every picture equals the single-process decode and the oracle's chained decode"""
+    port = 29500 + (os.getpid() + world * 11 + n_streams) % 2000
+    mp.spawn(_worker_gpu, args=(world, port, str(tmp_path), n_streams), nprocs=world, join=True)
+    frames = _frames(10, GW, GH, GN, seed=950)
+    got = _collect(str(tmp_path), world, GN)
+    import test_looprestoration as TLR
+    exp = oracle_gop(frames)
+    for k in range(GN):
+        assert TLR.picture_equal(frames[k], got[k], exp[k]), "frame %d differs from the oracle's chained decode" % k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_streams", [1, 2])
+def test_gpu_single_rank_pipeline(n_streams):
+    """world = 1 on the GPU: band pipeline (events between the streams when two frames are in flight) vs the oracle"""
+    from dav1d_b200 import frame, shard, get_lib
+    import test_looprestoration as TLR
+    frames = _frames(8, GW, GH, 5, seed=960)
+    exp = oracle_gop(frames)
+
+    def make(S, rows):
+        return frame.FrameBuffers(S, band_rows=rows)
+    got = shard.decode_gop(frames, make, None, 0, 1, get_lib(), band_rows=128, n_streams=n_streams)
+    for k in range(5):
+        assert TLR.picture_equal(frames[k], got[k], exp[k]), k
