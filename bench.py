@@ -14,9 +14,11 @@ Workloads
              synthesised at the record level (no AV1 streams / encoder exist here).
              Mpixels = luma pixels (3840*2160 = 8.29 Mpx per frame).
   itx8x8     BASELINE config 0: 2^20 inv_txfm_add DCT_DCT 8x8 8-bit blocks (67.1 Mpx) per step.
-Multi-GPU: frames shard over GPUs (one frame per GPU per step, weak scaling); for the inter workload every
-rank's restored picture is all-gathered over NCCL after each step (the reference-picture broadcast: frame
-n+1.. may reference it), inside the timed region.
+Multi-GPU: ONE dependent stream of frames, frame n on rank n mod N (one frame per GPU per step, weak scaling); frame n
+predicts from the restored pictures of frames n-1 and n-2, which other ranks produce. A frame job is cut into bands of
+superblock rows; after each band the producer puts the rows that became final into its two consumers' landing buffers over
+NVLink peer memory and raises their progress flag, and a band starts when the references have progressed past the lowest
+row it reads (dav1d's check_tile rule; dav1d_b200/shard.py). Inside the timed region, also on the e2e leg.
 
 --impl reference times dav1d's own C functions (oracle/_ref, unmodified reference sources, HAVE_ASM=0:
 no nasm in this image) on the host cores: one frame per thread (dav1d's frame threading), all cores.
@@ -99,11 +101,16 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.proc = index, False, [], None
+        self.marks = []
+
+    def mark(self):
+        """remember how many samples had arrived (called at the start and the end of the device-timed region)"""
+        self.marks.append(len(self.samples))
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 f = [x.strip() for x in line.strip().split(",")]
@@ -131,8 +138,34 @@ class ClockSampler(threading.Thread):
         sm = sorted(int(float(s[0])) for s in self.samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
-                "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.samples[0][1])), "reasons": reasons,
+               "samples": len(sm)}
+        if len(self.marks) >= 2:
+            out["samples_in_timed_region"] = self.marks[1] - self.marks[0]
+        return out
+
+
+def host_threads():
+    """threads the CPU arm may really use: the scheduler affinity set capped by the cgroup CPU quota (os.cpu_count() reports the
+    machine, not the container: round 1's arm ran 64 threads on a box that gave it a quarter of that)"""
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = max(1, int(float(q) / float(per) + 0.5))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = max(1, int(q / per + 0.5))
+        except Exception:
+            pass
+    n = min(aff, quota) if quota else aff
+    return max(1, n), {"os_cpu_count": os.cpu_count(), "affinity": aff, "cgroup_quota": quota}
 
 
 def measured_peak():
@@ -258,7 +291,8 @@ def run_reference(args):
     if rank != 0:
         return
     from dav1d_b200 import synth
-    ncores = os.cpu_count() or 1
+    ncores, thr_info = host_threads()
+    arm_note = None
     if args.workload == "itx8x8":
         import refs
         n = 1 << 18
@@ -273,28 +307,32 @@ def run_reference(args):
         t = [step() for _ in range(args.steps)]
         ms = 1e3 * sum(t) / len(t)
         val = n * 64 / (ms * 1e-3) / 1e6
-        wl = "itx8x8: inv_txfm_add DCT_DCT 8x8 8-bit (BASELINE config 0), sample of 2^18 of the 2^20 blocks per step"
+        wl = ("itx8x8: 2^20 inv_txfm_add DCT_DCT 8x8 8-bit blocks per GPU per step (BASELINE config 0), "
+              "checkasm-style coefficients, 8192x8192 plane")
+        arm_note = "a sample of 2^18 of the 2^20 blocks per step"
         sample = "2^18 blocks/step, %d threads" % ncores
         kind = "reference"
     else:
         S = make_workload_frame(args.workload, 1)
         nthr = min(ncores, 64)
-        for _ in range(min(args.warmup, 1)):
+        for _ in range(args.warmup):
             cpu_frames(S, nthr, 1)
         vals, dts = [], []
         for _ in range(args.steps):
             v, dt, kind = cpu_frames(S, nthr, 1)
             vals.append(v); dts.append(dt)
         val = float(np.mean(vals)); ms = 1e3 * float(np.mean(dts))
-        wl = "%s: %s; reference arm: %d frames per step, one per host thread" % (args.workload, FRAME_WORKLOADS[args.workload]["desc"], nthr)
-        sample = "%d whole frames per step (one per thread, %d of %d cores), dav1d C path HAVE_ASM=0" % (nthr, nthr, ncores)
+        wl = "%s: %s" % (args.workload, FRAME_WORKLOADS[args.workload]["desc"])
+        arm_note = "%d independent frames of this workload per step, one per host thread (dav1d's frame threading without its inter-frame waits: an upper bound for the CPU)" % nthr
+        sample = "%d whole frames per step (one per thread; usable host threads: %r), dav1d C path HAVE_ASM=0 (no nasm in the image: not the AVX2 / AVX-512 path)" % (nthr, thr_info)
         ncores = nthr
     line = {"impl": "reference", "metric": "Mpixels/s", "value": val, "unit": "Mpixels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": FRAME_WORKLOADS.get(args.workload, {"dtype": "u8/i16->i32"})["dtype"], "data": "synthetic",
             "config": {"workload": wl, "l2": "n/a (host)"},
-            "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": ncores, "kind": kind, "sample": sample},
+            "arm_note": arm_note,
+            "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": ncores, "kind": kind, "sample": sample, "host": thr_info},
             "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -330,7 +368,7 @@ def run_stream(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from dav1d_b200 import obu, stream
     W = STREAM_WORKLOADS[args.workload]
-    nthr = int(os.environ.get("B200_STREAM_THREADS", min(os.cpu_count() or 1, 32)))     # dav1d worker threads, both arms
+    nthr = int(os.environ.get("B200_STREAM_THREADS", min(host_threads()[0], 32)))     # dav1d worker threads, both arms
     mfd = min(8, W["frames"], nthr)
     gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=2, **k)) if W.get("inter") else obu.intra_stream
     fg = int(W.get("film_grain", 0))
@@ -575,7 +613,7 @@ def run_ours_frame(args):
                            "GBps": sum(alg[run_keys[k]] for k in stage_ms if k in ("pred", "comp", "itx", "intra")) / (recon_ms * 1e-3) / 1e9},
                  "postfilter": {"ms": post_ms, "Mpixels/s": px_per_step / (post_ms * 1e-3) / 1e6,
                                 "GBps": sum(alg[run_keys[k]] for k in stage_ms if k in ("deblock", "cdef", "lr", "fg")) / (post_ms * 1e-3) / 1e9}}
-        nthr = min(os.cpu_count() or 1, 32)
+        nthr = min(host_threads()[0], 32)
         v, dt, kind = cpu_frames(Ss[0], nthr, 1)
         cpu = {"value": v, "unit": "Mpixels/s", "cores": nthr, "kind": kind,
                "sample": "%d whole frames of this workload, one per thread (frame threading), dav1d C path HAVE_ASM=0 (no nasm in image), %.1f s" % (nthr, dt)}
@@ -600,6 +638,209 @@ def run_ours_frame(args):
                         "d2h_bytes_per_step": int(fbs[0].d2h_bytes)},
                 "gpu_launches": int(launches), "clocks": sampler.summary()}
         emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def planes_differ(S, a, b):
+    """first (plane, row) where the visible area of two pictures of frame S differs, or None"""
+    ssh, ssv = [0, S["ss_hor"], S["ss_hor"]], [0, S["ss_ver"], S["ss_ver"]]
+    for pl in range(3):
+        h, w = (S["H"] + ssv[pl]) >> ssv[pl], (S["W"] + ssh[pl]) >> ssh[pl]
+        o, st = S["off"][pl], S["stride"][pl]
+        A = a[o:o + h * st].reshape(h, st)[:, :w]; B = b[o:o + h * st].reshape(h, st)[:, :w]
+        if not np.array_equal(A, B):
+            return pl, int(np.where((A != B).any(axis=1))[0][0])
+    return None
+
+
+def dev_to_numpy(lib, ptr, like):
+    out = np.empty_like(like)
+    lib.check(lib.b200_copy_async(out.ctypes.data, ptr, out.nbytes, None), "b200_copy_async")
+    lib.check(lib.b200_frame_wait(None), "b200_frame_wait")
+    return out
+
+
+def run_ours_gop(args):
+    """the inter workloads: one dependent stream of frames over the ranks (dav1d_b200/shard.py)"""
+    torch, dist, world, rank, local = dist_setup()
+    from dav1d_b200 import frame, shard, get_lib
+    lib = get_lib()
+    wl = FRAME_WORKLOADS[args.workload]
+    W, H = wl["W"], wl["H"]
+    px_per_frame = W * H
+    whole = -(-H // 64) * 64
+    # bands: one GPU decodes whole frames (nothing to wait for: stream order is the dependency); over several GPUs a frame
+    # is cut into bands of superblock rows so that frame n+1 starts on its GPU while frame n is still being decoded
+    band_rows = int(os.environ.get("B200_BAND_ROWS", str(whole if world == 1 else (256 if H > 2400 else 128))))
+    band_rows = min(whole, max(64, band_rows // 64 * 64))
+    n_streams = max(1, int(os.environ.get("B200_FRAMES_IN_FLIGHT", "1")))
+    nsets = int(os.environ.get("B200_NSETS", "3" if args.workload == "8k10_full" else "6"))
+    nsets = -(-nsets // n_streams) * n_streams
+    distinct = min(nsets, int(os.environ.get("B200_DISTINCT", "2" if args.workload == "8k10_full" else "3")))
+    Ss = [make_workload_frame(args.workload, 1 + rank * 16 + k) for k in range(distinct)]
+    sets = [workload_buffers(args.workload, Ss[k % distinct], band_rows=band_rows, **OURS) for k in range(nsets)]
+    x = shard.PeerExchange(lib, dist, rank, world, Ss[0]["pic"].nbytes, 2) if world > 1 else None
+    pipe = shard.GopPipeline(lib, rank, world, sets, exchange=x, n_refs=2, n_streams=n_streams)
+    main = torch.cuda.current_stream()
+    tstreams = [t for t, _ in pipe.streams] + ([pipe.copy_stream[0]] if pipe.copy_stream[0] is not None else [])
+
+    def sync_all():
+        pipe.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- parity before timing: this rank's first frame (global frame `rank`) against the reference's own functions
+    # (oracle/_ref: dav1d's C path over the same records), given the references this rank holds for it — synthetic ones
+    # before the stream starts, otherwise the rows its producers put into the landing buffers
+    pipe.submit()
+    sync_all()
+    parity = None
+    if not int(os.environ.get("B200_SKIP_PARITY", "0")):
+        import refs
+        if refs.have_ref():
+            S0 = dict(Ss[0])
+            S0["refs"] = []
+            for d in (1, 2):
+                kind, mseq = pipe.ref_source(rank, d)
+                S0["refs"].append(Ss[0]["refs"][d - 1] if kind == "own" else
+                                  dev_to_numpy(lib, x.landing_ptr(d, mseq % shard.K_SLOTS) if kind == "remote" else sets[mseq % nsets].picture_ptr(pipe.ref_name), Ss[0]["pic"]))
+            fbr = workload_buffers(args.workload, S0, lib=object(), alloc=frame.NumpyAlloc())
+            fn = refs.ref().refdrv_frame_run_8bpc if S0["bpc"] == 8 else refs.ref().refdrv_frame_run_16bpc
+            fn(C.byref(fbr.job))
+            bad = planes_differ(S0, sets[0].output(pipe.ref_name), fbr.output(fbr.ref_name))
+            if bad is None and fbr.out_name != fbr.ref_name:
+                bad = planes_differ(S0, sets[0].output(sets[0].out_name), fbr.output(fbr.out_name))
+            ok = torch.tensor([0 if bad is None else 1], device="cuda")
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MAX)
+            if int(ok.item()):
+                raise SystemExit("bench: parity check failed on rank %d: frame %d differs from the reference at (plane, row) %r" % (rank, rank, bad))
+            parity = "frame n = rank of the stream on every rank (%dx%d, the bench workload itself), restored%s picture byte-identical to dav1d's C functions (oracle/_ref) given the same records and references" % (W, H, " and grained" if wl["fg"] else "")
+        else:
+            parity = "skipped: oracle/_ref not built"
+
+    def block(nframes):
+        for _ in range(nframes):
+            pipe.submit()
+
+    block(args.warmup)
+    sync_all()
+    # inner repetitions: the timed region lasts at least ~0.6 s whatever --steps is (clock samples, launch noise)
+    t0 = time.perf_counter()
+    block(args.steps)
+    sync_all()
+    est = time.perf_counter() - t0
+    reps = max(1, int(np.ceil(float(os.environ.get("B200_MIN_TIMED_S", "0.6")) / max(est, 1e-4))))
+    if world > 1:
+        tr = torch.tensor([reps], device="cuda")
+        dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        reps = int(tr.item())
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.15)
+    put0 = pipe.bytes_put
+    launches0 = lib.b200_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark()
+    ev0.record(main)
+    for t in tstreams:
+        t.wait_stream(main)             # the timed region starts on every stream after ev0
+    block(args.steps * reps)
+    for t in tstreams:
+        main.wait_stream(t)             # ... and ends when every stream (incl. the puts) has drained
+    ev1.record(main)
+    sync_all()
+    sampler.mark()
+    launches = lib.b200_launch_count() - launches0
+    t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / (args.steps * reps)
+    value = world * px_per_frame / (ms_per_step * 1e-3) / 1e6
+    put_per_frame = (pipe.bytes_put - put0) // max(1, args.steps * reps)
+
+    stage_ms = stage_times(torch, lib, sets, nsets)
+
+    # ---- end to end: the same stream of frames, every frame's records from pinned host memory (H2D) and its output picture
+    # back to the host (D2H), the reference exchange between the GPUs included; host clock, max over ranks
+    pipe.enable_host_io()
+    block(max(2, nsets)); sync_all()
+    e2e_frames = max(2 * nsets, int(0.4 / max(ms_per_step * 1e-3, 1e-5) / 2))
+    t0 = time.perf_counter()
+    block(e2e_frames)
+    pipe.sync()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_frames
+    t = torch.tensor([e2e_ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * px_per_frame / (float(t.item()) * 1e-3) / 1e6
+    sampler.stop()
+    sampler.join(timeout=2)
+    sync_all()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        fb0 = sets[0]
+        alg = frame_algorithmic_bytes(fb0.S, fused=bool(fb0.job.n_cfused))
+        key = {"pred": "mc", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg", "intra": "intra"}
+        stages = {n: {"ms": ms, "algorithmic_bytes": alg[key[n]], "GBps": alg[key[n]] / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                      "frac": alg[key[n]] / (ms * 1e-3) / 1e9 / peak if ms > 0 else None} for n, ms in stage_ms.items()}
+        tot_ms = sum(stage_ms.values())
+        # the kernel the roofline object is about: the stage furthest from the roofline among those that matter (>= 10 % of the frame)
+        cand = [n for n in stages if stage_ms[n] >= 0.10 * tot_ms] or list(stages)
+        dom = min(cand, key=lambda n: stages[n]["frac"])
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "frame_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic = (tj.get(args.workload) or {}).get(dom) if isinstance(tj.get(args.workload), dict) else None
+        total_alg = sum(alg[key[k]] for k in stage_ms)
+        grp = lambda names: {"ms": sum(stage_ms[k] for k in stage_ms if k in names),
+                             "Mpixels/s": px_per_frame / (sum(stage_ms[k] for k in stage_ms if k in names) * 1e-3) / 1e6,
+                             "GBps": sum(alg[key[k]] for k in stage_ms if k in names) / (sum(stage_ms[k] for k in stage_ms if k in names) * 1e-3) / 1e9}
+        split = {"recon": grp(("pred", "comp", "itx", "intra")), "postfilter": grp(("deblock", "cdef", "lr", "fg"))}
+        cpu = None
+        if world == 1:
+            nthr, thr_info = host_threads()
+            nthr = min(nthr, 32)
+            v, dt, kind = cpu_frames(Ss[0], nthr, 1)
+            cpu = {"value": v, "unit": "Mpixels/s", "cores": nthr, "kind": kind, "host": thr_info,
+                   "sample": "%d whole frames of this workload, one per thread (frame threading), dav1d C path HAVE_ASM=0 (no nasm in image), %.1f s" % (nthr, dt)}
+        line = {"metric": "Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+                "config": {"workload": "%s: %s" % (args.workload, wl["desc"]),
+                           "stream": "one dependent stream: frame n on rank n mod %d predicts from the restored pictures of frames n-1 and n-2" % world,
+                           "inner_reps": reps, "timed_region_ms": ms_per_step * args.steps * reps,
+                           "frames_in_flight_per_gpu": n_streams, "band_rows": band_rows, "bands_per_frame": pipe.nb,
+                           "l2": "%d rotating frame sets per GPU (~%d MB) > 126 MB L2" % (nsets, nsets * ((2 + 2 + fb0.job.run_cdef + fb0.job.run_lr + fb0.job.run_fg) * Ss[0]["pic"].nbytes + Ss[0]["coefs"].nbytes) // 1000000),
+                           "records": {"pred_blocks": int(len(Ss[0]["pred"])), "compound": int(len(Ss[0]["comp"]) + len(Ss[0]["comp2"])),
+                                       "tx_blocks": int(sum(len(a) for a in Ss[0]["itx"].values())), "coefs": int(len(Ss[0]["coefs"])),
+                                       "intra_tx_blocks": int(len(Ss[0].get("intra_tx", [])) if Ss[0].get("intra_tx") is not None else 0)},
+                           "upload": "per coded transform block the coefficients 0..eob in scan order (expanded on the device inside the timed job) + block records + masks/levels",
+                           "exchange": ("per band, the producer puts the restored rows that became final into the landing buffers of the ranks decoding frames n+1 and n+2 "
+                                        "(cudaMemcpyAsync over NVLink peer memory, CUDA IPC) and raises their progress flag; consumers wait on the flag value of the lowest row a band reads "
+                                        "(dav1d check_tile rule); %d bytes put per frame per rank, inside the timed region and inside e2e" % put_per_frame) if world > 1 else "none (one GPU: stream order is the dependency)",
+                           "exchange_bytes_per_step": int(put_per_frame) * world,
+                           "parity_checked": parity,
+                           "roofline_kernel_rule": "stage with the lowest HBM fraction among stages >= 10 % of the frame time"},
+                "parity_checked": parity,
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                             "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                             "whole_frame": {"algorithmic_bytes": total_alg, "GBps": total_alg / (ms_per_step * 1e-3) / 1e9,
+                                             "frac": total_alg / (ms_per_step * 1e-3) / 1e9 / peak},
+                             "stages": stages, "split": split},
+                "cpu_baseline": cpu,
+                "e2e": {"value": e2e_val, "unit": "Mpixels/s", "h2d_bytes_per_step": int(fb0.h2d_bytes) * world,
+                        "d2h_bytes_per_step": int(fb0.d2h_bytes) * world, "frames_timed": e2e_frames},
+                "gpu_launches": int(launches), "clocks": sampler.summary()}
+        emit(line)
+    if x is not None:
+        x.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -721,7 +962,7 @@ def run_ours_itx(args):
         n = 1 << 18
         blocks, coefs, pic = make_itx8x8(1, n, 8192)
         st = (C.c_int32 * 3)(8192, 8192, 8192)
-        ncores = os.cpu_count() or 1
+        ncores = host_threads()[0]
         lib_r = refs.ref()
         lib_r.refdrv_itx_add_batch(255, 1, blocks.ctypes.data, n, coefs.ctypes.data, pic.ctypes.data, st, 0, ncores)
         reps, tot = 0, 0.0
@@ -773,11 +1014,15 @@ def main():
     if args.workload in STREAM_WORKLOADS:
         return run_stream(args)
     if args.impl == "reference":
-        args.steps = min(args.steps, 5)      # bounded: each step is tens of whole 4K frames on the CPU
-        run_reference(args)
+        run_reference(args)                  # every step is bounded (one frame per host thread); --steps / --warmup are honoured
     else:
         args.warmup = max(args.warmup, 3)
-        (run_ours_itx if args.workload == "itx8x8" else run_ours_frame)(args)
+        if args.workload == "itx8x8":
+            run_ours_itx(args)
+        elif FRAME_WORKLOADS[args.workload].get("intra"):
+            run_ours_frame(args)
+        else:
+            run_ours_gop(args)
 
 
 if __name__ == "__main__":

@@ -179,9 +179,22 @@ class GopPipeline:
         self.submitted = 0
         self.set_seq = [-1] * self.n_sets
         self.bytes_put = 0
+        self.up_stream = self.down_stream = (None, None)
         if host_io:
-            for s in sets:
+            self.enable_host_io()
+
+    def enable_host_io(self):
+        """end-to-end mode: every frame's records come from pinned host memory (own upload stream, so that frame n+1's
+        records travel while frame n is being reconstructed) and its output picture goes back to the host (own download stream)"""
+        A = self.sets[0].alloc
+        for s in self.sets:
+            if not getattr(s, "_host", None):
                 s.prepare_host(); s._host = True
+        self.up_stream, self.down_stream = A.new_stream(), A.new_stream()
+        ev = self.lib.b200_event_create
+        self.ev_up = [ev() for _ in self.sets]
+        self.ev_down = [ev() for _ in self.sets]
+        self.host_io = True
 
     def band_needed(self, need_luma, need_chroma):
         """first band of the producer after which rows [0, need) of both plane classes are final"""
@@ -223,6 +236,8 @@ class GopPipeline:
                     rs = r // world
                     if rs < seq and (rs % len(self.streams)) != sidx:
                         lib.check(lib.b200_stream_wait_event(st, self.ev_done[rs % self.n_sets]), "wait")
+            if self.host_io and self.down_stream[1] is not None:
+                lib.check(lib.b200_stream_wait_event(st, self.ev_down[si]), "wait")     # its output picture has left
         self.set_seq[si] = seq
         # ---- reference pointers
         srcs = []
@@ -236,8 +251,14 @@ class GopPipeline:
             else:
                 fb.job.mc.ref[d - 1] = fb.keep["ref%d" % (d - 1)][1]
         if self.host_io:
+            us = self.up_stream[1] if self.up_stream[1] is not None else st
+            if us is not st:
+                lib.check(lib.b200_stream_wait_event(us, self.ev_done[si]), "wait")     # the set's previous frame no longer reads its records
             for u in fb._ups:
-                lib.check(lib.b200_copy_async(u.dev, u.host, u.bytes, st), "h2d")
+                lib.check(lib.b200_copy_async(u.dev, u.host, u.bytes, us), "h2d")
+            if us is not st:
+                lib.check(lib.b200_event_record(self.ev_up[si], us), "record")
+                lib.check(lib.b200_stream_wait_event(st, self.ev_up[si]), "wait")
         S = self.S
         ph = [S["H"], (S["H"] + S["ss_ver"]) >> S["ss_ver"]]
         consumers = [(d, (rank + d) % world) for d in range(1, self.n_refs + 1)
@@ -288,10 +309,15 @@ class GopPipeline:
             kind, mseq = srcs[d - 1]
             if kind == "remote":
                 x.signal_ack((rank - d) % world, d, mseq + 1, st)
-        if self.host_io:
-            for dn in fb._downs:
-                lib.check(lib.b200_copy_async(dn.host, dn.dev, dn.bytes, st), "d2h")
         lib.check(lib.b200_event_record(self.ev_done[si], st), "record")
+        if self.host_io:
+            ds = self.down_stream[1] if self.down_stream[1] is not None else st
+            if ds is not st:
+                lib.check(lib.b200_stream_wait_event(ds, self.ev_done[si]), "wait")
+            for dn in fb._downs:
+                lib.check(lib.b200_copy_async(dn.host, dn.dev, dn.bytes, ds), "d2h")
+            if ds is not st:
+                lib.check(lib.b200_event_record(self.ev_down[si], ds), "record")
         if world > 1:
             lib.check(lib.b200_event_record(self.ev_puts[si], self.copy_stream[1]), "record")
         return seq
@@ -310,8 +336,9 @@ class GopPipeline:
     def sync(self):
         for _, h in self.streams:
             self.lib.check(self.lib.b200_frame_wait(h), "b200_frame_wait")
-        if self.copy_stream[1] is not None:
-            self.lib.check(self.lib.b200_frame_wait(self.copy_stream[1]), "b200_frame_wait")
+        for h in (self.copy_stream[1], self.up_stream[1], self.down_stream[1]):
+            if h is not None:
+                self.lib.check(self.lib.b200_frame_wait(h), "b200_frame_wait")
 
     def output(self, seq, name=None):
         return self.sets[seq % self.n_sets].output(name or self.ref_name)

@@ -1,0 +1,44 @@
+#!/bin/bash
+# Round-2 gpurun driver. usage: tools/gpu_r2.sh <section> ...   (outputs under gpurun_out/)
+set -u
+mkdir -p gpurun_out
+what=" $* "
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+nproc > gpurun_out/nproc.txt; cat /sys/fs/cgroup/cpu.max >> gpurun_out/nproc.txt 2>&1
+run_bench() { # name, env..., -- args
+  local name=$1; shift
+  ( timeout 600 env "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err ) ; echo "bench_$name rc=$?"
+}
+if [[ $what == *" newtests "* ]]; then
+  timeout 900 python -m pytest tests/test_multigpu.py tests/test_frame.py -x -q -m gpu 2>&1 | tail -25 > gpurun_out/pytest_new.txt
+  cat gpurun_out/pytest_new.txt | tail -5
+fi
+if [[ $what == *" tests "* ]]; then
+  timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 > gpurun_out/pytest_gpu.txt
+  tail -5 gpurun_out/pytest_gpu.txt
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1; tail -2 gpurun_out/smoke.txt
+fi
+if [[ $what == *" bench1 "* ]]; then
+  run_bench n1_default python bench.py --steps 20 --warmup 5
+  run_bench n1_2fl_b512 B200_FRAMES_IN_FLIGHT=2 B200_BAND_ROWS=512 python bench.py --steps 20 --warmup 5
+  run_bench n1_2fl_b256 B200_FRAMES_IN_FLIGHT=2 B200_BAND_ROWS=256 python bench.py --steps 20 --warmup 5
+  run_bench n1_1fl_b128 B200_FRAMES_IN_FLIGHT=1 B200_BAND_ROWS=128 python bench.py --steps 20 --warmup 5
+fi
+if [[ $what == *" benchref "* ]]; then
+  run_bench ref python bench.py --impl reference --steps 3 --warmup 1
+fi
+if [[ $what == *" bench2gpu "* ]]; then
+  for wl in 4k8_inter 8k10_full; do
+    ( timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 20 --warmup 5 --workload $wl > gpurun_out/bench_n2_$wl.json 2> gpurun_out/bench_n2_$wl.err ); echo "n2 $wl rc=$?"
+  done
+fi
+if [[ $what == *" benchNgpu "* ]]; then
+  N=${B200_N:-8}
+  for wl in 8k10_full 4k8_inter; do
+    ( timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 20 --warmup 5 --workload $wl > gpurun_out/bench_n${N}_$wl.json 2> gpurun_out/bench_n${N}_$wl.err ); echo "n$N $wl rc=$?"
+  done
+fi
+echo done > gpurun_out/done.txt
+for f in gpurun_out/bench_*.json; do echo "$f: $(head -c 600 $f)"; done
+for f in gpurun_out/bench_*.err; do if [ -s $f ]; then echo "== $f"; tail -5 $f; fi; done
+true
