@@ -35,7 +35,7 @@ static __constant__ uint32_t c_recip16[64] = { 0, 65536, 32768, 21846, 16384, 13
 #else
 static const uint32_t c_recip16[64] = { 0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048, 1986, 1928, 1873, 1821, 1772, 1725, 1681, 1639, 1599, 1561, 1525, 1490, 1457, 1425, 1395, 1366, 1338, 1311, 1286, 1261, 1237, 1214, 1192, 1171, 1150, 1130, 1111, 1093, 1075, 1058, 1041 };
 #endif
-B200_DEV unsigned recip16(int d) { return d < 64 ? (unsigned)c_recip16[d] : (65536u + d - 1) / d; }
+B200_DEV unsigned recip16(int d) { return d < 64 ? (unsigned)c_recip16[d] : (d & (d - 1)) ? (65536u + d - 1) / d : 65536u >> (31 - __clz(d)); }
 
 // pixel / coefficient types per bit-depth class (reference include/common/bitdepth.h:42-86)
 template <bool HBD> struct Bd;

@@ -266,33 +266,221 @@ B200_DEV void mc_subblock(McSmem<HBD> &sm, const int lane, const typename Bd<HBD
         mc_passes<HBD, 8>(sm, lane, sw, sh, nr, shift0, t.has_h, t.has_v, t.fh, t.fv, t.fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, tw);
 }
 
+// ---- put / prep, register-column form ------------------------------------------------------------------
+// One warp per prediction block; a lane owns an ITEM = one output column x R consecutive rows. It filters the R (+7)
+// source rows of its column horizontally straight from the reference picture (three aligned 32-bit words per row,
+// realigned with funnel shifts, 2 dp4a — 10/12-bit: five words, 4 dp2a), keeps those `mid` values in registers and
+// runs the vertical filter from them. No shared memory, no barriers, no int16 round trip: neighbouring lanes read the
+// same words (L1 hits), every load of an item is independent (memory-level parallelism instead of occupancy), and a
+// row store is one contiguous segment per warp. R is chosen per block shape so that small blocks still spread over
+// the lanes: the redundant horizontal work of short items ((R + 7) / R rows) is cheaper than idle lanes.
+// (Round 1's kernel staged a window in shared memory and made two passes over an int16 tile: 58.8 M warp
+// instructions per 4K frame, mostly per-block set-up and tile traffic of small blocks. This form: ~3x fewer.)
+template <bool HBD> struct McSrc {
+    typedef typename Bd<HBD>::pixel pixel;
+    const pixel *ref; int rs, rw, rh;
+};
+
+struct McOut {             // where an item's outputs go: pixels (put) or int16 (prep)
+    void *px; int ds; int16_t *tmp; int tw; bool is_prep;
+};
+
+// horizontally filtered value from the aligned words at `p` (first tap's sample is `al` samples into the first word)
+template <bool HBD>
+B200_DEV int mc_hfilter_words(const unsigned char *p, const unsigned al_shift, const int fh_lo, const int fh_hi, const int rnd, const int sh)
+{
+    const unsigned *wp = (const unsigned *)p;
+    if constexpr (!HBD) {
+        const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        const unsigned lo = __funnelshift_r(w0, w1, al_shift), hi = __funnelshift_r(w1, w2, al_shift);
+        return dp4a_us(hi, fh_hi, dp4a_us(lo, fh_lo, rnd)) >> sh;
+    } else {
+        const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+        const unsigned a0 = __funnelshift_r(w0, w1, al_shift), a1 = __funnelshift_r(w1, w2, al_shift);
+        const unsigned a2 = __funnelshift_r(w2, w3, al_shift), a3 = __funnelshift_r(w3, w4, al_shift);
+        int acc = dp2a_us<false>(a0, fh_lo, rnd);
+        acc = dp2a_us<true>(a1, fh_lo, acc);
+        acc = dp2a_us<false>(a2, fh_hi, acc);
+        acc = dp2a_us<true>(a3, fh_hi, acc);
+        return acc >> sh;
+    }
+}
+
+// final rounding of one output (reference src/mc_tmpl.c: put / prep after the last pass)
+template <bool HAS_H, bool HAS_V>
+B200_DEV int mc_finish(const int v, const int fsh, const int ib, const int bias, const int bdmax, const bool is_prep)
+{
+    if (HAS_V) {
+        if (HAS_H) return is_prep ? RND_SH(v, fsh) - bias : iclip(RND_SH(v, fsh + ib), 0, bdmax);
+        return is_prep ? RND_SH(v, fsh - ib) - bias : iclip(RND_SH(v, fsh), 0, bdmax);
+    }
+    if (HAS_H) return is_prep ? v - bias : iclip((v + ((1 << ib) >> 1)) >> ib, 0, bdmax);
+    return is_prep ? (v << ib) - bias : v;
+}
+
+// interior blocks: every word an item reads lies inside the reference plane. Straight-line code per item (no branch
+// between the loads of different rows: the loads of a whole item are in flight together).
+template <bool HBD, int R, bool HAS_H, bool HAS_V>
+B200_DEV void mc_block_items(const McSrc<HBD> &S, const int lane, const int w, const int h, const int sx, const int sy,
+                             const McTaps &t, const int ib, const int bias, const int bdmax, const McOut &o)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    constexpr int PX = HBD ? 2 : 1, PPW = HBD ? 2 : 4;
+    const int fh_lo = (t.fh[0] & 0xff) | (t.fh[1] & 0xff) << 8 | (t.fh[2] & 0xff) << 16 | (t.fh[3] & 0xff) << 24;
+    const int fh_hi = (t.fh[4] & 0xff) | (t.fh[5] & 0xff) << 8 | (t.fh[6] & 0xff) << 16 | (t.fh[7] & 0xff) << 24;
+    const int hsh = t.fsh - ib, hrnd = (1 << hsh) >> 1;             // horizontal pass: RND_SH(sum, fsh - ib)
+    const int ngroups = h / R, items = w * ngroups;                    // R divides h (mc_item_rows)
+    const unsigned magic_w = recip16(w);                               // exact it / w: w is 2^k, 12 or 24 and it < 8192
+    const int gx = sx - (HAS_H ? 3 : 0), gy = sy - (HAS_V ? 3 : 0);
+    const int rsb = S.rs * PX;
+    constexpr int NR = HAS_V ? R + 7 : R;
+    for (int it = lane; it < items; it += 32) {
+        const int g = (int)(((unsigned)it * magic_w) >> 16), x = it - g * w, y0 = g * R;
+        const int b0 = gx + x;
+        const unsigned char *ip = (const unsigned char *)S.ref + (ptrdiff_t)(gy + y0) * rsb + (HAS_H ? (b0 & ~(PPW - 1)) : b0) * PX;
+        const unsigned al = HAS_H ? (b0 & (PPW - 1)) * (HBD ? 16 : 8) : 0;
+        int mid[NR];
+#pragma unroll
+        for (int r = 0; r < NR; r++) {
+            const unsigned char *rp = ip + (ptrdiff_t)r * rsb;
+            if (HAS_H) mid[r] = mc_hfilter_words<HBD>(rp, al, fh_lo, fh_hi, hrnd, hsh);
+            else mid[r] = (int)*(const pixel *)rp;
+        }
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            int v;
+            if (HAS_V) {
+                v = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) v += t.fv[k] * mid[j + k];
+            } else v = mid[j];
+            const int out = mc_finish<HAS_H, HAS_V>(v, t.fsh, ib, bias, bdmax, o.is_prep);
+            if (o.is_prep) o.tmp[(y0 + j) * o.tw + x] = (int16_t)out;
+            else ((pixel *)o.px)[(ptrdiff_t)(y0 + j) * o.ds + x] = (pixel)out;
+        }
+    }
+}
+
+// blocks whose window leaves the reference plane (or whose plane is not word addressable): per-sample clamped loads
+// = dav1d's emu_edge (reference src/mc_tmpl.c:868-916) folded in. One compact instantiation (4-row items, run-time
+// filter flags): a few percent of the blocks of a frame take this path.
+template <bool HBD>
+B200_DEV void mc_block_items_edge(const McSrc<HBD> &S, const int lane, const int w, const int h, const int sx, const int sy,
+                                  const McTaps &t, const int ib, const int bias, const int bdmax, const McOut &o)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    constexpr int R = 4;
+    const bool has_h = t.has_h, has_v = t.has_v;
+    const int hsh = t.fsh - ib, hrnd = (1 << hsh) >> 1;
+    const int ngroups = (h + R - 1) / R, items = w * ngroups;
+    const unsigned magic_w = recip16(w);
+    const int gx = sx - (has_h ? 3 : 0), gy = sy - (has_v ? 3 : 0);
+    const int nr = has_v ? R + 7 : R;
+    for (int it = lane; it < items; it += 32) {
+        const int g = (int)(((unsigned)it * magic_w) >> 16), x = it - g * w, y0 = g * R;
+        int mid[R + 7];
+#pragma unroll
+        for (int r = 0; r < R + 7; r++) {
+            mid[r] = 0;
+            if (r < nr) {
+                const pixel *rp = S.ref + (ptrdiff_t)iclip(gy + y0 + r, 0, S.rh - 1) * S.rs;
+                if (has_h) {
+                    int acc = hrnd;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc += t.fh[k] * (int)rp[iclip(gx + x + k, 0, S.rw - 1)];
+                    mid[r] = acc >> hsh;
+                } else mid[r] = (int)rp[iclip(gx + x, 0, S.rw - 1)];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            int v;
+            if (has_v) {
+                v = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) v += t.fv[k] * mid[j + k];
+            } else v = mid[j];
+            int out;
+            if (has_v) out = has_h ? mc_finish<true, true>(v, t.fsh, ib, bias, bdmax, o.is_prep) : mc_finish<false, true>(v, t.fsh, ib, bias, bdmax, o.is_prep);
+            else out = has_h ? mc_finish<true, false>(v, t.fsh, ib, bias, bdmax, o.is_prep) : mc_finish<false, false>(v, t.fsh, ib, bias, bdmax, o.is_prep);
+            if (y0 + j >= h) break;
+            if (o.is_prep) o.tmp[(y0 + j) * o.tw + x] = (int16_t)out;
+            else ((pixel *)o.px)[(ptrdiff_t)(y0 + j) * o.ds + x] = (pixel)out;
+        }
+    }
+}
+
+// rows of an item: the largest R for which the block still gives every lane an item (an item costs ~9 instructions per
+// source row + ~12 per output; idle lanes cost the same as busy ones)
+B200_DEV int mc_item_rows(int w, int h)
+{
+    const int a = w * h;
+    int R = a >= 512 ? 16 : a >= 256 ? 8 : a >= 128 ? 4 : a >= 64 ? 2 : 1;
+    while (h & (R - 1)) R >>= 1;        // whole items only (h is 2^k, or 12 / 24 for OBMC neighbour predictions)
+    return R;
+}
+
+template <bool HBD, bool HAS_H, bool HAS_V>
+B200_DEV void mc_block_dispatch(const McSrc<HBD> &S, int lane, int w, int h, int sx, int sy, const McTaps &t, int ib, int bias,
+                                int bdmax, const McOut &o)
+{
+    switch (mc_item_rows(w, h)) {
+    case 16: mc_block_items<HBD, 16, HAS_H, HAS_V>(S, lane, w, h, sx, sy, t, ib, bias, bdmax, o); break;
+    case 8:  mc_block_items<HBD, 8, HAS_H, HAS_V>(S, lane, w, h, sx, sy, t, ib, bias, bdmax, o); break;
+    case 4:  mc_block_items<HBD, 4, HAS_H, HAS_V>(S, lane, w, h, sx, sy, t, ib, bias, bdmax, o); break;
+    case 2:  mc_block_items<HBD, 2, HAS_H, HAS_V>(S, lane, w, h, sx, sy, t, ib, bias, bdmax, o); break;
+    default: mc_block_items<HBD, 1, HAS_H, HAS_V>(S, lane, w, h, sx, sy, t, ib, bias, bdmax, o); break;
+    }
+}
+
+// is every sample (and every aligned word) the block's items read inside the reference plane?
+template <bool HBD>
+B200_DEV bool mc_window_interior(const McSrc<HBD> &S, int sx, int sy, int w, int h, bool has_h, bool has_v)
+{
+    constexpr int PPW = HBD ? 2 : 4;
+    if ((S.rs & (PPW - 1)) || (((uintptr_t)S.ref) & 3)) return false;
+    const int gx = sx - (has_h ? 3 : 0), gy = sy - (has_v ? 3 : 0);
+    const int nc = w + (has_h ? 7 : 0), nr = h + (has_v ? 7 : 0);
+    if (gx < 0 || gy < 0 || gx + nc > S.rw || gy + nr > S.rh) return false;
+    // the realigning loads read whole words: from the word holding the first tap to one word past the one holding the last
+    // tap; all of it must lie inside the row's pitch (the bottom row has nothing behind it to run into)
+    return !has_h || (gx & ~(PPW - 1)) + ((nc + (gx & (PPW - 1)) + PPW - 1) & ~(PPW - 1)) + PPW <= S.rs;
+}
+
 template <bool HBD>
 __global__ void __launch_bounds__(kMcWarps * 32, B200_MC_MINB)
 mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
-    __shared__ McSmem<HBD> smem[kMcWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bi = blockIdx.x * kMcWarps + warp;
     if (bi >= n_blocks) return;
-    McSmem<HBD> &sm = smem[warp];
     const B200McBlock b = blocks[bi];
     const int w = b.w, h = b.h, pl = b.plane;
-    const pixel *__restrict__ ref = (const pixel *)fr.ref[b.ref] + fr.ref_plane_off[pl];
-    const int rs = fr.ref_stride[pl], rw = fr.ref_w[pl], rh = fr.ref_h[pl];
+    McSrc<HBD> S;
+    S.ref = (const pixel *)fr.ref[b.ref] + fr.ref_plane_off[pl];
+    S.rs = fr.ref_stride[pl]; S.rw = fr.ref_w[pl]; S.rh = fr.ref_h[pl];
     const int ib = inter_bits<HBD>(bdmax);
     const int bias = HBD ? 8192 : 0;
-    const bool is_prep = b.op == 1;
     McTaps t;
     mc_taps(t, b.filter2d, b.mx, b.my, w, h);
     // op 2: "put" into the dense pixel scratch (pitch w) that the blend stages read (OBMC neighbour predictions)
-    pixel *const dpx = b.op == 2 ? (pixel *)fr.px_tmp : (pixel *)fr.dst;
-    const int ds = b.op == 2 ? w : fr.dst_stride[pl];
-    for (int sy0 = 0; sy0 < h; sy0 += kMcSub)
-        for (int sx0 = 0; sx0 < w; sx0 += kMcSub)
-            mc_subblock<HBD>(sm, lane, ref, rs, rw, rh, b.src_x + sx0, b.src_y + sy0, imin(kMcSub, w - sx0), imin(kMcSub, h - sy0),
-                             t, ib, bias, is_prep, bdmax, dpx + b.dst_off + (ptrdiff_t)sy0 * ds + sx0, ds,
-                             fr.tmp + b.dst_off + sy0 * w + sx0, w);
+    McOut o;
+    o.is_prep = b.op == 1;
+    o.px = (b.op == 2 ? (pixel *)fr.px_tmp : (pixel *)fr.dst) + b.dst_off;
+    o.ds = b.op == 2 ? w : fr.dst_stride[pl];
+    o.tmp = fr.tmp + b.dst_off; o.tw = w;
+    if (!mc_window_interior<HBD>(S, b.src_x, b.src_y, w, h, t.has_h, t.has_v)) {
+        mc_block_items_edge<HBD>(S, lane, w, h, b.src_x, b.src_y, t, ib, bias, bdmax, o);
+        return;
+    }
+    if (t.has_h) {
+        if (t.has_v) mc_block_dispatch<HBD, true, true>(S, lane, w, h, b.src_x, b.src_y, t, ib, bias, bdmax, o);
+        else mc_block_dispatch<HBD, true, false>(S, lane, w, h, b.src_x, b.src_y, t, ib, bias, bdmax, o);
+    } else {
+        if (t.has_v) mc_block_dispatch<HBD, false, true>(S, lane, w, h, b.src_x, b.src_y, t, ib, bias, bdmax, o);
+        else mc_block_dispatch<HBD, false, false>(S, lane, w, h, b.src_x, b.src_y, t, ib, bias, bdmax, o);
+    }
 }
 
 // ---- fused compound prediction -----------------------------------------------------------------------
