@@ -676,12 +676,16 @@ def run_ours_gop(args):
     band_rows = min(whole, max(64, band_rows // 64 * 64))
     n_streams = max(1, int(os.environ.get("B200_FRAMES_IN_FLIGHT", "1")))
     nsets = int(os.environ.get("B200_NSETS", "3" if args.workload == "8k10_full" else "6"))
-    nsets = -(-nsets // n_streams) * n_streams
+    # a banded frame is hundreds of launches, waits and copies: replayed as one CUDA graph per frame (the host would otherwise
+    # be the bottleneck: ~100 us of launch calls per band)
+    graphs = bool(int(os.environ.get("B200_GRAPHS", "1" if -(-H // band_rows) > 1 else "0")))
+    mult = n_streams * (2 if graphs and n_streams % 2 else 1)       # graph replay: an even number of sets (fixed landing slots per set)
+    nsets = -(-nsets // mult) * mult
     distinct = min(nsets, int(os.environ.get("B200_DISTINCT", "2" if args.workload == "8k10_full" else "3")))
     Ss = [make_workload_frame(args.workload, 1 + rank * 16 + k) for k in range(distinct)]
     sets = [workload_buffers(args.workload, Ss[k % distinct], band_rows=band_rows, **OURS) for k in range(nsets)]
     x = shard.PeerExchange(lib, dist, rank, world, Ss[0]["pic"].nbytes, 2) if world > 1 else None
-    pipe = shard.GopPipeline(lib, rank, world, sets, exchange=x, n_refs=2, n_streams=n_streams)
+    pipe = shard.GopPipeline(lib, rank, world, sets, exchange=x, n_refs=2, n_streams=n_streams, graphs=graphs)
     main = torch.cuda.current_stream()
     tstreams = [t for t, _ in pipe.streams] + ([pipe.copy_stream[0]] if pipe.copy_stream[0] is not None else [])
 
@@ -817,6 +821,7 @@ def run_ours_gop(args):
                            "stream": "one dependent stream: frame n on rank n mod %d predicts from the restored pictures of frames n-1 and n-2" % world,
                            "inner_reps": reps, "timed_region_ms": ms_per_step * args.steps * reps,
                            "frames_in_flight_per_gpu": n_streams, "band_rows": band_rows, "bands_per_frame": pipe.nb,
+                           "cuda_graphs": "one graph launch per frame (bands, waits, puts captured once per frame set; flag values derived on the device from the frame's sequence word)" if graphs else "off",
                            "l2": "%d rotating frame sets per GPU (~%d MB) > 126 MB L2" % (nsets, nsets * ((2 + 2 + fb0.job.run_cdef + fb0.job.run_lr + fb0.job.run_fg) * Ss[0]["pic"].nbytes + Ss[0]["coefs"].nbytes) // 1000000),
                            "records": {"pred_blocks": int(len(Ss[0]["pred"])), "compound": int(len(Ss[0]["comp"]) + len(Ss[0]["comp2"])),
                                        "tx_blocks": int(sum(len(a) for a in Ss[0]["itx"].values())), "coefs": int(len(Ss[0]["coefs"])),

@@ -258,6 +258,12 @@ _SIGS = {
     "b200_copy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200_flag_signal": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "b200_flag_wait_geq": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "b200_flag_signal_rel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "b200_flag_wait_geq_rel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "b200_graph_begin": (C.c_int, [C.c_void_p]),
+    "b200_graph_end": (C.c_void_p, [C.c_void_p]),
+    "b200_graph_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200_graph_destroy": (None, [C.c_void_p]),
     "b200_event_create": (C.c_void_p, []),
     "b200_event_destroy": (None, [C.c_void_p]),
     "b200_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -183,6 +183,22 @@ __global__ void flag_wait_kernel(const uint32_t *flag, uint32_t value)
         __nanosleep(200);
     }
 }
+__global__ void flag_signal_rel_kernel(uint32_t *flag, const uint32_t *base, int sub, int shift, int add)
+{
+    const uint32_t value = ((*(volatile const uint32_t *)base - (uint32_t)sub) << shift) + (uint32_t)add;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(value) : "memory");
+}
+__global__ void flag_wait_rel_kernel(const uint32_t *flag, const uint32_t *base, int sub, int shift, int add)
+{
+    const uint32_t value = ((*(volatile const uint32_t *)base - (uint32_t)sub) << shift) + (uint32_t)add;
+    uint32_t v;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - value) >= 0) break;
+        __nanosleep(200);
+    }
+}
 // cuStreamWaitValue32 through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned);
 WaitValue32Fn wait_value_fn()
@@ -277,6 +293,82 @@ int b200_flag_wait_geq(const uint32_t *flag, uint32_t value, void *stream)
     if ((int32_t)(*flag - value) < 0) { b200_set_error("b200_flag_wait_geq: flag %u < %u (the emulator executes in program order)", *flag, value); return -1; }
 #endif
     return 0;
+}
+
+int b200_flag_signal_rel(uint32_t *flag, const uint32_t *base, int32_t sub, int32_t shift, int32_t add, void *stream)
+{
+#ifndef B200_EMU
+    flag_signal_rel_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, base, sub, shift, add);
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+#else
+    (void)stream;
+    *flag = ((*base - (uint32_t)sub) << shift) + (uint32_t)add;
+#endif
+    return 0;
+}
+
+int b200_flag_wait_geq_rel(const uint32_t *flag, const uint32_t *base, int32_t sub, int32_t shift, int32_t add, void *stream)
+{
+#ifndef B200_EMU
+    flag_wait_rel_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, base, sub, shift, add);
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+#else
+    (void)stream;
+    const uint32_t value = ((*base - (uint32_t)sub) << shift) + (uint32_t)add;
+    if ((int32_t)(*flag - value) < 0) { b200_set_error("b200_flag_wait_geq_rel: flag %u < %u (the emulator executes in program order)", *flag, value); return -1; }
+#endif
+    return 0;
+}
+
+int b200_graph_begin(void *stream)
+{
+#ifndef B200_EMU
+    B200_CUDA_OK(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeRelaxed));
+    return 0;
+#else
+    (void)stream;
+    b200_set_error("b200_graph_begin: no graphs on the host emulator");
+    return -1;
+#endif
+}
+
+void *b200_graph_end(void *stream)
+{
+#ifndef B200_EMU
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &g);
+    if (e != cudaSuccess || !g) { b200_set_error("b200_graph_end: cudaStreamEndCapture -> %s", cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    cudaGraphExec_t x = nullptr;
+    e = cudaGraphInstantiate(&x, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { b200_set_error("b200_graph_end: cudaGraphInstantiate -> %s", cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    return (void *)x;
+#else
+    (void)stream;
+    return nullptr;
+#endif
+}
+
+int b200_graph_launch(void *graph_exec, void *stream)
+{
+#ifndef B200_EMU
+    B200_CUDA_OK(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    return 0;
+#else
+    (void)graph_exec; (void)stream;
+    return -1;
+#endif
+}
+
+void b200_graph_destroy(void *graph_exec)
+{
+#ifndef B200_EMU
+    if (graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)graph_exec);
+#else
+    (void)graph_exec;
+#endif
 }
 
 void *b200_event_create(void)

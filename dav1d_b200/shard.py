@@ -87,6 +87,20 @@ class PeerExchange:
     def wait_ack(self, d, value, stream):
         self.lib.check(self.lib.b200_flag_wait_geq(self.arena + self.ack_flag_off(d), value, stream), "b200_flag_wait_geq")
 
+    # the same with values derived on the device from a sequence word (graph replay; see GopPipeline):
+    # progress value = ((seq - wrap) << SEQ_SHIFT) + bands, acknowledgement value = seq - wrap + 1
+    def signal_progress_rel(self, consumer, d, base, bands, stream):
+        self.lib.check(self.lib.b200_flag_signal_rel(self.peer[consumer] + self.prog_flag_off(d), base, 0, SEQ_SHIFT, bands, stream), "b200_flag_signal_rel")
+
+    def wait_progress_rel(self, d, base, wrap, bands, stream):
+        self.lib.check(self.lib.b200_flag_wait_geq_rel(self.arena + self.prog_flag_off(d), base, wrap, SEQ_SHIFT, bands, stream), "b200_flag_wait_geq_rel")
+
+    def signal_ack_rel(self, producer, d, base, wrap, stream):
+        self.lib.check(self.lib.b200_flag_signal_rel(self.peer[producer] + self.ack_flag_off(d), base, wrap, 0, 1, stream), "b200_flag_signal_rel")
+
+    def wait_ack_rel(self, d, base, back, add, stream):
+        self.lib.check(self.lib.b200_flag_wait_geq_rel(self.arena + self.ack_flag_off(d), base, back, 0, add, stream), "b200_flag_wait_geq_rel")
+
     def close(self):
         for r, p in self.peer.items():
             if r != self.rank:
@@ -151,10 +165,12 @@ class GopPipeline:
     """This rank's share of a dependent group of pictures. Frame `seq` of this rank is global frame n = seq * world + rank;
     it is decoded in set seq % n_sets (a FrameBuffers with band plan) and predicts from frames n-1 .. n-n_refs.
 
-    make_buffers(i) -> FrameBuffers (band_rows set) for set i; all sets share geometry. exchange: PeerExchange /
-    DistExchange / None (world == 1)."""
+    sets: FrameBuffers (band_rows set), all of one geometry. exchange: PeerExchange / DistExchange / None (world == 1).
+    graphs: from a set's second frame on, the frame's whole schedule (bands, waits, puts, host copies) is replayed as ONE
+    CUDA graph launch; what changes from frame to frame — the flag values — is derived on the device from the set's
+    sequence word (b200_flag_*_rel). Needs an even number of sets (a set then always uses the same landing slots)."""
 
-    def __init__(self, lib, rank, world, sets, exchange=None, n_refs=2, n_streams=1, host_io=False, n_total=None):
+    def __init__(self, lib, rank, world, sets, exchange=None, n_refs=2, n_streams=1, host_io=False, n_total=None, graphs=False):
         self.n_total = n_total          # frames in the group of pictures (None: endless stream): later frames do not exist as consumers
         self.lib, self.rank, self.world, self.sets, self.x, self.n_refs = lib, rank, world, sets, exchange, n_refs
         self.n_sets = len(sets)
@@ -164,9 +180,10 @@ class GopPipeline:
         self.nb = fb.n_bands()
         assert self.nb >= 1 and all(s.n_bands() == self.nb for s in sets)
         self.ref_name = fb.ref_name
-        self.host_io = host_io
+        self.host_io = False
         A = fb.alloc
         self.streams = [A.new_stream() for _ in range(max(1, n_streams))]          # (keep, handle)
+        assert self.n_sets % len(self.streams) == 0, "a set must always run on the same stream"
         self.copy_stream = A.new_stream() if world > 1 else (None, None)
         # progress after each band, per plane class (luma, chroma): what a consumer's `need` is compared with
         self.prog = np.array([[fb.band_progress(k, 0), fb.band_progress(k, 1)] for k in range(self.nb)], np.int64)
@@ -175,13 +192,31 @@ class GopPipeline:
         self.ev_band = [[ev() for _ in range(self.nb)] for _ in sets] if len(self.streams) > 1 else None
         self.ev_done = [ev() for _ in sets]
         self.ev_puts = [ev() for _ in sets] if world > 1 else None
-        self.ev_band_copy = [ev() for _ in sets] if world > 1 else None
+        self.ev_fork = [ev() for _ in sets]
+        self.ev_up = [ev() for _ in sets]
+        self.ev_down = [ev() for _ in sets]
         self.submitted = 0
         self.set_seq = [-1] * self.n_sets
         self.bytes_put = 0
+        self.put_bytes_per_frame = 0
         self.up_stream = self.down_stream = (None, None)
+        self.graphs = bool(graphs)
+        self.graph = [None] * self.n_sets
+        self.words = None
+        if self.graphs:
+            assert n_total is None, "graph replay is for endless streams (every later frame of a set looks the same)"
+            assert self.n_sets % K_SLOTS == 0 or world == 1, "graph replay needs a set to always use the same landing slots"
+            self.words = lib.b200_dev_alloc(8192)        # per set: sequence word at 64 * set, local progress flag at 4096 + 64 * set
+            lib.check(lib.b200_dev_memset(self.words, 0, 8192, None), "b200_dev_memset")
+            lib.check(lib.b200_frame_wait(None), "b200_frame_wait")
         if host_io:
             self.enable_host_io()
+
+    def seq_word(self, si):
+        return self.words + 64 * si
+
+    def local_flag(self, si):
+        return self.words + 4096 + 64 * si
 
     def enable_host_io(self):
         """end-to-end mode: every frame's records come from pinned host memory (own upload stream, so that frame n+1's
@@ -191,10 +226,11 @@ class GopPipeline:
             if not getattr(s, "_host", None):
                 s.prepare_host(); s._host = True
         self.up_stream, self.down_stream = A.new_stream(), A.new_stream()
-        ev = self.lib.b200_event_create
-        self.ev_up = [ev() for _ in self.sets]
-        self.ev_down = [ev() for _ in self.sets]
         self.host_io = True
+        for g in self.graph:                      # the captured schedules did not contain the copies
+            if g:
+                self.lib.b200_graph_destroy(g)
+        self.graph = [None] * self.n_sets
 
     def band_needed(self, need_luma, need_chroma):
         """first band of the producer after which rows [0, need) of both plane classes are final"""
@@ -215,19 +251,16 @@ class GopPipeline:
 
     def submit(self):
         """enqueue this rank's next frame (all its bands, waits and puts); returns its local sequence number"""
-        lib, x, world, rank = self.lib, self.x, self.world, self.rank
+        lib, world, rank = self.lib, self.world, self.rank
         seq = self.submitted
         self.submitted += 1
-        n = seq * world + rank
         si = seq % self.n_sets
-        fb = self.sets[si]
         sidx = seq % len(self.streams)
         st = self.streams[sidx][1]
         # ---- the set is free again: its previous frame finished, its puts left, nobody predicts from it any more
+        # (always outside a captured graph: these are dependencies on other frames' work)
         if self.set_seq[si] >= 0:
             prev = self.set_seq[si]
-            if (prev % len(self.streams)) != sidx:
-                lib.check(lib.b200_stream_wait_event(st, self.ev_done[si]), "wait")
             if world > 1:
                 lib.check(lib.b200_stream_wait_event(st, self.ev_puts[si]), "wait")
             for d in range(1, self.n_refs + 1):                 # local frames that predicted from it
@@ -236,9 +269,37 @@ class GopPipeline:
                     rs = r // world
                     if rs < seq and (rs % len(self.streams)) != sidx:
                         lib.check(lib.b200_stream_wait_event(st, self.ev_done[rs % self.n_sets]), "wait")
-            if self.host_io and self.down_stream[1] is not None:
+            if self.host_io:
                 lib.check(lib.b200_stream_wait_event(st, self.ev_down[si]), "wait")     # its output picture has left
+        replay = self.graphs and self.set_seq[si] >= 0
         self.set_seq[si] = seq
+        if replay:
+            if self.graph[si] is None:
+                before = self.bytes_put
+                lib.check(lib.b200_graph_begin(st), "b200_graph_begin")
+                self._enqueue(seq, st, sidx, rel=True)
+                g = lib.b200_graph_end(st)
+                if not g:
+                    raise RuntimeError("b200_graph_end: " + lib.b200_last_error().decode())
+                self.graph[si] = g
+                self.put_bytes_per_frame = self.bytes_put - before
+            else:
+                self.bytes_put += self.put_bytes_per_frame
+            lib.check(lib.b200_flag_signal(self.seq_word(si), seq, st), "b200_flag_signal")
+            lib.check(lib.b200_graph_launch(self.graph[si], st), "b200_graph_launch")
+        else:
+            self._enqueue(seq, st, sidx, rel=False)
+        lib.check(lib.b200_event_record(self.ev_done[si], st), "record")
+        return seq
+
+    def _enqueue(self, seq, st, sidx, rel):
+        """one frame's schedule on stream st. rel: flag values come from the set's sequence word on the device (capturable)"""
+        lib, x, world, rank = self.lib, self.x, self.world, self.rank
+        n = seq * world + rank
+        si = seq % self.n_sets
+        fb = self.sets[si]
+        multi = len(self.streams) > 1
+        base = self.seq_word(si) if rel else None
         # ---- reference pointers
         srcs = []
         for d in range(1, self.n_refs + 1):
@@ -249,18 +310,20 @@ class GopPipeline:
             elif kind == "remote":
                 fb.job.mc.ref[d - 1] = x.landing_ptr(d, mseq % K_SLOTS)
             else:
+                assert not rel
                 fb.job.mc.ref[d - 1] = fb.keep["ref%d" % (d - 1)][1]
+        fork = lambda other: (lib.check(lib.b200_event_record(self.ev_fork[si], st), "record"),
+                              lib.check(lib.b200_stream_wait_event(other, self.ev_fork[si]), "wait"))
         if self.host_io:
-            us = self.up_stream[1] if self.up_stream[1] is not None else st
-            if us is not st:
+            us = self.up_stream[1]
+            if rel:
+                fork(us)                                        # inside a graph the copies hang off the frame's own stream
+            else:
                 lib.check(lib.b200_stream_wait_event(us, self.ev_done[si]), "wait")     # the set's previous frame no longer reads its records
             for u in fb._ups:
                 lib.check(lib.b200_copy_async(u.dev, u.host, u.bytes, us), "h2d")
-            if us is not st:
-                lib.check(lib.b200_event_record(self.ev_up[si], us), "record")
-                lib.check(lib.b200_stream_wait_event(st, self.ev_up[si]), "wait")
-        S = self.S
-        ph = [S["H"], (S["H"] + S["ss_ver"]) >> S["ss_ver"]]
+            lib.check(lib.b200_event_record(self.ev_up[si], us), "record")
+            lib.check(lib.b200_stream_wait_event(st, self.ev_up[si]), "wait")
         consumers = [(d, (rank + d) % world) for d in range(1, self.n_refs + 1)
                      if (rank + d) % world != rank and (self.n_total is None or n + d < self.n_total)] if world > 1 else []
         if isinstance(x, DistExchange):       # tell the exchange what the producers of my references will send
@@ -270,6 +333,8 @@ class GopPipeline:
                     for k in range(self.nb):
                         x.expect(d, mseq % K_SLOTS, (mseq << SEQ_SHIFT) + k + 1, self._band_ranges(k))
         waited = [-1] * (self.n_refs + 1)
+        cs = self.copy_stream[1]
+        forked_copy = False
         for k in range(self.nb):
             # ---- dependencies of band k: each reference must be final down to the lowest row the band reads
             for d in range(1, self.n_refs + 1):
@@ -280,47 +345,68 @@ class GopPipeline:
                 if kn <= waited[d]:
                     continue
                 waited[d] = kn
+                wrap = seq - mseq
                 if kind == "local":
                     if (mseq % len(self.streams)) != sidx:
-                        lib.check(lib.b200_stream_wait_event(st, self.ev_band[mseq % self.n_sets][kn]), "wait")
+                        if rel:
+                            lib.check(lib.b200_flag_wait_geq_rel(self.local_flag(mseq % self.n_sets), base, wrap, SEQ_SHIFT, kn + 1, st), "wait")
+                        else:
+                            lib.check(lib.b200_stream_wait_event(st, self.ev_band[mseq % self.n_sets][kn]), "wait")
+                elif rel:
+                    x.wait_progress_rel(d, base, wrap, kn + 1, st)
                 else:
                     x.wait_progress(d, (mseq << SEQ_SHIFT) + kn + 1, st)
             fb.run_band(k, st)
-            if self.ev_band is not None:
-                lib.check(lib.b200_event_record(self.ev_band[si][k], st), "record")
+            if multi:
+                if self.graphs:     # local consumers on the other stream wait on a flag (events recorded inside a graph are not visible outside)
+                    if rel:
+                        lib.check(lib.b200_flag_signal_rel(self.local_flag(si), base, 0, SEQ_SHIFT, k + 1, st), "signal")
+                    else:
+                        lib.check(lib.b200_flag_signal(self.local_flag(si), (seq << SEQ_SHIFT) + k + 1, st), "signal")
+                if not rel:
+                    lib.check(lib.b200_event_record(self.ev_band[si][k], st), "record")
             # ---- put the rows that became final into the consumers' landing buffers, then raise their flag
             if consumers:
-                cs = self.copy_stream[1]
-                lib.check(lib.b200_event_record(self.ev_band_copy[si], st), "record")
-                lib.check(lib.b200_stream_wait_event(cs, self.ev_band_copy[si]), "wait")
+                fork(cs)
+                forked_copy = True
                 src_keep, src_ptr = fb.keep[self.ref_name]
                 for d, c in consumers:
-                    if k == 0 and seq >= K_SLOTS:
-                        x.wait_ack(d, seq - K_SLOTS + 1, cs)          # the slot's previous occupant has been consumed
+                    if k == 0:                      # the slot's previous occupant has been consumed
+                        if rel:
+                            x.wait_ack_rel(d, base, K_SLOTS, 1, cs)
+                        elif seq >= K_SLOTS:
+                            x.wait_ack(d, seq - K_SLOTS + 1, cs)
                     for a, b in self._band_ranges(k):
                         if isinstance(x, DistExchange):
                             x.put(c, d, seq % K_SLOTS, a, b, src_ptr, cs, src_keep=src_keep)
                         else:
                             x.put(c, d, seq % K_SLOTS, a, b, src_ptr, cs)
                         self.bytes_put += b - a
-                    x.signal_progress(c, d, (seq << SEQ_SHIFT) + k + 1, cs)
+                    if rel:
+                        x.signal_progress_rel(c, d, base, k + 1, cs)
+                    else:
+                        x.signal_progress(c, d, (seq << SEQ_SHIFT) + k + 1, cs)
         # ---- the frame is enqueued: acknowledge the references (their slots may be overwritten once this point is reached)
         for d in range(1, self.n_refs + 1):
             kind, mseq = srcs[d - 1]
             if kind == "remote":
-                x.signal_ack((rank - d) % world, d, mseq + 1, st)
-        lib.check(lib.b200_event_record(self.ev_done[si], st), "record")
+                if rel:
+                    x.signal_ack_rel((rank - d) % world, d, base, seq - mseq, st)
+                else:
+                    x.signal_ack((rank - d) % world, d, mseq + 1, st)
         if self.host_io:
-            ds = self.down_stream[1] if self.down_stream[1] is not None else st
-            if ds is not st:
-                lib.check(lib.b200_stream_wait_event(ds, self.ev_done[si]), "wait")
+            ds = self.down_stream[1]
+            fork(ds)
             for dn in fb._downs:
                 lib.check(lib.b200_copy_async(dn.host, dn.dev, dn.bytes, ds), "d2h")
-            if ds is not st:
-                lib.check(lib.b200_event_record(self.ev_down[si], ds), "record")
+            lib.check(lib.b200_event_record(self.ev_down[si], ds), "record")
+            if rel:
+                lib.check(lib.b200_stream_wait_event(st, self.ev_down[si]), "wait")       # join: a graph has one end
         if world > 1:
-            lib.check(lib.b200_event_record(self.ev_puts[si], self.copy_stream[1]), "record")
-        return seq
+            if forked_copy or not rel:
+                lib.check(lib.b200_event_record(self.ev_puts[si], cs), "record")
+            if rel and forked_copy:
+                lib.check(lib.b200_stream_wait_event(st, self.ev_puts[si]), "wait")       # join
 
     def _band_ranges(self, k):
         """byte ranges of the restored picture that became final with band k (per plane: rows [progress(k-1), progress(k)))"""

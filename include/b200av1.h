@@ -641,6 +641,17 @@ B200_API int b200_ipc_close(void *peer_ptr);
 B200_API int b200_copy_async(void *dst, const void *src, size_t bytes, void *stream);
 B200_API int b200_flag_signal(uint32_t *flag, uint32_t value, void *stream);           /* flag: device memory, local or peer */
 B200_API int b200_flag_wait_geq(const uint32_t *flag, uint32_t value, void *stream);   /* flag: local device memory */
+/* The same flag operations with the value taken from device memory when the operation EXECUTES:
+ * value = ((*base - sub) << shift) + add. A frame's whole schedule (bands, puts, waits) can then be captured once into a
+ * CUDA graph and replayed for every later frame of the set: only the word at `base` (the frame's sequence number) changes. */
+B200_API int b200_flag_signal_rel(uint32_t *flag, const uint32_t *base, int32_t sub, int32_t shift, int32_t add, void *stream);
+B200_API int b200_flag_wait_geq_rel(const uint32_t *flag, const uint32_t *base, int32_t sub, int32_t shift, int32_t add, void *stream);
+/* CUDA graphs for C hosts: everything enqueued on `stream` (and on streams joined to it through events) between begin and
+ * end is recorded instead of executed; b200_graph_end returns an executable graph (NULL on failure). */
+B200_API int b200_graph_begin(void *stream);
+B200_API void *b200_graph_end(void *stream);
+B200_API int b200_graph_launch(void *graph_exec, void *stream);
+B200_API void b200_graph_destroy(void *graph_exec);
 B200_API void *b200_event_create(void);
 B200_API void b200_event_destroy(void *event);
 B200_API int b200_event_record(void *event, void *stream);

@@ -9,9 +9,18 @@ run_bench() { # name, env..., -- args
   local name=$1; shift
   ( timeout 600 env "$@" > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err ) ; echo "bench_$name rc=$?"
 }
+if [[ $what == *" probe "* ]]; then
+  timeout 120 python tools/peer_probe.py 2 > gpurun_out/probe_waitvalue.txt 2>&1; echo "probe rc=$?"; tail -12 gpurun_out/probe_waitvalue.txt
+  B200_FLAG_KERNELS=1 timeout 120 python tools/peer_probe.py 2 > gpurun_out/probe_kernels.txt 2>&1; echo "probe(kernels) rc=$?"; tail -12 gpurun_out/probe_kernels.txt
+fi
+if [[ $what == *" gopprobe "* ]]; then
+  for cfg in "2 1 0" "2 1 1" "2 2 1" "1 2 1"; do
+    timeout 90 python tools/gop_probe.py $cfg > "gpurun_out/gop_probe_${cfg// /_}.txt" 2>&1; echo "gop_probe $cfg rc=$?"; grep -E "PARITY|STALL|flags|synced|Error|error" "gpurun_out/gop_probe_${cfg// /_}.txt" | head -8
+  done
+fi
 if [[ $what == *" newtests "* ]]; then
-  timeout 900 python -m pytest tests/test_multigpu.py tests/test_frame.py -x -q -m gpu 2>&1 | tail -25 > gpurun_out/pytest_new.txt
-  cat gpurun_out/pytest_new.txt | tail -5
+  timeout 600 python -m pytest tests/test_multigpu.py -x -v -m gpu --timeout 150 > gpurun_out/pytest_multigpu.txt 2>&1; echo "multigpu tests rc=$?"; tail -15 gpurun_out/pytest_multigpu.txt
+  timeout 600 python -m pytest tests/test_frame.py tests/test_mc.py -x -q -m gpu --timeout 300 > gpurun_out/pytest_new.txt 2>&1; echo "frame/mc tests rc=$?"; tail -5 gpurun_out/pytest_new.txt
 fi
 if [[ $what == *" tests "* ]]; then
   timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 > gpurun_out/pytest_gpu.txt
