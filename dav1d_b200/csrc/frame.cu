@@ -205,7 +205,11 @@ WaitValue32Fn wait_value_fn()
 {
     static WaitValue32Fn fn = [] {
         void *p = nullptr;
-        if (getenv("B200_FLAG_KERNELS")) return (WaitValue32Fn) nullptr;
+        // Default: a polling kernel. cuStreamWaitValue32 parks the stream's whole hardware work queue on the semaphore: any
+        // other stream that shares the queue (the copy stream that still has to deliver the rows the peer is waiting for)
+        // stops too, which deadlocked two ranks waiting for each other (gop_probe, round 2). A polling kernel only
+        // occupies one thread; kernels of other streams keep being dispatched. B200_WAIT_VALUE=1 selects the memory op.
+        if (!getenv("B200_WAIT_VALUE")) return (WaitValue32Fn) nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
         cudaGetLastError();

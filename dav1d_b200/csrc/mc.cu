@@ -28,27 +28,7 @@ template <bool HBD> B200_DEV int inter_bits(int bdmax) {
 
 #define RND_SH(v, sh) (((v) + ((1 << (sh)) >> 1)) >> (sh))
 
-// ---- put / prep ---------------------------------------------------------------------------------
-// One warp per prediction block (4 blocks per CTA), blocks larger than 32x32 walked in 32x32 sub-blocks:
-//   1. the source window (sub-block + 3/4 taps of margin on filtered axes) is staged in the warp's shared
-//      memory: 32-bit aligned words straight from the reference when the window lies inside the plane,
-//      per-sample clamped loads otherwise (= dav1d's emu_edge, reference src/mc_tmpl.c:868-916);
-//   2. horizontal pass: an item = S consecutive columns of one window row, lanes run along rows (odd word
-//      pitch: conflict-free), sliding the 8-tap window through registers -> int16 `mid` tile;
-//   3. vertical pass: an item = S consecutive rows of one column, lanes run along x (conflict-free reads,
-//      coalesced stores), same sliding window, final rounding / clip / prep bias.
-// S = 1 / 2 / 4 / 8 by sub-block area so that small blocks still fill the warp. Bilinear is the same machinery
-// with the taps {16-m, m} at positions 3, 4 and a base shift of 4 instead of 6.
 constexpr int kMcWarps = 4;
-constexpr int kMcSub = 32, kMcWin = kMcSub + 7;          // sub-block edge, window edge
-constexpr int kMcMidPitch = kMcSub + 2;                   // int16 elements; (pitch * 2 / 4) odd
-
-template <bool HBD> struct alignas(16) McSmem {
-    typedef typename Bd<HBD>::pixel pixel;
-    static constexpr int kRawPitch = HBD ? 42 : 44;       // elements; word pitch 21 / 11 (odd)
-    pixel raw[kMcWin * kRawPitch];
-    int16_t mid[kMcWin * kMcMidPitch];
-};
 
 // sum of 4 unsigned bytes of `px` times 4 signed bytes of `taps`, plus acc
 B200_DEV int dp4a_us(unsigned px, int taps, int acc) {
@@ -72,119 +52,6 @@ template <bool HI> B200_DEV int dp2a_us(unsigned px, int taps, int acc) {
     else asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(taps), "r"(acc));
     return d;
 #endif
-}
-
-template <bool HBD, int S>
-B200_DEV void mc_passes(McSmem<HBD> &sm, const int lane, const int sw, const int sh, const int nr, const int shift0,
-                        const bool has_h, const bool has_v, const int (&fh)[8], const int (&fv)[8], const int fsh,
-                        const int ib, const int bias, const bool is_prep, const int bdmax,
-                        typename Bd<HBD>::pixel *dpx, const int ds, int16_t *dtmp, const int tw)
-{
-    typedef typename Bd<HBD>::pixel pixel;
-    constexpr int RP = McSmem<HBD>::kRawPitch;
-    // ---- horizontal: mid[r][x] for r < nr, x < sw
-    const int fh_lo = (fh[0] & 0xff) | (fh[1] & 0xff) << 8 | (fh[2] & 0xff) << 16 | (fh[3] & 0xff) << 24;
-    const int fh_hi = (fh[4] & 0xff) | (fh[5] & 0xff) << 8 | (fh[6] & 0xff) << 16 | (fh[7] & 0xff) << 24;
-    const int ngx = (sw + S - 1) / S;
-    const unsigned magic_r = recip16(nr);       // exact it / nr for it < 65536 / nr (it < 39 * 32)
-    for (int it = lane; it < nr * ngx; it += 32) {
-        const int g = (int)((it * magic_r) >> 16), r = it - g * nr;
-        const int x0 = g * S;
-        const pixel *row = &sm.raw[r * RP + shift0 + x0];
-        int16_t *m = &sm.mid[r * kMcMidPitch + x0];
-        if (has_h) {
-            if constexpr (!HBD) {
-                // 8-bit: the S+7 source bytes as aligned words, realigned once to the item's first byte, then per
-                // output two funnel shifts + two dp4a (4 taps each) instead of 8 loads + 8 multiply-adds
-                constexpr int NW = (S + 7 + 3) / 4 + 1;
-                const int b0 = shift0 + x0;
-                const unsigned *rw = (const unsigned *)&sm.raw[r * RP + (b0 & ~3)];
-                unsigned wv[NW + 1];
-#pragma unroll
-                for (int k = 0; k < NW; k++) wv[k] = rw[k];
-                wv[NW] = 0;
-                const unsigned sh8 = (b0 & 3) * 8;
-                unsigned a[NW];
-#pragma unroll
-                for (int k = 0; k < NW; k++) a[k] = __funnelshift_r(wv[k], wv[k + 1], sh8);
-#pragma unroll
-                for (int j = 0; j < S; j++) {
-                    const unsigned lo = __funnelshift_r(a[j >> 2], a[(j >> 2) + 1], (j & 3) * 8);
-                    const unsigned hi = __funnelshift_r(a[(j >> 2) + 1], a[(j >> 2) + 2 < NW ? (j >> 2) + 2 : NW - 1], (j & 3) * 8);
-                    const int sacc = dp4a_us(hi, fh_hi, dp4a_us(lo, fh_lo, 0));
-                    if (x0 + j < sw) m[j] = (int16_t)RND_SH(sacc, fsh - ib);
-                }
-            } else {
-                // 10/12-bit: pixel pairs as words, realigned once to the item's first sample; per output 4 dp2a
-                constexpr int NW = (S + 7 + 1) / 2 + 1;
-                const int b0 = shift0 + x0;
-                const unsigned *rw = (const unsigned *)&sm.raw[r * RP + (b0 & ~1)];
-                unsigned wv[NW + 1];
-#pragma unroll
-                for (int k = 0; k < NW; k++) wv[k] = rw[k];
-                wv[NW] = 0;
-                const unsigned sh16 = (b0 & 1) * 16;
-                unsigned a[NW + 1];
-#pragma unroll
-                for (int k = 0; k < NW; k++) a[k] = __funnelshift_r(wv[k], wv[k + 1], sh16);
-                a[NW] = 0;
-#pragma unroll
-                for (int j = 0; j < S; j++) {
-                    const int q = j >> 1;
-                    unsigned p0, p1, p2, p3;
-                    if (j & 1) {
-                        p0 = __funnelshift_r(a[q], a[q + 1], 16); p1 = __funnelshift_r(a[q + 1], a[q + 2], 16);
-                        p2 = __funnelshift_r(a[q + 2], a[q + 3], 16); p3 = __funnelshift_r(a[q + 3], a[q + 4 < NW ? q + 4 : NW], 16);
-                    } else { p0 = a[q]; p1 = a[q + 1]; p2 = a[q + 2]; p3 = a[q + 3]; }
-                    int sacc = dp2a_us<false>(p0, fh_lo, 0);
-                    sacc = dp2a_us<true>(p1, fh_lo, sacc);
-                    sacc = dp2a_us<false>(p2, fh_hi, sacc);
-                    sacc = dp2a_us<true>(p3, fh_hi, sacc);
-                    if (x0 + j < sw) m[j] = (int16_t)RND_SH(sacc, fsh - ib);
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < S; j++) if (x0 + j < sw) m[j] = (int16_t)row[j];
-        }
-    }
-    __syncwarp();
-    // ---- vertical + store
-    const int ngy = (sh + S - 1) / S;
-    const unsigned magic_w = recip16(sw);
-    for (int it = lane; it < sw * ngy; it += 32) {
-        const int g = (int)((it * magic_w) >> 16), x = it - g * sw;
-        const int y0 = g * S;
-        const int16_t *m = &sm.mid[y0 * kMcMidPitch + x];
-        int out[S];
-        if (has_v) {
-            int win[S + 7];
-#pragma unroll
-            for (int k = 0; k < S + 7; k++) win[k] = (y0 + k < nr) ? m[k * kMcMidPitch] : 0;
-#pragma unroll
-            for (int j = 0; j < S; j++) {
-                int sacc = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) sacc += fv[k] * win[j + k];
-                if (has_h) out[j] = is_prep ? RND_SH(sacc, fsh) - bias : iclip(RND_SH(sacc, fsh + ib), 0, bdmax);
-                else       out[j] = is_prep ? RND_SH(sacc, fsh - ib) - bias : iclip(RND_SH(sacc, fsh), 0, bdmax);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < S; j++) {
-                const int a = (y0 + j < nr) ? m[j * kMcMidPitch] : 0;
-                if (has_h) out[j] = is_prep ? a - bias : iclip((a + ((1 << ib) >> 1)) >> ib, 0, bdmax);
-                else       out[j] = is_prep ? (a << ib) - bias : a;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < S; j++) {
-            if (y0 + j >= sh) break;
-            if (is_prep) dtmp[(y0 + j) * tw + x] = (int16_t)out[j];
-            else dpx[(ptrdiff_t)(y0 + j) * ds + x] = (pixel)out[j];
-        }
-    }
-    __syncwarp();
 }
 
 #ifndef B200_MC_MINB
@@ -219,51 +86,6 @@ B200_DEV void mc_taps(McTaps &t, int filter2d, int mx, int my, int w, int h)
             for (int k = 0; k < 8; k++) t.fv[k] = b200_mc_subpel_filters[idx][my - 1][k];
         }
     }
-}
-
-// one sub-block (<= 32x32) of one prediction by one warp: stage the source window, run the two passes.
-// (sx, sy): reference sample of the sub-block's top-left output; put -> dsub / ds, prep -> tsub / tw.
-template <bool HBD>
-B200_DEV void mc_subblock(McSmem<HBD> &sm, const int lane, const typename Bd<HBD>::pixel *__restrict__ ref, const int rs,
-                          const int rw, const int rh, const int sx, const int sy, const int sw, const int sh,
-                          const McTaps &t, const int ib, const int bias, const bool is_prep, const int bdmax,
-                          typename Bd<HBD>::pixel *dsub, const int ds, int16_t *tsub, const int tw)
-{
-    constexpr int RP = McSmem<HBD>::kRawPitch;
-    constexpr int PPW = HBD ? 2 : 4;                       // pixels per 32-bit word
-    const bool words_ok = ((rs & (PPW - 1)) == 0) && ((((uintptr_t)ref) & 3) == 0);
-    const int nc = sw + (t.has_h ? 7 : 0), nr = sh + (t.has_v ? 7 : 0);
-    const int gx = sx - (t.has_h ? 3 : 0), gy = sy - (t.has_v ? 3 : 0);
-    int shift0 = 0;
-    if (words_ok && gx >= 0 && gy >= 0 && gx + nc <= rw && gy + nr <= rh &&
-        (((gx & ~(PPW - 1)) + ((nc + (gx & (PPW - 1)) + PPW - 1) & ~(PPW - 1))) <= rs)) {
-        // interior: aligned words, the window starts `shift0` samples into the tile row
-        shift0 = gx & (PPW - 1);
-        const int nw = (nc + shift0 + PPW - 1) / PPW;
-        const int gxa = gx - shift0;
-        const unsigned magic = recip16(nw);
-        for (int it = lane; it < nr * nw; it += 32) {
-            const int r = (int)((it * magic) >> 16), c = it - r * nw;
-            const unsigned v = *(const unsigned *)(ref + (ptrdiff_t)(gy + r) * rs + gxa + c * PPW);
-            *(unsigned *)&sm.raw[r * RP + c * PPW] = v;
-        }
-    } else {
-        const unsigned magic = recip16(nc);
-        for (int it = lane; it < nr * nc; it += 32) {
-            const int r = (int)((it * magic) >> 16), c = it - r * nc;
-            sm.raw[r * RP + c] = ref[(ptrdiff_t)iclip(gy + r, 0, rh - 1) * rs + iclip(gx + c, 0, rw - 1)];
-        }
-    }
-    __syncwarp();
-    const int area = sw * sh;
-    if (B200_MC_S1 && area <= 32)
-        mc_passes<HBD, 1>(sm, lane, sw, sh, nr, shift0, t.has_h, t.has_v, t.fh, t.fv, t.fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, tw);
-    else if (area <= 64)
-        mc_passes<HBD, 2>(sm, lane, sw, sh, nr, shift0, t.has_h, t.has_v, t.fh, t.fv, t.fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, tw);
-    else if (area <= 256)
-        mc_passes<HBD, 4>(sm, lane, sw, sh, nr, shift0, t.has_h, t.has_v, t.fh, t.fv, t.fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, tw);
-    else
-        mc_passes<HBD, 8>(sm, lane, sw, sh, nr, shift0, t.has_h, t.has_v, t.fh, t.fv, t.fsh, ib, bias, is_prep, bdmax, dsub, ds, tsub, tw);
 }
 
 // ---- put / prep, register-column form ------------------------------------------------------------------
@@ -318,99 +140,147 @@ B200_DEV int mc_finish(const int v, const int fsh, const int ib, const int bias,
     return is_prep ? (v << ib) - bias : v;
 }
 
-// interior blocks: every word an item reads lies inside the reference plane. Straight-line code per item (no branch
-// between the loads of different rows: the loads of a whole item are in flight together).
+// per-prediction constants of an item computation
+template <bool HBD> struct McPred {
+    McSrc<HBD> S;
+    McTaps t;
+    int fh_lo, fh_hi;        // horizontal taps packed as signed bytes (dp4a / dp2a operands)
+    int gx, gy;              // reference sample of output (0, 0)'s first tap
+    int hsh, hrnd;           // horizontal pass: (sum + hrnd) >> hsh = RND_SH(sum, fsh - intermediate_bits)
+    bool interior;
+};
+
+template <bool HBD>
+B200_DEV void mc_pred_setup(McPred<HBD> &P, const B200McFrame &fr, int ref, int pl, int filter2d, int mx, int my, int w, int h,
+                            int sx, int sy, int ib)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    P.S.ref = (const pixel *)fr.ref[ref] + fr.ref_plane_off[pl];
+    P.S.rs = fr.ref_stride[pl]; P.S.rw = fr.ref_w[pl]; P.S.rh = fr.ref_h[pl];
+    mc_taps(P.t, filter2d, mx, my, w, h);
+    P.fh_lo = (P.t.fh[0] & 0xff) | (P.t.fh[1] & 0xff) << 8 | (P.t.fh[2] & 0xff) << 16 | (P.t.fh[3] & 0xff) << 24;
+    P.fh_hi = (P.t.fh[4] & 0xff) | (P.t.fh[5] & 0xff) << 8 | (P.t.fh[6] & 0xff) << 16 | (P.t.fh[7] & 0xff) << 24;
+    P.gx = sx - (P.t.has_h ? 3 : 0); P.gy = sy - (P.t.has_v ? 3 : 0);
+    P.hsh = P.t.fsh - ib; P.hrnd = (1 << P.hsh) >> 1;
+    // is every sample (and every aligned word) the block's items read inside the reference plane?
+    constexpr int PPW = HBD ? 2 : 4;
+    const int nc = w + (P.t.has_h ? 7 : 0), nr = h + (P.t.has_v ? 7 : 0);
+    bool in = !(P.S.rs & (PPW - 1)) && !(((uintptr_t)P.S.ref) & 3) && P.gx >= 0 && P.gy >= 0 && P.gx + nc <= P.S.rw && P.gy + nr <= P.S.rh;
+    // the realigning loads read whole words: from the word holding the first tap to one word past the one holding the last
+    // tap; all of it must lie inside the row's pitch (the bottom row has nothing behind it to run into)
+    if (in && P.t.has_h) in = (P.gx & ~(PPW - 1)) + ((nc + (P.gx & (PPW - 1)) + PPW - 1) & ~(PPW - 1)) + PPW <= P.S.rs;
+    P.interior = in;
+}
+
+// the R vertical-pass sums (or horizontal values / plain samples without a vertical filter) of the item at column x, rows
+// y0 .. y0 + R - 1. Interior form: straight-line code, no branch between the loads of different rows, so that the loads
+// of a whole item are in flight together.
 template <bool HBD, int R, bool HAS_H, bool HAS_V>
-B200_DEV void mc_block_items(const McSrc<HBD> &S, const int lane, const int w, const int h, const int sx, const int sy,
-                             const McTaps &t, const int ib, const int bias, const int bdmax, const McOut &o)
+B200_DEV void mc_item_interior(const McPred<HBD> &P, const int x, const int y0, int (&v)[R])
 {
     typedef typename Bd<HBD>::pixel pixel;
     constexpr int PX = HBD ? 2 : 1, PPW = HBD ? 2 : 4;
-    const int fh_lo = (t.fh[0] & 0xff) | (t.fh[1] & 0xff) << 8 | (t.fh[2] & 0xff) << 16 | (t.fh[3] & 0xff) << 24;
-    const int fh_hi = (t.fh[4] & 0xff) | (t.fh[5] & 0xff) << 8 | (t.fh[6] & 0xff) << 16 | (t.fh[7] & 0xff) << 24;
-    const int hsh = t.fsh - ib, hrnd = (1 << hsh) >> 1;             // horizontal pass: RND_SH(sum, fsh - ib)
-    const int ngroups = h / R, items = w * ngroups;                    // R divides h (mc_item_rows)
-    const unsigned magic_w = recip16(w);                               // exact it / w: w is 2^k, 12 or 24 and it < 8192
-    const int gx = sx - (HAS_H ? 3 : 0), gy = sy - (HAS_V ? 3 : 0);
-    const int rsb = S.rs * PX;
     constexpr int NR = HAS_V ? R + 7 : R;
-    for (int it = lane; it < items; it += 32) {
-        const int g = (int)(((unsigned)it * magic_w) >> 16), x = it - g * w, y0 = g * R;
-        const int b0 = gx + x;
-        const unsigned char *ip = (const unsigned char *)S.ref + (ptrdiff_t)(gy + y0) * rsb + (HAS_H ? (b0 & ~(PPW - 1)) : b0) * PX;
-        const unsigned al = HAS_H ? (b0 & (PPW - 1)) * (HBD ? 16 : 8) : 0;
-        int mid[NR];
+    const int rsb = P.S.rs * PX;
+    const int b0 = P.gx + x;
+    const unsigned char *ip = (const unsigned char *)P.S.ref + (ptrdiff_t)(P.gy + y0) * rsb + (HAS_H ? (b0 & ~(PPW - 1)) : b0) * PX;
+    const unsigned al = HAS_H ? (b0 & (PPW - 1)) * (HBD ? 16 : 8) : 0;
+    int mid[NR];
 #pragma unroll
-        for (int r = 0; r < NR; r++) {
-            const unsigned char *rp = ip + (ptrdiff_t)r * rsb;
-            if (HAS_H) mid[r] = mc_hfilter_words<HBD>(rp, al, fh_lo, fh_hi, hrnd, hsh);
-            else mid[r] = (int)*(const pixel *)rp;
-        }
+    for (int r = 0; r < NR; r++) {
+        const unsigned char *rp = ip + (ptrdiff_t)r * rsb;
+        if (HAS_H) mid[r] = mc_hfilter_words<HBD>(rp, al, P.fh_lo, P.fh_hi, P.hrnd, P.hsh);
+        else mid[r] = (int)*(const pixel *)rp;
+    }
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-            int v;
-            if (HAS_V) {
-                v = 0;
+    for (int j = 0; j < R; j++) {
+        if (HAS_V) {
+            int a = 0;
 #pragma unroll
-                for (int k = 0; k < 8; k++) v += t.fv[k] * mid[j + k];
-            } else v = mid[j];
-            const int out = mc_finish<HAS_H, HAS_V>(v, t.fsh, ib, bias, bdmax, o.is_prep);
-            if (o.is_prep) o.tmp[(y0 + j) * o.tw + x] = (int16_t)out;
-            else ((pixel *)o.px)[(ptrdiff_t)(y0 + j) * o.ds + x] = (pixel)out;
-        }
+            for (int k = 0; k < 8; k++) a += P.t.fv[k] * mid[j + k];
+            v[j] = a;
+        } else v[j] = mid[j];
     }
 }
 
 // blocks whose window leaves the reference plane (or whose plane is not word addressable): per-sample clamped loads
-// = dav1d's emu_edge (reference src/mc_tmpl.c:868-916) folded in. One compact instantiation (4-row items, run-time
-// filter flags): a few percent of the blocks of a frame take this path.
-template <bool HBD>
-B200_DEV void mc_block_items_edge(const McSrc<HBD> &S, const int lane, const int w, const int h, const int sx, const int sy,
-                                  const McTaps &t, const int ib, const int bias, const int bdmax, const McOut &o)
+// = dav1d's emu_edge (reference src/mc_tmpl.c:868-916) folded in. Compact (run-time filter flags, row loop not unrolled
+// over the filter cases): a few percent of the blocks of a frame take this path.
+template <bool HBD, int R>
+B200_DEV void mc_item_edge(const McPred<HBD> &P, const int x, const int y0, int (&v)[R])
 {
     typedef typename Bd<HBD>::pixel pixel;
-    constexpr int R = 4;
-    const bool has_h = t.has_h, has_v = t.has_v;
-    const int hsh = t.fsh - ib, hrnd = (1 << hsh) >> 1;
-    const int ngroups = (h + R - 1) / R, items = w * ngroups;
-    const unsigned magic_w = recip16(w);
-    const int gx = sx - (has_h ? 3 : 0), gy = sy - (has_v ? 3 : 0);
+    const bool has_h = P.t.has_h, has_v = P.t.has_v;
     const int nr = has_v ? R + 7 : R;
+    int mid[R + 7];
+#pragma unroll
+    for (int r = 0; r < R + 7; r++) {
+        mid[r] = 0;
+        if (r < nr) {
+            const pixel *rp = P.S.ref + (ptrdiff_t)iclip(P.gy + y0 + r, 0, P.S.rh - 1) * P.S.rs;
+            if (has_h) {
+                int acc = P.hrnd;
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc += P.t.fh[k] * (int)rp[iclip(P.gx + x + k, 0, P.S.rw - 1)];
+                mid[r] = acc >> P.hsh;
+            } else mid[r] = (int)rp[iclip(P.gx + x, 0, P.S.rw - 1)];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        if (has_v) {
+            int a = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) a += P.t.fv[k] * mid[j + k];
+            v[j] = a;
+        } else v[j] = mid[j];
+    }
+}
+
+// run-time dispatch on the filter flags (warp uniform: one block per warp)
+template <bool HBD, int R>
+B200_DEV void mc_item(const McPred<HBD> &P, const int x, const int y0, int (&v)[R])
+{
+    if (!P.interior) { mc_item_edge<HBD, R>(P, x, y0, v); return; }
+    if (P.t.has_h) {
+        if (P.t.has_v) mc_item_interior<HBD, R, true, true>(P, x, y0, v);
+        else mc_item_interior<HBD, R, true, false>(P, x, y0, v);
+    } else {
+        if (P.t.has_v) mc_item_interior<HBD, R, false, true>(P, x, y0, v);
+        else mc_item_interior<HBD, R, false, false>(P, x, y0, v);
+    }
+}
+
+B200_DEV int mc_finish_rt(const McTaps &t, const int v, const int ib, const int bias, const int bdmax, const bool is_prep)
+{
+    if (t.has_v) return t.has_h ? mc_finish<true, true>(v, t.fsh, ib, bias, bdmax, is_prep) : mc_finish<false, true>(v, t.fsh, ib, bias, bdmax, is_prep);
+    return t.has_h ? mc_finish<true, false>(v, t.fsh, ib, bias, bdmax, is_prep) : mc_finish<false, false>(v, t.fsh, ib, bias, bdmax, is_prep);
+}
+
+// put / prep of one block: the items of the block dealt to the lanes
+template <bool HBD, int R, bool HAS_H, bool HAS_V, bool INTERIOR>
+B200_DEV void mc_block_items(const McPred<HBD> &P, const int lane, const int w, const int h, const int ib, const int bias,
+                             const int bdmax, const McOut &o)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    const int items = w * (h / R);                                     // R divides h (mc_item_rows)
+    const unsigned magic_w = recip16(w);                               // exact it / w: w is 2^k, 12 or 24 and it < 8192
     for (int it = lane; it < items; it += 32) {
         const int g = (int)(((unsigned)it * magic_w) >> 16), x = it - g * w, y0 = g * R;
-        int mid[R + 7];
-#pragma unroll
-        for (int r = 0; r < R + 7; r++) {
-            mid[r] = 0;
-            if (r < nr) {
-                const pixel *rp = S.ref + (ptrdiff_t)iclip(gy + y0 + r, 0, S.rh - 1) * S.rs;
-                if (has_h) {
-                    int acc = hrnd;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) acc += t.fh[k] * (int)rp[iclip(gx + x + k, 0, S.rw - 1)];
-                    mid[r] = acc >> hsh;
-                } else mid[r] = (int)rp[iclip(gx + x, 0, S.rw - 1)];
-            }
-        }
+        int v[R];
+        if (INTERIOR) mc_item_interior<HBD, R, HAS_H, HAS_V>(P, x, y0, v);
+        else mc_item_edge<HBD, R>(P, x, y0, v);
 #pragma unroll
         for (int j = 0; j < R; j++) {
-            int v;
-            if (has_v) {
-                v = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) v += t.fv[k] * mid[j + k];
-            } else v = mid[j];
-            int out;
-            if (has_v) out = has_h ? mc_finish<true, true>(v, t.fsh, ib, bias, bdmax, o.is_prep) : mc_finish<false, true>(v, t.fsh, ib, bias, bdmax, o.is_prep);
-            else out = has_h ? mc_finish<true, false>(v, t.fsh, ib, bias, bdmax, o.is_prep) : mc_finish<false, false>(v, t.fsh, ib, bias, bdmax, o.is_prep);
-            if (y0 + j >= h) break;
+            const int out = INTERIOR ? mc_finish<HAS_H, HAS_V>(v[j], P.t.fsh, ib, bias, bdmax, o.is_prep)
+                                     : mc_finish_rt(P.t, v[j], ib, bias, bdmax, o.is_prep);
             if (o.is_prep) o.tmp[(y0 + j) * o.tw + x] = (int16_t)out;
             else ((pixel *)o.px)[(ptrdiff_t)(y0 + j) * o.ds + x] = (pixel)out;
         }
     }
 }
 
-// rows of an item: the largest R for which the block still gives every lane an item (an item costs ~9 instructions per
+// rows of an item: the largest R for which the block still gives every lane an item (an item costs ~10 instructions per
 // source row + ~12 per output; idle lanes cost the same as busy ones)
 B200_DEV int mc_item_rows(int w, int h)
 {
@@ -421,30 +291,15 @@ B200_DEV int mc_item_rows(int w, int h)
 }
 
 template <bool HBD, bool HAS_H, bool HAS_V>
-B200_DEV void mc_block_dispatch(const McSrc<HBD> &S, int lane, int w, int h, int sx, int sy, const McTaps &t, int ib, int bias,
-                                int bdmax, const McOut &o)
+B200_DEV void mc_block_dispatch(const McPred<HBD> &P, int lane, int w, int h, int ib, int bias, int bdmax, const McOut &o)
 {
     switch (mc_item_rows(w, h)) {
-    case 16: mc_block_items<HBD, 16, HAS_H, HAS_V>(S, lane, w, h, sx, sy, t, ib, bias, bdmax, o); break;
-    case 8:  mc_block_items<HBD, 8, HAS_H, HAS_V>(S, lane, w, h, sx, sy, t, ib, bias, bdmax, o); break;
-    case 4:  mc_block_items<HBD, 4, HAS_H, HAS_V>(S, lane, w, h, sx, sy, t, ib, bias, bdmax, o); break;
-    case 2:  mc_block_items<HBD, 2, HAS_H, HAS_V>(S, lane, w, h, sx, sy, t, ib, bias, bdmax, o); break;
-    default: mc_block_items<HBD, 1, HAS_H, HAS_V>(S, lane, w, h, sx, sy, t, ib, bias, bdmax, o); break;
+    case 16: mc_block_items<HBD, 16, HAS_H, HAS_V, true>(P, lane, w, h, ib, bias, bdmax, o); break;
+    case 8:  mc_block_items<HBD, 8, HAS_H, HAS_V, true>(P, lane, w, h, ib, bias, bdmax, o); break;
+    case 4:  mc_block_items<HBD, 4, HAS_H, HAS_V, true>(P, lane, w, h, ib, bias, bdmax, o); break;
+    case 2:  mc_block_items<HBD, 2, HAS_H, HAS_V, true>(P, lane, w, h, ib, bias, bdmax, o); break;
+    default: mc_block_items<HBD, 1, HAS_H, HAS_V, true>(P, lane, w, h, ib, bias, bdmax, o); break;
     }
-}
-
-// is every sample (and every aligned word) the block's items read inside the reference plane?
-template <bool HBD>
-B200_DEV bool mc_window_interior(const McSrc<HBD> &S, int sx, int sy, int w, int h, bool has_h, bool has_v)
-{
-    constexpr int PPW = HBD ? 2 : 4;
-    if ((S.rs & (PPW - 1)) || (((uintptr_t)S.ref) & 3)) return false;
-    const int gx = sx - (has_h ? 3 : 0), gy = sy - (has_v ? 3 : 0);
-    const int nc = w + (has_h ? 7 : 0), nr = h + (has_v ? 7 : 0);
-    if (gx < 0 || gy < 0 || gx + nc > S.rw || gy + nr > S.rh) return false;
-    // the realigning loads read whole words: from the word holding the first tap to one word past the one holding the last
-    // tap; all of it must lie inside the row's pitch (the bottom row has nothing behind it to run into)
-    return !has_h || (gx & ~(PPW - 1)) + ((nc + (gx & (PPW - 1)) + PPW - 1) & ~(PPW - 1)) + PPW <= S.rs;
 }
 
 template <bool HBD>
@@ -457,110 +312,136 @@ mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, const __gri
     if (bi >= n_blocks) return;
     const B200McBlock b = blocks[bi];
     const int w = b.w, h = b.h, pl = b.plane;
-    McSrc<HBD> S;
-    S.ref = (const pixel *)fr.ref[b.ref] + fr.ref_plane_off[pl];
-    S.rs = fr.ref_stride[pl]; S.rw = fr.ref_w[pl]; S.rh = fr.ref_h[pl];
     const int ib = inter_bits<HBD>(bdmax);
     const int bias = HBD ? 8192 : 0;
-    McTaps t;
-    mc_taps(t, b.filter2d, b.mx, b.my, w, h);
+    McPred<HBD> P;
+    mc_pred_setup<HBD>(P, fr, b.ref, pl, b.filter2d, b.mx, b.my, w, h, b.src_x, b.src_y, ib);
     // op 2: "put" into the dense pixel scratch (pitch w) that the blend stages read (OBMC neighbour predictions)
     McOut o;
     o.is_prep = b.op == 1;
     o.px = (b.op == 2 ? (pixel *)fr.px_tmp : (pixel *)fr.dst) + b.dst_off;
     o.ds = b.op == 2 ? w : fr.dst_stride[pl];
     o.tmp = fr.tmp + b.dst_off; o.tw = w;
-    if (!mc_window_interior<HBD>(S, b.src_x, b.src_y, w, h, t.has_h, t.has_v)) {
-        mc_block_items_edge<HBD>(S, lane, w, h, b.src_x, b.src_y, t, ib, bias, bdmax, o);
+    if (!P.interior) {
+        // 4-row items (2 / 1 when the height asks for it): (4 + 7) / 4 source rows per output row, one instantiation each
+        if (!(h & 3)) mc_block_items<HBD, 4, false, false, false>(P, lane, w, h, ib, bias, bdmax, o);
+        else if (!(h & 1)) mc_block_items<HBD, 2, false, false, false>(P, lane, w, h, ib, bias, bdmax, o);
+        else mc_block_items<HBD, 1, false, false, false>(P, lane, w, h, ib, bias, bdmax, o);
         return;
     }
-    if (t.has_h) {
-        if (t.has_v) mc_block_dispatch<HBD, true, true>(S, lane, w, h, b.src_x, b.src_y, t, ib, bias, bdmax, o);
-        else mc_block_dispatch<HBD, true, false>(S, lane, w, h, b.src_x, b.src_y, t, ib, bias, bdmax, o);
+    if (P.t.has_h) {
+        if (P.t.has_v) mc_block_dispatch<HBD, true, true>(P, lane, w, h, ib, bias, bdmax, o);
+        else mc_block_dispatch<HBD, true, false>(P, lane, w, h, ib, bias, bdmax, o);
     } else {
-        if (t.has_v) mc_block_dispatch<HBD, false, true>(S, lane, w, h, b.src_x, b.src_y, t, ib, bias, bdmax, o);
-        else mc_block_dispatch<HBD, false, false>(S, lane, w, h, b.src_x, b.src_y, t, ib, bias, bdmax, o);
+        if (P.t.has_v) mc_block_dispatch<HBD, false, true>(P, lane, w, h, ib, bias, bdmax, o);
+        else mc_block_dispatch<HBD, false, false>(P, lane, w, h, ib, bias, bdmax, o);
     }
 }
 
 // ---- fused compound prediction -----------------------------------------------------------------------
-// Both predictions of a compound block and their combination in one pass: the two int16 intermediates of a
-// 32x32 sub-block stay in the warp's shared memory instead of making the round trip through mc.tmp in HBM
-// (prep store + compound load: 4 bytes per sample each way), and the separate compound launch disappears.
-// Same arithmetic as prep + avg / w_avg / mask / w_mask (reference src/mc_tmpl.c:628-781): bit-identical.
+// Both predictions of a compound block and their combination in one pass, item by item in registers: a lane computes
+// the R int16-precision values of its column from the first reference, then from the second, and combines them
+// (avg / w_avg / mask / w_mask, reference src/mc_tmpl.c:628-781) — no int16 round trip through mc.tmp (2 x 2 bytes
+// written and read back per sample) and no separate compound launch. Same arithmetic as prep + compound: bit-identical.
+// w_mask sums the mask over horizontal pairs (neighbouring lanes: one shuffle) and, for 4:2:0, row pairs (same lane).
+template <bool HBD, int R>
+B200_DEV void mc_comp_fused_items(const McPred<HBD> (&P)[2], const int lane, const B200CompFusedBlock &b, const int ib,
+                                  const int bias, const int bdmax, typename Bd<HBD>::pixel *dpx, const int ds, uint8_t *mask)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    const int w = b.w, h = b.h, op = b.op;
+    const int items = w * (h / R);
+    const unsigned magic_w = recip16(w);
+    const int bitdepth = 32 - __clz(bdmax);
+    const int ss_hor = op >= B200_COMP_W_MASK_422, ss_ver = op == B200_COMP_W_MASK_420;
+    for (int it0 = 0; it0 < items; it0 += 32) {
+        const bool active = it0 + lane < items;
+        const int it = active ? it0 + lane : items - 1;               // idle lanes of the last round redo the last item (w_mask shuffles need the whole warp)
+        const int g = (int)(((unsigned)it * magic_w) >> 16), x = it - g * w, y0 = g * R;
+        int a[R], c[R];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            int v[R];
+            mc_item<HBD, R>(P[r], x, y0, v);
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const int p = mc_finish_rt(P[r].t, v[j], ib, bias, bdmax, true);
+                if (r == 0) a[j] = p; else c[j] = p;
+            }
+        }
+        if (op <= B200_COMP_MASK) {
+            if (!active) continue;
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                int o;
+                if (op == B200_COMP_AVG) o = (a[j] + c[j] + (1 << ib) + bias * 2) >> (ib + 1);
+                else if (op == B200_COMP_W_AVG) o = (a[j] * b.param + c[j] * (16 - b.param) + (8 << ib) + bias * 16) >> (ib + 4);
+                else { const int m = mask[(y0 + j) * w + x]; o = (a[j] * m + c[j] * (64 - m) + (32 << ib) + bias * 64) >> (ib + 6); }
+                dpx[(ptrdiff_t)(y0 + j) * ds + x] = (pixel)iclip(o, 0, bdmax);
+            }
+        } else {
+            // w_mask: derive the blend mask from |tmp1 - tmp2|, blend, emit the (sub-sampled) mask
+            const int sign = b.param;
+            const int shc = ib + 6, rnd = (32 << ib) + bias * 64;
+            const int mask_sh = bitdepth + ib - 4, mask_rnd = 1 << (mask_sh - 5);
+            const int mw = ss_hor ? w >> 1 : w;                        // pitch of the emitted mask
+            int m[R];
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const int d = a[j] - c[j];
+                m[j] = imin(38 + ((iabs(d) + mask_rnd) >> mask_sh), 64);
+                if (active) dpx[(ptrdiff_t)(y0 + j) * ds + x] = (pixel)iclip((d * m[j] + c[j] * 64 + rnd) >> shc, 0, bdmax);
+            }
+            if (!ss_hor) {
+                if (active) {
+#pragma unroll
+                    for (int j = 0; j < R; j++) mask[(y0 + j) * w + x] = (uint8_t)m[j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < R; j++) m[j] += __shfl_xor_sync(0xffffffffu, m[j], 1);       // x and x ^ 1 are neighbouring lanes (w is even)
+                if (active && !(x & 1)) {
+                    if (ss_ver) {
+                        if constexpr (R >= 2) {
+#pragma unroll
+                            for (int j = 0; j < R; j += 2) mask[((y0 + j) >> 1) * mw + (x >> 1)] = (uint8_t)((m[j] + m[j + 1] + 2 - sign) >> 2);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < R; j++) mask[(y0 + j) * mw + (x >> 1)] = (uint8_t)((m[j] + 1 - sign) >> 1);
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <bool HBD>
 __global__ void __launch_bounds__(kMcWarps * 32, B200_MC_MINB)
 mc_comp_fused_kernel(const B200CompFusedBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
-    __shared__ McSmem<HBD> smem[kMcWarps];
-    __shared__ int16_t s_pred[kMcWarps][2][kMcSub * kMcSub];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bi = blockIdx.x * kMcWarps + warp;
     if (bi >= n_blocks) return;
-    McSmem<HBD> &sm = smem[warp];
     const B200CompFusedBlock b = blocks[bi];
-    const int w = b.w, h = b.h, pl = b.plane, op = b.op;
-    const int rs = fr.ref_stride[pl], rw = fr.ref_w[pl], rh = fr.ref_h[pl];
+    const int w = b.w, h = b.h, pl = b.plane;
     const int ib = inter_bits<HBD>(bdmax);
     const int bias = HBD ? 8192 : 0;
-    const int bitdepth = 32 - __clz(bdmax);
+    McPred<HBD> P[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) mc_pred_setup<HBD>(P[r], fr, b.ref[r], pl, b.filter2d, b.mx[r], b.my[r], w, h, b.src_x[r], b.src_y[r], ib);
     pixel *const dpx = (pixel *)fr.dst + b.dst_off;
     const int ds = fr.dst_stride[pl];
     uint8_t *const mask = fr.mask + b.mask_off;
-    const int ss_hor = op >= B200_COMP_W_MASK_422, ss_ver = op == B200_COMP_W_MASK_420;
-    for (int sy0 = 0; sy0 < h; sy0 += kMcSub)
-        for (int sx0 = 0; sx0 < w; sx0 += kMcSub) {
-            const int sw = imin(kMcSub, w - sx0), sh = imin(kMcSub, h - sy0);
-#pragma unroll 1
-            for (int r = 0; r < 2; r++) {
-                const pixel *__restrict__ ref = (const pixel *)fr.ref[b.ref[r]] + fr.ref_plane_off[pl];
-                McTaps t;
-                mc_taps(t, b.filter2d, b.mx[r], b.my[r], w, h);
-                mc_subblock<HBD>(sm, lane, ref, rs, rw, rh, b.src_x[r] + sx0, b.src_y[r] + sy0, sw, sh, t, ib, bias, true, bdmax,
-                                 nullptr, 0, s_pred[warp][r], sw);
-            }
-            __syncwarp();
-            const int16_t *t1 = s_pred[warp][0], *t2 = s_pred[warp][1];
-            if (op <= B200_COMP_MASK) {
-                for (int i = lane; i < sw * sh; i += 32) {
-                    const int y = i / sw, x = i - y * sw;
-                    const int a = t1[i], c = t2[i];
-                    int v;
-                    if (op == B200_COMP_AVG) v = (a + c + (1 << ib) + bias * 2) >> (ib + 1);
-                    else if (op == B200_COMP_W_AVG) v = (a * b.param + c * (16 - b.param) + (8 << ib) + bias * 16) >> (ib + 4);
-                    else { const int m = mask[(sy0 + y) * w + sx0 + x]; v = (a * m + c * (64 - m) + (32 << ib) + bias * 64) >> (ib + 6); }
-                    dpx[(ptrdiff_t)(sy0 + y) * ds + sx0 + x] = (pixel)iclip(v, 0, bdmax);
-                }
-            } else {
-                // w_mask: derive the blend mask from |tmp1 - tmp2|, blend, emit the (sub-sampled) mask
-                const int sign = b.param;
-                const int shc = ib + 6, rnd = (32 << ib) + bias * 64;
-                const int mask_sh = bitdepth + ib - 4, mask_rnd = 1 << (mask_sh - 5);
-                const int qw = sw >> 1, qh = ss_ver ? sh >> 1 : sh;
-                const int mw = ss_hor ? w >> 1 : w;                    // pitch of the emitted mask
-                for (int i = lane; i < qw * qh; i += 32) {
-                    const int qy = i / qw, qx = i - qy * qw;
-                    const int x = qx * 2;
-                    int msum = 0;
-                    for (int rr = 0; rr <= ss_ver; rr++) {
-                        const int y = ss_ver ? qy * 2 + rr : qy;
-#pragma unroll
-                        for (int k = 0; k < 2; k++) {
-                            const int idx = y * sw + x + k;
-                            const int c = t2[idx], d = t1[idx] - c;
-                            const int m = imin(38 + ((iabs(d) + mask_rnd) >> mask_sh), 64);
-                            dpx[(ptrdiff_t)(sy0 + y) * ds + sx0 + x + k] = (pixel)iclip((d * m + c * 64 + rnd) >> shc, 0, bdmax);
-                            if (!ss_hor) mask[(sy0 + y) * w + sx0 + x + k] = (uint8_t)m;
-                            msum += m;
-                        }
-                    }
-                    if (ss_ver)      mask[((sy0 >> 1) + qy) * mw + (sx0 >> 1) + qx] = (uint8_t)((msum + 2 - sign) >> 2);
-                    else if (ss_hor) mask[(sy0 + qy) * mw + (sx0 >> 1) + qx] = (uint8_t)((msum + 1 - sign) >> 1);
-                }
-            }
-            __syncwarp();
-        }
+    int R = imin(mc_item_rows(w, h), 8);                  // two predictions' worth of registers per item
+    if (b.op == B200_COMP_W_MASK_420 && R < 2) R = 2;     // row pairs stay inside an item (h is even)
+    switch (R) {
+    case 8:  mc_comp_fused_items<HBD, 8>(P, lane, b, ib, bias, bdmax, dpx, ds, mask); break;
+    case 4:  mc_comp_fused_items<HBD, 4>(P, lane, b, ib, bias, bdmax, dpx, ds, mask); break;
+    case 2:  mc_comp_fused_items<HBD, 2>(P, lane, b, ib, bias, bdmax, dpx, ds, mask); break;
+    default: mc_comp_fused_items<HBD, 1>(P, lane, b, ib, bias, bdmax, dpx, ds, mask); break;
+    }
 }
 
 // ---- scaled references -----------------------------------------------------------------------------

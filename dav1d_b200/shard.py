@@ -182,6 +182,8 @@ class GopPipeline:
         self.ref_name = fb.ref_name
         self.host_io = False
         A = fb.alloc
+        # streams that may sit in a flag wait must not share a hardware work queue with the streams that feed the peers:
+        # the package sets CUDA_DEVICE_MAX_CONNECTIONS=32 before CUDA starts (dav1d_b200/__init__.py)
         self.streams = [A.new_stream() for _ in range(max(1, n_streams))]          # (keep, handle)
         assert self.n_sets % len(self.streams) == 0, "a set must always run on the same stream"
         self.copy_stream = A.new_stream() if world > 1 else (None, None)
@@ -261,7 +263,8 @@ class GopPipeline:
         # (always outside a captured graph: these are dependencies on other frames' work)
         if self.set_seq[si] >= 0:
             prev = self.set_seq[si]
-            if world > 1:
+            replayed = self.graph[si] is not None          # its last frame ran as a graph: puts and host copies were joined inside it
+            if world > 1 and not replayed:
                 lib.check(lib.b200_stream_wait_event(st, self.ev_puts[si]), "wait")
             for d in range(1, self.n_refs + 1):                 # local frames that predicted from it
                 r = (prev * world + rank) + d
@@ -269,7 +272,7 @@ class GopPipeline:
                     rs = r // world
                     if rs < seq and (rs % len(self.streams)) != sidx:
                         lib.check(lib.b200_stream_wait_event(st, self.ev_done[rs % self.n_sets]), "wait")
-            if self.host_io:
+            if self.host_io and not replayed:
                 lib.check(lib.b200_stream_wait_event(st, self.ev_down[si]), "wait")     # its output picture has left
         replay = self.graphs and self.set_seq[si] >= 0
         self.set_seq[si] = seq

@@ -14,7 +14,7 @@ if [[ $what == *" probe "* ]]; then
   B200_FLAG_KERNELS=1 timeout 120 python tools/peer_probe.py 2 > gpurun_out/probe_kernels.txt 2>&1; echo "probe(kernels) rc=$?"; tail -12 gpurun_out/probe_kernels.txt
 fi
 if [[ $what == *" gopprobe "* ]]; then
-  for cfg in "2 1 0" "2 1 1" "2 2 1" "1 2 1"; do
+  for cfg in ${B200_PROBE_CFGS:-"2 1 0" "2 1 1" "2 2 1"}; do
     timeout 90 python tools/gop_probe.py $cfg > "gpurun_out/gop_probe_${cfg// /_}.txt" 2>&1; echo "gop_probe $cfg rc=$?"; grep -E "PARITY|STALL|flags|synced|Error|error" "gpurun_out/gop_probe_${cfg// /_}.txt" | head -8
   done
 fi
@@ -35,6 +35,9 @@ if [[ $what == *" bench1 "* ]]; then
 fi
 if [[ $what == *" benchref "* ]]; then
   run_bench ref python bench.py --impl reference --steps 3 --warmup 1
+fi
+if [[ $what == *" mgtests "* ]]; then
+  timeout 500 python -m pytest tests/test_multigpu.py -x -v -m gpu --timeout 200 > gpurun_out/pytest_multigpu.txt 2>&1; echo "multigpu tests rc=$?"; tail -8 gpurun_out/pytest_multigpu.txt
 fi
 if [[ $what == *" bench2gpu "* ]]; then
   for wl in 4k8_inter 8k10_full; do
