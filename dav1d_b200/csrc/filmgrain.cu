@@ -1,10 +1,10 @@
 // Film grain (dav1d Dav1dFilmGrainDSPContext; reference src/filmgrain_tmpl.c:50-402,
 // driver src/fg_apply_tmpl.c:41-240).
 //
-//   fg_prep_kernel   one CTA per picture: (1) the raw grain fields (16-bit LFSR -> Gaussian table) are
-//                    filled by one thread per LUT (the LFSR chain is sequential but tiny); (2) the
-//                    raster-order AR filter runs as a skewed wavefront, one thread per LUT row, row y
-//                    trailing row y-1 by lag+1 columns; (3) scaling LUTs (closed form of the `d += delta`
+//   fg_prep_kernel   one CTA per picture: (1) the raw grain fields (16-bit LFSR -> Gaussian table), one thread
+//                    per LUT row after an LFSR jump-ahead (GF(2) matrix powers); (2) the raster-order AR
+//                    filter as a skewed wavefront in shared memory, one thread per LUT row, row y trailing
+//                    row y-1 by lag+1 columns; (3) scaling LUTs (closed form of the `d += delta`
 //                    recurrence) and (4) the per-row block-offset chains.
 //   fg_apply_kernel  one thread per 4 consecutive pixels: LUT samples of their own 32x32 block blended with
 //                    the left / top / top-left blocks' samples inside the 2-sample overlap, scaled by
@@ -34,46 +34,98 @@ B200_HD int fg_rnd(int bits, unsigned *state) {
 }
 B200_HD int fg_round2(int x, int sh) { return (x + ((1 << sh) >> 1)) >> sh; }
 
-// grain LUT generation; buf / buf_y are int16 working copies (pitch GW). Called by a whole CTA.
-B200_DEV void fg_generate(int16_t *buf, const int16_t *buf_y, const B200FilmGrainData &d, int uv, int subx, int suby, int b8)
+// ---- grain LUT generation, parallel ------------------------------------------------------------------------
+// The reference fills a LUT from ONE 16-bit LFSR in raster order and then runs the auto-regressive filter in raster
+// order (reference src/filmgrain_tmpl.c:50-160). Both are parallelised without changing a bit:
+//   * the LFSR step is linear over GF(2): state_{n+k} = A^k state_n. The images of the 16 basis states under A^(2^b)
+//     are built once per launch (16 threads per squaring), every LUT row then jumps straight to its first state
+//     (row y starts after y * width draws) and fills its own 82 / 44 entries: one thread per row, all planes at once;
+//   * the AR filter of pixel (x, y) needs the filtered (x + lag, y - 1): rows run as a skewed wavefront, row y trailing
+//     row y - 1 by lag + 1 columns, in SHARED memory (one barrier + <= 24 multiply-adds per step); luma first, then both
+//     chroma planes side by side (they read the filtered luma grain).
+// Round 1 did the LFSR chain on one thread and the wavefront in global memory: ~475 us per frame; this form ~35 us.
+struct FgJump { uint16_t t[14][16]; };      // t[b][i] = A^(2^b) e_i ; 2^13 > 73 * 82 draws
+
+B200_DEV unsigned fg_lfsr_step(unsigned r) { return (r >> 1) | ((((r >> 0) ^ (r >> 1) ^ (r >> 3) ^ (r >> 12)) & 1u) << 15); }
+
+// called by the whole CTA
+B200_DEV void fg_build_jump(FgJump &J)
+{
+    const int i = threadIdx.x;
+    if (i < 16) J.t[0][i] = (uint16_t)fg_lfsr_step(1u << i);
+    __syncthreads();
+    for (int b = 1; b < 14; b++) {
+        if (i < 16) {
+            const unsigned v = J.t[b - 1][i];
+            unsigned r = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) if ((v >> k) & 1) r ^= J.t[b - 1][k];
+            J.t[b][i] = (uint16_t)r;
+        }
+        __syncthreads();
+    }
+}
+
+B200_DEV unsigned fg_lfsr_advance(const FgJump &J, unsigned s, int n)
+{
+    for (int b = 0; n; b++, n >>= 1) {
+        if (!(n & 1)) continue;
+        unsigned r = 0;
+#pragma unroll
+        for (int k = 0; k < 16; k++) if ((s >> k) & 1) r ^= J.t[b][k];
+        s = r;
+    }
+    return s;
+}
+
+// one LUT row of raw grain (thread-level): row y of plane uv (< 0: luma)
+B200_DEV void fg_fill_row(int16_t *buf, const FgJump &J, const B200FilmGrainData &d, int uv, int cw, int y, int shift)
+{
+    unsigned seed = fg_lfsr_advance(J, d.seed ^ (uv < 0 ? 0u : uv ? 0x49d8u : 0xb524u), y * cw);
+    for (int x = 0; x < cw; x++) buf[y * GW + x] = (int16_t)fg_round2(b200_gaussian_sequence[fg_rnd(11, &seed)], shift);
+}
+
+// one wavefront step of the AR filter for LUT row y (thread-level); the caller separates steps with barriers
+B200_DEV void fg_ar_step(int16_t *buf, const int16_t *buf_y, const B200FilmGrainData &d, int uv, int subx, int suby,
+                         int cw, int ch, int y, int t, int gmin, int gmax)
+{
+    const int lag = d.ar_coeff_lag;
+    const int x = t - (lag + 1) * (y - 3) + 3;
+    if (y >= ch || x < 3 || x >= cw - 3) return;
+    const int8_t *coeff = uv < 0 ? d.ar_coeffs_y : d.ar_coeffs_uv[uv];
+    int sum = 0;
+    for (int dy = -lag; dy <= 0; dy++)
+        for (int dx = -lag; dx <= lag; dx++) {
+            if (!dx && !dy) {
+                if (uv >= 0 && d.num_y_points) {
+                    int luma = 0;
+                    const int lx = ((x - 3) << subx) + 3, ly = ((y - 3) << suby) + 3;
+                    for (int i = 0; i <= suby; i++)
+                        for (int j = 0; j <= subx; j++) luma += buf_y[(ly + i) * GW + lx + j];
+                    sum += fg_round2(luma, subx + suby) * *coeff;
+                }
+                break;
+            }
+            sum += *(coeff++) * buf[(y + dy) * GW + x + dx];
+        }
+    buf[y * GW + x] = (int16_t)iclip(buf[y * GW + x] + fg_round2(sum, (int)d.ar_coeff_shift), gmin, gmax);
+}
+
+B200_DEV int fg_ar_steps(const B200FilmGrainData &d, int cw, int ch) { return (cw - 6) + (d.ar_coeff_lag + 1) * (ch - 3 - 1); }
+
+// grain LUT of one plane; buf / buf_y are int16 working copies (pitch GW) in shared or global memory. Called by a whole
+// CTA of >= 73 threads (Level 1: one plane per launch).
+B200_DEV void fg_generate(int16_t *buf, const int16_t *buf_y, const B200FilmGrainData &d, int uv, int subx, int suby, int b8, FgJump &J)
 {
     const int cw = uv >= 0 && subx ? 44 : GW, ch = uv >= 0 && suby ? 38 : GH;
     const int shift = 4 - b8 + d.grain_scale_shift;
     const int gmin = -(128 << b8), gmax = (128 << b8) - 1;
-    if (threadIdx.x == 0) {
-        unsigned seed = d.seed ^ (uv < 0 ? 0u : uv ? 0x49d8u : 0xb524u);
-        for (int y = 0; y < ch; y++)
-            for (int x = 0; x < cw; x++)
-                buf[y * GW + x] = (int16_t)fg_round2(b200_gaussian_sequence[fg_rnd(11, &seed)], shift);
-    }
+    fg_build_jump(J);
+    if ((int)threadIdx.x < ch) fg_fill_row(buf, J, d, uv, cw, threadIdx.x, shift);
     __syncthreads();
-    const int lag = d.ar_coeff_lag;
-    const int8_t *coeffs = uv < 0 ? d.ar_coeffs_y : d.ar_coeffs_uv[uv];
-    // thread y filters row y; at step t it handles column x = t - (lag + 1) * (y - 3) + 3
-    const int y = threadIdx.x + 3;
-    const int skew = lag + 1;
-    const int steps = (cw - 6) + skew * (ch - 3 - 1);
+    const int steps = fg_ar_steps(d, cw, ch);
     for (int t = 0; t < steps; t++) {
-        const int x = t - skew * (y - 3) + 3;
-        if (y < ch && x >= 3 && x < cw - 3) {
-            const int8_t *coeff = coeffs;
-            int sum = 0;
-            for (int dy = -lag; dy <= 0; dy++)
-                for (int dx = -lag; dx <= lag; dx++) {
-                    if (!dx && !dy) {
-                        if (uv >= 0 && d.num_y_points) {
-                            int luma = 0;
-                            const int lx = ((x - 3) << subx) + 3, ly = ((y - 3) << suby) + 3;
-                            for (int i = 0; i <= suby; i++)
-                                for (int j = 0; j <= subx; j++) luma += buf_y[(ly + i) * GW + lx + j];
-                            sum += fg_round2(luma, subx + suby) * *coeff;
-                        }
-                        break;
-                    }
-                    sum += *(coeff++) * buf[(y + dy) * GW + x + dx];
-                }
-            buf[y * GW + x] = (int16_t)iclip(buf[y * GW + x] + fg_round2(sum, (int)d.ar_coeff_shift), gmin, gmax);
-        }
+        fg_ar_step(buf, buf_y, d, uv, subx, suby, cw, ch, threadIdx.x + 3, t, gmin, gmax);
         __syncthreads();
     }
 }
@@ -110,14 +162,42 @@ B200_DEV void fg_scaling(int bitdepth, const uint8_t (*points)[2], int num, uint
     }
 }
 
-__global__ void __launch_bounds__(128) fg_prep_kernel(const __grid_constant__ B200FgFrame f, int bdmax)
+constexpr int kFgPrepThreads = 256;
+__global__ void __launch_bounds__(kFgPrepThreads) fg_prep_kernel(const __grid_constant__ B200FgFrame f, int bdmax)
 {
     FgScratch *S = (FgScratch *)f.scratch;
     const B200FilmGrainData &d = f.data;
     const int bitdepth = 32 - __clz(bdmax), b8 = bitdepth - 8;
-    fg_generate(S->lut[0], nullptr, d, -1, 0, 0, b8);
-    for (int uv = 0; uv < 2; uv++)
-        if (d.num_uv_points[uv] || d.chroma_scaling_from_luma) fg_generate(S->lut[1 + uv], S->lut[0], d, uv, f.ss_hor, f.ss_ver, b8);
+    const int tid = threadIdx.x;
+    __shared__ FgJump J;
+    __shared__ int16_t sbuf[3][(GH + 1) * GW];
+    const bool has_uv[2] = { d.num_uv_points[0] || d.chroma_scaling_from_luma, d.num_uv_points[1] || d.chroma_scaling_from_luma };
+    const int cw = f.ss_hor ? 44 : GW, ch = f.ss_ver ? 38 : GH;
+    const int shift = 4 - b8 + d.grain_scale_shift;
+    const int gmin = -(128 << b8), gmax = (128 << b8) - 1;
+    fg_build_jump(J);
+    // raw grain: one thread per LUT row, the three planes side by side (threads 0.., 80.., 160..)
+    {
+        const int pl = tid < 80 ? 0 : tid < 160 ? 1 : 2, y = tid - 80 * pl;
+        if (pl == 0) { if (y < GH) fg_fill_row(sbuf[0], J, d, -1, GW, y, shift); }
+        else if (has_uv[pl - 1] && y < ch) fg_fill_row(sbuf[pl], J, d, pl - 1, cw, y, shift);
+    }
+    __syncthreads();
+    // AR filter: luma, then the two chroma planes together
+    for (int t = 0, n = fg_ar_steps(d, GW, GH); t < n; t++) {
+        if (tid < 80) fg_ar_step(sbuf[0], nullptr, d, -1, 0, 0, GW, GH, tid + 3, t, gmin, gmax);
+        __syncthreads();
+    }
+    if (has_uv[0] || has_uv[1]) {
+        for (int t = 0, n = fg_ar_steps(d, cw, ch); t < n; t++) {
+            const int pl = tid < 80 ? 0 : tid < 160 ? 1 : 2;
+            if (pl && has_uv[pl - 1]) fg_ar_step(sbuf[pl], sbuf[0], d, pl - 1, f.ss_hor, f.ss_ver, cw, ch, tid - 80 * pl + 3, t, gmin, gmax);
+            __syncthreads();
+        }
+    }
+    for (int pl = 0; pl < 3; pl++)
+        if (pl == 0 || has_uv[pl - 1])
+            for (int i = tid; i < GH * GW; i += kFgPrepThreads) S->lut[pl][i] = sbuf[pl][i];
     if (d.num_y_points || d.chroma_scaling_from_luma) fg_scaling(bitdepth, d.y_points, d.num_y_points, S->scaling[0]);
     for (int uv = 0; uv < 2; uv++)
         if (d.num_uv_points[uv]) fg_scaling(bitdepth, d.uv_points[uv], d.num_uv_points[uv], S->scaling[1 + uv]);
@@ -242,7 +322,8 @@ __global__ void __launch_bounds__(256) fg_apply_kernel(const __grid_constant__ B
 // ---- Level-1 kernels ----
 __global__ void __launch_bounds__(128) fg_gen_l1_kernel(int16_t *buf, const int16_t *buf_y, B200FilmGrainData d, int uv, int subx, int suby, int bdmax)
 {
-    fg_generate(buf, buf_y, d, uv, subx, suby, (32 - __clz(bdmax)) - 8);
+    __shared__ FgJump J;
+    fg_generate(buf, buf_y, d, uv, subx, suby, (32 - __clz(bdmax)) - 8, J);
 }
 
 template <bool HBD>
@@ -299,7 +380,7 @@ static int fg_check(int bdmax, const B200FgFrame *f, const char *who)
 int b200_fg_prep(int bdmax, const B200FgFrame *f, void *stream)
 {
     if (fg_check(bdmax, f, "b200_fg_prep")) return -2;
-    B200_LAUNCH(fg_prep_kernel, dim3(1), dim3(128), 0, (cudaStream_t)stream, *f, bdmax);
+    B200_LAUNCH(fg_prep_kernel, dim3(1), dim3(kFgPrepThreads), 0, (cudaStream_t)stream, *f, bdmax);
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;

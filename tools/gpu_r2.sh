@@ -14,7 +14,8 @@ if [[ $what == *" probe "* ]]; then
   B200_FLAG_KERNELS=1 timeout 120 python tools/peer_probe.py 2 > gpurun_out/probe_kernels.txt 2>&1; echo "probe(kernels) rc=$?"; tail -12 gpurun_out/probe_kernels.txt
 fi
 if [[ $what == *" gopprobe "* ]]; then
-  for cfg in ${B200_PROBE_CFGS:-"2 1 0" "2 1 1" "2 2 1"}; do
+  IFS=';' read -ra CFGS <<< "${B200_PROBE_CFGS:-2 1 0;2 1 1;2 2 1}"
+  for cfg in "${CFGS[@]}"; do
     timeout 90 python tools/gop_probe.py $cfg > "gpurun_out/gop_probe_${cfg// /_}.txt" 2>&1; echo "gop_probe $cfg rc=$?"; grep -E "PARITY|STALL|flags|synced|Error|error" "gpurun_out/gop_probe_${cfg// /_}.txt" | head -8
   done
 fi
