@@ -204,6 +204,7 @@ class GopPipeline:
         self.up_stream = self.down_stream = (None, None)
         self.graphs = bool(graphs)
         self.graph = [None] * self.n_sets
+        self.last_replayed = [False] * self.n_sets
         self.words = None
         if self.graphs:
             assert n_total is None, "graph replay is for endless streams (every later frame of a set looks the same)"
@@ -263,7 +264,7 @@ class GopPipeline:
         # (always outside a captured graph: these are dependencies on other frames' work)
         if self.set_seq[si] >= 0:
             prev = self.set_seq[si]
-            replayed = self.graph[si] is not None          # its last frame ran as a graph: puts and host copies were joined inside it
+            replayed = self.last_replayed[si]              # its last frame ran as a graph: puts and host copies were joined inside it
             if world > 1 and not replayed:
                 lib.check(lib.b200_stream_wait_event(st, self.ev_puts[si]), "wait")
             for d in range(1, self.n_refs + 1):                 # local frames that predicted from it
@@ -275,6 +276,7 @@ class GopPipeline:
             if self.host_io and not replayed:
                 lib.check(lib.b200_stream_wait_event(st, self.ev_down[si]), "wait")     # its output picture has left
         replay = self.graphs and self.set_seq[si] >= 0
+        self.last_replayed[si] = replay
         self.set_seq[si] = seq
         if replay:
             if self.graph[si] is None:

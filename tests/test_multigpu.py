@@ -157,11 +157,73 @@ def test_gpu_single_rank_pipeline(n_streams):
     """world = 1 on the GPU: band pipeline (events between the streams when two frames are in flight) vs the oracle"""
     from dav1d_b200 import frame, shard, get_lib
     import test_looprestoration as TLR
-    frames = _frames(8, GW, GH, 5, seed=960)
+    frames = _frames(8, GW, GH, 6, seed=960)
     exp = oracle_gop(frames)
 
     def make(S, rows):
         return frame.FrameBuffers(S, band_rows=rows)
     got = shard.decode_gop(frames, make, None, 0, 1, get_lib(), band_rows=128, n_streams=n_streams)
-    for k in range(5):
+    for k in range(6):
         assert TLR.picture_equal(frames[k], got[k], exp[k]), k
+
+
+# ------------------------------------------------------------------------------------------ GPU: CUDA graph replay
+def _endless_frames(world, n_sets, total):
+    """the frame sequence an endless pipeline decodes: rank r's set i holds a fixed synthetic frame, global frame n uses
+    set (n // world) % n_sets of rank n % world"""
+    base = {(r, i): _frames(8, GW, GH, 1, seed=970 + 16 * r + i)[0] for r in range(world) for i in range(n_sets)}
+    return base, [base[(n % world, (n // world) % n_sets)] for n in range(total)]
+
+
+def _worker_graph(rank, world, port, outdir, n_streams, per_rank):
+    sys.path.insert(0, os.path.dirname(__file__))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dav1d_b200 import frame, shard, get_lib
+        lib = get_lib()
+        n_sets = 4
+        base, _ = _endless_frames(world, n_sets, 0)
+        sets = [frame.FrameBuffers(base[(rank, i)], band_rows=64, compact=True) for i in range(n_sets)]
+        x = shard.PeerExchange(lib, dist, rank, world, base[(0, 0)]["pic"].nbytes, 2) if world > 1 else None
+        pipe = shard.GopPipeline(lib, rank, world, sets, exchange=x, n_streams=n_streams, graphs=True)
+        for _ in range(per_rank):
+            pipe.submit()
+        pipe.sync()
+        if world > 1:
+            dist.barrier()
+        # the last n_sets frames of this rank are still resident
+        out = {str((per_rank - n_sets + i) * world + rank): pipe.output(per_rank - n_sets + i) for i in range(n_sets)}
+        np.savez(os.path.join(outdir, "g%d.npz" % rank), **out)
+        if x is not None:
+            x.close()
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(240)
+@pytest.mark.parametrize("world,n_streams", [(1, 1), (1, 2), (2, 1), (2, 2)])
+def test_gpu_graph_replay_matches_oracle(tmp_path, world, n_streams):
+    """from a set's second frame on the band schedule is ONE CUDA graph launch per frame (flag values derived on the device
+    from the frame's sequence word): the pictures decoded that way equal the oracle's chained decode of the same stream"""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    per_rank = 10                      # sets are used 2.5 times: eager, captured + replayed, replayed
+    port = 29500 + (os.getpid() + world * 13 + n_streams) % 2000
+    if world == 1:
+        _worker_graph(0, 1, port, str(tmp_path), n_streams, per_rank)
+    else:
+        mp.spawn(_worker_graph, args=(world, port, str(tmp_path), n_streams, per_rank), nprocs=world, join=True)
+    import test_looprestoration as TLR
+    _, seq = _endless_frames(world, 4, per_rank * world)
+    exp = oracle_gop(seq)
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), "g%d.npz" % r))
+        assert len(z.files) == 4
+        for k in z.files:
+            assert TLR.picture_equal(seq[int(k)], z[k], exp[int(k)]), "frame %s (rank %d) differs from the oracle's chained decode" % (k, r)
