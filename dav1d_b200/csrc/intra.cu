@@ -342,6 +342,226 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
 }
 
 
+// ---- warp-per-block dataflow (round 2) -----------------------------------------------------------------------
+// The same machine with a WARP as the unit instead of a CTA: every warp of the persistent grid takes tickets on its own,
+// polls the done map, gathers its edges, predicts, transforms and publishes without a single CTA barrier. ncu on the
+// CTA-per-block kernel (profiles/r01_intra_sb_v5.md) showed half of all stall samples in bar.sync — one warp ran the
+// transform while three waited — and instruction-cache misses from 48 K inlined instructions. Here the independent
+// blocks of a wavefront run side by side inside a CTA (4 warps = 4 blocks), only __syncwarp separates the phases of a
+// block, and the 1-D transforms are out-of-line (one copy per length, shared by the row and the column pass and by all
+// block shapes). The flags are written after a device-scope fence and read with volatile loads + fence, pixels of
+// neighbours are read through L2 (ld.cg): the same publication protocol as before.
+constexpr int kIwWarps = 4;
+template <bool HBD> struct IwShared {
+    typedef typename Bd<HBD>::pixel pixel;
+    typedef typename Bd<HBD>::coef coef;
+    IpShared S;                       // edge array, scratch of the directional / filter predictors
+    int itx[32 * 65];                 // transform tile (ItxGeom: SH rows of pitch W + 1, at most 32 x 65)
+    coef cf[32 * 32];
+    int16_t ac[32 * 32];
+    pixel px[64 * 64];                // the block being reconstructed (pitch = its width)
+};
+
+template <bool HBD>
+__global__ void __launch_bounds__(kIwWarps * 32) intra_warp_kernel(const __grid_constant__ IntraBatch B, const int bdmax)
+{
+    const IntraParams &P = B.p[blockIdx.y];
+    typedef typename Bd<HBD>::pixel pixel;
+    typedef typename Bd<HBD>::coef coef;
+    typedef IpWarp G;
+#ifdef B200_EMU
+    IwShared<HBD> *const all = (IwShared<HBD> *)B200_EMU_DYN_SMEM;
+#else
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    IwShared<HBD> *const all = (IwShared<HBD> *)dyn_smem;
+#endif
+    IwShared<HBD> &W = all[threadIdx.x >> 5];
+    IpShared &S = W.S;
+    pixel *const s_px = W.px;
+    int16_t *const s_ac = W.ac;
+    coef *const s_cf = W.cf;
+    const int lane = threadIdx.x & 31;
+    const IntraFrameDev &f = P.f;
+    const int bitdepth = 32 - __clz(bdmax);
+    int *const tl = S.edge + 128;
+
+    for (;;) {
+        int ti = 0;
+        if (lane == 0) ti = atomicAdd(((int *)P.scratch), 1);
+        ti = __shfl_sync(0xffffffffu, ti, 0);
+        if (ti >= P.n) break;
+        const B200IntraTx r = P.tx[ti];
+        const int pl = r.plane, st = f.stride[pl];
+        const int tw = c_tx_w4[r.tx], th = c_tx_h4[r.tx];              // 4-sample units
+        const int w = tw * 4, h = th * 4;
+        const int x = r.x4, y = r.y4, xe = r.xend4, ye = r.yend4;
+        const bool have_left = r.flags & B200_INTRA_HAVE_LEFT, have_top = r.flags & B200_INTRA_HAVE_TOP;
+        const bool have_tr = have_top && x + tw < xe && (r.flags & B200_INTRA_TOP_HAS_RIGHT);
+        const bool have_bl = have_left && y + th < ye && (r.flags & B200_INTRA_LEFT_HAS_BOTTOM);
+        const bool is_cfl = r.mode == B200_INTRA_MODE_CFL && r.cfl_alpha != 0;
+        const bool is_ii = r.mode == B200_INTRA_MODE_II, is_resid = r.mode == B200_INTRA_MODE_RESID, is_pal = r.mode == B200_INTRA_MODE_PAL;
+        uint8_t *const dmap = (P.scratch + P.done_off[pl]);
+        const int mw = f.w4[pl];
+        const int ncf = imin(w, 32) * imin(h, 32);
+        coef *const gcf = (coef *)f.d_coef + r.coef_off;
+        // coefficients: in flight while the warp waits for its neighbours
+        if (r.eob >= 0) for (int i = lane; i < ncf; i += 32) s_cf[i] = gcf[i];
+
+        // ---- wait for the neighbours whose pixels the edge array reads
+        {
+            const int n_left = is_resid ? 0 : have_left ? imin(th, ye - y) + (have_bl ? imin(th, ye - y - th) : 0) : 0;
+            const int n_top = is_resid ? 0 : have_top ? imin(tw, xe - x) + (have_tr ? imin(tw, xe - x - tw) : 0) : 0;
+            const int n_tl = !is_resid && have_left && have_top;
+            const int self_w = imin(tw, mw - x), n_self = is_resid ? self_w * imin(th, f.h4[pl] - y) : 0;
+            const int want = is_resid ? 2 : 1;       // a residual-only record waits for its own cells to be "predicted" (2)
+            int n_luma = 0, lw4 = 0, lx4 = 0, ly4 = 0;
+            if (is_cfl) {
+                lx4 = x << f.ss_hor; ly4 = y << f.ss_ver;
+                lw4 = imin((tw - r.cfl_w_pad) << f.ss_hor, f.w4[0] - lx4);
+                const int lh4 = imin((th - r.cfl_h_pad) << f.ss_ver, f.h4[0] - ly4);
+                n_luma = lw4 * lh4;
+            }
+            for (int c = lane; c < n_left + n_top + n_tl + n_luma + n_self; c += 32) {
+                const uint8_t *cell;
+                if (c >= n_left + n_top + n_tl + n_luma) { const int k = c - n_left - n_top - n_tl - n_luma; cell = dmap + (y + k / self_w) * mw + x + k % self_w; }
+                else if (c < n_left) cell = dmap + (y + c) * mw + x - 1;
+                else if (c < n_left + n_top) cell = dmap + (y - 1) * mw + x + (c - n_left);
+                else if (c < n_left + n_top + n_tl) cell = dmap + (y - 1) * mw + x - 1;
+                else { const int k = c - n_left - n_top - n_tl; cell = (P.scratch + P.done_off[0]) + (ly4 + k / lw4) * f.w4[0] + lx4 + k % lw4; }
+                unsigned ns = B200_POLL_NS0, spins = 0;
+                while (ld_cell(cell) != want) {
+                    __nanosleep(ns); if (ns < B200_POLL_NSMAX) ns += ns >> 1;
+                    if (++spins > (1u << 23)) intra_stuck();      // seconds: records are not in a valid order
+                }
+            }
+            __threadfence();              // acquire side
+            __syncwarp();
+        }
+
+        pixel *const dst = (pixel *)f.pic + r.dst_off;
+        // ---- dav1d_prepare_intra_edges: mode conversion (:97-120)
+        int mode = r.mode, angle = r.angle;
+        if (is_ii) { mode = r.angle; angle = 0; }                              // inter-intra: the predictor is in `angle`
+        if (is_resid || is_pal) mode = 0;
+        if (mode == B200_INTRA_MODE_CFL) mode = 0;                             // DC_PRED (:1446, :1373)
+        if (mode >= 1 && mode <= 8) {                                          // VERT_PRED .. VERT_LEFT_PRED
+            const int base = mode == 1 ? 90 : mode == 2 ? 180 : mode == 3 ? 45 : mode == 4 ? 135 : mode == 5 ? 113
+                           : mode == 6 ? 157 : mode == 7 ? 203 : 67;
+            angle = base + 3 * angle;
+            if (angle <= 90) mode = angle < 90 && have_top ? B200_Z1_PRED : B200_VERT_PRED;
+            else if (angle < 180) mode = B200_Z2_PRED;
+            else mode = angle > 180 && have_left ? B200_Z3_PRED : B200_HOR_PRED;
+        } else if (mode == 0) {
+            mode = have_left ? (have_top ? B200_DC_PRED : B200_LEFT_DC_PRED) : (have_top ? B200_TOP_DC_PRED : B200_DC_128_PRED);
+        } else if (mode == 12) {
+            mode = have_left ? (have_top ? B200_PAETH_PRED : B200_HOR_PRED) : (have_top ? B200_VERT_PRED : B200_DC_128_PRED);
+        }
+        // ---- edge gather (every part is filled; the predictors read only what the reference fills)
+        if (!is_resid && !is_pal) {
+            const pixel *const top = dst - st;
+            const int half = (1 << bitdepth) >> 1;
+            const int lpx = imin(h, (ye - y) << 2), lpx2 = imin(h, (ye - y - th) << 2);
+            const int tpx = imin(w, (xe - x) << 2), tpx2 = imin(w, (xe - x - tw) << 2);
+            const int left_fill = have_top ? ld_px<HBD>(top) : half + 1;
+            const int top_fill = have_left ? ld_px<HBD>(dst - 1) : half - 1;
+            for (int i = lane; i < 2 * h; i += 32) {                            // tl[-(1+i)]: left, then bottom-left
+                int v;
+                if (i < h) v = have_left ? ld_px<HBD>(dst + (ptrdiff_t)imin(i, lpx - 1) * st - 1) : left_fill;
+                else if (have_bl) v = ld_px<HBD>(dst + (ptrdiff_t)(h + imin(i - h, lpx2 - 1)) * st - 1);
+                else v = have_left ? ld_px<HBD>(dst + (ptrdiff_t)(lpx - 1) * st - 1) : left_fill;
+                tl[-(1 + i)] = v;
+            }
+            for (int i = lane; i < 2 * w; i += 32) {                            // tl[1+i]: top, then top-right
+                int v;
+                if (i < w) v = have_top ? ld_px<HBD>(top + imin(i, tpx - 1)) : top_fill;
+                else if (have_tr) v = ld_px<HBD>(top + w + imin(i - w, tpx2 - 1));
+                else v = have_top ? ld_px<HBD>(top + tpx - 1) : top_fill;
+                tl[1 + i] = v;
+            }
+            if (lane == 0)
+                tl[0] = have_left ? (have_top ? ld_px<HBD>(top - 1) : ld_px<HBD>(dst - 1)) : (have_top ? ld_px<HBD>(top) : half);
+            // CFL: the (sub-sampled, padded) luma block -> s_ac, mean removed
+            if (is_cfl) {
+                const pixel *ypx = (const pixel *)f.pic + r.luma_off;
+                const int ssh = f.ss_hor, ssv = f.ss_ver, ys = f.stride[0];
+                int part = 0;
+                for (int i = lane; i < w * h; i += 32) {
+                    const int yy = i / w, xx = i - yy * w;
+                    const int sy = imin(yy, h - 4 * r.cfl_h_pad - 1), sx = imin(xx, w - 4 * r.cfl_w_pad - 1);
+                    const pixel *p = ypx + (ptrdiff_t)(sy << ssv) * ys + (sx << ssh);
+                    int sacc = ld_px<HBD>(p);
+                    if (ssh) sacc += ld_px<HBD>(p + 1);
+                    if (ssv) { sacc += ld_px<HBD>(p + ys); if (ssh) sacc += ld_px<HBD>(p + ys + 1); }
+                    sacc <<= 1 + !ssv + !ssh;
+                    s_ac[i] = (int16_t)sacc;
+                    part += sacc;
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                const int log2sz = (__ffs(w) - 1) + (__ffs(h) - 1);
+                const int dc = (part + ((1 << log2sz) >> 1)) >> log2sz;
+                __syncwarp();
+                for (int i = lane; i < w * h; i += 32) s_ac[i] = (int16_t)(s_ac[i] - dc);
+            }
+            __syncwarp();
+            if (lane == 0 && mode == B200_Z2_PRED && tw + th >= 6 && (r.angle_flags & 1024))
+                tl[0] = ((tl[-1] + tl[1]) * 5 + tl[0] * 6 + 8) >> 4;
+            __syncwarp();
+        }
+
+        // ---- predict into the shared tile
+        if (is_resid) {
+            // residual only: the tile is what the inter-intra record of this block left in the picture (another SM wrote it)
+            for (int i = lane; i < w * h; i += 32) { const int yy = i / w, xx = i - yy * w; s_px[i] = (pixel)ld_px<HBD>(dst + (ptrdiff_t)yy * st + xx); }
+        } else if (is_pal) {
+            // palette: 8 colours, then the index map (two 4-bit indices per byte, low nibble first)
+            const pixel *const colours = (const pixel *)(f.pal + r.luma_off);
+            const uint8_t *const idx = f.pal + r.luma_off + 8 * sizeof(pixel);
+            for (int i = lane; i < w * h; i += 32) s_px[i] = colours[(idx[i >> 1] >> ((i & 1) * 4)) & 7];
+        } else if (is_cfl) {
+            ipred_cfl_pred_body<HBD, G>(S, s_px, w, w, h, mode, r.cfl_alpha, s_ac, bdmax);
+        } else {
+            const int a = (mode == B200_FILTER_PRED ? r.angle : angle) | r.angle_flags;
+            ipred_pred_body<HBD, G>(S, s_px, w, w, h, mode, a, r.max_w, r.max_h, bdmax);
+        }
+        __syncwarp();
+        if (is_ii) {
+            // inter-intra: blend the intra prediction into the inter prediction already in the picture (earlier launch),
+            // dst = (inter * (64 - m) + intra * m + 32) >> 6 (dsp->mc.blend, reference src/mc_tmpl.c:683-694)
+            const uint8_t *const msk = f.mask + r.luma_off;
+            for (int i = lane; i < w * h; i += 32) {
+                const int yy = i / w, xx = i - yy * w, m = msk[i];
+                s_px[i] = (pixel)(((int)dst[(ptrdiff_t)yy * st + xx] * (64 - m) + (int)s_px[i] * m + 32) >> 6);
+            }
+            __syncwarp();
+        }
+
+        // ---- residual, added in the shared tile
+        if (r.eob >= 0) {
+            switch (r.tx) {
+#define X(TX, TW, TH, SH) case TX: itx_add_warp<TW, TH, TX, SH, HBD>(W.itx, s_cf, s_px, TW, r.eob, r.txtp, bdmax); break;
+            B200_ITX_SIZES(X)
+#undef X
+            }
+            if (f.zero_coefs)
+                for (int i = lane; i < ncf; i += 32) gcf[i] = 0;
+        }
+        // ---- write the block, publish
+        for (int i = lane; i < w * h; i += 32) {
+            const int yy = i / w, xx = i - yy * w;
+            dst[(ptrdiff_t)yy * st + xx] = s_px[i];
+        }
+        __syncwarp();
+        {
+            const int cw = imin(tw, mw - x), chh = imin(th, f.h4[pl] - y);
+            const uint8_t state = (is_ii || is_pal) && r.cfl_alpha ? 2 : 1;   // 2: predicted, the block's residual records follow
+            if (lane < cw * chh || lane == 0) __threadfence();                  // the warp barrier above ordered every lane's stores before it
+            for (int c = lane; c < cw * chh; c += 32) *(volatile uint8_t *)(dmap + (y + c / cw) * mw + x + c % cw) = state;
+        }
+        __syncwarp();
+    }
+}
+
 // ---- superblock-granular variant -------------------------------------------------------------------------
 // A CTA takes a whole 64x64 superblock (ticket order = wavefront order of superblocks) and reconstructs its
 // transform blocks one after the other in decode order on a shared-memory canvas (superblock + the row above,
@@ -589,6 +809,7 @@ int b200_intra_frames(int bdmax, const B200IntraFrame *frames, const B200IntraTx
 {
     if (bdmax != 255 && bdmax != 1023 && bdmax != 4095) { b200_set_error("b200_intra_frames: bad bitdepth_max"); return -2; }
     const size_t px = bdmax > 255 ? 2 : 1;
+    static const bool use_cta_kernel = getenv("B200_INTRA_CTA") != nullptr;      // round-1 CTA-per-block kernel (A/B measurements)
     for (int mode = 0; mode < 2; mode++)          // 0: per-transform-block dataflow, 1: superblock-granular
     for (int base = 0; base < n_frames; ) {
         IntraBatch B;
@@ -621,7 +842,20 @@ int b200_intra_frames(int bdmax, const B200IntraFrame *frames, const B200IntraTx
         }
         base = i;
         if (!nb) continue;
-        if (mode == 0) {
+        if (mode == 0 && !use_cta_kernel) {
+            // warp-per-block: a CTA carries kIwWarps blocks, so the same number of blocks in flight needs a quarter of the CTAs
+            const size_t iw = kIwWarps * (bdmax > 255 ? sizeof(IwShared<true>) : sizeof(IwShared<false>));
+#ifndef B200_EMU
+            static bool iw_attr[2] = { false, false };
+            if (!iw_attr[bdmax > 255]) {
+                if (bdmax > 255) B200_CUDA_OK(cudaFuncSetAttribute(intra_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iw));
+                else B200_CUDA_OK(cudaFuncSetAttribute(intra_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iw));
+                iw_attr[bdmax > 255] = true;
+            }
+#endif
+            if (bdmax > 255) { auto k = intra_warp_kernel<true>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIwWarps * 32), iw, (cudaStream_t)stream, B, bdmax); }
+            else { auto k = intra_warp_kernel<false>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIwWarps * 32), iw, (cudaStream_t)stream, B, bdmax); }
+        } else if (mode == 0) {
             if (bdmax > 255) { auto k = intra_frame_kernel<true>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIpT), 0, (cudaStream_t)stream, B, bdmax); }
             else { auto k = intra_frame_kernel<false>; B200_LAUNCH(k, dim3(grid, nb), dim3(kIpT), 0, (cudaStream_t)stream, B, bdmax); }
         } else {

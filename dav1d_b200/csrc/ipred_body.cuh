@@ -1,5 +1,5 @@
 // Device-side bodies of the intra predictors, shared by the batched ipred kernel (ipred.cu) and the fused
-// intra reconstruction kernel (intra.cu). A CTA of kIpT threads works on one block; the edge array lives in
+// intra reconstruction kernel (intra.cu). A group of threads (a CTA of kIpT threads, or one warp) works on one block; the edge array lives in
 // shared memory as ints (tl = IpShared::edge + 128, valid for tl[-(w+h) .. w+h]).
 #pragma once
 #include "host_util.h"
@@ -15,6 +15,19 @@ namespace b200 {
 #define B200_IPT 128
 #endif
 constexpr int kIpT = B200_IPT;   // threads per block
+
+// who works on a block: a whole CTA of kIpT threads (batched ipred kernel, round-1 intra kernels) or one warp (the
+// warp-per-block intra kernel: independent blocks of a wavefront side by side in one CTA, no CTA barriers)
+struct IpCta {
+    static B200_DEV int tid() { return threadIdx.x; }
+    static constexpr int size = kIpT;
+    static B200_DEV void sync() { __syncthreads(); }
+};
+struct IpWarp {
+    static B200_DEV int tid() { return threadIdx.x & 31; }
+    static constexpr int size = 32;
+    static B200_DEV void sync() { __syncwarp(); }
+};
 
 B200_DEV int ip_filter_strength(int wh, int angle, int is_sm) {
     if (is_sm) {
@@ -34,8 +47,9 @@ B200_DEV int ip_upsample(int wh, int angle, int is_sm) { return angle < 40 && wh
 static __constant__ uint8_t c_edge_kernel[3][5] = { { 0, 4, 8, 4, 0 }, { 0, 5, 6, 5, 0 }, { 2, 4, 4, 4, 2 } };
 
 // out[i], i in [0, sz): in[clamp(i)] or the 5-tap smoothed value inside [lim_from, lim_to)
+template <class G = IpCta>
 B200_DEV void ip_edge_filter(int *out, int sz, int lim_from, int lim_to, const int *in, int from, int to, int strength) {
-    for (int i = threadIdx.x; i < sz; i += kIpT) {
+    for (int i = G::tid(); i < sz; i += G::size) {
         if (i < imin(sz, lim_from) || i >= imin(lim_to, sz)) { out[i] = in[iclip(i, from, to - 1)]; continue; }
         int s = 0;
 #pragma unroll
@@ -43,8 +57,9 @@ B200_DEV void ip_edge_filter(int *out, int sz, int lim_from, int lim_to, const i
         out[i] = (s + 8) >> 4;
     }
 }
+template <class G = IpCta>
 B200_DEV void ip_edge_upsample(int *out, int hsz, const int *in, int from, int to, int bdmax) {
-    for (int i = threadIdx.x; i < hsz; i += kIpT) {
+    for (int i = G::tid(); i < hsz; i += G::size) {
         out[i * 2] = in[iclip(i, from, to - 1)];
         if (i < hsz - 1) {
             const int s = -in[iclip(i - 1, from, to - 1)] + 9 * in[iclip(i, from, to - 1)] +
@@ -79,16 +94,16 @@ struct IpShared {
 };
 
 // cfl_ac: (sub-sampled, padded) luma -> zero-mean int16 ac[w * h]   (reference src/ipred_tmpl.c:657-715)
-template <bool HBD>
+template <bool HBD, class G = IpCta>
 B200_DEV void ipred_cfl_ac_body(IpShared &S, const typename Bd<HBD>::pixel *ypx, int ys, int ssh, int ssv, int w, int h,
                                 int w_pad, int h_pad, int16_t *ac)
 {
     typedef typename Bd<HBD>::pixel pixel;
-    const int tid = threadIdx.x;
+    const int tid = G::tid();
     int *const s_tile = S.tile;
     int &s_dc = S.dc;
         int part = 0;
-        for (int i = tid; i < w * h; i += kIpT) {
+        for (int i = tid; i < w * h; i += G::size) {
             const int y = i / w, x = i - y * w;
             const int sy = imin(y, h - 4 * h_pad - 1), sx = imin(x, w - 4 * w_pad - 1);
             const pixel *p = ypx + (ptrdiff_t)(sy << ssv) * ys + (sx << ssh);
@@ -100,31 +115,31 @@ B200_DEV void ipred_cfl_ac_body(IpShared &S, const typename Bd<HBD>::pixel *ypx,
             part += s;
         }
         s_tile[tid] = part;
-        __syncthreads();
+        G::sync();
         if (tid == 0) {
             const int log2sz = (__ffs(w) - 1) + (__ffs(h) - 1);
             int sum = (1 << log2sz) >> 1;
-            for (int i = 0; i < kIpT; i++) sum += s_tile[i];
+            for (int i = 0; i < G::size; i++) sum += s_tile[i];
             s_dc = sum >> log2sz;
         }
-        __syncthreads();
+        G::sync();
         const int dc = s_dc;
-        for (int i = tid; i < w * h; i += kIpT) ac[i] = (int16_t)(ac[i] - dc);
+        for (int i = tid; i < w * h; i += G::size) ac[i] = (int16_t)(ac[i] - dc);
 }
 
 // cfl_pred: dc of the edges + alpha * ac   (reference src/ipred_tmpl.c:71-84, 717-760)
-template <bool HBD>
+template <bool HBD, class G = IpCta>
 B200_DEV void ipred_cfl_pred_body(IpShared &S, typename Bd<HBD>::pixel *dst, int st, int w, int h, int mode, int alpha,
                                   const int16_t *ac, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
-    const int tid = threadIdx.x;
+    const int tid = G::tid();
     int *const tl = S.edge + 128;
     int &s_dc = S.dc;
         if (tid == 0) s_dc = ip_dc(tl, w, h, mode, bdmax, HBD);
-        __syncthreads();
+        G::sync();
         const int dc = s_dc;
-        for (int i = tid; i < w * h; i += kIpT) {
+        for (int i = tid; i < w * h; i += G::size) {
             const int y = i / w, x = i - y * w;
             const int diff = alpha * ac[i];
             const int m = (iabs(diff) + 32) >> 6;
@@ -133,12 +148,12 @@ B200_DEV void ipred_cfl_pred_body(IpShared &S, typename Bd<HBD>::pixel *dst, int
 }
 
 // the 14 predictors; `angle` carries dav1d's flags (|512 smooth neighbour, |1024 edge filter enabled), FILTER: index
-template <bool HBD>
+template <bool HBD, class G = IpCta>
 B200_DEV void ipred_pred_body(IpShared &S, typename Bd<HBD>::pixel *dst, int st, int w, int h, int mode, int angle_in,
                               int max_w, int max_h, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
-    const int tid = threadIdx.x;
+    const int tid = G::tid();
     int *const tl = S.edge + 128;
     int *const s_aux = S.aux;
     int *const s_tile = S.tile;
@@ -148,18 +163,18 @@ B200_DEV void ipred_pred_body(IpShared &S, typename Bd<HBD>::pixel *dst, int st,
     switch (mode) {
     case B200_DC_PRED: case B200_TOP_DC_PRED: case B200_LEFT_DC_PRED: case B200_DC_128_PRED: {
         if (tid == 0) s_dc = ip_dc(tl, w, h, mode, bdmax, HBD);
-        __syncthreads();
+        G::sync();
         const int dc = s_dc;
-        for (int i = tid; i < w * h; i += kIpT) dst[(ptrdiff_t)(i / w) * st + (i % w)] = (pixel)dc;
+        for (int i = tid; i < w * h; i += G::size) dst[(ptrdiff_t)(i / w) * st + (i % w)] = (pixel)dc;
         break; }
     case B200_VERT_PRED:
-        for (int i = tid; i < w * h; i += kIpT) dst[(ptrdiff_t)(i / w) * st + (i % w)] = (pixel)tl[1 + (i % w)];
+        for (int i = tid; i < w * h; i += G::size) dst[(ptrdiff_t)(i / w) * st + (i % w)] = (pixel)tl[1 + (i % w)];
         break;
     case B200_HOR_PRED:
-        for (int i = tid; i < w * h; i += kIpT) dst[(ptrdiff_t)(i / w) * st + (i % w)] = (pixel)tl[-(1 + i / w)];
+        for (int i = tid; i < w * h; i += G::size) dst[(ptrdiff_t)(i / w) * st + (i % w)] = (pixel)tl[-(1 + i / w)];
         break;
     case B200_PAETH_PRED:
-        for (int i = tid; i < w * h; i += kIpT) {
+        for (int i = tid; i < w * h; i += G::size) {
             const int y = i / w, x = i - y * w;
             const int l = tl[-(y + 1)], t = tl[1 + x], c = tl[0], base = l + t - c;
             const int ld = iabs(l - base), td = iabs(t - base), cd = iabs(c - base);
@@ -168,7 +183,7 @@ B200_DEV void ipred_pred_body(IpShared &S, typename Bd<HBD>::pixel *dst, int st,
         break;
     case B200_SMOOTH_PRED: case B200_SMOOTH_V_PRED: case B200_SMOOTH_H_PRED: {
         const int right = tl[w], bottom = tl[-h];
-        for (int i = tid; i < w * h; i += kIpT) {
+        for (int i = tid; i < w * h; i += G::size) {
             const int y = i / w, x = i - y * w;
             const int wv = b200_sm_weights[h + y], wh = b200_sm_weights[w + x];
             int v;
@@ -184,12 +199,12 @@ B200_DEV void ipred_pred_body(IpShared &S, typename Bd<HBD>::pixel *dst, int st,
         const int up = eief ? ip_upsample(w + h, 90 - angle, is_sm) : 0;
         const int fs = (!up && eief) ? ip_filter_strength(w + h, 90 - angle, is_sm) : 0;
         const int *top; int max_base_x;
-        if (up) { ip_edge_upsample(s_aux, w + h, &tl[1], -1, w + imin(w, h), bdmax); top = s_aux; max_base_x = 2 * (w + h) - 2; dx <<= 1; }
-        else if (fs) { ip_edge_filter(s_aux, w + h, 0, w + h, &tl[1], -1, w + imin(w, h), fs); top = s_aux; max_base_x = w + h - 1; }
+        if (up) { ip_edge_upsample<G>(s_aux, w + h, &tl[1], -1, w + imin(w, h), bdmax); top = s_aux; max_base_x = 2 * (w + h) - 2; dx <<= 1; }
+        else if (fs) { ip_edge_filter<G>(s_aux, w + h, 0, w + h, &tl[1], -1, w + imin(w, h), fs); top = s_aux; max_base_x = w + h - 1; }
         else { top = &tl[1]; max_base_x = w + imin(w, h) - 1; }
-        __syncthreads();
+        G::sync();
         const int inc = 1 + up;
-        for (int i = tid; i < w * h; i += kIpT) {
+        for (int i = tid; i < w * h; i += G::size) {
             const int y = i / w, x = i - y * w;
             const int xpos = dx * (y + 1), frac = xpos & 0x3E, base = (xpos >> 6) + x * inc;
             dst[(ptrdiff_t)y * st + x] = (pixel)(base < max_base_x ? (top[base] * (64 - frac) + top[base + 1] * frac + 32) >> 6 : top[max_base_x]);
@@ -201,24 +216,24 @@ B200_DEV void ipred_pred_body(IpShared &S, typename Bd<HBD>::pixel *dst, int st,
         const int up_l = eief ? ip_upsample(w + h, 180 - angle, is_sm) : 0;
         const int up_a = eief ? ip_upsample(w + h, angle - 90, is_sm) : 0;
         int *const e = s_aux + 128;               // e[-2h .. 2w]
-        if (up_a) { ip_edge_upsample(e, w + 1, tl, 0, w + 1, bdmax); dx <<= 1; }
+        if (up_a) { ip_edge_upsample<G>(e, w + 1, tl, 0, w + 1, bdmax); dx <<= 1; }
         else {
             const int fs = eief ? ip_filter_strength(w + h, angle - 90, is_sm) : 0;
-            if (fs) ip_edge_filter(&e[1], w, 0, b.max_w, &tl[1], -1, w, fs);
-            else for (int i = tid; i < w; i += kIpT) e[1 + i] = tl[1 + i];
+            if (fs) ip_edge_filter<G>(&e[1], w, 0, b.max_w, &tl[1], -1, w, fs);
+            else for (int i = tid; i < w; i += G::size) e[1 + i] = tl[1 + i];
         }
-        if (up_l) { ip_edge_upsample(&e[-h * 2], h + 1, &tl[-h], 0, h + 1, bdmax); dy <<= 1; }
+        if (up_l) { ip_edge_upsample<G>(&e[-h * 2], h + 1, &tl[-h], 0, h + 1, bdmax); dy <<= 1; }
         else {
             const int fs = eief ? ip_filter_strength(w + h, 180 - angle, is_sm) : 0;
-            if (fs) ip_edge_filter(&e[-h], h, h - b.max_h, h, &tl[-h], 0, h + 1, fs);
-            else for (int i = tid; i < h; i += kIpT) e[-h + i] = tl[-h + i];
+            if (fs) ip_edge_filter<G>(&e[-h], h, h - b.max_h, h, &tl[-h], 0, h + 1, fs);
+            else for (int i = tid; i < h; i += G::size) e[-h + i] = tl[-h + i];
         }
-        __syncthreads();
+        G::sync();
         if (tid == 0) e[0] = tl[0];               // after the upsamplers (which also write e[0])
-        __syncthreads();
+        G::sync();
         const int inc_x = 1 + up_a;
         const int *left = &e[-(1 + up_l)];
-        for (int i = tid; i < w * h; i += kIpT) {
+        for (int i = tid; i < w * h; i += G::size) {
             const int y = i / w, x = i - y * w;
             const int xpos = ((1 + up_a) << 6) - dx * (y + 1);
             const int base_x = (xpos >> 6) + x * inc_x, frac_x = xpos & 0x3E;
@@ -238,12 +253,12 @@ B200_DEV void ipred_pred_body(IpShared &S, typename Bd<HBD>::pixel *dst, int st,
         const int up = eief ? ip_upsample(w + h, angle - 180, is_sm) : 0;
         const int fs = (!up && eief) ? ip_filter_strength(w + h, angle - 180, is_sm) : 0;
         const int *left; int max_base_y;
-        if (up) { ip_edge_upsample(s_aux, w + h, &tl[-(w + h)], imax(w - h, 0), w + h + 1, bdmax); left = &s_aux[2 * (w + h) - 2]; max_base_y = 2 * (w + h) - 2; dy <<= 1; }
-        else if (fs) { ip_edge_filter(s_aux, w + h, 0, w + h, &tl[-(w + h)], imax(w - h, 0), w + h + 1, fs); left = &s_aux[w + h - 1]; max_base_y = w + h - 1; }
+        if (up) { ip_edge_upsample<G>(s_aux, w + h, &tl[-(w + h)], imax(w - h, 0), w + h + 1, bdmax); left = &s_aux[2 * (w + h) - 2]; max_base_y = 2 * (w + h) - 2; dy <<= 1; }
+        else if (fs) { ip_edge_filter<G>(s_aux, w + h, 0, w + h, &tl[-(w + h)], imax(w - h, 0), w + h + 1, fs); left = &s_aux[w + h - 1]; max_base_y = w + h - 1; }
         else { left = &tl[-1]; max_base_y = h + imin(w, h) - 1; }
-        __syncthreads();
+        G::sync();
         const int inc = 1 + up;
-        for (int i = tid; i < w * h; i += kIpT) {
+        for (int i = tid; i < w * h; i += G::size) {
             const int y = i / w, x = i - y * w;
             const int ypos = dy * (x + 1), frac = ypos & 0x3E, base = (ypos >> 6) + y * inc;
             dst[(ptrdiff_t)y * st + x] = (pixel)(base < max_base_y ? (left[-base] * (64 - frac) + left[-(base + 1)] * frac + 32) >> 6 : left[-max_base_y]);
@@ -253,7 +268,7 @@ B200_DEV void ipred_pred_body(IpShared &S, typename Bd<HBD>::pixel *dst, int st,
         const int8_t *flt = b200_filter_intra_taps[angle & 511];
         const int uw = w >> 2, uh = h >> 1;
         for (int d = 0; d < uw + uh - 1; d++) {
-            for (int ux = tid; ux < uw; ux += kIpT) {
+            for (int ux = tid; ux < uw; ux += G::size) {
                 const int uy = d - ux;
                 if (uy < 0 || uy >= uh) continue;
                 const int x = ux * 4, y = uy * 2;
@@ -272,7 +287,7 @@ B200_DEV void ipred_pred_body(IpShared &S, typename Bd<HBD>::pixel *dst, int st,
                     dst[(ptrdiff_t)(y + (k >> 2)) * st + x + (k & 3)] = (pixel)v;
                 }
             }
-            __syncthreads();
+            G::sync();
         }
         break; }
     }

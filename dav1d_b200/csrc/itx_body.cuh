@@ -238,6 +238,81 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
     }
 }
 
+// One transform block by ONE warp (the warp-per-block intra kernel): the same two passes as itx_add_body — lane = coefficient
+// row, padded tile `t` (>= SH * (W + 1) words), lane = picture column (64-wide blocks: two rounds) — through the out-of-line
+// 1-D passes, so that all block sizes of a kernel share one copy of each butterfly network.
+template <int W, int H, int TX, int SHIFT, bool HBD>
+B200_DEV void itx_add_warp(int *const t, typename Bd<HBD>::coef *const cf, typename Bd<HBD>::pixel *const dst, const int stride,
+                           const int eob, const int txtp, const int bitdepth_max)
+{
+    typedef ItxGeom<W, H> G;
+    typedef typename Bd<HBD>::pixel pixel;
+    const int lane = threadIdx.x & 31;
+    constexpr int rnd = (1 << SHIFT) >> 1;
+    const bool is_wht = (W == 4 && H == 4) && txtp == B200_WHT_WHT;
+    const bool dc_only = !is_wht && eob < (txtp == 0 ? 1 : 0);
+    int row_lo, col_lo;
+    if (HBD) { row_lo = (int)((unsigned)~bitdepth_max << 7); col_lo = (int)((unsigned)~bitdepth_max << 5); }
+    else row_lo = col_lo = -32768;
+    const int row_hi = ~row_lo, col_hi = ~col_lo;
+    const int t_first = is_wht ? 0 : c_tx_first[txtp & 15];
+    const int t_second = is_wht ? 0 : c_tx_second[txtp & 15];
+    if (dc_only) {
+        int dc = (int)cf[0];
+        if (G::RECT2) dc = (dc * 181 + 128) >> 8;
+        dc = (dc * 181 + 128) >> 8;
+        dc = (dc + rnd) >> SHIFT;
+        dc = (dc * 181 + 128 + 2048) >> 12;
+        for (int i = lane; i < W * H; i += 32) {
+            pixel *p = dst + (ptrdiff_t)(i / W) * stride + (i % W);
+            *p = (pixel)iclip((int)*p + dc, 0, bitdepth_max);
+        }
+        return;
+    }
+    if (lane < G::SH) {
+        const int y = lane;
+        if (is_wht) {
+            if constexpr (W == 4 && H == 4) {
+                int c[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) c[x] = (int)cf[y + x * 4] >> 2;
+                iwht4(c);
+#pragma unroll
+                for (int x = 0; x < 4; x++) t[y * G::P + x] = c[x];
+            }
+        } else {
+            int last;       // rows past this bound are zero by definition (reference src/itx_tmpl.c:86-105)
+            if (t_second == TX1D_IDENTITY && t_first != TX1D_IDENTITY) last = imin(G::SH - 1, eob);
+            else if (t_first == TX1D_IDENTITY && t_second != TX1D_IDENTITY) last = eob >> (G::LW + 2);
+            else last = b200_lnz_col[b200_lnz_col_off[TX] + eob];
+            if (y <= last) itx_row_pass_shared<W, HBD>(cf + y, G::SH, t + y * G::P, G::RECT2, SHIFT, t_first, row_lo, row_hi, col_lo, col_hi);
+            else {
+#pragma unroll
+                for (int x = 0; x < W; x++) t[y * G::P + x] = 0;
+            }
+        }
+    }
+    __syncwarp();
+    for (int x = lane; x < W; x += 32) {
+        if (is_wht) {
+            if constexpr (W == 4 && H == 4) {
+                int c[4];
+#pragma unroll
+                for (int y = 0; y < 4; y++) c[y] = t[y * G::P + x];
+                iwht4(c);
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    pixel *p = dst + (ptrdiff_t)y * stride + x;
+                    *p = (pixel)iclip((int)*p + c[y], 0, bitdepth_max);
+                }
+            }
+        } else {
+            itx_col_pass_shared<H, HBD>(t + x, G::P, dst + x, stride, t_second, col_lo, col_hi, bitdepth_max);
+        }
+    }
+    __syncwarp();
+}
+
 // tx -> (w, h, inter-pass shift): reference src/itx_tmpl.c:160-178
 #define B200_ITX_SIZES(X) \
     X(4, 64, 64, 2) X(11, 32, 64, 1) X(12, 64, 32, 1) X(17, 16, 64, 2) X(18, 64, 16, 2) X(3, 32, 32, 2) X(9, 16, 32, 1) \

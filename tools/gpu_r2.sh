@@ -34,6 +34,22 @@ if [[ $what == *" bench1 "* ]]; then
   run_bench n1_2fl_b256 B200_FRAMES_IN_FLIGHT=2 B200_BAND_ROWS=256 python bench.py --steps 20 --warmup 5
   run_bench n1_1fl_b128 B200_FRAMES_IN_FLIGHT=1 B200_BAND_ROWS=128 python bench.py --steps 20 --warmup 5
 fi
+if [[ $what == *" tests2 "* ]]; then
+  timeout 900 python -m pytest tests/test_intra.py tests/test_filmgrain.py tests/test_frame.py tests/test_mc.py tests/test_ipred.py -x -q -m gpu --timeout 300 > gpurun_out/pytest_tests2.txt 2>&1; echo "tests2 rc=$?"; tail -4 gpurun_out/pytest_tests2.txt
+fi
+if [[ $what == *" benchA "* ]]; then
+  run_bench n1_default python bench.py --steps 20 --warmup 5
+  run_bench n1_fused B200_FUSED=1 python bench.py --steps 20 --warmup 5
+  run_bench intra python bench.py --workload 1080p8_intra --steps 10 --warmup 3
+  run_bench intra_cta B200_INTRA_CTA=1 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
+  run_bench 4k10 python bench.py --workload 4k10_full --steps 20 --warmup 5
+fi
+if [[ $what == *" profmc "* ]]; then
+  export B200_SKIP_PARITY=1 B200_MIN_TIMED_S=0.005 B200_NSETS=2 B200_DISTINCT=2
+  timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 40 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:mc_pred_kernel -s 3 -c 2 -f -o gpurun_out/prof_mc python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_mc.log 2>&1; echo "ncu mc rc=$?"
+  unset B200_SKIP_PARITY B200_MIN_TIMED_S B200_NSETS B200_DISTINCT
+fi
 if [[ $what == *" benchref "* ]]; then
   run_bench ref python bench.py --impl reference --steps 3 --warmup 1
 fi
