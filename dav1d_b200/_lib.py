@@ -160,6 +160,16 @@ class FrameBand(C.Structure):
                [("itx", (C.c_int32 * 2) * 19)]
 
 
+class PutRange(C.Structure):
+    """struct B200PutRange"""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p * 2), ("bytes", C.c_uint64)]
+
+
+class PutFlag(C.Structure):
+    """struct B200PutFlag"""
+    _fields_ = [("flag", C.c_void_p), ("base", C.c_void_p), ("sub", C.c_int32), ("shift", C.c_int32), ("add", C.c_int32), ("pad", C.c_int32)]
+
+
 class Xfer(C.Structure):
     _fields_ = [("host", C.c_void_p), ("dev", C.c_void_p), ("bytes", C.c_uint64)]
 
@@ -258,6 +268,7 @@ _SIGS = {
     "b200_copy_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200_flag_signal": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "b200_flag_wait_geq": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "b200_put_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "b200_flag_signal_rel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b200_flag_wait_geq_rel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "b200_graph_begin": (C.c_int, [C.c_void_p]),

@@ -199,6 +199,41 @@ __global__ void flag_wait_rel_kernel(const uint32_t *flag, const uint32_t *base,
         __nanosleep(200);
     }
 }
+struct PutArgs { B200PutRange r[3]; B200PutFlag f[2]; int n_ranges, n_flags; uint32_t *counter; };
+constexpr int kPutThreads = 256;
+__global__ void __launch_bounds__(kPutThreads) put_rows_kernel(const __grid_constant__ PutArgs a)
+{
+    const int tid = blockIdx.x * kPutThreads + threadIdx.x, nt = gridDim.x * kPutThreads;
+    for (int k = 0; k < a.n_ranges; k++) {
+        const unsigned char *src = (const unsigned char *)a.r[k].src;
+        unsigned char *d0 = (unsigned char *)a.r[k].dst[0], *d1 = (unsigned char *)a.r[k].dst[1];
+        const size_t n = a.r[k].bytes;
+        // head up to the first 16-byte boundary, 16-byte body, tail (src and dst share their alignment modulo 16)
+        size_t head = (16 - ((uintptr_t)src & 15)) & 15;
+        if (head > n) head = n;
+        const size_t body = (n - head) >> 4;
+        for (size_t i = tid; i < head; i += nt) { const unsigned char v = src[i]; if (d0) d0[i] = v; if (d1) d1[i] = v; }
+        const uint4 *s4 = (const uint4 *)(src + head);
+        uint4 *p0 = d0 ? (uint4 *)(d0 + head) : nullptr, *p1 = d1 ? (uint4 *)(d1 + head) : nullptr;
+        for (size_t i = tid; i < body; i += nt) { const uint4 v = s4[i]; if (p0) p0[i] = v; if (p1) p1[i] = v; }
+        for (size_t i = head + (body << 4) + tid; i < n; i += nt) { const unsigned char v = src[i]; if (d0) d0[i] = v; if (d1) d1[i] = v; }
+    }
+    // publish: every thread's stores -> system-scope fence -> CTA barrier -> one count per CTA; the last CTA raises the flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(a.counter, 1u) + 1;
+        if (done == gridDim.x) {
+            *a.counter = 0;                       // ready for the next launch on this stream
+            __threadfence_system();
+            for (int k = 0; k < a.n_flags; k++) {
+                const B200PutFlag &f = a.f[k];
+                const uint32_t value = f.base ? ((*(volatile const uint32_t *)f.base - (uint32_t)f.sub) << f.shift) + (uint32_t)f.add : (uint32_t)f.add;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(f.flag), "r"(value) : "memory");
+            }
+        }
+    }
+}
 // cuStreamWaitValue32 through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned);
 WaitValue32Fn wait_value_fn()
@@ -264,6 +299,36 @@ int b200_ipc_close(void *p)
 int b200_copy_async(void *dst, const void *src, size_t bytes, void *stream)
 {
     if (bytes) B200_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return 0;
+}
+
+int b200_put_rows(const B200PutRange *ranges, int n_ranges, const B200PutFlag *flags, int n_flags, uint32_t *counter, void *stream)
+{
+    if (n_ranges < 0 || n_ranges > 3 || n_flags < 0 || n_flags > 2 || !counter) { b200_set_error("b200_put_rows: bad arguments"); return -2; }
+#ifndef B200_EMU
+    PutArgs a;
+    memset(&a, 0, sizeof(a));
+    size_t total = 0;
+    for (int k = 0; k < n_ranges; k++) {
+        a.r[k] = ranges[k]; total += ranges[k].bytes;
+        for (int d = 0; d < 2; d++)
+            if (ranges[k].dst[d] && (((uintptr_t)ranges[k].dst[d] ^ (uintptr_t)ranges[k].src) & 15)) { b200_set_error("b200_put_rows: src / dst alignment differs"); return -2; }
+    }
+    for (int k = 0; k < n_flags; k++) a.f[k] = flags[k];
+    a.n_ranges = n_ranges; a.n_flags = n_flags; a.counter = counter;
+    // enough CTAs to keep the NVLink stores of one band flowing, few enough to leave the SMs to the reconstruction
+    const int grid = (int)(total >> 16) < 1 ? 1 : (int)(total >> 16) > 32 ? 32 : (int)(total >> 16);
+    put_rows_kernel<<<grid, kPutThreads, 0, (cudaStream_t)stream>>>(a);
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+#else
+    (void)stream; (void)counter;
+    for (int k = 0; k < n_ranges; k++)
+        for (int d = 0; d < 2; d++)
+            if (ranges[k].dst[d]) memcpy(ranges[k].dst[d], ranges[k].src, ranges[k].bytes);
+    for (int k = 0; k < n_flags; k++)
+        *flags[k].flag = flags[k].base ? ((*flags[k].base - (uint32_t)flags[k].sub) << flags[k].shift) + (uint32_t)flags[k].add : (uint32_t)flags[k].add;
+#endif
     return 0;
 }
 

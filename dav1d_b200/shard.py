@@ -35,7 +35,8 @@ class PeerExchange:
     maps the arenas of the ranks it sends to (rank + d) and of those it acknowledges to (rank - d)."""
 
     def __init__(self, lib, dist, rank, world, pic_bytes, n_refs):
-        self.lib, self.rank, self.world, self.n_refs, self.pic_bytes = lib, rank, world, n_refs, pic_bytes
+        self.lib, self.rank, self.world, self.n_refs = lib, rank, world, n_refs
+        self.pic_bytes = pic_bytes = (pic_bytes + 255) & ~255      # slot pitch: landing buffers keep the source's alignment (b200_put_rows)
         self.arena_bytes = FLAG_BYTES + n_refs * K_SLOTS * pic_bytes
         self.arena = lib.b200_dev_alloc(self.arena_bytes)
         if not self.arena:
@@ -77,6 +78,27 @@ class PeerExchange:
 
     def signal_progress(self, consumer, d, value, stream):
         self.lib.check(self.lib.b200_flag_signal(self.peer[consumer] + self.prog_flag_off(d), value, stream), "b200_flag_signal")
+
+    def put_band(self, consumers, slot, ranges, src_ptr, seq, bands, base, counter, stream):
+        """one band's put to all its consumers in one launch (b200_put_rows): `ranges` byte ranges of the picture at src_ptr
+        into landing slot `slot` of every (d, rank) in `consumers`, then their progress flags = (seq << SEQ_SHIFT) + bands
+        (seq read from the device word `base` when given: graph replay)"""
+        from . import _lib
+        assert len(consumers) <= 2 and len(ranges) <= 3
+        R = (_lib.PutRange * len(ranges))()
+        for i, (a, b) in enumerate(ranges):
+            R[i].src = src_ptr + a
+            R[i].bytes = b - a
+            for j, (d, c) in enumerate(consumers):
+                R[i].dst[j] = self.peer[c] + self.landing_off(d, slot) + a
+        F = (_lib.PutFlag * len(consumers))()
+        for j, (d, c) in enumerate(consumers):
+            F[j].flag = self.peer[c] + self.prog_flag_off(d)
+            if base is not None:
+                F[j].base, F[j].sub, F[j].shift, F[j].add = base, 0, SEQ_SHIFT, bands
+            else:
+                F[j].base, F[j].add = None, (seq << SEQ_SHIFT) + bands
+        self.lib.check(self.lib.b200_put_rows(R, len(ranges), F, len(consumers), counter, stream), "b200_put_rows")
 
     def wait_progress(self, d, value, stream, **_):
         self.lib.check(self.lib.b200_flag_wait_geq(self.arena + self.prog_flag_off(d), value, stream), "b200_flag_wait_geq")
@@ -206,6 +228,9 @@ class GopPipeline:
         self.graph = [None] * self.n_sets
         self.last_replayed = [False] * self.n_sets
         self.words = None
+        self.aux_words = lib.b200_dev_alloc(64 * max(self.n_sets, 1))      # per set: CTA counter of its put kernel
+        lib.check(lib.b200_dev_memset(self.aux_words, 0, 64 * max(self.n_sets, 1), None), "b200_dev_memset")
+        lib.check(lib.b200_frame_wait(None), "b200_frame_wait")
         if self.graphs:
             assert n_total is None, "graph replay is for endless streams (every later frame of a set looks the same)"
             assert self.n_sets % K_SLOTS == 0 or world == 1, "graph replay needs a set to always use the same landing slots"
@@ -220,6 +245,9 @@ class GopPipeline:
 
     def local_flag(self, si):
         return self.words + 4096 + 64 * si
+
+    def put_counter(self, si):
+        return self.aux_words + 64 * si
 
     def enable_host_io(self):
         """end-to-end mode: every frame's records come from pinned host memory (own upload stream, so that frame n+1's
@@ -375,22 +403,21 @@ class GopPipeline:
                 fork(cs)
                 forked_copy = True
                 src_keep, src_ptr = fb.keep[self.ref_name]
-                for d, c in consumers:
-                    if k == 0:                      # the slot's previous occupant has been consumed
+                if k == 0:                          # the slots' previous occupants have been consumed
+                    for d, c in consumers:
                         if rel:
                             x.wait_ack_rel(d, base, K_SLOTS, 1, cs)
                         elif seq >= K_SLOTS:
                             x.wait_ack(d, seq - K_SLOTS + 1, cs)
-                    for a, b in self._band_ranges(k):
-                        if isinstance(x, DistExchange):
+                ranges = self._band_ranges(k)
+                self.bytes_put += sum(b - a for a, b in ranges) * len(consumers)
+                if isinstance(x, DistExchange):
+                    for d, c in consumers:
+                        for a, b in ranges:
                             x.put(c, d, seq % K_SLOTS, a, b, src_ptr, cs, src_keep=src_keep)
-                        else:
-                            x.put(c, d, seq % K_SLOTS, a, b, src_ptr, cs)
-                        self.bytes_put += b - a
-                    if rel:
-                        x.signal_progress_rel(c, d, base, k + 1, cs)
-                    else:
                         x.signal_progress(c, d, (seq << SEQ_SHIFT) + k + 1, cs)
+                else:       # one launch: rows to every consumer over NVLink, then their flags
+                    x.put_band(consumers, seq % K_SLOTS, ranges, src_ptr, seq, k + 1, base, self.put_counter(si), cs)
         # ---- the frame is enqueued: acknowledge the references (their slots may be overwritten once this point is reached)
         for d in range(1, self.n_refs + 1):
             kind, mseq = srcs[d - 1]

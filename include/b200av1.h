@@ -641,6 +641,16 @@ B200_API int b200_ipc_close(void *peer_ptr);
 B200_API int b200_copy_async(void *dst, const void *src, size_t bytes, void *stream);
 B200_API int b200_flag_signal(uint32_t *flag, uint32_t value, void *stream);           /* flag: device memory, local or peer */
 B200_API int b200_flag_wait_geq(const uint32_t *flag, uint32_t value, void *stream);   /* flag: local device memory */
+/* One band's whole put in ONE launch: copies up to 3 byte ranges (the rows of the three planes that became final) to up to
+ * two destinations each (the landing buffers of the ranks decoding frames n+1 and n+2: peer pointers, stores travel over
+ * NVLink) and, when the last CTA has finished, raises those ranks' progress flags behind a system-scope fence. Replaces 6
+ * cudaMemcpyAsync + 2 flag kernels per band (~10 us each on the copy engines: the exchange, not the reconstruction, set the
+ * pace of a banded frame). `src` and `dst` must have the same alignment modulo 16 bytes. Flag value: add, or
+ * ((*base - sub) << shift) + add when base != NULL. `counter`: a zero-initialised device word owned by the caller's stream. */
+typedef struct B200PutRange { const void *src; void *dst[2]; uint64_t bytes; } B200PutRange;
+typedef struct B200PutFlag { uint32_t *flag; const uint32_t *base; int32_t sub, shift, add, pad; } B200PutFlag;
+B200_API int b200_put_rows(const B200PutRange *ranges, int n_ranges, const B200PutFlag *flags, int n_flags,
+                           uint32_t *counter, void *stream);
 /* The same flag operations with the value taken from device memory when the operation EXECUTES:
  * value = ((*base - sub) << shift) + add. A frame's whole schedule (bands, puts, waits) can then be captured once into a
  * CUDA graph and replayed for every later frame of the set: only the word at `base` (the frame's sequence number) changes. */
