@@ -672,9 +672,13 @@ def run_ours_gop(args):
     whole = -(-H // 64) * 64
     # bands: one GPU decodes whole frames (nothing to wait for: stream order is the dependency); over several GPUs a frame
     # is cut into bands of superblock rows so that frame n+1 starts on its GPU while frame n is still being decoded
-    band_rows = int(os.environ.get("B200_BAND_ROWS", str(whole if world == 1 else (256 if H > 2400 else 128))))
+    # ... the band height: a band of frame n+1 may start once frame n has restored ~144 luma rows more than the band's bottom
+    # (motion reach + filter taps + the rows the post filters still hold back), i.e. frame n+1 trails frame n by about
+    # (144 + band) rows; N ranks stay busy when N such lags fit into a frame, hence ~H / 3N rows per band — as few bands as
+    # that allows, because every band is a dozen more (small) launches
+    band_rows = int(os.environ.get("B200_BAND_ROWS", str(whole if world == 1 else H // (3 * world))))
     band_rows = min(whole, max(64, band_rows // 64 * 64))
-    n_streams = max(1, int(os.environ.get("B200_FRAMES_IN_FLIGHT", "1")))
+    n_streams = max(1, int(os.environ.get("B200_FRAMES_IN_FLIGHT", "1" if world == 1 else "2")))
     nsets = int(os.environ.get("B200_NSETS", "3" if args.workload == "8k10_full" else "6"))
     # a banded frame is hundreds of launches, waits and copies: replayed as one CUDA graph per frame (the host would otherwise
     # be the bottleneck: ~100 us of launch calls per band)

@@ -118,6 +118,10 @@ class Level1Decoder:
         if self.dll.b200l1_set_backend(backend.encode(), mask) != 0:
             raise RuntimeError("b200l1_set_backend(%s) failed" % backend)
 
+    def c_slots_left(self):
+        """(slots still on dav1d's C functions after the back end's init, slots replaced): the first must be 0"""
+        return int(self.dll.b200l1_c_slots_left()), int(self.dll.b200l1_slots_replaced())
+
     def decode(self, tus, **kw):
         kw.setdefault("n_threads", 1)            # the Level-1 thunks serialise on one lock anyway
         kw.setdefault("max_frame_delay", 1)

@@ -20,14 +20,15 @@ static uint64_t g_clock;            /* LRU stamps of the frame-context and pictu
 
 API int b200hook_set_backend(const char *path)
 {
-    pthread_mutex_lock(&g_lock);
-    g_be_ok = 0;
+    /* build the table locally, publish it with one release store: a thread that sees g_be_ok set sees every pointer.
+     * (Rebinding while frames are in flight is not supported: the old table is simply kept.) */
+    B200Backend be;
+    memset(&be, 0, sizeof(be));
     void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
-    if (!h) { fprintf(stderr, "b200hook: cannot load back end %s: %s\n", path, dlerror()); pthread_mutex_unlock(&g_lock); return -1; }
-    memset(&g_be, 0, sizeof(g_be));
-    g_be.handle = h;
-#define SYM(field, name) do { *(void **)&g_be.field = dlsym(h, name); \
-        if (!g_be.field) { fprintf(stderr, "b200hook: back end lacks %s\n", name); pthread_mutex_unlock(&g_lock); return -1; } } while (0)
+    if (!h) { fprintf(stderr, "b200hook: cannot load back end %s: %s\n", path, dlerror()); return -1; }
+    be.handle = h;
+#define SYM(field, name) do { *(void **)&be.field = dlsym(h, name); \
+        if (!be.field) { fprintf(stderr, "b200hook: back end lacks %s\n", name); dlclose(h); return -1; } } while (0)
     SYM(last_error, "b200_last_error");
     SYM(dev_alloc, "b200_dev_alloc"); SYM(dev_free, "b200_dev_free");
     SYM(host_alloc, "b200_host_alloc"); SYM(host_free, "b200_host_free");
@@ -37,13 +38,15 @@ API int b200hook_set_backend(const char *path)
     SYM(struct_size, "b200_struct_size");
 #undef SYM
     /* binding self-check: the structs this file was compiled with are the ones the library was compiled with */
-    if (g_be.struct_size(9) != (int)sizeof(B200FrameJob) || g_be.struct_size(14) != (int)sizeof(B200IntraTx) ||
-        g_be.struct_size(10) != (int)sizeof(B200Av1Filter) || g_be.struct_size(11) != (int)sizeof(B200Av1Restoration)) {
+    if (be.struct_size(9) != (int)sizeof(B200FrameJob) || be.struct_size(14) != (int)sizeof(B200IntraTx) ||
+        be.struct_size(10) != (int)sizeof(B200Av1Filter) || be.struct_size(11) != (int)sizeof(B200Av1Restoration)) {
         fprintf(stderr, "b200hook: ABI struct size mismatch with %s\n", path);
-        pthread_mutex_unlock(&g_lock);
+        dlclose(h);
         return -1;
     }
-    g_be_ok = 1;
+    pthread_mutex_lock(&g_lock);
+    g_be = be;
+    __atomic_store_n(&g_be_ok, 1, __ATOMIC_RELEASE);
     pthread_mutex_unlock(&g_lock);
     return 0;
 }
@@ -58,9 +61,17 @@ void b200hook_job_leave(void) { if (g_serialize) pthread_mutex_unlock(&g_job_loc
 
 const B200Backend *b200hook_backend(void)
 {
-    if (!g_be_ok) {
-        const char *env = getenv("B200AV1_LIB");
-        if (!env || b200hook_set_backend(env)) {
+    if (!__atomic_load_n(&g_be_ok, __ATOMIC_ACQUIRE)) {
+        /* lazy binding from the environment, once: concurrent first calls serialise here and the losers find it bound */
+        static pthread_mutex_t once = PTHREAD_MUTEX_INITIALIZER;
+        pthread_mutex_lock(&once);
+        int ok = __atomic_load_n(&g_be_ok, __ATOMIC_ACQUIRE);
+        if (!ok) {
+            const char *env = getenv("B200AV1_LIB");
+            ok = env && !b200hook_set_backend(env);
+        }
+        pthread_mutex_unlock(&once);
+        if (!ok) {
             fprintf(stderr, "b200hook: no back end loaded (b200hook_set_backend / B200AV1_LIB) - frame fails\n");
             return NULL;
         }
@@ -152,18 +163,41 @@ void b200hook_refpic_wait(HookRefPic *r)
 
 /* Frame contexts come and go with dav1d_open / dav1d_close (there is no hook for either): a context that is not in the
  * table takes over the least recently used idle slot, together with that slot's buffers. */
+/* a thread's cached slot: the slot's `users` count says how many threads may take the lock-free path to it; the count is
+ * released when the thread caches another slot or exits (pthread key destructor) */
+static pthread_key_t g_tls_key;
+static pthread_once_t g_tls_once = PTHREAD_ONCE_INIT;
+static unsigned g_epoch;            /* bumped by b200hook_release: references taken before it are void */
+static void tls_release(void *p)
+{
+    HookFrame *const h = p;
+    if (!h) return;
+    pthread_mutex_lock(&g_lock);
+    if (h->users > 0 && h->epoch == g_epoch) h->users--;
+    pthread_mutex_unlock(&g_lock);
+}
+static void tls_init(void) { pthread_key_create(&g_tls_key, tls_release); }
+
 HookFrame *b200hook_frame(const void *key)
 {
-    /* called by every hook, i.e. once per block: the thread's last answer is almost always still right (a slot is only
-     * handed to another key while it is idle), so the table lock is taken once per tile superblock row, not per block */
+    /* called by every hook, i.e. once per block: the thread's last answer is still right as long as this thread holds a
+     * `users` reference on the slot (a slot somebody caches is never handed to another key), so the table lock is taken
+     * once per frame and thread, not per block */
     static __thread const void *tl_key;
     static __thread HookFrame *tl_slot;
-    if (tl_key == key && tl_slot && __atomic_load_n(&tl_slot->key, __ATOMIC_ACQUIRE) == key) {
-        tl_slot->last_use = g_clock;
+    static __thread unsigned tl_epoch;
+    if (tl_key == key && tl_slot && tl_epoch == __atomic_load_n(&g_epoch, __ATOMIC_ACQUIRE) &&
+        __atomic_load_n(&tl_slot->key, __ATOMIC_ACQUIRE) == key) {
+        __atomic_store_n(&tl_slot->last_use, __atomic_load_n(&g_clock, __ATOMIC_RELAXED), __ATOMIC_RELAXED);
         return tl_slot;
     }
+    pthread_once(&g_tls_once, tls_init);
     HookFrame *r = NULL, *lru = NULL;
     pthread_mutex_lock(&g_lock);
+    if (tl_slot) {
+        if (tl_epoch == g_epoch && tl_slot->users > 0) tl_slot->users--;
+        tl_slot = NULL; tl_key = NULL; pthread_setspecific(g_tls_key, NULL);
+    }
     for (int i = 0; i < 64 && !r; i++)
         if (g_frames[i].key == key) r = &g_frames[i];
     for (int i = 0; i < 64 && !r; i++)
@@ -181,7 +215,7 @@ HookFrame *b200hook_frame(const void *key)
         for (int tries = 0; tries < 64 && !r; tries++) {
             for (int i = 0; i < 64; i++) {
                 HookFrame *const h = &g_frames[i];
-                if (h->pinned || h->last_use <= floor_use) continue;
+                if (h->pinned || h->users || h->last_use <= floor_use) continue;
                 if (!pass && (h->started || h->tile_sbrows_done)) continue;
                 if (!lru || h->last_use < lru->last_use) lru = h;
             }
@@ -196,9 +230,10 @@ HookFrame *b200hook_frame(const void *key)
         }
     }
     if (!r) fprintf(stderr, "b200hook: no frame-context slot available\n");
-    if (r) r->last_use = ++g_clock;
+    if (r) { r->last_use = ++g_clock; r->users++; r->epoch = g_epoch; pthread_setspecific(g_tls_key, r); }
+    tl_epoch = g_epoch;
     pthread_mutex_unlock(&g_lock);
-    tl_key = key; tl_slot = r;
+    tl_key = r ? key : NULL; tl_slot = r;
     return r;
 }
 
@@ -311,6 +346,7 @@ API void b200hook_get_stats(B200HookStats *out, int reset)
 API void b200hook_release(void)
 {
     pthread_mutex_lock(&g_lock);
+    __atomic_add_fetch(&g_epoch, 1, __ATOMIC_RELEASE);
     for (int i = 0; i < 64; i++) {
         HookFrame *h = &g_frames[i];
         if (!h->key) continue;

@@ -57,6 +57,10 @@ typedef struct HookFrame {
     int started, is_inter, n_ii;
     unsigned refs_used;            /* bit k: some prediction of this frame reads reference k (f->refp[k]) */
     int pinned;                    /* never recycled for another key (the output-stage slots) */
+    unsigned epoch;                /* b200hook_release generation the `users` references belong to */
+    int users;                     /* threads whose thread-local cache points at this slot (under the table lock): only a slot
+                                      nobody caches may be handed to another key — the lock-free fast path of b200hook_frame
+                                      is taken by exactly those threads */
     const void *cur_pic;           /* f->cur.data[0] of the frame being emitted: a different picture means the previous frame of this
                                       context was abandoned half way (flush / close) and its records are stale */
     uint64_t last_use;             /* slot recycling: least recently used idle slot is taken over (its buffers are kept) */

@@ -94,11 +94,14 @@ static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *c
         const int ss_ver = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
         const size_t aw4 = (f->bw + 31) & ~31, ah4 = (f->bh + 31) & ~31;
         const size_t cells = aw4 * ah4 + (f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I400 ? 2 * ((aw4 >> ss_hor) * (ah4 >> ss_ver)) : 0);
-        hf->cap_tx = (int)cells; hf->cap_coef = cells * 16;
+        /* + the block-level records that come on top of the per-transform-block ones: a palette or inter-intra block emits
+         * one PAL / II record per plane before its RESID records, and such a block covers at least one 8x8 luma area (2x2
+         * cells: 4 luma + the chroma cells) — a quarter of the cells bounds their number (+ slack for ragged frame edges) */
+        hf->cap_tx = (int)(cells + cells / 4 + 64); hf->cap_coef = cells * 16;
         /* palette blocks: 8 bytes of packed indices per 4x4 cell + 8 palette entries per block (>= 1 cell) */
         hf->cap_pal = f->frame_hdr->allow_screen_content_tools ? cells * (8 + 8 * sizeof(pixel)) : 0;
         hf->n_pal = 0;
-        if (b200hook_buf_reserve(&hf->tx, cells * sizeof(B200IntraTx), 1, 0) ||
+        if (b200hook_buf_reserve(&hf->tx, (size_t)hf->cap_tx * sizeof(B200IntraTx), 1, 0) ||
             b200hook_buf_reserve(&hf->coef, cells * 16 * sizeof(coef), 1, 0) ||
             (hf->cap_pal && b200hook_buf_reserve(&hf->pal, hf->cap_pal, 1, 0))) {
             __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
@@ -108,6 +111,21 @@ static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *c
     }
     pthread_mutex_unlock(&hf->lock);
 }
+
+/* the job copies these dav1d structures byte for byte into their B200 twins (include/b200av1.h): a dav1d version or
+ * configuration with another layout must not compile */
+_Static_assert(sizeof(Av1Filter) == sizeof(B200Av1Filter), "Av1Filter layout");
+_Static_assert(offsetof(Av1Filter, filter_uv) == offsetof(B200Av1Filter, filter_uv) && offsetof(Av1Filter, cdef_idx) == offsetof(B200Av1Filter, cdef_idx) &&
+               offsetof(Av1Filter, noskip_mask) == offsetof(B200Av1Filter, noskip_mask), "Av1Filter members");
+_Static_assert(sizeof(Av1Restoration) == sizeof(B200Av1Restoration) && sizeof(Av1RestorationUnit) == sizeof(B200RestorationUnit), "Av1Restoration layout");
+_Static_assert(offsetof(Av1RestorationUnit, filter_h) == offsetof(B200RestorationUnit, filter_h) && offsetof(Av1RestorationUnit, filter_v) == offsetof(B200RestorationUnit, filter_v) &&
+               offsetof(Av1RestorationUnit, sgr_weights) == offsetof(B200RestorationUnit, sgr_weights), "Av1RestorationUnit members");
+_Static_assert(sizeof(Dav1dFilmGrainData) == sizeof(B200FilmGrainData), "Dav1dFilmGrainData layout");
+_Static_assert(offsetof(Dav1dFilmGrainData, ar_coeffs_y) == offsetof(B200FilmGrainData, ar_coeffs_y) && offsetof(Dav1dFilmGrainData, ar_coeff_shift) == offsetof(B200FilmGrainData, ar_coeff_shift) &&
+               offsetof(Dav1dFilmGrainData, uv_mult) == offsetof(B200FilmGrainData, uv_mult) && offsetof(Dav1dFilmGrainData, clip_to_restricted_range) == offsetof(B200FilmGrainData, clip_to_restricted_range),
+               "Dav1dFilmGrainData members");
+_Static_assert(sizeof(((Av1FilterLUT *)0)->e) == sizeof(((B200FilterLUT *)0)->e) && sizeof(((Av1FilterLUT *)0)->i) == sizeof(((B200FilterLUT *)0)->i) &&
+               sizeof(((Av1FilterLUT *)0)->sharp) == sizeof(((B200FilterLUT *)0)->sharp), "Av1FilterLUT members");
 
 /* ---- one transform block -> one record ------------------------------------------------------------------ */
 typedef struct TxCtx {

@@ -15,6 +15,7 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include "src/internal.h"
 
 #define API __attribute__((visibility("default")))
@@ -44,15 +45,43 @@ static void *sym(const char *name)
     return p;
 }
 
+/* Every member of the seven DSP contexts is a function pointer, so a context is an array of slots. After dav1d's own init
+ * a slot is either NULL (a combination AV1 does not define) or one of dav1d's C functions; after the back end's init every
+ * non-NULL slot must point somewhere else. A slot the back end forgot would silently keep running on the CPU and the stream
+ * tests would still pass: count them (b200l1_c_slots_left) and name them on stderr. */
+static int g_c_slots_left, g_slots_replaced;
+API int b200l1_c_slots_left(void) { return g_c_slots_left; }
+API int b200l1_slots_replaced(void) { return g_slots_replaced; }
+
+static void check_replaced(const char *family, int bd, void *const *before, void *const *after, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        if (!before[i]) continue;
+        if (after[i] == before[i]) {
+            g_c_slots_left++;
+            fprintf(stderr, "b200l1: %s_%dbpc slot %zu of %zu is still dav1d's C function\n", family, bd, i, n);
+        } else g_slots_replaced++;
+    }
+}
+
+#define HOOK_BODY(bit, family, Type, bd, CALL_REF, CALL_B200) \
+        CALL_REF; \
+        if (g_families & (bit)) { \
+            void *before[sizeof(Type) / sizeof(void *)]; \
+            _Static_assert(sizeof(Type) % sizeof(void *) == 0, "context is an array of function pointers"); \
+            memcpy(before, c, sizeof(Type)); \
+            CALL_B200; \
+            check_replaced(#family, bd, before, (void *const *)c, sizeof(Type) / sizeof(void *)); \
+        }
 #define HOOK0(bit, family, Type, bd) \
     void b200l1_##family##_dsp_init_##bd##bpc(Type *const c) { \
-        dav1d_##family##_dsp_init_##bd##bpc(c); \
-        if (g_families & (bit)) ((void (*)(void *))sym("b200_" #family "_dsp_init_" #bd "bpc"))(c); \
+        HOOK_BODY(bit, family, Type, bd, dav1d_##family##_dsp_init_##bd##bpc(c), \
+                  ((void (*)(void *))sym("b200_" #family "_dsp_init_" #bd "bpc"))(c)) \
     }
 #define HOOK1(bit, family, Type, bd) \
     void b200l1_##family##_dsp_init_##bd##bpc(Type *const c, const int bpc) { \
-        dav1d_##family##_dsp_init_##bd##bpc(c, bpc); \
-        if (g_families & (bit)) ((void (*)(void *, int))sym("b200_" #family "_dsp_init_" #bd "bpc"))(c, bpc); \
+        HOOK_BODY(bit, family, Type, bd, dav1d_##family##_dsp_init_##bd##bpc(c, bpc), \
+                  ((void (*)(void *, int))sym("b200_" #family "_dsp_init_" #bd "bpc"))(c, bpc)) \
     }
 
 HOOK1(1, itx, Dav1dInvTxfmDSPContext, 8)

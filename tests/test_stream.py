@@ -489,6 +489,9 @@ def _level1_case(dec, launches):
         r1, _, out1 = dec.decode(tus, apply_grain=1)
         assert r0 == len(tus) and r1 == r0 and np.array_equal(out0, out1), gen.__name__
     assert launches() - n0 > 1000, "the DSP calls did not reach the back end"
+    # no slot that dav1d defines may be left on dav1d's own C function (it would run on the CPU and still "pass")
+    left, replaced = dec.c_slots_left()
+    assert left == 0 and replaced > 400, "Level-1 tables: %d slots still on dav1d's C functions (%d replaced)" % (left, replaced)
 
 
 @pytest.mark.emu

@@ -44,8 +44,13 @@ if [[ $what == *" benchA "* ]]; then
   run_bench intra_cta B200_INTRA_CTA=1 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
   run_bench 4k10 python bench.py --workload 4k10_full --steps 20 --warmup 5
 fi
+if [[ $what == *" benchI "* ]]; then
+  run_bench intra_warp B200_INTRA_SB=0 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
+  run_bench intra_warp_g16 B200_INTRA_SB=0 B200_INTRA_GRID=16 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
+  run_bench intra_cta B200_INTRA_SB=0 B200_INTRA_CTA=1 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
+fi
 if [[ $what == *" profmc "* ]]; then
-  export B200_SKIP_PARITY=1 B200_MIN_TIMED_S=0.005 B200_NSETS=2 B200_DISTINCT=2
+  export B200_SKIP_PARITY=1 B200_MIN_TIMED_S=0.005 B200_NSETS=3 B200_DISTINCT=1
   timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 40 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:mc_pred_kernel -s 3 -c 2 -f -o gpurun_out/prof_mc python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_mc.log 2>&1; echo "ncu mc rc=$?"
   unset B200_SKIP_PARITY B200_MIN_TIMED_S B200_NSETS B200_DISTINCT
