@@ -217,6 +217,9 @@ FRAME_WORKLOADS = {
     "4k8_inter": dict(bpc=8, W=3840, H=2160, fg=False, dtype="u8/i16->i32",
                       desc="one 3840x2160 8-bit 4:2:0 inter frame per GPU per step: prediction (put/prep+compound, 2 refs) + "
                            "inverse transforms + deblock + CDEF + loop restoration (BASELINE configs[2])"),
+    "4k8_mixed": dict(bpc=8, W=3840, H=2160, fg=False, dtype="u8/i16->i32", p_intra=0.10,
+                      desc="4k8_inter with 10 % of the blocks intra coded (what real inter frames contain): the inter stages, then the "
+                           "dependency-driven intra kernel on top of them (done map pre-marked for the inter cells), then the post filters"),
     "4k10_full": dict(bpc=10, W=3840, H=2160, fg=True, dtype="u16/i32->i32",
                       desc="one 3840x2160 10-bit 4:2:0 inter frame per GPU per step, full pipeline: prediction + inverse "
                            "transforms + deblock + CDEF + loop restoration + film grain (BASELINE configs[3])"),
@@ -237,7 +240,7 @@ def make_workload_frame(name, seed):
     wl = FRAME_WORKLOADS[name]
     if wl.get("intra"):
         return synth.make_intra_frame(np.random.default_rng(seed), wl["bpc"], wl["W"], wl["H"])
-    return synth.make_inter_frame(np.random.default_rng(seed), wl["bpc"], wl["W"], wl["H"], film_grain=wl["fg"])
+    return synth.make_inter_frame(np.random.default_rng(seed), wl["bpc"], wl["W"], wl["H"], film_grain=wl["fg"], p_intra=wl.get("p_intra", 0.0))
 
 
 def workload_buffers(name, S, **kw):
@@ -267,7 +270,8 @@ def cpu_frames(S, n_threads, reps, use_ref=True):
     else:
         import test_frame
         fn, kind = None, "port"
-    wl = next((k for k, v in FRAME_WORKLOADS.items() if v.get("intra")), None) if S.get("intra_tx") is not None else "4k8_inter"
+    intra_only = S.get("intra_tx") is not None and not len(S["pred"])
+    wl = next((k for k, v in FRAME_WORKLOADS.items() if v.get("intra")), None) if intra_only else "4k8_inter"
     fbs = [workload_buffers(wl, S, lib=object(), alloc=frame.NumpyAlloc()) for _ in range(n_threads)] if fn else None
 
     def work(i):
@@ -1018,7 +1022,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k10_full", "8k10_full", "1080p8_intra", "itx8x8"] + sorted(STREAM_WORKLOADS))
+    ap.add_argument("--workload", default="4k8_inter", choices=["4k8_inter", "4k8_mixed", "4k10_full", "8k10_full", "1080p8_intra", "itx8x8"] + sorted(STREAM_WORKLOADS))
     args = ap.parse_args()
     if args.workload in STREAM_WORKLOADS:
         return run_stream(args)

@@ -112,8 +112,9 @@ int b200_frame_run_band(const B200FrameJob *j, const B200FrameBand *b, void *str
         b200_set_error("b200_frame_run_band: band [%d, %d) must be 64-row aligned (last band: down to the picture height %d)", b->y0, b->y1, H);
         return -2;
     }
-    if (j->n_intra > 0) { b200_set_error("b200_frame_run_band: intra records are not band-sliced (use b200_frame_run)"); return -2; }
     const bool first = b->y0 == 0;
+    // intra records form a dependency graph over the whole frame: they run with a band only when that band IS the frame
+    if (j->n_intra > 0 && !(first && b->last)) { b200_set_error("b200_frame_run_band: intra records are not band-sliced (one band, or b200_frame_run)"); return -2; }
 #ifndef B200_EMU
     bool fg_forked = false;
     if (first && j->run_fg) {       // grain LUTs depend on the frame header only: beside the first band, joined before the last one's apply
@@ -144,6 +145,7 @@ int b200_frame_run_band(const B200FrameJob *j, const B200FrameBand *b, void *str
         itx_n[t] = j->d_itx[t] ? b->itx[t][1] : 0;
     }
     if ((r = b200_itx_add_frame(bd, itx_p, itx_n, j->d_coef, j->mc.dst, j->itx_stride, j->zero_coefs, stream))) return r;
+    if (j->n_intra > 0 && (r = b200_intra_frame(bd, &j->intra, j->d_intra, j->n_intra, stream))) return r;
     // sweeps: what this band's reconstruction makes final. Deblock: the band's own rows (a row-edge filter at y1 will still
     // change rows >= y1 - 6). CDEF tile rows (32 luma rows, reading 2 more on each side): those ending at or above y1 - 32.
     // Loop restoration tile rows (32 rows inside the 64-row stripes that end at 64 k - 8, reading CDEF output up to 3 rows

@@ -135,7 +135,9 @@ def band_plan(S, band_rows, compact=False, fused=False):
         cc, ex = synth.compact_coefs(S2)
         # compact_coefs emits its records size class after size class, each in the (band-sorted) order of S2["itx"][tx]
         eb = np.concatenate([np.repeat(np.arange(nb), itx_ranges[tx][1]) for tx in range(19) if len(S2["itx"][tx])]) if len(ex) else np.zeros(0, np.int64)
-        assert len(eb) == len(ex)
+        # ... followed by the intra records' blocks (mixed frames: a single band only, see b200_frame_run_band)
+        assert len(eb) == len(ex) or (nb == 1 and len(eb) < len(ex))
+        eb = np.concatenate([eb, np.zeros(len(ex) - len(eb), np.int64)]).astype(np.int64)
         order = np.argsort(eb, kind="stable")
         cnt = np.bincount(eb, minlength=nb)
         expand = (cc, ex[order])
@@ -299,6 +301,9 @@ class FrameBuffers:
             else:
                 j.d_intra = up("intra_tx", S["intra_tx"]); j.n_intra = len(S["intra_tx"])
                 self.uploads.append(("intra_tx", S["intra_tx"]))
+                if S.get("done_init") is not None:       # a frame that mixes inter and intra blocks: inter cells are final already
+                    it.done_init = up("done_init", S["done_init"])
+                    self.uploads.append(("done_init", S["done_init"]))
             n_intra = 1
         # post filters
         j.run_lf, j.run_cdef, j.run_lr = int(run_lf), int(run_cdef), int(run_lr)

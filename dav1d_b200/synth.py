@@ -13,9 +13,10 @@ AV1FILTER_DT = np.dtype([("filter_y", "<u2", (2, 32, 3, 2)), ("filter_uv", "<u2"
 assert AV1FILTER_DT.itemsize == 1348
 
 
-def random_tiling(rng, w4, h4, max_log=4, min_log=0, p_split=0.55):
+def random_tiling(rng, w4, h4, max_log=4, min_log=0, p_split=0.55, order=None):
     """Random block tiling of a w4 x h4 grid of 4x4 units. Returns int arrays (h4, w4):
-    bx, by (origin of the block covering each unit) and lw, lh (log2 of block width/height in units)."""
+    bx, by (origin of the block covering each unit) and lw, lh (log2 of block width/height in units).
+    `order`: a list that receives the blocks (x, y, lw, lh) in decode order (superblock raster, partition recursion)."""
     bx = np.zeros((h4, w4), np.int32); by = np.zeros((h4, w4), np.int32)
     lw = np.zeros((h4, w4), np.int8); lh = np.zeros((h4, w4), np.int8)
     S = 1 << max_log
@@ -23,6 +24,8 @@ def random_tiling(rng, w4, h4, max_log=4, min_log=0, p_split=0.55):
     def fill(x, y, lwv, lhv):
         x1, y1 = min(w4, x + (1 << lwv)), min(h4, y + (1 << lhv))
         bx[y:y1, x:x1] = x; by[y:y1, x:x1] = y; lw[y:y1, x:x1] = lwv; lh[y:y1, x:x1] = lhv
+        if order is not None:
+            order.append((x, y, lwv, lhv))
 
     def rec(x, y, lwv, lhv):
         if x >= w4 or y >= h4:
@@ -290,9 +293,12 @@ def make_film_grain(rng, full=True):
 
 
 def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.3, p_skip=0.25, min_log=1, max_log=4,
-                     film_grain=False):
+                     film_grain=False, p_intra=0.0):
     """Synthetic inter frame: every block is predicted from `n_refs` reference pictures (single or
-    compound), carries a residual (unless skipped) and the frame has deblock / CDEF / LR parameters."""
+    compound), carries a residual (unless skipped) and the frame has deblock / CDEF / LR parameters.
+    p_intra > 0: that share of the blocks is intra coded instead (what real inter frames contain): B200IntraTx records
+    (S["intra_tx"], wavefront order among themselves) + S["done_init"], the done map in which every cell of an inter block
+    is final before the intra kernel starts (include/b200av1.h, B200IntraFrame.done_init)."""
     bd = (1 << bpc) - 1
     dt = np.uint8 if bpc == 8 else np.uint16
     cdt = np.int16 if bpc == 8 else np.int32
@@ -302,10 +308,34 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
     w4, h4 = S["w4"], S["h4"]
     ssh, ssv = [0, ss_hor, ss_hor], [0, ss_ver, ss_ver]
     refs = [smooth_picture(rng, total, bd, dt) for _ in range(n_refs)]
-    bx, by, lw, lh = random_tiling(rng, w4, h4, max_log=max_log, min_log=min_log)
-    key = by.astype(np.int64) * 65536 + bx
-    _, first = np.unique(key, return_index=True)
-    blocks = [(int(bx.flat[i]), int(by.flat[i]), int(lw.flat[i]), int(lh.flat[i])) for i in first]
+    decode_order = []
+    bx, by, lw, lh = random_tiling(rng, w4, h4, max_log=max_log, min_log=min_log, order=decode_order)
+    if p_intra > 0:
+        blocks = [b for b in decode_order if b[0] < w4 and b[1] < h4]      # intra blocks need their neighbours first: decode order
+    else:
+        key = by.astype(np.int64) * 65536 + bx
+        _, first = np.unique(key, return_index=True)
+        blocks = [(int(bx.flat[i]), int(by.flat[i]), int(lw.flat[i]), int(lh.flat[i])) for i in first]
+    intra_recs = []
+    pw4 = [w4, (w4 + ss_hor) >> ss_hor, (w4 + ss_hor) >> ss_hor]; ph4 = [h4, (h4 + ss_ver) >> ss_ver, (h4 + ss_ver) >> ss_ver]
+    edge_filter = int(rng.integers(0, 2)) if p_intra > 0 else 0
+
+    def add_intra(pl, x, y, tlw, tlh, mode, angle, skip):
+        """one intra transform block of plane pl at (x, y) [plane 4-sample units] (cf. make_intra_frame.add)"""
+        r = np.zeros(1, INTRA_TX_DT)[0]
+        r["dst_off"] = off[pl] + y * 4 * stride[pl] + x * 4
+        r["x4"], r["y4"], r["xend4"], r["yend4"] = x, y, pw4[pl], ph4[pl]
+        if pl == 0:
+            r["max_w"], r["max_h"] = 4 * w4 - 4 * x, 4 * h4 - 4 * y
+        else:
+            r["max_w"] = (4 * w4 + ss_hor - 4 * (x << ss_hor)) >> ss_hor
+            r["max_h"] = (4 * h4 + ss_ver - 4 * (y << ss_ver)) >> ss_ver
+        r["angle_flags"] = edge_filter << 10
+        r["tx"] = TX_FROM_WH[(4 << tlw, 4 << tlh)]
+        r["mode"], r["angle"], r["plane"] = mode, angle, pl
+        r["flags"] = (1 if x > 0 else 0) | (2 if y > 0 else 0)        # top-right / bottom-left never used: always a valid choice
+        r["eob"] = -1 if skip else 0                                  # residual filled in below
+        intra_recs.append(r)
 
     pred, comp, comp2 = [], [], []
     pred_single, cfused, cfused2 = [], [], []  # the same predictions for the fused compound kernel
@@ -324,6 +354,32 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
 
     for (x4, y4, lwv, lhv) in blocks:
         bw, bh = 4 << lwv, 4 << lhv
+        if p_intra > 0 and rng.random() < p_intra:
+            # ---- an intra block inside the inter frame: predicted from its reconstructed neighbours at transform-block
+            # granularity (the neighbours may be inter blocks: final before the intra kernel starts)
+            skip = rng.random() < p_skip
+            skip_map[y4:y4 + (1 << lhv), x4:x4 + (1 << lwv)] = skip
+            cwb, chb = min(1 << lwv, w4 - x4), min(1 << lhv, h4 - y4)
+            m = int(rng.integers(0, 13)); ang = int(rng.integers(-3, 4)) if 1 <= m <= 8 else 0
+            tlw, tlh = min(lwv, 4), min(lhv, 4)
+            if rng.random() < 0.4 and tlw > 0 and tlh > 0:
+                tlw -= 1; tlh -= 1
+            for yy in range(0, chb, 1 << tlh):
+                for xx in range(0, cwb, 1 << tlw):
+                    paint(ty, x4 + xx, y4 + yy, tlw, tlh, h4, w4)
+                    add_intra(0, x4 + xx, y4 + yy, tlw, tlh, m, ang, skip)
+            clw, clh = max(lwv - ss_hor, 0), max(lhv - ss_ver, 0)
+            cx4, cy4 = x4 >> ss_hor, y4 >> ss_ver
+            ccw, cch = (cwb + ss_hor) >> ss_hor, (chb + ss_ver) >> ss_ver
+            um = int(rng.integers(0, 13)); uang = int(rng.integers(-3, 4)) if 1 <= um <= 8 else 0
+            ctl, cth = min(clw, 3), min(clh, 3)
+            for pl in (1, 2):
+                for yy in range(0, cch, 1 << cth):
+                    for xx in range(0, ccw, 1 << ctl):
+                        if pl == 1:
+                            paint(tuv, cx4 + xx, cy4 + yy, ctl, cth, ch4, cw4)
+                        add_intra(pl, cx4 + xx, cy4 + yy, ctl, cth, um, uang, skip)
+            continue
         compound = rng.random() < p_compound
         mv = [(int(rng.integers(-512, 513)), int(rng.integers(-512, 513))) for _ in range(2)]   # 1/8 luma pixels
         if rng.random() < 0.05:
@@ -428,6 +484,57 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
         itx_arrays[tx] = arr
         coef_chunks.append(c.astype(cdt).reshape(-1))
         coef_off += n * ncf
+    intra_extra = {}
+    if intra_recs:
+        tx = np.array(intra_recs, INTRA_TX_DT)
+        for t in range(19):
+            sel = np.nonzero((tx["tx"] == t) & (tx["eob"] >= 0))[0]
+            if not len(sel):
+                continue
+            k = len(sel)
+            sw, sh = _L.tx_coef_dims(t)
+            ncf = sw * sh
+            legal = [tp for tp in range(10) if _L.itx_defined(t, tp)]
+            txtp = rng.choice(legal, k, p=None if len(legal) == 1 else [0.55] + [0.45 / (len(legal) - 1)] * (len(legal) - 1))
+            scan = scan_table(t)
+            inv = np.empty(ncf, np.int64); inv[scan] = np.arange(ncf)
+            eob = np.minimum((rng.exponential(ncf / 10.0, k)).astype(np.int64), ncf - 1)
+            eob[rng.random(k) < 0.25] = 0
+            pos = inv[None, :]
+            c = np.rint(rng.laplace(0.0, (bd + 1) / 2.0 * 0.25, (k, ncf)) / (1.0 + pos / 6.0)).astype(np.int64)
+            c[pos > eob[:, None]] = 0
+            c[np.arange(k), scan[eob]] = np.where(c[np.arange(k), scan[eob]] == 0, 1, c[np.arange(k), scan[eob]])
+            tx["coef_off"][sel] = coef_off + np.arange(k) * ncf
+            tx["eob"][sel] = eob; tx["txtp"][sel] = txtp
+            coef_chunks.append(c.astype(cdt).reshape(-1))
+            coef_off += k * ncf
+        # wavefront numbers among the intra records (cells of inter blocks are final from the start: depth 0)
+        wave_map = [np.zeros((ph4[p], pw4[p]), np.int32) for p in range(3)]
+        covered = [np.zeros((ph4[p], pw4[p]), bool) for p in range(3)]
+        wave = np.zeros(len(tx), np.int64)
+        for i in range(len(tx)):
+            r = tx[i]
+            pl, x, y = int(r["plane"]), int(r["x4"]), int(r["y4"])
+            tw, th = _L.TX_W[r["tx"]] // 4, _L.TX_H[r["tx"]] // 4
+            wm = wave_map[pl]
+            dep = 0
+            if x > 0:
+                dep = max(dep, int(wm[y:y + min(th, ph4[pl] - y), x - 1].max()))
+            if y > 0:
+                dep = max(dep, int(wm[y - 1, x:x + min(tw, pw4[pl] - x)].max()))
+            if x > 0 and y > 0:
+                dep = max(dep, int(wm[y - 1, x - 1]))
+            wave[i] = dep + 1
+            wm[y:y + th, x:x + tw] = dep + 1
+            covered[pl][y:y + th, x:x + tw] = True
+        # done map image (b200_intra_scratch_bytes layout): 256 zero bytes, then one byte per 4x4 cell of plane 0, 1, 2,
+        # each map padded to a multiple of 256 bytes; 1 = final before the kernel starts (not covered by an intra record)
+        parts = [np.zeros(256, np.uint8)]
+        for p in range(3):
+            mcell = (~covered[p]).astype(np.uint8).reshape(-1)
+            parts.append(np.concatenate([mcell, np.zeros((-len(mcell)) % 256, np.uint8)]))
+        intra_extra = dict(intra_tx=tx[np.argsort(wave, kind="stable")].copy(), intra_tx_decode_order=tx, intra_waves=int(wave.max()),
+                           done_init=np.concatenate(parts))
     coefs = np.concatenate(coef_chunks) if coef_chunks else np.zeros(1, cdt)
 
     def to_arr(lst, dtp):
@@ -445,6 +552,7 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
              comp2=by_area(to_arr(comp2, COMP_BLOCK_DT)), pred_single=by_area(to_arr(pred_single, MC_BLOCK_DT)),
              cfused=by_area(to_arr(cfused, COMP_FUSED_DT)), cfused2=by_area(to_arr(cfused2, COMP_FUSED_DT)),
              itx=itx_arrays, coefs=coefs, tmp_len=tmp_off + 64, mask=rng.integers(0, 65, max(1, mask_off)).astype(np.uint8))
+    S.update(intra_extra)
     S["pic"] = np.zeros(total, dt)                     # the picture being reconstructed
     # post-filter records from the transform tilings
     S["masks"] = build_lf_masks(w4, h4, tuple(ty), tuple(tuv), ss_hor, ss_ver)

@@ -39,6 +39,14 @@ def oracle_frame(S, run_lf=True, run_cdef=True, run_lr=True):
         a = S["itx"][tx]
         if len(a):
             assert o.oracle_itx_add_batch(bd, tx, a.ctypes.data, len(a), coefs.ctypes.data, pic.ctypes.data, st, 0) == 0
+    if S.get("intra_tx") is not None and len(S["intra_tx"]):
+        # intra blocks of a mixed frame: record by record, after every inter block is in the picture
+        import test_intra as TI
+        fr_i = TI.intra_frame_struct(S, pic, coefs)
+        tx = np.ascontiguousarray(S["intra_tx_decode_order"])
+        fn = o.oracle_intra_frame
+        fn.restype = None
+        fn(C.c_int(bd), C.byref(fr_i), C.c_void_p(tx.ctypes.data), C.c_int(len(tx)))
     out = {"recon": pic.copy()}
     S2 = dict(S); S2["pic"] = pic
     if run_lf:
@@ -172,6 +180,38 @@ def test_gpu_frame_bands(bpc, W, H, ssh, ssv):
     exp = oracle_frame(S)
     for fb in _banded_variants(S):
         fb.run_bands()
+        fb.alloc.sync()
+        check_frame(S, fb, exp)
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("bpc,W,H", [(8, 264, 200), (10, 200, 136)])
+def test_emu_mixed_frame(bpc, W, H):
+    """an inter frame in which a share of the blocks is intra coded (what real inter frames contain): the intra kernel runs
+    on top of the inter stages from a pre-marked done map; equals the oracle, whole-frame and as a single band"""
+    S = synth.make_inter_frame(np.random.default_rng(650 + bpc), bpc, W, H, p_intra=0.25, film_grain=bpc > 8)
+    assert len(S["intra_tx"]) > 30 and S["intra_waves"] > 2
+    exp = oracle_frame(S)
+    S0 = dict(S); S0["intra_tx"] = S["intra_tx"][:0]
+    assert not np.array_equal(exp["recon"], oracle_frame(S0)["recon"])
+    kw = dict(lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
+    fb = frame.FrameBuffers(S, **kw)
+    fb.run()
+    check_frame(S, fb, exp)
+    fb1 = frame.FrameBuffers(S, band_rows=-(-H // 64) * 64, compact=True, **kw)      # the pipeline's whole-frame band
+    assert fb1.n_bands() == 1
+    fb1.run_bands()
+    check_frame(S, fb1, exp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bpc,W,H", [(8, 648, 520), (10, 1288, 720)])
+def test_gpu_mixed_frame(bpc, W, H):
+    S = synth.make_inter_frame(np.random.default_rng(660 + bpc), bpc, W, H, p_intra=0.15, film_grain=bpc > 8)
+    exp = oracle_frame(S)
+    for kw in (dict(), dict(band_rows=-(-H // 64) * 64, compact=True)):
+        fb = frame.FrameBuffers(S, **kw)
+        fb.run_bands() if kw else fb.run()
         fb.alloc.sync()
         check_frame(S, fb, exp)
 
