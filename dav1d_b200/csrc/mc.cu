@@ -69,6 +69,10 @@ B200_DEV void mc_taps(McTaps &t, int filter2d, int mx, int my, int w, int h)
     t.has_h = mx != 0; t.has_v = my != 0; t.fsh = bilin ? 4 : 6;
 #pragma unroll
     for (int k = 0; k < 8; k++) t.fh[k] = t.fv[k] = 0;
+    // an axis without a fractional phase gets the identity filter (1 << fsh at the centre tap): every block then runs the
+    // same horizontal + vertical code, and the result is the reference's "no filter on this axis" arithmetic exactly
+    // (sum = px << fsh, so each rounding shift of the filtered form reduces to the shift of the unfiltered form)
+    t.fh[3] = t.fv[3] = 1 << t.fsh;
     if (bilin) {
         t.fh[3] = 16 - mx; t.fh[4] = mx; t.fv[3] = 16 - my; t.fv[4] = my;
     } else {
@@ -89,15 +93,18 @@ B200_DEV void mc_taps(McTaps &t, int filter2d, int mx, int my, int w, int h)
 }
 
 // ---- put / prep, register-column form ------------------------------------------------------------------
-// One warp per prediction block; a lane owns an ITEM = one output column x R consecutive rows. It filters the R (+7)
-// source rows of its column horizontally straight from the reference picture (three aligned 32-bit words per row,
-// realigned with funnel shifts, 2 dp4a — 10/12-bit: five words, 4 dp2a), keeps those `mid` values in registers and
-// runs the vertical filter from them. No shared memory, no barriers, no int16 round trip: neighbouring lanes read the
-// same words (L1 hits), every load of an item is independent (memory-level parallelism instead of occupancy), and a
-// row store is one contiguous segment per warp. R is chosen per block shape so that small blocks still spread over
-// the lanes: the redundant horizontal work of short items ((R + 7) / R rows) is cheaper than idle lanes.
-// (Round 1's kernel staged a window in shared memory and made two passes over an int16 tile: 58.8 M warp
-// instructions per 4K frame, mostly per-block set-up and tile traffic of small blocks. This form: ~3x fewer.)
+// One warp per prediction block; a lane owns an ITEM = one output column x R consecutive rows. It walks the R + 7 source
+// rows of its column from top to bottom: each row is filtered horizontally straight from the reference picture (three
+// aligned 32-bit words, realigned with funnel shifts, 2 dp4a — 10/12-bit: five words, 4 dp2a) and its value is
+// scattered into the 8 running vertical sums it contributes to (a ring of 8 accumulators: row r feeds outputs r-7 .. r);
+// the sum of output r-7 is complete after row r and is rounded and stored at once. No shared memory, no barriers, no
+// int16 tile: neighbouring lanes read the same words (L1 hits), a row store is one contiguous segment per warp, and the
+// code is ONE loop body of 8 rows for every block shape and filter (an axis without a fractional phase runs the identity
+// filter), a couple of hundred instructions.
+// History: round 1 staged a window in shared memory and made two passes over an int16 tile (58.8 M warp instructions per
+// 4K frame, 81 us). A first register form kept all R + 7 row values in registers, fully unrolled per item height and per
+// filter case: 37 M instructions but 157 KB of straight-line code; ncu showed `no_instruction` (instruction-cache misses)
+// as the top stall and 105 us. The rolling ring keeps the instruction count and fits the instruction cache.
 template <bool HBD> struct McSrc {
     typedef typename Bd<HBD>::pixel pixel;
     const pixel *ref; int rs, rw, rh;
@@ -107,46 +114,13 @@ struct McOut {             // where an item's outputs go: pixels (put) or int16 
     void *px; int ds; int16_t *tmp; int tw; bool is_prep;
 };
 
-// horizontally filtered value from the aligned words at `p` (first tap's sample is `al` samples into the first word)
-template <bool HBD>
-B200_DEV int mc_hfilter_words(const unsigned char *p, const unsigned al_shift, const int fh_lo, const int fh_hi, const int rnd, const int sh)
-{
-    const unsigned *wp = (const unsigned *)p;
-    if constexpr (!HBD) {
-        const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
-        const unsigned lo = __funnelshift_r(w0, w1, al_shift), hi = __funnelshift_r(w1, w2, al_shift);
-        return dp4a_us(hi, fh_hi, dp4a_us(lo, fh_lo, rnd)) >> sh;
-    } else {
-        const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-        const unsigned a0 = __funnelshift_r(w0, w1, al_shift), a1 = __funnelshift_r(w1, w2, al_shift);
-        const unsigned a2 = __funnelshift_r(w2, w3, al_shift), a3 = __funnelshift_r(w3, w4, al_shift);
-        int acc = dp2a_us<false>(a0, fh_lo, rnd);
-        acc = dp2a_us<true>(a1, fh_lo, acc);
-        acc = dp2a_us<false>(a2, fh_hi, acc);
-        acc = dp2a_us<true>(a3, fh_hi, acc);
-        return acc >> sh;
-    }
-}
-
-// final rounding of one output (reference src/mc_tmpl.c: put / prep after the last pass)
-template <bool HAS_H, bool HAS_V>
-B200_DEV int mc_finish(const int v, const int fsh, const int ib, const int bias, const int bdmax, const bool is_prep)
-{
-    if (HAS_V) {
-        if (HAS_H) return is_prep ? RND_SH(v, fsh) - bias : iclip(RND_SH(v, fsh + ib), 0, bdmax);
-        return is_prep ? RND_SH(v, fsh - ib) - bias : iclip(RND_SH(v, fsh), 0, bdmax);
-    }
-    if (HAS_H) return is_prep ? v - bias : iclip((v + ((1 << ib) >> 1)) >> ib, 0, bdmax);
-    return is_prep ? (v << ib) - bias : v;
-}
-
 // per-prediction constants of an item computation
 template <bool HBD> struct McPred {
     McSrc<HBD> S;
-    McTaps t;
+    int fv[8];               // vertical taps
     int fh_lo, fh_hi;        // horizontal taps packed as signed bytes (dp4a / dp2a operands)
     int gx, gy;              // reference sample of output (0, 0)'s first tap
-    int hsh, hrnd;           // horizontal pass: (sum + hrnd) >> hsh = RND_SH(sum, fsh - intermediate_bits)
+    int fsh, hsh, hrnd;      // base shift; horizontal pass: (sum + hrnd) >> hsh = RND_SH(sum, fsh - intermediate_bits)
     bool interior;
 };
 
@@ -157,148 +131,144 @@ B200_DEV void mc_pred_setup(McPred<HBD> &P, const B200McFrame &fr, int ref, int 
     typedef typename Bd<HBD>::pixel pixel;
     P.S.ref = (const pixel *)fr.ref[ref] + fr.ref_plane_off[pl];
     P.S.rs = fr.ref_stride[pl]; P.S.rw = fr.ref_w[pl]; P.S.rh = fr.ref_h[pl];
-    mc_taps(P.t, filter2d, mx, my, w, h);
-    P.fh_lo = (P.t.fh[0] & 0xff) | (P.t.fh[1] & 0xff) << 8 | (P.t.fh[2] & 0xff) << 16 | (P.t.fh[3] & 0xff) << 24;
-    P.fh_hi = (P.t.fh[4] & 0xff) | (P.t.fh[5] & 0xff) << 8 | (P.t.fh[6] & 0xff) << 16 | (P.t.fh[7] & 0xff) << 24;
-    P.gx = sx - (P.t.has_h ? 3 : 0); P.gy = sy - (P.t.has_v ? 3 : 0);
-    P.hsh = P.t.fsh - ib; P.hrnd = (1 << P.hsh) >> 1;
-    // is every sample (and every aligned word) the block's items read inside the reference plane?
+    McTaps t;
+    mc_taps(t, filter2d, mx, my, w, h);
+#pragma unroll
+    for (int k = 0; k < 8; k++) P.fv[k] = t.fv[k];
+    P.fh_lo = (t.fh[0] & 0xff) | (t.fh[1] & 0xff) << 8 | (t.fh[2] & 0xff) << 16 | (t.fh[3] & 0xff) << 24;
+    P.fh_hi = (t.fh[4] & 0xff) | (t.fh[5] & 0xff) << 8 | (t.fh[6] & 0xff) << 16 | (t.fh[7] & 0xff) << 24;
+    P.gx = sx - 3; P.gy = sy - 3;
+    P.fsh = t.fsh; P.hsh = t.fsh - ib; P.hrnd = (1 << P.hsh) >> 1;
+    // is every sample (and every aligned word) the block's items read inside the reference plane? The window is always the
+    // 8-tap one (w + 7) x (h + 7): samples under the zero taps of an identity / 4-tap / bilinear filter are read, not used
     constexpr int PPW = HBD ? 2 : 4;
-    const int nc = w + (P.t.has_h ? 7 : 0), nr = h + (P.t.has_v ? 7 : 0);
+    const int nc = w + 7, nr = h + 7;
     bool in = !(P.S.rs & (PPW - 1)) && !(((uintptr_t)P.S.ref) & 3) && P.gx >= 0 && P.gy >= 0 && P.gx + nc <= P.S.rw && P.gy + nr <= P.S.rh;
     // the realigning loads read whole words: from the word holding the first tap to one word past the one holding the last
     // tap; all of it must lie inside the row's pitch (the bottom row has nothing behind it to run into)
-    if (in && P.t.has_h) in = (P.gx & ~(PPW - 1)) + ((nc + (P.gx & (PPW - 1)) + PPW - 1) & ~(PPW - 1)) + PPW <= P.S.rs;
+    if (in) in = (P.gx & ~(PPW - 1)) + ((nc + (P.gx & (PPW - 1)) + PPW - 1) & ~(PPW - 1)) + PPW <= P.S.rs;
     P.interior = in;
 }
 
-// the R vertical-pass sums (or horizontal values / plain samples without a vertical filter) of the item at column x, rows
-// y0 .. y0 + R - 1. Interior form: straight-line code, no branch between the loads of different rows, so that the loads
-// of a whole item are in flight together.
-template <bool HBD, int R, bool HAS_H, bool HAS_V>
-B200_DEV void mc_item_interior(const McPred<HBD> &P, const int x, const int y0, int (&v)[R])
+// horizontally filtered value of window row r (0 = first tap row of the item) at column b0 (= first tap's sample).
+// INTERIOR: aligned words at ip + r * pitch; otherwise per-sample loads clamped to the plane = dav1d's emu_edge
+// (reference src/mc_tmpl.c:868-916) folded in (a few percent of the blocks of a frame).
+template <bool HBD, bool INTERIOR>
+B200_DEV int mc_hrow(const McPred<HBD> &P, const unsigned char *ip, const int rsb, const unsigned al, const int row, const int b0)
 {
     typedef typename Bd<HBD>::pixel pixel;
-    constexpr int PX = HBD ? 2 : 1, PPW = HBD ? 2 : 4;
-    constexpr int NR = HAS_V ? R + 7 : R;
-    const int rsb = P.S.rs * PX;
-    const int b0 = P.gx + x;
-    const unsigned char *ip = (const unsigned char *)P.S.ref + (ptrdiff_t)(P.gy + y0) * rsb + (HAS_H ? (b0 & ~(PPW - 1)) : b0) * PX;
-    const unsigned al = HAS_H ? (b0 & (PPW - 1)) * (HBD ? 16 : 8) : 0;
-    int mid[NR];
-#pragma unroll
-    for (int r = 0; r < NR; r++) {
-        const unsigned char *rp = ip + (ptrdiff_t)r * rsb;
-        if (HAS_H) mid[r] = mc_hfilter_words<HBD>(rp, al, P.fh_lo, P.fh_hi, P.hrnd, P.hsh);
-        else mid[r] = (int)*(const pixel *)rp;
-    }
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-        if (HAS_V) {
-            int a = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) a += P.t.fv[k] * mid[j + k];
-            v[j] = a;
-        } else v[j] = mid[j];
-    }
-}
-
-// blocks whose window leaves the reference plane (or whose plane is not word addressable): per-sample clamped loads
-// = dav1d's emu_edge (reference src/mc_tmpl.c:868-916) folded in. Compact (run-time filter flags, row loop not unrolled
-// over the filter cases): a few percent of the blocks of a frame take this path.
-template <bool HBD, int R>
-B200_DEV void mc_item_edge(const McPred<HBD> &P, const int x, const int y0, int (&v)[R])
-{
-    typedef typename Bd<HBD>::pixel pixel;
-    const bool has_h = P.t.has_h, has_v = P.t.has_v;
-    const int nr = has_v ? R + 7 : R;
-    int mid[R + 7];
-#pragma unroll
-    for (int r = 0; r < R + 7; r++) {
-        mid[r] = 0;
-        if (r < nr) {
-            const pixel *rp = P.S.ref + (ptrdiff_t)iclip(P.gy + y0 + r, 0, P.S.rh - 1) * P.S.rs;
-            if (has_h) {
-                int acc = P.hrnd;
-#pragma unroll
-                for (int k = 0; k < 8; k++) acc += P.t.fh[k] * (int)rp[iclip(P.gx + x + k, 0, P.S.rw - 1)];
-                mid[r] = acc >> P.hsh;
-            } else mid[r] = (int)rp[iclip(P.gx + x, 0, P.S.rw - 1)];
+    if constexpr (INTERIOR) {
+        const unsigned *wp = (const unsigned *)(ip + (ptrdiff_t)row * rsb);
+        if constexpr (!HBD) {
+            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
+            const unsigned lo = __funnelshift_r(w0, w1, al), hi = __funnelshift_r(w1, w2, al);
+            return dp4a_us(hi, P.fh_hi, dp4a_us(lo, P.fh_lo, P.hrnd)) >> P.hsh;
+        } else {
+            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+            const unsigned a0 = __funnelshift_r(w0, w1, al), a1 = __funnelshift_r(w1, w2, al);
+            const unsigned a2 = __funnelshift_r(w2, w3, al), a3 = __funnelshift_r(w3, w4, al);
+            int acc = dp2a_us<false>(a0, P.fh_lo, P.hrnd);
+            acc = dp2a_us<true>(a1, P.fh_lo, acc);
+            acc = dp2a_us<false>(a2, P.fh_hi, acc);
+            acc = dp2a_us<true>(a3, P.fh_hi, acc);
+            return acc >> P.hsh;
         }
-    }
-#pragma unroll
-    for (int j = 0; j < R; j++) {
-        if (has_v) {
-            int a = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) a += P.t.fv[k] * mid[j + k];
-            v[j] = a;
-        } else v[j] = mid[j];
-    }
-}
-
-// run-time dispatch on the filter flags (warp uniform: one block per warp)
-template <bool HBD, int R>
-B200_DEV void mc_item(const McPred<HBD> &P, const int x, const int y0, int (&v)[R])
-{
-    if (!P.interior) { mc_item_edge<HBD, R>(P, x, y0, v); return; }
-    if (P.t.has_h) {
-        if (P.t.has_v) mc_item_interior<HBD, R, true, true>(P, x, y0, v);
-        else mc_item_interior<HBD, R, true, false>(P, x, y0, v);
     } else {
-        if (P.t.has_v) mc_item_interior<HBD, R, false, true>(P, x, y0, v);
-        else mc_item_interior<HBD, R, false, false>(P, x, y0, v);
-    }
-}
-
-B200_DEV int mc_finish_rt(const McTaps &t, const int v, const int ib, const int bias, const int bdmax, const bool is_prep)
-{
-    if (t.has_v) return t.has_h ? mc_finish<true, true>(v, t.fsh, ib, bias, bdmax, is_prep) : mc_finish<false, true>(v, t.fsh, ib, bias, bdmax, is_prep);
-    return t.has_h ? mc_finish<true, false>(v, t.fsh, ib, bias, bdmax, is_prep) : mc_finish<false, false>(v, t.fsh, ib, bias, bdmax, is_prep);
-}
-
-// put / prep of one block: the items of the block dealt to the lanes
-template <bool HBD, int R, bool HAS_H, bool HAS_V, bool INTERIOR>
-B200_DEV void mc_block_items(const McPred<HBD> &P, const int lane, const int w, const int h, const int ib, const int bias,
-                             const int bdmax, const McOut &o)
-{
-    typedef typename Bd<HBD>::pixel pixel;
-    const int items = w * (h / R);                                     // R divides h (mc_item_rows)
-    const unsigned magic_w = recip16(w);                               // exact it / w: w is 2^k, 12 or 24 and it < 8192
-    for (int it = lane; it < items; it += 32) {
-        const int g = (int)(((unsigned)it * magic_w) >> 16), x = it - g * w, y0 = g * R;
-        int v[R];
-        if (INTERIOR) mc_item_interior<HBD, R, HAS_H, HAS_V>(P, x, y0, v);
-        else mc_item_edge<HBD, R>(P, x, y0, v);
+        const pixel *rp = P.S.ref + (ptrdiff_t)iclip(P.gy + row, 0, P.S.rh - 1) * P.S.rs;
+        unsigned p[8];
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-            const int out = INTERIOR ? mc_finish<HAS_H, HAS_V>(v[j], P.t.fsh, ib, bias, bdmax, o.is_prep)
-                                     : mc_finish_rt(P.t, v[j], ib, bias, bdmax, o.is_prep);
-            if (o.is_prep) o.tmp[(y0 + j) * o.tw + x] = (int16_t)out;
-            else ((pixel *)o.px)[(ptrdiff_t)(y0 + j) * o.ds + x] = (pixel)out;
+        for (int k = 0; k < 8; k++) p[k] = rp[iclip(b0 + k, 0, P.S.rw - 1)];
+        if constexpr (!HBD) {
+            const unsigned lo = p[0] | p[1] << 8 | p[2] << 16 | p[3] << 24, hi = p[4] | p[5] << 8 | p[6] << 16 | p[7] << 24;
+            return dp4a_us(hi, P.fh_hi, dp4a_us(lo, P.fh_lo, P.hrnd)) >> P.hsh;
+        } else {
+            int acc = dp2a_us<false>(p[0] | p[1] << 16, P.fh_lo, P.hrnd);
+            acc = dp2a_us<true>(p[2] | p[3] << 16, P.fh_lo, acc);
+            acc = dp2a_us<false>(p[4] | p[5] << 16, P.fh_hi, acc);
+            acc = dp2a_us<true>(p[6] | p[7] << 16, P.fh_hi, acc);
+            return acc >> P.hsh;
         }
     }
 }
 
-// rows of an item: the largest R for which the block still gives every lane an item (an item costs ~10 instructions per
-// source row + ~12 per output; idle lanes cost the same as busy ones)
+// The rolling vertical filter of NP predictions in lockstep (1: put / prep, 2: compound). emit(j, v[NP]) receives the
+// complete vertical sums of output row y0 + j, j = 0 .. R - 1 in order. Window row r (r = 0 .. R + 6) feeds output j = r - k
+// with tap k; output j lives in accumulator j & 7 until row j + 7 has been added.
+template <bool HBD, bool INTERIOR, int NP, class Emit>
+B200_DEV void mc_item_roll(const McPred<HBD> (&P)[NP], const int x, const int y0, const int R, Emit emit)
+{
+    constexpr int PX = HBD ? 2 : 1, PPW = HBD ? 2 : 4;
+    const unsigned char *ip[NP]; int rsb[NP], b0[NP]; unsigned al[NP];
+    int acc[NP][8];
+#pragma unroll
+    for (int n = 0; n < NP; n++) {
+        rsb[n] = P[n].S.rs * PX;
+        b0[n] = P[n].gx + x;
+        ip[n] = (const unsigned char *)P[n].S.ref + (ptrdiff_t)(P[n].gy + y0) * rsb[n] + (b0[n] & ~(PPW - 1)) * PX;
+        al[n] = (b0[n] & (PPW - 1)) * (HBD ? 16 : 8);
+    }
+    // rows 0 .. 6: no output completes yet
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+#pragma unroll
+        for (int n = 0; n < NP; n++) {
+            const int m = mc_hrow<HBD, INTERIOR>(P[n], ip[n], rsb[n], al[n], INTERIOR ? r : y0 + r, b0[n]);
+            acc[n][r] = P[n].fv[0] * m;
+#pragma unroll
+            for (int k = 1; k <= r; k++) acc[n][r - k] += P[n].fv[k] * m;
+        }
+    }
+    // rows 7 .. R + 6, eight per trip: row 7 + 8 g + i completes output 8 g + i, held in accumulator i
+    for (int rb = 7; rb < R + 7; rb += 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = rb + i;
+            if (r >= R + 7) break;
+            int v[NP];
+#pragma unroll
+            for (int n = 0; n < NP; n++) {
+                const int m = mc_hrow<HBD, INTERIOR>(P[n], ip[n], rsb[n], al[n], INTERIOR ? r : y0 + r, b0[n]);
+#pragma unroll
+                for (int k = 1; k < 8; k++) acc[n][(7 + i - k) & 7] += P[n].fv[k] * m;
+                v[n] = acc[n][i];                                  // output r - 7: all eight taps are in
+                acc[n][(7 + i) & 7] = P[n].fv[0] * m;              // output r starts in the slot output r - 8 left long ago
+            }
+            emit(r - 7, v);
+        }
+    }
+}
+
+// final rounding of one output (reference src/mc_tmpl.c: put / prep after the second pass)
+B200_DEV int mc_finish(const int v, const int fsh, const int ib, const int bias, const int bdmax, const bool is_prep)
+{
+    return is_prep ? RND_SH(v, fsh) - bias : iclip(RND_SH(v, fsh + ib), 0, bdmax);
+}
+
+// rows of an item: as many as still give every lane an item (an item costs ~20 instructions per source row, R + 7 of
+// them, + ~5 per output; idle lanes cost the same as busy ones), a power of two that divides the height
 B200_DEV int mc_item_rows(int w, int h)
 {
-    const int a = w * h;
-    int R = a >= 512 ? 16 : a >= 256 ? 8 : a >= 128 ? 4 : a >= 64 ? 2 : 1;
+    int R = imin(32, imax(1, (w * h) >> 5));
+    R = 1 << (31 - __clz(R));
     while (h & (R - 1)) R >>= 1;        // whole items only (h is 2^k, or 12 / 24 for OBMC neighbour predictions)
     return R;
 }
 
-template <bool HBD, bool HAS_H, bool HAS_V>
-B200_DEV void mc_block_dispatch(const McPred<HBD> &P, int lane, int w, int h, int ib, int bias, int bdmax, const McOut &o)
+template <bool HBD, bool INTERIOR>
+B200_DEV void mc_block_items(const McPred<HBD> (&P)[1], const int lane, const int w, const int h, const int ib, const int bias,
+                             const int bdmax, const McOut &o)
 {
-    switch (mc_item_rows(w, h)) {
-    case 16: mc_block_items<HBD, 16, HAS_H, HAS_V, true>(P, lane, w, h, ib, bias, bdmax, o); break;
-    case 8:  mc_block_items<HBD, 8, HAS_H, HAS_V, true>(P, lane, w, h, ib, bias, bdmax, o); break;
-    case 4:  mc_block_items<HBD, 4, HAS_H, HAS_V, true>(P, lane, w, h, ib, bias, bdmax, o); break;
-    case 2:  mc_block_items<HBD, 2, HAS_H, HAS_V, true>(P, lane, w, h, ib, bias, bdmax, o); break;
-    default: mc_block_items<HBD, 1, HAS_H, HAS_V, true>(P, lane, w, h, ib, bias, bdmax, o); break;
+    typedef typename Bd<HBD>::pixel pixel;
+    const int R = mc_item_rows(w, h);
+    const int items = w * (h / R);
+    const unsigned magic_w = recip16(w);                               // exact it / w: w is 2^k, 12 or 24 and it < 8192
+    for (int it = lane; it < items; it += 32) {
+        const int g = (int)(((unsigned)it * magic_w) >> 16), x = it - g * w, y0 = g * R;
+        mc_item_roll<HBD, INTERIOR, 1>(P, x, y0, R, [&](const int j, const int (&v)[1]) {
+            const int out = mc_finish(v[0], P[0].fsh, ib, bias, bdmax, o.is_prep);
+            if (o.is_prep) o.tmp[(y0 + j) * o.tw + x] = (int16_t)out;
+            else ((pixel *)o.px)[(ptrdiff_t)(y0 + j) * o.ds + x] = (pixel)out;
+        });
     }
 }
 
@@ -314,110 +284,76 @@ mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, const __gri
     const int w = b.w, h = b.h, pl = b.plane;
     const int ib = inter_bits<HBD>(bdmax);
     const int bias = HBD ? 8192 : 0;
-    McPred<HBD> P;
-    mc_pred_setup<HBD>(P, fr, b.ref, pl, b.filter2d, b.mx, b.my, w, h, b.src_x, b.src_y, ib);
+    McPred<HBD> P[1];
+    mc_pred_setup<HBD>(P[0], fr, b.ref, pl, b.filter2d, b.mx, b.my, w, h, b.src_x, b.src_y, ib);
     // op 2: "put" into the dense pixel scratch (pitch w) that the blend stages read (OBMC neighbour predictions)
     McOut o;
     o.is_prep = b.op == 1;
     o.px = (b.op == 2 ? (pixel *)fr.px_tmp : (pixel *)fr.dst) + b.dst_off;
     o.ds = b.op == 2 ? w : fr.dst_stride[pl];
     o.tmp = fr.tmp + b.dst_off; o.tw = w;
-    if (!P.interior) {
-        // 4-row items (2 / 1 when the height asks for it): (4 + 7) / 4 source rows per output row, one instantiation each
-        if (!(h & 3)) mc_block_items<HBD, 4, false, false, false>(P, lane, w, h, ib, bias, bdmax, o);
-        else if (!(h & 1)) mc_block_items<HBD, 2, false, false, false>(P, lane, w, h, ib, bias, bdmax, o);
-        else mc_block_items<HBD, 1, false, false, false>(P, lane, w, h, ib, bias, bdmax, o);
-        return;
-    }
-    if (P.t.has_h) {
-        if (P.t.has_v) mc_block_dispatch<HBD, true, true>(P, lane, w, h, ib, bias, bdmax, o);
-        else mc_block_dispatch<HBD, true, false>(P, lane, w, h, ib, bias, bdmax, o);
-    } else {
-        if (P.t.has_v) mc_block_dispatch<HBD, false, true>(P, lane, w, h, ib, bias, bdmax, o);
-        else mc_block_dispatch<HBD, false, false>(P, lane, w, h, ib, bias, bdmax, o);
-    }
+    if (P[0].interior) mc_block_items<HBD, true>(P, lane, w, h, ib, bias, bdmax, o);
+    else mc_block_items<HBD, false>(P, lane, w, h, ib, bias, bdmax, o);
 }
 
 // ---- fused compound prediction -----------------------------------------------------------------------
-// Both predictions of a compound block and their combination in one pass, item by item in registers: a lane computes
-// the R int16-precision values of its column from the first reference, then from the second, and combines them
-// (avg / w_avg / mask / w_mask, reference src/mc_tmpl.c:628-781) — no int16 round trip through mc.tmp (2 x 2 bytes
-// written and read back per sample) and no separate compound launch. Same arithmetic as prep + compound: bit-identical.
-// w_mask sums the mask over horizontal pairs (neighbouring lanes: one shuffle) and, for 4:2:0, row pairs (same lane).
-template <bool HBD, int R>
+// Both predictions of a compound block and their combination in one pass: the two rolling filters run in lockstep, so
+// the two int16-precision values of an output row are complete together and are combined on the spot (avg / w_avg /
+// mask / w_mask, reference src/mc_tmpl.c:628-781) — no int16 round trip through mc.tmp (2 x 2 bytes written and read
+// back per sample) and no separate compound launch. Same arithmetic as prep + compound: bit-identical.
+// w_mask sums the mask over horizontal pairs (neighbouring lanes: one shuffle) and, for 4:2:0, row pairs (same lane,
+// consecutive outputs).
+template <bool HBD, bool INTERIOR>
 B200_DEV void mc_comp_fused_items(const McPred<HBD> (&P)[2], const int lane, const B200CompFusedBlock &b, const int ib,
                                   const int bias, const int bdmax, typename Bd<HBD>::pixel *dpx, const int ds, uint8_t *mask)
 {
     typedef typename Bd<HBD>::pixel pixel;
     const int w = b.w, h = b.h, op = b.op;
+    int R = mc_item_rows(w, h);
+    if (op == B200_COMP_W_MASK_420 && R < 2) R = 2;       // row pairs stay inside an item (h is even)
     const int items = w * (h / R);
     const unsigned magic_w = recip16(w);
     const int bitdepth = 32 - __clz(bdmax);
     const int ss_hor = op >= B200_COMP_W_MASK_422, ss_ver = op == B200_COMP_W_MASK_420;
+    const int sign = b.param, wt = b.param;
+    const int shc = ib + 6, rnd = (32 << ib) + bias * 64;
+    const int mask_sh = bitdepth + ib - 4, mask_rnd = 1 << (mask_sh - 5);
+    const int mw = ss_hor ? w >> 1 : w;                                // pitch of an emitted mask
     for (int it0 = 0; it0 < items; it0 += 32) {
         const bool active = it0 + lane < items;
         const int it = active ? it0 + lane : items - 1;               // idle lanes of the last round redo the last item (w_mask shuffles need the whole warp)
         const int g = (int)(((unsigned)it * magic_w) >> 16), x = it - g * w, y0 = g * R;
-        int a[R], c[R];
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            int v[R];
-            mc_item<HBD, R>(P[r], x, y0, v);
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-                const int p = mc_finish_rt(P[r].t, v[j], ib, bias, bdmax, true);
-                if (r == 0) a[j] = p; else c[j] = p;
-            }
-        }
-        if (op <= B200_COMP_MASK) {
-            if (!active) continue;
-#pragma unroll
-            for (int j = 0; j < R; j++) {
+        int m_prev = 0;
+        mc_item_roll<HBD, INTERIOR, 2>(P, x, y0, R, [&](const int j, const int (&v)[2]) {
+            const int a = mc_finish(v[0], P[0].fsh, ib, bias, bdmax, true), c = mc_finish(v[1], P[1].fsh, ib, bias, bdmax, true);
+            const int y = y0 + j;
+            if (op <= B200_COMP_MASK) {
                 int o;
-                if (op == B200_COMP_AVG) o = (a[j] + c[j] + (1 << ib) + bias * 2) >> (ib + 1);
-                else if (op == B200_COMP_W_AVG) o = (a[j] * b.param + c[j] * (16 - b.param) + (8 << ib) + bias * 16) >> (ib + 4);
-                else { const int m = mask[(y0 + j) * w + x]; o = (a[j] * m + c[j] * (64 - m) + (32 << ib) + bias * 64) >> (ib + 6); }
-                dpx[(ptrdiff_t)(y0 + j) * ds + x] = (pixel)iclip(o, 0, bdmax);
-            }
-        } else {
-            // w_mask: derive the blend mask from |tmp1 - tmp2|, blend, emit the (sub-sampled) mask
-            const int sign = b.param;
-            const int shc = ib + 6, rnd = (32 << ib) + bias * 64;
-            const int mask_sh = bitdepth + ib - 4, mask_rnd = 1 << (mask_sh - 5);
-            const int mw = ss_hor ? w >> 1 : w;                        // pitch of the emitted mask
-            int m[R];
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-                const int d = a[j] - c[j];
-                m[j] = imin(38 + ((iabs(d) + mask_rnd) >> mask_sh), 64);
-                if (active) dpx[(ptrdiff_t)(y0 + j) * ds + x] = (pixel)iclip((d * m[j] + c[j] * 64 + rnd) >> shc, 0, bdmax);
-            }
-            if (!ss_hor) {
-                if (active) {
-#pragma unroll
-                    for (int j = 0; j < R; j++) mask[(y0 + j) * w + x] = (uint8_t)m[j];
-                }
+                if (op == B200_COMP_AVG) o = (a + c + (1 << ib) + bias * 2) >> (ib + 1);
+                else if (op == B200_COMP_W_AVG) o = (a * wt + c * (16 - wt) + (8 << ib) + bias * 16) >> (ib + 4);
+                else { const int m = mask[y * w + x]; o = (a * m + c * (64 - m) + (32 << ib) + bias * 64) >> (ib + 6); }
+                if (active) dpx[(ptrdiff_t)y * ds + x] = (pixel)iclip(o, 0, bdmax);
             } else {
-#pragma unroll
-                for (int j = 0; j < R; j++) m[j] += __shfl_xor_sync(0xffffffffu, m[j], 1);       // x and x ^ 1 are neighbouring lanes (w is even)
-                if (active && !(x & 1)) {
+                // w_mask: derive the blend mask from |tmp1 - tmp2|, blend, emit the (sub-sampled) mask
+                const int d = a - c;
+                int m = imin(38 + ((iabs(d) + mask_rnd) >> mask_sh), 64);
+                if (active) dpx[(ptrdiff_t)y * ds + x] = (pixel)iclip((d * m + c * 64 + rnd) >> shc, 0, bdmax);
+                if (!ss_hor) {
+                    if (active) mask[y * w + x] = (uint8_t)m;
+                } else {
+                    m += __shfl_xor_sync(0xffffffffu, m, 1);           // x and x ^ 1 are neighbouring lanes (w is even)
                     if (ss_ver) {
-                        if constexpr (R >= 2) {
-#pragma unroll
-                            for (int j = 0; j < R; j += 2) mask[((y0 + j) >> 1) * mw + (x >> 1)] = (uint8_t)((m[j] + m[j + 1] + 2 - sign) >> 2);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < R; j++) mask[(y0 + j) * mw + (x >> 1)] = (uint8_t)((m[j] + 1 - sign) >> 1);
-                    }
+                        if (j & 1) { if (active && !(x & 1)) mask[(y >> 1) * mw + (x >> 1)] = (uint8_t)((m_prev + m + 2 - sign) >> 2); }
+                        else m_prev = m;
+                    } else if (active && !(x & 1)) mask[y * mw + (x >> 1)] = (uint8_t)((m + 1 - sign) >> 1);
                 }
             }
-        }
+        });
     }
 }
 
 template <bool HBD>
-__global__ void __launch_bounds__(kMcWarps * 32, B200_MC_MINB)
+__global__ void __launch_bounds__(kMcWarps * 32, 4)          // two rings + two tap sets: 128 registers, no spills
 mc_comp_fused_kernel(const B200CompFusedBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
     typedef typename Bd<HBD>::pixel pixel;
@@ -434,14 +370,8 @@ mc_comp_fused_kernel(const B200CompFusedBlock *__restrict__ blocks, int n_blocks
     pixel *const dpx = (pixel *)fr.dst + b.dst_off;
     const int ds = fr.dst_stride[pl];
     uint8_t *const mask = fr.mask + b.mask_off;
-    int R = imin(mc_item_rows(w, h), 8);                  // two predictions' worth of registers per item
-    if (b.op == B200_COMP_W_MASK_420 && R < 2) R = 2;     // row pairs stay inside an item (h is even)
-    switch (R) {
-    case 8:  mc_comp_fused_items<HBD, 8>(P, lane, b, ib, bias, bdmax, dpx, ds, mask); break;
-    case 4:  mc_comp_fused_items<HBD, 4>(P, lane, b, ib, bias, bdmax, dpx, ds, mask); break;
-    case 2:  mc_comp_fused_items<HBD, 2>(P, lane, b, ib, bias, bdmax, dpx, ds, mask); break;
-    default: mc_comp_fused_items<HBD, 1>(P, lane, b, ib, bias, bdmax, dpx, ds, mask); break;
-    }
+    if (P[0].interior && P[1].interior) mc_comp_fused_items<HBD, true>(P, lane, b, ib, bias, bdmax, dpx, ds, mask);
+    else mc_comp_fused_items<HBD, false>(P, lane, b, ib, bias, bdmax, dpx, ds, mask);
 }
 
 // ---- scaled references -----------------------------------------------------------------------------
