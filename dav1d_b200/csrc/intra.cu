@@ -356,10 +356,13 @@ template <bool HBD> struct IwShared {
     typedef typename Bd<HBD>::pixel pixel;
     typedef typename Bd<HBD>::coef coef;
     IpShared S;                       // edge array, scratch of the directional / filter predictors
-    int itx[32 * 65];                 // transform tile (ItxGeom: SH rows of pitch W + 1, at most 32 x 65)
+    union {                           // first the transform tile (ItxGeom: SH rows of pitch W + 1, at most 32 x 65) while the residual
+        int itx[32 * 65];             // is computed, then (the residual sits in `resid`) the prediction of the block (pitch = its width)
+        pixel px[64 * 64];
+    } u;
+    int16_t resid[64 * 64];           // the block's residual, transformed while the warp still waits for its neighbours
     coef cf[32 * 32];
     int16_t ac[32 * 32];
-    pixel px[64 * 64];                // the block being reconstructed (pitch = its width)
 };
 
 template <bool HBD>
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(kIwWarps * 32) intra_warp_kernel(const __grid_
 #endif
     IwShared<HBD> &W = all[threadIdx.x >> 5];
     IpShared &S = W.S;
-    pixel *const s_px = W.px;
+    pixel *const s_px = W.u.px;
     int16_t *const s_ac = W.ac;
     coef *const s_cf = W.cf;
     const int lane = threadIdx.x & 31;
@@ -404,8 +407,20 @@ __global__ void __launch_bounds__(kIwWarps * 32) intra_warp_kernel(const __grid_
         const int mw = f.w4[pl];
         const int ncf = imin(w, 32) * imin(h, 32);
         coef *const gcf = (coef *)f.d_coef + r.coef_off;
-        // coefficients: in flight while the warp waits for its neighbours
-        if (r.eob >= 0) for (int i = lane; i < ncf; i += 32) s_cf[i] = gcf[i];
+        // The residual does not depend on the neighbours: inverse transform NOW, into an int16 tile, off the dependency chain
+        // (the chain of a frame is ~1000 blocks deep; what stays on it is poll -> edge loads -> predict -> add -> store -> publish)
+        if (r.eob >= 0) {
+            for (int i = lane; i < ncf; i += 32) s_cf[i] = gcf[i];
+            __syncwarp();
+            switch (r.tx) {
+#define X(TX, TW, TH, SH) case TX: itx_add_warp<TW, TH, TX, SH, HBD>(W.u.itx, s_cf, (pixel *)nullptr, TW, r.eob, r.txtp, bdmax, W.resid); break;
+            B200_ITX_SIZES(X)
+#undef X
+            }
+            if (f.zero_coefs)
+                for (int i = lane; i < ncf; i += 32) gcf[i] = 0;
+            __syncwarp();
+        }
 
         // ---- wait for the neighbours whose pixels the edge array reads
         {
@@ -536,20 +551,17 @@ __global__ void __launch_bounds__(kIwWarps * 32) intra_warp_kernel(const __grid_
             __syncwarp();
         }
 
-        // ---- residual, added in the shared tile
+        // ---- prediction + residual -> picture, publish
         if (r.eob >= 0) {
-            switch (r.tx) {
-#define X(TX, TW, TH, SH) case TX: itx_add_warp<TW, TH, TX, SH, HBD>(W.itx, s_cf, s_px, TW, r.eob, r.txtp, bdmax); break;
-            B200_ITX_SIZES(X)
-#undef X
+            for (int i = lane; i < w * h; i += 32) {
+                const int yy = i / w, xx = i - yy * w;
+                dst[(ptrdiff_t)yy * st + xx] = (pixel)iclip((int)s_px[i] + W.resid[i], 0, bdmax);
             }
-            if (f.zero_coefs)
-                for (int i = lane; i < ncf; i += 32) gcf[i] = 0;
-        }
-        // ---- write the block, publish
-        for (int i = lane; i < w * h; i += 32) {
-            const int yy = i / w, xx = i - yy * w;
-            dst[(ptrdiff_t)yy * st + xx] = s_px[i];
+        } else {
+            for (int i = lane; i < w * h; i += 32) {
+                const int yy = i / w, xx = i - yy * w;
+                dst[(ptrdiff_t)yy * st + xx] = s_px[i];
+            }
         }
         __syncwarp();
         {

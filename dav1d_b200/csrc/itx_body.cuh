@@ -56,9 +56,12 @@ __device__ __noinline__ void itx_row_pass_shared(const typename Bd<HBD>::coef *c
     for (int x = 0; x < W; x++) trow[x] = iclip((c[x] + rnd) >> shift, col_lo, col_hi);
 }
 
+// resid != nullptr: the residual column ((c + 8) >> 4, before the add) goes to the int16 tile `resid` (pitch `stride`)
+// instead of being added to the picture column: the warp-per-block intra kernel transforms a block's coefficients
+// while it is still waiting for the neighbours its prediction needs
 template <int H, bool HBD>
 __device__ __noinline__ void itx_col_pass_shared(const int *tcol, int pitch, typename Bd<HBD>::pixel *dcol, int stride,
-                                                 int t_second, int col_lo, int col_hi, int bitdepth_max)
+                                                 int t_second, int col_lo, int col_hi, int bitdepth_max, int16_t *resid = nullptr)
 {
     typedef typename Bd<HBD>::pixel pixel;
     constexpr int SH = H < 32 ? H : 32;
@@ -66,6 +69,11 @@ __device__ __noinline__ void itx_col_pass_shared(const int *tcol, int pitch, typ
 #pragma unroll
     for (int y = 0; y < H; y++) c[y] = y < SH ? tcol[y * pitch] : 0;
     tx1d_apply<H>(c, t_second, col_lo, col_hi);
+    if (resid) {
+#pragma unroll
+        for (int y = 0; y < H; y++) resid[y * stride] = (int16_t)((c[y] + 8) >> 4);
+        return;
+    }
 #pragma unroll
     for (int y = 0; y < H; y++)
         dcol[(ptrdiff_t)y * stride] = (pixel)iclip((int)dcol[(ptrdiff_t)y * stride] + ((c[y] + 8) >> 4), 0, bitdepth_max);
@@ -241,9 +249,10 @@ B200_DEV void itx_add_body(const int cta, int *const smem, const B200ItxBlock *_
 // One transform block by ONE warp (the warp-per-block intra kernel): the same two passes as itx_add_body — lane = coefficient
 // row, padded tile `t` (>= SH * (W + 1) words), lane = picture column (64-wide blocks: two rounds) — through the out-of-line
 // 1-D passes, so that all block sizes of a kernel share one copy of each butterfly network.
+// resid != nullptr: nothing is added; the W x H residual goes to the dense int16 tile `resid` (pitch W).
 template <int W, int H, int TX, int SHIFT, bool HBD>
 B200_DEV void itx_add_warp(int *const t, typename Bd<HBD>::coef *const cf, typename Bd<HBD>::pixel *const dst, const int stride,
-                           const int eob, const int txtp, const int bitdepth_max)
+                           const int eob, const int txtp, const int bitdepth_max, int16_t *const resid = nullptr)
 {
     typedef ItxGeom<W, H> G;
     typedef typename Bd<HBD>::pixel pixel;
@@ -263,6 +272,12 @@ B200_DEV void itx_add_warp(int *const t, typename Bd<HBD>::coef *const cf, typen
         dc = (dc * 181 + 128) >> 8;
         dc = (dc + rnd) >> SHIFT;
         dc = (dc * 181 + 128 + 2048) >> 12;
+        if (resid) {
+            // (saturated: |residual| >= 2^15 clips the 12-bit sum exactly like the full value)
+            for (int i = lane; i < W * H; i += 32) resid[i] = (int16_t)iclip(dc, -32768, 32767);
+            __syncwarp();
+            return;
+        }
         for (int i = lane; i < W * H; i += 32) {
             pixel *p = dst + (ptrdiff_t)(i / W) * stride + (i % W);
             *p = (pixel)iclip((int)*p + dc, 0, bitdepth_max);
@@ -302,12 +317,13 @@ B200_DEV void itx_add_warp(int *const t, typename Bd<HBD>::coef *const cf, typen
                 iwht4(c);
 #pragma unroll
                 for (int y = 0; y < 4; y++) {
+                    if (resid) { resid[y * W + x] = (int16_t)iclip(c[y], -32768, 32767); continue; }
                     pixel *p = dst + (ptrdiff_t)y * stride + x;
                     *p = (pixel)iclip((int)*p + c[y], 0, bitdepth_max);
                 }
             }
         } else {
-            itx_col_pass_shared<H, HBD>(t + x, G::P, dst + x, stride, t_second, col_lo, col_hi, bitdepth_max);
+            itx_col_pass_shared<H, HBD>(t + x, G::P, dst + x, stride, t_second, col_lo, col_hi, bitdepth_max, resid ? resid + x : nullptr);
         }
     }
     __syncwarp();

@@ -44,6 +44,12 @@ if [[ $what == *" benchA "* ]]; then
   run_bench intra_cta B200_INTRA_CTA=1 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
   run_bench 4k10 python bench.py --workload 4k10_full --steps 20 --warmup 5
 fi
+if [[ $what == *" benchB "* ]]; then
+  run_bench n1_default python bench.py --steps 20 --warmup 5
+  run_bench n1_fused B200_FUSED=1 python bench.py --steps 20 --warmup 5
+  run_bench n1_mixed python bench.py --workload 4k8_mixed --steps 20 --warmup 5
+  run_bench 4k10 python bench.py --workload 4k10_full --steps 20 --warmup 5
+fi
 if [[ $what == *" benchI "* ]]; then
   run_bench intra_warp B200_INTRA_SB=0 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
   run_bench intra_warp_g16 B200_INTRA_SB=0 B200_INTRA_GRID=16 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
