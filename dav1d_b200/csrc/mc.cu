@@ -55,7 +55,7 @@ template <bool HI> B200_DEV int dp2a_us(unsigned px, int taps, int acc) {
 }
 
 #ifndef B200_MC_MINB
-#define B200_MC_MINB 6
+#define B200_MC_MINB 5
 #endif
 #ifndef B200_MC_S1
 #define B200_MC_S1 0
@@ -150,51 +150,54 @@ B200_DEV void mc_pred_setup(McPred<HBD> &P, const B200McFrame &fr, int ref, int 
     P.interior = in;
 }
 
-// horizontally filtered value of window row r (0 = first tap row of the item) at column b0 (= first tap's sample).
-// INTERIOR: aligned words at ip + r * pitch; otherwise per-sample loads clamped to the plane = dav1d's emu_edge
-// (reference src/mc_tmpl.c:868-916) folded in (a few percent of the blocks of a frame).
+// the aligned words (or, outside the plane interior, the clamped samples packed the same way) of window row `row` that
+// the horizontal filter of column b0 needs: loaded for a whole group of rows before any of them is filtered, so that a
+// lane has 8 rows of loads in flight (ncu on the row-at-a-time form: long_scoreboard was 8 of 12 stall cycles per issue)
+template <bool HBD> struct McRowWords { unsigned w[HBD ? 5 : 3]; };
+
 template <bool HBD, bool INTERIOR>
-B200_DEV int mc_hrow(const McPred<HBD> &P, const unsigned char *ip, const int rsb, const unsigned al, const int row, const int b0)
+B200_DEV void mc_load_row(McRowWords<HBD> &W, const McPred<HBD> &P, const unsigned char *ip, const int rsb, const int row, const int b0)
 {
     typedef typename Bd<HBD>::pixel pixel;
     if constexpr (INTERIOR) {
         const unsigned *wp = (const unsigned *)(ip + (ptrdiff_t)row * rsb);
-        if constexpr (!HBD) {
-            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
-            const unsigned lo = __funnelshift_r(w0, w1, al), hi = __funnelshift_r(w1, w2, al);
-            return dp4a_us(hi, P.fh_hi, dp4a_us(lo, P.fh_lo, P.hrnd)) >> P.hsh;
-        } else {
-            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-            const unsigned a0 = __funnelshift_r(w0, w1, al), a1 = __funnelshift_r(w1, w2, al);
-            const unsigned a2 = __funnelshift_r(w2, w3, al), a3 = __funnelshift_r(w3, w4, al);
-            int acc = dp2a_us<false>(a0, P.fh_lo, P.hrnd);
-            acc = dp2a_us<true>(a1, P.fh_lo, acc);
-            acc = dp2a_us<false>(a2, P.fh_hi, acc);
-            acc = dp2a_us<true>(a3, P.fh_hi, acc);
-            return acc >> P.hsh;
-        }
+#pragma unroll
+        for (int k = 0; k < (HBD ? 5 : 3); k++) W.w[k] = wp[k];
     } else {
+        // per-sample loads clamped to the plane = dav1d's emu_edge (reference src/mc_tmpl.c:868-916) folded in
         const pixel *rp = P.S.ref + (ptrdiff_t)iclip(P.gy + row, 0, P.S.rh - 1) * P.S.rs;
         unsigned p[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) p[k] = rp[iclip(b0 + k, 0, P.S.rw - 1)];
-        if constexpr (!HBD) {
-            const unsigned lo = p[0] | p[1] << 8 | p[2] << 16 | p[3] << 24, hi = p[4] | p[5] << 8 | p[6] << 16 | p[7] << 24;
-            return dp4a_us(hi, P.fh_hi, dp4a_us(lo, P.fh_lo, P.hrnd)) >> P.hsh;
-        } else {
-            int acc = dp2a_us<false>(p[0] | p[1] << 16, P.fh_lo, P.hrnd);
-            acc = dp2a_us<true>(p[2] | p[3] << 16, P.fh_lo, acc);
-            acc = dp2a_us<false>(p[4] | p[5] << 16, P.fh_hi, acc);
-            acc = dp2a_us<true>(p[6] | p[7] << 16, P.fh_hi, acc);
-            return acc >> P.hsh;
-        }
+        if constexpr (!HBD) { W.w[0] = p[0] | p[1] << 8 | p[2] << 16 | p[3] << 24; W.w[1] = p[4] | p[5] << 8 | p[6] << 16 | p[7] << 24; W.w[2] = 0; }
+        else { W.w[0] = p[0] | p[1] << 16; W.w[1] = p[2] | p[3] << 16; W.w[2] = p[4] | p[5] << 16; W.w[3] = p[6] | p[7] << 16; W.w[4] = 0; }
+    }
+}
+
+// horizontal filter of one loaded row: realign (al = bit offset of the first tap inside the first word; 0 for the packed
+// samples of the clamped form), 2 dp4a / 4 dp2a, rounding shift
+template <bool HBD>
+B200_DEV int mc_hfilter(const McRowWords<HBD> &W, const McPred<HBD> &P, const unsigned al)
+{
+    if constexpr (!HBD) {
+        const unsigned lo = __funnelshift_r(W.w[0], W.w[1], al), hi = __funnelshift_r(W.w[1], W.w[2], al);
+        return dp4a_us(hi, P.fh_hi, dp4a_us(lo, P.fh_lo, P.hrnd)) >> P.hsh;
+    } else {
+        const unsigned a0 = __funnelshift_r(W.w[0], W.w[1], al), a1 = __funnelshift_r(W.w[1], W.w[2], al);
+        const unsigned a2 = __funnelshift_r(W.w[2], W.w[3], al), a3 = __funnelshift_r(W.w[3], W.w[4], al);
+        int acc = dp2a_us<false>(a0, P.fh_lo, P.hrnd);
+        acc = dp2a_us<true>(a1, P.fh_lo, acc);
+        acc = dp2a_us<false>(a2, P.fh_hi, acc);
+        acc = dp2a_us<true>(a3, P.fh_hi, acc);
+        return acc >> P.hsh;
     }
 }
 
 // The rolling vertical filter of NP predictions in lockstep (1: put / prep, 2: compound). emit(j, v[NP]) receives the
 // complete vertical sums of output row y0 + j, j = 0 .. R - 1 in order. Window row r (r = 0 .. R + 6) feeds output j = r - k
-// with tap k; output j lives in accumulator j & 7 until row j + 7 has been added.
-template <bool HBD, bool INTERIOR, int NP, class Emit>
+// with tap k; output j lives in accumulator j & 7 until row j + 7 has been added. Rows are processed in groups whose
+// loads are all issued first: the 7 rows before the first output, then RG = min(R, 8) rows per group.
+template <bool HBD, bool INTERIOR, int NP, int RG, class Emit>
 B200_DEV void mc_item_roll(const McPred<HBD> (&P)[NP], const int x, const int y0, const int R, Emit emit)
 {
     constexpr int PX = HBD ? 2 : 1, PPW = HBD ? 2 : 4;
@@ -205,37 +208,55 @@ B200_DEV void mc_item_roll(const McPred<HBD> (&P)[NP], const int x, const int y0
         rsb[n] = P[n].S.rs * PX;
         b0[n] = P[n].gx + x;
         ip[n] = (const unsigned char *)P[n].S.ref + (ptrdiff_t)(P[n].gy + y0) * rsb[n] + (b0[n] & ~(PPW - 1)) * PX;
-        al[n] = (b0[n] & (PPW - 1)) * (HBD ? 16 : 8);
+        al[n] = INTERIOR ? (b0[n] & (PPW - 1)) * (HBD ? 16 : 8) : 0;
     }
-    // rows 0 .. 6: no output completes yet
+    {   // rows 0 .. 6: no output completes yet
+        McRowWords<HBD> W[NP][7];
 #pragma unroll
-    for (int r = 0; r < 7; r++) {
+        for (int r = 0; r < 7; r++)
 #pragma unroll
-        for (int n = 0; n < NP; n++) {
-            const int m = mc_hrow<HBD, INTERIOR>(P[n], ip[n], rsb[n], al[n], INTERIOR ? r : y0 + r, b0[n]);
-            acc[n][r] = P[n].fv[0] * m;
+            for (int n = 0; n < NP; n++) mc_load_row<HBD, INTERIOR>(W[n][r], P[n], ip[n], rsb[n], INTERIOR ? r : y0 + r, b0[n]);
 #pragma unroll
-            for (int k = 1; k <= r; k++) acc[n][r - k] += P[n].fv[k] * m;
-        }
+        for (int r = 0; r < 7; r++)
+#pragma unroll
+            for (int n = 0; n < NP; n++) {
+                const int m = mc_hfilter<HBD>(W[n][r], P[n], al[n]);
+                acc[n][r] = P[n].fv[0] * m;
+#pragma unroll
+                for (int k = 1; k <= r; k++) acc[n][r - k] += P[n].fv[k] * m;
+            }
     }
-    // rows 7 .. R + 6, eight per trip: row 7 + 8 g + i completes output 8 g + i, held in accumulator i
-    for (int rb = 7; rb < R + 7; rb += 8) {
+    // rows 7 .. R + 6, RG per trip (R is a multiple of RG): row 7 + 8 g + i completes output 8 g + i, held in accumulator i
+    for (int rb = 7; rb < R + 7; rb += RG) {
+        McRowWords<HBD> W[NP][RG];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int r = rb + i;
-            if (r >= R + 7) break;
+        for (int i = 0; i < RG; i++)
+#pragma unroll
+            for (int n = 0; n < NP; n++) mc_load_row<HBD, INTERIOR>(W[n][i], P[n], ip[n], rsb[n], INTERIOR ? rb + i : y0 + rb + i, b0[n]);
+#pragma unroll
+        for (int i = 0; i < RG; i++) {
             int v[NP];
 #pragma unroll
             for (int n = 0; n < NP; n++) {
-                const int m = mc_hrow<HBD, INTERIOR>(P[n], ip[n], rsb[n], al[n], INTERIOR ? r : y0 + r, b0[n]);
+                const int m = mc_hfilter<HBD>(W[n][i], P[n], al[n]);
 #pragma unroll
                 for (int k = 1; k < 8; k++) acc[n][(7 + i - k) & 7] += P[n].fv[k] * m;
-                v[n] = acc[n][i];                                  // output r - 7: all eight taps are in
-                acc[n][(7 + i) & 7] = P[n].fv[0] * m;              // output r starts in the slot output r - 8 left long ago
+                v[n] = acc[n][i];                                  // output rb + i - 7: all eight taps are in
+                acc[n][(7 + i) & 7] = P[n].fv[0] * m;              // output rb + i starts in the slot output rb + i - 8 left long ago
             }
-            emit(r - 7, v);
+            emit(rb + i - 7, v);
         }
     }
+}
+
+// run-time item height -> group size (R is a power of two)
+template <bool HBD, bool INTERIOR, int NP, class Emit>
+B200_DEV void mc_item_roll_any(const McPred<HBD> (&P)[NP], const int x, const int y0, const int R, Emit emit)
+{
+    if (R >= 8) mc_item_roll<HBD, INTERIOR, NP, 8>(P, x, y0, R, emit);
+    else if (R == 4) mc_item_roll<HBD, INTERIOR, NP, 4>(P, x, y0, R, emit);
+    else if (R == 2) mc_item_roll<HBD, INTERIOR, NP, 2>(P, x, y0, R, emit);
+    else mc_item_roll<HBD, INTERIOR, NP, 1>(P, x, y0, R, emit);
 }
 
 // final rounding of one output (reference src/mc_tmpl.c: put / prep after the second pass)
@@ -264,7 +285,7 @@ B200_DEV void mc_block_items(const McPred<HBD> (&P)[1], const int lane, const in
     const unsigned magic_w = recip16(w);                               // exact it / w: w is 2^k, 12 or 24 and it < 8192
     for (int it = lane; it < items; it += 32) {
         const int g = (int)(((unsigned)it * magic_w) >> 16), x = it - g * w, y0 = g * R;
-        mc_item_roll<HBD, INTERIOR, 1>(P, x, y0, R, [&](const int j, const int (&v)[1]) {
+        mc_item_roll_any<HBD, INTERIOR, 1>(P, x, y0, R, [&](const int j, const int (&v)[1]) {
             const int out = mc_finish(v[0], P[0].fsh, ib, bias, bdmax, o.is_prep);
             if (o.is_prep) o.tmp[(y0 + j) * o.tw + x] = (int16_t)out;
             else ((pixel *)o.px)[(ptrdiff_t)(y0 + j) * o.ds + x] = (pixel)out;
@@ -324,7 +345,7 @@ B200_DEV void mc_comp_fused_items(const McPred<HBD> (&P)[2], const int lane, con
         const int it = active ? it0 + lane : items - 1;               // idle lanes of the last round redo the last item (w_mask shuffles need the whole warp)
         const int g = (int)(((unsigned)it * magic_w) >> 16), x = it - g * w, y0 = g * R;
         int m_prev = 0;
-        mc_item_roll<HBD, INTERIOR, 2>(P, x, y0, R, [&](const int j, const int (&v)[2]) {
+        mc_item_roll_any<HBD, INTERIOR, 2>(P, x, y0, R, [&](const int j, const int (&v)[2]) {
             const int a = mc_finish(v[0], P[0].fsh, ib, bias, bdmax, true), c = mc_finish(v[1], P[1].fsh, ib, bias, bdmax, true);
             const int y = y0 + j;
             if (op <= B200_COMP_MASK) {
