@@ -254,20 +254,25 @@ B200_DEV void lr_wiener_regs(const typename Bd<HBD>::pixel *C, const typename Bd
     const int woff = (b0 & ~(PPW - 1)) * PX;
     const unsigned al = (b0 & (PPW - 1)) * (HBD ? 16 : 8);
     const int vbase = -(1 << (bitdepth + (rbv - 1))) + (1 << (rbv - 1));
-    auto hrow = [&](const int Yv) -> int {
+    // the words of one virtual source row (rows inside the stripe from the CDEF output, the two rows beyond it from the
+    // deblocked picture, clamped at the picture's top / bottom); all 14 rows of an item are loaded before any is filtered
+    struct Row { unsigned w[HBD ? 5 : 3]; };
+    auto load = [&](Row &W, const int Yv) {
         const pixel *base = C; int Y = Yv;
         if (Y < y0s) { if (have_top) { base = D; Y = imax(Y, y0s - 2); } else Y = y0s; }
         else if (Y >= y1s) { if (have_bot) { base = D; Y = imin(imin(Y, y1s + 1), h - 1); } else Y = y1s - 1; }
         const unsigned *wp = (const unsigned *)((const unsigned char *)(base + (ptrdiff_t)Y * st) + woff);
+#pragma unroll
+        for (int k = 0; k < (HBD ? 5 : 3); k++) W.w[k] = wp[k];
+    };
+    auto hfilter = [&](const Row &W) -> int {
         int sum;
         if constexpr (!HBD) {
-            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
-            const unsigned lo = __funnelshift_r(w0, w1, al), hi = __funnelshift_r(w1, w2, al);
+            const unsigned lo = __funnelshift_r(W.w[0], W.w[1], al), hi = __funnelshift_r(W.w[1], W.w[2], al);
             sum = lr_dp4a_us(hi, t_hi, lr_dp4a_us(lo, t_lo, hbase)) + (int)(lo >> 24) * 128;
         } else {
-            const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-            const unsigned a0 = __funnelshift_r(w0, w1, al), a1 = __funnelshift_r(w1, w2, al);
-            const unsigned a2 = __funnelshift_r(w2, w3, al), a3 = __funnelshift_r(w3, w4, al);
+            const unsigned a0 = __funnelshift_r(W.w[0], W.w[1], al), a1 = __funnelshift_r(W.w[1], W.w[2], al);
+            const unsigned a2 = __funnelshift_r(W.w[2], W.w[3], al), a3 = __funnelshift_r(W.w[3], W.w[4], al);
             sum = lr_dp2a_us<false>(a0, t_lo, hbase);
             sum = lr_dp2a_us<true>(a1, t_lo, sum);
             sum = lr_dp2a_us<false>(a2, t_hi, sum);
@@ -279,10 +284,13 @@ B200_DEV void lr_wiener_regs(const typename Bd<HBD>::pixel *C, const typename Bd
     int acc[8];
     const int Y0 = ty0 + r0 - 3;                              // virtual row of window row 0
     pixel *const out = O + (ptrdiff_t)(ty0 + r0) * st + x0 + x;
+    Row W[14];
+#pragma unroll
+    for (int r = 0; r < 14; r++) load(W[r], Y0 + imin(r, R + 5));      // (rows past a short last item: reloaded, not used)
     // window rows 0 .. 5: no output completes yet
 #pragma unroll
     for (int r = 0; r < 6; r++) {
-        const int m = hrow(Y0 + r);
+        const int m = hfilter(W[r]);
         acc[r] = P.fv[0] * m;
 #pragma unroll
         for (int k = 1; k <= r; k++) acc[r - k] += P.fv[k] * m;
@@ -291,7 +299,7 @@ B200_DEV void lr_wiener_regs(const typename Bd<HBD>::pixel *C, const typename Bd
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         if (i >= R) break;
-        const int m = hrow(Y0 + 6 + i);
+        const int m = hfilter(W[6 + i]);
 #pragma unroll
         for (int k = 1; k < 7; k++) acc[(6 + i - k) & 7] += P.fv[k] * m;
         out[(ptrdiff_t)i * st] = (pixel)iclip((acc[i] + vbase) >> rbv, 0, bdmax);
@@ -304,7 +312,7 @@ struct LrGrid { int base[3], nx[3]; unsigned nx_recip[3]; int ty0[3]; };   // fl
 
 template <bool HBD>
 #ifndef B200_LR_MINB
-#define B200_LR_MINB 6
+#define B200_LR_MINB 4
 #endif
 __global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(const __grid_constant__ B200LrFrame f, const __grid_constant__ LrGrid lg, int bdmax)
 {
