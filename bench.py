@@ -695,7 +695,8 @@ def run_ours_gop(args):
     x = shard.PeerExchange(lib, dist, rank, world, Ss[0]["pic"].nbytes, 2) if world > 1 else None
     pipe = shard.GopPipeline(lib, rank, world, sets, exchange=x, n_refs=2, n_streams=n_streams, graphs=graphs)
     main = torch.cuda.current_stream()
-    tstreams = [t for t, _ in pipe.streams] + ([pipe.copy_stream[0]] if pipe.copy_stream[0] is not None else [])
+    tstreams = [t for t, _ in pipe.streams] + ([pipe.copy_stream[0]] if pipe.copy_stream[0] is not None else []) + \
+               [t for t, _ in (pipe.post_streams or [])]
 
     def sync_all():
         pipe.sync()

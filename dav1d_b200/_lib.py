@@ -261,6 +261,7 @@ _SIGS = {
     "b200_frame_wait": (C.c_int, [C.c_void_p]),
     # ---- band-sliced job + cross-GPU exchange
     "b200_frame_run_band": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200_frame_run_band_phase": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_band_progress": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "b200_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_ipc_open": (C.c_void_p, [C.c_void_p]),

@@ -105,7 +105,13 @@ int b200_band_progress(const B200FrameJob *j, int y1, int last, int plane)
 
 int b200_frame_run_band(const B200FrameJob *j, const B200FrameBand *b, void *stream)
 {
+    return b200_frame_run_band_phase(j, b, B200_BAND_RECON | B200_BAND_POST, stream);
+}
+
+int b200_frame_run_band_phase(const B200FrameJob *j, const B200FrameBand *b, int phases, void *stream)
+{
     int r;
+    const bool do_recon = phases & B200_BAND_RECON, do_post = phases & B200_BAND_POST;
     const int bd = j->bitdepth_max;
     const int H = job_luma_h(j);
     if ((b->y0 & 63) || b->y0 < 0 || b->y1 <= b->y0 || (!b->last && (b->y1 & 63)) || (b->last && b->y1 < H)) {
@@ -115,16 +121,19 @@ int b200_frame_run_band(const B200FrameJob *j, const B200FrameBand *b, void *str
     const bool first = b->y0 == 0;
     // intra records form a dependency graph over the whole frame: they run with a band only when that band IS the frame
     if (j->n_intra > 0 && !(first && b->last)) { b200_set_error("b200_frame_run_band: intra records are not band-sliced (one band, or b200_frame_run)"); return -2; }
+    // (the grain LUTs belong to the post phase: its stream forks the preparation beside the first band and joins it before
+    // the last band's application)
 #ifndef B200_EMU
     bool fg_forked = false;
-    if (first && j->run_fg) {       // grain LUTs depend on the frame header only: beside the first band, joined before the last one's apply
+    if (do_post && first && j->run_fg) {       // grain LUTs depend on the frame header only
         SideStream *fs = side_stream_for((cudaStream_t)stream, 0);
         if (fs && fs->fork((cudaStream_t)stream)) { if ((r = b200_fg_prep(bd, &j->fg, fs->side))) return r; fg_forked = true; }
     }
-    if (first && j->run_fg && !fg_forked && (r = b200_fg_prep(bd, &j->fg, stream))) return r;
+    if (do_post && first && j->run_fg && !fg_forked && (r = b200_fg_prep(bd, &j->fg, stream))) return r;
 #else
-    if (first && j->run_fg && (r = b200_fg_prep(bd, &j->fg, stream))) return r;
+    if (do_post && first && j->run_fg && (r = b200_fg_prep(bd, &j->fg, stream))) return r;
 #endif
+    if (do_recon) {
     if (first && j->n_expand > 0) B200_CUDA_OK(cudaMemsetAsync(j->d_coef, 0, j->coef_bytes, (cudaStream_t)stream));
 #define SUB(ptr, rng) ((ptr) ? (ptr) + (rng)[0] : (ptr)), ((ptr) ? (rng)[1] : 0)
     if (j->n_expand > 0 && (r = b200_coef_expand(bd, SUB(j->d_expand, b->expand), j->d_ccoef, j->d_coef, stream))) return r;
@@ -146,6 +155,8 @@ int b200_frame_run_band(const B200FrameJob *j, const B200FrameBand *b, void *str
     }
     if ((r = b200_itx_add_frame(bd, itx_p, itx_n, j->d_coef, j->mc.dst, j->itx_stride, j->zero_coefs, stream))) return r;
     if (j->n_intra > 0 && (r = b200_intra_frame(bd, &j->intra, j->d_intra, j->n_intra, stream))) return r;
+    }
+    if (!do_post) return 0;
     // sweeps: what this band's reconstruction makes final. Deblock: the band's own rows (a row-edge filter at y1 will still
     // change rows >= y1 - 6). CDEF tile rows (32 luma rows, reading 2 more on each side): those ending at or above y1 - 32.
     // Loop restoration tile rows (32 rows inside the 64-row stripes that end at 64 k - 8, reading CDEF output up to 3 rows

@@ -371,6 +371,11 @@ class FrameBuffers:
         st = self.alloc.stream() if stream is None else stream
         self.lib.check(self.lib.b200_frame_run_band(C.byref(self.job), C.byref(self.bands[k]), st), "b200_frame_run_band")
 
+    def run_band_phase(self, k, phases, stream=None):
+        """1 = reconstruction of band k, 2 = its post filters (b200_frame_run_band_phase)"""
+        st = self.alloc.stream() if stream is None else stream
+        self.lib.check(self.lib.b200_frame_run_band_phase(C.byref(self.job), C.byref(self.bands[k]), phases, st), "b200_frame_run_band_phase")
+
     def run_bands(self, stream=None):
         for k in range(len(self.bands)):
             self.run_band(k, stream)

@@ -209,6 +209,10 @@ class GopPipeline:
         self.streams = [A.new_stream() for _ in range(max(1, n_streams))]          # (keep, handle)
         assert self.n_sets % len(self.streams) == 0, "a set must always run on the same stream"
         self.copy_stream = A.new_stream() if world > 1 else (None, None)
+        # a banded frame runs as two chains: the reconstruction of band k+1 beside the post filters of band k (every band is
+        # a dozen small dependent launches; ~7 us of launch latency and drain each: the chain length, not the work, sets
+        # the pace of a band — measured: 7 bands on one stream cost 1.0 ms against 0.38 ms for the unbanded frame)
+        self.post_streams = [A.new_stream() for _ in self.streams] if self.nb > 1 else None
         # progress after each band, per plane class (luma, chroma): what a consumer's `need` is compared with
         self.prog = np.array([[fb.band_progress(k, 0), fb.band_progress(k, 1)] for k in range(self.nb)], np.int64)
         # events: per set and band (local consumers on another stream), per set "frame done", "puts done"
@@ -217,6 +221,8 @@ class GopPipeline:
         self.ev_done = [ev() for _ in sets]
         self.ev_puts = [ev() for _ in sets] if world > 1 else None
         self.ev_fork = [ev() for _ in sets]
+        self.ev_recon = [ev() for _ in sets]
+        self.ev_post = [ev() for _ in sets]
         self.ev_up = [ev() for _ in sets]
         self.ev_down = [ev() for _ in sets]
         self.submitted = 0
@@ -368,6 +374,11 @@ class GopPipeline:
         waited = [-1] * (self.n_refs + 1)
         cs = self.copy_stream[1]
         forked_copy = False
+        ps = self.post_streams[sidx][1] if self.post_streams is not None else None      # post-filter chain (None: one chain)
+        if ps is not None and ps == st:
+            ps = None
+        fork_from = lambda src, other: (lib.check(lib.b200_event_record(self.ev_fork[si], src), "record"),
+                                        lib.check(lib.b200_stream_wait_event(other, self.ev_fork[si]), "wait"))
         for k in range(self.nb):
             # ---- dependencies of band k: each reference must be final down to the lowest row the band reads
             for d in range(1, self.n_refs + 1):
@@ -389,18 +400,26 @@ class GopPipeline:
                     x.wait_progress_rel(d, base, wrap, kn + 1, st)
                 else:
                     x.wait_progress(d, (mseq << SEQ_SHIFT) + kn + 1, st)
-            fb.run_band(k, st)
+            if ps is None:
+                fb.run_band(k, st)
+                qs = st                     # the stream on which band k's restored rows are final
+            else:
+                fb.run_band_phase(k, 1, st)
+                lib.check(lib.b200_event_record(self.ev_recon[si], st), "record")
+                lib.check(lib.b200_stream_wait_event(ps, self.ev_recon[si]), "wait")
+                fb.run_band_phase(k, 2, ps)
+                qs = ps
             if multi:
                 if self.graphs:     # local consumers on the other stream wait on a flag (events recorded inside a graph are not visible outside)
                     if rel:
-                        lib.check(lib.b200_flag_signal_rel(self.local_flag(si), base, 0, SEQ_SHIFT, k + 1, st), "signal")
+                        lib.check(lib.b200_flag_signal_rel(self.local_flag(si), base, 0, SEQ_SHIFT, k + 1, qs), "signal")
                     else:
-                        lib.check(lib.b200_flag_signal(self.local_flag(si), (seq << SEQ_SHIFT) + k + 1, st), "signal")
+                        lib.check(lib.b200_flag_signal(self.local_flag(si), (seq << SEQ_SHIFT) + k + 1, qs), "signal")
                 if not rel:
-                    lib.check(lib.b200_event_record(self.ev_band[si][k], st), "record")
+                    lib.check(lib.b200_event_record(self.ev_band[si][k], qs), "record")
             # ---- put the rows that became final into the consumers' landing buffers, then raise their flag
             if consumers:
-                fork(cs)
+                fork_from(qs, cs)
                 forked_copy = True
                 src_keep, src_ptr = fb.keep[self.ref_name]
                 if k == 0:                          # the slots' previous occupants have been consumed
@@ -426,6 +445,9 @@ class GopPipeline:
                     x.signal_ack_rel((rank - d) % world, d, base, seq - mseq, st)
                 else:
                     x.signal_ack((rank - d) % world, d, mseq + 1, st)
+        if ps is not None:                  # the post chain joins: what follows on st (acknowledged above: only the
+            lib.check(lib.b200_event_record(self.ev_post[si], ps), "record")      # reconstruction reads the references)
+            lib.check(lib.b200_stream_wait_event(st, self.ev_post[si]), "wait")
         if self.host_io:
             ds = self.down_stream[1]
             fork(ds)
@@ -454,7 +476,7 @@ class GopPipeline:
     def sync(self):
         for _, h in self.streams:
             self.lib.check(self.lib.b200_frame_wait(h), "b200_frame_wait")
-        for h in (self.copy_stream[1], self.up_stream[1], self.down_stream[1]):
+        for h in [self.copy_stream[1], self.up_stream[1], self.down_stream[1]] + [p[1] for p in (self.post_streams or [])]:
             if h is not None:
                 self.lib.check(self.lib.b200_frame_wait(h), "b200_frame_wait")
 

@@ -624,6 +624,12 @@ typedef struct B200FrameBand {
     int32_t itx[B200_N_RECT_TX_SIZES][2];
 } B200FrameBand;
 B200_API int b200_frame_run_band(const B200FrameJob *job, const B200FrameBand *band, void *stream);
+/* The two halves of a band for callers that pipeline them on two streams: B200_BAND_RECON = coefficient expansion,
+ * prediction, compound, blends, transforms (reads the references, writes the band's rows of the reconstruction);
+ * B200_BAND_POST = deblock / CDEF / LR / grain rows (needs RECON of the same band and POST of the previous band). The
+ * reconstruction of band k+1 then runs beside the post filters of band k. */
+enum { B200_BAND_RECON = 1, B200_BAND_POST = 2 };
+B200_API int b200_frame_run_band_phase(const B200FrameJob *job, const B200FrameBand *band, int phases, void *stream);
 /* rows of plane `plane` of the restored picture (lr.dst, or cdef.dst / the reconstruction when later stages are off) that
  * are final once the band ending at luma row y1 has run (`last` != 0: the plane height) */
 B200_API int b200_band_progress(const B200FrameJob *job, int y1, int last, int plane);
