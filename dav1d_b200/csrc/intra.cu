@@ -848,7 +848,8 @@ int b200_intra_frames(int bdmax, const B200IntraFrame *frames, const B200IntraTx
             else
                 B200_CUDA_OK(cudaMemsetAsync(base_p, 0, mode ? 256 + (size_t)f->sb_w * f->sb_h : L.total, (cudaStream_t)stream));
             const int units = mode ? f->n_sb : n_tx[i];
-            const int want = f->grid > 0 ? f->grid : (mode ? 16 : kIntraGrid);
+            // warp-per-block kernel: two CTAs (8 blocks in flight) per SM fit its shared memory
+            const int want = f->grid > 0 ? f->grid : (mode ? 16 : (use_cta_kernel ? kIntraGrid : 2 * kIntraGrid));
             grid = imax(grid, units < want ? units : want);
             if (mode) dyn = intra_canvas_bytes(f, px);
         }

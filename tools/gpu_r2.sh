@@ -61,6 +61,12 @@ if [[ $what == *" benchC "* ]]; then
   run_bench intra_warp_g32 B200_INTRA_SB=0 B200_INTRA_GRID=32 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
   run_bench n1_mixed python bench.py --workload 4k8_mixed --steps 20 --warmup 5
 fi
+if [[ $what == *" benchD "* ]]; then
+  run_bench n1_default python bench.py --steps 20 --warmup 5
+  run_bench n1_1fl_b320 B200_FRAMES_IN_FLIGHT=1 B200_BAND_ROWS=320 python bench.py --steps 20 --warmup 5
+  run_bench n1_2fl_b576 B200_FRAMES_IN_FLIGHT=2 B200_BAND_ROWS=576 python bench.py --steps 20 --warmup 5
+  run_bench n1_2fl_b320 B200_FRAMES_IN_FLIGHT=2 B200_BAND_ROWS=320 python bench.py --steps 20 --warmup 5
+fi
 if [[ $what == *" benchI "* ]]; then
   run_bench intra_warp B200_INTRA_SB=0 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
   run_bench intra_warp_g16 B200_INTRA_SB=0 B200_INTRA_GRID=16 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
