@@ -210,6 +210,7 @@ template <bool HBD>
 #endif
 __global__ void __launch_bounds__(kCdefThreads, B200_CDEF_MINB) cdef_frame_kernel(const __grid_constant__ B200CdefFrame f, int bdmax, int tile_row0)
 {
+    B200_PDL_ENTRY();
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ CdefShared S;
     const int tid = threadIdx.x;
@@ -426,8 +427,8 @@ int cdef_frame_rows(int bdmax, const B200CdefFrame *f, int t0, int t1, cudaStrea
     t0 = imax(t0, 0); t1 = imin(t1, (f->bh + 7) / 8);
     if (t1 <= t0) return 0;
     dim3 grid((f->bw + 15) / 16, t1 - t0);
-    if (bdmax > 255) { auto k = cdef_frame_kernel<true>; B200_LAUNCH(k, grid, dim3(kCdefThreads), 0, stream, *f, bdmax, t0); }
-    else { auto k = cdef_frame_kernel<false>; B200_LAUNCH(k, grid, dim3(kCdefThreads), 0, stream, *f, bdmax, t0); }
+    if (bdmax > 255) { auto k = cdef_frame_kernel<true>; B200_LAUNCH_PDL(k, grid, dim3(kCdefThreads), 0, stream, *f, bdmax, t0); }
+    else { auto k = cdef_frame_kernel<false>; B200_LAUNCH_PDL(k, grid, dim3(kCdefThreads), 0, stream, *f, bdmax, t0); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -14,6 +14,7 @@ template <class coef>
 __global__ void __launch_bounds__(128) coef_expand_kernel(const B200CoefBlock *__restrict__ recs, int n,
                                                           const coef *__restrict__ compact, coef *__restrict__ dense)
 {
+    B200_PDL_ENTRY();
     const int wi = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (wi >= n) return;
     const B200CoefBlock r = recs[wi];
@@ -34,8 +35,8 @@ int b200_coef_expand(int bitdepth_max, const B200CoefBlock *d_blocks, int n_bloc
     if (n_blocks <= 0) return 0;
     using namespace b200;
     const dim3 grid((n_blocks + 3) / 4);
-    if (bitdepth_max > 255) { auto k = coef_expand_kernel<int32_t>; B200_LAUNCH(k, grid, dim3(128), 0, (cudaStream_t)stream, d_blocks, n_blocks, (const int32_t *)d_compact, (int32_t *)d_dense); }
-    else { auto k = coef_expand_kernel<int16_t>; B200_LAUNCH(k, grid, dim3(128), 0, (cudaStream_t)stream, d_blocks, n_blocks, (const int16_t *)d_compact, (int16_t *)d_dense); }
+    if (bitdepth_max > 255) { auto k = coef_expand_kernel<int32_t>; B200_LAUNCH_PDL(k, grid, dim3(128), 0, (cudaStream_t)stream, d_blocks, n_blocks, (const int32_t *)d_compact, (int32_t *)d_dense); }
+    else { auto k = coef_expand_kernel<int16_t>; B200_LAUNCH_PDL(k, grid, dim3(128), 0, (cudaStream_t)stream, d_blocks, n_blocks, (const int16_t *)d_compact, (int16_t *)d_dense); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -249,6 +249,7 @@ B200_DEV int fg_pixel_grain(const B200FilmGrainData &d, const int16_t *lut, cons
 template <bool HBD>
 __global__ void __launch_bounds__(256) fg_apply_kernel(const __grid_constant__ B200FgFrame f, int bdmax)
 {
+    B200_PDL_ENTRY();
     typedef typename Bd<HBD>::pixel pixel;
     const int pl = blockIdx.z;
     const B200FilmGrainData &d = f.data;
@@ -390,8 +391,8 @@ int b200_fg_apply(int bdmax, const B200FgFrame *f, void *stream)
 {
     if (fg_check(bdmax, f, "b200_fg_apply")) return -2;
     dim3 grid((f->w + 127) / 128, (f->h + 7) / 8, 3);
-    if (bdmax > 255) { auto k = fg_apply_kernel<true>; B200_LAUNCH(k, grid, dim3(32, 8), 0, (cudaStream_t)stream, *f, bdmax); }
-    else { auto k = fg_apply_kernel<false>; B200_LAUNCH(k, grid, dim3(32, 8), 0, (cudaStream_t)stream, *f, bdmax); }
+    if (bdmax > 255) { auto k = fg_apply_kernel<true>; B200_LAUNCH_PDL(k, grid, dim3(32, 8), 0, (cudaStream_t)stream, *f, bdmax); }
+    else { auto k = fg_apply_kernel<false>; B200_LAUNCH_PDL(k, grid, dim3(32, 8), 0, (cudaStream_t)stream, *f, bdmax); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -23,6 +23,7 @@ itx_add_kernel(const B200ItxBlock *__restrict__ blocks, int n_blocks,
                typename Bd<HBD>::coef *__restrict__ coefs, typename Bd<HBD>::pixel *__restrict__ pic,
                int stride0, int stride1, int stride2, int bitdepth_max, int zero_coefs)
 {
+    B200_PDL_ENTRY();
     typedef ItxGeom<W, H> G;
     __shared__ int tile[ItxGeom<W, H>::BPC * G::SLOT];
     itx_add_body<W, H, TX, SHIFT, HBD>(blockIdx.x, tile, blocks, n_blocks, coefs, pic, stride0, stride1, stride2,
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(kItxWarps * 32, ItxClass<BIG>::kMinCtas)
 itx_add_grouped_kernel(const __grid_constant__ ItxGroups g, typename Bd<HBD>::coef *__restrict__ coefs, typename Bd<HBD>::pixel *__restrict__ pic,
                        int stride0, int stride1, int stride2, int bitdepth_max, int zero_coefs)
 {
+    B200_PDL_ENTRY();
     __shared__ int tile[ItxClass<BIG>::kTileWords];
     const int c = blockIdx.x;
 #define X(TX, W, H, SH) \
@@ -82,11 +84,11 @@ int launch_itx_grouped(bool hbd, const void *const *blocks, const int32_t *n, vo
 #undef X
         if (!total) continue;
         if (hbd) {
-            if (big) { auto k = itx_add_grouped_kernel<true, true>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int32_t *)coefs, (uint16_t *)pic, st[0], st[1], st[2], bdmax, zero); }
-            else { auto k = itx_add_grouped_kernel<true, false>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int32_t *)coefs, (uint16_t *)pic, st[0], st[1], st[2], bdmax, zero); }
+            if (big) { auto k = itx_add_grouped_kernel<true, true>; B200_LAUNCH_PDL(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int32_t *)coefs, (uint16_t *)pic, st[0], st[1], st[2], bdmax, zero); }
+            else { auto k = itx_add_grouped_kernel<true, false>; B200_LAUNCH_PDL(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int32_t *)coefs, (uint16_t *)pic, st[0], st[1], st[2], bdmax, zero); }
         } else {
-            if (big) { auto k = itx_add_grouped_kernel<false, true>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int16_t *)coefs, (uint8_t *)pic, st[0], st[1], st[2], bdmax, zero); }
-            else { auto k = itx_add_grouped_kernel<false, false>; B200_LAUNCH(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int16_t *)coefs, (uint8_t *)pic, st[0], st[1], st[2], bdmax, zero); }
+            if (big) { auto k = itx_add_grouped_kernel<false, true>; B200_LAUNCH_PDL(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int16_t *)coefs, (uint8_t *)pic, st[0], st[1], st[2], bdmax, zero); }
+            else { auto k = itx_add_grouped_kernel<false, false>; B200_LAUNCH_PDL(k, dim3(total), dim3(kItxWarps * 32), 0, stream, g, (int16_t *)coefs, (uint8_t *)pic, st[0], st[1], st[2], bdmax, zero); }
         }
         b200_count_launch();
     }

@@ -121,6 +121,7 @@ B200_DEV int lf_width(const B200Av1Filter &m, int plane, int dir, int b, int a, 
 template <bool HBD>
 __global__ void __launch_bounds__(256) lf_cols_kernel(const __grid_constant__ B200LfFrame f, int bdmax, int ya4, int yb4)
 {
+    B200_PDL_ENTRY();
     typedef typename Bd<HBD>::pixel pixel;
     const int plane = blockIdx.z;
     if (plane ? !f.filter_uv : !f.filter_y) return;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(256) lf_cols_kernel(const __grid_constant__ B2
 template <bool HBD>
 __global__ void __launch_bounds__(256) lf_rows_kernel(const __grid_constant__ B200LfFrame f, int bdmax, int ya4, int yb4)
 {
+    B200_PDL_ENTRY();
     typedef typename Bd<HBD>::pixel pixel;
     const int plane = blockIdx.z;
     if (plane ? !f.filter_uv : !f.filter_y) return;
@@ -208,11 +210,11 @@ int lf_frame_rows(int bdmax, const B200LfFrame *f, int ya4, int yb4, cudaStream_
     dim3 g1((w4 + 31) / 32, (n4 + 7) / 8, 3), b1(32, 8);
     dim3 g2((w4 * 4 + 127) / 128, (n4 + 1) / 2, 3), b2(128, 2);
     if (bdmax > 255) {
-        auto k1 = lf_cols_kernel<true>; B200_LAUNCH(k1, g1, b1, 0, stream, *f, bdmax, ya4, yb4);
-        auto k2 = lf_rows_kernel<true>; B200_LAUNCH(k2, g2, b2, 0, stream, *f, bdmax, ya4, yb4);
+        auto k1 = lf_cols_kernel<true>; B200_LAUNCH_PDL(k1, g1, b1, 0, stream, *f, bdmax, ya4, yb4);
+        auto k2 = lf_rows_kernel<true>; B200_LAUNCH_PDL(k2, g2, b2, 0, stream, *f, bdmax, ya4, yb4);
     } else {
-        auto k1 = lf_cols_kernel<false>; B200_LAUNCH(k1, g1, b1, 0, stream, *f, bdmax, ya4, yb4);
-        auto k2 = lf_rows_kernel<false>; B200_LAUNCH(k2, g2, b2, 0, stream, *f, bdmax, ya4, yb4);
+        auto k1 = lf_cols_kernel<false>; B200_LAUNCH_PDL(k1, g1, b1, 0, stream, *f, bdmax, ya4, yb4);
+        auto k2 = lf_rows_kernel<false>; B200_LAUNCH_PDL(k2, g2, b2, 0, stream, *f, bdmax, ya4, yb4);
     }
     b200_count_launch(); b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());

@@ -316,6 +316,7 @@ template <bool HBD>
 #endif
 __global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(const __grid_constant__ B200LrFrame f, const __grid_constant__ LrGrid lg, int bdmax)
 {
+    B200_PDL_ENTRY();
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ LrShared sm;
     const int bid = blockIdx.x;
@@ -467,8 +468,8 @@ int lr_frame_rows(int bdmax, const B200LrFrame *f, int r0, int r1, cudaStream_t 
     }
     if (!total) return 0;
     dim3 grid(total);
-    if (bdmax > 255) { auto k = lr_frame_kernel<true>; B200_LAUNCH(k, grid, dim3(256), 0, stream, *f, lg, bdmax); }
-    else { auto k = lr_frame_kernel<false>; B200_LAUNCH(k, grid, dim3(256), 0, stream, *f, lg, bdmax); }
+    if (bdmax > 255) { auto k = lr_frame_kernel<true>; B200_LAUNCH_PDL(k, grid, dim3(256), 0, stream, *f, lg, bdmax); }
+    else { auto k = lr_frame_kernel<false>; B200_LAUNCH_PDL(k, grid, dim3(256), 0, stream, *f, lg, bdmax); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;

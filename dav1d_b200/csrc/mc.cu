@@ -297,6 +297,7 @@ template <bool HBD>
 __global__ void __launch_bounds__(kMcWarps * 32, B200_MC_MINB)
 mc_pred_kernel(const B200McBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
+    B200_PDL_ENTRY();
     typedef typename Bd<HBD>::pixel pixel;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bi = blockIdx.x * kMcWarps + warp;
@@ -377,6 +378,7 @@ template <bool HBD>
 __global__ void __launch_bounds__(kMcWarps * 32, 4)          // two rings + two tap sets: 128 registers, no spills
 mc_comp_fused_kernel(const B200CompFusedBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
+    B200_PDL_ENTRY();
     typedef typename Bd<HBD>::pixel pixel;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bi = blockIdx.x * kMcWarps + warp;
@@ -404,6 +406,7 @@ template <bool HBD>
 __global__ void __launch_bounds__(256)
 mc_scaled_kernel(const B200McScaledBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
+    B200_PDL_ENTRY();
     typedef typename Bd<HBD>::pixel pixel;
     const B200McScaledBlock b = blocks[blockIdx.x];
     const int w = b.w, h = b.h, pl = b.plane;
@@ -467,6 +470,7 @@ template <bool HBD>
 __global__ void __launch_bounds__(128)
 mc_comp_kernel(const B200CompBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
+    B200_PDL_ENTRY();
     typedef typename Bd<HBD>::pixel pixel;
     const B200CompBlock b = blocks[blockIdx.x];
     const int w = b.w, h = b.h, op = b.op;
@@ -546,6 +550,7 @@ template <bool HBD>
 __global__ void __launch_bounds__(128)
 mc_blend_kernel(const B200BlendBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
+    B200_PDL_ENTRY();
     typedef typename Bd<HBD>::pixel pixel;
     const B200BlendBlock b = blocks[blockIdx.x];
     const int w = b.w, h = b.h, op = b.op;
@@ -571,6 +576,7 @@ template <bool HBD>
 __global__ void __launch_bounds__(kWarpWarps * 32)
 mc_warp_kernel(const B200WarpBlock *__restrict__ blocks, int n_blocks, const __grid_constant__ B200McFrame fr, int bdmax)
 {
+    B200_PDL_ENTRY();
     typedef typename Bd<HBD>::pixel pixel;
     __shared__ int mid[kWarpWarps][15 * 8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -653,8 +659,8 @@ extern "C" {
 int b200_mc_batch(int bitdepth_max, const B200McFrame *frame, const B200McBlock *d_blocks, int n, void *stream) {
     if (check_bd(bitdepth_max, "b200_mc_batch")) return -2;
     if (n <= 0) return 0;
-    if (bitdepth_max > 255) { auto k = mc_pred_kernel<true>; B200_LAUNCH(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
-    else { auto k = mc_pred_kernel<false>; B200_LAUNCH(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    if (bitdepth_max > 255) { auto k = mc_pred_kernel<true>; B200_LAUNCH_PDL(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_pred_kernel<false>; B200_LAUNCH_PDL(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -662,8 +668,8 @@ int b200_mc_batch(int bitdepth_max, const B200McFrame *frame, const B200McBlock 
 int b200_mc_scaled_batch(int bitdepth_max, const B200McFrame *frame, const B200McScaledBlock *d_blocks, int n, void *stream) {
     if (check_bd(bitdepth_max, "b200_mc_scaled_batch")) return -2;
     if (n <= 0) return 0;
-    if (bitdepth_max > 255) { auto k = mc_scaled_kernel<true>; B200_LAUNCH(k, dim3(n), dim3(256), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
-    else { auto k = mc_scaled_kernel<false>; B200_LAUNCH(k, dim3(n), dim3(256), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    if (bitdepth_max > 255) { auto k = mc_scaled_kernel<true>; B200_LAUNCH_PDL(k, dim3(n), dim3(256), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_scaled_kernel<false>; B200_LAUNCH_PDL(k, dim3(n), dim3(256), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -671,8 +677,8 @@ int b200_mc_scaled_batch(int bitdepth_max, const B200McFrame *frame, const B200M
 int b200_mc_comp_fused_batch(int bitdepth_max, const B200McFrame *frame, const B200CompFusedBlock *d_blocks, int n, void *stream) {
     if (check_bd(bitdepth_max, "b200_mc_comp_fused_batch")) return -2;
     if (n <= 0) return 0;
-    if (bitdepth_max > 255) { auto k = mc_comp_fused_kernel<true>; B200_LAUNCH(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
-    else { auto k = mc_comp_fused_kernel<false>; B200_LAUNCH(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    if (bitdepth_max > 255) { auto k = mc_comp_fused_kernel<true>; B200_LAUNCH_PDL(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_comp_fused_kernel<false>; B200_LAUNCH_PDL(k, dim3((n + kMcWarps - 1) / kMcWarps), dim3(kMcWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -680,8 +686,8 @@ int b200_mc_comp_fused_batch(int bitdepth_max, const B200McFrame *frame, const B
 int b200_mc_comp_batch(int bitdepth_max, const B200McFrame *frame, const B200CompBlock *d_blocks, int n, void *stream) {
     if (check_bd(bitdepth_max, "b200_mc_comp_batch")) return -2;
     if (n <= 0) return 0;
-    if (bitdepth_max > 255) { auto k = mc_comp_kernel<true>; B200_LAUNCH(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
-    else { auto k = mc_comp_kernel<false>; B200_LAUNCH(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    if (bitdepth_max > 255) { auto k = mc_comp_kernel<true>; B200_LAUNCH_PDL(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_comp_kernel<false>; B200_LAUNCH_PDL(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -689,8 +695,8 @@ int b200_mc_comp_batch(int bitdepth_max, const B200McFrame *frame, const B200Com
 int b200_mc_blend_batch(int bitdepth_max, const B200McFrame *frame, const B200BlendBlock *d_blocks, int n, void *stream) {
     if (check_bd(bitdepth_max, "b200_mc_blend_batch")) return -2;
     if (n <= 0) return 0;
-    if (bitdepth_max > 255) { auto k = mc_blend_kernel<true>; B200_LAUNCH(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
-    else { auto k = mc_blend_kernel<false>; B200_LAUNCH(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    if (bitdepth_max > 255) { auto k = mc_blend_kernel<true>; B200_LAUNCH_PDL(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_blend_kernel<false>; B200_LAUNCH_PDL(k, dim3(n), dim3(128), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -699,8 +705,8 @@ int b200_mc_warp_batch(int bitdepth_max, const B200McFrame *frame, const B200War
     if (check_bd(bitdepth_max, "b200_mc_warp_batch")) return -2;
     if (n <= 0) return 0;
     const int grid = (n + kWarpWarps - 1) / kWarpWarps;
-    if (bitdepth_max > 255) { auto k = mc_warp_kernel<true>; B200_LAUNCH(k, dim3(grid), dim3(kWarpWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
-    else { auto k = mc_warp_kernel<false>; B200_LAUNCH(k, dim3(grid), dim3(kWarpWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    if (bitdepth_max > 255) { auto k = mc_warp_kernel<true>; B200_LAUNCH_PDL(k, dim3(grid), dim3(kWarpWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
+    else { auto k = mc_warp_kernel<false>; B200_LAUNCH_PDL(k, dim3(grid), dim3(kWarpWarps * 32), 0, (cudaStream_t)stream, d_blocks, n, *frame, bitdepth_max); }
     b200_count_launch();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
