@@ -225,8 +225,8 @@ FRAME_WORKLOADS = {
                            "transforms + deblock + CDEF + loop restoration + film grain (BASELINE configs[3])"),
     "8k10_full": dict(bpc=10, W=7680, H=4320, fg=True, dtype="u16/i32->i32",
                       desc="one 7680x4320 10-bit 4:2:0 inter frame per GPU per step, full pipeline incl. film grain "
-                           "(BASELINE configs[4]: with --gpus N every rank reconstructs its own frame and the restored pictures "
-                           "are exchanged over NCCL as reference pictures)"),
+                           "(BASELINE configs[4]: with --gpus N the frames of one dependent stream go round the ranks and every "
+                           "restored picture reaches the two ranks that predict from it band by band over NVLink)"),
     "1080p8_intra": dict(bpc=8, W=1920, H=1080, fg=False, dtype="u8/i16->i32", intra=True, frames_per_step=int(os.environ.get("B200_INTRA_FPS", "96")),
                          desc="one 1920x1080 8-bit 4:2:0 intra-only frame per GPU per step: device-side edge preparation + "
                               "intra prediction + inverse transforms (dependency-driven kernel) + deblock (BASELINE configs[1]); a step is %s "
@@ -680,8 +680,9 @@ def run_ours_gop(args):
     # (motion reach + filter taps + the rows the post filters still hold back), i.e. frame n+1 trails frame n by about
     # (144 + band) rows; N ranks stay busy when N such lags fit into a frame, hence ~H / 3N rows per band — as few bands as
     # that allows, because every band is a dozen more (small) launches
-    band_rows = int(os.environ.get("B200_BAND_ROWS", str(whole if world == 1 else H // (3 * world))))
-    band_rows = min(whole, max(64, band_rows // 64 * 64))
+    n_bands = min(2 * world + 1, max(2, H // 256))          # ... and no more than ~256-row bands: a band costs ~55 us of launch chain
+    band_rows = int(os.environ.get("B200_BAND_ROWS", str(whole if world == 1 else -(-H // n_bands))))
+    band_rows = min(whole, max(64, -(-band_rows // 64) * 64))
     n_streams = max(1, int(os.environ.get("B200_FRAMES_IN_FLIGHT", "1" if world == 1 else "2")))
     nsets = int(os.environ.get("B200_NSETS", "3" if args.workload == "8k10_full" else "6"))
     # a banded frame is hundreds of launches, waits and copies: replayed as one CUDA graph per frame (the host would otherwise
@@ -693,6 +694,8 @@ def run_ours_gop(args):
     Ss = [make_workload_frame(args.workload, 1 + rank * 16 + k) for k in range(distinct)]
     sets = [workload_buffers(args.workload, Ss[k % distinct], band_rows=band_rows, **OURS) for k in range(nsets)]
     x = shard.PeerExchange(lib, dist, rank, world, Ss[0]["pic"].nbytes, 2) if world > 1 else None
+    # programmatic dependent launch pays on one chain of whole-frame launches; parked CTAs hurt when chains share the GPU
+    lib.b200_set_pdl(1 if (-(-H // band_rows) == 1 and n_streams == 1) else 0)
     pipe = shard.GopPipeline(lib, rank, world, sets, exchange=x, n_refs=2, n_streams=n_streams, graphs=graphs)
     main = torch.cuda.current_stream()
     tstreams = [t for t, _ in pipe.streams] + ([pipe.copy_stream[0]] if pipe.copy_stream[0] is not None else []) + \

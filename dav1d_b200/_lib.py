@@ -181,6 +181,7 @@ _SIGS = {
     "b200_version": (C.c_int, []),
     "b200_last_error": (C.c_char_p, []),
     "b200_launch_count": (C.c_uint64, []),
+    "b200_set_pdl": (None, [C.c_int]),
     "b200_itx_dsp_init_8bpc": (None, [C.c_void_p, C.c_int]),
     "b200_itx_dsp_init_16bpc": (None, [C.c_void_p, C.c_int]),
     "b200_inv_txfm_add": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -30,12 +30,19 @@ void b200_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void b200_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<int> g_pdl{-1};
+bool b200_pdl_enabled() {
+    int v = g_pdl.load(std::memory_order_relaxed);
+    if (v < 0) { v = getenv("B200_NO_PDL") ? 0 : 1; g_pdl.store(v, std::memory_order_relaxed); }
+    return v != 0;
+}
 
 extern "C" {
 
 int b200_version(void) { return 100; }
 const char *b200_last_error(void) { return g_err; }
 uint64_t b200_launch_count(void) { return g_launches.load(); }
+void b200_set_pdl(int on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 void *b200_dev_alloc(size_t bytes) {
     void *p = nullptr;

@@ -9,8 +9,11 @@
 // previous kernel's last wave drains (they park in b200_pdl_entry() until it has completed and its writes are visible), so
 // the launch latency and the ramp-up of every stage overlap the tail of the stage before it. A frame is a chain of a dozen
 // dependent launches (a band of a frame another dozen): ~7 us of latency + drain each was a fifth of the 4K frame time.
-// Every kernel launched this way calls b200_pdl_entry() before anything else (every thread, before any return).
-inline bool b200_pdl_enabled() { static const bool on = !getenv("B200_NO_PDL"); return on; }
+// Every kernel launched this way calls B200_PDL_ENTRY() before anything else (every thread, before any return).
+// It pays on ONE chain of kernels (whole-frame jobs: -3 % frame time); when several chains share the GPU (banded frames:
+// reconstruction and post-filter chains, two frames in flight) the parked CTAs take the slots the other chain's kernels
+// would have used (measured: +10 ... +30 % frame time), so the pipeline turns it off there (b200_set_pdl).
+bool b200_pdl_enabled();         // capi.cu: b200_set_pdl() / B200_NO_PDL
 template <class... KArgs, class... Args>
 inline void b200_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args)
 {

@@ -204,115 +204,12 @@ B200_DEV void lr_unit_params(const B200RestorationUnit &u, bool hbd, LrTileParam
     }
 }
 
-// sum of 4 unsigned bytes of `px` times 4 signed bytes of `taps`, plus acc
-B200_DEV int lr_dp4a_us(unsigned px, int taps, int acc) {
-#ifdef B200_EMU
-    return __dp4a_us(px, taps, acc);
-#else
-    int d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(taps), "r"(acc));
-    return d;
-#endif
-}
-// two unsigned halfwords of `px` times signed bytes {0,1} (HI = false) or {2,3} (HI = true) of `taps`, plus acc
-template <bool HI> B200_DEV int lr_dp2a_us(unsigned px, int taps, int acc) {
-#ifdef B200_EMU
-    const int t0 = (int8_t)(taps >> (HI ? 16 : 0)), t1 = (int8_t)(taps >> (HI ? 24 : 8));
-    return acc + (int)(px & 0xffff) * t0 + (int)(px >> 16) * t1;
-#else
-    int d;
-    if (HI) asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(taps), "r"(acc));
-    else asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(px), "r"(taps), "r"(acc));
-    return d;
-#endif
-}
-
-// Wiener restoration of one tile in registers (no shared-memory staging, no barriers): a thread owns one output column x 8
-// consecutive rows, walks the 14 source rows of its column top to bottom — each filtered horizontally straight from the
-// (virtual) source picture: aligned words, funnel shifts, dp4a / dp2a, the centre sample's * 128 added separately so that
-// every tap fits a signed byte — and scatters the value into the running vertical sums it contributes to (ring of 8
-// accumulators, output j is complete after row j + 6). Same arithmetic as lr_tile_compute's Wiener branch
-// (reference src/looprestoration_tmpl.c:46-132); tiles that touch the left / right picture edge take the staged path.
-template <bool HBD>
-B200_DEV void lr_wiener_regs(const typename Bd<HBD>::pixel *C, const typename Bd<HBD>::pixel *D, typename Bd<HBD>::pixel *O, const int st,
-                             const int x0, const int ty0, const int tw, const int th, const int y0s, const int y1s, const int h,
-                             const bool have_top, const bool have_bot, const LrTileParams &P, const int bdmax)
-{
-    typedef typename Bd<HBD>::pixel pixel;
-    constexpr int PX = HBD ? 2 : 1, PPW = HBD ? 2 : 4;
-    const int x = threadIdx.x & 63, r0 = (threadIdx.x >> 6) * 8;
-    if (x >= tw || r0 >= th) return;
-    const int R = imin(8, th - r0);
-    const int bitdepth = HBD ? 32 - __clz(bdmax) : 8;
-    const int rbh = 3 + (bitdepth == 12) * 2, rbv = 11 - (bitdepth == 12) * 2;
-    const int clip_hi = (1 << (bitdepth + 1 + 7 - rbh)) - 1;
-    const int c3 = P.fh[3] - (HBD ? 128 : 0);                 // centre tap without the 128 (added from the sample itself)
-    const int t_lo = (P.fh[0] & 0xff) | (P.fh[1] & 0xff) << 8 | (P.fh[2] & 0xff) << 16 | (c3 & 0xff) << 24;
-    const int t_hi = (P.fh[4] & 0xff) | (P.fh[5] & 0xff) << 8 | (P.fh[6] & 0xff) << 16;
-    const int hbase = (1 << (bitdepth + 6)) + (1 << (rbh - 1));
-    const int b0 = x0 + x - 3;
-    const int woff = (b0 & ~(PPW - 1)) * PX;
-    const unsigned al = (b0 & (PPW - 1)) * (HBD ? 16 : 8);
-    const int vbase = -(1 << (bitdepth + (rbv - 1))) + (1 << (rbv - 1));
-    // the words of one virtual source row (rows inside the stripe from the CDEF output, the two rows beyond it from the
-    // deblocked picture, clamped at the picture's top / bottom); all 14 rows of an item are loaded before any is filtered
-    struct Row { unsigned w[HBD ? 5 : 3]; };
-    auto load = [&](Row &W, const int Yv) {
-        const pixel *base = C; int Y = Yv;
-        if (Y < y0s) { if (have_top) { base = D; Y = imax(Y, y0s - 2); } else Y = y0s; }
-        else if (Y >= y1s) { if (have_bot) { base = D; Y = imin(imin(Y, y1s + 1), h - 1); } else Y = y1s - 1; }
-        const unsigned *wp = (const unsigned *)((const unsigned char *)(base + (ptrdiff_t)Y * st) + woff);
-#pragma unroll
-        for (int k = 0; k < (HBD ? 5 : 3); k++) W.w[k] = wp[k];
-    };
-    auto hfilter = [&](const Row &W) -> int {
-        int sum;
-        if constexpr (!HBD) {
-            const unsigned lo = __funnelshift_r(W.w[0], W.w[1], al), hi = __funnelshift_r(W.w[1], W.w[2], al);
-            sum = lr_dp4a_us(hi, t_hi, lr_dp4a_us(lo, t_lo, hbase)) + (int)(lo >> 24) * 128;
-        } else {
-            const unsigned a0 = __funnelshift_r(W.w[0], W.w[1], al), a1 = __funnelshift_r(W.w[1], W.w[2], al);
-            const unsigned a2 = __funnelshift_r(W.w[2], W.w[3], al), a3 = __funnelshift_r(W.w[3], W.w[4], al);
-            sum = lr_dp2a_us<false>(a0, t_lo, hbase);
-            sum = lr_dp2a_us<true>(a1, t_lo, sum);
-            sum = lr_dp2a_us<false>(a2, t_hi, sum);
-            sum = lr_dp2a_us<true>(a3, t_hi, sum);
-            sum += (int)(a1 >> 16) * 128;
-        }
-        return iclip(sum >> rbh, 0, clip_hi);
-    };
-    int acc[8];
-    const int Y0 = ty0 + r0 - 3;                              // virtual row of window row 0
-    pixel *const out = O + (ptrdiff_t)(ty0 + r0) * st + x0 + x;
-    Row W[14];
-#pragma unroll
-    for (int r = 0; r < 14; r++) load(W[r], Y0 + imin(r, R + 5));      // (rows past a short last item: reloaded, not used)
-    // window rows 0 .. 5: no output completes yet
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-        const int m = hfilter(W[r]);
-        acc[r] = P.fv[0] * m;
-#pragma unroll
-        for (int k = 1; k <= r; k++) acc[r - k] += P.fv[k] * m;
-    }
-    // window rows 6 .. R + 5: row 6 + i completes output i (accumulator i) and starts output 6 + i (accumulator (6 + i) & 7)
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        if (i >= R) break;
-        const int m = hfilter(W[6 + i]);
-#pragma unroll
-        for (int k = 1; k < 7; k++) acc[(6 + i - k) & 7] += P.fv[k] * m;
-        out[(ptrdiff_t)i * st] = (pixel)iclip((acc[i] + vbase) >> rbv, 0, bdmax);
-        acc[(6 + i) & 7] = P.fv[0] * m;
-    }
-}
-
 struct LrGrid { int base[3], nx[3]; unsigned nx_recip[3]; int ty0[3]; };   // flattened tile list: plane p owns CTAs base[p] .. , nx[p] tiles per row;
                                                                // nx_recip = ceil(2^32 / nx): local / nx == mulhi(local, nx_recip) while local * nx < 2^32
 
 template <bool HBD>
 #ifndef B200_LR_MINB
-#define B200_LR_MINB 4
+#define B200_LR_MINB 6
 #endif
 __global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(const __grid_constant__ B200LrFrame f, const __grid_constant__ LrGrid lg, int bdmax)
 {
@@ -374,15 +271,9 @@ __global__ void __launch_bounds__(256, B200_LR_MINB) lr_frame_kernel(const __gri
         }
         return;
     }
+    // stage the virtual source: rows ty0-3 .. ty0+th+2, cols x0-3 .. x0+tw+2
     const bool have_top = y0s > 0, have_bot = y1s < h;
     constexpr int PPW = HBD ? 2 : 4;                                 // samples per 32-bit word
-    // Wiener tiles away from the left / right picture edge: in registers, straight from the pictures (the realigning loads
-    // read whole words from the one holding column x0 - 3 to two words past it per thread: inside the row's pitch)
-    if (P.type == 1 && x0 >= 4 && x0 + tw + 4 <= w && x0 + tw + 12 <= st && !(st & (PPW - 1)) && !(((uintptr_t)C | (uintptr_t)D) & 3)) {
-        lr_wiener_regs<HBD>(C, D, O, st, x0, ty0, tw, th, y0s, y1s, h, have_top, have_bot, P, bdmax);
-        return;
-    }
-    // stage the virtual source: rows ty0-3 .. ty0+th+2, cols x0-3 .. x0+tw+2
     const bool interior = x0 >= 4 && x0 + tw + 4 <= w && !(tw & 3) && !(x0 & 3) && !(st & (PPW - 1)) &&
                           !(((uintptr_t)C | (uintptr_t)D) & 3);
     if (interior) {
@@ -453,6 +344,8 @@ int lr_frame_rows(int bdmax, const B200LrFrame *f, int r0, int r1, cudaStream_t 
         if (f->unit_size_log2[i] < 5 || f->unit_size_log2[i] > 8) { b200_set_error("b200_lr_frame: bad unit size"); return -2; }
     const int n_stripes = (f->h + 8 + 63) / 64;
     r0 = imax(r0, 0); r1 = imin(r1, 2 * n_stripes);
+    // (A register-only path for Wiener tiles — rolling ring as in mc.cu, dp4a horizontal pass, no staging — was measured
+    // in round 2: 67.6 us, the same as this staged form, 74.9 us with all rows loaded up front at lower occupancy. Dropped.)
     LrGrid lg;
     int total = 0;
     for (int p = 0; p < 3; p++) {

@@ -33,6 +33,10 @@ B200_API int b200_version(void);
 B200_API const char *b200_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 B200_API uint64_t b200_launch_count(void);
+/* programmatic dependent launch between the kernels of a frame job (default on; B200_NO_PDL=1 in the environment turns it
+ * off): worth ~3 % on a single chain of whole-frame jobs, a loss when several chains of small launches share the GPU
+ * (banded frames on two streams) — the frame pipeline switches it per configuration */
+B200_API void b200_set_pdl(int on);
 
 /* Device / pinned-host memory and streams for C hosts (a dav1d build has no other way to own HBM): thin
  * wrappers over cudaMalloc / cudaMallocHost / cudaStreamCreate. NULL on failure (b200_last_error() says why). */
