@@ -50,12 +50,16 @@ static inline double bitfn(now_ms)(void)
 
 /* device picture geometry derived from the host picture: same strides, planes back to back */
 typedef struct PicGeom { int stride[3]; uint32_t off[3]; int rows[3]; size_t bytes; } PicGeom;
+/* Monochrome (4:0:0): the device picture keeps two dummy chroma planes in 4:2:0 geometry (the frame-wide sweeps walk three
+ * planes; nothing is predicted or transformed into them, chroma deblocking is off, nothing of them is downloaded), so the
+ * luma path is exactly the 4:2:0 one. */
 static void bitfn(pic_geom)(const Dav1dFrameContext *const f, PicGeom *const g)
 {
-    const int ss_ver = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
+    const int mono = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I400;
+    const int ss_ver = mono || f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
     const int rows = (f->cur.p.h + 127) & ~127;
     g->stride[0] = (int)PXSTRIDE(f->cur.stride[0]);
-    g->stride[1] = g->stride[2] = (int)PXSTRIDE(f->cur.stride[1]);
+    g->stride[1] = g->stride[2] = mono ? g->stride[0] : (int)PXSTRIDE(f->cur.stride[1]);
     g->rows[0] = rows; g->rows[1] = g->rows[2] = rows >> ss_ver;
     g->off[0] = 0;
     g->off[1] = (uint32_t)g->stride[0] * rows;
@@ -84,8 +88,6 @@ static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *c
         HookRefPic *const out = b200hook_refpic(f->cur.data[0], g.bytes, 1);
         if (out) b200hook_refpic_set_ready(out, 0);
         else __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
-        if (f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I400)      /* the post-filter sweeps always walk three planes */
-            __atomic_fetch_or(&hf->unsupported, 512, __ATOMIC_RELAXED);
         if (f->frame_hdr->width[0] != f->frame_hdr->width[1])        /* super-resolution: no upscaling stage in the frame job yet */
             __atomic_fetch_or(&hf->unsupported, 1024, __ATOMIC_RELAXED);
         /* intra records and coefficients are appended without a lock by every tile thread of the frame (slots are taken
@@ -749,13 +751,14 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         fprintf(stderr, "b200hook: frame uses tools the emitters do not translate yet (%s%s%s%s)\n",
                 hf->unsupported & 1 ? " palette" : "", hf->unsupported & 2 ? " inter" : "",
                 hf->unsupported & 4 ? " single-pass-decoding" : "", hf->unsupported & 8 ? " out-of-memory" : "");
-        fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 scaled reference, 64 intra block copy, 256 inter-intra block size, 512 monochrome, 1024 super-resolution)\n", hf->unsupported);
+        fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 scaled reference, 64 intra block copy, 256 inter-intra block size, 1024 super-resolution)\n", hf->unsupported);
         return -1;
     }
     PicGeom g;
     bitfn(pic_geom)(f, &g);
     const Dav1dFrameHeader *const hdr = f->frame_hdr;
-    const int ss_ver = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    const int mono = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I400;         /* dummy 4:2:0 chroma planes on the device (pic_geom) */
+    const int ss_ver = mono || f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
     const int n_sb128 = f->sb128w * f->sb128h;
     const size_t mask_bytes = (size_t)n_sb128 * sizeof(Av1Filter), level_bytes = (size_t)n_sb128 * 32 * 32 * 4;
     const size_t lr_bytes = (size_t)f->sr_sb128w * f->sb128h * sizeof(Av1Restoration);
@@ -882,7 +885,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     for (int p = 0; p < 3; p++) { j.lf.plane_off[p] = g.off[p]; j.lf.stride[p] = g.stride[p]; }
     j.lf.w4 = f->w4; j.lf.h4 = f->h4; j.lf.sb128w = f->sb128w; j.lf.b4_stride = (int)f->b4_stride;
     j.lf.ss_hor = ss_hor; j.lf.ss_ver = ss_ver; j.lf.sb128 = f->seq_hdr->sb128;
-    j.lf.filter_y = do_lf; j.lf.filter_uv = hdr->loopfilter.level_u || hdr->loopfilter.level_v;
+    j.lf.filter_y = do_lf; j.lf.filter_uv = !mono && (hdr->loopfilter.level_u || hdr->loopfilter.level_v);
     j.lf.mask = (const B200Av1Filter *)hf->mask.dev;
     j.lf.level = (const uint8_t (*)[4])hf->level.dev;
     memcpy(j.lf.lut.e, f->lf.lim_lut.e, 64); memcpy(j.lf.lut.i, f->lf.lim_lut.i, 64);
@@ -904,7 +907,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     j.lr.w = f->sr_cur.p.p.w; j.lr.h = f->sr_cur.p.p.h; j.lr.ss_hor = ss_hor; j.lr.ss_ver = ss_ver;
     j.lr.sb128 = f->seq_hdr->sb128; j.lr.sr_sb128w = f->sr_sb128w;
     j.lr.unit_size_log2[0] = hdr->restoration.unit_size[0]; j.lr.unit_size_log2[1] = hdr->restoration.unit_size[1];
-    j.lr.restore_planes = f->lf.restore_planes;
+    j.lr.restore_planes = mono ? f->lf.restore_planes & 1 : f->lf.restore_planes;
     j.lr.lr_mask = (const B200Av1Restoration *)hf->lr_mask.dev;
 
     B200Xfer up[48];          /* 6 fixed + 8 inter lists + 19 transform sizes + done map: 34 at most */
@@ -930,7 +933,8 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     uint8_t *const out = outp->dev;
     B200Xfer down[3];
     uint64_t d2h = 0, h2d = 0;
-    for (int p = 0; p < 3; p++) {
+    const int n_down = mono ? 1 : 3;
+    for (int p = 0; p < n_down; p++) {
         const int rows = p ? (f->cur.p.h + ss_ver) >> ss_ver : f->cur.p.h;
         down[p].host = f->cur.data[p];
         down[p].dev = out + (size_t)g.off[p] * sizeof(pixel);
@@ -940,7 +944,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     for (int i = 0; i < n_up; i++) h2d += up[i].bytes;
     const double t0 = bitfn(now_ms)();
     b200hook_job_enter();
-    const int r = be->frame_run_host(&j, up, n_up, down, 3, hf->stream);
+    const int r = be->frame_run_host(&j, up, n_up, down, n_down, hf->stream);
     b200hook_job_leave();
     if (r) { fprintf(stderr, "b200hook: b200_frame_run_host failed (%d): %s\n", r, be->last_error()); return -1; }
     uint64_t n_rec = (uint64_t)hf->n_tx + hf->n_pred + hf->n_comp + hf->n_comp2 + hf->n_warp + hf->n_blend + hf->n_blend2;
@@ -994,14 +998,15 @@ static void bitfn(fg_whole_picture)(Dav1dPicture *const out, const Dav1dPicture 
 {
     const B200Backend *const be = b200hook_backend();
     HookRefPic *const src = b200hook_refpic(in->data[0], 0, 0);
-    if (!be || !src || !src->dev || out->stride[0] != in->stride[0] || out->stride[1] != in->stride[1]) {
+    if (!be || !src || !src->dev || out->stride[0] != in->stride[0] || (in->p.layout != DAV1D_PIXEL_LAYOUT_I400 && out->stride[1] != in->stride[1])) {
         fprintf(stderr, "b200hook: film grain: the picture is not resident on the device (or the output copy has another layout)\n");
         abort();                                    /* no error channel here (void, like dav1d's), no CPU fallback */
     }
     b200hook_refpic_wait(src);
-    const int ss_ver = in->p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = in->p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    const int mono = in->p.layout == DAV1D_PIXEL_LAYOUT_I400;            /* device picture: dummy 4:2:0 chroma planes (pic_geom) */
+    const int ss_ver = mono || in->p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = in->p.layout != DAV1D_PIXEL_LAYOUT_I444;
     const int rows = (in->p.h + 127) & ~127;
-    const int st0 = (int)PXSTRIDE(in->stride[0]), st1 = (int)PXSTRIDE(in->stride[1]);
+    const int st0 = (int)PXSTRIDE(in->stride[0]), st1 = mono ? st0 : (int)PXSTRIDE(in->stride[1]);
     const uint32_t off1 = (uint32_t)st0 * rows, off2 = off1 + (uint32_t)st1 * (rows >> ss_ver);
     const size_t bytes = ((size_t)off2 + (size_t)st1 * (rows >> ss_ver)) * sizeof(pixel);
     static const char fg_slot_key = 0;

@@ -118,9 +118,11 @@ def test_screen_content_stream_emu_matches_stock_dav1d(emu_decoder, case):
 
 
 @pytest.mark.emu
-@pytest.mark.parametrize("case", [("444", 8, 0, 0, 0), ("444", 10, 1, 1, 1), ("444", 12, 1, 0, 0), ("420", 12, 1, 1, 1)])
+@pytest.mark.parametrize("case", [("444", 8, 0, 0, 0), ("444", 10, 1, 1, 1), ("444", 12, 1, 0, 0), ("420", 12, 1, 1, 1),
+                                  ("400", 8, 0, 0, 0), ("400", 10, 1, 1, 0), ("400", 12, 1, 0, 1)])
 def test_other_layouts_and_12bit_stream_emu_matches_stock_dav1d(emu_decoder, case):
-    """profile 1 (4:4:4) and profile 2 (12 bit) streams: same hooks, chroma at full resolution / 12-bit clipping ranges.
+    """profile 1 (4:4:4) and profile 2 (12 bit) streams: same hooks, chroma at full resolution / 12-bit clipping ranges;
+    monochrome (4:0:0): luma only, the device picture carries two dummy chroma planes for the frame-wide sweeps.
     (4:2:2 cannot be driven with random payloads: its illegal partitions make the decoder reject the tile.)"""
     layout, bpc, inter, fg, sc = case
     gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=2, **k)) if inter else obu.intra_stream
@@ -205,7 +207,7 @@ def test_unused_references_are_not_waited_for(emu_decoder, seed):
     rng = np.random.default_rng(seed)
     w, h = int(rng.integers(4, 30)) * 8 + int(rng.choice([0, 0, 2, 6])), int(rng.integers(4, 22)) * 8 + int(rng.choice([0, 0, 4]))
     kw = dict(bpc=int(rng.choice([8, 10, 12])), sb128=int(rng.integers(0, 2)), log2_cols=int(rng.integers(0, 2)), log2_rows=int(rng.integers(0, 2)),
-              film_grain=int(rng.integers(0, 2)), screen_content=int(rng.integers(0, 2)), layout=str(rng.choice(["420", "420", "444"])),
+              film_grain=int(rng.integers(0, 2)), screen_content=int(rng.integers(0, 2)), layout=str(rng.choice(["420", "420", "444", "400"])),
               segmentation=int(rng.integers(0, 2)))
     tus = obu.inter_stream(seed, w, h, n_frames=int(rng.integers(2, 7)), motion_modes=int(rng.integers(0, 3)), global_motion=int(rng.integers(0, 2)),
                            hidden_every=int(rng.choice([0, 0, 2, 3])), intra_only_every=int(rng.choice([0, 0, 0, 4])), **kw)
@@ -225,13 +227,10 @@ def test_super_resolution_stream_fails_loudly(emu_decoder):
     emu_decoder.stats(reset=True)
 
 
-def test_monochrome_stream_fails_loudly(emu_decoder):
-    """4:0:0 is not supported by the whole-frame post filters (they walk three planes): the hooked decoder must report an
-    error, not decode something else"""
-    tus = obu.intra_stream(5, 128, 128, n_frames=1, layout="400")
-    assert _ref_decode(tus)[0] == 1
-    assert emu_decoder.decode(tus)[0] < 0
-    emu_decoder.stats(reset=True)
+def test_monochrome_stream_decodes(emu_decoder):
+    """4:0:0 (was refused in round 1): key frames through the hooked decoder, byte-identical to stock dav1d"""
+    tus = obu.intra_stream(5, 128, 128, n_frames=2, layout="400")
+    _check(emu_decoder, tus, 2)
 
 
 @pytest.mark.emu
