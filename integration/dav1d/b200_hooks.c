@@ -9,7 +9,25 @@
 #include <string.h>
 #include "b200_hooks.h"
 
+#include "dav1d/dav1d.h"
+
 #define API __attribute__((visibility("default")))
+
+/* The record emitters run in dav1d's pass 2 (frame_thread.pass == 2: the frame's symbols were decoded in pass 1 and its
+ * coefficients sit in frame_thread.cf). dav1d only decodes in two passes with more than one frame context (reference
+ * src/thread_task.c:741-744, src/decode.c:2801-2896), and the number of frame contexts is min(max_frame_delay, n_threads)
+ * or ceil(sqrt(n_threads)) (src/lib.c). A caller that asks for one thread / no frame delay would get the single-pass mode,
+ * which the emitters cannot serve (they would have to run the entropy decoder themselves): open with two threads and two
+ * frame contexts instead — same pictures, one frame more of output delay. lib.c's own dav1d_open is renamed by the Makefile. */
+int b200real_dav1d_open(Dav1dContext **c_out, const Dav1dSettings *s);
+API int dav1d_open(Dav1dContext **const c_out, const Dav1dSettings *const s)
+{
+    if (!s) return b200real_dav1d_open(c_out, s);
+    Dav1dSettings s2 = *s;
+    if (s2.n_threads == 1) s2.n_threads = 2;
+    if (s2.max_frame_delay == 1) s2.max_frame_delay = 2;
+    return b200real_dav1d_open(c_out, &s2);
+}
 
 static B200Backend g_be;
 static int g_be_ok;

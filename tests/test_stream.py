@@ -233,6 +233,17 @@ def test_monochrome_stream_decodes(emu_decoder):
     _check(emu_decoder, tus, 2)
 
 
+@pytest.mark.parametrize("n_threads,delay", [(1, 1), (1, 0), (4, 1), (2, 0)])
+def test_single_threaded_settings_decode(emu_decoder, n_threads, delay):
+    """one thread / no frame delay used to put dav1d in single-pass mode, which the emitters cannot serve (every frame
+    failed as unsupported): the hooked library's dav1d_open now keeps two frame contexts, and the pictures match"""
+    tus = obu.inter_stream(11, 192, 136, n_frames=5, motion_modes=1, film_grain=1)
+    r0, _, out0 = _ref_decode(tus, n_threads=1, max_frame_delay=1, apply_grain=1)
+    r1, _, out1 = emu_decoder.decode(tus, n_threads=n_threads, max_frame_delay=delay, apply_grain=1)
+    assert r0 == 5 and r1 == r0 and np.array_equal(out0, out1)
+    emu_decoder.stats(reset=True)
+
+
 @pytest.mark.emu
 def test_stream_many_decoders_recycle_slots(emu_decoder):
     """frame contexts and host pictures of closed decoders must not exhaust the hook's tables (each decode opens a new
