@@ -192,6 +192,9 @@ def frame_algorithmic_bytes(S, fused=False):
     else:
         c = np.concatenate([S["comp"], S["comp2"]])
         comp = (c["w"].astype(np.int64) * c["h"] * (4 + px)).sum()
+    # 8x8 warps: 15x15 window read + 8x8 written; blends: prediction (pixel scratch) read + picture read-modify-write
+    warp = len(S["warp"]) * (15 * 15 + 64) * px if "warp" in S else 0
+    blend = sum(int((S[n]["w"].astype(np.int64) * S[n]["h"]).sum()) * 3 * px for n in ("blend", "blend2") if n in S)
     itx = 0
     from dav1d_b200 import levels as L
     for tx in range(19):
@@ -207,7 +210,7 @@ def frame_algorithmic_bytes(S, fused=False):
         # prediction written + edge read; residual: coefficients read + picture read-modify-write
         intra = int(((tw * th + 2 * (tw + th) + 1) * px).sum() +
                     ((np.minimum(tw, 32) * np.minimum(th, 32) * cps + 2 * tw * th * px) * coded).sum())
-    return {"intra": intra, "mc": int(foot + out), "comp": int(comp), "itx": int(itx), "deblock": int(4 * samples * px),
+    return {"intra": intra, "mc": int(foot + out), "warp": int(warp), "blend": int(blend), "comp": int(comp), "itx": int(itx), "deblock": int(4 * samples * px),
             "cdef": int(2 * samples * px), "lr": int(2 * samples * px),
             "fg": int((2 * samples + luma) * px) if S.get("fg") is not None else 0,   # + luma re-read by the chroma planes
             "samples": int(samples)}
@@ -217,9 +220,11 @@ FRAME_WORKLOADS = {
     "4k8_inter": dict(bpc=8, W=3840, H=2160, fg=False, dtype="u8/i16->i32",
                       desc="one 3840x2160 8-bit 4:2:0 inter frame per GPU per step: prediction (put/prep+compound, 2 refs) + "
                            "inverse transforms + deblock + CDEF + loop restoration (BASELINE configs[2])"),
-    "4k8_mixed": dict(bpc=8, W=3840, H=2160, fg=False, dtype="u8/i16->i32", p_intra=0.10,
-                      desc="4k8_inter with 10 % of the blocks intra coded (what real inter frames contain): the inter stages, then the "
-                           "dependency-driven intra kernel on top of them (done map pre-marked for the inter cells), then the post filters"),
+    "4k8_mixed": dict(bpc=8, W=3840, H=2160, fg=False, dtype="u8/i16->i32", p_intra=0.10, p_obmc=0.10, p_warp=0.05, p_ii=0.05,
+                      desc="4k8_inter with the block mix of real inter frames: 10 % of the blocks intra coded, and of the single-reference "
+                           "blocks 10 % with overlapped block motion compensation, 5 % warped, 5 % inter-intra: the inter stages (incl. warp "
+                           "and the two blend stages), then the dependency-driven intra kernel on top of them (done map pre-marked for the "
+                           "inter cells), then the post filters"),
     "4k10_full": dict(bpc=10, W=3840, H=2160, fg=True, dtype="u16/i32->i32",
                       desc="one 3840x2160 10-bit 4:2:0 inter frame per GPU per step, full pipeline: prediction + inverse "
                            "transforms + deblock + CDEF + loop restoration + film grain (BASELINE configs[3])"),
@@ -240,7 +245,8 @@ def make_workload_frame(name, seed):
     wl = FRAME_WORKLOADS[name]
     if wl.get("intra"):
         return synth.make_intra_frame(np.random.default_rng(seed), wl["bpc"], wl["W"], wl["H"])
-    return synth.make_inter_frame(np.random.default_rng(seed), wl["bpc"], wl["W"], wl["H"], film_grain=wl["fg"], p_intra=wl.get("p_intra", 0.0))
+    return synth.make_inter_frame(np.random.default_rng(seed), wl["bpc"], wl["W"], wl["H"], film_grain=wl["fg"],
+                                  **{k: wl[k] for k in ("p_intra", "p_obmc", "p_warp", "p_ii") if k in wl})
 
 
 def workload_buffers(name, S, **kw):
@@ -601,7 +607,7 @@ def run_ours_frame(args):
         alg = frame_algorithmic_bytes(Ss[0], fused=bool(fbs[0].job.n_cfused))
         stages = {}
         for name, ms in stage_ms.items():
-            key = {"pred": "mc", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg", "intra": "intra"}[name]
+            key = {"pred": "mc", "warp": "warp", "blend": "blend", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg", "intra": "intra"}[name]
             stages[name] = {"ms": ms, "algorithmic_bytes": alg[key], "GBps": alg[key] / (ms * 1e-3) / 1e9 if ms > 0 else None}
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         traffic = None
@@ -609,12 +615,12 @@ def run_ours_frame(args):
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(dom)
         achieved = stages[dom]["GBps"]
-        run_keys = {"pred": "mc", "comp": "comp", "itx": "itx", "intra": "intra", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg"}
+        run_keys = {"pred": "mc", "warp": "warp", "blend": "blend", "comp": "comp", "itx": "itx", "intra": "intra", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg"}
         total_alg = sum(alg[run_keys[k]] for k in stage_ms)
-        recon_ms = sum(v for k, v in stage_ms.items() if k in ("pred", "comp", "itx", "intra"))
+        recon_ms = sum(v for k, v in stage_ms.items() if k in ("pred", "warp", "blend", "comp", "itx", "intra"))
         post_ms = sum(v for k, v in stage_ms.items() if k in ("deblock", "cdef", "lr", "fg"))
         split = {"recon": {"ms": recon_ms, "Mpixels/s": px_per_step / (recon_ms * 1e-3) / 1e6,
-                           "GBps": sum(alg[run_keys[k]] for k in stage_ms if k in ("pred", "comp", "itx", "intra")) / (recon_ms * 1e-3) / 1e9},
+                           "GBps": sum(alg[run_keys[k]] for k in stage_ms if k in ("pred", "warp", "blend", "comp", "itx", "intra")) / (recon_ms * 1e-3) / 1e9},
                  "postfilter": {"ms": post_ms, "Mpixels/s": px_per_step / (post_ms * 1e-3) / 1e6,
                                 "GBps": sum(alg[run_keys[k]] for k in stage_ms if k in ("deblock", "cdef", "lr", "fg")) / (post_ms * 1e-3) / 1e9}}
         nthr = min(host_threads()[0], 32)
@@ -802,7 +808,7 @@ def run_ours_gop(args):
         peak, peak_src = measured_peak()
         fb0 = sets[0]
         alg = frame_algorithmic_bytes(fb0.S, fused=bool(fb0.job.n_cfused))
-        key = {"pred": "mc", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg", "intra": "intra"}
+        key = {"pred": "mc", "warp": "warp", "blend": "blend", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg", "intra": "intra"}
         stages = {n: {"ms": ms, "algorithmic_bytes": alg[key[n]], "GBps": alg[key[n]] / (ms * 1e-3) / 1e9 if ms > 0 else None,
                       "frac": alg[key[n]] / (ms * 1e-3) / 1e9 / peak if ms > 0 else None} for n, ms in stage_ms.items()}
         tot_ms = sum(stage_ms.values())
@@ -818,7 +824,7 @@ def run_ours_gop(args):
         grp = lambda names: {"ms": sum(stage_ms[k] for k in stage_ms if k in names),
                              "Mpixels/s": px_per_frame / (sum(stage_ms[k] for k in stage_ms if k in names) * 1e-3) / 1e6,
                              "GBps": sum(alg[key[k]] for k in stage_ms if k in names) / (sum(stage_ms[k] for k in stage_ms if k in names) * 1e-3) / 1e9}
-        split = {"recon": grp(("pred", "comp", "itx", "intra")), "postfilter": grp(("deblock", "cdef", "lr", "fg"))}
+        split = {"recon": grp(("pred", "warp", "blend", "comp", "itx", "intra")), "postfilter": grp(("deblock", "cdef", "lr", "fg"))}
         cpu = None
         if world == 1:
             nthr, thr_info = host_threads()
@@ -869,6 +875,11 @@ def stage_times(torch, lib, fbs, nsets, reps=6):
     stages = []
     if j0.n_pred:
         stages.append(("pred", lambda j, bd, st: lib.b200_mc_batch(bd, C.byref(j.mc), j.d_pred, j.n_pred, st)))
+    if j0.n_warp:
+        stages.append(("warp", lambda j, bd, st: lib.b200_mc_warp_batch(bd, C.byref(j.mc), j.d_warp, j.n_warp, st)))
+    if j0.n_blend or j0.n_blend2:
+        stages.append(("blend", lambda j, bd, st: (lib.b200_mc_blend_batch(bd, C.byref(j.mc), j.d_blend, j.n_blend, st),
+                                                   lib.b200_mc_blend_batch(bd, C.byref(j.mc), j.d_blend2, j.n_blend2, st))))
     if j0.n_cfused or j0.n_cfused2:
         stages.append(("comp", lambda j, bd, st: (lib.b200_mc_comp_fused_batch(bd, C.byref(j.mc), j.d_cfused, j.n_cfused, st),
                                                   lib.b200_mc_comp_fused_batch(bd, C.byref(j.mc), j.d_cfused2, j.n_cfused2, st))))

@@ -108,14 +108,27 @@ def band_plan(S, band_rows, compact=False, fused=False):
             tmp_y[t1] = yy; tmp_y[t2] = yy
         S2[name], f, c, _ = sort_by_band(a, y)
         ranges[name] = (f, c)
+    # blends (OBMC): they tell where the overlapped predictions (op 2, addressed in `px_tmp`) belong; 8x8 warps
+    lap_y = {}
+    for name in ("blend", "blend2", "warp"):
+        if name in S:
+            a = S[name]
+            y = luma_y(a["dst_off"], a["plane"]) if len(a) else np.zeros(0, np.int64)
+            if name != "warp":
+                for t, yy in zip(a["tmp_off"].tolist(), y.tolist()):
+                    lap_y[t] = yy
+            S2[name], f, c, _ = sort_by_band(a, y)
+            ranges[name] = (f, c)
     pname = "pred_single" if (fused and "cfused" in S) else "pred"
     a = S[pname]
     y = np.zeros(len(a), np.int64)
-    put = a["op"] != 1
+    put, prep, lap = a["op"] == 0, a["op"] == 1, a["op"] == 2
     if put.any():
         y[put] = luma_y(a["dst_off"][put], a["plane"][put])
-    if (~put).any():
-        y[~put] = [tmp_y[t] for t in a["dst_off"][~put].tolist()]
+    if prep.any():
+        y[prep] = [tmp_y[t] for t in a["dst_off"][prep].tolist()]
+    if lap.any():
+        y[lap] = [lap_y[t] for t in a["dst_off"][lap].tolist()]
     S2[pname], f, c, pband = sort_by_band(a, y)
     ranges["pred"] = (f, c)
     for name in ("cfused", "cfused2"):
@@ -215,7 +228,7 @@ class FrameBuffers:
             for k, b in enumerate(plan):
                 fbn = self.bands[k]
                 fbn.y0, fbn.y1, fbn.last = b["y0"], b["y1"], b["last"]
-                for name in ("pred", "comp", "comp2", "cfused", "cfused2", "expand"):
+                for name in ("pred", "warp", "comp", "comp2", "blend", "blend2", "cfused", "cfused2", "expand"):
                     if name in b:
                         getattr(fbn, name)[0], getattr(fbn, name)[1] = b[name]
                 for tx in range(19):
@@ -247,7 +260,7 @@ class FrameBuffers:
             j.mc.ref_plane_off[p] = S["off"][p]; j.mc.ref_stride[p] = S["stride"][p]
             j.mc.ref_w[p] = (S["W"] + ssh[p]) >> ssh[p]; j.mc.ref_h[p] = (S["H"] + ssv[p]) >> ssv[p]
             j.mc.dst_stride[p] = S["stride"][p]; j.itx_stride[p] = S["stride"][p]
-        j.mc.dst, j.mc.tmp, j.mc.mask, j.mc.px_tmp = p0, tmp, mask, None
+        j.mc.dst, j.mc.tmp, j.mc.mask, j.mc.px_tmp = p0, tmp, mask, (zeros("px_tmp", S["px_tmp_len"] * px) if S.get("px_tmp_len") else None)
         self.uploads = []          # (name, host array) re-sent per frame on the end-to-end path
 
         def rec(field_ptr, field_n, name, arr):
@@ -262,6 +275,9 @@ class FrameBuffers:
             rec("d_pred", "n_pred", "pred", S["pred"])
             rec("d_comp", "n_comp", "comp", S["comp"])
             rec("d_comp2", "n_comp2", "comp2", S["comp2"])
+        for name in ("warp", "blend", "blend2"):      # warped blocks; OBMC blends (stage 1: rows from above, stage 2: columns from the left)
+            if name in S:
+                rec("d_" + name, "n_" + name, name, S[name])
         for tx in range(19):
             a = S["itx"][tx]
             if len(a):
@@ -285,6 +301,7 @@ class FrameBuffers:
             it = j.intra
             it.pic, it.d_coef, it.zero_coefs, it.grid = p0, j.d_coef, 0, intra_grid
             it.ss_hor, it.ss_ver = S["ss_hor"], S["ss_ver"]
+            it.mask = mask                            # blend masks of inter-intra (II) records
             for p in range(3):
                 it.stride[p] = S["stride"][p]
                 it.w4[p] = S["w4"] >> ssh[p]; it.h4[p] = S["h4"] >> ssv[p]
@@ -353,6 +370,7 @@ class FrameBuffers:
             n_fg = 2
         self.job = j
         self.n_launches = (1 if j.n_pred else 0) + (1 if j.n_comp else 0) + (1 if j.n_comp2 else 0) + \
+            (1 if j.n_warp else 0) + (1 if j.n_blend else 0) + (1 if j.n_blend2 else 0) + \
             (1 if j.n_cfused else 0) + (1 if j.n_cfused2 else 0) + \
             (1 if any(j.n_itx[tx] for tx in (4, 11, 12, 17, 18)) else 0) + \
             (1 if any(j.n_itx[tx] for tx in range(19) if tx not in (4, 11, 12, 17, 18)) else 0) + 2 * int(run_lf) + int(run_cdef) + int(run_lr) + n_fg + n_intra

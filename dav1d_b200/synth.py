@@ -238,6 +238,10 @@ COMP_FUSED_DT = np.dtype([("dst_off", "<u4"), ("mask_off", "<u4"), ("src_x", "<i
 assert COMP_FUSED_DT.itemsize == 40
 ITX_BLOCK_DT = np.dtype([("dst_off", "<u4"), ("coef_off", "<u4"), ("eob", "<i2"), ("txtp", "u1"), ("plane", "u1")])
 assert MC_BLOCK_DT.itemsize == 20 and COMP_BLOCK_DT.itemsize == 24 and ITX_BLOCK_DT.itemsize == 12
+BLEND_BLOCK_DT = np.dtype([("dst_off", "<u4"), ("tmp_off", "<u4"), ("mask_off", "<u4"), ("w", "u1"), ("h", "u1"), ("op", "u1"), ("plane", "u1")])
+WARP_BLOCK_DT = np.dtype([("dst_off", "<u4"), ("src_x", "<i4"), ("src_y", "<i4"), ("mx", "<i4"), ("my", "<i4"), ("abcd", "<i2", (4,)),
+                          ("tmp_stride", "<u2"), ("op", "u1"), ("plane", "u1"), ("ref", "u1"), ("pad", "u1", (3,))])
+assert BLEND_BLOCK_DT.itemsize == 16 and WARP_BLOCK_DT.itemsize == 36
 TX_FROM_WH = {(_L.TX_W[t], _L.TX_H[t]): t for t in range(19)}
 _scans = None
 
@@ -293,9 +297,13 @@ def make_film_grain(rng, full=True):
 
 
 def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.3, p_skip=0.25, min_log=1, max_log=4,
-                     film_grain=False, p_intra=0.0):
+                     film_grain=False, p_intra=0.0, p_obmc=0.0, p_warp=0.0, p_ii=0.0):
     """Synthetic inter frame: every block is predicted from `n_refs` reference pictures (single or
     compound), carries a residual (unless skipped) and the frame has deblock / CDEF / LR parameters.
+    p_obmc / p_warp / p_ii: share of the single-reference blocks of 8x8 luma samples and more that use overlapped block
+    motion compensation (predictions with the neighbours' motion blended over the top rows / left columns: B200McBlock op 2
+    + B200BlendBlock, what obmc() does, reference src/recon_tmpl.c:1052-1113), an affine warp (B200WarpBlock per 8x8,
+    warp_affine :1115-1165) or an inter-intra blend (B200_INTRA_MODE_II + RESID records, :1601-1626, 1737-1777).
     p_intra > 0: that share of the blocks is intra coded instead (what real inter frames contain): B200IntraTx records
     (S["intra_tx"], wavefront order among themselves) + S["done_init"], the done map in which every cell of an inter block
     is final before the intra kernel starts (include/b200av1.h, B200IntraFrame.done_init)."""
@@ -310,7 +318,7 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
     refs = [smooth_picture(rng, total, bd, dt) for _ in range(n_refs)]
     decode_order = []
     bx, by, lw, lh = random_tiling(rng, w4, h4, max_log=max_log, min_log=min_log, order=decode_order)
-    if p_intra > 0:
+    if p_intra > 0 or p_ii > 0:
         blocks = [b for b in decode_order if b[0] < w4 and b[1] < h4]      # intra blocks need their neighbours first: decode order
     else:
         key = by.astype(np.int64) * 65536 + bx
@@ -319,6 +327,8 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
     intra_recs = []
     pw4 = [w4, (w4 + ss_hor) >> ss_hor, (w4 + ss_hor) >> ss_hor]; ph4 = [h4, (h4 + ss_ver) >> ss_ver, (h4 + ss_ver) >> ss_ver]
     edge_filter = int(rng.integers(0, 2)) if p_intra > 0 else 0
+    warp, blend, blend2 = [], [], []
+    px_tmp_off = 0
 
     def add_intra(pl, x, y, tlw, tlh, mode, angle, skip):
         """one intra transform block of plane pl at (x, y) [plane 4-sample units] (cf. make_intra_frame.add)"""
@@ -336,6 +346,7 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
         r["flags"] = (1 if x > 0 else 0) | (2 if y > 0 else 0)        # top-right / bottom-left never used: always a valid choice
         r["eob"] = -1 if skip else 0                                  # residual filled in below
         intra_recs.append(r)
+        return r
 
     pred, comp, comp2 = [], [], []
     pred_single, cfused, cfused2 = [], [], []  # the same predictions for the fused compound kernel
@@ -381,6 +392,16 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
                         add_intra(pl, cx4 + xx, cy4 + yy, ctl, cth, um, uang, skip)
             continue
         compound = rng.random() < p_compound
+        motion = None
+        inside = x4 + (1 << lwv) <= w4 and y4 + (1 << lhv) <= h4
+        if not compound and inside and min(bw, bh) >= 8 and (p_obmc or p_warp or p_ii):
+            u = rng.random()
+            if u < p_warp:
+                motion = "warp"
+            elif u < p_warp + p_obmc:
+                motion = "obmc"
+            elif u < p_warp + p_obmc + p_ii and max(bw, bh) <= 32 and max(bw, bh) <= 2 * min(bw, bh):
+                motion = "ii"
         mv = [(int(rng.integers(-512, 513)), int(rng.integers(-512, 513))) for _ in range(2)]   # 1/8 luma pixels
         if rng.random() < 0.05:
             mv[0] = (mv[0][0] & ~7, mv[0][1] & ~7)                                              # integer-pel sometimes
@@ -408,9 +429,43 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
                 srcs.append((sx, sy, mx, my))
                 if compound:
                     pred.append((tmp_off, sx, sy, w, h, mx, my, f2d, 1, pl, rf[k])); offs.append(tmp_off); tmp_off += w * h
+                elif motion == "warp" and min(w, h) >= 8:
+                    # one record per 8x8 of the block; the matrix of the block is shared, the per-8x8 positions / phases are
+                    # what warp_affine derives from it (here: drawn, the kernel does not care where they come from)
+                    abcd = [int(v) for v in rng.integers(-2048, 2049, 4)]
+                    for yy in range(0, h, 8):
+                        for xx in range(0, w, 8):
+                            warp.append((dst_off + yy * stride[pl] + xx, sx + xx + int(rng.integers(-2, 3)), sy + yy + int(rng.integers(-2, 3)),
+                                         int(rng.integers(0, 1 << 16)) & ~0x3f, int(rng.integers(0, 1 << 16)) & ~0x3f, abcd, 0, 0, pl, rf[k], (0, 0, 0)))
                 else:
                     pred.append((dst_off, sx, sy, w, h, mx, my, f2d, 0, pl, rf[k]))
                     pred_single.append(pred[-1])
+            if motion == "obmc":
+                # predictions with the motion of the block above over the top rows (3/4 of half the block height are computed,
+                # blend_h blends them) and of the block to the left over the left columns (blend_v)
+                def lap(wl, hl):
+                    nonlocal px_tmp_off
+                    mvx, mvy = int(rng.integers(-512, 513)), int(rng.integers(-512, 513))
+                    sxl, mxl = (px + (mvx >> 3), (mvx & 7) << 1) if (pl == 0 or not ss_hor) else (px + (mvx >> 4), mvx & 15)
+                    syl, myl = (py + (mvy >> 3), (mvy & 7) << 1) if (pl == 0 or not ss_ver) else (py + (mvy >> 4), mvy & 15)
+                    rec = (px_tmp_off, sxl, syl, wl, hl, mxl, myl, int(rng.integers(0, 10)), 2, pl, int(rng.integers(0, n_refs)))
+                    pred.append(rec); pred_single.append(rec)
+                    o = px_tmp_off; px_tmp_off += wl * hl
+                    return o
+                h_mul, v_mul = 4 >> ssh[pl], 4 >> ssv[pl]
+                if y4 > 0:
+                    oh4 = min(1 << lhv, 16) >> 1
+                    o = lap(w, ((oh4 * 3 + 3) >> 2) * v_mul)
+                    blend.append((dst_off, o, 0, w, v_mul * oh4, 2, pl))
+                if x4 > 0:
+                    ow4 = min(1 << lwv, 16) >> 1
+                    o = lap(h_mul * ow4, h)
+                    blend2.append((dst_off, o, 0, h_mul * ow4, h, 1, pl))
+            if motion == "ii":
+                r = add_intra(pl, (x4 * 4 >> ssh[pl]) >> 2, (y4 * 4 >> ssv[pl]) >> 2, 0, 0, 15, int(rng.choice([0, 1, 2, 9])), True)
+                r["tx"] = TX_FROM_WH[(w, h)]
+                r["luma_off"] = mask_off; mask_off += w * h
+                intra_recs[-1] = r
             if compound:
                 def fused(moff, op_, par):
                     return (dst_off, moff, (srcs[0][0], srcs[1][0]), (srcs[0][1], srcs[1][1]), w, h, (srcs[0][2], srcs[1][2]),
@@ -434,6 +489,11 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
         # residual: transform tiling of the block (var-tx split depth <= 1), capped at 64
         skip = rng.random() < p_skip
         skip_map[y4:y4 + (1 << lhv), x4:x4 + (1 << lwv)] = skip
+        if motion == "ii":
+            # the residual of an inter-intra block goes through the intra machine as RESID records (after the blend); the II
+            # records just appended say whether any follow
+            for r in intra_recs[-3:]:
+                r["cfl_alpha"] = 0 if skip else 1
         tlw, tlh = min(lwv, 4), min(lhv, 4)
         if rng.random() < 0.3 and tlw > 0 and tlh > 0:
             tlw -= 1; tlh -= 1
@@ -442,7 +502,10 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
                 paint(ty, xx, yy, tlw, tlh, h4, w4)
                 if not skip and xx < w4 and yy < h4:
                     tx = TX_FROM_WH[(4 << tlw, 4 << tlh)]
-                    itx[tx].append((off[0] + yy * 4 * stride[0] + xx * 4, 0))
+                    if motion == "ii":
+                        add_intra(0, xx, yy, tlw, tlh, 16, 0, False)
+                    else:
+                        itx[tx].append((off[0] + yy * 4 * stride[0] + xx * 4, 0))
         # chroma: one transform per block, capped at 32 (64x64 luma -> 32x32 chroma)
         clw, clh = max(lwv - ss_hor, 0), max(lhv - ss_ver, 0)
         cx4, cy4 = x4 >> ss_hor, y4 >> ss_ver
@@ -453,7 +516,10 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
                 if not skip and xx < cw4 and yy < ch4:
                     tx = TX_FROM_WH[(4 << ctl, 4 << cth)]
                     for pl in (1, 2):
-                        itx[tx].append((off[pl] + yy * 4 * stride[pl] + xx * 4, pl))
+                        if motion == "ii":
+                            add_intra(pl, xx, yy, ctl, cth, 16, 0, False)
+                        else:
+                            itx[tx].append((off[pl] + yy * 4 * stride[pl] + xx * 4, pl))
 
     # ---- coefficient stream (vectorised per transform size) ----
     coef_chunks, itx_arrays, coef_off = [], {}, 0
@@ -518,6 +584,10 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
             tw, th = _L.TX_W[r["tx"]] // 4, _L.TX_H[r["tx"]] // 4
             wm = wave_map[pl]
             dep = 0
+            if r["mode"] == 16:                        # RESID: after the II record that predicted these cells
+                wave[i] = int(wm[y:y + th, x:x + tw].max()) + 1
+                wm[y:y + th, x:x + tw] = wave[i]
+                continue
             if x > 0:
                 dep = max(dep, int(wm[y:y + min(th, ph4[pl] - y), x - 1].max()))
             if y > 0:
@@ -552,6 +622,9 @@ def make_inter_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, n_refs=2, p_compound=0.
              comp2=by_area(to_arr(comp2, COMP_BLOCK_DT)), pred_single=by_area(to_arr(pred_single, MC_BLOCK_DT)),
              cfused=by_area(to_arr(cfused, COMP_FUSED_DT)), cfused2=by_area(to_arr(cfused2, COMP_FUSED_DT)),
              itx=itx_arrays, coefs=coefs, tmp_len=tmp_off + 64, mask=rng.integers(0, 65, max(1, mask_off)).astype(np.uint8))
+    if warp or blend or blend2:
+        S.update(warp=to_arr(warp, WARP_BLOCK_DT), blend=by_area(to_arr(blend, BLEND_BLOCK_DT)), blend2=by_area(to_arr(blend2, BLEND_BLOCK_DT)),
+                 px_tmp_len=px_tmp_off + 64)
     S.update(intra_extra)
     S["pic"] = np.zeros(total, dt)                     # the picture being reconstructed
     # post-filter records from the transform tilings

@@ -392,7 +392,10 @@ ORACLE_API void oracle_mc_batch(int bdmax, const OracleMcFrame *f, const OracleM
         oracle_emu_edge(b->w + 7, b->h + 7, f->ref_w[pl], f->ref_h[pl], b->src_x - 3, b->src_y - 3, win,
                         135 * (ptrdiff_t)px, ref, f->ref_stride[pl] * (ptrdiff_t)px, bdmax);
         const uint8_t *src = win + (3 * 135 + 3) * px;
-        if (b->op) oracle_mc_prep(f->tmp + b->dst_off, src, 135 * (ptrdiff_t)px, b->w, b->h, b->mx, b->my, b->filter2d, bdmax);
+        if (b->op == 2)       /* put into the pixel scratch (pitch w): the overlapped predictions of obmc(), src/recon_tmpl.c:1052-1113 */
+            oracle_mc_put((uint8_t *)f->px_tmp + (size_t)b->dst_off * px, b->w * (ptrdiff_t)px, src, 135 * (ptrdiff_t)px, b->w, b->h,
+                          b->mx, b->my, b->filter2d, bdmax);
+        else if (b->op) oracle_mc_prep(f->tmp + b->dst_off, src, 135 * (ptrdiff_t)px, b->w, b->h, b->mx, b->my, b->filter2d, bdmax);
         else oracle_mc_put((uint8_t *)f->dst + (size_t)b->dst_off * px, f->dst_stride[pl] * (ptrdiff_t)px, src,
                            135 * (ptrdiff_t)px, b->w, b->h, b->mx, b->my, b->filter2d, bdmax);
     }

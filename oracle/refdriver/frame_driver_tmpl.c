@@ -236,8 +236,28 @@ API void bitfn(refdrv_frame_run)(const B200FrameJob *const j)
         } else {
             src = ref + (ptrdiff_t)dy * j->mc.ref_stride[pl] + dx;
         }
-        if (b->op) mc.mct[b->filter2d](j->mc.tmp + b->dst_off, src, rs, w, h, mx, my HIGHBD_TAIL_SUFFIX);
+        if (b->op == 2)       /* obmc()'s `lap` prediction: a put into the pixel scratch, pitch w (src/recon_tmpl.c:1052-1113) */
+            mc.mc[b->filter2d]((pixel *)j->mc.px_tmp + b->dst_off, w * (ptrdiff_t)sizeof(pixel), src, rs, w, h, mx, my HIGHBD_TAIL_SUFFIX);
+        else if (b->op) mc.mct[b->filter2d](j->mc.tmp + b->dst_off, src, rs, w, h, mx, my HIGHBD_TAIL_SUFFIX);
         else mc.mc[b->filter2d](dst + b->dst_off, j->mc.dst_stride[pl] * (ptrdiff_t)sizeof(pixel), src, rs, w, h, mx, my HIGHBD_TAIL_SUFFIX);
+    }
+    /* warped blocks: emu_edge of the 15x15 window when it leaves the picture, then warp8x8 / warp8x8t (warp_affine,
+     * src/recon_tmpl.c:1115-1165) */
+    for (int i = 0; i < j->n_warp; i++) {
+        const B200WarpBlock *b = &j->d_warp[i];
+        const int pl = b->plane, iw = j->mc.ref_w[pl], ih = j->mc.ref_h[pl], dx = b->src_x, dy = b->src_y;
+        const pixel *ref = (const pixel *)j->mc.ref[b->ref] + j->mc.ref_plane_off[pl];
+        ptrdiff_t rs = j->mc.ref_stride[pl] * (ptrdiff_t)sizeof(pixel);
+        const pixel *src;
+        if (dx < 3 || dx + 8 + 4 > iw || dy < 3 || dy + 8 + 4 > ih) {
+            mc.emu_edge(15, 15, iw, ih, dx - 3, dy - 3, emu, 32 * sizeof(pixel), ref, rs);
+            src = &emu[32 * 3 + 3];
+            rs = 32 * sizeof(pixel);
+        } else {
+            src = ref + (ptrdiff_t)dy * j->mc.ref_stride[pl] + dx;
+        }
+        if (b->op) mc.warp8x8t(j->mc.tmp + b->dst_off, b->tmp_stride, src, rs, b->abcd, b->mx, b->my HIGHBD_TAIL_SUFFIX);
+        else mc.warp8x8(dst + b->dst_off, j->mc.dst_stride[pl] * (ptrdiff_t)sizeof(pixel), src, rs, b->abcd, b->mx, b->my HIGHBD_TAIL_SUFFIX);
     }
     for (int pass = 0; pass < 2; pass++) {
         const B200CompBlock *cb = pass ? j->d_comp2 : j->d_comp;
@@ -253,6 +273,20 @@ API void bitfn(refdrv_frame_run)(const B200FrameJob *const j)
             case B200_COMP_MASK:  mc.mask(d, ds, t1, t2, cb->w, cb->h, m HIGHBD_TAIL_SUFFIX); break;
             default: mc.w_mask[cb->op - B200_COMP_W_MASK_444](d, ds, t1, t2, cb->w, cb->h, m, cb->param HIGHBD_TAIL_SUFFIX); break;
             }
+        }
+    }
+    /* blends: every blend_h (predictions of the blocks above), then every blend_v (blocks to the left), as obmc() orders them
+     * inside a block; blocks do not overlap, so the order across blocks is free */
+    for (int pass = 0; pass < 2; pass++) {
+        const B200BlendBlock *bb = pass ? j->d_blend2 : j->d_blend;
+        const int n = pass ? j->n_blend2 : j->n_blend;
+        for (int i = 0; i < n; i++, bb++) {
+            pixel *d = dst + bb->dst_off;
+            const ptrdiff_t ds = j->mc.dst_stride[bb->plane] * (ptrdiff_t)sizeof(pixel);
+            const pixel *lap = (const pixel *)j->mc.px_tmp + bb->tmp_off;
+            if (bb->op == B200_BLEND_H) mc.blend_h(d, ds, lap, bb->w, bb->h);
+            else if (bb->op == B200_BLEND_V) mc.blend_v(d, ds, lap, bb->w, bb->h);
+            else mc.blend(d, ds, lap, bb->w, bb->h, j->mc.mask + bb->mask_off);
         }
     }
     for (int tx = 0; tx < N_RECT_TX_SIZES; tx++) {

@@ -30,9 +30,16 @@ def oracle_frame(S, run_lf=True, run_cdef=True, run_lr=True):
         fr.ref_w[p] = (S["W"] + ssh[p]) >> ssh[p]; fr.ref_h[p] = (S["H"] + ssv[p]) >> ssv[p]
         fr.dst_stride[p] = S["stride"][p]
     fr.dst, fr.tmp, fr.mask = pic.ctypes.data, tmp.ctypes.data, mask.ctypes.data
+    px_tmp = np.zeros(S.get("px_tmp_len", 1), pic.dtype)
+    fr.px_tmp = px_tmp.ctypes.data
     o.oracle_mc_batch(bd, C.byref(fr), S["pred"].ctypes.data, len(S["pred"]))
+    if "warp" in S:
+        o.oracle_mc_warp_batch(bd, C.byref(fr), S["warp"].ctypes.data, len(S["warp"]))
     o.oracle_mc_comp_batch(bd, C.byref(fr), S["comp"].ctypes.data, len(S["comp"]))
     o.oracle_mc_comp_batch(bd, C.byref(fr), S["comp2"].ctypes.data, len(S["comp2"]))
+    for name in ("blend", "blend2"):            # OBMC: rows from the blocks above, then columns from the blocks to the left
+        if name in S:
+            o.oracle_mc_blend_batch(bd, C.byref(fr), S[name].ctypes.data, len(S[name]))
     st = (C.c_int32 * 3)(*S["stride"])
     coefs = S["coefs"].copy()
     for tx in range(19):
@@ -43,6 +50,7 @@ def oracle_frame(S, run_lf=True, run_cdef=True, run_lr=True):
         # intra blocks of a mixed frame: record by record, after every inter block is in the picture
         import test_intra as TI
         fr_i = TI.intra_frame_struct(S, pic, coefs)
+        fr_i.mask = mask.ctypes.data
         tx = np.ascontiguousarray(S["intra_tx_decode_order"])
         fn = o.oracle_intra_frame
         fn.restype = None
@@ -216,6 +224,62 @@ def test_gpu_mixed_frame(bpc, W, H):
         check_frame(S, fb, exp)
 
 
+MOTION = dict(p_obmc=0.2, p_warp=0.15, p_ii=0.15)
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("bpc,W,H,p_intra", [(8, 264, 200, 0.1), (10, 200, 136, 0.0), (8, 328, 264, 0.0)])
+def test_emu_motion_mode_frame(bpc, W, H, p_intra):
+    """the remaining inter tools of real frames in the synthetic records: overlapped block motion compensation (op-2 predictions
+    + blend_h / blend_v stages), affine warps (8x8 records) and inter-intra blends (II + RESID records of the intra machine),
+    alone and next to intra blocks; equals the oracle; without intra-machine records also cut into bands"""
+    S = synth.make_inter_frame(np.random.default_rng(670 + bpc + H), bpc, W, H, p_intra=p_intra, film_grain=bpc > 8, **MOTION)
+    assert len(S["warp"]) > 10 and len(S["blend"]) > 10 and len(S["blend2"]) > 10 and (S["intra_tx"]["mode"] == 15).sum() > 5
+    assert (S["intra_tx"]["mode"] == 16).sum() > 5 and (S["pred"]["op"] == 2).sum() > 20
+    exp = oracle_frame(S)
+    for drop in ("warp", "blend", "blend2"):         # every list matters
+        S0 = dict(S); S0[drop] = S[drop][:0]
+        assert not np.array_equal(exp["recon"], oracle_frame(S0)["recon"]), drop
+    kw = dict(lib=refs.emu_lib(), alloc=frame.NumpyAlloc())
+    fb = frame.FrameBuffers(S, **kw)
+    fb.run()
+    check_frame(S, fb, exp)
+    fb1 = frame.FrameBuffers(S, band_rows=-(-H // 64) * 64, compact=True, **kw)
+    fb1.run_bands()
+    check_frame(S, fb1, exp)
+
+
+@pytest.mark.emu
+def test_emu_motion_mode_frame_bands():
+    """OBMC and warp records sorted into 64-row bands (inter-intra needs the intra machine: whole-frame band only)"""
+    S = synth.make_inter_frame(np.random.default_rng(681), 8, 264, 328, p_obmc=0.25, p_warp=0.2)
+    assert "intra_tx" not in S and len(S["warp"]) and len(S["blend"])
+    exp = oracle_frame(S)
+    for rows in (64, 128):
+        fb = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc(), band_rows=rows, compact=True)
+        assert fb.n_bands() > 2
+        fb.run_bands()
+        check_frame(S, fb, exp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bpc,W,H,p_intra", [(8, 648, 520, 0.1), (10, 1288, 720, 0.05)])
+def test_gpu_motion_mode_frame(bpc, W, H, p_intra):
+    S = synth.make_inter_frame(np.random.default_rng(690 + bpc), bpc, W, H, p_intra=p_intra, film_grain=bpc > 8, **MOTION)
+    exp = oracle_frame(S)
+    for kw in (dict(), dict(band_rows=-(-H // 64) * 64, compact=True)):
+        fb = frame.FrameBuffers(S, **kw)
+        fb.run_bands() if kw else fb.run()
+        fb.alloc.sync()
+        check_frame(S, fb, exp)
+    S = synth.make_inter_frame(np.random.default_rng(691 + bpc), bpc, W, H, p_obmc=0.25, p_warp=0.2)
+    exp = oracle_frame(S)
+    fb = frame.FrameBuffers(S, band_rows=128, compact=True)
+    fb.run_bands()
+    fb.alloc.sync()
+    check_frame(S, fb, exp)
+
+
 def reference_frame(S):
     """the same job through the reference's own functions on the CPU (oracle/refdriver: refdrv_frame_run)"""
     fb = frame.FrameBuffers(S, lib=object(), alloc=frame.NumpyAlloc())
@@ -230,6 +294,12 @@ def test_oracle_frame_vs_reference_functions(bpc, W, H, ssh, ssv):
     if not refs.have_ref():
         pytest.skip("reference build (oracle/_ref) not present")
     S = synth.make_inter_frame(np.random.default_rng(620 + bpc), bpc, W, H, ssh, ssv, film_grain=bpc > 8)
+    exp = oracle_frame(S)
+    fb = reference_frame(S)
+    check_frame(S, fb, exp)
+    # ... and with intra blocks, OBMC, warps and inter-intra blends in the records
+    S = synth.make_inter_frame(np.random.default_rng(625 + bpc), bpc, W, H, ssh, ssv, p_intra=0.1, **MOTION)
+    S["intra_tx"] = S["intra_tx_decode_order"]
     exp = oracle_frame(S)
     fb = reference_frame(S)
     check_frame(S, fb, exp)

@@ -95,6 +95,14 @@ if [[ $what == *" benchNgpu "* ]]; then
     ( timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 20 --warmup 5 --workload $wl > gpurun_out/bench_n${N}_$wl.json 2> gpurun_out/bench_n${N}_$wl.err ); echo "n$N $wl rc=$?"
   done
 fi
+if [[ $what == *" bandsweep "* ]]; then
+  # band height vs throughput of the dependent stream at N ranks (the chain bound is ~2 band times per frame)
+  N=${B200_N:-4}
+  for cfg in "4k8_inter 128" "4k8_inter 192" "4k8_inter 320" "8k10_full 128" "8k10_full 192"; do
+    set -- $cfg
+    ( B200_SKIP_PARITY=1 B200_BAND_ROWS=$2 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus $N --steps 16 --warmup 4 --workload $1 > gpurun_out/bench_n${N}_$1_b$2.json 2> gpurun_out/bench_n${N}_$1_b$2.err ); echo "n$N $1 b$2 rc=$?"
+  done
+fi
 echo done > gpurun_out/done.txt
 for f in gpurun_out/bench_*.json; do echo "$f: $(head -c 600 $f)"; done
 for f in gpurun_out/bench_*.err; do if [ -s $f ]; then echo "== $f"; tail -5 $f; fi; done
