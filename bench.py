@@ -687,7 +687,11 @@ def run_ours_gop(args):
     # (144 + band) rows; N ranks stay busy when N such lags fit into a frame, hence ~H / 3N rows per band — as few bands as
     # that allows, because every band is a dozen more (small) launches
     n_bands = min(2 * world + 1, max(2, H // 256))          # ... and no more than ~256-row bands: a band costs ~55 us of launch chain
-    band_rows = int(os.environ.get("B200_BAND_ROWS", str(whole if world == 1 else -(-H // n_bands))))
+    # ... from 4 ranks on the stream is bound by the frame-to-frame lag (one band period + the launch chains of a band's
+    # reconstruction and post filters + 2 bands of work), not by GPU time: measured at N=4 (profiles/r02_bench_n4_*): 4K
+    # 0.369 / 0.282 / 0.315 ms per frame with 128 / 192 / 320-row bands, 8K 0.686 / 0.606 with 128 / 192, 0.558 with 320 (N=8)
+    default_rows = whole if world == 1 else -(-H // n_bands) if world < 4 else (192 if H <= 2160 else 320)
+    band_rows = int(os.environ.get("B200_BAND_ROWS", str(default_rows)))
     band_rows = min(whole, max(64, -(-band_rows // 64) * 64))
     n_streams = max(1, int(os.environ.get("B200_FRAMES_IN_FLIGHT", "1" if world == 1 else "2")))
     nsets = int(os.environ.get("B200_NSETS", "3" if args.workload == "8k10_full" else "6"))

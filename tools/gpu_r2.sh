@@ -103,6 +103,24 @@ if [[ $what == *" bandsweep "* ]]; then
     ( B200_SKIP_PARITY=1 B200_BAND_ROWS=$2 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus $N --steps 16 --warmup 4 --workload $1 > gpurun_out/bench_n${N}_$1_b$2.json 2> gpurun_out/bench_n${N}_$1_b$2.err ); echo "n$N $1 b$2 rc=$?"
   done
 fi
+if [[ $what == *" final "* ]]; then
+  # round-end pass on one GPU: every GPU test, smoke, the bench lines the docs quote, launch list, ncu --set full of every
+  # frame-path kernel (8-bit and 10-bit instantiations, film grain, the intra machine, warp / blend)
+  timeout 1200 python -m pytest tests -x -q -m gpu --timeout 300 2>&1 | tail -25 > gpurun_out/pytest_gpu.txt; tail -3 gpurun_out/pytest_gpu.txt
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1; tail -2 gpurun_out/smoke.txt
+  run_bench n1_default python bench.py
+  export B200_SKIP_PARITY=1 B200_MIN_TIMED_S=0.005 B200_NSETS=3 B200_DISTINCT=1
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 60 --csv --log-file gpurun_out/launches_4k8.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+  timeout 400 ncu --set full --clock-control none -k regex:"mc_|itx_|lf_|cdef_|lr_|coef_" -s 36 -c 12 -f -o gpurun_out/prof_4k8 python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_4k8.log 2>&1; echo "ncu 4k8 rc=$?"
+  timeout 400 ncu --set full --clock-control none -k regex:"mc_|itx_|lf_|cdef_|lr_|coef_|fg_" -s 42 -c 14 -f -o gpurun_out/prof_4k10 python bench.py --workload 4k10_full --steps 2 --warmup 3 > gpurun_out/ncu_4k10.log 2>&1; echo "ncu 4k10 rc=$?"
+  timeout 500 ncu --set full --clock-control none -k regex:"intra_|mc_warp|mc_blend" -s 12 -c 4 -f -o gpurun_out/prof_mixed python bench.py --workload 4k8_mixed --steps 2 --warmup 3 > gpurun_out/ncu_mixed.log 2>&1; echo "ncu mixed rc=$?"
+  unset B200_SKIP_PARITY B200_MIN_TIMED_S B200_NSETS B200_DISTINCT
+  run_bench n1_mixed python bench.py --workload 4k8_mixed --steps 20 --warmup 5
+  run_bench n1_4k10 python bench.py --workload 4k10_full --steps 20 --warmup 5
+  run_bench n1_8k10 python bench.py --workload 8k10_full --steps 10 --warmup 3
+  run_bench n1_intra_warp B200_INTRA_SB=0 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
+  ls -la gpurun_out/*.ncu-rep
+fi
 echo done > gpurun_out/done.txt
 for f in gpurun_out/bench_*.json; do echo "$f: $(head -c 600 $f)"; done
 for f in gpurun_out/bench_*.err; do if [ -s $f ]; then echo "== $f"; tail -5 $f; fi; done
