@@ -900,8 +900,8 @@ def stage_times(torch, lib, fbs, nsets, reps=6):
         stages.append(("cdef", lambda j, bd, st: lib.b200_cdef_frame(bd, C.byref(j.cdef), st)))
     if j0.run_lr:
         stages.append(("lr", lambda j, bd, st: lib.b200_lr_frame(bd, C.byref(j.lr), st)))
-    if j0.run_fg:   # apply only: the LUT preparation overlaps reconstruction on the side stream in the real job
-        stages.append(("fg", lambda j, bd, st: lib.b200_fg_apply(bd, C.byref(j.fg), st)))
+    if j0.run_fg:   # grain templates + scaling LUT, then the blend; in the job the preparation runs on a side stream beside reconstruction
+        stages.append(("fg", lambda j, bd, st: (lib.b200_fg_prep(bd, C.byref(j.fg), st), lib.b200_fg_apply(bd, C.byref(j.fg), st))))
     acc = {n: 0.0 for n, _ in stages}
     st = torch.cuda.current_stream().cuda_stream
     for r in range(reps):

@@ -59,9 +59,10 @@ def obu(obu_type, payload):
 OBU_SEQ_HDR, OBU_TD, OBU_FRAME_HDR, OBU_FRAME = 1, 2, 3, 6
 
 
-# 4:2:2 is expressible in the headers below, but random tile payloads are not legal 4:2:2 streams: partitions whose
-# chroma blocks would be 2 samples wide are forbidden there and the decoder rejects them (reference src/decode.c,
-# decode_sb). The stream generators therefore offer 4:2:0, 4:4:4 and 4:0:0.
+# 4:2:2 (layout="422") is expressible in the headers below, but random tile payloads are only sometimes legal 4:2:2 streams:
+# partitions whose chroma blocks would be 2 samples wide are forbidden there and the decoder rejects them (reference
+# src/decode.c, decode_sb). Small frames (a few superblocks) pass for a good share of the seeds: callers draw seeds until
+# the stock decoder accepts the stream (tests/test_stream.py::_valid_422).
 def _profile(bpc, layout):
     """seq_profile for a bit depth / chroma layout: 0 = 4:2:0 (and 4:0:0) 8 / 10 bit, 1 = 4:4:4 8 / 10 bit, 2 = 4:2:2 and everything 12 bit"""
     if bpc == 12 or layout == "422":

@@ -233,6 +233,31 @@ def test_monochrome_stream_decodes(emu_decoder):
     _check(emu_decoder, tus, 2)
 
 
+def _valid_422(kind, w, h, bpc, want, **kw):
+    """random tile payloads are only sometimes legal 4:2:2 streams (partitions whose chroma blocks would be 2 samples wide are
+    forbidden, reference src/decode.c decode_sb): draw seeds until stock dav1d accepts `want` of them"""
+    out = []
+    for seed in range(400):
+        tus = obu.intra_stream(seed, w, h, n_frames=1, bpc=bpc, layout="422", **kw) if kind == "intra" else \
+            obu.inter_stream(seed, w, h, n_frames=3, bpc=bpc, layout="422", **kw)
+        if _ref_decode(tus)[0] == (1 if kind == "intra" else 3):
+            out.append(tus)
+            if len(out) == want:
+                break
+    return out
+
+
+@pytest.mark.parametrize("kind,w,h,bpc,kw", [("intra", 64, 64, 8, {}), ("intra", 128, 128, 10, dict(film_grain=1)), ("intra", 192, 128, 12, {}),
+                                             ("inter", 64, 64, 10, dict(motion_modes=1)), ("inter", 128, 64, 8, dict(motion_modes=1, film_grain=1)),
+                                             ("inter", 128, 64, 12, dict(motion_modes=2))])
+def test_422_streams_decode(emu_decoder, kind, w, h, bpc, kw):
+    """4:2:2 (ss_hor = 1, ss_ver = 0) key and inter frames through the hooked decoder, byte-identical to stock dav1d"""
+    streams = _valid_422(kind, w, h, bpc, 3, **kw)
+    assert len(streams) == 3
+    for tus in streams:
+        _check(emu_decoder, tus, 1 if kind == "intra" else 3, apply_grain=1)
+
+
 @pytest.mark.parametrize("n_threads,delay", [(1, 1), (1, 0), (4, 1), (2, 0)])
 def test_single_threaded_settings_decode(emu_decoder, n_threads, delay):
     """one thread / no frame delay used to put dav1d in single-pass mode, which the emitters cannot serve (every frame
