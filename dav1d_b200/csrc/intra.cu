@@ -95,6 +95,36 @@ B200_DEV void prefetch_l2(const void *p) {
 #endif
 }
 
+// Intra block copy: one sample of mc[FILTER_2D_BILINEAR] (put_bilin_c, reference src/mc_tmpl.c:434-490) read from the picture
+// being reconstructed, source coordinates clamped to the plane area like emu_edge (mc(), src/recon_tmpl.c:956-977 with
+// w = f->bw * 4 >> ss_hor, h = f->bh * 4 >> ss_ver). L2 loads: other SMs wrote the source.
+template <bool HBD, class Frame>
+__device__ __forceinline__ int ibc_sample(const Frame &f, const B200IntraTx &r, const int pl, const int xx, const int yy,
+                                          const int bitdepth, const int bdmax)
+{
+    typedef typename Bd<HBD>::pixel pixel;
+    const int st = f.stride[pl], pw = f.w4[pl] * 4, ph = f.h4[pl] * 4;
+    const int mx = r.cfl_w_pad, my = r.cfl_h_pad;
+    const int sx = (int)(r.luma_off & 0xffff) + xx, sy = (int)(r.luma_off >> 16) + yy;
+    // the plane starts where this block's row 0 / column 0 is, minus its own position
+    const pixel *const plane = (const pixel *)f.pic + r.dst_off - ((ptrdiff_t)r.y4 * 4 * st + r.x4 * 4);
+    const int x0 = iclip(sx, 0, pw - 1), x1 = iclip(sx + 1, 0, pw - 1), y0 = iclip(sy, 0, ph - 1), y1 = iclip(sy + 1, 0, ph - 1);
+    const int ib = bitdepth == 12 ? 2 : 4;                       // intermediate_bits
+    const int a = ld_px<HBD>(plane + (ptrdiff_t)y0 * st + x0);
+    if (!mx && !my) return a;
+    if (mx && !my) {
+        const int b = ld_px<HBD>(plane + (ptrdiff_t)y0 * st + x1);
+        const int px = (16 * a + mx * (b - a) + ((1 << (4 - ib)) >> 1)) >> (4 - ib);
+        return iclip((px + ((1 << ib) >> 1)) >> ib, 0, bdmax);
+    }
+    const int c = ld_px<HBD>(plane + (ptrdiff_t)y1 * st + x0);
+    if (!mx) return iclip((16 * a + my * (c - a) + 8) >> 4, 0, bdmax);
+    const int b = ld_px<HBD>(plane + (ptrdiff_t)y0 * st + x1), d = ld_px<HBD>(plane + (ptrdiff_t)y1 * st + x1);
+    const int m0 = (16 * a + mx * (b - a) + ((1 << (4 - ib)) >> 1)) >> (4 - ib);
+    const int m1 = (16 * c + mx * (d - c) + ((1 << (4 - ib)) >> 1)) >> (4 - ib);
+    return iclip((16 * m0 + my * (m1 - m0) + ((1 << (4 + ib)) >> 1)) >> (4 + ib), 0, bdmax);
+}
+
 template <bool HBD>
 #ifndef B200_POLL_NS0
 #define B200_POLL_NS0 32
@@ -144,6 +174,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
         const bool have_bl = have_left && y + th < ye && (r.flags & B200_INTRA_LEFT_HAS_BOTTOM);
         const bool is_cfl = r.mode == B200_INTRA_MODE_CFL && r.cfl_alpha != 0;
         const bool is_ii = r.mode == B200_INTRA_MODE_II, is_resid = r.mode == B200_INTRA_MODE_RESID, is_pal = r.mode == B200_INTRA_MODE_PAL;
+        const bool is_ibc = r.mode == B200_INTRA_MODE_IBC;
         const uint8_t *const dmap = (P.scratch + P.done_off[pl]);
         const int mw = f.w4[pl];
         // coefficients: loads issued before the wait, parked in shared memory after it (off the dependency chain)
@@ -158,9 +189,18 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
         // ---- wait for the neighbours whose pixels the edge array reads
         {
             // a residual-only record waits for its own cells to be "predicted" (2), everything else for final neighbours (1)
-            const int n_left = is_resid ? 0 : have_left ? imin(th, ye - y) + (have_bl ? imin(th, ye - y - th) : 0) : 0;
-            const int n_top = is_resid ? 0 : have_top ? imin(tw, xe - x) + (have_tr ? imin(tw, xe - x - tw) : 0) : 0;
-            const int n_tl = !is_resid && have_left && have_top;
+            const bool no_edges = is_resid || is_ibc;
+            const int n_left = no_edges ? 0 : have_left ? imin(th, ye - y) + (have_bl ? imin(th, ye - y - th) : 0) : 0;
+            const int n_top = no_edges ? 0 : have_top ? imin(tw, xe - x) + (have_tr ? imin(tw, xe - x - tw) : 0) : 0;
+            const int n_tl = !no_edges && have_left && have_top;
+            // intra block copy: every cell of the source rectangle (one sample more where the bilinear phase is not 0)
+            int n_src = 0, sc_x0 = 0, sc_y0 = 0, sc_w = 1;
+            if (is_ibc) {
+                const int sx = r.luma_off & 0xffff, sy = r.luma_off >> 16;
+                sc_x0 = imin(sx >> 2, mw - 1); sc_y0 = imin(sy >> 2, f.h4[pl] - 1);
+                sc_w = imin((sx + w - 1 + (r.cfl_w_pad != 0)) >> 2, mw - 1) - sc_x0 + 1;
+                n_src = sc_w * (imin((sy + h - 1 + (r.cfl_h_pad != 0)) >> 2, f.h4[pl] - 1) - sc_y0 + 1);
+            }
             const int self_w = imin(tw, mw - x), n_self = is_resid ? self_w * imin(th, f.h4[pl] - y) : 0;
             const int want = is_resid ? 2 : 1;
             int n_luma = 0, lw4 = 0, lx4 = 0, ly4 = 0;
@@ -172,9 +212,10 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
             }
             // only warp 0 polls (the other warps park at the barrier and cost no issue slots)
             if (tid < 32) {
-                for (int c = tid; c < n_left + n_top + n_tl + n_luma + n_self; c += 32) {
+                for (int c = tid; c < n_left + n_top + n_tl + n_luma + n_self + n_src; c += 32) {
                     const uint8_t *cell;
-                    if (c >= n_left + n_top + n_tl + n_luma) { const int k = c - n_left - n_top - n_tl - n_luma; cell = dmap + (y + k / self_w) * mw + x + k % self_w; }
+                    if (c >= n_left + n_top + n_tl + n_luma + n_self) { const int k = c - n_left - n_top - n_tl - n_luma - n_self; cell = dmap + (sc_y0 + k / sc_w) * mw + sc_x0 + k % sc_w; }
+                    else if (c >= n_left + n_top + n_tl + n_luma) { const int k = c - n_left - n_top - n_tl - n_luma; cell = dmap + (y + k / self_w) * mw + x + k % self_w; }
                     else if (c < n_left) cell = dmap + (y + c) * mw + x - 1;
                     else if (c < n_left + n_top) cell = dmap + (y - 1) * mw + x + (c - n_left);
                     else if (c < n_left + n_top + n_tl) cell = dmap + (y - 1) * mw + x - 1;
@@ -199,7 +240,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
         // ---- dav1d_prepare_intra_edges: mode conversion (:97-120)
         int mode = r.mode, angle = r.angle;
         if (is_ii) { mode = r.angle; angle = 0; }                              // inter-intra: the predictor is in `angle`
-        if (is_resid || is_pal) mode = 0;
+        if (is_resid || is_pal || is_ibc) mode = 0;
         if (mode == B200_INTRA_MODE_CFL) mode = 0;                             // DC_PRED (:1446, :1373)
         if (mode >= 1 && mode <= 8) {                                          // VERT_PRED .. VERT_LEFT_PRED
             const int base = mode == 1 ? 90 : mode == 2 ? 180 : mode == 3 ? 45 : mode == 4 ? 135 : mode == 5 ? 113
@@ -280,6 +321,8 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
             const pixel *const colours = (const pixel *)(f.pal + r.luma_off);
             const uint8_t *const idx = f.pal + r.luma_off + 8 * sizeof(pixel);
             for (int i = tid; i < w * h; i += kIpT) s_px[i] = colours[(idx[i >> 1] >> ((i & 1) * 4)) & 7];
+        } else if (is_ibc) {
+            for (int i = tid; i < w * h; i += kIpT) s_px[i] = (pixel)ibc_sample<HBD>(f, r, pl, i % w, i / w, bitdepth, bdmax);
         } else if (is_cfl) {
             const int dc = S.dc;
             for (int i = tid; i < w * h; i += kIpT) s_ac[i] = (int16_t)(s_ac[i] - dc);
@@ -327,7 +370,7 @@ __global__ void __launch_bounds__(kIpT, B200_INTRA_MINB) intra_frame_kernel(cons
             __syncwarp();
             uint8_t *const dm = (P.scratch + P.done_off[pl]);
             const int cw = imin(tw, mw - x), chh = imin(th, f.h4[pl] - y);
-            const uint8_t state = (is_ii || is_pal) && r.cfl_alpha ? 2 : 1;   // 2: predicted, the block's residual records follow
+            const uint8_t state = (is_ii || is_pal || is_ibc) && r.cfl_alpha ? 2 : 1;   // 2: predicted, the block's residual records follow
             for (int c = tid; c < cw * chh; c += 32) *(volatile uint8_t *)(dm + (y + c / cw) * mw + x + c % cw) = state;
         }
         // ---- hand over to the next record
@@ -403,6 +446,7 @@ __global__ void __launch_bounds__(kIwWarps * 32) intra_warp_kernel(const __grid_
         const bool have_bl = have_left && y + th < ye && (r.flags & B200_INTRA_LEFT_HAS_BOTTOM);
         const bool is_cfl = r.mode == B200_INTRA_MODE_CFL && r.cfl_alpha != 0;
         const bool is_ii = r.mode == B200_INTRA_MODE_II, is_resid = r.mode == B200_INTRA_MODE_RESID, is_pal = r.mode == B200_INTRA_MODE_PAL;
+        const bool is_ibc = r.mode == B200_INTRA_MODE_IBC;
         uint8_t *const dmap = (P.scratch + P.done_off[pl]);
         const int mw = f.w4[pl];
         const int ncf = imin(w, 32) * imin(h, 32);
@@ -424,9 +468,18 @@ __global__ void __launch_bounds__(kIwWarps * 32) intra_warp_kernel(const __grid_
 
         // ---- wait for the neighbours whose pixels the edge array reads
         {
-            const int n_left = is_resid ? 0 : have_left ? imin(th, ye - y) + (have_bl ? imin(th, ye - y - th) : 0) : 0;
-            const int n_top = is_resid ? 0 : have_top ? imin(tw, xe - x) + (have_tr ? imin(tw, xe - x - tw) : 0) : 0;
-            const int n_tl = !is_resid && have_left && have_top;
+            const bool no_edges = is_resid || is_ibc;
+            const int n_left = no_edges ? 0 : have_left ? imin(th, ye - y) + (have_bl ? imin(th, ye - y - th) : 0) : 0;
+            const int n_top = no_edges ? 0 : have_top ? imin(tw, xe - x) + (have_tr ? imin(tw, xe - x - tw) : 0) : 0;
+            const int n_tl = !no_edges && have_left && have_top;
+            // intra block copy: every cell of the source rectangle (one sample more where the bilinear phase is not 0)
+            int n_src = 0, sc_x0 = 0, sc_y0 = 0, sc_w = 1;
+            if (is_ibc) {
+                const int sx = r.luma_off & 0xffff, sy = r.luma_off >> 16;
+                sc_x0 = imin(sx >> 2, mw - 1); sc_y0 = imin(sy >> 2, f.h4[pl] - 1);
+                sc_w = imin((sx + w - 1 + (r.cfl_w_pad != 0)) >> 2, mw - 1) - sc_x0 + 1;
+                n_src = sc_w * (imin((sy + h - 1 + (r.cfl_h_pad != 0)) >> 2, f.h4[pl] - 1) - sc_y0 + 1);
+            }
             const int self_w = imin(tw, mw - x), n_self = is_resid ? self_w * imin(th, f.h4[pl] - y) : 0;
             const int want = is_resid ? 2 : 1;       // a residual-only record waits for its own cells to be "predicted" (2)
             int n_luma = 0, lw4 = 0, lx4 = 0, ly4 = 0;
@@ -436,9 +489,10 @@ __global__ void __launch_bounds__(kIwWarps * 32) intra_warp_kernel(const __grid_
                 const int lh4 = imin((th - r.cfl_h_pad) << f.ss_ver, f.h4[0] - ly4);
                 n_luma = lw4 * lh4;
             }
-            for (int c = lane; c < n_left + n_top + n_tl + n_luma + n_self; c += 32) {
+            for (int c = lane; c < n_left + n_top + n_tl + n_luma + n_self + n_src; c += 32) {
                 const uint8_t *cell;
-                if (c >= n_left + n_top + n_tl + n_luma) { const int k = c - n_left - n_top - n_tl - n_luma; cell = dmap + (y + k / self_w) * mw + x + k % self_w; }
+                if (c >= n_left + n_top + n_tl + n_luma + n_self) { const int k = c - n_left - n_top - n_tl - n_luma - n_self; cell = dmap + (sc_y0 + k / sc_w) * mw + sc_x0 + k % sc_w; }
+                else if (c >= n_left + n_top + n_tl + n_luma) { const int k = c - n_left - n_top - n_tl - n_luma; cell = dmap + (y + k / self_w) * mw + x + k % self_w; }
                 else if (c < n_left) cell = dmap + (y + c) * mw + x - 1;
                 else if (c < n_left + n_top) cell = dmap + (y - 1) * mw + x + (c - n_left);
                 else if (c < n_left + n_top + n_tl) cell = dmap + (y - 1) * mw + x - 1;
@@ -457,7 +511,7 @@ __global__ void __launch_bounds__(kIwWarps * 32) intra_warp_kernel(const __grid_
         // ---- dav1d_prepare_intra_edges: mode conversion (:97-120)
         int mode = r.mode, angle = r.angle;
         if (is_ii) { mode = r.angle; angle = 0; }                              // inter-intra: the predictor is in `angle`
-        if (is_resid || is_pal) mode = 0;
+        if (is_resid || is_pal || is_ibc) mode = 0;
         if (mode == B200_INTRA_MODE_CFL) mode = 0;                             // DC_PRED (:1446, :1373)
         if (mode >= 1 && mode <= 8) {                                          // VERT_PRED .. VERT_LEFT_PRED
             const int base = mode == 1 ? 90 : mode == 2 ? 180 : mode == 3 ? 45 : mode == 4 ? 135 : mode == 5 ? 113
@@ -472,7 +526,7 @@ __global__ void __launch_bounds__(kIwWarps * 32) intra_warp_kernel(const __grid_
             mode = have_left ? (have_top ? B200_PAETH_PRED : B200_HOR_PRED) : (have_top ? B200_VERT_PRED : B200_DC_128_PRED);
         }
         // ---- edge gather (every part is filled; the predictors read only what the reference fills)
-        if (!is_resid && !is_pal) {
+        if (!is_resid && !is_pal && !is_ibc) {
             const pixel *const top = dst - st;
             const int half = (1 << bitdepth) >> 1;
             const int lpx = imin(h, (ye - y) << 2), lpx2 = imin(h, (ye - y - th) << 2);
@@ -533,6 +587,8 @@ __global__ void __launch_bounds__(kIwWarps * 32) intra_warp_kernel(const __grid_
             const pixel *const colours = (const pixel *)(f.pal + r.luma_off);
             const uint8_t *const idx = f.pal + r.luma_off + 8 * sizeof(pixel);
             for (int i = lane; i < w * h; i += 32) s_px[i] = colours[(idx[i >> 1] >> ((i & 1) * 4)) & 7];
+        } else if (is_ibc) {
+            for (int i = lane; i < w * h; i += 32) s_px[i] = (pixel)ibc_sample<HBD>(f, r, pl, i % w, i / w, bitdepth, bdmax);
         } else if (is_cfl) {
             ipred_cfl_pred_body<HBD, G>(S, s_px, w, w, h, mode, r.cfl_alpha, s_ac, bdmax);
         } else {
@@ -566,7 +622,7 @@ __global__ void __launch_bounds__(kIwWarps * 32) intra_warp_kernel(const __grid_
         __syncwarp();
         {
             const int cw = imin(tw, mw - x), chh = imin(th, f.h4[pl] - y);
-            const uint8_t state = (is_ii || is_pal) && r.cfl_alpha ? 2 : 1;   // 2: predicted, the block's residual records follow
+            const uint8_t state = (is_ii || is_pal || is_ibc) && r.cfl_alpha ? 2 : 1;   // 2: predicted, the block's residual records follow
             if (lane < cw * chh || lane == 0) __threadfence();                  // the warp barrier above ordered every lane's stores before it
             for (int c = lane; c < cw * chh; c += 32) *(volatile uint8_t *)(dmap + (y + c / cw) * mw + x + c % cw) = state;
         }

@@ -124,7 +124,7 @@ def _tile_log2(sz, tgt):
 
 
 def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout="420",
-                  segmentation=0):
+                  segmentation=0, intrabc=0):
     """tile info, quantizer, segmentation, delta q / lf, loop filter, CDEF, loop restoration (same syntax in key and
     inter frames when primary_ref_frame is NONE)"""
     # tile info (uniform)
@@ -182,7 +182,12 @@ def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restor
         b.f(1, 1 if delta_q else 0)          # delta_q_present
         if delta_q:
             b.f(2, int(rng.integers(0, 4)))
-            b.f(1, 1); b.f(2, int(rng.integers(0, 4))); b.f(1, int(rng.integers(0, 2)))   # delta_lf present, res, multi
+            if not intrabc:
+                b.f(1, 1); b.f(2, int(rng.integers(0, 4))); b.f(1, int(rng.integers(0, 2)))   # delta_lf present, res, multi
+    # a frame that allows intra block copy carries no loop filter, CDEF or restoration parameters: the picture it copies
+    # from is the unfiltered one, so the filters are off (reference src/obu.c:807, 835, 879, 895)
+    if intrabc:
+        return cols, rows, tile_w, tile_h, sbw, sbh
     # loop filter
     lf = [int(rng.integers(1, 64)), int(rng.integers(1, 64)), int(rng.integers(0, 64)), int(rng.integers(0, 64))] if lf is None else lf
     b.f(6, lf[0]); b.f(6, lf[1])
@@ -235,7 +240,7 @@ def _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_byt
 
 def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None, lf=None, cdef=True,
               restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0, screen_content=0, layout="420",
-              intra_only=None, segmentation=0, super_res=0):
+              intra_only=None, segmentation=0, super_res=0, intrabc=0):
     """One shown key frame (OBU_FRAME), or with intra_only=(order_hint, refresh_frame_flags) a shown INTRA_ONLY frame
     (intra coded, but it only replaces the reference slots it names). Returns the OBU bytes. `cdef_on` / `restoration_on` must match the sequence
     header (the fields are absent when the sequence disables the tool)."""
@@ -254,10 +259,11 @@ def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb
     if super_res:
         b.f(1, 1); b.f(3, int(rng.integers(0, 8)))   # use_superres, coded_denom
     b.f(1, 0)                                # render_and_frame_size_different
+    intrabc = 1 if (intrabc and screen_content and not super_res) else 0
     if screen_content and not super_res:
-        b.f(1, 0)                            # allow_intrabc
+        b.f(1, intrabc)                      # allow_intrabc
     b.f(1, 0)                                # disable_frame_end_update_cdf
-    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout, segmentation)
+    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout, segmentation, intrabc)
     b.f(1, 1)                                # tx_mode_select
     b.f(1, int(rng.integers(0, 2)))          # reduced_tx_set
     if film_grain_seq:

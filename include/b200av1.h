@@ -481,7 +481,15 @@ enum { B200_INTRA_MODE_FILTER = 13, B200_INTRA_MODE_CFL = 14,   /* besides enum 
         * the whole block (`tx` = the block's size); `luma_off` = byte offset into B200IntraFrame.pal of 8 palette entries
         * (pixels) followed by the w x h index map, two 4-bit indices per byte, low nibble first, pitch w / 2 (dav1d's
         * packed pal_idx). Like II it carries no residual: RESID records follow when cfl_alpha != 0. */
-       B200_INTRA_MODE_PAL = 17 };
+       B200_INTRA_MODE_PAL = 17,
+       /* intra block copy (reference src/recon_tmpl.c:1583-1596, src/decode.c:1286-1345): the block is predicted from an
+        * already reconstructed area of the SAME picture with dav1d's bilinear put (luma vectors are whole samples, sub-sampled
+        * chroma may sit on a half sample). An IBC record covers the whole block (`tx` = its size, blocks wider / taller than
+        * 64 come as several records); `luma_off` = source position in this plane, (y << 16) | x, samples; cfl_w_pad /
+        * cfl_h_pad = the mx / my phase handed to mc[FILTER_2D_BILINEAR] (0 or 8). Source samples are clamped to the plane
+        * area w4 * 4 x h4 * 4 (emu_edge). The record waits until every 4x4 cell it reads is final. Like II it carries no
+        * residual: RESID records follow when cfl_alpha != 0. Per-transform-block schedule only (not with B200IntraFrame.sb). */
+       B200_INTRA_MODE_IBC = 18 };
 typedef struct B200IntraTx {
     uint32_t dst_off;              /* sample offset of the transform block in the picture (plane offset included) */
     uint32_t coef_off;             /* into d_coef, dav1d's transposed layout, min(w,32) x min(h,32) */

@@ -279,7 +279,12 @@ int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int
         const int x = r->x4, y = r->y4, tw = k_tx_w4[r->tx], th = k_tx_h4[r->tx], xe = r->xend4, ye = r->yend4;
         const int hl = r->flags & B200_INTRA_HAVE_LEFT, ht = r->flags & B200_INTRA_HAVE_TOP;
         int dep = 0;
-        if (r->mode == B200_INTRA_MODE_RESID) {           /* waits for the inter-intra record that covers it */
+        if (r->mode == B200_INTRA_MODE_IBC) {             /* waits for every cell its source rectangle touches */
+            const int sx = r->luma_off & 0xffff, sy = r->luma_off >> 16;
+            const int x1 = mini((sx + tw * 4 - 1 + (r->cfl_w_pad != 0)) >> 2, mw - 1), y1 = mini((sy + th * 4 - 1 + (r->cfl_h_pad != 0)) >> 2, mh - 1);
+            for (int yy = mini(sy >> 2, mh - 1); yy <= y1; yy++)
+                for (int xx = mini(sx >> 2, mw - 1); xx <= x1; xx++) { const int v = m[(size_t)yy * mw + xx]; if (v > dep) dep = v; }
+        } else if (r->mode == B200_INTRA_MODE_RESID) {    /* waits for the inter-intra record that covers it */
             for (int yy = y; yy < y + th && yy < mh; yy++)
                 for (int xx = x; xx < x + tw && xx < mw; xx++) { const int v = m[(size_t)yy * mw + xx]; if (v > dep) dep = v; }
         } else if (hl) {
@@ -333,7 +338,7 @@ void b200hook_decode_frame_exit(struct Dav1dFrameContext *const f, const int ret
             if (out) b200hook_refpic_set_ready(out, 1);
             h->started = 0; h->tile_sbrows_done = 0; h->n_tx = 0; h->n_coef = 0; h->unsupported = 0;
             h->n_pred = h->n_comp = h->n_comp2 = h->n_warp = h->n_blend = h->n_blend2 = 0;
-            h->n_tmp16 = 0; h->n_pxtmp = 0; h->is_inter = 0; h->n_ii = 0; h->n_pal = 0; h->refs_used = 0;
+            h->n_tmp16 = 0; h->n_pxtmp = 0; h->is_inter = 0; h->n_ii = 0; h->n_ibc = 0; h->n_pal = 0; h->refs_used = 0;
             memset(h->n_itx, 0, sizeof(h->n_itx));
         }
         pthread_mutex_unlock(&h->lock);
@@ -341,13 +346,13 @@ void b200hook_decode_frame_exit(struct Dav1dFrameContext *const f, const int ret
     dav1d_decode_frame_exit(f, retval);
 }
 
-void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[9], double prep_ms)
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[10], double prep_ms)
 {
     pthread_mutex_lock(&g_lock);
     g_stats.frames++; g_stats.records += records; g_stats.coefs += coefs;
     g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += d2h; g_stats.device_ms += ms;
     g_stats.intra_tx += kinds[0]; g_stats.pred += kinds[1]; g_stats.comp += kinds[2]; g_stats.warp += kinds[3];
-    g_stats.host_prep_ms += prep_ms; g_stats.interintra += kinds[7]; g_stats.palette_bytes += kinds[8];
+    g_stats.host_prep_ms += prep_ms; g_stats.interintra += kinds[7]; g_stats.palette_bytes += kinds[8]; g_stats.ibc += kinds[9];
     g_stats.blend += kinds[4]; g_stats.itx += kinds[5]; g_stats.inter_frames += kinds[6];
     pthread_mutex_unlock(&g_lock);
 }

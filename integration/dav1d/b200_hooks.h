@@ -54,7 +54,7 @@ typedef struct HookFrame {
     HookBuf warp, blend, blend2, pxtmp;      /* warped-motion 8x8 blocks; OBMC: blend_h stage, blend_v stage, pixel scratch (device only) */
     int n_pred, n_comp, n_comp2, n_itx[19], n_warp, n_blend, n_blend2;
     size_t n_tmp16, n_cmask, n_pxtmp;
-    int started, is_inter, n_ii;
+    int started, is_inter, n_ii, n_ibc;
     unsigned refs_used;            /* bit k: some prediction of this frame reads reference k (f->refp[k]) */
     int pinned;                    /* never recycled for another key (the output-stage slots) */
     unsigned epoch;                /* b200hook_release generation the `users` references belong to */
@@ -88,7 +88,8 @@ typedef struct B200HookStats {
     double host_prep_ms;            /* frame completion on the host before the job: mask fix-ups, wavefront sort, staging */
     uint64_t interintra;            /* inter-intra records (a subset of intra_tx) */
     uint64_t palette_bytes;         /* palettes + index maps shipped for palette blocks */
+    uint64_t ibc;                   /* intra block copy records (a subset of intra_tx) */
 } B200HookStats;
-void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[9], double prep_ms);
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[10], double prep_ms);
 
 #endif

@@ -76,7 +76,7 @@ static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *c
         /* the context's previous frame never completed (dav1d flushed or closed while it was being reconstructed) */
         hf->tile_sbrows_done = 0; hf->n_tx = 0; hf->n_coef = 0; hf->unsupported = 0;
         hf->n_pred = hf->n_comp = hf->n_comp2 = hf->n_warp = hf->n_blend = hf->n_blend2 = 0;
-        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->is_inter = 0; hf->n_ii = 0; hf->refs_used = 0;
+        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->is_inter = 0; hf->n_ii = 0; hf->n_ibc = 0; hf->refs_used = 0;
         memset(hf->n_itx, 0, sizeof(hf->n_itx));
         hf->started = 0;
     }
@@ -474,6 +474,43 @@ static int bitfn(emit_interintra)(TxCtx *const c, const enum BlockSize bs, const
     return 0;
 }
 
+/* intra block copy (reference :1583-1596; the vector was clipped to the decoded part of the tile in src/decode.c:1286-1345):
+ * mc() with the current picture as reference and the bilinear filter, bw4 x bh4 luma units at (bx, by), written as IBC records
+ * of the intra machine (one per <= 64x64 piece whose shape is a transform size); the residual follows as RESID records */
+static int bitfn(emit_ibc)(TxCtx *const c, const int pl, const uint32_t dst_off, const int bw4, const int bh4,
+                           const int bx, const int by, const mv mv)
+{
+    HookFrame *const hf = c->hf;
+    const Dav1dFrameContext *const f = c->t->f;
+    const Dav1dTileState *const ts = c->t->ts;
+    const int ss_ver = pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    const int h_mul = 4 >> ss_hor, v_mul = 4 >> ss_ver;
+    const int w = bw4 * h_mul, h = bh4 * v_mul;
+    const int dx = bx * h_mul + (mv.x >> (3 + ss_hor)), dy = by * v_mul + (mv.y >> (3 + ss_ver));
+    const int mx = (mv.x & (15 >> !ss_hor)) << !ss_hor, my = (mv.y & (15 >> !ss_ver)) << !ss_ver;
+    if (dx < 0 || dy < 0 || dx + w > 65535 || dy + h > 65535) { __atomic_fetch_or(&hf->unsupported, 64, __ATOMIC_RELAXED); return 0; }
+    int cw = imin(w, 64), ch = imin(h, 64);
+    while (cw > 4 * ch) cw >>= 1;           /* e.g. the 8x64 chroma block of a 4:2:2 16x64 block: no such transform shape */
+    while (ch > 4 * cw) ch >>= 1;
+    const int tx = bitfn(tx_of_dims)(cw >> 2, ch >> 2);
+    if (tx < 0) { __atomic_fetch_or(&hf->unsupported, 64, __ATOMIC_RELAXED); return 0; }
+    const int px4 = (bx * h_mul) >> 2, py4 = (by * v_mul) >> 2;
+    for (int yy = 0; yy < h; yy += ch)
+        for (int xx = 0; xx < w; xx += cw) {
+            B200IntraTx *const r = bitfn(new_record)(hf);
+            if (!r) return -1;
+            r->mode = B200_INTRA_MODE_IBC; r->plane = pl; r->tx = tx; r->eob = -1; r->flags = 0;
+            r->dst_off = dst_off + (uint32_t)yy * c->g.stride[pl] + xx;
+            r->x4 = px4 + (xx >> 2); r->y4 = py4 + (yy >> 2);
+            r->xend4 = ts->tiling.col_end >> ss_hor; r->yend4 = ts->tiling.row_end >> ss_ver;
+            r->luma_off = ((uint32_t)(dy + yy) << 16) | (uint32_t)(dx + xx);
+            r->cfl_w_pad = mx; r->cfl_h_pad = my;
+            r->cfl_alpha = !c->b->skip;           /* residual records follow */
+            __atomic_fetch_add(&hf->n_ibc, 1, __ATOMIC_RELAXED);
+        }
+    return 0;
+}
+
 static int bitfn(emit_itx)(TxCtx *const c, const int tx, const int pl, const uint32_t dst_off, const int chroma)
 {
     HookFrame *const hf = c->hf;
@@ -548,8 +585,16 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
 
     bitfn(frame_started)(hf, f);
     pthread_mutex_lock(&hf->lock);          /* protects the inter record lists; intra records / coefficients are lock-free */
+    if (IS_KEY_OR_INTRA(f->frame_hdr)) {
+        /* intra block copy: prediction and residual both go through the intra machine (the source is this very picture) */
+        c.ii = 1;
+        if (bitfn(emit_ibc)(&c, 0, ydst, bw4, bh4, bx, by, b->mv[0])) goto out;
+        if (has_chroma)
+            for (int pl = 1; pl <= 2; pl++)
+                if (bitfn(emit_ibc)(&c, pl, g->off[pl] + uvrel, bw4 << (bw4 == ss_hor), bh4 << (bh4 == ss_ver), bx & ~ss_hor, by & ~ss_ver, b->mv[0])) goto out;
+        goto residual;
+    }
     hf->is_inter = 1;
-    if (IS_KEY_OR_INTRA(f->frame_hdr)) { __atomic_fetch_or(&hf->unsupported, 64, __ATOMIC_RELAXED); goto out; }          /* intra block copy */
     if (b->comp_type == COMP_INTER_NONE) {
         const enum Filter2d filter_2d = b->filter2d;
         const int warp = (b->inter_mode == GLOBALMV && f->gmv_warp_allowed[b->ref[0]]) ||
@@ -659,6 +704,7 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
             }
         }
     }
+residual:
     /* residual (:1888-1983) */
     if (!b->skip) {
         const TxfmInfo *const uvtx = &dav1d_txfm_dimensions[b->uvtx], *const ytx = &dav1d_txfm_dimensions[b->max_ytx];
@@ -751,7 +797,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         fprintf(stderr, "b200hook: frame uses tools the emitters do not translate yet (%s%s%s%s)\n",
                 hf->unsupported & 1 ? " palette" : "", hf->unsupported & 2 ? " inter" : "",
                 hf->unsupported & 4 ? " single-pass-decoding" : "", hf->unsupported & 8 ? " out-of-memory" : "");
-        fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 scaled reference, 64 intra block copy, 256 inter-intra block size, 1024 super-resolution)\n", hf->unsupported);
+        fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 scaled reference, 64 intra block copy out of range, 256 inter-intra block size, 1024 super-resolution)\n", hf->unsupported);
         return -1;
     }
     PicGeom g;
@@ -951,8 +997,8 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     uint64_t n_itx = 0;
     for (int t = 0; t < N_RECT_TX_SIZES; t++) n_itx += hf->n_itx[t];
     n_rec += n_itx;
-    const uint64_t kinds[9] = { (uint64_t)hf->n_tx, (uint64_t)hf->n_pred, (uint64_t)hf->n_comp + hf->n_comp2, (uint64_t)hf->n_warp,
-                                (uint64_t)hf->n_blend + hf->n_blend2, n_itx, (uint64_t)inter, (uint64_t)hf->n_ii, (uint64_t)hf->n_pal };
+    const uint64_t kinds[10] = { (uint64_t)hf->n_tx, (uint64_t)hf->n_pred, (uint64_t)hf->n_comp + hf->n_comp2, (uint64_t)hf->n_warp,
+                                (uint64_t)hf->n_blend + hf->n_blend2, n_itx, (uint64_t)inter, (uint64_t)hf->n_ii, (uint64_t)hf->n_pal, (uint64_t)hf->n_ibc };
     b200hook_account(n_rec, hf->n_coef, h2d, d2h, bitfn(now_ms)() - t0, kinds, t0 - t_enter);
     return 0;
 }
@@ -974,7 +1020,7 @@ void bitfn(b200hook_backup_ipred_edge)(Dav1dTaskContext *const t)
         if (outp) b200hook_refpic_set_ready(outp, 1);       /* also after a failure: nobody may wait for ever */
         hf->tile_sbrows_done = 0; hf->n_tx = 0; hf->n_coef = 0; hf->unsupported = 0;
         hf->n_pred = hf->n_comp = hf->n_comp2 = hf->n_warp = hf->n_blend = hf->n_blend2 = 0;
-        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->started = 0; hf->is_inter = 0; hf->n_ii = 0; hf->refs_used = 0;
+        hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->started = 0; hf->is_inter = 0; hf->n_ii = 0; hf->n_ibc = 0; hf->refs_used = 0;
         memset(hf->n_itx, 0, sizeof(hf->n_itx));
     }
     pthread_mutex_unlock(&hf->lock);

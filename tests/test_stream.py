@@ -258,6 +258,34 @@ def test_422_streams_decode(emu_decoder, kind, w, h, bpc, kw):
         _check(emu_decoder, tus, 1 if kind == "intra" else 3, apply_grain=1)
 
 
+def _valid_intrabc(w, h, want, n_frames=2, **kw):
+    """random payloads in frames that allow intra block copy are legal only when no vector ends up inside the current
+    superblock (reference src/decode.c:1286-1345 returns an error otherwise): draw seeds until stock dav1d accepts `want`"""
+    out = []
+    for seed in range(400):
+        tus = obu.intra_stream(seed, w, h, n_frames=n_frames, screen_content=1, intrabc=1, **kw)
+        if _ref_decode(tus)[0] == n_frames:
+            out.append(tus)
+            if len(out) == want:
+                break
+    return out
+
+
+@pytest.mark.parametrize("w,h,kw", [(128, 128, dict(bpc=8)), (192, 128, dict(bpc=10)), (256, 192, dict(bpc=8, layout="444", log2_cols=1)),
+                                    (384, 256, dict(bpc=12, sb128=1)), (320, 192, dict(bpc=10)), (128, 128, dict(bpc=8, layout="422")),
+                                    (256, 256, dict(bpc=8, layout="400"))])
+def test_intra_block_copy_streams_decode(emu_decoder, w, h, kw):
+    """key frames with allow_intrabc (was refused in round 1): blocks predicted from the reconstructed part of the same picture
+    go through the intra machine as IBC records (bilinear put, half-sample chroma phases included) + RESID records"""
+    streams = _valid_intrabc(w, h, 3, **kw)
+    assert len(streams) == 3
+    n_ibc = 0
+    for tus in streams:
+        _check(emu_decoder, tus, 2)
+        n_ibc += emu_decoder.last_stats["ibc"]
+    assert n_ibc > 0, "no intra block copy block in any of the streams"
+
+
 @pytest.mark.parametrize("n_threads,delay", [(1, 1), (1, 0), (4, 1), (2, 0)])
 def test_single_threaded_settings_decode(emu_decoder, n_threads, delay):
     """one thread / no frame delay used to put dav1d in single-pass mode, which the emitters cannot serve (every frame
@@ -337,6 +365,24 @@ def test_inter_stream_gpu_matches_stock_dav1d(gpu_decoder, case):
     w, h, bpc, sb128, lc, lr, nf, mm = case
     tus = obu.inter_stream(2000 + (hash(case) & 0xfff), w, h, n_frames=nf, bpc=bpc, sb128=sb128, log2_cols=lc, log2_rows=lr, motion_modes=mm)
     _check(gpu_decoder, tus, nf)
+
+
+@pytest.mark.gpu
+def test_new_layouts_and_intra_block_copy_gpu(gpu_decoder):
+    """round 2 on the device: 4:0:0 and 4:2:2 streams, key frames with intra block copy, one thread / no frame delay"""
+    _check(gpu_decoder, obu.intra_stream(5, 256, 192, n_frames=2, layout="400"), 2)
+    _check(gpu_decoder, obu.inter_stream(7, 320, 192, n_frames=4, layout="400", motion_modes=1, film_grain=1), 4, apply_grain=1)
+    for kind, w, h, bpc, kw in (("intra", 128, 128, 10, dict(film_grain=1)), ("inter", 128, 64, 8, dict(motion_modes=1))):
+        for tus in _valid_422(kind, w, h, bpc, 2, **kw):
+            _check(gpu_decoder, tus, 1 if kind == "intra" else 3, apply_grain=1)
+    n_ibc = 0
+    for w, h, kw in ((320, 192, dict(bpc=10)), (256, 192, dict(bpc=8, layout="444", log2_cols=1)), (128, 128, dict(bpc=8, layout="422"))):
+        for tus in _valid_intrabc(w, h, 2, **kw):
+            _check(gpu_decoder, tus, 2)
+            n_ibc += gpu_decoder.last_stats["ibc"]
+    assert n_ibc > 0
+    tus = obu.inter_stream(11, 192, 136, n_frames=5, motion_modes=1)
+    _check(gpu_decoder, tus, 5, n_threads=1, max_frame_delay=1)
 
 
 @pytest.mark.gpu

@@ -121,6 +121,24 @@ if [[ $what == *" final "* ]]; then
   run_bench n1_intra_warp B200_INTRA_SB=0 python bench.py --workload 1080p8_intra --steps 10 --warmup 3
   ls -la gpurun_out/*.ncu-rep
 fi
+if [[ $what == *" final2 "* ]]; then
+  # the GPU tests again (new stream tests), ncu --set full of every frame-path kernel dumped to CSV on the box (the reports
+  # themselves are tens of MB), the bench lines in full
+  timeout 600 python -m pytest tests -x -q -m gpu --timeout 300 2>&1 | tail -25 > gpurun_out/pytest_gpu.txt; tail -3 gpurun_out/pytest_gpu.txt
+  export B200_SKIP_PARITY=1 B200_MIN_TIMED_S=0.005 B200_NSETS=3 B200_DISTINCT=1
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 60 --csv --log-file gpurun_out/launches_4k8.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+  timeout 400 ncu --set full --clock-control none -k regex:"mc_|itx_|lf_|cdef_|lr_|coef_" -s 36 -c 12 -f -o /tmp/prof_4k8 python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_4k8.log 2>&1; echo "ncu 4k8 rc=$?"
+  timeout 400 ncu --set full --clock-control none -k regex:"mc_|itx_|lf_|cdef_|lr_|coef_|fg_" -s 42 -c 14 -f -o /tmp/prof_4k10 python bench.py --workload 4k10_full --steps 2 --warmup 3 > gpurun_out/ncu_4k10.log 2>&1; echo "ncu 4k10 rc=$?"
+  timeout 500 ncu --set full --clock-control none -k regex:"intra_|mc_warp|mc_blend" -s 12 -c 4 -f -o /tmp/prof_mixed python bench.py --workload 4k8_mixed --steps 2 --warmup 3 > gpurun_out/ncu_mixed.log 2>&1; echo "ncu mixed rc=$?"
+  unset B200_SKIP_PARITY B200_MIN_TIMED_S B200_NSETS B200_DISTINCT
+  for n in 4k8 4k10 mixed; do ncu -i /tmp/prof_$n.ncu-rep --page raw --csv > gpurun_out/prof_$n.csv 2>/dev/null; done
+  ls -la /tmp/*.ncu-rep gpurun_out/*.csv
+  run_bench n1_default python bench.py
+  run_bench n1_mixed python bench.py --workload 4k8_mixed --steps 20 --warmup 5
+  run_bench n1_4k10 python bench.py --workload 4k10_full --steps 20 --warmup 5
+  run_bench n1_8k10 python bench.py --workload 8k10_full --steps 10 --warmup 3
+  du -sh gpurun_out
+fi
 echo done > gpurun_out/done.txt
 for f in gpurun_out/bench_*.json; do echo "$f: $(head -c 600 $f)"; done
 for f in gpurun_out/bench_*.err; do if [ -s $f ]; then echo "== $f"; tail -5 $f; fi; done
