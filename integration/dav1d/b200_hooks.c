@@ -20,12 +20,25 @@
  * which the emitters cannot serve (they would have to run the entropy decoder themselves): open with two threads and two
  * frame contexts instead — same pictures, one frame more of output delay. lib.c's own dav1d_open is renamed by the Makefile. */
 int b200real_dav1d_open(Dav1dContext **c_out, const Dav1dSettings *s);
+int dav1d_default_picture_alloc(Dav1dPicture *p, void *cookie);       /* src/picture.c: what dav1d_default_settings installs */
+static int pinned_pic_alloc(Dav1dPicture *p, void *cookie);
+static void pinned_pic_release(Dav1dPicture *p, void *cookie);
+static int backend_bound_quietly(void);
 API int dav1d_open(Dav1dContext **const c_out, const Dav1dSettings *const s)
 {
     if (!s) return b200real_dav1d_open(c_out, s);
     Dav1dSettings s2 = *s;
     if (s2.n_threads == 1) s2.n_threads = 2;
     if (s2.max_frame_delay == 1) s2.max_frame_delay = 2;
+    /* output pictures in page-locked memory (a Dav1dPicAllocator, reference include/dav1d/picture.h:107-146), unless the caller
+     * brought an allocator of its own: the copy of a finished picture into it is then a true asynchronous copy on the frame's
+     * stream, and the worker thread that submitted the job is not held up by it (B200HOOK_PINNED_PICS=0 keeps dav1d's pool) */
+    const char *const e = getenv("B200HOOK_PINNED_PICS");
+    if (s2.allocator.alloc_picture_callback == dav1d_default_picture_alloc && (!e || atoi(e) != 0) && backend_bound_quietly()) {
+        s2.allocator.cookie = NULL;
+        s2.allocator.alloc_picture_callback = pinned_pic_alloc;
+        s2.allocator.release_picture_callback = pinned_pic_release;
+    }
     return b200real_dav1d_open(c_out, &s2);
 }
 
@@ -53,6 +66,9 @@ API int b200hook_set_backend(const char *path)
     SYM(stream_create, "b200_stream_create"); SYM(stream_destroy, "b200_stream_destroy");
     SYM(intra_scratch_bytes, "b200_intra_scratch_bytes");
     SYM(frame_run_host, "b200_frame_run_host");
+    SYM(frame_submit_host, "b200_frame_submit_host"); SYM(frame_wait, "b200_frame_wait"); SYM(copy_async, "b200_copy_async");
+    SYM(event_create, "b200_event_create"); SYM(event_destroy, "b200_event_destroy");
+    SYM(event_record, "b200_event_record"); SYM(stream_wait_event, "b200_stream_wait_event");
     SYM(struct_size, "b200_struct_size");
 #undef SYM
     /* binding self-check: the structs this file was compiled with are the ones the library was compiled with */
@@ -76,6 +92,76 @@ static pthread_mutex_t g_job_lock = PTHREAD_MUTEX_INITIALIZER;
 API void b200hook_set_serialize(int on) { g_serialize = on; }
 void b200hook_job_enter(void) { if (g_serialize) pthread_mutex_lock(&g_job_lock); }
 void b200hook_job_leave(void) { if (g_serialize) pthread_mutex_unlock(&g_job_lock); }
+
+static int backend_bound_quietly(void)
+{
+    if (__atomic_load_n(&g_be_ok, __ATOMIC_ACQUIRE)) return 1;
+    const char *env = getenv("B200AV1_LIB");
+    return env && b200hook_backend() != NULL;
+}
+
+/* ---- page-locked output pictures -------------------------------------------------------------------------------------
+ * Same layout as dav1d_default_picture_alloc (reference src/picture.c:46-78: planes back to back in one allocation, 128-sample
+ * aligned dimensions, 64 bytes more when a stride would be a multiple of 1024) — pic_geom() of the emitters derives the
+ * device picture from the host strides. Buffers come from a pool (cudaHostAlloc costs about a millisecond); released
+ * pictures go back to it, b200hook_release() frees the idle ones. */
+static struct { void *ptr; size_t cap; int used; } g_pin_pool[128];
+static pthread_mutex_t g_pin_lock = PTHREAD_MUTEX_INITIALIZER;
+static int pinned_pic_alloc(Dav1dPicture *const p, void *const cookie)
+{
+    (void)cookie;
+    const B200Backend *const be = b200hook_backend();
+    if (!be) return -12;
+    const int hbd = p->p.bpc > 8;
+    const int aligned_w = (p->p.w + 127) & ~127, aligned_h = (p->p.h + 127) & ~127;
+    const int has_chroma = p->p.layout != DAV1D_PIXEL_LAYOUT_I400;
+    const int ss_ver = p->p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = p->p.layout != DAV1D_PIXEL_LAYOUT_I444;
+    ptrdiff_t y_stride = (ptrdiff_t)aligned_w << hbd;
+    ptrdiff_t uv_stride = has_chroma ? y_stride >> ss_hor : 0;
+    if (!(y_stride & 1023)) y_stride += DAV1D_PICTURE_ALIGNMENT;
+    if (!(uv_stride & 1023) && has_chroma) uv_stride += DAV1D_PICTURE_ALIGNMENT;
+    const size_t y_sz = (size_t)y_stride * aligned_h, uv_sz = (size_t)uv_stride * (aligned_h >> ss_ver);
+    const size_t need = y_sz + 2 * uv_sz + DAV1D_PICTURE_ALIGNMENT;
+    int slot = -1, empty = -1;
+    pthread_mutex_lock(&g_pin_lock);
+    for (int i = 0; i < 128; i++) {
+        if (!g_pin_pool[i].ptr) { if (empty < 0) empty = i; continue; }
+        if (!g_pin_pool[i].used && g_pin_pool[i].cap >= need && (slot < 0 || g_pin_pool[i].cap < g_pin_pool[slot].cap)) slot = i;
+    }
+    if (slot < 0 && empty < 0)                      /* pool full of buffers that are too small: drop an idle one */
+        for (int i = 0; i < 128 && empty < 0; i++)
+            if (!g_pin_pool[i].used) { be->host_free(g_pin_pool[i].ptr); g_pin_pool[i].ptr = NULL; empty = i; }
+    if (slot < 0 && empty >= 0) {
+        void *const mem = be->host_alloc(need);
+        if (mem) { g_pin_pool[empty].ptr = mem; g_pin_pool[empty].cap = need; slot = empty; }
+    }
+    if (slot >= 0) g_pin_pool[slot].used = 1;
+    pthread_mutex_unlock(&g_pin_lock);
+    if (slot < 0) { fprintf(stderr, "b200hook: no page-locked memory for a picture: %s\n", be->last_error()); return -12; }
+    uint8_t *const buf = g_pin_pool[slot].ptr;
+    p->stride[0] = y_stride; p->stride[1] = uv_stride;
+    p->allocator_data = (void *)(intptr_t)(slot + 1);
+    p->data[0] = buf;
+    p->data[1] = has_chroma ? buf + y_sz : NULL;
+    p->data[2] = has_chroma ? buf + y_sz + uv_sz : NULL;
+    return 0;
+}
+static void pinned_pic_release(Dav1dPicture *const p, void *const cookie)
+{
+    (void)cookie;
+    const int slot = (int)(intptr_t)p->allocator_data - 1;
+    if (slot < 0 || slot >= 128) return;
+    pthread_mutex_lock(&g_pin_lock);
+    g_pin_pool[slot].used = 0;
+    pthread_mutex_unlock(&g_pin_lock);
+}
+static void pinned_pool_trim(void)
+{
+    pthread_mutex_lock(&g_pin_lock);
+    for (int i = 0; i < 128; i++)
+        if (g_pin_pool[i].ptr && !g_pin_pool[i].used && g_be_ok) { g_be.host_free(g_pin_pool[i].ptr); g_pin_pool[i].ptr = NULL; g_pin_pool[i].cap = 0; }
+    pthread_mutex_unlock(&g_pin_lock);
+}
 
 const B200Backend *b200hook_backend(void)
 {
@@ -152,9 +238,10 @@ HookRefPic *b200hook_refpic(const void *key, size_t bytes, int create)
             if (!r)                              /* only pictures of abandoned frames (never completed) are left: oldest one */
                 for (int i = 0; i < 64; i++)
                     if (!r || g_refs[i].last_use < r->last_use) r = &g_refs[i];
-            r->key = key; r->ready = 0;
+            r->key = key; r->ready = 0; r->submitted = 0;
         }
     }
+    if (r && create && !r->event) r->event = be->event_create();      /* NULL = no events: consumers then wait for `ready` on the host */
     if (r) r->last_use = ++g_clock;
     if (r && create && r->bytes < bytes) {
         if (r->dev) be->dev_free(r->dev);
@@ -169,8 +256,28 @@ void b200hook_refpic_set_ready(HookRefPic *r, int ready)
 {
     pthread_mutex_lock(&g_lock);
     r->ready = ready;
+    if (ready) r->submitted = 1;                /* nobody may wait for ever, whatever happened to the job */
     pthread_cond_broadcast(&g_ref_cond);
     pthread_mutex_unlock(&g_lock);
+}
+void b200hook_refpic_set_submitted(HookRefPic *r, int submitted)
+{
+    pthread_mutex_lock(&g_lock);
+    r->submitted = submitted;
+    pthread_cond_broadcast(&g_ref_cond);
+    pthread_mutex_unlock(&g_lock);
+}
+void b200hook_refpic_wait_submitted(HookRefPic *r)
+{
+    pthread_mutex_lock(&g_lock);
+    while (!r->submitted && !r->ready) pthread_cond_wait(&g_ref_cond, &g_lock);
+    pthread_mutex_unlock(&g_lock);
+}
+int b200hook_async(void)
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("B200HOOK_ASYNC"); v = !e || atoi(e) != 0; }
+    return v;
 }
 void b200hook_refpic_wait(HookRefPic *r)
 {
@@ -233,7 +340,7 @@ HookFrame *b200hook_frame(const void *key)
         for (int tries = 0; tries < 64 && !r; tries++) {
             for (int i = 0; i < 64; i++) {
                 HookFrame *const h = &g_frames[i];
-                if (h->pinned || h->users || h->last_use <= floor_use) continue;
+                if (h->pinned || h->users || h->pending || h->last_use <= floor_use) continue;      /* pending: its job still uses the buffers */
                 if (!pass && (h->started || h->tile_sbrows_done)) continue;
                 if (!lru || h->last_use < lru->last_use) lru = h;
             }
@@ -322,9 +429,28 @@ int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int
 /* dav1d's "this frame is over" (completed, failed or flushed; reference src/decode.c:3242, called from src/thread_task.c and
  * src/lib.c:588, which are compiled with the call renamed to this wrapper). A frame that ends without having been handed to
  * the device leaves half a frame of records in its slot: drop them, and release anybody waiting for its picture. */
+#include <time.h>
+static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+
+/* The frame's job was enqueued when its last tile superblock row had been emitted (run_frame); here — in the frame's exit
+ * handler, the last thing dav1d does before the picture may be output or the context reused — the host waits for it.
+ * In between, later frames have ordered their jobs behind this one on the device (event) without any host-side wait.
+ * Called with h->lock held. */
+int b200hook_frame_finish(HookFrame *const h)
+{
+    if (!h->pending) return 0;
+    const B200Backend *const be = b200hook_backend();
+    int r = be ? be->frame_wait(h->stream) : -1;
+    if (r) fprintf(stderr, "b200hook: device job failed (%d): %s\n", r, be ? be->last_error() : "no back end");
+    b200hook_account(h->pend_rec, h->pend_coef, h->pend_h2d, h->pend_d2h, now_ms() - h->t_submit, h->pend_kinds, h->pend_prep_ms);
+    if (h->pending_out) b200hook_refpic_set_ready(h->pending_out, 1);
+    h->pending = 0; h->pending_out = NULL;
+    return r;
+}
+
 struct Dav1dFrameContext;
 void dav1d_decode_frame_exit(struct Dav1dFrameContext *f, int retval);
-void b200hook_decode_frame_exit(struct Dav1dFrameContext *const f, const int retval)
+void b200hook_decode_frame_exit(struct Dav1dFrameContext *const f, int retval)
 {
     HookFrame *h = NULL;
     pthread_mutex_lock(&g_lock);
@@ -333,6 +459,7 @@ void b200hook_decode_frame_exit(struct Dav1dFrameContext *const f, const int ret
     pthread_mutex_unlock(&g_lock);
     if (h) {
         pthread_mutex_lock(&h->lock);
+        if (b200hook_frame_finish(h) && !retval) retval = -22;      /* DAV1D_ERR(EINVAL): the frame is reported as a decoding error */
         if (h->started) {
             HookRefPic *const out = h->cur_pic ? b200hook_refpic(h->cur_pic, 0, 0) : NULL;
             if (out) b200hook_refpic_set_ready(out, 1);
@@ -373,6 +500,7 @@ API void b200hook_release(void)
     for (int i = 0; i < 64; i++) {
         HookFrame *h = &g_frames[i];
         if (!h->key) continue;
+        if (h->pending && h->stream && g_be_ok) g_be.frame_wait(h->stream);       /* nothing may still read the buffers below */
         b200hook_buf_free(&h->tx); b200hook_buf_free(&h->tx_sorted); b200hook_buf_free(&h->coef); b200hook_buf_free(&h->mask);
         b200hook_buf_free(&h->level); b200hook_buf_free(&h->lr_mask); b200hook_buf_free(&h->scratch);
         for (int p = 0; p < 3; p++) b200hook_buf_free(&h->pic[p]);
@@ -387,7 +515,9 @@ API void b200hook_release(void)
     }
     for (int i = 0; i < 64; i++) {
         if (g_refs[i].dev && g_be_ok) g_be.dev_free(g_refs[i].dev);
+        if (g_refs[i].event && g_be_ok) g_be.event_destroy(g_refs[i].event);
         memset(&g_refs[i], 0, sizeof(g_refs[i]));
     }
     pthread_mutex_unlock(&g_lock);
+    pinned_pool_trim();
 }

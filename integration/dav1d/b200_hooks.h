@@ -26,6 +26,13 @@ typedef struct B200Backend {
     void (*stream_destroy)(void *);
     size_t (*intra_scratch_bytes)(const B200IntraFrame *);
     int (*frame_run_host)(const B200FrameJob *, const B200Xfer *, int, const B200Xfer *, int, void *);
+    int (*frame_submit_host)(const B200FrameJob *, const B200Xfer *, int, const B200Xfer *, int, void *);
+    int (*frame_wait)(void *);
+    int (*copy_async)(void *, const void *, size_t, void *);
+    void *(*event_create)(void);
+    void (*event_destroy)(void *);
+    int (*event_record)(void *, void *);
+    int (*stream_wait_event)(void *, void *);
     int (*struct_size)(int);
 } B200Backend;
 const B200Backend *b200hook_backend(void);   /* NULL (after logging) when no back end is loaded: the decode fails */
@@ -65,6 +72,12 @@ typedef struct HookFrame {
                                       context was abandoned half way (flush / close) and its records are stale */
     uint64_t last_use;             /* slot recycling: least recently used idle slot is taken over (its buffers are kept) */
     void *stream;
+    /* a submitted job that has not been waited for yet (the frame's exit handler does): its output picture and what the
+     * statistics will be told once it is done */
+    int pending;
+    struct HookRefPic *pending_out;
+    double t_submit, pend_prep_ms;
+    uint64_t pend_rec, pend_coef, pend_h2d, pend_d2h, pend_kinds[10];
     /* statistics */
     uint64_t frames, records;
 } HookFrame;
@@ -75,10 +88,17 @@ void *b200hook_append(HookBuf *b, int *n, size_t elem);
 
 /* device pictures that outlive their frame context: every decoded picture, keyed by the host picture's data[0]
  * (dav1d recycles a host buffer only when no reference to it is left, so a key is reused only for a dead picture) */
-typedef struct HookRefPic { const void *key; void *dev; size_t bytes; int ready; uint64_t last_use; } HookRefPic;
+/* submitted: the picture's job is enqueued on its frame context's stream and `event` marks the end of its kernels — later
+ * frames order their own jobs behind it on the device (b200_stream_wait_event) without waiting on the host; ready: the job
+ * and the copy into the host picture are complete */
+typedef struct HookRefPic { const void *key; void *dev; size_t bytes; int ready, submitted; void *event; uint64_t last_use; } HookRefPic;
 HookRefPic *b200hook_refpic(const void *key, size_t bytes, int create);
 void b200hook_refpic_set_ready(HookRefPic *r, int ready);
 void b200hook_refpic_wait(HookRefPic *r);
+void b200hook_refpic_set_submitted(HookRefPic *r, int submitted);
+void b200hook_refpic_wait_submitted(HookRefPic *r);
+int b200hook_async(void);                /* B200HOOK_ASYNC != 0 (default): jobs are waited for in the frame's exit handler */
+int b200hook_frame_finish(HookFrame *h); /* waits for the slot's pending job, accounts it, marks its picture ready */
 void b200hook_job_enter(void);
 void b200hook_job_leave(void);
 

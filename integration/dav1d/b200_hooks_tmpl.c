@@ -838,6 +838,8 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     void *const p0 = !will_lr && !will_cdef ? outp->dev : hf->pic[0].dev;
     j.mc.dst = p0;
     const int inter = hf->is_inter;
+    HookRefPic *rps[7];
+    int n_rps = 0;
     if (inter) {
         for (int k = 0; k < 7; k++) {
             /* only the references some block really predicts from: dav1d made this frame wait for those (their pass 2 has
@@ -847,7 +849,10 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
             if (!key || !(hf->refs_used & (1u << k))) continue;
             HookRefPic *const rp = b200hook_refpic(key, 0, 0);
             if (!rp || !rp->dev) { fprintf(stderr, "b200hook: reference %d was not decoded by this back end\n", k); return -1; }
-            b200hook_refpic_wait(rp);          /* its device job (another frame context) must have finished */
+            /* its device job (another frame context) must have been enqueued: this job is ordered behind it on the device
+             * (event), the host does not wait for it to finish. Without events: wait for the finished picture. */
+            if (rp->event && b200hook_async()) { b200hook_refpic_wait_submitted(rp); rps[n_rps++] = rp; }
+            else b200hook_refpic_wait(rp);
             j.mc.ref[k] = rp->dev;
         }
         for (int p = 0; p < 3; p++) {
@@ -989,17 +994,34 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     }
     for (int i = 0; i < n_up; i++) h2d += up[i].bytes;
     const double t0 = bitfn(now_ms)();
+    /* enqueue: the frame's records (they depend on nothing on the device, so they go up while earlier frames still compute),
+     * the wait for the reference pictures' jobs, the job, the event later frames will wait on, the copy into the host picture.
+     * Nothing here waits on the host: that happens in the frame's exit handler (b200hook_frame_finish). */
     b200hook_job_enter();
-    const int r = be->frame_run_host(&j, up, n_up, down, n_down, hf->stream);
+    int r = 0;
+    for (int i = 0; i < n_up && !r; i++)
+        if (up[i].bytes) r = be->copy_async(up[i].dev, up[i].host, up[i].bytes, hf->stream);
+    for (int i = 0; i < n_rps && !r; i++) r = be->stream_wait_event(hf->stream, rps[i]->event);
+    if (!r) r = be->frame_submit_host(&j, NULL, 0, NULL, 0, hf->stream);
+    if (!r && outp->event) r = be->event_record(outp->event, hf->stream);
+    for (int i = 0; i < n_down && !r; i++) r = be->copy_async(down[i].host, down[i].dev, down[i].bytes, hf->stream);
     b200hook_job_leave();
-    if (r) { fprintf(stderr, "b200hook: b200_frame_run_host failed (%d): %s\n", r, be->last_error()); return -1; }
+    if (r) {
+        fprintf(stderr, "b200hook: submitting the frame job failed (%d): %s\n", r, be->last_error());
+        be->frame_wait(hf->stream);             /* whatever was enqueued must not outlive the buffers */
+        return -1;
+    }
     uint64_t n_rec = (uint64_t)hf->n_tx + hf->n_pred + hf->n_comp + hf->n_comp2 + hf->n_warp + hf->n_blend + hf->n_blend2;
     uint64_t n_itx = 0;
     for (int t = 0; t < N_RECT_TX_SIZES; t++) n_itx += hf->n_itx[t];
     n_rec += n_itx;
     const uint64_t kinds[10] = { (uint64_t)hf->n_tx, (uint64_t)hf->n_pred, (uint64_t)hf->n_comp + hf->n_comp2, (uint64_t)hf->n_warp,
                                 (uint64_t)hf->n_blend + hf->n_blend2, n_itx, (uint64_t)inter, (uint64_t)hf->n_ii, (uint64_t)hf->n_pal, (uint64_t)hf->n_ibc };
-    b200hook_account(n_rec, hf->n_coef, h2d, d2h, bitfn(now_ms)() - t0, kinds, t0 - t_enter);
+    hf->pending = 1; hf->pending_out = outp; hf->t_submit = t0; hf->pend_prep_ms = t0 - t_enter;
+    hf->pend_rec = n_rec; hf->pend_coef = hf->n_coef; hf->pend_h2d = h2d; hf->pend_d2h = d2h;
+    memcpy(hf->pend_kinds, kinds, sizeof(kinds));
+    b200hook_refpic_set_submitted(outp, 1);
+    if (!b200hook_async()) return b200hook_frame_finish(hf) ? -1 : 0;     /* B200HOOK_ASYNC=0: one job at a time per context, host waits here */
     return 0;
 }
 
@@ -1014,10 +1036,11 @@ void bitfn(b200hook_backup_ipred_edge)(Dav1dTaskContext *const t)
     if (t->frame_thread.pass != 2) __atomic_fetch_or(&hf->unsupported, 4, __ATOMIC_RELAXED);
     const int total = f->sbh * f->frame_hdr->tiling.cols;
     if (++hf->tile_sbrows_done >= total) {
-        if (bitfn(run_frame)(hf, f))
+        if (bitfn(run_frame)(hf, f)) {
             atomic_fetch_or(&f->task_thread.error, 1);      /* the frame is reported as a decoding error */
-        HookRefPic *const outp = b200hook_refpic(f->cur.data[0], 0, 0);
-        if (outp) b200hook_refpic_set_ready(outp, 1);       /* also after a failure: nobody may wait for ever */
+            HookRefPic *const outp = b200hook_refpic(f->cur.data[0], 0, 0);
+            if (outp && !hf->pending) b200hook_refpic_set_ready(outp, 1);       /* after a failure nobody may wait for ever */
+        }
         hf->tile_sbrows_done = 0; hf->n_tx = 0; hf->n_coef = 0; hf->unsupported = 0;
         hf->n_pred = hf->n_comp = hf->n_comp2 = hf->n_warp = hf->n_blend = hf->n_blend2 = 0;
         hf->n_tmp16 = 0; hf->n_pxtmp = 0; hf->started = 0; hf->is_inter = 0; hf->n_ii = 0; hf->n_ibc = 0; hf->refs_used = 0;

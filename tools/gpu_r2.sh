@@ -139,6 +139,15 @@ if [[ $what == *" final2 "* ]]; then
   run_bench n1_8k10 python bench.py --workload 8k10_full --steps 10 --warmup 3
   du -sh gpurun_out
 fi
+if [[ $what == *" async "* ]]; then
+  # the hooked decoder with asynchronous submission (events between frame jobs, page-locked output pictures): stream tests,
+  # then the stream workloads with and without it, and the stock decoder beside them
+  timeout 300 python -m pytest tests/test_stream.py -x -q -m gpu --timeout 120 2>&1 | tail -6 > gpurun_out/pytest_stream_gpu.txt; tail -3 gpurun_out/pytest_stream_gpu.txt
+  run_bench stream1080p8_inter python bench.py --workload stream1080p8_inter --steps 3 --warmup 1
+  run_bench stream1080p8_inter_sync B200HOOK_ASYNC=0 B200HOOK_PINNED_PICS=0 python bench.py --workload stream1080p8_inter --steps 3 --warmup 1
+  run_bench stream4k8_inter python bench.py --workload stream4k8_inter --steps 3 --warmup 1
+  run_bench ref_stream1080p8_inter python bench.py --impl reference --workload stream1080p8_inter --steps 3 --warmup 1
+fi
 echo done > gpurun_out/done.txt
 for f in gpurun_out/bench_*.json; do echo "$f: $(head -c 600 $f)"; done
 for f in gpurun_out/bench_*.err; do if [ -s $f ]; then echo "== $f"; tail -5 $f; fi; done
