@@ -148,6 +148,10 @@ if [[ $what == *" async "* ]]; then
   run_bench stream4k8_inter python bench.py --workload stream4k8_inter --steps 3 --warmup 1
   run_bench ref_stream1080p8_inter python bench.py --impl reference --workload stream1080p8_inter --steps 3 --warmup 1
 fi
+if [[ $what == *" async4k "* ]]; then
+  run_bench stream4k8_inter_sync B200HOOK_ASYNC=0 B200HOOK_PINNED_PICS=0 python bench.py --workload stream4k8_inter --steps 2 --warmup 1
+  run_bench ref_stream4k8_inter python bench.py --impl reference --workload stream4k8_inter --steps 2 --warmup 1
+fi
 echo done > gpurun_out/done.txt
 for f in gpurun_out/bench_*.json; do echo "$f: $(head -c 600 $f)"; done
 for f in gpurun_out/bench_*.err; do if [ -s $f ]; then echo "== $f"; tail -5 $f; fi; done
