@@ -217,6 +217,47 @@ void *b200hook_append(HookBuf *b, int *n, size_t elem)
     return p;
 }
 
+int b200hook_tiles_reset(HookFrame *const hf, const int n_tiles)
+{
+    if (n_tiles > hf->cap_tiles) {
+        HookTile *const nt = realloc(hf->tiles, (size_t)n_tiles * sizeof(*nt));
+        if (!nt) return -1;
+        memset(nt + hf->cap_tiles, 0, (size_t)(n_tiles - hf->cap_tiles) * sizeof(*nt));
+        hf->tiles = nt; hf->cap_tiles = n_tiles;
+    }
+    hf->n_tiles = n_tiles;
+    for (int t = 0; t < hf->cap_tiles; t++)
+        for (int l = 0; l < B200L_COUNT; l++) hf->tiles[t].l[l].n = 0;
+    return 0;
+}
+void *b200hook_tile_append(HookFrame *const hf, const int tile, const int list, const size_t elem)
+{
+    if ((unsigned)tile >= (unsigned)hf->n_tiles) return NULL;
+    HookList *const L = &hf->tiles[tile].l[list];
+    if (L->n == L->cap) {
+        const int cap = L->cap ? 2 * L->cap : 256;
+        uint8_t *const d = realloc(L->data, (size_t)cap * elem);
+        if (!d) return NULL;
+        L->data = d; L->cap = cap;
+    }
+    void *const p = L->data + (size_t)L->n++ * elem;
+    memset(p, 0, elem);
+    return p;
+}
+int b200hook_tiles_gather(HookFrame *const hf, const int list, HookBuf *const dst, const size_t elem)
+{
+    size_t total = 0;
+    for (int t = 0; t < hf->n_tiles; t++) total += (size_t)hf->tiles[t].l[list].n;
+    if (b200hook_buf_reserve(dst, (total ? total : 1) * elem, 1, 0)) return -1;
+    uint8_t *o = dst->host;
+    for (int t = 0; t < hf->n_tiles; t++) {
+        const HookList *const L = &hf->tiles[t].l[list];
+        if (L->n) memcpy(o, L->data, (size_t)L->n * elem);
+        o += (size_t)L->n * elem;
+    }
+    return (int)total;
+}
+
 static HookRefPic g_refs[64];
 static pthread_cond_t g_ref_cond = PTHREAD_COND_INITIALIZER;
 HookRefPic *b200hook_refpic(const void *key, size_t bytes, int create)
@@ -371,13 +412,21 @@ static const uint8_t k_tx_w4[19] = { 1, 2, 4, 8, 16, 1, 2, 2, 4, 4, 8, 8, 16, 1,
 static const uint8_t k_tx_h4[19] = { 1, 2, 4, 8, 16, 2, 1, 4, 2, 8, 4, 16, 8, 4, 1, 8, 2, 16, 4 };
 static inline int mini(int a, int b) { return a < b ? a : b; }
 int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int32_t w4[3], const int32_t h4[3],
-                       int ss_hor, int ss_ver)
+                       int ss_hor, int ss_ver, void **scratch, size_t *scratch_cap)
 {
     size_t cells = 0, off[3];
     for (int p = 0; p < 3; p++) { off[p] = cells; cells += (size_t)w4[p] * h4[p]; }
-    int32_t *const map = calloc(cells, sizeof(*map));
-    int32_t *const wave = malloc((size_t)(n + 1) * sizeof(*wave));
-    if (!map || !wave) { free(map); free(wave); return -1; }
+    /* the cell map (several MB at 4K) and the wave numbers live in a buffer the frame context keeps: a fresh calloc per
+     * frame cost more in page faults than the sort itself */
+    const size_t need = (cells + (size_t)n + 1) * sizeof(int32_t);
+    if (*scratch_cap < need) {
+        free(*scratch);
+        *scratch = malloc(need + need / 4);
+        *scratch_cap = *scratch ? need + need / 4 : 0;
+        if (!*scratch) return -1;
+    }
+    int32_t *const map = *scratch, *const wave = map + cells;
+    memset(map, 0, cells * sizeof(*map));
     int n_waves = 0;
     for (int i = 0; i < n; i++) {
         const B200IntraTx *const r = &in[i];
@@ -418,11 +467,11 @@ int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int
             for (int xx = x; xx < x + tw && xx < mw; xx++) m[(size_t)yy * mw + xx] = wv;
     }
     int32_t *const start = calloc((size_t)n_waves + 2, sizeof(*start));
-    if (!start) { free(map); free(wave); return -1; }
+    if (!start) return -1;
     for (int i = 0; i < n; i++) start[wave[i] + 1]++;
     for (int k = 1; k <= n_waves + 1; k++) start[k] += start[k - 1];
     for (int i = 0; i < n; i++) out[start[wave[i]]++] = in[i];
-    free(start); free(map); free(wave);
+    free(start);
     return n_waves;
 }
 
@@ -510,6 +559,10 @@ API void b200hook_release(void)
         b200hook_buf_free(&h->pal);
         b200hook_buf_free(&h->warp); b200hook_buf_free(&h->blend); b200hook_buf_free(&h->blend2); b200hook_buf_free(&h->pxtmp);
         if (h->stream && g_be_ok) g_be.stream_destroy(h->stream);
+        for (int t = 0; t < h->cap_tiles; t++)
+            for (int l = 0; l < B200L_COUNT; l++) free(h->tiles[t].l[l].data);
+        free(h->tiles);
+        free(h->sort_scratch);
         pthread_mutex_destroy(&h->lock);
         memset(h, 0, sizeof(*h));
     }

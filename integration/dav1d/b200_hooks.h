@@ -42,6 +42,15 @@ typedef struct HookBuf { void *host, *dev; size_t cap; } HookBuf;
 int b200hook_buf_reserve(HookBuf *b, size_t bytes, int need_host, int keep);
 void b200hook_buf_free(HookBuf *b);
 
+/* Inter records are appended per TILE: a tile is reconstructed by one thread at a time, so its lists need no lock, and the
+ * tile threads of a frame no longer serialise on the frame's mutex once per block (with 8 threads on a 16-tile 4K frame that
+ * mutex made pass 2 effectively single threaded). Plain host memory, grown by doubling, kept across frames; the lists of all
+ * tiles are concatenated into the pinned upload buffers when the frame completes (the order of the records inside a stage does
+ * not matter: blocks do not overlap). */
+enum { B200L_PRED, B200L_COMP, B200L_COMP2, B200L_WARP, B200L_BLEND, B200L_BLEND2, B200L_ITX, B200L_COUNT = B200L_ITX + 19 };
+typedef struct HookList { uint8_t *data; int n, cap; } HookList;
+typedef struct HookTile { HookList l[B200L_COUNT]; } HookTile;
+
 /* per frame context (dav1d's n_fc frames in flight): the records of the frame being reconstructed */
 typedef struct HookFrame {
     const void *key;               /* the Dav1dFrameContext this slot serves */
@@ -59,7 +68,11 @@ typedef struct HookFrame {
     HookBuf pal;                             /* palettes + packed index maps of palette blocks (slots taken atomically) */
     size_t n_pal, cap_pal;
     HookBuf warp, blend, blend2, pxtmp;      /* warped-motion 8x8 blocks; OBMC: blend_h stage, blend_v stage, pixel scratch (device only) */
-    int n_pred, n_comp, n_comp2, n_itx[19], n_warp, n_blend, n_blend2;
+    int n_pred, n_comp, n_comp2, n_itx[19], n_warp, n_blend, n_blend2;       /* totals over the tiles, known when the frame completes */
+    HookTile *tiles;
+    int n_tiles, cap_tiles;
+    void *sort_scratch;            /* cell map + wave numbers of b200hook_wave_sort, kept across frames */
+    size_t sort_scratch_cap;
     size_t n_tmp16, n_cmask, n_pxtmp;
     int started, is_inter, n_ii, n_ibc;
     unsigned refs_used;            /* bit k: some prediction of this frame reads reference k (f->refp[k]) */
@@ -83,8 +96,11 @@ typedef struct HookFrame {
 } HookFrame;
 HookFrame *b200hook_frame(const void *key);
 int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int32_t w4[3], const int32_t h4[3],
-                       int ss_hor, int ss_ver);
+                       int ss_hor, int ss_ver, void **scratch, size_t *scratch_cap);
 void *b200hook_append(HookBuf *b, int *n, size_t elem);
+int b200hook_tiles_reset(HookFrame *hf, int n_tiles);
+void *b200hook_tile_append(HookFrame *hf, int tile, int list, size_t elem);
+int b200hook_tiles_gather(HookFrame *hf, int list, HookBuf *dst, size_t elem);      /* total number of records, < 0 on failure */
 
 /* device pictures that outlive their frame context: every decoded picture, keyed by the host picture's data[0]
  * (dav1d recycles a host buffer only when no reference to it is left, so a key is reused only for a dead picture) */

@@ -82,6 +82,7 @@ static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *c
     }
     if (!hf->started) {
         hf->cur_pic = f->cur.data[0];
+        if (b200hook_tiles_reset(hf, f->frame_hdr->tiling.cols * f->frame_hdr->tiling.rows)) __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
         hf->n_cmask = (sizeof(dav1d_masks) + 63) & ~(size_t)63;      /* dav1d's wedge tables sit at the head of the mask buffer */
         PicGeom g;
         bitfn(pic_geom)(f, &g);
@@ -342,6 +343,9 @@ out:;
 }
 
 /* ---- inter blocks (what dav1d_recon_b_inter does, reference src/recon_tmpl.c:1557-1985) -------------------- */
+/* the tile the calling thread is reconstructing (set on entry of the inter hook): its record lists are this thread's alone */
+static __thread int bitfn(tl_tile);
+#define TILE_REC(list, type) ((type *)b200hook_tile_append(hf, bitfn(tl_tile), (list), sizeof(type)))
 /* one motion-compensated prediction: the arguments of the reference's mc() (:938-988), as a B200McBlock.
  * Source samples outside the reference plane are clamped by the kernel (= emu_edge). */
 static int bitfn(emit_mc)(HookFrame *const hf, const Dav1dFrameContext *const f, const int op, const uint32_t dst_off,
@@ -354,7 +358,7 @@ static int bitfn(emit_mc)(HookFrame *const hf, const Dav1dFrameContext *const f,
     const int ss_hor = !!pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
     const int h_mul = 4 >> ss_hor, v_mul = 4 >> ss_ver;
     const int mx = mv.x & (15 >> !ss_hor), my = mv.y & (15 >> !ss_ver);
-    B200McBlock *const r = b200hook_append(&hf->pred, &hf->n_pred, sizeof(*r));
+    B200McBlock *const r = TILE_REC(B200L_PRED, B200McBlock);
     if (!r) return -1;
     r->dst_off = dst_off;
     r->src_x = bx * h_mul + (mv.x >> (3 + ss_hor));
@@ -362,7 +366,7 @@ static int bitfn(emit_mc)(HookFrame *const hf, const Dav1dFrameContext *const f,
     r->w = bw4 * h_mul; r->h = bh4 * v_mul;
     r->mx = mx << !ss_hor; r->my = my << !ss_ver;
     r->filter2d = filter_2d; r->op = op; r->plane = pl; r->ref = refidx;      /* op: 0 put, 1 prep, 2 put into the pixel scratch */
-    hf->refs_used |= 1u << refidx;
+    __atomic_fetch_or(&hf->refs_used, 1u << refidx, __ATOMIC_RELAXED);
     return 0;
 }
 
@@ -384,7 +388,7 @@ static int bitfn(emit_warp)(HookFrame *const hf, const Dav1dFrameContext *const 
         for (int x = 0; x < b_dim[0] * h_mul; x += 8) {
             const int src_x = t->bx * 4 + ((x + 4) << ss_hor);
             const int64_t mvx = ((int64_t)mat[2] * src_x + mat3_y) >> ss_hor, mvy = ((int64_t)mat[4] * src_x + mat5_y) >> ss_ver;
-            B200WarpBlock *const r = b200hook_append(&hf->warp, &hf->n_warp, sizeof(*r));
+            B200WarpBlock *const r = TILE_REC(B200L_WARP, B200WarpBlock);
             if (!r) return -1;
             r->dst_off = dst_off + (uint32_t)y * pitch + x;
             r->src_x = (int)(mvx >> 16) - 4; r->src_y = (int)(mvy >> 16) - 4;
@@ -392,7 +396,7 @@ static int bitfn(emit_warp)(HookFrame *const hf, const Dav1dFrameContext *const 
             r->my = (((int)mvy & 0xffff) - wmp->u.p.gamma * 4 - wmp->u.p.delta * 4) & ~0x3f;
             for (int k = 0; k < 4; k++) r->abcd[k] = wmp->u.abcd[k];
             r->tmp_stride = pitch; r->op = op; r->plane = pl; r->ref = refidx;
-            hf->refs_used |= 1u << refidx;
+            __atomic_fetch_or(&hf->refs_used, 1u << refidx, __ATOMIC_RELAXED);
         }
     }
     return 0;
@@ -415,11 +419,10 @@ static int bitfn(emit_obmc)(HookFrame *const hf, const Dav1dFrameContext *const 
             const int step4 = iclip(dav1d_block_dimensions[a_r->bs][0], 2, 16);
             if (a_r->ref.ref[0] > 0) {
                 const int ow4 = imin(step4, b_dim[0]), oh4 = imin(b_dim[1], 16) >> 1;
-                const uint32_t scratch = (uint32_t)hf->n_pxtmp;
-                hf->n_pxtmp += (size_t)(ow4 * h_mul) * (((oh4 * 3 + 3) >> 2) * v_mul);
+                const uint32_t scratch = (uint32_t)__atomic_fetch_add(&hf->n_pxtmp, (size_t)(ow4 * h_mul) * (((oh4 * 3 + 3) >> 2) * v_mul), __ATOMIC_RELAXED);
                 if (bitfn(emit_mc)(hf, f, 2, scratch, ow4, (oh4 * 3 + 3) >> 2, t->bx + x, t->by, pl, a_r->mv.mv[0], a_r->ref.ref[0] - 1,
                                    dav1d_filter_2d[t->a->filter[1][bx4 + x + 1]][t->a->filter[0][bx4 + x + 1]])) return -1;
-                B200BlendBlock *const bl = b200hook_append(&hf->blend, &hf->n_blend, sizeof(*bl));
+                B200BlendBlock *const bl = TILE_REC(B200L_BLEND, B200BlendBlock);
                 if (!bl) return -1;
                 bl->dst_off = dst_off + x * h_mul; bl->tmp_off = scratch;
                 bl->w = h_mul * ow4; bl->h = v_mul * oh4; bl->op = B200_BLEND_H; bl->plane = pl;
@@ -433,11 +436,10 @@ static int bitfn(emit_obmc)(HookFrame *const hf, const Dav1dFrameContext *const 
             const int step4 = iclip(dav1d_block_dimensions[l_r->bs][1], 2, 16);
             if (l_r->ref.ref[0] > 0) {
                 const int ow4 = imin(b_dim[0], 16) >> 1, oh4 = imin(step4, b_dim[1]);
-                const uint32_t scratch = (uint32_t)hf->n_pxtmp;
-                hf->n_pxtmp += (size_t)(ow4 * h_mul) * (oh4 * v_mul);
+                const uint32_t scratch = (uint32_t)__atomic_fetch_add(&hf->n_pxtmp, (size_t)(ow4 * h_mul) * (oh4 * v_mul), __ATOMIC_RELAXED);
                 if (bitfn(emit_mc)(hf, f, 2, scratch, ow4, oh4, t->bx, t->by + y, pl, l_r->mv.mv[0], l_r->ref.ref[0] - 1,
                                    dav1d_filter_2d[t->l.filter[1][by4 + y + 1]][t->l.filter[0][by4 + y + 1]])) return -1;
-                B200BlendBlock *const bl = b200hook_append(&hf->blend2, &hf->n_blend2, sizeof(*bl));
+                B200BlendBlock *const bl = TILE_REC(B200L_BLEND2, B200BlendBlock);
                 if (!bl) return -1;
                 bl->dst_off = dst_off + (uint32_t)(y * v_mul) * dst_stride; bl->tmp_off = scratch;
                 bl->w = h_mul * ow4; bl->h = v_mul * oh4; bl->op = B200_BLEND_V; bl->plane = pl;
@@ -530,7 +532,7 @@ static int bitfn(emit_itx)(TxCtx *const c, const int tx, const int pl, const uin
     memset(&tmp, 0, sizeof(tmp));
     if (bitfn(take_residual)(c, &tmp, &dav1d_txfm_dimensions[tx], chroma)) return -1;
     if (tmp.eob < 0) return 0;
-    B200ItxBlock *const r = b200hook_append(&hf->itx[tx], &hf->n_itx[tx], sizeof(*r));
+    B200ItxBlock *const r = TILE_REC(B200L_ITX + tx, B200ItxBlock);
     if (!r) return -1;
     r->dst_off = dst_off; r->coef_off = tmp.coef_off; r->eob = tmp.eob; r->txtp = tmp.txtp; r->plane = pl;
     return 0;
@@ -584,7 +586,7 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
     int rc = -1;
 
     bitfn(frame_started)(hf, f);
-    pthread_mutex_lock(&hf->lock);          /* protects the inter record lists; intra records / coefficients are lock-free */
+    bitfn(tl_tile) = (int)(t->ts - f->ts);  /* no lock: inter records go to this tile's lists, intra records / coefficients / scratch offsets are taken atomically */
     if (IS_KEY_OR_INTRA(f->frame_hdr)) {
         /* intra block copy: prediction and residual both go through the intra machine (the source is this very picture) */
         c.ii = 1;
@@ -594,7 +596,7 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
                 if (bitfn(emit_ibc)(&c, pl, g->off[pl] + uvrel, bw4 << (bw4 == ss_hor), bh4 << (bh4 == ss_ver), bx & ~ss_hor, by & ~ss_ver, b->mv[0])) goto out;
         goto residual;
     }
-    hf->is_inter = 1;
+    __atomic_store_n(&hf->is_inter, 1, __ATOMIC_RELAXED);
     if (b->comp_type == COMP_INTER_NONE) {
         const enum Filter2d filter_2d = b->filter2d;
         const int warp = (b->inter_mode == GLOBALMV && f->gmv_warp_allowed[b->ref[0]]) ||
@@ -666,16 +668,14 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
             const int pw = pl ? bw4 * 4 >> ss_hor : bw4 * 4, ph = pl ? bh4 * 4 >> ss_ver : bh4 * 4;
             uint32_t tmp_off[2];
             for (int i = 0; i < 2; i++) {
-                tmp_off[i] = (uint32_t)hf->n_tmp16;
-                hf->n_tmp16 += (size_t)pw * ph;
+                tmp_off[i] = (uint32_t)__atomic_fetch_add(&hf->n_tmp16, (size_t)pw * ph, __ATOMIC_RELAXED);
                 if (b->inter_mode == GLOBALMV_GLOBALMV && f->gmv_warp_allowed[b->ref[i]] && (!pl || imin(cbw4, cbh4) > 1)) {
                     if (bitfn(emit_warp)(hf, f, t, 1, tmp_off[i], pw, dim, pl, b->ref[i], &f->frame_hdr->gmv[b->ref[i]])) goto out;
                 } else if (bitfn(emit_mc)(hf, f, 1, tmp_off[i], bw4, bh4, bx, by, pl, b->mv[i], b->ref[i], filter_2d)) goto out;
             }
             const int seg = b->comp_type == COMP_INTER_SEG;
             /* chroma of a difference-weighted block reads the mask its luma block writes: second compound stage */
-            B200CompBlock *const r = (pl && seg) ? b200hook_append(&hf->comp2, &hf->n_comp2, sizeof(*r))
-                                                 : b200hook_append(&hf->comp, &hf->n_comp, sizeof(*r));
+            B200CompBlock *const r = (pl && seg) ? TILE_REC(B200L_COMP2, B200CompBlock) : TILE_REC(B200L_COMP, B200CompBlock);
             if (!r) goto out;
             r->dst_off = pl ? g->off[pl] + uvrel : ydst;
             r->w = pw; r->h = ph; r->plane = pl;
@@ -689,9 +689,8 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
                     if (seg) {
                         /* w_mask writes the (sub-sampled) mask the chroma planes blend with */
                         r->op = B200_COMP_W_MASK_444 + chr_layout_idx; r->param = b->mask_sign;
-                        hf->n_cmask = (hf->n_cmask + 63) & ~(size_t)63;
-                        r->mask_off = mask_off = (uint32_t)hf->n_cmask;
-                        hf->n_cmask += (size_t)(bw4 * 4 >> ss_hor) * (bh4 * 4 >> ss_ver);
+                        /* the counter stays a multiple of 64 (it starts as one and grows by rounded sizes) */
+                        r->mask_off = mask_off = (uint32_t)__atomic_fetch_add(&hf->n_cmask, ((size_t)(bw4 * 4 >> ss_hor) * (bh4 * 4 >> ss_ver) + 63) & ~(size_t)63, __ATOMIC_RELAXED);
                     } else {
                         r->op = B200_COMP_MASK;
                         r->mask_off = (uint32_t)(WEDGE_MASK(0, bs, 0, b->wedge_idx) - (const uint8_t *)&dav1d_masks);
@@ -727,7 +726,6 @@ residual:
     rc = 0;
 out:
     if (rc) __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
-    pthread_mutex_unlock(&hf->lock);
     return 0;       /* problems are reported when the frame completes (the whole frame fails, loudly) */
 }
 
@@ -791,6 +789,10 @@ static void bitfn(fix_tile_edges)(const Dav1dFrameContext *const f, Av1Filter *c
 static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const f)
 {
     const double t_enter = bitfn(now_ms)();
+    /* B200HOOK_PROF=1: where the host-side completion of a frame spends its time (stderr, one line per frame) */
+    static int prof = -1;
+    if (prof < 0) { const char *e = getenv("B200HOOK_PROF"); prof = e && atoi(e) != 0; }
+    double tp[6] = { t_enter, t_enter, t_enter, t_enter, t_enter, t_enter };
     const B200Backend *const be = b200hook_backend();
     if (!be) return -1;
     if (hf->unsupported) {
@@ -819,6 +821,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     bitfn(fix_tile_edges)(f, (Av1Filter *)hf->mask.host);
     memcpy(hf->level.host, f->lf.level, level_bytes);
     memcpy(hf->lr_mask.host, f->lf.lr_mask, lr_bytes);
+    tp[1] = bitfn(now_ms)();
 
     B200FrameJob j;
     memset(&j, 0, sizeof(j));
@@ -855,6 +858,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
             else b200hook_refpic_wait(rp);
             j.mc.ref[k] = rp->dev;
         }
+        tp[2] = bitfn(now_ms)();
         for (int p = 0; p < 3; p++) {
             j.mc.ref_plane_off[p] = g.off[p]; j.mc.ref_stride[p] = g.stride[p];
             j.mc.ref_w[p] = p ? (f->cur.p.w + ss_hor) >> ss_hor : f->cur.p.w;
@@ -862,12 +866,13 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         }
         if (b200hook_buf_reserve(&hf->tmp16, (hf->n_tmp16 + 1) * sizeof(int16_t), 0, 0) ||
             b200hook_buf_reserve(&hf->cmask, hf->n_cmask + 64, 1, 0) ||
-            b200hook_buf_reserve(&hf->pred, (size_t)imax(hf->n_pred, 1) * sizeof(B200McBlock), 1, 1) ||
-            b200hook_buf_reserve(&hf->comp, (size_t)imax(hf->n_comp, 1) * sizeof(B200CompBlock), 1, 1) ||
-            b200hook_buf_reserve(&hf->comp2, (size_t)imax(hf->n_comp2, 1) * sizeof(B200CompBlock), 1, 1) ||
-            b200hook_buf_reserve(&hf->warp, (size_t)imax(hf->n_warp, 1) * sizeof(B200WarpBlock), 1, 1) ||
-            b200hook_buf_reserve(&hf->blend, (size_t)imax(hf->n_blend, 1) * sizeof(B200BlendBlock), 1, 1) ||
-            b200hook_buf_reserve(&hf->blend2, (size_t)imax(hf->n_blend2, 1) * sizeof(B200BlendBlock), 1, 1) ||
+            /* the tiles' record lists, concatenated into the pinned upload buffers */
+            (hf->n_pred = b200hook_tiles_gather(hf, B200L_PRED, &hf->pred, sizeof(B200McBlock))) < 0 ||
+            (hf->n_comp = b200hook_tiles_gather(hf, B200L_COMP, &hf->comp, sizeof(B200CompBlock))) < 0 ||
+            (hf->n_comp2 = b200hook_tiles_gather(hf, B200L_COMP2, &hf->comp2, sizeof(B200CompBlock))) < 0 ||
+            (hf->n_warp = b200hook_tiles_gather(hf, B200L_WARP, &hf->warp, sizeof(B200WarpBlock))) < 0 ||
+            (hf->n_blend = b200hook_tiles_gather(hf, B200L_BLEND, &hf->blend, sizeof(B200BlendBlock))) < 0 ||
+            (hf->n_blend2 = b200hook_tiles_gather(hf, B200L_BLEND2, &hf->blend2, sizeof(B200BlendBlock))) < 0 ||
             b200hook_buf_reserve(&hf->pxtmp, (hf->n_pxtmp + 1) * sizeof(pixel), 0, 0))
             return -1;
         memcpy(hf->cmask.host, &dav1d_masks, sizeof(dav1d_masks));
@@ -880,10 +885,12 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         j.d_blend = (const B200BlendBlock *)hf->blend.dev; j.n_blend = hf->n_blend;
         j.d_blend2 = (const B200BlendBlock *)hf->blend2.dev; j.n_blend2 = hf->n_blend2;
         for (int t = 0; t < N_RECT_TX_SIZES; t++) {
+            if ((hf->n_itx[t] = b200hook_tiles_gather(hf, B200L_ITX + t, &hf->itx[t], sizeof(B200ItxBlock))) < 0) return -1;
             if (!hf->n_itx[t]) continue;
             j.d_itx[t] = (const B200ItxBlock *)hf->itx[t].dev; j.n_itx[t] = hf->n_itx[t];
         }
     }
+    tp[3] = bitfn(now_ms)();
     j.d_coef = hf->coef.dev;
     for (int p = 0; p < 3; p++) { j.itx_stride[p] = g.stride[p]; j.mc.dst_stride[p] = g.stride[p]; }
     /* intra reconstruction */
@@ -918,6 +925,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         }
         j.intra.done_init = (const uint8_t *)hf->done_init.dev;
     }
+    tp[4] = bitfn(now_ms)();
     /* decode order -> wavefront order (B200HOOK_WAVE_SORT=0 keeps decode order, which is also valid) */
     const HookBuf *txb = &hf->tx;
     static int wave_sort = -1;
@@ -925,10 +933,13 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     if (wave_sort && hf->n_tx > 0) {
         if (b200hook_buf_reserve(&hf->tx_sorted, (size_t)hf->n_tx * sizeof(B200IntraTx), 1, 0)) return -1;
         if (b200hook_wave_sort((const B200IntraTx *)hf->tx.host, (B200IntraTx *)hf->tx_sorted.host, hf->n_tx,
-                               j.intra.w4, j.intra.h4, ss_hor, ss_ver) < 0) return -1;
+                               j.intra.w4, j.intra.h4, ss_hor, ss_ver, &hf->sort_scratch, &hf->sort_scratch_cap) < 0) return -1;
         txb = &hf->tx_sorted;
         j.d_intra = (const B200IntraTx *)txb->dev;
     }
+    tp[5] = bitfn(now_ms)();
+    if (prof) fprintf(stderr, "b200hook prof: masks %.2f  ref-submit wait %.2f  gather %.2f  done map %.2f  wave sort %.2f ms (%d intra records)\n",
+                      tp[1] - tp[0], tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4], hf->n_tx);
     /* deblock (reference src/recon_tmpl.c:1987-2027), in place on p0 */
     const int do_lf = (f->c->inloop_filters & DAV1D_INLOOPFILTER_DEBLOCK) && (hdr->loopfilter.level_y[0] || hdr->loopfilter.level_y[1]);
     j.run_lf = do_lf;

@@ -452,7 +452,11 @@ def test_hook_wavefront_sort_is_a_valid_order():
     w4 = (C.c_int32 * 3)(S["w4"], S["w4"] >> 1, S["w4"] >> 1)
     h4 = (C.c_int32 * 3)(S["h4"], S["h4"] >> 1, S["h4"] >> 1)
     dll.b200hook_wave_sort.restype = C.c_int
-    waves = dll.b200hook_wave_sort(tx.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n, w4, h4, 1, 1)
+    scratch, cap = C.c_void_p(), C.c_size_t(0)          # the caller keeps the sort's scratch buffer between frames (freed with libc below)
+    for _ in range(2):                                   # the second call reuses the buffer
+        waves = dll.b200hook_wave_sort(tx.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), n, w4, h4, 1, 1, C.byref(scratch), C.byref(cap))
+    assert scratch.value and cap.value >= 4 * (n + 1)
+    C.CDLL(None).free(scratch)
     assert waves == S["intra_waves"], (waves, S["intra_waves"])          # same depth as the generator's own numbering
     # same multiset of records, and every record's dependency cells are owned by earlier records
     assert sorted(out.tobytes()[i * tx.itemsize:(i + 1) * tx.itemsize] for i in range(n)) == \
