@@ -146,11 +146,16 @@ static int pinned_pic_alloc(Dav1dPicture *const p, void *const cookie)
     p->data[2] = has_chroma ? buf + y_sz + uv_sz : NULL;
     return 0;
 }
+void b200hook_refpic_forget(const void *key);
 static void pinned_pic_release(Dav1dPicture *const p, void *const cookie)
 {
     (void)cookie;
     const int slot = (int)(intptr_t)p->allocator_data - 1;
     if (slot < 0 || slot >= 128) return;
+    /* dav1d dropped its last reference to the picture: nothing decodes from it or outputs it any more, so its device copy's
+     * table entry is free for the next picture (its device buffer is kept for reuse). With dav1d's own allocator there is no
+     * such signal and the table falls back to least-recently-used recycling. */
+    b200hook_refpic_forget(p->data[0]);
     pthread_mutex_lock(&g_pin_lock);
     g_pin_pool[slot].used = 0;
     pthread_mutex_unlock(&g_pin_lock);
@@ -269,8 +274,11 @@ HookRefPic *b200hook_refpic(const void *key, size_t bytes, int create)
     for (int i = 0; i < 64 && !r; i++)
         if (g_refs[i].key == key) r = &g_refs[i];
     if (!r && create) {
-        for (int i = 0; i < 64 && !r; i++)
-            if (!g_refs[i].key) { r = &g_refs[i]; memset(r, 0, sizeof(*r)); r->key = key; }
+        /* a free entry: one whose device buffer is already large enough if there is one (the buffer and event of a forgotten
+         * picture stay with its entry) */
+        for (int i = 0; i < 64; i++)
+            if (!g_refs[i].key && (!r || (r->bytes < bytes && g_refs[i].bytes >= bytes))) r = &g_refs[i];
+        if (r) { r->key = key; r->ready = 0; r->submitted = 0; }
         if (!r) {
             /* host pictures of closed decoders never come back: recycle the least recently used entry (the live set —
              * 8 reference slots + frames in flight + pictures waiting for output — is far smaller than the table) */
@@ -292,6 +300,14 @@ HookRefPic *b200hook_refpic(const void *key, size_t bytes, int create)
     }
     pthread_mutex_unlock(&g_lock);
     return r;
+}
+void b200hook_refpic_forget(const void *const key)
+{
+    if (!key) return;
+    pthread_mutex_lock(&g_lock);
+    for (int i = 0; i < 64; i++)
+        if (g_refs[i].key == key) { g_refs[i].key = NULL; g_refs[i].ready = 0; g_refs[i].submitted = 0; }
+    pthread_mutex_unlock(&g_lock);
 }
 void b200hook_refpic_set_ready(HookRefPic *r, int ready)
 {

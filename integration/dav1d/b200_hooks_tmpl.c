@@ -1077,24 +1077,28 @@ void bitfn(b200hook_filter_sbrow_lr)(Dav1dFrameContext *const f, const int sby) 
 static void bitfn(fg_whole_picture)(Dav1dPicture *const out, const Dav1dPicture *const in)
 {
     const B200Backend *const be = b200hook_backend();
-    HookRefPic *const src = b200hook_refpic(in->data[0], 0, 0);
-    if (!be || !src || !src->dev || out->stride[0] != in->stride[0] || (in->p.layout != DAV1D_PIXEL_LAYOUT_I400 && out->stride[1] != in->stride[1])) {
-        fprintf(stderr, "b200hook: film grain: the picture is not resident on the device (or the output copy has another layout)\n");
-        abort();                                    /* no error channel here (void, like dav1d's), no CPU fallback */
-    }
-    b200hook_refpic_wait(src);
+    if (!be) { fprintf(stderr, "b200hook: film grain: no back end\n"); abort(); }      /* no error channel here (void, like dav1d's), no CPU fallback */
     const int mono = in->p.layout == DAV1D_PIXEL_LAYOUT_I400;            /* device picture: dummy 4:2:0 chroma planes (pic_geom) */
     const int ss_ver = mono || in->p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = in->p.layout != DAV1D_PIXEL_LAYOUT_I444;
     const int rows = (in->p.h + 127) & ~127;
     const int st0 = (int)PXSTRIDE(in->stride[0]), st1 = mono ? st0 : (int)PXSTRIDE(in->stride[1]);
     const uint32_t off1 = (uint32_t)st0 * rows, off2 = off1 + (uint32_t)st1 * (rows >> ss_ver);
     const size_t bytes = ((size_t)off2 + (size_t)st1 * (rows >> ss_ver)) * sizeof(pixel);
+    const int npl = mono ? 1 : 3;
+    /* normally the decoded picture is still in HBM (keyed by its host buffer). It is not when it was decoded elsewhere and
+     * handed to the public dav1d_apply_grain, or after b200hook_release(): then the host picture goes up first. */
+    HookRefPic *const src = b200hook_refpic(in->data[0], 0, 0);
+    const char *const force = getenv("B200HOOK_FG_UPLOAD");                /* tests: take the upload path although the picture is resident */
+    const int resident = src && src->dev && src->bytes >= bytes && !(force && atoi(force));
+    if (resident) b200hook_refpic_wait(src);
+    const int same_pitch = out->stride[0] == in->stride[0] && (mono || out->stride[1] == in->stride[1]);
     static const char fg_slot_key = 0;
     HookFrame *const hf = b200hook_frame(&fg_slot_key);                  /* a slot of its own for the output stage */
-    if (!hf) abort();
+    if (!hf) { fprintf(stderr, "b200hook: film grain: no slot\n"); abort(); }
     hf->pinned = 1;
     pthread_mutex_lock(&hf->lock);
     if ((!hf->stream && !(hf->stream = be->stream_create())) || b200hook_buf_reserve(&hf->pic[0], bytes, 0, 0) ||
+        (!resident && b200hook_buf_reserve(&hf->pic[1], bytes, 0, 0)) ||
         b200hook_buf_reserve(&hf->scratch, B200_FG_SCRATCH_BYTES, 0, 0)) {
         fprintf(stderr, "b200hook: film grain: %s\n", be->last_error());
         abort();
@@ -1107,25 +1111,33 @@ static void bitfn(fg_whole_picture)(Dav1dPicture *const out, const Dav1dPicture 
     j.bitdepth_max = (1 << in->p.bpc) - 1;
 #endif
     j.run_fg = 1;
-    j.fg.in = src->dev; j.fg.out = hf->pic[0].dev; j.fg.scratch = hf->scratch.dev;
+    j.fg.in = resident ? src->dev : hf->pic[1].dev; j.fg.out = hf->pic[0].dev; j.fg.scratch = hf->scratch.dev;
     j.fg.plane_off[0] = 0; j.fg.plane_off[1] = off1; j.fg.plane_off[2] = off2;
     j.fg.stride[0] = st0; j.fg.stride[1] = j.fg.stride[2] = st1;
     j.fg.w = in->p.w; j.fg.h = in->p.h; j.fg.ss_hor = ss_hor; j.fg.ss_ver = ss_ver;
     j.fg.is_id = in->seq_hdr->mtrx == DAV1D_MC_IDENTITY;
     memcpy(&j.fg.data, &in->frame_hdr->film_grain.data, sizeof(j.fg.data));
-    B200Xfer down[3];
-    const int npl = in->p.layout == DAV1D_PIXEL_LAYOUT_I400 ? 1 : 3;
-    for (int p = 0; p < npl; p++) {
-        const int prow = p ? (in->p.h + ss_ver) >> ss_ver : in->p.h;
-        down[p].host = out->data[p];
-        down[p].dev = (uint8_t *)hf->pic[0].dev + (size_t)j.fg.plane_off[p] * sizeof(pixel);
-        down[p].bytes = (uint64_t)prow * j.fg.stride[p] * sizeof(pixel);
-    }
     b200hook_job_enter();
-    const int r = be->frame_run_host(&j, NULL, 0, down, npl, hf->stream);
+    int r = 0;
+    for (int p = 0; p < npl && !resident && !r; p++) {
+        const int prow = p ? (in->p.h + ss_ver) >> ss_ver : in->p.h;
+        r = be->copy_async((uint8_t *)hf->pic[1].dev + (size_t)j.fg.plane_off[p] * sizeof(pixel), in->data[p],
+                           (size_t)prow * j.fg.stride[p] * sizeof(pixel), hf->stream);
+    }
+    if (!r) r = be->frame_submit_host(&j, NULL, 0, NULL, 0, hf->stream);
+    for (int p = 0; p < npl && !r; p++) {
+        const int prow = p ? (in->p.h + ss_ver) >> ss_ver : in->p.h, pw = p ? (in->p.w + ss_hor) >> ss_hor : in->p.w;
+        const uint8_t *const d = (const uint8_t *)hf->pic[0].dev + (size_t)j.fg.plane_off[p] * sizeof(pixel);
+        if (same_pitch) r = be->copy_async(out->data[p], d, (size_t)prow * j.fg.stride[p] * sizeof(pixel), hf->stream);
+        else            /* an output copy with another pitch (a caller's own allocator): row by row */
+            for (int y = 0; y < prow && !r; y++)
+                r = be->copy_async((uint8_t *)out->data[p] + (ptrdiff_t)y * out->stride[!!p], d + (size_t)y * j.fg.stride[p] * sizeof(pixel),
+                                   (size_t)pw * sizeof(pixel), hf->stream);
+    }
+    const int r2 = be->frame_wait(hf->stream);
     b200hook_job_leave();
     pthread_mutex_unlock(&hf->lock);
-    if (r) { fprintf(stderr, "b200hook: film grain job failed: %s\n", be->last_error()); abort(); }
+    if (r || r2) { fprintf(stderr, "b200hook: film grain job failed: %s\n", be->last_error()); abort(); }
 }
 
 void bitfn(b200hook_apply_grain)(const Dav1dFilmGrainDSPContext *const dsp, Dav1dPicture *const out, const Dav1dPicture *const in)

@@ -286,6 +286,20 @@ def test_intra_block_copy_streams_decode(emu_decoder, w, h, kw):
     assert n_ibc > 0, "no intra block copy block in any of the streams"
 
 
+def test_film_grain_on_a_picture_that_is_not_resident(emu_decoder):
+    """film grain on a picture without a device copy (decoded elsewhere and handed to dav1d_apply_grain, or after
+    b200hook_release): the host picture is uploaded first instead of aborting the process (B200HOOK_FG_UPLOAD forces that path)"""
+    tus = obu.inter_stream(77, 200, 136, n_frames=4, bpc=10, film_grain=1)
+    r0, _, out0 = _ref_decode(tus, apply_grain=1)
+    os.environ["B200HOOK_FG_UPLOAD"] = "1"
+    try:
+        r1, _, out1 = emu_decoder.decode(tus, apply_grain=1)
+    finally:
+        del os.environ["B200HOOK_FG_UPLOAD"]
+    assert r0 == 4 and r1 == r0 and np.array_equal(out0, out1)
+    emu_decoder.stats(reset=True)
+
+
 @pytest.mark.parametrize("n_threads,delay", [(1, 1), (1, 0), (4, 1), (2, 0)])
 def test_single_threaded_settings_decode(emu_decoder, n_threads, delay):
     """one thread / no frame delay used to put dav1d in single-pass mode, which the emitters cannot serve (every frame
