@@ -18,11 +18,17 @@ class ItxBlock(C.Structure):
                 ("txtp", C.c_uint8), ("plane", C.c_uint8)]
 
 
+class RefGeom(C.Structure):
+    """struct B200RefGeom: planes of a reference picture whose size differs from the frame's (scaled references)"""
+    _fields_ = [("plane_off", C.c_uint32 * 3), ("stride", C.c_int32 * 3), ("w", C.c_int32 * 3), ("h", C.c_int32 * 3)]
+
+
 class McFrame(C.Structure):
     """struct B200McFrame"""
     _fields_ = [("ref", C.c_void_p * 8), ("ref_plane_off", C.c_uint32 * 3), ("ref_stride", C.c_int32 * 3),
                 ("ref_w", C.c_int32 * 3), ("ref_h", C.c_int32 * 3), ("dst", C.c_void_p),
-                ("dst_stride", C.c_int32 * 3), ("tmp", C.c_void_p), ("mask", C.c_void_p), ("px_tmp", C.c_void_p)]
+                ("dst_stride", C.c_int32 * 3), ("tmp", C.c_void_p), ("mask", C.c_void_p), ("px_tmp", C.c_void_p),
+                ("scaled_mask", C.c_uint32), ("pad_geom", C.c_uint32), ("ref_geom", RefGeom * 8)]
 
 
 class McBlock(C.Structure):

@@ -410,15 +410,18 @@ mc_scaled_kernel(const B200McScaledBlock *__restrict__ blocks, int n_blocks, con
     typedef typename Bd<HBD>::pixel pixel;
     const B200McScaledBlock b = blocks[blockIdx.x];
     const int w = b.w, h = b.h, pl = b.plane;
-    const pixel *__restrict__ ref = (const pixel *)fr.ref[b.ref] + fr.ref_plane_off[pl];
-    const int rs = fr.ref_stride[pl], rw1 = fr.ref_w[pl] - 1, rh1 = fr.ref_h[pl] - 1;
+    // a reference of another size brings its own plane geometry
+    const bool own = (fr.scaled_mask >> b.ref) & 1;
+    const pixel *__restrict__ ref = (const pixel *)fr.ref[b.ref] + (own ? fr.ref_geom[b.ref].plane_off[pl] : fr.ref_plane_off[pl]);
+    const int rs = own ? fr.ref_geom[b.ref].stride[pl] : fr.ref_stride[pl];
+    const int rw1 = (own ? fr.ref_geom[b.ref].w[pl] : fr.ref_w[pl]) - 1, rh1 = (own ? fr.ref_geom[b.ref].h[pl] : fr.ref_h[pl]) - 1;
     const int ib = inter_bits<HBD>(bdmax);
     const int bias = HBD ? 8192 : 0;
-    const bool bilin = b.filter2d == 9, is_prep = b.op != 0;
+    const bool bilin = b.filter2d == 9, is_prep = b.op == 1;
     const int th = bilin ? 0 : c_f2d_h[b.filter2d], tv = bilin ? 0 : c_f2d_v[b.filter2d];
     const int hidx = w > 4 ? th : 3 + (th & 1), vidx = h > 4 ? tv : 3 + (tv & 1);
-    pixel *const dpx = (pixel *)fr.dst;
-    const int ds = fr.dst_stride[pl];
+    pixel *const dpx = b.op == 2 ? (pixel *)fr.px_tmp : (pixel *)fr.dst;      // op 2: the overlapped predictions of OBMC
+    const int ds = b.op == 2 ? w : fr.dst_stride[pl];
     for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
         const int y = i / w, x = i - y * w;
         const int px = b.mx + x * b.dx, py = b.my + y * b.dy;

@@ -376,9 +376,11 @@ def _poc_diff(bits, a, b):
 def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None,
                 lf=None, cdef=True, restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0,
                 refresh=None, switchable_motion_mode=0, warped_motion_seq=0, comp_refs=1, allow_warped_motion=0, layout="420",
-                show_frame=1, global_motion=0, segmentation=0):
+                show_frame=1, global_motion=0, segmentation=0, max_size=None):
     """One shown inter frame (OBU_FRAME), primary_ref_frame = NONE. `ref_hints` = order hints held by the 8 reference slots
-    (updated in place for the slots this frame refreshes). Global motion is identity."""
+    (updated in place for the slots this frame refreshes). Global motion is identity. max_size = (W, H) of the sequence
+    header when this frame is coded at another size (w, h): frame_size_override with an explicit size, so that its references
+    — decoded at other sizes — are scaled references (reference src/obu.c read_frame_size, src/recon_tmpl.c:991-1046)."""
     bits = 7
     b = BitWriter()
     b.f(1, 0)                                # show_existing_frame
@@ -387,7 +389,8 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
         b.f(1, 1)                            # showable_frame: a later show_existing_frame header outputs it
     b.f(1, 0)                                # error_resilient_mode
     b.f(1, 0)                                # disable_cdf_update
-    b.f(1, 0)                                # frame_size_override
+    override = max_size is not None and tuple(max_size) != (w, h)
+    b.f(1, 1 if override else 0)             # frame_size_override
     b.f(bits, order_hint)
     b.f(3, 7)                                # primary_ref_frame NONE
     refresh = int(rng.integers(1, 256)) if refresh is None else refresh
@@ -396,6 +399,11 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
     refidx = [int(rng.integers(0, 8)) for _ in range(7)]
     for r in refidx:
         b.f(3, r)
+    if override:
+        for _ in range(7):
+            b.f(1, 0)                        # found_ref: the size is not taken from a reference ...
+        wn, hn = max(1, int(max_size[0] - 1).bit_length()), max(1, int(max_size[1] - 1).bit_length())
+        b.f(wn, w - 1); b.f(hn, h - 1)       # ... but written out (frame_width_minus_1, frame_height_minus_1)
     b.f(1, 0)                                # render_and_frame_size_different
     hp = int(rng.integers(0, 2))
     b.f(1, hp)                               # allow_high_precision_mv
@@ -456,7 +464,7 @@ def show_existing_frame(slot):
 
 
 def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, film_grain=0, screen_content=0, layout="420",
-                 hidden_every=0, intra_only_every=0, **kw):
+                 hidden_every=0, intra_only_every=0, sizes=None, **kw):
     """Temporal units: one key frame, then n_frames - 1 inter frames (single and compound references incl. wedge /
     difference-weighted masks and distance weights, switchable interpolation filters, variable transform trees, intra
     blocks; identity global motion). motion_modes=1 additionally enables the per-block motion mode (overlapped block
@@ -490,5 +498,9 @@ def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=
             tus.append(temporal_unit(hid, shown))
             tus.append(temporal_unit(show_existing_frame(7)))
         else:
-            tus.append(temporal_unit(inter_frame(rng, w, h, i % 128, hints, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, **kw)))
+            # sizes = [(w, h), ...]: inter frame i is coded at sizes[(i - 1) % len(sizes)] (each within a factor 2 down / 16 up of
+            # every picture still held as a reference, as AV1 requires): its references are then scaled references
+            fw, fh = sizes[(i - 1) % len(sizes)] if sizes else (w, h)
+            tus.append(temporal_unit(inter_frame(rng, fw, fh, i % 128, hints, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows,
+                                                 max_size=(w, h) if sizes else None, **kw)))
     return tus

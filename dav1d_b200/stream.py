@@ -19,7 +19,7 @@ class HookStats(C.Structure):
     _fields_ = [("frames", C.c_uint64), ("records", C.c_uint64), ("coefs", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("device_ms", C.c_double), ("intra_tx", C.c_uint64), ("pred", C.c_uint64),
                 ("comp", C.c_uint64), ("warp", C.c_uint64), ("blend", C.c_uint64), ("itx", C.c_uint64),
-                ("inter_frames", C.c_uint64), ("host_prep_ms", C.c_double), ("interintra", C.c_uint64), ("palette_bytes", C.c_uint64), ("ibc", C.c_uint64)]
+                ("inter_frames", C.c_uint64), ("host_prep_ms", C.c_double), ("interintra", C.c_uint64), ("palette_bytes", C.c_uint64), ("ibc", C.c_uint64), ("scaled", C.c_uint64)]
 
 
 def build_hooked(verbose=False):

@@ -112,6 +112,11 @@ B200_API int b200_itx_add_batch_host(int bitdepth_max, int tx, const B200ItxBloc
  * ref_plane_off/ref_stride/ref_w/ref_h describe the planes (in pixels). Source coordinates that
  * fall outside [0,ref_w) x [0,ref_h) are clamped — exactly the replicate padding dav1d's
  * emu_edge builds for such blocks (reference src/recon_tmpl.c:960-977, src/mc_tmpl.c:868-916). */
+typedef struct B200RefGeom {     /* a reference picture whose size is not the current frame's (scaled references) */
+    uint32_t plane_off[3];
+    int32_t stride[3];
+    int32_t w[3], h[3];
+} B200RefGeom;
 typedef struct B200McFrame {
     const void *ref[8];          /* device base pointer per reference slot */
     uint32_t ref_plane_off[3];
@@ -122,6 +127,11 @@ typedef struct B200McFrame {
     int16_t *tmp;                /* device int16 scratch: prep outputs / compound inputs */
     uint8_t *mask;               /* device uint8 scratch: w_mask outputs, mask / blend inputs */
     const void *px_tmp;          /* device pixel scratch: blend inputs (OBMC / inter-intra predictions); written by B200McBlock op 2 */
+    uint32_t scaled_mask;        /* bit k: reference k has another size than the frame being decoded and its planes are described by
+                                    ref_geom[k] instead of ref_plane_off / ref_stride / ref_w / ref_h. Only B200McScaledBlock records
+                                    may name such a reference (reference src/recon_tmpl.c:991-1046, f->svc[refidx]). */
+    uint32_t pad_geom;
+    B200RefGeom ref_geom[8];
 } B200McFrame;
 
 /* one prediction block: dav1d's mc[filter2d] (op 0, "put") or mct[filter2d] (op 1, "prep") */
@@ -203,7 +213,7 @@ typedef struct B200McScaledBlock {
     uint16_t mx, my;             /* 0 .. 1023 */
     uint16_t dx, dy;             /* 1 .. 2048 */
     uint8_t w, h;                /* 2 .. 128 */
-    uint8_t filter2d, op, plane, ref;
+    uint8_t filter2d, op, plane, ref;      /* op: 0 put, 1 prep (int16 into tmp), 2 put into px_tmp (pitch w) like B200McBlock */
     uint8_t pad[2];
 } B200McScaledBlock;
 B200_API int b200_mc_scaled_batch(int bitdepth_max, const B200McFrame *frame, const B200McScaledBlock *d_blocks,

@@ -538,13 +538,13 @@ void b200hook_decode_frame_exit(struct Dav1dFrameContext *const f, int retval)
     dav1d_decode_frame_exit(f, retval);
 }
 
-void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[10], double prep_ms)
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[11], double prep_ms)
 {
     pthread_mutex_lock(&g_lock);
     g_stats.frames++; g_stats.records += records; g_stats.coefs += coefs;
     g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += d2h; g_stats.device_ms += ms;
     g_stats.intra_tx += kinds[0]; g_stats.pred += kinds[1]; g_stats.comp += kinds[2]; g_stats.warp += kinds[3];
-    g_stats.host_prep_ms += prep_ms; g_stats.interintra += kinds[7]; g_stats.palette_bytes += kinds[8]; g_stats.ibc += kinds[9];
+    g_stats.host_prep_ms += prep_ms; g_stats.interintra += kinds[7]; g_stats.palette_bytes += kinds[8]; g_stats.ibc += kinds[9]; g_stats.scaled += kinds[10];
     g_stats.blend += kinds[4]; g_stats.itx += kinds[5]; g_stats.inter_frames += kinds[6];
     pthread_mutex_unlock(&g_lock);
 }
@@ -574,6 +574,7 @@ API void b200hook_release(void)
         b200hook_buf_free(&h->tmp16); b200hook_buf_free(&h->cmask); b200hook_buf_free(&h->done_init);
         b200hook_buf_free(&h->pal);
         b200hook_buf_free(&h->warp); b200hook_buf_free(&h->blend); b200hook_buf_free(&h->blend2); b200hook_buf_free(&h->pxtmp);
+        b200hook_buf_free(&h->scaled);
         if (h->stream && g_be_ok) g_be.stream_destroy(h->stream);
         for (int t = 0; t < h->cap_tiles; t++)
             for (int l = 0; l < B200L_COUNT; l++) free(h->tiles[t].l[l].data);

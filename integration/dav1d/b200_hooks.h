@@ -47,7 +47,7 @@ void b200hook_buf_free(HookBuf *b);
  * mutex made pass 2 effectively single threaded). Plain host memory, grown by doubling, kept across frames; the lists of all
  * tiles are concatenated into the pinned upload buffers when the frame completes (the order of the records inside a stage does
  * not matter: blocks do not overlap). */
-enum { B200L_PRED, B200L_COMP, B200L_COMP2, B200L_WARP, B200L_BLEND, B200L_BLEND2, B200L_ITX, B200L_COUNT = B200L_ITX + 19 };
+enum { B200L_PRED, B200L_COMP, B200L_COMP2, B200L_WARP, B200L_BLEND, B200L_BLEND2, B200L_SCALED, B200L_ITX, B200L_COUNT = B200L_ITX + 19 };
 typedef struct HookList { uint8_t *data; int n, cap; } HookList;
 typedef struct HookTile { HookList l[B200L_COUNT]; } HookTile;
 
@@ -68,6 +68,8 @@ typedef struct HookFrame {
     HookBuf pal;                             /* palettes + packed index maps of palette blocks (slots taken atomically) */
     size_t n_pal, cap_pal;
     HookBuf warp, blend, blend2, pxtmp;      /* warped-motion 8x8 blocks; OBMC: blend_h stage, blend_v stage, pixel scratch (device only) */
+    HookBuf scaled;                          /* predictions from references of another size (B200McScaledBlock) */
+    int n_scaled;
     int n_pred, n_comp, n_comp2, n_itx[19], n_warp, n_blend, n_blend2;       /* totals over the tiles, known when the frame completes */
     HookTile *tiles;
     int n_tiles, cap_tiles;
@@ -90,7 +92,7 @@ typedef struct HookFrame {
     int pending;
     struct HookRefPic *pending_out;
     double t_submit, pend_prep_ms;
-    uint64_t pend_rec, pend_coef, pend_h2d, pend_d2h, pend_kinds[10];
+    uint64_t pend_rec, pend_coef, pend_h2d, pend_d2h, pend_kinds[11];
     /* statistics */
     uint64_t frames, records;
 } HookFrame;
@@ -125,7 +127,8 @@ typedef struct B200HookStats {
     uint64_t interintra;            /* inter-intra records (a subset of intra_tx) */
     uint64_t palette_bytes;         /* palettes + index maps shipped for palette blocks */
     uint64_t ibc;                   /* intra block copy records (a subset of intra_tx) */
+    uint64_t scaled;                /* predictions from references of another size */
 } B200HookStats;
-void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[10], double prep_ms);
+void b200hook_account(uint64_t records, uint64_t coefs, uint64_t h2d, uint64_t d2h, double ms, const uint64_t kinds[11], double prep_ms);
 
 #endif

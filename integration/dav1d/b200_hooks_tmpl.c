@@ -353,10 +353,28 @@ static int bitfn(emit_mc)(HookFrame *const hf, const Dav1dFrameContext *const f,
                           const int refidx, const enum Filter2d filter_2d)
 {
     const Dav1dThreadPicture *const refp = &f->refp[refidx];
-    if (refp->p.p.w != f->cur.p.w || refp->p.p.h != f->cur.p.h) { __atomic_fetch_or(&hf->unsupported, 32, __ATOMIC_RELAXED); return 0; }   /* scaled reference */
     const int ss_ver = !!pl && f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
     const int ss_hor = !!pl && f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
     const int h_mul = 4 >> ss_hor, v_mul = 4 >> ss_ver;
+    if (refp->p.p.w != f->cur.p.w || refp->p.p.h != f->cur.p.h) {
+        /* a reference of another size (the scaled branch of mc(), reference :991-1046): the block's position in the reference
+         * in 1/1024 sample units and the per-sample steps of f->svc[refidx]; the kernel clamps its loads to the reference
+         * plane (= the emu_edge window of the reference) */
+        const int orig_pos_y = (by * v_mul << 4) + mv.y * (1 << !ss_ver), orig_pos_x = (bx * h_mul << 4) + mv.x * (1 << !ss_hor);
+        const int64_t tx = (int64_t)orig_pos_x * f->svc[refidx][0].scale + (f->svc[refidx][0].scale - 0x4000) * 8;
+        const int64_t ty = (int64_t)orig_pos_y * f->svc[refidx][1].scale + (f->svc[refidx][1].scale - 0x4000) * 8;
+        const int pos_x = apply_sign64((int)((llabs(tx) + 128) >> 8), tx) + 32, pos_y = apply_sign64((int)((llabs(ty) + 128) >> 8), ty) + 32;
+        B200McScaledBlock *const r = TILE_REC(B200L_SCALED, B200McScaledBlock);
+        if (!r) return -1;
+        r->dst_off = dst_off;
+        r->src_x = pos_x >> 10; r->src_y = pos_y >> 10;
+        r->mx = pos_x & 0x3ff; r->my = pos_y & 0x3ff;
+        r->dx = f->svc[refidx][0].step; r->dy = f->svc[refidx][1].step;
+        r->w = bw4 * h_mul; r->h = bh4 * v_mul;
+        r->filter2d = filter_2d; r->op = op; r->plane = pl; r->ref = refidx;
+        __atomic_fetch_or(&hf->refs_used, 1u << refidx, __ATOMIC_RELAXED);
+        return 0;
+    }
     const int mx = mv.x & (15 >> !ss_hor), my = mv.y & (15 >> !ss_ver);
     B200McBlock *const r = TILE_REC(B200L_PRED, B200McBlock);
     if (!r) return -1;
@@ -799,7 +817,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         fprintf(stderr, "b200hook: frame uses tools the emitters do not translate yet (%s%s%s%s)\n",
                 hf->unsupported & 1 ? " palette" : "", hf->unsupported & 2 ? " inter" : "",
                 hf->unsupported & 4 ? " single-pass-decoding" : "", hf->unsupported & 8 ? " out-of-memory" : "");
-        fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 scaled reference, 64 intra block copy out of range, 256 inter-intra block size, 1024 super-resolution)\n", hf->unsupported);
+        fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 warp from a scaled reference, 64 intra block copy out of range, 256 inter-intra block size, 1024 super-resolution)\n", hf->unsupported);
         return -1;
     }
     PicGeom g;
@@ -857,6 +875,21 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
             if (rp->event && b200hook_async()) { b200hook_refpic_wait_submitted(rp); rps[n_rps++] = rp; }
             else b200hook_refpic_wait(rp);
             j.mc.ref[k] = rp->dev;
+            const Dav1dPicture *const rpic = &f->refp[k].p;
+            if (rpic->p.w != f->cur.p.w || rpic->p.h != f->cur.p.h) {
+                /* a reference of another size: its own plane geometry (the layout pic_geom() gives a picture of its size) */
+                B200RefGeom *const rg = &j.mc.ref_geom[k];
+                const int rrows = (rpic->p.h + 127) & ~127;
+                rg->stride[0] = (int)PXSTRIDE(rpic->stride[0]);
+                rg->stride[1] = rg->stride[2] = mono ? rg->stride[0] : (int)PXSTRIDE(rpic->stride[1]);
+                rg->plane_off[0] = 0; rg->plane_off[1] = (uint32_t)rg->stride[0] * rrows;
+                rg->plane_off[2] = rg->plane_off[1] + (uint32_t)rg->stride[1] * (rrows >> ss_ver);
+                for (int p = 0; p < 3; p++) {
+                    rg->w[p] = p ? (rpic->p.w + ss_hor) >> ss_hor : rpic->p.w;
+                    rg->h[p] = p ? (rpic->p.h + ss_ver) >> ss_ver : rpic->p.h;
+                }
+                j.mc.scaled_mask |= 1u << k;
+            }
         }
         tp[2] = bitfn(now_ms)();
         for (int p = 0; p < 3; p++) {
@@ -873,6 +906,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
             (hf->n_warp = b200hook_tiles_gather(hf, B200L_WARP, &hf->warp, sizeof(B200WarpBlock))) < 0 ||
             (hf->n_blend = b200hook_tiles_gather(hf, B200L_BLEND, &hf->blend, sizeof(B200BlendBlock))) < 0 ||
             (hf->n_blend2 = b200hook_tiles_gather(hf, B200L_BLEND2, &hf->blend2, sizeof(B200BlendBlock))) < 0 ||
+            (hf->n_scaled = b200hook_tiles_gather(hf, B200L_SCALED, &hf->scaled, sizeof(B200McScaledBlock))) < 0 ||
             b200hook_buf_reserve(&hf->pxtmp, (hf->n_pxtmp + 1) * sizeof(pixel), 0, 0))
             return -1;
         memcpy(hf->cmask.host, &dav1d_masks, sizeof(dav1d_masks));
@@ -884,6 +918,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         j.d_warp = (const B200WarpBlock *)hf->warp.dev; j.n_warp = hf->n_warp;
         j.d_blend = (const B200BlendBlock *)hf->blend.dev; j.n_blend = hf->n_blend;
         j.d_blend2 = (const B200BlendBlock *)hf->blend2.dev; j.n_blend2 = hf->n_blend2;
+        j.d_scaled = (const B200McScaledBlock *)hf->scaled.dev; j.n_scaled = hf->n_scaled;
         for (int t = 0; t < N_RECT_TX_SIZES; t++) {
             if ((hf->n_itx[t] = b200hook_tiles_gather(hf, B200L_ITX + t, &hf->itx[t], sizeof(B200ItxBlock))) < 0) return -1;
             if (!hf->n_itx[t]) continue;
@@ -986,6 +1021,7 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         UP(hf->warp, (size_t)hf->n_warp * sizeof(B200WarpBlock));
         UP(hf->blend, (size_t)hf->n_blend * sizeof(B200BlendBlock));
         UP(hf->blend2, (size_t)hf->n_blend2 * sizeof(B200BlendBlock));
+        UP(hf->scaled, (size_t)hf->n_scaled * sizeof(B200McScaledBlock));
         UP(hf->cmask, sizeof(dav1d_masks));
         for (int t = 0; t < N_RECT_TX_SIZES; t++)
             if (hf->n_itx[t]) UP(hf->itx[t], (size_t)hf->n_itx[t] * sizeof(B200ItxBlock));
@@ -1022,12 +1058,12 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         be->frame_wait(hf->stream);             /* whatever was enqueued must not outlive the buffers */
         return -1;
     }
-    uint64_t n_rec = (uint64_t)hf->n_tx + hf->n_pred + hf->n_comp + hf->n_comp2 + hf->n_warp + hf->n_blend + hf->n_blend2;
+    uint64_t n_rec = (uint64_t)hf->n_tx + hf->n_pred + hf->n_comp + hf->n_comp2 + hf->n_warp + hf->n_blend + hf->n_blend2 + (inter ? hf->n_scaled : 0);
     uint64_t n_itx = 0;
     for (int t = 0; t < N_RECT_TX_SIZES; t++) n_itx += hf->n_itx[t];
     n_rec += n_itx;
-    const uint64_t kinds[10] = { (uint64_t)hf->n_tx, (uint64_t)hf->n_pred, (uint64_t)hf->n_comp + hf->n_comp2, (uint64_t)hf->n_warp,
-                                (uint64_t)hf->n_blend + hf->n_blend2, n_itx, (uint64_t)inter, (uint64_t)hf->n_ii, (uint64_t)hf->n_pal, (uint64_t)hf->n_ibc };
+    const uint64_t kinds[11] = { (uint64_t)hf->n_tx, (uint64_t)hf->n_pred, (uint64_t)hf->n_comp + hf->n_comp2, (uint64_t)hf->n_warp,
+                                (uint64_t)hf->n_blend + hf->n_blend2, n_itx, (uint64_t)inter, (uint64_t)hf->n_ii, (uint64_t)hf->n_pal, (uint64_t)hf->n_ibc, (uint64_t)(inter ? hf->n_scaled : 0) };
     hf->pending = 1; hf->pending_out = outp; hf->t_submit = t0; hf->pend_prep_ms = t0 - t_enter;
     hf->pend_rec = n_rec; hf->pend_coef = hf->n_coef; hf->pend_h2d = h2d; hf->pend_d2h = d2h;
     memcpy(hf->pend_kinds, kinds, sizeof(kinds));

@@ -286,6 +286,22 @@ def test_intra_block_copy_streams_decode(emu_decoder, w, h, kw):
     assert n_ibc > 0, "no intra block copy block in any of the streams"
 
 
+@pytest.mark.parametrize("w,h,sizes,kw", [(256, 192, [(192, 144), (256, 192), (160, 96)], dict(bpc=8)),
+                                          (320, 192, [(256, 160), (320, 192), (200, 120), (320, 176)], dict(bpc=10, motion_modes=1, film_grain=1)),
+                                          (256, 256, [(128, 128), (256, 256)], dict(bpc=8, motion_modes=2, layout="444")),
+                                          (192, 136, [(96, 72), (192, 136), (144, 100)], dict(bpc=12, log2_cols=1))])
+def test_scaled_reference_streams_decode(emu_decoder, w, h, sizes, kw):
+    """inter frames coded at changing sizes (was refused in round 1): their references have other sizes, so predictions are
+    B200McScaledBlock records (put, prep for compound blocks, pixel scratch for OBMC) against per-reference plane geometry
+    (B200McFrame.ref_geom) — byte-identical to stock dav1d, which runs mc_scaled / mct_scaled there (src/recon_tmpl.c:991-1046)"""
+    n_scaled = 0
+    for seed in range(3):
+        tus = obu.inter_stream(700 + seed, w, h, n_frames=6, sizes=sizes, **kw)
+        _check(emu_decoder, tus, 6, apply_grain=1)
+        n_scaled += emu_decoder.last_stats["scaled"]
+    assert n_scaled > 100, "hardly any scaled prediction in the streams"
+
+
 def test_film_grain_on_a_picture_that_is_not_resident(emu_decoder):
     """film grain on a picture without a device copy (decoded elsewhere and handed to dav1d_apply_grain, or after
     b200hook_release): the host picture is uploaded first instead of aborting the process (B200HOOK_FG_UPLOAD forces that path)"""
