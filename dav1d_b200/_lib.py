@@ -138,6 +138,13 @@ class IntraFrame(C.Structure):
                 ("sb_w", C.c_int32), ("sb_h", C.c_int32), ("sb", C.c_void_p), ("mask", C.c_void_p), ("pal", C.c_void_p), ("done_init", C.c_void_p)]
 
 
+class ResizeFrame(C.Structure):
+    """struct B200ResizeFrame"""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("src_plane_off", C.c_uint32 * 3), ("dst_plane_off", C.c_uint32 * 3),
+                ("src_stride", C.c_int32 * 3), ("dst_stride", C.c_int32 * 3), ("src_w", C.c_int32 * 3), ("dst_w", C.c_int32 * 3),
+                ("h", C.c_int32 * 3), ("dx", C.c_int32 * 3), ("mx0", C.c_int32 * 3), ("n_planes", C.c_int32), ("pad", C.c_int32)]
+
+
 class FrameJob(C.Structure):
     """struct B200FrameJob"""
     _fields_ = [("bitdepth_max", C.c_int32), ("zero_coefs", C.c_int32), ("mc", McFrame),
@@ -156,7 +163,8 @@ class FrameJob(C.Structure):
                 ("d_expand", C.c_void_p), ("n_expand", C.c_int32), ("pad8", C.c_int32), ("d_ccoef", C.c_void_p),
                 ("coef_bytes", C.c_uint64),
                 ("run_fg", C.c_int32), ("pad5", C.c_int32), ("fg", FgFrame),
-                ("d_blend2", C.c_void_p), ("n_blend2", C.c_int32), ("pad9", C.c_int32)]
+                ("d_blend2", C.c_void_p), ("n_blend2", C.c_int32), ("pad9", C.c_int32),
+                ("run_resize", C.c_int32), ("pad10", C.c_int32), ("resize", ResizeFrame * 2)]
 
 
 class FrameBand(C.Structure):
@@ -214,6 +222,7 @@ _SIGS = {
                                   C.c_int, C.c_int, C.c_int]),
     "b200_mc_emu_edge": (C.c_int, [C.c_ssize_t] * 6 + [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_int]),
     "b200_mc_resize": (C.c_int, [C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t] + [C.c_int] * 6),
+    "b200_resize_frame": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
     "b200_mc_dsp_init_8bpc": (None, [C.c_void_p]),
     "b200_mc_dsp_init_16bpc": (None, [C.c_void_p]),
     # ---- loopfilter
@@ -354,4 +363,4 @@ class Av1Restoration(C.Structure):
 
 
 ABI_STRUCTS = [McFrame, McBlock, CompBlock, BlendBlock, WarpBlock, ItxBlock, LfFrame, CdefFrame, LrFrame, FrameJob,
-               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame, McScaledBlock, CoefBlock, IntraSb, CompFusedBlock, FrameBand]
+               Av1Filter, Av1Restoration, FgFrame, FilmGrainData, IntraTx, IntraFrame, McScaledBlock, CoefBlock, IntraSb, CompFusedBlock, FrameBand, ResizeFrame]

@@ -46,6 +46,10 @@ static int frame_phase_post(const B200FrameJob *j, void *stream, void *fg_side)
     const int bd = j->bitdepth_max;
     if (j->run_lf && (r = b200_lf_frame(bd, &j->lf, stream))) return r;
     if (j->run_cdef && (r = b200_cdef_frame(bd, &j->cdef, stream))) return r;
+    if (j->run_resize) {                     // super-resolution: CDEF output (and the deblocked picture LR reads) upscaled
+        if ((r = b200_resize_frame(bd, &j->resize[0], stream))) return r;
+        if ((r = b200_resize_frame(bd, &j->resize[1], stream))) return r;
+    }
     if (j->run_lr && (r = b200_lr_frame(bd, &j->lr, stream))) return r;
     if (j->run_fg) {
 #ifndef B200_EMU
@@ -499,7 +503,7 @@ int b200_struct_size(int which)
     case 6: return sizeof(B200LfFrame); case 7: return sizeof(B200CdefFrame); case 8: return sizeof(B200LrFrame);
     case 9: return sizeof(B200FrameJob); case 10: return sizeof(B200Av1Filter); case 11: return sizeof(B200Av1Restoration);
     case 12: return sizeof(B200FgFrame); case 13: return sizeof(B200FilmGrainData);
-    case 14: return sizeof(B200IntraTx); case 15: return sizeof(B200IntraFrame); case 16: return sizeof(B200McScaledBlock); case 17: return sizeof(B200CoefBlock); case 18: return sizeof(B200IntraSb); case 19: return sizeof(B200CompFusedBlock); case 20: return sizeof(B200FrameBand);
+    case 14: return sizeof(B200IntraTx); case 15: return sizeof(B200IntraFrame); case 16: return sizeof(B200McScaledBlock); case 17: return sizeof(B200CoefBlock); case 18: return sizeof(B200IntraSb); case 19: return sizeof(B200CompFusedBlock); case 20: return sizeof(B200FrameBand); case 21: return sizeof(B200ResizeFrame);
     }
     return -1;
 }

@@ -647,6 +647,30 @@ __global__ void resize_kernel(typename Bd<HBD>::pixel *dst, const typename Bd<HB
     }
 }
 
+// whole planes, strided (the frame job's super-resolution stage): one thread per output sample, grid.y = plane
+template <bool HBD>
+__global__ void __launch_bounds__(256) resize_frame_kernel(const __grid_constant__ B200ResizeFrame fr, int bdmax)
+{
+    B200_PDL_ENTRY();
+    typedef typename Bd<HBD>::pixel pixel;
+    const int pl = blockIdx.y;
+    const int dst_w = fr.dst_w[pl], src_w = fr.src_w[pl], h = fr.h[pl], dx = fr.dx[pl], mx0 = fr.mx0[pl];
+    const pixel *const src = (const pixel *)fr.src + fr.src_plane_off[pl];
+    pixel *const dst = (pixel *)fr.dst + fr.dst_plane_off[pl];
+    const int ss = fr.src_stride[pl], ds = fr.dst_stride[pl];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dst_w * h; i += gridDim.x * blockDim.x) {
+        const int y = i / dst_w, x = i - y * dst_w;
+        const long long pos = (long long)mx0 + (long long)x * dx;
+        const int src_x = -1 + (int)(pos >> 14), mx = (int)(pos & 0x3fff);
+        const int8_t *F = b200_resize_filter[mx >> 8];
+        const pixel *const row = src + (ptrdiff_t)y * ss;
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += F[k] * (int)row[iclip(src_x - 3 + k, 0, src_w - 1)];
+        dst[(ptrdiff_t)y * ds + x] = (pixel)iclip((-s + 64) >> 7, 0, bdmax);
+    }
+}
+
 }  // namespace b200
 
 // =======================================================================================
@@ -941,6 +965,24 @@ int b200_mc_emu_edge(intptr_t bw, intptr_t bh, intptr_t iw, intptr_t ih, intptr_
     } while (0);
     free(stage);
     return rc;
+}
+
+int b200_resize_frame(int bitdepth_max, const B200ResizeFrame *fr, void *stream)
+{
+    if (check_bd(bitdepth_max, "b200_resize_frame")) return -2;
+    if (fr->n_planes <= 0) return 0;
+    if (fr->n_planes > 3 || !fr->src || !fr->dst) { b200_set_error("b200_resize_frame: bad arguments"); return -2; }
+    int most = 0;
+    for (int p = 0; p < fr->n_planes; p++) {
+        if (fr->dst_w[p] < 1 || fr->src_w[p] < 1 || fr->h[p] < 1) { b200_set_error("b200_resize_frame: bad geometry"); return -2; }
+        most = imax(most, fr->dst_w[p] * fr->h[p]);
+    }
+    const dim3 grid(imin((most + 255) / 256, 8 * 148), fr->n_planes);
+    if (bitdepth_max > 255) { auto k = resize_frame_kernel<true>; B200_LAUNCH_PDL(k, grid, dim3(256), 0, (cudaStream_t)stream, *fr, bitdepth_max); }
+    else { auto k = resize_frame_kernel<false>; B200_LAUNCH_PDL(k, grid, dim3(256), 0, (cudaStream_t)stream, *fr, bitdepth_max); }
+    b200_count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 int b200_mc_resize(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride, int dst_w, int h,

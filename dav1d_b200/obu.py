@@ -256,14 +256,17 @@ def key_frame(rng, w, h, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb
     b.f(7, 0 if intra_only is None else intra_only[0])   # order_hint
     if intra_only is not None:
         b.f(8, intra_only[1])                # refresh_frame_flags (a shown key frame refreshes all slots implicitly)
+    cw = w
     if super_res:
-        b.f(1, 1); b.f(3, int(rng.integers(0, 8)))   # use_superres, coded_denom
+        cd = int(rng.integers(0, 8))
+        b.f(1, 1); b.f(3, cd)                # use_superres, coded_denom: the frame is coded (cw wide) and upscaled to w after CDEF
+        cw = (w * 8 + (9 + cd) // 2) // (9 + cd)
     b.f(1, 0)                                # render_and_frame_size_different
     intrabc = 1 if (intrabc and screen_content and not super_res) else 0
     if screen_content and not super_res:
         b.f(1, intrabc)                      # allow_intrabc
     b.f(1, 0)                                # disable_frame_end_update_cdf
-    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout, segmentation, intrabc)
+    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, cw, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout, segmentation, intrabc)
     b.f(1, 1)                                # tx_mode_select
     b.f(1, int(rng.integers(0, 2)))          # reduced_tx_set
     if film_grain_seq:
@@ -376,7 +379,7 @@ def _poc_diff(bits, a, b):
 def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_rows=0, payload_bytes_per_sb64=3000, q=None,
                 lf=None, cdef=True, restoration=True, delta_q=True, cdef_on=1, restoration_on=1, film_grain_seq=0,
                 refresh=None, switchable_motion_mode=0, warped_motion_seq=0, comp_refs=1, allow_warped_motion=0, layout="420",
-                show_frame=1, global_motion=0, segmentation=0, max_size=None):
+                show_frame=1, global_motion=0, segmentation=0, max_size=None, super_res=0):
     """One shown inter frame (OBU_FRAME), primary_ref_frame = NONE. `ref_hints` = order hints held by the 8 reference slots
     (updated in place for the slots this frame refreshes). Global motion is identity. max_size = (W, H) of the sequence
     header when this frame is coded at another size (w, h): frame_size_override with an explicit size, so that its references
@@ -404,6 +407,14 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
             b.f(1, 0)                        # found_ref: the size is not taken from a reference ...
         wn, hn = max(1, int(max_size[0] - 1).bit_length()), max(1, int(max_size[1] - 1).bit_length())
         b.f(wn, w - 1); b.f(hn, h - 1)       # ... but written out (frame_width_minus_1, frame_height_minus_1)
+    cw = w
+    if super_res:                            # superres_params() of frame_size(): the sequence enables the tool, this frame may use it
+        use = int(rng.integers(0, 4) > 0)
+        b.f(1, use)
+        if use:
+            cd = int(rng.integers(0, 8))
+            b.f(3, cd)
+            cw = (w * 8 + (9 + cd) // 2) // (9 + cd)
     b.f(1, 0)                                # render_and_frame_size_different
     hp = int(rng.integers(0, 2))
     b.f(1, hp)                               # allow_high_precision_mv
@@ -413,7 +424,7 @@ def inter_frame(rng, w, h, order_hint, ref_hints, sb128=0, log2_cols=0, log2_row
         b.f(1, 0); b.f(2, int(rng.integers(0, 4)))
     b.f(1, switchable_motion_mode)
     b.f(1, 0)                                # disable_frame_end_update_cdf
-    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout, segmentation)
+    cols, rows, tile_w, tile_h, sbw, sbh = _frame_common(b, rng, cw, h, sb128, log2_cols, log2_rows, q, lf, cdef, restoration, delta_q, cdef_on, restoration_on, layout, segmentation)
     b.f(1, 1)                                # tx_mode_select
     b.f(1, comp_refs)                        # reference_select
     if comp_refs:                            # skip_mode_present exists only when two suitable references do (src/obu.c:929-987)
@@ -464,7 +475,7 @@ def show_existing_frame(slot):
 
 
 def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=0, motion_modes=0, film_grain=0, screen_content=0, layout="420",
-                 hidden_every=0, intra_only_every=0, sizes=None, **kw):
+                 hidden_every=0, intra_only_every=0, sizes=None, super_res=0, **kw):
     """Temporal units: one key frame, then n_frames - 1 inter frames (single and compound references incl. wedge /
     difference-weighted masks and distance weights, switchable interpolation filters, variable transform trees, intra
     blocks; identity global motion). motion_modes=1 additionally enables the per-block motion mode (overlapped block
@@ -472,19 +483,21 @@ def inter_stream(seed, w, h, n_frames=3, bpc=8, sb128=0, log2_cols=0, log2_rows=
     every k-th inter frame a hidden future frame (decoded early, referenced with backward prediction, output later by a
     show_existing_frame header)."""
     rng = np.random.default_rng(seed)
-    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=1 if motion_modes >= 2 else 0, warped_motion=1 if motion_modes else 0, film_grain=film_grain, screen_content=screen_content, layout=layout)
+    seq = sequence_header(w, h, bpc=bpc, sb128=sb128, inter_intra=1 if motion_modes >= 2 else 0, warped_motion=1 if motion_modes else 0, film_grain=film_grain, screen_content=screen_content, layout=layout, super_res=super_res)
     kw = dict(kw, layout=layout)
+    if super_res:                            # every frame may then be coded narrower and upscaled; its references keep their upscaled size
+        kw = dict(kw, super_res=1)
     if motion_modes:
         kw = dict(kw, switchable_motion_mode=1, warped_motion_seq=1, allow_warped_motion=1)
     if film_grain:
         kw = dict(kw, film_grain_seq=1)
     hints = [0] * 8
-    tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, film_grain_seq=film_grain, screen_content=screen_content, layout=layout))]
+    tus = [temporal_unit(seq, key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, film_grain_seq=film_grain, screen_content=screen_content, layout=layout, super_res=super_res))]
     for i in range(1, n_frames):
         if intra_only_every and i % intra_only_every == 0:
             refresh = int(rng.integers(1, 255))
             tus.append(temporal_unit(key_frame(rng, w, h, sb128=sb128, log2_cols=log2_cols, log2_rows=log2_rows, film_grain_seq=film_grain,
-                                               screen_content=screen_content, layout=layout, intra_only=(i % 128, refresh))))
+                                               screen_content=screen_content, layout=layout, intra_only=(i % 128, refresh), super_res=super_res)))
             for k in range(8):
                 if refresh & (1 << k):
                     hints[k] = i % 128

@@ -105,6 +105,18 @@ B200_API int b200_itx_add_batch_host(int bitdepth_max, int tx, const B200ItxBloc
                                      const int32_t stride_px[3], int zero_coefs);
 
 /* ==== mc (Dav1dMCDSPContext, reference src/mc.h:38-162, src/mc_tmpl.c) ================== */
+/* horizontal upscaling of whole planes with dav1d's `resize` (reference src/mc_tmpl.c:918-944): per plane dst_w samples per row
+ * from src_w, position step dx and start mx0 in 1/16384 sample units (f->resize_step / f->resize_start) */
+typedef struct B200ResizeFrame {
+    const void *src; void *dst;              /* device pictures */
+    uint32_t src_plane_off[3], dst_plane_off[3];
+    int32_t src_stride[3], dst_stride[3];    /* samples */
+    int32_t src_w[3], dst_w[3], h[3];
+    int32_t dx[3], mx0[3];
+    int32_t n_planes, pad;
+} B200ResizeFrame;
+B200_API int b200_resize_frame(int bitdepth_max, const B200ResizeFrame *frame, void *stream);
+
 #define B200_N_2D_FILTERS 10          /* enum Filter2d, reference src/levels.h:184-196 (9 = bilinear) */
 
 /* ---- mc: Level 2 (batched, device-resident) ---- */
@@ -613,6 +625,12 @@ typedef struct B200FrameJob {
     B200FgFrame fg;
     const B200BlendBlock *d_blend2;      /* second blend stage, after d_blend: OBMC blends the predictions of the blocks above */
     int32_t n_blend2, pad9;              /* (blend_h, stage 1) and then those of the blocks to the left (blend_v, stage 2) */
+    /* super-resolution (reference src/recon_tmpl.c:2053-2086, src/lf_apply_tmpl.c:73-87): after CDEF the frame, coded at a
+     * reduced width, is upscaled horizontally; loop restoration (lr.*) then runs on the upscaled pictures. resize[0] upscales the
+     * CDEF output (or the deblocked picture when CDEF is off), resize[1] the deblocked picture loop restoration reads its
+     * stripe-boundary rows from (n_planes = 0: not needed). */
+    int32_t run_resize, pad10;
+    B200ResizeFrame resize[2];
 } B200FrameJob;
 B200_API int b200_frame_run(const B200FrameJob *job, void *stream);
 /* n independent jobs of the same bit depth on one stream: reconstruction of every job, then ONE batched intra launch
@@ -621,7 +639,7 @@ B200_API int b200_frame_run_batch(const B200FrameJob *const *jobs, int n_jobs, v
 /* sizeof() of the ABI structs as compiled into the library (binding self-check): 0 McFrame, 1 McBlock, 2 CompBlock,
  * 3 BlendBlock, 4 WarpBlock, 5 ItxBlock, 6 LfFrame, 7 CdefFrame, 8 LrFrame, 9 FrameJob, 10 Av1Filter, 11 Av1Restoration,
  * 12 FgFrame, 13 FilmGrainData, 14 IntraTx, 15 IntraFrame, 16 McScaledBlock, 17 CoefBlock, 18 IntraSb, 19 CompFusedBlock,
- * 20 FrameBand */
+ * 20 FrameBand, 21 ResizeFrame */
 B200_API int b200_struct_size(int which);
 
 /* ==== band-sliced frame job + cross-GPU reference exchange ===================== */

@@ -574,7 +574,7 @@ API void b200hook_release(void)
         b200hook_buf_free(&h->tmp16); b200hook_buf_free(&h->cmask); b200hook_buf_free(&h->done_init);
         b200hook_buf_free(&h->pal);
         b200hook_buf_free(&h->warp); b200hook_buf_free(&h->blend); b200hook_buf_free(&h->blend2); b200hook_buf_free(&h->pxtmp);
-        b200hook_buf_free(&h->scaled);
+        b200hook_buf_free(&h->scaled); b200hook_buf_free(&h->sr[0]); b200hook_buf_free(&h->sr[1]);
         if (h->stream && g_be_ok) g_be.stream_destroy(h->stream);
         for (int t = 0; t < h->cap_tiles; t++)
             for (int l = 0; l < B200L_COUNT; l++) free(h->tiles[t].l[l].data);

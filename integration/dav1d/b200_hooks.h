@@ -69,6 +69,7 @@ typedef struct HookFrame {
     size_t n_pal, cap_pal;
     HookBuf warp, blend, blend2, pxtmp;      /* warped-motion 8x8 blocks; OBMC: blend_h stage, blend_v stage, pixel scratch (device only) */
     HookBuf scaled;                          /* predictions from references of another size (B200McScaledBlock) */
+    HookBuf sr[2];                           /* super-resolution: the upscaled deblocked / CDEF pictures loop restoration reads (device only) */
     int n_scaled;
     int n_pred, n_comp, n_comp2, n_itx[19], n_warp, n_blend, n_blend2;       /* totals over the tiles, known when the frame completes */
     HookTile *tiles;

@@ -53,26 +53,30 @@ typedef struct PicGeom { int stride[3]; uint32_t off[3]; int rows[3]; size_t byt
 /* Monochrome (4:0:0): the device picture keeps two dummy chroma planes in 4:2:0 geometry (the frame-wide sweeps walk three
  * planes; nothing is predicted or transformed into them, chroma deblocking is off, nothing of them is downloaded), so the
  * luma path is exactly the 4:2:0 one. */
-static void bitfn(pic_geom)(const Dav1dFrameContext *const f, PicGeom *const g)
+static void bitfn(geom_of)(const Dav1dPicture *const p, PicGeom *const g)
 {
-    const int mono = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I400;
-    const int ss_ver = mono || f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420;
-    const int rows = (f->cur.p.h + 127) & ~127;
-    g->stride[0] = (int)PXSTRIDE(f->cur.stride[0]);
-    g->stride[1] = g->stride[2] = mono ? g->stride[0] : (int)PXSTRIDE(f->cur.stride[1]);
+    const int mono = p->p.layout == DAV1D_PIXEL_LAYOUT_I400;
+    const int ss_ver = mono || p->p.layout == DAV1D_PIXEL_LAYOUT_I420;
+    const int rows = (p->p.h + 127) & ~127;
+    g->stride[0] = (int)PXSTRIDE(p->stride[0]);
+    g->stride[1] = g->stride[2] = mono ? g->stride[0] : (int)PXSTRIDE(p->stride[1]);
     g->rows[0] = rows; g->rows[1] = g->rows[2] = rows >> ss_ver;
     g->off[0] = 0;
     g->off[1] = (uint32_t)g->stride[0] * rows;
     g->off[2] = g->off[1] + (uint32_t)g->stride[1] * g->rows[1];
     g->bytes = ((size_t)g->off[2] + (size_t)g->stride[2] * g->rows[2]) * sizeof(pixel);
 }
+/* the picture being reconstructed (coded size) ... */
+static void bitfn(pic_geom)(const Dav1dFrameContext *const f, PicGeom *const g) { bitfn(geom_of)(&f->cur, g); }
+/* ... and the one that is output and referenced: the same picture, or with super-resolution the upscaled one (f->sr_cur) */
+#define OUT_KEY(f) ((const void *)(f)->sr_cur.p.data[0])
 
 /* first pass-2 hook call of a frame: its output picture (keyed by the host buffer) is not valid any more / yet */
 static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *const f)
 {
-    if (__atomic_load_n(&hf->started, __ATOMIC_ACQUIRE) && hf->cur_pic == f->cur.data[0]) return;
+    if (__atomic_load_n(&hf->started, __ATOMIC_ACQUIRE) && hf->cur_pic == OUT_KEY(f)) return;
     pthread_mutex_lock(&hf->lock);
-    if (hf->started && hf->cur_pic != f->cur.data[0]) {
+    if (hf->started && hf->cur_pic != OUT_KEY(f)) {
         /* the context's previous frame never completed (dav1d flushed or closed while it was being reconstructed) */
         hf->tile_sbrows_done = 0; hf->n_tx = 0; hf->n_coef = 0; hf->unsupported = 0;
         hf->n_pred = hf->n_comp = hf->n_comp2 = hf->n_warp = hf->n_blend = hf->n_blend2 = 0;
@@ -81,16 +85,14 @@ static void bitfn(frame_started)(HookFrame *const hf, const Dav1dFrameContext *c
         hf->started = 0;
     }
     if (!hf->started) {
-        hf->cur_pic = f->cur.data[0];
+        hf->cur_pic = OUT_KEY(f);
         if (b200hook_tiles_reset(hf, f->frame_hdr->tiling.cols * f->frame_hdr->tiling.rows)) __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
         hf->n_cmask = (sizeof(dav1d_masks) + 63) & ~(size_t)63;      /* dav1d's wedge tables sit at the head of the mask buffer */
         PicGeom g;
-        bitfn(pic_geom)(f, &g);
-        HookRefPic *const out = b200hook_refpic(f->cur.data[0], g.bytes, 1);
+        bitfn(geom_of)(&f->sr_cur.p, &g);
+        HookRefPic *const out = b200hook_refpic(OUT_KEY(f), g.bytes, 1);
         if (out) b200hook_refpic_set_ready(out, 0);
         else __atomic_fetch_or(&hf->unsupported, 8, __ATOMIC_RELAXED);
-        if (f->frame_hdr->width[0] != f->frame_hdr->width[1])        /* super-resolution: no upscaling stage in the frame job yet */
-            __atomic_fetch_or(&hf->unsupported, 1024, __ATOMIC_RELAXED);
         /* intra records and coefficients are appended without a lock by every tile thread of the frame (slots are taken
          * with atomic counters), so their buffers are sized for the worst case up front: one record per 4x4 cell of each
          * plane, 16 coefficients per cell, over the 128-aligned frame area */
@@ -820,9 +822,11 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
         fprintf(stderr, "b200hook: unsupported mask 0x%x (16 warped motion, 32 warp from a scaled reference, 64 intra block copy out of range, 256 inter-intra block size, 1024 super-resolution)\n", hf->unsupported);
         return -1;
     }
-    PicGeom g;
+    PicGeom g, gs;            /* the picture as coded; the picture that is output / referenced (wider with super-resolution) */
     bitfn(pic_geom)(f, &g);
+    bitfn(geom_of)(&f->sr_cur.p, &gs);
     const Dav1dFrameHeader *const hdr = f->frame_hdr;
+    const int superres = hdr->width[0] != hdr->width[1];
     const int mono = f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I400;         /* dummy 4:2:0 chroma planes on the device (pic_geom) */
     const int ss_ver = mono || f->cur.p.layout == DAV1D_PIXEL_LAYOUT_I420, ss_hor = f->cur.p.layout != DAV1D_PIXEL_LAYOUT_I444;
     const int n_sb128 = f->sb128w * f->sb128h;
@@ -850,13 +854,17 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
 #endif
     /* the finished picture goes into a buffer that outlives this frame context (later frames predict from it); the
      * other stages ping-pong through the context's own pictures */
-    HookRefPic *const outp = b200hook_refpic(f->cur.data[0], g.bytes, 1);
+    HookRefPic *const outp = b200hook_refpic(OUT_KEY(f), gs.bytes, 1);
     if (!outp) return -1;
     const int will_cdef = f->seq_hdr->cdef && (f->c->inloop_filters & DAV1D_INLOOPFILTER_CDEF);
     const int will_lr = f->lf.restore_planes && (f->c->inloop_filters & DAV1D_INLOOPFILTER_RESTORATION);
+    /* super-resolution: reconstruction, deblocking and CDEF stay in the context's own pictures (coded width); the upscaled CDEF
+     * picture u1 is the output itself unless loop restoration follows, which reads u1 and the upscaled deblocked picture u0 */
+    if (superres && (b200hook_buf_reserve(&hf->sr[0], gs.bytes, 0, 0) || b200hook_buf_reserve(&hf->sr[1], gs.bytes, 0, 0))) return -1;
+    void *const u0 = superres ? hf->sr[0].dev : NULL, *const u1 = superres ? (will_lr ? hf->sr[1].dev : outp->dev) : NULL;
     void *const p2 = will_lr ? outp->dev : hf->pic[2].dev;
-    void *const p1 = !will_lr && will_cdef ? outp->dev : hf->pic[1].dev;
-    void *const p0 = !will_lr && !will_cdef ? outp->dev : hf->pic[0].dev;
+    void *const p1 = !superres && !will_lr && will_cdef ? outp->dev : hf->pic[1].dev;
+    void *const p0 = !superres && !will_lr && !will_cdef ? outp->dev : hf->pic[0].dev;
     j.mc.dst = p0;
     const int inter = hf->is_inter;
     HookRefPic *rps[7];
@@ -999,8 +1007,27 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     /* loop restoration (:2100-2109), -> p2 */
     const int do_lr = f->lf.restore_planes && (f->c->inloop_filters & DAV1D_INLOOPFILTER_RESTORATION);
     j.run_lr = do_lr;
-    j.lr.cdef = do_cdef ? p1 : p0; j.lr.dbl = p0; j.lr.dst = p2;
-    for (int p = 0; p < 3; p++) { j.lr.plane_off[p] = g.off[p]; j.lr.stride[p] = g.stride[p]; }
+    j.lr.cdef = superres ? u1 : do_cdef ? p1 : p0; j.lr.dbl = superres ? u0 : p0; j.lr.dst = p2;
+    for (int p = 0; p < 3; p++) { j.lr.plane_off[p] = gs.off[p]; j.lr.stride[p] = gs.stride[p]; }
+    if (superres) {
+        /* the upscaling stage (dav1d_filter_sbrow_resize, :2053-2086; the rows loop restoration keeps of the deblocked picture
+         * are upscaled the same way, src/lf_apply_tmpl.c:73-87) */
+        j.run_resize = 1;
+        for (int k = 0; k < 2; k++) {
+            B200ResizeFrame *const rz = &j.resize[k];
+            if (k && !do_lr) break;                      /* nobody reads the upscaled deblocked picture */
+            rz->src = k ? p0 : (do_cdef ? p1 : p0); rz->dst = k ? u0 : u1;
+            rz->n_planes = mono ? 1 : 3;
+            for (int p = 0; p < 3; p++) {
+                const int sh = p && ss_hor, sv = p && ss_ver;
+                rz->src_plane_off[p] = g.off[p]; rz->dst_plane_off[p] = gs.off[p];
+                rz->src_stride[p] = g.stride[p]; rz->dst_stride[p] = gs.stride[p];
+                rz->src_w[p] = (4 * f->bw + sh) >> sh; rz->dst_w[p] = (f->sr_cur.p.p.w + sh) >> sh;
+                rz->h[p] = (f->cur.p.h + sv) >> sv;
+                rz->dx[p] = f->resize_step[!!p]; rz->mx0[p] = f->resize_start[!!p];
+            }
+        }
+    }
     j.lr.w = f->sr_cur.p.p.w; j.lr.h = f->sr_cur.p.p.h; j.lr.ss_hor = ss_hor; j.lr.ss_ver = ss_ver;
     j.lr.sb128 = f->seq_hdr->sb128; j.lr.sr_sb128w = f->sr_sb128w;
     j.lr.unit_size_log2[0] = hdr->restoration.unit_size[0]; j.lr.unit_size_log2[1] = hdr->restoration.unit_size[1];
@@ -1034,9 +1061,9 @@ static int bitfn(run_frame)(HookFrame *const hf, const Dav1dFrameContext *const 
     const int n_down = mono ? 1 : 3;
     for (int p = 0; p < n_down; p++) {
         const int rows = p ? (f->cur.p.h + ss_ver) >> ss_ver : f->cur.p.h;
-        down[p].host = f->cur.data[p];
-        down[p].dev = out + (size_t)g.off[p] * sizeof(pixel);
-        down[p].bytes = (uint64_t)rows * g.stride[p] * sizeof(pixel);
+        down[p].host = f->sr_cur.p.data[p];
+        down[p].dev = out + (size_t)gs.off[p] * sizeof(pixel);
+        down[p].bytes = (uint64_t)rows * gs.stride[p] * sizeof(pixel);
         d2h += down[p].bytes;
     }
     for (int i = 0; i < n_up; i++) h2d += up[i].bytes;
@@ -1085,7 +1112,7 @@ void bitfn(b200hook_backup_ipred_edge)(Dav1dTaskContext *const t)
     if (++hf->tile_sbrows_done >= total) {
         if (bitfn(run_frame)(hf, f)) {
             atomic_fetch_or(&f->task_thread.error, 1);      /* the frame is reported as a decoding error */
-            HookRefPic *const outp = b200hook_refpic(f->cur.data[0], 0, 0);
+            HookRefPic *const outp = b200hook_refpic(OUT_KEY(f), 0, 0);
             if (outp && !hf->pending) b200hook_refpic_set_ready(outp, 1);       /* after a failure nobody may wait for ever */
         }
         hf->tile_sbrows_done = 0; hf->n_tx = 0; hf->n_coef = 0; hf->unsupported = 0;

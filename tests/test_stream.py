@@ -219,12 +219,27 @@ def test_unused_references_are_not_waited_for(emu_decoder, seed):
     emu_decoder.stats(reset=True)
 
 
-def test_super_resolution_stream_fails_loudly(emu_decoder):
-    """super-resolution needs an upscaling stage the frame job does not have yet: an error, not a wrong picture"""
-    tus = obu.intra_stream(3, 256, 192, n_frames=1, super_res=1)
-    assert _ref_decode(tus)[0] == 1
-    assert emu_decoder.decode(tus)[0] < 0
-    emu_decoder.stats(reset=True)
+@pytest.mark.parametrize("w,h,kw", [(256, 192, dict(bpc=8)), (328, 200, dict(bpc=10, log2_cols=1)), (192, 136, dict(bpc=12, layout="444")),
+                                    (256, 192, dict(bpc=8, layout="400")), (320, 192, dict(bpc=8, film_grain=1))])
+def test_super_resolution_key_frames_decode(emu_decoder, w, h, kw):
+    """super-resolution (was refused until round 2): the frame is coded narrower, upscaled after CDEF by the job's resize stage
+    (both the CDEF picture and the deblocked picture loop restoration reads), restored and output at full width"""
+    for seed in range(3):
+        tus = obu.intra_stream(900 + seed, w, h, n_frames=2, super_res=1, **kw)
+        _check(emu_decoder, tus, 2, apply_grain=1)
+
+
+@pytest.mark.parametrize("w,h,kw", [(256, 192, dict(bpc=8)), (328, 200, dict(bpc=10, log2_cols=1, motion_modes=1)),
+                                    (192, 136, dict(bpc=12, layout="444", motion_modes=2)), (320, 192, dict(bpc=8, film_grain=1, intra_only_every=3))])
+def test_super_resolution_inter_streams_decode(emu_decoder, w, h, kw):
+    """inter frames with super-resolution: every reference is the upscaled picture of an earlier frame while the frame itself
+    is coded narrower, so all of its predictions are scaled predictions"""
+    n_scaled = 0
+    for seed in range(2):
+        tus = obu.inter_stream(950 + seed, w, h, n_frames=6, super_res=1, **kw)
+        _check(emu_decoder, tus, 6, apply_grain=1)
+        n_scaled += emu_decoder.last_stats["scaled"]
+    assert n_scaled > 100
 
 
 def test_monochrome_stream_decodes(emu_decoder):
