@@ -222,7 +222,17 @@ typedef void *cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
-static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = n ? aligned_alloc(256, (n + 255) & ~(size_t)255) : nullptr; return cudaSuccess; }
+// "device" memory is poisoned on allocation (like real device memory it is NOT zero): a kernel that reads what nothing wrote
+// shows up as a mismatch in the emulator tests too (B200_EMU_POISON=0 switches the fill off)
+static inline cudaError_t cudaMalloc(void **p, size_t n)
+{
+    const size_t sz = (n + 255) & ~(size_t)255;
+    *p = n ? aligned_alloc(256, sz) : nullptr;
+    static int poison = -1;
+    if (poison < 0) { const char *e = getenv("B200_EMU_POISON"); poison = !e || atoi(e) != 0; }
+    if (*p && poison) memset(*p, 0xA5, sz);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMallocHost(void **p, size_t n) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
