@@ -171,6 +171,8 @@ def main(argv=None):
     ap.add_argument("--filmgrain", type=int, default=1, help="apply film grain (dav1d --filmgrain)")
     ap.add_argument("--backend", default="b200", help="b200 (default) or the path of another build of the libb200av1 C ABI")
     ap.add_argument("--one-job-at-a-time", action="store_true", help="serialise the device jobs (for back ends that are not re-entrant)")
+    ap.add_argument("--frametimes", metavar="FILE", help="write one line per output frame: nanoseconds since the previous one (like `dav1d --frametimes`)")
+    ap.add_argument("-q", "--quiet", action="store_true", help="no progress / speed line")
     args = ap.parse_args(argv)
     if bool(args.input) == bool(args.synth):
         ap.error("give exactly one of -i / --synth")
@@ -185,8 +187,15 @@ def main(argv=None):
     t0 = time.perf_counter()
     dec = stream.HookedDecoder(backend=None if args.backend == "b200" else args.backend, serialize=args.one_job_at_a_time)
     n, info, packed = dec.decode(tus, **kw)
+    times = dec.output_times_ns()
     dec.release()
     dt = time.perf_counter() - t0
+    if args.frametimes:
+        # tools/dav1d.c synchronize(): elapsed time between consecutive output frames, in nanoseconds, one per line
+        with open(args.frametimes, "w") as fh:
+            last = 0
+            for t in times:
+                fh.write("%d\n" % (t - last)); last = t
     if n < 0:
         print("decoding failed: dav1d error %d" % n, file=sys.stderr)
         return 1
@@ -204,7 +213,10 @@ def main(argv=None):
             print("md5 mismatch: %s != %s" % (digest, args.verify), file=sys.stderr)
             return 2
     px = sum(int(w) * int(h) for w, h, _, _ in info)
-    print("decoded %d frames in %.3f s (%.1f fps, %.1f Mpixels/s)" % (n, dt, n / dt, px / dt / 1e6), file=sys.stderr)
+    if not args.quiet:
+        # tools/dav1d.c print_stats(): "Decoded n/num frames (100.0%) - x fps" (the decoder's own clock: first byte in to last frame out)
+        d_fps = 1e9 * n / times[-1] if times and times[-1] else n / dt
+        print("Decoded %d/%d frames (100.0%%) - %.2f fps (%.1f Mpixels/s; %.3f s incl. start-up)" % (n, n, d_fps, px * d_fps / max(n, 1) / 1e6, dt), file=sys.stderr)
     return 0
 
 

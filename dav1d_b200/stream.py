@@ -89,6 +89,13 @@ class HookedDecoder:
     def decode(self, tus, **kw):
         return decode_stream(self.dll, tus, **kw)
 
+    def output_times_ns(self):
+        """when each picture of the last decode() came out of dav1d_get_picture: nanoseconds since the call began"""
+        buf = (C.c_uint64 * 4096)()
+        self.dll.refdrv_output_times_ns.restype = C.c_int
+        n = self.dll.refdrv_output_times_ns(buf, 4096)
+        return [int(buf[i]) for i in range(n)]
+
     def stats(self, reset=False):
         s = HookStats()
         self.dll.b200hook_get_stats(C.byref(s), 1 if reset else 0)

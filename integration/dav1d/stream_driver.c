@@ -12,9 +12,23 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "dav1d/dav1d.h"
 
 #define API __attribute__((visibility("default")))
+
+/* when each picture of the last refdrv_decode_stream call came out of dav1d_get_picture, nanoseconds since the call began
+ * (what tools/dav1d.c's --frametimes is made of, reference tools/dav1d.c:94-116) */
+#define MAX_TIMES 4096
+static uint64_t g_out_ns[MAX_TIMES];
+static int g_n_out;
+static uint64_t now_ns(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; }
+API int refdrv_output_times_ns(uint64_t *out, int max)
+{
+    const int n = g_n_out < max ? g_n_out : max;
+    for (int i = 0; i < n; i++) out[i] = g_out_ns[i];
+    return n;
+}
 
 static void nop_free(const uint8_t *d, void *c) { (void)d; (void)c; }
 
@@ -48,6 +62,8 @@ API int refdrv_decode_stream(const uint8_t *data, const uint64_t *tu_sz, int n_t
     s.n_threads = n_threads;
     s.max_frame_delay = max_frame_delay;
     s.apply_grain = apply_grain;
+    const uint64_t t_begin = now_ns();
+    g_n_out = 0;
     int res = dav1d_open(&c, &s);
     if (res < 0) return res;
     int n_pics = 0;
@@ -74,6 +90,7 @@ API int refdrv_decode_stream(const uint8_t *data, const uint64_t *tu_sz, int n_t
                 if (r == DAV1D_ERR(EAGAIN)) { if (i < n_tu || ++again >= 2) break; continue; }
                 again = 0;
                 if (r < 0) { res = r; if (i < n_tu) dav1d_data_unref(&d); goto done; }
+                if (g_n_out < MAX_TIMES) g_out_ns[g_n_out++] = now_ns() - t_begin;
                 if (n_pics < max_pics) {
                     const size_t n = pack(&p, out + pos, (size_t)out_cap - pos, info + 4 * n_pics);
                     if (!n) { dav1d_picture_unref(&p); res = DAV1D_ERR(ENOMEM); if (i < n_tu) dav1d_data_unref(&d); goto done; }

@@ -562,6 +562,12 @@ def test_cli_md5_y4m_and_obu_file_roundtrip(tmp_path, capsys):
     r0, info0, out0 = _ref_decode(tus, apply_grain=1)
     want, n = cli.md5_of(cli.frames_of(info0, out0))
     assert r0 == 3 and n == 3 and got == want
+    # --frametimes: one line per output frame (nanoseconds since the previous one), and the "Decoded n/n frames - x fps" line of tools/dav1d.c
+    ft = str(tmp_path / "ft.txt")
+    assert cli.main(common + ["--muxer", "null", "--frametimes", ft]) == 0
+    lines = open(ft).read().split()
+    assert len(lines) == 3 and all(int(v) >= 0 for v in lines) and sum(map(int, lines)) > 0
+    assert "Decoded 3/3 frames (100.0%) - " in capsys.readouterr().err
     # the same stream wrapped in IVF and in Annex B (size-less OBUs) demuxes to the same temporal units and the same md5
     ivf = b"DKIF" + (0).to_bytes(2, "little") + (32).to_bytes(2, "little") + b"AV01" + (208).to_bytes(2, "little") + \
           (144).to_bytes(2, "little") + (25).to_bytes(4, "little") + (1).to_bytes(4, "little") + (3).to_bytes(4, "little") + bytes(4)
