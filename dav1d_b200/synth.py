@@ -696,11 +696,17 @@ def ordered_tiling(rng, w4, h4, max_log=4, min_log=1, p_split=0.6):
     return out
 
 
-def make_intra_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, p_skip=0.2, p_cfl=0.25):
+MODE_RESID, MODE_IBC = 16, 18
+
+
+def make_intra_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, p_skip=0.2, p_cfl=0.25, p_ibc=0.0):
     """Synthetic intra-only frame (BASELINE configs[1]): every block intra predicted (all 13 modes with angle deltas,
     filter-intra, CFL) at transform-block granularity + residual, deblocking parameters. W, H multiples of 8
     (dav1d's f->bw / f->bh are even). Availability of the top-right / bottom-left neighbours follows decode order
-    geometrically (a superset of the bitstream rule; what matters to the kernels is that it is consistent)."""
+    geometrically (a superset of the bitstream rule; what matters to the kernels is that it is consistent).
+    p_ibc: that share of the blocks below the first superblock row is an intra block copy instead (B200_INTRA_MODE_IBC, one
+    record per plane + RESID records): copied, with dav1d's bilinear put, from anywhere in the superblock rows above — whole
+    luma samples, hence half-sample phases in sub-sampled chroma for odd vectors (reference src/recon_tmpl.c:1583-1596)."""
     assert W % 8 == 0 and H % 8 == 0
     bd = (1 << bpc) - 1
     dt = np.uint8 if bpc == 8 else np.uint16
@@ -754,11 +760,51 @@ def make_intra_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, p_skip=0.2, p_cfl=0.25)
             r["luma_off"] = off[0] + (by4 & ~ss_ver) * 4 * stride[0] + (bx4 & ~ss_hor) * 4
         recs.append(r)
 
+    def add_ibc(pl, x, y, tw, th, sx, sy, mx, my, resid):
+        """an IBC record of plane pl: block at (x, y), tw x th [4-sample units], source sample position (sx, sy) + phase"""
+        r = np.zeros(1, INTRA_TX_DT)[0]
+        r["dst_off"] = off[pl] + y * 4 * stride[pl] + x * 4
+        r["x4"], r["y4"], r["xend4"], r["yend4"] = x, y, pw4[pl], ph4[pl]
+        r["tx"] = TX_FROM_WH[(4 * tw, 4 * th)]
+        r["mode"], r["plane"], r["eob"] = MODE_IBC, pl, -1
+        r["luma_off"] = (sy << 16) | sx
+        r["cfl_w_pad"], r["cfl_h_pad"], r["cfl_alpha"] = mx, my, 1 if resid else 0
+        order[pl][y:y + th, x:x + tw] = len(recs)
+        recs.append(r)
+
     for (x4, y4, lwv, lhv) in ordered_tiling(rng, w4, h4):
         bw4, bh4 = 1 << lwv, 1 << lhv
         cw, chh = min(bw4, w4 - x4), min(bh4, h4 - y4)                         # clipped block size (w4, h4 in :1188)
         skip = rng.random() < p_skip
         small = bw4 <= 8 and bh4 <= 8
+        if p_ibc and y4 >= 16 and cw == bw4 and chh == bh4 and rng.random() < p_ibc:
+            # ---- intra block copy from the superblock rows above (all of them are reconstructed: superblock raster order)
+            sx = int(rng.integers(0, 4 * w4 - 4 * bw4 + 1)); sy = int(rng.integers(0, (y4 >> 4) * 64 - 4 * bh4 + 1))
+            dx, dy = sx - 4 * x4, sy - 4 * y4                                   # the (whole-sample) luma vector
+            add_ibc(0, x4, y4, bw4, bh4, sx, sy, 0, 0, not skip)
+            ymode[y4:y4 + bh4, x4:x4 + bw4] = 0; uvmode[y4:y4 + bh4, x4:x4 + bw4] = 0
+            tlw, tlh = min(lwv, 4), min(lhv, 4)
+            if rng.random() < 0.5 and tlw > 0 and tlh > 0:
+                tlw -= 1; tlh -= 1
+            for yy in range(0, bh4, 1 << tlh):
+                for xx in range(0, bw4, 1 << tlw):
+                    paint(ty, x4 + xx, y4 + yy, tlw, tlh, h4, w4)
+                    if not skip:
+                        add(0, x4 + xx, y4 + yy, tlw, tlh, MODE_RESID, 0, 0, False, x4, y4)
+            clw, clh = lwv - ss_hor, lhv - ss_ver
+            cx4, cy4 = x4 >> ss_hor, y4 >> ss_ver
+            ctl, cth = min(clw, 3), min(clh, 3)
+            for pl in (1, 2):
+                # chroma: mv >> (3 + ss) whole samples, (mv & 15) the phase of the bilinear filter (mc(), :948-956)
+                csx = (cx4 * 4 + (dx >> 1)) if ss_hor else sx; csy = (cy4 * 4 + (dy >> 1)) if ss_ver else sy
+                add_ibc(pl, cx4, cy4, 1 << clw, 1 << clh, csx, csy, (dx & 1) * 8 if ss_hor else 0, (dy & 1) * 8 if ss_ver else 0, not skip)
+                for yy in range(0, 1 << clh, 1 << cth):
+                    for xx in range(0, 1 << clw, 1 << ctl):
+                        if pl == 1:
+                            paint(tuv, cx4 + xx, cy4 + yy, ctl, cth, ch4, cw4)
+                        if not skip:
+                            add(pl, cx4 + xx, cy4 + yy, ctl, cth, MODE_RESID, 0, 0, False, x4, y4)
+            continue
         # ---- luma
         m = int(rng.integers(0, 13))
         ang = int(rng.integers(-3, 4)) if 1 <= m <= 8 else 0
@@ -845,6 +891,17 @@ def make_intra_frame(rng, bpc, W, H, ss_hor=1, ss_ver=1, p_skip=0.2, p_cfl=0.25)
         wm = wave_map[pl]
         fl = int(r["flags"])
         dep = 0
+        if r["mode"] == MODE_RESID:                     # after the record that predicted these cells
+            wave[i] = int(wm[y:y + th, x:x + tw].max()) + 1
+            wm[y:y + th, x:x + tw] = wave[i]
+            continue
+        if r["mode"] == MODE_IBC:                       # after every cell its source rectangle touches
+            sx, sy = int(r["luma_off"]) & 0xffff, int(r["luma_off"]) >> 16
+            x1 = min((sx + 4 * tw - 1 + (1 if r["cfl_w_pad"] else 0)) >> 2, pw4[pl] - 1)
+            y1 = min((sy + 4 * th - 1 + (1 if r["cfl_h_pad"] else 0)) >> 2, ph4[pl] - 1)
+            wave[i] = int(wm[min(sy >> 2, ph4[pl] - 1):y1 + 1, min(sx >> 2, pw4[pl] - 1):x1 + 1].max()) + 1
+            wm[y:y + th, x:x + tw] = wave[i]
+            continue
         if fl & 1:
             nrow = min(th, ph4[pl] - y) + (min(th, ph4[pl] - y - th) if (fl & 8) and y + th < ph4[pl] else 0)
             dep = max(dep, int(wm[y:y + nrow, x - 1].max()))

@@ -19,6 +19,9 @@ void oracle_cfl_pred(int mode, void *dst, ptrdiff_t stride_bytes, const void *to
 void oracle_pal_pred(void *dst, ptrdiff_t stride_bytes, const void *pal, const uint8_t *idx, int w, int h, int bdmax);
 void oracle_blend(void *dst, ptrdiff_t dst_stride, const void *tmp, int w, int h, const uint8_t *mask, int bdmax);
 int oracle_inv_txfm_add(void *dst, ptrdiff_t stride_bytes, void *coeff, int eob, int tx, int txtp, int bdmax);
+void oracle_emu_edge(intptr_t bw, intptr_t bh, intptr_t iw, intptr_t ih, intptr_t x, intptr_t y, void *dst, ptrdiff_t dst_stride,
+                     const void *ref, ptrdiff_t ref_stride, int bdmax);
+void oracle_mc_put(void *dst, ptrdiff_t dst_stride, const void *src, ptrdiff_t src_stride, int w, int h, int mx, int my, int filter2d, int bdmax);
 
 static const uint8_t k_w4[19] = { 1, 2, 4, 8, 16, 1, 2, 2, 4, 4, 8, 8, 16, 1, 4, 2, 8, 4, 16 };
 static const uint8_t k_h4[19] = { 1, 2, 4, 8, 16, 2, 1, 4, 2, 8, 4, 16, 8, 4, 1, 8, 2, 16, 4 };
@@ -97,6 +100,14 @@ ORACLE_API void oracle_intra_frame(int bdmax, const B200IntraFrame *f, const B20
         } else if (r->mode == B200_INTRA_MODE_PAL) {
             const uint8_t *pd = f->pal + r->luma_off;
             oracle_pal_pred(dst, st * (ptrdiff_t)px, pd, pd + 8 * px, w, h, bdmax);
+        } else if (r->mode == B200_INTRA_MODE_IBC) {
+            /* intra block copy: mc() with the picture itself as reference and the bilinear filter (reference
+             * src/recon_tmpl.c:1583-1596, 938-988): emu_edge window against the plane area w4*4 x h4*4, then put_bilin */
+            static __thread uint8_t win[72 * 72 * 2];
+            const int pl = r->plane, sx = (int)(r->luma_off & 0xffff), sy = (int)(r->luma_off >> 16);
+            const uint8_t *plane = (const uint8_t *)f->pic + ((size_t)r->dst_off - ((size_t)r->y4 * 4 * st + (size_t)r->x4 * 4)) * px;
+            oracle_emu_edge(w + 7, h + 7, f->w4[pl] * 4, f->h4[pl] * 4, sx - 3, sy - 3, win, 72 * (ptrdiff_t)px, plane, st * (ptrdiff_t)px, bdmax);
+            oracle_mc_put(dst, st * (ptrdiff_t)px, win + (3 * 72 + 3) * px, 72 * (ptrdiff_t)px, w, h, r->cfl_w_pad, r->cfl_h_pad, 9, bdmax);
         } else if (r->mode == B200_INTRA_MODE_II) {
             /* the predictor named by `angle` over the whole block into a scratch, then dsp->mc.blend with the mask */
             uint16_t tmp16[64 * 64];

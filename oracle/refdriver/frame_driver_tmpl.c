@@ -424,6 +424,23 @@ static void bitfn(intra_records)(const int bitdepth_max, const B200IntraFrame *c
             /* the reference's own pal_pred over the whole block (src/recon_tmpl.c:1220) */
             const pixel *const pal = (const pixel *)(fr->pal + r->luma_off);
             ip.pal_pred(dst, stride, pal, (const uint8_t *)(pal + 8), t->w * 4, t->h * 4);
+        } else if (r->mode == B200_INTRA_MODE_IBC) {
+            /* the reference's own mc() route for intra block copy (src/recon_tmpl.c:1583-1596, 956-988): emu_edge when the
+             * footprint leaves the plane area, then mc[FILTER_2D_BILINEAR] */
+            ALIGN_STK_64(pixel, emu, 192 * 72,);
+            const int pl = r->plane, w = t->w * 4, h = t->h * 4, mx = r->cfl_w_pad, my = r->cfl_h_pad;
+            const int dx = (int)(r->luma_off & 0xffff), dy = (int)(r->luma_off >> 16), iw = fr->w4[pl] * 4, ih = fr->h4[pl] * 4;
+            const pixel *const plane = (const pixel *)fr->pic + r->dst_off - ((ptrdiff_t)r->y4 * 4 * fr->stride[pl] + r->x4 * 4);
+            const pixel *src;
+            ptrdiff_t rs = stride;
+            if (dx < !!mx * 3 || dy < !!my * 3 || dx + w + !!mx * 4 > iw || dy + h + !!my * 4 > ih) {
+                mcd.emu_edge(w + !!mx * 7, h + !!my * 7, iw, ih, dx - !!mx * 3, dy - !!my * 3, emu, 192 * sizeof(pixel), plane, stride);
+                src = &emu[192 * !!my * 3 + !!mx * 3];
+                rs = 192 * sizeof(pixel);
+            } else {
+                src = plane + (ptrdiff_t)dy * fr->stride[pl] + dx;
+            }
+            mcd.mc[FILTER_2D_BILINEAR](dst, stride, src, rs, w, h, mx, my HIGHBD_TAIL_SUFFIX);
         } else if (r->mode == B200_INTRA_MODE_II) {
             /* the reference's own edge preparation, predictor and blend (src/recon_tmpl.c:1601-1626) */
             pixel tmp[64 * 64];

@@ -6,6 +6,7 @@ intra_pred / cfl_ac / cfl_pred and itxfm_add functions driven record by record (
 kernel is then checked against the oracle, with the records in decode order and in wavefront order.
 """
 import ctypes as C
+import os
 import numpy as np
 import pytest
 
@@ -96,6 +97,49 @@ def test_emu_intra_frame(bpc, W, H, ssh, ssv):
     got = run_lib(refs.emu_lib(), frame.NumpyAlloc(), S, sb=True)            # superblock-granular schedule
     ok, where = planes_equal(S, exp, got)
     assert ok, ("sb", where)
+
+
+IBC_CASES = [(8, 328, 264, 1, 1), (10, 264, 200, 1, 1), (12, 200, 264, 0, 0), (8, 264, 264, 1, 0)]
+
+
+@pytest.mark.emu
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", IBC_CASES)
+def test_intra_block_copy_oracle_reference_and_kernel(bpc, W, H, ssh, ssv):
+    """intra block copy records (B200_INTRA_MODE_IBC + RESID): blocks copied with the bilinear put from arbitrary (unaligned,
+    odd-vector) positions in the superblock rows above; the oracle's restatement, dav1d's own emu_edge + mc[BILINEAR] and the
+    intra machine (wavefront order and decode order, both kernels) give the same picture"""
+    S = synth.make_intra_frame(np.random.default_rng(740 + bpc + W), bpc, W, H, ssh, ssv, p_ibc=0.3)
+    t = S["intra_tx"]
+    assert (t["mode"] == synth.MODE_IBC).sum() > 12 and (t["mode"] == synth.MODE_RESID).sum() > 12
+    if ssh:
+        assert ((t["mode"] == synth.MODE_IBC) & (t["cfl_w_pad"] == 8)).sum() > 3, "no half-sample chroma phase"
+    exp = oracle_intra(S)
+    S0 = dict(S); S0["intra_tx"] = t[t["mode"] != synth.MODE_IBC]
+    assert not planes_equal(S, exp, oracle_intra(S0))[0]                   # the copies matter
+    if refs.have_ref():
+        ok, where = planes_equal(S, reference_intra(S), exp)
+        assert ok, ("reference", where)
+    for order in ("intra_tx", "intra_tx_decode_order"):
+        got = run_lib(refs.emu_lib(), frame.NumpyAlloc(), S, order=order, compact=order == "intra_tx")
+        ok, where = planes_equal(S, exp, got)
+        assert ok, (order, where)
+    os.environ["B200_INTRA_CTA"] = "1"                                       # the CTA-per-block kernel (read once per process:
+    try:                                                                     # effective only if this is the first intra launch)
+        got = run_lib(refs.emu_lib(), frame.NumpyAlloc(), S)
+    finally:
+        del os.environ["B200_INTRA_CTA"]
+    ok, where = planes_equal(S, exp, got)
+    assert ok, ("cta", where)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bpc,W,H,ssh,ssv", IBC_CASES[:2] + [(8, 1288, 720, 1, 1)])
+def test_gpu_intra_block_copy(bpc, W, H, ssh, ssv):
+    S = synth.make_intra_frame(np.random.default_rng(760 + bpc + W), bpc, W, H, ssh, ssv, p_ibc=0.3)
+    exp = oracle_intra(S)
+    got = run_lib(None, None, S)
+    ok, where = planes_equal(S, exp, got)
+    assert ok, where
 
 
 def check_batch(lib, alloc_fn, n, bpc=8, W=136, H=72, with_lf=True):
