@@ -175,6 +175,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# stage name (stage_times) -> key of frame_algorithmic_bytes
+STAGE_BYTES_KEY = {"pred": "mc", "warp": "warp", "blend": "blend", "comp": "comp", "itx": "itx", "intra": "intra", "deblock": "deblock",
+                   "cdef": "cdef", "lr": "lr", "fg": "fg"}
+STAGE_NAMES = tuple(STAGE_BYTES_KEY)          # every name stage_times() can return
+
+
 def frame_algorithmic_bytes(S, fused=False):
     """SURVEY.md §8(d) accounting for one frame, per stage (bytes); px = bytes per pixel."""
     px = S["pic"].itemsize
@@ -607,7 +613,7 @@ def run_ours_frame(args):
         alg = frame_algorithmic_bytes(Ss[0], fused=bool(fbs[0].job.n_cfused))
         stages = {}
         for name, ms in stage_ms.items():
-            key = {"pred": "mc", "warp": "warp", "blend": "blend", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg", "intra": "intra"}[name]
+            key = STAGE_BYTES_KEY[name]
             stages[name] = {"ms": ms, "algorithmic_bytes": alg[key], "GBps": alg[key] / (ms * 1e-3) / 1e9 if ms > 0 else None}
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         traffic = None
@@ -615,7 +621,7 @@ def run_ours_frame(args):
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(dom)
         achieved = stages[dom]["GBps"]
-        run_keys = {"pred": "mc", "warp": "warp", "blend": "blend", "comp": "comp", "itx": "itx", "intra": "intra", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg"}
+        run_keys = STAGE_BYTES_KEY
         total_alg = sum(alg[run_keys[k]] for k in stage_ms)
         recon_ms = sum(v for k, v in stage_ms.items() if k in ("pred", "warp", "blend", "comp", "itx", "intra"))
         post_ms = sum(v for k, v in stage_ms.items() if k in ("deblock", "cdef", "lr", "fg"))
@@ -812,7 +818,7 @@ def run_ours_gop(args):
         peak, peak_src = measured_peak()
         fb0 = sets[0]
         alg = frame_algorithmic_bytes(fb0.S, fused=bool(fb0.job.n_cfused))
-        key = {"pred": "mc", "warp": "warp", "blend": "blend", "comp": "comp", "itx": "itx", "deblock": "deblock", "cdef": "cdef", "lr": "lr", "fg": "fg", "intra": "intra"}
+        key = STAGE_BYTES_KEY
         stages = {n: {"ms": ms, "algorithmic_bytes": alg[key[n]], "GBps": alg[key[n]] / (ms * 1e-3) / 1e9 if ms > 0 else None,
                       "frac": alg[key[n]] / (ms * 1e-3) / 1e9 / peak if ms > 0 else None} for n, ms in stage_ms.items()}
         tot_ms = sum(stage_ms.values())
