@@ -105,7 +105,8 @@ static int backend_bound_quietly(void)
  * aligned dimensions, 64 bytes more when a stride would be a multiple of 1024) — pic_geom() of the emitters derives the
  * device picture from the host strides. Buffers come from a pool (cudaHostAlloc costs about a millisecond); released
  * pictures go back to it, b200hook_release() frees the idle ones. */
-static struct { void *ptr; size_t cap; int used; } g_pin_pool[128];
+#define PIN_POOL 1024
+static struct { void *ptr; size_t cap; int used; } g_pin_pool[PIN_POOL];
 static pthread_mutex_t g_pin_lock = PTHREAD_MUTEX_INITIALIZER;
 static int pinned_pic_alloc(Dav1dPicture *const p, void *const cookie)
 {
@@ -124,12 +125,12 @@ static int pinned_pic_alloc(Dav1dPicture *const p, void *const cookie)
     const size_t need = y_sz + 2 * uv_sz + DAV1D_PICTURE_ALIGNMENT;
     int slot = -1, empty = -1;
     pthread_mutex_lock(&g_pin_lock);
-    for (int i = 0; i < 128; i++) {
+    for (int i = 0; i < PIN_POOL; i++) {
         if (!g_pin_pool[i].ptr) { if (empty < 0) empty = i; continue; }
         if (!g_pin_pool[i].used && g_pin_pool[i].cap >= need && (slot < 0 || g_pin_pool[i].cap < g_pin_pool[slot].cap)) slot = i;
     }
     if (slot < 0 && empty < 0)                      /* pool full of buffers that are too small: drop an idle one */
-        for (int i = 0; i < 128 && empty < 0; i++)
+        for (int i = 0; i < PIN_POOL && empty < 0; i++)
             if (!g_pin_pool[i].used) { be->host_free(g_pin_pool[i].ptr); g_pin_pool[i].ptr = NULL; empty = i; }
     if (slot < 0 && empty >= 0) {
         void *const mem = be->host_alloc(need);
@@ -151,7 +152,7 @@ static void pinned_pic_release(Dav1dPicture *const p, void *const cookie)
 {
     (void)cookie;
     const int slot = (int)(intptr_t)p->allocator_data - 1;
-    if (slot < 0 || slot >= 128) return;
+    if (slot < 0 || slot >= PIN_POOL) return;
     /* dav1d dropped its last reference to the picture: nothing decodes from it or outputs it any more, so its device copy's
      * table entry is free for the next picture (its device buffer is kept for reuse). With dav1d's own allocator there is no
      * such signal and the table falls back to least-recently-used recycling. */
@@ -163,7 +164,7 @@ static void pinned_pic_release(Dav1dPicture *const p, void *const cookie)
 static void pinned_pool_trim(void)
 {
     pthread_mutex_lock(&g_pin_lock);
-    for (int i = 0; i < 128; i++)
+    for (int i = 0; i < PIN_POOL; i++)
         if (g_pin_pool[i].ptr && !g_pin_pool[i].used && g_be_ok) { g_be.host_free(g_pin_pool[i].ptr); g_pin_pool[i].ptr = NULL; g_pin_pool[i].cap = 0; }
     pthread_mutex_unlock(&g_pin_lock);
 }
