@@ -132,16 +132,6 @@ def test_intra_block_copy_oracle_reference_and_kernel(bpc, W, H, ssh, ssv):
     assert ok, ("cta", where)
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("bpc,W,H,ssh,ssv", IBC_CASES[:2] + [(8, 1288, 720, 1, 1)])
-def test_gpu_intra_block_copy(bpc, W, H, ssh, ssv):
-    S = synth.make_intra_frame(np.random.default_rng(760 + bpc + W), bpc, W, H, ssh, ssv, p_ibc=0.3)
-    exp = oracle_intra(S)
-    got = run_lib(None, None, S)
-    ok, where = planes_equal(S, exp, got)
-    assert ok, where
-
-
 def check_batch(lib, alloc_fn, n, bpc=8, W=136, H=72, with_lf=True):
     """n different frames through b200_frame_run_batch (one intra launch for all of them) against the oracle"""
     import test_loopfilter as TLF

@@ -431,25 +431,6 @@ def test_new_layouts_and_intra_block_copy_gpu(gpu_decoder):
 
 
 @pytest.mark.gpu
-def test_scaled_references_and_super_resolution_gpu(gpu_decoder):
-    """on the device: frames coded at changing sizes (scaled predictions against per-reference geometry) and super-resolution
-    (resize stage before loop restoration; later frames predict from the upscaled pictures), key and inter frames"""
-    n_scaled = 0
-    for seed, (w, h, sizes, kw) in enumerate([(256, 192, [(192, 144), (256, 192), (160, 96)], dict(bpc=8)),
-                                              (320, 192, [(256, 160), (320, 192), (200, 120), (320, 176)], dict(bpc=10, motion_modes=1, film_grain=1))]):
-        tus = obu.inter_stream(700 + seed, w, h, n_frames=6, sizes=sizes, **kw)
-        _check(gpu_decoder, tus, 6, apply_grain=1)
-        n_scaled += gpu_decoder.last_stats["scaled"]
-    for seed, (w, h, kw) in enumerate([(328, 200, dict(bpc=10, log2_cols=1)), (256, 192, dict(bpc=8, layout="400")), (320, 192, dict(bpc=8, film_grain=1))]):
-        _check(gpu_decoder, obu.intra_stream(900 + seed, w, h, n_frames=2, super_res=1, **kw), 2, apply_grain=1)
-    for seed, (w, h, kw) in enumerate([(256, 192, dict(bpc=8)), (328, 200, dict(bpc=10, log2_cols=1, motion_modes=1))]):
-        tus = obu.inter_stream(950 + seed, w, h, n_frames=6, super_res=1, **kw)
-        _check(gpu_decoder, tus, 6, apply_grain=1)
-        n_scaled += gpu_decoder.last_stats["scaled"]
-    assert n_scaled > 100
-
-
-@pytest.mark.gpu
 def test_stream_gpu_many_frames_in_flight(gpu_decoder):
     """8 frame contexts, 32 threads, decoders opened again and again (slot recycling), device jobs of several frames
     overlapping on their own streams"""
