@@ -74,7 +74,7 @@ def _collect(outdir, world, n):
 
 
 @pytest.mark.emu
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_ranks_shard_a_dependent_gop(tmp_path, world):
     port = 29500 + (os.getpid() + world * 7) % 2000
     mp.spawn(_worker_emu, args=(world, port, str(tmp_path)), nprocs=world, join=True)
