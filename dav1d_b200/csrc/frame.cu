@@ -125,6 +125,7 @@ int b200_frame_run_band_phase(const B200FrameJob *j, const B200FrameBand *b, int
     const bool first = b->y0 == 0;
     // intra records form a dependency graph over the whole frame: they run with a band only when that band IS the frame
     if (j->n_intra > 0 && !(first && b->last)) { b200_set_error("b200_frame_run_band: intra records are not band-sliced (one band, or b200_frame_run)"); return -2; }
+    if (j->run_resize) { b200_set_error("b200_frame_run_band: the super-resolution stage is not band-sliced (b200_frame_run)"); return -2; }
     // (the grain LUTs belong to the post phase: its stream forks the preparation beside the first band and joins it before
     // the last band's application)
 #ifndef B200_EMU
