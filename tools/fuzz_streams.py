@@ -5,7 +5,7 @@ motion modes, global motion, segmentation, hidden / intra-only frames, changing 
 random thread counts / frames in flight through integration/_ref/libdav1d_b200.so bound to the host-emulator build of the CUDA
 sources, and through oracle/_ref (stock dav1d); every output picture must be byte-identical. Streams the stock decoder rejects
 (random payloads are not always legal, e.g. 4:2:2 or intra block copy) are skipped.
-usage: tools/fuzz_streams.py [n_streams] [first_seed]"""
+usage: tools/fuzz_streams.py [n_streams] [first_seed] [big]      (big: frames up to 1000x560 instead of 420x290)"""
 import importlib.util
 import os
 import sys
@@ -20,13 +20,16 @@ from dav1d_b200 import obu, stream   # noqa: E402
 import test_stream as TS         # noqa: E402
 
 
+BIG = len(sys.argv) > 3 and sys.argv[3] == "big"
+
+
 def draw(seed):
     rng = np.random.default_rng(seed)
     inter = rng.random() < 0.65
     layout = str(rng.choice(["420", "420", "420", "444", "400", "422"]))
     small = layout == "422"
-    w = int(rng.integers(8, 18 if small else 52)) * 8 + int(rng.choice([0, 0, 2, 6]))
-    h = int(rng.integers(8, 18 if small else 36)) * 8 + int(rng.choice([0, 0, 4]))
+    w = int(rng.integers(8, 18 if small else 125 if BIG else 52)) * 8 + int(rng.choice([0, 0, 2, 6]))
+    h = int(rng.integers(8, 18 if small else 70 if BIG else 36)) * 8 + int(rng.choice([0, 0, 4]))
     kw = dict(bpc=int(rng.choice([8, 10, 12])), sb128=int(rng.integers(0, 2)), log2_cols=int(rng.integers(0, 3)), log2_rows=int(rng.integers(0, 2)),
               film_grain=int(rng.integers(0, 2)), layout=layout)
     sc = int(rng.random() < 0.3)
