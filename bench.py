@@ -271,6 +271,11 @@ OURS = dict(compact=True, fused=bool(int(os.environ.get("B200_FUSED", "0"))))   
 
 
 # ------------------------------------------------------------------------------ reference arm / cpu baseline
+def cpu_reps(S, n_threads, target_s=20.0):
+    """frames per thread so that the CPU sample is ~target_s of CPU work (the C path does ~27 Mpixels/s per thread)"""
+    return max(1, int(round(target_s / (n_threads * S["W"] * S["H"] / 27e6))))
+
+
 def cpu_frames(S, n_threads, reps, use_ref=True):
     """`n_threads` frames in parallel, one per thread (frame threading), each through the reference's own
     functions (oracle/refdriver refdrv_frame_run) or, when oracle/_ref is absent, the oracle port."""
@@ -630,9 +635,10 @@ def run_ours_frame(args):
                  "postfilter": {"ms": post_ms, "Mpixels/s": px_per_step / (post_ms * 1e-3) / 1e6,
                                 "GBps": sum(alg[run_keys[k]] for k in stage_ms if k in ("deblock", "cdef", "lr", "fg")) / (post_ms * 1e-3) / 1e9}}
         nthr = min(host_threads()[0], 32)
-        v, dt, kind = cpu_frames(Ss[0], nthr, 1)
+        cr = cpu_reps(Ss[0], nthr)
+        v, dt, kind = cpu_frames(Ss[0], nthr, cr)
         cpu = {"value": v, "unit": "Mpixels/s", "cores": nthr, "kind": kind,
-               "sample": "%d whole frames of this workload, one per thread (frame threading), dav1d C path HAVE_ASM=0 (no nasm in image), %.1f s" % (nthr, dt)}
+               "sample": "%d whole frames of this workload, %d per thread on %d threads (frame threading), dav1d C path HAVE_ASM=0 (no nasm in image), %.1f s wall, ~%.0f s of CPU work" % (nthr * cr, cr, nthr, dt, dt * nthr)}
         line = {"metric": "Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": FRAME_WORKLOADS[args.workload]["dtype"], "data": "synthetic",
@@ -839,9 +845,10 @@ def run_ours_gop(args):
         if world == 1:
             nthr, thr_info = host_threads()
             nthr = min(nthr, 32)
-            v, dt, kind = cpu_frames(Ss[0], nthr, 1)
+            cr = cpu_reps(Ss[0], nthr)
+            v, dt, kind = cpu_frames(Ss[0], nthr, cr)
             cpu = {"value": v, "unit": "Mpixels/s", "cores": nthr, "kind": kind, "host": thr_info,
-                   "sample": "%d whole frames of this workload, one per thread (frame threading), dav1d C path HAVE_ASM=0 (no nasm in image), %.1f s" % (nthr, dt)}
+                   "sample": "%d whole frames of this workload, %d per thread on %d threads (frame threading), dav1d C path HAVE_ASM=0 (no nasm in image), %.1f s wall, ~%.0f s of CPU work" % (nthr * cr, cr, nthr, dt, dt * nthr)}
         line = {"metric": "Mpixels/s", "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
