@@ -374,6 +374,17 @@ STREAM_WORKLOADS = {
     "stream4k8_inter": dict(W=3840, H=2160, bpc=8, frames=8, log2_cols=2, log2_rows=2, inter=1,
                             desc="AV1 elementary stream, 1 key frame + 7 inter frames 3840x2160 8-bit 4:2:0, 4x4 tiles, all inter tools of "
                                  "stream1080p8_inter, decoded through dav1d's public API (host front end = unmodified dav1d, back end = libb200av1)"),
+    # the same streams with statistics closer to encoder-made video: 60 % skipped blocks, half of the coded transform blocks all zero,
+    # short end-of-block positions, 10 % intra blocks (tests/streamgen.py: the reference decoder chooses and range-encodes the symbols)
+    "stream1080p8_sparse": dict(W=1920, H=1080, bpc=8, frames=16, log2_cols=2, log2_rows=1, inter=1,
+                                gen=dict(p_skip=0.6, p_txskip=0.5, eob_draws=4, p_intra=0.1),
+                                desc="AV1 elementary stream, 1 key frame + 15 inter frames 1920x1080 8-bit 4:2:0, 4x2 tiles, every tool of "
+                                     "stream1080p8_inter, symbols chosen by the stream generator (60 % skipped blocks, 50 % all-zero transform "
+                                     "blocks, short end-of-block positions, 10 % intra blocks) instead of a random payload; decoded through dav1d's public API"),
+    "stream4k8_sparse": dict(W=3840, H=2160, bpc=8, frames=8, log2_cols=2, log2_rows=2, inter=1,
+                             gen=dict(p_skip=0.6, p_txskip=0.5, eob_draws=4, p_intra=0.1),
+                             desc="AV1 elementary stream, 1 key frame + 7 inter frames 3840x2160 8-bit 4:2:0, 4x4 tiles, the statistics of "
+                                  "stream1080p8_sparse; decoded through dav1d's public API"),
     "stream4k10": dict(W=3840, H=2160, bpc=10, frames=6, log2_cols=2, log2_rows=2, inter=1, film_grain=1,
                        desc="AV1 elementary stream, 1 key frame + 5 inter frames 3840x2160 10-bit 4:2:0, 4x4 tiles, all inter tools of "
                             "stream1080p8_inter plus film grain on every frame (the full pipeline of BASELINE configs[3]) decoded through "
@@ -393,7 +404,13 @@ def run_stream(args):
     mfd = min(8, W["frames"], nthr)
     gen = (lambda *a, **k: obu.inter_stream(*a, motion_modes=2, **k)) if W.get("inter") else obu.intra_stream
     fg = int(W.get("film_grain", 0))
-    tus = gen(100 + rank, W["W"], W["H"], n_frames=W["frames"], bpc=W["bpc"], log2_cols=W["log2_cols"], log2_rows=W["log2_rows"], film_grain=fg)
+    build = lambda: gen(100 + rank, W["W"], W["H"], n_frames=W["frames"], bpc=W["bpc"], log2_cols=W["log2_cols"], log2_rows=W["log2_rows"], film_grain=fg)
+    if W.get("gen"):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import streamgen                 # workload synthesis only (test infrastructure): the generator is not on any measured path
+        tus = streamgen.generate(build, seed=100 + rank, check=False, **W["gen"])[0]
+    else:
+        tus = build()
     px = W["W"] * W["H"] * W["frames"]
     stream.decode_stream.capacity = (W["W"] * W["H"] * 3 // 2) * (2 if W["bpc"] > 8 else 1) * W["frames"] + (1 << 20)
     steps = min(args.steps, 10)

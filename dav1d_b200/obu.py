@@ -220,6 +220,11 @@ def _frame_common(b, rng, w, h, sb128, log2_cols, log2_rows, q, lf, cdef, restor
     return cols, rows, tile_w, tile_h, sbw, sbh
 
 
+# stream generator (tests/streamgen.py): an iterator of tile payloads that replace the random ones (the random bytes are
+# still drawn, so that every later header choice is the same as in the run that produced the payloads)
+PAYLOADS = None
+
+
 def _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_bytes_per_sb64):
     b.align()
     n_tiles = cols * rows
@@ -232,8 +237,10 @@ def _tile_group(b, rng, cols, rows, tile_w, tile_h, sbw, sbh, sb128, payload_byt
         nsb = (min(sbw, (tc + 1) * tile_w) - tc * tile_w) * (min(sbh, (tr + 1) * tile_h) - tr * tile_h)
         n = max(64, (payload_bytes_per_sb64 << (2 * sb128)) * nsb)   # the symbol decoder must never run dry (src/decode.c:2743)
         data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        if PAYLOADS is not None:
+            data = next(PAYLOADS)
         if t < n_tiles - 1:
-            out += int(n - 1).to_bytes(4, "little")
+            out += int(len(data) - 1).to_bytes(4, "little")
         out += data
     return bytes(out)
 

@@ -371,8 +371,8 @@ HookFrame *b200hook_frame(const void *key)
     static __thread unsigned tl_epoch;
     if (tl_key == key && tl_slot && tl_epoch == __atomic_load_n(&g_epoch, __ATOMIC_ACQUIRE) &&
         __atomic_load_n(&tl_slot->key, __ATOMIC_ACQUIRE) == key) {
-        __atomic_store_n(&tl_slot->last_use, __atomic_load_n(&g_clock, __ATOMIC_RELAXED), __ATOMIC_RELAXED);
-        return tl_slot;
+        return tl_slot;       /* no write here (it would be one store per block and thread to a line all tile threads read): a slot
+                                 somebody caches (`users`) is never taken over, its LRU stamp is refreshed by the slow path */
     }
     pthread_once(&g_tls_once, tls_init);
     HookFrame *r = NULL, *lru = NULL;

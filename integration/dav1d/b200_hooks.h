@@ -55,10 +55,9 @@ typedef struct HookTile { HookList l[B200L_COUNT]; } HookTile;
 typedef struct HookFrame {
     const void *key;               /* the Dav1dFrameContext this slot serves */
     pthread_mutex_t lock;
-    int n_tx, cap_tx;              /* B200IntraTx records emitted so far (tx.host); slots are taken atomically */
-    size_t n_coef, cap_coef;       /* coefficients staged so far (coef.host), in elements; taken atomically */
+    int cap_tx;                    /* capacity of tx.host in B200IntraTx records (n_tx below: slots are taken atomically) */
+    size_t cap_coef;               /* capacity of coef.host in elements (n_coef below) */
     int tile_sbrows_done;          /* completed pass-2 tile superblock rows of the current frame */
-    int unsupported;               /* a block used a tool the emitters do not translate yet */
     HookBuf tx, tx_sorted, coef, mask, level, lr_mask, pic[3], scratch;
     /* inter frames: prediction / compound / transform records (B200McBlock, B200CompBlock x 2 stages, B200ItxBlock
      * per transform size), the int16 scratch of the compound predictions (device only), the mask buffer (dav1d's
@@ -66,7 +65,7 @@ typedef struct HookFrame {
      * (cells of inter blocks are "done" before it starts) */
     HookBuf pred, comp, comp2, itx[19], tmp16, cmask, done_init;
     HookBuf pal;                             /* palettes + packed index maps of palette blocks (slots taken atomically) */
-    size_t n_pal, cap_pal;
+    size_t cap_pal;
     HookBuf warp, blend, blend2, pxtmp;      /* warped-motion 8x8 blocks; OBMC: blend_h stage, blend_v stage, pixel scratch (device only) */
     HookBuf scaled;                          /* predictions from references of another size (B200McScaledBlock) */
     HookBuf sr[2];                           /* super-resolution: the upscaled deblocked / CDEF pictures loop restoration reads (device only) */
@@ -76,9 +75,7 @@ typedef struct HookFrame {
     int n_tiles, cap_tiles;
     void *sort_scratch;            /* cell map + wave numbers of b200hook_wave_sort, kept across frames */
     size_t sort_scratch_cap;
-    size_t n_tmp16, n_cmask, n_pxtmp;
-    int started, is_inter, n_ii, n_ibc;
-    unsigned refs_used;            /* bit k: some prediction of this frame reads reference k (f->refp[k]) */
+    int started;
     int pinned;                    /* never recycled for another key (the output-stage slots) */
     unsigned epoch;                /* b200hook_release generation the `users` references belong to */
     int users;                     /* threads whose thread-local cache points at this slot (under the table lock): only a slot
@@ -96,6 +93,18 @@ typedef struct HookFrame {
     uint64_t pend_rec, pend_coef, pend_h2d, pend_d2h, pend_kinds[11];
     /* statistics */
     uint64_t frames, records;
+    /* What every tile thread of a frame WRITES while it emits blocks lives on cache lines of its own, away from what the
+     * threads only read per block (key, started, cur_pic, buffer pointers, capacities): with 8 - 16 threads on one frame a
+     * shared line that is written once per block costs more than the emission itself. */
+    int n_tx __attribute__((aligned(64)));             /* B200IntraTx records emitted so far (tx.host) */
+    size_t n_coef __attribute__((aligned(64)));        /* coefficients staged so far (coef.host), in elements */
+    size_t n_pal;                  /* bytes taken in the palette buffer */
+    size_t n_tmp16, n_cmask, n_pxtmp;                  /* scratch offsets handed out to compound / OBMC / mask records */
+    int n_ii, n_ibc;
+    int unsupported;               /* a block used a tool the emitters do not translate (written at most a few times) */
+    int is_inter;
+    unsigned refs_used;            /* bit k: some prediction of this frame reads reference k (f->refp[k]) */
+    char pad_tail[64];
 } HookFrame;
 HookFrame *b200hook_frame(const void *key);
 int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int32_t w4[3], const int32_t h4[3],

@@ -374,7 +374,7 @@ static int bitfn(emit_mc)(HookFrame *const hf, const Dav1dFrameContext *const f,
         r->dx = f->svc[refidx][0].step; r->dy = f->svc[refidx][1].step;
         r->w = bw4 * h_mul; r->h = bh4 * v_mul;
         r->filter2d = filter_2d; r->op = op; r->plane = pl; r->ref = refidx;
-        __atomic_fetch_or(&hf->refs_used, 1u << refidx, __ATOMIC_RELAXED);
+        if (!(__atomic_load_n(&hf->refs_used, __ATOMIC_RELAXED) & (1u << refidx))) __atomic_fetch_or(&hf->refs_used, 1u << refidx, __ATOMIC_RELAXED);      /* written once per reference, not once per block: the line is shared by every tile thread */
         return 0;
     }
     const int mx = mv.x & (15 >> !ss_hor), my = mv.y & (15 >> !ss_ver);
@@ -386,7 +386,7 @@ static int bitfn(emit_mc)(HookFrame *const hf, const Dav1dFrameContext *const f,
     r->w = bw4 * h_mul; r->h = bh4 * v_mul;
     r->mx = mx << !ss_hor; r->my = my << !ss_ver;
     r->filter2d = filter_2d; r->op = op; r->plane = pl; r->ref = refidx;      /* op: 0 put, 1 prep, 2 put into the pixel scratch */
-    __atomic_fetch_or(&hf->refs_used, 1u << refidx, __ATOMIC_RELAXED);
+    if (!(__atomic_load_n(&hf->refs_used, __ATOMIC_RELAXED) & (1u << refidx))) __atomic_fetch_or(&hf->refs_used, 1u << refidx, __ATOMIC_RELAXED);      /* written once per reference, not once per block: the line is shared by every tile thread */
     return 0;
 }
 
@@ -416,7 +416,7 @@ static int bitfn(emit_warp)(HookFrame *const hf, const Dav1dFrameContext *const 
             r->my = (((int)mvy & 0xffff) - wmp->u.p.gamma * 4 - wmp->u.p.delta * 4) & ~0x3f;
             for (int k = 0; k < 4; k++) r->abcd[k] = wmp->u.abcd[k];
             r->tmp_stride = pitch; r->op = op; r->plane = pl; r->ref = refidx;
-            __atomic_fetch_or(&hf->refs_used, 1u << refidx, __ATOMIC_RELAXED);
+            if (!(__atomic_load_n(&hf->refs_used, __ATOMIC_RELAXED) & (1u << refidx))) __atomic_fetch_or(&hf->refs_used, 1u << refidx, __ATOMIC_RELAXED);      /* written once per reference, not once per block: the line is shared by every tile thread */
         }
     }
     return 0;
@@ -616,7 +616,7 @@ int bitfn(b200hook_recon_b_inter)(Dav1dTaskContext *const t, const enum BlockSiz
                 if (bitfn(emit_ibc)(&c, pl, g->off[pl] + uvrel, bw4 << (bw4 == ss_hor), bh4 << (bh4 == ss_ver), bx & ~ss_hor, by & ~ss_ver, b->mv[0])) goto out;
         goto residual;
     }
-    __atomic_store_n(&hf->is_inter, 1, __ATOMIC_RELAXED);
+    if (!__atomic_load_n(&hf->is_inter, __ATOMIC_RELAXED)) __atomic_store_n(&hf->is_inter, 1, __ATOMIC_RELAXED);
     if (b->comp_type == COMP_INTER_NONE) {
         const enum Filter2d filter_2d = b->filter2d;
         const int warp = (b->inter_mode == GLOBALMV && f->gmv_warp_allowed[b->ref[0]]) ||
