@@ -236,19 +236,13 @@ int b200hook_tiles_reset(HookFrame *const hf, const int n_tiles)
         for (int l = 0; l < B200L_COUNT; l++) hf->tiles[t].l[l].n = 0;
     return 0;
 }
-void *b200hook_tile_append(HookFrame *const hf, const int tile, const int list, const size_t elem)
+void *b200hook_tile_grow(HookList *const L, const size_t elem)
 {
-    if ((unsigned)tile >= (unsigned)hf->n_tiles) return NULL;
-    HookList *const L = &hf->tiles[tile].l[list];
-    if (L->n == L->cap) {
-        const int cap = L->cap ? 2 * L->cap : 256;
-        uint8_t *const d = realloc(L->data, (size_t)cap * elem);
-        if (!d) return NULL;
-        L->data = d; L->cap = cap;
-    }
-    void *const p = L->data + (size_t)L->n++ * elem;
-    memset(p, 0, elem);
-    return p;
+    const int cap = L->cap ? 2 * L->cap : 256;
+    uint8_t *const d = realloc(L->data, (size_t)cap * elem);
+    if (!d) return NULL;
+    L->data = d; L->cap = cap;
+    return d;
 }
 int b200hook_tiles_gather(HookFrame *const hf, const int list, HookBuf *const dst, const size_t elem)
 {

@@ -111,8 +111,18 @@ int b200hook_wave_sort(const B200IntraTx *in, B200IntraTx *out, int n, const int
                        int ss_hor, int ss_ver, void **scratch, size_t *scratch_cap);
 void *b200hook_append(HookBuf *b, int *n, size_t elem);
 int b200hook_tiles_reset(HookFrame *hf, int n_tiles);
-void *b200hook_tile_append(HookFrame *hf, int tile, int list, size_t elem);
 int b200hook_tiles_gather(HookFrame *hf, int list, HookBuf *dst, size_t elem);      /* total number of records, < 0 on failure */
+void *b200hook_tile_grow(HookList *L, size_t elem);
+/* one record at the end of a tile's list (zeroed); inline: it is called once or more per block */
+static inline void *b200hook_tile_append(HookFrame *const hf, const int tile, const int list, const size_t elem)
+{
+    if ((unsigned)tile >= (unsigned)hf->n_tiles) return NULL;
+    HookList *const L = &hf->tiles[tile].l[list];
+    if (L->n == L->cap && !b200hook_tile_grow(L, elem)) return NULL;
+    void *const p = L->data + (size_t)L->n++ * elem;
+    __builtin_memset(p, 0, elem);
+    return p;
+}
 
 /* device pictures that outlive their frame context: every decoded picture, keyed by the host picture's data[0]
  * (dav1d recycles a host buffer only when no reference to it is left, so a key is reused only for a dead picture) */
