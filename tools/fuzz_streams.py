@@ -4,7 +4,10 @@ dav1d_b200/obu.py drawn at random: bit depth, layout, superblock size, tiles, fi
 motion modes, global motion, segmentation, hidden / intra-only frames, changing frame sizes, super-resolution), decoded with
 random thread counts / frames in flight through integration/_ref/libdav1d_b200.so bound to the host-emulator build of the CUDA
 sources, and through oracle/_ref (stock dav1d); every output picture must be byte-identical. Streams the stock decoder rejects
-(random payloads are not always legal, e.g. 4:2:2 or intra block copy) are skipped.
+(random payloads are not always legal, e.g. 4:2:2 or intra block copy) are skipped. Every other stream goes through the stream
+generator first (tests/streamgen.py: symbols chosen and range-encoded by the reference decoder itself), with a random policy for
+skipped blocks / sparse coefficients / intra share — and, for 4:2:2, frames of any size, since the generator avoids the
+partitions that are illegal there.
 usage: tools/fuzz_streams.py [n_streams] [first_seed] [big]      (big: frames up to 1000x560 instead of 420x290)"""
 import importlib.util
 import os
@@ -18,6 +21,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import refs                      # noqa: E402
 from dav1d_b200 import obu, stream   # noqa: E402
 import test_stream as TS         # noqa: E402
+import streamgen                 # noqa: E402
 
 
 BIG = len(sys.argv) > 3 and sys.argv[3] == "big"
@@ -27,7 +31,8 @@ def draw(seed):
     rng = np.random.default_rng(seed)
     inter = rng.random() < 0.65
     layout = str(rng.choice(["420", "420", "420", "444", "400", "422"]))
-    small = layout == "422"
+    use_gen = streamgen.have_generator() and rng.random() < 0.5
+    small = layout == "422" and not use_gen
     w = int(rng.integers(8, 18 if small else 125 if BIG else 52)) * 8 + int(rng.choice([0, 0, 2, 6]))
     h = int(rng.integers(8, 18 if small else 70 if BIG else 36)) * 8 + int(rng.choice([0, 0, 4]))
     kw = dict(bpc=int(rng.choice([8, 10, 12])), sb128=int(rng.integers(0, 2)), log2_cols=int(rng.integers(0, 3)), log2_rows=int(rng.integers(0, 2)),
@@ -44,14 +49,14 @@ def draw(seed):
             kw["sizes"] = [(int(rng.choice(ws)), int(rng.choice(hs))) for _ in range(4)]
         elif u < 0.45:
             kw["super_res"] = 1
-        return "inter", w, h, kw
+        return "inter", w, h, kw, use_gen
     kw.update(n_frames=int(rng.integers(1, 4)), screen_content=sc, segmentation=int(rng.integers(0, 2)))
     u = rng.random()
     if sc and u < 0.5:
         kw["intrabc"] = 1
     elif u < 0.7 or not sc and u < 0.4:
         kw["super_res"] = 1
-    return "intra", w, h, kw
+    return "intra", w, h, kw, use_gen
 
 
 def main():
@@ -65,8 +70,19 @@ def main():
     kinds = {}
     t0 = time.time()
     for seed in range(first, first + n):
-        kind, w, h, kw = draw(seed)
-        tus = (obu.inter_stream if kind == "inter" else obu.intra_stream)(seed, w, h, **kw)
+        kind, w, h, kw, use_gen = draw(seed)
+        build = lambda: (obu.inter_stream if kind == "inter" else obu.intra_stream)(seed, w, h, **kw)
+        if use_gen:
+            prng = np.random.default_rng(seed + 13)
+            pol = dict(p_skip=float(prng.choice([-1, 0.3, 0.7, 0.9])), p_intra=float(prng.choice([-1, 0.02, 0.2, 0.6])),
+                       p_txskip=float(prng.choice([-1, 0.5, 0.8])), eob_draws=int(prng.choice([1, 2, 6])))
+            try:
+                tus = streamgen.generate(build, seed=seed, check=False, apply_grain=1, layout422=kw["layout"] == "422", tries=6, **pol)[0]
+            except RuntimeError:
+                skipped += 1
+                continue
+        else:
+            tus = build()
         r0, i0, o0 = TS._ref_decode(tus, apply_grain=1)
         if r0 <= 0:
             skipped += 1
@@ -81,6 +97,7 @@ def main():
                 kinds[k] = kinds.get(k, 0) + int(st[k] > 0)
             for k in ("super_res", "sizes"):
                 kinds[k] = kinds.get(k, 0) + int(k in kw)
+            kinds["generated"] = kinds.get("generated", 0) + int(use_gen)
             kinds[kw["layout"]] = kinds.get(kw["layout"], 0) + 1
         else:
             bad += 1
