@@ -47,3 +47,14 @@ def test_scaled_references_and_super_resolution_gpu(gpu_decoder):
     assert n_scaled > 100
 
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["gen_422_10bit_all_tools", "gen_sparse_8bit", "inter_444_12bit"])
+def test_golden_streams_round2_gpu_md5(gpu_decoder, name):
+    """generator-made golden streams (4:2:2 at a real frame size with every inter tool and film grain; encoder-like sparse
+    statistics) and the 4:4:4 12-bit one: the committed md5 of stock dav1d's output, no reference / oracle needed on the box"""
+    from test_stream import _golden, _md5
+    tus, want = _golden()[name]
+    assert _md5(gpu_decoder.decode(tus, apply_grain=1)) == (want["md5"], want["frames"])
+    gpu_decoder.stats(reset=True)
