@@ -147,7 +147,8 @@ def band_plan(S, band_rows, compact=False, fused=False):
         from . import synth
         cc, ex = synth.compact_coefs(S2)
         # compact_coefs emits its records size class after size class, each in the (band-sorted) order of S2["itx"][tx]
-        eb = np.concatenate([np.repeat(np.arange(nb), itx_ranges[tx][1]) for tx in range(19) if len(S2["itx"][tx])]) if len(ex) else np.zeros(0, np.int64)
+        per_tx = [np.repeat(np.arange(nb), itx_ranges[tx][1]) for tx in range(19) if len(S2["itx"][tx])]       # empty: every inter block skipped
+        eb = np.concatenate(per_tx) if per_tx else np.zeros(0, np.int64)
         # ... followed by the intra records' blocks (mixed frames: a single band only, see b200_frame_run_band)
         assert len(eb) == len(ex) or (nb == 1 and len(eb) < len(ex))
         eb = np.concatenate([eb, np.zeros(len(ex) - len(eb), np.int64)]).astype(np.int64)

@@ -250,6 +250,19 @@ def test_emu_motion_mode_frame(bpc, W, H, p_intra):
 
 
 @pytest.mark.emu
+def test_emu_mixed_frame_whose_inter_blocks_are_all_skipped():
+    """found by tools/fuzz_frames.py: no inter transform block at all, coefficients only in the intra blocks — the band plan of the
+    whole-frame band (compact upload) used to fail on the empty list"""
+    S = synth.make_inter_frame(np.random.default_rng(702), 8, 200, 136, p_skip=0.2, p_intra=0.3)
+    S["itx"] = {t: a[:0] for t, a in S["itx"].items()}          # as if every inter block had been skipped
+    assert (S["intra_tx"]["eob"] >= 0).sum() > 10
+    exp = oracle_frame(S)
+    fb = frame.FrameBuffers(S, lib=refs.emu_lib(), alloc=frame.NumpyAlloc(), band_rows=192, compact=True)
+    fb.run_bands()
+    check_frame(S, fb, exp)
+
+
+@pytest.mark.emu
 def test_emu_motion_mode_frame_bands():
     """OBMC and warp records sorted into 64-row bands (inter-intra needs the intra machine: whole-frame band only)"""
     S = synth.make_inter_frame(np.random.default_rng(681), 8, 264, 328, p_obmc=0.25, p_warp=0.2)
