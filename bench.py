@@ -720,6 +720,8 @@ def run_ours_gop(args):
     # reconstruction and post filters + 2 bands of work), not by GPU time: measured at N=4 (profiles/r02_bench_n4_*): 4K
     # 0.369 / 0.282 / 0.315 ms per frame with 128 / 192 / 320-row bands, 8K 0.686 / 0.606 with 128 / 192, 0.558 with 320 (N=8)
     default_rows = whole if world == 1 else -(-H // n_bands) if world < 4 else (192 if H <= 2160 else 320)
+    if wl.get("p_intra") or wl.get("p_ii"):
+        default_rows = whole             # intra-machine records form a dependency graph over the frame: such frames are not cut into bands
     band_rows = int(os.environ.get("B200_BAND_ROWS", str(default_rows)))
     band_rows = min(whole, max(64, -(-band_rows // 64) * 64))
     n_streams = max(1, int(os.environ.get("B200_FRAMES_IN_FLIGHT", "1" if world == 1 else "2")))
