@@ -93,6 +93,35 @@ def test_ranks_shard_a_dependent_gop(tmp_path, world):
     assert not np.array_equal(lone.output(), got[1])
 
 
+def _mixed_frames():
+    from dav1d_b200 import synth
+    return [synth.make_inter_frame(np.random.default_rng(40 + k), 8, 200, 136, p_intra=0.15, p_obmc=0.2, p_warp=0.1, p_ii=0.1) for k in range(6)]
+
+
+def _worker_emu_mixed(rank, world, port, outdir):
+    sys.path.insert(0, os.path.dirname(__file__))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pics = _decode_emu(rank, world, _mixed_frames(), band_rows=192)          # 136 rows: the band is the whole frame
+        np.savez(os.path.join(outdir, "r%d.npz" % rank), **{str(k): v for k, v in pics.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.emu
+def test_ranks_shard_mixed_frames_as_one_band(tmp_path):
+    """frames with intra-machine records (intra blocks, inter-intra) and OBMC / warps over two ranks: such frames are not cut
+    into bands (the band is the frame), the exchange and the dependency rule are the same"""
+    port = 29500 + (os.getpid() + 31) % 2000
+    mp.spawn(_worker_emu_mixed, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    exp = oracle_gop(_mixed_frames())
+    got = _collect(str(tmp_path), 2, 6)
+    for k, (a, b) in enumerate(zip(exp, got)):
+        assert np.array_equal(a, b), "frame %d" % k
+
+
 @pytest.mark.emu
 def test_single_rank_pipeline_two_band_sizes():
     """world = 1: the band pipeline is just a chained decode; 64- and 128-row bands agree with the oracle"""
