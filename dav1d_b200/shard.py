@@ -196,7 +196,10 @@ class GopPipeline:
         self.n_total = n_total          # frames in the group of pictures (None: endless stream): later frames do not exist as consumers
         self.lib, self.rank, self.world, self.sets, self.x, self.n_refs = lib, rank, world, sets, exchange, n_refs
         self.n_sets = len(sets)
-        assert self.n_sets * world > n_refs, "a set would be overwritten while later frames still predict from it"
+        # sets are reused round-robin in an endless stream: a set must not be overwritten while later frames still predict from
+        # it; a finite group of pictures that keeps every owned frame in a set of its own (decode_gop) never reuses one
+        reused = n_total is None or len(range(rank, n_total, world)) > self.n_sets
+        assert not reused or self.n_sets * world > n_refs, "a set would be overwritten while later frames still predict from it"
         fb = sets[0]
         self.S = fb.S
         self.nb = fb.n_bands()
