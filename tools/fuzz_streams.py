@@ -8,7 +8,10 @@ sources, and through oracle/_ref (stock dav1d); every output picture must be byt
 generator first (tests/streamgen.py: symbols chosen and range-encoded by the reference decoder itself), with a random policy for
 skipped blocks / sparse coefficients / intra share — and, for 4:2:2, frames of any size, since the generator avoids the
 partitions that are illegal there.
-usage: tools/fuzz_streams.py [n_streams] [first_seed] [big]      (big: frames up to 1000x560 instead of 420x290)"""
+usage: tools/fuzz_streams.py [n_streams] [first_seed] [big | level1]
+   big: frames up to 1000x560 instead of 420x290;  level1: small frames through integration/_ref/libdav1d_b200_l1.so instead — dav1d's
+   own reconstruction code on the B200 function tables (every Dav1dDSPContext slot incl. mc_scaled / resize / emu_edge / warp / blend),
+   one emulated kernel launch per DSP call"""
 import importlib.util
 import os
 import sys
@@ -25,6 +28,7 @@ import streamgen                 # noqa: E402
 
 
 BIG = len(sys.argv) > 3 and sys.argv[3] == "big"
+LEVEL1 = len(sys.argv) > 3 and sys.argv[3] == "level1"
 
 
 def draw(seed):
@@ -33,8 +37,8 @@ def draw(seed):
     layout = str(rng.choice(["420", "420", "420", "444", "400", "422"]))
     use_gen = streamgen.have_generator() and rng.random() < 0.5
     small = layout == "422" and not use_gen
-    w = int(rng.integers(8, 18 if small else 125 if BIG else 52)) * 8 + int(rng.choice([0, 0, 2, 6]))
-    h = int(rng.integers(8, 18 if small else 70 if BIG else 36)) * 8 + int(rng.choice([0, 0, 4]))
+    w = int(rng.integers(8, 18 if small or LEVEL1 else 125 if BIG else 52)) * 8 + int(rng.choice([0, 0, 2, 6]))
+    h = int(rng.integers(8, 14 if LEVEL1 else 18 if small else 70 if BIG else 36)) * 8 + int(rng.choice([0, 0, 4]))
     kw = dict(bpc=int(rng.choice([8, 10, 12])), sb128=int(rng.integers(0, 2)), log2_cols=int(rng.integers(0, 3)), log2_rows=int(rng.integers(0, 2)),
               film_grain=int(rng.integers(0, 2)), layout=layout)
     sc = int(rng.random() < 0.3)
@@ -65,7 +69,7 @@ def main():
     refs.emu_lib()
     spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "emu", "build_emu.py"))
     m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
-    dec = stream.HookedDecoder(backend=m.build(), serialize=True)
+    dec = stream.Level1Decoder(backend=m.build()) if LEVEL1 else stream.HookedDecoder(backend=m.build(), serialize=True)
     ok = skipped = bad = 0
     kinds = {}
     t0 = time.time()
@@ -89,8 +93,12 @@ def main():
             continue
         rng = np.random.default_rng(seed + 7)
         thr = int(rng.choice([1, 2, 3, 4, 8, 16])); mfd = int(rng.choice([1, 2, 4, 8]))
-        r1, i1, o1 = dec.decode(tus, apply_grain=1, n_threads=thr, max_frame_delay=mfd)
-        st = dec.stats(reset=True)
+        if LEVEL1:
+            r1, i1, o1 = dec.decode(tus, apply_grain=1)
+            st = dict(ibc=0, scaled="sizes" in kw or ("super_res" in kw and kind == "inter"), interintra=0, warp=0, blend=0, palette_bytes=0)
+        else:
+            r1, i1, o1 = dec.decode(tus, apply_grain=1, n_threads=thr, max_frame_delay=mfd)
+            st = dec.stats(reset=True)
         if r1 == r0 and np.array_equal(i0, i1) and np.array_equal(o0, o1):
             ok += 1
             for k in ("ibc", "scaled", "interintra", "warp", "blend", "palette_bytes"):
@@ -102,6 +110,8 @@ def main():
         else:
             bad += 1
             print("MISMATCH seed %d: %s %dx%d %r threads %d delay %d -> stock %d frames, hooked %d" % (seed, kind, w, h, kw, thr, mfd, r0, r1), flush=True)
+    if LEVEL1:
+        print("level 1: %d emulated kernel launches behind the DSP tables; slots (left on C, replaced) = %r" % (int(refs.emu_lib().b200_launch_count()), dec.c_slots_left()))
     print("fuzz: %d streams identical, %d rejected by stock dav1d (skipped), %d MISMATCHES in %.0f s; streams with: %s"
           % (ok, skipped, bad, time.time() - t0, ", ".join("%s %d" % kv for kv in sorted(kinds.items()))))
     return 1 if bad else 0
